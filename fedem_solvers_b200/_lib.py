@@ -1,0 +1,90 @@
+"""ctypes binding of libfedem_b200.so (the C ABI declared in include/fedem_b200.h).
+
+The library is the product; nothing here computes.  Loading fails loudly when the CUDA
+extension has not been built -- there is deliberately no CPU fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class FsrError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libfedem_b200.so")
+
+
+class FsrSam(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nnod", "nel", "ndof", "ndof1", "ndof2", "ngen", "neq", "nceq",
+                                        "nmmnpc", "nmmceq")] + [
+        ("madof", C.POINTER(C.c_int)), ("msc", C.POINTER(C.c_int)), ("mpmnpc", C.POINTER(C.c_int)),
+        ("mmnpc", C.POINTER(C.c_int)), ("melcon", C.POINTER(C.c_int)), ("mpmceq", C.POINTER(C.c_int)),
+        ("mmceq", C.POINTER(C.c_int)), ("ttcc", C.POINTER(C.c_double)), ("meqn", C.POINTER(C.c_int)),
+        ("meqn1", C.POINTER(C.c_int)), ("meqn2", C.POINTER(C.c_int))]
+
+
+class FsrElmData(C.Structure):
+    _fields_ = [("xyz", C.POINTER(C.c_double)), ("emod", C.POINTER(C.c_double)),
+                ("rny", C.POINTER(C.c_double)), ("thk", C.POINTER(C.c_double)),
+                ("elmid", C.POINTER(C.c_int)), ("beam", C.POINTER(C.c_double))]
+
+
+class FsrOptions(C.Structure):
+    _fields_ = [("device", C.c_int), ("stressForm", C.c_int), ("step_tile", C.c_int),
+                ("reserved", C.c_int * 5)]
+
+
+# every symbol include/fedem_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int)
+SYMBOLS = [
+    ("fsr_part_create", C.c_int, [C.POINTER(_P), C.POINTER(FsrSam), C.POINTER(FsrElmData), C.POINTER(FsrOptions)]),
+    ("fsr_set_recovery", C.c_int, [_P, _D, C.c_int, _D, C.c_int]),
+    ("fsr_part_destroy", None, [_P]),
+    ("fsr_num_result_points", C.c_int, [_P]),
+    ("fsr_result_point_offsets", C.c_int, [_P, _I]),
+    ("fsr_ndim", C.c_int, [_P]),
+    ("fsr_recover", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
+    ("fsr_recover_dev", C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    ("fsr_reset_envelope", C.c_int, [_P]),
+    ("fsr_get_envelope", C.c_int, [_P, _D, _D]),
+    ("fsr_envelope_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    ("fsr_recover_step_full", C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
+    ("fsr_expand", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
+    ("fsr_fatigue", C.c_int, [C.c_int, _D, C.c_int, C.c_int, C.c_double, _D, C.c_double, C.c_int, _D, _I, _I]),
+    ("fsr_fatigue_dev", C.c_int, [C.c_int, _P, C.c_size_t, C.c_int, C.c_int, C.c_double, _D, C.c_double,
+                                  C.c_int, _P, _P, _P, _P]),
+    ("fsr_last_error", C.c_char_p, []),
+    ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
+    ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),
+]
+
+
+def load_library():
+    """Loads libfedem_b200.so and declares all prototypes.  Raises FsrError if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise FsrError(f"{path} not found: build the CUDA extension first (./build.sh or "
+                       "__graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    """Raises on fatal (<0) return codes; returns the warning count otherwise."""
+    if rc < 0:
+        msg = load_library().fsr_last_error().decode(errors="replace")
+        raise FsrError(f"{what} failed (code {rc}): {msg}")
+    return rc

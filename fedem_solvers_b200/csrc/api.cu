@@ -1,0 +1,387 @@
+// api.cu -- the extern "C" boundary of libfedem_b200.so (see include/fedem_b200.h) and the host
+// orchestration of the step-tiled pipeline:  pack Q -> K1 (DMMA expansion) -> K2 (element
+// kernels with fused envelope) per tile of steps.
+#include <cstdarg>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace fsr {
+
+static thread_local char g_err[1024] = "";
+long long g_launches = 0;
+
+void set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int nstrp_of(int type)
+{
+  switch (type) {
+    case 21: case 23: return 6;
+    case 22: case 24: return 8;
+    case 41: return 10;
+    default: return 0;  // beams (11) carry section forces only: nstrp = 0 (elStressModule.f90:161-164)
+  }
+}
+
+static bool supported_type(int type) { return type == 24 || type == 23 || type == 41 || type == 11; }
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static void free_family(FamilyData& f)
+{
+  cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed);
+  cudaFree(f.aux);
+  f = FamilyData();
+}
+
+static int ensure_batch_buffers(fsr_part* p, bool need_vm_tile)
+{
+  if (!p->Qt) FSR_CUDA(cudaMalloc(&p->Qt, sizeof(double) * (size_t)p->step_tile * p->ldk));
+  if (!p->U) FSR_CUDA(cudaMalloc(&p->U, sizeof(double) * (size_t)p->nrows_pad * p->step_tile));
+  if (need_vm_tile && !p->vm_tile && p->npts > 0)
+    FSR_CUDA(cudaMalloc(&p->vm_tile, sizeof(double) * (size_t)p->step_tile * p->npts));
+  return FSR_OK;
+}
+
+static int choose_step_tile(fsr_part* p, int requested)
+{
+  if (requested > 0) return round_up(requested, 64);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 512;
+  // per step: U row slice + vm staging; keep half of the free memory for everything else
+  double per_step = 8.0 * ((double)p->nrows_pad + (double)p->npts + p->ldk);
+  long long t = (long long)(0.5 * (double)free_b / per_step);
+  if (t > 1024) t = 1024;
+  if (t < 64) t = 64;
+  return (int)(t / 64 * 64);
+}
+
+}  // namespace fsr
+
+using namespace fsr;
+
+extern "C" {
+
+const char* fsr_last_error(void) { return g_err; }
+
+long long fsr_kernel_launches(int reset)
+{
+  long long n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+int fsr_part_create(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, const fsr_options* opt)
+{
+  if (!out || !sam || !elm) { set_error("fsr_part_create: null argument"); return FSR_ERR_ARG; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    set_error("no CUDA device available: this library has no CPU fallback");
+    return FSR_ERR_CUDA;
+  }
+  int dev = opt ? opt->device : 0;
+  if (dev < 0 || dev >= ndev) { set_error("device %d out of range (0..%d)", dev, ndev - 1); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  FSR_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    return FSR_ERR_CUDA;
+  }
+  if (sam->nnod < 1 || sam->nel < 0 || sam->ndof < 1 || !sam->madof || !sam->mpmnpc || !sam->mmnpc ||
+      !sam->melcon || !sam->meqn || !sam->msc || !elm->xyz || !elm->emod || !elm->rny || !elm->thk) {
+    set_error("fsr_part_create: incomplete SAM / element data");
+    return FSR_ERR_ARG;
+  }
+  if (sam->nceq > 0 && (!sam->mpmceq || !sam->mmceq || !sam->ttcc)) {
+    set_error("fsr_part_create: nceq > 0 but constraint arrays missing");
+    return FSR_ERR_ARG;
+  }
+
+  fsr_part* p = new fsr_part();
+  p->device = dev;
+  p->nnod = sam->nnod; p->nel = sam->nel; p->ndof = sam->ndof; p->ndof1 = sam->ndof1;
+  p->ndof2 = sam->ndof2; p->ngen = sam->ngen; p->neq = sam->neq; p->nceq = sam->nceq;
+  p->ndim = sam->ndof2 + sam->ngen;
+  p->stressForm = opt ? opt->stressForm : 0;
+  // ldk: multiple of 4 with ldk % 8 == 4 (bank-conflict-free fragment loads in K1)
+  p->ldk = round_up(std::max(p->ndim, 1), 4);
+  if (p->ldk % 8 == 0) p->ldk += 4;
+  p->nrows_pad = round_up(p->ndof, 128);
+
+  // result point offsets in SAM (processing) order, stressRoutines.f90:169-331
+  p->ptoff_host.assign((size_t)sam->nel + 1, 0);
+  p->melcon_host.assign(sam->melcon, sam->melcon + sam->nel);
+  p->sam_keep.keep(sam);
+  int n = 0, nskipped = 0;
+  for (int e = 0; e < sam->nel; ++e) {
+    p->ptoff_host[e] = n;
+    if (elm->elmid && elm->elmid[e] < 1) continue;
+    if (!supported_type(sam->melcon[e])) { ++nskipped; continue; }
+    n += nstrp_of(sam->melcon[e]);
+  }
+  p->ptoff_host[sam->nel] = n;
+  p->npts = n;
+  (void)nskipped;
+
+  int rc = FSR_OK;
+  auto fail = [&](int code) { fsr_part_destroy(p); return code; };
+  if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(FSR_ERR_CUDA); }
+  for (int i = 0; i < 4; ++i)
+    if (cudaEventCreate(&p->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail(FSR_ERR_CUDA); }
+
+  auto up = [&](double** dst, const double* src, size_t cnt) -> int {
+    FSR_CUDA(cudaMalloc(dst, sizeof(double) * std::max<size_t>(cnt, 1)));
+    FSR_CUDA(cudaMemcpyAsync(*dst, src, sizeof(double) * cnt, cudaMemcpyHostToDevice, p->stream));
+    return FSR_OK;
+  };
+  if ((rc = up(&p->xyz, elm->xyz, (size_t)3 * sam->nnod))) return fail(rc);
+  if ((rc = up(&p->emod, elm->emod, (size_t)sam->nel))) return fail(rc);
+  if ((rc = up(&p->rny, elm->rny, (size_t)sam->nel))) return fail(rc);
+  if ((rc = up(&p->thk, elm->thk, (size_t)sam->nel))) return fail(rc);
+
+  if (cudaMalloc(&p->R, sizeof(double) * (size_t)p->nrows_pad * p->ldk) != cudaSuccess ||
+      cudaMalloc(&p->env_max, sizeof(double) * std::max(p->npts, 1)) != cudaSuccess ||
+      cudaMalloc(&p->env_min, sizeof(double) * std::max(p->npts, 1)) != cudaSuccess) {
+    set_error("device allocation failed (R: %zu bytes)", sizeof(double) * (size_t)p->nrows_pad * p->ldk);
+    return fail(FSR_ERR_ALLOC);
+  }
+  if ((rc = build_shell_operators(p, sam, elm))) return fail(rc);
+  if ((rc = build_solid_operators(p, sam, elm))) return fail(rc);
+  if ((rc = build_beam_operators(p, sam, elm))) return fail(rc);
+  if ((rc = fsr_reset_envelope(p))) return fail(rc);
+
+  // count failed elements (they get hugeVal results, the run continues)
+  p->nfailed = 0;
+  for (int f = 0; f < FAM_COUNT; ++f) {
+    FamilyData& fd = p->fam[f];
+    if (fd.nelt == 0) continue;
+    std::vector<unsigned char> h(fd.nelt);
+    if (cudaMemcpy(h.data(), fd.failed, fd.nelt, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy of element status failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(FSR_ERR_CUDA); }
+    for (unsigned char c : h) p->nfailed += c ? 1 : 0;
+  }
+  p->step_tile = choose_step_tile(p, opt ? opt->step_tile : 0);
+  *out = p;
+  return p->nfailed;
+}
+
+void fsr_part_destroy(fsr_part* p)
+{
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  cudaFree(p->xyz); cudaFree(p->emod); cudaFree(p->rny); cudaFree(p->thk);
+  cudaFree(p->R); cudaFree(p->Qt); cudaFree(p->U); cudaFree(p->vm_tile); cudaFree(p->Qstage);
+  cudaFree(p->env_max); cudaFree(p->env_min);
+  for (int f = 0; f < FAM_COUNT; ++f) free_family(p->fam[f]);
+  if (p->pinned) cudaFreeHost(p->pinned);
+  for (int i = 0; i < 4; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int fsr_set_recovery(fsr_part* p, const double* B, int ldB, const double* E, int ldE)
+{
+  if (!p) { set_error("fsr_set_recovery: null handle"); return FSR_ERR_ARG; }
+  if (p->ndof1 > 0 && p->ndof2 > 0 && (!B || ldB < p->ndof1)) { set_error("fsr_set_recovery: bad B / ldB"); return FSR_ERR_ARG; }
+  if (p->ndof1 > 0 && p->ngen > 0 && (!E || ldE < p->ndof1)) { set_error("fsr_set_recovery: bad E / ldE"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  if (!p->sam_keep.valid) { set_error("fsr_set_recovery: SAM maps missing"); return FSR_ERR_STATE; }
+  fsr_sam sam = p->sam_keep.view();
+  return build_row_operator(p, &sam, B, ldB, E, ldE);
+}
+
+int fsr_num_result_points(const fsr_part* p) { return p ? p->npts : FSR_ERR_ARG; }
+int fsr_ndim(const fsr_part* p) { return p ? p->ndim : FSR_ERR_ARG; }
+int fsr_result_point_offsets(const fsr_part* p, int* off)
+{
+  if (!p || !off) return FSR_ERR_ARG;
+  std::copy(p->ptoff_host.begin(), p->ptoff_host.end(), off);
+  return FSR_OK;
+}
+
+int fsr_reset_envelope(fsr_part* p)
+{
+  if (!p) return FSR_ERR_ARG;
+  FSR_CUDA(cudaSetDevice(p->device));
+  std::vector<double> hmin((size_t)std::max(p->npts, 1), kHuge);
+  FSR_CUDA(cudaMemsetAsync(p->env_max, 0, sizeof(double) * std::max(p->npts, 1), p->stream));
+  FSR_CUDA(cudaMemcpyAsync(p->env_min, hmin.data(), sizeof(double) * hmin.size(), cudaMemcpyHostToDevice, p->stream));
+  FSR_CUDA(cudaStreamSynchronize(p->stream));
+  return FSR_OK;
+}
+
+int fsr_get_envelope(fsr_part* p, double* vm_max, double* vm_min)
+{
+  if (!p) return FSR_ERR_ARG;
+  FSR_CUDA(cudaSetDevice(p->device));
+  FSR_CUDA(cudaStreamSynchronize(p->stream));
+  if (vm_max) FSR_CUDA(cudaMemcpy(vm_max, p->env_max, sizeof(double) * p->npts, cudaMemcpyDeviceToHost));
+  if (vm_min) FSR_CUDA(cudaMemcpy(vm_min, p->env_min, sizeof(double) * p->npts, cudaMemcpyDeviceToHost));
+  return FSR_OK;
+}
+
+int fsr_envelope_dev(fsr_part* p, double** vm_max_dev, double** vm_min_dev)
+{
+  if (!p) return FSR_ERR_ARG;
+  if (vm_max_dev) *vm_max_dev = p->env_max;
+  if (vm_min_dev) *vm_min_dev = p->env_min;
+  return FSR_OK;
+}
+
+// One tile of steps, everything on `s`.  vm_dev may be NULL (envelope only).
+static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, double* vm_dev, size_t ld_vm,
+                    cudaStream_t s, bool timed)
+{
+  int nsteps_pad = round_up(nsteps, 64);
+  int rc;
+  if (timed) cudaEventRecord(p->ev[0], s);
+  if ((rc = launch_pack_q(p, Q_dev, ldq, nsteps, nsteps_pad, s))) return rc;
+  if ((rc = launch_k1(p, nsteps_pad, s))) return rc;
+  if (timed) cudaEventRecord(p->ev[1], s);
+  if ((rc = launch_k2_shell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_tet10_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if (timed) cudaEventRecord(p->ev[2], s);
+  return FSR_OK;
+}
+
+int fsr_recover_dev(fsr_part* p, const double* Q_dev, int ldq, int nsteps, double* vm_hist_dev,
+                    size_t ld_vm, void* stream)
+{
+  if (!p || !Q_dev || nsteps < 0 || ldq < p->ndim) { set_error("fsr_recover_dev: bad arguments"); return FSR_ERR_ARG; }
+  if (!p->have_R) { set_error("fsr_recover_dev: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  if (vm_hist_dev && ld_vm < (size_t)p->npts) { set_error("fsr_recover_dev: ld_vm < number of result points"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, false);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+  for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
+    int nt = std::min(p->step_tile, nsteps - t0);
+    rc = run_tile(p, Q_dev + (size_t)t0 * ldq, ldq, nt, vm_hist_dev ? vm_hist_dev + (size_t)t0 * ld_vm : nullptr,
+                  ld_vm, s, false);
+    if (rc) return rc;
+  }
+  return FSR_OK;
+}
+
+int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hist)
+{
+  if (!p || !Q || nsteps < 0 || ldq < p->ndim) { set_error("fsr_recover: bad arguments"); return FSR_ERR_ARG; }
+  if (!p->have_R) { set_error("fsr_recover: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, vm_hist != nullptr);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  size_t qbytes = sizeof(double) * (size_t)ldq * nsteps;
+  if (p->Qstage_cap < qbytes) {
+    cudaFree(p->Qstage); p->Qstage = nullptr; p->Qstage_cap = 0;
+    FSR_CUDA(cudaMalloc(&p->Qstage, std::max<size_t>(qbytes, 8)));
+    p->Qstage_cap = qbytes;
+  }
+  p->t_k1 = p->t_k2 = p->t_other = 0.0;
+  cudaEventRecord(p->ev[3], s);
+  FSR_CUDA(cudaMemcpyAsync(p->Qstage, Q, qbytes, cudaMemcpyHostToDevice, s));
+  for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
+    int nt = std::min(p->step_tile, nsteps - t0);
+    rc = run_tile(p, p->Qstage + (size_t)t0 * ldq, ldq, nt, vm_hist ? p->vm_tile : nullptr, (size_t)p->npts, s, true);
+    if (rc) return rc;
+    if (vm_hist)
+      FSR_CUDA(cudaMemcpyAsync(vm_hist + (size_t)t0 * p->npts, p->vm_tile, sizeof(double) * (size_t)nt * p->npts,
+                               cudaMemcpyDeviceToHost, s));
+    FSR_CUDA(cudaStreamSynchronize(s));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&b, p->ev[1], p->ev[2]);
+    p->t_k1 += a; p->t_k2 += b;
+  }
+  FSR_CUDA(cudaStreamSynchronize(s));
+  return FSR_OK;
+}
+
+int fsr_expand(fsr_part* p, const double* Q, int ldq, int nsteps, double* U_host)
+{
+  if (!p || !Q || !U_host || nsteps < 0 || ldq < p->ndim) { set_error("fsr_expand: bad arguments"); return FSR_ERR_ARG; }
+  if (!p->have_R) { set_error("fsr_expand: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, false);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  size_t qbytes = sizeof(double) * (size_t)ldq * nsteps;
+  double* dQ = nullptr;
+  FSR_CUDA(cudaMalloc(&dQ, std::max<size_t>(qbytes, 8)));
+  FSR_CUDA(cudaMemcpyAsync(dQ, Q, qbytes, cudaMemcpyHostToDevice, s));
+  std::vector<double> tile;
+  for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
+    int nt = std::min(p->step_tile, nsteps - t0);
+    int nsteps_pad = round_up(nt, 64);
+    if ((rc = launch_pack_q(p, dQ + (size_t)t0 * ldq, ldq, nt, nsteps_pad, s))) { cudaFree(dQ); return rc; }
+    if ((rc = launch_k1(p, nsteps_pad, s))) { cudaFree(dQ); return rc; }
+    // U is [dof][t]; hand back step-major [t][dof]
+    tile.resize((size_t)p->ndof * p->step_tile);
+    FSR_CUDA(cudaMemcpyAsync(tile.data(), p->U, sizeof(double) * tile.size(), cudaMemcpyDeviceToHost, s));
+    FSR_CUDA(cudaStreamSynchronize(s));
+    for (int t = 0; t < nt; ++t)
+      for (int d = 0; d < p->ndof; ++d) U_host[(size_t)(t0 + t) * p->ndof + d] = tile[(size_t)d * p->step_tile + t];
+  }
+  cudaFree(dQ);
+  return FSR_OK;
+}
+
+int fsr_recover_step_full(fsr_part* p, const double* q, double* resmat, double* stress, double* strain,
+                          double* sres, double* sv)
+{
+  if (!p || !q) { set_error("fsr_recover_step_full: bad arguments"); return FSR_ERR_ARG; }
+  if (!p->have_R) { set_error("fsr_recover_step_full: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, false);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  double* dq = nullptr;
+  FSR_CUDA(cudaMalloc(&dq, sizeof(double) * p->ndim));
+  FSR_CUDA(cudaMemcpyAsync(dq, q, sizeof(double) * p->ndim, cudaMemcpyHostToDevice, s));
+  if ((rc = launch_pack_q(p, dq, p->ndim, 1, 64, s))) { cudaFree(dq); return rc; }
+  if ((rc = launch_k1(p, 64, s))) { cudaFree(dq); return rc; }
+  size_t np = (size_t)std::max(p->npts, 1);
+  double *d_res = nullptr, *d_sig = nullptr, *d_eps = nullptr, *d_sr = nullptr;
+  FSR_CUDA(cudaMalloc(&d_res, sizeof(double) * 8 * np));
+  FSR_CUDA(cudaMalloc(&d_sig, sizeof(double) * 6 * np));
+  FSR_CUDA(cudaMalloc(&d_eps, sizeof(double) * 6 * np));
+  FSR_CUDA(cudaMalloc(&d_sr, sizeof(double) * 24 * (size_t)std::max(p->nel, 1)));
+  FSR_CUDA(cudaMemsetAsync(d_res, 0, sizeof(double) * 8 * np, s));
+  FSR_CUDA(cudaMemsetAsync(d_sig, 0, sizeof(double) * 6 * np, s));
+  FSR_CUDA(cudaMemsetAsync(d_eps, 0, sizeof(double) * 6 * np, s));
+  FSR_CUDA(cudaMemsetAsync(d_sr, 0, sizeof(double) * 24 * (size_t)std::max(p->nel, 1), s));
+  rc = launch_k2_full(p, d_res, d_sig, d_eps, d_sr, s);
+  if (rc == FSR_OK) {
+    if (resmat) cudaMemcpyAsync(resmat, d_res, sizeof(double) * 8 * p->npts, cudaMemcpyDeviceToHost, s);
+    if (stress) cudaMemcpyAsync(stress, d_sig, sizeof(double) * 6 * p->npts, cudaMemcpyDeviceToHost, s);
+    if (strain) cudaMemcpyAsync(strain, d_eps, sizeof(double) * 6 * p->npts, cudaMemcpyDeviceToHost, s);
+    if (sres) cudaMemcpyAsync(sres, d_sr, sizeof(double) * 24 * p->nel, cudaMemcpyDeviceToHost, s);
+    if (sv) {
+      // column t = 0 of U[dof][t]
+      cudaMemcpy2DAsync(sv, sizeof(double), p->U, sizeof(double) * p->step_tile, sizeof(double), p->ndof,
+                        cudaMemcpyDeviceToHost, s);
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("fsr_recover_step_full: %s", cudaGetErrorString(cudaGetLastError())); rc = FSR_ERR_CUDA; }
+  }
+  cudaFree(dq); cudaFree(d_res); cudaFree(d_sig); cudaFree(d_eps); cudaFree(d_sr);
+  return rc;
+}
+
+int fsr_last_timing(fsr_part* p, double* t_ms, int n)
+{
+  if (!p || !t_ms) return FSR_ERR_ARG;
+  double v[3] = {p->t_k1, p->t_k2, p->t_other};
+  int m = std::min(n, 3);
+  for (int i = 0; i < m; ++i) t_ms[i] = v[i];
+  return m;
+}
+
+}  // extern "C"

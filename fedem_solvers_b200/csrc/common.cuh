@@ -1,0 +1,159 @@
+// common.cuh -- shared declarations of the B200 stress-recovery library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fedem_b200.h"
+
+namespace fsr {
+
+void set_error(const char* fmt, ...);
+extern long long g_launches;
+
+#define FSR_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      fsr::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                     cudaGetErrorString(e_));                                       \
+      return FSR_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define FSR_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    ++fsr::g_launches;                                                              \
+    cudaError_t e_ = cudaGetLastError();                                            \
+    if (e_ != cudaSuccess) {                                                        \
+      fsr::set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__,       \
+                     cudaGetErrorString(e_));                                       \
+      return FSR_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+constexpr double kHuge = 1.7976931348623157e308;  // hugeVal_p = huge(1.0_dp)
+constexpr double kEpsDiv0 = 2.220446049250313e-16; // epsDiv0_p = epsilon(1.0_dp)
+
+// One FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
+// Fragment ownership (g = lane>>2, t = lane&3): a = A[g][t], b = B[t][g], c = C[g][2t..2t+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Element families handled by the K2 kernels.  A family fixes the operator shape:
+// MT m-tiles of 8 rows, KT k-tiles of 4 element DOFs.
+enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_COUNT = 4 };
+
+struct FamilyData {
+  int nelt = 0;          // elements of this family (active only)
+  int nenod = 0, nndof = 0, nstrp = 0, ncmp = 0;
+  int MT = 0, KT = 0;    // operator tiles
+  int* elem = nullptr;   // [nelt] 0-based element index in SAM order
+  int* edof = nullptr;   // [nelt][KT*4] 0-based row of U for each element DOF (padding -> 0)
+  int* ptoff = nullptr;  // [nelt] first result point (or element slot for beams)
+  double* Sfrag = nullptr;      // [nelt][MT][KT][32] operator in DMMA A-fragment order
+  unsigned char* failed = nullptr; // [nelt] 1 = operator build failed -> hugeVal results
+  double* aux = nullptr; // per-element scalars needed by the full-output kernels
+  int naux = 0;
+};
+
+}  // namespace fsr
+
+namespace fsr {
+// Host copies of the SAM index maps that fsr_set_recovery needs after fsr_part_create returned
+// (the caller may free its arrays in between).
+struct SamKeep {
+  bool valid = false;
+  int nnod = 0, nel = 0, ndof = 0, ndof1 = 0, ndof2 = 0, ngen = 0, neq = 0, nceq = 0;
+  std::vector<int> msc, meqn, meqn1, meqn2, mpmceq, mmceq;
+  std::vector<double> ttcc;
+  void keep(const fsr_sam* s)
+  {
+    nnod = s->nnod; nel = s->nel; ndof = s->ndof; ndof1 = s->ndof1; ndof2 = s->ndof2;
+    ngen = s->ngen; neq = s->neq; nceq = s->nceq;
+    msc.assign(s->msc, s->msc + ndof);
+    meqn.assign(s->meqn, s->meqn + ndof);
+    if (ndof1 > 0) meqn1.assign(s->meqn1, s->meqn1 + ndof1);
+    if (ndof2 > 0) meqn2.assign(s->meqn2, s->meqn2 + ndof2);
+    if (nceq > 0) {
+      mpmceq.assign(s->mpmceq, s->mpmceq + nceq + 1);
+      int nm = s->nmmceq > 0 ? s->nmmceq : mpmceq[nceq] - 1;
+      mmceq.assign(s->mmceq, s->mmceq + nm);
+      ttcc.assign(s->ttcc, s->ttcc + nm);
+    }
+    valid = true;
+  }
+  fsr_sam view() const
+  {
+    fsr_sam v;
+    memset(&v, 0, sizeof(v));
+    v.nnod = nnod; v.nel = nel; v.ndof = ndof; v.ndof1 = ndof1; v.ndof2 = ndof2; v.ngen = ngen;
+    v.neq = neq; v.nceq = nceq; v.nmmceq = (int)mmceq.size();
+    v.msc = msc.data(); v.meqn = meqn.data(); v.meqn1 = meqn1.data(); v.meqn2 = meqn2.data();
+    v.mpmceq = mpmceq.data(); v.mmceq = mmceq.data(); v.ttcc = ttcc.data();
+    return v;
+  }
+};
+}  // namespace fsr
+
+struct fsr_part {
+  int device = 0;
+  int nnod = 0, nel = 0, ndof = 0, ndof1 = 0, ndof2 = 0, ngen = 0, neq = 0, nceq = 0, ndim = 0;
+  int ldk = 0;         // padded reduced dimension (multiple of 4, == 4 mod 8: conflict-free smem)
+  int nrows_pad = 0;   // ndof padded to the K1 row tile
+  int npts = 0;        // result points
+  int stressForm = 0;
+  int step_tile = 0;   // steps per device batch
+  std::vector<int> ptoff_host;  // [nel+1]
+  std::vector<int> melcon_host;
+  fsr::SamKeep sam_keep;
+  // device model data
+  double* xyz = nullptr;    // [3*nnod]
+  double* emod = nullptr;   // [nel]
+  double* rny = nullptr;    // [nel]
+  double* thk = nullptr;    // [nel]
+  // recovery operator
+  double* R = nullptr;      // [nrows_pad][ldk] row-major, zero padded
+  bool have_R = false;
+  // per-batch buffers
+  double* Qt = nullptr;     // [step_tile][ldk]
+  double* U = nullptr;      // [nrows_pad][step_tile]  (row = nodal DOF, t fastest)
+  double* vm_tile = nullptr;// [step_tile][npts] staging for host output
+  double* Qstage = nullptr; // device copy of the caller's Q (host API)
+  size_t Qstage_cap = 0;
+  double* env_max = nullptr;
+  double* env_min = nullptr;
+  fsr::FamilyData fam[fsr::FAM_COUNT];
+  int nfailed = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double t_k1 = 0, t_k2 = 0, t_other = 0;
+  double* pinned = nullptr; size_t pinned_cap = 0;
+};
+
+namespace fsr {
+// k1_expand.cu
+int build_row_operator(fsr_part* p, const fsr_sam* sam, const double* B, int ldB, const double* E,
+                       int ldE);
+int launch_pack_q(fsr_part* p, const double* Q_dev, int ldq, int nsteps, int nsteps_pad,
+                  cudaStream_t s);
+int launch_k1(fsr_part* p, int nsteps_pad, cudaStream_t s);
+// k2_*.cu
+int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int build_beam_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int launch_k2_shell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm,
+                       cudaStream_t s);
+int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm,
+                       cudaStream_t s);
+int launch_beam_full(fsr_part* p, double* sres, cudaStream_t s);
+int launch_k2_full(fsr_part* p, double* resmat, double* stress, double* strain, double* sres,
+                   cudaStream_t s);
+}  // namespace fsr

@@ -1,0 +1,195 @@
+// k2_full.cu -- the full per-step result set (one step, every derived measure), generic over the
+// element families.  This is the B200 counterpart of what fedem_stress computes per element when
+// all of -SR -stress -strain -vmStress -maxPStress ... are switched on
+// (reference src/vpmStress/stressRoutines.f90:234-331): stress and strain tensors at every result
+// point, von Mises / max & min principal / max shear of both (calcVonMises, calcPrincipalVals,
+// src/vpmStress/strainAndStressUtils.f90:484-555 -> FFaTensorTransforms.C:33-67,242-296 ->
+// FFa::cubicSolve, FFaMath.C:61-142, same branch structure), and the shell stress resultants.
+// Not the throughput path (that is the von Mises + envelope kernel of each family); one thread
+// per result point, operator rows read back from the A-fragment stream.
+#include "common.cuh"
+
+namespace fsr {
+
+__device__ __forceinline__ size_t frag_at(int row, int col, int KT)
+{
+  return ((size_t)((row >> 3) * KT + (col >> 2)) << 5) + ((row & 7) << 2) + (col & 3);
+}
+
+// FFa::cubicSolve (FFaMath.C:61-142): same case analysis, same tolerances.
+__device__ int cubic_solve(double A, double B, double C, double D, double* X)
+{
+  const double epsilon = 1.0e-16;
+  if (fabs(A) > epsilon) {
+    const double epsmall = 1.0e-96;  // pow(epsilon, 6)
+    double P = (C - B * B / (3.0 * A)) / (3.0 * A);
+    double Q = ((2.0 * B * B / (27.0 * A) - C / 3.0) * B / A + D) / (A + A);
+    double W = Q * Q + P * P * P;
+    if (W <= -epsmall && P < 0.0) {
+      double FI = acos(-Q / sqrt(-P * P * P));
+      X[0] = 2.0 * sqrt(-P) * cos(FI / 3.0);
+      X[1] = -2.0 * sqrt(-P) * cos((FI + 3.14159265358979323846) / 3.0);
+      X[2] = -2.0 * sqrt(-P) * cos((FI - 3.14159265358979323846) / 3.0);
+    } else if (fabs(W) < epsmall && Q <= 0.0) {
+      X[0] = 2.0 * pow(-Q, 1.0 / 3.0);
+      X[1] = -0.5 * X[0];
+      X[2] = X[1];
+    } else if (W > -epsmall && Q + sqrt(W) <= 0.0 && Q - sqrt(W) <= 0.0) {
+      X[0] = pow(-Q + sqrt(W), 1.0 / 3.0) + pow(-Q - sqrt(W), 1.0 / 3.0);
+      X[1] = -0.5 * X[0];
+      X[2] = X[1];
+    } else if (W >= epsmall && fabs(Q) > epsmall && P > 0.0) {
+      double FI = atan(sqrt(P * P * P) / fabs(Q));
+      double KI = atan(copysign(pow(tan(0.5 * FI), 1.0 / 3.0), Q));
+      X[0] = -2.0 * sqrt(P) / tan(KI + KI);
+      X[1] = -0.5 * X[0];
+      X[2] = X[1];
+    } else
+      return -3;
+    W = B / (3.0 * A);
+    X[0] -= W; X[1] -= W; X[2] -= W;
+    return 3;
+  } else if (fabs(B) > epsilon) {
+    const double epsmall = 1.0e-64;  // pow(epsilon, 4)
+    double P = C * C - 4.0 * B * D;
+    if (P > 0.0) {
+      double Q = sqrt(P);
+      X[0] = (-C + Q) / (B + B);
+      X[1] = (-C - Q) / (B + B);
+    } else if (P > -epsmall) {
+      X[0] = -C / (B + B);
+      X[1] = X[0];
+    } else
+      return -2;
+    return 2;
+  } else if (fabs(C) > epsilon) {
+    X[0] = -D / C;
+    return 1;
+  }
+  return 0;
+}
+
+// principalValues (FFaTensorTransforms.C:229-286).  On failure P keeps its previous content,
+// like the reference (the Fortran caller then reads stale values).
+__device__ void principal_values(int ncmp, const double* S, double* P)
+{
+  if (ncmp == 3) {
+    double Cq = -(S[0] + S[1]);
+    double Dq = S[0] * S[1] - S[2] * S[2];
+    double X[3];
+    if (cubic_solve(0.0, 1.0, Cq, Dq, X) != 2) return;
+    if (X[0] < X[1]) { double t = X[0]; X[0] = X[1]; X[1] = t; }
+    P[0] = X[0]; P[1] = X[1];
+  } else if (ncmp == 6) {
+    double s11 = S[0], s22 = S[1], s33 = S[2], s12 = S[3], s13 = S[4], s23 = S[5];
+    double B = -(s11 + s22 + s33);
+    double C = s11 * s22 + s11 * s33 + s22 * s33 - s12 * s12 - s13 * s13 - s23 * s23;
+    double D = s11 * s23 * s23 + s22 * s13 * s13 + s33 * s12 * s12 - s11 * s22 * s33 - 2.0 * s12 * s13 * s23;
+    double X[3];
+    if (cubic_solve(1.0, B, C, D, X) != 3) return;
+    double t;
+    if (X[0] < X[1]) { t = X[0]; X[0] = X[1]; X[1] = t; }
+    if (X[1] < X[2]) { t = X[1]; X[1] = X[2]; X[2] = t; }
+    if (X[0] < X[1]) { t = X[0]; X[0] = X[1]; X[1] = t; }
+    P[0] = X[0]; P[1] = X[1]; P[2] = X[2];
+  } else
+    P[0] = S[0];
+}
+
+__device__ double von_mises(int ncmp, const double* S)
+{
+  if (ncmp == 3) return sqrt(S[0] * S[0] + S[1] * S[1] - S[0] * S[1] + 3.0 * S[2] * S[2]);
+  if (ncmp == 6)
+    return sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2] - S[0] * S[1] - S[1] * S[2] - S[2] * S[0] +
+                3.0 * (S[3] * S[3] + S[4] * S[4] + S[5] * S[5]));
+  return S[0];
+}
+
+// layout: 0 = shells (row = comp*8 + point), 1 = solids (row = point*ncmp + comp)
+__global__ void k2_full_kernel(const double* __restrict__ U, size_t ldu, const double* __restrict__ Sfrag,
+                               const int* __restrict__ edof, const int* __restrict__ ptoff,
+                               const int* __restrict__ elem, const unsigned char* __restrict__ failed,
+                               const double* __restrict__ aux, int naux, int nelt, int nstrp, int ncmp,
+                               int nedof, int MT, int KT, int layout, int nenod,
+                               double* __restrict__ resmat, double* __restrict__ stress,
+                               double* __restrict__ strain, double* __restrict__ sres)
+{
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nelt * nstrp) return;
+  const int i = idx / nstrp, pnt = idx % nstrp;
+  const size_t pt = (size_t)ptoff[i] + pnt;
+  const double* S = Sfrag + (size_t)i * MT * KT * 32;
+  const int* ed = edof + (size_t)i * KT * 4;
+  double sig[6] = {0, 0, 0, 0, 0, 0}, eps[6] = {0, 0, 0, 0, 0, 0};
+  if (failed[i]) {
+    for (int k = 0; k < 8; ++k) resmat[8 * pt + k] = kHuge;
+    for (int k = 0; k < 6; ++k) { stress[6 * pt + k] = kHuge; strain[6 * pt + k] = kHuge; }
+    if (ncmp == 3 && pnt < nenod) for (int k = 0; k < 6; ++k) sres[(size_t)24 * elem[i] + 6 * pnt + k] = kHuge;
+    return;
+  }
+  for (int c = 0; c < ncmp; ++c) {
+    const int row = layout == 0 ? c * 8 + pnt : pnt * ncmp + c;
+    double s = 0.0;
+    for (int col = 0; col < nedof; ++col) s += S[frag_at(row, col, KT)] * U[(size_t)ed[col] * ldu];
+    sig[c] = s;
+  }
+  const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
+  if (ncmp == 3) {
+    // isoMat2Dinv (isoMatModule.f90:41-57), then tensorial shear (elStressModule.f90:244-248)
+    eps[0] = sig[0] / E - nu / E * sig[1];
+    eps[1] = -nu / E * sig[0] + sig[1] / E;
+    eps[2] = 0.5 * (2.0 * (1.0 + nu) / E * sig[2]);
+  } else {
+    // isoMat3Dinv (isoMatModule.f90:95-120), then tensorial shear (elStressModule.f90:249-251)
+    eps[0] = (sig[0] - nu * (sig[1] + sig[2])) / E;
+    eps[1] = (sig[1] - nu * (sig[0] + sig[2])) / E;
+    eps[2] = (sig[2] - nu * (sig[0] + sig[1])) / E;
+    const double g2 = 2.0 * (1.0 + nu) / E;
+    eps[3] = 0.5 * g2 * sig[3]; eps[4] = 0.5 * g2 * sig[4]; eps[5] = 0.5 * g2 * sig[5];
+  }
+  for (int k = 0; k < 6; ++k) { stress[6 * pt + k] = sig[k]; strain[6 * pt + k] = eps[k]; }
+  const int np = ncmp == 3 ? 2 : 3;
+  double P[3] = {0, 0, 0};
+  resmat[8 * pt + 0] = von_mises(ncmp, sig);
+  principal_values(ncmp, sig, P);
+  resmat[8 * pt + 1] = P[0]; resmat[8 * pt + 2] = P[np - 1]; resmat[8 * pt + 3] = 0.5 * (P[0] - P[np - 1]);
+  resmat[8 * pt + 4] = von_mises(ncmp, eps);
+  principal_values(ncmp, eps, P);
+  resmat[8 * pt + 5] = P[0]; resmat[8 * pt + 6] = P[np - 1]; resmat[8 * pt + 7] = 0.5 * (P[0] - P[np - 1]);
+
+  // shell stress resultants at node pnt from the top (pnt) and bottom (nenod+pnt) stresses
+  // (STR22a, elStressModule.f90:826-831; STR23 :976-979 is the same relation inverted)
+  if (ncmp == 3 && pnt < nenod) {
+    const double t = aux[(size_t)i * naux + 2];
+    double bot[3];
+    for (int c = 0; c < 3; ++c) {
+      const int row = c * 8 + nenod + pnt;
+      double s = 0.0;
+      for (int col = 0; col < nedof; ++col) s += S[frag_at(row, col, KT)] * U[(size_t)ed[col] * ldu];
+      bot[c] = s;
+    }
+    double* sr = sres + (size_t)24 * elem[i] + 6 * pnt;
+    for (int c = 0; c < 3; ++c) {
+      sr[c] = (sig[c] + bot[c]) * 0.5 * t;
+      sr[3 + c] = (sig[c] - bot[c]) * 0.5 * t * t / 6.0;
+    }
+  }
+}
+
+int launch_k2_full(fsr_part* p, double* resmat, double* stress, double* strain, double* sres, cudaStream_t s)
+{
+  for (int fi = 0; fi < FAM_COUNT; ++fi) {
+    FamilyData& f = p->fam[fi];
+    if (f.nelt == 0 || f.nstrp == 0) continue;
+    int total = f.nelt * f.nstrp;
+    int layout = (fi == FAM_TET10) ? 1 : 0;
+    k2_full_kernel<<<(total + 127) / 128, 128, 0, s>>>(p->U, (size_t)p->step_tile, f.Sfrag, f.edof, f.ptoff,
+                                                      f.elem, f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
+                                                      f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod, resmat,
+                                                      stress, strain, sres);
+    FSR_LAUNCH_CHECK();
+  }
+  return launch_beam_full(p, sres, s);
+}
+
+}  // namespace fsr

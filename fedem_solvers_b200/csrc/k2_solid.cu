@@ -1,0 +1,285 @@
+// k2_solid.cu -- K2 for the 10-node tetrahedron (type 41) on sm_100a.
+//
+// Reference: STR41 -> ITET32 -> DN1031 / JACI31 (src/vpmStress/elStressModule.f90:1308-1375,
+// src/Femlib/itet.f:7-87,701-997, src/Femlib/jaci31.f) re-evaluates ten 3x3 Jacobian inverses per
+// element per step.  Here the 60x30 stress operator sigma(6,10) = S_e . v(3,10) is built once
+// (default -stressForm 0: direct evaluation at the nodes; otherwise 4 Gauss points with the
+// reference's REAL*4 abscissae, extrapolated with alpha_p/beta_p) and applied per step tile with
+// DMMA.8x8x4: rows packed densely (row = 6*node + component, 60 of 64 used, K = 30 of 32), the
+// accumulators are transposed through shared memory so that one lane sees all six components of
+// a node for the von Mises evaluation (FFaTensorTransforms.C:38-43) and the fused envelope.
+#include "common.cuh"
+
+namespace fsr {
+
+__device__ __forceinline__ size_t frag_index8(int row, int col, int KT)
+{
+  return ((size_t)((row >> 3) * KT + (col >> 2)) << 5) + ((row & 7) << 2) + (col & 3);
+}
+
+// shape-function derivatives w.r.t. the volume coordinates L1..L3 (L4 eliminated), itet.f:48-84
+__device__ void tet10_dn(double L1, double L2, double L3, double L4, double d1[10], double d2[10],
+                         double d3[10])
+{
+  d1[0] = 4. * L1 - 1.; d1[1] = 4. * L2; d1[2] = 0.; d1[3] = 0.; d1[4] = 0.; d1[5] = 4. * L3;
+  d1[6] = 4. * (L4 - L1); d1[7] = -4. * L2; d1[8] = -4. * L3; d1[9] = -4. * L4 + 1.;
+  d2[0] = 0.; d2[1] = 4. * L1; d2[2] = 4. * L2 - 1.; d2[3] = 4. * L3; d2[4] = 0.; d2[5] = 0.;
+  d2[6] = -4. * L1; d2[7] = 4. * (L4 - L2); d2[8] = -4. * L3; d2[9] = -4. * L4 + 1.;
+  d3[0] = 0.; d3[1] = 0.; d3[2] = 0.; d3[3] = 4. * L2; d3[4] = 4. * L3 - 1.; d3[5] = 4. * L1;
+  d3[6] = -4. * L1; d3[7] = -4. * L2; d3[8] = 4. * L4 - 4. * L3; d3[9] = -4. * L4 + 1.;
+}
+
+struct Tet10Points {
+  int npt;            // evaluation points (10 nodes, or 4 Gauss points)
+  double L[10][3];    // volume coordinates L1..L3 of each evaluation point
+  double W[10][10];   // sigma(node p) = sum_g W[p][g] * sigma(evaluation point g)
+};
+
+__global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
+                                       const int* __restrict__ conn /* [nelt][10] */,
+                                       const double* __restrict__ xyz, const double* __restrict__ emod,
+                                       const double* __restrict__ rny, const Tet10Points* __restrict__ pts,
+                                       double* __restrict__ Sfrag, unsigned char* __restrict__ failed,
+                                       double* __restrict__ aux)
+{
+  const int KT = 8;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelt) return;
+  const int e = elem[i];
+  double* S = Sfrag + (size_t)i * 8 * KT * 32;
+  double X[10], Y[10], Z[10];
+  for (int k = 0; k < 10; ++k) {
+    int n = conn[i * 10 + k];
+    X[k] = xyz[3 * n]; Y[k] = xyz[3 * n + 1]; Z[k] = xyz[3 * n + 2];
+  }
+  const double E = emod[e], nu = rny[e];
+  aux[i * 2] = E; aux[i * 2 + 1] = nu;
+  const double D = E * (1. - nu) / ((1. + nu) * (1. - 2. * nu));
+  const double D1 = D * nu / (1. - nu);
+  const double D2 = D * (1. - 2. * nu) / (2. * (1. - nu));
+  bool ok = true;
+  const int npt = pts->npt;
+
+  for (int gpt = 0; gpt < npt; ++gpt) {
+    const double L1 = pts->L[gpt][0], L2 = pts->L[gpt][1], L3 = pts->L[gpt][2];
+    const double L4 = 1.0 - L1 - L2 - L3;
+    double d1[10], d2[10], d3[10];
+    tet10_dn(L1, L2, L3, L4, d1, d2, d3);
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < 10; ++k) {
+      J[0][0] += d1[k] * X[k]; J[0][1] += d1[k] * Y[k]; J[0][2] += d1[k] * Z[k];
+      J[1][0] += d2[k] * X[k]; J[1][1] += d2[k] * Y[k]; J[1][2] += d2[k] * Z[k];
+      J[2][0] += d3[k] * X[k]; J[2][1] += d3[k] * Y[k]; J[2][2] += d3[k] * Z[k];
+    }
+    double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) +
+                 J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+                 J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    if (fabs(det) <= 2.2250738585072014e-308 * 100.0) { ok = false; det = 1.0; }
+    double I[3][3];
+    I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+    I[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) / det;
+    I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+    I[1][0] = (J[2][0] * J[1][2] - J[2][2] * J[1][0]) / det;
+    I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+    I[1][2] = (J[1][0] * J[0][2] - J[1][2] * J[0][0]) / det;
+    I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+    I[2][1] = (J[2][0] * J[0][1] - J[2][1] * J[0][0]) / det;
+    I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    for (int j = 0; j < 10; ++j) {
+      const double bx = I[0][0] * d1[j] + I[0][1] * d2[j] + I[0][2] * d3[j];
+      const double by = I[1][0] * d1[j] + I[1][1] * d2[j] + I[1][2] * d3[j];
+      const double bz = I[2][0] * d1[j] + I[2][1] * d2[j] + I[2][2] * d3[j];
+      // D*B block of node j: rows xx,yy,zz,xy,xz,yz ; columns u,v,w  (itet.f:917-934)
+      const double db[6][3] = {{D * bx, D1 * by, D1 * bz},  {D1 * bx, D * by, D1 * bz},
+                               {D1 * bx, D1 * by, D * bz},  {D2 * by, D2 * bx, 0.0},
+                               {D2 * bz, 0.0, D2 * bx},     {0.0, D2 * bz, D2 * by}};
+      for (int p = 0; p < 10; ++p) {
+        const double w = pts->W[p][gpt];
+        if (w == 0.0) continue;
+        for (int c = 0; c < 6; ++c)
+          for (int d = 0; d < 3; ++d) S[frag_index8(p * 6 + c, 3 * j + d, KT)] += w * db[c][d];
+      }
+    }
+  }
+  if (!ok)
+    for (int k = 0; k < 8 * KT * 32; ++k) S[k] = 0.0;
+  failed[i] = ok ? 0 : 1;
+}
+
+// one warp per element; 8 m-tiles x 8 k-tiles of operator fragments live in registers
+__global__ void __launch_bounds__(256, 1)
+k2_tet10_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
+                   const double* __restrict__ Sfrag, const int* __restrict__ edof,
+                   const int* __restrict__ ptoff, const unsigned char* __restrict__ failed, int nelt,
+                   double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
+                   double* __restrict__ env_min)
+{
+  constexpr int KT = 8, MT = 8;
+  __shared__ __align__(16) double sig_s[8][64 * 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= nelt) return;
+  double* sig = sig_s[warp];
+
+  double a[MT][KT];
+  const double* sf = Sfrag + (size_t)i * MT * KT * 32 + lane;
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < KT; ++j) a[m][j] = __ldg(sf + (size_t)(m * KT + j) * 32);
+  const double* urow[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) urow[j] = U + (size_t)__ldg(edof + (size_t)i * KT * 4 + j * 4 + t4) * ldu + g;
+
+  const bool bad = failed[i] != 0;
+  const size_t pt0 = (size_t)ptoff[i];
+  // the (node, step-in-tile) pairs this lane evaluates: idx = lane + 32 r -> node = idx/8, step = idx%8
+  const int st = lane & 7, pl = lane >> 3;
+  double emax[3] = {0.0, 0.0, 0.0}, emin[3] = {kHuge, kHuge, kHuge};
+
+  const int ntiles = nsteps_pad >> 3;
+  double b[KT], bn[KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j) b[j] = urow[j][0];
+  for (int nt = 0; nt < ntiles; ++nt) {
+    if (nt + 1 < ntiles) {
+#pragma unroll
+      for (int j = 0; j < KT; ++j) bn[j] = urow[j][(nt + 1) * 8];
+    }
+    double c[MT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) c[m][0] = c[m][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < KT; ++j)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) dmma884(c[m][0], c[m][1], a[m][j], b[j]);
+    // transpose through shared memory: sig[row][step]
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+      *reinterpret_cast<double2*>(sig + (m * 8 + g) * 8 + 2 * t4) = make_double2(c[m][0], c[m][1]);
+    __syncwarp();
+    const int t = nt * 8 + st;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int p = pl + 4 * r;
+      if (p < 10) {
+        const double* s6 = sig + (p * 6) * 8 + st;
+        const double s11 = s6[0], s22 = s6[8], s33 = s6[16], s12 = s6[24], s13 = s6[32], s23 = s6[40];
+        double v = sqrt(s11 * s11 + s22 * s22 + s33 * s33 - s11 * s22 - s22 * s33 - s33 * s11 +
+                        3.0 * (s12 * s12 + s13 * s13 + s23 * s23));
+        if (bad) v = kHuge;
+        if (t < nsteps) {
+          if (vm) vm[(size_t)t * ld_vm + pt0 + p] = v;
+          emax[r] = fmax(emax[r], v);
+          emin[r] = fmin(emin[r], v);
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < KT; ++j) b[j] = bn[j];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      emax[r] = fmax(emax[r], __shfl_xor_sync(0xffffffffu, emax[r], o));
+      emin[r] = fmin(emin[r], __shfl_xor_sync(0xffffffffu, emin[r], o));
+    }
+    const int p = pl + 4 * r;
+    if (st == 0 && p < 10 && nsteps > 0) {
+      if (emax[r] > env_max[pt0 + p]) env_max[pt0 + p] = emax[r];
+      if (emin[r] < env_min[pt0 + p]) env_min[pt0 + p] = emin[r];
+    }
+  }
+}
+
+int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
+{
+  cudaStream_t s = p->stream;
+  FamilyData& f = p->fam[FAM_TET10];
+  f.nenod = 10; f.nndof = 3; f.nstrp = 10; f.ncmp = 6; f.MT = 8; f.KT = 8;
+  std::vector<int> elem, conn, edof, ptoff;
+  for (int e = 0; e < sam->nel; ++e) {
+    if (sam->melcon[e] != 41) continue;
+    if (elm->elmid && elm->elmid[e] < 1) continue;
+    int ip0 = sam->mpmnpc[e] - 1, nn = sam->mpmnpc[e + 1] - sam->mpmnpc[e];
+    if (nn != 10) { set_error("TET10 element %d has %d nodes", e + 1, nn); return FSR_ERR_ARG; }
+    elem.push_back(e);
+    ptoff.push_back(p->ptoff_host[e]);
+    size_t base = edof.size();
+    edof.resize(base + 32, 0);
+    for (int k = 0; k < 10; ++k) {
+      int n = sam->mmnpc[ip0 + k] - 1;
+      if (n < 0 || n >= sam->nnod) { set_error("element %d: node index out of range", e + 1); return FSR_ERR_ARG; }
+      conn.push_back(n);
+      int js = sam->madof[n] - 1, nd = sam->madof[n + 1] - sam->madof[n];
+      if (nd < 3) { set_error("element %d: node %d has %d DOFs, solid needs 3", e + 1, n + 1, nd); return FSR_ERR_ARG; }
+      for (int d = 0; d < 3; ++d) edof[base + (size_t)k * 3 + d] = js + d;
+    }
+  }
+  f.nelt = (int)elem.size();
+  f.naux = 2;
+  if (f.nelt == 0) return FSR_OK;
+
+  // evaluation points and node extrapolation weights (itet.f:822-877, elStressModule.f90:1357-1368)
+  Tet10Points h;
+  memset(&h, 0, sizeof(h));
+  if (p->stressForm == 0) {
+    h.npt = 10;
+    const double L[10][3] = {{1, 0, 0}, {.5, .5, 0}, {0, 1, 0}, {0, .5, .5}, {0, 0, 1},
+                             {.5, 0, .5}, {.5, 0, 0}, {0, .5, 0}, {0, 0, .5}, {0, 0, 0}};
+    memcpy(h.L, L, sizeof(L));
+    for (int q = 0; q < 10; ++q) h.W[q][q] = 1.0;
+  } else {
+    h.npt = 4;
+    const double al = (double)0.585410196625f, be = (double)0.138196601125f;  // REAL*4 literals
+    const double L[4][3] = {{al, be, be}, {be, al, be}, {be, be, al}, {be, be, be}};
+    memcpy(h.L, L, sizeof(L));
+    const double ap = 1.927051062810166, bp = -0.309017015969668;
+    const int corner[4] = {0, 2, 4, 9};
+    for (int c = 0; c < 4; ++c)
+      for (int gq = 0; gq < 4; ++gq) h.W[corner[c]][gq] = (c == gq) ? ap : bp;
+    const int mid[6][3] = {{1, 0, 2}, {3, 2, 4}, {5, 4, 0}, {6, 0, 9}, {7, 2, 9}, {8, 4, 9}};
+    for (auto& m : mid)
+      for (int gq = 0; gq < 4; ++gq) h.W[m[0]][gq] = 0.5 * (h.W[m[1]][gq] + h.W[m[2]][gq]);
+  }
+  Tet10Points* d_pts = nullptr;
+  int* d_conn = nullptr;
+  FSR_CUDA(cudaMalloc(&d_pts, sizeof(Tet10Points)));
+  FSR_CUDA(cudaMemcpyAsync(d_pts, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMalloc(&f.elem, sizeof(int) * elem.size()));
+  FSR_CUDA(cudaMalloc(&f.edof, sizeof(int) * edof.size()));
+  FSR_CUDA(cudaMalloc(&f.ptoff, sizeof(int) * ptoff.size()));
+  FSR_CUDA(cudaMalloc(&f.failed, f.nelt));
+  FSR_CUDA(cudaMalloc(&f.Sfrag, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32));
+  FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
+  FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
+  FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(f.ptoff, ptoff.data(), sizeof(int) * ptoff.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
+  build_tet10_ops_kernel<<<(f.nelt + 63) / 64, 64, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny,
+                                                         d_pts, f.Sfrag, f.failed, f.aux);
+  FSR_LAUNCH_CHECK();
+  FSR_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_conn);
+  cudaFree(d_pts);
+  return FSR_OK;
+}
+
+int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s)
+{
+  FamilyData& f = p->fam[FAM_TET10];
+  if (f.nelt == 0) return FSR_OK;
+  const int warps = 8;
+  k2_tet10_vm_kernel<<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+      p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
+      ld_vm, p->env_max, p->env_min);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+
+}  // namespace fsr

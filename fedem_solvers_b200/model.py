@@ -1,0 +1,303 @@
+"""Host-side model containers (the data the reference keeps in SamType and in the FE-model
+singleton) and seeded synthetic part generators for the BASELINE.json configurations.
+
+Index arrays are 1-based exactly as the reference stores them in the .fsm file
+(src/vpmStress/samStressModule.f90:273-316), so the same arrays can be handed to the C ABI, to
+the Fortran driver and to the CPU oracle unchanged."""
+from dataclasses import dataclass, field
+import numpy as np
+
+I32 = np.int32
+F64 = np.float64
+
+
+@dataclass
+class SamData:
+    """SamType subset (src/vpmCommon/samModule.f90:27-66) as read by initiateSAM."""
+    nnod: int
+    nel: int
+    ndof: int
+    ndof1: int
+    ndof2: int
+    ngen: int
+    neq: int
+    nceq: int
+    madof: np.ndarray
+    msc: np.ndarray
+    mpmnpc: np.ndarray
+    mmnpc: np.ndarray
+    melcon: np.ndarray
+    meqn: np.ndarray
+    meqn1: np.ndarray
+    meqn2: np.ndarray
+    mpmceq: np.ndarray = field(default_factory=lambda: np.ones(1, I32))
+    mmceq: np.ndarray = field(default_factory=lambda: np.zeros(0, I32))
+    ttcc: np.ndarray = field(default_factory=lambda: np.zeros(0, F64))
+    minex: np.ndarray = None
+
+    @property
+    def ndim(self):
+        return self.ndof2 + self.ngen
+
+    def dof_pos_in2(self):
+        """invertEqPartition, src/vpmCommon/samModule.f90:960-970."""
+        pos = {int(eq): j + 1 for j, eq in enumerate(self.meqn2)}
+        return np.array([pos[int(self.meqn[d])] for d in np.nonzero(self.msc == 2)[0]], I32)
+
+
+@dataclass
+class ElementData:
+    """What ffl_getcoor/getmat/getthick/getbeamsection/getpinflags/getelmid deliver
+    (fedem-foundation/src/FFlLib/FFlLinkHandler_F.C:699-1193)."""
+    xyz: np.ndarray          # [nnod, 3]
+    emod: np.ndarray         # [nel]
+    rny: np.ndarray          # [nel]
+    thk: np.ndarray          # [nel]
+    elmid: np.ndarray = None # [nel] external ids (<1: skipped)
+    beam: np.ndarray = None  # [nel, 32] beam data (type 11)
+
+
+@dataclass
+class PartModel:
+    sam: SamData
+    elm: ElementData
+    B: np.ndarray = None     # [ndof1, ndof2] column-major (Fortran order)
+    E: np.ndarray = None     # [ndof1, ngen]  column-major
+    name: str = ""
+
+    def nstrp(self):
+        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10}
+        n = np.array([tab.get(int(t), 0) for t in self.sam.melcon], I32)
+        if self.elm.elmid is not None:
+            n[self.elm.elmid < 1] = 0
+        return n
+
+
+# ------------------------------------------------------------------------------------------
+# SAM bookkeeping for a synthetic part
+# ------------------------------------------------------------------------------------------
+def _build_sam(nnod, ndof_per_node, conn_list, types, ext_nodes, fixed_dofs=(), constraints=(),
+               rng=None, shuffle_eq=False):
+    """conn_list: list of 1-based node arrays per element; ext_nodes: 1-based external nodes;
+    fixed_dofs: 0-based DOF indices that are suppressed; constraints: list of
+    (dependent_dof0, [(master_dof0, coeff), ...])."""
+    ndpn = np.full(nnod, ndof_per_node, I32) if np.isscalar(ndof_per_node) else np.asarray(ndof_per_node, I32)
+    madof = np.concatenate([[1], 1 + np.cumsum(ndpn)]).astype(I32)
+    ndof = int(madof[-1] - 1)
+    msc = np.ones(ndof, I32)
+    for n in ext_nodes:
+        msc[madof[n - 1] - 1: madof[n] - 1] = 2
+    dep = {d: terms for d, terms in constraints}
+    for d in fixed_dofs:
+        msc[d] = 0
+    for d in dep:
+        msc[d] = 0  # dependent DOFs carry status 0 in msc; meqn holds -iceq
+    free = np.nonzero(msc > 0)[0]
+    neq = len(free)
+    eqno = np.arange(1, neq + 1)
+    if shuffle_eq and rng is not None:
+        eqno = rng.permutation(eqno)
+    meqn = np.zeros(ndof, I32)
+    meqn[free] = eqno
+    mpmceq = [1]
+    mmceq, ttcc = [], []
+    for ic, (d, terms) in enumerate(dep.items(), start=1):
+        meqn[d] = -ic
+        mmceq.append(d + 1)       # first entry: the dependent DOF itself with c0
+        ttcc.append(0.0)
+        for m, c in terms:
+            mmceq.append(m + 1)
+            ttcc.append(c)
+        mpmceq.append(len(mmceq) + 1)
+    int_dofs = np.nonzero(msc == 1)[0]
+    ext_dofs = np.nonzero(msc == 2)[0]
+    meqn1 = meqn[int_dofs].copy()
+    meqn2 = meqn[ext_dofs].copy()
+    if shuffle_eq and rng is not None:
+        meqn1 = rng.permutation(meqn1)
+        meqn2 = rng.permutation(meqn2)
+    mpmnpc = np.concatenate([[1], 1 + np.cumsum([len(c) for c in conn_list])]).astype(I32)
+    mmnpc = np.concatenate(conn_list).astype(I32) if len(conn_list) else np.zeros(0, I32)
+    return SamData(nnod=nnod, nel=len(conn_list), ndof=ndof, ndof1=len(int_dofs), ndof2=len(ext_dofs),
+                   ngen=0, neq=neq, nceq=len(dep), madof=madof, msc=msc, mpmnpc=mpmnpc, mmnpc=mmnpc,
+                   melcon=np.asarray(types, I32), meqn=meqn, meqn1=meqn1.astype(I32),
+                   meqn2=meqn2.astype(I32), mpmceq=np.asarray(mpmceq, I32),
+                   mmceq=np.asarray(mmceq, I32), ttcc=np.asarray(ttcc, F64),
+                   minex=np.arange(1, nnod + 1, dtype=I32))
+
+
+def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0):
+    """Synthetic [B|E]: smooth low-order cosine fields over the part, one per reduced DOF, with
+    a random per-component scale -- cheap to generate at 6M rows, and every internal DOF row is a
+    distinct, well-scaled linear combination of the reduced DOFs."""
+    int_dofs = np.nonzero(sam.msc == 1)[0]
+    # internal row k corresponds to equation meqn1[k]; map equation -> dof
+    eq2dof = np.zeros(sam.neq + 1, np.int64)
+    nz = np.nonzero(sam.meqn > 0)[0]
+    eq2dof[sam.meqn[nz]] = nz
+    rows_dof = eq2dof[sam.meqn1]                       # dof of each B row
+    node_of_dof = np.searchsorted(sam.madof, rows_dof + 1, side="right") - 1
+    comp = rows_dof - (sam.madof[node_of_dof] - 1)
+    lo, hi = xyz.min(0), xyz.max(0)
+    span = np.where(hi - lo > 0, hi - lo, 1.0)
+    u = (xyz[node_of_dof] - lo) / span                 # normalised coordinates in [0,1]
+    ncol = sam.ndof2 + ngen
+    M = np.empty((sam.ndof1, ncol), F64, order="F")
+    cscale = np.array([1.0, 1.0, 1.0, 0.5, 0.5, 0.5])
+    for j in range(ncol):
+        f = rng.integers(0, 4, 3) * np.pi
+        ph = rng.uniform(0, 2 * np.pi, 3)
+        a = rng.normal(0.0, 1.0, 6) * cscale
+        M[:, j] = amp * a[comp] * np.cos(f[0] * u[:, 0] + ph[0]) * np.cos(f[1] * u[:, 1] + ph[1]) * \
+            np.cos(f[2] * u[:, 2] + ph[2])
+    B = np.asfortranarray(M[:, :sam.ndof2])
+    E = np.asfortranarray(M[:, sam.ndof2:])
+    return B, E
+
+
+def reduced_history(ndim, nsteps, seed, amp=1.0e-3, dt=1.0e-3):
+    """Band-limited synthetic reduced history Q [ndim x nsteps] (Fortran order): sum of 8
+    sinusoids per reduced DOF, amplitude ~amp."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(nsteps) * dt
+    Q = np.zeros((ndim, nsteps), F64, order="F")
+    for _ in range(8):
+        w = rng.uniform(2.0, 60.0, ndim) * 2 * np.pi
+        ph = rng.uniform(0, 2 * np.pi, ndim)
+        a = rng.normal(0.0, amp / 3.0, ndim)
+        Q += a[:, None] * np.sin(w[:, None] * t[None, :] + ph[:, None])
+    return Q
+
+
+# ------------------------------------------------------------------------------------------
+# part generators
+# ------------------------------------------------------------------------------------------
+def plate_part(nx, ny, ngen=10, seed=1, tri_fraction=0.0, n_ext=4, jitter=0.02, lx=1.0, ly=1.0,
+               thickness=0.01, emod=2.1e11, rny=0.3, warp=0.0, shuffle_eq=False, n_fixed=0,
+               n_constraints=0, with_recovery=True):
+    """Flat (or slightly warped) plate of nx x ny ANDES quads (type 24), optionally a fraction of
+    the cells split into two ANDES triangles (type 23).  n_ext corner/edge nodes are external
+    (6 DOFs each).  Config C1: plate_part(70, 70); config C2: plate_part(1000, 1000, ngen=50, n_ext=8)."""
+    rng = np.random.default_rng(seed)
+    nnx, nny = nx + 1, ny + 1
+    nnod = nnx * nny
+    gx, gy = np.meshgrid(np.linspace(0, lx, nnx), np.linspace(0, ly, nny), indexing="xy")
+    xyz = np.zeros((nnod, 3), F64)
+    xyz[:, 0] = gx.ravel()
+    xyz[:, 1] = gy.ravel()
+    hx, hy = lx / nx, ly / ny
+    interior = np.ones((nny, nnx), bool)
+    interior[0, :] = interior[-1, :] = interior[:, 0] = interior[:, -1] = False
+    m = interior.ravel()
+    xyz[m, 0] += rng.uniform(-jitter, jitter, m.sum()) * hx
+    xyz[m, 1] += rng.uniform(-jitter, jitter, m.sum()) * hy
+    if warp:
+        xyz[:, 2] = warp * np.sin(np.pi * xyz[:, 0] / lx) * np.sin(np.pi * xyz[:, 1] / ly)
+    # cells
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    n1 = (iy * nnx + ix + 1).ravel()
+    quads = np.stack([n1, n1 + 1, n1 + 1 + nnx, n1 + nnx], 1).astype(I32)
+    ncell = nx * ny
+    split = np.zeros(ncell, bool)
+    if tri_fraction > 0:
+        split = rng.random(ncell) < tri_fraction
+    conn, types = [], []
+    if not split.any():
+        conn = list(quads)
+        types = np.full(ncell, 24, I32)
+    else:
+        types = []
+        for c in range(ncell):
+            q = quads[c]
+            if split[c]:
+                conn.append(q[[0, 1, 2]]); types.append(23)
+                conn.append(q[[0, 2, 3]]); types.append(23)
+            else:
+                conn.append(q); types.append(24)
+        types = np.asarray(types, I32)
+    corners = [1, nnx, nnod, nnod - nnx + 1]
+    extra = [nnx // 2 + 1, nnod - nnx // 2, (nny // 2) * nnx + 1, (nny // 2 + 1) * nnx]
+    ext_nodes = (corners + extra)[:n_ext]
+    ext_set = set(ext_nodes)
+    fixed, cons = [], []
+    if n_fixed or n_constraints:
+        cand = [n for n in rng.permutation(np.arange(1, nnod + 1)) if n not in ext_set]
+        for n in cand[:n_fixed]:
+            fixed.append(6 * (n - 1) + int(rng.integers(0, 6)))
+        used = set(fixed)
+        for n in cand[n_fixed:n_fixed + n_constraints]:
+            d = 6 * (n - 1) + int(rng.integers(0, 6))
+            masters = []
+            for mnode in rng.choice(cand[n_fixed + n_constraints:], 3, replace=False):
+                md = 6 * (int(mnode) - 1) + int(rng.integers(0, 6))
+                if md not in used:
+                    masters.append((md, float(rng.normal())))
+            cons.append((d, masters))
+            used.add(d)
+    sam = _build_sam(nnod, 6, conn, types, ext_nodes, fixed, cons, rng, shuffle_eq)
+    sam.ngen = ngen
+    nel = sam.nel
+    elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64),
+                      thk=np.full(nel, thickness, F64), elmid=np.arange(1, nel + 1, dtype=I32))
+    part = PartModel(sam=sam, elm=elm, name=f"plate{nx}x{ny}")
+    if with_recovery:
+        part.B, part.E = _smooth_recovery_matrices(sam, xyz, ngen, rng)
+    return part
+
+
+_TET_SPLIT = [(0, 1, 3, 7), (0, 1, 7, 5), (0, 5, 7, 4), (1, 2, 3, 7), (1, 6, 7, 5), (1, 2, 7, 6)]
+
+
+def tet10_block(nx, ny, nz, ngen=10, seed=3, n_ext=4, jitter=0.05, emod=2.1e11, rny=0.3,
+                shuffle_eq=False, with_recovery=True):
+    """Structured block of nx*ny*nz hexahedral cells, each split into 6 ten-node tetrahedra
+    (type 41), FEDEM node order: corners 1,3,5,10, mid-edges 2,4,6,7,8,9 (itet.f label 300).
+    Mid-edge nodes get a small jitter so edges are curved (non-constant Jacobians)."""
+    rng = np.random.default_rng(seed)
+    # vertex grid on doubled indices so mid-edge nodes are addressable
+    NX, NY, NZ = 2 * nx + 1, 2 * ny + 1, 2 * nz + 1
+    node_id = {}
+    coords = []
+
+    def nid(i, j, k):
+        key = (i, j, k)
+        if key not in node_id:
+            node_id[key] = len(coords) + 1
+            p = np.array([i / 2.0, j / 2.0, k / 2.0])
+            if (i % 2) + (j % 2) + (k % 2) > 0:
+                p = p + rng.uniform(-jitter, jitter, 3) * 0.5
+            coords.append(p)
+        return node_id[key]
+
+    conn = []
+    for cz in range(nz):
+        for cy in range(ny):
+            for cx in range(nx):
+                v = [(2 * cx + dx, 2 * cy + dy, 2 * cz + dz) for dz in (0, 2) for dy in (0, 2) for dx in (0, 2)]
+                # v index: dx + 2*dy/2... -> order (0,0,0),(2,0,0),(0,2,0),(2,2,0),(0,0,2),...
+                hexv = [v[0], v[1], v[3], v[2], v[4], v[5], v[7], v[6]]
+                for t in _TET_SPLIT:
+                    a, b, c, d = (hexv[q] for q in t)
+                    # orientation: positive volume for (a,b,c,d) with L4 at d
+                    pa, pb, pc, pd = (np.array(x, float) for x in (a, b, c, d))
+                    if np.dot(np.cross(pb - pa, pc - pa), pd - pa) < 0:
+                        b, c = c, b
+                    mid = lambda p, q: tuple((np.array(p) + np.array(q)) // 2)
+                    n = [nid(*a), nid(*mid(a, b)), nid(*b), nid(*mid(b, c)), nid(*c), nid(*mid(c, a)),
+                         nid(*mid(a, d)), nid(*mid(b, d)), nid(*mid(c, d)), nid(*d)]
+                    conn.append(np.asarray(n, I32))
+    xyz = np.asarray(coords, F64)
+    nnod = len(coords)
+    # external nodes: corner vertices of the block
+    cand = [(0, 0, 0), (NX - 1, 0, 0), (0, NY - 1, 0), (NX - 1, NY - 1, NZ - 1), (0, 0, NZ - 1),
+            (NX - 1, NY - 1, 0), (0, NY - 1, NZ - 1), (NX - 1, 0, NZ - 1)]
+    ext_nodes = [node_id[c] for c in cand[:n_ext]]
+    sam = _build_sam(nnod, 3, conn, np.full(len(conn), 41, I32), ext_nodes, rng=rng, shuffle_eq=shuffle_eq)
+    sam.ngen = ngen
+    nel = sam.nel
+    elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64),
+                      thk=np.zeros(nel, F64), elmid=np.arange(1, nel + 1, dtype=I32))
+    part = PartModel(sam=sam, elm=elm, name=f"tet10_{nx}x{ny}x{nz}")
+    if with_recovery:
+        part.B, part.E = _smooth_recovery_matrices(sam, xyz, ngen, rng)
+    return part

@@ -1,0 +1,161 @@
+"""Host-side mirror of the reference's recovery driver interface, on top of the C ABI.
+
+``StressRecovery`` plays the role of one FE part inside ``fedem_stress``
+(src/vpmStress/stress.f90:112-435) or of one entry of the solver's recovery list
+(src/vpmSolver/stressRecoveryModule.f90:517-768,991-1225): it is created from the SAM data and
+the element data (initiateSAM + ffl_*), receives the B and E matrices (openBandEmatrices) and is
+then driven with a window of the reduced history.  Method names follow the reference routines
+they replace; argument meaning and error behaviour (negative = fatal, positive = number of
+failed elements which get hugeVal results) follow ``ierr`` of the Fortran."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import FsrSam, FsrElmData, FsrOptions, check
+from .model import PartModel
+
+F64 = np.float64
+I32 = np.int32
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+class StressRecovery:
+    def __init__(self, part: PartModel, device=0, stress_form=0, step_tile=0):
+        self._lib = _lib.load_library()
+        self._h = C.c_void_p()
+        s, e = part.sam, part.elm
+        self._keep = []
+
+        def ci(a):
+            a = np.ascontiguousarray(a, I32)
+            self._keep.append(a)
+            return a
+
+        def cd(a):
+            a = np.ascontiguousarray(a, F64)
+            self._keep.append(a)
+            return a
+
+        sam = FsrSam(nnod=s.nnod, nel=s.nel, ndof=s.ndof, ndof1=s.ndof1, ndof2=s.ndof2, ngen=s.ngen,
+                     neq=s.neq, nceq=s.nceq, nmmnpc=len(s.mmnpc), nmmceq=len(s.mmceq))
+        sam.madof = _ip(ci(s.madof)); sam.msc = _ip(ci(s.msc)); sam.mpmnpc = _ip(ci(s.mpmnpc))
+        sam.mmnpc = _ip(ci(s.mmnpc)); sam.melcon = _ip(ci(s.melcon)); sam.mpmceq = _ip(ci(s.mpmceq))
+        sam.mmceq = _ip(ci(s.mmceq if len(s.mmceq) else np.zeros(1, I32)))
+        sam.ttcc = _dp(cd(s.ttcc if len(s.ttcc) else np.zeros(1)))
+        sam.meqn = _ip(ci(s.meqn)); sam.meqn1 = _ip(ci(s.meqn1 if s.ndof1 else np.zeros(1, I32)))
+        sam.meqn2 = _ip(ci(s.meqn2 if s.ndof2 else np.zeros(1, I32)))
+        elm = FsrElmData()
+        elm.xyz = _dp(cd(e.xyz)); elm.emod = _dp(cd(e.emod)); elm.rny = _dp(cd(e.rny)); elm.thk = _dp(cd(e.thk))
+        elm.elmid = _ip(ci(e.elmid)) if e.elmid is not None else None
+        elm.beam = _dp(cd(e.beam)) if e.beam is not None else None
+        opt = FsrOptions(device=device, stressForm=stress_form, step_tile=step_tile)
+        rc = self._lib.fsr_part_create(C.byref(self._h), C.byref(sam), C.byref(elm), C.byref(opt))
+        self.n_failed = check(rc, "fsr_part_create")
+        self._keep = []
+        self.ndim = self._lib.fsr_ndim(self._h)
+        self.npts = self._lib.fsr_num_result_points(self._h)
+        self.ndof = s.ndof
+        self.nel = s.nel
+        if part.B is not None or part.E is not None:
+            self.open_B_and_E_matrices(part.B, part.E)
+
+    # ---- openBandEmatrices (displacementModule.f90:645-790) --------------------------------
+    def open_B_and_E_matrices(self, B, E):
+        B = np.asfortranarray(B, F64) if B is not None and B.size else None
+        E = np.asfortranarray(E, F64) if E is not None and E.size else None
+        ldB = B.shape[0] if B is not None else 0
+        ldE = E.shape[0] if E is not None else 0
+        check(self._lib.fsr_set_recovery(self._h, _dp(B), ldB, _dp(E), ldE), "fsr_set_recovery")
+
+    # ---- stress.f90:361-435 time loop, batched ----------------------------------------------
+    def recover(self, Q, want_history=True):
+        """Q: [ndim, nsteps] (column = [finit; vg] of a step).  Returns the von Mises history
+        [nsteps, npts] (row s = resMat(1,:) of step s, stressRoutines.f90:273-276) or None."""
+        Q = np.asfortranarray(Q, F64)
+        assert Q.shape[0] == self.ndim, (Q.shape, self.ndim)
+        nsteps = Q.shape[1]
+        vm = np.empty((nsteps, self.npts), F64) if want_history else None
+        check(self._lib.fsr_recover(self._h, _dp(Q), Q.shape[0], nsteps, _dp(vm)), "fsr_recover")
+        return vm
+
+    def recover_dev(self, q_ptr, ldq, nsteps, vm_ptr=None, ld_vm=0, stream=None):
+        """Device-pointer variant (torch tensors: pass .data_ptr()); asynchronous."""
+        check(self._lib.fsr_recover_dev(self._h, C.c_void_p(q_ptr), ldq, nsteps,
+                                        C.c_void_p(vm_ptr) if vm_ptr else None, ld_vm,
+                                        C.c_void_p(stream) if stream else None), "fsr_recover_dev")
+
+    def reset_envelope(self):
+        check(self._lib.fsr_reset_envelope(self._h), "fsr_reset_envelope")
+
+    def envelope(self):
+        """Running (max, min) of von Mises per result point (strainCoatModule.f90:159-166,410-420)."""
+        mx = np.empty(self.npts, F64); mn = np.empty(self.npts, F64)
+        check(self._lib.fsr_get_envelope(self._h, _dp(mx), _dp(mn)), "fsr_get_envelope")
+        return mx, mn
+
+    def envelope_dev_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        check(self._lib.fsr_envelope_dev(self._h, C.byref(a), C.byref(b)), "fsr_envelope_dev")
+        return a.value, b.value
+
+    # ---- calcIntDisplacements for a batch ------------------------------------------------------
+    def calc_int_displacements(self, Q):
+        Q = np.asfortranarray(Q, F64)
+        nsteps = Q.shape[1]
+        U = np.empty((nsteps, self.ndof), F64)
+        check(self._lib.fsr_expand(self._h, _dp(Q), Q.shape[0], nsteps, _dp(U)), "fsr_expand")
+        return U
+
+    # ---- calcStresses with every output switch on, one step -------------------------------------
+    def calc_stresses(self, q):
+        q = np.ascontiguousarray(q, F64)
+        res = dict(resmat=np.zeros((self.npts, 8), F64), stress=np.zeros((self.npts, 6), F64),
+                   strain=np.zeros((self.npts, 6), F64), sres=np.zeros((self.nel, 24), F64),
+                   sv=np.zeros(self.ndof, F64))
+        rc = self._lib.fsr_recover_step_full(self._h, _dp(q), _dp(res["resmat"]), _dp(res["stress"]),
+                                             _dp(res["strain"]), _dp(res["sres"]), _dp(res["sv"]))
+        check(rc, "fsr_recover_step_full")
+        return res
+
+    def result_point_offsets(self):
+        off = np.zeros(self.nel + 1, I32)
+        check(self._lib.fsr_result_point_offsets(self._h, _ip(off)), "fsr_result_point_offsets")
+        return off
+
+    def last_timing(self):
+        t = np.zeros(3, F64)
+        self._lib.fsr_last_timing(self._h, _dp(t), 3)
+        return dict(k1_ms=t[0], k2_ms=t[1], other_ms=t[2])
+
+    def close(self):
+        if self._h:
+            self._lib.fsr_part_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fatigue(hist, gate, curve, bin_size=0.0, nbins=0, device=0):
+    """ffp_getdamage / ffp_getnumcycles for many gages at once
+    (fedem-foundation/src/FFpLib/FFpFatigue/FFpFatigue_F.C:81-141).
+    hist: [ngage, nsteps].  Returns (damage[ngage], ncycles[ngage], bins[ngage, nbins] or None)."""
+    lib = _lib.load_library()
+    hist = np.ascontiguousarray(hist, F64)
+    ng, ns = hist.shape
+    curve = np.ascontiguousarray(curve, F64)
+    damage = np.zeros(ng, F64); ncyc = np.zeros(ng, I32)
+    bins = np.zeros((ng, nbins), I32) if nbins > 0 else None
+    check(lib.fsr_fatigue(device, _dp(hist), ng, ns, float(gate), _dp(curve), float(bin_size), nbins,
+                          _dp(damage), _ip(ncyc), _ip(bins)), "fsr_fatigue")
+    return damage, ncyc, bins

@@ -1,0 +1,177 @@
+/*
+ * fedem_b200.h -- C ABI of the B200-native stress-recovery library (libfedem_b200.so).
+ *
+ * This is the drop-in boundary for the fedem_stress / fedem_gage hot path of
+ * SAP-archive/fedem-solvers: plain pointers and sizes, no C++/torch types, callable from
+ * Fortran through ISO_C_BINDING (fortran/fedem_b200_mod.f90), from C/C++ and from Python/ctypes.
+ * Each entry point names the reference routine(s) it replaces (paths relative to the reference
+ * checkout).  The reference calls those routines once per time step; this library is batched:
+ * the caller collects the reduced history Q for a window of steps and makes one call.
+ *
+ * Conventions (identical to what the reference stores, so a Fortran caller passes its arrays
+ * untouched): all index arrays are 1-based as in the .fsm file; matrices are column-major;
+ * host pointers unless the name says _dev.  Every function returns 0 on success, <0 on a fatal
+ * error (message via fsr_last_error), >0 as a warning count (e.g. number of failed elements,
+ * which get hugeVal results like stressRoutines.f90:237-241,264-268).
+ *
+ * There is NO CPU fallback: every call fails with FSR_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef FEDEM_B200_H
+#define FEDEM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSR_OK 0
+#define FSR_ERR_ARG (-1)
+#define FSR_ERR_CUDA (-2)
+#define FSR_ERR_ALLOC (-3)
+#define FSR_ERR_STATE (-4)
+#define FSR_ERR_LIMIT (-5)
+
+#define FSR_NBEAM 32 /* doubles of beam data per element, see fsr_elmdata.beam */
+
+typedef struct fsr_part fsr_part; /* opaque per-superelement handle (one FE part on one GPU) */
+
+/* SamType subset (src/vpmCommon/samModule.f90:27-66) exactly as initiateSAM reads it from the
+ * .fsm file (src/vpmStress/samStressModule.f90:273-316), BEFORE the msc remap of :245-256. */
+typedef struct fsr_sam {
+  int nnod, nel, ndof, ndof1, ndof2, ngen, neq, nceq, nmmnpc, nmmceq;
+  const int *madof;  /* [nnod+1] */
+  const int *msc;    /* [ndof] status codes as stored: 2 = external, 1 = free, 0 = fixed */
+  const int *mpmnpc; /* [nel+1]  */
+  const int *mmnpc;  /* [nmmnpc] */
+  const int *melcon; /* [nel]    */
+  const int *mpmceq; /* [nceq+1] (may be NULL if nceq == 0) */
+  const int *mmceq;  /* [nmmceq] */
+  const double *ttcc;/* [nmmceq] */
+  const int *meqn;   /* [ndof]   */
+  const int *meqn1;  /* [ndof1]  */
+  const int *meqn2;  /* [ndof2]  */
+} fsr_sam;
+
+/* What the reference pulls per element, per step, from the FE model through
+ * ffl_getcoor / ffl_getmat / ffl_getthick / ffl_getbeamsection / ffl_getpinflags / ffl_getelmid
+ * (fedem-foundation/src/FFlLib/FFlLinkHandler_F.C:699-1193); here handed over once. */
+typedef struct fsr_elmdata {
+  const double *xyz;  /* [3*nnod] x,y,z of every internal node (node order of madof)          */
+  const double *emod; /* [nel] Young's modulus                                               */
+  const double *rny;  /* [nel] Poisson's ratio                                               */
+  const double *thk;  /* [nel] shell thickness (ffl_getthick: uniform over the element)      */
+  const int *elmid;   /* [nel] external element id; < 1 = not in the -group selection; NULL = all */
+  const double *beam; /* [nel*FSR_NBEAM] for type-11 elements, else ignored; may be NULL.
+                         [0:5) X(1:5), [5:10) Y(1:5), [10:15) Z(1:5) as ffl_getcoor returns them
+                         for beams (ends incl. eccentricity, Z-direction point, the two nodes);
+                         [15:29) BSEC(1:14) of ffl_getbeamsection; [29] IPA, [30] IPB pin flags */
+} fsr_elmdata;
+
+/* Arithmetic-changing options of fedem_stress (src/vpmStress/stressmain.C:68-79) + run control */
+typedef struct fsr_options {
+  int device;     /* CUDA device ordinal                                                    */
+  int stressForm; /* -stressForm (solids): 0 = nodal evaluation (default), else Gauss extrap. */
+  int step_tile;  /* time steps per device batch (0 = automatic from free HBM)              */
+  int reserved[5];
+} fsr_options;
+
+/* Output selection bits = the -vmStress ... switches of stressmain.C:46-60 */
+#define FSR_OUT_VMSTRESS 0x001
+#define FSR_OUT_MAXPSTRESS 0x002
+#define FSR_OUT_MINPSTRESS 0x004
+#define FSR_OUT_MAXSSTRESS 0x008
+#define FSR_OUT_VMSTRAIN 0x010
+#define FSR_OUT_MAXPSTRAIN 0x020
+#define FSR_OUT_MINPSTRAIN 0x040
+#define FSR_OUT_MAXSSTRAIN 0x080
+#define FSR_OUT_STRESS 0x100
+#define FSR_OUT_STRAIN 0x200
+#define FSR_OUT_SR 0x400
+#define FSR_OUT_DEFORMATION 0x800
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+
+/* Replaces initiateSAM (src/vpmStress/samStressModule.f90:39-263: dofPosIn2, index maps) and
+ * the per-step ffl_* lookups + element-matrix rebuilds of ElStress
+ * (src/vpmStress/elStressModule.f90:129-229): uploads the model and builds every element's
+ * stress operator once on the GPU. */
+int fsr_part_create(fsr_part **part, const fsr_sam *sam, const fsr_elmdata *elm,
+                    const fsr_options *opt);
+
+/* Replaces openBandEmatrices (src/vpmStress/displacementModule.f90:645-790): takes the
+ * reducer's B (ndof1 x ndof2, leading dimension ldB) and E (ndof1 x ngen, ldE) as dmOpen
+ * holds them in core and folds dofPosIn2, meqn1/meqn2 scatter and disExpand (constraint
+ * equations) into one row operator R[ndof x (ndof2+ngen)] in nodal DOF order on the GPU. */
+int fsr_set_recovery(fsr_part *part, const double *B, int ldB, const double *E, int ldE);
+
+void fsr_part_destroy(fsr_part *part);
+
+/* ---- sizes ------------------------------------------------------------------------------- */
+int fsr_num_result_points(const fsr_part *part);           /* sum of nstrp over active elements */
+int fsr_result_point_offsets(const fsr_part *part, int *off /* [nel+1] */);
+int fsr_ndim(const fsr_part *part);                        /* ndof2 + ngen (mpar(24))            */
+
+/* ---- the hot path --------------------------------------------------------------------------
+ * Replaces the time loop body of stress.f90:361-435: calcIntDisplacements
+ * (displacementModule.f90:931-1024) + calcStresses (stressRoutines.f90:48-342) for nsteps
+ * steps at once.  Q is ndim x nsteps column-major, column s = [finit(1:ndof2); vg(1:ngen)] of
+ * step s (what readSupElDisplacements/BuildFinit deliver, supElTypeModule.f90:1067-1114).
+ *  vm_hist : optional [nsteps x npts] step-major von Mises stress of every result point
+ *            (row s = the reference's resMat(1,:) of step s for all elements in SAM order);
+ *            NULL = keep only the envelopes.
+ * The running envelopes (strainCoatModule.f90:159-166,410-420 semantics: max starts at 0,
+ * min at hugeVal) accumulate across calls until fsr_reset_envelope. */
+int fsr_recover(fsr_part *part, const double *Q, int ldq, int nsteps, double *vm_hist);
+
+/* Same, with Q already resident on the device (ldq-strided) and the von Mises history left on
+ * the device: vm_hist_dev is [nsteps x ld_vm] step-major or NULL.  Asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream). */
+int fsr_recover_dev(fsr_part *part, const double *Q_dev, int ldq, int nsteps,
+                    double *vm_hist_dev, size_t ld_vm, void *stream);
+
+int fsr_reset_envelope(fsr_part *part);
+int fsr_get_envelope(fsr_part *part, double *vm_max, double *vm_min); /* host [npts] each */
+int fsr_envelope_dev(fsr_part *part, double **vm_max_dev, double **vm_min_dev);
+
+/* Full result set for ONE step (what fedem_stress writes per step when all of -SR -stress
+ * -strain -vmStress ... are on, stressRoutines.f90:234-331).  q = [finit; vg] (ndim).
+ *  resmat [8 x npts] col-major per point: vmStress,maxP,minP,maxShear, then the same for strain
+ *  stress/strain [6 x npts] (first ncmp rows used; tensorial shear strain as ElStress :244-253)
+ *  sres [12 x nel] SR(1:6, node 1:2) stress resultants / beam section forces
+ *  sv [ndof] expanded nodal displacements (calcIntDisplacements output).  Any may be NULL. */
+int fsr_recover_step_full(fsr_part *part, const double *q, double *resmat, double *stress,
+                          double *strain, double *sres, double *sv);
+
+/* Expansion only (calcIntDisplacements for a batch): U_host [nsteps x ndof] step-major. */
+int fsr_expand(fsr_part *part, const double *Q, int ldq, int nsteps, double *U_host);
+
+/* ---- strain gages + fatigue (fedem_gage path) ------------------------------------------------
+ * Replaces ffp_addpoint / ffp_getdamage / ffp_getnumcycles
+ * (fedem-foundation/src/FFpLib/FFpFatigue/FFpFatigue_F.C:37-141) for ngage independent scalar
+ * histories at once: PVX peak-valley extraction, rainflow counting, Miner sum on a two-slope
+ * NorSok S-N curve, cycle histogram with the bin edges of reportDamage
+ * (src/vpmStress/strainGageModule.f90:827-848: s0 = 0, s1 = s0 + binSize, ...).
+ *  hist   [ngage x nsteps] gage-major (one contiguous history per gage), host
+ *  curve  {loga1, loga2, m1, m2}
+ *  damage [ngage]; ncycles [ngage] counted cycles; bins [ngage x nbins] (may be NULL) */
+int fsr_fatigue(int device, const double *hist, int ngage, int nsteps, double gate,
+                const double *curve, double bin_size, int nbins, double *damage, int *ncycles,
+                int *bins);
+int fsr_fatigue_dev(int device, const double *hist_dev, size_t ld_hist, int ngage, int nsteps,
+                    double gate, const double *curve, double bin_size, int nbins,
+                    double *damage_dev, int *ncycles_dev, int *bins_dev, void *stream);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+const char *fsr_last_error(void);
+/* Number of kernels this library launched since the counter was last reset (bench evidence). */
+long long fsr_kernel_launches(int reset);
+/* Device time (ms) of the last fsr_recover* call split per kernel family: t[0]=K1 expansion,
+ * t[1]=K2 element kernels (+fused envelope), t[2]=copies/other; measured with CUDA events on
+ * the library's stream.  Returns number of entries written. */
+int fsr_last_timing(fsr_part *part, double *t_ms, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEDEM_B200_H */

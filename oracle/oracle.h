@@ -1,0 +1,134 @@
+/*
+ * oracle.h -- CPU restatement of the reference's stress-recovery path (FP64, plain C).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
+ * and only as the checker / reported CPU baseline.  The product path (fedem_solvers_b200)
+ * never links or calls this library and fails loudly without its CUDA extension.
+ *
+ * Every function follows, statement by statement, the reference routine cited above it
+ * (paths relative to the SAP-archive/fedem-solvers checkout).  The reference's Fortran cannot
+ * be compiled in this image (no Fortran compiler), so this restatement is pinned by
+ *   (1) the reference's own known-answer tests re-expressed in tests/ (testBmatrix.pf mat-vec),
+ *   (2) the reference's own C++ (tensor invariants, cubicSolve, PVX / rainflow / S-N damage)
+ *       compiled unmodified from /root/reference into oracle/_ref/ and compared bit-for-bit,
+ *   (3) physics patch tests (rigid-body -> zero stress, uniform stretch, pure bending).
+ * For the element types in the configs (11, 23, 24, 41) the reference holds NO unit-level
+ * golden vector: parity for those is "unpinned by reference goldens" and
+ * rests on this statement-level restatement.
+ *
+ * Conventions: all index arrays are 1-based exactly as stored in the reference's .fsm file
+ * (madof, mpmnpc, mmnpc, meqn, ...); matrices are Fortran column-major unless noted.
+ */
+#ifndef FEDEM_ORACLE_H
+#define FEDEM_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#include <float.h>
+#define ORC_HUGE DBL_MAX        /* hugeVal_p = huge(1.0_dp), src/vpmUtilities/kindModule.f90:38 */
+#define ORC_EPSDIV0 DBL_EPSILON /* epsDiv0_p = epsilon(1.0_dp), kindModule.f90:44 */
+
+/* The subset of SamType (src/vpmCommon/samModule.f90:27-66) the recovery path reads. */
+typedef struct orc_sam {
+  int nnod, nel, ndof, ndof1, ndof2, neq, nceq, ngen;
+  const int *madof;     /* [nnod+1] first DOF of each node                         */
+  const int *mpmnpc;    /* [nel+1]  pointers into mmnpc                            */
+  const int *mmnpc;     /* [nmmnpc] element connectivity (internal node numbers)   */
+  const int *melcon;    /* [nel]    element type codes (11, 23, 24, 41, ...)       */
+  const int *meqn;      /* [ndof]   DOF -> equation number (<0: -constraint eq.)   */
+  const int *meqn1;     /* [ndof1]  equation numbers of the internal DOFs          */
+  const int *meqn2;     /* [ndof2]  equation numbers of the external DOFs          */
+  const int *dofPosIn2; /* [ndof2]  see orc_dof_pos_in2                            */
+  const int *mpmceq;    /* [nceq+1] */
+  const int *mmceq;     /* [nmmceq] */
+  const double *ttcc;   /* [nmmceq] */
+} orc_sam;
+
+/* Per-element data the reference fetches through ffl_getcoor/getmat/getthick/getbeamsection
+ * (fedem-foundation/src/FFlLib/FFlLinkHandler_F.C:745-1193). */
+typedef struct orc_elmdata {
+  const double *xyz;      /* [3*nnod] nodal coordinates x,y,z per internal node            */
+  const double *emod;     /* [nel] Young's modulus                                         */
+  const double *rny;      /* [nel] Poisson's ratio                                         */
+  const double *thk;      /* [nel] shell thickness (ffl_getthick returns it for all nodes) */
+  const int    *elmid;    /* [nel] external element id, <1: element is skipped (or NULL)   */
+  const double *beam;     /* [nel*ORC_NBEAM] beam data, see orc_str11 (or NULL)            */
+} orc_elmdata;
+#define ORC_NBEAM 32
+
+/* ---- expansion (K1) ---- */
+void orc_dof_pos_in2(int ndof, int ndof2, const int *msc, const int *meqn,
+                     const int *meqn2, int *dofPosIn2);
+void orc_mat_times_vec(int nrows, int ncols, const double *A, const double *x,
+                       double *y, int do_initialize);
+void orc_dis_expand(const orc_sam *sam, const double *sveq, double *svdof);
+int orc_calc_int_displacements(const orc_sam *sam, const double *Bmat, const double *Emat,
+                               const double *finit, const double *vg, double *work,
+                               double *sv);
+
+/* ---- element routines (K2) ---- */
+int orc_extract_ev(int iel, const orc_sam *sam, const double *sv, double *ev, int evsize);
+void orc_iso_mat2d(double emod, double rnu, double C[9]);
+void orc_iso_mat2d_inv(double emod, double rnu, double C[9]);
+int orc_pmat_stiff(int nnod, const double *x, const double *y, const double *z, double *pmat);
+int orc_shell_element_axes(int nenod, const double *X, const double *Y, const double *Z,
+                           double V1[3], double V2[3], double V3[3]);
+int orc_shell_stress_trans(const double VX[3], const double VZ[3], double T[4]);
+void orc_strain_disp_quad4(int nndof, const double *xEl, const double *yEl, const double *zEl,
+                           const double T_el[9], double xi, double eta, double zPos,
+                           double *B_el);
+void orc_strain_disp_cst(int nndof, const double *xEl, const double *yEl, const double *zEl,
+                         const double T_el[9], double zPos, double *B_el);
+int orc_str24(const double xg[4], const double yg[4], const double zg[4], double emod,
+              double rny, const double thk[4], double ev[24], double SR[24], double SS[24],
+              double sigma[24], double epsil[24]);
+int orc_str23(const double xg[3], const double yg[3], const double zg[3], double emod,
+              double rny, const double thk[3], const double ev[18], double SR[18],
+              double SS[18], double sigma[18], double epsil[18]);
+int orc_str41(const double xg[10], const double yg[10], const double zg[10], double emod,
+              double rny, int stressForm, const double v[30], double sigma[60],
+              double epsil[60]);
+int orc_str11(const double *beam, const double ev[12], double SF[12]);
+int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed,
+                  double *V, double *S, double *Sigma, double *Epsil, int *nenod, int *nstrp);
+
+/* ---- invariants ---- */
+double orc_von_mises(int N, const double *S);
+int orc_cubic_solve(double A, double B, double C, double D, double *X);
+int orc_principal_values(int N, const double *S, double *P);
+double orc_max_shear_value(double pmax, double pmin);
+void orc_rotate2d(const double *S, const double *rotMx, double *out);
+void orc_calc_von_mises(const double *inTensor, int ncomp, int nstrp, double *vm);
+void orc_calc_principal_vals(const double *inTensor, int ncomp, int nstrp, double *maxP,
+                             double *minP, double *maxS);
+
+/* ---- whole-part loop (calcStresses) ---- */
+int orc_result_point_offsets(const orc_sam *sam, const int *elmid, int *off);
+int orc_calc_stresses(const orc_sam *sam, const orc_elmdata *ed, const double *sv,
+                      const int *ptoff, double *resmat, double *stress, double *strain,
+                      double *sres, int nthreads);
+int orc_recover_history(const orc_sam *sam, const orc_elmdata *ed, const double *Bmat,
+                        const double *Emat, const double *Q, int nsteps, const int *ptoff,
+                        double *vm_hist, double *env_max, double *env_min, int nthreads);
+
+/* ---- strain rosettes / gages ---- */
+void orc_principle_strains2d(const double epsC[3], double *eps1, double *eps2,
+                             double *gammaMax, double *alpha1, double *alphaGamma);
+void orc_principle_stresses2d(const double sigC[3], double *sig1, double *sig2,
+                              double *tauMax, double *alpha1, double *alphaTau);
+
+/* ---- fatigue (K3) ---- */
+int orc_pvx(const double *data, int n, double gate, double *turns);
+int orc_rainflow(const double *turns, int nturns, double gate, double *cyc_first,
+                 double *cyc_second);
+double orc_sn_norsok(double s, double loga1, double loga2, double m1, double m2);
+double orc_damage(const double *cyc_first, const double *cyc_second, int ncyc, double loga1,
+                  double loga2, double m1, double m2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

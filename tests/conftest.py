@@ -1,0 +1,26 @@
+import os
+import sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_bind
+    return oracle_bind.Oracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    import oracle_bind
+    r = oracle_bind.Reference()
+    if not r.available:
+        pytest.skip("oracle/_ref/libfedem_ref.so not built (reference sources absent)")
+    return r

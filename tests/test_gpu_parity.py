@@ -1,0 +1,114 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerance: BASELINE.json north_star -- <= 1e-10 relative on FP64 stresses
+(max|gpu - oracle| <= 1e-10 * max|oracle| per result quantity per part)."""
+import numpy as np
+import pytest
+
+from fedem_solvers_b200 import StressRecovery
+from fedem_solvers_b200.model import plate_part, tet10_block, reduced_history
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-10
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _check_part(oracle, part, nsteps, seed, step_tile=0):
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, nsteps, seed=seed)
+    vm_o, mx_o, mn_o = oracle.recover_history(b, Q)
+    rec = StressRecovery(part, step_tile=step_tile)
+    assert rec.npts == b["npts"]
+    assert np.array_equal(rec.result_point_offsets(), b["ptoff"])
+    vm_g = rec.recover(Q)
+    mx_g, mn_g = rec.envelope()
+    assert rel_err(vm_g, vm_o) <= TOL, rel_err(vm_g, vm_o)
+    assert rel_err(mx_g, mx_o) <= TOL
+    assert rel_err(mn_g, mn_o) <= TOL
+    # expansion alone (calcIntDisplacements)
+    U = rec.calc_int_displacements(Q[:, :3])
+    for s in range(3):
+        sv = oracle.expand(b, Q[:, s])
+        assert rel_err(U[s], sv) <= TOL
+    # full result set of one step
+    full = rec.calc_stresses(Q[:, 1])
+    ref = oracle.calc_stresses(b, oracle.expand(b, Q[:, 1]))
+    assert rel_err(full["sv"], oracle.expand(b, Q[:, 1])) <= TOL
+    for key in ("stress", "strain"):
+        assert rel_err(full[key], ref[key]) <= TOL, (key, rel_err(full[key], ref[key]))
+    for k, name in enumerate(["vmStress", "maxPStress", "minPStress", "maxSStress", "vmStrain",
+                              "maxPStrain", "minPStrain", "maxSStrain"]):
+        e = rel_err(full["resmat"][:, k], ref["resmat"][:, k])
+        assert e <= 1e-9 if "P" in name else e <= TOL, (name, e)
+    rec.close()
+    return vm_g
+
+
+def test_quad_plate_small(oracle):
+    part = plate_part(9, 7, ngen=5, seed=11, shuffle_eq=True, n_fixed=4, n_constraints=3, warp=0.05)
+    _check_part(oracle, part, nsteps=37, seed=3)
+
+
+def test_quad_plate_multi_tile(oracle):
+    """step window larger than the device batch: tiles of 64 steps, ragged last tile"""
+    part = plate_part(8, 8, ngen=4, seed=12)
+    _check_part(oracle, part, nsteps=150, seed=4, step_tile=64)
+
+
+def test_tet10_block_small(oracle):
+    part = tet10_block(3, 2, 2, ngen=6, seed=5, shuffle_eq=True)
+    _check_part(oracle, part, nsteps=21, seed=6)
+
+
+def test_config1_plate(oracle):
+    """BASELINE config 1: 70x70 ANDES quads, 5,041 nodes, 4 external nodes, 10 modes; the oracle
+    covers a 40-step sample of the 1,000-step history (it rebuilds every element every step)."""
+    part = plate_part(70, 70, ngen=10, seed=1)
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 1000, seed=1)
+    rec = StressRecovery(part)
+    vm_g = rec.recover(Q)
+    mx_g, mn_g = rec.envelope()
+    sample = np.arange(0, 1000, 25)
+    vm_o, _, _ = oracle.recover_history(b, Q[:, sample], nthreads=8)
+    assert rel_err(vm_g[sample], vm_o) <= TOL
+    # envelope is the running max/min of the history it produced (max starts at 0, min at huge)
+    assert np.array_equal(mx_g, np.maximum(vm_g.max(0), 0.0))
+    assert np.array_equal(mn_g, vm_g.min(0))
+    rec.close()
+
+
+def test_envelope_accumulates_and_resets(oracle):
+    part = plate_part(5, 5, ngen=3, seed=2)
+    Q = reduced_history(part.sam.ndim, 64, seed=9)
+    rec = StressRecovery(part)
+    vm1 = rec.recover(Q[:, :32])
+    vm2 = rec.recover(Q[:, 32:])
+    mx, mn = rec.envelope()
+    allvm = np.vstack([vm1, vm2])
+    assert np.array_equal(mx, allvm.max(0)) and np.array_equal(mn, allvm.min(0))
+    rec.reset_envelope()
+    rec.recover(Q[:, :1], want_history=False)
+    mx, mn = rec.envelope()
+    assert np.array_equal(mx, vm1[0]) and np.array_equal(mn, vm1[0])
+    rec.close()
+
+
+def test_degenerate_element_gets_huge(oracle):
+    """failed element -> hugeVal results, run continues (stressRoutines.f90:237-241,264-268)"""
+    part = plate_part(4, 4, ngen=2, seed=8)
+    n = part.sam.mmnpc[part.sam.mpmnpc[5] - 1: part.sam.mpmnpc[6] - 1]
+    part.elm.xyz[n[2] - 1] = part.elm.xyz[n[0] - 1]   # collapse a diagonal: zero normal
+    part.elm.xyz[n[3] - 1] = part.elm.xyz[n[1] - 1]
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 4, seed=1)
+    vm_o, _, _ = oracle.recover_history(b, Q)
+    rec = StressRecovery(part)
+    assert rec.n_failed >= 1
+    vm_g = rec.recover(Q)
+    bad = vm_o >= 1e300
+    assert bad.any() and np.array_equal(bad, vm_g >= 1e300)
+    assert rel_err(vm_g[~bad], vm_o[~bad]) <= TOL
+    rec.close()
