@@ -45,6 +45,7 @@ SYMBOLS = [
     ("fsr_part_create", C.c_int, [C.POINTER(_P), C.POINTER(FsrSam), C.POINTER(FsrElmData), C.POINTER(FsrOptions)]),
     ("fsr_set_recovery", C.c_int, [_P, _D, C.c_int, _D, C.c_int]),
     ("fsr_part_destroy", None, [_P]),
+    ("fsr_set_stream", C.c_int, [_P, _P]),
     ("fsr_num_result_points", C.c_int, [_P]),
     ("fsr_result_point_offsets", C.c_int, [_P, _I]),
     ("fsr_ndim", C.c_int, [_P]),
@@ -53,6 +54,7 @@ SYMBOLS = [
     ("fsr_reset_envelope", C.c_int, [_P]),
     ("fsr_get_envelope", C.c_int, [_P, _D, _D]),
     ("fsr_envelope_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    ("fsr_copy_envelope_dev", C.c_int, [_P, _P, _P, _P]),
     ("fsr_recover_step_full", C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
     ("fsr_expand", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
     ("fsr_fatigue", C.c_int, [C.c_int, _D, C.c_int, C.c_int, C.c_double, _D, C.c_double, C.c_int, _D, _I, _I]),
@@ -61,6 +63,7 @@ SYMBOLS = [
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),
+    ("fsr_timing_reset", C.c_int, [_P]),
 ]
 
 

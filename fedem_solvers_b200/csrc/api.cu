@@ -183,7 +183,8 @@ void fsr_part_destroy(fsr_part* p)
   for (int f = 0; f < FAM_COUNT; ++f) free_family(p->fam[f]);
   if (p->pinned) cudaFreeHost(p->pinned);
   for (int i = 0; i < 4; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
-  if (p->stream) cudaStreamDestroy(p->stream);
+  for (auto& tr : p->evring) for (int i = 0; i < 3; ++i) if (tr[i]) cudaEventDestroy(tr[i]);
+  if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
 
@@ -196,6 +197,17 @@ int fsr_set_recovery(fsr_part* p, const double* B, int ldB, const double* E, int
   if (!p->sam_keep.valid) { set_error("fsr_set_recovery: SAM maps missing"); return FSR_ERR_STATE; }
   fsr_sam sam = p->sam_keep.view();
   return build_row_operator(p, &sam, B, ldB, E, ldE);
+}
+
+int fsr_set_stream(fsr_part* p, void* stream)
+{
+  if (!p) return FSR_ERR_ARG;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+  p->stream = (cudaStream_t)stream;
+  p->own_stream = false;
+  return FSR_OK;
 }
 
 int fsr_num_result_points(const fsr_part* p) { return p ? p->npts : FSR_ERR_ARG; }
@@ -228,6 +240,18 @@ int fsr_get_envelope(fsr_part* p, double* vm_max, double* vm_min)
   return FSR_OK;
 }
 
+int fsr_copy_envelope_dev(fsr_part* p, double* vm_max_dst_dev, double* vm_min_dst_dev, void* stream)
+{
+  if (!p) return FSR_ERR_ARG;
+  FSR_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+  if (vm_max_dst_dev)
+    FSR_CUDA(cudaMemcpyAsync(vm_max_dst_dev, p->env_max, sizeof(double) * p->npts, cudaMemcpyDeviceToDevice, s));
+  if (vm_min_dst_dev)
+    FSR_CUDA(cudaMemcpyAsync(vm_min_dst_dev, p->env_min, sizeof(double) * p->npts, cudaMemcpyDeviceToDevice, s));
+  return FSR_OK;
+}
+
 int fsr_envelope_dev(fsr_part* p, double** vm_max_dev, double** vm_min_dev)
 {
   if (!p) return FSR_ERR_ARG;
@@ -242,13 +266,20 @@ static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
 {
   int nsteps_pad = round_up(nsteps, 64);
   int rc;
-  if (timed) cudaEventRecord(p->ev[0], s);
+  cudaEvent_t* ev = nullptr;
+  if (timed && p->ntimed < (int)(sizeof(p->evring) / sizeof(p->evring[0]))) {
+    ev = p->evring[p->ntimed];
+    for (int i = 0; i < 3; ++i)
+      if (!ev[i]) FSR_CUDA(cudaEventCreate(&ev[i]));
+    ++p->ntimed;
+  }
+  if (ev) cudaEventRecord(ev[0], s);
   if ((rc = launch_pack_q(p, Q_dev, ldq, nsteps, nsteps_pad, s))) return rc;
   if ((rc = launch_k1(p, nsteps_pad, s))) return rc;
-  if (timed) cudaEventRecord(p->ev[1], s);
+  if (ev) cudaEventRecord(ev[1], s);
   if ((rc = launch_k2_shell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if ((rc = launch_k2_tet10_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
-  if (timed) cudaEventRecord(p->ev[2], s);
+  if (ev) cudaEventRecord(ev[2], s);
   return FSR_OK;
 }
 
@@ -265,7 +296,7 @@ int fsr_recover_dev(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
     int nt = std::min(p->step_tile, nsteps - t0);
     rc = run_tile(p, Q_dev + (size_t)t0 * ldq, ldq, nt, vm_hist_dev ? vm_hist_dev + (size_t)t0 * ld_vm : nullptr,
-                  ld_vm, s, false);
+                  ld_vm, s, true);
     if (rc) return rc;
   }
   return FSR_OK;
@@ -285,8 +316,7 @@ int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hi
     FSR_CUDA(cudaMalloc(&p->Qstage, std::max<size_t>(qbytes, 8)));
     p->Qstage_cap = qbytes;
   }
-  p->t_k1 = p->t_k2 = p->t_other = 0.0;
-  cudaEventRecord(p->ev[3], s);
+  p->ntimed = 0;
   FSR_CUDA(cudaMemcpyAsync(p->Qstage, Q, qbytes, cudaMemcpyHostToDevice, s));
   for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
     int nt = std::min(p->step_tile, nsteps - t0);
@@ -295,11 +325,7 @@ int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hi
     if (vm_hist)
       FSR_CUDA(cudaMemcpyAsync(vm_hist + (size_t)t0 * p->npts, p->vm_tile, sizeof(double) * (size_t)nt * p->npts,
                                cudaMemcpyDeviceToHost, s));
-    FSR_CUDA(cudaStreamSynchronize(s));
-    float a = 0, b = 0;
-    cudaEventElapsedTime(&a, p->ev[0], p->ev[1]);
-    cudaEventElapsedTime(&b, p->ev[1], p->ev[2]);
-    p->t_k1 += a; p->t_k2 += b;
+    if (vm_hist) FSR_CUDA(cudaStreamSynchronize(s));  // vm_tile is reused by the next tile
   }
   FSR_CUDA(cudaStreamSynchronize(s));
   return FSR_OK;
@@ -378,10 +404,26 @@ int fsr_recover_step_full(fsr_part* p, const double* q, double* resmat, double* 
 int fsr_last_timing(fsr_part* p, double* t_ms, int n)
 {
   if (!p || !t_ms) return FSR_ERR_ARG;
-  double v[3] = {p->t_k1, p->t_k2, p->t_other};
+  cudaSetDevice(p->device);
+  double v[3] = {0.0, 0.0, (double)p->ntimed};
+  for (int k = 0; k < p->ntimed; ++k) {
+    cudaEvent_t* ev = p->evring[k];
+    if (cudaEventSynchronize(ev[2]) != cudaSuccess) { set_error("fsr_last_timing: event sync failed"); return FSR_ERR_CUDA; }
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    v[0] += a; v[1] += b;
+  }
   int m = std::min(n, 3);
   for (int i = 0; i < m; ++i) t_ms[i] = v[i];
   return m;
+}
+
+int fsr_timing_reset(fsr_part* p)
+{
+  if (!p) return FSR_ERR_ARG;
+  p->ntimed = 0;
+  return FSR_OK;
 }
 
 }  // extern "C"

@@ -133,8 +133,10 @@ struct fsr_part {
   fsr::FamilyData fam[fsr::FAM_COUNT];
   int nfailed = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  double t_k1 = 0, t_k2 = 0, t_other = 0;
+  cudaEvent_t evring[256][3] = {};  // per-tile event triplets: start, after K1, after K2
+  int ntimed = 0;
   double* pinned = nullptr; size_t pinned_cap = 0;
 };
 

@@ -116,8 +116,13 @@ def _build_sam(nnod, ndof_per_node, conn_list, types, ext_nodes, fixed_dofs=(), 
     if shuffle_eq and rng is not None:
         meqn1 = rng.permutation(meqn1)
         meqn2 = rng.permutation(meqn2)
-    mpmnpc = np.concatenate([[1], 1 + np.cumsum([len(c) for c in conn_list])]).astype(I32)
-    mmnpc = np.concatenate(conn_list).astype(I32) if len(conn_list) else np.zeros(0, I32)
+    if isinstance(conn_list, np.ndarray) and conn_list.ndim == 2:  # uniform connectivity, fast path
+        nper = conn_list.shape[1]
+        mpmnpc = (1 + nper * np.arange(conn_list.shape[0] + 1, dtype=np.int64)).astype(I32)
+        mmnpc = np.ascontiguousarray(conn_list, I32).ravel()
+    else:
+        mpmnpc = np.concatenate([[1], 1 + np.cumsum([len(c) for c in conn_list])]).astype(I32)
+        mmnpc = np.concatenate(conn_list).astype(I32) if len(conn_list) else np.zeros(0, I32)
     return SamData(nnod=nnod, nel=len(conn_list), ndof=ndof, ndof1=len(int_dofs), ndof2=len(ext_dofs),
                    ngen=0, neq=neq, nceq=len(dep), madof=madof, msc=msc, mpmnpc=mpmnpc, mmnpc=mmnpc,
                    melcon=np.asarray(types, I32), meqn=meqn, meqn1=meqn1.astype(I32),
@@ -144,12 +149,30 @@ def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0):
     ncol = sam.ndof2 + ngen
     M = np.empty((sam.ndof1, ncol), F64, order="F")
     cscale = np.array([1.0, 1.0, 1.0, 0.5, 0.5, 0.5])
-    for j in range(ncol):
-        f = rng.integers(0, 4, 3) * np.pi
-        ph = rng.uniform(0, 2 * np.pi, 3)
-        a = rng.normal(0.0, 1.0, 6) * cscale
-        M[:, j] = amp * a[comp] * np.cos(f[0] * u[:, 0] + ph[0]) * np.cos(f[1] * u[:, 1] + ph[1]) * \
-            np.cos(f[2] * u[:, 2] + ph[2])
+    # cos(f*u + ph) = cos(f*u) cos(ph) - sin(f*u) sin(ph): tabulate the four harmonics per axis once
+    ctab = [[np.cos(m * np.pi * u[:, ax]) for m in range(4)] for ax in range(3)]
+    stab = [[np.sin(m * np.pi * u[:, ax]) for m in range(4)] for ax in range(3)]
+    fs = rng.integers(0, 4, (ncol, 3))
+    phs = rng.uniform(0, 2 * np.pi, (ncol, 3))
+    amps = rng.normal(0.0, 1.0, (ncol, 6)) * cscale
+
+    def fill(j):
+        col = M[:, j]
+        np.take(amp * amps[j], comp, out=col)
+        tmp = np.empty(sam.ndof1, F64)
+        for ax in range(3):
+            np.multiply(ctab[ax][fs[j, ax]], np.cos(phs[j, ax]), out=tmp)
+            tmp -= stab[ax][fs[j, ax]] * np.sin(phs[j, ax])
+            col *= tmp
+
+    if sam.ndof1 * ncol > 5_000_000:
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            list(ex.map(fill, range(ncol)))
+    else:
+        for j in range(ncol):
+            fill(j)
     B = np.asfortranarray(M[:, :sam.ndof2])
     E = np.asfortranarray(M[:, sam.ndof2:])
     return B, E
@@ -203,7 +226,7 @@ def plate_part(nx, ny, ngen=10, seed=1, tri_fraction=0.0, n_ext=4, jitter=0.02, 
         split = rng.random(ncell) < tri_fraction
     conn, types = [], []
     if not split.any():
-        conn = list(quads)
+        conn = quads
         types = np.full(ncell, 24, I32)
     else:
         types = []

@@ -94,11 +94,22 @@ class StressRecovery:
     def reset_envelope(self):
         check(self._lib.fsr_reset_envelope(self._h), "fsr_reset_envelope")
 
-    def envelope(self):
+    def set_stream(self, stream_ptr):
+        """Run all later calls on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._lib.fsr_set_stream(self._h, C.c_void_p(stream_ptr) if stream_ptr else None), "fsr_set_stream")
+
+    def envelope(self, out_max=None, out_min=None):
         """Running (max, min) of von Mises per result point (strainCoatModule.f90:159-166,410-420)."""
-        mx = np.empty(self.npts, F64); mn = np.empty(self.npts, F64)
+        mx = out_max if out_max is not None else np.empty(self.npts, F64)
+        mn = out_min if out_min is not None else np.empty(self.npts, F64)
         check(self._lib.fsr_get_envelope(self._h, _dp(mx), _dp(mn)), "fsr_get_envelope")
         return mx, mn
+
+    def copy_envelope_dev(self, max_ptr, min_ptr, stream=None):
+        """Envelopes into caller-owned device buffers (torch tensors: .data_ptr()), asynchronous."""
+        check(self._lib.fsr_copy_envelope_dev(self._h, C.c_void_p(max_ptr) if max_ptr else None,
+                                              C.c_void_p(min_ptr) if min_ptr else None,
+                                              C.c_void_p(stream) if stream else None), "fsr_copy_envelope_dev")
 
     def envelope_dev_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()
@@ -132,7 +143,10 @@ class StressRecovery:
     def last_timing(self):
         t = np.zeros(3, F64)
         self._lib.fsr_last_timing(self._h, _dp(t), 3)
-        return dict(k1_ms=t[0], k2_ms=t[1], other_ms=t[2])
+        return dict(k1_ms=t[0], k2_ms=t[1], tiles=int(t[2]))
+
+    def timing_reset(self):
+        self._lib.fsr_timing_reset(self._h)
 
     def close(self):
         if self._h:

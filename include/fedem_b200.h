@@ -107,6 +107,10 @@ int fsr_set_recovery(fsr_part *part, const double *B, int ldB, const double *E, 
 
 void fsr_part_destroy(fsr_part *part);
 
+/* Makes every later call on this handle run on the caller's stream (cudaStream_t as void*;
+ * NULL = the legacy default stream) instead of the handle's private stream. */
+int fsr_set_stream(fsr_part *part, void *stream);
+
 /* ---- sizes ------------------------------------------------------------------------------- */
 int fsr_num_result_points(const fsr_part *part);           /* sum of nstrp over active elements */
 int fsr_result_point_offsets(const fsr_part *part, int *off /* [nel+1] */);
@@ -133,12 +137,15 @@ int fsr_recover_dev(fsr_part *part, const double *Q_dev, int ldq, int nsteps,
 int fsr_reset_envelope(fsr_part *part);
 int fsr_get_envelope(fsr_part *part, double *vm_max, double *vm_min); /* host [npts] each */
 int fsr_envelope_dev(fsr_part *part, double **vm_max_dev, double **vm_min_dev);
+/* device-to-device copy of the envelopes into caller-owned device buffers ([npts] each, either
+ * may be NULL), asynchronous on `stream` -- the hand-over point to an NCCL gather. */
+int fsr_copy_envelope_dev(fsr_part *part, double *vm_max_dst_dev, double *vm_min_dst_dev, void *stream);
 
 /* Full result set for ONE step (what fedem_stress writes per step when all of -SR -stress
  * -strain -vmStress ... are on, stressRoutines.f90:234-331).  q = [finit; vg] (ndim).
  *  resmat [8 x npts] col-major per point: vmStress,maxP,minP,maxShear, then the same for strain
  *  stress/strain [6 x npts] (first ncmp rows used; tensorial shear strain as ElStress :244-253)
- *  sres [12 x nel] SR(1:6, node 1:2) stress resultants / beam section forces
+ *  sres [24 x nel] SR(1:6, node 1:4) shell stress resultants / SF(1:6, 1:2) beam section forces
  *  sv [ndof] expanded nodal displacements (calcIntDisplacements output).  Any may be NULL. */
 int fsr_recover_step_full(fsr_part *part, const double *q, double *resmat, double *stress,
                           double *strain, double *sres, double *sv);
@@ -166,10 +173,13 @@ int fsr_fatigue_dev(int device, const double *hist_dev, size_t ld_hist, int ngag
 const char *fsr_last_error(void);
 /* Number of kernels this library launched since the counter was last reset (bench evidence). */
 long long fsr_kernel_launches(int reset);
-/* Device time (ms) of the last fsr_recover* call split per kernel family: t[0]=K1 expansion,
- * t[1]=K2 element kernels (+fused envelope), t[2]=copies/other; measured with CUDA events on
- * the library's stream.  Returns number of entries written. */
+/* Device time (ms), summed over the step tiles launched since the last fsr_timing_reset (or the
+ * start of the last fsr_recover), split per kernel family: t[0] = Q packing + K1 expansion,
+ * t[1] = K2 element kernels (+fused envelope), t[2] = number of tiles timed.  Measured with CUDA
+ * events recorded on the stream the kernels were launched on; synchronises on the last event.
+ * Returns the number of entries written. */
 int fsr_last_timing(fsr_part *part, double *t_ms, int n);
+int fsr_timing_reset(fsr_part *part);
 
 #ifdef __cplusplus
 }

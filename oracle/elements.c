@@ -218,6 +218,10 @@ int orc_recover_history(const orc_sam *sam, const orc_elmdata *ed, const double 
   double *sv = (double *)malloc(sizeof(double) * (size_t)sam->ndof);
   double *resmat = (double *)malloc(sizeof(double) * 8 * (size_t)(npts > 0 ? npts : 1));
   if (!work || !sv || !resmat) { free(work); free(sv); free(resmat); return -1; }
+  {
+    extern int orc_threads;
+    orc_threads = nthreads > 0 ? nthreads : 1;
+  }
   if (env_max) for (int p = 0; p < npts; p++) env_max[p] = 0.0;
   if (env_min) for (int p = 0; p < npts; p++) env_min[p] = ORC_HUGE;
   for (int s = 0; s < nsteps; s++) {

@@ -5,6 +5,8 @@
 #include "oracle.h"
 #include <string.h>
 
+int orc_threads = 1; /* host threads for the bench variant; 1 = the reference's serial loop */
+
 /* samModule.f90:964-970: for the i2-th DOF with status code 2 (in nodal DOF order),
  * dofPosIn2(i2) = findloc(meqn2, meqn(idof)) (1-based position, 0 if absent). */
 void orc_dof_pos_in2(int ndof, int ndof2, const int *msc, const int *meqn,
@@ -28,10 +30,18 @@ void orc_mat_times_vec(int nrows, int ncols, const double *A, const double *x,
 {
   if (nrows < 1 || ncols < 1) return;
   if (do_initialize) memset(y, 0, sizeof(double) * (size_t)nrows);
-  for (int i = 0; i < ncols; i++) {
-    const double *col = A + (size_t)i * (size_t)nrows;
-    const double xi = x[i];
-    for (int r = 0; r < nrows; r++) y[r] = y[r] + col[r] * xi;
+  /* Row blocks may run on several host threads (bench "all host cores" variant); every y[r]
+   * still accumulates its columns in the reference's order i = 1..ncols. */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(orc_threads > 0 ? orc_threads : 1)
+#endif
+  for (int r0 = 0; r0 < nrows; r0 += 4096) {
+    int r1 = r0 + 4096 < nrows ? r0 + 4096 : nrows;
+    for (int i = 0; i < ncols; i++) {
+      const double *col = A + (size_t)i * (size_t)nrows;
+      const double xi = x[i];
+      for (int r = r0; r < r1; r++) y[r] = y[r] + col[r] * xi;
+    }
   }
 }
 
