@@ -268,8 +268,63 @@ __global__ void build_quad_ops_kernel(int nelt, const int* __restrict__ elem,
 // ------------------------------------------------------------------------------------------
 // K2 apply: von Mises + envelope for shell families (3 m-tiles: xx, yy, xy at 8 points)
 // ------------------------------------------------------------------------------------------
-template <int KT>
-__global__ void __launch_bounds__(256)
+// The FP64 tensor pipe is the shared resource here (DMMA and scalar FP64 issue to the same pipe and
+// a DMMA holds the dispatch port for its 16 cycles), so every non-DMMA instruction in the step loop
+// costs wall time: the loop body is written for minimum instruction count -- row pointers bumped
+// once per four tiles with immediate offsets in between, register double-buffering without moves,
+// a Newton square root on MUFU.RSQ64H instead of the IEEE slow path, compare/select envelopes.
+
+// sqrt(x) for x >= 0 to < 1 ulp-ish (two Newton steps on the 2^-22 hardware seed); 0 for x < 1e-290
+__device__ __forceinline__ double sqrt_pos(double x)
+{
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double y = x * r, h = 0.5 * r;
+  double e = fma(-h, y, 0.5);
+  y = fma(y, e, y);
+  h = fma(h, e, h);
+  e = fma(-y, y, x);
+  y = fma(e, h, y);
+  return x > 1.0e-290 ? y : 0.0;
+}
+
+template <int KT, bool WRITE_VM, bool GUARD>
+__device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const double (&b)[KT], double*& vmp0,
+                                           double*& vmp1, size_t ld8, int t0, int nsteps, double& emax,
+                                           double& emin)
+{
+  double c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+#pragma unroll
+    for (int m = 0; m < 3; ++m) dmma884(c[m][0], c[m][1], a[m][j], b[j]);
+  // von Mises, FFaTensorTransforms.C:33-36: sqrt(s11^2 + s22^2 - s11*s22 + 3*s12^2)
+  double q0 = fma(c[2][0] * 3.0, c[2][0], fma(-c[0][0], c[1][0], fma(c[1][0], c[1][0], c[0][0] * c[0][0])));
+  double q1 = fma(c[2][1] * 3.0, c[2][1], fma(-c[0][1], c[1][1], fma(c[1][1], c[1][1], c[0][1] * c[0][1])));
+  double v0 = sqrt_pos(q0), v1 = sqrt_pos(q1);
+  if (GUARD) {
+    if (t0 < nsteps) {
+      if (WRITE_VM) *vmp0 = v0;
+      emax = v0 > emax ? v0 : emax;
+      emin = v0 < emin ? v0 : emin;
+    }
+    if (t0 + 1 < nsteps) {
+      if (WRITE_VM) *vmp1 = v1;
+      emax = v1 > emax ? v1 : emax;
+      emin = v1 < emin ? v1 : emin;
+    }
+  } else {
+    if (WRITE_VM) { *vmp0 = v0; *vmp1 = v1; }
+    const bool p = v0 > v1;
+    const double hi = p ? v0 : v1, lo = p ? v1 : v0;
+    emax = hi > emax ? hi : emax;
+    emin = lo < emin ? lo : emin;
+  }
+  if (WRITE_VM) { vmp0 += ld8; vmp1 += ld8; }
+}
+
+template <int KT, bool WRITE_VM>
+__global__ void __launch_bounds__(256, 2)
 k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
                    const double* __restrict__ Sfrag, const int* __restrict__ edof,
                    const int* __restrict__ ptoff, const unsigned char* __restrict__ failed,
@@ -280,6 +335,17 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
   const int g = lane >> 2, t4 = lane & 3;
   const int i = blockIdx.x * (blockDim.x >> 5) + warp;
   if (i >= nelt) return;
+  const bool live = g < nstrp;
+  const size_t pt = (size_t)ptoff[i] + (live ? g : 0);
+
+  if (failed[i]) {  // operator build failed: hugeVal results (stressRoutines.f90:264-268)
+    if (live) {
+      if (WRITE_VM)
+        for (int t = t4; t < nsteps; t += 4) vm[(size_t)t * ld_vm + pt] = kHuge;
+      if (t4 == 0 && nsteps > 0) { env_max[pt] = kHuge; if (kHuge < env_min[pt]) env_min[pt] = kHuge; }
+    }
+    return;
+  }
 
   // operator fragments: resident for the whole step tile
   double a[3][KT];
@@ -290,48 +356,58 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
     for (int j = 0; j < KT; ++j) a[m][j] = __ldg(sf + (size_t)(m * KT + j) * 32);
 
   // this lane's DOF row of U for each k-tile (B fragment: row k = t4, column n = g)
-  const double* urow[KT];
+  const double* up[KT];
 #pragma unroll
-  for (int j = 0; j < KT; ++j) urow[j] = U + (size_t)__ldg(edof + (size_t)i * KT * 4 + j * 4 + t4) * ldu + g;
+  for (int j = 0; j < KT; ++j) up[j] = U + (size_t)__ldg(edof + (size_t)i * KT * 4 + j * 4 + t4) * ldu + g;
 
-  const bool bad = failed[i] != 0;
-  const bool live = g < nstrp;
-  const size_t pt = (size_t)ptoff[i] + g;
   double emax = 0.0, emin = kHuge;  // neutral w.r.t. the stored envelope (max starts at 0)
+  // lane owns point g at steps t0 = 8*tile + 2*t4 and t0 + 1; padded lanes (g >= nstrp) write to a
+  // valid dummy location guarded below by `live`
+  double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
+  double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
+  const size_t ld8 = ld_vm * 8;
 
-  const int ntiles = nsteps_pad >> 3;
-  double b[KT], bn[KT];
+  const int ntiles = nsteps_pad >> 3;            // multiple of 8
+  const int nfull = ((nsteps >> 3) >> 2) << 2;   // tiles (in groups of 4) with all 8 steps valid
+  double b0[KT], b1[KT];
 #pragma unroll
-  for (int j = 0; j < KT; ++j) b[j] = urow[j][0];
+  for (int j = 0; j < KT; ++j) b0[j] = up[j][0];
 
-  for (int nt = 0; nt < ntiles; ++nt) {
-    if (nt + 1 < ntiles) {
+  if (live) {
+    int nt = 0;
+    for (; nt < nfull; nt += 4) {
 #pragma unroll
-      for (int j = 0; j < KT; ++j) bn[j] = urow[j][(nt + 1) * 8];
+      for (int j = 0; j < KT; ++j) b1[j] = up[j][8];
+      shell_tile<KT, WRITE_VM, false>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin);
+#pragma unroll
+      for (int j = 0; j < KT; ++j) b0[j] = up[j][16];
+      shell_tile<KT, WRITE_VM, false>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin);
+#pragma unroll
+      for (int j = 0; j < KT; ++j) b1[j] = up[j][24];
+      shell_tile<KT, WRITE_VM, false>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin);
+#pragma unroll
+      for (int j = 0; j < KT; ++j) { up[j] += 32; b0[j] = up[j][0]; }  // U rows carry 64 doubles of slack
+      shell_tile<KT, WRITE_VM, false>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin);
     }
-    double c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (; nt < ntiles && nt * 8 < nsteps; ++nt) {  // ragged tail: guarded stores
 #pragma unroll
-    for (int j = 0; j < KT; ++j)
+      for (int j = 0; j < KT; ++j) { up[j] += 8; b1[j] = up[j][0]; }
+      shell_tile<KT, WRITE_VM, true>(a, b0, vmp0, vmp1, ld8, nt * 8 + 2 * t4, nsteps, emax, emin);
 #pragma unroll
-      for (int m = 0; m < 3; ++m) dmma884(c[m][0], c[m][1], a[m][j], b[j]);
-
-    // lane owns point g at steps t0, t0+1
-    const int t0 = nt * 8 + 2 * t4;
-    double v0 = sqrt(c[0][0] * c[0][0] + c[1][0] * c[1][0] - c[0][0] * c[1][0] + 3.0 * c[2][0] * c[2][0]);
-    double v1 = sqrt(c[0][1] * c[0][1] + c[1][1] * c[1][1] - c[0][1] * c[1][1] + 3.0 * c[2][1] * c[2][1]);
-    if (bad) { v0 = kHuge; v1 = kHuge; }
-    if (live) {
-      if (t0 < nsteps) {
-        if (vm) vm[(size_t)t0 * ld_vm + pt] = v0;
-        emax = fmax(emax, v0); emin = fmin(emin, v0);
-      }
-      if (t0 + 1 < nsteps) {
-        if (vm) vm[(size_t)(t0 + 1) * ld_vm + pt] = v1;
-        emax = fmax(emax, v1); emin = fmin(emin, v1);
-      }
+      for (int j = 0; j < KT; ++j) b0[j] = b1[j];
     }
+  } else {
+    // lanes of padded result points (triangles: g = 6,7) still feed the MMAs
+    int nt = 0;
+    double dmax = 0.0, dmin = 0.0;
+    double *d0 = nullptr, *d1 = nullptr;
+    for (; nt < ntiles && nt * 8 < nsteps; ++nt) {
 #pragma unroll
-    for (int j = 0; j < KT; ++j) b[j] = bn[j];
+      for (int j = 0; j < KT; ++j) { up[j] += 8; b1[j] = up[j][0]; }
+      shell_tile<KT, false, false>(a, b0, d0, d1, 0, 0, 0, dmax, dmin);
+#pragma unroll
+      for (int j = 0; j < KT; ++j) b0[j] = b1[j];
+    }
   }
   // combine the four lanes that share a result point, then fold into the stored envelope
   emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
@@ -426,9 +502,14 @@ int launch_k2_shell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
   {
     FamilyData& f = p->fam[FAM_QUAD];
     if (f.nelt > 0) {
-      k2_shell_vm_kernel<6><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-          p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt,
-          f.nstrp, vm_dev, ld_vm, p->env_max, p->env_min);
+      if (vm_dev)
+        k2_shell_vm_kernel<6, true><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt,
+            f.nstrp, vm_dev, ld_vm, p->env_max, p->env_min);
+      else
+        k2_shell_vm_kernel<6, false><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt,
+            f.nstrp, vm_dev, ld_vm, p->env_max, p->env_min);
       FSR_LAUNCH_CHECK();
     }
   }
