@@ -32,6 +32,12 @@ class FsrElmData(C.Structure):
                 ("elmid", C.POINTER(C.c_int)), ("beam", C.POINTER(C.c_double))]
 
 
+class FsrRosette(C.Structure):
+    _fields_ = [("id", C.c_int), ("numnod", C.c_int), ("ngage", C.c_int), ("zero_init", C.c_int),
+                ("nodes", C.c_int * 4), ("rpos", C.c_double * 12), ("zpos", C.c_double), ("emod", C.c_double),
+                ("nu", C.c_double), ("alpha_gages", C.c_double), ("gate", C.c_double), ("sncurve", C.c_double * 4)]
+
+
 class FsrOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("stressForm", C.c_int), ("step_tile", C.c_int),
                 ("reserved", C.c_int * 5)]
@@ -60,6 +66,28 @@ SYMBOLS = [
     ("fsr_fatigue", C.c_int, [C.c_int, _D, C.c_int, C.c_int, C.c_double, _D, C.c_double, C.c_int, _D, _I, _I]),
     ("fsr_fatigue_dev", C.c_int, [C.c_int, _P, C.c_size_t, C.c_int, C.c_int, C.c_double, _D, C.c_double,
                                   C.c_int, _P, _P, _P, _P]),
+    ("fsr_fatigue_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_double, _D, C.c_double, C.c_int, C.c_int]),
+    ("fsr_fatigue_set_gage_params", C.c_int, [_P, _D, _D]),
+    ("fsr_fatigue_reset", C.c_int, [_P]),
+    ("fsr_fatigue_locate_dev", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, _I, _P]),
+    ("fsr_fatigue_feed_dev", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, _P]),
+    ("fsr_fatigue_finish", C.c_int, [_P, _D, _I, _I, _I]),
+    ("fsr_fatigue_finish_dev", C.c_int, [_P, _P]),
+    ("fsr_fatigue_results_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    ("fsr_fatigue_destroy", None, [_P]),
+    ("fsr_vms_size", C.c_int, [_P]),
+    ("fsr_get_vms", C.c_int, [_P, _D, _D, C.c_int]),
+    ("fsr_gage_create", C.c_int, [C.POINTER(_P), _P, C.POINTER(FsrRosette), C.c_int]),
+    ("fsr_gage_num_series", C.c_int, [_P]),
+    ("fsr_gage_get_bcart", C.c_int, [_P, _D]),
+    ("fsr_gage_recover", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
+    ("fsr_gage_recover_dev", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    ("fsr_gage_fatigue", C.c_int, [_P, _D, C.c_int, C.c_int, C.c_double, C.c_double, _D, C.c_double, C.c_int,
+                                   _D, _I, _I, _I]),
+    ("fsr_gage_fatigue_begin", C.c_int, [_P, C.c_double, C.c_double, _D, C.c_double, C.c_int, C.c_int]),
+    ("fsr_gage_fatigue_feed_dev", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _I, _P]),
+    ("fsr_gage_fatigue_end", C.c_int, [_P, _D, _I, _I, _I]),
+    ("fsr_gage_destroy", None, [_P]),
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),

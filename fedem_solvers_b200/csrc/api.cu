@@ -120,6 +120,14 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, 
   p->ptoff_host.assign((size_t)sam->nel + 1, 0);
   p->melcon_host.assign(sam->melcon, sam->melcon + sam->nel);
   p->sam_keep.keep(sam);
+  p->madof_host.assign(sam->madof, sam->madof + sam->nnod + 1);
+  p->xyz_host.assign(elm->xyz, elm->xyz + (size_t)3 * sam->nnod);
+  p->nenod_host.resize((size_t)sam->nel);
+  p->active_host.resize((size_t)sam->nel);
+  for (int e = 0; e < sam->nel; ++e) {
+    p->nenod_host[e] = sam->mpmnpc[e + 1] - sam->mpmnpc[e];
+    p->active_host[e] = (elm->elmid && elm->elmid[e] < 1) ? 0 : 1;
+  }
   int n = 0, nskipped = 0;
   for (int e = 0; e < sam->nel; ++e) {
     p->ptoff_host[e] = n;
@@ -399,6 +407,42 @@ int fsr_recover_step_full(fsr_part* p, const double* q, double* resmat, double* 
   }
   cudaFree(dq); cudaFree(d_res); cudaFree(d_sig); cudaFree(d_eps); cudaFree(d_sr);
   return rc;
+}
+
+int fsr_vms_size(const fsr_part* p)
+{
+  if (!p) return FSR_ERR_ARG;
+  int n = 0;
+  for (int e = 0; e < p->nel; ++e) {
+    const int nstrp = p->ptoff_host[e + 1] - p->ptoff_host[e];
+    if (nstrp > 0) n += 3 + nstrp;
+  }
+  return n;
+}
+
+int fsr_get_vms(fsr_part* p, const double* q, double* vms, int nvms)
+{
+  if (!p || !q || !vms) { set_error("fsr_get_vms: bad arguments"); return FSR_ERR_ARG; }
+  if (nvms < fsr_vms_size(p)) { set_error("fsr_get_vms: array too small (%d < %d)", nvms, fsr_vms_size(p)); return FSR_ERR_ARG; }
+  std::vector<double> vm((size_t)std::max(p->npts, 1));
+  // the envelope belongs to the batched history: keep it untouched by this single-step query
+  std::vector<double> emax((size_t)std::max(p->npts, 1)), emin((size_t)std::max(p->npts, 1));
+  int rc = fsr_get_envelope(p, emax.data(), emin.data());
+  if (rc < 0) return rc;
+  rc = fsr_recover(p, q, p->ndim, 1, vm.data());
+  if (rc < 0) return rc;
+  FSR_CUDA(cudaMemcpy(p->env_max, emax.data(), sizeof(double) * p->npts, cudaMemcpyHostToDevice));
+  FSR_CUDA(cudaMemcpy(p->env_min, emin.data(), sizeof(double) * p->npts, cudaMemcpyHostToDevice));
+  size_t k = 0;
+  for (int e = 0; e < p->nel; ++e) {
+    const int nstrp = p->ptoff_host[e + 1] - p->ptoff_host[e];
+    if (nstrp <= 0) continue;
+    vms[k++] = (double)(e + 1);
+    vms[k++] = (double)p->nenod_host[e];
+    vms[k++] = (double)nstrp;
+    for (int i = 0; i < nstrp; ++i) vms[k++] = vm[(size_t)p->ptoff_host[e] + i];
+  }
+  return FSR_OK;
 }
 
 int fsr_last_timing(fsr_part* p, double* t_ms, int n)

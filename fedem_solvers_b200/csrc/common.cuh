@@ -113,6 +113,14 @@ struct fsr_part {
   int step_tile = 0;   // steps per device batch
   std::vector<int> ptoff_host;  // [nel+1]
   std::vector<int> melcon_host;
+  std::vector<int> madof_host;      // [nnod+1] (gage setup, in-core vms layout)
+  std::vector<int> nenod_host;      // [nel] nodes per element
+  std::vector<int> active_host;     // [nel] 1 = element takes part (elmid >= 1 or no elmid given)
+  std::vector<double> xyz_host;     // [3*nnod] (gage setup)
+  // external-DOF sources of every nodal DOF row of R: row d receives w * finit(extcol[j]) for each
+  // (j, w) in [ext_rowptr[d], ext_rowptr[d+1]); kept for the gage operator (k3_gage.cu)
+  std::vector<int> ext_rowptr, ext_j, extcol;
+  std::vector<double> ext_w;
   fsr::SamKeep sam_keep;
   // device model data
   double* xyz = nullptr;    // [3*nnod]
@@ -147,6 +155,11 @@ int build_row_operator(fsr_part* p, const fsr_sam* sam, const double* B, int ldB
 int launch_pack_q(fsr_part* p, const double* Q_dev, int ldq, int nsteps, int nsteps_pad,
                   cudaStream_t s);
 int launch_k1(fsr_part* p, int nsteps_pad, cudaStream_t s);
+// the same GEMM on any row-major operator: U[nrows_pad x ldu] = R[nrows_pad x ldk] . Qt[nsteps_pad x ldk]^T
+int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nrows_pad, int nsteps_pad, size_t ldu,
+                  cudaStream_t s);
+int launch_pack_q_raw(double* Qt, int ldk, const double* Q_dev, int ldq, int ndim, int nsteps, int nsteps_pad,
+                      cudaStream_t s);
 // k2_*.cu
 int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);

@@ -115,6 +115,16 @@ int build_row_operator(fsr_part* p, const fsr_sam* sam, const double* B, int ldB
     }
     rowptr[d + 1] = (int)src.size();
   }
+  // external sources per row, for the gage operator (ElDispFromSupElDisp puts the unit of external
+  // DOF i at meqn2(i), displacementModule.f90:1170)
+  p->ext_rowptr.assign((size_t)ndof + 1, 0);
+  p->ext_j.clear(); p->ext_w.clear();
+  for (int d = 0; d < ndof; ++d) {
+    for (int ip = rowptr[d]; ip < rowptr[d + 1]; ++ip)
+      if (src[ip] < 0) { p->ext_j.push_back(-src[ip] - 1); p->ext_w.push_back(w[ip]); }
+    p->ext_rowptr[d + 1] = (int)p->ext_j.size();
+  }
+  p->extcol.assign(extcol.begin(), extcol.end());
   if (src.empty()) { src.push_back(0); w.push_back(0.0); }
 
   int *d_rowptr = nullptr, *d_src = nullptr, *d_bcol = nullptr, *d_extcol = nullptr;
@@ -168,14 +178,20 @@ __global__ void pack_q_kernel(double* __restrict__ Qt, int ldk, const double* __
   Qt[idx] = (k < ndim && s < nsteps) ? Q[(size_t)s * ldq + k] : 0.0;
 }
 
+int launch_pack_q_raw(double* Qt, int ldk, const double* Q_dev, int ldq, int ndim, int nsteps, int nsteps_pad,
+                      cudaStream_t s)
+{
+  size_t total = (size_t)nsteps_pad * ldk;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  pack_q_kernel<<<blocks, 256, 0, s>>>(Qt, ldk, Q_dev, (size_t)ldq, ndim, nsteps, nsteps_pad);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+
 int launch_pack_q(fsr_part* p, const double* Q_dev, int ldq, int nsteps, int nsteps_pad,
                   cudaStream_t s)
 {
-  size_t total = (size_t)nsteps_pad * p->ldk;
-  unsigned blocks = (unsigned)((total + 255) / 256);
-  pack_q_kernel<<<blocks, 256, 0, s>>>(p->Qt, p->ldk, Q_dev, (size_t)ldq, p->ndim, nsteps, nsteps_pad);
-  FSR_LAUNCH_CHECK();
-  return FSR_OK;
+  return launch_pack_q_raw(p->Qt, p->ldk, Q_dev, ldq, p->ndim, nsteps, nsteps_pad, s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -311,25 +327,34 @@ static size_t k1_smem_bytes(int ldk)
   return ((size_t)K1_BM * ldk + (size_t)2 * K1_BN * ldk) * sizeof(double) + 3 * sizeof(uint64_t) + 64;
 }
 
-int launch_k1(fsr_part* p, int nsteps_pad, cudaStream_t s)
+int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nrows_pad, int nsteps_pad, size_t ldu,
+                  cudaStream_t s)
 {
   static bool attr_set = false;
-  size_t smem = k1_smem_bytes(p->ldk);
+  size_t smem = k1_smem_bytes(ldk);
   if (smem > 227 * 1024) {
-    set_error("reduced dimension ndim=%d too large for the resident-K expansion kernel (needs %zu B smem)",
-              p->ndim, smem);
+    set_error("reduced dimension (padded %d) too large for the resident-K expansion kernel (needs %zu B smem)",
+              ldk, smem);
     return FSR_ERR_LIMIT;
   }
   if (!attr_set) {
     FSR_CUDA(cudaFuncSetAttribute(k1_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (nsteps_pad % K1_BN != 0) { set_error("internal: nsteps_pad not a multiple of %d", K1_BN); return FSR_ERR_ARG; }
-  unsigned blocks = (unsigned)(p->nrows_pad / K1_BM);
-  k1_expand_kernel<<<blocks, K1_THREADS, smem, s>>>(p->R, p->Qt, p->U, p->ldk, nsteps_pad,
-                                                     (size_t)p->step_tile);
+  if (nsteps_pad % K1_BN != 0 || nrows_pad % K1_BM != 0) {
+    set_error("internal: K1 tile mismatch (%d rows, %d steps)", nrows_pad, nsteps_pad);
+    return FSR_ERR_ARG;
+  }
+  unsigned blocks = (unsigned)(nrows_pad / K1_BM);
+  if (blocks == 0) return FSR_OK;
+  k1_expand_kernel<<<blocks, K1_THREADS, smem, s>>>(R, Qt, U, ldk, nsteps_pad, ldu);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
+}
+
+int launch_k1(fsr_part* p, int nsteps_pad, cudaStream_t s)
+{
+  return launch_k1_raw(p->R, p->Qt, p->U, p->ldk, p->nrows_pad, nsteps_pad, (size_t)p->step_tile, s);
 }
 
 }  // namespace fsr

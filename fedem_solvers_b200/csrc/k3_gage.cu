@@ -1,0 +1,537 @@
+// k3_gage.cu -- strain rosettes / strain gages on sm_100a (the fedem_gage path, config 5).
+//
+// Reference: InitStrainRosette builds, per rosette, Bcart(3 x ndim) = Teps . B_el(z) . T_el . H_el
+// (src/vpmStress/strainRosetteModule.f90:587-812, H_el from ElDispFromSupElDisp,
+// displacementModule.f90:1096-1202) and then evaluates, every time step and one rosette after the
+// other, epsC = Bcart . finit + epsCInit, sigmaC = C . epsC, the gage legs, Mohr's circle and the
+// von Mises values (calcRosetteStrains :251-324, evaluateStrainGages :225-248), pushing
+// sigmaP(1) and every leg stress into a per-gage std::vector for rainflow counting
+// (AddFatiguePoints, strainGageModule.f90:691-716).
+//
+// Here:  * setup (once): the small geometric factor bscr(3 x <=24) per rosette is formed on the
+//          host exactly like InitStrainRosette does; Bcart = bscr . R[rows of the rosette nodes]
+//          is formed on the GPU from the row operator R that fsr_set_recovery left there (R is
+//          H_el for every node at once);
+//        * per tile of time steps: ALL rosettes at once as one FP64 tensor-core GEMM
+//          eps[3 nros x T] = Bcart[3 nros x ndim] . Q[ndim x T] (the K1 DMMA kernel, TMA staged),
+//          then one thread per (rosette, step) finishes sigmaC, gage legs, principal values,
+//          angles, von Mises and writes the fatigue series (max principal + legs, scaled to MPa)
+//          gage-major, which the K3 rainflow kernels (k3_fatigue.cu) consume tile by tile.
+// Nothing per-step is kept on the host and no history is ever stored whole.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+#define FSR_GAGE_NVAL_ 24
+
+struct fsr_gages {
+  fsr_part* part = nullptr;
+  int device = 0, nros = 0, ndim = 0, ldk = 0;
+  int nrows_pad = 0;   // 3*nros padded to the K1 row tile
+  int tile = 0;        // steps per device batch
+  double* Bcart = nullptr;    // [nrows_pad][ldk] row-major, zero padded (row = 3*r + component)
+  double* Qt = nullptr;       // [tile][ldk]
+  double* eps = nullptr;      // [nrows_pad][tile]
+  double* hist = nullptr;     // [4*nros][tile] fatigue series, gage-major
+  double* values = nullptr;   // [tile][nros][NVAL] staging for host output
+  double* Qstage = nullptr; size_t Qstage_cap = 0;
+  double* cmat = nullptr;     // [nros][4]: C11, C12, C33, unused
+  double* tg = nullptr;       // [nros][9] Teps_NfromC of up to three legs
+  double* eps0 = nullptr;     // [nros][3] epsCInit
+  int* ngage = nullptr;       // [nros]
+  int* zero_init = nullptr;   // [nros] 1 = epsCInit still to be taken from the first step
+  bool zero_pending = false;
+  std::vector<fsr_rosette> ros;
+  fsr_fatigue_state* fat = nullptr;  // streaming rainflow state of 4*nros series
+  double to_mpa = 1.0;
+  cudaStream_t stream = nullptr;
+};
+
+namespace fsr {
+
+// Bcart[3r+j][c] = sum_i bscr[r][j][i] * R[row(r,i)][c]; one block per rosette, threads over c
+__global__ void gage_bcart_kernel(double* __restrict__ Bcart, int ldk, const double* __restrict__ R,
+                                  const double* __restrict__ bscr /* [nros][3][24] */,
+                                  const int* __restrict__ rows /* [nros][24] 0-based, -1 = unused */, int nros)
+{
+  const int r = blockIdx.x;
+  if (r >= nros) return;
+  for (int c = threadIdx.x; c < ldk; c += blockDim.x) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int i = 0; i < 24; ++i) {
+      const int row = rows[r * 24 + i];
+      if (row < 0) break;
+      const double h = R[(size_t)row * ldk + c];
+      a0 += bscr[(r * 3 + 0) * 24 + i] * h;
+      a1 += bscr[(r * 3 + 1) * 24 + i] * h;
+      a2 += bscr[(r * 3 + 2) * 24 + i] * h;
+    }
+    Bcart[(size_t)(3 * r + 0) * ldk + c] = a0;
+    Bcart[(size_t)(3 * r + 1) * ldk + c] = a1;
+    Bcart[(size_t)(3 * r + 2) * ldk + c] = a2;
+  }
+}
+
+// epsCInit = -Bcart . finit(first step) for rosettes with zeroInit (calcZeroStartRosetteStrains,
+// strainRosetteModule.f90:327-353); eps holds Bcart . Q of the current tile, column 0 = first step
+__global__ void gage_zero_init_kernel(const double* __restrict__ eps, size_t ldu, int nros, int* __restrict__ zero_init,
+                                      double* __restrict__ eps0)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nros || !zero_init[r]) return;
+  for (int j = 0; j < 3; ++j) eps0[3 * r + j] = -eps[(size_t)(3 * r + j) * ldu];
+  zero_init[r] = 0;
+}
+
+// one thread per (step, rosette), steps fastest: coalesced reads of eps rows and writes of hist rows
+__global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int nros, int nsteps,
+                                 const double* __restrict__ cmat, const double* __restrict__ tg,
+                                 const double* __restrict__ eps0, const int* __restrict__ ngage, double to_mpa,
+                                 double* __restrict__ hist, size_t ld_hist, double* __restrict__ values)
+{
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nros * nsteps) return;
+  const int t = (int)(idx % nsteps), r = (int)(idx / nsteps);
+  double e[3], s[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) e[j] = eps[(size_t)(3 * r + j) * ldu + t] + eps0[3 * r + j];
+  const double C11 = cmat[4 * r], C12 = cmat[4 * r + 1], C33 = cmat[4 * r + 2];
+  s[0] = C11 * e[0] + C12 * e[1];
+  s[1] = C12 * e[0] + C11 * e[1];
+  s[2] = C33 * e[2];
+  const int ng = ngage[r];
+  double eg[3] = {0, 0, 0}, sg[3] = {0, 0, 0};
+  for (int i = 0; i < ng; ++i) {
+    const double* T = tg + 9 * r + 3 * i;
+    eg[i] = T[0] * e[0] + T[1] * e[1] + T[2] * e[2];
+    sg[i] = T[0] * s[0] + T[1] * s[1] + T[2] * s[2];
+  }
+  // PrincipleStrains2D / PrincipleStresses2D (strainAndStressUtils.f90:14-98)
+  double origo = (e[0] + e[1]) * 0.5, d12 = e[0] - e[1], exy = e[2] * 0.5;
+  double radius = sqrt(d12 * d12 + e[2] * e[2]) * 0.5;
+  const double ep1 = origo + radius, ep2 = origo - radius, gmax = radius * 2.0;
+  double alpha1 = 0.0, alphaG = 0.0;
+  if (fabs(exy) > kEpsDiv0 || fabs(d12) > kEpsDiv0) {
+    alpha1 = atan2(exy, d12) * 0.5;
+    alphaG = atan2(d12, exy) * 0.5;
+  }
+  origo = (s[0] + s[1]) * 0.5; d12 = s[0] - s[1];
+  radius = sqrt(d12 * d12 + 4.0 * s[2] * s[2]) * 0.5;
+  const double sp1 = origo + radius, sp2 = origo - radius, tmax = radius;
+  // fatigue series: sigmaP(1) and the leg stresses in MPa (strainGageModule.f90:711-716)
+  hist[(size_t)(4 * r) * ld_hist + t] = sp1 * to_mpa;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) hist[(size_t)(4 * r + 1 + i) * ld_hist + t] = sg[i] * to_mpa;
+  if (values) {
+    double* v = values + ((size_t)t * nros + r) * FSR_GAGE_NVAL_;
+    v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+    v[3] = ep1; v[4] = ep2; v[5] = fabs(ep1) > fabs(ep2) ? ep1 : ep2;
+    v[6] = gmax; v[7] = sqrt(ep1 * ep1 + ep2 * ep2 - ep1 * ep2);
+    v[8] = alpha1; v[9] = alphaG;
+    v[10] = s[0]; v[11] = s[1]; v[12] = s[2];
+    v[13] = sp1; v[14] = sp2; v[15] = fabs(sp1) > fabs(sp2) ? sp1 : sp2;
+    v[16] = tmax; v[17] = sqrt(sp1 * sp1 + sp2 * sp2 - sp1 * sp2);
+    v[18] = eg[0]; v[19] = eg[1]; v[20] = eg[2];
+    v[21] = sg[0]; v[22] = sg[1]; v[23] = sg[2];
+  }
+}
+
+// ---- host geometry (InitStrainRosette up to bscr, strainRosetteModule.f90:630-724) ------------
+struct H3 { double x, y, z; };
+static H3 hsub(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static H3 hcross(H3 a, H3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+static double hdot(H3 a, H3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static bool hnormalize(H3& a)
+{
+  double l2 = hdot(a, a);
+  if (!(l2 > kEpsDiv0 * kEpsDiv0)) return false;
+  double l = std::sqrt(l2);
+  a = {a.x / l, a.y / l, a.z / l};
+  return true;
+}
+
+// bscr[3][24] (row j, column i), rows[24] (0-based nodal DOF, -1 padded)
+static int rosette_bscr(const fsr_part* p, const fsr_rosette& ro, double* bscr, int* rows)
+{
+  const int nn = ro.numnod;
+  if (nn != 3 && nn != 4) { set_error("rosette %d: %d nodes (3 or 4 expected)", ro.id, nn); return FSR_ERR_ARG; }
+  H3 X[4];
+  int nd[4], nNDof = 0;
+  for (int i = 0; i < nn; ++i) {
+    const int n = ro.nodes[i];
+    if (n < 1 || n > p->nnod) { set_error("rosette %d: node %d out of range", ro.id, n); return FSR_ERR_ARG; }
+    X[i] = {p->xyz_host[3 * (size_t)(n - 1)], p->xyz_host[3 * (size_t)(n - 1) + 1], p->xyz_host[3 * (size_t)(n - 1) + 2]};
+    nd[i] = p->madof_host[n] - p->madof_host[n - 1];
+    nNDof = std::max(nNDof, nd[i]);
+  }
+  if (nNDof > 6 || nNDof < 3) { set_error("rosette %d: unsupported nodal DOF count %d", ro.id, nNDof); return FSR_ERR_ARG; }
+  // element axes (getShellElementAxes, strainAndStressUtils.f90:339-434)
+  H3 ex, ey, ez;
+  if (nn == 3) { ex = hsub(X[1], X[0]); ez = hcross(ex, hsub(X[2], X[0])); }
+  else ez = hcross(hsub(X[2], X[0]), hsub(X[3], X[1]));
+  if (!hnormalize(ez)) { set_error("rosette %d: degenerate element normal", ro.id); return FSR_ERR_ARG; }
+  if (nn == 4) { ex = hsub(X[1], X[0]); ey = hcross(ez, ex); ex = hcross(ey, ez); }
+  if (!hnormalize(ex)) { set_error("rosette %d: degenerate element x-axis", ro.id); return FSR_ERR_ARG; }
+  ey = hcross(ez, ex);
+  const double T[3][3] = {{ex.x, ex.y, ex.z}, {ey.x, ey.y, ey.z}, {ez.x, ez.y, ez.z}};
+  // c = T_el(1:2,:) . posInGl(:,1:2); Teps rotates element-axes strains to rosette axes (:655-664)
+  double c[2][2];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) c[i][j] = T[i][0] * ro.rpos[3 * j] + T[i][1] * ro.rpos[3 * j + 1] + T[i][2] * ro.rpos[3 * j + 2];
+  const double Te[3][3] = {{c[0][0] * c[0][0], c[1][0] * c[1][0], c[0][0] * c[1][0]},
+                           {c[0][1] * c[0][1], c[1][1] * c[1][1], c[0][1] * c[1][1]},
+                           {2.0 * c[0][0] * c[0][1], 2.0 * c[1][1] * c[1][0], c[0][0] * c[1][1] + c[0][1] * c[1][0]}};
+  // in-plane shape-function gradients at the gage position (StrainDispCST / StrainDispQuad4 at xi=eta=0)
+  double sx[4], sy[4];
+  if (nn == 3) {
+    double xl[3][3] = {{0}}, yl[3][3] = {{0}};
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        if (a != b) { H3 d = hsub(X[a], X[b]); xl[a][b] = hdot(ex, d); yl[a][b] = hdot(ey, d); }
+    const double a2 = xl[1][0] * yl[2][0] - xl[2][0] * yl[1][0];
+    sx[0] = yl[1][2] / a2; sx[1] = yl[2][0] / a2; sx[2] = yl[0][1] / a2;
+    sy[0] = -xl[1][2] / a2; sy[1] = -xl[2][0] / a2; sy[2] = -xl[0][1] / a2;
+  } else {
+    double xl[4] = {0, 0, 0, 0}, yl[4] = {0, 0, 0, 0};
+    for (int k = 1; k < 4; ++k) { H3 d = hsub(X[k], X[0]); xl[k] = hdot(ex, d); yl[k] = hdot(ey, d); }
+    const double dxi[4] = {-0.25, 0.25, 0.25, -0.25}, det[4] = {-0.25, -0.25, 0.25, 0.25};
+    double j11 = 0, j12 = 0, j21 = 0, j22 = 0;
+    for (int k = 0; k < 4; ++k) { j11 += dxi[k] * xl[k]; j12 += dxi[k] * yl[k]; j21 += det[k] * xl[k]; j22 += det[k] * yl[k]; }
+    const double dj = j11 * j22 - j21 * j12;
+    const double i11 = j22 / dj, i22 = j11 / dj, i12 = -j12 / dj, i21 = -j21 / dj;
+    for (int k = 0; k < 4; ++k) { sx[k] = i11 * dxi[k] + i12 * det[k]; sy[k] = i21 * dxi[k] + i22 * det[k]; }
+  }
+  const bool bend = nNDof >= 5 && std::fabs(ro.zpos) > kEpsDiv0;
+  for (int k = 0; k < 3 * 24; ++k) bscr[k] = 0.0;
+  for (int k = 0; k < 24; ++k) rows[k] = -1;
+  int col = 0;
+  for (int n = 0; n < nn; ++n) {
+    // local B block of node n: columns (u, v, w, rx, ry, rz) in element axes
+    double Bl[3][6] = {{0}};
+    Bl[0][0] = sx[n]; Bl[2][0] = sy[n]; Bl[1][1] = sy[n]; Bl[2][1] = sx[n];
+    if (bend)
+      for (int r = 0; r < 3; ++r) { Bl[r][3] = -ro.zpos * Bl[r][1]; Bl[r][4] = ro.zpos * Bl[r][0]; }
+    // to global DOF directions, three DOFs at a time: B . T_el (:697-707)
+    for (int j = 0; j + 3 <= nd[n]; j += 3) {
+      for (int b = 0; b < 3; ++b) {
+        double g[3];
+        for (int r = 0; r < 3; ++r) g[r] = Bl[r][j] * T[0][b] + Bl[r][j + 1] * T[1][b] + Bl[r][j + 2] * T[2][b];
+        for (int r = 0; r < 3; ++r) bscr[r * 24 + col + j + b] = Te[r][0] * g[0] + Te[r][1] * g[1] + Te[r][2] * g[2];
+      }
+    }
+    for (int d = 0; d < nd[n]; ++d) rows[col + d] = p->madof_host[ro.nodes[n] - 1] - 1 + d;
+    col += nd[n];
+    if (col > 24) { set_error("rosette %d: more than 24 element DOFs", ro.id); return FSR_ERR_ARG; }
+  }
+  return FSR_OK;
+}
+
+// Teps_NfromC of leg i (InitStrainGages, strainGageModule.f90:645-661; vec_to_mat through the
+// quaternion of rotationModule.f90:393-428,478-497)
+static void gage_direction(const fsr_rosette& ro, int leg, double* out)
+{
+  const double* X = ro.rpos; const double* Y = ro.rpos + 3; const double* Z = ro.rpos + 6;
+  double rv[3];
+  for (int k = 0; k < 3; ++k) rv[k] = leg * ro.alpha_gages * Z[k];
+  const double eps_th = 0.0005;
+  const double thh = 0.5 * std::sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+  double fac;
+  if (thh < eps_th) { const double f1 = thh / eps_th; fac = f1 * std::sin(eps_th) / eps_th + 1.0 - f1; }
+  else fac = std::sin(thh) / thh;
+  double q[4] = {std::cos(thh), rv[0] * fac * 0.5, rv[1] * fac * 0.5, rv[2] * fac * 0.5};
+  for (int pass = 0; pass < 2; ++pass) {
+    const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (double& v : q) v /= nq;
+  }
+  const double Rm[3][3] = {
+      {2.0 * (q[1] * q[1] + q[0] * q[0]) - 1.0, 2.0 * (q[1] * q[2] - q[3] * q[0]), 2.0 * (q[1] * q[3] + q[2] * q[0])},
+      {2.0 * (q[2] * q[1] + q[3] * q[0]), 2.0 * (q[2] * q[2] + q[0] * q[0]) - 1.0, 2.0 * (q[2] * q[3] - q[1] * q[0])},
+      {2.0 * (q[3] * q[1] - q[2] * q[0]), 2.0 * (q[3] * q[2] + q[1] * q[0]), 2.0 * (q[3] * q[3] + q[0] * q[0]) - 1.0}};
+  double v[3];
+  for (int k = 0; k < 3; ++k) v[k] = Rm[k][0] * X[0] + Rm[k][1] * X[1] + Rm[k][2] * X[2];
+  const double c = v[0] * X[0] + v[1] * X[1] + v[2] * X[2];
+  const double s = v[0] * Y[0] + v[1] * Y[1] + v[2] * Y[2];
+  out[0] = c * c; out[1] = s * s; out[2] = c * s;
+}
+
+static int gage_buffers(fsr_gages* g, bool want_values)
+{
+  if (!g->Qt) FSR_CUDA(cudaMalloc(&g->Qt, sizeof(double) * (size_t)g->tile * g->ldk));
+  if (!g->eps) FSR_CUDA(cudaMalloc(&g->eps, sizeof(double) * ((size_t)g->nrows_pad * g->tile + 64)));
+  if (!g->hist) FSR_CUDA(cudaMalloc(&g->hist, sizeof(double) * (size_t)4 * std::max(g->nros, 1) * g->tile));
+  if (want_values && !g->values)
+    FSR_CUDA(cudaMalloc(&g->values, sizeof(double) * (size_t)g->tile * std::max(g->nros, 1) * FSR_GAGE_NVAL_));
+  return FSR_OK;
+}
+
+// Q tile (device) -> eps -> per-step values + fatigue series
+static int gage_tile(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, double* values_dev, cudaStream_t s)
+{
+  const int nsteps_pad = (nsteps + 63) / 64 * 64;
+  int rc;
+  if ((rc = launch_pack_q_raw(g->Qt, g->ldk, Q_dev, ldq, g->ndim, nsteps, nsteps_pad, s))) return rc;
+  if ((rc = launch_k1_raw(g->Bcart, g->Qt, g->eps, g->ldk, g->nrows_pad, nsteps_pad, (size_t)g->tile, s))) return rc;
+  if (g->zero_pending) {
+    gage_zero_init_kernel<<<(g->nros + 127) / 128, 128, 0, s>>>(g->eps, (size_t)g->tile, g->nros, g->zero_init, g->eps0);
+    FSR_LAUNCH_CHECK();
+    g->zero_pending = false;
+  }
+  const size_t total = (size_t)g->nros * nsteps;
+  if (total > 0) {
+    gage_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g->eps, (size_t)g->tile, g->nros, nsteps, g->cmat,
+                                                                    g->tg, g->eps0, g->ngage, g->to_mpa, g->hist,
+                                                                    (size_t)g->tile, values_dev);
+    FSR_LAUNCH_CHECK();
+  }
+  return FSR_OK;
+}
+
+static int stage_q(fsr_gages* g, const double* Q, int ldq, int nsteps, cudaStream_t s)
+{
+  const size_t qbytes = sizeof(double) * (size_t)ldq * nsteps;
+  if (g->Qstage_cap < qbytes) {
+    cudaFree(g->Qstage); g->Qstage = nullptr; g->Qstage_cap = 0;
+    FSR_CUDA(cudaMalloc(&g->Qstage, std::max<size_t>(qbytes, 8)));
+    g->Qstage_cap = qbytes;
+  }
+  FSR_CUDA(cudaMemcpyAsync(g->Qstage, Q, qbytes, cudaMemcpyHostToDevice, s));
+  return FSR_OK;
+}
+
+}  // namespace fsr
+
+using namespace fsr;
+
+extern "C" {
+
+void fsr_gage_destroy(fsr_gages* g)
+{
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  if (g->fat) fsr_fatigue_destroy(g->fat);
+  cudaFree(g->Bcart); cudaFree(g->Qt); cudaFree(g->eps); cudaFree(g->hist); cudaFree(g->values);
+  cudaFree(g->Qstage); cudaFree(g->cmat); cudaFree(g->tg); cudaFree(g->eps0); cudaFree(g->ngage);
+  cudaFree(g->zero_init);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+int fsr_gage_create(fsr_gages** out, fsr_part* p, const fsr_rosette* ros, int nros)
+{
+  if (!out || !p || (nros > 0 && !ros) || nros < 0) { set_error("fsr_gage_create: bad arguments"); return FSR_ERR_ARG; }
+  *out = nullptr;
+  if (!p->have_R) { set_error("fsr_gage_create: call fsr_set_recovery first (Bcart needs the B and E matrices)"); return FSR_ERR_STATE; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  fsr_gages* g = new fsr_gages();
+  g->part = p; g->device = p->device; g->nros = nros; g->ndim = p->ndim; g->ldk = p->ldk;
+  g->nrows_pad = (3 * nros + 127) / 128 * 128;
+  g->tile = 512;
+  g->ros.assign(ros, ros + nros);
+  auto fail = [&](int code) { fsr_gage_destroy(g); return code; };
+  if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(FSR_ERR_CUDA); }
+
+  const size_t nr = (size_t)std::max(nros, 1);
+  std::vector<double> bscr(nr * 72), cmat(nr * 4, 0.0), tg(nr * 9, 0.0), eps0(nr * 3, 0.0);
+  std::vector<int> rows(nr * 24, -1), ngage(nr, 0), zinit(nr, 0);
+  for (int r = 0; r < nros; ++r) {
+    const fsr_rosette& ro = ros[r];
+    int rc = rosette_bscr(p, ro, &bscr[(size_t)r * 72], &rows[(size_t)r * 24]);
+    if (rc) return fail(rc);
+    if (ro.ngage < 0 || ro.ngage > 3) { set_error("rosette %d: %d gages (0..3 expected)", ro.id, ro.ngage); return fail(FSR_ERR_ARG); }
+    ngage[r] = ro.ngage;
+    zinit[r] = ro.zero_init ? 1 : 0;
+    if (ro.zero_init) g->zero_pending = true;
+    // isoMat2D (isoMatModule.f90:21-38)
+    cmat[4 * (size_t)r] = ro.emod / (1.0 - ro.nu * ro.nu);
+    cmat[4 * (size_t)r + 1] = ro.nu * cmat[4 * (size_t)r];
+    cmat[4 * (size_t)r + 2] = 0.5 * ro.emod / (1.0 + ro.nu);
+    for (int i = 0; i < ro.ngage; ++i) gage_direction(ro, i, &tg[9 * (size_t)r + 3 * i]);
+  }
+  double* d_bscr = nullptr; int* d_rows = nullptr;
+  bool ok = cudaMalloc(&g->Bcart, sizeof(double) * (size_t)g->nrows_pad * g->ldk) == cudaSuccess &&
+            cudaMalloc(&g->cmat, sizeof(double) * cmat.size()) == cudaSuccess &&
+            cudaMalloc(&g->tg, sizeof(double) * tg.size()) == cudaSuccess &&
+            cudaMalloc(&g->eps0, sizeof(double) * eps0.size()) == cudaSuccess &&
+            cudaMalloc(&g->ngage, sizeof(int) * ngage.size()) == cudaSuccess &&
+            cudaMalloc(&g->zero_init, sizeof(int) * zinit.size()) == cudaSuccess &&
+            cudaMalloc(&d_bscr, sizeof(double) * bscr.size()) == cudaSuccess &&
+            cudaMalloc(&d_rows, sizeof(int) * rows.size()) == cudaSuccess;
+  if (!ok) { set_error("fsr_gage_create: device allocation failed"); cudaFree(d_bscr); cudaFree(d_rows); return fail(FSR_ERR_ALLOC); }
+  cudaStream_t s = g->stream;
+  cudaMemcpyAsync(g->cmat, cmat.data(), sizeof(double) * cmat.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(g->tg, tg.data(), sizeof(double) * tg.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(g->eps0, eps0.data(), sizeof(double) * eps0.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(g->ngage, ngage.data(), sizeof(int) * ngage.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(g->zero_init, zinit.data(), sizeof(int) * zinit.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_bscr, bscr.data(), sizeof(double) * bscr.size(), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(g->Bcart, 0, sizeof(double) * (size_t)g->nrows_pad * g->ldk, s);
+  if (nros > 0) {
+    gage_bcart_kernel<<<nros, 128, 0, s>>>(g->Bcart, g->ldk, p->R, d_bscr, d_rows, nros);
+    ++g_launches;
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(d_bscr); cudaFree(d_rows);
+  if (e != cudaSuccess) { set_error("fsr_gage_create: %s", cudaGetErrorString(e)); return fail(FSR_ERR_CUDA); }
+
+  // ElDispFromSupElDisp puts the unit response of external DOF i at equation meqn2(i)
+  // (displacementModule.f90:1170) whereas calcIntDisplacements (and therefore R) associates
+  // finit(i) with meqn2(dofPosIn2(i)).  Identical whenever meqn2 is in nodal order; otherwise move
+  // the unit entries so that Bcart equals the reference's.
+  bool permuted = false;
+  for (size_t j = 0; j < p->extcol.size(); ++j) permuted = permuted || p->extcol[j] != (int)j;
+  if (permuted && nros > 0 && !p->ext_rowptr.empty()) {
+    std::vector<double> hb((size_t)g->nrows_pad * g->ldk);
+    FSR_CUDA(cudaMemcpy(hb.data(), g->Bcart, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < nros; ++r)
+      for (int i = 0; i < 24 && rows[(size_t)r * 24 + i] >= 0; ++i) {
+        const int d = rows[(size_t)r * 24 + i];
+        for (int ip = p->ext_rowptr[d]; ip < p->ext_rowptr[d + 1]; ++ip) {
+          const int j = p->ext_j[ip];
+          const double w = p->ext_w[ip];
+          for (int c3 = 0; c3 < 3; ++c3) {
+            const double b = bscr[(size_t)r * 72 + c3 * 24 + i] * w;
+            hb[(size_t)(3 * r + c3) * g->ldk + j] += b;
+            hb[(size_t)(3 * r + c3) * g->ldk + p->extcol[j]] -= b;
+          }
+        }
+      }
+    FSR_CUDA(cudaMemcpy(g->Bcart, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice));
+  }
+  *out = g;
+  return FSR_OK;
+}
+
+int fsr_gage_num_series(const fsr_gages* g) { return g ? 4 * g->nros : FSR_ERR_ARG; }
+
+int fsr_gage_get_bcart(fsr_gages* g, double* bcart)
+{
+  if (!g || !bcart) { set_error("fsr_gage_get_bcart: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  std::vector<double> hb((size_t)g->nrows_pad * g->ldk);
+  FSR_CUDA(cudaMemcpy(hb.data(), g->Bcart, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost));
+  for (int r = 0; r < g->nros; ++r)
+    for (int c = 0; c < g->ndim; ++c)
+      for (int j = 0; j < 3; ++j) bcart[(size_t)r * 3 * g->ndim + (size_t)c * 3 + j] = hb[(size_t)(3 * r + j) * g->ldk + c];
+  return FSR_OK;
+}
+
+int fsr_gage_recover_dev(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, double* values_dev, void* stream)
+{
+  if (!g || !Q_dev || nsteps < 0 || ldq < g->ndim) { set_error("fsr_gage_recover_dev: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  int rc = gage_buffers(g, false);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+  for (int t0 = 0; t0 < nsteps; t0 += g->tile) {
+    const int nt = std::min(g->tile, nsteps - t0);
+    rc = gage_tile(g, Q_dev + (size_t)t0 * ldq, ldq, nt,
+                   values_dev ? values_dev + (size_t)t0 * g->nros * FSR_GAGE_NVAL_ : nullptr, s);
+    if (rc) return rc;
+  }
+  return FSR_OK;
+}
+
+int fsr_gage_recover(fsr_gages* g, const double* Q, int ldq, int nsteps, double* values)
+{
+  if (!g || !Q || nsteps < 0 || ldq < g->ndim) { set_error("fsr_gage_recover: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  int rc = gage_buffers(g, values != nullptr);
+  if (rc) return rc;
+  cudaStream_t s = g->stream;
+  if ((rc = stage_q(g, Q, ldq, nsteps, s))) return rc;
+  for (int t0 = 0; t0 < nsteps; t0 += g->tile) {
+    const int nt = std::min(g->tile, nsteps - t0);
+    if ((rc = gage_tile(g, g->Qstage + (size_t)t0 * ldq, ldq, nt, values ? g->values : nullptr, s))) return rc;
+    if (values) {
+      FSR_CUDA(cudaMemcpyAsync(values + (size_t)t0 * g->nros * FSR_GAGE_NVAL_, g->values,
+                               sizeof(double) * (size_t)nt * g->nros * FSR_GAGE_NVAL_, cudaMemcpyDeviceToHost, s));
+      FSR_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  FSR_CUDA(cudaStreamSynchronize(s));
+  return FSR_OK;
+}
+
+int fsr_gage_fatigue_begin(fsr_gages* g, double to_mpa, double default_gate, const double* default_curve,
+                           double bin_size, int nbins, int stack_cap)
+{
+  if (!g || !default_curve) { set_error("fsr_gage_fatigue_begin: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  if (g->fat) { fsr_fatigue_destroy(g->fat); g->fat = nullptr; }
+  g->to_mpa = to_mpa;
+  int rc = fsr_fatigue_create(&g->fat, g->device, 4 * g->nros, default_gate, default_curve, bin_size, nbins, stack_cap);
+  if (rc) return rc;
+  // per-rosette gate / S-N data override the defaults when given (> 0), reportDamage
+  // (strainGageModule.f90:806-812): m2 has no per-rosette default rule, it is taken as given
+  std::vector<double> gate((size_t)4 * std::max(g->nros, 1)), curve((size_t)16 * std::max(g->nros, 1));
+  for (int r = 0; r < g->nros; ++r) {
+    const fsr_rosette& ro = g->ros[r];
+    double c[4];
+    for (int k = 0; k < 4; ++k) c[k] = ro.sncurve[k];
+    for (int k = 0; k < 3; ++k) if (c[k] <= 0.0) c[k] = default_curve[k];
+    if (c[3] <= 0.0) c[3] = default_curve[3];
+    for (int k = 0; k < 4; ++k) {
+      gate[4 * (size_t)r + k] = ro.gate > 0.0 ? ro.gate : default_gate;
+      for (int m = 0; m < 4; ++m) curve[16 * (size_t)r + 4 * k + m] = c[m];
+    }
+  }
+  if (g->nros > 0) rc = fsr_fatigue_set_gage_params(g->fat, gate.data(), curve.data());
+  return rc;
+}
+
+int fsr_gage_fatigue_feed_dev(fsr_gages* g, const double* Q_dev, int ldq, int step0, int nsteps, int mode,
+                              int* n_pending, void* stream)
+{
+  if (!g || !g->fat || !Q_dev || nsteps < 0 || ldq < g->ndim) { set_error("fsr_gage_fatigue_feed_dev: bad arguments / no fsr_gage_fatigue_begin"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  int rc = gage_buffers(g, false);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+  int pend_total = 0;
+  for (int t0 = 0; t0 < nsteps; t0 += g->tile) {
+    const int nt = std::min(g->tile, nsteps - t0);
+    if ((rc = gage_tile(g, Q_dev + (size_t)t0 * ldq, ldq, nt, nullptr, s))) return rc;
+    if (mode == 0) {
+      int pend = 0;
+      rc = fsr_fatigue_locate_dev(g->fat, g->hist, (size_t)g->tile, FSR_HIST_GAGE_MAJOR, step0 + t0, nt,
+                                  n_pending ? &pend : nullptr, s);
+      pend_total = pend;
+      if (rc) return rc;
+      if (n_pending && pend == 0) break;
+    } else if ((rc = fsr_fatigue_feed_dev(g->fat, g->hist, (size_t)g->tile, FSR_HIST_GAGE_MAJOR, step0 + t0, nt, s)))
+      return rc;
+  }
+  if (n_pending) *n_pending = pend_total;
+  return FSR_OK;
+}
+
+int fsr_gage_fatigue_end(fsr_gages* g, double* damage, int* ncycles, int* bins, int* status)
+{
+  if (!g || !g->fat) { set_error("fsr_gage_fatigue_end: no fsr_gage_fatigue_begin"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  FSR_CUDA(cudaStreamSynchronize(g->stream));
+  return fsr_fatigue_finish(g->fat, damage, ncycles, bins, status);
+}
+
+int fsr_gage_fatigue(fsr_gages* g, const double* Q, int ldq, int nsteps, double to_mpa, double gate,
+                     const double* curve, double bin_size, int nbins, double* damage, int* ncycles, int* bins,
+                     int* status)
+{
+  if (!g || !Q || nsteps < 0 || ldq < g->ndim || !curve) { set_error("fsr_gage_fatigue: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  int rc = fsr_gage_fatigue_begin(g, to_mpa, gate, curve, bin_size, nbins, std::min(nsteps + 8, 1 << 16));
+  if (rc) return rc;
+  cudaStream_t s = g->stream;
+  if ((rc = stage_q(g, Q, ldq, nsteps, s))) return rc;
+  // zero-start strains must come from the first step in BOTH passes: remember the flags
+  int pend = 0;
+  if ((rc = fsr_gage_fatigue_feed_dev(g, g->Qstage, ldq, 0, nsteps, 0, &pend, s))) return rc;
+  if ((rc = fsr_gage_fatigue_feed_dev(g, g->Qstage, ldq, 0, nsteps, 1, nullptr, s))) return rc;
+  FSR_CUDA(cudaStreamSynchronize(s));
+  return fsr_fatigue_finish(g->fat, damage, ncycles, bins, status);
+}
+
+}  // extern "C"

@@ -324,3 +324,39 @@ def tet10_block(nx, ny, nz, ngen=10, seed=3, n_ext=4, jitter=0.05, emod=2.1e11, 
     if with_recovery:
         part.B, part.E = _smooth_recovery_matrices(sam, xyz, ngen, rng)
     return part
+
+
+# ------------------------------------------------------------------------------------------
+# strain rosettes on a shell part (config C5)
+# ------------------------------------------------------------------------------------------
+def rosettes_on_part(part, nros, seed=5, rtype="TRIPLE_GAGE_45", zero_init_fraction=0.0, top_surface=True):
+    """nros rosettes on randomly chosen shell elements (types 23/24) of `part`, placed like the
+    reference's strain coats on the element surface (zPos = +-t/2), rosette X axis at a random
+    in-plane angle, explicit position matrix as in the .fsi input format."""
+    from .gage import Rosette
+    rng = np.random.default_rng(seed)
+    sam, elm = part.sam, part.elm
+    shells = np.nonzero((sam.melcon == 24) | (sam.melcon == 23))[0]
+    pick = rng.choice(shells, nros, replace=len(shells) < nros)
+    out = []
+    for k, e in enumerate(pick):
+        nodes = sam.mmnpc[sam.mpmnpc[e] - 1: sam.mpmnpc[e + 1] - 1]
+        X = elm.xyz[nodes - 1]
+        if len(nodes) == 4:
+            n = np.cross(X[2] - X[0], X[3] - X[1])
+        else:
+            n = np.cross(X[1] - X[0], X[2] - X[0])
+        n = n / np.linalg.norm(n)
+        ex = X[1] - X[0]
+        ex = ex - n * (ex @ n)
+        ex /= np.linalg.norm(ex)
+        ey = np.cross(n, ex)
+        ang = rng.uniform(0, 2 * np.pi)
+        xr = np.cos(ang) * ex + np.sin(ang) * ey
+        yr = np.cross(n, xr)
+        rpos = np.stack([xr, yr, n, X.mean(0)], 1)
+        t = float(elm.thk[e])
+        out.append(Rosette(id=k + 1, nodes=[int(v) for v in nodes], rpos=rpos, type=rtype,
+                           zpos=(0.5 * t if top_surface else -0.5 * t), emod=float(elm.emod[e]),
+                           nu=float(elm.rny[e]), zero_init=bool(rng.random() < zero_init_fraction)))
+    return out

@@ -173,3 +173,57 @@ def fatigue(hist, gate, curve, bin_size=0.0, nbins=0, device=0):
     check(lib.fsr_fatigue(device, _dp(hist), ng, ns, float(gate), _dp(curve), float(bin_size), nbins,
                           _dp(damage), _ip(ncyc), _ip(bins)), "fsr_fatigue")
     return damage, ncyc, bins
+
+
+class FatigueCounter:
+    """Streaming PVX + rainflow + damage for ngage histories resident on one GPU: the batched,
+    device-side form of ffp_addpoint ... ffp_getdamage (FFpFatigue_F.C:37-124).  Tiles of time steps
+    are device arrays (torch tensors: pass .data_ptr()); see include/fedem_b200.h for the locate /
+    feed protocol."""
+    GAGE_MAJOR, STEP_MAJOR = 0, 1
+
+    def __init__(self, ngage, gate, curve, bin_size=0.0, nbins=0, stack_cap=0, device=0):
+        self._lib = _lib.load_library()
+        self._h = C.c_void_p()
+        self.ngage, self.nbins = ngage, nbins
+        curve = np.ascontiguousarray(curve, F64)
+        check(self._lib.fsr_fatigue_create(C.byref(self._h), device, ngage, float(gate), _dp(curve),
+                                           float(bin_size), nbins, stack_cap), "fsr_fatigue_create")
+
+    def set_gage_params(self, gate=None, curve=None):
+        g = np.ascontiguousarray(gate, F64) if gate is not None else None
+        c = np.ascontiguousarray(curve, F64) if curve is not None else None
+        check(self._lib.fsr_fatigue_set_gage_params(self._h, _dp(g), _dp(c)), "fsr_fatigue_set_gage_params")
+
+    def reset(self):
+        check(self._lib.fsr_fatigue_reset(self._h), "fsr_fatigue_reset")
+
+    def locate(self, hist_ptr, ld, layout, step0, nsteps, stream=None, want_pending=True):
+        n = C.c_int(-1)
+        check(self._lib.fsr_fatigue_locate_dev(self._h, C.c_void_p(hist_ptr), ld, layout, step0, nsteps,
+                                               C.byref(n) if want_pending else None,
+                                               C.c_void_p(stream) if stream else None), "fsr_fatigue_locate_dev")
+        return n.value
+
+    def feed(self, hist_ptr, ld, layout, step0, nsteps, stream=None):
+        check(self._lib.fsr_fatigue_feed_dev(self._h, C.c_void_p(hist_ptr), ld, layout, step0, nsteps,
+                                             C.c_void_p(stream) if stream else None), "fsr_fatigue_feed_dev")
+
+    def finish(self):
+        """Returns dict(damage, ncycles, bins, status) as host arrays."""
+        damage = np.zeros(self.ngage, F64); ncyc = np.zeros(self.ngage, I32); status = np.zeros(self.ngage, I32)
+        bins = np.zeros((self.ngage, self.nbins), I32) if self.nbins > 0 else None
+        nwarn = check(self._lib.fsr_fatigue_finish(self._h, _dp(damage), _ip(ncyc), _ip(bins), _ip(status)),
+                      "fsr_fatigue_finish")
+        return dict(damage=damage, ncycles=ncyc, bins=bins, status=status, nwarn=nwarn)
+
+    def close(self):
+        if self._h:
+            self._lib.fsr_fatigue_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

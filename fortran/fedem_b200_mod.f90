@@ -1,0 +1,399 @@
+!! fedem_b200_mod.f90 -- ISO_C_BINDING interface to libfedem_b200.so (include/fedem_b200.h).
+!!
+!! This is the thin layer the reference's Fortran host code (src/vpmStress/stress.f90, gage.f90,
+!! src/vpmSolver/stressRecoveryModule.f90) uses to call the B200 kernels: every C entry point is
+!! bound by its exact name; derived types mirror the C structs member by member.  Index arrays
+!! are passed exactly as SamType holds them (1-based, src/vpmCommon/samModule.f90:27-66); real
+!! arrays are real(c_double) = real(dp).  See fortran/stress_b200_driver.f90 for the call
+!! sequence that replaces the time loop of stress.f90:357-435 and INTEGRATION.md for the build.
+!!
+!! No Fortran compiler exists in the build image, so this file is delivered as source;
+!! tests/test_abi_cpu.py checks that it binds every symbol the header declares, and
+!! tests/c_abi_driver.c exercises the identical symbols from plain C.
+
+module fedem_b200_mod
+
+  use, intrinsic :: iso_c_binding
+
+  implicit none
+
+  integer(c_int), parameter :: FSR_OK = 0, FSR_ERR_ARG = -1, FSR_ERR_CUDA = -2
+  integer(c_int), parameter :: FSR_ERR_ALLOC = -3, FSR_ERR_STATE = -4, FSR_ERR_LIMIT = -5
+  integer(c_int), parameter :: FSR_NBEAM = 32
+  integer(c_int), parameter :: FSR_HIST_GAGE_MAJOR = 0, FSR_HIST_STEP_MAJOR = 1
+  integer(c_int), parameter :: FSR_GAGE_NVAL = 24
+
+  !> struct fsr_sam: the SamType subset read by initiateSAM (samStressModule.f90:273-316)
+  type, bind(C) :: fsr_sam
+     integer(c_int) :: nnod, nel, ndof, ndof1, ndof2, ngen, neq, nceq, nmmnpc, nmmceq
+     type(c_ptr)    :: madof, msc, mpmnpc, mmnpc, melcon, mpmceq, mmceq, ttcc, meqn, meqn1, meqn2
+  end type fsr_sam
+
+  !> struct fsr_elmdata: what ffl_getcoor/getmat/getthick/getbeamsection/getpinflags/getelmid return
+  type, bind(C) :: fsr_elmdata
+     type(c_ptr) :: xyz, emod, rny, thk, elmid, beam
+  end type fsr_elmdata
+
+  !> struct fsr_options
+  type, bind(C) :: fsr_options
+     integer(c_int) :: device, stressForm, step_tile
+     integer(c_int) :: reserved(5)
+  end type fsr_options
+
+  !> struct fsr_rosette: one strain rosette (strainGageModule.f90:184-237, &STRAIN_ROSETTE)
+  type, bind(C) :: fsr_rosette
+     integer(c_int) :: id, numnod, ngage, zero_init
+     integer(c_int) :: nodes(4)
+     real(c_double) :: rpos(12), zpos, emod, nu, alpha_gages, gate
+     real(c_double) :: sncurve(4)
+  end type fsr_rosette
+
+  interface
+
+     ! ---- life cycle ----------------------------------------------------------------------
+     function fsr_part_create (part, sam, elm, opt) bind(C,name="fsr_part_create") result(ierr)
+       import :: c_ptr, c_int, fsr_sam, fsr_elmdata, fsr_options
+       type(c_ptr)      , intent(out) :: part
+       type(fsr_sam)    , intent(in)  :: sam
+       type(fsr_elmdata), intent(in)  :: elm
+       type(fsr_options), intent(in)  :: opt
+       integer(c_int) :: ierr
+     end function fsr_part_create
+
+     function fsr_set_recovery (part, B, ldB, E, ldE) bind(C,name="fsr_set_recovery") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: part
+       real(c_double), intent(in) :: B(*), E(*)
+       integer(c_int), value      :: ldB, ldE
+       integer(c_int) :: ierr
+     end function fsr_set_recovery
+
+     subroutine fsr_part_destroy (part) bind(C,name="fsr_part_destroy")
+       import :: c_ptr
+       type(c_ptr), value :: part
+     end subroutine fsr_part_destroy
+
+     function fsr_set_stream (part, stream) bind(C,name="fsr_set_stream") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part, stream
+       integer(c_int) :: ierr
+     end function fsr_set_stream
+
+     ! ---- sizes -----------------------------------------------------------------------------
+     function fsr_num_result_points (part) bind(C,name="fsr_num_result_points") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: n
+     end function fsr_num_result_points
+
+     function fsr_result_point_offsets (part, off) bind(C,name="fsr_result_point_offsets") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value       :: part
+       integer(c_int), intent(out) :: off(*)
+       integer(c_int) :: ierr
+     end function fsr_result_point_offsets
+
+     function fsr_ndim (part) bind(C,name="fsr_ndim") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: n
+     end function fsr_ndim
+
+     function fsr_vms_size (part) bind(C,name="fsr_vms_size") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: n
+     end function fsr_vms_size
+
+     ! ---- the hot path ----------------------------------------------------------------------
+     function fsr_recover (part, Q, ldq, nsteps, vm_hist) bind(C,name="fsr_recover") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: part
+       real(c_double), intent(in) :: Q(ldq,*)
+       integer(c_int), value      :: ldq, nsteps
+       type(c_ptr)   , value      :: vm_hist   !< c_loc of a real(dp) array, or c_null_ptr
+       integer(c_int) :: ierr
+     end function fsr_recover
+
+     function fsr_recover_dev (part, Q_dev, ldq, nsteps, vm_hist_dev, ld_vm, stream) &
+          &                   bind(C,name="fsr_recover_dev") result(ierr)
+       import :: c_ptr, c_int, c_size_t
+       type(c_ptr)      , value :: part, Q_dev, vm_hist_dev, stream
+       integer(c_int)   , value :: ldq, nsteps
+       integer(c_size_t), value :: ld_vm
+       integer(c_int) :: ierr
+     end function fsr_recover_dev
+
+     function fsr_reset_envelope (part) bind(C,name="fsr_reset_envelope") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: ierr
+     end function fsr_reset_envelope
+
+     function fsr_get_envelope (part, vm_max, vm_min) bind(C,name="fsr_get_envelope") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: part
+       real(c_double), intent(out) :: vm_max(*), vm_min(*)
+       integer(c_int) :: ierr
+     end function fsr_get_envelope
+
+     function fsr_envelope_dev (part, vm_max_dev, vm_min_dev) bind(C,name="fsr_envelope_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value       :: part
+       type(c_ptr), intent(out) :: vm_max_dev, vm_min_dev
+       integer(c_int) :: ierr
+     end function fsr_envelope_dev
+
+     function fsr_copy_envelope_dev (part, vm_max_dst_dev, vm_min_dst_dev, stream) &
+          &                         bind(C,name="fsr_copy_envelope_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part, vm_max_dst_dev, vm_min_dst_dev, stream
+       integer(c_int) :: ierr
+     end function fsr_copy_envelope_dev
+
+     function fsr_recover_step_full (part, q, resmat, stress, strain, sres, sv) &
+          &                         bind(C,name="fsr_recover_step_full") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: part
+       real(c_double), intent(in) :: q(*)
+       type(c_ptr)   , value      :: resmat, stress, strain, sres, sv  !< c_loc(array) or c_null_ptr
+       integer(c_int) :: ierr
+     end function fsr_recover_step_full
+
+     function fsr_get_vms (part, q, vms, nvms) bind(C,name="fsr_get_vms") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: part
+       real(c_double), intent(in)  :: q(*)
+       real(c_double), intent(out) :: vms(*)
+       integer(c_int), value       :: nvms
+       integer(c_int) :: ierr
+     end function fsr_get_vms
+
+     function fsr_expand (part, Q, ldq, nsteps, U_host) bind(C,name="fsr_expand") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: part
+       real(c_double), intent(in)  :: Q(ldq,*)
+       integer(c_int), value       :: ldq, nsteps
+       real(c_double), intent(out) :: U_host(*)
+       integer(c_int) :: ierr
+     end function fsr_expand
+
+     ! ---- strain gages (fedem_gage path) ----------------------------------------------------
+     function fsr_gage_create (gages, part, ros, nros) bind(C,name="fsr_gage_create") result(ierr)
+       import :: c_ptr, c_int, fsr_rosette
+       type(c_ptr)      , intent(out) :: gages
+       type(c_ptr)      , value       :: part
+       type(fsr_rosette), intent(in)  :: ros(*)
+       integer(c_int)   , value       :: nros
+       integer(c_int) :: ierr
+     end function fsr_gage_create
+
+     function fsr_gage_num_series (gages) bind(C,name="fsr_gage_num_series") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: gages
+       integer(c_int) :: n
+     end function fsr_gage_num_series
+
+     function fsr_gage_get_bcart (gages, bcart) bind(C,name="fsr_gage_get_bcart") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: gages
+       real(c_double), intent(out) :: bcart(*)
+       integer(c_int) :: ierr
+     end function fsr_gage_get_bcart
+
+     function fsr_gage_recover (gages, Q, ldq, nsteps, values) bind(C,name="fsr_gage_recover") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: gages
+       real(c_double), intent(in) :: Q(ldq,*)
+       integer(c_int), value      :: ldq, nsteps
+       type(c_ptr)   , value      :: values    !< c_loc of real(dp) (FSR_GAGE_NVAL,nros,nsteps) or c_null_ptr
+       integer(c_int) :: ierr
+     end function fsr_gage_recover
+
+     function fsr_gage_recover_dev (gages, Q_dev, ldq, nsteps, values_dev, stream) &
+          &                        bind(C,name="fsr_gage_recover_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value :: gages, Q_dev, values_dev, stream
+       integer(c_int), value :: ldq, nsteps
+       integer(c_int) :: ierr
+     end function fsr_gage_recover_dev
+
+     function fsr_gage_fatigue (gages, Q, ldq, nsteps, to_mpa, gate, curve, bin_size, nbins, damage, &
+          &                    ncycles, bins, status) bind(C,name="fsr_gage_fatigue") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: gages
+       real(c_double), intent(in) :: Q(ldq,*), curve(4)
+       integer(c_int), value      :: ldq, nsteps, nbins
+       real(c_double), value      :: to_mpa, gate, bin_size
+       type(c_ptr)   , value      :: damage, ncycles, bins, status
+       integer(c_int) :: ierr
+     end function fsr_gage_fatigue
+
+     function fsr_gage_fatigue_begin (gages, to_mpa, default_gate, default_curve, bin_size, nbins, &
+          &                          stack_cap) bind(C,name="fsr_gage_fatigue_begin") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: gages
+       real(c_double), value      :: to_mpa, default_gate, bin_size
+       real(c_double), intent(in) :: default_curve(4)
+       integer(c_int), value      :: nbins, stack_cap
+       integer(c_int) :: ierr
+     end function fsr_gage_fatigue_begin
+
+     function fsr_gage_fatigue_feed_dev (gages, Q_dev, ldq, step0, nsteps, mode, n_pending, stream) &
+          &                             bind(C,name="fsr_gage_fatigue_feed_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value :: gages, Q_dev, n_pending, stream
+       integer(c_int), value :: ldq, step0, nsteps, mode
+       integer(c_int) :: ierr
+     end function fsr_gage_fatigue_feed_dev
+
+     function fsr_gage_fatigue_end (gages, damage, ncycles, bins, status) &
+          &                        bind(C,name="fsr_gage_fatigue_end") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: gages, damage, ncycles, bins, status
+       integer(c_int) :: ierr
+     end function fsr_gage_fatigue_end
+
+     subroutine fsr_gage_destroy (gages) bind(C,name="fsr_gage_destroy")
+       import :: c_ptr
+       type(c_ptr), value :: gages
+     end subroutine fsr_gage_destroy
+
+     ! ---- fatigue (ffp_addpoint / ffp_getdamage / ffp_getnumcycles) ---------------------------
+     function fsr_fatigue (device, hist, ngage, nsteps, gate, curve, bin_size, nbins, damage, &
+          &               ncycles, bins) bind(C,name="fsr_fatigue") result(ierr)
+       import :: c_ptr, c_int, c_double
+       integer(c_int), value       :: device, ngage, nsteps, nbins
+       real(c_double), intent(in)  :: hist(nsteps,*), curve(4)
+       real(c_double), value       :: gate, bin_size
+       real(c_double), intent(out) :: damage(*)
+       integer(c_int), intent(out) :: ncycles(*)
+       type(c_ptr)   , value       :: bins
+       integer(c_int) :: ierr
+     end function fsr_fatigue
+
+     function fsr_fatigue_dev (device, hist_dev, ld_hist, ngage, nsteps, gate, curve, bin_size, nbins, &
+          &                   damage_dev, ncycles_dev, bins_dev, stream) &
+          &                   bind(C,name="fsr_fatigue_dev") result(ierr)
+       import :: c_ptr, c_int, c_double, c_size_t
+       integer(c_int)   , value      :: device, ngage, nsteps, nbins
+       type(c_ptr)      , value      :: hist_dev, damage_dev, ncycles_dev, bins_dev, stream
+       integer(c_size_t), value      :: ld_hist
+       real(c_double)   , value      :: gate, bin_size
+       real(c_double)   , intent(in) :: curve(4)
+       integer(c_int) :: ierr
+     end function fsr_fatigue_dev
+
+     function fsr_fatigue_create (f, device, ngage, gate, curve, bin_size, nbins, stack_cap) &
+          &                      bind(C,name="fsr_fatigue_create") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , intent(out) :: f
+       integer(c_int), value       :: device, ngage, nbins, stack_cap
+       real(c_double), value       :: gate, bin_size
+       real(c_double), intent(in)  :: curve(4)
+       integer(c_int) :: ierr
+     end function fsr_fatigue_create
+
+     function fsr_fatigue_set_gage_params (f, gate, curve) bind(C,name="fsr_fatigue_set_gage_params") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: f, gate, curve
+       integer(c_int) :: ierr
+     end function fsr_fatigue_set_gage_params
+
+     function fsr_fatigue_reset (f) bind(C,name="fsr_fatigue_reset") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: f
+       integer(c_int) :: ierr
+     end function fsr_fatigue_reset
+
+     function fsr_fatigue_locate_dev (f, hist_dev, ld, layout, step0, nsteps, n_pending, stream) &
+          &                          bind(C,name="fsr_fatigue_locate_dev") result(ierr)
+       import :: c_ptr, c_int, c_size_t
+       type(c_ptr)      , value :: f, hist_dev, stream
+       integer(c_size_t), value :: ld
+       integer(c_int)   , value :: layout, step0, nsteps
+       integer(c_int)   , intent(out) :: n_pending
+       integer(c_int) :: ierr
+     end function fsr_fatigue_locate_dev
+
+     function fsr_fatigue_feed_dev (f, hist_dev, ld, layout, step0, nsteps, stream) &
+          &                        bind(C,name="fsr_fatigue_feed_dev") result(ierr)
+       import :: c_ptr, c_int, c_size_t
+       type(c_ptr)      , value :: f, hist_dev, stream
+       integer(c_size_t), value :: ld
+       integer(c_int)   , value :: layout, step0, nsteps
+       integer(c_int) :: ierr
+     end function fsr_fatigue_feed_dev
+
+     function fsr_fatigue_finish (f, damage, ncycles, bins, status) bind(C,name="fsr_fatigue_finish") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: f, damage, ncycles, bins, status
+       integer(c_int) :: ierr
+     end function fsr_fatigue_finish
+
+     function fsr_fatigue_finish_dev (f, stream) bind(C,name="fsr_fatigue_finish_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: f, stream
+       integer(c_int) :: ierr
+     end function fsr_fatigue_finish_dev
+
+     function fsr_fatigue_results_dev (f, damage_dev, ncycles_dev, bins_dev, status_dev) &
+          &                           bind(C,name="fsr_fatigue_results_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value       :: f
+       type(c_ptr), intent(out) :: damage_dev, ncycles_dev, bins_dev, status_dev
+       integer(c_int) :: ierr
+     end function fsr_fatigue_results_dev
+
+     subroutine fsr_fatigue_destroy (f) bind(C,name="fsr_fatigue_destroy")
+       import :: c_ptr
+       type(c_ptr), value :: f
+     end subroutine fsr_fatigue_destroy
+
+     ! ---- diagnostics ------------------------------------------------------------------------
+     function fsr_last_error () bind(C,name="fsr_last_error") result(msg)
+       import :: c_ptr
+       type(c_ptr) :: msg    !< NUL-terminated C string, see fsr_error_message below
+     end function fsr_last_error
+
+     function fsr_kernel_launches (reset) bind(C,name="fsr_kernel_launches") result(n)
+       import :: c_int, c_long_long
+       integer(c_int), value :: reset
+       integer(c_long_long) :: n
+     end function fsr_kernel_launches
+
+     function fsr_last_timing (part, t_ms, n) bind(C,name="fsr_last_timing") result(m)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: part
+       real(c_double), intent(out) :: t_ms(*)
+       integer(c_int), value       :: n
+       integer(c_int) :: m
+     end function fsr_last_timing
+
+     function fsr_timing_reset (part) bind(C,name="fsr_timing_reset") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: ierr
+     end function fsr_timing_reset
+
+  end interface
+
+contains
+
+  !> Copies the library's last error text into a Fortran string (for reportError).
+  subroutine fsr_error_message (text)
+    character(len=*), intent(out) :: text
+    character(kind=c_char), pointer :: p(:)
+    type(c_ptr) :: cmsg
+    integer     :: i
+    text = ' '
+    cmsg = fsr_last_error()
+    if (.not. c_associated(cmsg)) return
+    call c_f_pointer (cmsg, p, [len(text)])
+    do i = 1, len(text)
+       if (p(i) == c_null_char) exit
+       text(i:i) = p(i)
+    end do
+  end subroutine fsr_error_message
+
+end module fedem_b200_mod

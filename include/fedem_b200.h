@@ -150,6 +150,15 @@ int fsr_copy_envelope_dev(fsr_part *part, double *vm_max_dst_dev, double *vm_min
 int fsr_recover_step_full(fsr_part *part, const double *q, double *resmat, double *stress,
                           double *strain, double *sres, double *sv);
 
+/* The in-core von Mises state that fedempy reads through getPartStressStateSize /
+ * savePartStressState (src/vpmSolver/solverInterface.C:946,993 -> getGroupVMSsize / getStress,
+ * src/vpmSolver/stressRecoveryModule.f90:203-280,718-747): for every active element that has
+ * stress points, in SAM order, [iel, nenod, nstrp, vm(1..nstrp)] as doubles
+ * (stressRoutines.f90:324-331).  fsr_vms_size returns the array length, fsr_get_vms fills it
+ * for the step whose reduced displacements are q = [finit; vg]. */
+int fsr_vms_size(const fsr_part *part);
+int fsr_get_vms(fsr_part *part, const double *q, double *vms, int nvms);
+
 /* Expansion only (calcIntDisplacements for a batch): U_host [nsteps x ndof] step-major. */
 int fsr_expand(fsr_part *part, const double *Q, int ldq, int nsteps, double *U_host);
 
@@ -168,6 +177,86 @@ int fsr_fatigue(int device, const double *hist, int ngage, int nsteps, double ga
 int fsr_fatigue_dev(int device, const double *hist_dev, size_t ld_hist, int ngage, int nsteps,
                     double gate, const double *curve, double bin_size, int nbins,
                     double *damage_dev, int *ncycles_dev, int *bins_dev, void *stream);
+
+/* Streaming form of the same (what ffp_addpoint does sample by sample, FFpFatigue_F.C:37-44, but
+ * without ever holding a whole history): a handle owns ngage per-gage states on one GPU and is fed
+ * tiles of time steps in order.  Because the reference's PVX starts at the FIRST turning point,
+ * which it finds by a look-ahead scan (FFpPVXprocessor::locateFirstTP, FFpFatigue.C:129-163), the
+ * caller runs fsr_fatigue_locate_dev over the leading tiles until *n_pending == 0 (normally the
+ * first tile) and then fsr_fatigue_feed_dev over ALL tiles from step 0.
+ *  layout FSR_HIST_GAGE_MAJOR: hist_dev[g*ld + t]; FSR_HIST_STEP_MAJOR: hist_dev[t*ld + g];
+ *  step0 = global index of the tile's first step.
+ * fsr_fatigue_finish closes the residue (processFinish, FFpFatigue.C:274-320) and returns
+ *  damage[ngage], ncycles[ngage], bins[ngage x nbins] (-1 like ffp_getnumcycles when there are no
+ *  cycles or the bin starts above the largest range), status[ngage]: 0 ok, 1 = the reference's
+ *  closure failure (cycles counted so far are kept, as ffp_getdamage ignores it), 2 = residue
+ *  stack capacity exceeded (results -1).  Return value: number of gages with status != 0. */
+typedef struct fsr_fatigue_state fsr_fatigue_state;
+#define FSR_HIST_GAGE_MAJOR 0
+#define FSR_HIST_STEP_MAJOR 1
+int fsr_fatigue_create(fsr_fatigue_state **f, int device, int ngage, double gate, const double *curve,
+                       double bin_size, int nbins, int stack_cap /* 0 = 1024 points per gage */);
+/* per-gage gate values [ngage] and S-N curves [ngage x 4] (rosette%gateValue / %snCurve,
+ * strainRosetteModule.f90:36-37); either may be NULL to keep the common value */
+int fsr_fatigue_set_gage_params(fsr_fatigue_state *f, const double *gate, const double *curve);
+int fsr_fatigue_reset(fsr_fatigue_state *f);
+int fsr_fatigue_locate_dev(fsr_fatigue_state *f, const double *hist_dev, size_t ld, int layout, int step0,
+                           int nsteps, int *n_pending, void *stream);
+int fsr_fatigue_feed_dev(fsr_fatigue_state *f, const double *hist_dev, size_t ld, int layout, int step0,
+                         int nsteps, void *stream);
+int fsr_fatigue_finish(fsr_fatigue_state *f, double *damage, int *ncycles, int *bins, int *status);
+int fsr_fatigue_finish_dev(fsr_fatigue_state *f, void *stream); /* asynchronous; results stay on device */
+int fsr_fatigue_results_dev(fsr_fatigue_state *f, double **damage_dev, int **ncycles_dev, int **bins_dev,
+                            int **status_dev);
+void fsr_fatigue_destroy(fsr_fatigue_state *f);
+
+/* ---- strain rosettes (fedem_gage) ------------------------------------------------------------
+ * One &STRAIN_ROSETTE record as readStrainGageData delivers it
+ * (src/vpmStress/strainGageModule.f90:107-237): nodes are INTERNAL node numbers (1-based, as in
+ * mmnpc), rpos = posInGl(3,4) column-major (rosette X, Y, Z axes and position; the .fsi format
+ * gives it explicitly), ngage / alpha_gages from the rosette type (SINGLE_GAGE 1/0,
+ * DOUBLE_GAGE_90 2/pi/2, TRIPLE_GAGE_60 3/pi/3, TRIPLE_GAGE_45 3/pi/4), gate and sncurve
+ * <= 0 = use the run's defaults (reportDamage, strainGageModule.f90:806-812). */
+typedef struct fsr_rosette {
+  int id, numnod, ngage, zero_init;
+  int nodes[4];
+  double rpos[12];
+  double zpos, emod, nu, alpha_gages, gate;
+  double sncurve[4]; /* loga1, loga2, m1, m2 */
+} fsr_rosette;
+typedef struct fsr_gages fsr_gages;
+/* values per rosette and step written by fsr_gage_recover: [0:3) epsC, [3:6) epsP (max, min,
+ * signed abs max), 6 gammaMax, 7 epsVM, 8 alpha1, 9 alphaGamma, [10:13) sigmaC, [13:16) sigmaP,
+ * 16 tauMax, 17 sigmaVM, [18:21) gage strains, [21:24) gage stresses
+ * (StrainRosetteType, strainRosetteModule.f90:29-58; calcRosetteStrains :251-324) */
+#define FSR_GAGE_NVAL 24
+
+/* Replaces ElDispFromSupElDisp + InitStrainRosette + InitStrainGages (gage.f90:169-232,
+ * displacementModule.f90:1096-1202, strainRosetteModule.f90:587-812, strainGageModule.f90:604-661):
+ * Bcart(3 x ndim) of every rosette, on the GPU, from the row operator of `part` (which must have
+ * had fsr_set_recovery).  The part may be destroyed afterwards (like closeBandEmatrices, gage.f90:256). */
+int fsr_gage_create(fsr_gages **gages, fsr_part *part, const fsr_rosette *ros, int nros);
+int fsr_gage_num_series(const fsr_gages *gages); /* 4 per rosette: max principal stress, legs 1-3 */
+int fsr_gage_get_bcart(fsr_gages *gages, double *bcart /* [nros][3 x ndim] column-major */);
+/* Replaces the time loop body of gage.f90:293-355 (CalcZeroStartRosetteStrains,
+ * CalcRosetteStrains) for nsteps steps: values [nsteps][nros][FSR_GAGE_NVAL] (may be NULL). */
+int fsr_gage_recover(fsr_gages *gages, const double *Q, int ldq, int nsteps, double *values);
+int fsr_gage_recover_dev(fsr_gages *gages, const double *Q_dev, int ldq, int nsteps,
+                         double *values_dev, void *stream);
+/* Replaces AddFatiguePoints + reportDamage (strainGageModule.f90:691-716,778-862): rainflow and
+ * damage of sigmaP(1)*toMPa and every leg stress*toMPa; series 4*r = rosette r max principal,
+ * 4*r+k = leg k (unused legs: no cycles).  damage/ncycles/status [4*nros], bins [4*nros x nbins]. */
+int fsr_gage_fatigue(fsr_gages *gages, const double *Q, int ldq, int nsteps, double to_mpa,
+                     double gate, const double *curve, double bin_size, int nbins, double *damage,
+                     int *ncycles, int *bins, int *status);
+/* streaming form for a device-resident history (see fsr_fatigue_locate_dev for the protocol):
+ * mode 0 = locate pass (stops at the first tile after which *n_pending == 0), 1 = counting pass */
+int fsr_gage_fatigue_begin(fsr_gages *gages, double to_mpa, double default_gate,
+                           const double *default_curve, double bin_size, int nbins, int stack_cap);
+int fsr_gage_fatigue_feed_dev(fsr_gages *gages, const double *Q_dev, int ldq, int step0, int nsteps,
+                              int mode, int *n_pending, void *stream);
+int fsr_gage_fatigue_end(fsr_gages *gages, double *damage, int *ncycles, int *bins, int *status);
+void fsr_gage_destroy(fsr_gages *gages);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);

@@ -115,6 +115,23 @@ int orc_recover_history(const orc_sam *sam, const orc_elmdata *ed, const double 
                         double *vm_hist, double *env_max, double *env_min, int nthreads);
 
 /* ---- strain rosettes / gages ---- */
+/* One &STRAIN_ROSETTE record (strainGageModule.f90:107-237); same layout as fsr_rosette. */
+typedef struct orc_rosette {
+  int id, numnod, ngage, zero_init;
+  int nodes[4];          /* internal node numbers, 1-based */
+  double rpos[12];       /* posInGl(3,4) column-major: X, Y, Z axis of the rosette, position */
+  double zpos, emod, nu, alpha_gages, gate;
+  double sncurve[4];
+} orc_rosette;
+#define ORC_GAGE_NVAL 24
+void orc_gage_directions(const orc_rosette *ros, double *Tg);
+int orc_rosette_bscr(const orc_rosette *ros, const orc_sam *sam, const double *xyz, double *bscr,
+                     int *rows, int *nElDof_out);
+int orc_rosette_bcart(const orc_rosette *ros, const orc_sam *sam, const double *xyz,
+                      const double *Bmat, const double *Emat, double *Bcart);
+void orc_calc_rosette_strains(const double *Bcart, int ndim, const double *finit,
+                              const double epsCInit[3], double emod, double nu,
+                              const double sigmaC0[3], const double *Tg, int ngage, double *out);
 void orc_principle_strains2d(const double epsC[3], double *eps1, double *eps2,
                              double *gammaMax, double *alpha1, double *alphaGamma);
 void orc_principle_stresses2d(const double sigC[3], double *sig1, double *sig2,

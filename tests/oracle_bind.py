@@ -34,6 +34,12 @@ class OrcElm(C.Structure):
     _fields_ = [("xyz", _D), ("emod", _D), ("rny", _D), ("thk", _D), ("elmid", _I), ("beam", _D)]
 
 
+class OrcRosette(C.Structure):
+    _fields_ = [("id", C.c_int), ("numnod", C.c_int), ("ngage", C.c_int), ("zero_init", C.c_int),
+                ("nodes", C.c_int * 4), ("rpos", C.c_double * 12), ("zpos", C.c_double), ("emod", C.c_double),
+                ("nu", C.c_double), ("alpha_gages", C.c_double), ("gate", C.c_double), ("sncurve", C.c_double * 4)]
+
+
 def ensure_built():
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
@@ -140,6 +146,62 @@ class Oracle:
                                           _ip(b["ptoff"]), _dp(vm), _dp(mx), _dp(mn), nthreads)
         assert rc == 0
         return vm, mx[:npts], mn[:npts]
+
+    # ---- strain rosettes (fedem_gage) -----------------------------------------------------
+    def _ros(self, r):
+        c = r.to_c()   # fsr_rosette and orc_rosette share their layout
+        o = OrcRosette()
+        C.memmove(C.byref(o), C.byref(c), C.sizeof(o))
+        return o
+
+    def rosette_bcart(self, b, ros):
+        """InitStrainRosette: Bcart [3, ndim] from ElDispFromSupElDisp and the rosette geometry."""
+        part = b["part"]; s = part.sam
+        B = np.asfortranarray(part.B, F64) if part.B is not None and part.B.size else np.zeros((1, 1), order="F")
+        E = np.asfortranarray(part.E, F64) if part.E is not None and part.E.size else np.zeros((1, 1), order="F")
+        out = np.zeros((s.ndim, 3), F64)
+        o = self._ros(ros)
+        self.lib.orc_rosette_bcart.argtypes = [C.POINTER(OrcRosette), C.POINTER(OrcSam), _D, _D, _D, _D]
+        rc = self.lib.orc_rosette_bcart(C.byref(o), C.byref(b["sam"]), b["elm"].xyz, _dp(B), _dp(E), _dp(out))
+        assert rc == 0, rc
+        return np.ascontiguousarray(out.T)
+
+    def rosette_history(self, b, ros, Q, Bcart=None):
+        """gage.f90:293-355 for one rosette: values [nsteps, 24] (zero-start strains honoured)."""
+        Bc = self.rosette_bcart(b, ros) if Bcart is None else Bcart
+        Bf = np.asfortranarray(Bc)
+        o = self._ros(ros)
+        Tg = np.zeros(9, F64)
+        self.lib.orc_gage_directions.argtypes = [C.POINTER(OrcRosette), _D]
+        self.lib.orc_gage_directions(C.byref(o), _dp(Tg))
+        self.lib.orc_calc_rosette_strains.argtypes = [_D, C.c_int, _D, _D, C.c_double, C.c_double, _D, _D, C.c_int, _D]
+        Q = np.asfortranarray(Q, F64)
+        ns = Q.shape[1]
+        out = np.zeros((ns, 24), F64)
+        eps0 = np.zeros(3, F64); sig0 = np.zeros(3, F64)
+        if ros.zero_init:
+            eps0 = -(Bc @ Q[:, 0])          # calcZeroStartRosetteStrains
+        for t in range(ns):
+            q = np.ascontiguousarray(Q[:, t])
+            self.lib.orc_calc_rosette_strains(_dp(Bf), Q.shape[0], _dp(q), _dp(eps0), ros.emod, ros.nu, _dp(sig0),
+                                              _dp(Tg), o.ngage, _dp(out[t]))
+        return out
+
+    def series_fatigue(self, x, gate, curve, bin_size=0.0, nbins=0):
+        """ffp_getdamage + ffp_getnumcycles on one history -> (damage, ncycles, bins, ok)."""
+        tp = self.pvx(x, gate)
+        cyc = self.rainflow(tp, gate)
+        if cyc is None:
+            return 0.0, 0, np.full(nbins, -1, I32), False
+        d = self.damage(cyc, curve) if len(cyc) else 0.0
+        r = np.abs(cyc[:, 0] - cyc[:, 1]) if len(cyc) else np.zeros(0)
+        bins = np.zeros(nbins, I32)
+        lo = 0.0
+        for k in range(nbins):
+            hi = lo + bin_size
+            bins[k] = -1 if (len(r) == 0 or lo > r.max()) else int(((r >= lo) & (r < hi)).sum())
+            lo = hi
+        return d, len(cyc), bins, True
 
     # ---- invariants / fatigue -------------------------------------------------------------
     def von_mises(self, S):
