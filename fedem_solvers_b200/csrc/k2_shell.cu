@@ -266,6 +266,344 @@ __global__ void build_quad_ops_kernel(int nelt, const int* __restrict__ elem,
 }
 
 // ------------------------------------------------------------------------------------------
+// Operator build: ANDES triangle (type 23)
+// ------------------------------------------------------------------------------------------
+// In-place inverse of a column-major N x N matrix: LU with partial pivoting, then the inverse
+// from the factors -- the job DINV12 (src/Femlib/dinv12.f:9-25) gives to LAPACK DGETRF/DGETRI
+// (an un-vendored system library in the reference; pivot-order rounding is O(1e-15) relative).
+template <int N>
+__device__ bool lu_invert(double* a)
+{
+  int piv[N];
+  double inv[N * N], col[N];
+  for (int k = 0; k < N; ++k) {
+    int p = k;
+    double big = fabs(a[k + N * k]);
+    for (int i = k + 1; i < N; ++i)
+      if (fabs(a[i + N * k]) > big) { big = fabs(a[i + N * k]); p = i; }
+    piv[k] = p;
+    if (a[p + N * k] == 0.0) return false;
+    if (p != k)
+      for (int j = 0; j < N; ++j) { double t = a[k + N * j]; a[k + N * j] = a[p + N * j]; a[p + N * j] = t; }
+    for (int i = k + 1; i < N; ++i) a[i + N * k] /= a[k + N * k];
+    for (int j = k + 1; j < N; ++j)
+      for (int i = k + 1; i < N; ++i) a[i + N * j] -= a[i + N * k] * a[k + N * j];
+  }
+  for (int c = 0; c < N; ++c) {
+    for (int i = 0; i < N; ++i) col[i] = (i == c) ? 1.0 : 0.0;
+    for (int k = 0; k < N; ++k)
+      if (piv[k] != k) { double t = col[k]; col[k] = col[piv[k]]; col[piv[k]] = t; }
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < i; ++k) col[i] -= a[i + N * k] * col[k];
+    for (int i = N - 1; i >= 0; --i) {
+      for (int k = i + 1; k < N; ++k) col[i] -= a[i + N * k] * col[k];
+      col[i] /= a[i + N * i];
+    }
+    for (int i = 0; i < N; ++i) inv[i + N * c] = col[i];
+  }
+  for (int k = 0; k < N * N; ++k) a[k] = inv[k];
+  return true;
+}
+
+// Membrane "kappa" matrix of the hybrid triangle, AKM(7 x 9) = F^-1 A with the IOP = 1 edge
+// displacement variant (HLST31, src/Femlib/hlst.f:102-243).  x, y: local corner coordinates,
+// Ei: inverse of the 3x3 constitutive matrix (column-major), thk: mean thickness.
+__device__ bool tri_membrane_kappa(double* AKM, const double* Ei, const double* x, const double* y, double thk)
+{
+  const int nxt[3] = {1, 2, 0};
+  double c[3], s[3], sl[3], xl[3], yl[3];
+  double area = 0.5 * (x[0] * y[1] + x[1] * y[2] + x[2] * y[0] - x[0] * y[2] - x[1] * y[0] - x[2] * y[1]);
+  if (area < 0.0) return false;
+  for (int i = 0; i < 3; ++i) {
+    const int j = nxt[i];
+    sl[i] = sqrt((x[j] - x[i]) * (x[j] - x[i]) + (y[j] - y[i]) * (y[j] - y[i]));
+    s[i] = (x[i] - x[j]) / sl[i];
+    c[i] = (y[j] - y[i]) / sl[i];
+  }
+  const double x0 = (x[0] + x[1] + x[2]) / 3., y0 = (y[0] + y[1] + y[2]) / 3.;
+  for (int i = 0; i < 3; ++i) { xl[i] = x[i] - x0; yl[i] = y[i] - y0; }
+  double f = area / (12. * thk);
+  const double P20 = f * (xl[0] * xl[0] + xl[1] * xl[1] + xl[2] * xl[2]);
+  const double P11 = f * (xl[0] * yl[0] + xl[1] * yl[1] + xl[2] * yl[2]);
+  const double P02 = f * (yl[0] * yl[0] + yl[1] * yl[1] + yl[2] * yl[2]);
+#define EI(i, j) Ei[(i - 1) + 3 * (j - 1)]
+#define FM(i, j) F7[(i - 1) + 7 * (j - 1)]
+#define AM(i, j) A[(i - 1) + 7 * (j - 1)]
+  double F7[49], A[63];
+  for (int k = 0; k < 49; ++k) F7[k] = 0.0;
+  for (int k = 0; k < 63; ++k) A[k] = 0.0;
+  f = area / thk;
+  FM(1, 1) = f * EI(1, 1); FM(1, 2) = f * EI(1, 2); FM(2, 2) = f * EI(2, 2);
+  FM(1, 3) = f * EI(1, 3); FM(2, 3) = f * EI(2, 3); FM(3, 3) = f * EI(3, 3);
+  FM(4, 4) = EI(1, 1) * P20 - 2. * EI(1, 3) * P11 + EI(3, 3) * P02;
+  FM(4, 5) = EI(1, 2) * P20 - EI(2, 3) * P11;
+  FM(5, 5) = EI(2, 2) * P20;
+  FM(4, 6) = EI(1, 1) * P11 - EI(1, 3) * P02;
+  FM(5, 6) = EI(1, 2) * P11;
+  FM(6, 6) = EI(1, 1) * P02;
+  FM(4, 7) = -EI(1, 3) * P20 + (EI(1, 2) + EI(3, 3)) * P11 - EI(2, 3) * P02;
+  FM(5, 7) = EI(2, 2) * P11 - EI(2, 3) * P20;
+  FM(6, 7) = EI(1, 2) * P02 - EI(1, 3) * P11;
+  FM(7, 7) = EI(2, 2) * P02 - 2. * EI(2, 3) * P11 + EI(3, 3) * P20;
+  for (int i = 1; i <= 7; ++i)
+    for (int j = i; j <= 7; ++j) FM(j, i) = FM(i, j);
+  if (!lu_invert<7>(F7)) return false;
+  for (int K = 0; K < 3; ++K) {
+    const double ck = c[K], sk = s[K], l = sl[K];
+    const double C2 = ck * ck, S2 = sk * sk, SC = sk * ck;
+    const double CX = ck * xl[K], CY = ck * yl[K], SX = sk * xl[K], SY = sk * yl[K];
+    const double l2 = l * l, A1 = l / 2.;
+    for (int end = 0; end < 2; ++end) {
+      // end 0: the edge's first node (K), end 1: its second node
+      const int J = 3 * (end == 0 ? K : nxt[K]) + 1;
+      const double sgn = end == 0 ? 1.0 : -1.0;
+      const double A4 = -sgn * ck * l2 / 12., A5 = -sgn * sk * l2 / 12.;
+      const double B4 = end == 0 ? -ck * l2 * l / 30. : ck * l2 * l / 20.;
+      const double B5 = end == 0 ? -sk * l2 * l / 30. : sk * l2 * l / 20.;
+      const double B1 = end == 0 ? l2 / 6. : l2 / 3., B2 = 0., B3 = B1;
+      AM(1, J) += A1 * ck;
+      AM(3, J) += A1 * sk;
+      AM(4, J) += A1 * (CX - SY) - 2. * B1 * SC - B2 * C2;
+      AM(5, J) += -B2 * S2;
+      AM(6, J) += A1 * CY + B1 * C2;
+      AM(7, J) += -A1 * SX + B1 * S2 + 2. * B2 * SC;
+      AM(2, J + 1) += A1 * sk;
+      AM(3, J + 1) += A1 * ck;
+      AM(4, J + 1) += -A1 * CY - 2. * B2 * SC - B3 * C2;
+      AM(5, J + 1) += A1 * SX - B3 * S2;
+      AM(6, J + 1) += B2 * C2;
+      AM(7, J + 1) += A1 * (SY - CX) + B2 * S2 + 2. * B3 * SC;
+      AM(1, J + 2) += A4 * ck;
+      AM(2, J + 2) += A5 * sk;
+      AM(3, J + 2) += A4 * sk + A5 * ck;
+      AM(4, J + 2) += A4 * (CX - SY) - A5 * CY - 2. * B4 * SC - B5 * C2;
+      AM(5, J + 2) += A5 * SX - B5 * S2;
+      AM(6, J + 2) += A4 * CY + B4 * C2;
+      AM(7, J + 2) += -A4 * SX + A5 * (SY - CX) + B4 * S2 + 2. * B5 * SC;
+    }
+  }
+  for (int i = 1; i <= 7; ++i)
+    for (int j = 1; j <= 9; ++j) {
+      double acc = FM(i, 1) * AM(1, j);
+      for (int k = 2; k <= 7; ++k) acc += FM(i, k) * AM(k, j);
+      AKM[(i - 1) + 7 * (j - 1)] = acc;
+    }
+#undef FM
+#undef AM
+  return true;
+}
+
+// Bending "kappa" matrix AKB(9 x 9) = Fb^-1 G T (TEBA31, src/Femlib/nyteba.f:7-331).  The 7-point
+// rule is kept in the REAL*4 precision of the reference's DATA statements (nyteba.f:35-43).
+__device__ bool tri_bending_kappa(double* AKB, const double* Ei, const double* x, const double* y, const double* th)
+{
+  const int nxt[3] = {1, 2, 0};
+  const double za = (double)0.33333333f, zb = (double)0.05971587f, zc = (double)0.47014206f,
+               zd = (double)0.79742699f, ze = (double)0.10128651f;
+  const double Z1[7] = {za, zb, zc, zc, zd, ze, ze}, Z2[7] = {za, zc, zb, zc, ze, zd, ze},
+               Z3[7] = {za, zc, zc, zb, ze, ze, zd};
+  const double wa = (double)0.225f, wb = (double)0.13239415f, wc = (double)0.12593918f;
+  const double W[7] = {wa, wb, wb, wb, wc, wc, wc};
+  double c[3], s[3], sl[3];
+  const double area = 0.5 * (x[0] * y[1] + x[1] * y[2] + x[2] * y[0] - x[0] * y[2] - x[1] * y[0] - x[2] * y[1]);
+  if (area <= 0.0) return false;
+  for (int i = 0; i < 3; ++i) {
+    const int j = nxt[i];
+    sl[i] = sqrt((x[j] - x[i]) * (x[j] - x[i]) + (y[j] - y[i]) * (y[j] - y[i]));
+    s[i] = (x[i] - x[j]) / sl[i];
+    c[i] = (y[j] - y[i]) / sl[i];
+  }
+  const double RL11 = 0.5 * (y[1] - y[2]) / area, RL12 = 0.5 * (y[2] - y[0]) / area;
+  const double RL21 = 0.5 * (x[2] - x[1]) / area, RL22 = 0.5 * (x[0] - x[2]) / area;
+  double Bq[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 7; ++k) {
+    const double t = th[0] * Z1[k] + th[1] * Z2[k] + th[2] * Z3[k];
+    if (t <= 0.0) return false;
+    const double f = 12. * area * W[k] / (t * t * t);
+    const double z[3] = {Z1[k], Z2[k], Z3[k]};
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) Bq[i + 3 * j] += f * z[i] * z[j];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 3; ++j) Bq[j + 3 * i] = Bq[i + 3 * j];
+  double EK[81], G[108], T[108], GT[81];
+#define EKM(i, j) EK[(i - 1) + 9 * (j - 1)]
+#define GM(i, j) G[(i - 1) + 9 * (j - 1)]
+#define TM(i, j) T[(i - 1) + 12 * (j - 1)]
+  for (int II = 1; II <= 3; ++II)
+    for (int JJ = II; JJ <= 3; ++JJ)
+      for (int i = 1; i <= 3; ++i)
+        for (int j = 1; j <= 3; ++j) EKM(3 * II - 3 + i, 3 * JJ - 3 + j) = EI(II, JJ) * Bq[(i - 1) + 3 * (j - 1)];
+  for (int i = 1; i <= 9; ++i)
+    for (int j = i; j <= 9; ++j) EKM(j, i) = EKM(i, j);
+  if (!lu_invert<9>(EK)) return false;
+  for (int k = 0; k < 108; ++k) { G[k] = 0.0; T[k] = 0.0; }
+  for (int I = 1; I <= 3; ++I) {
+    const int K = nxt[nxt[I - 1]] + 1;
+    GM(I, I) = s[K - 1] * c[K - 1] - s[I - 1] * c[I - 1];
+    GM(I + 3, I) = -GM(I, I);
+    GM(I + 6, I) = c[I - 1] * c[I - 1] - s[I - 1] * s[I - 1] - c[K - 1] * c[K - 1] + s[K - 1] * s[K - 1];
+  }
+  for (int I = 1; I <= 3; ++I) {
+    const int J = I + 3;
+    const double ci = c[I - 1], si = s[I - 1];
+    const double SS = si * si * ci, CC = ci * ci * si, CS = ci * ci - si * si;
+    GM(1, J) = (ci + SS) * RL11 - CC * RL21;
+    GM(2, J) = (ci + SS) * RL12 - CC * RL22;
+    GM(3, J) = -(ci + SS) * (RL11 + RL12) + CC * (RL21 + RL22);
+    GM(4, J) = (si + CC) * RL21 - SS * RL11;
+    GM(5, J) = (si + CC) * RL22 - SS * RL12;
+    GM(6, J) = -(si + CC) * (RL21 + RL22) + SS * (RL11 + RL12);
+    GM(7, J) = si * RL11 + ci * RL21 - CS * (si * RL11 - ci * RL21);
+    GM(8, J) = ci * RL22 + si * RL12 - CS * (si * RL12 - ci * RL22);
+    GM(9, J) = -si * (RL11 + RL12) - ci * (RL21 + RL22);
+    GM(9, J) = GM(9, J) + CS * (si * (RL11 + RL12) - ci * (RL21 + RL22));
+  }
+  for (int I = 1; I <= 3; ++I) {
+    const int J = nxt[I - 1] + 1, N = 2 * I + 5;
+    const double ci = c[I - 1], si = s[I - 1];
+    GM(I, N) = ci * ci; GM(I + 3, N) = si * si; GM(I + 6, N) = 2. * si * ci;
+    GM(J, N + 1) = ci * ci; GM(J + 3, N + 1) = si * si; GM(J + 6, N + 1) = 2. * si * ci;
+  }
+  for (int I = 1; I <= 3; ++I) {
+    const int J = nxt[I - 1] + 1;
+    const double l = sl[I - 1], SS = s[I - 1] * l, CC = c[I - 1] * l;
+    TM(I, 3 * I - 2) = 1.;
+    TM(I + 3, 3 * I - 2) = l / 2.;
+    TM(I + 3, 3 * I - 1) = -l * SS / 12.;
+    TM(I + 3, 3 * I) = l * CC / 12.;
+    TM(I + 3, 3 * J - 2) = l / 2.;
+    TM(I + 3, 3 * J - 1) = l * SS / 12.;
+    TM(I + 3, 3 * J) = -l * CC / 12.;
+    TM(2 * I + 5, 3 * I - 1) = -CC / 3.;
+    TM(2 * I + 5, 3 * I) = -SS / 3.;
+    TM(2 * I + 5, 3 * J - 1) = -CC / 6.;
+    TM(2 * I + 5, 3 * J) = -SS / 6.;
+    TM(2 * I + 6, 3 * I - 1) = -CC / 6.;
+    TM(2 * I + 6, 3 * I) = -SS / 6.;
+    TM(2 * I + 6, 3 * J - 1) = -CC / 3.;
+    TM(2 * I + 6, 3 * J) = -SS / 3.;
+  }
+  // (w, dw/dx, dw/dy) -> (w, theta_x, theta_y): swap the two rotation columns with a sign change
+  for (int I = 1; I <= 3; ++I) {
+    const int J = 3 * I - 1, K = J + 1;
+    for (int M = 1; M <= 12; ++M) { const double f = TM(M, J); TM(M, J) = TM(M, K); TM(M, K) = -f; }
+  }
+  for (int I = 1; I <= 9; ++I)
+    for (int J = 1; J <= 9; ++J) {
+      double acc = 0.;
+      for (int K = 1; K <= 12; ++K) acc += GM(I, K) * TM(K, J);
+      GT[(I - 1) + 9 * (J - 1)] = acc;
+    }
+  for (int I = 1; I <= 9; ++I)
+    for (int J = 1; J <= 9; ++J) {
+      double acc = 0.;
+      for (int K = 1; K <= 9; ++K) acc += EKM(I, K) * GT[(K - 1) + 9 * (J - 1)];
+      AKB[(I - 1) + 9 * (J - 1)] = acc;
+    }
+#undef EKM
+#undef GM
+#undef TM
+#undef EI
+  return true;
+}
+
+// One thread per triangle: STR23 (src/vpmStress/elStressModule.f90:901-999) as a 6-point x 3-component
+// x 18-DOF operator.  FTSA31 (ftsa.f:53-104) gives the two kappa matrices, FTSA32 (:196-260) their
+// centroid stress matrices with ZZ = 1./3. in REAL*4, FTS38 (fts.f:446-490) the split of the nodal
+// vector into membrane (u, v, rz) and bending (w, rx, ry) parts in the DIRC30 axes
+// (beamaux.f:209-260); top / bottom stresses = (N +- 6 M / t) / t at every node.
+__global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, const int* __restrict__ conn,
+                                     const double* __restrict__ xyz, const double* __restrict__ emod,
+                                     const double* __restrict__ rny, const double* __restrict__ thk,
+                                     double* __restrict__ Sfrag, unsigned char* __restrict__ failed,
+                                     double* __restrict__ aux)
+{
+  const int KT = 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelt) return;
+  const int e = elem[i];
+  double* S = Sfrag + (size_t)i * 3 * KT * 32;
+  V3 X[3];
+  for (int k = 0; k < 3; ++k) {
+    const int n = conn[i * 3 + k];
+    X[k] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
+  }
+  const double E = emod[e], nu = rny[e], t = thk[e];
+  aux[i * 4 + 0] = E; aux[i * 4 + 1] = nu; aux[i * 4 + 2] = t; aux[i * 4 + 3] = 0.0;
+  bool ok = true;
+  // isoMat2D and its LU inverse (HLST31/TEBA31 invert the matrix they are given)
+  const double C11 = E / (1.0 - nu * nu);
+  double Ei[9] = {C11, nu * C11, 0., nu * C11, C11, 0., 0., 0., 0.5 * E / (1.0 + nu)};
+  ok = lu_invert<3>(Ei);
+  // local corner coordinates (ftsa.f:60-80)
+  const V3 d21 = vsub(X[1], X[0]), d31 = vsub(X[2], X[0]);
+  const double L21 = sqrt(vdot(d21, d21)), L31 = sqrt(vdot(d31, d31));
+  const double cosg = vdot(d31, d21) / (L31 * L21);
+  const double a1 = 1. - cosg * cosg;
+  const double sing = a1 <= 0.0 ? 0. : sqrt(a1);
+  const double xl[3] = {0., L21, L31 * cosg}, yl[3] = {0., 0., L31 * sing};
+  const double th[3] = {t, t, t};
+  double AKM[63], AKB[81];
+  if (ok) ok = tri_membrane_kappa(AKM, Ei, xl, yl, (t + t + t) / 3.);
+  if (ok) ok = tri_bending_kappa(AKB, Ei, xl, yl, th);
+  // output-system rotation from the triangle axes (x along 1->2, not projected)
+  V3 ex = d21, ez = vcross(d21, d31);
+  double l2 = vdot(ez, ez);
+  if (l2 > kEpsDiv0 * kEpsDiv0) ez = vscale(ez, 1.0 / sqrt(l2)); else ok = false;
+  l2 = vdot(ex, ex);
+  if (l2 > kEpsDiv0 * kEpsDiv0) ex = vscale(ex, 1.0 / sqrt(l2)); else ok = false;
+  double ca = 1.0, sa = 0.0;
+  if (ok) ok = stress_rotation(ex, ez, ca, sa);
+  if (!ok) { failed[i] = 1; return; }  // Sfrag was zeroed by the caller
+
+  // centroid stress matrices (HLST32, hlst.f:330-352; TEBA32, nyteba.f:333-364), ZZ = REAL*4 1./3.
+  const double zz = (double)(1.f / 3.f);
+  const double x0 = (xl[0] + xl[1] + xl[2]) / 3., y0 = (yl[0] + yl[1] + yl[2]) / 3.;
+  double rx = 0., ry = 0.;
+  for (int k = 0; k < 3; ++k) { rx += (xl[k] - x0) * zz; ry += (yl[k] - y0) * zz; }
+  double SMM[3][9], SMB[3][9];
+  for (int j = 0; j < 9; ++j) {
+    const double* a = AKM + 7 * j;
+    SMM[0][j] = a[0] + rx * a[3] + ry * a[5];
+    SMM[1][j] = a[1] + rx * a[4] + ry * a[6];
+    SMM[2][j] = a[2] - ry * a[3] - rx * a[6];
+    for (int r = 0; r < 3; ++r) SMB[r][j] = zz * AKB[3 * r + 9 * j] + zz * AKB[3 * r + 1 + 9 * j] + zz * AKB[3 * r + 2 + 9 * j];
+  }
+  // direction cosines (DIRC30): rows = local x (1->2), y, z; every row renormalised
+  V3 cz = vcross(ex, d31);
+  cz = vscale(cz, 1.0 / sqrt(vdot(cz, cz)));
+  V3 cy = vcross(cz, ex);
+  cy = vscale(cy, 1.0 / sqrt(vdot(cy, cy)));
+  const double Cd[3][3] = {{ex.x, ex.y, ex.z}, {cy.x, cy.y, cy.z}, {cz.x, cz.y, cz.z}};
+  for (int n = 0; n < 3; ++n)
+    for (int d = 0; d < 6; ++d) {
+      const int k = d % 3;
+      double N[3], M[3];
+      for (int r = 0; r < 3; ++r) {
+        if (d < 3) {  // translation: (u, v) -> membrane, w -> bending
+          N[r] = SMM[r][3 * n] * Cd[0][k] + SMM[r][3 * n + 1] * Cd[1][k];
+          M[r] = SMB[r][3 * n] * Cd[2][k];
+        } else {      // rotation: (rx, ry) -> bending, rz -> membrane
+          M[r] = SMB[r][3 * n + 1] * Cd[0][k] + SMB[r][3 * n + 2] * Cd[1][k];
+          N[r] = SMM[r][3 * n + 2] * Cd[2][k];
+        }
+      }
+      rot2d(N[0], N[1], N[2], ca, sa);
+      rot2d(M[0], M[1], M[2], ca, sa);
+      const int col = 6 * n + d;
+      for (int r = 0; r < 3; ++r) {
+        const double top = (N[r] + M[r] * 6.0 / t) / t, bot = (N[r] - M[r] * 6.0 / t) / t;
+        for (int pnt = 0; pnt < 3; ++pnt) {
+          S[frag_index(8 * r + pnt, col, KT)] = top;
+          S[frag_index(8 * r + 3 + pnt, col, KT)] = bot;
+        }
+      }
+    }
+  failed[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // K2 apply: von Mises + envelope for shell families (3 m-tiles: xx, yy, xy at 8 points)
 // ------------------------------------------------------------------------------------------
 // The FP64 tensor pipe is the shared resource here (DMMA and scalar FP64 issue to the same pipe and
@@ -288,10 +626,13 @@ __device__ __forceinline__ double sqrt_pos(double x)
   return x > 1.0e-290 ? y : 0.0;
 }
 
-template <int KT, bool WRITE_VM, bool GUARD>
+// `live` = this lane's result point exists (triangles use 6 of the 8 rows of an m-tile).  Every lane
+// of the warp must reach every mma.sync, so dead lanes run the same loop and only their stores and
+// envelope updates are predicated off (ALL_LIVE = true for quads compiles the predicate away).
+template <int KT, bool WRITE_VM, bool GUARD, bool ALL_LIVE>
 __device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const double (&b)[KT], double*& vmp0,
                                            double*& vmp1, size_t ld8, int t0, int nsteps, double& emax,
-                                           double& emin)
+                                           double& emin, bool live)
 {
   double c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
@@ -302,19 +643,20 @@ __device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const doubl
   double q0 = fma(c[2][0] * 3.0, c[2][0], fma(-c[0][0], c[1][0], fma(c[1][0], c[1][0], c[0][0] * c[0][0])));
   double q1 = fma(c[2][1] * 3.0, c[2][1], fma(-c[0][1], c[1][1], fma(c[1][1], c[1][1], c[0][1] * c[0][1])));
   double v0 = sqrt_pos(q0), v1 = sqrt_pos(q1);
+  const bool wr = ALL_LIVE || live;
   if (GUARD) {
     if (t0 < nsteps) {
-      if (WRITE_VM) *vmp0 = v0;
+      if (WRITE_VM && wr) *vmp0 = v0;
       emax = v0 > emax ? v0 : emax;
       emin = v0 < emin ? v0 : emin;
     }
     if (t0 + 1 < nsteps) {
-      if (WRITE_VM) *vmp1 = v1;
+      if (WRITE_VM && wr) *vmp1 = v1;
       emax = v1 > emax ? v1 : emax;
       emin = v1 < emin ? v1 : emin;
     }
   } else {
-    if (WRITE_VM) { *vmp0 = v0; *vmp1 = v1; }
+    if (WRITE_VM && wr) { *vmp0 = v0; *vmp1 = v1; }
     const bool p = v0 > v1;
     const double hi = p ? v0 : v1, lo = p ? v1 : v0;
     emax = hi > emax ? hi : emax;
@@ -323,7 +665,7 @@ __device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const doubl
   if (WRITE_VM) { vmp0 += ld8; vmp1 += ld8; }
 }
 
-template <int KT, bool WRITE_VM>
+template <int KT, bool WRITE_VM, bool ALL_LIVE>
 __global__ void __launch_bounds__(256, 2)
 k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
                    const double* __restrict__ Sfrag, const int* __restrict__ edof,
@@ -334,11 +676,11 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int i = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i >= nelt) return;
-  const bool live = g < nstrp;
+  if (i >= nelt) return;  // whole warp
+  const bool live = ALL_LIVE || g < nstrp;
   const size_t pt = (size_t)ptoff[i] + (live ? g : 0);
 
-  if (failed[i]) {  // operator build failed: hugeVal results (stressRoutines.f90:264-268)
+  if (failed[i]) {  // operator build failed: hugeVal results (stressRoutines.f90:264-268); whole warp
     if (live) {
       if (WRITE_VM)
         for (int t = t4; t < nsteps; t += 4) vm[(size_t)t * ld_vm + pt] = kHuge;
@@ -361,8 +703,7 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
   for (int j = 0; j < KT; ++j) up[j] = U + (size_t)__ldg(edof + (size_t)i * KT * 4 + j * 4 + t4) * ldu + g;
 
   double emax = 0.0, emin = kHuge;  // neutral w.r.t. the stored envelope (max starts at 0)
-  // lane owns point g at steps t0 = 8*tile + 2*t4 and t0 + 1; padded lanes (g >= nstrp) write to a
-  // valid dummy location guarded below by `live`
+  // lane owns point g at steps t0 = 8*tile + 2*t4 and t0 + 1
   double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
   double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
   const size_t ld8 = ld_vm * 8;
@@ -373,41 +714,27 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
 #pragma unroll
   for (int j = 0; j < KT; ++j) b0[j] = up[j][0];
 
-  if (live) {
-    int nt = 0;
-    for (; nt < nfull; nt += 4) {
+  int nt = 0;
+  for (; nt < nfull; nt += 4) {
 #pragma unroll
-      for (int j = 0; j < KT; ++j) b1[j] = up[j][8];
-      shell_tile<KT, WRITE_VM, false>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin);
+    for (int j = 0; j < KT; ++j) b1[j] = up[j][8];
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
 #pragma unroll
-      for (int j = 0; j < KT; ++j) b0[j] = up[j][16];
-      shell_tile<KT, WRITE_VM, false>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin);
+    for (int j = 0; j < KT; ++j) b0[j] = up[j][16];
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
 #pragma unroll
-      for (int j = 0; j < KT; ++j) b1[j] = up[j][24];
-      shell_tile<KT, WRITE_VM, false>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin);
+    for (int j = 0; j < KT; ++j) b1[j] = up[j][24];
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
 #pragma unroll
-      for (int j = 0; j < KT; ++j) { up[j] += 32; b0[j] = up[j][0]; }  // U rows carry 64 doubles of slack
-      shell_tile<KT, WRITE_VM, false>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin);
-    }
-    for (; nt < ntiles && nt * 8 < nsteps; ++nt) {  // ragged tail: guarded stores
+    for (int j = 0; j < KT; ++j) { up[j] += 32; b0[j] = up[j][0]; }  // U rows carry 64 doubles of slack
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
+  }
+  for (; nt < ntiles && nt * 8 < nsteps; ++nt) {  // ragged tail: guarded stores
 #pragma unroll
-      for (int j = 0; j < KT; ++j) { up[j] += 8; b1[j] = up[j][0]; }
-      shell_tile<KT, WRITE_VM, true>(a, b0, vmp0, vmp1, ld8, nt * 8 + 2 * t4, nsteps, emax, emin);
+    for (int j = 0; j < KT; ++j) { up[j] += 8; b1[j] = up[j][0]; }
+    shell_tile<KT, WRITE_VM, true, ALL_LIVE>(a, b0, vmp0, vmp1, ld8, nt * 8 + 2 * t4, nsteps, emax, emin, live);
 #pragma unroll
-      for (int j = 0; j < KT; ++j) b0[j] = b1[j];
-    }
-  } else {
-    // lanes of padded result points (triangles: g = 6,7) still feed the MMAs
-    int nt = 0;
-    double dmax = 0.0, dmin = 0.0;
-    double *d0 = nullptr, *d1 = nullptr;
-    for (; nt < ntiles && nt * 8 < nsteps; ++nt) {
-#pragma unroll
-      for (int j = 0; j < KT; ++j) { up[j] += 8; b1[j] = up[j][0]; }
-      shell_tile<KT, false, false>(a, b0, d0, d1, 0, 0, 0, dmax, dmin);
-#pragma unroll
-      for (int j = 0; j < KT; ++j) b0[j] = b1[j];
-    }
+    for (int j = 0; j < KT; ++j) b0[j] = b1[j];
   }
   // combine the four lanes that share a result point, then fold into the stored envelope
   emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
@@ -493,27 +820,50 @@ int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
       cudaFree(d_conn);
     }
   }
+  // ---- triangles (type 23) ----
+  {
+    FamilyData& f = p->fam[FAM_TRI];
+    f.nenod = 3; f.nndof = 6; f.nstrp = 6; f.ncmp = 3; f.MT = 3; f.KT = 5;
+    std::vector<int> elem, conn, edof, ptoff;
+    int rc = gather_family(p, sam, elm, 23, 3, 6, f.KT, elem, conn, edof, ptoff);
+    if (rc) return rc;
+    int* d_conn = nullptr;
+    rc = upload_family(f, elem, conn, edof, ptoff, 4, &d_conn, s);
+    if (rc) return rc;
+    if (f.nelt > 0) {
+      build_tri_ops_kernel<<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny,
+                                                           p->thk, f.Sfrag, f.failed, f.aux);
+      FSR_LAUNCH_CHECK();
+      FSR_CUDA(cudaStreamSynchronize(s));
+      cudaFree(d_conn);
+    }
+  }
+  return FSR_OK;
+}
+
+template <int KT, bool ALL_LIVE>
+static int launch_shell_family(fsr_part* p, FamilyData& f, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm,
+                               cudaStream_t s)
+{
+  const int warps = 8;
+  if (f.nelt == 0) return FSR_OK;
+  if (vm_dev)
+    k2_shell_vm_kernel<KT, true, ALL_LIVE><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, f.nstrp, vm_dev,
+        ld_vm, p->env_max, p->env_min);
+  else
+    k2_shell_vm_kernel<KT, false, ALL_LIVE><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, f.nstrp, vm_dev,
+        ld_vm, p->env_max, p->env_min);
+  FSR_LAUNCH_CHECK();
   return FSR_OK;
 }
 
 int launch_k2_shell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s)
 {
-  const int warps = 8;
-  {
-    FamilyData& f = p->fam[FAM_QUAD];
-    if (f.nelt > 0) {
-      if (vm_dev)
-        k2_shell_vm_kernel<6, true><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt,
-            f.nstrp, vm_dev, ld_vm, p->env_max, p->env_min);
-      else
-        k2_shell_vm_kernel<6, false><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt,
-            f.nstrp, vm_dev, ld_vm, p->env_max, p->env_min);
-      FSR_LAUNCH_CHECK();
-    }
-  }
-  return FSR_OK;
+  int rc = launch_shell_family<5, false>(p, p->fam[FAM_TRI], nsteps, nsteps_pad, vm_dev, ld_vm, s);
+  if (rc) return rc;
+  return launch_shell_family<6, true>(p, p->fam[FAM_QUAD], nsteps, nsteps_pad, vm_dev, ld_vm, s);
 }
 
 }  // namespace fsr

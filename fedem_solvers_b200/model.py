@@ -271,56 +271,104 @@ def plate_part(nx, ny, ngen=10, seed=1, tri_fraction=0.0, n_ext=4, jitter=0.02, 
 _TET_SPLIT = [(0, 1, 3, 7), (0, 1, 7, 5), (0, 5, 7, 4), (1, 2, 3, 7), (1, 6, 7, 5), (1, 2, 7, 6)]
 
 
+def beam_record(x1, x2, zdir, emod=2.1e11, gmod=8.0e10, area=1.0e-4, iy=2.0e-9, iz=1.0e-9, it=2.5e-9,
+                kxy=0.85, kxz=0.8, sy=0.0, sz=0.0, efflen=0.0, phi=0.0, ecc1=(0, 0, 0), ecc2=(0, 0, 0),
+                rho=7850.0, pin_a=0, pin_b=0):
+    """The 32 doubles a type-11 element carries over the C ABI (fsr_elmdata.beam): X(1:5), Y(1:5), Z(1:5)
+    as ffl_getcoor delivers them for BEAM2 (FFlLinkHandler_F.C:766-812: ends incl. eccentricity, point on
+    the local Z axis, the two nodes), BSEC(1:14) of ffl_getbeamsection (:1131-1188; the shear factors
+    stored inverted), pin flags."""
+    x1, x2, zdir = (np.asarray(v, F64) for v in (x1, x2, zdir))
+    e1, e2 = np.asarray(ecc1, F64), np.asarray(ecc2, F64)
+    P = np.stack([x1 + e1, x2 + e2, x1 + zdir + e1, x1, x2])      # [5, 3]
+    ixx = iy + iz
+    bsec = [rho, emod, gmod, area, iy, iz, it, ixx if ixx > 0 else it, 1.0 / kxy if kxy > 0 else 0.0,
+            1.0 / kxz if kxz > 0 else 0.0, sy, sz, efflen, phi]
+    return np.concatenate([P[:, 0], P[:, 1], P[:, 2], bsec, [pin_a, pin_b, 0.0]])
+
+
 def tet10_block(nx, ny, nz, ngen=10, seed=3, n_ext=4, jitter=0.05, emod=2.1e11, rny=0.3,
-                shuffle_eq=False, with_recovery=True):
+                shuffle_eq=False, with_recovery=True, n_beams=0):
     """Structured block of nx*ny*nz hexahedral cells, each split into 6 ten-node tetrahedra
     (type 41), FEDEM node order: corners 1,3,5,10, mid-edges 2,4,6,7,8,9 (itet.f label 300).
-    Mid-edge nodes get a small jitter so edges are curved (non-constant Jacobians)."""
+    Mid-edge nodes get a small jitter so edges are curved (non-constant Jacobians).  n_beams BEAM2
+    stiffeners (type 11) run along random cell edges; their nodes carry 6 DOFs like in a real model
+    (the solids use the first three), some with eccentricities, shear-centre offsets and a rotated
+    principal axis so that every branch of BEAM31 is exercised (config C3)."""
     rng = np.random.default_rng(seed)
-    # vertex grid on doubled indices so mid-edge nodes are addressable
     NX, NY, NZ = 2 * nx + 1, 2 * ny + 1, 2 * nz + 1
-    node_id = {}
-    coords = []
+    # nodes of the doubled grid that are used by the 6-tet split: all vertices, edge mids, face-diagonal
+    # mids and the cell-diagonal mid -- numbered in the order the elements first touch them
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cells = np.stack([iz.ravel(order="F"), iy.ravel(order="F"), ix.ravel(order="F")], 1)  # cz, cy, cx loops
+    order = np.lexsort((cells[:, 2], cells[:, 1], cells[:, 0]))
+    cells = cells[order]
+    dv = np.array([(dx, dy, dz) for dz in (0, 2) for dy in (0, 2) for dx in (0, 2)])
+    hexsel = [0, 1, 3, 2, 4, 5, 7, 6]
+    tets = []
+    for t in _TET_SPLIT:
+        a, b, c, d = (dv[hexsel[q]] for q in t)
+        if np.dot(np.cross(b - a, c - a), d - a) < 0:
+            b, c = c, b
+        mid = lambda p, q: (p + q) // 2
+        tets.append(np.stack([a, mid(a, b), b, mid(b, c), c, mid(c, a), mid(a, d), mid(b, d), mid(c, d), d]))
+    tets = np.stack(tets)                                            # [6, 10, 3] offsets in the doubled grid
+    base = 2 * cells[:, [2, 1, 0]]                                   # [ncell, 3] (x, y, z)
+    gidx = base[:, None, None, :] + tets[None]                       # [ncell, 6, 10, 3]
+    key = (gidx[..., 2].astype(np.int64) * NY + gidx[..., 1]) * NX + gidx[..., 0]
+    flat = key.reshape(-1)
+    uniq, first = np.unique(flat, return_index=True)
+    rank = np.empty(len(uniq), np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+    node = rank[np.searchsorted(uniq, flat)] + 1                     # numbering by first appearance
+    conn = node.reshape(-1, 10).astype(I32)
+    nnod = len(uniq)
+    kk = uniq[np.argsort(first, kind="stable")]
+    gi = np.stack([kk % NX, (kk // NX) % NY, kk // (NX * NY)], 1)
+    xyz = gi / 2.0
+    odd = (gi % 2).sum(1) > 0
+    xyz[odd] += rng.uniform(-jitter, jitter, (int(odd.sum()), 3)) * 0.5
+    node_of = {int(k): i + 1 for i, k in enumerate(kk)}
 
     def nid(i, j, k):
-        key = (i, j, k)
-        if key not in node_id:
-            node_id[key] = len(coords) + 1
-            p = np.array([i / 2.0, j / 2.0, k / 2.0])
-            if (i % 2) + (j % 2) + (k % 2) > 0:
-                p = p + rng.uniform(-jitter, jitter, 3) * 0.5
-            coords.append(p)
-        return node_id[key]
+        return node_of[(k * NY + j) * NX + i]
 
-    conn = []
-    for cz in range(nz):
-        for cy in range(ny):
-            for cx in range(nx):
-                v = [(2 * cx + dx, 2 * cy + dy, 2 * cz + dz) for dz in (0, 2) for dy in (0, 2) for dx in (0, 2)]
-                # v index: dx + 2*dy/2... -> order (0,0,0),(2,0,0),(0,2,0),(2,2,0),(0,0,2),...
-                hexv = [v[0], v[1], v[3], v[2], v[4], v[5], v[7], v[6]]
-                for t in _TET_SPLIT:
-                    a, b, c, d = (hexv[q] for q in t)
-                    # orientation: positive volume for (a,b,c,d) with L4 at d
-                    pa, pb, pc, pd = (np.array(x, float) for x in (a, b, c, d))
-                    if np.dot(np.cross(pb - pa, pc - pa), pd - pa) < 0:
-                        b, c = c, b
-                    mid = lambda p, q: tuple((np.array(p) + np.array(q)) // 2)
-                    n = [nid(*a), nid(*mid(a, b)), nid(*b), nid(*mid(b, c)), nid(*c), nid(*mid(c, a)),
-                         nid(*mid(a, d)), nid(*mid(b, d)), nid(*mid(c, d)), nid(*d)]
-                    conn.append(np.asarray(n, I32))
-    xyz = np.asarray(coords, F64)
-    nnod = len(coords)
-    # external nodes: corner vertices of the block
     cand = [(0, 0, 0), (NX - 1, 0, 0), (0, NY - 1, 0), (NX - 1, NY - 1, NZ - 1), (0, 0, NZ - 1),
             (NX - 1, NY - 1, 0), (0, NY - 1, NZ - 1), (NX - 1, 0, NZ - 1)]
-    ext_nodes = [node_id[c] for c in cand[:n_ext]]
-    sam = _build_sam(nnod, 3, conn, np.full(len(conn), 41, I32), ext_nodes, rng=rng, shuffle_eq=shuffle_eq)
+    ext_nodes = [nid(*c) for c in cand[:n_ext]]
+    types = np.full(len(conn), 41, I32)
+    ndpn = np.full(nnod, 3, I32)
+    beams = []
+    conn_list = conn
+    if n_beams > 0:
+        conn_list = [c for c in conn]
+        for b in range(n_beams):
+            ax = int(rng.integers(0, 3))
+            c0 = [int(rng.integers(0, n + (0 if a == ax else 1))) for a, n in enumerate((nx, ny, nz))]
+            p0 = [2 * v for v in c0]
+            p1 = list(p0); p1[ax] += 2
+            n1, n2 = nid(*p0), nid(*p1)
+            ndpn[n1 - 1] = ndpn[n2 - 1] = 6
+            zdir = np.roll(np.array([0.0, 0.3, 1.0]), ax) + rng.normal(0, 0.1, 3)
+            kw = {}
+            if b % 3 == 1:
+                kw = dict(ecc1=rng.normal(0, 0.02, 3), ecc2=rng.normal(0, 0.02, 3), sy=0.004, sz=-0.003)
+            if b % 3 == 2:
+                kw = dict(phi=25.0, sy=0.002, sz=0.001, efflen=0.9)
+            beams.append((len(conn_list), beam_record(xyz[n1 - 1], xyz[n2 - 1], zdir, **kw)))
+            conn_list.append(np.array([n1, n2], I32))
+        types = np.concatenate([types, np.full(n_beams, 11, I32)])
+    sam = _build_sam(nnod, ndpn if n_beams > 0 else 3, conn_list, types, ext_nodes, rng=rng, shuffle_eq=shuffle_eq)
     sam.ngen = ngen
     nel = sam.nel
+    beam = None
+    if beams:
+        beam = np.zeros((nel, 32), F64)
+        for e, rec in beams:
+            beam[e] = rec
     elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64),
-                      thk=np.zeros(nel, F64), elmid=np.arange(1, nel + 1, dtype=I32))
-    part = PartModel(sam=sam, elm=elm, name=f"tet10_{nx}x{ny}x{nz}")
+                      thk=np.zeros(nel, F64), elmid=np.arange(1, nel + 1, dtype=I32), beam=beam)
+    part = PartModel(sam=sam, elm=elm, name=f"tet10_{nx}x{ny}x{nz}" + (f"+{n_beams}beams" if n_beams else ""))
     if with_recovery:
         part.B, part.E = _smooth_recovery_matrices(sam, xyz, ngen, rng)
     return part

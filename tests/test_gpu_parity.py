@@ -62,6 +62,61 @@ def test_tet10_block_small(oracle):
     _check_part(oracle, part, nsteps=21, seed=6)
 
 
+def test_tri_quad_mixed_plate(oracle):
+    """ANDES triangles (type 23: two LU inversions per element, REAL*4 Gauss rule) mixed with quads"""
+    part = plate_part(9, 8, ngen=6, seed=13, tri_fraction=0.5, shuffle_eq=True, n_fixed=3, n_constraints=2, warp=0.04)
+    assert (part.sam.melcon == 23).sum() > 20 and (part.sam.melcon == 24).sum() > 20
+    _check_part(oracle, part, nsteps=70, seed=5)
+
+
+def test_all_triangles_ragged_tile(oracle):
+    part = plate_part(6, 5, ngen=3, seed=14, tri_fraction=1.0)
+    _check_part(oracle, part, nsteps=129, seed=6, step_tile=64)
+
+
+def test_tet10_with_beams(oracle):
+    """config-3-shaped part: TET10 + BEAM2 stiffeners (eccentricities, shear-centre offsets, rotated
+    principal axes, effective length).  Beams give section forces only (nstrp = 0)."""
+    part = tet10_block(3, 2, 2, ngen=6, seed=5, shuffle_eq=True, n_beams=9)
+    _check_part(oracle, part, nsteps=21, seed=6)
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 2, seed=3)
+    rec = StressRecovery(part)
+    full = rec.calc_stresses(Q[:, 1])
+    ref = oracle.calc_stresses(b, oracle.expand(b, Q[:, 1]))
+    beams = np.nonzero(part.sam.melcon == 11)[0]
+    assert len(beams) == 9
+    sf_g, sf_o = full["sres"][beams, :12], ref["sres"][beams]
+    assert np.abs(sf_o).max() > 0
+    for k in range(12):   # compare per section-force component (forces and moments differ in scale)
+        assert np.abs(sf_g[:, k] - sf_o[:, k]).max() <= TOL * np.abs(sf_o[:, k % 6::6]).max(), k
+    rec.close()
+
+
+def test_tet10_gauss_extrapolation(oracle):
+    """-stressForm 1: 4 Gauss points with the reference's REAL*4 abscissae, extrapolated to the nodes"""
+    part = tet10_block(2, 2, 1, ngen=4, seed=8)
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 9, seed=2)
+    rec = StressRecovery(part, stress_form=1)
+    vm_g = rec.recover(Q)
+    import ctypes as C
+    from oracle_bind import _dp
+    X = part.elm.xyz
+    for e in (0, 5, part.sam.nel - 1):
+        nodes = part.sam.mmnpc[part.sam.mpmnpc[e] - 1: part.sam.mpmnpc[e + 1] - 1] - 1
+        for s in (0, 8):
+            sv = oracle.expand(b, Q[:, s])
+            v = np.ascontiguousarray(np.stack([sv[3 * n: 3 * n + 3] for n in nodes]).ravel())
+            xg, yg, zg = (np.ascontiguousarray(X[nodes, k]) for k in range(3))
+            sig = np.zeros(60); eps = np.zeros(60)
+            assert oracle.lib.orc_str41(_dp(xg), _dp(yg), _dp(zg), part.elm.emod[e], part.elm.rny[e], 1, _dp(v), _dp(sig), _dp(eps)) == 0
+            vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(10)])
+            p0 = rec.result_point_offsets()[e]
+            assert rel_err(vm_g[s, p0:p0 + 10], vm_o) <= TOL
+    rec.close()
+
+
 def test_config1_plate(oracle):
     """BASELINE config 1: 70x70 ANDES quads, 5,041 nodes, 4 external nodes, 10 modes; the oracle
     covers a 40-step sample of the 1,000-step history (it rebuilds every element every step)."""
