@@ -8,9 +8,11 @@ Workload : BASELINE.json configs[1] -- synthetic 1000x1000 ANDES-quad plate (1,0
            full-field von Mises + envelope.  One bench "step" = one pass of the hot path
            (Q pack -> K1 DMMA expansion -> K2 element kernel with fused envelope) over one batch
            of --tile time steps (default 500), so the default --steps 20 covers the 10,000-step
-           history once.  At N > 1 GPUs the part grows with N (one 1000x1000 element block per
-           rank: weak scaling); the reduced history is broadcast from rank 0 with NCCL every step
-           and the per-block envelopes are gathered to rank 0 at the end, inside the timed region.
+           history once.  At N > 1 GPUs ONE part of N x 1,000,000 elements (a 1000 x 1000N plate) is
+           cut into N element blocks by fedem_solvers_b200.partition (weak scaling: the per-GPU block
+           stays at the named size); rank r recovers block r.  The reduced history is broadcast
+           from rank 0 with NCCL every step and the per-block envelopes are gathered to rank 0 at
+           the end, both inside the timed region.
 
 Arms     : default           this repo's CUDA path through the C ABI (libfedem_b200.so)
            --impl reference  the reference's CPU algorithm (oracle/ restatement; the reference's
@@ -48,6 +50,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-nx", type=int, default=160)
     ap.add_argument("--cpu-sample-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--elem-order", type=int, default=0, help="0 = Morton order (default), 1 = SAM order")
     return ap.parse_args()
 
 
@@ -164,9 +167,22 @@ def run_b200(args, rank, world, local_rank):
     tile = args.tile
     nsteps_total = tile * (args.steps + args.warmup)
     # ---- setup (untimed): the rank's element block, recovery matrices, reduced history ----
-    part = plate_part(args.nx, args.nx, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2 + rank)
+    if world == 1:
+        part = plate_part(args.nx, args.nx, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2)
+    else:
+        # one part, `world` element blocks: the rank builds the (matrix-free) part, cuts its block and
+        # generates only its own rows of the synthetic [B|E]
+        from fedem_solvers_b200.partition import split_elements, sub_part
+        from fedem_solvers_b200.model import synthetic_recovery
+        whole = plate_part(args.nx, args.nx * world, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2, ly=float(world),
+                           with_recovery=False)
+        bbox = (whole.elm.xyz.min(0), whole.elm.xyz.max(0))
+        e0, e1 = split_elements(whole, world)[rank]
+        part = sub_part(whole, e0, e1, with_matrices=False).part
+        del whole
+        part.B, part.E = synthetic_recovery(part, bbox=bbox)
     nel, ndim = part.sam.nel, part.sam.ndim
-    rec = StressRecovery(part, device=local_rank, step_tile=((tile + 63) // 64) * 64)
+    rec = StressRecovery(part, device=local_rank, step_tile=((tile + 63) // 64) * 64, elem_order=args.elem_order)
     npts = rec.npts
     part.B = part.E = None  # host copies no longer needed
     stream = torch.cuda.current_stream()
@@ -279,7 +295,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: {args.nx}x{args.nx} ANDES-quad plate per GPU ({nel} elements, "
+        "config": {"workload": f"C2: {args.nx}x{args.nx} ANDES-quad plate block per GPU ({nel} elements, "
                                f"{part.sam.ndof} DOF), n_red=48+50, {tile} time steps per bench step "
                                f"({tile * args.steps} steps timed), full-field von Mises + envelope",
                    "elements_per_gpu": nel, "ndof_per_gpu": int(part.sam.ndof), "n_red": ndim,

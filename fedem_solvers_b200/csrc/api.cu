@@ -33,6 +33,52 @@ static bool supported_type(int type) { return type == 24 || type == 23 || type =
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+static inline unsigned spread10(unsigned v)  // 10 bits -> every third bit
+{
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// The reference walks the elements in SAM order (stressRoutines.f90:169).  Elements that share nodes
+// read the same rows of U, so the K2 kernels process them in Morton order of their centroids: the
+// rows a warp needs were just touched by its neighbours and are still in L2.  Results keep their SAM
+// positions (ptoff), only the order of evaluation changes.
+std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int type)
+{
+  std::vector<int> el;
+  for (int e = 0; e < sam->nel; ++e)
+    if (sam->melcon[e] == type && !(elm->elmid && elm->elmid[e] < 1)) el.push_back(e);
+  if (p->elem_order != 0 || el.size() < 2) return el;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int n = 0; n < sam->nnod; ++n)
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::min(lo[k], elm->xyz[3 * (size_t)n + k]);
+      hi[k] = std::max(hi[k], elm->xyz[3 * (size_t)n + k]);
+    }
+  double inv[3];
+  for (int k = 0; k < 3; ++k) inv[k] = hi[k] > lo[k] ? 1023.999 / (hi[k] - lo[k]) : 0.0;
+  std::vector<std::pair<unsigned, int>> key(el.size());
+  for (size_t i = 0; i < el.size(); ++i) {
+    const int e = el[i], ip0 = sam->mpmnpc[e] - 1, nn = sam->mpmnpc[e + 1] - sam->mpmnpc[e];
+    double c[3] = {0, 0, 0};
+    for (int k = 0; k < nn; ++k) {
+      const int n = sam->mmnpc[ip0 + k] - 1;
+      if (n < 0 || n >= sam->nnod) continue;  // reported by the family builder
+      for (int d = 0; d < 3; ++d) c[d] += elm->xyz[3 * (size_t)n + d];
+    }
+    unsigned q[3];
+    for (int d = 0; d < 3; ++d) q[d] = (unsigned)((c[d] / std::max(nn, 1) - lo[d]) * inv[d]);
+    key[i] = {spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2), e};
+  }
+  std::stable_sort(key.begin(), key.end());
+  for (size_t i = 0; i < el.size(); ++i) el[i] = key[i].second;
+  return el;
+}
+
 static void free_family(FamilyData& f)
 {
   cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed);
@@ -111,6 +157,7 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, 
   p->ndof2 = sam->ndof2; p->ngen = sam->ngen; p->neq = sam->neq; p->nceq = sam->nceq;
   p->ndim = sam->ndof2 + sam->ngen;
   p->stressForm = opt ? opt->stressForm : 0;
+  p->elem_order = opt ? opt->reserved[0] : 0;
   // ldk: multiple of 4 with ldk % 8 == 4 (bank-conflict-free fragment loads in K1)
   p->ldk = round_up(std::max(p->ndim, 1), 4);
   if (p->ldk % 8 == 0) p->ldk += 4;

@@ -110,6 +110,8 @@ struct fsr_part {
   int nrows_pad = 0;   // ndof padded to the K1 row tile
   int npts = 0;        // result points
   int stressForm = 0;
+  int elem_order = 0;  // 0 = elements processed in Morton order of their centroids (L2 reuse of shared
+                       // nodes), 1 = SAM order.  Outputs are always in SAM order.
   int step_tile = 0;   // steps per device batch
   std::vector<int> ptoff_host;  // [nel+1]
   std::vector<int> melcon_host;
@@ -160,6 +162,8 @@ int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nro
                   cudaStream_t s);
 int launch_pack_q_raw(double* Qt, int ldk, const double* Q_dev, int ldq, int ndim, int nsteps, int nsteps_pad,
                       cudaStream_t s);
+// api.cu: active elements of one type, in processing order (see fsr_part::elem_order)
+std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int type);
 // k2_*.cu
 int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);

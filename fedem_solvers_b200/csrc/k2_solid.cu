@@ -201,9 +201,7 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FamilyData& f = p->fam[FAM_TET10];
   f.nenod = 10; f.nndof = 3; f.nstrp = 10; f.ncmp = 6; f.MT = 8; f.KT = 8;
   std::vector<int> elem, conn, edof, ptoff;
-  for (int e = 0; e < sam->nel; ++e) {
-    if (sam->melcon[e] != 41) continue;
-    if (elm->elmid && elm->elmid[e] < 1) continue;
+  for (int e : elements_of_type(p, sam, elm, 41)) {
     int ip0 = sam->mpmnpc[e] - 1, nn = sam->mpmnpc[e + 1] - sam->mpmnpc[e];
     if (nn != 10) { set_error("TET10 element %d has %d nodes", e + 1, nn); return FSR_ERR_ARG; }
     elem.push_back(e);

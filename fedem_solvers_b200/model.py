@@ -64,6 +64,7 @@ class PartModel:
     B: np.ndarray = None     # [ndof1, ndof2] column-major (Fortran order)
     E: np.ndarray = None     # [ndof1, ngen]  column-major
     name: str = ""
+    recovery_seed: int = 0   # seed of the synthetic [B|E] fields (synthetic_recovery)
 
     def nstrp(self):
         tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10}
@@ -131,10 +132,13 @@ def _build_sam(nnod, ndof_per_node, conn_list, types, ext_nodes, fixed_dofs=(), 
                    minex=np.arange(1, nnod + 1, dtype=I32))
 
 
-def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0):
+def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0, bbox=None):
     """Synthetic [B|E]: smooth low-order cosine fields over the part, one per reduced DOF, with
     a random per-component scale -- cheap to generate at 6M rows, and every internal DOF row is a
-    distinct, well-scaled linear combination of the reduced DOFs."""
+    distinct, well-scaled linear combination of the reduced DOFs.  A row depends
+    only on its node's coordinates, its DOF component and the per-column parameters drawn from `rng`,
+    so an element block of a part (partition.sub_part) can generate exactly its own rows when given
+    the whole part's bounding box."""
     int_dofs = np.nonzero(sam.msc == 1)[0]
     # internal row k corresponds to equation meqn1[k]; map equation -> dof
     eq2dof = np.zeros(sam.neq + 1, np.int64)
@@ -143,7 +147,7 @@ def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0):
     rows_dof = eq2dof[sam.meqn1]                       # dof of each B row
     node_of_dof = np.searchsorted(sam.madof, rows_dof + 1, side="right") - 1
     comp = rows_dof - (sam.madof[node_of_dof] - 1)
-    lo, hi = xyz.min(0), xyz.max(0)
+    lo, hi = (xyz.min(0), xyz.max(0)) if bbox is None else (np.asarray(bbox[0], F64), np.asarray(bbox[1], F64))
     span = np.where(hi - lo > 0, hi - lo, 1.0)
     u = (xyz[node_of_dof] - lo) / span                 # normalised coordinates in [0,1]
     ncol = sam.ndof2 + ngen
@@ -263,8 +267,9 @@ def plate_part(nx, ny, ngen=10, seed=1, tri_fraction=0.0, n_ext=4, jitter=0.02, 
     elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64),
                       thk=np.full(nel, thickness, F64), elmid=np.arange(1, nel + 1, dtype=I32))
     part = PartModel(sam=sam, elm=elm, name=f"plate{nx}x{ny}")
+    part.recovery_seed = seed
     if with_recovery:
-        part.B, part.E = _smooth_recovery_matrices(sam, xyz, ngen, rng)
+        part.B, part.E = synthetic_recovery(part)
     return part
 
 
@@ -369,9 +374,16 @@ def tet10_block(nx, ny, nz, ngen=10, seed=3, n_ext=4, jitter=0.05, emod=2.1e11, 
     elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64),
                       thk=np.zeros(nel, F64), elmid=np.arange(1, nel + 1, dtype=I32), beam=beam)
     part = PartModel(sam=sam, elm=elm, name=f"tet10_{nx}x{ny}x{nz}" + (f"+{n_beams}beams" if n_beams else ""))
+    part.recovery_seed = seed
     if with_recovery:
-        part.B, part.E = _smooth_recovery_matrices(sam, xyz, ngen, rng)
+        part.B, part.E = synthetic_recovery(part)
     return part
+
+
+def synthetic_recovery(part, bbox=None):
+    """(B, E) of a synthetic part (or of an element block of it, given the whole part's bbox)."""
+    rng = np.random.default_rng([int(getattr(part, "recovery_seed", 0)), 7719])
+    return _smooth_recovery_matrices(part.sam, part.elm.xyz, part.sam.ngen, rng, bbox=bbox)
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,107 @@
+!! stress_b200_driver.f90 -- how the reference's Fortran host code calls the B200 library.
+!!
+!! This is the replacement for the time loop of src/vpmStress/stress.f90:357-435: instead of
+!!   do while (ffr_getnextstep(...)); readSupElDisplacements; calcIntDisplacements; calcStresses
+!! per time step, the driver collects the reduced displacements of a window of steps into
+!! Q(ndim,nWin) and makes ONE call.  Everything before the loop (ffl_init, initiateSAM,
+!! readSolverData, openBandEmatrices, ffr_init, readResponsePointers, writeStressHeader) and the
+!! .frs writer stay as they are; the arrays handed over are the reference's own (SamType members,
+!! ffl_* results, the in-core B and E of DiskMatrixType%vala).
+!!
+!! Delivered as source: the build image has no Fortran compiler (see DESIGN.md section 1).
+
+subroutine stress_b200 (sam, xyz, emod, rny, thk, elmid, beam, Bmat, Emat, ngen, &
+     &                  triads, sup, rPointers, startTime, stopTime, tInc, lpu, ierr)
+
+  use, intrinsic :: iso_c_binding
+  use fedem_b200_mod
+  use SamModule                 , only : SamType
+  use TriadTypeModule           , only : TriadType
+  use SupElTypeModule           , only : SupElType
+  use DisplacementModule        , only : readSupElDisplacements
+  use FFrExtractorInterface     , only : ffr_getnextstep
+  use KindModule                , only : dp, i8
+  use ReportErrorModule         , only : reportError, error_p, debugFileOnly_p
+
+  implicit none
+
+  type(SamType)  , intent(in), target :: sam
+  real(dp)       , intent(in), target :: xyz(:,:), emod(:), rny(:), thk(:), beam(:,:)
+  integer        , intent(in), target :: elmid(:)
+  real(dp)       , intent(in)         :: Bmat(:,:), Emat(:,:)
+  integer        , intent(in)         :: ngen, lpu
+  type(TriadType), intent(inout)      :: triads(:)
+  type(SupElType), intent(inout)      :: sup
+  integer        , intent(in)         :: rPointers(:)
+  real(dp)       , intent(in)         :: startTime, stopTime, tInc
+  integer        , intent(out)        :: ierr
+
+  integer, parameter  :: nWin = 512        !< time steps per device batch
+  type(fsr_sam)       :: csam
+  type(fsr_elmdata)   :: celm
+  type(fsr_options)   :: copt
+  type(c_ptr)         :: part
+  real(dp), allocatable, target :: Q(:,:), vm(:,:), vmMax(:), vmMin(:)
+  real(dp)            :: currTime
+  integer(i8)         :: iStep
+  integer             :: ndim, npts, n
+  character(len=512)  :: msg
+
+  !! --- model hand-over (replaces initiateSAM's index work and the per-step ffl_* lookups)
+  csam%nnod = sam%nnod;  csam%nel = sam%nel;  csam%ndof = sam%ndof
+  csam%ndof1 = sam%ndof1; csam%ndof2 = sam%ndof2; csam%ngen = ngen
+  csam%neq = sam%neq;  csam%nceq = sam%nceq
+  csam%nmmnpc = size(sam%mmnpc);  csam%nmmceq = size(sam%mmceq)
+  csam%madof  = c_loc(sam%madof);  csam%msc   = c_loc(sam%msc)
+  csam%mpmnpc = c_loc(sam%mpmnpc); csam%mmnpc = c_loc(sam%mmnpc)
+  csam%melcon = c_loc(sam%melcon); csam%mpmceq = c_loc(sam%mpmceq)
+  csam%mmceq  = c_loc(sam%mmceq);  csam%ttcc  = c_loc(sam%ttcc)
+  csam%meqn   = c_loc(sam%meqn);   csam%meqn1 = c_loc(sam%meqn1)
+  csam%meqn2  = c_loc(sam%meqn2)
+  celm%xyz = c_loc(xyz);  celm%emod = c_loc(emod);  celm%rny = c_loc(rny)
+  celm%thk = c_loc(thk);  celm%elmid = c_loc(elmid); celm%beam = c_loc(beam)
+  copt%device = 0;  copt%stressForm = 0;  copt%step_tile = nWin;  copt%reserved = 0
+
+  ierr = fsr_part_create(part,csam,celm,copt)
+  if (ierr < 0) goto 900
+  if (ierr > 0) write(lpu,"('  ** ',I8,' elements failed; they get hugeVal results')") ierr
+
+  !! --- replaces openBandEmatrices: B and E go to the GPU once
+  ierr = fsr_set_recovery(part,Bmat,size(Bmat,1),Emat,size(Emat,1))
+  if (ierr < 0) goto 900
+
+  ndim = fsr_ndim(part)
+  npts = fsr_num_result_points(part)
+  allocate(Q(ndim,nWin),vm(npts,nWin),vmMax(npts),vmMin(npts))
+
+  !! --- the time loop, batched
+  n = 0
+  currTime = startTime - 1.0_dp
+  do while (ffr_getnextstep(startTime,stopTime,tInc,currTime,iStep))
+     call readSupElDisplacements (triads,sup,rPointers,0,lpu,ierr)   ! fills sup%finit, sup%genDOFs%ur
+     if (ierr /= 0) goto 900
+     n = n + 1
+     Q(1:sam%ndof2,n) = sup%finit(1:sam%ndof2)
+     if (ngen > 0) Q(sam%ndof2+1:ndim,n) = sup%genDOFs%ur(1:ngen)
+     if (n == nWin) then
+        ierr = fsr_recover(part,Q,ndim,n,c_loc(vm))    ! von Mises of every result point, n steps
+        if (ierr < 0) goto 900
+        !! ... writeStrMeasureDB for the n steps (saveStressModule) ...
+        n = 0
+     end if
+  end do
+  if (n > 0) then
+     ierr = fsr_recover(part,Q,ndim,n,c_loc(vm))
+     if (ierr < 0) goto 900
+  end if
+
+  ierr = fsr_get_envelope(part,vmMax,vmMin)
+  call fsr_part_destroy (part)
+  return
+
+900 call fsr_error_message (msg)
+  call reportError (error_p,trim(msg),addString='stress_b200')
+  call reportError (debugFileOnly_p,'stress_b200')
+  call fsr_part_destroy (part)
+
+end subroutine stress_b200

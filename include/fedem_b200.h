@@ -73,7 +73,8 @@ typedef struct fsr_options {
   int device;     /* CUDA device ordinal                                                    */
   int stressForm; /* -stressForm (solids): 0 = nodal evaluation (default), else Gauss extrap. */
   int step_tile;  /* time steps per device batch (0 = automatic from free HBM)              */
-  int reserved[5];
+  int reserved[5];/* [0]: element processing order, 0 = Morton order of the centroids (default,
+                     L2 reuse of shared nodes), 1 = SAM order; results are in SAM order either way */
 } fsr_options;
 
 /* Output selection bits = the -vmStress ... switches of stressmain.C:46-60 */

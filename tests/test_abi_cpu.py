@@ -55,3 +55,34 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle_bind" not in src and "liboracle" not in src and "orc_" not in src, f
+
+
+def _build_c_driver():
+    import subprocess
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "c_abi_driver")
+    src = os.path.join(ROOT, "tests", "c_abi_driver.c")
+    libdir = os.path.join(ROOT, "fedem_solvers_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", libdir, "-lfedem_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+def test_plain_c_caller_links_and_fails_loudly_without_gpu():
+    """a C translation unit that sees only include/fedem_b200.h compiles, links and runs"""
+    import subprocess
+    exe = _build_c_driver()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        assert "no usable B200" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_on_gpu():
+    import subprocess
+    exe = _build_c_driver()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C ABI driver OK" in r.stdout, r.stdout + r.stderr

@@ -58,6 +58,14 @@ int main(){
       printf("DMMA.8x8x4 warps/blk %d blk/SM %d : %.2f TFLOP/s (%.3f ms)\n", wpb,bps, fl/ms*1e-9, ms);
     }
   }
+  // dependent-chain probe: one warp per SM, NACC independent accumulators -> DMMA latency
+  {
+    int iters=20000; float ms;
+    #define LAT(N) dmma_loop<N><<<nsm,32>>>(out,100,1.0); CK(cudaDeviceSynchronize()); cudaEventRecord(e0); \
+      dmma_loop<N><<<nsm,32>>>(out,iters,1.0); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms,e0,e1); \
+      printf("DMMA chain probe NACC=%d: %.1f cycles per DMMA per warp (clock %d kHz)\n", N, ms*1e-3*p.clockRate*1e3/(double)(iters*N), p.clockRate);
+    LAT(1) LAT(2) LAT(3) LAT(4) LAT(6) LAT(8)
+  }
   for(int wpb=4; wpb<=8; wpb*=2){
     for(int bps=1;bps<=4;bps*=2){
       int iters=20000; float ms;
