@@ -49,7 +49,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // Element families handled by the K2 kernels.  A family fixes the operator shape:
 // MT m-tiles of 8 rows, KT k-tiles of 4 element DOFs.
-enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_COUNT = 4 };
+enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_COUNT = 5 };
 
 struct FamilyData {
   int nelt = 0;          // elements of this family (active only)
@@ -168,6 +168,8 @@ std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const f
 int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_beam_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);
 int launch_k2_shell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm,
                        cudaStream_t s);
 int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm,

@@ -1,0 +1,276 @@
+// k2_hex20.cu -- K2 for the 20-node hexahedron (type 43) on sm_100a, and the generic "large solid"
+// apply kernel (operator too big for registers: 120 x 60 for HEX20).
+//
+// Reference: STR43 -> IHEX32 -> DN2031 / JACI31 (src/vpmStress/elStressModule.f90:1472-1584,
+// src/Femlib/ihex.f:224-560,2433-2545, src/Femlib/jaci31.f) evaluates 27 (or 8) Jacobian inverses
+// per element per step.  Here the stress operator sigma(6,20) = S_e . v(3,20) is built once:
+// -stressForm 0 = direct evaluation at the 20 nodes; otherwise the 2x2x2 Gauss points (abscissa in
+// the reference's REAL*4 precision, ihex.f:364-365) extrapolated tri-linearly with
+// (1 +- sqrt3 xi_n)(1 +- sqrt3 eta_n)(1 +- sqrt3 zeta_n)/8 (elStressModule.f90:1563-1577).
+// Apply: one CTA (4 warps) per element; the operator lives in shared memory in DMMA A-fragment
+// order (57.6 KB), the element's 60 rows of U are staged per 8-step tile, each warp owns a share
+// of the 15 m-tiles, accumulators are transposed through shared memory so that one thread sees the
+// six components of a node for von Mises (FFaTensorTransforms.C:38-43) and the fused envelope.
+#include "common.cuh"
+
+namespace fsr {
+
+__device__ __forceinline__ size_t frag_index_g(int row, int col, int KT)
+{
+  return ((size_t)((row >> 3) * KT + (col >> 2)) << 5) + ((row & 7) << 2) + (col & 3);
+}
+
+__constant__ double c_hx[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+__constant__ double c_he[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+__constant__ double c_hz[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+
+// serendipity shape-function derivatives w.r.t. (xi, eta, zeta), node order of DN2031
+__device__ void hex20_dn(double xi, double et, double ze, double* dx, double* de, double* dz)
+{
+  for (int i = 0; i < 20; ++i) {
+    const double a = c_hx[i], b = c_he[i], c = c_hz[i];
+    if (a != 0.0 && b != 0.0 && c != 0.0) {           // corner
+      dx[i] = .125 * a * (1. + et * b) * (1. + ze * c) * (2. * xi * a + et * b + ze * c - 1.);
+      de[i] = .125 * b * (1. + xi * a) * (1. + ze * c) * (xi * a + 2. * et * b + ze * c - 1.);
+      dz[i] = .125 * c * (1. + xi * a) * (1. + et * b) * (xi * a + et * b + 2. * ze * c - 1.);
+    } else if (a == 0.0) {                             // mid-edge along xi
+      dx[i] = -.5 * xi * (1. + et * b) * (1. + ze * c);
+      de[i] = .25 * b * (1. - xi * xi) * (1. + ze * c);
+      dz[i] = .25 * c * (1. - xi * xi) * (1. + et * b);
+    } else if (b == 0.0) {                             // mid-edge along eta
+      dx[i] = .25 * a * (1. - et * et) * (1. + ze * c);
+      de[i] = -.5 * et * (1. + xi * a) * (1. + ze * c);
+      dz[i] = .25 * c * (1. + xi * a) * (1. - et * et);
+    } else {                                           // mid-edge along zeta
+      dx[i] = .25 * a * (1. + et * b) * (1. - ze * ze);
+      de[i] = .25 * b * (1. + xi * a) * (1. - ze * ze);
+      dz[i] = -.5 * ze * (1. + xi * a) * (1. + et * b);
+    }
+  }
+}
+
+__global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, const int* __restrict__ conn,
+                                       const double* __restrict__ xyz, const double* __restrict__ emod,
+                                       const double* __restrict__ rny, int stressForm, double* __restrict__ Sfrag,
+                                       unsigned char* __restrict__ failed, double* __restrict__ aux)
+{
+  constexpr int KT = 15, MT = 15;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelt) return;
+  const int e = elem[i];
+  double* S = Sfrag + (size_t)i * MT * KT * 32;
+  double X[20], Y[20], Z[20];
+  for (int k = 0; k < 20; ++k) {
+    const int n = conn[i * 20 + k];
+    X[k] = xyz[3 * n]; Y[k] = xyz[3 * n + 1]; Z[k] = xyz[3 * n + 2];
+  }
+  const double E = emod[e], nu = rny[e];
+  aux[i * 2] = E; aux[i * 2 + 1] = nu;
+  const double D = E * (1. - nu) / ((1. + nu) * (1. - 2. * nu));
+  const double D1 = D * nu / (1. - nu);
+  const double D2 = D * (1. - 2. * nu) / (2. * (1. - nu));
+  const double gp = (double)0.577350269189626f;  // REAL*4 literal of ihex.f:364-365
+  const double s3 = sqrt(3.0);
+  const int npt = stressForm == 0 ? 20 : 8;
+  bool ok = true;
+  for (int q = 0; q < npt && ok; ++q) {
+    double xi, et, ze;
+    if (stressForm == 0) { xi = c_hx[q]; et = c_he[q]; ze = c_hz[q]; }
+    else { xi = (q & 1) ? gp : -gp; et = (q & 2) ? gp : -gp; ze = (q & 4) ? gp : -gp; }
+    double dx[20], de[20], dz[20];
+    hex20_dn(xi, et, ze, dx, de, dz);
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < 20; ++k) {
+      J[0][0] += dx[k] * X[k]; J[0][1] += dx[k] * Y[k]; J[0][2] += dx[k] * Z[k];
+      J[1][0] += de[k] * X[k]; J[1][1] += de[k] * Y[k]; J[1][2] += de[k] * Z[k];
+      J[2][0] += dz[k] * X[k]; J[2][1] += dz[k] * Y[k]; J[2][2] += dz[k] * Z[k];
+    }
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    if (fabs(det) <= 2.2250738585072014e-308 * 100.0) { ok = false; break; }
+    double I[3][3];
+    I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+    I[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) / det;
+    I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+    I[1][0] = (J[2][0] * J[1][2] - J[2][2] * J[1][0]) / det;
+    I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+    I[1][2] = (J[1][0] * J[0][2] - J[1][2] * J[0][0]) / det;
+    I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+    I[2][1] = (J[2][0] * J[0][1] - J[2][1] * J[0][0]) / det;
+    I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    for (int j = 0; j < 20; ++j) {
+      const double bx = I[0][0] * dx[j] + I[0][1] * de[j] + I[0][2] * dz[j];
+      const double by = I[1][0] * dx[j] + I[1][1] * de[j] + I[1][2] * dz[j];
+      const double bz = I[2][0] * dx[j] + I[2][1] * de[j] + I[2][2] * dz[j];
+      // D*B block of node j: rows xx,yy,zz,xy,xz,yz ; columns u,v,w  (ihex.f:430-450)
+      const double db[6][3] = {{D * bx, D1 * by, D1 * bz}, {D1 * bx, D * by, D1 * bz}, {D1 * bx, D1 * by, D * bz},
+                               {D2 * by, D2 * bx, 0.0},    {D2 * bz, 0.0, D2 * bx},    {0.0, D2 * bz, D2 * by}};
+      if (stressForm == 0) {
+        for (int c = 0; c < 6; ++c)
+          for (int d = 0; d < 3; ++d) S[frag_index_g(q * 6 + c, 3 * j + d, KT)] = db[c][d];
+      } else {
+        for (int n = 0; n < 20; ++n) {
+          const double w = (1.0 + ((q & 1) ? 1.0 : -1.0) * (s3 * c_hx[n])) * (1.0 + ((q & 2) ? 1.0 : -1.0) * (s3 * c_he[n])) *
+                           (1.0 + ((q & 4) ? 1.0 : -1.0) * (s3 * c_hz[n])) * 0.125;
+          for (int c = 0; c < 6; ++c)
+            for (int d = 0; d < 3; ++d) S[frag_index_g(n * 6 + c, 3 * j + d, KT)] += db[c][d] * w;
+        }
+      }
+    }
+  }
+  if (!ok)
+    for (int k = 0; k < MT * KT * 32; ++k) S[k] = 0.0;
+  failed[i] = ok ? 0 : 1;
+}
+
+// Generic solid apply: NEN nodes, 6 stress components per node, 3 DOFs per node.
+template <int NEN>
+__global__ void __launch_bounds__(128)
+k2_solid_smem_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
+                        const double* __restrict__ Sfrag, const int* __restrict__ edof, const int* __restrict__ ptoff,
+                        const unsigned char* __restrict__ failed, int nelt, double* __restrict__ vm, size_t ld_vm,
+                        double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  constexpr int NROW = 6 * NEN, NCOL = 3 * NEN;
+  constexpr int MT = (NROW + 7) / 8, KT = (NCOL + 3) / 4;
+  constexpr int NITEM = NEN * 8;                       // (node, step-in-tile) pairs per tile
+  constexpr int IPT = (NITEM + 127) / 128;             // items per thread
+  extern __shared__ __align__(16) double smem[];
+  double* sS = smem;                                   // [MT][KT][32] operator fragments
+  double* sU = sS + MT * KT * 32;                      // [KT*4][8]   displacement tile
+  double* sSig = sU + KT * 4 * 8;                      // [MT*8][8]   stresses of the tile
+  int* sDof = reinterpret_cast<int*>(sSig + MT * 8 * 8);  // [KT*4]
+  const int i = blockIdx.x;
+  if (i >= nelt) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const double* src = Sfrag + (size_t)i * MT * KT * 32;
+  for (int k = tid; k < MT * KT * 32; k += 128) sS[k] = src[k];
+  for (int k = tid; k < KT * 4; k += 128) sDof[k] = edof[(size_t)i * KT * 4 + k];
+  const bool bad = failed[i] != 0;
+  const size_t pt0 = (size_t)ptoff[i];
+  double emax[IPT], emin[IPT];
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) { emax[r] = 0.0; emin[r] = kHuge; }
+  __syncthreads();
+  const int ntiles = nsteps_pad >> 3;
+  for (int nt = 0; nt < ntiles && nt * 8 < nsteps; ++nt) {
+    // stage the element's rows of U for these 8 steps (64-byte segments)
+    for (int k = tid; k < KT * 4 * 8; k += 128) {
+      const int row = k >> 3, s = k & 7;
+      sU[k] = row < NCOL ? U[(size_t)sDof[row] * ldu + (size_t)nt * 8 + s] : 0.0;
+    }
+    __syncthreads();
+    for (int m = warp; m < MT; m += 4) {               // warp-uniform: every lane reaches each mma
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll 5
+      for (int j = 0; j < KT; ++j) dmma884(c0, c1, sS[(m * KT + j) * 32 + lane], sU[(4 * j + t4) * 8 + g]);
+      *reinterpret_cast<double2*>(sSig + (m * 8 + g) * 8 + 2 * t4) = make_double2(c0, c1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      const int idx = tid + 128 * r;
+      if (idx < NITEM) {
+        const int p = idx >> 3, s = idx & 7, t = nt * 8 + s;
+        const double* s6 = sSig + (p * 6) * 8 + s;
+        const double s11 = s6[0], s22 = s6[8], s33 = s6[16], s12 = s6[24], s13 = s6[32], s23 = s6[40];
+        double v = sqrt(s11 * s11 + s22 * s22 + s33 * s33 - s11 * s22 - s22 * s33 - s33 * s11 +
+                        3.0 * (s12 * s12 + s13 * s13 + s23 * s23));
+        if (bad) v = kHuge;
+        if (t < nsteps) {
+          if (vm) vm[(size_t)t * ld_vm + pt0 + p] = v;
+          emax[r] = fmax(emax[r], v);
+          emin[r] = fmin(emin[r], v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // the 8 lanes that share a node are consecutive: reduce, lane with step 0 folds into the envelope
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      emax[r] = fmax(emax[r], __shfl_xor_sync(0xffffffffu, emax[r], o));
+      emin[r] = fmin(emin[r], __shfl_xor_sync(0xffffffffu, emin[r], o));
+    }
+    const int idx = tid + 128 * r;
+    if (idx < NITEM && (idx & 7) == 0 && nsteps > 0) {
+      const int p = idx >> 3;
+      if (emax[r] > env_max[pt0 + p]) env_max[pt0 + p] = emax[r];
+      if (emin[r] < env_min[pt0 + p]) env_min[pt0 + p] = emin[r];
+    }
+  }
+}
+
+template <int NEN>
+static size_t solid_smem_bytes()
+{
+  constexpr int MT = (6 * NEN + 7) / 8, KT = (3 * NEN + 3) / 4;
+  return sizeof(double) * (MT * KT * 32 + KT * 4 * 8 + MT * 8 * 8) + sizeof(int) * KT * 4;
+}
+
+int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
+{
+  cudaStream_t s = p->stream;
+  FamilyData& f = p->fam[FAM_HEX20];
+  f.nenod = 20; f.nndof = 3; f.nstrp = 20; f.ncmp = 6; f.MT = 15; f.KT = 15;
+  std::vector<int> elem, conn, edof, ptoff;
+  for (int e : elements_of_type(p, sam, elm, 43)) {
+    const int ip0 = sam->mpmnpc[e] - 1, nn = sam->mpmnpc[e + 1] - sam->mpmnpc[e];
+    if (nn != 20) { set_error("HEX20 element %d has %d nodes", e + 1, nn); return FSR_ERR_ARG; }
+    elem.push_back(e);
+    ptoff.push_back(p->ptoff_host[e]);
+    const size_t base = edof.size();
+    edof.resize(base + 60, 0);
+    for (int k = 0; k < 20; ++k) {
+      const int n = sam->mmnpc[ip0 + k] - 1;
+      if (n < 0 || n >= sam->nnod) { set_error("element %d: node index out of range", e + 1); return FSR_ERR_ARG; }
+      conn.push_back(n);
+      const int js = sam->madof[n] - 1, nd = sam->madof[n + 1] - sam->madof[n];
+      if (nd < 3) { set_error("element %d: node %d has %d DOFs, solid needs 3", e + 1, n + 1, nd); return FSR_ERR_ARG; }
+      for (int d = 0; d < 3; ++d) edof[base + (size_t)k * 3 + d] = js + d;
+    }
+  }
+  f.nelt = (int)elem.size();
+  f.naux = 2;
+  if (f.nelt == 0) return FSR_OK;
+  int* d_conn = nullptr;
+  FSR_CUDA(cudaMalloc(&f.elem, sizeof(int) * elem.size()));
+  FSR_CUDA(cudaMalloc(&f.edof, sizeof(int) * edof.size()));
+  FSR_CUDA(cudaMalloc(&f.ptoff, sizeof(int) * ptoff.size()));
+  FSR_CUDA(cudaMalloc(&f.failed, f.nelt));
+  FSR_CUDA(cudaMalloc(&f.Sfrag, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32));
+  FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
+  FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
+  FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(f.ptoff, ptoff.data(), sizeof(int) * ptoff.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
+  build_hex20_ops_kernel<<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny, p->stressForm,
+                                                         f.Sfrag, f.failed, f.aux);
+  FSR_LAUNCH_CHECK();
+  FSR_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_conn);
+  return FSR_OK;
+}
+
+int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s)
+{
+  FamilyData& f = p->fam[FAM_HEX20];
+  if (f.nelt == 0) return FSR_OK;
+  static bool attr = false;
+  const size_t smem = solid_smem_bytes<20>();
+  if (!attr) {
+    FSR_CUDA(cudaFuncSetAttribute(k2_solid_smem_vm_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  k2_solid_smem_vm_kernel<20><<<f.nelt, 128, smem, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof,
+                                                       f.ptoff, f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+
+}  // namespace fsr

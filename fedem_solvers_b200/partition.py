@@ -19,8 +19,8 @@ F64 = np.float64
 # relative cost of one element.step = K1 rows it brings (nodal DOFs x n_red, shared with neighbours)
 # + its K2 operator (rows x cols of the padded DMMA operator)
 ELEMENT_COST = {24: 24 * 24 + 6 * 98, 22: 24 * 24 + 6 * 98, 23: 24 * 20 + 3 * 98, 21: 24 * 20 + 3 * 98,
-                41: 64 * 32 + 4 * 98, 11: 12 * 12}
-NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10}
+                41: 64 * 32 + 4 * 98, 43: 120 * 60 + 12 * 98, 11: 12 * 12}
+NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 43: 20}
 
 
 def element_costs(melcon):

@@ -30,7 +30,12 @@ int orc_extract_ev(int iel, const orc_sam *sam, const double *sv, double *ev, in
     if (nd > nndof) nd = nndof;
     int iedof = nedof + 1;
     nedof = nedof + nd;
-    if (nedof < evsize) /* sic: strict '<' as in the reference */
+    /* The reference tests NEDOF < size(EV) with EV(60) (stressRoutines.f90:86,93): for the one
+     * element type with exactly 60 DOFs, HEX20, the 20th node is then NOT copied and keeps whatever
+     * the previous element left in EV(58:60).  That stale read cannot be a parity target (it depends
+     * on the element visited before); DELIBERATE DEVIATION: '<=' here and in the CUDA path, i.e. all
+     * 20 nodes are used.  Identical for every other element type (NEDOF < 60).  See DESIGN.md 9. */
+    if (nedof <= evsize)
       for (int k = 0; k < nd; k++) ev[iedof - 1 + k] = sv[js - 1 + k];
   }
   if (nedof > evsize) nedof = evsize - nedof;
@@ -54,7 +59,7 @@ static void get_coor(int iel, const orc_sam *sam, const orc_elmdata *ed, int n, 
 int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed,
                   double *V, double *S, double *Sigma, double *Epsil, int *nenod, int *nstrp)
 {
-  double x[10], y[10], z[10], thk[4], SS[24];
+  double x[20], y[20], z[20], thk[4], SS[24];
   int ierr = 0;
   *nenod = 0;
   *nstrp = 0;
@@ -91,6 +96,12 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     get_coor(iel, sam, ed, 10, x, y, z);
     ierr = orc_str41(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
     break;
+  case 43:
+    *nenod = 20;
+    *nstrp = 20;
+    get_coor(iel, sam, ed, 20, x, y, z);
+    ierr = orc_str43(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
+    break;
   default:
     return 0; /* silently ignore all other element types */
   }
@@ -123,6 +134,7 @@ static int nstrp_of(int t) /* elStressModule.f90:159-229 */
   case 21: case 23: return 6;
   case 22: case 24: return 8;
   case 41: return 10;
+  case 43: return 20;
   }
   return 0;
 }

@@ -91,6 +91,9 @@ int orc_str23(const double xg[3], const double yg[3], const double zg[3], double
 int orc_str41(const double xg[10], const double yg[10], const double zg[10], double emod,
               double rny, int stressForm, const double v[30], double sigma[60],
               double epsil[60]);
+int orc_str43(const double xg[20], const double yg[20], const double zg[20], double emod,
+              double rny, int stressForm, const double v[60], double sigma[120],
+              double epsil[120]);
 int orc_str11(const double *beam, const double ev[12], double SF[12]);
 int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed,
                   double *V, double *S, double *Sigma, double *Epsil, int *nenod, int *nstrp);

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from fedem_solvers_b200 import StressRecovery
-from fedem_solvers_b200.model import plate_part, tet10_block, reduced_history
+from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, reduced_history
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
@@ -114,6 +114,35 @@ def test_tet10_gauss_extrapolation(oracle):
             vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(10)])
             p0 = rec.result_point_offsets()[e]
             assert rel_err(vm_g[s, p0:p0 + 10], vm_o) <= TOL
+    rec.close()
+
+
+def test_hex20_block(oracle):
+    """20-node hexahedra (type 43): 120 x 60 operator through the shared-memory solid kernel"""
+    part = hex20_block(3, 2, 2, ngen=5, seed=6, shuffle_eq=True)
+    _check_part(oracle, part, nsteps=27, seed=7)
+
+
+def test_hex20_gauss_extrapolation(oracle):
+    import ctypes as C
+    from oracle_bind import _dp, _D
+    part = hex20_block(2, 1, 2, ngen=3, seed=9)
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 5, seed=2)
+    rec = StressRecovery(part, stress_form=2)
+    vm_g = rec.recover(Q)
+    oracle.lib.orc_str43.argtypes = [_D, _D, _D, C.c_double, C.c_double, C.c_int, _D, _D, _D]
+    X = part.elm.xyz
+    for e in range(part.sam.nel):
+        nodes = part.sam.mmnpc[part.sam.mpmnpc[e] - 1: part.sam.mpmnpc[e + 1] - 1] - 1
+        sv = oracle.expand(b, Q[:, 3])
+        v = np.ascontiguousarray(np.stack([sv[3 * n: 3 * n + 3] for n in nodes]).ravel())
+        xg, yg, zg = (np.ascontiguousarray(X[nodes, k]) for k in range(3))
+        sig = np.zeros(120); eps = np.zeros(120)
+        assert oracle.lib.orc_str43(_dp(xg), _dp(yg), _dp(zg), part.elm.emod[e], part.elm.rny[e], 2, _dp(v), _dp(sig), _dp(eps)) == 0
+        vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(20)])
+        p0 = rec.result_point_offsets()[e]
+        assert rel_err(vm_g[3, p0:p0 + 20], vm_o) <= TOL
     rec.close()
 
 
