@@ -350,6 +350,63 @@ module fedem_b200_mod
        type(c_ptr), value :: f
      end subroutine fsr_fatigue_destroy
 
+     ! ---- file formats and history assembly (host only) ---------------------------------------
+     function fsr_fmx_write (path, tag, checksum, A, n, single_precision) bind(C,name="fsr_fmx_write") result(ierr)
+       import :: c_char, c_int, c_double, c_long_long
+       character(kind=c_char), intent(in) :: path(*), tag(*)   !< NUL-terminated
+       integer(c_int)        , value      :: checksum, single_precision
+       real(c_double)        , intent(in) :: A(*)
+       integer(c_long_long)  , value      :: n
+       integer(c_int) :: ierr
+     end function fsr_fmx_write
+
+     function fsr_fmx_read (path, tag_out, tag_cap, checksum, is_single, A, n) bind(C,name="fsr_fmx_read") result(ierr)
+       import :: c_char, c_int, c_double, c_long_long
+       character(kind=c_char), intent(in)  :: path(*)
+       character(kind=c_char), intent(out) :: tag_out(*)
+       integer(c_int)        , value       :: tag_cap
+       integer(c_int)        , intent(out) :: checksum, is_single
+       real(c_double)        , intent(out) :: A(*)
+       integer(c_long_long)  , value       :: n
+       integer(c_int) :: ierr
+     end function fsr_fmx_read
+
+     function fsr_fsm_read_mpar (path, checksum, mpar, cap) bind(C,name="fsr_fsm_read_mpar") result(npar)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in)  :: path(*)
+       integer(c_int)        , intent(out) :: checksum, mpar(*)
+       integer(c_int)        , value       :: cap
+       integer(c_int) :: npar
+     end function fsr_fsm_read_mpar
+
+     function fsr_fsm_read (path, madof, minex, mnnn, msc, mpmnpc, mmnpc, melcon, mpmceq, mmceq, ttcc, &
+          &                meqn, meqn1, meqn2) bind(C,name="fsr_fsm_read") result(ierr)
+       import :: c_char, c_ptr, c_int
+       character(kind=c_char), intent(in) :: path(*)
+       type(c_ptr), value :: madof, minex, mnnn, msc, mpmnpc, mmnpc, melcon, mpmceq, mmceq, ttcc, meqn, meqn1, meqn2
+       integer(c_int) :: ierr
+     end function fsr_fsm_read
+
+     function fsr_fsm_write (path, checksum, npar, mpar, madof, minex, mnnn, msc, mpmnpc, mmnpc, melcon, &
+          &                 mpmceq, mmceq, ttcc, meqn, meqn1, meqn2) bind(C,name="fsr_fsm_write") result(ierr)
+       import :: c_char, c_ptr, c_int
+       character(kind=c_char), intent(in) :: path(*)
+       integer(c_int)        , value      :: checksum, npar
+       integer(c_int)        , intent(in) :: mpar(*)
+       type(c_ptr), value :: madof, minex, mnnn, msc, mpmnpc, mmnpc, melcon, mpmceq, mmceq, ttcc, meqn, meqn1, meqn2
+       integer(c_int) :: ierr
+     end function fsr_fsm_write
+
+     function fsr_build_finit (nsteps, ntriads, sup_tr, triad_ur, tr_undef, ndofs, first_dof, ngen, gen_ur, &
+          &                   gen_first_dof, Q, ldq) bind(C,name="fsr_build_finit") result(ierr)
+       import :: c_int, c_double
+       integer(c_int), value       :: nsteps, ntriads, ngen, gen_first_dof, ldq
+       real(c_double), intent(in)  :: sup_tr(3,4,*), triad_ur(3,4,ntriads,*), tr_undef(3,4,*), gen_ur(ngen,*)
+       integer(c_int), intent(in)  :: ndofs(*), first_dof(*)
+       real(c_double), intent(out) :: Q(ldq,*)
+       integer(c_int) :: ierr
+     end function fsr_build_finit
+
      ! ---- diagnostics ------------------------------------------------------------------------
      function fsr_last_error () bind(C,name="fsr_last_error") result(msg)
        import :: c_ptr

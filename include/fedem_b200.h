@@ -259,6 +259,39 @@ int fsr_gage_fatigue_feed_dev(fsr_gages *gages, const double *Q_dev, int ldq, in
 int fsr_gage_fatigue_end(fsr_gages *gages, double *damage, int *ncycles, int *bins, int *status);
 void fsr_gage_destroy(fsr_gages *gages);
 
+/* ---- file formats and history assembly on the drop-in surface (host only) -------------------
+ * Tagged binary files as written by writeTagDB / read by readTagDB (src/vpmUtilities/binaryDB.c:
+ * 643-733; header layout FFaTag.C:192-297): 30-char tag, 0x1234 endian mark, 8-byte checksum field,
+ * ";1.0;\n" (46 bytes), raw arrays.  Files of the other endianness are swapped on read.
+ *
+ * .fmx (dmOpen, src/vpmUtilities/diskMatrixModule.f90:263-301): column-major values; the dimensions
+ * come from the .fsm.  tag NULL = "#FEDEM disk matrix" (the E-matrix uses "#FEDEM generalized
+ * modes", displacementModule.f90:667); single_precision appends " SP" and stores floats. */
+int fsr_fmx_write(const char *path, const char *tag, int checksum, const double *A, long long n,
+                  int single_precision);
+int fsr_fmx_read(const char *path, char *tag_out, int tag_cap, int *checksum, int *is_single,
+                 double *A, long long n);
+/* .fsm (saveSAM, src/vpmReducer/samReducerModule.f90:586-672; readSAMarrays,
+ * src/vpmStress/samStressModule.f90:273-316).  fsr_fsm_read_mpar returns npar and the first `cap`
+ * entries of mpar (mpar(1)=nnod, (2)=nel, (3)=ndof, (4)=ndof1, (5)=ndof2, (7)=nceq, (11)=neq,
+ * (15)=nmmnpc, (16)=nmmceq, (18)=part base id, (22)=ngen, (24)=ndim); the caller sizes the arrays
+ * and calls fsr_fsm_read (NULL = skip that array). */
+int fsr_fsm_read_mpar(const char *path, int *checksum, int *mpar, int cap);
+int fsr_fsm_read(const char *path, int *madof, int *minex, int *mnnn, int *msc, int *mpmnpc,
+                 int *mmnpc, int *melcon, int *mpmceq, int *mmceq, double *ttcc, int *meqn,
+                 int *meqn1, int *meqn2);
+int fsr_fsm_write(const char *path, int checksum, int npar, const int *mpar, const int *madof,
+                  const int *minex, const int *mnnn, const int *msc, const int *mpmnpc,
+                  const int *mmnpc, const int *melcon, const int *mpmceq, const int *mmceq,
+                  const double *ttcc, const int *meqn, const int *meqn1, const int *meqn2);
+/* BuildFinit (src/vpmCommon/supElTypeModule.f90:1067-1114) for nsteps steps at once: co-rotated
+ * deformational displacements of the triads + the component-mode amplitudes = the columns of Q.
+ * 3x4 position matrices column-major: sup_tr [nsteps][12], triad_ur [nsteps][ntriads][12],
+ * tr_undef [ntriads][12]; ndofs/first_dof [ntriads] (first_dof 1-based); gen_ur [nsteps][ngen]. */
+int fsr_build_finit(int nsteps, int ntriads, const double *sup_tr, const double *triad_ur,
+                    const double *tr_undef, const int *ndofs, const int *first_dof, int ngen,
+                    const double *gen_ur, int gen_first_dof, double *Q, int ldq);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);
 /* Number of kernels this library launched since the counter was last reset (bench evidence). */
