@@ -48,7 +48,8 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=1000, help="plate is nx x nx quads per rank")
     ap.add_argument("--tile", type=int, default=500, help="time steps per bench step")
     ap.add_argument("--cpu-sample-nx", type=int, default=160)
-    ap.add_argument("--cpu-sample-steps", type=int, default=6)
+    ap.add_argument("--cpu-sample-steps", type=int, default=0,
+                    help="time steps of the CPU sample (0 = 128 for cpu_baseline ~10 s on one thread, 48 per reference-arm step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--elem-order", type=int, default=0, help="0 = Morton order (default), 1 = SAM order")
     return ap.parse_args()
@@ -129,7 +130,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nx, ns = args.cpu_sample_nx, args.cpu_sample_steps
+    nx, ns = args.cpu_sample_nx, args.cpu_sample_steps or 48
     cs = CpuSample(nx, ns * (args.steps + args.warmup))
     for i in range(args.warmup):
         cs.run(i * ns, ns, cores)
@@ -224,6 +225,10 @@ def run_b200(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         device_step(i)
+    if world > 1:  # bring up NCCL's point-to-point channels (gather = send/recv) before the timed region
+        env = torch.empty((2, npts), dtype=torch.float64, device=dev)
+        rec.copy_envelope_dev(env[0].data_ptr(), env[1].data_ptr(), stream.cuda_stream)
+        dist.gather(env, gather_buf, dst=0)
     sync_all()
     rec.reset_envelope()
     rec.timing_reset()
@@ -237,7 +242,6 @@ def run_b200(args, rank, world, local_rank):
     for i in range(args.steps):
         device_step(args.warmup + i)
     if world > 1:  # per-part envelopes gathered to rank 0 over NVLink
-        env = torch.empty((2, npts), dtype=torch.float64, device=dev)
         rec.copy_envelope_dev(env[0].data_ptr(), env[1].data_ptr(), stream.cuda_stream)
         dist.gather(env, gather_buf, dst=0)
     e1.record()
@@ -316,14 +320,15 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": launches, "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cs = CpuSample(args.cpu_sample_nx, args.cpu_sample_steps + 1)
+        ncs = args.cpu_sample_steps or 128
+        cs = CpuSample(args.cpu_sample_nx, ncs + 1)
         cs.run(0, 1, 1)
-        dt = cs.run(1, args.cpu_sample_steps, 1)
-        v, n_el = cs.nel * args.cpu_sample_steps / dt, cs.nel
+        dt = cs.run(1, ncs, 1)
+        v, n_el = cs.nel * ncs / dt, cs.nel
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{args.cpu_sample_nx}x{args.cpu_sample_nx}-quad sub-plate ({n_el} elements, n_red=98) x "
-                      f"{args.cpu_sample_steps} time steps, {dt:.1f} s, single thread like the serial reference "
+                      f"{ncs} time steps, {dt:.1f} s, single thread like the serial reference "
                       "(oracle C restatement; the reference's Fortran cannot be built in this image)"}
     print(json.dumps(line), flush=True)
     if world > 1:

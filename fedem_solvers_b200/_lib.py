@@ -94,6 +94,18 @@ SYMBOLS = [
     ("fsr_fsm_read", C.c_int, [C.c_char_p, _I, _I, _I, _I, _I, _I, _I, _I, _I, _D, _I, _I, _I]),
     ("fsr_fsm_write", C.c_int, [C.c_char_p, C.c_int, C.c_int, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _D, _I, _I, _I]),
     ("fsr_build_finit", C.c_int, [C.c_int, C.c_int, _D, _D, _D, _I, _I, C.c_int, _D, C.c_int, _D, C.c_int]),
+    ("fsr_frs_open", C.c_int, [C.POINTER(_P), C.POINTER(C.c_char_p), C.c_int]),
+    ("fsr_frs_close", None, [_P]),
+    ("fsr_frs_num_steps", C.c_int, [_P]),
+    ("fsr_frs_get_steps", C.c_int, [_P, _I, _D, C.c_int]),
+    ("fsr_frs_find", C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
+    ("fsr_frs_var_size", C.c_int, [_P, C.c_int]),
+    ("fsr_frs_read", C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, C.c_int, C.c_int]),
+    ("fsr_frs_reduced_history", C.c_int, [_P, C.c_int, C.c_int, _I, _I, _I, _D, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          _D, C.c_int]),
+    ("fsr_frs_create", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_char_p, C.c_longlong]),
+    ("fsr_frs_write_step", C.c_int, [_P, C.c_int, C.c_double, _P]),
+    ("fsr_frs_finish", C.c_int, [_P]),
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),

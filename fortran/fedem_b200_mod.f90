@@ -407,6 +407,93 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_build_finit
 
+     ! ---- .frs results database (replaces ffr_init/ffr_findptr/ffr_getdata for the recovery path) ----
+     function fsr_frs_open (db, paths, nfiles) bind(C,name="fsr_frs_open") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr)   , intent(out) :: db
+       type(c_ptr)   , intent(in)  :: paths(*)   !< c_loc of NUL-terminated file names
+       integer(c_int), value       :: nfiles
+       integer(c_int) :: ierr
+     end function fsr_frs_open
+
+     subroutine fsr_frs_close (db) bind(C,name="fsr_frs_close")
+       import :: c_ptr
+       type(c_ptr), value :: db
+     end subroutine fsr_frs_close
+
+     function fsr_frs_num_steps (db) bind(C,name="fsr_frs_num_steps") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: db
+       integer(c_int) :: n
+     end function fsr_frs_num_steps
+
+     function fsr_frs_get_steps (db, stepno, time, cap) bind(C,name="fsr_frs_get_steps") result(n)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: db
+       integer(c_int), intent(out) :: stepno(*)
+       real(c_double), intent(out) :: time(*)
+       integer(c_int), value       :: cap
+       integer(c_int) :: n
+     end function fsr_frs_get_steps
+
+     function fsr_frs_find (db, var_path, og_type, base_id) bind(C,name="fsr_frs_find") result(handle)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr)           , value      :: db
+       character(kind=c_char), intent(in) :: var_path(*), og_type(*)
+       integer(c_int)        , value      :: base_id
+       integer(c_int) :: handle
+     end function fsr_frs_find
+
+     function fsr_frs_var_size (db, handle) bind(C,name="fsr_frs_var_size") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value :: db
+       integer(c_int), value :: handle
+       integer(c_int) :: n
+     end function fsr_frs_var_size
+
+     function fsr_frs_read (db, handle, step0, nsteps, data, nw, ld) bind(C,name="fsr_frs_read") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: db
+       integer(c_int), value       :: handle, step0, nsteps, nw, ld
+       real(c_double), intent(out) :: data(ld,*)
+       integer(c_int) :: ierr
+     end function fsr_frs_read
+
+     function fsr_frs_reduced_history (db, sup_base_id, ntriads, triad_base_id, ndofs, first_dof, tr_undef, ngen, &
+          &                           gen_first_dof, step0, nsteps, Q, ldq) &
+          &                           bind(C,name="fsr_frs_reduced_history") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: db
+       integer(c_int), value       :: sup_base_id, ntriads, ngen, gen_first_dof, step0, nsteps, ldq
+       integer(c_int), intent(in)  :: triad_base_id(*), ndofs(*), first_dof(*)
+       real(c_double), intent(in)  :: tr_undef(3,4,*)
+       real(c_double), intent(out) :: Q(ldq,*)
+       integer(c_int) :: ierr
+     end function fsr_frs_reduced_history
+
+     function fsr_frs_create (w, path, checksum, header_text, payload_bytes) bind(C,name="fsr_frs_create") result(ierr)
+       import :: c_ptr, c_char, c_int, c_long_long
+       type(c_ptr)           , intent(out) :: w
+       character(kind=c_char), intent(in)  :: path(*), header_text(*)
+       integer(c_int)        , value       :: checksum
+       integer(c_long_long)  , value       :: payload_bytes
+       integer(c_int) :: ierr
+     end function fsr_frs_create
+
+     function fsr_frs_write_step (w, stepno, time, payload) bind(C,name="fsr_frs_write_step") result(n)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value :: w, payload
+       integer(c_int), value :: stepno
+       real(c_double), value :: time
+       integer(c_int) :: n
+     end function fsr_frs_write_step
+
+     function fsr_frs_finish (w) bind(C,name="fsr_frs_finish") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: w
+       integer(c_int) :: ierr
+     end function fsr_frs_finish
+
      ! ---- diagnostics ------------------------------------------------------------------------
      function fsr_last_error () bind(C,name="fsr_last_error") result(msg)
        import :: c_ptr

@@ -292,6 +292,42 @@ int fsr_build_finit(int nsteps, int ntriads, const double *sup_tr, const double 
                     const double *tr_undef, const int *ndofs, const int *first_dof, int ngen,
                     const double *gen_ur, int gen_first_dof, double *Q, int ldq);
 
+/* .frs results database, reader side = what the recovery path uses of FFrExtractor through
+ * ffr_init / ffr_findptr / ffr_getdata / ffr_setposition / ffr_increment
+ * (fedem-foundation/src/FFrLib/FFrExtractor_F.C:33-263; header grammar FFrResultContainer.C:234-528,
+ * record layout :534-585, time keys :714-860).  One handle owns any number of files (the solver
+ * splits its output over th_p_*.frs / th_s_*.frs); the time steps are the sorted union of the
+ * physical-time keys of all files.
+ *  fsr_frs_find  : var_path = item-group names and the variable name joined by '|', og_type =
+ *                  "Triad", "Part", ... (NULL/"" = a top-level variable), base_id = the object's base
+ *                  id.  Returns a variable handle >= 0, or -1 when no file holds it.
+ *  fsr_frs_read  : nw values of that variable for steps [step0, step0+nsteps) into data[s*ld + i]
+ *                  (FLOAT 32/64 and INT 8..64 on file -> double); error if a step lacks the variable
+ *                  or it is shorter than nw (ffr_getdata's ierr). */
+typedef struct fsr_frs fsr_frs;
+int fsr_frs_open(fsr_frs **db, const char *const *paths, int nfiles);
+void fsr_frs_close(fsr_frs *db);
+int fsr_frs_num_steps(const fsr_frs *db);
+int fsr_frs_get_steps(const fsr_frs *db, int *stepno, double *time, int cap); /* returns the step count */
+int fsr_frs_find(fsr_frs *db, const char *var_path, const char *og_type, int base_id);
+int fsr_frs_var_size(const fsr_frs *db, int handle);
+int fsr_frs_read(fsr_frs *db, int handle, int step0, int nsteps, double *data, int nw, int ld);
+/* readSupElDisplacements (src/vpmStress/displacementModule.f90:434-524) for a window of steps:
+ * "Position matrix" of every triad (6 DOFs; "Position" for 3-DOF triads) and of the part,
+ * "Generalized displacement" of the part, then BuildFinit -> Q[ldq x nsteps].  Arguments as
+ * fsr_build_finit; *_base_id = the base ids the solver wrote the objects with. */
+int fsr_frs_reduced_history(fsr_frs *db, int sup_base_id, int ntriads, const int *triad_base_id,
+                            const int *ndofs, const int *first_dof, const double *tr_undef, int ngen,
+                            int gen_first_dof, int step0, int nsteps, double *Q, int ldq);
+/* .frs writer core (src/vpmCommon/rdbModule.f90: openRDBfile :268-403, writeTimeStepDB :669-736):
+ * tag line, the caller's text header (heading lines, VARIABLES:, DATABLOCKS: sections), "DATA:",
+ * then per step int32 step number + double time + payload_bytes of the caller's record. */
+typedef struct fsr_frs_writer fsr_frs_writer;
+int fsr_frs_create(fsr_frs_writer **w, const char *path, int checksum, const char *header_text,
+                   long long payload_bytes);
+int fsr_frs_write_step(fsr_frs_writer *w, int stepno, double time, const void *payload); /* returns steps written */
+int fsr_frs_finish(fsr_frs_writer *w);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);
 /* Number of kernels this library launched since the counter was last reset (bench evidence). */
