@@ -106,6 +106,15 @@ SYMBOLS = [
     ("fsr_frs_create", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_char_p, C.c_longlong]),
     ("fsr_frs_write_step", C.c_int, [_P, C.c_int, C.c_double, _P]),
     ("fsr_frs_finish", C.c_int, [_P]),
+    ("fsr_ftl_open", C.c_int, [C.POINTER(_P), C.c_char_p]),
+    ("fsr_ftl_close", None, [_P]),
+    ("fsr_ftl_version", C.c_int, [_P]),
+    ("fsr_ftl_activate_groups", C.c_int, [_P, C.c_char_p]),
+    ("fsr_ftl_sizes", C.c_int, [_P, _I]),
+    ("fsr_ftl_get_nodes", C.c_int, [_P, _I, _I, _I, _I, _D]),
+    ("fsr_ftl_get_topology", C.c_int, [_P, C.c_int, _I, _I, _I]),
+    ("fsr_ftl_get_elmdata", C.c_int, [_P, _D, _D, _D, _D, _I, _D, _I]),
+    ("fsr_ftl_ext2int", C.c_int, [_P, C.c_int, C.c_int]),
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),

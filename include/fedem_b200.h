@@ -328,6 +328,38 @@ int fsr_frs_create(fsr_frs_writer **w, const char *path, int checksum, const cha
 int fsr_frs_write_step(fsr_frs_writer *w, int stepno, double time, const void *payload); /* returns steps written */
 int fsr_frs_finish(fsr_frs_writer *w);
 
+/* ---- FE part file (.ftl) ----------------------------------------------------------------------
+ * Replaces what fedem_stress pulls from the FE-model singleton through ffl_init (stress.f90:111 ->
+ * fedem-foundation/src/FFlLib/FFlLinkHandler_F.C:56-160) and, per element per step, through ffl_getcoor /
+ * ffl_getmat / ffl_getthick / ffl_getbeamsection / ffl_getpinflags / ffl_getelmid (:699-1193): reads the
+ * .ftl text file (grammar FFlIOAdaptors/FFlFedemReader.C:456-763) once and returns the same numbers as
+ * flat arrays in SAM order, i.e. the members of fsr_elmdata.
+ *  fsr_ftl_sizes        : sz[12] = nnod, nel, ndof, nmnpc, nmat, nxnod, npbeam, nrgd, nrbar, nwavgm, nprop,
+ *                         ncons exactly as ffl_getsize (:367-431); returns the number of elements whose
+ *                         calculation flag is on (its ierr).  initiateSAM compares these with the .fsm
+ *                         (samStressModule.f90:118-135).
+ *  fsr_ftl_activate_groups : the -group option, "55", "<33,22,44>", "<PMAT 33, PTHICK 55>" (FFlUtils.C:18-61);
+ *                         returns the number of non-existing groups that were ignored.
+ *  fsr_ftl_get_nodes    : ffl_getnodes (:459-556): madof [nnod+1], minex [nnod], mnode [nnod], msc [ndof],
+ *                         xyz [nnod][3] (extra nodes of pinned beam ends last, minex < 0); returns nnod.
+ *  fsr_ftl_get_topology : ffl_gettopol (:558-672): melcon [nel] (21/22 -> 23/24 when use_andes), mpmnpc
+ *                         [nel+1], mmnpc [nmnpc]; returns nel.
+ *  fsr_ftl_get_elmdata  : emod, rny, rho, thk [nel]; elmid [nel] (negative: outside the -group selection);
+ *                         beam [nel][FSR_NBEAM]; status [nel] (0 ok, -2 no material, -3 invalid Poisson's
+ *                         ratio / no beam section, -4 no shell thickness); returns the number of elements
+ *                         with status != 0 (those get hugeVal results, stressRoutines.f90:237-241). */
+typedef struct fsr_ftl fsr_ftl;
+int fsr_ftl_open(fsr_ftl **ftl, const char *path);
+void fsr_ftl_close(fsr_ftl *ftl);
+int fsr_ftl_version(const fsr_ftl *ftl);
+int fsr_ftl_activate_groups(fsr_ftl *ftl, const char *groups);
+int fsr_ftl_sizes(const fsr_ftl *ftl, int *sz);
+int fsr_ftl_get_nodes(const fsr_ftl *ftl, int *madof, int *minex, int *mnode, int *msc, double *xyz);
+int fsr_ftl_get_topology(const fsr_ftl *ftl, int use_andes, int *melcon, int *mpmnpc, int *mmnpc);
+int fsr_ftl_get_elmdata(const fsr_ftl *ftl, double *emod, double *rny, double *rho, double *thk, int *elmid,
+                        double *beam, int *status);
+int fsr_ftl_ext2int(const fsr_ftl *ftl, int is_node, int id); /* ffl_ext2int (:716-737) */
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);
 /* Number of kernels this library launched since the counter was last reset (bench evidence). */
