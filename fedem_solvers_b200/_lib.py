@@ -38,6 +38,13 @@ class FsrRosette(C.Structure):
                 ("nu", C.c_double), ("alpha_gages", C.c_double), ("gate", C.c_double), ("sncurve", C.c_double * 4)]
 
 
+class FsrRdbOptions(C.Structure):
+    _fields_ = [("out_mask", C.c_uint), ("double_precision", C.c_int), ("rdbinc", C.c_int), ("part_base_id", C.c_int),
+                ("part_user_id", C.c_int), ("part_descr", C.c_char_p), ("model_file", C.c_char_p),
+                ("link_file", C.c_char_p), ("elmid", C.POINTER(C.c_int)), ("module_name", C.c_char_p),
+                ("minex", C.POINTER(C.c_int)), ("sup_tr_init", C.POINTER(C.c_double))]
+
+
 class FsrOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("stressForm", C.c_int), ("step_tile", C.c_int),
                 ("reserved", C.c_int * 5)]
@@ -115,6 +122,14 @@ SYMBOLS = [
     ("fsr_ftl_get_topology", C.c_int, [_P, C.c_int, _I, _I, _I]),
     ("fsr_ftl_get_elmdata", C.c_int, [_P, _D, _D, _D, _D, _I, _D, _I]),
     ("fsr_ftl_ext2int", C.c_int, [_P, C.c_int, C.c_int]),
+    ("fsr_rdb_create", C.c_int, [C.POINTER(_P), _P, C.c_char_p, C.POINTER(FsrRdbOptions)]),
+    ("fsr_rdb_build_header", C.c_int, [C.c_int, _I, C.c_int, _I, C.POINTER(FsrRdbOptions), C.c_char_p, C.c_int, C.POINTER(C.c_longlong)]),
+    ("fsr_rdb_step_bytes", C.c_longlong, [_P]),
+    ("fsr_rdb_header", C.c_int, [_P, C.c_char_p, C.c_int]),
+    ("fsr_rdb_path", C.c_int, [_P, C.c_char_p, C.c_int]),
+    ("fsr_rdb_write_steps", C.c_int, [_P, _D, C.c_int, C.c_int, _I, _D, _D]),
+    ("fsr_total_nodal_displacement", None, [_D, _D, C.c_int, _D, _D, _D]),
+    ("fsr_rdb_close", C.c_int, [_P]),
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),

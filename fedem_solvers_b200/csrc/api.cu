@@ -87,7 +87,7 @@ static void free_family(FamilyData& f)
   f = FamilyData();
 }
 
-static int ensure_batch_buffers(fsr_part* p, bool need_vm_tile)
+int ensure_batch_buffers(fsr_part* p, bool need_vm_tile)
 {
   if (!p->Qt) FSR_CUDA(cudaMalloc(&p->Qt, sizeof(double) * (size_t)p->step_tile * p->ldk));
   if (!p->U) FSR_CUDA(cudaMalloc(&p->U, sizeof(double) * ((size_t)p->nrows_pad * p->step_tile + 64)));  // +64: prefetch slack

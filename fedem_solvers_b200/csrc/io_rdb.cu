@@ -1,0 +1,707 @@
+// io_rdb.cu -- the stress results database (.frs) of fedem_stress, written straight from the GPU.
+//
+// Reference: writeStressHeader / writeElementsHeader / writeBeamHeader / writeShellHeader / writeSolidHeader
+// (src/vpmStress/saveStressModule.f90:120-247,625-752,764-966,978-1186,1198-1347) build the text header in
+// three scratch files (variables, item groups, data blocks; src/vpmCommon/rdbModule.f90:191-251,418-463),
+// then calcStresses (src/vpmStress/stressRoutines.f90:169-331) writes, per time step and per element in
+// SAM order: the stress resultants SR(6,nenod) when -SR is on (writeStressDB, saveStressModule.f90:1527-1567)
+// and, per result point, [stress tensor][strain tensor][the selected ones of vmStress, maxP, minP, maxShear,
+// vmStrain, maxP, minP, maxShear] (writeStrMeasureDB :1579-1633), each value as float unless -double.
+//
+// Here the record of a whole tile of time steps is formed on the device: K1 expands the tile, the record
+// kernels evaluate every element result point for every step of the tile and drop the selected values at
+// their slot of the step record (slot-major, step fastest: coalesced reads of U and coalesced writes), one
+// tiled transpose turns that into step-major float/double records, and the host only adds the 12-byte
+// step key (int32 step number + float64 time, writeTimeStepDB rdbModule.f90:669-736) in front of each.
+#include <algorithm>
+#include <cstdarg>
+#include <ctime>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+#include "common.cuh"
+#include "invariants.cuh"
+#include "io_tagged.cuh"
+
+namespace fsr {
+
+int ensure_batch_buffers(fsr_part* p, bool need_vm_tile);
+
+struct RecLayout {
+  int sr, stress, strain;   // 1 = written
+  int mask;                 // bit j = resMat row j+1 written
+  int nsel;                 // popcount(mask)
+  int def;                  // 0 = no nodal output, 1 = deformational displacements, 3 = + total displacements
+};
+
+__device__ __forceinline__ size_t frag_at2(int row, int col, int KT)
+{
+  return ((size_t)((row >> 3) * KT + (col >> 2)) << 5) + ((row & 7) << 2) + (col & 3);
+}
+
+// One thread per (result point, step); step is the fastest index so that the U reads of a warp are one
+// contiguous segment per DOF row and the record writes one contiguous segment per slot.
+// rec[slot * ldt + t].  layout: 0 = shells (operator row = comp*8 + point), 1 = solids (row = point*ncmp + comp)
+__global__ void record_points_kernel(const double* __restrict__ U, size_t ldu, int nt, const double* __restrict__ Sfrag,
+                                     const int* __restrict__ edof, const long long* __restrict__ roff,
+                                     const unsigned char* __restrict__ failed, const double* __restrict__ aux, int naux,
+                                     int nelt, int nstrp, int ncmp, int nedof, int MT, int KT, int layout, int nenod,
+                                     RecLayout L, double* __restrict__ rec, size_t ldt)
+{
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long ip = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (t >= nt || ip >= (long long)nelt * nstrp) return;
+  const int i = (int)(ip / nstrp), pnt = (int)(ip % nstrp);
+  const long long base = roff[i];
+  if (base < 0) return;
+  const int srsize = L.sr && ncmp == 3 ? 6 * nenod : 0;
+  const int ptsize = (L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel;
+  double* out = rec + (size_t)(base + srsize + (long long)pnt * ptsize) * ldt + t;
+  double* srout = rec + (size_t)(base + 6 * pnt) * ldt + t;
+  if (failed[i]) {   // stressRoutines.f90:237-241,264-268: hugeVal for everything that is written
+    for (int k = 0; k < ptsize; ++k) out[(size_t)k * ldt] = kHuge;
+    if (srsize && pnt < nenod) for (int k = 0; k < 6; ++k) srout[(size_t)k * ldt] = kHuge;
+    return;
+  }
+  const double* S = Sfrag + (size_t)i * MT * KT * 32;
+  const int* ed = edof + (size_t)i * KT * 4;
+  double sig[6] = {0, 0, 0, 0, 0, 0}, eps[6] = {0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < ncmp; ++c) {
+    const int row = layout == 0 ? c * 8 + pnt : pnt * ncmp + c;
+    double s = 0.0;
+    for (int col = 0; col < nedof; ++col) s += S[frag_at2(row, col, KT)] * U[(size_t)ed[col] * ldu + t];
+    sig[c] = s;
+  }
+  const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
+  if (ncmp == 3) {
+    eps[0] = sig[0] / E - nu / E * sig[1];
+    eps[1] = -nu / E * sig[0] + sig[1] / E;
+    eps[2] = 0.5 * (2.0 * (1.0 + nu) / E * sig[2]);
+  } else {
+    eps[0] = (sig[0] - nu * (sig[1] + sig[2])) / E;
+    eps[1] = (sig[1] - nu * (sig[0] + sig[2])) / E;
+    eps[2] = (sig[2] - nu * (sig[0] + sig[1])) / E;
+    const double g2 = 2.0 * (1.0 + nu) / E;
+    eps[3] = 0.5 * g2 * sig[3]; eps[4] = 0.5 * g2 * sig[4]; eps[5] = 0.5 * g2 * sig[5];
+  }
+  int k = 0;
+  if (L.stress) for (int c = 0; c < ncmp; ++c) out[(size_t)(k++) * ldt] = sig[c];
+  if (L.strain) for (int c = 0; c < ncmp; ++c) out[(size_t)(k++) * ldt] = eps[c];
+  if (L.nsel) {
+    const int np = ncmp == 3 ? 2 : 3;
+    double r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, P[3] = {0, 0, 0};
+    if (L.mask & 0x01) r[0] = von_mises(ncmp, sig);
+    if (L.mask & 0x0e) { principal_values(ncmp, sig, P); r[1] = P[0]; r[2] = P[np - 1]; r[3] = 0.5 * (P[0] - P[np - 1]); }
+    if (L.mask & 0x10) r[4] = von_mises(ncmp, eps);
+    if (L.mask & 0xe0) { P[0] = P[1] = P[2] = 0.0; principal_values(ncmp, eps, P); r[5] = P[0]; r[6] = P[np - 1]; r[7] = 0.5 * (P[0] - P[np - 1]); }
+    for (int j = 0; j < 8; ++j) if (L.mask & (1 << j)) out[(size_t)(k++) * ldt] = r[j];
+  }
+  if (srsize && pnt < nenod) {   // shell stress resultants from the top and bottom stresses (k2_full.cu)
+    const double th = aux[(size_t)i * naux + 2];
+    for (int c = 0; c < 3; ++c) {
+      const int row = c * 8 + nenod + pnt;
+      double s = 0.0;
+      for (int col = 0; col < nedof; ++col) s += S[frag_at2(row, col, KT)] * U[(size_t)ed[col] * ldu + t];
+      srout[(size_t)c * ldt] = (sig[c] + s) * 0.5 * th;
+      srout[(size_t)(3 + c) * ldt] = (sig[c] - s) * 0.5 * th * th / 6.0;
+    }
+  }
+}
+
+struct BeamOp12 { double S[12][12]; };
+
+// beam section forces SF(6,2) (STR11, elStressModule.f90:402-515): 12 rows per beam
+__global__ void record_beams_kernel(const double* __restrict__ U, size_t ldu, int nt, const BeamOp12* __restrict__ ops,
+                                    const int* __restrict__ edof, const long long* __restrict__ roff,
+                                    const unsigned char* __restrict__ failed, int nelt, double* __restrict__ rec, size_t ldt)
+{
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long ir = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (t >= nt || ir >= (long long)nelt * 12) return;
+  const int i = (int)(ir / 12), r = (int)(ir % 12);
+  if (roff[i] < 0) return;
+  double acc = 0.0;
+  for (int c = 0; c < 12; ++c) acc += ops[i].S[r][c] * U[(size_t)edof[i * 12 + c] * ldu + t];
+  rec[(size_t)(roff[i] + r) * ldt + t] = failed[i] ? kHuge : acc;
+}
+
+// ---- rotation utilities of src/vpmUtilities/rotationModule.f90 (vec_to_quat :393-428, quat_to_mat :478-497,
+// mat_to_quat :441-470, quat_to_vec :505-533), matrices column-major a[i + 3*j] like the Fortran arrays
+__host__ __device__ inline void rot_vec_to_mat(const double* v, double* R)
+{
+  const double eps = 0.0005;
+  const double thh = 0.5 * sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const double sthh = sin(thh), cthh = cos(thh);
+  double q[4];
+  bool ok = true;
+  if (thh > 1.0e6 && fabs(1.0 - cthh * cthh - sthh * sthh) > 0.00001) { q[0] = 1.0; q[1] = q[2] = q[3] = 0.0; ok = false; }
+  if (ok) {
+    double fac;
+    if (thh < eps) { const double f1 = thh / eps; fac = f1 * sin(eps) / eps + 1.0 - f1; }
+    else fac = sthh / thh;
+    q[0] = cthh; q[1] = v[0] * fac * 0.5; q[2] = v[1] * fac * 0.5; q[3] = v[2] * fac * 0.5;
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) q[i] /= n;
+  }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+  R[0] = 2.0 * (q[1] * q[1] + q[0] * q[0]) - 1.0;
+  R[4] = 2.0 * (q[2] * q[2] + q[0] * q[0]) - 1.0;
+  R[8] = 2.0 * (q[3] * q[3] + q[0] * q[0]) - 1.0;
+  R[3] = 2.0 * (q[1] * q[2] - q[3] * q[0]);
+  R[6] = 2.0 * (q[1] * q[3] + q[2] * q[0]);
+  R[7] = 2.0 * (q[2] * q[3] - q[1] * q[0]);
+  R[1] = 2.0 * (q[2] * q[1] + q[3] * q[0]);
+  R[2] = 2.0 * (q[3] * q[1] - q[2] * q[0]);
+  R[5] = 2.0 * (q[3] * q[2] + q[1] * q[0]);
+}
+
+__host__ __device__ inline void rot_mat_to_vec(const double* R, double* v)
+{
+  const double eps = 0.0005;
+  double q[4];
+  const double trace = R[0] + R[4] + R[8];
+  int imax = 0;
+  if (R[4] > R[4 * imax]) imax = 1;
+  if (R[8] > R[4 * imax]) imax = 2;
+  if (trace > R[4 * imax]) {
+    q[0] = sqrt(1.0 + trace) * 0.5;
+    q[1] = (R[2 + 3 * 1] - R[1 + 3 * 2]) / (4.0 * q[0]);
+    q[2] = (R[0 + 3 * 2] - R[2 + 3 * 0]) / (4.0 * q[0]);
+    q[3] = (R[1 + 3 * 0] - R[0 + 3 * 1]) / (4.0 * q[0]);
+  } else {
+    const int i = imax, j = (imax + 1) % 3, k = (imax + 2) % 3;
+    q[i + 1] = sqrt(R[i + 3 * i] * 0.5 + (1.0 - trace) * 0.25);
+    q[0] = (R[k + 3 * j] - R[j + 3 * k]) / (4.0 * q[i + 1]);
+    q[j + 1] = (R[j + 3 * i] + R[i + 3 * j]) / (4.0 * q[i + 1]);
+    q[k + 1] = (R[k + 3 * i] + R[i + 3 * k]) / (4.0 * q[i + 1]);
+  }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+  const double cthh = q[0], sthh = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double thh = sthh < 0.7 ? asin(sthh) : acos(cthh);
+  double fac;
+  if (thh < eps) { const double f1 = thh / eps; fac = f1 * eps / sin(eps) + 1.0 - f1; }
+  else if (sthh >= 1.0) fac = thh;
+  else fac = thh / sthh;
+  for (int i = 0; i < 3; ++i) v[i] = q[i + 1] * fac * 2.0;
+}
+
+// calcTotalNodalDisplacement (src/vpmStress/displacementModule.f90:1694-1745): x0 = nodal coordinates, u = the
+// node's 3 or 6 deformational displacements, T = current and T0 = initial 3x4 position matrix of the part
+__host__ __device__ inline void total_nodal_displacement(const double* x0, const double* u, int nd, const double* T,
+                                                         const double* T0, double* utot)
+{
+  for (int i = 0; i < 3; ++i) {
+    const double a = T[i] * (x0[0] + u[0]) + T[i + 3] * (x0[1] + u[1]) + T[i + 6] * (x0[2] + u[2]) + T[i + 9];
+    const double b = T0[i] * x0[0] + T0[i + 3] * x0[1] + T0[i + 6] * x0[2] + T0[i + 9];
+    utot[i] = a - b;
+  }
+  if (nd < 6) return;
+  double dR[9], A[9], M[9];
+  rot_vec_to_mat(u + 3, dR);
+  for (int i = 0; i < 3; ++i)       // A = dR . T(:,1:3)
+    for (int j = 0; j < 3; ++j) A[i + 3 * j] = dR[i] * T[3 * j] + dR[i + 3] * T[1 + 3 * j] + dR[i + 6] * T[2 + 3 * j];
+  for (int i = 0; i < 3; ++i)       // deltaRot(T0, A) = mat_to_vec(A . T0^T)
+    for (int j = 0; j < 3; ++j) M[i + 3 * j] = A[i] * T0[j] + A[i + 3] * T0[j + 3] + A[i + 6] * T0[j + 6];
+  rot_mat_to_vec(M, utot + 3);
+}
+
+// writeDisplacementDB (saveStressModule.f90:1437-1515): per node the deformational displacements sv(j:k) and,
+// with -deformation in the current reference (iDef = 3), the total displacements.  One thread per (node, step).
+__global__ void record_nodes_kernel(const double* __restrict__ U, size_t ldu, int nt, int nnod, const int* __restrict__ madof,
+                                    const long long* __restrict__ nslot, const double* __restrict__ xyz,
+                                    const double* __restrict__ supTr, const double* __restrict__ supTr0, int total,
+                                    double* __restrict__ rec, size_t ldt)
+{
+  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+  const int n = blockIdx.x * blockDim.y + threadIdx.y;
+  if (t >= nt || n >= nnod) return;
+  const long long base = nslot[n];
+  if (base < 0) return;
+  const int j = madof[n] - 1, nd = madof[n + 1] - madof[n] > 5 ? 6 : 3;
+  double u[6] = {0, 0, 0, 0, 0, 0}, ut[6];
+  for (int d = 0; d < nd; ++d) { u[d] = U[(size_t)(j + d) * ldu + t]; rec[(size_t)(base + d) * ldt + t] = u[d]; }
+  if (!total) return;
+  double T[12], T0[12];
+  for (int i = 0; i < 12; ++i) { T[i] = supTr[(size_t)t * 12 + i]; T0[i] = supTr0[i]; }
+  total_nodal_displacement(xyz + 3 * (size_t)n, u, nd, T, T0, ut);
+  for (int d = 0; d < nd; ++d) rec[(size_t)(base + nd + d) * ldt + t] = ut[d];
+}
+
+// rec[slot][t] (double) -> out[t][slot] as float or double
+template <class T>
+__global__ void record_transpose_kernel(const double* __restrict__ rec, size_t ldt, long long nslot, int nt, T* __restrict__ out)
+{
+  __shared__ double tile[32][33];
+  const long long s0 = (long long)blockIdx.x * 32;
+  const int t0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long s = s0 + j;
+    const int t = t0 + threadIdx.x;
+    if (s < nslot && t < nt) tile[j][threadIdx.x] = rec[(size_t)s * ldt + t];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j;
+    const long long s = s0 + threadIdx.x;
+    if (s < nslot && t < nt) out[(size_t)t * nslot + s] = (T)tile[threadIdx.x][j];
+  }
+}
+
+static void appendf(std::string& s, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  s += buf;
+}
+
+}  // namespace fsr
+
+using namespace fsr;
+
+struct fsr_rdb {
+  fsr_part* part = nullptr;
+  FILE* f = nullptr;
+  std::string header, path;
+  RecLayout L{};
+  int dbl = 0;
+  long long nslot = 0;                 // values per step record
+  long long* roff[FAM_COUNT] = {};     // device: record slot of each family element (-1 = not written)
+  double* rec = nullptr;               // [nslot][tile] slot-major staging
+  void* out = nullptr;                 // [tile][nslot] float/double records
+  void* host = nullptr;                // pinned copy
+  int tile = 0;
+  long long steps_written = 0;
+  long long* node_slot = nullptr;      // device [nnod] record slot of each node's displacements (-1 = none)
+  int* madof = nullptr;                // device [nnod+1]
+  double* supTr0 = nullptr;            // device [12] initial part position (total displacements)
+  double* supTr = nullptr;             // device [tile][12]
+  ~fsr_rdb()
+  {
+    if (f) fclose(f);
+    for (auto& r : roff) cudaFree(r);
+    cudaFree(rec); cudaFree(out); cudaFree(node_slot); cudaFree(madof); cudaFree(supTr0); cudaFree(supTr);
+    if (host) cudaFreeHost(host);
+  }
+};
+
+namespace {
+
+// The three scratch files of rdbModule.f90 (ivard, iitem, idatd) as strings + the id bookkeeping of HeaderId
+struct HeaderBuilder {
+  std::string vard, item, datd;
+  int nvar = 0, nig = 0, nbit = 32;
+  int idSR1 = 0, idSR2 = 0, idSF1 = 0, idSF2 = 0, idStress[4] = {0, 0, 0, 0}, idStrain[4] = {0, 0, 0, 0}, idMeasure[8] = {};
+
+  void vardef(int& id, const char* name, const char* unit, const char* type, int n, const char* comps)
+  {
+    if (id) return;
+    id = ++nvar;   // format 601: '<',i3,';"',a,'";',a,';FLOAT;',i2,';',a,';(',i1,');((',a,'))>'
+    appendf(vard, "<%3d;\"%s\";%s;FLOAT;%2d;%s;(%1d);((%s))>\n", id, name, unit, nbit, type, n, comps);
+  }
+  void scalardef(int& id, const char* name, const char* unit)
+  {
+    if (id) return;
+    id = ++nvar;   // format 605
+    appendf(vard, "<%3d;\"%s\";%s;FLOAT;%2d;SCALAR>\n", id, name, unit, nbit);
+  }
+  void tensor(bool strain, int dim)
+  {
+    int& id = strain ? idStrain[dim] : idStress[dim];
+    const char* nm = strain ? "Strain" : "Stress";
+    const char* un = strain ? "NONE" : "FORCE/AREA";
+    if (dim == 2)
+      vardef(id, nm, un, "TENSOR2", 3, strain ? "\"epsilon_xx\",\"epsilon_yy\",\"epsilon_xy\"" : "\"sigma_xx\",\"sigma_yy\",\"sigma_xy\"");
+    else
+      vardef(id, nm, un, "TENSOR3", 6,
+             strain ? "\"epsilon_xx\",\"epsilon_yy\",\"epsilon_zz\",\"epsilon_xy\",\"epsilon_xz\",\"epsilon_yz\""
+                    : "\"sigma_xx\",\"sigma_yy\",\"sigma_zz\",\"sigma_xy\",\"sigma_xz\",\"sigma_yz\"");
+  }
+  // the per-point variable list shared by shells and solids (writeShellHeader :1048-1166, writeSolidHeader :1221-1330)
+  std::string point_vars(const RecLayout& L, int dim)
+  {
+    static const char* names[8] = {"Von Mises stress", "Max principal stress", "Min principal stress", "Max shear stress",
+                                   "Von Mises strain", "Max principal strain", "Min principal strain", "Max shear strain"};
+    std::string v;
+    if (L.stress) { tensor(false, dim); appendf(v, "<%3d>", idStress[dim]); }
+    if (L.strain) { tensor(true, dim); appendf(v, "<%3d>", idStrain[dim]); }
+    for (int j = 0; j < 8; ++j)
+      if (L.mask & (1 << j)) { scalardef(idMeasure[j], names[j], j < 4 ? "FORCE/AREA" : "NONE"); appendf(v, "<%3d>", idMeasure[j]); }
+    return v;
+  }
+  void node_lines(int n, const std::string& vars) { for (int i = 1; i <= n; ++i) appendf(item, "      [;%2d;%s]\n", i, vars.c_str()); }
+
+  int beam(const RecLayout& L)
+  {
+    const int ig = ++nig;
+    appendf(item, "[%3d;\"BEAM2\";\n", ig);
+    if (L.sr) {
+      vardef(idSF1, "Beam sectional force", "FORCE", "VEC3", 3, "\"N\",\"V_y\",\"V_z\"");
+      vardef(idSF2, "Beam sectional moment", "FORCE*LENGTH", "VEC3", 3, "\"M_x\",\"M_y\",\"M_z\"");
+      std::string v;
+      appendf(v, "<%3d><%3d>", idSF1, idSF2);
+      item += "  [;\"Element nodes\";\n    [;\"Basic\";\n";
+      node_lines(2, v);
+      item += "    ]\n  ]\n";
+    }
+    item += "]\n";
+    return ig;
+  }
+  int shell(const RecLayout& L, const char* type, int nelnod)
+  {
+    const int ig = ++nig;
+    appendf(item, "[%3d;\"%s\";\n  [;\"Element nodes\";\n", ig, type);
+    if (L.sr) {
+      vardef(idSR1, "Shell stress resultant force", "FORCE/LENGTH", "TENSOR2", 3, "\"n_xx\",\"n_yy\",\"n_xy\"");
+      vardef(idSR2, "Shell stress resultant moment", "FORCE*LENGTH/LENGTH", "TENSOR2", 3, "\"m_xx\",\"m_yy\",\"m_xy\"");
+      std::string v;
+      appendf(v, "<%3d><%3d>", idSR1, idSR2);
+      item += "    [;\"Basic\";\n";
+      node_lines(nelnod, v);
+      item += "    ]\n";
+    }
+    if (L.stress || L.strain || L.nsel) {
+      const std::string v = point_vars(L, nelnod > 4 ? 3 : 2);
+      for (const char* side : {"Top", "Bottom"}) {
+        appendf(item, "    [;\"%s\";\n", side);
+        node_lines(nelnod, v);
+        item += "    ]\n";
+      }
+    }
+    item += "  ]\n]\n";
+    return ig;
+  }
+  int solid(const RecLayout& L, const char* type, int nelnod)
+  {
+    const int ig = ++nig;
+    appendf(item, "[%3d;\"%s\";\n  [;\"Element nodes\";\n    [;\"Basic\";\n", ig, type);
+    node_lines(nelnod, point_vars(L, 3));
+    item += "    ]\n  ]\n]\n";
+    return ig;
+  }
+};
+
+// header text + record slot of every element (-1 = not written); returns the number of values per step
+static long long build_header(int nnod, const int* madof, int nel, const int* melcon, const int* active,
+                              const fsr_rdb_options* o, const RecLayout& L, std::string& header, std::vector<long long>& slot,
+                              std::vector<long long>& node_slot)
+{
+  HeaderBuilder hb;
+  hb.nbit = o->double_precision ? 64 : 32;
+  // openHeaderFiles (rdbModule.f90:191-251)
+  char host[96] = "unknown", date[32] = "";
+  gethostname(host, sizeof(host) - 1);
+  const char* user = getenv("USER");
+  time_t now = time(nullptr);
+  strftime(date, sizeof(date), "%d %b %Y %H:%M:%S", localtime(&now));
+  if (o->model_file) appendf(hb.vard, " AssociatedModelFileName = %s;\n", o->model_file);
+  if (o->link_file) appendf(hb.vard, " ModelName               = %s;\n", o->link_file);
+  hb.vard += " InformationText         = response data base file;\n";
+  appendf(hb.vard, " User                    = %s;\n", user ? user : "unknown");
+  appendf(hb.vard, " Computer                = %s;\n", host);
+  appendf(hb.vard, " DateTime                = %s;\n", date);
+  hb.vard += " UsedTime                = 00:00:00.00;\n";
+  appendf(hb.vard, " Module                  = %s;\n", o->module_name ? o->module_name : "fedem_stress");
+  hb.vard += " ModuleVersion           = B200 1.0;\nVARIABLES:\n";
+  // writeTimeStepHeader (rdbModule.f90:633-650)
+  hb.nvar = 2;
+  hb.vard += "<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n";
+  hb.datd = "DATABLOCKS:\n<1><2>\n";
+  // writeIdHeader('Part',sup%id,idatd,.true.) (idTypeModule.f90:103-143)
+  hb.datd += "{\"Part\";";
+  if (o->part_base_id > 0) appendf(hb.datd, "%d;", o->part_base_id); else hb.datd += ";";
+  if (o->part_user_id > 0) appendf(hb.datd, "%d;", o->part_user_id); else hb.datd += ";";
+  if (o->part_descr && *o->part_descr) appendf(hb.datd, "\"%s\";\n", o->part_descr); else hb.datd += ";\n";
+  long long nslot = 0;
+  node_slot.assign((size_t)std::max(nnod, 1), -1);
+  if (L.def) {   // writeNodesHeader (saveStressModule.f90:438-537), deformations as nodal data
+    int idDis[2] = {0, 0}, idRot[2] = {0, 0}, id3 = 0, id6 = 0;
+    const bool tot = L.def > 1;
+    hb.datd += "  [;\"Nodes\";\n";
+    for (int n = 0; n < nnod; ++n) {
+      const int nd = madof[n + 1] - madof[n];
+      if (nd < 3) continue;
+      hb.vardef(idDis[0], "Translational deformation", "LENGTH", "VEC3", 3, "\"d_x\",\"d_y\",\"d_z\"");
+      if (tot) hb.vardef(idDis[1], "Total translation", "LENGTH", "VEC3", 3, "\"u_x\",\"u_y\",\"u_z\"");
+      int ig = 0, nv = 0;
+      if (nd > 5) {
+        hb.vardef(idRot[0], "Angular deformation", "ANGLE", "ROT3", 3, "\"theta_x\",\"theta_y\",\"theta_z\"");
+        if (tot) hb.vardef(idRot[1], "Total rotation", "ANGLE", "ROT3", 3, "\"theta_x\",\"theta_y\",\"theta_z\"");
+        if (!id6) {
+          id6 = ++hb.nig;
+          if (tot) appendf(hb.item, "[%3d;\"Dynamic response\";<%3d><%3d><%3d><%3d>]\n", id6, idDis[0], idRot[0], idDis[1], idRot[1]);
+          else appendf(hb.item, "[%3d;\"Dynamic response\";<%3d><%3d>]\n", id6, idDis[0], idRot[0]);
+        }
+        ig = id6; nv = tot ? 12 : 6;
+      } else {
+        if (!id3) {
+          id3 = ++hb.nig;
+          if (tot) appendf(hb.item, "[%3d;\"Dynamic response\";<%3d><%3d>]\n", id3, idDis[0], idDis[1]);
+          else appendf(hb.item, "[%3d;\"Dynamic response\";<%3d>]\n", id3, idDis[0]);
+        }
+        ig = id3; nv = tot ? 6 : 3;
+      }
+      appendf(hb.datd, "    [;%8d;[%3d]]\n", o->minex ? o->minex[n] : n + 1, ig);
+      node_slot[(size_t)n] = nslot;
+      nslot += nv;
+    }
+    hb.datd += "  ]\n";
+  }
+  // writeElementsHeader (saveStressModule.f90:625-752) + the record slot of every element
+  slot.assign((size_t)std::max(nel, 1), -1);
+  int ig[64] = {};
+  const bool elements = L.sr || L.stress || L.strain || L.nsel;
+  if (elements) hb.datd += "  [;\"Elements\";\n";
+  if (!elements) nel = 0;
+  for (int e = 0; e < nel; ++e) {
+    const int elmno = o->elmid ? o->elmid[e] : e + 1;
+    if (elmno <= 0 || (active && !active[e])) continue;
+    const int t = melcon[e];
+    int nelnod = 0, ncmp = 0;
+    switch (t) {
+      case 11: if (!L.sr) continue; if (!ig[t]) ig[t] = hb.beam(L); nelnod = 2; break;
+      case 21: case 23: if (!ig[21]) ig[21] = hb.shell(L, "TRI3", 3); nelnod = 3; ncmp = 3; break;
+      case 22: case 24: if (!ig[22]) ig[22] = hb.shell(L, "QUAD4", 4); nelnod = 4; ncmp = 3; break;
+      case 41: if (!ig[t]) ig[t] = hb.solid(L, "TET10", 10); nelnod = 10; ncmp = 6; break;
+      case 43: if (!ig[t]) ig[t] = hb.solid(L, "HEX20", 20); nelnod = 20; ncmp = 6; break;
+      default: continue;   // element types without a stress operator in this library
+    }
+    const int key = t == 23 ? 21 : t == 24 ? 22 : t;
+    appendf(hb.datd, "    [;%8d;[%3d]]\n", elmno, ig[key]);
+    slot[(size_t)e] = nslot;
+    if (t == 11) nslot += 12;
+    else {
+      const int nstrp = ncmp == 3 ? 2 * nelnod : nelnod;
+      nslot += (L.sr && ncmp == 3 ? 6 * nelnod : 0) + (long long)nstrp * ((L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel);
+    }
+  }
+  if (elements) hb.datd += "  ]\n";
+  hb.datd += "}\n";
+  header = hb.vard + hb.item + hb.datd;
+  return nslot;
+}
+
+static int layout_from_options(const fsr_rdb_options* o, RecLayout& L)
+{
+  L = RecLayout{};
+  L.sr = (o->out_mask & FSR_OUT_SR) ? 1 : 0;
+  L.stress = (o->out_mask & FSR_OUT_STRESS) ? 1 : 0;
+  L.strain = (o->out_mask & FSR_OUT_STRAIN) ? 1 : 0;
+  L.mask = (int)(o->out_mask & 0xff);
+  for (int j = 0; j < 8; ++j) L.nsel += (L.mask >> j) & 1;
+  if (o->out_mask & FSR_OUT_DEFORMATION) L.def = o->sup_tr_init ? 3 : 1;
+  if (!(L.sr || L.stress || L.strain || L.nsel || L.def)) { set_error("no result output requested"); return FSR_ERR_ARG; }
+  return FSR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Host only: the header text and record size for a part given by its element type codes (SAM melcon) and
+// external element ids.  header may be NULL / cap 0 to query the length.  Returns the header length.
+int fsr_rdb_build_header(int nnod, const int* madof, int nel, const int* melcon, const fsr_rdb_options* o, char* header, int cap,
+                         long long* step_bytes)
+{
+  if (nel < 0 || !melcon || !o || ((o->out_mask & FSR_OUT_DEFORMATION) && (nnod < 0 || !madof))) { set_error("fsr_rdb_build_header: bad arguments"); return FSR_ERR_ARG; }
+  RecLayout L;
+  int rc = layout_from_options(o, L);
+  if (rc) return rc;
+  std::string h;
+  std::vector<long long> slot, node_slot;
+  const long long nslot = build_header(nnod, madof, nel, melcon, nullptr, o, L, h, slot, node_slot);
+  if (step_bytes) *step_bytes = 12 + nslot * (o->double_precision ? 8 : 4);
+  if (header && cap > 0) { strncpy(header, h.c_str(), (size_t)cap - 1); header[cap - 1] = 0; }
+  return (int)h.size();
+}
+
+int fsr_rdb_create(fsr_rdb** out, fsr_part* p, const char* path, const fsr_rdb_options* o)
+{
+  if (!out || !p || !path || !o) { set_error("fsr_rdb_create: bad arguments"); return FSR_ERR_ARG; }
+  *out = nullptr;
+  RecLayout L;
+  int rc0 = layout_from_options(o, L);
+  if (rc0) return rc0;
+  FSR_CUDA(cudaSetDevice(p->device));
+  std::string header;
+  std::vector<long long> slot, node_slot;
+  const long long nslot = build_header(p->nnod, p->madof_host.data(), p->nel, p->melcon_host.data(), p->active_host.data(), o, L,
+                                       header, slot, node_slot);
+  if (nslot == 0) { set_error("fsr_rdb_create: none of the active elements has the requested results"); return FSR_ERR_ARG; }
+
+  fsr_rdb* r = new fsr_rdb;
+  r->part = p; r->L = L; r->dbl = o->double_precision ? 1 : 0; r->nslot = nslot;
+  r->header = header;
+  // openRDBfile (rdbModule.f90:268-403): <name>_<rdbinc>.<ext>
+  r->path = path;
+  if (o->rdbinc > 0) {
+    const size_t dot = r->path.rfind('.');
+    const size_t sep = r->path.rfind('/');
+    char inc[16];
+    snprintf(inc, sizeof(inc), "_%d", o->rdbinc);
+    if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) r->path.insert(dot, inc);
+    else r->path += inc;
+  }
+  TaggedFile tf;
+  int rc = tf.open_write(r->path.c_str(), "#FEDEM response data", 0u);
+  if (rc) { delete r; return rc; }
+  if (fputs(r->header.c_str(), tf.f) < 0 || fputs("DATA:", tf.f) < 0) { set_error("%s: write error", r->path.c_str()); delete r; return FSR_ERR_ARG; }
+  r->f = tf.f;
+  tf.f = nullptr;
+  // per family: record slot of each of its elements
+  for (int fi = 0; fi < FAM_COUNT; ++fi) {
+    FamilyData& f = p->fam[fi];
+    if (f.nelt == 0) continue;
+    std::vector<int> elem((size_t)f.nelt);
+    if (cudaMemcpy(elem.data(), f.elem, sizeof(int) * f.nelt, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("fsr_rdb_create: cudaMemcpy failed"); delete r; return FSR_ERR_CUDA; }
+    std::vector<long long> ro((size_t)f.nelt);
+    for (int i = 0; i < f.nelt; ++i) ro[(size_t)i] = slot[(size_t)elem[(size_t)i]];
+    if (cudaMalloc(&r->roff[fi], sizeof(long long) * f.nelt) != cudaSuccess ||
+        cudaMemcpy(r->roff[fi], ro.data(), sizeof(long long) * f.nelt, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
+    }
+  }
+  if (L.def) {
+    if (cudaMalloc(&r->node_slot, sizeof(long long) * std::max(p->nnod, 1)) != cudaSuccess ||
+        cudaMalloc(&r->madof, sizeof(int) * (p->nnod + 1)) != cudaSuccess ||
+        cudaMemcpy(r->node_slot, node_slot.data(), sizeof(long long) * p->nnod, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(r->madof, p->madof_host.data(), sizeof(int) * (p->nnod + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
+    }
+    if (L.def > 1 && (cudaMalloc(&r->supTr0, sizeof(double) * 12) != cudaSuccess ||
+                      cudaMemcpy(r->supTr0, o->sup_tr_init, sizeof(double) * 12, cudaMemcpyHostToDevice) != cudaSuccess)) {
+      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
+    }
+  }
+  // step tile of the record buffers: bounded by the part's step tile and by ~1/4 of the free memory
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const double per_step = (double)nslot * (8.0 + (r->dbl ? 8.0 : 4.0));
+  long long tile = (long long)(0.25 * (double)free_b / per_step);
+  tile = std::max<long long>(1, std::min<long long>(tile, p->step_tile));
+  if (tile >= 32) tile = tile / 32 * 32;
+  r->tile = (int)tile;
+  const size_t vb = r->dbl ? 8 : 4;
+  if (cudaMalloc(&r->rec, sizeof(double) * (size_t)nslot * r->tile) != cudaSuccess ||
+      cudaMalloc(&r->out, vb * (size_t)nslot * r->tile) != cudaSuccess ||
+      cudaMallocHost(&r->host, vb * (size_t)nslot * r->tile) != cudaSuccess ||
+      (L.def > 1 && cudaMalloc(&r->supTr, sizeof(double) * 12 * r->tile) != cudaSuccess)) {
+    set_error("fsr_rdb_create: cannot allocate the record buffers (%lld values x %d steps)", nslot, r->tile);
+    delete r;
+    return FSR_ERR_ALLOC;
+  }
+  *out = r;
+  return FSR_OK;
+}
+
+long long fsr_rdb_step_bytes(const fsr_rdb* r) { return r ? 12 + r->nslot * (r->dbl ? 8 : 4) : 0; }
+
+int fsr_rdb_header(const fsr_rdb* r, char* buf, int cap)
+{
+  if (!r) return FSR_ERR_ARG;
+  if (buf && cap > 0) { strncpy(buf, r->header.c_str(), (size_t)cap - 1); buf[cap - 1] = 0; }
+  return (int)r->header.size();
+}
+
+int fsr_rdb_path(const fsr_rdb* r, char* buf, int cap)
+{
+  if (!r) return FSR_ERR_ARG;
+  if (buf && cap > 0) { strncpy(buf, r->path.c_str(), (size_t)cap - 1); buf[cap - 1] = 0; }
+  return (int)r->path.size();
+}
+
+int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const int* stepno, const double* time,
+                        const double* sup_tr)
+{
+  if (!r || !r->f || !Q || nsteps < 0 || !stepno || !time) { set_error("fsr_rdb_write_steps: bad arguments"); return FSR_ERR_ARG; }
+  if (r->L.def > 1 && !sup_tr) { set_error("fsr_rdb_write_steps: total displacements need the part position matrix of every step"); return FSR_ERR_ARG; }
+  fsr_part* p = r->part;
+  if (ldq < p->ndim) { set_error("fsr_rdb_write_steps: ldq < ndim"); return FSR_ERR_ARG; }
+  if (!p->have_R) { set_error("fsr_rdb_write_steps: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, false);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  double* dQ = nullptr;
+  const size_t vb = r->dbl ? 8 : 4;
+  for (int t0 = 0; t0 < nsteps; t0 += r->tile) {
+    const int nt = std::min(r->tile, nsteps - t0);
+    const int nt_pad = (nt + 63) / 64 * 64;
+    if (!dQ) FSR_CUDA(cudaMalloc(&dQ, sizeof(double) * (size_t)ldq * r->tile));
+    FSR_CUDA(cudaMemcpyAsync(dQ, Q + (size_t)t0 * ldq, sizeof(double) * (size_t)ldq * nt, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_pack_q(p, dQ, ldq, nt, nt_pad, s)) || (rc = launch_k1(p, nt_pad, s))) { cudaFree(dQ); return rc; }
+    const size_t ldt = (size_t)r->tile;
+    dim3 blk(32, 8);
+    if (r->L.def) {
+      if (r->L.def > 1) FSR_CUDA(cudaMemcpyAsync(r->supTr, sup_tr + (size_t)t0 * 12, sizeof(double) * 12 * nt, cudaMemcpyHostToDevice, s));
+      dim3 grd((p->nnod + 7) / 8, (nt + 31) / 32);
+      record_nodes_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, p->nnod, r->madof, r->node_slot, p->xyz, r->supTr,
+                                              r->supTr0, r->L.def > 1, r->rec, ldt);
+      ++g_launches;
+    }
+    for (int fi = 0; fi < FAM_COUNT; ++fi) {
+      FamilyData& f = p->fam[fi];
+      if (f.nelt == 0) continue;
+      if (fi == FAM_BEAM) {
+        if (!r->L.sr) continue;
+        dim3 grd((unsigned)(((long long)f.nelt * 12 + 7) / 8), (nt + 31) / 32);
+        record_beams_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, reinterpret_cast<const BeamOp12*>(f.Sfrag), f.edof,
+                                                r->roff[fi], f.failed, f.nelt, r->rec, ldt);
+      } else {
+        if (f.nstrp == 0) continue;
+        dim3 grd((unsigned)(((long long)f.nelt * f.nstrp + 7) / 8), (nt + 31) / 32);
+        const int layout = (fi == FAM_TET10 || fi == FAM_HEX20) ? 1 : 0;
+        record_points_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, f.Sfrag, f.edof, r->roff[fi], f.failed, f.aux,
+                                                 f.naux, f.nelt, f.nstrp, f.ncmp, f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod,
+                                                 r->L, r->rec, ldt);
+      }
+      ++g_launches;
+      if (cudaGetLastError() != cudaSuccess) { set_error("record kernel launch failed"); cudaFree(dQ); return FSR_ERR_CUDA; }
+    }
+    dim3 tb(32, 8), tg((unsigned)((r->nslot + 31) / 32), (nt + 31) / 32);
+    if (r->dbl) record_transpose_kernel<double><<<tg, tb, 0, s>>>(r->rec, ldt, r->nslot, nt, (double*)r->out);
+    else record_transpose_kernel<float><<<tg, tb, 0, s>>>(r->rec, ldt, r->nslot, nt, (float*)r->out);
+    ++g_launches;
+    if (cudaMemcpyAsync(r->host, r->out, vb * (size_t)r->nslot * nt, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("fsr_rdb_write_steps: %s", cudaGetErrorString(cudaGetLastError()));
+      cudaFree(dQ);
+      return FSR_ERR_CUDA;
+    }
+    for (int t = 0; t < nt; ++t) {
+      const int is = stepno[t0 + t];
+      const double tm = time[t0 + t];
+      if (fwrite(&is, 4, 1, r->f) != 1 || fwrite(&tm, 8, 1, r->f) != 1 ||
+          fwrite((const char*)r->host + vb * (size_t)r->nslot * t, vb, (size_t)r->nslot, r->f) != (size_t)r->nslot) {
+        set_error("%s: write error", r->path.c_str());
+        cudaFree(dQ);
+        return FSR_ERR_ARG;
+      }
+      ++r->steps_written;
+    }
+  }
+  cudaFree(dQ);
+  return FSR_OK;
+}
+
+void fsr_total_nodal_displacement(const double* x0, const double* u, int nd, const double* T, const double* T0, double* utot)
+{
+  total_nodal_displacement(x0, u, nd, T, T0, utot);
+}
+
+int fsr_rdb_close(fsr_rdb* r)
+{
+  if (!r) return FSR_ERR_ARG;
+  int rc = FSR_OK;
+  if (r->f && fclose(r->f) != 0) { set_error("%s: close error", r->path.c_str()); rc = FSR_ERR_ARG; }
+  r->f = nullptr;
+  delete r;
+  return rc;
+}
+
+}  // extern "C"

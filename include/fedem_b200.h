@@ -360,6 +360,52 @@ int fsr_ftl_get_elmdata(const fsr_ftl *ftl, double *emod, double *rny, double *r
                         double *beam, int *status);
 int fsr_ftl_ext2int(const fsr_ftl *ftl, int is_node, int id); /* ffl_ext2int (:716-737) */
 
+/* ---- stress results database (.frs), written from the GPU ------------------------------------------
+ * Replaces writeStressHeader (src/vpmStress/saveStressModule.f90:120-247, header grammar :625-1430) and the
+ * per-element writeStressDB / writeStrMeasureDB calls of calcStresses (stressRoutines.f90:234-310,
+ * saveStressModule.f90:1527-1633): the file has the reference's text header (meta data, VARIABLES:, item
+ * group definitions, DATABLOCKS: with the Part's "Elements" list) and, per time step, int32 step number +
+ * float64 time + [per node the 3 or 6 deformational (and total) displacements if FSR_OUT_DEFORMATION,
+ * writeDisplacementDB :1437-1515] + for every element in SAM order [SR(6,nenod) if FSR_OUT_SR] then per result point
+ * [stress][strain][selected measures], float32 unless double_precision.  fsr_rdb_write_steps recovers a
+ * whole window of steps on the device (K1 + record kernels) and appends their records.
+ * The file name gets the reference's "_<rdbinc>" suffix before the extension when rdbinc > 0
+ * (openRDBfile, src/vpmCommon/rdbModule.f90:305-322). */
+typedef struct fsr_rdb_options {
+  unsigned out_mask;      /* FSR_OUT_* bits: -SR -stress -strain -vmStress ... (stressmain.C:46-60)       */
+  int double_precision;   /* -double                                                                     */
+  int rdbinc;             /* -rdbinc                                                                     */
+  int part_base_id, part_user_id;
+  const char *part_descr; /* sup%id%descr (the link file name when there is no solver input file)        */
+  const char *model_file; /* AssociatedModelFileName, may be NULL                                        */
+  const char *link_file;  /* ModelName (-linkfile), may be NULL                                          */
+  const int *elmid;       /* [nel] external element ids as ffl_getelmid (< 1: skipped); NULL = 1..nel    */
+  const char *module_name;/* NULL = "fedem_stress"                                                       */
+  const int *minex;       /* [nnod] external node ids (FSR_OUT_DEFORMATION); NULL = 1..nnod              */
+  const double *sup_tr_init; /* [12] column-major 3x4 initial position of the part (sup%supTrInit): with
+                             FSR_OUT_DEFORMATION also the total displacements are written, as the current
+                             reference does (iDef = 3, stress.f90:292; calcTotalNodalDisplacement,
+                             displacementModule.f90:1694-1745); NULL = deformational displacements only   */
+} fsr_rdb_options;
+typedef struct fsr_rdb fsr_rdb;
+int fsr_rdb_create(fsr_rdb **rdb, fsr_part *part, const char *path, const fsr_rdb_options *opt);
+/* host only: the header text and the bytes per step for a part given by its SAM element type codes (melcon)
+ * and opt->elmid; header may be NULL to query the length, which is returned */
+int fsr_rdb_build_header(int nnod, const int *madof, int nel, const int *melcon, const fsr_rdb_options *opt,
+                         char *header, int cap, long long *step_bytes);
+long long fsr_rdb_step_bytes(const fsr_rdb *rdb);            /* bytes per time step incl. the 12-byte key */
+int fsr_rdb_header(const fsr_rdb *rdb, char *buf, int cap);  /* the text header; returns its length      */
+int fsr_rdb_path(const fsr_rdb *rdb, char *buf, int cap);    /* the actual file name                     */
+/* sup_tr [nsteps][12]: column-major 3x4 position matrix of the part at every step; only read when the
+ * total displacements are written (opt->sup_tr_init given), else may be NULL */
+int fsr_rdb_write_steps(fsr_rdb *rdb, const double *Q, int ldq, int nsteps, const int *stepno,
+                        const double *time, const double *sup_tr);
+/* calcTotalNodalDisplacement for one node on the host (the same code the record kernel runs): x0[3], u[nd],
+ * nd = 3 or 6, T / T0 = current / initial 3x4 position matrices; utot[nd] */
+void fsr_total_nodal_displacement(const double *x0, const double *u, int nd, const double *T, const double *T0,
+                                  double *utot);
+int fsr_rdb_close(fsr_rdb *rdb);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);
 /* Number of kernels this library launched since the counter was last reset (bench evidence). */

@@ -158,8 +158,8 @@ int orc_result_point_offsets(const orc_sam *sam, const int *elmid, int *off)
  * resmat : [8 x npts] column-major per point: vmStress, maxP, minP, maxShear (stress), then
  *          the same four for strain (stressRoutines.f90:273-287); hugeVal for failed elements.
  * stress/strain : [6 x npts] (ncmp leading entries used), may be NULL.
- * sres   : [12 x nel] stress resultants / beam section forces SR(6, <=2 nodes stored: the
- *          first two nodes), may be NULL.
+ * sres   : [24 x nel] stress resultants SR(6, node 1..4) of the thin shells / beam section forces
+ *          SF(6,2), may be NULL.
  * Returns number of failed elements. */
 int orc_calc_stresses(const orc_sam *sam, const orc_elmdata *ed, const double *sv,
                       const int *ptoff, double *resmat, double *stress, double *strain,
@@ -182,7 +182,7 @@ int orc_calc_stresses(const orc_sam *sam, const orc_elmdata *ed, const double *s
     if (lerr > 0)
       lerr = orc_el_stress(iel, t, sam, ed, EV, SR, Stress, Strain, &nenod, &nstrp);
     if (sres && nenod > 0)
-      for (int k = 0; k < 12; k++) sres[(size_t)12 * (iel - 1) + k] = lerr > 0 ? ORC_HUGE : SR[k];
+      for (int k = 0; k < 24; k++) sres[(size_t)24 * (iel - 1) + k] = lerr > 0 ? ORC_HUGE : SR[k];
     if (ncmp > 0 && nstrp > 0) {
       int p0 = ptoff[iel - 1];
       if (lerr > 0) {

@@ -125,7 +125,7 @@ class Oracle:
         s = b["part"].sam
         npts = max(b["npts"], 1)
         out = dict(resmat=np.zeros((npts, 8), F64), stress=np.zeros((npts, 6), F64),
-                   strain=np.zeros((npts, 6), F64), sres=np.zeros((s.nel, 12), F64))
+                   strain=np.zeros((npts, 6), F64), sres=np.zeros((s.nel, 24), F64))
         sv = np.ascontiguousarray(sv, F64)
         out["nfail"] = self.lib.orc_calc_stresses(C.byref(b["sam"]), C.byref(b["elm"]), _dp(sv), _ip(b["ptoff"]),
                                                   _dp(out["resmat"]), _dp(out["stress"]), _dp(out["strain"]),

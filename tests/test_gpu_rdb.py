@@ -1,0 +1,181 @@
+"""GPU parity of the stress results database written from the device (csrc/io_rdb.cu): the file is read back
+through the product's .frs reader and (when built) the reference's own FFrLib, and every value is compared with
+the CPU oracle's calcStresses of the same step: <= 1e-10 relative in -double files, float32 rounding of the
+oracle's value otherwise."""
+import os
+import numpy as np
+import pytest
+
+from fedem_solvers_b200 import StressRecovery
+from fedem_solvers_b200.frs import FrsReader
+from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, reduced_history
+from fedem_solvers_b200.rdb import StressRdb, out_mask
+from test_rdb_cpu import NAMES, NENOD, MEASURES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import oracle_bind
+    return oracle_bind.Oracle()
+
+
+def _close(a, b, scale, double):
+    if double:
+        return np.abs(a - b).max() <= TOL * scale
+    # float file: the stored value is the float32 rounding of a double within TOL of the oracle's
+    return np.abs(a - b).max() <= 1.3e-7 * scale
+
+
+def _check(oracle, part, tmp_path, mask, double, nsteps, total=False, step_tile=0, rdbinc=2):
+    b = oracle.bind_part(part)
+    sam = part.sam
+    Q = reduced_history(sam.ndim, nsteps, seed=4)
+    rng = np.random.default_rng(3)
+    rec = StressRecovery(part, step_tile=step_tile)
+    stepno = np.arange(10, 10 + nsteps)
+    time = 0.01 * stepno
+    sup_tr = tr0 = None
+    if total:
+        from scipy.spatial.transform import Rotation
+        tr0 = np.hstack([Rotation.from_rotvec([0.1, -0.2, 0.3]).as_matrix(), [[1.0], [2.0], [3.0]]])
+        sup_tr = np.stack([np.hstack([Rotation.from_rotvec(rng.normal(0, 0.5, 3)).as_matrix(), rng.normal(0, 1, (3, 1))])
+                           for _ in range(nsteps)])
+    path = str(tmp_path / "part_stress.frs")
+    with StressRdb(rec, path, mask, double=double, rdbinc=rdbinc, base_id=21, user_id=3, descr=part.name,
+                   link_file=part.name + ".ftl", elmid=part.elm.elmid, minex=sam.minex, sup_tr_init=tr0) as rdb:
+        assert rdb.path.endswith(f"part_stress_{rdbinc}.frs")
+        half = nsteps // 2   # two calls: records append
+        rdb.write_steps(Q[:, :half], stepno[:half], time[:half], None if sup_tr is None else sup_tr[:half])
+        rdb.write_steps(Q[:, half:], stepno[half:], time[half:], None if sup_tr is None else sup_tr[half:])
+        step_bytes, out_path = rdb.step_bytes, rdb.path
+    raw = open(out_path, "rb").read()
+    hsize = raw.find(b"\nDATA:") + 6
+    assert len(raw) - hsize == nsteps * step_bytes
+    rd = FrsReader(out_path)
+    assert rd.nsteps == nsteps and np.array_equal(rd.step_numbers, stepno) and np.allclose(rd.times, time, rtol=0, atol=0)
+    ref = None
+    try:
+        from test_frs_cpu import RefFrs, REF_LIB
+        if os.path.exists(REF_LIB):
+            ref = RefFrs([out_path])
+    except Exception:
+        ref = None
+    # the oracle's results of every step
+    o = []
+    for s in range(nsteps):
+        sv = oracle.expand(b, Q[:, s])
+        r = oracle.calc_stresses(b, sv)
+        r["sv"] = sv
+        o.append(r)
+    ptoff = b["ptoff"]
+    sel = [j for j in range(8) if mask & (1 << j)]
+    sr_on, st_on, sn_on, def_on = bool(mask & 0x400), bool(mask & 0x100), bool(mask & 0x200), bool(mask & 0x800)
+    scale = {k: max(np.abs(np.stack([x[k] for x in o])).max(), 1e-300) for k in ("stress", "strain", "sv")}
+    shells = np.nonzero(sam.melcon > 20)[0]
+    if len(shells) and sam.melcon[shells[0]] < 30:
+        allsr = np.stack([x["sres"][shells] for x in o]).reshape(nsteps, len(shells), 4, 6)
+        scale["srf"], scale["srm"] = np.abs(allsr[..., :3]).max(), np.abs(allsr[..., 3:]).max()
+    n_checked = 0
+
+    def check(p, want, sc):
+        nonlocal n_checked
+        h = rd.find(p, "Part", 21)
+        assert h is not None, p
+        got = rd.read(h)
+        assert got.shape == want.shape, p
+        assert _close(got, want, sc, double), (p, np.abs(got - want).max(), sc)
+        if ref is not None and n_checked % 7 == 0:
+            ok, g2 = ref.read(p, "Part", 21, ref.keys(), want.shape[1])
+            assert ok == nsteps and np.array_equal(g2, got), p
+        n_checked += 1
+
+    elems = list(range(sam.nel))
+    if sam.nel > 60:
+        elems = sorted(set(rng.choice(sam.nel, 50, replace=False)) | {0, sam.nel - 1} | set(np.nonzero(sam.melcon == 11)[0][:5]))
+    for e in elems:
+        t = int(sam.melcon[e])
+        if part.elm.elmid is not None and part.elm.elmid[e] <= 0:
+            assert rd.find(f"Elements|{abs(part.elm.elmid[e])}|{NAMES[t]}|Element nodes|Basic|1|Stress", "Part", 21) is None
+            continue
+        p = f"Elements|{part.elm.elmid[e]}|{NAMES[t]}|Element nodes|"
+        nn = NENOD[t]
+        if t == 11:
+            if sr_on:
+                sf = np.stack([x["sres"][e, :12] for x in o])     # [nsteps, 12]
+                for n in range(2):
+                    check(p + f"Basic|{n + 1}|Beam sectional force", sf[:, 6 * n:6 * n + 3], np.abs(sf[:, 0::6]).max() + np.abs(sf[:, :3]).max())
+                    check(p + f"Basic|{n + 1}|Beam sectional moment", sf[:, 6 * n + 3:6 * n + 6], np.abs(sf[:, 3:6]).max() + np.abs(sf[:, 9:]).max())
+            continue
+        shell = t < 30
+        ncmp = 3 if shell else 6
+        sides = ("Top", "Bottom") if shell else ("Basic",)
+        if shell and sr_on:
+            sr = np.stack([x["sres"][e] for x in o])      # [nsteps, 24] = SR(6, node)
+            for n in range(nn):
+                check(p + f"Basic|{n + 1}|Shell stress resultant force", sr[:, 6 * n:6 * n + 3], scale["srf"])
+                check(p + f"Basic|{n + 1}|Shell stress resultant moment", sr[:, 6 * n + 3:6 * n + 6], scale["srm"])
+        for si, side in enumerate(sides):
+            for n in (0, nn - 1):
+                pt = ptoff[e] + si * nn + n
+                q = p + f"{side}|{n + 1}|"
+                if st_on:
+                    check(q + "Stress", np.stack([x["stress"][pt, :ncmp] for x in o]), scale["stress"])
+                if sn_on:
+                    check(q + "Strain", np.stack([x["strain"][pt, :ncmp] for x in o]), scale["strain"])
+                for j in sel:
+                    # principal values: trigonometric cubic, 1e-9
+                    sc = (scale["stress"] if j < 4 else scale["strain"]) * (1.0 if j in (0, 4) or shell else 10.0)
+                    check(q + MEASURES[j], np.stack([x["resmat"][pt, j:j + 1] for x in o]), sc)
+    if def_on:
+        from oracle_bind import _dp
+        import ctypes as C
+        for n in sorted(set(rng.choice(sam.nnod, min(sam.nnod, 25), replace=False)) | {0, sam.nnod - 1}):
+            j0, nd = sam.madof[n] - 1, sam.madof[n + 1] - sam.madof[n]
+            p = f"Nodes|{sam.minex[n]}|Dynamic response|"
+            u = np.stack([x["sv"][j0:j0 + nd] for x in o])
+            check(p + "Translational deformation", u[:, :3], scale["sv"])
+            if nd > 5:
+                check(p + "Angular deformation", u[:, 3:6], scale["sv"])
+            if total:
+                ut = np.zeros((nsteps, 6))
+                for s in range(nsteps):
+                    x0 = np.ascontiguousarray(part.elm.xyz[n])
+                    oracle.lib.orc_total_nodal_displacement(_dp(x0), _dp(np.ascontiguousarray(u[s])), 6 if nd > 5 else 3,
+                                                            _dp(np.ascontiguousarray(sup_tr[s].T.ravel())),
+                                                            _dp(np.ascontiguousarray(tr0.T.ravel())), _dp(ut[s]))
+                check(p + "Total translation", ut[:, :3], np.abs(ut[:, :3]).max())
+                if nd > 5:
+                    check(p + "Total rotation", ut[:, 3:], np.abs(ut[:, 3:]).max())
+    assert n_checked > 10
+    if ref is not None:
+        ref.close()
+    rec.close()
+    return n_checked
+
+
+def test_plate_von_mises_float_file(oracle, tmp_path):
+    part = plate_part(9, 8, ngen=6, seed=2, tri_fraction=0.3, warp=0.02)
+    _check(oracle, part, tmp_path, out_mask(vmStress=True), False, nsteps=11)
+
+
+def test_plate_everything_double_with_total_displacements(oracle, tmp_path):
+    part = plate_part(7, 6, ngen=5, seed=3, tri_fraction=0.5, warp=0.02)
+    part.elm.elmid = part.elm.elmid.copy()
+    part.elm.elmid[[3, 17]] *= -1     # outside the -group selection: absent from the file
+    mask = out_mask(SR=True, stress=True, strain=True, vmStress=True, maxPStress=True, minPStress=True, maxSStress=True,
+                    vmStrain=True, maxPStrain=True, minPStrain=True, maxSStrain=True, deformation=True)
+    _check(oracle, part, tmp_path, mask, True, nsteps=9, total=True)
+
+
+def test_tets_and_beams_multi_tile(oracle, tmp_path):
+    part = tet10_block(3, 2, 2, ngen=6, seed=5, n_beams=7)
+    mask = out_mask(SR=True, stress=True, vmStress=True, maxPStress=True, deformation=True)
+    _check(oracle, part, tmp_path, mask, True, nsteps=150, step_tile=64)   # 3 record tiles, the last one ragged
+
+
+def test_hex20_strain_measures_float(oracle, tmp_path):
+    part = hex20_block(2, 2, 1, ngen=4, seed=6)
+    _check(oracle, part, tmp_path, out_mask(strain=True, vmStrain=True, maxSStrain=True), False, nsteps=5)
