@@ -48,6 +48,16 @@ module fedem_b200_mod
      real(c_double) :: sncurve(4)
   end type fsr_rosette
 
+  !> struct fsr_rdb_options: what writeStressHeader takes from the command line and from sup%id
+  type, bind(C) :: fsr_rdb_options
+     integer(c_int) :: out_mask, double_precision, rdbinc, part_base_id, part_user_id
+     type(c_ptr)    :: part_descr, model_file, link_file   !< NUL-terminated C strings (c_loc of a c_char array)
+     type(c_ptr)    :: elmid                               !< integer(c_int) elmid(nel)
+     type(c_ptr)    :: module_name
+     type(c_ptr)    :: minex                               !< integer(c_int) minex(nnod)
+     type(c_ptr)    :: sup_tr_init                         !< real(c_double) supTrInit(3,4)
+  end type fsr_rdb_options
+
   interface
 
      ! ---- life cycle ----------------------------------------------------------------------
@@ -493,6 +503,139 @@ module fedem_b200_mod
        type(c_ptr), value :: w
        integer(c_int) :: ierr
      end function fsr_frs_finish
+
+     ! ---- FE part file (.ftl): replaces ffl_init + the per-element ffl_get* calls -------------
+     function fsr_ftl_open (ftl, path) bind(C,name="fsr_ftl_open") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr)           , intent(out) :: ftl
+       character(kind=c_char), intent(in)  :: path(*)
+       integer(c_int) :: ierr
+     end function fsr_ftl_open
+
+     subroutine fsr_ftl_close (ftl) bind(C,name="fsr_ftl_close")
+       import :: c_ptr
+       type(c_ptr), value :: ftl
+     end subroutine fsr_ftl_close
+
+     function fsr_ftl_version (ftl) bind(C,name="fsr_ftl_version") result(iver)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: ftl
+       integer(c_int) :: iver
+     end function fsr_ftl_version
+
+     function fsr_ftl_activate_groups (ftl, groups) bind(C,name="fsr_ftl_activate_groups") result(nignored)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr)           , value      :: ftl
+       character(kind=c_char), intent(in) :: groups(*)
+       integer(c_int) :: nignored
+     end function fsr_ftl_activate_groups
+
+     function fsr_ftl_sizes (ftl, sz) bind(C,name="fsr_ftl_sizes") result(nael)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value       :: ftl
+       integer(c_int), intent(out) :: sz(12)
+       integer(c_int) :: nael
+     end function fsr_ftl_sizes
+
+     function fsr_ftl_get_nodes (ftl, madof, minex, mnode, msc, xyz) bind(C,name="fsr_ftl_get_nodes") result(nnod)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: ftl
+       integer(c_int), intent(out) :: madof(*), minex(*), mnode(*), msc(*)
+       real(c_double), intent(out) :: xyz(3,*)
+       integer(c_int) :: nnod
+     end function fsr_ftl_get_nodes
+
+     function fsr_ftl_get_topology (ftl, use_andes, melcon, mpmnpc, mmnpc) bind(C,name="fsr_ftl_get_topology") result(nel)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value       :: ftl
+       integer(c_int), value       :: use_andes
+       integer(c_int), intent(out) :: melcon(*), mpmnpc(*), mmnpc(*)
+       integer(c_int) :: nel
+     end function fsr_ftl_get_topology
+
+     function fsr_ftl_get_elmdata (ftl, emod, rny, rho, thk, elmid, beam, status) &
+          &                       bind(C,name="fsr_ftl_get_elmdata") result(nbad)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: ftl
+       real(c_double), intent(out) :: emod(*), rny(*), rho(*), thk(*), beam(32,*)
+       integer(c_int), intent(out) :: elmid(*), status(*)
+       integer(c_int) :: nbad
+     end function fsr_ftl_get_elmdata
+
+     function fsr_ftl_ext2int (ftl, is_node, id) bind(C,name="fsr_ftl_ext2int") result(intid)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value :: ftl
+       integer(c_int), value :: is_node, id
+       integer(c_int) :: intid
+     end function fsr_ftl_ext2int
+
+     ! ---- stress results database: replaces writeStressHeader + writeStressDB/writeStrMeasureDB ----
+     function fsr_rdb_create (rdb, part, path, opt) bind(C,name="fsr_rdb_create") result(ierr)
+       import :: c_ptr, c_char, c_int, fsr_rdb_options
+       type(c_ptr)           , intent(out) :: rdb
+       type(c_ptr)           , value       :: part
+       character(kind=c_char), intent(in)  :: path(*)
+       type(fsr_rdb_options) , intent(in)  :: opt
+       integer(c_int) :: ierr
+     end function fsr_rdb_create
+
+     function fsr_rdb_build_header (nnod, madof, nel, melcon, opt, header, cap, step_bytes) &
+          &                        bind(C,name="fsr_rdb_build_header") result(nchar)
+       import :: c_ptr, c_char, c_int, c_long_long, fsr_rdb_options
+       integer(c_int)        , value       :: nnod, nel, cap
+       integer(c_int)        , intent(in)  :: madof(*), melcon(*)
+       type(fsr_rdb_options) , intent(in)  :: opt
+       character(kind=c_char), intent(out) :: header(*)
+       integer(c_long_long)  , intent(out) :: step_bytes
+       integer(c_int) :: nchar
+     end function fsr_rdb_build_header
+
+     function fsr_rdb_step_bytes (rdb) bind(C,name="fsr_rdb_step_bytes") result(nbytes)
+       import :: c_ptr, c_long_long
+       type(c_ptr), value :: rdb
+       integer(c_long_long) :: nbytes
+     end function fsr_rdb_step_bytes
+
+     function fsr_rdb_header (rdb, buf, cap) bind(C,name="fsr_rdb_header") result(nchar)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr)           , value       :: rdb
+       character(kind=c_char), intent(out) :: buf(*)
+       integer(c_int)        , value       :: cap
+       integer(c_int) :: nchar
+     end function fsr_rdb_header
+
+     function fsr_rdb_path (rdb, buf, cap) bind(C,name="fsr_rdb_path") result(nchar)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr)           , value       :: rdb
+       character(kind=c_char), intent(out) :: buf(*)
+       integer(c_int)        , value       :: cap
+       integer(c_int) :: nchar
+     end function fsr_rdb_path
+
+     !> Q(ldq,nsteps) = [finit; vg] of every step of the window, supTr(3,4,nsteps) (only read when the
+     !> total displacements are written)
+     function fsr_rdb_write_steps (rdb, Q, ldq, nsteps, stepno, time, supTr) &
+          &                       bind(C,name="fsr_rdb_write_steps") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: rdb
+       real(c_double), intent(in) :: Q(ldq,*), time(*), supTr(3,4,*)
+       integer(c_int), value      :: ldq, nsteps
+       integer(c_int), intent(in) :: stepno(*)
+       integer(c_int) :: ierr
+     end function fsr_rdb_write_steps
+
+     subroutine fsr_total_nodal_displacement (x0, u, nd, T, T0, utot) bind(C,name="fsr_total_nodal_displacement")
+       import :: c_int, c_double
+       real(c_double), intent(in)  :: x0(3), u(*), T(3,4), T0(3,4)
+       integer(c_int), value       :: nd
+       real(c_double), intent(out) :: utot(*)
+     end subroutine fsr_total_nodal_displacement
+
+     function fsr_rdb_close (rdb) bind(C,name="fsr_rdb_close") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: rdb
+       integer(c_int) :: ierr
+     end function fsr_rdb_close
 
      ! ---- diagnostics ------------------------------------------------------------------------
      function fsr_last_error () bind(C,name="fsr_last_error") result(msg)
