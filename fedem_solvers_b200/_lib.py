@@ -122,6 +122,10 @@ SYMBOLS = [
     ("fsr_ftl_get_topology", C.c_int, [_P, C.c_int, _I, _I, _I]),
     ("fsr_ftl_get_elmdata", C.c_int, [_P, _D, _D, _D, _D, _I, _D, _I]),
     ("fsr_ftl_ext2int", C.c_int, [_P, C.c_int, C.c_int]),
+    ("fsr_fsi_open", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
+    ("fsr_fsi_close", None, [_P]),
+    ("fsr_fsi_part", C.c_int, [_P, _I, C.c_char_p, C.c_int, _I, _I, _D, _D, C.c_char_p, C.c_int]),
+    ("fsr_fsi_triads", C.c_int, [_P, _I, _I, _I, _I, _D, _D]),
     ("fsr_rdb_create", C.c_int, [C.POINTER(_P), _P, C.c_char_p, C.POINTER(FsrRdbOptions)]),
     ("fsr_rdb_build_header", C.c_int, [C.c_int, _I, C.c_int, _I, C.POINTER(FsrRdbOptions), C.c_char_p, C.c_int, C.POINTER(C.c_longlong)]),
     ("fsr_rdb_step_bytes", C.c_longlong, [_P]),
@@ -130,6 +134,22 @@ SYMBOLS = [
     ("fsr_rdb_write_steps", C.c_int, [_P, _D, C.c_int, C.c_int, _I, _D, _D]),
     ("fsr_total_nodal_displacement", None, [_D, _D, C.c_int, _D, _D, _D]),
     ("fsr_rdb_close", C.c_int, [_P]),
+    ("initSolverArgs", None, [C.c_int, C.POINTER(C.c_char_p)]),
+    ("solveStress", C.c_int, []),
+    ("fsr_select_steps", C.c_int, [_D, C.c_int, C.c_double, C.c_double, C.c_double, _I, C.c_int]),
+    ("fsr_cmdline_reset", None, []),
+    ("fsr_stress_define_options", None, []),
+    ("fsr_cmdline_add_bool", None, [C.c_char_p, C.c_int]),
+    ("fsr_cmdline_add_int", None, [C.c_char_p, C.c_int]),
+    ("fsr_cmdline_add_double", None, [C.c_char_p, C.c_double]),
+    ("fsr_cmdline_add_string", None, [C.c_char_p, C.c_char_p]),
+    ("fsr_cmdline_init", None, [C.c_int, C.POINTER(C.c_char_p)]),
+    ("fsr_cmdline_read_file", C.c_int, [C.c_char_p]),
+    ("fsr_cmdline_get_bool", C.c_int, [C.c_char_p]),
+    ("fsr_cmdline_get_int", C.c_int, [C.c_char_p]),
+    ("fsr_cmdline_get_double", C.c_double, [C.c_char_p]),
+    ("fsr_cmdline_get_string", C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
+    ("fsr_cmdline_is_set", C.c_int, [C.c_char_p]),
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),

@@ -1,0 +1,435 @@
+// stress_driver.cu -- the fedem_stress program flow on top of the library's own entry points (host code).
+//
+// Reference: main() of src/vpmStress/stressmain.C:16-83 (the option table), initSolverArgs / solveStress
+// (src/vpmStress/stressInterface.C:86-116 -> cmdLineArgInit, readOptionFiles) and subroutine stress
+// (src/vpmStress/stress.f90:17-493).  The reference walks the time steps one by one (readSupElDisplacements,
+// calcIntDisplacements, calcStresses, a few hundred small fwrites per step); here the time steps selected by
+// -statm/-stotm/-tinc are collected first (ffr_getnextstep semantics), their reduced displacements are read
+// and assembled in windows (readSupElDisplacements + BuildFinit batched), and each window makes one trip to the
+// GPU (K1 expansion + record kernels) from which the finished .frs records come back.
+//
+// Exported with the reference's names so that the same launcher / fedempy code can drive it:
+//   initSolverArgs(argc, argv), solveStress().
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <unistd.h>
+#include <vector>
+
+#include "cmdline.hpp"
+#include "common.cuh"
+
+using namespace fsr;
+
+namespace {
+
+CmdLine g_cmd;
+bool g_stress_options_defined = false;
+
+std::string strip_ext_add(const std::string& link, const char* suffix)
+{
+  if (link.empty()) return std::string("fedem") + suffix;
+  const size_t dot = link.rfind('.');
+  return (dot == std::string::npos ? link : link.substr(0, dot)) + suffix;
+}
+
+// getFileName (src/vpmStress/displacementModule.f90:87-117)
+std::string file_name(const char* option, const char* suffix)
+{
+  std::string name = g_cmd.get_string(option);
+  if (name.empty() && suffix) name = strip_ext_add(g_cmd.get_string("linkfile"), suffix);
+  return name;
+}
+
+// FFaTokenizer(files,'<','>',','): "<a,b,c>" -> a b c
+std::vector<std::string> file_list(const std::string& s)
+{
+  std::vector<std::string> out;
+  if (s.empty()) return out;
+  if (s[0] != '<') { out.push_back(s); return out; }
+  std::string tok;
+  for (size_t i = 1; i < s.size() && s[i] != '>'; ++i) {
+    if (s[i] == ',') { if (!tok.empty()) out.push_back(tok); tok.clear(); }
+    else if (!isspace((unsigned char)s[i]) && s[i] != '"') tok += s[i];
+  }
+  if (!tok.empty()) out.push_back(tok);
+  return out;
+}
+
+struct Log {
+  FILE* f = nullptr;
+  clock_t t0 = clock();
+  void open(const std::string& path, const char* heading)
+  {
+    f = fopen(path.c_str(), "w");
+    if (f) fprintf(f, "\n     %s (B200)\n\n", heading);
+  }
+  void line(const char* fmt, ...)
+  {
+    va_list ap;
+    va_start(ap, fmt);
+    if (f) { va_list cp; va_copy(cp, ap); vfprintf(f, fmt, cp); va_end(cp); fputc('\n', f); }
+    vprintf(fmt, ap);
+    putchar('\n');
+    va_end(ap);
+  }
+  ~Log() { if (f) fclose(f); }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ffr_getnextstep over a sorted key list (fedem-foundation/src/FFrLib/FFrExtractorInterface.f90:134-170,
+// ffr_setposition = first key >= wanted - FLT_EPSILON, clamped to the ends, FFrResultContainer.C:953-1010):
+// the indices of the time steps the stress loop visits.  Returns their number (out may be NULL).
+int fsr_select_steps(const double* times, int n, double start, double stop, double tinc, int* out, int cap)
+{
+  if (n < 0 || (n > 0 && !times)) { set_error("fsr_select_steps: bad arguments"); return FSR_ERR_ARG; }
+  const double tol = 1.0e-12, huge = 1.7976931348623157e308, feps = 1.1920928955078125e-07;
+  auto position = [&](double wanted) -> int {
+    if (n == 0) return -1;
+    if (times[0] > wanted) return 0;
+    if (wanted > times[n - 1]) return n - 1;
+    return (int)(std::upper_bound(times, times + n, wanted - feps) - times);
+  };
+  int count = 0, idx = -1;
+  double curr = start - 1.0, last = -huge;
+  for (;;) {
+    if (curr > stop - tol) break;
+    if (curr < start - tol) {
+      idx = position(start);
+      if (idx >= 0) { curr = times[idx]; start = curr; }
+      last = -huge;
+    } else if (tinc < tol) {
+      idx = idx + 1 < n ? idx + 1 : -1;
+      if (idx >= 0) curr = times[idx];
+    } else {
+      idx = position(curr + tinc);
+      if (idx >= 0) curr = times[idx];
+    }
+    const bool ok = curr < stop + tol && idx >= 0 && curr > last + tol;
+    last = curr;
+    if (!ok) break;
+    if (out && count < cap) out[count] = idx;
+    ++count;
+  }
+  return count;
+}
+
+// ---- the option parser behind a C face (tests compare it with the reference's FFaCmdLineArg) -------------
+void fsr_cmdline_reset(void) { g_cmd = CmdLine(); g_stress_options_defined = false; }
+void fsr_cmdline_add_bool(const char* n, int v) { g_cmd.add(n, v != 0, ""); }
+void fsr_cmdline_add_int(const char* n, int v) { g_cmd.add(n, v, ""); }
+void fsr_cmdline_add_double(const char* n, double v) { g_cmd.add(n, v, ""); }
+void fsr_cmdline_add_string(const char* n, const char* v) { g_cmd.add(n, v, ""); }
+void fsr_cmdline_init(int argc, char** argv) { g_cmd.init(argc, argv); }
+int fsr_cmdline_read_file(const char* path) { return g_cmd.read_options_file(path) ? 1 : 0; }
+int fsr_cmdline_get_bool(const char* n) { return g_cmd.get_bool(n) ? 1 : 0; }
+int fsr_cmdline_get_int(const char* n) { return g_cmd.get_int(n); }
+double fsr_cmdline_get_double(const char* n) { return g_cmd.get_double(n); }
+int fsr_cmdline_get_string(const char* n, char* out, int cap)
+{
+  const std::string s = g_cmd.get_string(n);
+  if (out && cap > 0) { strncpy(out, s.c_str(), (size_t)cap - 1); out[cap - 1] = 0; }
+  return (int)s.size();
+}
+int fsr_cmdline_is_set(const char* n) { return g_cmd.is_set(n) ? 1 : 0; }
+
+// The option table of fedem_stress: cmdLineArgInitStd + cmdLineArgInit (src/vpmCommon/cmdLineArgInitStd.C:72-90,
+// cmdLineArgInit.C:109-113) and stressmain.C:22-79, same names, defaults and help texts' meaning.
+void fsr_stress_define_options(void)
+{
+  CmdLine& c = g_cmd;
+  c.add("fao", "", "Read additional options from this file");
+  c.add("fco", "", "Read calculation options from this file");
+  c.add("fop", "", "Read output options from this file");
+  c.add("cwd", "", "Change working directory");
+  c.add("help", false, "Print out this help text");
+  c.add("helpAll", false, "Print out this help text\nincluding the private options, if any", false);
+  c.add("version", false, "Print out program version");
+  c.add("debug", 0, "Debug print switch");
+  c.add("terminal", 6, "File unit number for terminal output");
+  c.add("consolemsg", false, "Output error messages to console");
+  c.add("Bramsize", -1, "In-core size (MB) of displacement recovery matrix\n< 0: Use the same as in the reducer (default)\n= 0: Store full matrix in core");
+  c.add("dmramsize", -1, "Same as -Bramsize but in terms of double words", false);
+  c.add("linkId", 0, "Link base-ID number");
+  c.add("linkfile", "", "Name of link input file");
+  c.add("Bmatfile", "", "Name of B-matrix file");
+  c.add("eigfile", "", "Name of eigenvector file");
+  c.add("dispfile", "", "Name of gravitation displacement file");
+  c.add("resfile", "", "Name of result output file");
+  c.add("samfile", "", "Name of SAM data file");
+  c.add("fsifile", "fedem_solver.fsi", "Name of solver input file");
+  c.add("resStressFile", "", "Name of residual stress input file");
+  c.add("resStressSet", "", "Name of residual stress set");
+  c.add("frsfile", "", "Name of solver results database file");
+  c.add("rdbfile", "", "Name of stress results database file");
+  c.add("rdbinc", 1, "Increment number for the results database file");
+  c.add("VTFfile", "", "Name of VTF output file");
+  c.add("VTFoffset", 0, "VTF result block id offset");
+  c.add("VTFparts", 0, "Number of parts in VTF-file");
+  c.add("VTFavgelm", true, "Write averaged element results to VTF-file");
+  c.add("VTFinit", false, "Write initial state to VTF-file");
+  c.add("VTFdscale", 1.0, "Deformation scaling factor for VTF output");
+  c.add("double", false, "Save all results in double precision");
+  c.add("group", "", "List of element groups to do calculations for");
+  c.add("nodalForces", false, "Compute and print nodal forces");
+  c.add("SR", false, "Save stress resultants to results database");
+  c.add("stress", false, "Save stress tensors to results database");
+  c.add("strain", false, "Save strain tensors to results database");
+  c.add("vmStress", false, "Save von Mises stress to results database");
+  c.add("vmStrain", false, "Save von Mises strain to results database");
+  c.add("maxPStress", false, "Save max principal stress to results database");
+  c.add("maxPStrain", false, "Save max principal strain to results database");
+  c.add("minPStress", false, "Save min principal stress to results database");
+  c.add("minPStrain", false, "Save min principal strain to results database");
+  c.add("maxSStress", false, "Save max shear stress to results database");
+  c.add("maxSStrain", false, "Save max shear strain to results database");
+  c.add("deformation", false, "Save deformations to results database");
+  c.add("dumpDefNas", false, "Save deformations to Nastran bulk data files");
+  c.add("write_nodes", true, "Save deformations as nodal data");
+  c.add("write_vector", false, "Save deformations as vector data");
+  c.add("statm", 0.0, "Start time");
+  c.add("stotm", 1.0, "Stop time");
+  c.add("tinc", 0.1, "Time increment (= 0.0: process all time steps)");
+  c.add("stressForm", 0, "General stress formulation option\n= 0: Direct evaluation in nodes\n= 1: Volume averaged or mid-point evaluation\n= 2: Extrapolation from Gauss integration points", false);
+  c.add("ffqStressForm", 2, "Stress formulation for the FFQ shell", false);
+  c.add("fftStressForm", 1, "Stress formulation for the FFT shell", false);
+  c.add("useIncompatibleModes", false, "Linear hexahedron option", false);
+  // B200 additions
+  c.add("device", 0, "CUDA device ordinal");
+  c.add("stepTile", 0, "Time steps per device batch (0 = from free device memory)");
+  g_stress_options_defined = true;
+}
+
+void initSolverArgs(int argc, char** argv)
+{
+  g_cmd = CmdLine();
+  g_cmd.init(argc, argv);
+  fsr_stress_define_options();
+}
+
+#define FAIL(...) do { set_error(__VA_ARGS__); log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return -1; } while (0)
+#define CHECK(call) do { const int rc_ = (call); if (rc_ < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return rc_; } } while (0)
+
+int solveStress(void)
+{
+  if (!g_stress_options_defined) fsr_stress_define_options();
+  CmdLine& c = g_cmd;
+  // readOptionFilesStd (cmdLineArgInitStd.C:103-135)
+  const std::string cwd = c.get_string("cwd");
+  if (!cwd.empty() && chdir(cwd.c_str())) { perror(("fedem_stress: " + cwd).c_str()); return 1; }
+  for (const char* o : {"fao", "fco", "fop"}) { const std::string f = c.get_string(o); if (!f.empty()) c.read_options_file(f); }
+  if (c.get_bool("help") || c.get_bool("helpAll")) { printf("%s", c.help_text(c.get_bool("helpAll")).c_str()); return 0; }
+  if (c.get_bool("version")) { printf("fedem_stress B200 1.0\n"); return 0; }
+
+  Log log;
+  log.open(file_name("resfile", "_stress.res"), "Stress Recovery");
+  log.line("\n           ================> START OF PROGRAM STRESS <================");
+  if (c.is_set("resStressFile")) log.line("  ** Note: residual stress import (-resStressFile) is not part of this build; ignored");
+  if (c.is_set("VTFfile") && !c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
+  if (c.get_bool("dumpDefNas")) log.line("  ** Note: Nastran deformation dump (-dumpDefNas) is not part of this build; ignored");
+
+  // --- Read the link file (ffl_init)
+  const std::string linkfile = c.get_string("linkfile");
+  if (linkfile.empty()) FAIL("FE data file must be specified through -linkfile");
+  log.line("           --> Reading link files");
+  fsr_ftl* ftl = nullptr;
+  CHECK(fsr_ftl_open(&ftl, linkfile.c_str()));
+  struct FtlGuard { fsr_ftl* p; ~FtlGuard() { fsr_ftl_close(p); } } ftl_guard{ftl};
+  const std::string groups = c.get_string("group");
+  if (!groups.empty()) CHECK(fsr_ftl_activate_groups(ftl, groups.c_str()));
+  int fsz[12];
+  const int nael = fsr_ftl_sizes(ftl, fsz);
+
+  // --- Establish the SAM datastructure (initiateSAM, samStressModule.f90:39-263)
+  const std::string samfile = file_name("samfile", ".fsm");
+  int mpar[64] = {0}, cs_sam = 0;
+  CHECK(fsr_fsm_read_mpar(samfile.c_str(), &cs_sam, mpar, 64));
+  const int nnod = mpar[0], nel = mpar[1], ndof = mpar[2], ndof1 = mpar[3], ndof2 = mpar[4], nceq = mpar[6], neq = mpar[10],
+            nmmnpc = mpar[14], nmmceq = mpar[15], ngen = mpar[21];
+  if (fsz[0] != nnod || fsz[1] != nel || fsz[2] != ndof || fsz[3] < nmmnpc || fsz[5] != mpar[22])
+    FAIL("The FE data file %s does not match the SAM file %s (nnod %d/%d, nel %d/%d, ndof %d/%d, nmmnpc %d/%d, nxnod %d/%d)",
+         linkfile.c_str(), samfile.c_str(), fsz[0], nnod, fsz[1], nel, fsz[2], ndof, fsz[3], nmmnpc, fsz[5], mpar[22]);
+  std::vector<int> madof(nnod + 1), minex(std::max(nnod, 1)), mnnn(std::max(nnod, 1)), msc(std::max(ndof, 1)), mpmnpc(nel + 1),
+      mmnpc(std::max(nmmnpc, 1)), melcon(std::max(nel, 1)), mpmceq(nceq + 1), mmceq(std::max(nmmceq, 1)), meqn(std::max(ndof, 1)),
+      meqn1(std::max(ndof1, 1)), meqn2(std::max(ndof2, 1));
+  std::vector<double> ttcc(std::max(nmmceq, 1));
+  CHECK(fsr_fsm_read(samfile.c_str(), madof.data(), minex.data(), mnnn.data(), msc.data(), mpmnpc.data(), mmnpc.data(), melcon.data(),
+                     mpmceq.data(), mmceq.data(), ttcc.data(), meqn.data(), meqn1.data(), meqn2.data()));
+  log.line("           --> FE part: %d nodes, %d elements (%d active), %d DOFs (%d internal, %d external, %d component modes)", nnod, nel,
+           nael, ndof, ndof1, ndof2, ngen);
+
+  // --- element data in SAM order
+  std::vector<double> xyz(3 * (size_t)std::max(nnod, 1)), emod(std::max(nel, 1)), rny(std::max(nel, 1)), rho(std::max(nel, 1)),
+      thk(std::max(nel, 1)), beam((size_t)FSR_NBEAM * std::max(nel, 1));
+  std::vector<int> elmid(std::max(nel, 1)), estat(std::max(nel, 1));
+  CHECK(fsr_ftl_get_nodes(ftl, nullptr, nullptr, nullptr, nullptr, xyz.data()));
+  const int nbad = fsr_ftl_get_elmdata(ftl, emod.data(), rny.data(), rho.data(), thk.data(), elmid.data(), beam.data(), estat.data());
+  if (nbad > 0) log.line("  ** Warning: %d elements lack material / thickness / cross section data", nbad);
+
+  // --- Read superelement data from the solver input file (readSolverData)
+  int isup = c.get_int("linkId");
+  if (isup < 1) isup = mpar[17];
+  log.line("           --> Process Part; baseID (isup) = %d", isup);
+  int user_id = 0, ntriads = 0, ngen_fsi = 0, gen_first = 1;
+  char descr[256] = "", model_file[1024] = "";
+  double sup_pos[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}, grv[3] = {0, 0, 0};
+  std::vector<int> tb, tu, tnd, tfd;
+  std::vector<double> tru;
+  bool have_fsi = c.is_set("fsifile");
+  if (have_fsi) {
+    fsr_fsi* fsi = nullptr;
+    CHECK(fsr_fsi_open(&fsi, c.get_string("fsifile").c_str(), isup));
+    fsr_fsi_part(fsi, &user_id, descr, sizeof(descr), &ntriads, &ngen_fsi, sup_pos, grv, model_file, sizeof(model_file));
+    tb.resize(std::max(ntriads, 1)); tu.resize(tb.size()); tnd.resize(tb.size()); tfd.resize(tb.size()); tru.resize(12 * tb.size());
+    gen_first = fsr_fsi_triads(fsi, tb.data(), tu.data(), tnd.data(), tfd.data(), tru.data(), nullptr);
+    fsr_fsi_close(fsi);
+    if (gen_first - 1 != ndof2 || ngen_fsi != ngen)
+      FAIL("Part %d: the solver input file gives %d triad DOFs + %d component modes, the SAM file %d + %d", isup, gen_first - 1, ngen_fsi, ndof2, ngen);
+  } else
+    FAIL("No solver input file (-fsifile): reading expanded displacements directly from the results database is not part of this build");
+
+  // --- gravitation displacement modes (stress.f90:184-206): folded in as three extra "component modes"
+  const bool want_grav = std::sqrt(grv[0] * grv[0] + grv[1] * grv[1] + grv[2] * grv[2]) > 1.0e-8 && c.is_set("dispfile");
+  std::string dispfile = want_grav ? file_name("dispfile", "_V.fmx") : std::string();
+  bool lgrav = false;
+  if (want_grav) { FILE* t = fopen(dispfile.c_str(), "rb"); if (t) { lgrav = true; fclose(t); } }
+  const int nmodes = ngen + (lgrav ? 3 : 0);
+
+  // --- the part on the device
+  fsr_sam sam;
+  memset(&sam, 0, sizeof(sam));
+  sam.nnod = nnod; sam.nel = nel; sam.ndof = ndof; sam.ndof1 = ndof1; sam.ndof2 = ndof2; sam.ngen = nmodes; sam.neq = neq; sam.nceq = nceq;
+  sam.nmmnpc = nmmnpc; sam.nmmceq = nmmceq;
+  sam.madof = madof.data(); sam.msc = msc.data(); sam.mpmnpc = mpmnpc.data(); sam.mmnpc = mmnpc.data(); sam.melcon = melcon.data();
+  sam.mpmceq = mpmceq.data(); sam.mmceq = mmceq.data(); sam.ttcc = ttcc.data(); sam.meqn = meqn.data(); sam.meqn1 = meqn1.data();
+  sam.meqn2 = meqn2.data();
+  fsr_elmdata ed;
+  ed.xyz = xyz.data(); ed.emod = emod.data(); ed.rny = rny.data(); ed.thk = thk.data(); ed.elmid = elmid.data(); ed.beam = beam.data();
+  fsr_options po;
+  memset(&po, 0, sizeof(po));
+  po.device = c.get_int("device"); po.stressForm = c.get_int("stressForm"); po.step_tile = c.get_int("stepTile");
+  fsr_part* part = nullptr;
+  const int nfail = fsr_part_create(&part, &sam, &ed, &po);
+  if (nfail < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return nfail; }
+  struct PartGuard { fsr_part* p; ~PartGuard() { fsr_part_destroy(p); } } part_guard{part};
+  if (nfail > 0) log.line("  ** Warning: the stress operator of %d elements could not be formed; they get %g", nfail, kHuge);
+
+  // --- Open the B-matrix and the generalized modes files (openBandEmatrices)
+  if (!c.is_set("Bmatfile") && ndof2 > 0) log.line("  ** Note: -Bmatfile not given, using %s", file_name("Bmatfile", "_B.fmx").c_str());
+  {
+    std::vector<double> B((size_t)std::max(ndof1, 1) * std::max(ndof2, 1)), E((size_t)std::max(ndof1, 1) * std::max(nmodes, 1));
+    char tag[64];
+    int cs = 0, sp = 0;
+    if (ndof1 > 0 && ndof2 > 0) {
+      CHECK(fsr_fmx_read(file_name("Bmatfile", "_B.fmx").c_str(), tag, sizeof(tag), &cs, &sp, B.data(), (long long)ndof1 * ndof2));
+      if (cs != cs_sam) log.line("  ** Warning: checksum of the B-matrix file (%d) differs from the SAM file (%d)", cs, cs_sam);
+    }
+    if (ndof1 > 0 && ngen > 0) {
+      CHECK(fsr_fmx_read(file_name("eigfile", "_E.fmx").c_str(), tag, sizeof(tag), &cs, &sp, E.data(), (long long)ndof1 * ngen));
+      if (strcmp(tag, "#FEDEM generalized modes") != 0) FAIL("Invalid disk matrix file %s: file tag '%s'", file_name("eigfile", "_E.fmx").c_str(), tag);
+    }
+    if (lgrav) {   // readDoubleDB(chname,'displacement matrix',ndof1*3,vii) (stress.f90:199)
+      CHECK(fsr_fmx_read(dispfile.c_str(), tag, sizeof(tag), &cs, &sp, E.data() + (size_t)ndof1 * ngen, (long long)ndof1 * 3));
+      if (strcmp(tag, "#FEDEM displacement matrix") != 0) FAIL("%s is not a displacement matrix file, tag=%s", dispfile.c_str(), tag);
+      log.line("           --> Gravitation displacement modes read from %s", dispfile.c_str());
+    }
+    CHECK(fsr_set_recovery(part, ndof2 > 0 ? B.data() : nullptr, ndof1, nmodes > 0 ? E.data() : nullptr, ndof1));
+  }
+
+  // --- Open the solver results database (ffr_init) and select the time steps (ffr_getnextstep loop)
+  log.line("           --> Reading solver result files");
+  const std::vector<std::string> frs_files = file_list(c.get_string("frsfile"));
+  if (frs_files.empty()) FAIL("No results database files specified");
+  std::vector<const char*> fp;
+  for (const std::string& s : frs_files) fp.push_back(s.c_str());
+  fsr_frs* db = nullptr;
+  CHECK(fsr_frs_open(&db, fp.data(), (int)fp.size()));
+  struct FrsGuard { fsr_frs* p; ~FrsGuard() { fsr_frs_close(p); } } frs_guard{db};
+  const int nall = fsr_frs_num_steps(db);
+  std::vector<int> stepno(std::max(nall, 1));
+  std::vector<double> times(std::max(nall, 1));
+  fsr_frs_get_steps(db, stepno.data(), times.data(), nall);
+  const double statm = c.get_double("statm"), stotm = c.get_double("stotm"), tinc = c.get_double("tinc");
+  std::vector<int> sel(std::max(nall, 1));
+  const int nsel = fsr_select_steps(times.data(), nall, statm, stotm, tinc, sel.data(), nall);
+  log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
+
+  // --- Initialize the stress results database (writeStressHeader)
+  fsr_rdb_options ro;
+  memset(&ro, 0, sizeof(ro));
+  static const struct { const char* opt; unsigned bit; } kOut[] = {
+      {"vmStress", FSR_OUT_VMSTRESS}, {"maxPStress", FSR_OUT_MAXPSTRESS}, {"minPStress", FSR_OUT_MINPSTRESS},
+      {"maxSStress", FSR_OUT_MAXSSTRESS}, {"vmStrain", FSR_OUT_VMSTRAIN}, {"maxPStrain", FSR_OUT_MAXPSTRAIN},
+      {"minPStrain", FSR_OUT_MINPSTRAIN}, {"maxSStrain", FSR_OUT_MAXSSTRAIN}, {"stress", FSR_OUT_STRESS},
+      {"strain", FSR_OUT_STRAIN}, {"SR", FSR_OUT_SR}, {"deformation", FSR_OUT_DEFORMATION}};
+  for (const auto& k : kOut) if (c.get_bool(k.opt)) ro.out_mask |= k.bit;
+  if ((ro.out_mask & FSR_OUT_DEFORMATION) && (!c.get_bool("write_nodes") || c.get_bool("write_vector")))
+    log.line("  ** Note: deformations are written as nodal data (-write_vector is not part of this build)");
+  fsr_rdb* rdb = nullptr;
+  const std::string descr_s = descr[0] ? descr : linkfile;
+  if (ro.out_mask) {
+    log.line("           --> Writing result database headers");
+    ro.double_precision = c.get_bool("double") ? 1 : 0;
+    ro.rdbinc = c.get_int("rdbinc");
+    ro.part_base_id = isup; ro.part_user_id = user_id; ro.part_descr = descr_s.c_str();
+    ro.model_file = model_file; ro.link_file = linkfile.c_str();
+    ro.elmid = elmid.data(); ro.minex = minex.data(); ro.sup_tr_init = sup_pos;
+    CHECK(fsr_rdb_create(&rdb, part, file_name("rdbfile", ".frs").c_str(), &ro));
+    char path[1024];
+    fsr_rdb_path(rdb, path, sizeof(path));
+    log.line("           --> Results database file: %s (%lld bytes per time step)", path, fsr_rdb_step_bytes(rdb));
+  } else
+    log.line("  ** Note: no result output requested, only the von Mises envelope is computed");
+  struct RdbGuard { fsr_rdb*& p; ~RdbGuard() { if (p) fsr_rdb_close(p); } } rdb_guard{rdb};
+
+  // --- Time loop, in windows of consecutive selected steps
+  log.line("           --> Starting time loop");
+  const int ndim = ndof2 + nmodes, window = 256;
+  std::vector<double> Q((size_t)ndim * window), supTr(12 * (size_t)window), Qs((size_t)std::max(ndof2 + ngen, 1)), t_w(window);
+  std::vector<int> s_w(window);
+  std::vector<double> sup_all;
+  const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
+  for (int w0 = 0; w0 < nsel; w0 += window) {
+    const int nw = std::min(window, nsel - w0);
+    for (int k = 0; k < nw;) {   // runs of consecutive steps on file are read with one call
+      int run = 1;
+      while (k + run < nw && sel[w0 + k + run] == sel[w0 + k] + run) ++run;
+      double* q0 = Q.data() + (size_t)k * ndim;
+      CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[w0 + k], run, q0, ndim));
+      if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, sel[w0 + k], run, supTr.data() + 12 * (size_t)k, 12, 12));
+      k += run;
+    }
+    for (int k = 0; k < nw; ++k) {
+      s_w[k] = stepno[sel[w0 + k]];
+      t_w[k] = times[sel[w0 + k]];
+      if (lgrav) {   // g = matmul(grv, sup%supTr(:,1:3)) (stress.f90:412)
+        const double* T = supTr.data() + 12 * (size_t)k;
+        double* g = Q.data() + (size_t)k * ndim + ndof2 + ngen;
+        for (int j = 0; j < 3; ++j) g[j] = grv[0] * T[3 * j] + grv[1] * T[3 * j + 1] + grv[2] * T[3 * j + 2];
+      }
+    }
+    if (rdb) CHECK(fsr_rdb_write_steps(rdb, Q.data(), ndim, nw, s_w.data(), t_w.data(), supTr.data()));
+    else CHECK(fsr_recover(part, Q.data(), ndim, nw, nullptr));
+    log.line("           --> ......Simulation time : %12.5E  (%d of %d steps done)", t_w[nw - 1], w0 + nw, nsel);
+  }
+  if (!rdb && nsel > 0) {
+    std::vector<double> mx(std::max(fsr_num_result_points(part), 1)), mn(mx.size());
+    CHECK(fsr_get_envelope(part, mx.data(), mn.data()));
+    log.line("           --> largest von Mises stress over all result points and steps: %g", *std::max_element(mx.begin(), mx.end()));
+  }
+  log.line("           --> Time loop done. Closing database files");
+  if (rdb) { fsr_rdb* r = rdb; rdb = nullptr; CHECK(fsr_rdb_close(r)); }
+  log.line("           ================>  END OF PROGRAM STRESS  <================");
+  log.line("\n    Stress calculation successfully completed :-)  (%.2f s CPU)", (double)(clock() - log.t0) / CLOCKS_PER_SEC);
+  return 0;
+}
+
+}  // extern "C"

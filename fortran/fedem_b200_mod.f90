@@ -569,6 +569,40 @@ module fedem_b200_mod
        integer(c_int) :: intid
      end function fsr_ftl_ext2int
 
+     ! ---- solver input file (.fsi): replaces readSolverData ----------------------------------
+     function fsr_fsi_open (fsi, path, part_base_id) bind(C,name="fsr_fsi_open") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr)           , intent(out) :: fsi
+       character(kind=c_char), intent(in)  :: path(*)
+       integer(c_int)        , value       :: part_base_id
+       integer(c_int) :: ierr
+     end function fsr_fsi_open
+
+     subroutine fsr_fsi_close (fsi) bind(C,name="fsr_fsi_close")
+       import :: c_ptr
+       type(c_ptr), value :: fsi
+     end subroutine fsr_fsi_close
+
+     function fsr_fsi_part (fsi, user_id, descr, dcap, ntriads, ngen, supPos, gravity, model_file, mcap) &
+          &                bind(C,name="fsr_fsi_part") result(base_id)
+       import :: c_ptr, c_char, c_int, c_double
+       type(c_ptr)           , value       :: fsi
+       integer(c_int)        , intent(out) :: user_id, ntriads, ngen
+       character(kind=c_char), intent(out) :: descr(*), model_file(*)
+       integer(c_int)        , value       :: dcap, mcap
+       real(c_double)        , intent(out) :: supPos(3,4), gravity(3)
+       integer(c_int) :: base_id
+     end function fsr_fsi_part
+
+     function fsr_fsi_triads (fsi, base_id, user_id, ndofs, first_dof, trUndeformed, ur) &
+          &                  bind(C,name="fsr_fsi_triads") result(gen_first_dof)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: fsi
+       integer(c_int), intent(out) :: base_id(*), user_id(*), ndofs(*), first_dof(*)
+       real(c_double), intent(out) :: trUndeformed(3,4,*), ur(3,4,*)
+       integer(c_int) :: gen_first_dof
+     end function fsr_fsi_triads
+
      ! ---- stress results database: replaces writeStressHeader + writeStressDB/writeStrMeasureDB ----
      function fsr_rdb_create (rdb, part, path, opt) bind(C,name="fsr_rdb_create") result(ierr)
        import :: c_ptr, c_char, c_int, fsr_rdb_options

@@ -360,6 +360,24 @@ int fsr_ftl_get_elmdata(const fsr_ftl *ftl, double *emod, double *rny, double *r
                         double *beam, int *status);
 int fsr_ftl_ext2int(const fsr_ftl *ftl, int is_node, int id); /* ffl_ext2int (:716-737) */
 
+/* ---- solver input file (.fsi) -----------------------------------------------------------------------
+ * Replaces readSolverData (src/vpmStress/displacementModule.f90:138-229 -> InitiateSupEls1/InitiateTriads/
+ * InitiateSupEls2, src/vpmStress/initiateTriadAndSupElTypeModule.f90:34-319): from the Fortran namelist file of
+ * the dynamics run, the &SUP_EL record with id = part_base_id, its &TRIAD_UNDPOS and &TRIAD records, &HEADING
+ * modelFile and &ENVIRONMENT gravity.
+ *  fsr_fsi_part   : returns the part's base id; user id, description, numTriads, numGenDOFs, supPos as a
+ *                   column-major 3x4 matrix (= sup%supTr = sup%supTrInit), gravity[3], model file name.
+ *  fsr_fsi_triads : per triad in the order of triadIds (= the order of the reduced DOFs in finit): base id,
+ *                   user id, nDOFs, first reduced DOF (1-based), TrUndeformed and initial position ur
+ *                   (column-major 3x4 each); returns sup%genDOFs%firstDOF.  Arguments may be NULL. */
+typedef struct fsr_fsi fsr_fsi;
+int fsr_fsi_open(fsr_fsi **fsi, const char *path, int part_base_id);
+void fsr_fsi_close(fsr_fsi *fsi);
+int fsr_fsi_part(const fsr_fsi *fsi, int *user_id, char *descr, int dcap, int *ntriads, int *ngen,
+                 double *sup_pos, double *gravity, char *model_file, int mcap);
+int fsr_fsi_triads(const fsr_fsi *fsi, int *base_id, int *user_id, int *ndofs, int *first_dof,
+                   double *tr_undef, double *ur);
+
 /* ---- stress results database (.frs), written from the GPU ------------------------------------------
  * Replaces writeStressHeader (src/vpmStress/saveStressModule.f90:120-247, header grammar :625-1430) and the
  * per-element writeStressDB / writeStrMeasureDB calls of calcStresses (stressRoutines.f90:234-310,
@@ -405,6 +423,34 @@ int fsr_rdb_write_steps(fsr_rdb *rdb, const double *Q, int ldq, int nsteps, cons
 void fsr_total_nodal_displacement(const double *x0, const double *u, int nd, const double *T, const double *T0,
                                   double *utot);
 int fsr_rdb_close(fsr_rdb *rdb);
+
+/* ---- the fedem_stress program ------------------------------------------------------------------------
+ * The reference's launcher entry points, same names (src/vpmStress/stressInterface.C:86-116):
+ * initSolverArgs defines the option table of stressmain.C:22-79 (+ -fao/-fco/-fop/-cwd/-help/-debug ... of
+ * cmdLineArgInitStd.C / cmdLineArgInit.C) over the given arguments, solveStress runs subroutine stress
+ * (src/vpmStress/stress.f90): -linkfile .ftl, -samfile .fsm, -fsifile .fsi, -Bmatfile/-eigfile/-dispfile .fmx,
+ * -frsfile solver results, -statm/-stotm/-tinc, -group, -SR -stress -strain -vmStress ... -deformation -double,
+ * -rdbfile/-rdbinc stress results database.  Returns 0 on success.  bin/fedem_stress is main() over these. */
+void initSolverArgs(int argc, char **argv);
+int solveStress(void);
+/* ffr_getnextstep (fedem-foundation/src/FFrLib/FFrExtractorInterface.f90:134-170) over a sorted key list:
+ * indices of the time steps the stress loop visits for -statm start -stotm stop -tinc tinc; returns their
+ * number (out may be NULL) */
+int fsr_select_steps(const double *times, int n, double start, double stop, double tinc, int *out, int cap);
+/* the option parser (FFaCmdLineArg semantics) behind a C face, one global instance like the reference's */
+void fsr_cmdline_reset(void);
+void fsr_stress_define_options(void);
+void fsr_cmdline_add_bool(const char *name, int value);
+void fsr_cmdline_add_int(const char *name, int value);
+void fsr_cmdline_add_double(const char *name, double value);
+void fsr_cmdline_add_string(const char *name, const char *value);
+void fsr_cmdline_init(int argc, char **argv);
+int fsr_cmdline_read_file(const char *path);
+int fsr_cmdline_get_bool(const char *name);
+int fsr_cmdline_get_int(const char *name);
+double fsr_cmdline_get_double(const char *name);
+int fsr_cmdline_get_string(const char *name, char *out, int cap);
+int fsr_cmdline_is_set(const char *name);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);

@@ -5,7 +5,7 @@
 // ffl_getelmid entry points fedem_stress calls per element -- plus the reference's command-line parser
 // (FFaCmdLineArg), compiled where they lie under /root/reference by oracle/Makefile into
 // oracle/_ref/libfedem_ref_ffl.so.  No reference source is copied.  Used only by tests/ to check the
-// product's .ftl reader (csrc/io_ftl.cu) and option parser (csrc/cli_options.cu) value by value.
+// product's .ftl reader (csrc/io_ftl.cu) and option parser (csrc/cmdline.hpp) value by value.
 //
 // The few symbols FFlLib references from parts of the reference that are not on this path (VTF export,
 // the other FE file formats, the build-stamp module) are stubbed here.
@@ -62,6 +62,7 @@ int ref_cmdline_get_string(const char* name, char* out, int cap)
   out[cap - 1] = 0;
   return (int)v.size();
 }
+int ref_cmdline_read_file(const char* path) { return FFaCmdLineArg::instance()->readOptionsFile(path) ? 1 : 0; }
 int ref_cmdline_is_set(const char* name) { return FFaCmdLineArg::instance()->isOptionSetOnCmdLine(name) ? 1 : 0; }
 
 // ffl_full_init: read the .ftl file and activate the -group selection (stress.f90:111 -> ffl_init)

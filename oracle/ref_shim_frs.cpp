@@ -65,4 +65,19 @@ int ref_frs_read(void* h, const char* path, const char* og_type, int base_id, co
   return ok;
 }
 
+// ffr_setposition / ffr_increment (FFrExtractor_F.C:254-308) without the step-number read: the two moves the
+// Fortran ffr_getNextStep loop (FFrExtractorInterface.f90:134-170) is built from.  Return 0 or -1 (istep < 0).
+int ref_frs_setposition(void* h, double atime, double* btime)
+{
+  return static_cast<FFrExtractor*>(h)->positionRDB(atime, *btime, true) ? 0 : -1;
+}
+
+int ref_frs_increment(void* h, double* btime)
+{
+  FFrExtractor* rdb = static_cast<FFrExtractor*>(h);
+  const bool ok = rdb->incrementRDB();
+  *btime = rdb->getCurrentRDBPhysTime();
+  return ok ? 0 : -1;
+}
+
 }  // extern "C"

@@ -1,0 +1,144 @@
+"""End-to-end drop-in test of bin/fedem_stress on the GPU: the files a reducer + dynamics solver run leaves behind
+(.ftl FE part, _SAM.fsm, _B.fmx, _E.fmx, _V.fmx gravitation modes, fedem_solver.fsi, th_p_*.frs time history) are
+generated, the executable is run with the reference's command-line options (some of them through -fco/-fop
+option files), and its stress results database is read back and compared with the CPU oracle driven by the
+same reference-order recipe: readSupElDisplacements -> BuildFinit -> calcIntDisplacements -> calcStresses."""
+import os
+import subprocess
+import numpy as np
+import pytest
+
+from fedem_solvers_b200.files import save_part, write_fmx
+from fedem_solvers_b200.frs import FrsReader
+from fedem_solvers_b200.fsi import SolverPart, write_fsi
+from fedem_solvers_b200.ftl import write_ftl
+from fedem_solvers_b200.model import plate_part, tet10_block
+from test_frs_cpu import _write_solver_file, _build_finit_numpy
+from test_rdb_cpu import NAMES, NENOD, MEASURES
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "fedem_solvers_b200", "bin", "fedem_stress")
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import oracle_bind
+    return oracle_bind.Oracle()
+
+
+def _make_case(tmp_path, part, name, nsteps, gravity=None, seed=1):
+    """Writes every input file of a stress run for `part` into tmp_path; returns what the checks need."""
+    rng = np.random.default_rng(seed)
+    sam = part.sam
+    ntriads, ngen, base = sam.ndof2 // 6, sam.ngen, 40
+    assert ntriads * 6 == sam.ndof2
+    write_ftl(str(tmp_path / f"{name}.ftl"), part, groups={3: [int(i) for i in part.elm.elmid[: sam.nel // 2]]})
+    save_part(str(tmp_path / name), part, checksum=1234, part_id=base)
+    triads, tr_undef, sup, tri, gen = _write_solver_file(str(tmp_path / "th_p_1.frs"), rng, nsteps, ntriads, ngen, t0=0.0, dt=0.01,
+                                                         step0=1, sup_base=base)
+    ndofs, first = np.full(ntriads, 6), 1 + 6 * np.arange(ntriads)
+    sp = SolverPart(base_id=base, user_id=2, descr="Flexible part", ngen=ngen, sup_pos=sup[0], gravity=np.zeros(3), model_file="",
+                    triad_base_id=np.array([t[0] for t in triads]), triad_user_id=np.array([t[1] for t in triads]), ndofs=ndofs,
+                    first_dof=first, tr_undef=tr_undef, triad_ur=tri[0], gen_first_dof=0)
+    write_fsi(str(tmp_path / "fedem_solver.fsi"), [sp], gravity=gravity if gravity is not None else (0, 0, 0),
+              model_file="generated.fmm")
+    Q = _build_finit_numpy(sup, tri, tr_undef, ndofs, first, gen, sam.ndof2 + 1, sam.ndof2 + ngen)
+    V = None
+    if gravity is not None:
+        V = rng.normal(0, 1e-6, (sam.ndof1, 3))
+        write_fmx(str(tmp_path / f"{name}_V.fmx"), V, tag="#FEDEM displacement matrix", checksum=1234)
+    return dict(Q=Q, sup=sup, V=V, base=base, times=0.01 * np.arange(nsteps), stepno=1 + np.arange(nsteps))
+
+
+def _oracle_steps(oracle, part, case, steps, gravity=None):
+    b = oracle.bind_part(part)
+    out = []
+    for s in steps:
+        sv = oracle.expand(b, case["Q"][:, s])
+        if gravity is not None:   # vi += vii . g,  g = matmul(grv, supTr(:,1:3))  (stress.f90:412, displacementModule.f90:992-995)
+            g = np.asarray(gravity) @ case["sup"][s][:, :3]
+            vi = case["V"] @ g
+            sam = part.sam
+            sveq = np.zeros(sam.neq)
+            sveq[sam.meqn1 - 1] = vi
+            add = np.where(sam.meqn > 0, sveq[np.maximum(sam.meqn, 1) - 1], 0.0)
+            assert sam.nceq == 0
+            sv = sv + add
+        r = oracle.calc_stresses(b, sv)
+        r["sv"] = sv
+        out.append(r)
+    return b, out
+
+
+def _run(tmp_path, args):
+    r = subprocess.run([EXE, "-cwd", str(tmp_path)] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Stress calculation successfully completed" in r.stdout
+    return r.stdout
+
+
+def test_plate_all_results_with_option_files(oracle, tmp_path):
+    part = plate_part(8, 7, ngen=5, seed=21, tri_fraction=0.3, warp=0.02, n_ext=4)
+    case = _make_case(tmp_path, part, "plate", nsteps=40)
+    with open(tmp_path / "stress.fco", "w") as f:
+        f.write("# calculation options\n-linkfile plate.ftl -samfile plate_SAM.fsm\n-Bmatfile plate_B.fmx -eigfile plate_E.fmx\n"
+                "-fsifile fedem_solver.fsi -frsfile th_p_1.frs\n-statm 0.05 -stotm 0.30 -tinc 0.0\n")
+    with open(tmp_path / "stress.fop", "w") as f:
+        f.write("-rdbfile results/plate.frs -rdbinc 3 -double\n-SR -stress -strain -vmStress -maxPStress -minPStress -maxSStress\n"
+                "-vmStrain -maxPStrain -minPStrain -maxSStrain -deformation\n")
+    os.makedirs(tmp_path / "results")
+    _run(tmp_path, ["-fco", "stress.fco", "-fop", "stress.fop"])
+    rd = FrsReader(str(tmp_path / "results" / "plate_3.frs"))
+    steps = np.nonzero((case["times"] > 0.05 - 1e-9) & (case["times"] < 0.30 + 1e-9))[0]
+    assert np.array_equal(rd.step_numbers, case["stepno"][steps]) and np.allclose(rd.times, case["times"][steps], rtol=0, atol=1e-15)
+    b, o = _oracle_steps(oracle, part, case, steps)
+    sc = {k: np.abs(np.stack([x[k] for x in o])).max() for k in ("stress", "strain", "resmat", "sv", "sres")}
+    n = 0
+    for e in (0, 5, part.sam.nel // 2, part.sam.nel - 1):
+        t = int(part.sam.melcon[e]); nn = NENOD[t]
+        p = f"Elements|{part.elm.elmid[e]}|{NAMES[t]}|Element nodes|"
+        for si, side in enumerate(("Top", "Bottom")):
+            for k in range(nn):
+                pt = b["ptoff"][e] + si * nn + k
+                for var, key, w in (("Stress", "stress", 3), ("Strain", "strain", 3)):
+                    got = rd.read(rd.find(p + f"{side}|{k + 1}|{var}", "Part", case["base"]))
+                    want = np.stack([x[key][pt, :w] for x in o])
+                    assert np.abs(got - want).max() <= TOL * sc[key]
+                for j in range(8):
+                    got = rd.read(rd.find(p + f"{side}|{k + 1}|{MEASURES[j]}", "Part", case["base"]))
+                    want = np.stack([x["resmat"][pt, j:j + 1] for x in o])
+                    assert np.abs(got - want).max() <= TOL * (sc["stress"] if j < 4 else sc["strain"])
+                    n += 1
+        for k in range(nn):
+            got = rd.read(rd.find(p + f"Basic|{k + 1}|Shell stress resultant moment", "Part", case["base"]))
+            assert np.abs(got - np.stack([x["sres"][e, 6 * k + 3:6 * k + 6] for x in o])).max() <= TOL * sc["sres"]
+    for nd in (0, part.sam.nnod - 1):
+        got = rd.read(rd.find(f"Nodes|{part.sam.minex[nd]}|Dynamic response|Angular deformation", "Part", case["base"]))
+        j0 = part.sam.madof[nd] - 1
+        assert np.abs(got - np.stack([x["sv"][j0 + 3:j0 + 6] for x in o])).max() <= TOL * sc["sv"]
+        assert rd.find(f"Nodes|{part.sam.minex[nd]}|Dynamic response|Total translation", "Part", case["base"]) is not None
+    assert n > 100
+
+
+def test_tets_group_selection_gravity_and_time_increment(oracle, tmp_path):
+    part = tet10_block(2, 2, 2, ngen=4, seed=22, n_ext=4, n_beams=0)
+    # external nodes of the generator have 3 DOFs; triads need 6: use beams on the external nodes instead? keep it simple:
+    if part.sam.ndof2 % 6:
+        pytest.skip("generated part has 3-DOF external nodes")
+    case = _make_case(tmp_path, part, "block", nsteps=30, gravity=(0.0, 0.0, -9.81), seed=5)
+    _run(tmp_path, ["-linkfile", "block.ftl", "-frsfile", "<th_p_1.frs>", "-group", "3", "-vmStress", "-stress", "-statm", "0.0",
+                    "-stotm", "1.0", "-tinc", "0.03", "-dispfile", "block_V.fmx", "-rdbinc", "1"])
+    rd = FrsReader(str(tmp_path / "block_1.frs"))
+    steps = [0, 3, 6, 9, 12, 15, 18, 21, 24, 27]
+    assert np.array_equal(rd.step_numbers, case["stepno"][steps])
+    b, o = _oracle_steps(oracle, part, case, steps, gravity=(0.0, 0.0, -9.81))
+    sc = np.abs(np.stack([x["stress"] for x in o])).max()
+    half = part.sam.nel // 2
+    for e in (0, half - 1):
+        for k in (0, 9):
+            pt = b["ptoff"][e] + k
+            got = rd.read(rd.find(f"Elements|{part.elm.elmid[e]}|TET10|Element nodes|Basic|{k + 1}|Stress", "Part", case["base"]))
+            assert np.abs(got - np.stack([x["stress"][pt] for x in o])).max() <= 1.3e-7 * sc   # float file
+    assert rd.find(f"Elements|{part.elm.elmid[half]}|TET10|Element nodes|Basic|1|Stress", "Part", case["base"]) is None
