@@ -671,6 +671,102 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_rdb_close
 
+     ! ---- the fedem_stress program (same exported names as the reference's stressInterface.C) --
+     subroutine initSolverArgs (argc, argv) bind(C,name="initSolverArgs")
+       import :: c_int, c_ptr
+       integer(c_int), value :: argc
+       type(c_ptr)           :: argv(*)   !< C strings
+     end subroutine initSolverArgs
+
+     function solveStress () bind(C,name="solveStress") result(ierr)
+       import :: c_int
+       integer(c_int) :: ierr
+     end function solveStress
+
+     !> ffr_getNextStep loop over a sorted key list: indices (0-based) of the time steps to process
+     function fsr_select_steps (times, n, start, stop, tinc, out, cap) bind(C,name="fsr_select_steps") result(nsel)
+       import :: c_int, c_double
+       real(c_double), intent(in)  :: times(*)
+       integer(c_int), value       :: n, cap
+       real(c_double), value       :: start, stop, tinc
+       integer(c_int), intent(out) :: out(*)
+       integer(c_int) :: nsel
+     end function fsr_select_steps
+
+     subroutine fsr_cmdline_reset () bind(C,name="fsr_cmdline_reset")
+     end subroutine fsr_cmdline_reset
+
+     subroutine fsr_stress_define_options () bind(C,name="fsr_stress_define_options")
+     end subroutine fsr_stress_define_options
+
+     subroutine fsr_cmdline_add_bool (name, value) bind(C,name="fsr_cmdline_add_bool")
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int), value :: value
+     end subroutine fsr_cmdline_add_bool
+
+     subroutine fsr_cmdline_add_int (name, value) bind(C,name="fsr_cmdline_add_int")
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int), value :: value
+     end subroutine fsr_cmdline_add_int
+
+     subroutine fsr_cmdline_add_double (name, value) bind(C,name="fsr_cmdline_add_double")
+       import :: c_char, c_double
+       character(kind=c_char), intent(in) :: name(*)
+       real(c_double), value :: value
+     end subroutine fsr_cmdline_add_double
+
+     subroutine fsr_cmdline_add_string (name, value) bind(C,name="fsr_cmdline_add_string")
+       import :: c_char
+       character(kind=c_char), intent(in) :: name(*), value(*)
+     end subroutine fsr_cmdline_add_string
+
+     subroutine fsr_cmdline_init (argc, argv) bind(C,name="fsr_cmdline_init")
+       import :: c_int, c_ptr
+       integer(c_int), value :: argc
+       type(c_ptr)           :: argv(*)
+     end subroutine fsr_cmdline_init
+
+     function fsr_cmdline_read_file (path) bind(C,name="fsr_cmdline_read_file") result(ok)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: path(*)
+       integer(c_int) :: ok
+     end function fsr_cmdline_read_file
+
+     !> ffa_cmdlinearg_getbool / getint / getdouble / getstring / isSet
+     function fsr_cmdline_get_bool (name) bind(C,name="fsr_cmdline_get_bool") result(v)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int) :: v
+     end function fsr_cmdline_get_bool
+
+     function fsr_cmdline_get_int (name) bind(C,name="fsr_cmdline_get_int") result(v)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int) :: v
+     end function fsr_cmdline_get_int
+
+     function fsr_cmdline_get_double (name) bind(C,name="fsr_cmdline_get_double") result(v)
+       import :: c_char, c_double
+       character(kind=c_char), intent(in) :: name(*)
+       real(c_double) :: v
+     end function fsr_cmdline_get_double
+
+     function fsr_cmdline_get_string (name, out, cap) bind(C,name="fsr_cmdline_get_string") result(nchar)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in)  :: name(*)
+       character(kind=c_char), intent(out) :: out(*)
+       integer(c_int), value :: cap
+       integer(c_int) :: nchar
+     end function fsr_cmdline_get_string
+
+     function fsr_cmdline_is_set (name) bind(C,name="fsr_cmdline_is_set") result(v)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int) :: v
+     end function fsr_cmdline_is_set
+
      ! ---- diagnostics ------------------------------------------------------------------------
      function fsr_last_error () bind(C,name="fsr_last_error") result(msg)
        import :: c_ptr

@@ -44,6 +44,9 @@ def _make_case(tmp_path, part, name, nsteps, gravity=None, seed=1):
                     first_dof=first, tr_undef=tr_undef, triad_ur=tri[0], gen_first_dof=0)
     write_fsi(str(tmp_path / "fedem_solver.fsi"), [sp], gravity=gravity if gravity is not None else (0, 0, 0),
               model_file="generated.fmm")
+    # the .fsi file carries 10 significant digits: use the undeformed triad positions exactly as the program reads them
+    from fedem_solvers_b200.fsi import read_fsi
+    tr_undef = read_fsi(str(tmp_path / "fedem_solver.fsi"), base).tr_undef
     Q = _build_finit_numpy(sup, tri, tr_undef, ndofs, first, gen, sam.ndof2 + 1, sam.ndof2 + ngen)
     V = None
     if gravity is not None:
