@@ -47,6 +47,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// sqrt(x) for x >= 0 to < 1 ulp-ish (two Newton steps on the 2^-22 hardware seed); 0 for x < 1e-290
+__device__ __forceinline__ double sqrt_pos(double x)
+{
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double y = x * r, h = 0.5 * r;
+  double e = fma(-h, y, 0.5);
+  y = fma(y, e, y);
+  h = fma(h, e, h);
+  e = fma(-y, y, x);
+  y = fma(e, h, y);
+  return x > 1.0e-290 ? y : 0.0;
+}
+
 // Element families handled by the K2 kernels.  A family fixes the operator shape:
 // MT m-tiles of 8 rows, KT k-tiles of 4 element DOFs.
 enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_COUNT = 5 };
@@ -62,6 +76,7 @@ struct FamilyData {
   unsigned char* failed = nullptr; // [nelt] 1 = operator build failed -> hugeVal results
   double* aux = nullptr; // per-element scalars needed by the full-output kernels
   int naux = 0;
+  double* Gfrag = nullptr;      // solids: displacement-gradient operator in A-fragment order (k2_solid.cu)
 };
 
 }  // namespace fsr

@@ -612,20 +612,6 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
 // once per four tiles with immediate offsets in between, register double-buffering without moves,
 // a Newton square root on MUFU.RSQ64H instead of the IEEE slow path, compare/select envelopes.
 
-// sqrt(x) for x >= 0 to < 1 ulp-ish (two Newton steps on the 2^-22 hardware seed); 0 for x < 1e-290
-__device__ __forceinline__ double sqrt_pos(double x)
-{
-  double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double y = x * r, h = 0.5 * r;
-  double e = fma(-h, y, 0.5);
-  y = fma(y, e, y);
-  h = fma(h, e, h);
-  e = fma(-y, y, x);
-  y = fma(e, h, y);
-  return x > 1.0e-290 ? y : 0.0;
-}
-
 // `live` = this lane's result point exists (triangles use 6 of the 8 rows of an m-tile).  Every lane
 // of the warp must reach every mma.sync, so dead lanes run the same loop and only their stores and
 // envelope updates are predicated off (ALL_LIVE = true for quads compiles the predicate away).

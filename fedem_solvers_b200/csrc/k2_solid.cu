@@ -8,6 +8,18 @@
 // DMMA.8x8x4: rows packed densely (row = 6*node + component, 60 of 64 used, K = 30 of 32), the
 // accumulators are transposed through shared memory so that one lane sees all six components of
 // a node for the von Mises evaluation (FFaTensorTransforms.C:38-43) and the fused envelope.
+//
+// The von Mises + envelope kernel (the throughput path) does not apply that 60x30 operator.  sigma = D.B.v is
+// D . sym(grad u), and grad u at the 10 result points is [30 x 10] . [10 x 3]: the displacement-gradient
+// operator G (rows = node x derivative direction, columns = nodes; for Gauss-point extrapolation the
+// extrapolation weights are folded in, everything stays linear) applied to the nodal displacements as three
+// right-hand sides u, v, w.  That is 2*30*10*3 = 1,800 flops per element.step instead of 3,600, 12 A-fragments
+// in registers instead of 64, and the isotropic D (E, nu) is applied in the epilogue on the accumulators.
+// Rows are ordered so that lane (g, t4) of the DMMA accumulator layout owns all nine gradient entries of
+// node g at its two steps (m-tile d holds d/dx_d of nodes 0..7); nodes 8 and 9 share the fourth m-tile and
+// are completed with two warp shuffles.  The 60x30 operator is kept for the full-result / record kernels.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fsr {
@@ -29,6 +41,10 @@ __device__ void tet10_dn(double L1, double L2, double L3, double L4, double d1[1
   d3[6] = -4. * L1; d3[7] = -4. * L2; d3[8] = 4. * L4 - 4. * L3; d3[9] = -4. * L4 + 1.;
 }
 
+// row of the gradient operator for d/dx_d at result point p: m-tile d, row p for the first eight points;
+// points 8 and 9 share m-tile 3 (rows 3*(p-8)+d)
+__host__ __device__ __forceinline__ int tet10_grad_row(int p, int d) { return p < 8 ? d * 8 + p : 24 + (p - 8) * 3 + d; }
+
 struct Tet10Points {
   int npt;            // evaluation points (10 nodes, or 4 Gauss points)
   double L[10][3];    // volume coordinates L1..L3 of each evaluation point
@@ -40,13 +56,14 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
                                        const double* __restrict__ xyz, const double* __restrict__ emod,
                                        const double* __restrict__ rny, const Tet10Points* __restrict__ pts,
                                        double* __restrict__ Sfrag, unsigned char* __restrict__ failed,
-                                       double* __restrict__ aux)
+                                       double* __restrict__ aux, double* __restrict__ Gfrag)
 {
   const int KT = 8;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelt) return;
   const int e = elem[i];
   double* S = Sfrag + (size_t)i * 8 * KT * 32;
+  double* G = Gfrag + (size_t)i * 12 * 32;
   double X[10], Y[10], Z[10];
   for (int k = 0; k < 10; ++k) {
     int n = conn[i * 10 + k];
@@ -93,16 +110,20 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
       const double db[6][3] = {{D * bx, D1 * by, D1 * bz},  {D1 * bx, D * by, D1 * bz},
                                {D1 * bx, D1 * by, D * bz},  {D2 * by, D2 * bx, 0.0},
                                {D2 * bz, 0.0, D2 * bx},     {0.0, D2 * bz, D2 * by}};
+      const double bd[3] = {bx, by, bz};
       for (int p = 0; p < 10; ++p) {
         const double w = pts->W[p][gpt];
         if (w == 0.0) continue;
         for (int c = 0; c < 6; ++c)
           for (int d = 0; d < 3; ++d) S[frag_index8(p * 6 + c, 3 * j + d, KT)] += w * db[c][d];
+        for (int d = 0; d < 3; ++d) G[frag_index8(tet10_grad_row(p, d), j, 3)] += w * bd[d];
       }
     }
   }
-  if (!ok)
+  if (!ok) {
     for (int k = 0; k < 8 * KT * 32; ++k) S[k] = 0.0;
+    for (int k = 0; k < 12 * 32; ++k) G[k] = 0.0;
+  }
   failed[i] = ok ? 0 : 1;
 }
 
@@ -195,6 +216,159 @@ k2_tet10_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
   }
 }
 
+
+// von Mises of an isotropic solid from the displacement gradient H[c][d] = d u_c / d x_d.  With
+// sigma = lambda tr(eps) I + 2 mu eps (the D, D1, D2 of itet.f:917-934: D - D1 = 2 mu, D2 = mu) the hydrostatic
+// part drops out of von Mises: vm = 2 mu sqrt( ((exx-eyy)^2 + (eyy-ezz)^2 + (ezz-exx)^2)/2 + 3/4 (gxy^2 + gxz^2 + gyz^2) ),
+// the same number as FFaTensorTransforms::vonMises of the stress tensor up to rounding, at a third of the
+// FP64 instructions (DMMA and scalar FP64 share one pipe: every instruction here is wall time).
+__device__ __forceinline__ double solid_vm_from_gradient(const double (&H)[3][3], double mu2)
+{
+  const double a = H[0][0] - H[1][1], b = H[1][1] - H[2][2], c = H[2][2] - H[0][0];
+  const double gxy = H[0][1] + H[1][0], gxz = H[0][2] + H[2][0], gyz = H[1][2] + H[2][1];
+  const double dev = 0.5 * fma(a, a, fma(b, b, c * c));
+  const double shr = fma(gxy, gxy, fma(gxz, gxz, gyz * gyz));
+  return mu2 * sqrt_pos(fma(0.75, shr, dev));
+}
+
+// one warp per element: 4 m-tiles x 3 k-tiles of the gradient operator in registers, 36 DMMA per 8 steps.
+// Two 8-step tiles per loop trip: result points 0..7 are evaluated by their accumulator lanes after each tile,
+// result points 8 and 9 of both tiles (2 x 2 x 8 = 32 evaluations) are spread over the 32 lanes once per trip.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k2_tet10_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
+                        const double* __restrict__ Gfrag, const double* __restrict__ aux, const int* __restrict__ edof,
+                        const int* __restrict__ ptoff, const unsigned char* __restrict__ failed, int nelt,
+                        double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= nelt) return;
+
+  double a[4][3];
+  const double* gf = Gfrag + (size_t)i * 12 * 32 + lane;
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[m][j] = __ldg(gf + (size_t)(m * 3 + j) * 32);
+  // B operand: k = element node 4*j + t4 (nodes 10, 11 are padding: operator columns are zero), n = step g
+  int urow[3][3];      // row of U per (component, k-tile); addresses are formed at the load (saves 9 registers)
+  const int* ed = edof + (size_t)i * 32;
+  const double* Ug = U + g;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int node = 4 * j + t4;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) urow[c][j] = node < 10 ? __ldg(ed + 3 * node + c) : 0;
+  }
+  const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
+  const double mu2 = E / (1.0 + nu);            // 2 mu = D - D1
+  const bool bad = failed[i] != 0;
+  const size_t pt0 = (size_t)ptoff[i];
+  // the (tile parity, point 8/9, step) evaluation of this lane in the second phase and its source lanes
+  const int par2 = lane >> 4, node2 = (lane >> 3) & 1, step2 = lane & 7;
+  const int src0 = ((3 * node2) << 2) | (step2 >> 1);     // lane holding d/dx of that point at that step pair
+  const bool odd2 = step2 & 1;
+  double emax = 0.0, emin = kHuge, emax2 = 0.0, emin2 = kHuge;
+
+  const int ntiles = nsteps_pad >> 3;
+  double b[3][3], bn[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) b[c][j] = Ug[(size_t)urow[c][j] * ldu];
+  for (int nt = 0; nt < ntiles; nt += 2) {
+    double x3[2][3][2];   // m-tile 3 accumulators (points 8, 9) of the two tiles of this trip
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int tile = nt + half;
+      if (tile + 1 < ntiles) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) bn[c][j] = Ug[(size_t)urow[c][j] * ldu + (tile + 1) * 8];
+      }
+      double acc[4][3][2];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[m][c][0] = acc[m][c][1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) dmma884(acc[m][c][0], acc[m][c][1], a[m][j], b[c][j]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int t = tile * 8 + 2 * t4 + q;
+        double H[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) H[c][d] = acc[d][c][q];
+        double v = solid_vm_from_gradient(H, mu2);
+        if (bad) v = kHuge;
+        if (t < nsteps) {
+          if (vm) vm[(size_t)t * ld_vm + pt0 + g] = v;
+          emax = fmax(emax, v);
+          emin = fmin(emin, v);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { x3[half][c][0] = acc[3][c][0]; x3[half][c][1] = acc[3][c][1]; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) b[c][j] = bn[c][j];
+    }
+    // points 8 and 9: rows 24 + 3 (p - 8) + d of the operator = accumulator lanes g = 3 (p - 8) + d
+    {
+      double H[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int src = src0 + 4 * d;
+          const double a0 = __shfl_sync(0xffffffffu, x3[0][c][0], src), a1 = __shfl_sync(0xffffffffu, x3[0][c][1], src);
+          const double b0 = __shfl_sync(0xffffffffu, x3[1][c][0], src), b1 = __shfl_sync(0xffffffffu, x3[1][c][1], src);
+          H[c][d] = par2 ? (odd2 ? b1 : b0) : (odd2 ? a1 : a0);
+        }
+      double v = solid_vm_from_gradient(H, mu2);
+      if (bad) v = kHuge;
+      const int t = (nt + par2) * 8 + step2;
+      if (t < nsteps) {
+        if (vm) vm[(size_t)t * ld_vm + pt0 + 8 + node2] = v;
+        emax2 = fmax(emax2, v);
+        emin2 = fmin(emin2, v);
+      }
+    }
+  }
+  // fold the four step-lanes of points 0..7, and the 16 (parity, step) lanes of points 8, 9
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) {
+    emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    if (o == 8) continue;
+    emax2 = fmax(emax2, __shfl_xor_sync(0xffffffffu, emax2, o));
+    emin2 = fmin(emin2, __shfl_xor_sync(0xffffffffu, emin2, o));
+  }
+  if (nsteps > 0) {
+    if (t4 == 0) {
+      if (emax > env_max[pt0 + g]) env_max[pt0 + g] = emax;
+      if (emin < env_min[pt0 + g]) env_min[pt0 + g] = emin;
+    }
+    if ((lane & 0x17) == 0) {
+      if (emax2 > env_max[pt0 + 8 + node2]) env_max[pt0 + 8 + node2] = emax2;
+      if (emin2 < env_min[pt0 + 8 + node2]) env_min[pt0 + 8 + node2] = emin2;
+    }
+  }
+}
+
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
 {
   cudaStream_t s = p->stream;
@@ -253,6 +427,8 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMalloc(&f.failed, f.nelt));
   FSR_CUDA(cudaMalloc(&f.Sfrag, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32));
   FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
+  FSR_CUDA(cudaMalloc(&f.Gfrag, sizeof(double) * (size_t)f.nelt * 12 * 32));
+  FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, sizeof(double) * (size_t)f.nelt * 12 * 32, s));
   FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
   FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
@@ -260,7 +436,7 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
   build_tet10_ops_kernel<<<(f.nelt + 63) / 64, 64, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny,
-                                                         d_pts, f.Sfrag, f.failed, f.aux);
+                                                         d_pts, f.Sfrag, f.failed, f.aux, f.Gfrag);
   FSR_LAUNCH_CHECK();
   FSR_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_conn);
@@ -273,9 +449,20 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
   FamilyData& f = p->fam[FAM_TET10];
   if (f.nelt == 0) return FSR_OK;
   const int warps = 8;
-  k2_tet10_vm_kernel<<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-      p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
-      ld_vm, p->env_max, p->env_min);
+  // FSR_TET10_DENSE=1 selects the dense 60x30 formulation (kept for A/B timing and as a cross-check)
+  static const bool dense = getenv("FSR_TET10_DENSE") && atoi(getenv("FSR_TET10_DENSE")) != 0;
+  if (dense)
+    k2_tet10_vm_kernel<<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
+        ld_vm, p->env_max, p->env_min);
+  else if (getenv("FSR_TET10_OCC1"))
+    k2_tet10_grad_vm_kernel<1><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
+        ld_vm, p->env_max, p->env_min);
+  else
+    k2_tet10_grad_vm_kernel<2><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
+        ld_vm, p->env_max, p->env_min);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }

@@ -1,0 +1,167 @@
+#!/usr/bin/env python
+"""bench_configs.py -- the BASELINE.json configurations that are NOT the headline line of bench.py, measured on one
+B200 with the same rules (CUDA events on the launching stream, >= 3 warm-up steps, inputs larger than L2):
+
+  c3  mixed 10-node-tet solid + beam part (default 2,000,000 tets + 2 % beams), von Mises + envelope
+      -> element.time-step evaluations/s, roofline of the TET10 kernel (320 algorithmic bytes per element.step)
+  c5  strain-gage rosette recovery with rainflow counting and damage (default 100,000 rosettes, 100,000 steps)
+      -> gage-point.time-step evaluations/s; the rosette GEMM against the FP64 peak, the streaming
+         PVX + rainflow kernel in samples/s and GB/s of history consumed (8 B per sample)
+  c1  the reference's own CPU-sized case (70 x 70 quads, n_red = 34, 1,000 steps) through the host API
+
+One JSON line per configuration on stdout.  These are profile lines (profiles/), not the driver's bench contract."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+HBM_PEAK = 6546.2
+try:
+    HBM_PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+DGEMM_PEAK = 35.45   # TFLOP/s, profiles/r01_fp64_peaks.txt
+
+
+def c3(args):
+    import torch
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import tet10_block, reduced_history
+    lib = load_library()
+    n = round((args.elements / 6) ** (1 / 3))
+    t0 = time.time()
+    part = tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)))
+    tile, steps, warm = args.tile, args.steps, 3
+    rec = StressRecovery(part, device=0, step_tile=((tile + 63) // 64) * 64)
+    setup = time.time() - t0
+    nel, ndim, npts = part.sam.nel, part.sam.ndim, rec.npts
+    ntet = int((part.sam.melcon == 41).sum())
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * (steps + warm), seed=3).T)).to(dev)
+    for i in range(warm):
+        rec.recover_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    torch.cuda.synchronize()
+    rec.reset_envelope(); rec.timing_reset(); lib.fsr_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        rec.recover_dev(Q[(warm + i) * tile:(warm + i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tm = rec.last_timing()
+    k2 = tm["k2_ms"] / max(tm["tiles"], 1)
+    k1 = tm["k1_ms"] / max(tm["tiles"], 1)
+    # envelope only: 240 B read per TET10 element.step (the 80 B of von Mises stay in registers -> envelope)
+    alg = 240.0 * ntet * tile
+    mx, mn = rec.envelope()
+    return {"config": "C3", "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
+            "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
+            "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2, {part.sam.ndof} DOF, n_red={ndim}, {tile} time "
+                        f"steps per step, von Mises envelope (no per-step history kept)",
+            "roofline": {"kernel": "k2_tet10_vm_kernel", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK,
+                         "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch": k2,
+                         "algorithmic_bytes_per_launch": alg,
+                         "dmma_tflops": 2.0 * 64 * 32 * ntet * tile / (k2 * 1e-3) / 1e12},
+            "k1": {"ms_per_launch": k1, "tflops": 2.0 * part.sam.ndof * ndim * tile / (k1 * 1e-3) / 1e12, "peak": DGEMM_PEAK},
+            "gpu_launches": int(lib.fsr_kernel_launches(0)), "setup_s": setup, "max_von_mises": float(mx.max())}
+
+
+def c5(args):
+    import torch
+    from fedem_solvers_b200 import StressRecovery, StrainGages, load_library
+    from fedem_solvers_b200.model import plate_part, reduced_history, rosettes_on_part
+    lib = load_library()
+    part = plate_part(200, 200, ngen=50, n_ext=8, seed=5)
+    rec = StressRecovery(part, device=0, step_tile=512)
+    ros = rosettes_on_part(part, args.gages, seed=5)
+    t0 = time.time()
+    g = StrainGages(rec, ros)
+    setup = time.time() - t0
+    rec.close()
+    ndim, tile = part.sam.ndim, args.tile
+    ntiles = args.nsteps // tile
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    # a band-limited random history with enough amplitude to produce cycles above the gate
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * ntiles, seed=5, amp=2.0e-3).T)).to(dev)
+    g.fatigue_begin(to_mpa=1.0e-6, gate=5.0, bin_size=10.0, nbins=8)
+    for i in range(min(3, ntiles)):   # warm-up on throw-away state
+        g.fatigue_feed_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, i * tile, tile, 1, stream.cuda_stream)
+    g.fatigue_end()
+    torch.cuda.synchronize()
+    lib.fsr_kernel_launches(1)
+    g.fatigue_begin(to_mpa=1.0e-6, gate=5.0, bin_size=10.0, nbins=8)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    pending, i = 1, 0
+    while pending and i < ntiles:   # locate pass (normally one tile)
+        pending = g.fatigue_feed_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, i * tile, tile, 0, stream.cuda_stream, want_pending=True)
+        i += 1
+    e1.record()
+    for i in range(ntiles):
+        g.fatigue_feed_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, i * tile, tile, 1, stream.cuda_stream)
+    res = g.fatigue_end()
+    e2.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e2)
+    nseries = 4 * args.gages
+    samples = float(nseries) * tile * ntiles
+    return {"config": "C5", "metric": "gage_point_timestep_evals_per_sec", "value": args.gages * tile * ntiles / (ms * 1e-3),
+            "unit": "rosette*steps/s", "n_gpus": 1, "ms_total": ms, "ms_locate_pass": e0.elapsed_time(e1), "dtype": "f64",
+            "workload": f"{args.gages} TRIPLE_GAGE_45 rosettes x {tile * ntiles} time steps (tiles of {tile}), n_red={ndim}: "
+                        "Bcart GEMM -> Mohr circle / leg stresses -> PVX + rainflow + Miner damage + 8-bin cycle histogram, "
+                        f"{nseries} series",
+            "rainflow": {"samples_per_s": samples / (ms * 1e-3), "history_gbs": 8.0 * samples / (ms * 1e-3) / 1e9,
+                         "hbm_frac_if_materialised": 8.0 * samples / (ms * 1e-3) / 1e9 / HBM_PEAK},
+            "gemm_tflops_equiv": 2.0 * 3 * args.gages * ndim * tile * ntiles / (ms * 1e-3) / 1e12,
+            "gpu_launches": int(lib.fsr_kernel_launches(0)), "setup_s": setup,
+            "cycles_total": int(res["ncycles"][res["ncycles"] > 0].sum()), "series_with_status": int((res["status"] != 0).sum()),
+            "damage_max": float(res["damage"].max())}
+
+
+def c1(args):
+    import torch
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import plate_part, reduced_history
+    lib = load_library()
+    part = plate_part(70, 70, ngen=10, n_ext=4, seed=1)
+    rec = StressRecovery(part, device=0)
+    Q = reduced_history(part.sam.ndim, 1000, seed=1)
+    rec.recover(Q[:, :64], want_history=False)
+    torch.cuda.synchronize()
+    rec.reset_envelope(); lib.fsr_kernel_launches(1)
+    t0 = time.perf_counter()
+    vm = rec.recover(Q, want_history=True)     # host in, host out: the whole 1,000-step von Mises history
+    mx, mn = rec.envelope()
+    dt = time.perf_counter() - t0
+    return {"config": "C1", "metric": "element_timestep_stress_evals_per_sec", "value": part.sam.nel * 1000 / dt,
+            "unit": "element*steps/s", "n_gpus": 1, "seconds": dt, "dtype": "f64",
+            "workload": f"70x70 ANDES quads ({part.sam.nel} elements, {part.sam.ndof} DOF), n_red={part.sam.ndim}, 1000 steps, "
+                        "host Q in -> full von Mises history + envelope back on the host (fsr_recover + fsr_get_envelope)",
+            "h2d_bytes": int(Q.nbytes), "d2h_bytes": int(vm.nbytes + mx.nbytes + mn.nbytes),
+            "gpu_launches": int(lib.fsr_kernel_launches(0))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["c1", "c3", "c5"])
+    ap.add_argument("--elements", type=int, default=2_000_000, help="c3: number of TET10 elements")
+    ap.add_argument("--tile", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--gages", type=int, default=100_000)
+    ap.add_argument("--nsteps", type=int, default=100_000)
+    args = ap.parse_args()
+    for c in args.configs:
+        print(json.dumps({"c1": c1, "c3": c3, "c5": c5}[c](args)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,9 +32,10 @@ def full(path):
         for m in METRICS:
             if m in d:
                 print(f"   {m:78s} {d[m]:>16s} {units[hdr.index(m)]}")
-        try:
-            tr = float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"])
-            print(f"   {'traffic = dram read + write':78s} {tr:16.4f} {units[hdr.index('dram__bytes_read.sum')]}")
+        try:   # the two columns may carry different units (Gbyte / Mbyte / Kbyte)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            tr = sum(float(d[m]) * scale[units[hdr.index(m)]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            print(f"   {'traffic = dram read + write':78s} {tr / 1e9:16.4f} Gbyte")
         except Exception:
             pass
 
