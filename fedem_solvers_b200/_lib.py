@@ -150,6 +150,13 @@ SYMBOLS = [
     ("fsr_cmdline_get_double", C.c_double, [C.c_char_p]),
     ("fsr_cmdline_get_string", C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     ("fsr_cmdline_is_set", C.c_int, [C.c_char_p]),
+    ("fsr_recovery_register", C.c_int, [C.c_int, _P, _I]),
+    ("fsr_recovery_unregister", C.c_int, [C.c_int]),
+    ("fsr_recovery_update", C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, _D]),
+    ("getPartDeformationStateSize", C.c_int, [C.c_int]),
+    ("getPartStressStateSize", C.c_int, [C.c_int]),
+    ("savePartDeformationState", C.c_bool, [C.c_int, _D, C.c_int]),
+    ("savePartStressState", C.c_bool, [C.c_int, _D, C.c_int]),
     ("fsr_last_error", C.c_char_p, []),
     ("fsr_kernel_launches", C.c_longlong, [C.c_int]),
     ("fsr_last_timing", C.c_int, [_P, _D, C.c_int]),

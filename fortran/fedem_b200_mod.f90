@@ -767,6 +767,55 @@ module fedem_b200_mod
        integer(c_int) :: v
      end function fsr_cmdline_is_set
 
+     ! ---- in-core part state (the solver's recovery list, polled by fedempy) ------------------
+     function fsr_recovery_register (base_id, part, minex) bind(C,name="fsr_recovery_register") result(ierr)
+       import :: c_ptr, c_int
+       integer(c_int), value      :: base_id
+       type(c_ptr)   , value      :: part
+       integer(c_int), intent(in) :: minex(*)
+       integer(c_int) :: ierr
+     end function fsr_recovery_register
+
+     function fsr_recovery_unregister (base_id) bind(C,name="fsr_recovery_unregister") result(ierr)
+       import :: c_int
+       integer(c_int), value :: base_id
+       integer(c_int) :: ierr
+     end function fsr_recovery_unregister
+
+     function fsr_recovery_update (base_id, istep, time, timeStep, q) bind(C,name="fsr_recovery_update") result(ierr)
+       import :: c_int, c_double
+       integer(c_int), value      :: base_id, istep
+       real(c_double), value      :: time, timeStep
+       real(c_double), intent(in) :: q(*)
+       integer(c_int) :: ierr
+     end function fsr_recovery_update
+
+     function getPartDeformationStateSize (bid) bind(C,name="getPartDeformationStateSize") result(ndat)
+       import :: c_int
+       integer(c_int), value :: bid
+       integer(c_int) :: ndat
+     end function getPartDeformationStateSize
+
+     function getPartStressStateSize (bid) bind(C,name="getPartStressStateSize") result(ndat)
+       import :: c_int
+       integer(c_int), value :: bid
+       integer(c_int) :: ndat
+     end function getPartStressStateSize
+
+     function savePartDeformationState (bid, data, ndat) bind(C,name="savePartDeformationState") result(ok)
+       import :: c_int, c_double, c_bool
+       integer(c_int), value       :: bid, ndat
+       real(c_double), intent(out) :: data(*)
+       logical(c_bool) :: ok
+     end function savePartDeformationState
+
+     function savePartStressState (bid, data, ndat) bind(C,name="savePartStressState") result(ok)
+       import :: c_int, c_double, c_bool
+       integer(c_int), value       :: bid, ndat
+       real(c_double), intent(out) :: data(*)
+       logical(c_bool) :: ok
+     end function savePartStressState
+
      ! ---- diagnostics ------------------------------------------------------------------------
      function fsr_last_error () bind(C,name="fsr_last_error") result(msg)
        import :: c_ptr

@@ -19,6 +19,7 @@
 #ifndef FEDEM_B200_H
 #define FEDEM_B200_H
 
+#include <stdbool.h>
 #include <stddef.h>
 
 #ifdef __cplusplus
@@ -451,6 +452,25 @@ int fsr_cmdline_get_int(const char *name);
 double fsr_cmdline_get_double(const char *name);
 int fsr_cmdline_get_string(const char *name, char *out, int cap);
 int fsr_cmdline_is_set(const char *name);
+
+/* ---- in-core part state for fedempy ----------------------------------------------------------------
+ * The four functions fedempy's FedemSolver.save_part_state / get_part_*_state_size call
+ * (PythonAPI/src/fedempy/solver.py:524-629), with the reference's names, argument lists and data layout
+ * (src/vpmSolver/solverInterface.C:940-1001 -> solverModule.f90:2183-2263 -> stressRecoveryModule.f90:115-267):
+ *  data[0:4] = step number, time, time step size, part base id; then
+ *  deformation: 3 translational deformations per node in SAM node order (0 for minex <= 0), size 3*nnod + 4;
+ *  stress     : the vms array of fsr_get_vms, size fsr_vms_size + 4.
+ * Sizes: -1 = no such part, -999 = no part registered at all (the reference's "not allocated").
+ * fsr_recovery_register makes a part known under its base id (minex [nnod] may be NULL);
+ * fsr_recovery_update is the solver's per-step recovery: it expands q = [finit; vg] of the converged step and
+ * evaluates the von Mises stresses on the device, keeping both in core for the save calls. */
+int fsr_recovery_register(int base_id, fsr_part *part, const int *minex);
+int fsr_recovery_unregister(int base_id);
+int fsr_recovery_update(int base_id, int step, double time, double time_step, const double *q);
+int getPartDeformationStateSize(int bid);
+int getPartStressStateSize(int bid);
+bool savePartDeformationState(int bid, double *data, int ndat);
+bool savePartStressState(int bid, double *data, int ndat);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 const char *fsr_last_error(void);

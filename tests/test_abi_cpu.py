@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     txt = open(os.path.join(ROOT, "include", "fedem_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(fsr_[a-z0-9_]+)\s*\(", txt)))
+    # fsr_* entry points + the exported names kept from the reference (stressInterface.C, solverInterface.C)
+    return sorted(set(re.findall(r"\b(fsr_[a-z0-9_]+|initSolverArgs|solveStress|(?:get|save)Part[A-Za-z]+)\s*\(", txt)))
 
 
 def test_header_symbols_are_exported():
@@ -31,7 +32,17 @@ def test_fortran_interface_covers_header():
     Fortran host code) binds every C entry point by its exact name."""
     f90 = open(os.path.join(ROOT, "fortran", "fedem_b200_mod.f90")).read().lower()
     for n in _declared_symbols():
-        assert f'name="{n}"' in f90 or f"name='{n}'" in f90, n
+        assert f'name="{n.lower()}"' in f90 or f"name='{n.lower()}'" in f90, n
+
+
+def test_part_state_entry_points_without_parts():
+    """getPartStressStateSize & co. before any part is registered: the reference's 'not allocated' answer."""
+    from fedem_solvers_b200 import _lib
+    lib = _lib.load_library()
+    assert lib.getPartDeformationStateSize(7) == -999 and lib.getPartStressStateSize(7) == -999
+    buf = np.zeros(8)
+    assert lib.savePartStressState(7, buf.ctypes.data_as(_lib._D), 8) and buf[3] == 7.0   # header only, like the reference
+    assert not lib.savePartStressState(7, buf.ctypes.data_as(_lib._D), 3)
 
 
 def test_no_gpu_fails_loudly():

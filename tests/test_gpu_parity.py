@@ -196,3 +196,45 @@ def test_degenerate_element_gets_huge(oracle):
     assert bad.any() and np.array_equal(bad, vm_g >= 1e300)
     assert rel_err(vm_g[~bad], vm_o[~bad]) <= TOL
     rec.close()
+
+
+def test_fedempy_part_state_entry_points(oracle):
+    """getPartStressStateSize / savePartStressState / savePartDeformationState (solverInterface.C:940-1001) over a
+    registered part: header [step, time, dt, baseId], then vms = [iel, nenod, nstrp, vm...] per element with stress
+    points / 3 deformations per node."""
+    import ctypes as C
+    from fedem_solvers_b200 import _lib
+    lib = _lib.load_library()
+    part = plate_part(6, 5, ngen=4, seed=9, tri_fraction=0.4)
+    b = oracle.bind_part(part)
+    rec = StressRecovery(part)
+    Q = reduced_history(part.sam.ndim, 3, seed=7)
+    minex = np.ascontiguousarray(part.sam.minex, np.int32).copy()
+    minex[2] = -3   # an internal beam-pin node: no output
+    assert lib.fsr_recovery_register(31, rec._h, minex.ctypes.data_as(_lib._I)) == 0
+    assert lib.getPartStressStateSize(32) == -1
+    nd, ns = lib.getPartDeformationStateSize(31), lib.getPartStressStateSize(31)
+    assert nd == 3 * part.sam.nnod + 4 and ns == 4 + sum(3 + n for n in part.nstrp() if n > 0)
+    q = np.ascontiguousarray(Q[:, 2])
+    assert lib.fsr_recovery_update(31, 12, 0.375, 0.005, q.ctypes.data_as(_lib._D)) == 0
+    d, s = np.zeros(nd), np.zeros(ns)
+    assert lib.savePartDeformationState(31, d.ctypes.data_as(_lib._D), nd) and lib.savePartStressState(31, s.ctypes.data_as(_lib._D), ns)
+    assert not lib.savePartStressState(31, s.ctypes.data_as(_lib._D), ns - 1)
+    assert list(d[:4]) == [12.0, 0.375, 0.005, 31.0] and list(s[:4]) == [12.0, 0.375, 0.005, 31.0]
+    sv = oracle.expand(b, q)
+    ref = oracle.calc_stresses(b, sv)
+    want = np.stack([sv[part.sam.madof[:-1] - 1 + k] for k in range(3)], 1)
+    want[2] = 0.0
+    assert np.abs(d[4:].reshape(-1, 3) - want).max() <= TOL * np.abs(sv).max()
+    k, scale = 4, np.abs(ref["resmat"][:, 0]).max()
+    for e in range(part.sam.nel):
+        n = int(part.nstrp()[e])
+        if n == 0:
+            continue
+        assert (s[k], s[k + 2]) == (e + 1, n)
+        p0 = b["ptoff"][e]
+        assert np.abs(s[k + 3:k + 3 + n] - ref["resmat"][p0:p0 + n, 0]).max() <= TOL * scale
+        k += 3 + n
+    assert k == ns
+    assert lib.fsr_recovery_unregister(31) == 0
+    rec.close()
