@@ -292,6 +292,13 @@ def run_b200(args, rank, world, local_rank):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k2_shell_vm_kernel<6>"]
+        if t["nx"] == args.nx and t["tile"] == tile:
+            traffic = {"bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"]}
+    except Exception:
+        pass
     achieved = QUAD_BYTES * nel * tile / (k2_ms * 1e-3) / 1e9
     k1_flops = 2.0 * part.sam.ndof * ndim * tile
     dgemm_peak = 35.45  # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt)
@@ -308,7 +315,8 @@ def run_b200(args, rank, world, local_rank):
                          (part.sam.ndof * tile * 8 / 1e9, npts * tile * 8 / 1e9)},
         "roofline": {"kernel": "k2_shell_vm_kernel<6> (ANDES quad von Mises + envelope)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": peak_src, "traffic": None, "ms_per_launch": k2_ms,
+                     "peak_source": peak_src, "traffic": traffic["bytes_per_launch"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None, "ms_per_launch": k2_ms,
                      "algorithmic_bytes_per_launch": QUAD_BYTES * nel * tile},
         "k1": {"kernel": "k1_expand_kernel (DMMA.8x8x4)", "bound": "fp64 tensor", "ms_per_launch": k1_ms,
                "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": dgemm_peak, "unit": "TFLOP/s",
