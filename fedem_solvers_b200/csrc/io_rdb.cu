@@ -469,6 +469,9 @@ static long long build_header(int nnod, const int* madof, int nel, const int* me
       case 22: case 24: if (!ig[22]) ig[22] = hb.shell(L, "QUAD4", 4); nelnod = 4; ncmp = 3; break;
       case 41: if (!ig[t]) ig[t] = hb.solid(L, "TET10", 10); nelnod = 10; ncmp = 6; break;
       case 43: if (!ig[t]) ig[t] = hb.solid(L, "HEX20", 20); nelnod = 20; ncmp = 6; break;
+      case 44: if (!ig[t]) ig[t] = hb.solid(L, "HEX8", 8); nelnod = 8; ncmp = 6; break;
+      case 45: if (!ig[t]) ig[t] = hb.solid(L, "TET4", 4); nelnod = 4; ncmp = 6; break;
+      case 46: if (!ig[t]) ig[t] = hb.solid(L, "WEDG6", 6); nelnod = 6; ncmp = 6; break;
       default: continue;   // element types without a stress operator in this library
     }
     const int key = t == 23 ? 21 : t == 24 ? 22 : t;
@@ -655,7 +658,7 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
       } else {
         if (f.nstrp == 0) continue;
         dim3 grd((unsigned)(((long long)f.nelt * f.nstrp + 7) / 8), (nt + 31) / 32);
-        const int layout = (fi == FAM_TET10 || fi == FAM_HEX20) ? 1 : 0;
+        const int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : 1;
         record_points_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, f.Sfrag, f.edof, r->roff[fi], f.failed, f.aux,
                                                  f.naux, f.nelt, f.nstrp, f.ncmp, f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod,
                                                  r->L, r->rec, ldt);

@@ -94,7 +94,7 @@ int launch_k2_full(fsr_part* p, double* resmat, double* stress, double* strain, 
     FamilyData& f = p->fam[fi];
     if (f.nelt == 0 || f.nstrp == 0) continue;
     int total = f.nelt * f.nstrp;
-    int layout = (fi == FAM_TET10 || fi == FAM_HEX20) ? 1 : 0;
+    int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : 1;
     k2_full_kernel<<<(total + 127) / 128, 128, 0, s>>>(p->U, (size_t)p->step_tile, f.Sfrag, f.edof, f.ptoff,
                                                       f.elem, f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
                                                       f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod, resmat,

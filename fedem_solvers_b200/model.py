@@ -67,7 +67,7 @@ class PartModel:
     recovery_seed: int = 0   # seed of the synthetic [B|E] fields (synthetic_recovery)
 
     def nstrp(self):
-        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 43: 20}
+        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 43: 20, 44: 8, 45: 4, 46: 6}
         n = np.array([tab.get(int(t), 0) for t in self.sam.melcon], I32)
         if self.elm.elmid is not None:
             n[self.elm.elmid < 1] = 0
@@ -414,6 +414,55 @@ def hex20_block(nx, ny, nz, ngen=8, seed=6, n_ext=4, jitter=0.04, emod=2.1e11, r
     elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64), thk=np.zeros(nel, F64),
                       elmid=np.arange(1, nel + 1, dtype=I32))
     part = PartModel(sam=sam, elm=elm, name=f"hex20_{nx}x{ny}x{nz}")
+    part.recovery_seed = seed
+    if with_recovery:
+        part.B, part.E = synthetic_recovery(part)
+    return part
+
+
+def linsolid_block(nx, ny, nz, ngen=6, seed=8, n_ext=4, jitter=0.08, emod=2.1e11, rny=0.3, shuffle_eq=False,
+                   kinds=(44, 45, 46), with_recovery=True):
+    """Structured block of nx*ny*nz cells filled, cell by cell in turn, with the linear solids of `kinds`:
+    one 8-node hexahedron (type 44, node order of HEXA32: bottom face counter-clockwise, then the top face),
+    six 4-node tetrahedra (type 45, positive volume as cstetbmat demands) or two 6-node wedges (type 46, bottom
+    triangle then top triangle).  Jittered nodes, so no element is a parallelepiped."""
+    rng = np.random.default_rng(seed)
+    NX, NY, NZ = nx + 1, ny + 1, nz + 1
+    nid = lambda i, j, k: 1 + i + NX * (j + NY * k)
+    gi = np.stack(np.meshgrid(np.arange(NX), np.arange(NY), np.arange(NZ), indexing="ij"), -1).reshape(-1, 3)
+    xyz = np.zeros((NX * NY * NZ, 3))
+    for i, j, k in gi:
+        xyz[nid(i, j, k) - 1] = (i, j, k)
+    xyz += rng.uniform(-jitter, jitter, xyz.shape)
+    conn, types = [], []
+    cell = 0
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                c = [nid(i, j, k), nid(i + 1, j, k), nid(i + 1, j + 1, k), nid(i, j + 1, k),
+                     nid(i, j, k + 1), nid(i + 1, j, k + 1), nid(i + 1, j + 1, k + 1), nid(i, j + 1, k + 1)]
+                t = kinds[cell % len(kinds)]
+                cell += 1
+                if t == 44:
+                    conn.append(np.array(c, I32)); types.append(44)
+                elif t == 46:
+                    for tri in ((0, 1, 2), (0, 2, 3)):
+                        conn.append(np.array([c[q] for q in tri] + [c[q + 4] for q in tri], I32)); types.append(46)
+                else:   # six tetrahedra around the cell diagonal 0-6
+                    for a, b in ((1, 2), (2, 3), (3, 7), (7, 4), (4, 5), (5, 1)):
+                        tet = [c[0], c[a], c[b], c[6]]
+                        X = xyz[np.array(tet) - 1]
+                        if np.dot(np.cross(X[1] - X[0], X[2] - X[0]), X[3] - X[0]) < 0:
+                            tet[1], tet[2] = tet[2], tet[1]
+                        conn.append(np.array(tet, I32)); types.append(45)
+    cand = [(0, 0, 0), (nx, 0, 0), (0, ny, 0), (nx, ny, nz), (0, 0, nz), (nx, ny, 0), (0, ny, nz), (nx, 0, nz)]
+    ext_nodes = [nid(*c) for c in cand[:n_ext]]
+    sam = _build_sam(len(xyz), 3, conn, np.asarray(types, I32), ext_nodes, rng=rng, shuffle_eq=shuffle_eq)
+    sam.ngen = ngen
+    nel = sam.nel
+    elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64), thk=np.zeros(nel, F64),
+                      elmid=np.arange(1, nel + 1, dtype=I32))
+    part = PartModel(sam=sam, elm=elm, name=f"linsolid_{nx}x{ny}x{nz}")
     part.recovery_seed = seed
     if with_recovery:
         part.B, part.E = synthetic_recovery(part)

@@ -102,6 +102,24 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     get_coor(iel, sam, ed, 20, x, y, z);
     ierr = orc_str43(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
     break;
+  case 44:
+    *nenod = 8;
+    *nstrp = 8;
+    get_coor(iel, sam, ed, 8, x, y, z);
+    ierr = orc_str44(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
+    break;
+  case 45:
+    *nenod = 4;
+    *nstrp = 4;
+    get_coor(iel, sam, ed, 4, x, y, z);
+    ierr = orc_str45(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], V, Sigma, Epsil);
+    break;
+  case 46:
+    *nenod = 6;
+    *nstrp = 6;
+    get_coor(iel, sam, ed, 6, x, y, z);
+    ierr = orc_str46(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
+    break;
   default:
     return 0; /* silently ignore all other element types */
   }
@@ -135,6 +153,9 @@ static int nstrp_of(int t) /* elStressModule.f90:159-229 */
   case 22: case 24: return 8;
   case 41: return 10;
   case 43: return 20;
+  case 44: return 8;
+  case 45: return 4;
+  case 46: return 6;
   }
   return 0;
 }

@@ -94,6 +94,14 @@ int orc_str41(const double xg[10], const double yg[10], const double zg[10], dou
 int orc_str43(const double xg[20], const double yg[20], const double zg[20], double emod,
               double rny, int stressForm, const double v[60], double sigma[120],
               double epsil[120]);
+/* linear solids (solids_lin.c): STR44 HEX8 (sigma/epsil (6,8)), STR45 TET4 ((6,4)), STR46 WEDG6 ((6,6)).
+ * Component order: HEX8 (xx,yy,zz,xy,xz,yz); TET4 and WEDG6 (xx,yy,zz,xy,yz,zx) as their B-matrices give it. */
+int orc_str44(const double *x, const double *y, const double *z, double emod, double rny, int stressForm, const double *v,
+              double *sigma, double *epsil);
+int orc_str45(const double *x, const double *y, const double *z, double emod, double rny, const double *v, double *sigma,
+              double *epsil);
+int orc_str46(const double *x, const double *y, const double *z, double emod, double rny, int stressForm, const double *v,
+              double *sigma, double *epsil);
 int orc_str11(const double *beam, const double ev[12], double SF[12]);
 int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed,
                   double *V, double *S, double *Sigma, double *Epsil, int *nenod, int *nstrp);

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from fedem_solvers_b200 import StressRecovery
-from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, reduced_history
+from fedem_solvers_b200.model import linsolid_block, plate_part, tet10_block, hex20_block, reduced_history
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
@@ -237,4 +237,49 @@ def test_fedempy_part_state_entry_points(oracle):
         k += 3 + n
     assert k == ns
     assert lib.fsr_recovery_unregister(31) == 0
+    rec.close()
+
+
+def test_linear_solids_hex8_tet4_wedg6(oracle):
+    """types 44, 45, 46: gradient-form von Mises kernel + dense full-result operator against the oracle"""
+    part = linsolid_block(3, 2, 2, ngen=5, seed=8, shuffle_eq=True)
+    assert {44, 45, 46} <= set(int(t) for t in part.sam.melcon)
+    _check_part(oracle, part, nsteps=70, seed=3)
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 2, seed=5)
+    rec = StressRecovery(part)
+    full = rec.calc_stresses(Q[:, 1])
+    ref = oracle.calc_stresses(b, oracle.expand(b, Q[:, 1]))
+    for k, tol in (("stress", TOL), ("strain", TOL), ("resmat", 1e-9)):
+        for c in range(ref[k].shape[1]):
+            sc = np.abs(ref[k][:, c % 4::4] if k == "resmat" else ref[k]).max()
+            assert np.abs(full[k][:, c] - ref[k][:, c]).max() <= tol * sc, (k, c)
+    rec.close()
+
+
+@pytest.mark.parametrize("form", [1, 2])
+def test_linear_solids_gauss_point_forms(oracle, form):
+    """-stressForm 1 (HEX8 volume average, WEDG6 mid-plane scheme) and 2 (extrapolation from the Gauss points)"""
+    import ctypes as C
+    from oracle_bind import _dp
+    part = linsolid_block(2, 2, 2, ngen=4, seed=9, kinds=(44, 46))
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 9, seed=2)
+    rec = StressRecovery(part, stress_form=form)
+    vm_g = rec.recover(Q)
+    X = part.elm.xyz
+    off = rec.result_point_offsets()
+    for e in range(part.sam.nel):
+        t = int(part.sam.melcon[e])
+        nodes = part.sam.mmnpc[part.sam.mpmnpc[e] - 1: part.sam.mpmnpc[e + 1] - 1] - 1
+        nn = len(nodes)
+        for s in (0, 8):
+            sv = oracle.expand(b, Q[:, s])
+            v = np.ascontiguousarray(np.stack([sv[3 * n: 3 * n + 3] for n in nodes]).ravel())
+            xg, yg, zg = (np.ascontiguousarray(X[nodes, k]) for k in range(3))
+            sig, eps = np.zeros(6 * nn), np.zeros(6 * nn)
+            fn = oracle.lib.orc_str44 if t == 44 else oracle.lib.orc_str46
+            assert fn(_dp(xg), _dp(yg), _dp(zg), C.c_double(part.elm.emod[e]), C.c_double(part.elm.rny[e]), form, _dp(v), _dp(sig), _dp(eps)) == 0
+            vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(nn)])
+            assert rel_err(vm_g[s, off[e]:off[e] + nn], vm_o) <= TOL, (t, e, s)
     rec.close()

@@ -8,7 +8,7 @@ import pytest
 
 from fedem_solvers_b200 import StressRecovery
 from fedem_solvers_b200.frs import FrsReader
-from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, reduced_history
+from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, linsolid_block, reduced_history
 from fedem_solvers_b200.rdb import StressRdb, out_mask
 from test_rdb_cpu import NAMES, NENOD, MEASURES
 
@@ -179,3 +179,9 @@ def test_tets_and_beams_multi_tile(oracle, tmp_path):
 def test_hex20_strain_measures_float(oracle, tmp_path):
     part = hex20_block(2, 2, 1, ngen=4, seed=6)
     _check(oracle, part, tmp_path, out_mask(strain=True, vmStrain=True, maxSStrain=True), False, nsteps=5)
+
+
+def test_linear_solids_all_measures_double(oracle, tmp_path):
+    part = linsolid_block(2, 2, 1, ngen=4, seed=7)
+    mask = out_mask(stress=True, strain=True, vmStress=True, maxPStress=True, minPStress=True, maxSStress=True, vmStrain=True)
+    _check(oracle, part, tmp_path, mask, True, nsteps=6)
