@@ -11,6 +11,8 @@
 // order (57.6 KB), the element's 60 rows of U are staged per 8-step tile, each warp owns a share
 // of the 15 m-tiles, accumulators are transposed through shared memory so that one thread sees the
 // six components of a node for von Mises (FFaTensorTransforms.C:38-43) and the fused envelope.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fsr {
@@ -52,13 +54,14 @@ __device__ void hex20_dn(double xi, double et, double ze, double* dx, double* de
 __global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, const int* __restrict__ conn,
                                        const double* __restrict__ xyz, const double* __restrict__ emod,
                                        const double* __restrict__ rny, int stressForm, double* __restrict__ Sfrag,
-                                       unsigned char* __restrict__ failed, double* __restrict__ aux)
+                                       unsigned char* __restrict__ failed, double* __restrict__ aux, double* __restrict__ Gfrag)
 {
   constexpr int KT = 15, MT = 15;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelt) return;
   const int e = elem[i];
   double* S = Sfrag + (size_t)i * MT * KT * 32;
+  double* G = Gfrag + (size_t)i * 9 * 5 * 32;   // displacement-gradient operator, see k2_hex20_grad_vm_kernel
   double X[20], Y[20], Z[20];
   for (int k = 0; k < 20; ++k) {
     const int n = conn[i * 20 + k];
@@ -105,22 +108,125 @@ __global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, c
       // D*B block of node j: rows xx,yy,zz,xy,xz,yz ; columns u,v,w  (ihex.f:430-450)
       const double db[6][3] = {{D * bx, D1 * by, D1 * bz}, {D1 * bx, D * by, D1 * bz}, {D1 * bx, D1 * by, D * bz},
                                {D2 * by, D2 * bx, 0.0},    {D2 * bz, 0.0, D2 * bx},    {0.0, D2 * bz, D2 * by}};
+      const double bd[3] = {bx, by, bz};
       if (stressForm == 0) {
         for (int c = 0; c < 6; ++c)
           for (int d = 0; d < 3; ++d) S[frag_index_g(q * 6 + c, 3 * j + d, KT)] = db[c][d];
+        for (int d = 0; d < 3; ++d) G[frag_index_g(((q >> 3) * 3 + d) * 8 + (q & 7), j, 5)] = bd[d];
       } else {
         for (int n = 0; n < 20; ++n) {
           const double w = (1.0 + ((q & 1) ? 1.0 : -1.0) * (s3 * c_hx[n])) * (1.0 + ((q & 2) ? 1.0 : -1.0) * (s3 * c_he[n])) *
                            (1.0 + ((q & 4) ? 1.0 : -1.0) * (s3 * c_hz[n])) * 0.125;
           for (int c = 0; c < 6; ++c)
             for (int d = 0; d < 3; ++d) S[frag_index_g(n * 6 + c, 3 * j + d, KT)] += db[c][d] * w;
+          for (int d = 0; d < 3; ++d) G[frag_index_g(((n >> 3) * 3 + d) * 8 + (n & 7), j, 5)] += bd[d] * w;
         }
       }
     }
   }
-  if (!ok)
+  if (!ok) {
     for (int k = 0; k < MT * KT * 32; ++k) S[k] = 0.0;
+    for (int k = 0; k < 9 * 5 * 32; ++k) G[k] = 0.0;
+  }
   failed[i] = ok ? 0 : 1;
+}
+
+// Displacement-gradient form of the HEX20 von Mises kernel (same idea as k2_tet10_grad_vm_kernel, k2_solid.cu):
+// sigma = D . sym(grad u) and grad u at the 20 result points = [60 x 20] . [20 x 3].  The result points are taken in
+// three blocks of 8 DMMA rows (the last one holds 4); per block 3 m-tiles (one per derivative direction) x 5 k-tiles,
+// so lane (g, t4) owns all nine gradient entries of point 8 pb + g at its two steps and no transposition is needed.
+// 135 DMMA per 8 steps instead of 225 for the dense 120 x 60 operator, which stays for the full-result path.
+// One warp per element; the 15 B fragments (u, v, w of the 20 nodes, 8 steps) stay in registers for the three
+// blocks, the A fragments of a block stream from L1/L2 (5.6 KB per element, re-read every tile).
+__global__ void __launch_bounds__(128, 3)
+k2_hex20_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Gfrag,
+                        const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff,
+                        const unsigned char* __restrict__ failed, int nelt, double* __restrict__ vm, size_t ld_vm,
+                        double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  constexpr int KT = 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= nelt) return;
+  const double* gf = Gfrag + (size_t)i * 9 * KT * 32 + lane;
+  const int* ed = edof + (size_t)i * 60;
+  const double* urow[3][KT];
+#pragma unroll
+  for (int j = 0; j < KT; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) urow[c][j] = U + (size_t)__ldg(ed + 3 * (4 * j + t4) + c) * ldu + g;
+  const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
+  const double mu2 = E / (1.0 + nu);
+  const bool bad = failed[i] != 0;
+  const size_t pt0 = (size_t)ptoff[i];
+  double emax[3] = {0.0, 0.0, 0.0}, emin[3] = {kHuge, kHuge, kHuge};
+  const int ntiles = nsteps_pad >> 3;
+  double b[3][KT], bn[3][KT];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < KT; ++j) b[c][j] = urow[c][j][0];
+  for (int nt = 0; nt < ntiles; ++nt) {
+    if (nt + 1 < ntiles) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < KT; ++j) bn[c][j] = urow[c][j][(nt + 1) * 8];
+    }
+#pragma unroll
+    for (int pb = 0; pb < 3; ++pb) {
+      double a[3][KT];
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int j = 0; j < KT; ++j) a[m][j] = __ldg(gf + (size_t)((pb * 3 + m) * KT + j) * 32);
+      double acc[3][3][2];
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[m][c][0] = acc[m][c][1] = 0.0;
+#pragma unroll
+      for (int j = 0; j < KT; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int m = 0; m < 3; ++m) dmma884(acc[m][c][0], acc[m][c][1], a[m][j], b[c][j]);
+      const bool live = pb < 2 || g < 4;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int t = nt * 8 + 2 * t4 + q;
+        const double da = acc[0][0][q] - acc[1][1][q], db = acc[1][1][q] - acc[2][2][q], dc = acc[2][2][q] - acc[0][0][q];
+        const double gxy = acc[1][0][q] + acc[0][1][q], gxz = acc[2][0][q] + acc[0][2][q], gyz = acc[2][1][q] + acc[1][2][q];
+        const double dev = 0.5 * fma(da, da, fma(db, db, dc * dc));
+        const double shr = fma(gxy, gxy, fma(gxz, gxz, gyz * gyz));
+        double v = mu2 * sqrt_pos(fma(0.75, shr, dev));
+        if (bad) v = kHuge;
+        if (live && t < nsteps) {
+          if (vm) vm[(size_t)t * ld_vm + pt0 + 8 * pb + g] = v;
+          emax[pb] = fmax(emax[pb], v);
+          emin[pb] = fmin(emin[pb], v);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < KT; ++j) b[c][j] = bn[c][j];
+  }
+#pragma unroll
+  for (int pb = 0; pb < 3; ++pb) {
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+      emax[pb] = fmax(emax[pb], __shfl_xor_sync(0xffffffffu, emax[pb], o));
+      emin[pb] = fmin(emin[pb], __shfl_xor_sync(0xffffffffu, emin[pb], o));
+    }
+    if (t4 == 0 && nsteps > 0 && (pb < 2 || g < 4)) {
+      const size_t pt = pt0 + 8 * pb + g;
+      if (emax[pb] > env_max[pt]) env_max[pt] = emax[pb];
+      if (emin[pb] < env_min[pt]) env_min[pt] = emin[pb];
+    }
+  }
 }
 
 // Generic solid apply: NEN nodes, 6 stress components per node, 3 DOFs per node.
@@ -243,6 +349,8 @@ int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMalloc(&f.failed, f.nelt));
   FSR_CUDA(cudaMalloc(&f.Sfrag, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32));
   FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
+  FSR_CUDA(cudaMalloc(&f.Gfrag, sizeof(double) * (size_t)f.nelt * 9 * 5 * 32));
+  FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, sizeof(double) * (size_t)f.nelt * 9 * 5 * 32, s));
   FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
   FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
@@ -250,7 +358,7 @@ int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
   build_hex20_ops_kernel<<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny, p->stressForm,
-                                                         f.Sfrag, f.failed, f.aux);
+                                                         f.Sfrag, f.failed, f.aux, f.Gfrag);
   FSR_LAUNCH_CHECK();
   FSR_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_conn);
@@ -261,6 +369,16 @@ int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
 {
   FamilyData& f = p->fam[FAM_HEX20];
   if (f.nelt == 0) return FSR_OK;
+  // FSR_HEX20_DENSE=1 selects the dense 120x60 shared-memory formulation (A/B timing, cross-check)
+  static const bool dense = getenv("FSR_HEX20_DENSE") && atoi(getenv("FSR_HEX20_DENSE")) != 0;
+  if (!dense) {
+    const int warps = 4;
+    k2_hex20_grad_vm_kernel<<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag,
+                                                                               f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
+                                                                               ld_vm, p->env_max, p->env_min);
+    FSR_LAUNCH_CHECK();
+    return FSR_OK;
+  }
   static bool attr = false;
   const size_t smem = solid_smem_bytes<20>();
   if (!attr) {

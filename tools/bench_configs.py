@@ -74,6 +74,47 @@ def c3(args):
             "gpu_launches": int(lib.fsr_kernel_launches(0)), "setup_s": setup, "max_von_mises": float(mx.max())}
 
 
+def chex(args):
+    """HEX20 block (type 43, named by the north_star): von Mises envelope, gradient-form kernel."""
+    import torch
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import hex20_block, reduced_history
+    lib = load_library()
+    n = round(args.hex_elements ** (1 / 3))
+    part = hex20_block(n, n, n, ngen=50, seed=6, n_ext=16)
+    tile, steps, warm = args.tile, args.steps, 3
+    rec = StressRecovery(part, device=0, step_tile=((tile + 63) // 64) * 64)
+    nel, ndim = part.sam.nel, part.sam.ndim
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * (steps + warm), seed=3).T)).to(dev)
+    for i in range(warm):
+        rec.recover_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    torch.cuda.synchronize()
+    rec.reset_envelope(); rec.timing_reset(); lib.fsr_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        rec.recover_dev(Q[(warm + i) * tile:(warm + i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tm = rec.last_timing()
+    k2, k1 = tm["k2_ms"] / max(tm["tiles"], 1), tm["k1_ms"] / max(tm["tiles"], 1)
+    alg = 480.0 * nel * tile
+    mx, mn = rec.envelope()
+    return {"config": "HEX20", "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
+            "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
+            "workload": f"{n}x{n}x{n} HEX20 ({nel} elements, {part.sam.ndof} DOF), n_red={ndim}, {tile} time steps per step, "
+                        "von Mises envelope",
+            "roofline": {"kernel": "k2_hex20_grad_vm_kernel" if not os.environ.get("FSR_HEX20_DENSE") else "k2_solid_smem_vm_kernel<20>",
+                         "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK, "unit": "GB/s",
+                         "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch": k2, "algorithmic_bytes_per_launch": alg},
+            "k1": {"ms_per_launch": k1, "tflops": 2.0 * part.sam.ndof * ndim * tile / (k1 * 1e-3) / 1e12, "peak": DGEMM_PEAK},
+            "gpu_launches": int(lib.fsr_kernel_launches(0)), "max_von_mises": float(mx.max())}
+
+
 def c5(args):
     import torch
     from fedem_solvers_b200 import StressRecovery, StrainGages, load_library
@@ -156,11 +197,12 @@ def main():
     ap.add_argument("--elements", type=int, default=2_000_000, help="c3: number of TET10 elements")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--hex-elements", type=int, default=250_000)
     ap.add_argument("--gages", type=int, default=100_000)
     ap.add_argument("--nsteps", type=int, default=100_000)
     args = ap.parse_args()
     for c in args.configs:
-        print(json.dumps({"c1": c1, "c3": c3, "c5": c5}[c](args)), flush=True)
+        print(json.dumps({"c1": c1, "c3": c3, "c5": c5, "hex20": chex}[c](args)), flush=True)
 
 
 if __name__ == "__main__":
