@@ -25,6 +25,7 @@ static int nstrp_of(int type)
     case 21: case 23: return 6;
     case 22: case 24: return 8;
     case 41: return 10;
+    case 42: return 15;
     case 43: return 20;
     case 44: return 8;
     case 45: return 4;
@@ -33,7 +34,7 @@ static int nstrp_of(int type)
   }
 }
 
-static bool supported_type(int type) { return type == 24 || type == 23 || type == 41 || (type >= 43 && type <= 46) || type == 11; }
+static bool supported_type(int type) { return type == 24 || type == 23 || (type >= 41 && type <= 46) || type == 11; }
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -217,6 +218,7 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, 
   if ((rc = build_beam_operators(p, sam, elm))) return fail(rc);
   if ((rc = build_hex20_operators(p, sam, elm))) return fail(rc);
   if ((rc = build_linsolid_operators(p, sam, elm))) return fail(rc);
+  if ((rc = build_wedg15_operators(p, sam, elm))) return fail(rc);
   if ((rc = fsr_reset_envelope(p))) return fail(rc);
 
   // count failed elements (they get hugeVal results, the run continues)
@@ -342,6 +344,7 @@ static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   if ((rc = launch_k2_tet10_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if ((rc = launch_k2_hex20_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if ((rc = launch_k2_linsolid_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_wedg15_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if (ev) cudaEventRecord(ev[2], s);
   return FSR_OK;
 }

@@ -63,7 +63,7 @@ __device__ __forceinline__ double sqrt_pos(double x)
 
 // Element families handled by the K2 kernels.  A family fixes the operator shape:
 // MT m-tiles of 8 rows, KT k-tiles of 4 element DOFs.
-enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_HEX8 = 5, FAM_TET4 = 6, FAM_WEDG6 = 7, FAM_COUNT = 8 };
+enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_HEX8 = 5, FAM_TET4 = 6, FAM_WEDG6 = 7, FAM_WEDG15 = 8, FAM_COUNT = 9 };
 
 struct FamilyData {
   int nelt = 0;          // elements of this family (active only)
@@ -184,6 +184,8 @@ int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_beam_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int build_wedg15_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int launch_k2_wedg15_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);
 int build_linsolid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int launch_k2_linsolid_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);
 int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);

@@ -468,6 +468,7 @@ static long long build_header(int nnod, const int* madof, int nel, const int* me
       case 21: case 23: if (!ig[21]) ig[21] = hb.shell(L, "TRI3", 3); nelnod = 3; ncmp = 3; break;
       case 22: case 24: if (!ig[22]) ig[22] = hb.shell(L, "QUAD4", 4); nelnod = 4; ncmp = 3; break;
       case 41: if (!ig[t]) ig[t] = hb.solid(L, "TET10", 10); nelnod = 10; ncmp = 6; break;
+      case 42: if (!ig[t]) ig[t] = hb.solid(L, "WEDG15", 15); nelnod = 15; ncmp = 6; break;
       case 43: if (!ig[t]) ig[t] = hb.solid(L, "HEX20", 20); nelnod = 20; ncmp = 6; break;
       case 44: if (!ig[t]) ig[t] = hb.solid(L, "HEX8", 8); nelnod = 8; ncmp = 6; break;
       case 45: if (!ig[t]) ig[t] = hb.solid(L, "TET4", 4); nelnod = 4; ncmp = 6; break;

@@ -11,7 +11,9 @@
 // order (57.6 KB), the element's 60 rows of U are staged per 8-step tile, each warp owns a share
 // of the 15 m-tiles, accumulators are transposed through shared memory so that one thread sees the
 // six components of a node for von Mises (FFaTensorTransforms.C:38-43) and the fused envelope.
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -138,29 +140,35 @@ __global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, c
 // 135 DMMA per 8 steps instead of 225 for the dense 120 x 60 operator, which stays for the full-result path.
 // One warp per element; the 15 B fragments (u, v, w of the 20 nodes, 8 steps) stay in registers for the three
 // blocks, the A fragments of a block stream from L1/L2 (5.6 KB per element, re-read every tile).
+// The same kernel serves the 15-node wedge (type 42): NPB = 2 blocks of result points, KT = 4 k-tiles (90 DMMA).
+template <int NPB, int KT, int NP, int NN>
 __global__ void __launch_bounds__(128, 3)
-k2_hex20_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Gfrag,
-                        const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff,
-                        const unsigned char* __restrict__ failed, int nelt, double* __restrict__ vm, size_t ld_vm,
-                        double* __restrict__ env_max, double* __restrict__ env_min)
+k2_bigsolid_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Gfrag,
+                           const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff,
+                           const unsigned char* __restrict__ failed, int nelt, double* __restrict__ vm, size_t ld_vm,
+                           double* __restrict__ env_max, double* __restrict__ env_min)
 {
-  constexpr int KT = 5;
+  constexpr int ESTRIDE = ((3 * NN + 3) / 4) * 4;   // edof row stride = 4 * (k-tiles of the dense operator)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int i = blockIdx.x * (blockDim.x >> 5) + warp;
   if (i >= nelt) return;
-  const double* gf = Gfrag + (size_t)i * 9 * KT * 32 + lane;
-  const int* ed = edof + (size_t)i * 60;
+  const double* gf = Gfrag + (size_t)i * 3 * NPB * KT * 32 + lane;
+  const int* ed = edof + (size_t)i * ESTRIDE;
   const double* urow[3][KT];
 #pragma unroll
-  for (int j = 0; j < KT; ++j)
+  for (int j = 0; j < KT; ++j) {
+    const int node = 4 * j + t4;   // nodes >= NN are padding: their operator columns are zero
 #pragma unroll
-    for (int c = 0; c < 3; ++c) urow[c][j] = U + (size_t)__ldg(ed + 3 * (4 * j + t4) + c) * ldu + g;
+    for (int c = 0; c < 3; ++c) urow[c][j] = U + (size_t)(node < NN ? __ldg(ed + 3 * node + c) : 0) * ldu + g;
+  }
   const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
   const double mu2 = E / (1.0 + nu);
   const bool bad = failed[i] != 0;
   const size_t pt0 = (size_t)ptoff[i];
-  double emax[3] = {0.0, 0.0, 0.0}, emin[3] = {kHuge, kHuge, kHuge};
+  double emax[NPB], emin[NPB];
+#pragma unroll
+  for (int pb = 0; pb < NPB; ++pb) { emax[pb] = 0.0; emin[pb] = kHuge; }
   const int ntiles = nsteps_pad >> 3;
   double b[3][KT], bn[3][KT];
 #pragma unroll
@@ -175,7 +183,7 @@ k2_hex20_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, in
         for (int j = 0; j < KT; ++j) bn[c][j] = urow[c][j][(nt + 1) * 8];
     }
 #pragma unroll
-    for (int pb = 0; pb < 3; ++pb) {
+    for (int pb = 0; pb < NPB; ++pb) {
       double a[3][KT];
 #pragma unroll
       for (int m = 0; m < 3; ++m)
@@ -192,7 +200,7 @@ k2_hex20_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, in
         for (int c = 0; c < 3; ++c)
 #pragma unroll
           for (int m = 0; m < 3; ++m) dmma884(acc[m][c][0], acc[m][c][1], a[m][j], b[c][j]);
-      const bool live = pb < 2 || g < 4;
+      const bool live = 8 * pb + g < NP;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int t = nt * 8 + 2 * t4 + q;
@@ -215,13 +223,13 @@ k2_hex20_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, in
       for (int j = 0; j < KT; ++j) b[c][j] = bn[c][j];
   }
 #pragma unroll
-  for (int pb = 0; pb < 3; ++pb) {
+  for (int pb = 0; pb < NPB; ++pb) {
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
       emax[pb] = fmax(emax[pb], __shfl_xor_sync(0xffffffffu, emax[pb], o));
       emin[pb] = fmin(emin[pb], __shfl_xor_sync(0xffffffffu, emin[pb], o));
     }
-    if (t4 == 0 && nsteps > 0 && (pb < 2 || g < 4)) {
+    if (t4 == 0 && nsteps > 0 && 8 * pb + g < NP) {
       const size_t pt = pt0 + 8 * pb + g;
       if (emax[pb] > env_max[pt]) env_max[pt] = emax[pb];
       if (emin[pb] < env_min[pt]) env_min[pt] = emin[pb];
@@ -373,7 +381,7 @@ int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
   static const bool dense = getenv("FSR_HEX20_DENSE") && atoi(getenv("FSR_HEX20_DENSE")) != 0;
   if (!dense) {
     const int warps = 4;
-    k2_hex20_grad_vm_kernel<<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag,
+    k2_bigsolid_grad_vm_kernel<3, 5, 20, 20><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag,
                                                                                f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
                                                                                ld_vm, p->env_max, p->env_min);
     FSR_LAUNCH_CHECK();
@@ -387,6 +395,201 @@ int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
   }
   k2_solid_smem_vm_kernel<20><<<f.nelt, 128, smem, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof,
                                                        f.ptoff, f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+
+// ---- 15-node wedge (type 42) -----------------------------------------------------------------------------------
+// Reference: STR42 -> IPRI32 -> DN1531 / JACI31 (src/vpmStress/elStressModule.f90:1381-1465, src/Femlib/ipri.f:391-767,
+// 2867-2971).  -stressForm 0 evaluates at the 15 nodes; otherwise at 3 mid-side points x 2 Gauss levels (abscissa in the
+// reference's REAL*4 precision, ipri.f "ZE(1)=-.577350269189626") with the linear extrapolation of STR42 (:1441-1462).
+struct Wedg15Points {
+  int npt;
+  double L[18][4];     // L1, L2, L3, zeta of each evaluation point
+  double W[15][18];    // result point p = sum_g W[p][g] * evaluation point g
+};
+
+__device__ void wedg15_dn(double RL1, double RL2, double RL3, double ZE, double* DNL1, double* DNL2, double* DNZE)
+{
+  const double RL1RL1 = RL1 * RL1, RL1RL2 = RL1 * RL2, RL1RL3 = RL1 * RL3, RL1ZE = RL1 * ZE, RL2RL2 = RL2 * RL2, RL2RL3 = RL2 * RL3,
+               RL2ZE = RL2 * ZE, RL3RL3 = RL3 * RL3, RL3ZE = RL3 * ZE, ZEZE = ZE * ZE;
+  DNL1[0] = -1. + 0.5 * ZE + 0.5 * ZEZE + 2. * RL1 - 2. * RL1ZE; DNL1[1] = 2. * RL2 - 2. * RL2ZE; DNL1[2] = 0.;
+  DNL1[3] = -2. * RL2 + 2. * RL2ZE; DNL1[4] = 1. - 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 + 2. * RL3ZE; DNL1[5] = 2. * (1. - ZE) * (RL3 - RL1);
+  DNL1[6] = 1. - ZEZE; DNL1[7] = 0.; DNL1[8] = -1. + ZEZE;
+  DNL1[9] = -1. - 0.5 * ZE + 0.5 * ZEZE + 2. * RL1 + 2. * RL1ZE; DNL1[10] = 2. * RL2 + 2. * RL2ZE; DNL1[11] = 0.;
+  DNL1[12] = -2. * RL2 - 2. * RL2ZE; DNL1[13] = 1. + 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 - 2. * RL3ZE; DNL1[14] = 2. * (1. + ZE) * (RL3 - RL1);
+  DNL2[0] = 0.; DNL2[1] = 2. * RL1 - 2. * RL1ZE; DNL2[2] = -1. + 0.5 * ZE + 0.5 * ZEZE + 2. * RL2 - 2. * RL2ZE;
+  DNL2[3] = 2. * (RL3 - RL2) * (1. - ZE); DNL2[4] = 1. - 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 + 2. * RL3ZE; DNL2[5] = -2. * RL1 + 2. * RL1ZE;
+  DNL2[6] = 0.; DNL2[7] = 1. - ZEZE; DNL2[8] = -1. + ZEZE;
+  DNL2[9] = 0.; DNL2[10] = 2. * RL1 + 2. * RL1ZE; DNL2[11] = -1. - 0.5 * ZE + 0.5 * ZEZE + 2. * RL2 + 2. * RL2ZE;
+  DNL2[12] = 2. * (RL3 - RL2) * (1. + ZE); DNL2[13] = 1. + 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 - 2. * RL3ZE; DNL2[14] = -2. * RL1 - 2. * RL1ZE;
+  DNZE[0] = 0.5 * RL1 + RL1ZE - RL1RL1; DNZE[1] = -2. * RL1RL2; DNZE[2] = 0.5 * RL2 + RL2ZE - RL2RL2;
+  DNZE[3] = -2. * RL2RL3; DNZE[4] = 0.5 * RL3 + RL3ZE - RL3RL3; DNZE[5] = -2. * RL1RL3;
+  DNZE[6] = -2. * RL1ZE; DNZE[7] = -2. * RL2ZE; DNZE[8] = -2. * RL3ZE;
+  DNZE[9] = -0.5 * RL1 + RL1ZE + RL1RL1; DNZE[10] = 2. * RL1RL2; DNZE[11] = -0.5 * RL2 + RL2ZE + RL2RL2;
+  DNZE[12] = 2. * RL2RL3; DNZE[13] = -0.5 * RL3 + RL3ZE + RL3RL3; DNZE[14] = 2. * RL1RL3;
+}
+
+__global__ void build_wedg15_ops_kernel(int nelt, const int* __restrict__ elem, const int* __restrict__ conn,
+                                        const double* __restrict__ xyz, const double* __restrict__ emod,
+                                        const double* __restrict__ rny, const Wedg15Points* __restrict__ pts,
+                                        double* __restrict__ Sfrag, double* __restrict__ Gfrag, unsigned char* __restrict__ failed,
+                                        double* __restrict__ aux)
+{
+  constexpr int MT = 12, KT = 12, KTG = 4;   // dense 90 x 45 operator; gradient operator 2 blocks x 3 x 8 rows, 16 columns
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelt) return;
+  const int e = elem[i];
+  double* S = Sfrag + (size_t)i * MT * KT * 32;
+  double* G = Gfrag + (size_t)i * 6 * KTG * 32;
+  double X[15], Y[15], Z[15];
+  for (int k = 0; k < 15; ++k) {
+    const int n = conn[i * 15 + k];
+    X[k] = xyz[3 * n]; Y[k] = xyz[3 * n + 1]; Z[k] = xyz[3 * n + 2];
+  }
+  const double E = emod[e], nu = rny[e];
+  aux[i * 2] = E; aux[i * 2 + 1] = nu;
+  const double D = E * (1. - nu) / ((1. + nu) * (1. - 2. * nu));
+  const double D1 = D * nu / (1. - nu);
+  const double D2 = D * (1. - 2. * nu) / (2. * (1. - nu));
+  bool ok = true;
+  for (int q = 0; q < pts->npt && ok; ++q) {
+    double dx[15], de[15], dz[15];
+    wedg15_dn(pts->L[q][0], pts->L[q][1], pts->L[q][2], pts->L[q][3], dx, de, dz);
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < 15; ++k) {
+      J[0][0] += dx[k] * X[k]; J[0][1] += dx[k] * Y[k]; J[0][2] += dx[k] * Z[k];
+      J[1][0] += de[k] * X[k]; J[1][1] += de[k] * Y[k]; J[1][2] += de[k] * Z[k];
+      J[2][0] += dz[k] * X[k]; J[2][1] += dz[k] * Y[k]; J[2][2] += dz[k] * Z[k];
+    }
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    if (fabs(det) <= 2.2250738585072014e-308 * 100.0) { ok = false; break; }
+    double I[3][3];
+    I[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det;
+    I[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) / det;
+    I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+    I[1][0] = (J[2][0] * J[1][2] - J[2][2] * J[1][0]) / det;
+    I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det;
+    I[1][2] = (J[1][0] * J[0][2] - J[1][2] * J[0][0]) / det;
+    I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
+    I[2][1] = (J[2][0] * J[0][1] - J[2][1] * J[0][0]) / det;
+    I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    for (int j = 0; j < 15; ++j) {
+      const double bd[3] = {I[0][0] * dx[j] + I[0][1] * de[j] + I[0][2] * dz[j], I[1][0] * dx[j] + I[1][1] * de[j] + I[1][2] * dz[j],
+                            I[2][0] * dx[j] + I[2][1] * de[j] + I[2][2] * dz[j]};
+      const double bx = bd[0], by = bd[1], bz = bd[2];
+      const double db[6][3] = {{D * bx, D1 * by, D1 * bz}, {D1 * bx, D * by, D1 * bz}, {D1 * bx, D1 * by, D * bz},
+                               {D2 * by, D2 * bx, 0.0},    {D2 * bz, 0.0, D2 * bx},    {0.0, D2 * bz, D2 * by}};
+      for (int n = 0; n < 15; ++n) {
+        const double w = pts->W[n][q];
+        if (w == 0.0) continue;
+        for (int c = 0; c < 6; ++c)
+          for (int d = 0; d < 3; ++d) S[frag_index_g(n * 6 + c, 3 * j + d, KT)] += db[c][d] * w;
+        for (int d = 0; d < 3; ++d) G[frag_index_g(((n >> 3) * 3 + d) * 8 + (n & 7), j, KTG)] += bd[d] * w;
+      }
+    }
+  }
+  if (!ok) {
+    for (int k = 0; k < MT * KT * 32; ++k) S[k] = 0.0;
+    for (int k = 0; k < 6 * KTG * 32; ++k) G[k] = 0.0;
+  }
+  failed[i] = ok ? 0 : 1;
+}
+
+int build_wedg15_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
+{
+  cudaStream_t s = p->stream;
+  FamilyData& f = p->fam[FAM_WEDG15];
+  f.nenod = 15; f.nndof = 3; f.nstrp = 15; f.ncmp = 6; f.MT = 12; f.KT = 12; f.naux = 2;
+  std::vector<int> elem, conn, edof, ptoff;
+  for (int e : elements_of_type(p, sam, elm, 42)) {
+    const int ip0 = sam->mpmnpc[e] - 1, nn = sam->mpmnpc[e + 1] - sam->mpmnpc[e];
+    if (nn != 15) { set_error("WEDG15 element %d has %d nodes", e + 1, nn); return FSR_ERR_ARG; }
+    elem.push_back(e);
+    ptoff.push_back(p->ptoff_host[e]);
+    const size_t base = edof.size();
+    edof.resize(base + 48, 0);
+    for (int k = 0; k < 15; ++k) {
+      const int n = sam->mmnpc[ip0 + k] - 1;
+      if (n < 0 || n >= sam->nnod) { set_error("element %d: node index out of range", e + 1); return FSR_ERR_ARG; }
+      conn.push_back(n);
+      const int js = sam->madof[n] - 1, nd = sam->madof[n + 1] - sam->madof[n];
+      if (nd < 3) { set_error("element %d: node %d has %d DOFs, solid needs 3", e + 1, n + 1, nd); return FSR_ERR_ARG; }
+      for (int d = 0; d < 3; ++d) edof[base + (size_t)k * 3 + d] = js + d;
+    }
+  }
+  f.nelt = (int)elem.size();
+  if (f.nelt == 0) return FSR_OK;
+  Wedg15Points h;
+  memset(&h, 0, sizeof(h));
+  const double RL[6][3] = {{1, 0, 0}, {.5, .5, 0}, {0, 1, 0}, {0, .5, .5}, {0, 0, 1}, {.5, 0, .5}};
+  if (p->stressForm == 0) {   // the 15 nodes: 6 at zeta = -1, corners at zeta = 0, 6 at zeta = +1
+    h.npt = 15;
+    for (int n = 0; n < 15; ++n) {
+      const int k = n < 6 ? n : n < 9 ? 2 * (n - 6) : n - 9;
+      for (int c = 0; c < 3; ++c) h.L[n][c] = RL[k][c];
+      h.L[n][3] = n < 6 ? -1.0 : n < 9 ? 0.0 : 1.0;
+      h.W[n][n] = 1.0;
+    }
+  } else {                    // IPRI32 with NSTRP = 3, NSTRPZ = 2, then the extrapolation of STR42 applied to unit vectors
+    h.npt = 6;
+    const double ze[2] = {(double)-.577350269189626f, (double).577350269189626f};
+    const int mid[3] = {1, 3, 5};   // RL1(1..3) of the NSTRP = 3 branch are the mid-side points
+    for (int l = 0; l < 2; ++l)
+      for (int k = 0; k < 3; ++k) {
+        for (int c = 0; c < 3; ++c) h.L[3 * l + k][c] = RL[mid[k]][c];
+        h.L[3 * l + k][3] = ze[l];
+      }
+    const double zm1 = 0.5 * sqrt(3.0) - 0.5, zp1 = zm1 + 1.0;
+    for (int g = 0; g < 6; ++g) {
+      double SG[6] = {0, 0, 0, 0, 0, 0}, EP[6], SI[15];
+      SG[g] = 1.0;
+      EP[0] = SG[2] + SG[0] - SG[1]; EP[1] = SG[1] + SG[0] - SG[2]; EP[2] = SG[1] + SG[2] - SG[0];
+      EP[3] = SG[5] + SG[3] - SG[4]; EP[4] = SG[4] + SG[3] - SG[5]; EP[5] = SG[4] + SG[5] - SG[3];
+      SI[0] = zp1 * EP[0] - zm1 * EP[3]; SI[2] = zp1 * EP[1] - zm1 * EP[4]; SI[4] = zp1 * EP[2] - zm1 * EP[5];
+      SI[9] = zp1 * EP[3] - zm1 * EP[0]; SI[11] = zp1 * EP[4] - zm1 * EP[1]; SI[13] = zp1 * EP[5] - zm1 * EP[2];
+      SI[1] = 0.5 * (SI[0] + SI[2]); SI[3] = 0.5 * (SI[2] + SI[4]); SI[5] = 0.5 * (SI[4] + SI[0]);
+      SI[6] = 0.5 * (SI[0] + SI[9]); SI[7] = 0.5 * (SI[2] + SI[11]); SI[8] = 0.5 * (SI[4] + SI[13]);
+      SI[10] = 0.5 * (SI[9] + SI[11]); SI[12] = 0.5 * (SI[11] + SI[13]); SI[14] = 0.5 * (SI[13] + SI[9]);
+      for (int n = 0; n < 15; ++n) h.W[n][g] = SI[n];
+    }
+  }
+  Wedg15Points* d_pts = nullptr;
+  int* d_conn = nullptr;
+  FSR_CUDA(cudaMalloc(&d_pts, sizeof(h)));
+  FSR_CUDA(cudaMemcpyAsync(d_pts, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMalloc(&f.elem, sizeof(int) * elem.size()));
+  FSR_CUDA(cudaMalloc(&f.edof, sizeof(int) * edof.size()));
+  FSR_CUDA(cudaMalloc(&f.ptoff, sizeof(int) * ptoff.size()));
+  FSR_CUDA(cudaMalloc(&f.failed, f.nelt));
+  FSR_CUDA(cudaMalloc(&f.Sfrag, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32));
+  FSR_CUDA(cudaMalloc(&f.Gfrag, sizeof(double) * (size_t)f.nelt * 6 * 4 * 32));
+  FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
+  FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
+  FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(f.ptoff, ptoff.data(), sizeof(int) * ptoff.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
+  FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, sizeof(double) * (size_t)f.nelt * 6 * 4 * 32, s));
+  build_wedg15_ops_kernel<<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny, d_pts, f.Sfrag, f.Gfrag,
+                                                          f.failed, f.aux);
+  FSR_LAUNCH_CHECK();
+  FSR_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_conn);
+  cudaFree(d_pts);
+  return FSR_OK;
+}
+
+int launch_k2_wedg15_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s)
+{
+  FamilyData& f = p->fam[FAM_WEDG15];
+  if (f.nelt == 0) return FSR_OK;
+  const int warps = 4;
+  k2_bigsolid_grad_vm_kernel<2, 4, 15, 15><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
+      p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev, ld_vm, p->env_max,
+      p->env_min);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }

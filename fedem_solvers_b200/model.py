@@ -67,7 +67,7 @@ class PartModel:
     recovery_seed: int = 0   # seed of the synthetic [B|E] fields (synthetic_recovery)
 
     def nstrp(self):
-        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 43: 20, 44: 8, 45: 4, 46: 6}
+        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
         n = np.array([tab.get(int(t), 0) for t in self.sam.melcon], I32)
         if self.elm.elmid is not None:
             n[self.elm.elmid < 1] = 0
@@ -414,6 +414,47 @@ def hex20_block(nx, ny, nz, ngen=8, seed=6, n_ext=4, jitter=0.04, emod=2.1e11, r
     elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64), thk=np.zeros(nel, F64),
                       elmid=np.arange(1, nel + 1, dtype=I32))
     part = PartModel(sam=sam, elm=elm, name=f"hex20_{nx}x{ny}x{nz}")
+    part.recovery_seed = seed
+    if with_recovery:
+        part.B, part.E = synthetic_recovery(part)
+    return part
+
+
+# WEDG15 node order (DN1531, src/Femlib/ipri.f:2867-2971): bottom triangle corner, mid, corner, mid, corner, mid; the three
+# mid-height corner nodes; the top triangle.  Offsets on the doubled grid for the two wedges of a cell.
+_W15_TRI = [[(0, 0), (1, 0), (2, 0), (2, 1), (2, 2), (1, 1)], [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]]
+_WEDG15 = [[(x, y, 0) for x, y in t] + [(t[0][0], t[0][1], 1), (t[2][0], t[2][1], 1), (t[4][0], t[4][1], 1)] +
+           [(x, y, 2) for x, y in t] for t in _W15_TRI]
+
+
+def wedg15_block(nx, ny, nz, ngen=6, seed=10, n_ext=4, jitter=0.04, emod=2.1e11, rny=0.3, shuffle_eq=False, with_recovery=True):
+    """Structured block of nx*ny*nz cells, each split into two 15-node wedges (type 42), jittered nodes."""
+    rng = np.random.default_rng(seed)
+    NX, NY, NZ = 2 * nx + 1, 2 * ny + 1, 2 * nz + 1
+    cz, cy, cx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = 2 * np.stack([cx.ravel(), cy.ravel(), cz.ravel()], 1)
+    off = np.asarray(_WEDG15)                                   # [2, 15, 3]
+    gidx = (base[:, None, None, :] + off[None]).reshape(-1, 15, 3)
+    key = (gidx[..., 2].astype(np.int64) * NY + gidx[..., 1]) * NX + gidx[..., 0]
+    flat = key.reshape(-1)
+    uniq, first = np.unique(flat, return_index=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(len(uniq), np.int64)
+    rank[order] = np.arange(len(uniq))
+    conn = (rank[np.searchsorted(uniq, flat)] + 1).reshape(-1, 15).astype(I32)
+    kk = uniq[order]
+    gi = np.stack([kk % NX, (kk // NX) % NY, kk // (NX * NY)], 1)
+    xyz = gi / 2.0 + rng.uniform(-jitter, jitter, (len(kk), 3)) * 0.5
+    node_of = {int(k): i + 1 for i, k in enumerate(kk)}
+    cand = [(0, 0, 0), (NX - 1, 0, 0), (0, NY - 1, 0), (NX - 1, NY - 1, NZ - 1), (0, 0, NZ - 1), (NX - 1, NY - 1, 0),
+            (0, NY - 1, NZ - 1), (NX - 1, 0, NZ - 1)]
+    ext_nodes = [node_of[(c[2] * NY + c[1]) * NX + c[0]] for c in cand[:n_ext]]
+    sam = _build_sam(len(kk), 3, conn, np.full(len(conn), 42, I32), ext_nodes, rng=rng, shuffle_eq=shuffle_eq)
+    sam.ngen = ngen
+    nel = sam.nel
+    elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64), thk=np.zeros(nel, F64),
+                      elmid=np.arange(1, nel + 1, dtype=I32))
+    part = PartModel(sam=sam, elm=elm, name=f"wedg15_{nx}x{ny}x{nz}")
     part.recovery_seed = seed
     if with_recovery:
         part.B, part.E = synthetic_recovery(part)

@@ -102,6 +102,12 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     get_coor(iel, sam, ed, 20, x, y, z);
     ierr = orc_str43(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
     break;
+  case 42:
+    *nenod = 15;
+    *nstrp = 15;
+    get_coor(iel, sam, ed, 15, x, y, z);
+    ierr = orc_str42(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], 0, V, Sigma, Epsil);
+    break;
   case 44:
     *nenod = 8;
     *nstrp = 8;
@@ -152,6 +158,7 @@ static int nstrp_of(int t) /* elStressModule.f90:159-229 */
   case 21: case 23: return 6;
   case 22: case 24: return 8;
   case 41: return 10;
+  case 42: return 15;
   case 43: return 20;
   case 44: return 8;
   case 45: return 4;

@@ -96,6 +96,9 @@ int orc_str43(const double xg[20], const double yg[20], const double zg[20], dou
               double epsil[120]);
 /* linear solids (solids_lin.c): STR44 HEX8 (sigma/epsil (6,8)), STR45 TET4 ((6,4)), STR46 WEDG6 ((6,6)).
  * Component order: HEX8 (xx,yy,zz,xy,xz,yz); TET4 and WEDG6 (xx,yy,zz,xy,yz,zx) as their B-matrices give it. */
+/* STR42 WEDG15 (sigma/epsil (6,15)), component order (xx,yy,zz,xy,xz,yz) */
+int orc_str42(const double *x, const double *y, const double *z, double emod, double rny, int stressForm, const double *v,
+              double *sigma, double *epsil);
 int orc_str44(const double *x, const double *y, const double *z, double emod, double rny, int stressForm, const double *v,
               double *sigma, double *epsil);
 int orc_str45(const double *x, const double *y, const double *z, double emod, double rny, const double *v, double *sigma,

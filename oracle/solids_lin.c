@@ -370,3 +370,161 @@ int orc_str44(const double *x, const double *y, const double *z, double emod, do
   }
   return 0;
 }
+
+/* ---- WEDG15 ---------------------------------------------------------------------------------------
+ * STR42 (src/vpmStress/elStressModule.f90:1381-1465) -> IPRI32 (src/Femlib/ipri.f:391-767) -> DN1531 (ipri.f:2867-2971),
+ * JACI31.  Component order (xx,yy,zz,xy,xz,yz).  The Fortran 77 source writes its abscissae as default-REAL literals
+ * (ZE = +-.577350269189626 in an IMPLICIT DOUBLE PRECISION unit is still a REAL*4 constant): reproduced with float casts. */
+static void dn1531(double *DNL1, double *DNL2, double *DNZE, double RL1, double RL2, double RL3, double ZE)
+{
+  double RL1RL1 = RL1 * RL1, RL1RL2 = RL1 * RL2, RL1RL3 = RL1 * RL3, RL1ZE = RL1 * ZE, RL2RL2 = RL2 * RL2, RL2RL3 = RL2 * RL3,
+         RL2ZE = RL2 * ZE, RL3RL3 = RL3 * RL3, RL3ZE = RL3 * ZE, ZEZE = ZE * ZE;
+#define D1_(i) DNL1[(i)-1]
+#define D2_(i) DNL2[(i)-1]
+#define DZ_(i) DNZE[(i)-1]
+  D1_(1) = -1. + 0.5 * ZE + 0.5 * ZEZE + 2. * RL1 - 2. * RL1ZE;
+  D1_(2) = 2. * RL2 - 2. * RL2ZE;
+  D1_(3) = 0.;
+  D1_(4) = -2. * RL2 + 2. * RL2ZE;
+  D1_(5) = 1. - 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 + 2. * RL3ZE;
+  D1_(6) = 2. * (1. - ZE) * (RL3 - RL1);
+  D1_(7) = 1. - ZEZE;
+  D1_(8) = 0.;
+  D1_(9) = -1. + ZEZE;
+  D1_(10) = -1. - 0.5 * ZE + 0.5 * ZEZE + 2. * RL1 + 2. * RL1ZE;
+  D1_(11) = 2. * RL2 + 2. * RL2ZE;
+  D1_(12) = 0.;
+  D1_(13) = -2. * RL2 - 2. * RL2ZE;
+  D1_(14) = 1. + 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 - 2. * RL3ZE;
+  D1_(15) = 2. * (1. + ZE) * (RL3 - RL1);
+  D2_(1) = 0.;
+  D2_(2) = 2. * RL1 - 2. * RL1ZE;
+  D2_(3) = -1. + 0.5 * ZE + 0.5 * ZEZE + 2. * RL2 - 2. * RL2ZE;
+  D2_(4) = 2. * (RL3 - RL2) * (1. - ZE);
+  D2_(5) = 1. - 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 + 2. * RL3ZE;
+  D2_(6) = -2. * RL1 + 2. * RL1ZE;
+  D2_(7) = 0.;
+  D2_(8) = 1. - ZEZE;
+  D2_(9) = -1. + ZEZE;
+  D2_(10) = 0.;
+  D2_(11) = 2. * RL1 + 2. * RL1ZE;
+  D2_(12) = -1. - 0.5 * ZE + 0.5 * ZEZE + 2. * RL2 + 2. * RL2ZE;
+  D2_(13) = 2. * (RL3 - RL2) * (1. + ZE);
+  D2_(14) = 1. + 0.5 * ZE - 0.5 * ZEZE - 2. * RL3 - 2. * RL3ZE;
+  D2_(15) = -2. * RL1 - 2. * RL1ZE;
+  DZ_(1) = 0.5 * RL1 + RL1ZE - RL1RL1;
+  DZ_(2) = -2. * RL1RL2;
+  DZ_(3) = 0.5 * RL2 + RL2ZE - RL2RL2;
+  DZ_(4) = -2. * RL2RL3;
+  DZ_(5) = 0.5 * RL3 + RL3ZE - RL3RL3;
+  DZ_(6) = -2. * RL1RL3;
+  DZ_(7) = -2. * RL1ZE;
+  DZ_(8) = -2. * RL2ZE;
+  DZ_(9) = -2. * RL3ZE;
+  DZ_(10) = -0.5 * RL1 + RL1ZE + RL1RL1;
+  DZ_(11) = 2. * RL1RL2;
+  DZ_(12) = -0.5 * RL2 + RL2ZE + RL2RL2;
+  DZ_(13) = 2. * RL2RL3;
+  DZ_(14) = -0.5 * RL3 + RL3ZE + RL3RL3;
+  DZ_(15) = 2. * RL1RL3;
+#undef D1_
+#undef D2_
+#undef DZ_
+}
+
+/* IPRI32 for NSTRP in {3, 6}, NSTRPZ in {2, 3}, IOPXP = IOPE0 = 0: SIG(6, NSTRP*NSTRPZ) */
+static int ipri32(double *SIG, const double *V, const double *XG, const double *YG, const double *ZG, double YOUNG, double RNY,
+                  int NSTRP, int NSTRPZ)
+{
+  double RL1[7] = {0}, RL2[7] = {0}, RL3[7] = {0}, ZE[3] = {0}, DNL1[15], DNL2[15], DNZE[15], JI[9], DETJ, B[3], DB[15][6][3];
+  double D = YOUNG * (1. - RNY) / ((1. + RNY) * (1. - 2. * RNY));
+  double D1 = D * RNY / (1. - RNY);
+  double D2 = D * (1. - 2. * RNY) / (2. * (1. - RNY));
+  int N = 0;
+  memset(SIG, 0, 6 * 21 * sizeof(double));
+  if (NSTRP == 3) {
+    RL1[0] = .5; RL2[0] = .5; RL3[0] = .0;
+    RL1[1] = .0; RL2[1] = .5; RL3[1] = .5;
+    RL1[2] = .5; RL2[2] = .0; RL3[2] = .5;
+  } else if (NSTRP == 6) {
+    RL1[0] = 1.0; RL1[1] = 0.5; RL2[1] = 0.5; RL2[2] = 1.0; RL2[3] = 0.5; RL3[3] = 0.5; RL3[4] = 1.0; RL1[5] = 0.5; RL3[5] = 0.5;
+  } else
+    return -1;
+  if (NSTRPZ == 2) { ZE[0] = (double)-.577350269189626f; ZE[1] = (double).577350269189626f; }
+  else if (NSTRPZ == 3) {
+    ZE[0] = (double)-.774596669241483f; ZE[2] = (double).774596669241483f;
+    if (NSTRP == 6) { ZE[0] = -1.0; ZE[2] = 1.0; }
+  } else
+    return -1;
+  for (int L = 1; L <= NSTRPZ; L++)
+    for (int K = 1; K <= NSTRP; K++) {
+      dn1531(DNL1, DNL2, DNZE, RL1[K - 1], RL2[K - 1], RL3[K - 1], ZE[L - 1]);
+      N = N + 1;
+      if (jaci31(JI, &DETJ, DNL1, DNL2, DNZE, XG, YG, ZG, 15) < 0) return -1;
+      for (int J = 1; J <= 15; J++) {
+        B[0] = A2(JI, 1, 1, 3) * DNL1[J - 1] + A2(JI, 1, 2, 3) * DNL2[J - 1] + A2(JI, 1, 3, 3) * DNZE[J - 1];
+        B[1] = A2(JI, 2, 1, 3) * DNL1[J - 1] + A2(JI, 2, 2, 3) * DNL2[J - 1] + A2(JI, 2, 3, 3) * DNZE[J - 1];
+        B[2] = A2(JI, 3, 1, 3) * DNL1[J - 1] + A2(JI, 3, 2, 3) * DNL2[J - 1] + A2(JI, 3, 3, 3) * DNZE[J - 1];
+        DB[J - 1][0][0] = D * B[0];  DB[J - 1][1][0] = D1 * B[0]; DB[J - 1][2][0] = DB[J - 1][1][0];
+        DB[J - 1][3][0] = D2 * B[1]; DB[J - 1][4][0] = D2 * B[2]; DB[J - 1][5][0] = 0.0;
+        DB[J - 1][0][1] = D1 * B[1]; DB[J - 1][1][1] = D * B[1];  DB[J - 1][2][1] = DB[J - 1][0][1];
+        DB[J - 1][3][1] = D2 * B[0]; DB[J - 1][4][1] = 0.0;       DB[J - 1][5][1] = DB[J - 1][4][0];
+        DB[J - 1][0][2] = D1 * B[2]; DB[J - 1][1][2] = DB[J - 1][0][2]; DB[J - 1][2][2] = D * B[2];
+        DB[J - 1][3][2] = 0.0;       DB[J - 1][4][2] = DB[J - 1][3][1]; DB[J - 1][5][2] = DB[J - 1][3][0];
+      }
+      for (int I = 1; I <= 15; I++) {
+        int I1 = (I - 1) * 3 + 1, I2 = I1 + 1, I3 = I2 + 1;
+        for (int J = 1; J <= 6; J++)
+          A2(SIG, J, N, 6) = A2(SIG, J, N, 6) + DB[I - 1][J - 1][0] * V[I1 - 1] + DB[I - 1][J - 1][1] * V[I2 - 1] + DB[I - 1][J - 1][2] * V[I3 - 1];
+      }
+    }
+  return 0;
+}
+
+int orc_str42(const double *x, const double *y, const double *z, double emod, double rny, int stressForm, const double *v,
+              double *sigma /* (6,15) */, double *epsil /* (6,15) */)
+{
+  double Einv[36], SIGG[6 * 21];
+  const double zm1 = 0.5 * sqrt(3.0) - 0.5, zp1 = zm1 + 1.0;
+  int n = stressForm == 0 ? 6 : 3, nZ = stressForm == 0 ? 3 : 2;
+  iso_mat3d_inv(emod, rny, Einv);
+  if (ipri32(SIGG, v, x, y, z, emod, rny, n, nZ) != 0) return 1;
+#define SG(c, p) A2(SIGG, c, p, 6)
+#define SI(c, p) A2(sigma, c, p, 6)
+#define EP(c, p) A2(epsil, c, p, 6)
+  for (int c = 1; c <= 6; c++) {
+    if (stressForm == 0) {
+      for (int p = 1; p <= 7; p++) SI(c, p) = SG(c, p);
+      SI(c, 8) = SG(c, 9);
+      SI(c, 9) = SG(c, 11);
+      for (int p = 10; p <= 15; p++) SI(c, p) = SG(c, p + 3);
+    } else {
+      EP(c, 1) = SG(c, 3) + SG(c, 1) - SG(c, 2);
+      EP(c, 2) = SG(c, 2) + SG(c, 1) - SG(c, 3);
+      EP(c, 3) = SG(c, 2) + SG(c, 3) - SG(c, 1);
+      EP(c, 4) = SG(c, 6) + SG(c, 4) - SG(c, 5);
+      EP(c, 5) = SG(c, 5) + SG(c, 4) - SG(c, 6);
+      EP(c, 6) = SG(c, 5) + SG(c, 6) - SG(c, 4);
+      SI(c, 1) = zp1 * EP(c, 1) - zm1 * EP(c, 4);
+      SI(c, 3) = zp1 * EP(c, 2) - zm1 * EP(c, 5);
+      SI(c, 5) = zp1 * EP(c, 3) - zm1 * EP(c, 6);
+      SI(c, 10) = zp1 * EP(c, 4) - zm1 * EP(c, 1);
+      SI(c, 12) = zp1 * EP(c, 5) - zm1 * EP(c, 2);
+      SI(c, 14) = zp1 * EP(c, 6) - zm1 * EP(c, 3);
+      SI(c, 2) = 0.5 * (SI(c, 1) + SI(c, 3));
+      SI(c, 4) = 0.5 * (SI(c, 3) + SI(c, 5));
+      SI(c, 6) = 0.5 * (SI(c, 5) + SI(c, 1));
+      SI(c, 7) = 0.5 * (SI(c, 1) + SI(c, 10));
+      SI(c, 8) = 0.5 * (SI(c, 3) + SI(c, 12));
+      SI(c, 9) = 0.5 * (SI(c, 5) + SI(c, 14));
+      SI(c, 11) = 0.5 * (SI(c, 10) + SI(c, 12));
+      SI(c, 13) = 0.5 * (SI(c, 12) + SI(c, 14));
+      SI(c, 15) = 0.5 * (SI(c, 14) + SI(c, 10));
+    }
+  }
+  for (int p = 1; p <= 15; p++) matvec6(Einv, &SI(1, p), &EP(1, p));
+  return 0;
+#undef SG
+#undef SI
+#undef EP
+}

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from fedem_solvers_b200 import StressRecovery
-from fedem_solvers_b200.model import linsolid_block, plate_part, tet10_block, hex20_block, reduced_history
+from fedem_solvers_b200.model import linsolid_block, wedg15_block, plate_part, tet10_block, hex20_block, reduced_history
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
@@ -282,4 +282,40 @@ def test_linear_solids_gauss_point_forms(oracle, form):
             assert fn(_dp(xg), _dp(yg), _dp(zg), C.c_double(part.elm.emod[e]), C.c_double(part.elm.rny[e]), form, _dp(v), _dp(sig), _dp(eps)) == 0
             vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(nn)])
             assert rel_err(vm_g[s, off[e]:off[e] + nn], vm_o) <= TOL, (t, e, s)
+    rec.close()
+
+
+@pytest.mark.parametrize("form", [0, 2])
+def test_wedg15_block(oracle, form):
+    """type 42: two-block gradient kernel + dense operator; -stressForm 2 = 3 x 2 Gauss points extrapolated (REAL*4 abscissa)"""
+    import ctypes as C
+    from oracle_bind import _dp
+    part = wedg15_block(2, 2, 1, ngen=5, seed=10, shuffle_eq=True)
+    b = oracle.bind_part(part)
+    if form == 0:
+        _check_part(oracle, part, nsteps=40, seed=4)
+        Q = reduced_history(part.sam.ndim, 2, seed=5)
+        rec = StressRecovery(part)
+        full = rec.calc_stresses(Q[:, 1])
+        ref = oracle.calc_stresses(b, oracle.expand(b, Q[:, 1]))
+        for k, tol in (("stress", TOL), ("strain", TOL), ("resmat", 1e-9)):
+            assert np.abs(full[k] - ref[k]).max() <= tol * np.abs(ref[k]).max() * (1 if k != "resmat" else 1), k
+        rec.close()
+        return
+    Q = reduced_history(part.sam.ndim, 9, seed=2)
+    rec = StressRecovery(part, stress_form=form)
+    vm_g = rec.recover(Q)
+    off = rec.result_point_offsets()
+    X = part.elm.xyz
+    for e in (0, 3, part.sam.nel - 1):
+        nodes = part.sam.mmnpc[part.sam.mpmnpc[e] - 1: part.sam.mpmnpc[e + 1] - 1] - 1
+        for s in (0, 8):
+            sv = oracle.expand(b, Q[:, s])
+            v = np.ascontiguousarray(np.stack([sv[3 * n: 3 * n + 3] for n in nodes]).ravel())
+            xg, yg, zg = (np.ascontiguousarray(X[nodes, k]) for k in range(3))
+            sig, eps = np.zeros(90), np.zeros(90)
+            assert oracle.lib.orc_str42(_dp(xg), _dp(yg), _dp(zg), C.c_double(part.elm.emod[e]), C.c_double(part.elm.rny[e]), form,
+                                        _dp(v), _dp(sig), _dp(eps)) == 0
+            vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(15)])
+            assert rel_err(vm_g[s, off[e]:off[e] + 15], vm_o) <= TOL, (e, s)
     rec.close()
