@@ -12,7 +12,7 @@
 // Data movement: a history tile is read exactly once per pass.  Step-major tiles (hist[t*ld + g],
 // what the rosette kernel writes) are read coalesced by consecutive threads; gage-major tiles
 // (hist[g*ld + t], what a host caller holds) are staged through shared memory with cp.async
-// (LDGSTS) as 32-step x 128-gage blocks, each gage row a 256-byte segment, double buffered, so
+// (LDGSTS) as 32-step x 128-gage blocks, each gage row a 256-byte segment (one buffer per block, five blocks per SM), so
 // that global reads stay coalesced although every thread walks its own row.  The work per sample is
 // a divergent state machine: the kernel is latency / issue bound, not HBM bound (8 B per sample).
 #include <algorithm>
@@ -33,6 +33,7 @@ struct GageState {
 
 constexpr int K3_THREADS = 128;
 constexpr int K3_CHUNK = 32;
+constexpr int K3_QCAP = 4;   // closed cycles a gage may queue between two convergent damage evaluations
 
 }  // namespace fsr
 
@@ -100,7 +101,7 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
                  const double* __restrict__ edges, double bin_size, int nbins, double* __restrict__ spill, int cap,
                  int* __restrict__ bins, int* __restrict__ pending)
 {
-  extern __shared__ double tiles[];  // LAYOUT 0: 2 x [32][129]
+  extern __shared__ double tiles[];  // LAYOUT 0: [32][129]
   const int g0 = blockIdx.x * K3_THREADS;
   const int g = g0 + threadIdx.x;
   const bool active = g < ngage;
@@ -123,7 +124,28 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
   int* mybins = (bins && nbins > 0) ? bins + (active ? g : 0) : nullptr;
   const size_t stride = (size_t)ngage;
 
-  auto count = [&](double a, double b) { count_cycle(a, b, p, s.sink, mybins, stride, edges); };
+  // Closed cycles are not evaluated where the rainflow rules find them: the S-N damage (log10 + pow) and the histogram
+  // search are by far the most expensive part of a sample, and inside the state machine they would run once per step in
+  // which ANY lane of the warp closes a cycle (~80 % of the steps at one cycle per 20 samples).  They are queued per gage
+  // (FIFO, so the order of the Miner sum is unchanged) and evaluated warp-convergently once per 32-step chunk: the warp
+  // then pays max-over-lanes evaluations per chunk instead of one per step.
+  __shared__ double q_a[MODE == 1 ? K3_QCAP : 1][K3_THREADS], q_b[MODE == 1 ? K3_QCAP : 1][K3_THREADS];
+  int qn = 0;
+  auto count = [&](double a, double b) {
+    if (qn == K3_QCAP) {   // more than K3_QCAP cycles since the last flush: drain in order (divergent, rare)
+      for (int k = 0; k < K3_QCAP; ++k) count_cycle(q_a[k][threadIdx.x], q_b[k][threadIdx.x], p, s.sink, mybins, stride, edges);
+      qn = 0;
+    }
+    q_a[qn][threadIdx.x] = a; q_b[qn][threadIdx.x] = b; ++qn;
+  };
+  auto flush = [&]() {     // reached by every lane of the warp
+    int m = qn;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int k = 0; k < m; ++k)
+      if (k < qn) count_cycle(q_a[k][threadIdx.x], q_b[k][threadIdx.x], p, s.sink, mybins, stride, edges);
+    qn = 0;
+  };
   auto emit = [&](double v) { s.rf.push(v, p.gate, myspill, stride, cap, count); };
   auto consume = [&](int i, double x) {
     if (MODE == 0) {
@@ -136,18 +158,19 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
 
   if (LAYOUT == 0) {
     const int nchunks = (nsteps + K3_CHUNK - 1) / K3_CHUNK;
-    double* tile[2] = {tiles, tiles + K3_CHUNK * (K3_THREADS + 1)};
-    stage_tile(tile[0], hist, ld, g0, ngage, 0, nsteps);
-    cp_async_commit();
+    // One staging buffer per block: the kernel is latency bound (a divergent state machine per lane), so the shared
+    // memory goes to occupancy -- five blocks per SM hide each other's staging waits -- rather than to double buffering
+    // inside a block (r01l profile: 2 blocks/SM, 12 % of the warp slots active with two 33 KB buffers).
     for (int c = 0; c < nchunks; ++c) {
-      if (c + 1 < nchunks) stage_tile(tile[(c + 1) & 1], hist, ld, g0, ngage, (c + 1) * K3_CHUNK, nsteps);
+      stage_tile(tiles, hist, ld, g0, ngage, c * K3_CHUNK, nsteps);
       cp_async_commit();
-      cp_async_wait<1>();
+      cp_async_wait<0>();
       __syncthreads();
       const int tn = min(K3_CHUNK, nsteps - c * K3_CHUNK);
-      const double* col = tile[c & 1] + threadIdx.x;
+      const double* col = tiles + threadIdx.x;
       if (!idle)
         for (int k = 0; k < tn && !idle; ++k) consume(step0 + c * K3_CHUNK + k, col[k * (K3_THREADS + 1)]);
+      if (MODE == 1) flush();
       // every gage of the block located: nothing left to read in this pass
       if (MODE == 0 && __syncthreads_and(idle)) break;
       if (MODE != 0) __syncthreads();
@@ -156,8 +179,8 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
   } else {
     const double* hp = hist + (active ? g : 0);
     int t = 0;
-    if (!idle) {
-      for (; t + 8 <= nsteps && !idle; t += 8) {
+    for (; t + 8 <= nsteps; t += 8) {   // warp-uniform trip count: the flush below needs every lane
+      if (!idle) {
         double xb[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) xb[k] = __ldg(hp + (size_t)(t + k) * ld);
@@ -165,8 +188,12 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
         for (int k = 0; k < 8; ++k)
           if (!idle) consume(step0 + t + k, xb[k]);
       }
-      for (; t < nsteps && !idle; ++t) consume(step0 + t, __ldg(hp + (size_t)t * ld));
+      if (MODE == 1 && (t & 31) == 24) flush();
+      if (MODE == 0 && __all_sync(0xffffffffu, idle)) break;
     }
+    if (!idle)
+      for (; t < nsteps && !idle; ++t) consume(step0 + t, __ldg(hp + (size_t)t * ld));
+    if (MODE == 1) flush();
   }
   if (active && (MODE == 1 || was_pending)) st[g] = s;
   if (MODE == 0 && pending) {
@@ -216,7 +243,7 @@ k3_finish_kernel(GageState* __restrict__ st, int ngage, const double* __restrict
     }
 }
 
-static size_t k3_smem(int layout) { return layout == 0 ? sizeof(double) * 2 * K3_CHUNK * (K3_THREADS + 1) : 0; }
+static size_t k3_smem(int layout) { return layout == 0 ? sizeof(double) * K3_CHUNK * (K3_THREADS + 1) : 0; }
 
 template <int MODE>
 static int launch_stream(fsr_fatigue_state* f, const double* hist, size_t ld, int layout, int step0, int nsteps,
