@@ -17,10 +17,10 @@ I32 = np.int32
 F64 = np.float64
 
 # relative cost of one element.step = K1 rows it brings (nodal DOFs x n_red, shared with neighbours)
-# + its K2 operator (rows x cols of the padded DMMA operator)
-ELEMENT_COST = {24: 24 * 24 + 6 * 98, 22: 24 * 24 + 6 * 98, 23: 24 * 20 + 3 * 98, 21: 24 * 20 + 3 * 98,
-                41: 64 * 32 + 4 * 98, 43: 120 * 60 + 12 * 98, 11: 12 * 12}
-NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 43: 20}
+# + its K2 kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/r01b, r01f, r01i:
+# quad 47 + 39, TET10 120 + 24, HEX20 331 + 66; the other types scaled by their DMMA counts)
+ELEMENT_COST = {24: 86.0, 22: 86.0, 23: 55.0, 21: 55.0, 41: 144.0, 42: 240.0, 43: 397.0, 44: 65.0, 45: 35.0, 46: 55.0, 11: 3.0}
+NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
 
 
 def element_costs(melcon):

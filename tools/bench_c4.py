@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""bench_c4.py -- BASELINE.json config 4: a mechanism with 6 flexible superelements of mixed size and element type,
+per-part stress recovery load-balanced across the GPUs of one box.
+
+  python tools/bench_c4.py                                      # 1 GPU
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_c4.py
+
+The reference runs one fedem_stress process per part (the parts are independent).  Here the parts are laid end to end by
+their measured element cost and the line is cut into N equal shares (partition.plan_work: element blocks can be cut
+anywhere, so the load is divisible); a rank recovers its pieces one after the other, every piece a self-contained
+element block (partition.sub_part) with the B/E rows of its own nodes.  Per step tile rank 0 broadcasts the reduced
+histories of all parts (NCCL), at the end the per-piece von Mises envelopes are gathered to rank 0 (NCCL gather), both
+inside the timed region.  Prints one JSON line on rank 0: whole-job element.steps/s, the per-rank device times (load
+balance) and the plan."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def build_parts(scale):
+    """Six parts of mixed size / type; `scale` multiplies the element counts (1.0 ~ 1.9 M elements in total)."""
+    from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, linsolid_block
+    s = scale ** 0.5
+    c = scale ** (1.0 / 3.0)
+    n = lambda v, f: max(2, int(round(v * f)))
+    return [
+        plate_part(n(800, s), n(800, s), ngen=40, n_ext=8, seed=41),                          # 640 k ANDES quads
+        plate_part(n(500, s), n(500, s), ngen=30, n_ext=6, seed=42, tri_fraction=0.5),        # 250 k quads + 250 k... tris
+        tet10_block(n(44, c), n(44, c), n(44, c), ngen=30, seed=43, n_ext=8, n_beams=2000),   # 511 k TET10 + beams
+        hex20_block(n(36, c), n(36, c), n(36, c), ngen=20, seed=44, n_ext=8),                 # 47 k HEX20
+        linsolid_block(n(40, c), n(40, c), n(40, c), ngen=20, seed=45, n_ext=8),              # HEX8 / TET4 / WEDG6 mix
+        plate_part(n(120, s), n(120, s), ngen=10, n_ext=4, seed=46),                          # a small one: 14 k quads
+    ]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--tile", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import reduced_history
+    from fedem_solvers_b200.partition import element_costs, plan_work, cost_fraction_to_elements, sub_part
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load_library()
+    t0 = time.time()
+    parts = build_parts(args.scale)          # every rank builds the (seeded, identical) parts and keeps only its pieces
+    costs = []
+    for p in parts:
+        c = element_costs(p.sam.melcon)
+        costs.append(float(c.sum()))
+    items, loads = plan_work(costs, world)
+    tile, steps, warm = args.tile, args.steps, args.warmup
+    pieces = []
+    for ip, f0, f1 in items[rank]:
+        e0, e1 = cost_fraction_to_elements(parts[ip], f0, f1)
+        if e1 <= e0:
+            continue
+        blk = sub_part(parts[ip], e0, e1, with_matrices=True).part
+        rec = StressRecovery(blk, device=local_rank, step_tile=((tile + 63) // 64) * 64)
+        pieces.append(dict(part=ip, e0=e0, e1=e1, rec=rec, nel=e1 - e0, npts=rec.npts))
+    nel_total = sum(p.sam.nel for p in parts)
+    ndims = [p.sam.ndim for p in parts]
+    del parts
+    stream = torch.cuda.current_stream()
+    for pc in pieces:
+        pc["rec"].set_stream(stream.cuda_stream)
+        pc["env"] = torch.empty((2, pc["npts"]), dtype=torch.float64, device=dev)
+    # reduced histories of all parts, concatenated: [steps, sum ndim]; rank 0 owns them
+    off = np.concatenate([[0], np.cumsum(ndims)])
+    nq = tile * (steps + warm)
+    Q = torch.empty((nq, int(off[-1])), dtype=torch.float64, device=dev)
+    if rank == 0:
+        Qh = np.concatenate([reduced_history(nd, nq, seed=50 + i).T for i, nd in enumerate(ndims)], axis=1)
+        Q.copy_(torch.from_numpy(np.ascontiguousarray(Qh)))
+    setup = time.time() - t0
+
+    def step(i):
+        q = Q[i * tile:(i + 1) * tile]
+        if world > 1:
+            dist.broadcast(q, src=0)
+        for pc in pieces:
+            ip = pc["part"]
+            qp = q[:, int(off[ip]):int(off[ip + 1])]      # [tile, ndim] view with row stride sum(ndim)
+            pc["rec"].recover_dev(qp.data_ptr(), int(off[-1]), tile, None, 0, stream.cuda_stream)
+
+    def gather():
+        for pc in pieces:
+            pc["rec"].copy_envelope_dev(pc["env"][0].data_ptr(), pc["env"][1].data_ptr(), stream.cuda_stream)
+        if world > 1:
+            mine = torch.cat([pc["env"] for pc in pieces], 1) if pieces else torch.empty((2, 0), dtype=torch.float64, device=dev)
+            counts = [None] * world
+            dist.all_gather_object(counts, int(mine.shape[1]))
+            bufs = [torch.empty((2, c), dtype=torch.float64, device=dev) for c in counts] if rank == 0 else None
+            dist.gather(mine, bufs, dst=0)
+
+    for i in range(warm):
+        step(i)
+    gather()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for pc in pieces:
+        pc["rec"].reset_envelope()
+        pc["rec"].timing_reset()
+    lib.fsr_kernel_launches(1)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for i in range(steps):
+        step(warm + i)
+    e1.record()
+    gather()
+    e2.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    my_compute, my_total = e0.elapsed_time(e1), e0.elapsed_time(e2)
+    t = torch.tensor([my_compute, my_total], dtype=torch.float64, device=dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allt, t)
+    else:
+        allt = [t]
+    if rank == 0:
+        comp = [float(x[0]) for x in allt]
+        tot = max(float(x[1]) for x in allt)
+        print(json.dumps({
+            "config": "C4", "metric": "element_timestep_stress_evals_per_sec", "value": nel_total * tile * steps / (tot * 1e-3),
+            "unit": "element*steps/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / steps, "dtype": "f64",
+            "scaling": "strong",
+            "workload": f"6 parts, {nel_total} elements in total (ANDES quads/triangles, TET10 + beams, HEX20, HEX8/TET4/WEDG6), "
+                        f"{tile} time steps per step, von Mises envelopes gathered to rank 0",
+            "rank_compute_ms_per_step": [c / steps for c in comp],
+            "load_imbalance": max(comp) / (sum(comp) / len(comp)) - 1.0,
+            "planned_load_share": [float(l / sum(loads)) for l in loads],
+            "plan": [[(ip, round(f0, 4), round(f1, 4)) for ip, f0, f1 in it] for it in items],
+            "gpu_launches_rank0": int(lib.fsr_kernel_launches(0)), "setup_s": setup}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
