@@ -101,15 +101,22 @@ def main():
             qp = q[:, int(off[ip]):int(off[ip + 1])]      # [tile, ndim] view with row stride sum(ndim)
             pc["rec"].recover_dev(qp.data_ptr(), int(off[-1]), tile, None, 0, stream.cuda_stream)
 
+    state = {}
+
     def gather():
         for pc in pieces:
             pc["rec"].copy_envelope_dev(pc["env"][0].data_ptr(), pc["env"][1].data_ptr(), stream.cuda_stream)
         if world > 1:
             mine = torch.cat([pc["env"] for pc in pieces], 1) if pieces else torch.empty((2, 0), dtype=torch.float64, device=dev)
-            counts = [None] * world
-            dist.all_gather_object(counts, int(mine.shape[1]))
-            bufs = [torch.empty((2, c), dtype=torch.float64, device=dev) for c in counts] if rank == 0 else None
-            dist.gather(mine, bufs, dst=0)
+            # NCCL gather wants equal shapes: pad every rank's envelope block to the largest one
+            if "gather_pad" not in state:
+                counts = [None] * world
+                dist.all_gather_object(counts, int(mine.shape[1]))
+                state["gather_pad"] = max(counts)
+                state["gather_bufs"] = [torch.empty((2, max(counts)), dtype=torch.float64, device=dev) for _ in counts] if rank == 0 else None
+                state["gather_mine"] = torch.zeros((2, max(counts)), dtype=torch.float64, device=dev)
+            state["gather_mine"][:, :mine.shape[1]].copy_(mine)
+            dist.gather(state["gather_mine"], state["gather_bufs"], dst=0)
 
     for i in range(warm):
         step(i)
