@@ -66,10 +66,10 @@ def c3(args):
             "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
             "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2, {part.sam.ndof} DOF, n_red={ndim}, {tile} time "
                         f"steps per step, von Mises envelope (no per-step history kept)",
-            "roofline": {"kernel": "k2_tet10_vm_kernel", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK,
+            "roofline": {"kernel": "k2_tet10_vm_kernel (dense 60x30)" if os.environ.get("FSR_TET10_DENSE") else "k2_tet10_grad_vm_kernel", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK,
                          "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch": k2,
                          "algorithmic_bytes_per_launch": alg,
-                         "dmma_tflops": 2.0 * 64 * 32 * ntet * tile / (k2 * 1e-3) / 1e12},
+                         "dmma_tflops_issued": (4096.0 if os.environ.get("FSR_TET10_DENSE") else 2304.0) * ntet * tile / (k2 * 1e-3) / 1e12},
             "k1": {"ms_per_launch": k1, "tflops": 2.0 * part.sam.ndof * ndim * tile / (k1 * 1e-3) / 1e12, "peak": DGEMM_PEAK},
             "gpu_launches": int(lib.fsr_kernel_launches(0)), "setup_s": setup, "max_von_mises": float(mx.max())}
 
@@ -191,6 +191,65 @@ def c1(args):
             "gpu_launches": int(lib.fsr_kernel_launches(0))}
 
 
+def c1cli(args):
+    """Config 1 through the drop-in executable: the files a reducer + solver run leaves behind (70 x 70 ANDES quads, 4 triads,
+    10 component modes, 1,000 time steps) -> bin/fedem_stress -vmStress (float .frs, the reference's default) -> wall time of
+    the whole program incl. reading the inputs, CUDA context creation and writing the 157 MB results database; next to it the
+    CPU restatement of the reference's time loop (oracle, single thread like fedem_stress) on the same history."""
+    import subprocess
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind
+    from test_frs_cpu import _write_solver_file, _build_finit_numpy
+    from fedem_solvers_b200.files import save_part
+    from fedem_solvers_b200.fsi import SolverPart, write_fsi, read_fsi
+    from fedem_solvers_b200.ftl import write_ftl
+    from fedem_solvers_b200.frs import FrsReader
+    from fedem_solvers_b200.model import plate_part
+    part = plate_part(70, 70, ngen=10, n_ext=4, seed=1)
+    d = tempfile.mkdtemp(prefix="c1cli_")
+    rng = np.random.default_rng(1)
+    nsteps, base = 1000, 40
+    write_ftl(os.path.join(d, "plate.ftl"), part)
+    save_part(os.path.join(d, "plate"), part, checksum=7, part_id=base)
+    triads, tr_undef, sup, tri, gen = _write_solver_file(os.path.join(d, "th_p_1.frs"), rng, nsteps, 4, 10, dt=0.001, step0=1, sup_base=base)
+    sp = SolverPart(base_id=base, user_id=1, descr="plate", ngen=10, sup_pos=sup[0], gravity=np.zeros(3), model_file="",
+                    triad_base_id=np.array([t[0] for t in triads]), triad_user_id=np.array([t[1] for t in triads]), ndofs=np.full(4, 6),
+                    first_dof=np.zeros(4, int), tr_undef=tr_undef, triad_ur=tri[0], gen_first_dof=0)
+    write_fsi(os.path.join(d, "fedem_solver.fsi"), [sp])
+    exe = os.path.join(ROOT, "fedem_solvers_b200", "bin", "fedem_stress")
+    cmd = [exe, "-cwd", d, "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs",
+           "-vmStress", "-statm", "0", "-stotm", "10", "-tinc", "0"]
+    subprocess.run(cmd, capture_output=True, text=True)          # first run: CUDA module load, page cache
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    wall = time.perf_counter() - t0
+    assert r.returncode == 0, r.stdout
+    out = os.path.join(d, "plate_1.frs")
+    rd = FrsReader(out)
+    assert rd.nsteps == nsteps
+    # the CPU restatement on the same reduced history
+    o = oracle_bind.Oracle()
+    b = o.bind_part(part)
+    tr = read_fsi(os.path.join(d, "fedem_solver.fsi"), base).tr_undef
+    Q = _build_finit_numpy(sup, tri, tr, np.full(4, 6), 1 + 6 * np.arange(4), gen, 25, 34)
+    ns_cpu = 100
+    t0 = time.perf_counter()
+    vm_o, _, _ = o.recover_history(b, Q[:, :ns_cpu], want_history=True, nthreads=1)
+    cpu = time.perf_counter() - t0
+    h = rd.find(f"Elements|{int(part.elm.elmid[17])}|QUAD4|Element nodes|Top|1|Von Mises stress", "Part", base)
+    got = rd.read(h)[:ns_cpu, 0]
+    p0 = b["ptoff"][17]
+    err = float(np.abs(got - vm_o[:, p0]).max() / np.abs(vm_o).max())
+    return {"config": "C1-cli", "metric": "element_timestep_stress_evals_per_sec", "value": part.sam.nel * nsteps / wall, "unit": "element*steps/s",
+            "n_gpus": 1, "seconds_wall": wall, "dtype": "f64 compute, f32 file",
+            "workload": f"bin/fedem_stress -vmStress on generated reducer/solver files: {part.sam.nel} ANDES quads, n_red=34, {nsteps} steps; "
+                        f"results database {os.path.getsize(out) / 1e6:.0f} MB",
+            "cpu_port": {"value": part.sam.nel * ns_cpu / cpu, "unit": "element*steps/s", "cores": 1, "seconds_for_1000_steps": cpu * nsteps / ns_cpu,
+                         "sample": f"oracle restatement of the reference time loop, {ns_cpu} of the {nsteps} steps, compute only (no file output)"},
+            "max_rel_diff_vs_oracle_float_file": err}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["c1", "c3", "c5"])
@@ -202,7 +261,7 @@ def main():
     ap.add_argument("--nsteps", type=int, default=100_000)
     args = ap.parse_args()
     for c in args.configs:
-        print(json.dumps({"c1": c1, "c3": c3, "c5": c5, "hex20": chex}[c](args)), flush=True)
+        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex}[c](args)), flush=True)
 
 
 if __name__ == "__main__":
