@@ -4,14 +4,19 @@
 !!   do while (ffr_getnextstep(...)); readSupElDisplacements; calcIntDisplacements; calcStresses
 !! per time step, the driver collects the reduced displacements of a window of steps into
 !! Q(ndim,nWin) and makes ONE call.  Everything before the loop (ffl_init, initiateSAM,
-!! readSolverData, openBandEmatrices, ffr_init, readResponsePointers, writeStressHeader) and the
-!! .frs writer stay as they are; the arrays handed over are the reference's own (SamType members,
-!! ffl_* results, the in-core B and E of DiskMatrixType%vala).
+!! readSolverData, openBandEmatrices, ffr_init, readResponsePointers) stays as it is; the arrays handed
+!! over are the reference's own (SamType members, ffl_* results, the in-core B and E of
+!! DiskMatrixType%vala).  The results database is written by the library: fsr_rdb_create replaces
+!! writeStressHeader (same header grammar), fsr_rdb_write_steps replaces writeTimeStepDB + the per-element
+!! writeStressDB / writeStrMeasureDB / writeDisplacementDB calls of a whole window of steps -- the records
+!! are formed on the device.  (A host that prefers to keep its own writer calls fsr_recover / fsr_recover_step_full
+!! instead and gets the arrays back; the library-only program is bin/fedem_stress, csrc/stress_driver.cu.)
 !!
 !! Delivered as source: the build image has no Fortran compiler (see DESIGN.md section 1).
 
 subroutine stress_b200 (sam, xyz, emod, rny, thk, elmid, beam, Bmat, Emat, ngen, &
-     &                  triads, sup, rPointers, startTime, stopTime, tInc, lpu, ierr)
+     &                  triads, sup, rPointers, startTime, stopTime, tInc, &
+     &                  rdbFile, outMask, lDouble, lpu, ierr)
 
   use, intrinsic :: iso_c_binding
   use fedem_b200_mod
@@ -34,14 +39,21 @@ subroutine stress_b200 (sam, xyz, emod, rny, thk, elmid, beam, Bmat, Emat, ngen,
   type(SupElType), intent(inout)      :: sup
   integer        , intent(in)         :: rPointers(:)
   real(dp)       , intent(in)         :: startTime, stopTime, tInc
+  character(len=*), intent(in)        :: rdbFile   !< -rdbfile
+  integer        , intent(in)         :: outMask   !< FSR_OUT_* bits from -SR -stress -strain -vmStress ...
+  logical        , intent(in)         :: lDouble   !< -double
   integer        , intent(out)        :: ierr
 
   integer, parameter  :: nWin = 512        !< time steps per device batch
   type(fsr_sam)       :: csam
   type(fsr_elmdata)   :: celm
   type(fsr_options)   :: copt
-  type(c_ptr)         :: part
-  real(dp), allocatable, target :: Q(:,:), vm(:,:), vmMax(:), vmMin(:)
+  type(fsr_rdb_options) :: ropt
+  type(c_ptr)         :: part, rdb
+  character(kind=c_char,len=:), allocatable, target :: cDescr
+  real(dp), allocatable, target :: Q(:,:), supTr(:,:,:), vmMax(:), vmMin(:), time(:)
+  integer , allocatable :: stepNo(:)
+  real(dp), target    :: supTrInit(3,4)
   real(dp)            :: currTime
   integer(i8)         :: iStep
   integer             :: ndim, npts, n
@@ -72,7 +84,18 @@ subroutine stress_b200 (sam, xyz, emod, rny, thk, elmid, beam, Bmat, Emat, ngen,
 
   ndim = fsr_ndim(part)
   npts = fsr_num_result_points(part)
-  allocate(Q(ndim,nWin),vm(npts,nWin),vmMax(npts),vmMin(npts))
+  allocate(Q(ndim,nWin),supTr(3,4,nWin),time(nWin),stepNo(nWin),vmMax(npts),vmMin(npts))
+
+  !! --- replaces writeStressHeader (saveStressModule.f90:120-247)
+  cDescr = trim(sup%id%descr)//c_null_char
+  supTrInit = sup%supTrInit
+  ropt%out_mask = outMask;  ropt%double_precision = merge(1,0,lDouble);  ropt%rdbinc = 1
+  ropt%part_base_id = sup%id%baseId;  ropt%part_user_id = sup%id%userId
+  ropt%part_descr = c_loc(cDescr);  ropt%model_file = c_null_ptr;  ropt%link_file = c_null_ptr
+  ropt%elmid = c_loc(elmid);  ropt%module_name = c_null_ptr
+  ropt%minex = c_loc(sam%minex);  ropt%sup_tr_init = c_loc(supTrInit)
+  ierr = fsr_rdb_create(rdb,part,trim(rdbFile)//c_null_char,ropt)
+  if (ierr < 0) goto 900
 
   !! --- the time loop, batched
   n = 0
@@ -83,19 +106,21 @@ subroutine stress_b200 (sam, xyz, emod, rny, thk, elmid, beam, Bmat, Emat, ngen,
      n = n + 1
      Q(1:sam%ndof2,n) = sup%finit(1:sam%ndof2)
      if (ngen > 0) Q(sam%ndof2+1:ndim,n) = sup%genDOFs%ur(1:ngen)
+     supTr(:,:,n) = sup%supTr;  time(n) = currTime;  stepNo(n) = int(iStep)
      if (n == nWin) then
-        ierr = fsr_recover(part,Q,ndim,n,c_loc(vm))    ! von Mises of every result point, n steps
+        !! K1 expansion + record kernels for n steps, records appended to the .frs file
+        ierr = fsr_rdb_write_steps(rdb,Q,ndim,n,stepNo,time,supTr)
         if (ierr < 0) goto 900
-        !! ... writeStrMeasureDB for the n steps (saveStressModule) ...
         n = 0
      end if
   end do
   if (n > 0) then
-     ierr = fsr_recover(part,Q,ndim,n,c_loc(vm))
+     ierr = fsr_rdb_write_steps(rdb,Q,ndim,n,stepNo,time,supTr)
      if (ierr < 0) goto 900
   end if
 
-  ierr = fsr_get_envelope(part,vmMax,vmMin)
+  ierr = fsr_rdb_close(rdb)
+  ierr = fsr_get_envelope(part,vmMax,vmMin)   ! running max/min of von Mises, if the caller wants them
   call fsr_part_destroy (part)
   return
 
