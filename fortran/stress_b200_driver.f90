@@ -120,7 +120,7 @@ subroutine stress_b200 (sam, xyz, emod, rny, thk, elmid, beam, Bmat, Emat, ngen,
   end if
 
   ierr = fsr_rdb_close(rdb)
-  ierr = fsr_get_envelope(part,vmMax,vmMin)   ! running max/min of von Mises, if the caller wants them
+  !! (the running von Mises envelopes of fsr_get_envelope belong to the fsr_recover path, not to the record path)
   call fsr_part_destroy (part)
   return
 
