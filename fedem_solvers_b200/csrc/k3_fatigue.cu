@@ -33,6 +33,7 @@ struct GageState {
 
 constexpr int K3_THREADS = 128;
 constexpr int K3_CHUNK = 32;
+constexpr int K3_TPCAP = 8;  // turning points a gage may queue between two convergent rainflow passes
 constexpr int K3_QCAP = 4;   // closed cycles a gage may queue between two convergent damage evaluations
 
 }  // namespace fsr
@@ -146,7 +147,28 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
       if (k < qn) count_cycle(q_a[k][threadIdx.x], q_b[k][threadIdx.x], p, s.sink, mybins, stride, edges);
     qn = 0;
   };
-  auto emit = [&](double v) { s.rf.push(v, p.gate, myspill, stride, cap, count); };
+  // The same separation one level up: the peak-valley filter only queues its turning points (FIFO per gage); the
+  // rainflow stack consumes them at the end of the chunk in a loop every lane of the warp runs together, so the three
+  // state machines (PVX, rainflow, damage) are three tight loops instead of one interleaved, divergent one.
+  __shared__ double q_tp[MODE == 1 ? K3_TPCAP : 1][K3_THREADS];
+  int qt = 0;
+  auto emit = [&](double v) {
+    if (qt == K3_TPCAP) {   // queue full: drain in order (divergent, rare)
+      for (int k = 0; k < K3_TPCAP; ++k) s.rf.push(q_tp[k][threadIdx.x], p.gate, myspill, stride, cap, count);
+      qt = 0;
+    }
+    q_tp[qt][threadIdx.x] = v; ++qt;
+  };
+  auto drain = [&]() {      // reached by every lane of the warp
+    int m = qt;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int k = 0; k < m; ++k)
+      if (k < qt) s.rf.push(q_tp[k][threadIdx.x], p.gate, myspill, stride, cap, count);
+    qt = 0;
+    flush();
+    if (s.rf.overflow) { s.status = 2; idle = true; }
+  };
   auto consume = [&](int i, double x) {
     if (MODE == 0) {
       if (s.loc.feed(x, p.gate)) idle = true;
@@ -170,7 +192,7 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
       const double* col = tiles + threadIdx.x;
       if (!idle)
         for (int k = 0; k < tn && !idle; ++k) consume(step0 + c * K3_CHUNK + k, col[k * (K3_THREADS + 1)]);
-      if (MODE == 1) flush();
+      if (MODE == 1) drain();
       // every gage of the block located: nothing left to read in this pass
       if (MODE == 0 && __syncthreads_and(idle)) break;
       if (MODE != 0) __syncthreads();
@@ -188,12 +210,12 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
         for (int k = 0; k < 8; ++k)
           if (!idle) consume(step0 + t + k, xb[k]);
       }
-      if (MODE == 1 && (t & 31) == 24) flush();
+      if (MODE == 1 && (t & 31) == 24) drain();
       if (MODE == 0 && __all_sync(0xffffffffu, idle)) break;
     }
     if (!idle)
       for (; t < nsteps && !idle; ++t) consume(step0 + t, __ldg(hp + (size_t)t * ld));
-    if (MODE == 1) flush();
+    if (MODE == 1) drain();
   }
   if (active && (MODE == 1 || was_pending)) st[g] = s;
   if (MODE == 0 && pending) {
