@@ -107,23 +107,26 @@ __global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int
     eg[i] = T[0] * e[0] + T[1] * e[1] + T[2] * e[2];
     sg[i] = T[0] * s[0] + T[1] * s[1] + T[2] * s[2];
   }
-  // PrincipleStrains2D / PrincipleStresses2D (strainAndStressUtils.f90:14-98)
-  double origo = (e[0] + e[1]) * 0.5, d12 = e[0] - e[1], exy = e[2] * 0.5;
-  double radius = sqrt(d12 * d12 + e[2] * e[2]) * 0.5;
-  const double ep1 = origo + radius, ep2 = origo - radius, gmax = radius * 2.0;
-  double alpha1 = 0.0, alphaG = 0.0;
-  if (fabs(exy) > kEpsDiv0 || fabs(d12) > kEpsDiv0) {
-    alpha1 = atan2(exy, d12) * 0.5;
-    alphaG = atan2(d12, exy) * 0.5;
-  }
-  origo = (s[0] + s[1]) * 0.5; d12 = s[0] - s[1];
-  radius = sqrt(d12 * d12 + 4.0 * s[2] * s[2]) * 0.5;
+  // PrincipleStresses2D (strainAndStressUtils.f90:57-98)
+  double origo = (s[0] + s[1]) * 0.5, d12 = s[0] - s[1];
+  double radius = sqrt(d12 * d12 + 4.0 * s[2] * s[2]) * 0.5;
   const double sp1 = origo + radius, sp2 = origo - radius, tmax = radius;
   // fatigue series: sigmaP(1) and the leg stresses in MPa (strainGageModule.f90:711-716)
   hist[(size_t)(4 * r) * ld_hist + t] = sp1 * to_mpa;
 #pragma unroll
   for (int i = 0; i < 3; ++i) hist[(size_t)(4 * r + 1 + i) * ld_hist + t] = sg[i] * to_mpa;
   if (values) {
+    // PrincipleStrains2D (strainAndStressUtils.f90:14-55): only the per-step result record needs the principal strains and
+    // the two atan2 angles, the fatigue pass (values == NULL) does not pay for them
+    origo = (e[0] + e[1]) * 0.5; d12 = e[0] - e[1];
+    const double exy = e[2] * 0.5;
+    radius = sqrt(d12 * d12 + e[2] * e[2]) * 0.5;
+    const double ep1 = origo + radius, ep2 = origo - radius, gmax = radius * 2.0;
+    double alpha1 = 0.0, alphaG = 0.0;
+    if (fabs(exy) > kEpsDiv0 || fabs(d12) > kEpsDiv0) {
+      alpha1 = atan2(exy, d12) * 0.5;
+      alphaG = atan2(d12, exy) * 0.5;
+    }
     double* v = values + ((size_t)t * nros + r) * FSR_GAGE_NVAL_;
     v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
     v[3] = ep1; v[4] = ep2; v[5] = fabs(ep1) > fabs(ep2) ? ep1 : ep2;
