@@ -59,7 +59,7 @@ static void get_coor(int iel, const orc_sam *sam, const orc_elmdata *ed, int n, 
 int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed,
                   double *V, double *S, double *Sigma, double *Epsil, int *nenod, int *nstrp)
 {
-  double x[20], y[20], z[20], thk[4], SS[24];
+  double x[20], y[20], z[20], thk[8], SS[24];
   int ierr = 0;
   *nenod = 0;
   *nstrp = 0;
@@ -89,6 +89,22 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     thk[0] = thk[1] = thk[2] = thk[3] = ed->thk[iel - 1];
     ierr = orc_str24(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, S, SS, Sigma,
                      Epsil);
+    break;
+  case 31:
+    *nenod = 6;
+    *nstrp = 12;
+    get_coor(iel, sam, ed, 6, x, y, z);
+    for (int k = 0; k < 6; k++) thk[k] = ed->thk[iel - 1];
+    memset(S, 0, sizeof(double) * 36);   /* "Nodal stress resultants ... maybe later", elStressModule.f90:1174-1176 */
+    ierr = orc_str31(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, Sigma, Epsil);
+    break;
+  case 32:
+    *nenod = 8;
+    *nstrp = 16;
+    get_coor(iel, sam, ed, 8, x, y, z);
+    for (int k = 0; k < 8; k++) thk[k] = ed->thk[iel - 1];
+    memset(S, 0, sizeof(double) * 48);
+    ierr = orc_str32(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, Sigma, Epsil);
     break;
   case 41:
     *nenod = 10;
@@ -157,6 +173,8 @@ static int nstrp_of(int t) /* elStressModule.f90:159-229 */
   case 11: return 0;
   case 21: case 23: return 6;
   case 22: case 24: return 8;
+  case 31: return 12;
+  case 32: return 16;
   case 41: return 10;
   case 42: return 15;
   case 43: return 20;

@@ -105,6 +105,12 @@ int orc_str45(const double *x, const double *y, const double *z, double emod, do
               double *epsil);
 int orc_str46(const double *x, const double *y, const double *z, double emod, double rny, int stressForm, const double *v,
               double *sigma, double *epsil);
+/* thick shells (thickshell.c): STR31 TRI6 (sigma/epsil (6,12)), STR32 QUAD8 ((6,16)); ev = 6 DOFs per node */
+int orc_str31(const double *xg, const double *yg, const double *zg, double emod, double rny, const double *thk,
+              const double *ev, double *sigma, double *epsil);
+int orc_str32(const double *xg, const double *yg, const double *zg, double emod, double rny, const double *thk,
+              const double *ev, double *sigma, double *epsil);
+void orc_rotate3d(const double *S, const double *rotMx, double *out);
 int orc_str11(const double *beam, const double ev[12], double SF[12]);
 int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed,
                   double *V, double *S, double *Sigma, double *Epsil, int *nenod, int *nstrp);
