@@ -24,6 +24,8 @@ static int nstrp_of(int type)
   switch (type) {
     case 21: case 23: return 6;
     case 22: case 24: return 8;
+    case 31: return 12;
+    case 32: return 16;
     case 41: return 10;
     case 42: return 15;
     case 43: return 20;
@@ -34,7 +36,7 @@ static int nstrp_of(int type)
   }
 }
 
-static bool supported_type(int type) { return type == 24 || type == 23 || (type >= 41 && type <= 46) || type == 11; }
+static bool supported_type(int type) { return type == 24 || type == 23 || type == 31 || type == 32 || (type >= 41 && type <= 46) || type == 11; }
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -86,7 +88,7 @@ std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const f
 
 static void free_family(FamilyData& f)
 {
-  cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed); cudaFree(f.Gfrag);
+  cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed); cudaFree(f.Gfrag); cudaFree(f.Efrag);
   cudaFree(f.aux);
   f = FamilyData();
 }
@@ -219,6 +221,7 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, 
   if ((rc = build_hex20_operators(p, sam, elm))) return fail(rc);
   if ((rc = build_linsolid_operators(p, sam, elm))) return fail(rc);
   if ((rc = build_wedg15_operators(p, sam, elm))) return fail(rc);
+  if ((rc = build_thickshell_operators(p, sam, elm))) return fail(rc);
   if ((rc = fsr_reset_envelope(p))) return fail(rc);
 
   // count failed elements (they get hugeVal results, the run continues)
@@ -345,6 +348,7 @@ static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   if ((rc = launch_k2_hex20_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if ((rc = launch_k2_linsolid_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if ((rc = launch_k2_wedg15_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_thickshell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if (ev) cudaEventRecord(ev[2], s);
   return FSR_OK;
 }

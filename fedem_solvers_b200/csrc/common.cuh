@@ -63,7 +63,7 @@ __device__ __forceinline__ double sqrt_pos(double x)
 
 // Element families handled by the K2 kernels.  A family fixes the operator shape:
 // MT m-tiles of 8 rows, KT k-tiles of 4 element DOFs.
-enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_HEX8 = 5, FAM_TET4 = 6, FAM_WEDG6 = 7, FAM_WEDG15 = 8, FAM_COUNT = 9 };
+enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_HEX8 = 5, FAM_TET4 = 6, FAM_WEDG6 = 7, FAM_WEDG15 = 8, FAM_TRI6 = 9, FAM_QUAD8 = 10, FAM_COUNT = 11 };
 
 struct FamilyData {
   int nelt = 0;          // elements of this family (active only)
@@ -77,6 +77,8 @@ struct FamilyData {
   double* aux = nullptr; // per-element scalars needed by the full-output kernels
   int naux = 0;
   double* Gfrag = nullptr;      // solids: displacement-gradient operator in A-fragment order (k2_solid.cu)
+  double* Efrag = nullptr;      // thick shells: strain operator, same shape as Sfrag (strain is not an isotropic function of
+                                // the global stress there, k2_thickshell.cu); NULL for every other family
 };
 
 }  // namespace fsr
@@ -186,6 +188,8 @@ int build_beam_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm
 int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_wedg15_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int launch_k2_wedg15_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);
+int build_thickshell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
+int launch_k2_thickshell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);
 int build_linsolid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int launch_k2_linsolid_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);
 int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s);

@@ -42,12 +42,13 @@ __device__ __forceinline__ size_t frag_at2(int row, int col, int KT)
 
 // One thread per (result point, step); step is the fastest index so that the U reads of a warp are one
 // contiguous segment per DOF row and the record writes one contiguous segment per slot.
-// rec[slot * ldt + t].  layout: 0 = shells (operator row = comp*8 + point), 1 = solids (row = point*ncmp + comp)
+// rec[slot * ldt + t].  layout: 0 = thin shells (operator row = comp*8 + point), 1 = solids (row = point*ncmp + comp),
+// 2 = thick shells (rows as solids, strain from its own operator Efrag, zero stress resultants)
 __global__ void record_points_kernel(const double* __restrict__ U, size_t ldu, int nt, const double* __restrict__ Sfrag,
                                      const int* __restrict__ edof, const long long* __restrict__ roff,
                                      const unsigned char* __restrict__ failed, const double* __restrict__ aux, int naux,
-                                     int nelt, int nstrp, int ncmp, int nedof, int MT, int KT, int layout, int nenod,
-                                     RecLayout L, double* __restrict__ rec, size_t ldt)
+                                     const double* __restrict__ Efrag, int nelt, int nstrp, int ncmp, int nedof, int MT, int KT,
+                                     int layout, int nenod, RecLayout L, double* __restrict__ rec, size_t ldt)
 {
   const int t = blockIdx.y * blockDim.x + threadIdx.x;
   const long long ip = (long long)blockIdx.x * blockDim.y + threadIdx.y;
@@ -55,7 +56,7 @@ __global__ void record_points_kernel(const double* __restrict__ U, size_t ldu, i
   const int i = (int)(ip / nstrp), pnt = (int)(ip % nstrp);
   const long long base = roff[i];
   if (base < 0) return;
-  const int srsize = L.sr && ncmp == 3 ? 6 * nenod : 0;
+  const int srsize = L.sr && layout != 1 ? 6 * nenod : 0;
   const int ptsize = (L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel;
   double* out = rec + (size_t)(base + srsize + (long long)pnt * ptsize) * ldt + t;
   double* srout = rec + (size_t)(base + 6 * pnt) * ldt + t;
@@ -74,7 +75,14 @@ __global__ void record_points_kernel(const double* __restrict__ U, size_t ldu, i
     sig[c] = s;
   }
   const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
-  if (ncmp == 3) {
+  if (layout == 2) {
+    const double* Es = Efrag + (size_t)i * MT * KT * 32;
+    for (int c = 0; c < ncmp; ++c) {
+      double s = 0.0;
+      for (int col = 0; col < nedof; ++col) s += Es[frag_at2(pnt * ncmp + c, col, KT)] * U[(size_t)ed[col] * ldu + t];
+      eps[c] = s;
+    }
+  } else if (ncmp == 3) {
     eps[0] = sig[0] / E - nu / E * sig[1];
     eps[1] = -nu / E * sig[0] + sig[1] / E;
     eps[2] = 0.5 * (2.0 * (1.0 + nu) / E * sig[2]);
@@ -97,7 +105,9 @@ __global__ void record_points_kernel(const double* __restrict__ U, size_t ldu, i
     if (L.mask & 0xe0) { P[0] = P[1] = P[2] = 0.0; principal_values(ncmp, eps, P); r[5] = P[0]; r[6] = P[np - 1]; r[7] = 0.5 * (P[0] - P[np - 1]); }
     for (int j = 0; j < 8; ++j) if (L.mask & (1 << j)) out[(size_t)(k++) * ldt] = r[j];
   }
-  if (srsize && pnt < nenod) {   // shell stress resultants from the top and bottom stresses (k2_full.cu)
+  if (srsize && pnt < nenod && layout == 2)   // thick shells: SR = 0 (STR31 / STR32, elStressModule.f90:1174-1176, 1296-1298)
+    for (int k = 0; k < 6; ++k) srout[(size_t)k * ldt] = 0.0;
+  if (srsize && pnt < nenod && layout == 0) {   // shell stress resultants from the top and bottom stresses (k2_full.cu)
     const double th = aux[(size_t)i * naux + 2];
     for (int c = 0; c < 3; ++c) {
       const int row = c * 8 + nenod + pnt;
@@ -463,10 +473,13 @@ static long long build_header(int nnod, const int* madof, int nel, const int* me
     if (elmno <= 0 || (active && !active[e])) continue;
     const int t = melcon[e];
     int nelnod = 0, ncmp = 0;
+    bool shell = false;
     switch (t) {
       case 11: if (!L.sr) continue; if (!ig[t]) ig[t] = hb.beam(L); nelnod = 2; break;
-      case 21: case 23: if (!ig[21]) ig[21] = hb.shell(L, "TRI3", 3); nelnod = 3; ncmp = 3; break;
-      case 22: case 24: if (!ig[22]) ig[22] = hb.shell(L, "QUAD4", 4); nelnod = 4; ncmp = 3; break;
+      case 21: case 23: if (!ig[21]) ig[21] = hb.shell(L, "TRI3", 3); nelnod = 3; ncmp = 3; shell = true; break;
+      case 22: case 24: if (!ig[22]) ig[22] = hb.shell(L, "QUAD4", 4); nelnod = 4; ncmp = 3; shell = true; break;
+      case 31: if (!ig[t]) ig[t] = hb.shell(L, "TRI6", 6); nelnod = 6; ncmp = 6; shell = true; break;
+      case 32: if (!ig[t]) ig[t] = hb.shell(L, "QUAD8", 8); nelnod = 8; ncmp = 6; shell = true; break;
       case 41: if (!ig[t]) ig[t] = hb.solid(L, "TET10", 10); nelnod = 10; ncmp = 6; break;
       case 42: if (!ig[t]) ig[t] = hb.solid(L, "WEDG15", 15); nelnod = 15; ncmp = 6; break;
       case 43: if (!ig[t]) ig[t] = hb.solid(L, "HEX20", 20); nelnod = 20; ncmp = 6; break;
@@ -480,8 +493,8 @@ static long long build_header(int nnod, const int* madof, int nel, const int* me
     slot[(size_t)e] = nslot;
     if (t == 11) nslot += 12;
     else {
-      const int nstrp = ncmp == 3 ? 2 * nelnod : nelnod;
-      nslot += (L.sr && ncmp == 3 ? 6 * nelnod : 0) + (long long)nstrp * ((L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel);
+      const int nstrp = shell ? 2 * nelnod : nelnod;
+      nslot += (L.sr && shell ? 6 * nelnod : 0) + (long long)nstrp * ((L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel);
     }
   }
   if (elements) hb.datd += "  ]\n";
@@ -659,9 +672,9 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
       } else {
         if (f.nstrp == 0) continue;
         dim3 grd((unsigned)(((long long)f.nelt * f.nstrp + 7) / 8), (nt + 31) / 32);
-        const int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : 1;
+        const int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : (fi == FAM_TRI6 || fi == FAM_QUAD8) ? 2 : 1;
         record_points_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, f.Sfrag, f.edof, r->roff[fi], f.failed, f.aux,
-                                                 f.naux, f.nelt, f.nstrp, f.ncmp, f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod,
+                                                 f.naux, f.Efrag, f.nelt, f.nstrp, f.ncmp, f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod,
                                                  r->L, r->rec, ldt);
       }
       ++g_launches;

@@ -21,7 +21,7 @@ __device__ __forceinline__ size_t frag_at(int row, int col, int KT)
 __global__ void k2_full_kernel(const double* __restrict__ U, size_t ldu, const double* __restrict__ Sfrag,
                                const int* __restrict__ edof, const int* __restrict__ ptoff,
                                const int* __restrict__ elem, const unsigned char* __restrict__ failed,
-                               const double* __restrict__ aux, int naux, int nelt, int nstrp, int ncmp,
+                               const double* __restrict__ aux, int naux, const double* __restrict__ Efrag, int nelt, int nstrp, int ncmp,
                                int nedof, int MT, int KT, int layout, int nenod,
                                double* __restrict__ resmat, double* __restrict__ stress,
                                double* __restrict__ strain, double* __restrict__ sres)
@@ -36,7 +36,7 @@ __global__ void k2_full_kernel(const double* __restrict__ U, size_t ldu, const d
   if (failed[i]) {
     for (int k = 0; k < 8; ++k) resmat[8 * pt + k] = kHuge;
     for (int k = 0; k < 6; ++k) { stress[6 * pt + k] = kHuge; strain[6 * pt + k] = kHuge; }
-    if (ncmp == 3 && pnt < nenod) for (int k = 0; k < 6; ++k) sres[(size_t)24 * elem[i] + 6 * pnt + k] = kHuge;
+    if ((ncmp == 3 && pnt < nenod) || (Efrag && pnt < 4)) for (int k = 0; k < 6; ++k) sres[(size_t)24 * elem[i] + 6 * pnt + k] = kHuge;
     return;
   }
   for (int c = 0; c < ncmp; ++c) {
@@ -46,7 +46,17 @@ __global__ void k2_full_kernel(const double* __restrict__ U, size_t ldu, const d
     sig[c] = s;
   }
   const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
-  if (ncmp == 3) {
+  if (Efrag) {
+    // thick shells: the strain has its own operator (local inverse constitutive matrix applied before the rotation to the
+    // global axes, STR31 / STR32 elStressModule.f90:1148-1160, 1260-1272; tensorial shear already folded in)
+    const double* Es = Efrag + (size_t)i * MT * KT * 32;
+    for (int c = 0; c < ncmp; ++c) {
+      double s = 0.0;
+      for (int col = 0; col < nedof; ++col) s += Es[frag_at(pnt * ncmp + c, col, KT)] * U[(size_t)ed[col] * ldu];
+      eps[c] = s;
+    }
+    if (pnt < 4) for (int k = 0; k < 6; ++k) sres[(size_t)24 * elem[i] + 6 * pnt + k] = 0.0;   // SR = 0 "maybe later" (:1174-1176)
+  } else if (ncmp == 3) {
     // isoMat2Dinv (isoMatModule.f90:41-57), then tensorial shear (elStressModule.f90:244-248)
     eps[0] = sig[0] / E - nu / E * sig[1];
     eps[1] = -nu / E * sig[0] + sig[1] / E;
@@ -96,7 +106,7 @@ int launch_k2_full(fsr_part* p, double* resmat, double* stress, double* strain, 
     int total = f.nelt * f.nstrp;
     int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : 1;
     k2_full_kernel<<<(total + 127) / 128, 128, 0, s>>>(p->U, (size_t)p->step_tile, f.Sfrag, f.edof, f.ptoff,
-                                                      f.elem, f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
+                                                      f.elem, f.failed, f.aux, f.naux, f.Efrag, f.nelt, f.nstrp, f.ncmp,
                                                       f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod, resmat,
                                                       stress, strain, sres);
     FSR_LAUNCH_CHECK();

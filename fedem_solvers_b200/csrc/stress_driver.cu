@@ -274,14 +274,12 @@ int solveStress(void)
   const int nbad = fsr_ftl_get_elmdata(ftl, emod.data(), rny.data(), rho.data(), thk.data(), elmid.data(), beam.data(), estat.data());
   if (nbad > 0) log.line("  ** Warning: %d elements lack material / thickness / cross section data", nbad);
   {   // element types with a stress routine in the reference but no operator in this library: say so loudly
-    int legacy = 0, thick = 0;
+    int legacy = 0;
     for (int e = 0; e < nel; ++e) {
       if (elmid[(size_t)e] < 1) continue;
       if (melcon[(size_t)e] == 21 || melcon[(size_t)e] == 22) ++legacy;
-      if (melcon[(size_t)e] == 31 || melcon[(size_t)e] == 32) ++thick;
     }
     if (legacy) log.line("  ** Warning: %d thin shells of type 21/22 (reduced without -useANDESformulation) get NO results: only the ANDES shells (23/24) are supported by this build", legacy);
-    if (thick) log.line("  ** Warning: %d thick shells of type 31/32 get NO results: not supported by this build", thick);
   }
 
   // --- Read superelement data from the solver input file (readSolverData)

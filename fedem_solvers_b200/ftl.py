@@ -122,6 +122,8 @@ def write_ftl(path, part, groups=None, rho=7850.0, comments=True):
     for e in range(sam.nel):
         t = int(sam.melcon[e])
         nodes = [int(minex[k - 1]) for k in sam.mmnpc[sam.mpmnpc[e] - 1: sam.mpmnpc[e + 1] - 1]]
+        if t == 31:   # the file lists a TRI6 around its perimeter; ffl_gettopol moves the mid-side nodes last
+            nodes = [nodes[0], nodes[3], nodes[1], nodes[4], nodes[2], nodes[5]]
         refs = []
         if t == 11:
             b = elm.beam[e]

@@ -67,7 +67,7 @@ class PartModel:
     recovery_seed: int = 0   # seed of the synthetic [B|E] fields (synthetic_recovery)
 
     def nstrp(self):
-        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
+        tab = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 31: 12, 32: 16, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
         n = np.array([tab.get(int(t), 0) for t in self.sam.melcon], I32)
         if self.elm.elmid is not None:
             n[self.elm.elmid < 1] = 0
@@ -504,6 +504,82 @@ def linsolid_block(nx, ny, nz, ngen=6, seed=8, n_ext=4, jitter=0.08, emod=2.1e11
     elm = ElementData(xyz=xyz, emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64), thk=np.zeros(nel, F64),
                       elmid=np.arange(1, nel + 1, dtype=I32))
     part = PartModel(sam=sam, elm=elm, name=f"linsolid_{nx}x{ny}x{nz}")
+    part.recovery_seed = seed
+    if with_recovery:
+        part.B, part.E = synthetic_recovery(part)
+    return part
+
+
+# thick shells on the doubled (u, v) grid of a cell: QUAD8 counter-clockwise from a corner (corner, mid-side, ...), the
+# cell centre unused; two TRI6 per cell in SAM order (3 corners, then the mid-sides 1-2, 2-3, 3-1), the cell centre is the
+# mid-side node of the shared diagonal
+_Q8 = [(0, 0), (1, 0), (2, 0), (2, 1), (2, 2), (1, 2), (0, 2), (0, 1)]
+_T6 = [[(0, 0), (2, 0), (2, 2), (1, 0), (2, 1), (1, 1)], [(0, 0), (2, 2), (0, 2), (1, 1), (1, 2), (0, 1)]]
+
+
+def thickshell_panel(nx, ny, ngen=6, seed=12, n_ext=4, jitter=0.1, emod=2.1e11, rny=0.3, thk=0.02, kinds=(31, 32),
+                     curvature=(0.15, 0.10, 0.05), rotation=None, shuffle_eq=False, with_recovery=True):
+    """Doubly curved panel of nx*ny cells meshed with 8-noded (type 32) and/or 6-noded (type 31) thick shells, 6 DOFs per
+    node; cells alternate between the requested kinds.  z = a u^2 + b v^2 + c u v over the unit-cell grid, nodes jittered in
+    (u, v) so that mid-side nodes stay well inside CHQA30's 1:3 bound; `rotation` (3x3) turns the whole panel, e.g. to put
+    shell normals along the global X axis (LNCS30's fallback branch)."""
+    rng = np.random.default_rng(seed)
+    NX, NY = 2 * nx + 1, 2 * ny + 1
+    conn_list, types = [], []
+    for j in range(ny):
+        for i in range(nx):
+            kind = kinds[(i + j) % len(kinds)]
+            pats = [_Q8] if kind == 32 else _T6
+            for pat in pats:
+                conn_list.append([(2 * j + dv) * NX + 2 * i + du for du, dv in pat])
+                types.append(kind)
+    flat = np.concatenate([np.asarray(c, np.int64) for c in conn_list])
+    uniq, first = np.unique(flat, return_index=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty(len(uniq), np.int64)
+    rank[order] = np.arange(len(uniq))
+    lookup = rank[np.searchsorted(uniq, flat)] + 1
+    conn, k = [], 0
+    for c in conn_list:
+        conn.append(lookup[k:k + len(c)].astype(I32))
+        k += len(c)
+    kk = uniq[order]
+    gu, gv = (kk % NX).astype(F64), (kk // NX).astype(F64)
+    corner = ((kk % NX) % 2 == 0) & ((kk // NX) % 2 == 0)
+    u = gu / 2.0 + np.where(corner, rng.uniform(-jitter, jitter, len(kk)), 0.0)
+    v = gv / 2.0 + np.where(corner, rng.uniform(-jitter, jitter, len(kk)), 0.0)
+    # mid-side / centre nodes: between their (jittered) neighbours, then shifted along the edge by up to +-10 % of it
+    cu, cv = {int(q): a for q, a in zip(kk, u)}, {int(q): a for q, a in zip(kk, v)}
+    for n, q in enumerate(kk):
+        if corner[n]:
+            continue
+        a, b = int(q % NX), int(q // NX)
+        if a % 2 == 1 and b % 2 == 0:
+            ends = [b * NX + a - 1, b * NX + a + 1]
+        elif a % 2 == 0 and b % 2 == 1:
+            ends = [(b - 1) * NX + a, (b + 1) * NX + a]
+        else:
+            ends = [(b - 1) * NX + a - 1, (b + 1) * NX + a + 1]
+        w = 0.5 + rng.uniform(-0.1, 0.1)
+        u[n] = (1 - w) * cu[ends[0]] + w * cu[ends[1]]
+        v[n] = (1 - w) * cv[ends[0]] + w * cv[ends[1]]
+    ca, cb, cc = curvature
+    xyz = np.stack([u, v, ca * u * u / max(nx, 1) + cb * v * v / max(ny, 1) + cc * u * v / max(nx, ny, 1)], 1)
+    if rotation is not None:
+        xyz = xyz @ np.asarray(rotation, F64).T
+    node_of = {int(q): i + 1 for i, q in enumerate(kk)}
+    cand = [(0, 0), (NX - 1, 0), (0, NY - 1), (NX - 1, NY - 1), (NX // 2 // 2 * 2, 0), (0, NY // 2 // 2 * 2)]
+    ext_nodes = []
+    for c in cand:
+        n = node_of.get(c[1] * NX + c[0])
+        if n is not None and n not in ext_nodes and len(ext_nodes) < n_ext:
+            ext_nodes.append(n)
+    sam = _build_sam(len(kk), 6, conn, np.asarray(types, I32), ext_nodes, rng=rng, shuffle_eq=shuffle_eq)
+    sam.ngen = ngen
+    nel = sam.nel
+    elm = ElementData(xyz=np.ascontiguousarray(xyz), emod=np.full(nel, emod, F64), rny=np.full(nel, rny, F64),
+                      thk=np.full(nel, thk, F64), elmid=np.arange(1, nel + 1, dtype=I32))
+    part = PartModel(sam=sam, elm=elm, name=f"thickshell_{nx}x{ny}")
     part.recovery_seed = seed
     if with_recovery:
         part.B, part.E = synthetic_recovery(part)

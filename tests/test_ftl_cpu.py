@@ -166,6 +166,13 @@ def test_generated_tet10_block_with_beams(tmp_path):
     _roundtrip(part, tmp_path, "tets.ftl")
 
 
+def test_generated_thick_shell_panel(tmp_path):
+    """TRI6 / QUAD8: the reference's ffl_gettopol moves the three mid-side nodes of a TRI6 last (FFlLinkHandler_F.C:657-664)"""
+    from fedem_solvers_b200.model import thickshell_panel
+    part = thickshell_panel(4, 3, ngen=3, seed=14, with_recovery=False)
+    _roundtrip(part, tmp_path, "panel.ftl")
+
+
 def test_generated_hex20_block_implicit_group(tmp_path):
     part = hex20_block(2, 2, 1, ngen=3, seed=13)
     mine, elm = _roundtrip(part, tmp_path, "hex.ftl", None, "<PMAT 1>")

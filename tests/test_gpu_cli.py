@@ -12,7 +12,7 @@ from fedem_solvers_b200.files import save_part, write_fmx
 from fedem_solvers_b200.frs import FrsReader
 from fedem_solvers_b200.fsi import SolverPart, write_fsi
 from fedem_solvers_b200.ftl import write_ftl
-from fedem_solvers_b200.model import plate_part, tet10_block
+from fedem_solvers_b200.model import plate_part, tet10_block, thickshell_panel
 from test_frs_cpu import _write_solver_file, _build_finit_numpy
 from test_rdb_cpu import NAMES, NENOD, MEASURES
 
@@ -145,3 +145,32 @@ def test_tets_group_selection_gravity_and_time_increment(oracle, tmp_path):
             got = rd.read(rd.find(f"Elements|{part.elm.elmid[e]}|TET10|Element nodes|Basic|{k + 1}|Stress", "Part", case["base"]))
             assert np.abs(got - np.stack([x["stress"][pt] for x in o])).max() <= 1.3e-7 * sc   # float file
     assert rd.find(f"Elements|{part.elm.elmid[half]}|TET10|Element nodes|Basic|1|Stress", "Part", case["base"]) is None
+
+
+def test_thick_shell_panel_through_the_executable(oracle, tmp_path):
+    """TRI6 / QUAD8 part: the .ftl lists a TRI6 around its perimeter (ffl_gettopol reorders the mid-side nodes last,
+    FFlLinkHandler_F.C:657-664); stress tensors (TENSOR3 in Top / Bottom groups) and von Mises in a float file."""
+    part = thickshell_panel(3, 3, ngen=4, seed=23, n_ext=4)
+    case = _make_case(tmp_path, part, "panel", nsteps=12)
+    out = _run(tmp_path, ["-linkfile", "panel.ftl", "-samfile", "panel_SAM.fsm", "-Bmatfile", "panel_B.fmx", "-eigfile", "panel_E.fmx",
+                          "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rdbfile", "panel.frs", "-stress", "-vmStress"])
+    assert "Warning" not in out
+    rd = FrsReader(str(tmp_path / "panel_1.frs"))
+    steps = np.arange(12)
+    assert np.array_equal(rd.step_numbers, case["stepno"])
+    b, o = _oracle_steps(oracle, part, case, steps)
+    sc = np.abs(np.stack([x["stress"] for x in o])).max()
+    n = 0
+    for e in range(part.sam.nel):
+        t = int(part.sam.melcon[e]); nn = NENOD[t]
+        p = f"Elements|{part.elm.elmid[e]}|{NAMES[t]}|Element nodes|"
+        for si, side in enumerate(("Top", "Bottom")):
+            for k in (0, nn // 2, nn - 1):
+                pt = b["ptoff"][e] + si * nn + k
+                got = rd.read(rd.find(p + f"{side}|{k + 1}|Stress", "Part", case["base"]))
+                want = np.stack([x["stress"][pt] for x in o])
+                assert got.shape == want.shape and np.abs(got - want).max() <= 1.3e-7 * sc
+                got = rd.read(rd.find(p + f"{side}|{k + 1}|Von Mises stress", "Part", case["base"]))
+                assert np.abs(got - np.stack([x["resmat"][pt, :1] for x in o])).max() <= 1.3e-7 * sc
+                n += 1
+    assert n > 50

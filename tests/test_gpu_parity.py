@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from fedem_solvers_b200 import StressRecovery
-from fedem_solvers_b200.model import linsolid_block, wedg15_block, plate_part, tet10_block, hex20_block, reduced_history
+from fedem_solvers_b200.model import thickshell_panel, linsolid_block, wedg15_block, plate_part, tet10_block, hex20_block, reduced_history
 
 pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
@@ -318,4 +318,38 @@ def test_wedg15_block(oracle, form):
                                         _dp(v), _dp(sig), _dp(eps)) == 0
             vm_o = np.array([oracle.von_mises(sig[6 * p: 6 * p + 6]) for p in range(15)])
             assert rel_err(vm_g[s, off[e]:off[e] + 15], vm_o) <= TOL, (e, s)
+    rec.close()
+
+
+@pytest.mark.parametrize("kinds", [(31, 32), (32,), (31,)])
+def test_thick_shells(oracle, kinds):
+    """types 31 / 32 (STR31 / STR32): dense stress + strain operators folded from the SCTS32 / SCQS32 stress matrices;
+    the oracle side of this pair is pinned by the reference's testThickShell.pf cases (tests/test_thickshell_cpu.py)"""
+    part = thickshell_panel(4, 3, ngen=5, seed=12, kinds=kinds, shuffle_eq=True)
+    _check_part(oracle, part, nsteps=70, seed=6)
+
+
+def test_thick_shells_with_normals_along_global_x(oracle):
+    """panel turned so that its normals lie along X: LNCS30 cannot put x' in the z'-X plane and falls through to the
+    z'-Y rule (scts.f:486-505), for the node systems and the sampling points alike"""
+    rot = np.array([[0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [-1.0, 0.0, 0.0]])
+    part = thickshell_panel(3, 3, ngen=4, seed=15, rotation=rot, curvature=(1e-5, 2e-5, 0.0))
+    _check_part(oracle, part, nsteps=12, seed=7)
+
+
+def test_thick_shell_with_bad_midside_node_gets_huge(oracle):
+    """CHQA30: a mid-side node at 1/5 of its edge fails the element (hugeVal), the others are unaffected"""
+    part = thickshell_panel(3, 2, ngen=3, seed=16, kinds=(32,))
+    n = part.sam.mmnpc[part.sam.mpmnpc[2] - 1: part.sam.mpmnpc[3] - 1] - 1
+    X = part.elm.xyz
+    X[n[1]] = X[n[0]] + 0.2 * (X[n[2]] - X[n[0]])
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 6, seed=2)
+    vm_o, _, _ = oracle.recover_history(b, Q)
+    rec = StressRecovery(part)
+    assert rec.n_failed >= 1
+    vm_g = rec.recover(Q)
+    bad = vm_o >= 1e300
+    assert bad.any() and not bad.all() and np.array_equal(bad, vm_g >= 1e300)
+    assert rel_err(vm_g[~bad], vm_o[~bad]) <= TOL
     rec.close()

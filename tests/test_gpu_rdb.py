@@ -8,7 +8,7 @@ import pytest
 
 from fedem_solvers_b200 import StressRecovery
 from fedem_solvers_b200.frs import FrsReader
-from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, linsolid_block, reduced_history
+from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, linsolid_block, thickshell_panel, reduced_history
 from fedem_solvers_b200.rdb import StressRdb, out_mask
 from test_rdb_cpu import NAMES, NENOD, MEASURES
 
@@ -109,10 +109,14 @@ def _check(oracle, part, tmp_path, mask, double, nsteps, total=False, step_tile=
                     check(p + f"Basic|{n + 1}|Beam sectional force", sf[:, 6 * n:6 * n + 3], np.abs(sf[:, 0::6]).max() + np.abs(sf[:, :3]).max())
                     check(p + f"Basic|{n + 1}|Beam sectional moment", sf[:, 6 * n + 3:6 * n + 6], np.abs(sf[:, 3:6]).max() + np.abs(sf[:, 9:]).max())
             continue
-        shell = t < 30
-        ncmp = 3 if shell else 6
+        shell = t < 40
+        ncmp = 3 if t < 30 else 6
         sides = ("Top", "Bottom") if shell else ("Basic",)
-        if shell and sr_on:
+        if shell and sr_on and t > 30:      # thick shells: SR = 0 for every node (STR31 / STR32 "maybe later")
+            for n in range(nn):
+                check(p + f"Basic|{n + 1}|Shell stress resultant force", np.zeros((nsteps, 3)), 1.0)
+                check(p + f"Basic|{n + 1}|Shell stress resultant moment", np.zeros((nsteps, 3)), 1.0)
+        elif shell and sr_on:
             sr = np.stack([x["sres"][e] for x in o])      # [nsteps, 24] = SR(6, node)
             for n in range(nn):
                 check(p + f"Basic|{n + 1}|Shell stress resultant force", sr[:, 6 * n:6 * n + 3], scale["srf"])
@@ -127,7 +131,7 @@ def _check(oracle, part, tmp_path, mask, double, nsteps, total=False, step_tile=
                     check(q + "Strain", np.stack([x["strain"][pt, :ncmp] for x in o]), scale["strain"])
                 for j in sel:
                     # principal values: trigonometric cubic, 1e-9
-                    sc = (scale["stress"] if j < 4 else scale["strain"]) * (1.0 if j in (0, 4) or shell else 10.0)
+                    sc = (scale["stress"] if j < 4 else scale["strain"]) * (1.0 if j in (0, 4) or t < 30 else 10.0)
                     check(q + MEASURES[j], np.stack([x["resmat"][pt, j:j + 1] for x in o]), sc)
     if def_on:
         from oracle_bind import _dp
@@ -185,3 +189,15 @@ def test_linear_solids_all_measures_double(oracle, tmp_path):
     part = linsolid_block(2, 2, 1, ngen=4, seed=7)
     mask = out_mask(stress=True, strain=True, vmStress=True, maxPStress=True, minPStress=True, maxSStress=True, vmStrain=True)
     _check(oracle, part, tmp_path, mask, True, nsteps=6)
+
+
+def test_thick_shells_everything_double(oracle, tmp_path):
+    part = thickshell_panel(3, 2, ngen=4, seed=13)
+    mask = out_mask(SR=True, stress=True, strain=True, vmStress=True, maxPStress=True, minPStress=True, maxSStress=True,
+                    vmStrain=True, maxPStrain=True, minPStrain=True, maxSStrain=True, deformation=True)
+    _check(oracle, part, tmp_path, mask, True, nsteps=7)
+
+
+def test_thick_shells_von_mises_float(oracle, tmp_path):
+    part = thickshell_panel(2, 3, ngen=3, seed=14)
+    _check(oracle, part, tmp_path, out_mask(vmStress=True, strain=True), False, nsteps=5)

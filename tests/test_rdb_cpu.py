@@ -19,8 +19,8 @@ from fedem_solvers_b200.rdb import build_header, out_mask, OUT
 from test_frs_cpu import RefFrs, FIXTURES, _header_text
 
 I32, F64 = np.int32, np.float64
-NAMES = {11: "BEAM2", 21: "TRI3", 23: "TRI3", 22: "QUAD4", 24: "QUAD4", 41: "TET10", 42: "WEDG15", 43: "HEX20", 44: "HEX8", 45: "TET4", 46: "WEDG6"}
-NENOD = {11: 2, 21: 3, 23: 3, 22: 4, 24: 4, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
+NAMES = {11: "BEAM2", 21: "TRI3", 23: "TRI3", 22: "QUAD4", 24: "QUAD4", 31: "TRI6", 32: "QUAD8", 41: "TET10", 42: "WEDG15", 43: "HEX20", 44: "HEX8", 45: "TET4", 46: "WEDG6"}
+NENOD = {11: 2, 21: 3, 23: 3, 22: 4, 24: 4, 31: 6, 32: 8, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
 MEASURES = ["Von Mises stress", "Max principal stress", "Min principal stress", "Max shear stress",
             "Von Mises strain", "Max principal strain", "Min principal strain", "Max shear strain"]
 
@@ -76,8 +76,8 @@ def _expected_slots(madof, melcon, elmid, minex, mask, total):
                 slots[p + f"Basic|{n + 1}|Beam sectional force"] = (k, 3); k += 3
                 slots[p + f"Basic|{n + 1}|Beam sectional moment"] = (k, 3); k += 3
             continue
-        shell = t < 30
-        ncmp = 3 if shell else 6
+        shell = t < 40
+        ncmp = 3 if t < 30 else 6
         if shell and sr:
             for n in range(nn):
                 slots[p + f"Basic|{n + 1}|Shell stress resultant force"] = (k, 3); k += 3
@@ -108,8 +108,8 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[f"mask{c['mask']:03x}{'d' if c['double'] else 'f'}" for c in CASES])
 def test_records_are_where_the_reference_reader_looks_for_them(tmp_path, case):
     rng = np.random.default_rng(case["mask"])
-    melcon = np.array([24, 24, 23, 11, 41, 22, 43, 21, 11, 51, 24, 44, 45, 46, 42], I32)   # 51: a mass element, never written
-    elmid = np.array([10, 11, 12, 13, 14, -15, 16, 17, 18, 19, 120, 121, 122, 123, 124], I32)   # -15: outside the -group selection
+    melcon = np.array([24, 24, 23, 11, 41, 22, 43, 21, 11, 51, 24, 44, 45, 46, 42, 32, 31], I32)   # 51: a mass element, never written
+    elmid = np.array([10, 11, 12, 13, 14, -15, 16, 17, 18, 19, 120, 121, 122, 123, 124, 125, 126], I32)   # -15: outside the -group selection
     ndofs = np.array([6, 6, 3, 6, 3, 3, 6, 0, 6], I32)                         # node 8 has no DOFs left
     madof = np.concatenate([[1], 1 + np.cumsum(ndofs)]).astype(I32)
     minex = np.array([1, 2, 5, 7, 8, 9, 20, 21, 300], I32)
