@@ -153,7 +153,7 @@ def test_thick_shell_panel_through_the_executable(oracle, tmp_path):
     part = thickshell_panel(3, 3, ngen=4, seed=23, n_ext=4)
     case = _make_case(tmp_path, part, "panel", nsteps=12)
     out = _run(tmp_path, ["-linkfile", "panel.ftl", "-samfile", "panel_SAM.fsm", "-Bmatfile", "panel_B.fmx", "-eigfile", "panel_E.fmx",
-                          "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rdbfile", "panel.frs", "-stress", "-vmStress"])
+                          "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rdbfile", "panel.frs", "-tinc", "0", "-stress", "-vmStress"])
     assert "Warning" not in out
     rd = FrsReader(str(tmp_path / "panel_1.frs"))
     steps = np.arange(12)
