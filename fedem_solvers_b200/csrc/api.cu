@@ -130,10 +130,28 @@ long long fsr_kernel_launches(int reset)
   return n;
 }
 
-int fsr_part_create(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, const fsr_options* opt)
+int fsr_part_create(fsr_part** out, const fsr_sam* sam_in, const fsr_elmdata* elm, const fsr_options* opt)
 {
-  if (!out || !sam || !elm) { set_error("fsr_part_create: null argument"); return FSR_ERR_ARG; }
+  if (!out || !sam_in || !elm) { set_error("fsr_part_create: null argument"); return FSR_ERR_ARG; }
   *out = nullptr;
+  // Legacy thin shells (types 21 FFT3 and 22 FFQ4, parts reduced with -useANDESformulation-): with the default stress
+  // formulations of fedem_stress (stressmain.C:72-78: -fftStressForm 1, -ffqStressForm 2) STR21 runs exactly the statements of
+  // STR23 (FTSA31 / FTSA32 / FTS38, elStressModule.f90:559-562,586-587 vs :935,953) and STR22 exactly those of STR24
+  // (pMatStiff projection + STR22a with 2 x 2 Gauss points, :675-686,717-722 vs :1039-1076), so they join those families.
+  // The other (private, non-default) formulations are not built: elements of such a run get NO results, like any
+  // unsupported type, and fedem_stress says so (stress_driver.cu).
+  const int ffq = opt && opt->reserved[1] ? opt->reserved[1] - 1 : 2, fft = opt && opt->reserved[2] ? opt->reserved[2] - 1 : 1;
+  std::vector<int> melcon_eff;
+  fsr_sam sam_eff = *sam_in;
+  if (sam_in->melcon && sam_in->nel > 0) {
+    melcon_eff.assign(sam_in->melcon, sam_in->melcon + sam_in->nel);
+    for (int& t : melcon_eff) {
+      if (t == 21) t = fft == 1 ? 23 : 0;
+      else if (t == 22) t = ffq == 2 ? 24 : 0;
+    }
+    sam_eff.melcon = melcon_eff.data();
+  }
+  const fsr_sam* sam = &sam_eff;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     set_error("no CUDA device available: this library has no CPU fallback");

@@ -273,13 +273,16 @@ int solveStress(void)
   CHECK(fsr_ftl_get_nodes(ftl, nullptr, nullptr, nullptr, nullptr, xyz.data()));
   const int nbad = fsr_ftl_get_elmdata(ftl, emod.data(), rny.data(), rho.data(), thk.data(), elmid.data(), beam.data(), estat.data());
   if (nbad > 0) log.line("  ** Warning: %d elements lack material / thickness / cross section data", nbad);
-  {   // element types with a stress routine in the reference but no operator in this library: say so loudly
-    int legacy = 0;
+  {   // legacy thin shells are recovered for the default stress formulations only (fsr_part_create): say so loudly otherwise
+    const int ffq = c.get_int("ffqStressForm"), fft = c.get_int("fftStressForm");
+    int nq = 0, nt = 0;
     for (int e = 0; e < nel; ++e) {
       if (elmid[(size_t)e] < 1) continue;
-      if (melcon[(size_t)e] == 21 || melcon[(size_t)e] == 22) ++legacy;
+      if (melcon[(size_t)e] == 22 && ffq != 2) ++nq;
+      if (melcon[(size_t)e] == 21 && fft != 1) ++nt;
     }
-    if (legacy) log.line("  ** Warning: %d thin shells of type 21/22 (reduced without -useANDESformulation) get NO results: only the ANDES shells (23/24) are supported by this build", legacy);
+    if (nq) log.line("  ** Warning: %d FFQ shells (type 22) get NO results: -ffqStressForm %d is not supported by this build (only the default, 2)", nq, ffq);
+    if (nt) log.line("  ** Warning: %d FFT shells (type 21) get NO results: -fftStressForm %d is not supported by this build (only the default, 1)", nt, fft);
   }
 
   // --- Read superelement data from the solver input file (readSolverData)
@@ -324,6 +327,7 @@ int solveStress(void)
   fsr_options po;
   memset(&po, 0, sizeof(po));
   po.device = c.get_int("device"); po.stressForm = c.get_int("stressForm"); po.step_tile = c.get_int("stepTile");
+  po.reserved[1] = c.get_int("ffqStressForm") + 1; po.reserved[2] = c.get_int("fftStressForm") + 1;
   fsr_part* part = nullptr;
   const int nfail = fsr_part_create(&part, &sam, &ed, &po);
   if (nfail < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return nfail; }

@@ -27,7 +27,7 @@ def _ip(a):
 
 
 class StressRecovery:
-    def __init__(self, part: PartModel, device=0, stress_form=0, step_tile=0, elem_order=0):
+    def __init__(self, part: PartModel, device=0, stress_form=0, step_tile=0, elem_order=0, ffq_stress_form=2, fft_stress_form=1):
         self._lib = _lib.load_library()
         self._h = C.c_void_p()
         s, e = part.sam, part.elm
@@ -57,6 +57,8 @@ class StressRecovery:
         elm.beam = _dp(cd(e.beam)) if e.beam is not None else None
         opt = FsrOptions(device=device, stressForm=stress_form, step_tile=step_tile)
         opt.reserved[0] = elem_order  # 0 = Morton order of element centroids, 1 = SAM order
+        opt.reserved[1] = ffq_stress_form + 1   # -ffqStressForm / -fftStressForm of the legacy shells (types 22 / 21)
+        opt.reserved[2] = fft_stress_form + 1
         rc = self._lib.fsr_part_create(C.byref(self._h), C.byref(sam), C.byref(elm), C.byref(opt))
         self.n_failed = check(rc, "fsr_part_create")
         self._keep = []

@@ -75,7 +75,12 @@ typedef struct fsr_options {
   int stressForm; /* -stressForm (solids): 0 = nodal evaluation (default), else Gauss extrap. */
   int step_tile;  /* time steps per device batch (0 = automatic from free HBM)              */
   int reserved[5];/* [0]: element processing order, 0 = Morton order of the centroids (default,
-                     L2 reuse of shared nodes), 1 = SAM order; results are in SAM order either way */
+                     L2 reuse of shared nodes), 1 = SAM order; results are in SAM order either way
+                     [1]: -ffqStressForm + 1 (legacy FFQ4 shells, type 22), 0 = the default formulation 2
+                     [2]: -fftStressForm + 1 (legacy FFT3 shells, type 21), 0 = the default formulation 1
+                     Types 21 / 22 are recovered for the default formulations only (then STR21 = STR23 and
+                     STR22 = STR24 statement by statement, elStressModule.f90:521-733); with another value
+                     those elements get no results */
 } fsr_options;
 
 /* Output selection bits = the -vmStress ... switches of stressmain.C:46-60 */

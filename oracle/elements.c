@@ -74,6 +74,7 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     Sigma[0] = 0.0;
     Epsil[0] = 0.0;
     break;
+  case 21: /* FFT3 with the default -fftStressForm 1: STR21 runs the statements of STR23 (elStressModule.f90:559-562,586-587) */
   case 23:
     *nenod = 3;
     *nstrp = 6;
@@ -82,6 +83,7 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     ierr = orc_str23(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, S, SS, Sigma,
                      Epsil);
     break;
+  case 22: /* FFQ4 with the default -ffqStressForm 2: STR22 = pMatStiff + STR22a(2), the statements of STR24 (:675-686,717-722) */
   case 24:
     *nenod = 4;
     *nstrp = 8;

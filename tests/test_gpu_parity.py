@@ -353,3 +353,18 @@ def test_thick_shell_with_bad_midside_node_gets_huge(oracle):
     assert bad.any() and not bad.all() and np.array_equal(bad, vm_g >= 1e300)
     assert rel_err(vm_g[~bad], vm_o[~bad]) <= TOL
     rec.close()
+
+
+def test_legacy_shells_default_formulations(oracle):
+    """types 21 / 22 (part reduced without the ANDES formulation): with the default -fftStressForm 1 / -ffqStressForm 2 the
+    reference's STR21 / STR22 run the statements of STR23 / STR24; any other formulation gives those elements no results"""
+    part = plate_part(6, 5, ngen=4, seed=17, tri_fraction=0.4, warp=0.02)
+    ref_vm = _check_part(oracle, part, nsteps=20, seed=8)
+    legacy = plate_part(6, 5, ngen=4, seed=17, tri_fraction=0.4, warp=0.02)
+    legacy.sam.melcon = legacy.sam.melcon - 2
+    assert set(np.unique(legacy.sam.melcon)) == {21, 22}
+    vm = _check_part(oracle, legacy, nsteps=20, seed=8)
+    assert np.array_equal(vm, ref_vm)
+    rec = StressRecovery(legacy, ffq_stress_form=1)      # FFQ quads drop out, the FFT triangles stay
+    assert rec.npts == 6 * int((legacy.sam.melcon == 21).sum())
+    rec.close()
