@@ -18,5 +18,6 @@ for p in "${pids[@]}"; do wait $p || { cat build/*.ptxas.log | grep -E "error" ;
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libfedem_b200.so build/api.o build/k1_expand.o build/k2_shell.o build/k2_solid.o build/k2_linsolid.o build/k2_hex20.o build/k2_thickshell.o build/k2_beam.o build/k2_full.o build/k3_fatigue.o build/k3_gage.o build/io_files.o build/io_frs.o build/io_ftl.o build/io_rdb.o build/io_fsi.o build/stress_driver.o build/solver_state.o -lcudart
 mkdir -p fedem_solvers_b200/bin
 g++ -O2 -o fedem_solvers_b200/bin/fedem_stress $SRC/stress_main.cpp -L$OUT -lfedem_b200 -Wl,-rpath,'$ORIGIN/../lib'
+g++ -O2 -o fedem_solvers_b200/bin/fedem_gage $SRC/gage_main.cpp -L$OUT -lfedem_b200 -Wl,-rpath,'$ORIGIN/../lib'
 make -s -C oracle all
 echo "built $OUT/libfedem_b200.so"

@@ -126,6 +126,7 @@ SYMBOLS = [
     ("fsr_fsi_close", None, [_P]),
     ("fsr_fsi_part", C.c_int, [_P, _I, C.c_char_p, C.c_int, _I, _I, _D, _D, C.c_char_p, C.c_int]),
     ("fsr_fsi_triads", C.c_int, [_P, _I, _I, _I, _I, _D, _D]),
+    ("fsr_fsi_read_rosettes", C.c_int, [C.c_char_p, C.c_int, C.POINTER(FsrRosette), _I, C.c_char_p, C.c_int, C.c_int]),
     ("fsr_rdb_create", C.c_int, [C.POINTER(_P), _P, C.c_char_p, C.POINTER(FsrRdbOptions)]),
     ("fsr_rdb_build_header", C.c_int, [C.c_int, _I, C.c_int, _I, C.POINTER(FsrRdbOptions), C.c_char_p, C.c_int, C.POINTER(C.c_longlong)]),
     ("fsr_rdb_step_bytes", C.c_longlong, [_P]),
@@ -136,6 +137,8 @@ SYMBOLS = [
     ("fsr_rdb_close", C.c_int, [_P]),
     ("initSolverArgs", None, [C.c_int, C.POINTER(C.c_char_p)]),
     ("solveStress", C.c_int, []),
+    ("solveGage", C.c_int, []),
+    ("fsr_gage_define_options", None, []),
     ("fsr_select_steps", C.c_int, [_D, C.c_int, C.c_double, C.c_double, C.c_double, _I, C.c_int]),
     ("fsr_cmdline_reset", None, []),
     ("fsr_stress_define_options", None, []),

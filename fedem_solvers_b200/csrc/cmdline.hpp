@@ -45,6 +45,7 @@ class CmdLine {
     for (auto& o : opts_) { Option& p = o.second; p.b = p.bdef; p.i = p.idef; p.d = p.ddef; p.s = p.sdef; p.is_set = false; }
   }
   void push(const std::string& arg) { args_.push_back(arg); }
+  void clear_options() { opts_.clear(); }   // keeps the (not yet evaluated) argument list
 
   bool read_options_file(const std::string& file)
   {

@@ -257,4 +257,63 @@ int fsr_fsi_triads(const fsr_fsi* h, int* base_id, int* user_id, int* ndofs, int
   return ndof + 1;
 }
 
+// ReadStrainGages (src/vpmStress/strainGageModule.f90:78-237) with thisLinkNumber present: every &STRAIN_ROSETTE record
+// of the file (id, extId, extDescr, linkId, type, zeroInit, numnod, nodes, rPos, zPos, Emod, nu, gateVal, snCurve);
+// a record whose linkId is not `link_base_id` is an input error there ("The part base ID does not match"), and so is
+// an unknown rosette type.  ros[k].nodes come back as the EXTERNAL node numbers of the file: the caller maps them with
+// ffl_ext2int and swaps them when the normal points the wrong way (checkRosette :479-521).  rPos(4,3) is filled in
+// Fortran order, i.e. the file lists posInGl row by row; rpos is posInGl(3,4) column-major.
+// user_id [cap], descr [cap][descr_stride] may be NULL.  Returns the number of records (ros may be NULL to count).
+int fsr_fsi_read_rosettes(const char* path, int link_base_id, fsr_rosette* ros, int* user_id, char* descr, int descr_stride, int cap)
+{
+  if (!path) { set_error("fsr_fsi_read_rosettes: bad arguments"); return FSR_ERR_ARG; }
+  std::vector<Record> recs;
+  if (!read_namelists(path, recs)) return FSR_ERR_ARG;
+  static const struct { const char* name; int ngage; double alpha; } kTypes[] = {
+      {"SINGLE_GAGE", 1, 0.0}, {"DOUBLE_GAGE_90", 2, 1.5707963267948966}, {"TRIPLE_GAGE_60", 3, 1.0471975511965976},
+      {"TRIPLE_GAGE_45", 3, 0.7853981633974483}};
+  int n = 0;
+  std::vector<int> iv;
+  std::vector<double> dv;
+  for (const Record& r : recs) {
+    if (r.group != "STRAIN_ROSETTE") continue;
+    if (ros && n < cap) {
+      fsr_rosette& o = ros[n];
+      memset(&o, 0, sizeof(o));
+      o.id = r.int1("id", 0);
+      const int link = r.int1("linkid", 0);
+      if (link != link_base_id) {
+        set_error("%s: STRAIN_ROSETTE %d (record %d): the part base ID %d does not match %d", path, o.id, n + 1, link, link_base_id);
+        return FSR_ERR_ARG;
+      }
+      std::string type = r.str("type");
+      while (!type.empty() && type.back() == ' ') type.pop_back();
+      int it = -1;
+      for (int k = 0; k < 4; ++k) if (strcasecmp(type.c_str(), kTypes[k].name) == 0) it = k;
+      if (it < 0) { set_error("%s: invalid rosette-type %s for Rosette %d", path, type.c_str(), o.id); return FSR_ERR_ARG; }
+      o.ngage = kTypes[it].ngage; o.alpha_gages = kTypes[it].alpha;
+      o.zero_init = r.int1("zeroinit", 0) > 0 ? 1 : 0;
+      o.numnod = r.int1("numnod", 0);
+      if (o.numnod < 3 || o.numnod > 4) { set_error("%s: Rosette %d has %d nodes (3 or 4 expected)", path, o.id, o.numnod); return FSR_ERR_ARG; }
+      if (!r.ints("nodes", iv) || (int)iv.size() < o.numnod) { set_error("%s: Rosette %d: nodes missing", path, o.id); return FSR_ERR_ARG; }
+      for (int k = 0; k < o.numnod; ++k) o.nodes[k] = iv[(size_t)k];
+      if (!r.reals("rpos", dv) || dv.size() < 12) { set_error("%s: Rosette %d: rPos needs 12 values", path, o.id); return FSR_ERR_ARG; }
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 4; ++j) o.rpos[i + 3 * j] = dv[(size_t)(4 * i + j)];
+      o.zpos = r.reals("zpos", dv) && !dv.empty() ? dv[0] : 0.0;
+      o.emod = r.reals("emod", dv) && !dv.empty() ? dv[0] : 0.0;
+      o.nu = r.reals("nu", dv) && !dv.empty() ? dv[0] : 0.0;
+      o.gate = r.reals("gateval", dv) && !dv.empty() ? dv[0] : 0.0;
+      if (r.reals("sncurve", dv)) for (size_t k = 0; k < 4 && k < dv.size(); ++k) o.sncurve[k] = dv[k];
+      if (user_id) { user_id[n] = r.ints("extid", iv) && !iv.empty() ? iv[0] : 0; }
+      if (descr && descr_stride > 0) {
+        const std::string d = r.str("extdescr");
+        strncpy(descr + (size_t)n * descr_stride, d.c_str(), (size_t)descr_stride - 1);
+        descr[(size_t)n * descr_stride + descr_stride - 1] = 0;
+      }
+    }
+    ++n;
+  }
+  return n;
+}
+
 }  // extern "C"

@@ -396,6 +396,33 @@ struct HeaderBuilder {
   }
 };
 
+}  // namespace
+
+namespace fsr {
+// openHeaderFiles (rdbModule.f90:191-251): the meta data lines that precede VARIABLES:
+std::string rdb_file_preamble(const char* module, const char* model_file, const char* link_file)
+{
+  std::string t;
+  char host[96] = "unknown", date[32] = "";
+  gethostname(host, sizeof(host) - 1);
+  const char* user = getenv("USER");
+  time_t now = time(nullptr);
+  strftime(date, sizeof(date), "%d %b %Y %H:%M:%S", localtime(&now));
+  if (model_file && *model_file) appendf(t, " AssociatedModelFileName = %s;\n", model_file);
+  if (link_file && *link_file) appendf(t, " ModelName               = %s;\n", link_file);
+  t += " InformationText         = response data base file;\n";
+  appendf(t, " User                    = %s;\n", user ? user : "unknown");
+  appendf(t, " Computer                = %s;\n", host);
+  appendf(t, " DateTime                = %s;\n", date);
+  t += " UsedTime                = 00:00:00.00;\n";
+  appendf(t, " Module                  = %s;\n", module);
+  t += " ModuleVersion           = B200 1.0;\n";
+  return t;
+}
+}  // namespace fsr
+
+namespace {
+
 // header text + record slot of every element (-1 = not written); returns the number of values per step
 static long long build_header(int nnod, const int* madof, int nel, const int* melcon, const int* active,
                               const fsr_rdb_options* o, const RecLayout& L, std::string& header, std::vector<long long>& slot,
@@ -403,21 +430,7 @@ static long long build_header(int nnod, const int* madof, int nel, const int* me
 {
   HeaderBuilder hb;
   hb.nbit = o->double_precision ? 64 : 32;
-  // openHeaderFiles (rdbModule.f90:191-251)
-  char host[96] = "unknown", date[32] = "";
-  gethostname(host, sizeof(host) - 1);
-  const char* user = getenv("USER");
-  time_t now = time(nullptr);
-  strftime(date, sizeof(date), "%d %b %Y %H:%M:%S", localtime(&now));
-  if (o->model_file) appendf(hb.vard, " AssociatedModelFileName = %s;\n", o->model_file);
-  if (o->link_file) appendf(hb.vard, " ModelName               = %s;\n", o->link_file);
-  hb.vard += " InformationText         = response data base file;\n";
-  appendf(hb.vard, " User                    = %s;\n", user ? user : "unknown");
-  appendf(hb.vard, " Computer                = %s;\n", host);
-  appendf(hb.vard, " DateTime                = %s;\n", date);
-  hb.vard += " UsedTime                = 00:00:00.00;\n";
-  appendf(hb.vard, " Module                  = %s;\n", o->module_name ? o->module_name : "fedem_stress");
-  hb.vard += " ModuleVersion           = B200 1.0;\nVARIABLES:\n";
+  hb.vard = rdb_file_preamble(o->module_name ? o->module_name : "fedem_stress", o->model_file, o->link_file) + "VARIABLES:\n";
   // writeTimeStepHeader (rdbModule.f90:633-650)
   hb.nvar = 2;
   hb.vard += "<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n";

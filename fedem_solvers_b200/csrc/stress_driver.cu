@@ -29,7 +29,7 @@ using namespace fsr;
 namespace {
 
 CmdLine g_cmd;
-bool g_stress_options_defined = false;
+bool g_stress_options_defined = false, g_gage_options_defined = false;
 
 std::string strip_ext_add(const std::string& link, const char* suffix)
 {
@@ -208,30 +208,99 @@ void fsr_stress_define_options(void)
   g_stress_options_defined = true;
 }
 
+// The option table of fedem_gage: the standard options + gagemain.C:22-61.
+void fsr_gage_define_options(void)
+{
+  CmdLine& c = g_cmd;
+  c.add("fao", "", "Read additional options from this file");
+  c.add("fco", "", "Read calculation options from this file");
+  c.add("fop", "", "Read output options from this file");
+  c.add("cwd", "", "Change working directory");
+  c.add("help", false, "Print out this help text");
+  c.add("helpAll", false, "Print out this help text\nincluding the private options, if any", false);
+  c.add("version", false, "Print out program version");
+  c.add("debug", 0, "Debug print switch");
+  c.add("terminal", 6, "File unit number for terminal output");
+  c.add("consolemsg", false, "Output error messages to console");
+  c.add("Bramsize", -1, "In-core size (MB) of displacement recovery matrix\n< 0: Use the same as in the reducer (default)\n= 0: Store full matrix in core");
+  c.add("dmramsize", -1, "Same as -Bramsize but in terms of double words", false);
+  c.add("linkId", 0, "Link base-ID number");
+  c.add("linkfile", "", "Name of link input file");
+  c.add("Bmatfile", "", "Name of B-matrix file");
+  c.add("eigfile", "", "Name of eigenvector file");
+  c.add("dispfile", "", "Name of gravitation displacement file");
+  c.add("resfile", "", "Name of results output file");
+  c.add("rdbfile", "", "Name of strain gage results database file");
+  c.add("rdbinc", 1, "Increment number for the results database file");
+  c.add("samfile", "", "Name of SAM data file");
+  c.add("fsifile", "fedem_solver.fsi", "Name of solver input file");
+  c.add("frsfile", "", "Name of solver results database file");
+  c.add("rosfile", "", "Name of strain rosette input file");
+  c.add("writeAsciiFiles", false, "Write rosette results to ASCII files");
+  c.add("deformation", false, "Save nodal deformations to results database");
+  c.add("nullify_start_rosettestrains", false, "Set start strains to zero for the rosettes");
+  c.add("statm", 0.0, "Start time");
+  c.add("stotm", 1.0, "Stop time");
+  c.add("tinc", 0.0, "Time increment (= 0.0: process all time steps)");
+  c.add("dac_sampleinc", 0.001, "Sampling increment for dac output files");
+  c.add("flushinc", -1.0, "Time between each database file flush\n< 0.0: Do not flush results database (let the OS decide)\n= 0.0: Flush at each time step, no external buffers\n> 0.0: Flush at specified time interval, use external buffers");
+  c.add("fatigue", 0, "Perform damage calculation on the gage stresses");
+  c.add("stressToMPaScale", 1.0e-6, "Scale factor scaling stresses to MPa");
+  c.add("gate", 25.0, "Stress gate value for the damage calculation [MPa]");
+  c.add("binSize", 10.0, "Bin size for stress cycle counting [MPa]");
+  c.add("loga1", 15.117, "Parameter log(a1) of the S-N curve");
+  c.add("loga2", 17.146, "Parameter log(a2) of the S-N curve");
+  c.add("m1", 4.0, "Parameter m1 of the S-N curve");
+  c.add("littleEndian", false, "Use Little Endian formatting of DAC files");
+  // B200 additions
+  c.add("device", 0, "CUDA device ordinal");
+  c.add("stepTile", 0, "Time steps per device batch (0 = from free device memory)");
+  g_gage_options_defined = true;
+}
+
 void initSolverArgs(int argc, char** argv)
 {
   g_cmd = CmdLine();
   g_cmd.init(argc, argv);
+  g_gage_options_defined = false;
   fsr_stress_define_options();
 }
 
-#define FAIL(...) do { set_error(__VA_ARGS__); log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return -1; } while (0)
-#define CHECK(call) do { const int rc_ = (call); if (rc_ < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return rc_; } } while (0)
+#define FAIL(...) do { set_error(__VA_ARGS__); log.line(" *** Error: %s", fsr_last_error()); log.line("\n    %s failed :-(", what); return -1; } while (0)
+#define CHECK(call) do { const int rc_ = (call); if (rc_ < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    %s failed :-(", what); return rc_; } } while (0)
 
-int solveStress(void)
+}  // extern "C"
+
+// subroutine stress (stress.f90:17-493) and subroutine gage (gage.f90:8-431) share everything up to the opened B and E
+// matrices and the time step selection: one body, `gage` switches the program specific parts.
+static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, const char* model_file,
+                     const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
+                     int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
+                     const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
+                     const std::vector<double>& times);
+
+static int run_program(bool gage)
 {
-  if (!g_stress_options_defined) fsr_stress_define_options();
+  const char* what = gage ? "Strain gage recovery" : "Stress calculation";
+  const char* prog = gage ? "fedem_gage" : "fedem_stress";
+  if (gage) {
+    if (!g_gage_options_defined) { g_cmd.clear_options(); g_stress_options_defined = false; fsr_gage_define_options(); }
+  } else if (!g_stress_options_defined)
+    fsr_stress_define_options();
   CmdLine& c = g_cmd;
   // readOptionFilesStd (cmdLineArgInitStd.C:103-135)
   const std::string cwd = c.get_string("cwd");
-  if (!cwd.empty() && chdir(cwd.c_str())) { perror(("fedem_stress: " + cwd).c_str()); return 1; }
+  if (!cwd.empty() && chdir(cwd.c_str())) { perror((std::string(prog) + ": " + cwd).c_str()); return 1; }
   for (const char* o : {"fao", "fco", "fop"}) { const std::string f = c.get_string(o); if (!f.empty()) c.read_options_file(f); }
   if (c.get_bool("help") || c.get_bool("helpAll")) { printf("%s", c.help_text(c.get_bool("helpAll")).c_str()); return 0; }
-  if (c.get_bool("version")) { printf("fedem_stress B200 1.0\n"); return 0; }
+  if (c.get_bool("version")) { printf("%s B200 1.0\n", prog); return 0; }
 
   Log log;
-  log.open(file_name("resfile", "_stress.res"), "Stress Recovery");
-  log.line("\n           ================> START OF PROGRAM STRESS <================");
+  log.open(file_name("resfile", gage ? "_gage.res" : "_stress.res"), gage ? "Strain Gage Recovery" : "Stress Recovery");
+  log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : "STRESS");
+  if (gage) {
+    if (c.get_bool("writeAsciiFiles")) log.line("  ** Note: ASCII / DAC rosette files (-writeAsciiFiles) are not part of this build; ignored");
+  } else
   if (c.is_set("resStressFile")) log.line("  ** Note: residual stress import (-resStressFile) is not part of this build; ignored");
   if (c.is_set("VTFfile") && !c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
   if (c.get_bool("dumpDefNas")) log.line("  ** Note: Nastran deformation dump (-dumpDefNas) is not part of this build; ignored");
@@ -273,7 +342,7 @@ int solveStress(void)
   CHECK(fsr_ftl_get_nodes(ftl, nullptr, nullptr, nullptr, nullptr, xyz.data()));
   const int nbad = fsr_ftl_get_elmdata(ftl, emod.data(), rny.data(), rho.data(), thk.data(), elmid.data(), beam.data(), estat.data());
   if (nbad > 0) log.line("  ** Warning: %d elements lack material / thickness / cross section data", nbad);
-  {   // legacy thin shells are recovered for the default stress formulations only (fsr_part_create): say so loudly otherwise
+  if (!gage) {   // legacy thin shells are recovered for the default stress formulations only (fsr_part_create): say so loudly otherwise
     const int ffq = c.get_int("ffqStressForm"), fft = c.get_int("fftStressForm");
     int nq = 0, nt = 0;
     for (int e = 0; e < nel; ++e) {
@@ -312,6 +381,10 @@ int solveStress(void)
   std::string dispfile = want_grav ? file_name("dispfile", "_V.fmx") : std::string();
   bool lgrav = false;
   if (want_grav) { FILE* t = fopen(dispfile.c_str(), "rb"); if (t) { lgrav = true; fclose(t); } }
+  if (gage && lgrav) {   // gage.f90:175-194 adds a constant strain offset from the static gravitation deflection
+    log.line("  ** Note: the static gravitation offset of the rosette strains (-dispfile) is not part of this build; ignored");
+    lgrav = false;
+  }
   const int nmodes = ngen + (lgrav ? 3 : 0);
 
   // --- the part on the device
@@ -327,7 +400,7 @@ int solveStress(void)
   fsr_options po;
   memset(&po, 0, sizeof(po));
   po.device = c.get_int("device"); po.stressForm = c.get_int("stressForm"); po.step_tile = c.get_int("stepTile");
-  po.reserved[1] = c.get_int("ffqStressForm") + 1; po.reserved[2] = c.get_int("fftStressForm") + 1;
+  if (!gage) { po.reserved[1] = c.get_int("ffqStressForm") + 1; po.reserved[2] = c.get_int("fftStressForm") + 1; }
   fsr_part* part = nullptr;
   const int nfail = fsr_part_create(&part, &sam, &ed, &po);
   if (nfail < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return nfail; }
@@ -373,6 +446,9 @@ int solveStress(void)
   std::vector<int> sel(std::max(nall, 1));
   const int nsel = fsr_select_steps(times.data(), nall, statm, stotm, tinc, sel.data(), nall);
   log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
+  if (gage)
+    return gage_part(c, log, what, part, ftl, db, isup, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
+                     sel, nsel, stepno, times);
 
   // --- Initialize the stress results database (writeStressHeader)
   fsr_rdb_options ro;
@@ -443,5 +519,191 @@ int solveStress(void)
   log.line("\n    Stress calculation successfully completed :-)  (%.2f s CPU)", (double)(clock() - log.t0) / CLOCKS_PER_SEC);
   return 0;
 }
+
+// --------------------------------------------------------------------------------------------------------------------
+// The fedem_gage specific part (gage.f90:136-150,196-247,278-400): rosette input, Bcart on the GPU, results database
+// (saveStrainGageModule.f90:23-268), fatigue report (reportDamage, strainGageModule.f90:778-862).
+static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, const char* model_file,
+                     const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
+                     int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
+                     const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
+                     const std::vector<double>& times)
+{
+  (void)minex;
+  // --- Initializing strain rosettes (readStrainGageData, checkRosette)
+  log.line("           --> Initializing strain rosettes");
+  const std::string rosfile = c.get_string("rosfile");
+  if (rosfile.empty()) FAIL("No strain rosette input file (-rosfile)");
+  if (rosfile.size() < 4 || rosfile.compare(rosfile.size() - 4, 4, ".fsi") != 0)
+    FAIL("%s: only the .fsi rosette format (&STRAIN_ROSETTE records) is part of this build, not the old rosette definition format", rosfile.c_str());
+  const int nros = fsr_fsi_read_rosettes(rosfile.c_str(), isup, nullptr, nullptr, nullptr, 0, 0);
+  if (nros < 0) CHECK(nros);
+  log.line("               Number of &STRAIN_ROSETTE =%6d", nros);
+  if (nros == 0) {
+    log.line("  ** Note: No strain rosettes on this link");
+    log.line("\n    %s successfully completed :-)", what);
+    return 0;
+  }
+  constexpr int kDescr = 128;
+  std::vector<fsr_rosette> ros((size_t)nros);
+  std::vector<int> ruser((size_t)nros);
+  std::vector<char> rdescr((size_t)nros * kDescr);
+  CHECK(fsr_fsi_read_rosettes(rosfile.c_str(), isup, ros.data(), ruser.data(), rdescr.data(), kDescr, nros));
+  for (int r = 0; r < nros; ++r) {
+    fsr_rosette& R = ros[(size_t)r];
+    int bad = 0;
+    for (int k = 0; k < R.numnod; ++k) {
+      R.nodes[k] = fsr_ftl_ext2int(ftl, 1, R.nodes[k]);
+      if (R.nodes[k] < 1) ++bad;
+    }
+    if (bad) FAIL("%d invalid node number(s) for Rosette %d", bad, R.id);
+    // checkOrientation (strainGageModule.f90:524-570): the element normal of the first three nodes must follow the rosette Z axis
+    const double* X[3];
+    for (int k = 0; k < 3; ++k) X[k] = &xyz[3 * (size_t)(R.nodes[k] - 1)];
+    const double a[3] = {X[1][0] - X[0][0], X[1][1] - X[0][1], X[1][2] - X[0][2]}, b[3] = {X[2][0] - X[0][0], X[2][1] - X[0][1], X[2][2] - X[0][2]};
+    const double vn[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    if (R.rpos[6] * vn[0] + R.rpos[7] * vn[1] + R.rpos[8] * vn[2] < 0.0) {
+      for (int k = 0; k < R.numnod / 2; ++k) std::swap(R.nodes[k], R.nodes[R.numnod - 1 - k]);
+      log.line("  ** Note: Nodal ordering for Rosette %d has been swapped", R.id);
+    }
+  }
+  if (c.get_bool("nullify_start_rosettestrains"))   // gage.f90:312-320: every rosette starts from zero strain at the first step
+    for (fsr_rosette& R : ros) R.zero_init = 1;
+  fsr_gages* gages = nullptr;
+  CHECK(fsr_gage_create(&gages, part, ros.data(), nros));
+  struct GageGuard { fsr_gages* p; ~GageGuard() { fsr_gage_destroy(p); } } gage_guard{gages};
+
+  // --- Writing result database headers (writeStrainGageHeader / writeRosetteHeader)
+  log.line("           --> Writing result database headers");
+  std::string hdr = rdb_file_preamble("fedem_gage", model_file, linkfile.c_str());
+  hdr += "VARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n"
+         "<3;\"Angle of maximum principal strain/stress\";ANGLE;FLOAT;32;SCALAR>\n<4;\"Angle of maximum shear\";ANGLE;FLOAT;32;SCALAR>\n"
+         "<5;\"Strain tensor\";NONE;FLOAT;32;TENSOR2;(3);((\"epsilon_x\",\"epsilon_y\",\"epsilon_xy\"))>\n"
+         "<6;\"Stress tensor\";FORCE/AREA;FLOAT;32;TENSOR2;(3);((\"sigma_x\",\"sigma_y\",\"sigma_xy\"))>\n"
+         "<7;\"Gage strain\";NONE;FLOAT;32;SCALAR>\n<8;\"Gage stress\";NONE;FLOAT;32;SCALAR>\n";
+  int maxg = 0;
+  for (const fsr_rosette& R : ros) maxg = std::max(maxg, R.ngage);
+  for (int j = 1; j <= maxg; ++j) { char b[64]; snprintf(b, sizeof(b), "[%d;\"Gage %d\";<7><8>]\n", j, j); hdr += b; }
+  hdr += "DATABLOCKS:\n<1><2>\n";
+  long long nval = 0;
+  for (int r = 0; r < nros; ++r) {
+    const fsr_rosette& R = ros[(size_t)r];
+    char b[512];
+    std::string line = "{\"Strain rosette\";";
+    if (R.id > 0) { snprintf(b, sizeof(b), "%d;", R.id); line += b; } else line += ";";
+    if (ruser[(size_t)r] > 0) { snprintf(b, sizeof(b), "%d;", ruser[(size_t)r]); line += b; } else line += ";";
+    const char* d = &rdescr[(size_t)r * kDescr];
+    if (*d) { snprintf(b, sizeof(b), "\"%s\";", d); line += b; } else line += ";";
+    line += "<3><4><5><6>";
+    for (int j = 1; j <= R.ngage; ++j) { snprintf(b, sizeof(b), "[%d]", j); line += b; }
+    hdr += line + "}\n";
+    nval += 8 + 2 * R.ngage;
+  }
+  if (c.get_bool("deformation"))
+    log.line("  ** Note: rosette node deformations, position and Euler angles (-deformation, rosette%%ur) are not part of this build");
+  std::string path = file_name("rdbfile", ".frs");
+  {   // openRDBfile (rdbModule.f90:268-403): <name>_<rdbinc>.<ext>
+    const int inc = c.get_int("rdbinc");
+    if (inc > 0) {
+      const size_t dot = path.rfind('.'), sep = path.rfind('/');
+      char b[16];
+      snprintf(b, sizeof(b), "_%d", inc);
+      if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) path.insert(dot, b);
+      else path += b;
+    }
+  }
+  fsr_frs_writer* w = nullptr;
+  CHECK(fsr_frs_create(&w, path.c_str(), 0, hdr.c_str(), 4 * nval));
+  struct WGuard { fsr_frs_writer*& p; ~WGuard() { if (p) fsr_frs_finish(p); } } w_guard{w};
+  log.line("           --> Results database file: %s (%lld bytes per time step)", path.c_str(), 12 + 4 * nval);
+
+  // --- Time loop in windows: reduced history (readSupElDisplacements + BuildFinit), rosette strains on the GPU
+  log.line("           --> Starting time loop");
+  const int ndim = ndof2 + ngen, window = 256;
+  const int iFatigue = c.get_int("fatigue");
+  std::vector<double> Qall(iFatigue > 0 ? (size_t)ndim * std::max(nsel, 1) : 0), Q((size_t)ndim * window),
+      vals((size_t)window * nros * FSR_GAGE_NVAL);
+  std::vector<float> recbuf((size_t)std::max<long long>(nval, 1));
+  for (int w0 = 0; w0 < nsel; w0 += window) {
+    const int nw = std::min(window, nsel - w0);
+    for (int k = 0; k < nw;) {
+      int run = 1;
+      while (k + run < nw && sel[(size_t)(w0 + k + run)] == sel[(size_t)(w0 + k)] + run) ++run;
+      CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[(size_t)(w0 + k)], run,
+                                    Q.data() + (size_t)k * ndim, ndim));
+      k += run;
+    }
+    if (iFatigue > 0) memcpy(Qall.data() + (size_t)w0 * ndim, Q.data(), sizeof(double) * (size_t)nw * ndim);
+    CHECK(fsr_gage_recover(gages, Q.data(), ndim, nw, vals.data()));
+    for (int k = 0; k < nw; ++k) {   // writeStrainGageDB (saveStrainGageModule.f90:196-262)
+      size_t n = 0;
+      for (int r = 0; r < nros; ++r) {
+        const double* v = vals.data() + ((size_t)k * nros + r) * FSR_GAGE_NVAL;
+        recbuf[n++] = (float)v[8]; recbuf[n++] = (float)v[9];
+        recbuf[n++] = (float)v[0]; recbuf[n++] = (float)v[1]; recbuf[n++] = (float)(0.5 * v[2]);
+        recbuf[n++] = (float)v[10]; recbuf[n++] = (float)v[11]; recbuf[n++] = (float)v[12];
+        for (int j = 0; j < ros[(size_t)r].ngage; ++j) { recbuf[n++] = (float)v[18 + j]; recbuf[n++] = (float)v[21 + j]; }
+      }
+      CHECK(fsr_frs_write_step(w, stepno[(size_t)sel[(size_t)(w0 + k)]], times[(size_t)sel[(size_t)(w0 + k)]], recbuf.data()));
+    }
+    log.line("           --> ......Simulation time : %12.5E  (%d of %d steps done)", times[(size_t)sel[(size_t)(w0 + nw - 1)]], w0 + nw, nsel);
+  }
+
+  // --- fatigue (AddFatiguePoints during the loop + reportDamage at the end)
+  if (iFatigue > 0 && nsel > 0) {
+    log.line("           --> Time loop done. Performing fatigue calculation");
+    const double to_mpa = c.get_double("stressToMPaScale"), gate = c.get_double("gate"), bin_size = c.get_double("binSize");
+    const double curve[4] = {c.get_double("loga1"), c.get_double("loga2"), c.get_double("m1"), 5.0};   // m2 = 5 (FFpSNCurve.H)
+    const int nser = 4 * nros;
+    std::vector<double> damage((size_t)nser);
+    std::vector<int> ncyc((size_t)nser), status((size_t)nser), bins;
+    int nbins = 64;
+    for (;;) {   // reportDamage walks the bins until every series answers -1 (no cycles left above the bin)
+      bins.assign((size_t)nser * nbins, 0);
+      CHECK(fsr_gage_fatigue(gages, Qall.data(), ndim, nsel, to_mpa, gate, curve, bin_size, nbins, damage.data(), ncyc.data(), bins.data(),
+                             status.data()));
+      bool open_end = false;
+      for (int s = 0; s < nser; ++s) if (bins[(size_t)s * nbins + nbins - 1] >= 0) open_end = true;
+      if (!open_end || nbins >= 65536) break;
+      nbins *= 4;
+    }
+    for (int r = 0; r < nros; ++r) {
+      const fsr_rosette& R = ros[(size_t)r];
+      const double g = R.gate > 0.0 ? R.gate : gate;
+      const double sn[4] = {R.sncurve[0] > 0.0 ? R.sncurve[0] : curve[0], R.sncurve[1] > 0.0 ? R.sncurve[1] : curve[1],
+                            R.sncurve[2] > 0.0 ? R.sncurve[2] : curve[2], R.sncurve[3]};
+      log.line("\n     ===== Computed damage in strain rosette =====\n           gate value :%12.5E\n           S-N curve  : log(a1) =%7.3f log(a2) =%7.3f m1 =%7.3f m2 =%7.3f"
+               "\n\n     Strain Rosette                      Max princ.  Gage 1      Gage 2  ...", g, sn[0], sn[1], sn[2], sn[3]);
+      char idtxt[64], row[256];
+      snprintf(idtxt, sizeof(idtxt), " [%d] %s", ruser[(size_t)r], &rdescr[(size_t)r * kDescr]);
+      int n = snprintf(row, sizeof(row), "    %-36.36s", idtxt);
+      for (int j = 0; j <= R.ngage; ++j) n += snprintf(row + n, sizeof(row) - (size_t)n, "%12.5E", damage[(size_t)(4 * r + j)]);
+      log.line("%s\n", row);
+      for (int b = 0; b < nbins; ++b) {
+        bool any_pos = false, any_open = false;
+        n = 0;
+        for (int j = 0; j <= R.ngage; ++j) {
+          const int cnt = bins[(size_t)(4 * r + j) * nbins + b];
+          if (cnt >= 0) { any_open = true; n += snprintf(row + n, sizeof(row) - (size_t)n, "%12d", cnt); if (cnt > 0) any_pos = true; }
+          else n += snprintf(row + n, sizeof(row) - (size_t)n, "%12s", "");
+        }
+        if (!any_open) break;
+        if (any_pos) log.line("     Stress cycles %7.2f -%7.2f%s", b * bin_size, (b + 1) * bin_size, row);
+      }
+      log.line("     =============================================\n");
+    }
+    log.line("           --> Closing database files");
+  } else
+    log.line("           --> Time loop done. Closing database files");
+  { fsr_frs_writer* x = w; w = nullptr; CHECK(fsr_frs_finish(x)); }
+  log.line("           ================>  END OF PROGRAM GAGE  <================");
+  log.line("\n    %s successfully completed :-)  (%.2f s CPU)", what, (double)(clock() - log.t0) / CLOCKS_PER_SEC);
+  return 0;
+}
+
+extern "C" {
+
+int solveStress(void) { return run_program(false); }
+int solveGage(void) { return run_program(true); }
 
 }  // extern "C"

@@ -56,6 +56,50 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 
 
+def write_rosette_file(path, rosettes, link_id, minex=None, user_ids=None, descr=None):
+    """The rosette input file of fedem_gage in .fsi format: one &STRAIN_ROSETTE record per rosette as the GUI writes them
+    (solverTests/InversePy/shell_strain/fedem_solver.fsi:162-177; rPos = posInGl row by row, 10 significant digits).
+    nodes are written as EXTERNAL node numbers (minex[internal - 1])."""
+    with open(path, "w") as f:
+        for k, r in enumerate(rosettes):
+            ext = [int(minex[n - 1]) if minex is not None else int(n) for n in r.nodes]
+            pos = np.asarray(r.rpos, F64)
+            f.write("&STRAIN_ROSETTE\n")
+            f.write(f"  id = {r.id}\n  extId = {user_ids[k] if user_ids is not None else r.id}\n")
+            f.write(f"  extDescr = '{descr[k] if descr is not None else 'rosette_%d' % r.id}'\n  linkId = {link_id}\n")
+            f.write(f"  type = '{r.type}'\n  zeroInit = {int(r.zero_init)}\n  numnod = {len(ext)}\n")
+            f.write("  nodes = " + " ".join(map(str, ext)) + "\n")
+            f.write("  rPos = " + "\n         ".join(" ".join(f"{v: .9e}" for v in pos[i]) for i in range(3)) + "\n")
+            f.write(f"  zPos = {r.zpos: .9e}\n  Emod = {r.emod: .9e}\n  nu   = {r.nu: .9e}\n")
+            if r.gate > 0.0:
+                f.write(f"  gateVal = {r.gate: .9e}\n")
+            if any(v > 0.0 for v in r.sncurve):
+                f.write("  snCurve = " + " ".join(f"{v: .9e}" for v in r.sncurve) + "\n")
+            f.write("/\n\n")
+
+
+def read_rosette_file(path, link_id):
+    """(rosettes with EXTERNAL node numbers, user ids, descriptions) through the library's ReadStrainGages."""
+    from ._lib import check, load_library
+    lib = load_library()
+    n = check(lib.fsr_fsi_read_rosettes(path.encode(), int(link_id), None, None, None, 0, 0), "fsr_fsi_read_rosettes")
+    arr = (FsrRosette * max(n, 1))()
+    uid = np.zeros(max(n, 1), I32)
+    buf = C.create_string_buffer(128 * max(n, 1))
+    check(lib.fsr_fsi_read_rosettes(path.encode(), int(link_id), arr, uid.ctypes.data_as(C.POINTER(C.c_int)), buf, 128, n),
+          "fsr_fsi_read_rosettes")
+    names = {round(a, 6): t for t, (g, a) in ROSETTE_TYPES.items()}
+    out = []
+    for k in range(n):
+        c = arr[k]
+        rpos = np.array([[c.rpos[3 * j + i] for j in range(4)] for i in range(3)])
+        t = "SINGLE_GAGE" if c.ngage == 1 else names[round(c.alpha_gages, 6)]
+        out.append(Rosette(id=c.id, nodes=[c.nodes[i] for i in range(c.numnod)], rpos=rpos, type=t, zpos=c.zpos, emod=c.emod,
+                           nu=c.nu, zero_init=bool(c.zero_init), gate=c.gate, sncurve=[c.sncurve[i] for i in range(4)]))
+    descr = [buf.raw[128 * k:128 * (k + 1)].split(b"\0")[0].decode() for k in range(n)]
+    return out, uid[:n].copy(), descr
+
+
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
 

@@ -603,6 +603,18 @@ module fedem_b200_mod
        integer(c_int) :: gen_first_dof
      end function fsr_fsi_triads
 
+     ! ReadStrainGages (strainGageModule.f90:78-237): the &STRAIN_ROSETTE records of a rosette input file
+     function fsr_fsi_read_rosettes (path, link_base_id, ros, user_id, descr, descr_stride, cap) &
+          &                         bind(C,name="fsr_fsi_read_rosettes") result(nros)
+       import :: c_ptr, c_char, c_int
+       character(kind=c_char), intent(in) :: path(*)
+       integer(c_int), value :: link_base_id, descr_stride, cap
+       type(c_ptr)   , value :: ros      ! type(fsr_rosette) array, or c_null_ptr to count
+       type(c_ptr)   , value :: user_id  ! integer(c_int) array or c_null_ptr
+       type(c_ptr)   , value :: descr    ! character buffer cap*descr_stride or c_null_ptr
+       integer(c_int) :: nros
+     end function fsr_fsi_read_rosettes
+
      ! ---- stress results database: replaces writeStressHeader + writeStressDB/writeStrMeasureDB ----
      function fsr_rdb_create (rdb, part, path, opt) bind(C,name="fsr_rdb_create") result(ierr)
        import :: c_ptr, c_char, c_int, fsr_rdb_options
@@ -698,6 +710,14 @@ module fedem_b200_mod
 
      subroutine fsr_stress_define_options () bind(C,name="fsr_stress_define_options")
      end subroutine fsr_stress_define_options
+
+     subroutine fsr_gage_define_options () bind(C,name="fsr_gage_define_options")
+     end subroutine fsr_gage_define_options
+
+     function solveGage () bind(C,name="solveGage") result(ierr)
+       import :: c_int
+       integer(c_int) :: ierr
+     end function solveGage
 
      subroutine fsr_cmdline_add_bool (name, value) bind(C,name="fsr_cmdline_add_bool")
        import :: c_char, c_int

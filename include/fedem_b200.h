@@ -383,6 +383,12 @@ int fsr_fsi_part(const fsr_fsi *fsi, int *user_id, char *descr, int dcap, int *n
                  double *sup_pos, double *gravity, char *model_file, int mcap);
 int fsr_fsi_triads(const fsr_fsi *fsi, int *base_id, int *user_id, int *ndofs, int *first_dof,
                    double *tr_undef, double *ur);
+/* ReadStrainGages (src/vpmStress/strainGageModule.f90:78-237): the &STRAIN_ROSETTE records of a rosette input file in
+ * .fsi format (gage.f90:137-139); ros[k].nodes are the EXTERNAL node numbers of the file (map them with
+ * fsr_ftl_ext2int; solveGage also applies checkRosette's orientation swap).  A record of another part or with an
+ * unknown type is an input error, as in the reference.  ros may be NULL to count.  Returns the record count. */
+int fsr_fsi_read_rosettes(const char *path, int link_base_id, fsr_rosette *ros, int *user_id, char *descr,
+                          int descr_stride, int cap);
 
 /* ---- stress results database (.frs), written from the GPU ------------------------------------------
  * Replaces writeStressHeader (src/vpmStress/saveStressModule.f90:120-247, header grammar :625-1430) and the
@@ -432,13 +438,19 @@ int fsr_rdb_close(fsr_rdb *rdb);
 
 /* ---- the fedem_stress program ------------------------------------------------------------------------
  * The reference's launcher entry points, same names (src/vpmStress/stressInterface.C:86-116):
- * initSolverArgs defines the option table of stressmain.C:22-79 (+ -fao/-fco/-fop/-cwd/-help/-debug ... of
+ * initSolverArgs (re)starts the option parser over the given arguments and defines the option table of stressmain.C:22-79 (+ -fao/-fco/-fop/-cwd/-help/-debug ... of
  * cmdLineArgInitStd.C / cmdLineArgInit.C) over the given arguments, solveStress runs subroutine stress
  * (src/vpmStress/stress.f90): -linkfile .ftl, -samfile .fsm, -fsifile .fsi, -Bmatfile/-eigfile/-dispfile .fmx,
  * -frsfile solver results, -statm/-stotm/-tinc, -group, -SR -stress -strain -vmStress ... -deformation -double,
  * -rdbfile/-rdbinc stress results database.  Returns 0 on success.  bin/fedem_stress is main() over these. */
 void initSolverArgs(int argc, char **argv);
 int solveStress(void);
+/* solveGage (src/vpmStress/stressInterface.C:118-123) runs subroutine gage (src/vpmStress/gage.f90) with the option
+ * table of gagemain.C:22-61: the same part / history inputs as solveStress, -rosfile with the &STRAIN_ROSETTE records
+ * (.fsi format), rosette strains and stresses of every selected step to -rdbfile (saveStrainGageModule.f90 grammar),
+ * -fatigue > 0: rainflow + damage report of sigmaP(1) and the gage legs in the -resfile (reportDamage).
+ * bin/fedem_gage is main() over initSolverArgs + solveGage. */
+int solveGage(void);
 /* ffr_getnextstep (fedem-foundation/src/FFrLib/FFrExtractorInterface.f90:134-170) over a sorted key list:
  * indices of the time steps the stress loop visits for -statm start -stotm stop -tinc tinc; returns their
  * number (out may be NULL) */
@@ -446,6 +458,7 @@ int fsr_select_steps(const double *times, int n, double start, double stop, doub
 /* the option parser (FFaCmdLineArg semantics) behind a C face, one global instance like the reference's */
 void fsr_cmdline_reset(void);
 void fsr_stress_define_options(void);
+void fsr_gage_define_options(void);   /* the option table of fedem_gage (gagemain.C:22-61) */
 void fsr_cmdline_add_bool(const char *name, int value);
 void fsr_cmdline_add_int(const char *name, int value);
 void fsr_cmdline_add_double(const char *name, double value);

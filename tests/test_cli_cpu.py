@@ -256,3 +256,54 @@ def test_executable_options_and_loud_failures(tmp_path):
     r = subprocess.run([EXE, "-cwd", str(tmp_path), "-linkfile", "nothere.ftl"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "Can not open FE data file nothere.ftl" in r.stdout
     assert os.path.exists(tmp_path / "nothere_stress.res")
+
+
+def test_rosette_file_reader(tmp_path):
+    """ReadStrainGages: written &STRAIN_ROSETTE records come back value for value (10 digits); the reference's own sample
+    (solverTests/InversePy/shell_strain/fedem_solver.fsi) parses; a record of another part or an unknown type is an error."""
+    from fedem_solvers_b200.gage import Rosette, write_rosette_file, read_rosette_file
+    rng = np.random.default_rng(5)
+    ros = []
+    for k, t in enumerate(["SINGLE_GAGE", "DOUBLE_GAGE_90", "TRIPLE_GAGE_60", "TRIPLE_GAGE_45"]):
+        Qm, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        ros.append(Rosette(id=40 + k, nodes=[3 + k, 9, 12] + ([20] if k % 2 else []), rpos=np.hstack([Qm, rng.standard_normal((3, 1))]),
+                           type=t, zpos=0.01 * k, emod=2.0e11 + k, nu=0.29, zero_init=bool(k & 1), gate=10.0 * k,
+                           sncurve=[12.0, 15.0, 3.0, 5.0] if k == 2 else [0.0] * 4))
+    path = str(tmp_path / "gages.fsi")
+    write_rosette_file(path, ros, link_id=16, user_ids=[7, 8, 9, 10], descr=["a b", "", "third", "x"])
+    back, uid, descr = read_rosette_file(path, 16)
+    assert len(back) == 4 and list(uid) == [7, 8, 9, 10] and descr == ["a b", "", "third", "x"]
+    for a, b in zip(ros, back):
+        assert (a.id, a.nodes, a.type, a.zero_init) == (b.id, b.nodes, b.type, b.zero_init)
+        assert np.allclose(a.rpos, b.rpos, rtol=0, atol=5e-10 * np.abs(a.rpos).max())
+        assert abs(a.emod - b.emod) <= 1e-9 * a.emod and abs(a.nu - b.nu) < 1e-9 and abs(a.gate - b.gate) < 1e-8
+        assert np.allclose(a.sncurve, b.sncurve)
+    lib = _lib.load_library()
+    assert lib.fsr_fsi_read_rosettes(path.encode(), 17, None, None, None, 0, 0) == 4      # counting does not look at the part
+    arr = (_lib.FsrRosette * 4)()
+    assert lib.fsr_fsi_read_rosettes(path.encode(), 17, arr, None, None, 0, 4) < 0
+    assert b"does not match" in lib.fsr_last_error()
+    open(path, "a").write("&STRAIN_ROSETTE\n id = 50\n linkId = 16\n type = 'QUAD_GAGE'\n numnod = 3\n nodes = 1 2 3\n rPos = 12*0.0\n/\n")
+    arr = (_lib.FsrRosette * 5)()
+    assert lib.fsr_fsi_read_rosettes(path.encode(), 16, arr, None, None, 0, 5) < 0
+    assert b"invalid rosette-type" in lib.fsr_last_error()
+    sample = "/root/reference/solverTests/InversePy/shell_strain/fedem_solver.fsi"
+    if os.path.exists(sample):
+        back, uid, descr = read_rosette_file(sample, 16)
+        assert len(back) >= 1 and back[0].id == 44 and back[0].type == "SINGLE_GAGE" and back[0].nodes == [4, 5, 10, 9]
+        assert descr[0] == "straingage_1" and uid[0] == 1
+        assert np.allclose(back[0].rpos, [[1, 0, 0, 3.5], [0, 1, 0, 0.1], [0, 0, 1, 0.1]]) and back[0].zpos == 0.1
+
+
+def test_gage_executable_options_and_loud_failures(tmp_path):
+    exe = os.path.join(os.path.dirname(EXE), "fedem_gage")
+    assert os.path.exists(exe), "build.sh did not produce bin/fedem_gage"
+    r = subprocess.run([exe, "-help"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0
+    for opt in ("-rosfile", "-fatigue", "-gate", "-binSize", "-loga1", "-loga2", "-m1", "-stressToMPaScale", "-nullify_start_rosettestrains",
+                "-linkfile", "-frsfile", "-rdbfile", "-tinc"):
+        assert opt + " " in r.stdout, opt
+    assert "-vmStress" not in r.stdout and "-group" not in r.stdout      # fedem_stress options are not fedem_gage options
+    r = subprocess.run([exe, "-cwd", str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "FE data file must be specified through -linkfile" in r.stdout and "Strain gage recovery failed" in r.stdout
+    assert os.path.exists(tmp_path / "fedem_gage.res")

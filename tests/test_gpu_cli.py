@@ -174,3 +174,75 @@ def test_thick_shell_panel_through_the_executable(oracle, tmp_path):
                 assert np.abs(got - np.stack([x["resmat"][pt, :1] for x in o])).max() <= 1.3e-7 * sc
                 n += 1
     assert n > 50
+
+
+def test_fedem_gage_executable(oracle, tmp_path):
+    """bin/fedem_gage on generated files: rosette input file (.fsi format, external node numbers, one rosette listed
+    against its normal -> checkRosette swap), strain gage results database read back and compared with the oracle's
+    calcRosetteStrains per step (float file), fatigue report of the -resfile against the oracle's PVX / rainflow / damage."""
+    import re
+    from fedem_solvers_b200.gage import write_rosette_file
+    from fedem_solvers_b200.model import rosettes_on_part
+    part = plate_part(7, 6, ngen=5, seed=31, tri_fraction=0.3, warp=0.02, n_ext=4)
+    part.sam.minex = (1000 + 3 * np.arange(part.sam.nnod)).astype(np.int32)     # external != internal node numbers
+    nsteps = 400
+    case = _make_case(tmp_path, part, "plate", nsteps=nsteps)
+    ros = rosettes_on_part(part, 5, seed=32, rtype="TRIPLE_GAGE_45") + rosettes_on_part(part, 3, seed=33, rtype="SINGLE_GAGE", zero_init_fraction=1.0)
+    for k, r in enumerate(ros):
+        r.id = 70 + k
+    ros[2].gate = 2.0
+    listed = [type(r)(**{**r.__dict__}) for r in ros]
+    listed[1].nodes = listed[1].nodes[::-1]       # against the rosette normal: fedem_gage swaps it back
+    write_rosette_file(str(tmp_path / "gages.fsi"), listed, link_id=case["base"], minex=part.sam.minex, user_ids=list(range(1, 9)))
+    exe = os.path.join(os.path.dirname(EXE), "fedem_gage")
+    r = subprocess.run([exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx",
+                        "-eigfile", "plate_E.fmx", "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rosfile", "gages.fsi",
+                        "-rdbfile", "gage.frs", "-rdbinc", "2", "-stotm", "100", "-fatigue", "1", "-gate", "1.0", "-binSize", "2.0",
+                        "-stressToMPaScale", "1.0e-6"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Strain gage recovery successfully completed" in r.stdout and "Nodal ordering for Rosette 71 has been swapped" in r.stdout
+    rd = FrsReader(str(tmp_path / "gage_2.frs"))
+    assert rd.nsteps == nsteps and np.array_equal(rd.step_numbers, case["stepno"])
+    b = oracle.bind_part(part)
+    Q = case["Q"]
+    res = open(tmp_path / "plate_gage.res").read()
+    blocks = res.split("===== Computed damage in strain rosette =====")[1:]
+    assert len(blocks) == len(ros)
+    ncyc = 0
+    for k, ro in enumerate(ros):
+        Vo = oracle.rosette_history(b, ro, Q)
+        ng = ro.to_c().ngage
+        sc_e, sc_s = np.abs(Vo[:, :3]).max(), np.abs(Vo[:, 10:13]).max()
+        def var(name, w):
+            h = rd.find(name, "Strain rosette", ro.id)
+            assert h is not None, name
+            got = rd.read(h)
+            assert got.shape == (nsteps, w), name
+            return got
+        eps = var("Strain tensor", 3)
+        want = Vo[:, :3].copy(); want[:, 2] *= 0.5
+        assert np.abs(eps - want).max() <= 1.3e-7 * sc_e
+        assert np.abs(var("Stress tensor", 3) - Vo[:, 10:13]).max() <= 1.3e-7 * sc_s
+        assert np.abs(var("Angle of maximum principal strain/stress", 1)[:, 0] - Vo[:, 8]).max() <= 1e-6
+        for j in range(ng):
+            assert np.abs(var(f"Gage {j + 1}|Gage strain", 1)[:, 0] - Vo[:, 18 + j]).max() <= 1.3e-7 * sc_e
+            assert np.abs(var(f"Gage {j + 1}|Gage stress", 1)[:, 0] - Vo[:, 21 + j]).max() <= 1.3e-7 * sc_s
+        assert rd.find(f"Gage {ng + 1}|Gage strain", "Strain rosette", ro.id) is None
+        # fatigue report: damage row of this rosette = max principal + legs
+        gate = ro.gate if ro.gate > 0 else 1.0
+        row = [l for l in blocks[k].splitlines() if re.search(r"E[+-]\d\d", l) and "gate value" not in l][0]
+        dmg = [float(x) for x in re.findall(r"-?\d\.\d{5}E[+-]\d\d", row)]
+        assert len(dmg) == 1 + ng
+        assert f"gate value :{gate:12.5E}" in blocks[k]
+        series = [Vo[:, 13] * 1e-6] + [Vo[:, 21 + j] * 1e-6 for j in range(ng)]
+        for j, x in enumerate(series):
+            d, n, bins, ok = oracle.series_fatigue(x, gate, (15.117, 17.146, 4.0, 5.0), 2.0, 40)
+            assert ok and abs(dmg[j] - d) <= 2e-5 * max(d, 1e-300) + 1e-300, (k, j, dmg[j], d)
+            ncyc += n
+        # cycle histogram lines: counts of the first series (max principal) in its column
+        d, n, bins, ok = oracle.series_fatigue(series[0], gate, (15.117, 17.146, 4.0, 5.0), 2.0, 40)
+        for bi, cnt in enumerate(bins):
+            m = re.search(rf"Stress cycles +{2.0 * bi:.2f} - *{2.0 * bi + 2.0:.2f}( .*)", blocks[k])
+            if cnt > 0:
+                assert m is not None and int(m.group(1)[:12]) == cnt, (k, bi, cnt)
+    assert ncyc > 200
