@@ -115,6 +115,48 @@ def chex(args):
             "gpu_launches": int(lib.fsr_kernel_launches(0)), "max_von_mises": float(mx.max())}
 
 
+def cthick(args):
+    """Thick-shell panel (types 32 QUAD8 and 31 TRI6): dense per-element operators, k2_dense6_vm_kernel."""
+    import torch
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import thickshell_panel, reduced_history
+    lib = load_library()
+    n = max(2, round((args.hex_elements / 1.5) ** 0.5))      # cells alternate QUAD8 / 2 x TRI6: 1.5 elements per cell
+    part = thickshell_panel(n, n, ngen=50, seed=12, n_ext=4)
+    tile, steps, warm = args.tile, args.steps, 3
+    rec = StressRecovery(part, device=0, step_tile=((tile + 63) // 64) * 64)
+    nel, ndim = part.sam.nel, part.sam.ndim
+    nq, nt = int((part.sam.melcon == 32).sum()), int((part.sam.melcon == 31).sum())
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * (steps + warm), seed=3).T)).to(dev)
+    for i in range(warm):
+        rec.recover_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    torch.cuda.synchronize()
+    rec.reset_envelope(); rec.timing_reset(); lib.fsr_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        rec.recover_dev(Q[(warm + i) * tile:(warm + i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tm = rec.last_timing()
+    k2, k1 = tm["k2_ms"] / max(tm["tiles"], 1), tm["k1_ms"] / max(tm["tiles"], 1)
+    alg = (512.0 * nq + 384.0 * nt) * tile
+    mx, mn = rec.envelope()
+    return {"config": "THICK", "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
+            "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
+            "workload": f"{n}x{n} cell panel, {nq} QUAD8 + {nt} TRI6 thick shells ({part.sam.ndof} DOF), n_red={ndim}, {tile} time steps "
+                        "per step, von Mises envelope",
+            "roofline": {"kernel": "k2_dense6_vm_kernel<16,48> + <12,36>", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9,
+                         "peak": HBM_PEAK, "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch_pair": k2,
+                         "algorithmic_bytes_per_launch_pair": alg},
+            "k1": {"ms_per_launch": k1, "tflops": 2.0 * part.sam.ndof * ndim * tile / (k1 * 1e-3) / 1e12, "peak": DGEMM_PEAK},
+            "gpu_launches": int(lib.fsr_kernel_launches(0)), "max_von_mises": float(mx.max())}
+
+
 def c5(args):
     import torch
     from fedem_solvers_b200 import StressRecovery, StrainGages, load_library
@@ -261,7 +303,7 @@ def main():
     ap.add_argument("--nsteps", type=int, default=100_000)
     args = ap.parse_args()
     for c in args.configs:
-        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex}[c](args)), flush=True)
+        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick}[c](args)), flush=True)
 
 
 if __name__ == "__main__":
