@@ -238,22 +238,40 @@ __device__ bool stress_matrix(double* sig, Mat3& L, const double* X, const doubl
   return true;
 }
 
+// extrapolation weights of STR31 (:1163-1168) / STR32 (:1275-1289): result point p of a surface = sum_g W[p][g] * sampling point g
+template <int NEN>
+__device__ void extrapolation_weights(double (*W)[NEN == 6 ? 3 : 4])
+{
+  constexpr int NG = NEN == 6 ? 3 : 4;
+  if constexpr (NEN == 6) {
+    const double w[6][3] = {{1, -1, 1}, {1, 1, -1}, {-1, 1, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int p = 0; p < 6; ++p) for (int g = 0; g < 3; ++g) W[p][g] = w[p][g];
+  } else {
+    const double sq3 = sqrt(3.0), f1 = 0.5 + 0.5 * sq3, f2 = 0.5 - 0.5 * sq3;
+    for (int p = 0; p < NEN; ++p) for (int g = 0; g < NG; ++g) W[p][g] = 0.0;
+    // sampling point g = (j-1)*2 + (i-1) of the (xi_i, eta_j) loop
+    W[0][0] = f1; W[0][3] = f2; W[2][1] = f1; W[2][2] = f2; W[4][3] = f1; W[4][0] = f2; W[6][2] = f1; W[6][1] = f2;
+    for (int p = 1; p < NEN; p += 2) for (int g = 0; g < NG; ++g) W[p][g] = 0.5 * (W[p - 1][g] + W[(p + 1) % NEN][g]);
+  }
+}
+
 // One thread per element: node systems, the 2 x NG sampling-point stress matrices, global rotation, extrapolation weights.
 template <int NEN>
 __global__ void build_thickshell_ops_kernel(int nelt, const int* __restrict__ elem, const int* __restrict__ conn,
                                             const double* __restrict__ xyz, const double* __restrict__ emod,
                                             const double* __restrict__ rny, const double* __restrict__ thk,
-                                            double* __restrict__ Sfrag, double* __restrict__ Efrag, unsigned char* __restrict__ failed,
-                                            double* __restrict__ aux)
+                                            double* __restrict__ Sfrag, double* __restrict__ Efrag, double* __restrict__ Gfrag,
+                                            unsigned char* __restrict__ failed, double* __restrict__ aux)
 {
   constexpr bool TRI = NEN == 6;
   constexpr int NG = TRI ? 3 : 4, NCOL = 6 * NEN, NROW = 12 * NEN;
-  constexpr int MT = (NROW + 7) / 8, KT = (NCOL + 3) / 4;
+  constexpr int MT = (NROW + 7) / 8, KT = (NCOL + 3) / 4, MTG = (12 * NG + 7) / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nelt) return;
   const int e = elem[i];
   double* S = Sfrag + (size_t)i * MT * KT * 32;
   double* Es = Efrag + (size_t)i * MT * KT * 32;
+  double* Gs = Gfrag + (size_t)i * MTG * KT * 32;   // global stresses at the 2 x NG sampling points: row = (k*NG + g)*6 + component
   double X[NEN], Y[NEN], Z[NEN];
   for (int k = 0; k < NEN; ++k) {
     const int n = conn[i * NEN + k];
@@ -277,16 +295,7 @@ __global__ void build_thickshell_ops_kernel(int nelt, const int* __restrict__ el
   ok = ok && midside_ok(X, Y, Z, TRI);
   // extrapolation weights: result point p of a surface = sum_g W[p][g] * sampling point g
   double W[NEN][NG];
-  if constexpr (TRI) {
-    const double w[6][3] = {{1, -1, 1}, {1, 1, -1}, {-1, 1, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    for (int p = 0; p < 6; ++p) for (int g = 0; g < 3; ++g) W[p][g] = w[p][g];
-  } else {
-    const double sq3 = sqrt(3.0), f1 = 0.5 + 0.5 * sq3, f2 = 0.5 - 0.5 * sq3;
-    for (int p = 0; p < NEN; ++p) for (int g = 0; g < NG; ++g) W[p][g] = 0.0;
-    // sampling point g = (j-1)*2 + (i-1) of the (xi_i, eta_j) loop
-    W[0][0] = f1; W[0][3] = f2; W[2][1] = f1; W[2][2] = f2; W[4][3] = f1; W[4][0] = f2; W[6][2] = f1; W[6][1] = f2;
-    for (int p = 1; p < NEN; p += 2) for (int g = 0; g < NG; ++g) W[p][g] = 0.5 * (W[p - 1][g] + W[(p + 1) % NEN][g]);
-  }
+  extrapolation_weights<NEN>(W);
   double sig[5 * 5 * NEN];
   const double sq3 = sqrt(3.0);
   for (int k = 0; k < 2 && ok; ++k) {
@@ -312,6 +321,7 @@ __global__ void build_thickshell_ops_kernel(int nelt, const int* __restrict__ el
         rotate3d(s6, L.m);
         rotate3d(e6, L.m);
         e6[3] *= 0.5; e6[4] *= 0.5; e6[5] *= 0.5;   // tensorial shear strain (ElStress, elStressModule.f90:248-252)
+        for (int c = 0; c < 6; ++c) Gs[frag_ix((k * NG + g) * 6 + c, j, KT)] = s6[c];
         for (int p = 0; p < NEN; ++p) {
           const double w = W[p][g];
           if (w == 0.0) continue;
@@ -324,8 +334,10 @@ __global__ void build_thickshell_ops_kernel(int nelt, const int* __restrict__ el
       }
     }
   }
-  if (!ok)
+  if (!ok) {
     for (int k = 0; k < MT * KT * 32; ++k) { S[k] = 0.0; Es[k] = 0.0; }
+    for (int k = 0; k < MTG * KT * 32; ++k) Gs[k] = 0.0;
+  }
   failed[i] = ok ? 0 : 1;
 }
 
@@ -405,6 +417,110 @@ k2_dense6_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int ns
   }
 }
 
+
+// The throughput kernel: von Mises + envelope from the SAMPLING-POINT operator (2 x NG points, 36 / 48 rows instead of the 72 / 96
+// rows of the nodal operator), the extrapolation to the nodes (STR31 :1163-1168, STR32 :1275-1289) done in the epilogue in the order
+// the reference does it (stress at the sampling points first, then the weighted sums).  One block of 4 warps per element, operator
+// fragments resident in shared memory (13 / 18 KB), 8-step tiles of U; every warp keeps the B fragment of a k-tile for its two m-tiles.
+template <int NEN>
+__global__ void __launch_bounds__(128)
+k2_thick_gauss_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Gfrag,
+                         const int* __restrict__ edof, const int* __restrict__ ptoff, const unsigned char* __restrict__ failed, int nelt,
+                         double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  constexpr int NG = NEN == 6 ? 3 : 4, NCOL = 6 * NEN, NPT = 2 * NEN;
+  constexpr int MTG = (12 * NG + 7) / 8, KT = (NCOL + 3) / 4;
+  constexpr int NITEM = NPT * 8;   // 96 / 128 (point, step) pairs per tile
+  extern __shared__ __align__(16) double smem[];
+  double* sS = smem;                       // [MTG][KT][32]
+  double* sU = sS + MTG * KT * 32;         // [2][KT*4][8]   double buffered displacement tile
+  double* sSig = sU + 2 * KT * 4 * 8;      // [MTG*8][8]
+  double* sW = sSig + MTG * 8 * 8;         // [NEN][NG]
+  int* sDof = reinterpret_cast<int*>(sW + NEN * NG);
+  const int i = blockIdx.x;
+  if (i >= nelt) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const double* src = Gfrag + (size_t)i * MTG * KT * 32;
+  for (int k = tid; k < MTG * KT * 32; k += 128) sS[k] = src[k];
+  for (int k = tid; k < KT * 4; k += 128) sDof[k] = edof[(size_t)i * KT * 4 + k];
+  if (tid == 0) extrapolation_weights<NEN>(reinterpret_cast<double (*)[NG]>(sW));
+  const bool bad = failed[i] != 0;
+  const size_t pt0 = (size_t)ptoff[i];
+  double emax = 0.0, emin = kHuge;
+  __syncthreads();
+  const int ntiles = min(nsteps_pad >> 3, (nsteps + 7) >> 3);
+  constexpr int NLD = (KT * 4 * 8 + 127) / 128;   // staged doubles per thread and tile
+  double r[NLD];
+  auto fetch = [&](int nt) {   // global -> registers; consumed by put() after the DMMAs so that the loads fly under them
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int k = tid + 128 * q, row = k >> 3, st = k & 7;
+      r[q] = (k < KT * 4 * 8 && row < NCOL) ? U[(size_t)sDof[row] * ldu + (size_t)nt * 8 + st] : 0.0;
+    }
+  };
+  auto put = [&](int buf) {
+    double* d = sU + buf * KT * 4 * 8;
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) { const int k = tid + 128 * q; if (k < KT * 4 * 8) d[k] = r[q]; }
+  };
+  if (ntiles > 0) { fetch(0); put(0); }
+  __syncthreads();
+  const int p = tid >> 3, s = tid & 7;       // epilogue item of this thread
+  const int ksurf = p / NEN, pn = p % NEN;
+  for (int nt = 0; nt < ntiles; ++nt) {
+    const double* u = sU + (nt & 1) * KT * 4 * 8;
+    if (nt + 1 < ntiles) fetch(nt + 1);
+    const int m0 = warp, m1 = warp + 4;                     // MTG <= 6: at most two m-tiles per warp
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 3
+    for (int j = 0; j < KT; ++j) {
+      const double b = u[(4 * j + t4) * 8 + g];
+      dmma884(c00, c01, sS[(m0 * KT + j) * 32 + lane], b);
+      if (m1 < MTG) dmma884(c10, c11, sS[(m1 * KT + j) * 32 + lane], b);   // warp-uniform
+    }
+    *reinterpret_cast<double2*>(sSig + (m0 * 8 + g) * 8 + 2 * t4) = make_double2(c00, c01);
+    if (m1 < MTG) *reinterpret_cast<double2*>(sSig + (m1 * 8 + g) * 8 + 2 * t4) = make_double2(c10, c11);
+    if (nt + 1 < ntiles) put((nt + 1) & 1);   // the other buffer: last read two barriers ago
+    __syncthreads();
+    if (tid < NITEM) {
+      double sg[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < NG; ++q) {
+        const double w = sW[pn * NG + q];
+        const double* r = sSig + ((ksurf * NG + q) * 6) * 8 + s;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sg[c] += w * r[c * 8];
+      }
+      double v = sqrt(sg[0] * sg[0] + sg[1] * sg[1] + sg[2] * sg[2] - sg[0] * sg[1] - sg[1] * sg[2] - sg[2] * sg[0] +
+                      3.0 * (sg[3] * sg[3] + sg[4] * sg[4] + sg[5] * sg[5]));
+      if (bad) v = kHuge;
+      const int t = nt * 8 + s;
+      if (t < nsteps) {
+        if (vm) vm[(size_t)t * ld_vm + pt0 + p] = v;
+        emax = fmax(emax, v);
+        emin = fmin(emin, v);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+  }
+  if (tid < NITEM && s == 0 && nsteps > 0) {
+    if (emax > env_max[pt0 + p]) env_max[pt0 + p] = emax;
+    if (emin < env_min[pt0 + p]) env_min[pt0 + p] = emin;
+  }
+}
+
+template <int NEN>
+constexpr size_t thick_gauss_smem()
+{
+  constexpr int NG = NEN == 6 ? 3 : 4, KT = (6 * NEN + 3) / 4, MTG = (12 * NG + 7) / 8;
+  return sizeof(double) * (MTG * KT * 32 + 2 * KT * 4 * 8 + MTG * 8 * 8 + NEN * NG) + sizeof(int) * KT * 4;
+}
+
 template <int NPT, int NCOL>
 constexpr size_t dense6_smem()
 {
@@ -446,6 +562,9 @@ int build_family(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int fa
   FSR_CUDA(cudaMalloc(&f.failed, f.nelt));
   FSR_CUDA(cudaMalloc(&f.Sfrag, opsz));
   FSR_CUDA(cudaMalloc(&f.Efrag, opsz));
+  const size_t gsz = sizeof(double) * (size_t)f.nelt * ((12 * (NEN == 6 ? 3 : 4) + 7) / 8) * f.KT * 32;
+  FSR_CUDA(cudaMalloc(&f.Gfrag, gsz));
+  FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, gsz, s));
   FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
   FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
   FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
@@ -455,7 +574,7 @@ int build_family(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int fa
   FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, opsz, s));
   FSR_CUDA(cudaMemsetAsync(f.Efrag, 0, opsz, s));
   build_thickshell_ops_kernel<NEN><<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny, p->thk, f.Sfrag,
-                                                                   f.Efrag, f.failed, f.aux);
+                                                                   f.Efrag, f.Gfrag, f.failed, f.aux);
   FSR_LAUNCH_CHECK();
   FSR_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_conn);
@@ -467,6 +586,21 @@ int launch_family(fsr_part* p, int fam, int nsteps, int nsteps_pad, double* vm_d
 {
   FamilyData& f = p->fam[fam];
   if (f.nelt == 0) return FSR_OK;
+  // FSR_THICK_DENSE=1 selects the nodal (dense 72x36 / 96x48) operator kernel (A/B timing, cross-check)
+  static const bool dense = getenv("FSR_THICK_DENSE") && atoi(getenv("FSR_THICK_DENSE")) != 0;
+  if (!dense) {
+    constexpr int NEN = NPT / 2;
+    static bool gattr = false;
+    constexpr size_t gsmem = thick_gauss_smem<NEN>();
+    if (!gattr) {
+      FSR_CUDA(cudaFuncSetAttribute(k2_thick_gauss_vm_kernel<NEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      gattr = true;
+    }
+    k2_thick_gauss_vm_kernel<NEN><<<f.nelt, 128, gsmem, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.edof, f.ptoff,
+                                                            f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min);
+    FSR_LAUNCH_CHECK();
+    return FSR_OK;
+  }
   static bool attr = false;
   constexpr size_t smem = dense6_smem<NPT, NCOL>();
   if (!attr) {
