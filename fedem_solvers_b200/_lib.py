@@ -95,6 +95,10 @@ SYMBOLS = [
     ("fsr_gage_fatigue_feed_dev", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _I, _P]),
     ("fsr_gage_fatigue_end", C.c_int, [_P, _D, _I, _I, _I]),
     ("fsr_gage_destroy", None, [_P]),
+    ("fsr_coat_begin", C.c_int, [_P, C.c_int, C.c_double]),
+    ("fsr_coat_feed", C.c_int, [_P, _D, C.c_int, C.c_int]),
+    ("fsr_coat_feed_dev", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    ("fsr_coat_end", C.c_int, [_P, _D, _D, _I]),
     ("fsr_fmx_write", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _D, C.c_longlong, C.c_int]),
     ("fsr_fmx_read", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, _I, _I, _D, C.c_longlong]),
     ("fsr_fsm_read_mpar", C.c_int, [C.c_char_p, _I, _I, C.c_int]),

@@ -45,6 +45,14 @@ struct fsr_gages {
   std::vector<fsr_rosette> ros;
   fsr_fatigue_state* fat = nullptr;  // streaming rainflow state of 4*nros series
   double to_mpa = 1.0;
+  // strain coat summary (k3 coat kernels below): running envelopes, angle bins [bin][rosette], biaxiality sums
+  int coat_nbin = 0;
+  double coat_gate = 0.0;
+  double* coat_env = nullptr;     // [8][nros]: epsMax, epsMin, sigMax, sigMin, gammaMax, tauMax, vmeMax, vmsMax
+  double* coat_bsum = nullptr;    // [2][nros]: sum and sum of squares of the biaxiality ratio
+  int* coat_nbiax = nullptr;      // [nros]
+  int* coat_nval = nullptr;       // [nbin][nros], -1 = bin not allocated yet
+  double* coat_bin = nullptr;     // [4][nbin][nros]: sigMax, sigMin, epsMax, epsMin of every bin
   cudaStream_t stream = nullptr;
 };
 
@@ -317,6 +325,7 @@ void fsr_gage_destroy(fsr_gages* g)
   cudaFree(g->Bcart); cudaFree(g->Qt); cudaFree(g->eps); cudaFree(g->hist); cudaFree(g->values);
   cudaFree(g->Qstage); cudaFree(g->cmat); cudaFree(g->tg); cudaFree(g->eps0); cudaFree(g->ngage);
   cudaFree(g->zero_init);
+  cudaFree(g->coat_env); cudaFree(g->coat_bsum); cudaFree(g->coat_nbiax); cudaFree(g->coat_nval); cudaFree(g->coat_bin);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -535,6 +544,218 @@ int fsr_gage_fatigue(fsr_gages* g, const double* Q, int ldq, int nsteps, double 
   if ((rc = fsr_gage_fatigue_feed_dev(g, g->Qstage, ldq, 0, nsteps, 1, nullptr, s))) return rc;
   FSR_CUDA(cudaStreamSynchronize(s));
   return fsr_fatigue_finish(g->fat, damage, ncycles, bins, status);
+}
+
+}  // extern "C"
+
+// ---- strain coat summary ---------------------------------------------------------------------------------------------------
+// calcStrainCoatData (src/vpmStress/strainCoatModule.f90:315-480) for every rosette as one coat result point: the running
+// envelopes (updateMax / updateMin, :349-364,410-420; max starts at 0, min at hugeVal, nullifyResults :142-170), the angle bins
+// of the principal directions (updateAngBin :436-478: nBin = -angleBins - 1 bins over 180 degrees; the bin of the largest
+// principal value counts the hit and tracks the range of sigmaP(1) / epsP(1), the bin of the smallest one, 90 degrees away, tracks
+// sigmaP(2) / epsP(2) without counting) and the biaxiality sums (updateBiAxial :421-434, gated on the signed abs-max principal
+// stress).  Sequential per point over the time steps, independent between points: one thread per rosette, state in HBM laid out
+// [bin][rosette].  calcAngleData (:481-547) and BiAxMean / BiAxStdDev (:672-704) finish it.
+namespace fsr {
+
+__global__ void coat_update_kernel(const double* __restrict__ values, int nros, int nsteps, int nbin, double gate,
+                                   double* __restrict__ env, double* __restrict__ bsum, int* __restrict__ nbiax,
+                                   int* __restrict__ nval, double* __restrict__ bin)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nros) return;
+  const double pi = 3.141592653589793238;
+  double e[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) e[k] = env[(size_t)k * nros + r];
+  double s1 = bsum[r], s2 = bsum[(size_t)nros + r];
+  int nb = nbiax[r];
+  const size_t plane = (size_t)nbin * nros;
+  for (int t = 0; t < nsteps; ++t) {
+    const double* v = values + ((size_t)t * nros + r) * FSR_GAGE_NVAL_;
+    const double epsP1 = v[3], epsP2 = v[4], sigP1 = v[13], sigP2 = v[14], sigP3 = v[15];
+    if (epsP1 > e[0]) e[0] = epsP1;
+    if (epsP2 < e[1]) e[1] = epsP2;
+    if (sigP1 > e[2]) e[2] = sigP1;
+    if (sigP2 < e[3]) e[3] = sigP2;
+    if (v[6] > e[4]) e[4] = v[6];
+    if (v[16] > e[5]) e[5] = v[16];
+    if (v[7] > e[6]) e[6] = v[7];
+    if (v[17] > e[7]) e[7] = v[17];
+    const double angle = v[8];
+    int iAng = (int)llround((angle / pi + 0.5) * nbin);   // nint: half away from zero
+    int jAng = (int)llround((angle / pi + 1.0) * nbin);
+    if (iAng < 1) iAng = nbin;
+    if (jAng > nbin) jAng = jAng - nbin;
+    {
+      const size_t ix = (size_t)(iAng - 1) * nros + r;
+      const int n = nval[ix];
+      if (n < 0) {
+        nval[ix] = 1;
+        bin[ix] = sigP1; bin[plane + ix] = sigP1; bin[2 * plane + ix] = epsP1; bin[3 * plane + ix] = epsP1;
+      } else {
+        nval[ix] = n + 1;
+        bin[ix] = fmax(bin[ix], sigP1); bin[plane + ix] = fmin(bin[plane + ix], sigP1);
+        bin[2 * plane + ix] = fmax(bin[2 * plane + ix], epsP1); bin[3 * plane + ix] = fmin(bin[3 * plane + ix], epsP1);
+      }
+    }
+    {
+      const size_t ix = (size_t)(jAng - 1) * nros + r;
+      if (nval[ix] < 0) {
+        nval[ix] = 0;
+        bin[ix] = sigP2; bin[plane + ix] = sigP2; bin[2 * plane + ix] = epsP2; bin[3 * plane + ix] = epsP2;
+      } else {
+        bin[ix] = fmax(bin[ix], sigP2); bin[plane + ix] = fmin(bin[plane + ix], sigP2);
+        bin[2 * plane + ix] = fmax(bin[2 * plane + ix], epsP2); bin[3 * plane + ix] = fmin(bin[3 * plane + ix], epsP2);
+      }
+    }
+    if (sigP3 > gate) {
+      const double biaxial = fabs(sigP1) > fabs(sigP2) ? sigP2 / sigP1 : sigP1 / sigP2;
+      s1 = s1 + biaxial;
+      s2 = s2 + biaxial * biaxial;
+      ++nb;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) env[(size_t)k * nros + r] = e[k];
+  bsum[r] = s1; bsum[(size_t)nros + r] = s2;
+  nbiax[r] = nb;
+}
+
+// calcAngleData with useOldRange = .false. + BiAxMean / BiAxStdDev; out [7][nros]: sRange(1), sRange(2), popAng, angSpd,
+// biaxial mean, biaxial standard deviation, (spare)
+__global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ nval, const double* __restrict__ bin,
+                                   const double* __restrict__ bsum, const int* __restrict__ nbiax, double* __restrict__ out)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nros) return;
+  const size_t plane = (size_t)nbin * nros;
+  const double binSize = 180.0 / nbin;
+  double sr1 = 0.0, sr2 = 0.0;
+  int iGap = 0, mVal = 0;
+  for (int i = 1; i <= nbin; ++i) {
+    const size_t ix = (size_t)(i - 1) * nros + r;
+    const int n = nval[ix];
+    if (n < 0) continue;
+    sr1 = fmax(sr1, bin[ix] - bin[plane + ix]);
+    sr2 = fmax(sr2, bin[2 * plane + ix] - bin[3 * plane + ix]);
+    if (n > mVal) { iGap = i; mVal = n; }
+  }
+  const double popAng = iGap * binSize - 90.0;
+  int firstGap = 0, maxGap = 0;
+  iGap = 0;
+  for (int i = 1; i <= nbin; ++i) {
+    const bool assoc = nval[(size_t)(i - 1) * nros + r] > 0;   // bins that only ever held the smaller principal value were freed
+    if (assoc) {
+      if (firstGap == 0) firstGap = i;
+      else if (iGap > 0) { maxGap = max(maxGap, i - iGap + 1); iGap = 0; }
+    } else if (iGap == 0 && firstGap > 0)
+      iGap = i;
+  }
+  if (iGap > 0) firstGap = firstGap + nbin - iGap + 1;
+  if (firstGap > maxGap) maxGap = firstGap;
+  out[r] = sr1; out[(size_t)nros + r] = sr2; out[(size_t)2 * nros + r] = popAng; out[(size_t)3 * nros + r] = 180.0 - maxGap * binSize;
+  const int nb = nbiax[r];
+  const double s1 = bsum[r], s2 = bsum[(size_t)nros + r];
+  out[(size_t)4 * nros + r] = s1 / (double)max(1, nb);
+  double sd = 0.0;
+  const double dnum = (double)nb;
+  if (dnum > 1.0) {
+    const double mean = s1 / dnum, dvar = s2 / dnum - mean * mean;
+    if (dvar > 0.0) sd = sqrt(dvar * dnum / (dnum - 1.0));
+  }
+  out[(size_t)5 * nros + r] = sd;
+}
+
+__global__ void coat_init_kernel(int nros, int nbin, double* env, double* bsum, int* nbiax, int* nval)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)nbin * nros) nval[i] = -1;
+  if (i < (size_t)nros) {
+    for (int k = 0; k < 8; ++k) env[(size_t)k * nros + i] = (k == 1 || k == 3) ? kHuge : 0.0;
+    bsum[i] = 0.0; bsum[(size_t)nros + i] = 0.0;
+    nbiax[i] = 0;
+  }
+}
+
+}  // namespace fsr
+
+extern "C" {
+
+int fsr_coat_begin(fsr_gages* g, int angle_bins, double biaxial_gate)
+{
+  if (!g || angle_bins < 3) { set_error("fsr_coat_begin: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  const int nbin = angle_bins - 1;   // allocate(angBin(angBinSize-1)), strainCoatModule.f90:297-299
+  const size_t nr = (size_t)std::max(g->nros, 1);
+  if (nbin != g->coat_nbin) {
+    cudaFree(g->coat_nval); cudaFree(g->coat_bin); g->coat_nval = nullptr; g->coat_bin = nullptr;
+  }
+  g->coat_nbin = nbin; g->coat_gate = biaxial_gate;
+  if (!g->coat_env) FSR_CUDA(cudaMalloc(&g->coat_env, sizeof(double) * 8 * nr));
+  if (!g->coat_bsum) FSR_CUDA(cudaMalloc(&g->coat_bsum, sizeof(double) * 2 * nr));
+  if (!g->coat_nbiax) FSR_CUDA(cudaMalloc(&g->coat_nbiax, sizeof(int) * nr));
+  if (!g->coat_nval) FSR_CUDA(cudaMalloc(&g->coat_nval, sizeof(int) * nr * nbin));
+  if (!g->coat_bin) FSR_CUDA(cudaMalloc(&g->coat_bin, sizeof(double) * 4 * nr * nbin));
+  const size_t n = nr * nbin;
+  fsr::coat_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g->stream>>>(g->nros, nbin, g->coat_env, g->coat_bsum, g->coat_nbiax, g->coat_nval);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+
+// the next nsteps steps of the reduced history (device): rosette strains / stresses (K1 GEMM + Mohr circle) -> coat update
+int fsr_coat_feed_dev(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, void* stream)
+{
+  if (!g || !Q_dev || nsteps < 0 || ldq < g->ndim || g->coat_nbin < 1) { set_error("fsr_coat_feed_dev: bad arguments (fsr_coat_begin first)"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  int rc = gage_buffers(g, true);
+  if (rc) return rc;
+  cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+  for (int t0 = 0; t0 < nsteps; t0 += g->tile) {
+    const int nt = std::min(g->tile, nsteps - t0);
+    if ((rc = gage_tile(g, Q_dev + (size_t)t0 * ldq, ldq, nt, g->values, s))) return rc;
+    if (g->nros > 0) {
+      fsr::coat_update_kernel<<<(g->nros + 127) / 128, 128, 0, s>>>(g->values, g->nros, nt, g->coat_nbin, g->coat_gate, g->coat_env, g->coat_bsum,
+                                                                  g->coat_nbiax, g->coat_nval, g->coat_bin);
+      FSR_LAUNCH_CHECK();
+    }
+  }
+  return FSR_OK;
+}
+
+int fsr_coat_feed(fsr_gages* g, const double* Q, int ldq, int nsteps)
+{
+  if (!g || !Q || nsteps < 0 || ldq < g->ndim) { set_error("fsr_coat_feed: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  int rc = stage_q(g, Q, ldq, nsteps, g->stream);
+  if (rc) return rc;
+  if ((rc = fsr_coat_feed_dev(g, g->Qstage, ldq, nsteps, g->stream))) return rc;
+  FSR_CUDA(cudaStreamSynchronize(g->stream));
+  return FSR_OK;
+}
+
+// env [8][nros] (epsMax, epsMin, sigMax, sigMin, gammaMax, tauMax, vmeMax, vmsMax), summary [6][nros] (stress range, strain range,
+// most popular angle [deg], angle spread [deg], biaxiality mean, biaxiality standard deviation), nbiax [nros]; any may be NULL
+int fsr_coat_end(fsr_gages* g, double* env, double* summary, int* nbiax)
+{
+  if (!g || g->coat_nbin < 1) { set_error("fsr_coat_end: bad arguments (fsr_coat_begin first)"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  const size_t nr = (size_t)std::max(g->nros, 1);
+  double* out = nullptr;
+  FSR_CUDA(cudaMalloc(&out, sizeof(double) * 6 * nr));
+  if (g->nros > 0) {
+    fsr::coat_finish_kernel<<<(g->nros + 127) / 128, 128, 0, g->stream>>>(g->nros, g->coat_nbin, g->coat_nval, g->coat_bin, g->coat_bsum,
+                                                                        g->coat_nbiax, out);
+    ++fsr::g_launches;
+  }
+  cudaError_t e = cudaSuccess;
+  if (env) e = cudaMemcpyAsync(env, g->coat_env, sizeof(double) * 8 * g->nros, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess && summary) e = cudaMemcpyAsync(summary, out, sizeof(double) * 6 * g->nros, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess && nbiax) e = cudaMemcpyAsync(nbiax, g->coat_nbiax, sizeof(int) * g->nros, cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g->stream);
+  cudaFree(out);
+  if (e != cudaSuccess) { set_error("fsr_coat_end: %s", cudaGetErrorString(e)); return FSR_ERR_CUDA; }
+  return FSR_OK;
 }
 
 }  // extern "C"

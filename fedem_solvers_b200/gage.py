@@ -173,6 +173,27 @@ class StrainGages:
         return dict(damage=dmg.reshape(-1, 4), ncycles=ncyc.reshape(-1, 4), status=status.reshape(-1, 4),
                     bins=bins.reshape(-1, 4, nb) if bins is not None else None, nwarn=nwarn)
 
+    # ---- strain coat recovery summary (calcStrainCoatData / calcAngleData, strainCoatModule.f90) ----
+    COAT_ENV = ("epsMax", "epsMin", "sigMax", "sigMin", "gammaMax", "tauMax", "vmeMax", "vmsMax")
+    COAT_SUMMARY = ("stressRange", "strainRange", "popAngle", "angSpread", "biAxMean", "biAxStdDev")
+
+    def coat_summary(self, Q, angle_bins=541, biaxial_gate=10.0, chunk=0):
+        """Envelopes, angle bins and biaxiality of every rosette over the history Q (fed in `chunk`-step calls when
+        chunk > 0: the state carries over).  Returns dict name -> [nros] arrays (+ 'nBiAxial')."""
+        Q = np.asfortranarray(Q, F64)
+        ns = Q.shape[1]
+        check(self._lib.fsr_coat_begin(self._h, int(angle_bins), float(biaxial_gate)), "fsr_coat_begin")
+        step = chunk if chunk > 0 else max(ns, 1)
+        for t0 in range(0, ns, step):
+            q = np.asfortranarray(Q[:, t0:t0 + step])
+            check(self._lib.fsr_coat_feed(self._h, _dp(q), q.shape[0], q.shape[1]), "fsr_coat_feed")
+        env, summ, nb = np.zeros((8, self.nros), F64), np.zeros((6, self.nros), F64), np.zeros(self.nros, I32)
+        check(self._lib.fsr_coat_end(self._h, _dp(env), _dp(summ), _ip(nb)), "fsr_coat_end")
+        out = {k: env[i] for i, k in enumerate(self.COAT_ENV)}
+        out.update({k: summ[i] for i, k in enumerate(self.COAT_SUMMARY)})
+        out["nBiAxial"] = nb
+        return out
+
     def recover_dev(self, q_ptr, ldq, nsteps, values_ptr=None, stream=None):
         check(self._lib.fsr_gage_recover_dev(self._h, C.c_void_p(q_ptr), ldq, nsteps,
                                              C.c_void_p(values_ptr) if values_ptr else None,

@@ -269,6 +269,37 @@ module fedem_b200_mod
        type(c_ptr), value :: gages
      end subroutine fsr_gage_destroy
 
+     ! ---- strain coat summary: replaces calcStrainCoatData / calcAngleData / BiAxMean / BiAxStdDev (strainCoatModule.f90) ----
+     function fsr_coat_begin (gages, angle_bins, biaxial_gate) bind(C,name="fsr_coat_begin") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value :: gages
+       integer(c_int), value :: angle_bins
+       real(c_double), value :: biaxial_gate
+       integer(c_int) :: ierr
+     end function fsr_coat_begin
+
+     function fsr_coat_feed (gages, Q, ldq, nsteps) bind(C,name="fsr_coat_feed") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value      :: gages
+       integer(c_int), value      :: ldq, nsteps
+       real(c_double), intent(in) :: Q(ldq,*)
+       integer(c_int) :: ierr
+     end function fsr_coat_feed
+
+     function fsr_coat_feed_dev (gages, Q_dev, ldq, nsteps, stream) bind(C,name="fsr_coat_feed_dev") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value :: gages, Q_dev, stream
+       integer(c_int), value :: ldq, nsteps
+       integer(c_int) :: ierr
+     end function fsr_coat_feed_dev
+
+     function fsr_coat_end (gages, env, summary, nbiax) bind(C,name="fsr_coat_end") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: gages
+       type(c_ptr), value :: env, summary, nbiax   ! real(c_double) env(nros,8), summary(nros,6), integer(c_int) nbiax(nros), or c_null_ptr
+       integer(c_int) :: ierr
+     end function fsr_coat_end
+
      ! ---- fatigue (ffp_addpoint / ffp_getdamage / ffp_getnumcycles) ---------------------------
      function fsr_fatigue (device, hist, ngage, nsteps, gate, curve, bin_size, nbins, damage, &
           &               ncycles, bins) bind(C,name="fsr_fatigue") result(ierr)

@@ -265,6 +265,21 @@ int fsr_gage_fatigue_feed_dev(fsr_gages *gages, const double *Q_dev, int ldq, in
 int fsr_gage_fatigue_end(fsr_gages *gages, double *damage, int *ncycles, int *bins, int *status);
 void fsr_gage_destroy(fsr_gages *gages);
 
+/* ---- strain coat summary (fedem_fpp's recovery-summary loop) -------------------------------------------
+ * calcStrainCoatData (src/vpmStress/strainCoatModule.f90:315-480) with every rosette of `gages` as one coat result
+ * point: running envelopes of the principal strains / stresses, max shear and von Mises (updateMax / updateMin, max
+ * from 0, min from hugeVal), the angle bins of the principal directions (updateAngBin: -angleBins - 1 bins over 180
+ * degrees) and the biaxiality sums gated on the signed abs-max principal stress (-biAxialGate); fsr_coat_end applies
+ * calcAngleData (:481-547, useOldRange = false) and BiAxMean / BiAxStdDev (:672-704).
+ *  env     [8][nros]  epsMax, epsMin, sigMax, sigMin, gammaMax, tauMax, vmeMax, vmsMax
+ *  summary [6][nros]  stress range, strain range (largest range inside one angle bin), most popular angle [deg],
+ *                     angle spread [deg], biaxiality mean, biaxiality standard deviation
+ *  nbiax   [nros]     number of steps above the biaxiality gate.            Any output may be NULL. */
+int fsr_coat_begin(fsr_gages *gages, int angle_bins /* -angleBins, 541 */, double biaxial_gate /* -biAxialGate, 10 */);
+int fsr_coat_feed(fsr_gages *gages, const double *Q, int ldq, int nsteps);
+int fsr_coat_feed_dev(fsr_gages *gages, const double *Q_dev, int ldq, int nsteps, void *stream);
+int fsr_coat_end(fsr_gages *gages, double *env, double *summary, int *nbiax);
+
 /* ---- file formats and history assembly on the drop-in surface (host only) -------------------
  * Tagged binary files as written by writeTagDB / read by readTagDB (src/vpmUtilities/binaryDB.c:
  * 643-733; header layout FFaTag.C:192-297): 30-char tag, 0x1234 endian mark, 8-byte checksum field,

@@ -152,6 +152,9 @@ int orc_rosette_bcart(const orc_rosette *ros, const orc_sam *sam, const double *
 void orc_calc_rosette_strains(const double *Bcart, int ndim, const double *finit,
                               const double epsCInit[3], double emod, double nu,
                               const double sigmaC0[3], const double *Tg, int ngage, double *out);
+/* strain coat recovery summary of one result point (coat.c) */
+int orc_coat_summary(const double *values, int nsteps, int angle_bins, double biaxial_gate, double *env, double *summary,
+                     int *nval_out);
 void orc_principle_strains2d(const double epsC[3], double *eps1, double *eps2,
                              double *gammaMax, double *alpha1, double *alphaGamma);
 void orc_principle_stresses2d(const double sigC[3], double *sig1, double *sig2,

@@ -111,3 +111,40 @@ def test_in_core_vms_layout(oracle):
         k += 3 + nstrp[e]
     assert k == n
     rec.close()
+
+
+def test_strain_coat_summary(oracle):
+    """calcStrainCoatData / calcAngleData / BiAxMean / BiAxStdDev per rosette on the GPU against the oracle's restatement fed with
+    the oracle's own rosette values: envelopes and ranges <= 1e-10, angle-bin derived quantities (most popular angle, angle
+    spread) and the gated step count identical; the state carries over between feed calls of ragged size."""
+    import ctypes as C
+    from oracle_bind import _dp, _ip
+    part = plate_part(6, 5, ngen=5, seed=41, tri_fraction=0.3, warp=0.02)
+    ros = rosettes_on_part(part, 40, seed=42, rtype="TRIPLE_GAGE_45", zero_init_fraction=0.2)
+    b = oracle.bind_part(part)
+    rec = StressRecovery(part)
+    g = StrainGages(rec, ros)
+    ns, nbins = 1500, 541
+    Q = reduced_history(part.sam.ndim, ns, seed=13, amp=2e-3)
+    Vo = [oracle.rosette_history(b, r, Q) for r in ros]
+    gate = float(np.median([np.abs(v[:, 15]).max() for v in Vo]) * 0.3)     # about a third of the steps above the gate
+    for chunk in (0, 333):
+        res = g.coat_summary(Q, angle_bins=nbins, biaxial_gate=gate, chunk=chunk)
+        f = oracle.lib.orc_coat_summary
+        f.restype = C.c_int
+        n_gated = 0
+        for i, r in enumerate(ros):
+            env, summ = np.zeros(8), np.zeros(6)
+            v = np.ascontiguousarray(Vo[i])
+            nb = f(_dp(v), ns, nbins, C.c_double(gate), _dp(env), _dp(summ), None)
+            sc_e, sc_s = np.abs(v[:, 3:6]).max(), np.abs(v[:, 13:16]).max()
+            for k, name in enumerate(g.COAT_ENV):
+                sc = sc_e if name in ("epsMax", "epsMin", "gammaMax", "vmeMax") else sc_s
+                assert abs(res[name][i] - env[k]) <= TOL * sc, (i, name, res[name][i], env[k])
+            assert abs(res["stressRange"][i] - summ[0]) <= TOL * sc_s and abs(res["strainRange"][i] - summ[1]) <= TOL * sc_e
+            assert res["popAngle"][i] == summ[2] and res["angSpread"][i] == summ[3], (i, res["popAngle"][i], summ[2], res["angSpread"][i], summ[3])
+            assert res["nBiAxial"][i] == nb
+            assert abs(res["biAxMean"][i] - summ[4]) <= 1e-9 and abs(res["biAxStdDev"][i] - summ[5]) <= 1e-9
+            n_gated += nb
+        assert 0.05 * ns * len(ros) < n_gated < 0.95 * ns * len(ros)
+    g.close(); rec.close()
