@@ -612,7 +612,7 @@ __global__ void coat_update_kernel(const double* __restrict__ values, int nros, 
     if (sigP3 > gate) {
       const double biaxial = fabs(sigP1) > fabs(sigP2) ? sigP2 / sigP1 : sigP1 / sigP2;
       s1 = s1 + biaxial;
-      s2 = s2 + biaxial * biaxial;
+      s2 = s2 + __dmul_rn(biaxial, biaxial);   // no FMA contraction: the sums are compared with the reference's arithmetic
       ++nb;
     }
   }
@@ -641,7 +641,7 @@ __global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ n
     sr2 = fmax(sr2, bin[2 * plane + ix] - bin[3 * plane + ix]);
     if (n > mVal) { iGap = i; mVal = n; }
   }
-  const double popAng = iGap * binSize - 90.0;
+  const double popAng = __dsub_rn(__dmul_rn((double)iGap, binSize), 90.0);   // unfused, like the reference's arithmetic
   int firstGap = 0, maxGap = 0;
   iGap = 0;
   for (int i = 1; i <= nbin; ++i) {
@@ -654,14 +654,14 @@ __global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ n
   }
   if (iGap > 0) firstGap = firstGap + nbin - iGap + 1;
   if (firstGap > maxGap) maxGap = firstGap;
-  out[r] = sr1; out[(size_t)nros + r] = sr2; out[(size_t)2 * nros + r] = popAng; out[(size_t)3 * nros + r] = 180.0 - maxGap * binSize;
+  out[r] = sr1; out[(size_t)nros + r] = sr2; out[(size_t)2 * nros + r] = popAng; out[(size_t)3 * nros + r] = __dsub_rn(180.0, __dmul_rn((double)maxGap, binSize));
   const int nb = nbiax[r];
   const double s1 = bsum[r], s2 = bsum[(size_t)nros + r];
   out[(size_t)4 * nros + r] = s1 / (double)max(1, nb);
   double sd = 0.0;
   const double dnum = (double)nb;
   if (dnum > 1.0) {
-    const double mean = s1 / dnum, dvar = s2 / dnum - mean * mean;
+    const double mean = s1 / dnum, dvar = __dsub_rn(s2 / dnum, __dmul_rn(mean, mean));
     if (dvar > 0.0) sd = sqrt(dvar * dnum / (dnum - 1.0));
   }
   out[(size_t)5 * nros + r] = sd;

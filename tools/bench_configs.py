@@ -210,6 +210,48 @@ def c5(args):
             "damage_max": float(res["damage"].max())}
 
 
+def ccoat(args):
+    """Strain coat recovery summary (envelopes + angle bins + biaxiality) of args.gages result points, device-resident history."""
+    import ctypes as C
+    import torch
+    from fedem_solvers_b200 import StressRecovery, StrainGages, load_library
+    from fedem_solvers_b200._lib import check
+    from fedem_solvers_b200.model import plate_part, reduced_history, rosettes_on_part
+    lib = load_library()
+    part = plate_part(200, 200, ngen=50, n_ext=8, seed=5)
+    rec = StressRecovery(part, device=0, step_tile=512)
+    ros = rosettes_on_part(part, args.gages, seed=5)
+    g = StrainGages(rec, ros)
+    rec.close()
+    ndim, tile = part.sam.ndim, args.tile
+    ntiles = max(4, min(args.nsteps, 20480) // tile)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * ntiles, seed=5, amp=2.0e-3).T)).to(dev)
+    check(lib.fsr_coat_begin(g._h, 541, 10.0e6), "fsr_coat_begin")
+    for i in range(3):
+        check(lib.fsr_coat_feed_dev(g._h, C.c_void_p(Q[i * tile:(i + 1) * tile].data_ptr()), ndim, tile, C.c_void_p(stream.cuda_stream)), "feed")
+    torch.cuda.synchronize()
+    check(lib.fsr_coat_begin(g._h, 541, 10.0e6), "fsr_coat_begin")
+    lib.fsr_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(ntiles):
+        check(lib.fsr_coat_feed_dev(g._h, C.c_void_p(Q[i * tile:(i + 1) * tile].data_ptr()), ndim, tile, C.c_void_p(stream.cuda_stream)), "feed")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    env, summ, nb = np.zeros((8, args.gages)), np.zeros((6, args.gages)), np.zeros(args.gages, np.int32)
+    check(lib.fsr_coat_end(g._h, env.ctypes.data_as(C.POINTER(C.c_double)), summ.ctypes.data_as(C.POINTER(C.c_double)),
+                           nb.ctypes.data_as(C.POINTER(C.c_int))), "fsr_coat_end")
+    return {"config": "COAT", "metric": "coat_point_timestep_evals_per_sec", "value": args.gages * tile * ntiles / (ms * 1e-3),
+            "unit": "point*steps/s", "n_gpus": 1, "ms_total": ms, "ms_per_tile": ms / ntiles, "dtype": "f64",
+            "workload": f"{args.gages} strain coat result points x {tile * ntiles} time steps (tiles of {tile}), n_red={ndim}: Bcart GEMM -> "
+                        "Mohr circle -> running envelopes + 540 angle bins per point + biaxiality sums",
+            "state_bytes": int(args.gages) * 540 * 36, "gpu_launches": int(lib.fsr_kernel_launches(0)),
+            "mean_angle_spread_deg": float(summ[3].mean()), "mean_gated_steps": float(nb.mean())}
+
+
 def c1(args):
     import torch
     from fedem_solvers_b200 import StressRecovery, load_library
@@ -303,7 +345,7 @@ def main():
     ap.add_argument("--nsteps", type=int, default=100_000)
     args = ap.parse_args()
     for c in args.configs:
-        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick}[c](args)), flush=True)
+        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick, "coat": ccoat}[c](args)), flush=True)
 
 
 if __name__ == "__main__":
