@@ -51,8 +51,8 @@ struct fsr_gages {
   double* coat_env = nullptr;     // [8][nros]: epsMax, epsMin, sigMax, sigMin, gammaMax, tauMax, vmeMax, vmsMax
   double* coat_bsum = nullptr;    // [2][nros]: sum and sum of squares of the biaxiality ratio
   int* coat_nbiax = nullptr;      // [nros]
-  int* coat_nval = nullptr;       // [nbin][nros], -1 = bin not allocated yet
-  double* coat_bin = nullptr;     // [4][nbin][nros]: sigMax, sigMin, epsMax, epsMin of every bin
+  int* coat_nval = nullptr;       // [nros][nbin] hit counts
+  unsigned long long* coat_bin = nullptr;   // [nros][4][nbin]: sigMax, sigMin, epsMax, epsMin of every bin, order-preserving encoding
   cudaStream_t stream = nullptr;
 };
 
@@ -93,14 +93,14 @@ __global__ void gage_zero_init_kernel(const double* __restrict__ eps, size_t ldu
 }
 
 // one thread per (step, rosette), steps fastest: coalesced reads of eps rows and writes of hist rows
-__global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int nros, int nsteps,
-                                 const double* __restrict__ cmat, const double* __restrict__ tg,
-                                 const double* __restrict__ eps0, const int* __restrict__ ngage, double to_mpa,
-                                 double* __restrict__ hist, size_t ld_hist, double* __restrict__ values)
+// One (rosette, step): strains -> stresses -> gage legs -> Mohr circle; the fatigue series go to hist, the full result record
+// (FSR_GAGE_NVAL values, only when WANT) to v[].
+template <bool WANT>
+__device__ __forceinline__ void gage_point(const double* __restrict__ eps, size_t ldu, int r, int t, const double* __restrict__ cmat,
+                                           const double* __restrict__ tg, const double* __restrict__ eps0,
+                                           const int* __restrict__ ngage, double to_mpa, double* __restrict__ hist, size_t ld_hist,
+                                           double* v)
 {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)nros * nsteps) return;
-  const int t = (int)(idx % nsteps), r = (int)(idx / nsteps);
   double e[3], s[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) e[j] = eps[(size_t)(3 * r + j) * ldu + t] + eps0[3 * r + j];
@@ -123,9 +123,9 @@ __global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int
   hist[(size_t)(4 * r) * ld_hist + t] = sp1 * to_mpa;
 #pragma unroll
   for (int i = 0; i < 3; ++i) hist[(size_t)(4 * r + 1 + i) * ld_hist + t] = sg[i] * to_mpa;
-  if (values) {
+  if (WANT) {
     // PrincipleStrains2D (strainAndStressUtils.f90:14-55): only the per-step result record needs the principal strains and
-    // the two atan2 angles, the fatigue pass (values == NULL) does not pay for them
+    // the two atan2 angles, the fatigue pass does not pay for them
     origo = (e[0] + e[1]) * 0.5; d12 = e[0] - e[1];
     const double exy = e[2] * 0.5;
     radius = sqrt(d12 * d12 + e[2] * e[2]) * 0.5;
@@ -135,7 +135,6 @@ __global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int
       alpha1 = atan2(exy, d12) * 0.5;
       alphaG = atan2(d12, exy) * 0.5;
     }
-    double* v = values + ((size_t)t * nros + r) * FSR_GAGE_NVAL_;
     v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
     v[3] = ep1; v[4] = ep2; v[5] = fabs(ep1) > fabs(ep2) ? ep1 : ep2;
     v[6] = gmax; v[7] = sqrt(ep1 * ep1 + ep2 * ep2 - ep1 * ep2);
@@ -145,6 +144,47 @@ __global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int
     v[16] = tmax; v[17] = sqrt(sp1 * sp1 + sp2 * sp2 - sp1 * sp2);
     v[18] = eg[0]; v[19] = eg[1]; v[20] = eg[2];
     v[21] = sg[0]; v[22] = sg[1]; v[23] = sg[2];
+  }
+}
+
+// fatigue pass: no result record, one thread per (rosette, step), step fastest (coalesced eps reads and hist writes)
+__global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int nros, int nsteps,
+                                 const double* __restrict__ cmat, const double* __restrict__ tg,
+                                 const double* __restrict__ eps0, const int* __restrict__ ngage, double to_mpa,
+                                 double* __restrict__ hist, size_t ld_hist)
+{
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nros * nsteps) return;
+  gage_point<false>(eps, ldu, (int)(idx / nsteps), (int)(idx % nsteps), cmat, tg, eps0, ngage, to_mpa, hist, ld_hist, nullptr);
+}
+
+// result-record pass: a block takes 32 steps x 4 rosettes, the records are staged in shared memory and written out as contiguous
+// runs.  LAYOUT 0: values[t][r][NVAL] (the host API's per-step record order: 4 x NVAL doubles per step are contiguous);
+// LAYOUT 1: values[r][t][NVAL] (the strain coat kernel's order: 32 x NVAL doubles per rosette are contiguous).
+template <int LAYOUT>
+__global__ void __launch_bounds__(128)
+gage_values_kernel(const double* __restrict__ eps, size_t ldu, int nros, int nsteps, const double* __restrict__ cmat,
+                   const double* __restrict__ tg, const double* __restrict__ eps0, const int* __restrict__ ngage, double to_mpa,
+                   double* __restrict__ hist, size_t ld_hist, double* __restrict__ values, size_t ld_t /* steps per rosette, LAYOUT 1 */)
+{
+  __shared__ double sv[4][32][FSR_GAGE_NVAL_];
+  const int tl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 4, t0 = blockIdx.y * 32;
+  const int r = r0 + rl, t = t0 + tl;
+  if (r < nros && t < nsteps) gage_point<true>(eps, ldu, r, t, cmat, tg, eps0, ngage, to_mpa, hist, ld_hist, sv[rl][tl]);
+  __syncthreads();
+  const int nr = min(4, nros - r0), nt = min(32, nsteps - t0);
+  if (LAYOUT == 0) {
+    for (int k = 0; k < nt; ++k) {
+      double* dst = values + ((size_t)(t0 + k) * nros + r0) * FSR_GAGE_NVAL_;
+      for (int j = threadIdx.x; j < nr * FSR_GAGE_NVAL_; j += 128) dst[j] = sv[j / FSR_GAGE_NVAL_][k][j % FSR_GAGE_NVAL_];
+    }
+  } else {
+    for (int k = 0; k < nr; ++k) {
+      double* dst = values + ((size_t)(r0 + k) * ld_t + t0) * FSR_GAGE_NVAL_;
+      const double* src = &sv[k][0][0];
+      for (int j = threadIdx.x; j < nt * FSR_GAGE_NVAL_; j += 128) dst[j] = src[j];
+    }
   }
 }
 
@@ -277,7 +317,7 @@ static int gage_buffers(fsr_gages* g, bool want_values)
 }
 
 // Q tile (device) -> eps -> per-step values + fatigue series
-static int gage_tile(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, double* values_dev, cudaStream_t s)
+static int gage_tile(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, double* values_dev, cudaStream_t s, int values_layout = 0)
 {
   const int nsteps_pad = (nsteps + 63) / 64 * 64;
   int rc;
@@ -289,10 +329,19 @@ static int gage_tile(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, dou
     g->zero_pending = false;
   }
   const size_t total = (size_t)g->nros * nsteps;
-  if (total > 0) {
+  if (total > 0 && !values_dev) {
     gage_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g->eps, (size_t)g->tile, g->nros, nsteps, g->cmat,
                                                                     g->tg, g->eps0, g->ngage, g->to_mpa, g->hist,
-                                                                    (size_t)g->tile, values_dev);
+                                                                    (size_t)g->tile);
+    FSR_LAUNCH_CHECK();
+  } else if (total > 0) {
+    const dim3 grid((unsigned)((g->nros + 3) / 4), (unsigned)((nsteps + 31) / 32));
+    if (values_layout == 0)
+      gage_values_kernel<0><<<grid, 128, 0, s>>>(g->eps, (size_t)g->tile, g->nros, nsteps, g->cmat, g->tg, g->eps0, g->ngage, g->to_mpa, g->hist,
+                                                 (size_t)g->tile, values_dev, 0);
+    else
+      gage_values_kernel<1><<<grid, 128, 0, s>>>(g->eps, (size_t)g->tile, g->nros, nsteps, g->cmat, g->tg, g->eps0, g->ngage, g->to_mpa, g->hist,
+                                                 (size_t)g->tile, values_dev, (size_t)nsteps);
     FSR_LAUNCH_CHECK();
   }
   return FSR_OK;
@@ -558,95 +607,115 @@ int fsr_gage_fatigue(fsr_gages* g, const double* Q, int ldq, int nsteps, double 
 // [bin][rosette].  calcAngleData (:481-547) and BiAxMean / BiAxStdDev (:672-704) finish it.
 namespace fsr {
 
+// doubles as order-preserving unsigned integers: max / min of the encodings = encoding of the max / min, so that the bin updates
+// (which commute: counts, max, min) can be done with native 64-bit integer atomics by the 32 lanes of a warp on different steps
+__device__ __forceinline__ unsigned long long coat_enc(double x)
+{
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+__device__ __forceinline__ double coat_dec(unsigned long long u)
+{
+  const long long b = (long long)u;
+  return __longlong_as_double(b ^ (((~b) >> 63) | (long long)0x8000000000000000ULL));
+}
+constexpr unsigned long long kCoatMaxInit = 0ULL, kCoatMinInit = ~0ULL;   // below / above the encoding of every double
+
+// One warp per result point; the point's bin block (nbin counts + 4 x nbin encoded doubles, contiguous in HBM) is streamed
+// through shared memory once per tile of steps: lanes take the steps t = lane, lane + 32, ... and update the bins with shared
+// memory atomics.  The envelopes and the biaxiality sums are lane-local and folded with shuffles at the end.
 __global__ void coat_update_kernel(const double* __restrict__ values, int nros, int nsteps, int nbin, double gate,
                                    double* __restrict__ env, double* __restrict__ bsum, int* __restrict__ nbiax,
-                                   int* __restrict__ nval, double* __restrict__ bin)
+                                   int* __restrict__ nval, unsigned long long* __restrict__ bin)
 {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) unsigned long long coat_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int r = blockIdx.x * wpb + warp;
   if (r >= nros) return;
+  const int nbp = (nbin + 1) & ~1;                            // counts padded to a multiple of 8 bytes
+  unsigned long long* sB = coat_smem + (size_t)warp * (4 * nbin + nbp / 2);
+  int* sN = reinterpret_cast<int*>(sB + 4 * nbin);
+  const unsigned long long* gB = bin + (size_t)r * 4 * nbin;
+  int* gN = nval + (size_t)r * nbin;
+  for (int i = lane; i < 4 * nbin; i += 32) sB[i] = gB[i];
+  for (int i = lane; i < nbin; i += 32) sN[i] = gN[i];
+  __syncwarp();
   const double pi = 3.141592653589793238;
-  double e[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) e[k] = env[(size_t)k * nros + r];
-  double s1 = bsum[r], s2 = bsum[(size_t)nros + r];
-  int nb = nbiax[r];
-  const size_t plane = (size_t)nbin * nros;
-  for (int t = 0; t < nsteps; ++t) {
-    const double* v = values + ((size_t)t * nros + r) * FSR_GAGE_NVAL_;
+  double e[8] = {0.0, kHuge, 0.0, kHuge, 0.0, 0.0, 0.0, 0.0};   // neutral w.r.t. the stored envelopes (max from 0, min from hugeVal)
+  double s1 = 0.0, s2 = 0.0;
+  int nb = 0;
+  for (int t = lane; t < nsteps; t += 32) {
+    const double* v = values + ((size_t)r * nsteps + t) * FSR_GAGE_NVAL_;   // [rosette][step][NVAL] (gage_values_kernel<1>)
     const double epsP1 = v[3], epsP2 = v[4], sigP1 = v[13], sigP2 = v[14], sigP3 = v[15];
-    if (epsP1 > e[0]) e[0] = epsP1;
-    if (epsP2 < e[1]) e[1] = epsP2;
-    if (sigP1 > e[2]) e[2] = sigP1;
-    if (sigP2 < e[3]) e[3] = sigP2;
-    if (v[6] > e[4]) e[4] = v[6];
-    if (v[16] > e[5]) e[5] = v[16];
-    if (v[7] > e[6]) e[6] = v[7];
-    if (v[17] > e[7]) e[7] = v[17];
+    e[0] = fmax(e[0], epsP1); e[1] = fmin(e[1], epsP2); e[2] = fmax(e[2], sigP1); e[3] = fmin(e[3], sigP2);
+    e[4] = fmax(e[4], v[6]); e[5] = fmax(e[5], v[16]); e[6] = fmax(e[6], v[7]); e[7] = fmax(e[7], v[17]);
     const double angle = v[8];
     int iAng = (int)llround((angle / pi + 0.5) * nbin);   // nint: half away from zero
     int jAng = (int)llround((angle / pi + 1.0) * nbin);
     if (iAng < 1) iAng = nbin;
     if (jAng > nbin) jAng = jAng - nbin;
-    {
-      const size_t ix = (size_t)(iAng - 1) * nros + r;
-      const int n = nval[ix];
-      if (n < 0) {
-        nval[ix] = 1;
-        bin[ix] = sigP1; bin[plane + ix] = sigP1; bin[2 * plane + ix] = epsP1; bin[3 * plane + ix] = epsP1;
-      } else {
-        nval[ix] = n + 1;
-        bin[ix] = fmax(bin[ix], sigP1); bin[plane + ix] = fmin(bin[plane + ix], sigP1);
-        bin[2 * plane + ix] = fmax(bin[2 * plane + ix], epsP1); bin[3 * plane + ix] = fmin(bin[3 * plane + ix], epsP1);
-      }
-    }
-    {
-      const size_t ix = (size_t)(jAng - 1) * nros + r;
-      if (nval[ix] < 0) {
-        nval[ix] = 0;
-        bin[ix] = sigP2; bin[plane + ix] = sigP2; bin[2 * plane + ix] = epsP2; bin[3 * plane + ix] = epsP2;
-      } else {
-        bin[ix] = fmax(bin[ix], sigP2); bin[plane + ix] = fmin(bin[plane + ix], sigP2);
-        bin[2 * plane + ix] = fmax(bin[2 * plane + ix], epsP2); bin[3 * plane + ix] = fmin(bin[3 * plane + ix], epsP2);
-      }
-    }
+    --iAng; --jAng;
+    atomicAdd(&sN[iAng], 1);
+    const unsigned long long s1e = coat_enc(sigP1), e1e = coat_enc(epsP1), s2e = coat_enc(sigP2), e2e = coat_enc(epsP2);
+    atomicMax(&sB[iAng], s1e); atomicMin(&sB[nbin + iAng], s1e); atomicMax(&sB[2 * nbin + iAng], e1e); atomicMin(&sB[3 * nbin + iAng], e1e);
+    atomicMax(&sB[jAng], s2e); atomicMin(&sB[nbin + jAng], s2e); atomicMax(&sB[2 * nbin + jAng], e2e); atomicMin(&sB[3 * nbin + jAng], e2e);
     if (sigP3 > gate) {
       const double biaxial = fabs(sigP1) > fabs(sigP2) ? sigP2 / sigP1 : sigP1 / sigP2;
       s1 = s1 + biaxial;
-      s2 = s2 + __dmul_rn(biaxial, biaxial);   // no FMA contraction: the sums are compared with the reference's arithmetic
+      s2 = s2 + __dmul_rn(biaxial, biaxial);
       ++nb;
     }
   }
+  __syncwarp();
+  unsigned long long* wB = bin + (size_t)r * 4 * nbin;
+  for (int i = lane; i < 4 * nbin; i += 32) wB[i] = sB[i];
+  for (int i = lane; i < nbin; i += 32) gN[i] = sN[i];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) env[(size_t)k * nros + r] = e[k];
-  bsum[r] = s1; bsum[(size_t)nros + r] = s2;
-  nbiax[r] = nb;
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double other = __shfl_xor_sync(0xffffffffu, e[k], o);
+      e[k] = (k == 1 || k == 3) ? fmin(e[k], other) : fmax(e[k], other);
+    }
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    nb += __shfl_xor_sync(0xffffffffu, nb, o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double old = env[(size_t)k * nros + r];
+      env[(size_t)k * nros + r] = (k == 1 || k == 3) ? fmin(old, e[k]) : fmax(old, e[k]);
+    }
+    bsum[r] += s1; bsum[(size_t)nros + r] += s2;
+    nbiax[r] += nb;
+  }
 }
 
-// calcAngleData with useOldRange = .false. + BiAxMean / BiAxStdDev; out [7][nros]: sRange(1), sRange(2), popAng, angSpd,
-// biaxial mean, biaxial standard deviation, (spare)
-__global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ nval, const double* __restrict__ bin,
+// calcAngleData with useOldRange = .false. + BiAxMean / BiAxStdDev; out [6][nros]: sRange(1), sRange(2), popAng, angSpd,
+// biaxial mean, biaxial standard deviation.  A bin is allocated once anything was folded into it (its max left the initial value);
+// bins that only ever held the smaller principal value (count 0) are freed before the gap search, as in the reference.
+__global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ nval, const unsigned long long* __restrict__ bin,
                                    const double* __restrict__ bsum, const int* __restrict__ nbiax, double* __restrict__ out)
 {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nros) return;
-  const size_t plane = (size_t)nbin * nros;
+  const unsigned long long* B = bin + (size_t)r * 4 * nbin;
+  const int* N = nval + (size_t)r * nbin;
   const double binSize = 180.0 / nbin;
   double sr1 = 0.0, sr2 = 0.0;
   int iGap = 0, mVal = 0;
   for (int i = 1; i <= nbin; ++i) {
-    const size_t ix = (size_t)(i - 1) * nros + r;
-    const int n = nval[ix];
-    if (n < 0) continue;
-    sr1 = fmax(sr1, bin[ix] - bin[plane + ix]);
-    sr2 = fmax(sr2, bin[2 * plane + ix] - bin[3 * plane + ix]);
-    if (n > mVal) { iGap = i; mVal = n; }
+    if (B[i - 1] == kCoatMaxInit) continue;
+    sr1 = fmax(sr1, coat_dec(B[i - 1]) - coat_dec(B[nbin + i - 1]));
+    sr2 = fmax(sr2, coat_dec(B[2 * nbin + i - 1]) - coat_dec(B[3 * nbin + i - 1]));
+    if (N[i - 1] > mVal) { iGap = i; mVal = N[i - 1]; }
   }
   const double popAng = __dsub_rn(__dmul_rn((double)iGap, binSize), 90.0);   // unfused, like the reference's arithmetic
   int firstGap = 0, maxGap = 0;
   iGap = 0;
   for (int i = 1; i <= nbin; ++i) {
-    const bool assoc = nval[(size_t)(i - 1) * nros + r] > 0;   // bins that only ever held the smaller principal value were freed
-    if (assoc) {
+    if (N[i - 1] > 0) {
       if (firstGap == 0) firstGap = i;
       else if (iGap > 0) { maxGap = max(maxGap, i - iGap + 1); iGap = 0; }
     } else if (iGap == 0 && firstGap > 0)
@@ -654,7 +723,8 @@ __global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ n
   }
   if (iGap > 0) firstGap = firstGap + nbin - iGap + 1;
   if (firstGap > maxGap) maxGap = firstGap;
-  out[r] = sr1; out[(size_t)nros + r] = sr2; out[(size_t)2 * nros + r] = popAng; out[(size_t)3 * nros + r] = __dsub_rn(180.0, __dmul_rn((double)maxGap, binSize));
+  out[r] = sr1; out[(size_t)nros + r] = sr2; out[(size_t)2 * nros + r] = popAng;
+  out[(size_t)3 * nros + r] = __dsub_rn(180.0, __dmul_rn((double)maxGap, binSize));
   const int nb = nbiax[r];
   const double s1 = bsum[r], s2 = bsum[(size_t)nros + r];
   out[(size_t)4 * nros + r] = s1 / (double)max(1, nb);
@@ -667,10 +737,15 @@ __global__ void coat_finish_kernel(int nros, int nbin, const int* __restrict__ n
   out[(size_t)5 * nros + r] = sd;
 }
 
-__global__ void coat_init_kernel(int nros, int nbin, double* env, double* bsum, int* nbiax, int* nval)
+__global__ void coat_init_kernel(int nros, int nbin, double* env, double* bsum, int* nbiax, int* nval, unsigned long long* bin)
 {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (size_t)nbin * nros) nval[i] = -1;
+  if (i < (size_t)nbin * nros) {
+    nval[i] = 0;
+    const size_t r = i / nbin, b = i % nbin;
+    unsigned long long* B = bin + r * 4 * nbin;
+    B[b] = kCoatMaxInit; B[nbin + b] = kCoatMinInit; B[2 * (size_t)nbin + b] = kCoatMaxInit; B[3 * (size_t)nbin + b] = kCoatMinInit;
+  }
   if (i < (size_t)nros) {
     for (int k = 0; k < 8; ++k) env[(size_t)k * nros + i] = (k == 1 || k == 3) ? kHuge : 0.0;
     bsum[i] = 0.0; bsum[(size_t)nros + i] = 0.0;
@@ -696,9 +771,9 @@ int fsr_coat_begin(fsr_gages* g, int angle_bins, double biaxial_gate)
   if (!g->coat_bsum) FSR_CUDA(cudaMalloc(&g->coat_bsum, sizeof(double) * 2 * nr));
   if (!g->coat_nbiax) FSR_CUDA(cudaMalloc(&g->coat_nbiax, sizeof(int) * nr));
   if (!g->coat_nval) FSR_CUDA(cudaMalloc(&g->coat_nval, sizeof(int) * nr * nbin));
-  if (!g->coat_bin) FSR_CUDA(cudaMalloc(&g->coat_bin, sizeof(double) * 4 * nr * nbin));
+  if (!g->coat_bin) FSR_CUDA(cudaMalloc(&g->coat_bin, sizeof(unsigned long long) * 4 * nr * nbin));
   const size_t n = nr * nbin;
-  fsr::coat_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g->stream>>>(g->nros, nbin, g->coat_env, g->coat_bsum, g->coat_nbiax, g->coat_nval);
+  fsr::coat_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g->stream>>>(g->nros, nbin, g->coat_env, g->coat_bsum, g->coat_nbiax, g->coat_nval, g->coat_bin);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }
@@ -713,10 +788,16 @@ int fsr_coat_feed_dev(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, vo
   cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
   for (int t0 = 0; t0 < nsteps; t0 += g->tile) {
     const int nt = std::min(g->tile, nsteps - t0);
-    if ((rc = gage_tile(g, Q_dev + (size_t)t0 * ldq, ldq, nt, g->values, s))) return rc;
+    if ((rc = gage_tile(g, Q_dev + (size_t)t0 * ldq, ldq, nt, g->values, s, 1))) return rc;   // records as [rosette][step][NVAL]
     if (g->nros > 0) {
-      fsr::coat_update_kernel<<<(g->nros + 127) / 128, 128, 0, s>>>(g->values, g->nros, nt, g->coat_nbin, g->coat_gate, g->coat_env, g->coat_bsum,
-                                                                  g->coat_nbiax, g->coat_nval, g->coat_bin);
+      const int nbin = g->coat_nbin;
+      const size_t per_warp = sizeof(unsigned long long) * (4 * (size_t)nbin + ((nbin + 1) & ~1) / 2);
+      int wpb = 4;
+      while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;      // two blocks per SM when they fit
+      if (per_warp * wpb > 227 * 1024) { set_error("fsr_coat_feed: %d angle bins do not fit the shared memory of an SM", nbin + 1); return FSR_ERR_ARG; }
+      FSR_CUDA(cudaFuncSetAttribute(fsr::coat_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
+      fsr::coat_update_kernel<<<(g->nros + wpb - 1) / wpb, wpb * 32, per_warp * wpb, s>>>(g->values, g->nros, nt, nbin, g->coat_gate, g->coat_env,
+                                                                                       g->coat_bsum, g->coat_nbiax, g->coat_nval, g->coat_bin);
       FSR_LAUNCH_CHECK();
     }
   }

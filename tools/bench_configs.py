@@ -238,12 +238,14 @@ def ccoat(args):
     e0.record()
     for i in range(ntiles):
         check(lib.fsr_coat_feed_dev(g._h, C.c_void_p(Q[i * tile:(i + 1) * tile].data_ptr()), ndim, tile, C.c_void_p(stream.cuda_stream)), "feed")
+    env, summ, nb = np.zeros((8, args.gages)), np.zeros((6, args.gages)), np.zeros(args.gages, np.int32)
+    # the work runs on the handle's own stream (torch's default stream handle is 0): fsr_coat_end synchronises it, so the
+    # events bracket launch -> results on the host
+    check(lib.fsr_coat_end(g._h, env.ctypes.data_as(C.POINTER(C.c_double)), summ.ctypes.data_as(C.POINTER(C.c_double)),
+                           nb.ctypes.data_as(C.POINTER(C.c_int))), "fsr_coat_end")
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    env, summ, nb = np.zeros((8, args.gages)), np.zeros((6, args.gages)), np.zeros(args.gages, np.int32)
-    check(lib.fsr_coat_end(g._h, env.ctypes.data_as(C.POINTER(C.c_double)), summ.ctypes.data_as(C.POINTER(C.c_double)),
-                           nb.ctypes.data_as(C.POINTER(C.c_int))), "fsr_coat_end")
     return {"config": "COAT", "metric": "coat_point_timestep_evals_per_sec", "value": args.gages * tile * ntiles / (ms * 1e-3),
             "unit": "point*steps/s", "n_gpus": 1, "ms_total": ms, "ms_per_tile": ms / ntiles, "dtype": "f64",
             "workload": f"{args.gages} strain coat result points x {tile * ntiles} time steps (tiles of {tile}), n_red={ndim}: Bcart GEMM -> "
