@@ -124,11 +124,11 @@ def test_strain_coat_summary(oracle):
     b = oracle.bind_part(part)
     rec = StressRecovery(part)
     g = StrainGages(rec, ros)
-    ns, nbins = 1500, 541
+    ns = 1500
     Q = reduced_history(part.sam.ndim, ns, seed=13, amp=2e-3)
     Vo = [oracle.rosette_history(b, r, Q) for r in ros]
     gate = float(np.median([np.abs(v[:, 15]).max() for v in Vo]) * 0.3)     # about a third of the steps above the gate
-    for chunk in (0, 333):
+    for chunk, nbins in ((0, 541), (333, 541), (97, 12)):      # 12 -> 11 bins: odd count, coarse bins
         res = g.coat_summary(Q, angle_bins=nbins, biaxial_gate=gate, chunk=chunk)
         f = oracle.lib.orc_coat_summary
         f.restype = C.c_int
