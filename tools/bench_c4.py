@@ -24,9 +24,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def build_parts(scale):
-    """Six parts of mixed size / type; `scale` multiplies the element counts (1.0 ~ 1.9 M elements in total)."""
+def build_parts(scale, which="c4"):
+    """Six parts of mixed size / type; `scale` multiplies the element counts (1.0 ~ 1.9 M elements in total).
+    which = "c3": BASELINE config 3 instead, ONE mixed TET10 + beam part of ~2 M elements (element-sharded over the ranks)."""
     from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, linsolid_block
+    if which == "c3":
+        n = max(2, int(round((2_000_000 * scale / 6) ** (1.0 / 3.0))))
+        return [tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)))]
     s = scale ** 0.5
     c = scale ** (1.0 / 3.0)
     n = lambda v, f: max(2, int(round(v * f)))
@@ -43,6 +47,7 @@ def build_parts(scale):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--parts", default="c4", choices=["c4", "c3"], help="c4: six mixed parts; c3: one 2 M TET10 + beam part")
     ap.add_argument("--tile", type=int, default=256)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
@@ -61,7 +66,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = load_library()
     t0 = time.time()
-    parts = build_parts(args.scale)          # every rank builds the (seeded, identical) parts and keeps only its pieces
+    parts = build_parts(args.scale, args.parts)          # every rank builds the (seeded, identical) parts and keeps only its pieces
     costs = []
     for p in parts:
         c = element_costs(p.sam.melcon)
@@ -149,10 +154,11 @@ def main():
         comp = [float(x[0]) for x in allt]
         tot = max(float(x[1]) for x in allt)
         print(json.dumps({
-            "config": "C4", "metric": "element_timestep_stress_evals_per_sec", "value": nel_total * tile * steps / (tot * 1e-3),
+            "config": "C4" if args.parts == "c4" else "C3-sharded", "metric": "element_timestep_stress_evals_per_sec", "value": nel_total * tile * steps / (tot * 1e-3),
             "unit": "element*steps/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / steps, "dtype": "f64",
             "scaling": "strong",
-            "workload": f"6 parts, {nel_total} elements in total (ANDES quads/triangles, TET10 + beams, HEX20, HEX8/TET4/WEDG6), "
+            "workload": (f"6 parts, {nel_total} elements in total (ANDES quads/triangles, TET10 + beams, HEX20, HEX8/TET4/WEDG6), "
+                         if args.parts == "c4" else f"one part, {nel_total} elements (TET10 + 2 % beams), cut into element blocks, ") +
                         f"{tile} time steps per step, von Mises envelopes gathered to rank 0",
             "rank_compute_ms_per_step": [c / steps for c in comp],
             "load_imbalance": max(comp) / (sum(comp) / len(comp)) - 1.0,
