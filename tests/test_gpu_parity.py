@@ -368,3 +368,30 @@ def test_legacy_shells_default_formulations(oracle):
     rec = StressRecovery(legacy, ffq_stress_form=1)      # FFQ quads drop out, the FFT triangles stay
     assert rec.npts == 6 * int((legacy.sam.melcon == 21).sum())
     rec.close()
+
+
+def test_edge_sizes(oracle):
+    """ragged / empty inputs: one step, zero steps, no component modes, a part whose elements are all outside the selection"""
+    part = plate_part(5, 4, ngen=0, seed=18, tri_fraction=0.5)            # no generalized DOFs: E matrix absent
+    assert part.sam.ngen == 0
+    _check_part(oracle, part, nsteps=3, seed=2)
+    part = plate_part(5, 4, ngen=3, seed=19)
+    b = oracle.bind_part(part)
+    rec = StressRecovery(part)
+    Q = reduced_history(part.sam.ndim, 1, seed=3)
+    vm_o, mx_o, mn_o = oracle.recover_history(b, Q)
+    vm_g = rec.recover(Q)                                                  # a single step
+    assert vm_g.shape == (1, rec.npts) and rel_err(vm_g, vm_o) <= TOL
+    rec.reset_envelope()
+    vm0 = rec.recover(Q[:, :0])                                            # no step at all: nothing happens
+    assert vm0.shape == (0, rec.npts)
+    mx, mn = rec.envelope()
+    assert (mx == 0.0).all() and (mn > 1e300).all()                        # untouched: max from 0, min from hugeVal
+    rec.close()
+    part.elm.elmid = -np.abs(part.elm.elmid)                               # every element outside the -group selection
+    rec = StressRecovery(part)
+    assert rec.npts == 0
+    assert rec.recover(Q).shape == (1, 0)
+    U = rec.calc_int_displacements(Q)                                      # the expansion still works
+    assert rel_err(U[0], oracle.expand(oracle.bind_part(part), Q[:, 0])) <= TOL
+    rec.close()
