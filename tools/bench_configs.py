@@ -157,6 +157,44 @@ def cthick(args):
             "gpu_launches": int(lib.fsr_kernel_launches(0)), "max_von_mises": float(mx.max())}
 
 
+def ctri(args):
+    """All-triangle ANDES plate (type 23): k2_shell_vm_kernel<5>, 192 algorithmic bytes per element.step."""
+    import torch
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import plate_part, reduced_history
+    lib = load_library()
+    n = max(2, round((args.elements / 2) ** 0.5))
+    part = plate_part(n, n, ngen=50, n_ext=8, seed=2, tri_fraction=1.0)
+    tile, steps, warm = args.tile, args.steps, 3
+    rec = StressRecovery(part, device=0, step_tile=((tile + 63) // 64) * 64)
+    nel, ndim = part.sam.nel, part.sam.ndim
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * (steps + warm), seed=3).T)).to(dev)
+    for i in range(warm):
+        rec.recover_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    torch.cuda.synchronize()
+    rec.reset_envelope(); rec.timing_reset(); lib.fsr_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        rec.recover_dev(Q[(warm + i) * tile:(warm + i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tm = rec.last_timing()
+    k2, k1 = tm["k2_ms"] / max(tm["tiles"], 1), tm["k1_ms"] / max(tm["tiles"], 1)
+    alg = 192.0 * nel * tile
+    return {"config": "TRI", "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
+            "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
+            "workload": f"{n}x{n} cells -> {nel} ANDES triangles ({part.sam.ndof} DOF), n_red={ndim}, {tile} time steps per step, von Mises envelope",
+            "roofline": {"kernel": "k2_shell_vm_kernel<5>", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK, "unit": "GB/s",
+                         "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch": k2, "algorithmic_bytes_per_launch": alg},
+            "k1": {"ms_per_launch": k1, "tflops": 2.0 * part.sam.ndof * ndim * tile / (k1 * 1e-3) / 1e12, "peak": DGEMM_PEAK},
+            "gpu_launches": int(lib.fsr_kernel_launches(0))}
+
+
 def c5(args):
     import torch
     from fedem_solvers_b200 import StressRecovery, StrainGages, load_library
@@ -347,7 +385,7 @@ def main():
     ap.add_argument("--nsteps", type=int, default=100_000)
     args = ap.parse_args()
     for c in args.configs:
-        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick, "coat": ccoat}[c](args)), flush=True)
+        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick, "coat": ccoat, "tri": ctri}[c](args)), flush=True)
 
 
 if __name__ == "__main__":
