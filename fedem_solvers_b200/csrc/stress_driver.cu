@@ -277,7 +277,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                      const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
                      int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
-                     const std::vector<double>& times);
+                     const std::vector<double>& times, bool lgrav, const double* grv);
 
 static int run_program(bool gage)
 {
@@ -381,10 +381,8 @@ static int run_program(bool gage)
   std::string dispfile = want_grav ? file_name("dispfile", "_V.fmx") : std::string();
   bool lgrav = false;
   if (want_grav) { FILE* t = fopen(dispfile.c_str(), "rb"); if (t) { lgrav = true; fclose(t); } }
-  if (gage && lgrav) {   // gage.f90:175-194 adds a constant strain offset from the static gravitation deflection
-    log.line("  ** Note: the static gravitation offset of the rosette strains (-dispfile) is not part of this build; ignored");
-    lgrav = false;
-  }
+  // gage.f90:175-194 adds the strains of the static gravitation deflection vgii = dis1Expand(V . g), g the gravitation vector of the
+  // solver input file (NOT turned with the part, unlike stress.f90:412): same three extra modes, constant amplitudes
   const int nmodes = ngen + (lgrav ? 3 : 0);
 
   // --- the part on the device
@@ -448,7 +446,7 @@ static int run_program(bool gage)
   log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
   if (gage)
     return gage_part(c, log, what, part, ftl, db, isup, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
-                     sel, nsel, stepno, times);
+                     sel, nsel, stepno, times, lgrav, grv);
 
   // --- Initialize the stress results database (writeStressHeader)
   fsr_rdb_options ro;
@@ -527,7 +525,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                      const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
                      int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
-                     const std::vector<double>& times)
+                     const std::vector<double>& times, bool lgrav, const double* grv)
 {
   (void)minex;
   // --- Initializing strain rosettes (readStrainGageData, checkRosette)
@@ -619,7 +617,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
 
   // --- Time loop in windows: reduced history (readSupElDisplacements + BuildFinit), rosette strains on the GPU
   log.line("           --> Starting time loop");
-  const int ndim = ndof2 + ngen, window = 256;
+  const int ndim = ndof2 + ngen + (lgrav ? 3 : 0), window = 256;
   const int iFatigue = c.get_int("fatigue");
   std::vector<double> Qall(iFatigue > 0 ? (size_t)ndim * std::max(nsel, 1) : 0), Q((size_t)ndim * window),
       vals((size_t)window * nros * FSR_GAGE_NVAL);
@@ -633,6 +631,8 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                                     Q.data() + (size_t)k * ndim, ndim));
       k += run;
     }
+    if (lgrav)
+      for (int k = 0; k < nw; ++k) for (int j = 0; j < 3; ++j) Q[(size_t)k * ndim + ndof2 + ngen + j] = grv[j];
     if (iFatigue > 0) memcpy(Qall.data() + (size_t)w0 * ndim, Q.data(), sizeof(double) * (size_t)nw * ndim);
     CHECK(fsr_gage_recover(gages, Q.data(), ndim, nw, vals.data()));
     for (int k = 0; k < nw; ++k) {   // writeStrainGageDB (saveStrainGageModule.f90:196-262)

@@ -246,3 +246,43 @@ def test_fedem_gage_executable(oracle, tmp_path):
             if cnt > 0:
                 assert m is not None and int(m.group(1)[:12]) == cnt, (k, bi, cnt)
     assert ncyc > 200
+
+
+def test_fedem_gage_with_gravitation_modes(oracle, tmp_path):
+    """-dispfile: the static gravitation deflection V . g (g = the solver input file's gravitation vector, not turned with
+    the part, gage.f90:175-194) adds a constant strain to every rosette that does not start from zero."""
+    import copy
+    from fedem_solvers_b200.gage import write_rosette_file
+    from fedem_solvers_b200.model import rosettes_on_part
+    part = plate_part(5, 5, ngen=3, seed=35, warp=0.02, n_ext=4)
+    grav = (0.0, 3.0, -9.81)
+    nsteps = 20
+    case = _make_case(tmp_path, part, "plate", nsteps=nsteps, gravity=grav)
+    ros = rosettes_on_part(part, 4, seed=36, rtype="DOUBLE_GAGE_90")
+    ros[3].zero_init = True
+    write_rosette_file(str(tmp_path / "gages.fsi"), ros, link_id=case["base"], minex=part.sam.minex)
+    exe = os.path.join(os.path.dirname(EXE), "fedem_gage")
+    r = subprocess.run([exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx",
+                        "-eigfile", "plate_E.fmx", "-dispfile", "plate_V.fmx", "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs",
+                        "-rosfile", "gages.fsi", "-rdbfile", "gage.frs", "-stotm", "100"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rd = FrsReader(str(tmp_path / "gage_1.frs"))
+    assert rd.nsteps == nsteps
+    # the oracle with the gravitation modes as three more component modes of constant amplitude g
+    gpart = copy.copy(part)
+    gpart.sam = copy.copy(part.sam)
+    gpart.sam.ngen = part.sam.ngen + 3
+    gpart.E = np.asfortranarray(np.hstack([part.E, case["V"]]))
+    b = oracle.bind_part(gpart)
+    Q = np.vstack([case["Q"], np.tile(np.asarray(grav)[:, None], (1, nsteps))])
+    for ro in ros:
+        Vo = oracle.rosette_history(b, ro, Q)
+        got = rd.read(rd.find("Stress tensor", "Strain rosette", ro.id))
+        assert np.abs(got - Vo[:, 10:13]).max() <= 1.3e-7 * np.abs(Vo[:, 10:13]).max()
+        got = rd.read(rd.find("Gage 2|Gage strain", "Strain rosette", ro.id))[:, 0]
+        assert np.abs(got - Vo[:, 19]).max() <= 1.3e-7 * np.abs(Vo[:, :3]).max()
+    # and the offset is really there: without the modes the first three rosettes would differ
+    b0 = oracle.bind_part(part)
+    V0 = oracle.rosette_history(b0, ros[0], case["Q"])
+    V1 = oracle.rosette_history(b, ros[0], Q)
+    assert np.abs(V1[:, 10:13] - V0[:, 10:13]).max() > 1e-3 * np.abs(V0[:, 10:13]).max()
