@@ -285,4 +285,4 @@ def test_fedem_gage_with_gravitation_modes(oracle, tmp_path):
     b0 = oracle.bind_part(part)
     V0 = oracle.rosette_history(b0, ros[0], case["Q"])
     V1 = oracle.rosette_history(b, ros[0], Q)
-    assert np.abs(V1[:, 10:13] - V0[:, 10:13]).max() > 1e-3 * np.abs(V0[:, 10:13]).max()
+    assert np.abs(V1[:, 10:13] - V0[:, 10:13]).max() > 100 * 1.3e-7 * np.abs(V0[:, 10:13]).max()      # far above the file's float rounding
