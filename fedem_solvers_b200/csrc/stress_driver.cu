@@ -277,7 +277,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                      const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
                      int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
-                     const std::vector<double>& times, bool lgrav, const double* grv);
+                     const std::vector<double>& times, bool lgrav, const double* grv, const std::vector<int>& madof);
 
 static int run_program(bool gage)
 {
@@ -446,7 +446,7 @@ static int run_program(bool gage)
   log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
   if (gage)
     return gage_part(c, log, what, part, ftl, db, isup, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
-                     sel, nsel, stepno, times, lgrav, grv);
+                     sel, nsel, stepno, times, lgrav, grv, madof);
 
   // --- Initialize the stress results database (writeStressHeader)
   fsr_rdb_options ro;
@@ -518,6 +518,46 @@ static int run_program(bool gage)
   return 0;
 }
 
+// getShellElementAxes (src/vpmStress/strainAndStressUtils.f90:339-434) for 3 or 4 nodes X[k][3]; axes V1, V2, V3.  Returns 0 if ok.
+static int shell_element_axes(int n, const double (*X)[3], double* V1, double* V2, double* V3)
+{
+  auto cross = [](const double* a, const double* b, double* c) { c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0]; };
+  auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  const double eps2 = kEpsDiv0 * kEpsDiv0;
+  if (n == 3) {
+    for (int k = 0; k < 3; ++k) { V1[k] = X[1][k] - X[0][k]; V2[k] = X[2][k] - X[0][k]; }
+  } else if (n == 4) {
+    for (int k = 0; k < 3; ++k) { V1[k] = X[2][k] - X[0][k]; V2[k] = X[3][k] - X[1][k]; }
+  } else
+    return -1;
+  cross(V1, V2, V3);
+  double vn = dot(V3, V3);
+  if (vn <= eps2) return 2;
+  vn = std::sqrt(vn);
+  for (int k = 0; k < 3; ++k) V3[k] /= vn;
+  if (n == 4) {
+    for (int k = 0; k < 3; ++k) V1[k] = X[1][k] - X[0][k];
+    cross(V3, V1, V2);
+    cross(V2, V3, V1);
+  }
+  vn = dot(V1, V1);
+  if (vn <= eps2) return 3;
+  vn = std::sqrt(vn);
+  for (int k = 0; k < 3; ++k) V1[k] /= vn;
+  cross(V3, V1, V2);
+  return 0;
+}
+
+// FFa_glbEulerZYX -> FaMat33::getEulerZYX (fedem-foundation/src/FFaLib/FFaAlgebra/FFaMat33.C:327-349), a = 3x3 column-major
+static void glb_euler_zyx(const double* a, double* ang)
+{
+  auto atan3 = [](double y, double x) { return std::fabs(y) > 1.0e-15 || std::fabs(x) > 1.0e-15 ? std::atan2(y, x) : 0.0; };   // FFaMath.H:44-47
+  const double a11 = a[0], a21 = a[1], a31 = a[2], a32 = a[5], a33 = a[8];
+  ang[2] = atan3(a21, a11);
+  ang[1] = -atan3(a31, std::hypot(a11, a21));
+  ang[0] = atan3(a32, a33);
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // The fedem_gage specific part (gage.f90:136-150,196-247,278-400): rosette input, Bcart on the GPU, results database
 // (saveStrainGageModule.f90:23-268), fatigue report (reportDamage, strainGageModule.f90:778-862).
@@ -525,7 +565,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                      const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
                      int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
-                     const std::vector<double>& times, bool lgrav, const double* grv)
+                     const std::vector<double>& times, bool lgrav, const double* grv, const std::vector<int>& madof)
 {
   (void)minex;
   // --- Initializing strain rosettes (readStrainGageData, checkRosette)
@@ -579,9 +619,27 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
          "<5;\"Strain tensor\";NONE;FLOAT;32;TENSOR2;(3);((\"epsilon_x\",\"epsilon_y\",\"epsilon_xy\"))>\n"
          "<6;\"Stress tensor\";FORCE/AREA;FLOAT;32;TENSOR2;(3);((\"sigma_x\",\"sigma_y\",\"sigma_xy\"))>\n"
          "<7;\"Gage strain\";NONE;FLOAT;32;SCALAR>\n<8;\"Gage stress\";NONE;FLOAT;32;SCALAR>\n";
+  // .fsi format: InitStrainRosette is called with calcDisp = .true. (gage.f90:203-214), so every rosette carries its node
+  // deformations (written with -deformation) and its position + Euler angles in the global system (always written)
+  const bool lDef = c.get_bool("deformation");
+  int nv = 8;
+  const int idDef = lDef ? ++nv : 0, idPos = ++nv, idAng = ++nv;
+  if (lDef) { char b[128]; snprintf(b, sizeof(b), "<%d;\"Deformation\";LENGTH;FLOAT;32;VEC3;(3);((\"d_x\",\"d_y\",\"d_z\"))>\n", idDef); hdr += b; }
+  { char b[256]; snprintf(b, sizeof(b), "<%d;\"Position\";LENGTH;FLOAT;32;VEC3;(3);((\"x\",\"y\",\"z\"))>\n<%d;\"Euler angles\";ANGLE;FLOAT;32;ROT3;(3);((\"eps_x\",\"eps_y\",\"eps_z\"))>\n", idPos, idAng); hdr += b; }
   int maxg = 0;
   for (const fsr_rosette& R : ros) maxg = std::max(maxg, R.ngage);
   for (int j = 1; j <= maxg; ++j) { char b[64]; snprintf(b, sizeof(b), "[%d;\"Gage %d\";<7><8>]\n", j, j); hdr += b; }
+  int nig = maxg;
+  std::vector<std::string> node_groups((size_t)nros);
+  if (lDef)   // writeItGDef(rdb,idNode,iFile,'Node'//StrId(globalNodes(j))) with idNode = 0: a new item group per rosette node
+    for (int r = 0; r < nros; ++r)
+      for (int k = 0; k < ros[(size_t)r].numnod; ++k) {
+        char b[96];
+        snprintf(b, sizeof(b), "[%d;\"Node%d\";<%d>]\n", ++nig, ros[(size_t)r].nodes[k], idDef);
+        hdr += b;
+        snprintf(b, sizeof(b), "[%d]", nig);
+        node_groups[(size_t)r] += b;
+      }
   hdr += "DATABLOCKS:\n<1><2>\n";
   long long nval = 0;
   for (int r = 0; r < nros; ++r) {
@@ -594,11 +652,21 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
     if (*d) { snprintf(b, sizeof(b), "\"%s\";", d); line += b; } else line += ";";
     line += "<3><4><5><6>";
     for (int j = 1; j <= R.ngage; ++j) { snprintf(b, sizeof(b), "[%d]", j); line += b; }
+    line += node_groups[(size_t)r];
+    snprintf(b, sizeof(b), "<%d><%d>", idPos, idAng);
+    line += b;
     hdr += line + "}\n";
-    nval += 8 + 2 * R.ngage;
+    nval += 8 + 2 * R.ngage + (lDef ? 3 * R.numnod : 0) + 6;
   }
-  if (c.get_bool("deformation"))
-    log.line("  ** Note: rosette node deformations, position and Euler angles (-deformation, rosette%%ur) are not part of this build");
+  // X0 and T0 of every rosette (InitStrainRosette, strainRosetteModule.f90:753-764): node coordinates and initial element axes
+  std::vector<double> X0((size_t)nros * 12), T0((size_t)nros * 9);
+  for (int r = 0; r < nros; ++r) {
+    const fsr_rosette& R = ros[(size_t)r];
+    double X[4][3];
+    for (int k = 0; k < R.numnod; ++k) for (int d = 0; d < 3; ++d) X[k][d] = X0[(size_t)r * 12 + 3 * k + d] = xyz[3 * (size_t)(R.nodes[k] - 1) + d];
+    double* T = &T0[(size_t)r * 9];      // columns = V1, V2, V3 (T0 = transpose(T_el), T_el rows = the element axes)
+    if (shell_element_axes(R.numnod, X, T, T + 3, T + 6)) FAIL("Could not calculate coordinate system for Rosette %d. Check the rosette definition.", R.id);
+  }
   std::string path = file_name("rdbfile", ".frs");
   {   // openRDBfile (rdbModule.f90:268-403): <name>_<rdbinc>.<ext>
     const int inc = c.get_int("rdbinc");
@@ -617,8 +685,13 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
 
   // --- Time loop in windows: reduced history (readSupElDisplacements + BuildFinit), rosette strains on the GPU
   log.line("           --> Starting time loop");
-  const int ndim = ndof2 + ngen + (lgrav ? 3 : 0), window = 256;
+  const int ndof = madof.back() - 1;
+  const int ndim = ndof2 + ngen + (lgrav ? 3 : 0);
+  const int window = (int)std::max<long long>(1, std::min<long long>(256, (64LL << 20) / std::max(ndof, 1)));   // <= 512 MB of expanded displacements
   const int iFatigue = c.get_int("fatigue");
+  std::vector<double> Uw((size_t)window * ndof), supTr(12 * (size_t)window);
+  for (int k = 0; k < window; ++k) { double* T = &supTr[12 * (size_t)k]; for (int j = 0; j < 12; ++j) T[j] = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0; }
+  const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
   std::vector<double> Qall(iFatigue > 0 ? (size_t)ndim * std::max(nsel, 1) : 0), Q((size_t)ndim * window),
       vals((size_t)window * nros * FSR_GAGE_NVAL);
   std::vector<float> recbuf((size_t)std::max<long long>(nval, 1));
@@ -629,12 +702,14 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
       while (k + run < nw && sel[(size_t)(w0 + k + run)] == sel[(size_t)(w0 + k)] + run) ++run;
       CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[(size_t)(w0 + k)], run,
                                     Q.data() + (size_t)k * ndim, ndim));
+      if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, sel[(size_t)(w0 + k)], run, supTr.data() + 12 * (size_t)k, 12, 12));
       k += run;
     }
     if (lgrav)
       for (int k = 0; k < nw; ++k) for (int j = 0; j < 3; ++j) Q[(size_t)k * ndim + ndof2 + ngen + j] = grv[j];
     if (iFatigue > 0) memcpy(Qall.data() + (size_t)w0 * ndim, Q.data(), sizeof(double) * (size_t)nw * ndim);
     CHECK(fsr_gage_recover(gages, Q.data(), ndim, nw, vals.data()));
+    CHECK(fsr_expand(part, Q.data(), ndim, nw, Uw.data()));   // nodal displacements for CalcRosetteDisplacements
     for (int k = 0; k < nw; ++k) {   // writeStrainGageDB (saveStrainGageModule.f90:196-262)
       size_t n = 0;
       for (int r = 0; r < nros; ++r) {
@@ -643,6 +718,36 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
         recbuf[n++] = (float)v[0]; recbuf[n++] = (float)v[1]; recbuf[n++] = (float)(0.5 * v[2]);
         recbuf[n++] = (float)v[10]; recbuf[n++] = (float)v[11]; recbuf[n++] = (float)v[12];
         for (int j = 0; j < ros[(size_t)r].ngage; ++j) { recbuf[n++] = (float)v[18 + j]; recbuf[n++] = (float)v[21 + j]; }
+        // CalcRosetteDisplacements (strainRosetteModule.f90:814-873): node deformations, position and Euler angles of the rosette
+        const fsr_rosette& R = ros[(size_t)r];
+        const double* u = Uw.data() + (size_t)k * ndof;
+        const double* S = &supTr[12 * (size_t)k];
+        double Xn[4][3], posR[3] = {0, 0, 0};
+        for (int i = 0; i < R.numnod; ++i) {
+          const double* d = u + (madof[(size_t)(R.nodes[i] - 1)] - 1);
+          for (int j = 0; j < 3; ++j) {
+            if (lDef) recbuf[n++] = (float)d[j];
+            posR[j] += d[j];
+            Xn[i][j] = X0[(size_t)r * 12 + 3 * i + j] + d[j];
+          }
+        }
+        for (int j = 0; j < 3; ++j) posR[j] = R.rpos[9 + j] + posR[j] / (double)R.numnod;
+        for (int j = 0; j < 3; ++j) recbuf[n++] = (float)(S[j] * posR[0] + S[3 + j] * posR[1] + S[6 + j] * posR[2] + S[9 + j]);   // matmul34
+        double Tn[9], Ti[9], Tg[9], ang[3];
+        if (shell_element_axes(R.numnod, Xn, Tn, Tn + 3, Tn + 6)) FAIL("Could not calculate the deformed coordinate system of Rosette %d", R.id);
+        const double* T0r = &T0[(size_t)r * 9];
+        for (int a = 0; a < 3; ++a) for (int b2 = 0; b2 < 3; ++b2) {   // Tinc = Tn . T0^T
+          double t = 0.0;
+          for (int q = 0; q < 3; ++q) t += Tn[a + 3 * q] * T0r[b2 + 3 * q];
+          Ti[a + 3 * b2] = t;
+        }
+        for (int a = 0; a < 3; ++a) for (int b2 = 0; b2 < 3; ++b2) {   // Tinc . supTr(:,1:3)
+          double t = 0.0;
+          for (int q = 0; q < 3; ++q) t += Ti[a + 3 * q] * S[q + 3 * b2];
+          Tg[a + 3 * b2] = t;
+        }
+        glb_euler_zyx(Tg, ang);
+        for (int j = 0; j < 3; ++j) recbuf[n++] = (float)ang[j];
       }
       CHECK(fsr_frs_write_step(w, stepno[(size_t)sel[(size_t)(w0 + k)]], times[(size_t)sel[(size_t)(w0 + k)]], recbuf.data()));
     }

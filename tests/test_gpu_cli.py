@@ -197,7 +197,7 @@ def test_fedem_gage_executable(oracle, tmp_path):
     exe = os.path.join(os.path.dirname(EXE), "fedem_gage")
     r = subprocess.run([exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx",
                         "-eigfile", "plate_E.fmx", "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rosfile", "gages.fsi",
-                        "-rdbfile", "gage.frs", "-rdbinc", "2", "-stotm", "100", "-fatigue", "1", "-gate", "1.0", "-binSize", "2.0",
+                        "-rdbfile", "gage.frs", "-rdbinc", "2", "-stotm", "100", "-deformation", "-fatigue", "1", "-gate", "1.0", "-binSize", "2.0",
                         "-stressToMPaScale", "1.0e-6"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Strain gage recovery successfully completed" in r.stdout and "Nodal ordering for Rosette 71 has been swapped" in r.stdout
@@ -228,6 +228,40 @@ def test_fedem_gage_executable(oracle, tmp_path):
             assert np.abs(var(f"Gage {j + 1}|Gage strain", 1)[:, 0] - Vo[:, 18 + j]).max() <= 1.3e-7 * sc_e
             assert np.abs(var(f"Gage {j + 1}|Gage stress", 1)[:, 0] - Vo[:, 21 + j]).max() <= 1.3e-7 * sc_s
         assert rd.find(f"Gage {ng + 1}|Gage strain", "Strain rosette", ro.id) is None
+        # CalcRosetteDisplacements: node deformations (-deformation), rosette position and Euler angles in the global system
+        import ctypes as C
+        from oracle_bind import _dp
+        nn = len(ro.nodes)
+        sam = part.sam
+        U = np.stack([oracle.expand(b, Q[:, s_]) for s_ in range(nsteps)])
+        disp = np.stack([U[:, sam.madof[n - 1] - 1: sam.madof[n - 1] + 2] for n in ro.nodes], 1)      # [nsteps, nn, 3]
+        for i, n in enumerate(ro.nodes):
+            got = var(f"Node{n}|Deformation", 3)
+            assert np.abs(got - disp[:, i]).max() <= 1.3e-7 * np.abs(U).max()
+        X0 = part.elm.xyz[np.asarray(ro.nodes) - 1]
+
+        def axes(X):
+            V = [np.zeros(3) for _ in range(3)]
+            x, y, z = (np.ascontiguousarray(X[:, k_]) for k_ in range(3))
+            assert oracle.lib.orc_shell_element_axes(nn, _dp(x), _dp(y), _dp(z), _dp(V[0]), _dp(V[1]), _dp(V[2])) == 0
+            return np.stack(V, 1)                                                                   # columns = axes
+        T0 = axes(X0)
+        want_pos, want_ang = np.zeros((nsteps, 3)), np.zeros((nsteps, 3))
+        ref_lib = os.path.join(ROOT, "oracle", "_ref", "libfedem_ref_frs.so")
+        euler = C.CDLL(ref_lib).ffa_glbeulerzyx_ if os.path.exists(ref_lib) else None
+        for s_ in range(nsteps):
+            S = case["sup"][s_]
+            posR = np.asarray(ro.rpos)[:, 3] + disp[s_].mean(0)
+            want_pos[s_] = S[:, :3] @ posR + S[:, 3]
+            Tg = axes(X0 + disp[s_]) @ T0.T @ S[:, :3]
+            if euler is not None:       # the reference's own FaMat33::getEulerZYX
+                a, ang = np.ascontiguousarray(Tg.T.reshape(-1)), np.zeros(3)
+                euler(_dp(a), _dp(ang))
+                want_ang[s_] = ang
+            else:
+                want_ang[s_] = [np.arctan2(Tg[2, 1], Tg[2, 2]), -np.arctan2(Tg[2, 0], np.hypot(Tg[0, 0], Tg[1, 0])), np.arctan2(Tg[1, 0], Tg[0, 0])]
+        assert np.abs(var("Position", 3) - want_pos).max() <= 1.3e-7 * np.abs(want_pos).max()
+        assert np.abs(var("Euler angles", 3) - want_ang).max() <= 2e-6
         # fatigue report: damage row of this rosette = max principal + legs
         gate = ro.gate if ro.gate > 0 else 1.0
         row = [l for l in blocks[k].splitlines() if re.search(r"E[+-]\d\d", l) and "gate value" not in l][0]
