@@ -70,6 +70,7 @@ SYMBOLS = [
     ("fsr_copy_envelope_dev", C.c_int, [_P, _P, _P, _P]),
     ("fsr_recover_step_full", C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
     ("fsr_expand", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
+    ("fsr_expand_rows", C.c_int, [_P, _D, C.c_int, C.c_int, _I, C.c_int, _D]),
     ("fsr_fatigue", C.c_int, [C.c_int, _D, C.c_int, C.c_int, C.c_double, _D, C.c_double, C.c_int, _D, _I, _I]),
     ("fsr_fatigue_dev", C.c_int, [C.c_int, _P, C.c_size_t, C.c_int, C.c_int, C.c_double, _D, C.c_double,
                                   C.c_int, _P, _P, _P, _P]),

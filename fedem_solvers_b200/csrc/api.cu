@@ -448,6 +448,48 @@ int fsr_expand(fsr_part* p, const double* Q, int ldq, int nsteps, double* U_host
   return FSR_OK;
 }
 
+// out[t][k] = U[rows[k]][t]: the expanded displacements of a few DOFs only (rosette nodes, monitored nodes)
+__global__ void gather_rows_kernel(const double* __restrict__ U, size_t ldu, const int* __restrict__ rows, int nrows, int nt,
+                                   double* __restrict__ out)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nrows * nt) return;
+  const int t = (int)(i % nt), k = (int)(i / nt);      // t fastest: coalesced reads of U
+  out[(size_t)t * nrows + k] = U[(size_t)rows[k] * ldu + t];
+}
+
+int fsr_expand_rows(fsr_part* p, const double* Q, int ldq, int nsteps, const int* rows, int nrows, double* out)
+{
+  if (!p || !Q || nsteps < 0 || ldq < p->ndim || nrows < 0 || (nrows > 0 && (!rows || !out))) { set_error("fsr_expand_rows: bad arguments"); return FSR_ERR_ARG; }
+  if (!p->have_R) { set_error("fsr_expand_rows: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  for (int k = 0; k < nrows; ++k)
+    if (rows[k] < 0 || rows[k] >= p->ndof) { set_error("fsr_expand_rows: DOF %d out of range (0..%d)", rows[k], p->ndof - 1); return FSR_ERR_ARG; }
+  if (nrows == 0 || nsteps == 0) return FSR_OK;
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, false);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  const size_t qbytes = sizeof(double) * (size_t)ldq * nsteps;
+  double *dQ = nullptr, *dout = nullptr;
+  int* drows = nullptr;
+  auto done = [&](int code) { cudaFree(dQ); cudaFree(dout); cudaFree(drows); return code; };
+  if (cudaMalloc(&dQ, qbytes) != cudaSuccess || cudaMalloc(&drows, sizeof(int) * nrows) != cudaSuccess ||
+      cudaMalloc(&dout, sizeof(double) * (size_t)nrows * p->step_tile) != cudaSuccess) { set_error("fsr_expand_rows: device allocation failed"); return done(FSR_ERR_ALLOC); }
+  cudaMemcpyAsync(dQ, Q, qbytes, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(drows, rows, sizeof(int) * nrows, cudaMemcpyHostToDevice, s);
+  for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
+    const int nt = std::min(p->step_tile, nsteps - t0);
+    if ((rc = launch_pack_q(p, dQ + (size_t)t0 * ldq, ldq, nt, round_up(nt, 64), s))) return done(rc);
+    if ((rc = launch_k1(p, round_up(nt, 64), s))) return done(rc);
+    const size_t n = (size_t)nrows * nt;
+    gather_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p->U, (size_t)p->step_tile, drows, nrows, nt, dout);
+    ++g_launches;
+    if (cudaMemcpyAsync(out + (size_t)t0 * nrows, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { set_error("fsr_expand_rows: %s", cudaGetErrorString(cudaGetLastError())); return done(FSR_ERR_CUDA); }
+  }
+  return done(FSR_OK);
+}
+
 int fsr_recover_step_full(fsr_part* p, const double* q, double* resmat, double* stress, double* strain,
                           double* sres, double* sv)
 {

@@ -687,9 +687,16 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
   log.line("           --> Starting time loop");
   const int ndof = madof.back() - 1;
   const int ndim = ndof2 + ngen + (lgrav ? 3 : 0);
-  const int window = (int)std::max<long long>(1, std::min<long long>(256, (64LL << 20) / std::max(ndof, 1)));   // <= 512 MB of expanded displacements
+  const int window = 256;
+  (void)ndof;
+  // the translational DOFs of the rosette nodes: the only rows of the expansion CalcRosetteDisplacements needs
+  std::vector<int> urows;
+  for (const fsr_rosette& R : ros)
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) urows.push_back(i < R.numnod ? madof[(size_t)(R.nodes[i] - 1)] - 1 + j : 0);
+  const int nur = (int)urows.size();   // 12 per rosette
   const int iFatigue = c.get_int("fatigue");
-  std::vector<double> Uw((size_t)window * ndof), supTr(12 * (size_t)window);
+  std::vector<double> Uw((size_t)window * nur), supTr(12 * (size_t)window);
   for (int k = 0; k < window; ++k) { double* T = &supTr[12 * (size_t)k]; for (int j = 0; j < 12; ++j) T[j] = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0; }
   const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
   std::vector<double> Qall(iFatigue > 0 ? (size_t)ndim * std::max(nsel, 1) : 0), Q((size_t)ndim * window),
@@ -709,7 +716,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
       for (int k = 0; k < nw; ++k) for (int j = 0; j < 3; ++j) Q[(size_t)k * ndim + ndof2 + ngen + j] = grv[j];
     if (iFatigue > 0) memcpy(Qall.data() + (size_t)w0 * ndim, Q.data(), sizeof(double) * (size_t)nw * ndim);
     CHECK(fsr_gage_recover(gages, Q.data(), ndim, nw, vals.data()));
-    CHECK(fsr_expand(part, Q.data(), ndim, nw, Uw.data()));   // nodal displacements for CalcRosetteDisplacements
+    CHECK(fsr_expand_rows(part, Q.data(), ndim, nw, urows.data(), nur, Uw.data()));   // node displacements for CalcRosetteDisplacements
     for (int k = 0; k < nw; ++k) {   // writeStrainGageDB (saveStrainGageModule.f90:196-262)
       size_t n = 0;
       for (int r = 0; r < nros; ++r) {
@@ -720,11 +727,11 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
         for (int j = 0; j < ros[(size_t)r].ngage; ++j) { recbuf[n++] = (float)v[18 + j]; recbuf[n++] = (float)v[21 + j]; }
         // CalcRosetteDisplacements (strainRosetteModule.f90:814-873): node deformations, position and Euler angles of the rosette
         const fsr_rosette& R = ros[(size_t)r];
-        const double* u = Uw.data() + (size_t)k * ndof;
+        const double* u = Uw.data() + (size_t)k * nur + 12 * (size_t)r;
         const double* S = &supTr[12 * (size_t)k];
         double Xn[4][3], posR[3] = {0, 0, 0};
         for (int i = 0; i < R.numnod; ++i) {
-          const double* d = u + (madof[(size_t)(R.nodes[i] - 1)] - 1);
+          const double* d = u + 3 * i;
           for (int j = 0; j < 3; ++j) {
             if (lDef) recbuf[n++] = (float)d[j];
             posR[j] += d[j];

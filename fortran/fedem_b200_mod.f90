@@ -188,6 +188,16 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_expand
 
+     function fsr_expand_rows (part, Q, ldq, nsteps, rows, nrows, out) bind(C,name="fsr_expand_rows") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: part
+       integer(c_int), value       :: ldq, nsteps, nrows
+       real(c_double), intent(in)  :: Q(ldq,*)
+       integer(c_int), intent(in)  :: rows(*)       ! 0-based nodal DOF indices
+       real(c_double), intent(out) :: out(nrows,*)  ! (nrows, nsteps)
+       integer(c_int) :: ierr
+     end function fsr_expand_rows
+
      ! ---- strain gages (fedem_gage path) ----------------------------------------------------
      function fsr_gage_create (gages, part, ros, nros) bind(C,name="fsr_gage_create") result(ierr)
        import :: c_ptr, c_int, fsr_rosette

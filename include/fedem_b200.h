@@ -168,6 +168,9 @@ int fsr_get_vms(fsr_part *part, const double *q, double *vms, int nvms);
 
 /* Expansion only (calcIntDisplacements for a batch): U_host [nsteps x ndof] step-major. */
 int fsr_expand(fsr_part *part, const double *Q, int ldq, int nsteps, double *U_host);
+/* The same for a few DOFs only (0-based indices into the nodal DOF vector): out [nsteps x nrows] step-major; what
+ * CalcRosetteDisplacements (strainRosetteModule.f90:846) needs of the H_el rows of the rosette nodes. */
+int fsr_expand_rows(fsr_part *part, const double *Q, int ldq, int nsteps, const int *rows, int nrows, double *out);
 
 /* ---- strain gages + fatigue (fedem_gage path) ------------------------------------------------
  * Replaces ffp_addpoint / ffp_getdamage / ffp_getnumcycles

@@ -395,3 +395,23 @@ def test_edge_sizes(oracle):
     U = rec.calc_int_displacements(Q)                                      # the expansion still works
     assert rel_err(U[0], oracle.expand(oracle.bind_part(part), Q[:, 0])) <= TOL
     rec.close()
+
+
+def test_expand_rows(oracle):
+    """fsr_expand_rows: the expansion of selected DOFs only (rosette nodes) equals those entries of the full expansion"""
+    import ctypes as C
+    from oracle_bind import _dp, _ip
+    part = plate_part(6, 6, ngen=4, seed=20, tri_fraction=0.2)
+    b = oracle.bind_part(part)
+    rec = StressRecovery(part, step_tile=64)
+    Q = np.asfortranarray(reduced_history(part.sam.ndim, 150, seed=4))          # three device tiles, the last one ragged
+    rows = np.array([0, 5, 17, part.sam.ndof - 1, 17, 40], np.int32)
+    out = np.zeros((150, len(rows)))
+    rc = rec._lib.fsr_expand_rows(rec._h, _dp(Q), Q.shape[0], 150, _ip(rows), len(rows), _dp(out))
+    assert rc == 0
+    for s_ in (0, 63, 64, 149):
+        sv = oracle.expand(b, Q[:, s_])
+        assert np.abs(out[s_] - sv[rows]).max() <= TOL * np.abs(sv).max()
+    bad = np.array([part.sam.ndof], np.int32)
+    assert rec._lib.fsr_expand_rows(rec._h, _dp(Q), Q.shape[0], 1, _ip(bad), 1, _dp(out)) < 0
+    rec.close()
