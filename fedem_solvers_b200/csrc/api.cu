@@ -438,11 +438,12 @@ int fsr_expand(fsr_part* p, const double* Q, int ldq, int nsteps, double* U_host
     if ((rc = launch_pack_q(p, dQ + (size_t)t0 * ldq, ldq, nt, nsteps_pad, s))) { cudaFree(dQ); return rc; }
     if ((rc = launch_k1(p, nsteps_pad, s))) { cudaFree(dQ); return rc; }
     // U is [dof][t]; hand back step-major [t][dof]
-    tile.resize((size_t)p->ndof * p->step_tile);
-    FSR_CUDA(cudaMemcpyAsync(tile.data(), p->U, sizeof(double) * tile.size(), cudaMemcpyDeviceToHost, s));
+    tile.resize((size_t)p->ndof * nt);   // only the nt live columns of every DOF row cross the bus
+    FSR_CUDA(cudaMemcpy2DAsync(tile.data(), sizeof(double) * nt, p->U, sizeof(double) * p->step_tile, sizeof(double) * nt, (size_t)p->ndof,
+                               cudaMemcpyDeviceToHost, s));
     FSR_CUDA(cudaStreamSynchronize(s));
     for (int t = 0; t < nt; ++t)
-      for (int d = 0; d < p->ndof; ++d) U_host[(size_t)(t0 + t) * p->ndof + d] = tile[(size_t)d * p->step_tile + t];
+      for (int d = 0; d < p->ndof; ++d) U_host[(size_t)(t0 + t) * p->ndof + d] = tile[(size_t)d * nt + t];
   }
   cudaFree(dQ);
   return FSR_OK;
