@@ -106,6 +106,7 @@ SYMBOLS = [
     ("fsr_fsm_read", C.c_int, [C.c_char_p, _I, _I, _I, _I, _I, _I, _I, _I, _I, _D, _I, _I, _I]),
     ("fsr_fsm_write", C.c_int, [C.c_char_p, C.c_int, C.c_int, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _D, _I, _I, _I]),
     ("fsr_build_finit", C.c_int, [C.c_int, C.c_int, _D, _D, _D, _I, _I, C.c_int, _D, C.c_int, _D, C.c_int]),
+    ("fsr_build_mode_finit", C.c_int, [C.c_int, _D, _I, _I, _D, C.c_int, C.c_int, _D, C.c_int, _D, C.c_int]),
     ("fsr_frs_open", C.c_int, [C.POINTER(_P), C.POINTER(C.c_char_p), C.c_int]),
     ("fsr_frs_close", None, [_P]),
     ("fsr_frs_num_steps", C.c_int, [_P]),

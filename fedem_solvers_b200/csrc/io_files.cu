@@ -210,4 +210,41 @@ int fsr_build_finit(int nsteps, int ntriads, const double* sup_tr, const double*
   return FSR_OK;
 }
 
+// readSupElModes (src/vpmStress/modesRoutines.f90:121-203): the columns of Q for a mode-shape expansion (fedem_modes = the K1
+// expansion with eigenvectors instead of a time history).  The solver stores the eigenvector components of every triad in global
+// directions ("Eigenvectors|Mode n" of the Triad, nDOFs x ncomp values; ncomp = 2 for damped modes: real and imaginary part) and
+// those of the component modes under the Part; per triad the translational and the rotational triple are turned into the part's
+// system with invert34(supTr)(:,1:3) = supTr(:,1:3)^T, the generalized DOFs are copied.
+//  sup_tr [12] column-major 3x4; triad_eig: concatenation over the triads of eigVec(nDOFs*ncomp) exactly as ffr_getData returns it
+//  (component l of triad i starts at offset n*(l-1)); gen_eig [ngen*ncomp]; Q [ldq x ncomp] column-major: column l = eigFinit(:,l).
+int fsr_build_mode_finit(int ntriads, const double* sup_tr, const int* ndofs, const int* first_dof, const double* triad_eig, int ngen,
+                         int gen_first_dof, const double* gen_eig, int ncomp, double* Q, int ldq)
+{
+  if (ntriads < 0 || !sup_tr || (ntriads > 0 && (!ndofs || !first_dof || !triad_eig)) || !Q || ncomp < 1 || (ngen > 0 && !gen_eig)) {
+    set_error("fsr_build_mode_finit: bad arguments");
+    return FSR_ERR_ARG;
+  }
+  size_t off = 0;
+  for (int t = 0; t < ntriads; ++t) {
+    const int n = ndofs[t], k = first_dof[t] - 1;
+    if (k < 0 || k + (n >= 6 ? 6 : n >= 3 ? 3 : 0) > ldq) { set_error("fsr_build_mode_finit: triad %d DOF range outside Q", t + 1); return FSR_ERR_ARG; }
+    for (int l = 0; l < ncomp; ++l) {
+      const double* e = triad_eig + off + (size_t)n * l;
+      double* q = Q + (size_t)ldq * l + k;
+      for (int h = 0; h < 2; ++h) {         // translations, then rotations
+        if (n < 3 * (h + 1)) break;
+        for (int i = 0; i < 3; ++i)         // tInv(i,:) = supTr(:,i)
+          q[3 * h + i] = sup_tr[3 * i] * e[3 * h] + sup_tr[3 * i + 1] * e[3 * h + 1] + sup_tr[3 * i + 2] * e[3 * h + 2];
+      }
+    }
+    off += (size_t)n * ncomp;
+  }
+  if (ngen > 0) {
+    if (gen_first_dof < 1 || gen_first_dof - 1 + ngen > ldq) { set_error("fsr_build_mode_finit: generalized DOF range outside Q"); return FSR_ERR_ARG; }
+    for (int l = 0; l < ncomp; ++l)
+      for (int k = 0; k < ngen; ++k) Q[(size_t)ldq * l + gen_first_dof - 1 + k] = gen_eig[(size_t)ngen * l + k];
+  }
+  return FSR_OK;
+}
+
 }  // extern "C"

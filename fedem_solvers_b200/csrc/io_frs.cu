@@ -376,6 +376,8 @@ static int frs_open_file(const char* path, FrsFile& F)
 struct FrsLoc {
   int file, var;
   long long byte_off;
+  int count = 0;   // > 0: an item group read as one array (ffr_findptr on a group path, e.g. "Eigenvectors|Mode  1"): values of all
+                   // its variables, which share one number format; 0: the variable's own size
 };
 
 }  // namespace fsr
@@ -391,9 +393,25 @@ struct fsr_frs {
 
 namespace fsr {
 
-static bool frs_find_in_file(const FrsFile& F, const std::vector<std::string>& path, const std::string& og_type, int base_id,
-                             int& var, long long& bit_off)
+// leaf variables below an item group, in record order; false when they do not share one number format
+static bool frs_group_span(const FrsFile& F, const FrsNode& n, int& first_var, int& count)
 {
+  if (n.var >= 0) {
+    const FrsVar& v = F.vars[(size_t)n.var];
+    if (first_var < 0) first_var = n.var;
+    else if (F.vars[(size_t)first_var].bits != v.bits || F.vars[(size_t)first_var].is_int != v.is_int) return false;
+    count += v.repeats;
+    return true;
+  }
+  for (int k : n.kids)
+    if (!frs_group_span(F, F.nodes[(size_t)k], first_var, count)) return false;
+  return true;
+}
+
+static bool frs_find_in_file(const FrsFile& F, const std::vector<std::string>& path, const std::string& og_type, int base_id,
+                             int& var, long long& bit_off, int& count)
+{
+  count = 0;
   if (og_type.empty()) {  // top-level variable
     if (path.size() != 1) return false;
     for (const FrsTopVar& t : F.top)
@@ -417,9 +435,15 @@ static bool frs_find_in_file(const FrsFile& F, const std::vector<std::string>& p
     off = o2;
     const FrsNode& n = F.nodes[(size_t)hit];
     if (lev + 1 == path.size()) {
-      if (n.var < 0) return false;  // the path ends on an item group
-      var = n.var;
       bit_off = off;
+      if (n.var < 0) {   // the path ends on an item group: all its values as one array (FFrExtractor reads a group that way)
+        int first = -1, cnt = 0;
+        if (!frs_group_span(F, n, first, cnt) || first < 0) return false;
+        var = first;
+        count = cnt;
+        return true;
+      }
+      var = n.var;
       return true;
     }
     if (n.var >= 0) return false;
@@ -436,7 +460,7 @@ static int frs_read_values(fsr_frs* db, int handle, int gstep, double* out, int 
     auto it = F.time_index.find(key);
     if (it == F.time_index.end()) continue;
     const FrsVar& v = F.vars[(size_t)L.var];
-    const int n = std::min(nw, v.repeats), nb = v.bits / 8;
+    const int n = std::min(nw, L.count > 0 ? L.count : v.repeats), nb = v.bits / 8;
     unsigned char buf[8];
     fseeko(F.f, (off_t)(F.header_size + (long long)it->second * F.step_size + L.byte_off), SEEK_SET);
     for (int i = 0; i < n; ++i) {
@@ -511,9 +535,9 @@ int fsr_frs_find(fsr_frs* db, const char* var_path, const char* og_type, int bas
   }
   std::vector<FrsLoc> locs;
   for (size_t i = 0; i < db->files.size(); ++i) {
-    int var;
+    int var, count;
     long long off;
-    if (frs_find_in_file(*db->files[i], path, og_type ? og_type : "", base_id, var, off)) locs.push_back({(int)i, var, off >> 3});
+    if (frs_find_in_file(*db->files[i], path, og_type ? og_type : "", base_id, var, off, count)) locs.push_back({(int)i, var, off >> 3, count});
   }
   if (locs.empty()) return -1;  // like a null pointer from ffr_findptr: not an error by itself
   db->handles.push_back(locs);
@@ -524,7 +548,7 @@ int fsr_frs_var_size(const fsr_frs* db, int handle)
 {
   if (!db || handle < 0 || handle >= (int)db->handles.size()) { set_error("fsr_frs_var_size: invalid handle"); return FSR_ERR_ARG; }
   const FrsLoc& L = db->handles[(size_t)handle][0];
-  return db->files[(size_t)L.file]->vars[(size_t)L.var].repeats;
+  return L.count > 0 ? L.count : db->files[(size_t)L.file]->vars[(size_t)L.var].repeats;
 }
 
 int fsr_frs_read(fsr_frs* db, int handle, int step0, int nsteps, double* data, int nw, int ld)

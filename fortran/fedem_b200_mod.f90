@@ -458,6 +458,17 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_build_finit
 
+     ! readSupElModes (modesRoutines.f90:121-203): eigenvector components -> columns of Q for a mode-shape expansion
+     function fsr_build_mode_finit (ntriads, supTr, ndofs, first_dof, triad_eig, ngen, gen_first_dof, gen_eig, ncomp, Q, ldq) &
+          &                        bind(C,name="fsr_build_mode_finit") result(ierr)
+       import :: c_int, c_double
+       integer(c_int), value       :: ntriads, ngen, gen_first_dof, ncomp, ldq
+       real(c_double), intent(in)  :: supTr(3,4), triad_eig(*), gen_eig(*)
+       integer(c_int), intent(in)  :: ndofs(*), first_dof(*)
+       real(c_double), intent(out) :: Q(ldq,*)
+       integer(c_int) :: ierr
+     end function fsr_build_mode_finit
+
      ! ---- .frs results database (replaces ffr_init/ffr_findptr/ffr_getdata for the recovery path) ----
      function fsr_frs_open (db, paths, nfiles) bind(C,name="fsr_frs_open") result(ierr)
        import :: c_ptr, c_int

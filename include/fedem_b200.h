@@ -315,6 +315,13 @@ int fsr_fsm_write(const char *path, int checksum, int npar, const int *mpar, con
 int fsr_build_finit(int nsteps, int ntriads, const double *sup_tr, const double *triad_ur,
                     const double *tr_undef, const int *ndofs, const int *first_dof, int ngen,
                     const double *gen_ur, int gen_first_dof, double *Q, int ldq);
+/* readSupElModes (src/vpmStress/modesRoutines.f90:121-203): the same for a mode shape -- fedem_modes is the K1 expansion
+ * (fsr_expand / fsr_recover) with eigenvectors as Q.  triad_eig = the "Eigenvectors|Mode n" variables of the part's triads as
+ * read from the solver results (global directions, nDOFs x ncomp values each, concatenated in triad order), gen_eig the
+ * Part's [ngen x ncomp]; ncomp = 1 (2 for damped modes: real and imaginary part).  Q [ldq x ncomp] column-major. */
+int fsr_build_mode_finit(int ntriads, const double *sup_tr, const int *ndofs, const int *first_dof,
+                         const double *triad_eig, int ngen, int gen_first_dof, const double *gen_eig, int ncomp,
+                         double *Q, int ldq);
 
 /* .frs results database, reader side = what the recovery path uses of FFrExtractor through
  * ffr_init / ffr_findptr / ffr_getdata / ffr_setposition / ffr_increment

@@ -284,3 +284,63 @@ def test_big_endian_file_is_swapped(tmp_path):
     assert np.array_equal(rd.read(rd.find("Position matrix", "Triad", 11)), vals[:, :12])
     assert np.array_equal(rd.read(rd.find("Generalized displacement", "Part", 7)), vals[:, 24:26])
     rd.close()
+
+
+def test_eigenvector_groups_of_a_real_solver_file_and_mode_finit():
+    """fedem_modes' inputs: readModesPointers asks for the ITEM GROUP "Eigenvectors|Mode  n" of every triad and reads it as one
+    array (translational + angular components); on the reference's own modal results file the product reader must return what
+    the reference's FFrExtractor returns.  fsr_build_mode_finit (readSupElModes) then turns the components into the part system."""
+    import ctypes as C
+    path = os.path.join(FIXTURES, "response_0001", "eigval_0001", "ev_p_3.frs")
+    if not os.path.exists(path):
+        pytest.skip("reference fixtures not present")
+    rd = FrsReader(path)
+    assert rd.nsteps == 2
+    ref = RefFrs([path]) if os.path.exists(REF_LIB) else None
+    keys = ref.keys() if ref else None
+    triads = [11, 12, 20, 48]
+    eig = {}
+    for mode in (1, 6):
+        for t in triads:
+            h = rd.find(f"Eigenvectors|Mode{mode:3d}", "Triad", t)
+            assert h is not None
+            got = rd.read(h)
+            assert got.shape == (2, 6)
+            tr = rd.read(rd.find(f"Eigenvectors|Mode{mode:3d}|Translational deformation", "Triad", t))
+            ro = rd.read(rd.find(f"Eigenvectors|Mode{mode:3d}|Angular deformation", "Triad", t))
+            assert np.array_equal(got, np.hstack([tr, ro]))
+            if ref:
+                ok, want = ref.read(f"Eigenvectors|Mode{mode:3d}", "Triad", t, keys, 6)
+                assert ok == 2 and np.array_equal(want, got)
+            eig[(mode, t)] = got
+    assert rd.find("Eigenvectors|Mode  7", "Triad", 11) is None
+    freq = rd.read(rd.find("Eigenvalues|Mode  1|Eigenfrequency", "Mechanism", 2))
+    assert freq.shape == (2, 1) and freq[0, 0] > 0
+    if ref:
+        ref.close()
+    # readSupElModes on the first time step of mode 1: four 6-DOF triads + 3 generalized DOFs, two components (damped form)
+    from fedem_solvers_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(7)
+    from scipy.spatial.transform import Rotation
+    sup = np.hstack([Rotation.from_rotvec([0.3, -0.2, 0.5]).as_matrix(), [[1.0], [2.0], [3.0]]])
+    ndofs = np.array([6, 6, 3, 6], np.int32)
+    first = np.array([1, 7, 13, 16], np.int32)
+    ncomp, ngen, gfirst = 2, 3, 22
+    vecs = [np.concatenate([eig[(1, t)][0][:n], eig[(6, t)][1][:n]]) for t, n in zip(triads, ndofs)]      # component 1, component 2
+    tri = np.ascontiguousarray(np.concatenate(vecs))
+    gen = rng.standard_normal(ngen * ncomp)
+    Q = np.zeros((24, ncomp), order="F")
+    _dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    rc = lib.fsr_build_mode_finit(4, _dp(np.ascontiguousarray(sup.T.reshape(-1))), _ip(ndofs), _ip(first), _dp(tri), ngen, gfirst, _dp(gen), ncomp, _dp(Q), 24)
+    assert rc == 0
+    tinv = sup[:, :3].T
+    for l in range(ncomp):
+        for v, n, k in zip(vecs, ndofs, first):
+            e = v[n * l: n * (l + 1)]
+            assert np.allclose(Q[k - 1:k + 2, l], tinv @ e[:3], rtol=0, atol=1e-16)
+            if n == 6:
+                assert np.allclose(Q[k + 2:k + 5, l], tinv @ e[3:6], rtol=0, atol=1e-16)
+        assert np.array_equal(Q[gfirst - 1:gfirst - 1 + ngen, l], gen[ngen * l: ngen * (l + 1)])
+    assert lib.fsr_build_mode_finit(4, _dp(np.ascontiguousarray(sup.T.reshape(-1))), _ip(ndofs), _ip(first), _dp(tri), ngen, 23, _dp(gen), ncomp, _dp(Q), 24) < 0
