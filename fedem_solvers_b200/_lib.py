@@ -117,6 +117,7 @@ SYMBOLS = [
     ("fsr_frs_reduced_history", C.c_int, [_P, C.c_int, C.c_int, _I, _I, _I, _D, C.c_int, C.c_int, C.c_int, C.c_int,
                                           _D, C.c_int]),
     ("fsr_frs_create", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_char_p, C.c_longlong]),
+    ("fsr_frs_create_tagged", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_longlong]),
     ("fsr_frs_write_step", C.c_int, [_P, C.c_int, C.c_double, _P]),
     ("fsr_frs_finish", C.c_int, [_P]),
     ("fsr_ftl_open", C.c_int, [C.POINTER(_P), C.c_char_p]),
@@ -144,6 +145,8 @@ SYMBOLS = [
     ("initSolverArgs", None, [C.c_int, C.POINTER(C.c_char_p)]),
     ("solveStress", C.c_int, []),
     ("solveGage", C.c_int, []),
+    ("solveModes", C.c_int, []),
+    ("fsr_modes_define_options", None, []),
     ("fsr_gage_define_options", None, []),
     ("fsr_select_steps", C.c_int, [_D, C.c_int, C.c_double, C.c_double, C.c_double, _I, C.c_int]),
     ("fsr_cmdline_reset", None, []),

@@ -182,7 +182,7 @@ int launch_pack_q_raw(double* Qt, int ldk, const double* Q_dev, int ldq, int ndi
 // api.cu: active elements of one type, in processing order (see fsr_part::elem_order)
 std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int type);
 // io_rdb.cu: the meta data lines of a results database header (openHeaderFiles)
-std::string rdb_file_preamble(const char* module, const char* model_file, const char* link_file);
+std::string rdb_file_preamble(const char* module, const char* model_file, const char* link_file, const char* info = nullptr);
 // k2_*.cu
 int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm);

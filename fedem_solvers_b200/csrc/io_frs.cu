@@ -615,9 +615,14 @@ struct fsr_frs_writer {
 
 int fsr_frs_create(fsr_frs_writer** w, const char* path, int checksum, const char* header_text, long long payload_bytes)
 {
-  if (!w || !path || !header_text || payload_bytes < 0) { set_error("fsr_frs_create: bad arguments"); return FSR_ERR_ARG; }
+  return fsr_frs_create_tagged(w, path, "#FEDEM response data", checksum, header_text, payload_bytes);
+}
+
+int fsr_frs_create_tagged(fsr_frs_writer** w, const char* path, const char* tag, int checksum, const char* header_text, long long payload_bytes)
+{
+  if (!w || !path || !tag || !header_text || payload_bytes < 0) { set_error("fsr_frs_create: bad arguments"); return FSR_ERR_ARG; }
   TaggedFile tf;
-  int rc = tf.open_write(path, "#FEDEM response data", (unsigned int)checksum);
+  int rc = tf.open_write(path, tag, (unsigned int)checksum);
   if (rc) return rc;
   if (fputs(header_text, tf.f) < 0 || fputs("DATA:", tf.f) < 0) { set_error("%s: write error", path); return FSR_ERR_ARG; }
   fsr_frs_writer* x = new fsr_frs_writer;

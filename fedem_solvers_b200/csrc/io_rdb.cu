@@ -400,7 +400,7 @@ struct HeaderBuilder {
 
 namespace fsr {
 // openHeaderFiles (rdbModule.f90:191-251): the meta data lines that precede VARIABLES:
-std::string rdb_file_preamble(const char* module, const char* model_file, const char* link_file)
+std::string rdb_file_preamble(const char* module, const char* model_file, const char* link_file, const char* info)
 {
   std::string t;
   char host[96] = "unknown", date[32] = "";
@@ -410,7 +410,7 @@ std::string rdb_file_preamble(const char* module, const char* model_file, const 
   strftime(date, sizeof(date), "%d %b %Y %H:%M:%S", localtime(&now));
   if (model_file && *model_file) appendf(t, " AssociatedModelFileName = %s;\n", model_file);
   if (link_file && *link_file) appendf(t, " ModelName               = %s;\n", link_file);
-  t += " InformationText         = response data base file;\n";
+  appendf(t, " InformationText         = %s;\n", info ? info : "response data base file");
   appendf(t, " User                    = %s;\n", user ? user : "unknown");
   appendf(t, " Computer                = %s;\n", host);
   appendf(t, " DateTime                = %s;\n", date);

@@ -29,7 +29,7 @@ using namespace fsr;
 namespace {
 
 CmdLine g_cmd;
-bool g_stress_options_defined = false, g_gage_options_defined = false;
+bool g_stress_options_defined = false, g_gage_options_defined = false, g_modes_options_defined = false;
 
 std::string strip_ext_add(const std::string& link, const char* suffix)
 {
@@ -258,11 +258,59 @@ void fsr_gage_define_options(void)
   g_gage_options_defined = true;
 }
 
+// The option table of fedem_modes: the standard options + modesmain.C:22-52.
+void fsr_modes_define_options(void)
+{
+  CmdLine& c = g_cmd;
+  c.add("fao", "", "Read additional options from this file");
+  c.add("fco", "", "Read calculation options from this file");
+  c.add("fop", "", "Read output options from this file");
+  c.add("cwd", "", "Change working directory");
+  c.add("help", false, "Print out this help text");
+  c.add("helpAll", false, "Print out this help text\nincluding the private options, if any", false);
+  c.add("version", false, "Print out program version");
+  c.add("debug", 0, "Debug print switch");
+  c.add("terminal", 6, "File unit number for terminal output");
+  c.add("consolemsg", false, "Output error messages to console");
+  c.add("Bramsize", -1, "In-core size (MB) of displacement recovery matrix\n< 0: Use the same as in the reducer (default)\n= 0: Store full matrix in core");
+  c.add("dmramsize", -1, "Same as -Bramsize but in terms of double words", false);
+  c.add("linkId", 0, "Link base-ID number");
+  c.add("linkfile", "", "Name of link input file");
+  c.add("Bmatfile", "", "Name of B-matrix file");
+  c.add("eigfile", "", "Name of eigenvector file");
+  c.add("dispfile", "", "Name of gravitation displacement file");
+  c.add("resfile", "", "Name of results output file");
+  c.add("samfile", "", "Name of SAM data file");
+  c.add("fsifile", "fedem_solver.fsi", "Name of solver input file");
+  c.add("frsfile", "", "Name of solver results database file");
+  c.add("rdbfile", "", "Name of modes results database file");
+  c.add("rdbinc", 1, "Increment number for the results database file");
+  c.add("VTFfile", "", "Name of VTF output file");
+  c.add("VTFoffset", 0, "VTF result block id offset");
+  c.add("VTFparts", 0, "Number of parts in VTF-file");
+  c.add("VTFexpress", false, "Write express VTF-files (one file per mode)");
+  c.add("VTFdscale", 1.0, "Deformation scaling factor for VTF output");
+  c.add("double", false, "Save all results in double precision");
+  c.add("damped", false, "Complex modes are calculated");
+  c.add("recover_modes", "", "List of mode numbers to expand");
+  c.add("write_nodes", false, "Save results as nodal data");
+  c.add("write_vector", true, "Save results as vector data");
+  c.add("energy_density", false, "Save scaled strain energy density");
+  c.add("stressForm", 0, "General stress formulation option", false);
+  c.add("ffqStressForm", 2, "Stress formulation for the FFQ shell", false);
+  c.add("fftStressForm", 1, "Stress formulation for the FFT shell", false);
+  c.add("useIncompatibleModes", false, "Linear hexahedron option", false);
+  c.add("device", 0, "CUDA device ordinal");
+  c.add("stepTile", 0, "Time steps per device batch (0 = from free device memory)");
+  g_modes_options_defined = true;
+}
+
 void initSolverArgs(int argc, char** argv)
 {
   g_cmd = CmdLine();
   g_cmd.init(argc, argv);
   g_gage_options_defined = false;
+  g_modes_options_defined = false;
   fsr_stress_define_options();
 }
 
@@ -279,12 +327,21 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
                      const std::vector<double>& times, bool lgrav, const double* grv, const std::vector<int>& madof);
 
-static int run_program(bool gage)
+static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_frs* db, int isup, int user_id, const char* descr,
+                      const char* model_file, const std::string& linkfile, const std::vector<int>& madof, const std::vector<int>& minex,
+                      int ndof2, int ngen, int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
+                      const std::vector<double>& tru, int gen_first, const std::vector<int>& stepno, const std::vector<double>& times, bool lgrav,
+                      const double* grv);
+
+static int run_program(int which)
 {
-  const char* what = gage ? "Strain gage recovery" : "Stress calculation";
-  const char* prog = gage ? "fedem_gage" : "fedem_stress";
+  const bool gage = which == 1, modes = which == 2;
+  const char* what = gage ? "Strain gage recovery" : modes ? "Modal recovery" : "Stress calculation";
+  const char* prog = gage ? "fedem_gage" : modes ? "fedem_modes" : "fedem_stress";
   if (gage) {
-    if (!g_gage_options_defined) { g_cmd.clear_options(); g_stress_options_defined = false; fsr_gage_define_options(); }
+    if (!g_gage_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_modes_options_defined = false; fsr_gage_define_options(); }
+  } else if (modes) {
+    if (!g_modes_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_gage_options_defined = false; fsr_modes_define_options(); }
   } else if (!g_stress_options_defined)
     fsr_stress_define_options();
   CmdLine& c = g_cmd;
@@ -296,8 +353,8 @@ static int run_program(bool gage)
   if (c.get_bool("version")) { printf("%s B200 1.0\n", prog); return 0; }
 
   Log log;
-  log.open(file_name("resfile", gage ? "_gage.res" : "_stress.res"), gage ? "Strain Gage Recovery" : "Stress Recovery");
-  log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : "STRESS");
+  log.open(file_name("resfile", gage ? "_gage.res" : modes ? "_modes.res" : "_stress.res"), gage ? "Strain Gage Recovery" : modes ? "Modal Recovery" : "Stress Recovery");
+  log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : modes ? "MODES" : "STRESS");
   if (gage) {
     if (c.get_bool("writeAsciiFiles")) log.line("  ** Note: ASCII / DAC rosette files (-writeAsciiFiles) are not part of this build; ignored");
   } else
@@ -342,7 +399,7 @@ static int run_program(bool gage)
   CHECK(fsr_ftl_get_nodes(ftl, nullptr, nullptr, nullptr, nullptr, xyz.data()));
   const int nbad = fsr_ftl_get_elmdata(ftl, emod.data(), rny.data(), rho.data(), thk.data(), elmid.data(), beam.data(), estat.data());
   if (nbad > 0) log.line("  ** Warning: %d elements lack material / thickness / cross section data", nbad);
-  if (!gage) {   // legacy thin shells are recovered for the default stress formulations only (fsr_part_create): say so loudly otherwise
+  if (which == 0) {   // legacy thin shells are recovered for the default stress formulations only (fsr_part_create): say so loudly otherwise
     const int ffq = c.get_int("ffqStressForm"), fft = c.get_int("fftStressForm");
     int nq = 0, nt = 0;
     for (int e = 0; e < nel; ++e) {
@@ -443,7 +500,10 @@ static int run_program(bool gage)
   const double statm = c.get_double("statm"), stotm = c.get_double("stotm"), tinc = c.get_double("tinc");
   std::vector<int> sel(std::max(nall, 1));
   const int nsel = fsr_select_steps(times.data(), nall, statm, stotm, tinc, sel.data(), nall);
-  log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
+  if (!modes) log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
+  if (modes)
+    return modes_part(c, log, what, part, db, isup, user_id, descr[0] ? descr : linkfile.c_str(), model_file, linkfile, madof, minex, ndof2, ngen, ntriads,
+                      tb, tnd, tfd, tru, gen_first, stepno, times, lgrav, grv);
   if (gage)
     return gage_part(c, log, what, part, ftl, db, isup, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
                      sel, nsel, stepno, times, lgrav, grv, madof);
@@ -813,9 +873,193 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
   return 0;
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// The fedem_modes specific part (modes.f90:236-460, stressInterface.C:30-83): the dynamic response and the requested eigenmodes at
+// the requested times, expanded with ONE K1 call per time (columns = response, mode 1 Re, mode 1 Im, mode 2 ...), written as vector
+// data to one modal results file (writeModesHeader :356-426, writeNodesHeader :541-595, writeDisplacementDB :1437-1515).
+static std::vector<std::string> bracket_tokens(const std::string& s)   // FFaTokenizer(s,'<','>',','), one nesting level kept
+{
+  std::vector<std::string> out;
+  size_t i = 0;
+  while (i < s.size() && isspace((unsigned char)s[i])) ++i;
+  if (i >= s.size()) return out;
+  if (s[i] != '<') { out.push_back(s.substr(i)); return out; }
+  int depth = 0;
+  std::string tok;
+  for (; i < s.size(); ++i) {
+    const char ch = s[i];
+    if (ch == '<') { if (depth++ > 0) tok += ch; }
+    else if (ch == '>') { if (--depth > 0) tok += ch; else { if (!tok.empty()) out.push_back(tok); break; } }
+    else if (ch == ',' && depth == 1) { if (!tok.empty()) out.push_back(tok); tok.clear(); }
+    else if (!isspace((unsigned char)ch) || depth > 1) tok += ch;
+  }
+  return out;
+}
+
+static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_frs* db, int isup, int user_id, const char* descr,
+                      const char* model_file, const std::string& linkfile, const std::vector<int>& madof, const std::vector<int>& minex,
+                      int ndof2, int ngen, int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
+                      const std::vector<double>& tru, int gen_first, const std::vector<int>& stepno, const std::vector<double>& times, bool lgrav,
+                      const double* grv)
+{
+  // --- -recover_modes <<t1,m1,m2,..>,<t2,..>> (convertModeOption, stressInterface.C:30-83)
+  const std::string opt = c.get_string("recover_modes");
+  const std::vector<std::string> tt = bracket_tokens(opt);
+  if (tt.empty()) FAIL("fedem_modes: No time steps, check option -recover_modes \"%s\"", opt.c_str());
+  std::vector<double> tsteps;
+  std::vector<int> modeNum;
+  for (size_t i = 0; i < tt.size(); ++i) {
+    const std::vector<std::string> mt = bracket_tokens(tt[i]);
+    if (mt.size() < 2) FAIL("fedem_modes: No modes at time step %zu check sub-token \"%s\" in -recover_modes", i, tt[i].c_str());
+    tsteps.push_back(atof(mt[0].c_str()));
+    std::vector<int> here;
+    for (size_t j = 1; j < mt.size(); ++j) here.push_back(atoi(mt[j].c_str()));
+    if (i == 0) modeNum = here;
+    else {
+      std::vector<int> a = modeNum, b = here;
+      std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+      if (a != b) FAIL("different mode lists at different times (one results file per mode, modes.f90:263-301) are not part of this build");
+    }
+  }
+  const int nMode = (int)modeNum.size();
+  if (c.get_bool("energy_density")) FAIL("-energy_density (one results file per mode with the scaled strain energy density) is not part of this build");
+  if (!c.get_bool("write_vector") || c.get_bool("write_nodes")) FAIL("only the vector form of the modal results (-write_vector without -write_nodes, the default) is part of this build");
+  if (!c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
+  const bool lComplex = c.get_bool("damped"), lDouble = c.get_bool("double");
+  const int ncomp = lComplex ? 2 : 1, nnod = (int)madof.size() - 1, ndof = madof.back() - 1;
+  int ntra = 0, nrot = 0;
+  for (int i = 0; i < nnod; ++i) {
+    if (madof[(size_t)i + 1] < madof[(size_t)i] + 3) FAIL("node %d has fewer than 3 DOFs: the vector form is impossible (initWriteDisp) and the nodal form is not part of this build", minex[(size_t)i]);
+    if (minex[(size_t)i] < 0) continue;   // internal beam nodes
+    ntra += 3;
+    if (madof[(size_t)i + 1] >= madof[(size_t)i] + 6) nrot += 3;
+  }
+
+  // --- result pointers of the eigenvectors (readModesPointers, modesRoutines.f90:47-119)
+  std::vector<int> hm((size_t)nMode * (ntriads + 1), -1);
+  for (int j = 0; j < nMode; ++j) {
+    char path[64];
+    snprintf(path, sizeof(path), "Eigenvectors|Mode%3d", modeNum[(size_t)j]);
+    for (int i = 0; i < ntriads; ++i)
+      if ((hm[(size_t)j * (ntriads + 1) + i] = fsr_frs_find(db, path, "Triad", tb[(size_t)i])) < 0)
+        FAIL("Can not find eigenvector components for Triad {%d} and Mode%3d", tb[(size_t)i], modeNum[(size_t)j]);
+    if (ngen > 0 && (hm[(size_t)j * (ntriads + 1) + ntriads] = fsr_frs_find(db, path, "Part", isup)) < 0)
+      FAIL("Can not find eigenvector components for Part {%d} (component modes) and Mode%3d", isup, modeNum[(size_t)j]);
+  }
+  const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
+
+  // --- Writing result database headers (writeModesHeader)
+  log.line("           --> Writing result database headers");
+  const int nbit = lDouble ? 64 : 32;
+  std::string hdr = rdb_file_preamble("fedem_modes", model_file, linkfile.c_str(), "modes data base file");
+  hdr += "VARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n";
+  char b[512];
+  snprintf(b, sizeof(b), "<%3d;\"Translational deformation\";LENGTH;FLOAT;%2d;VECTOR;(%8d)>\n", 3, nbit, ntra); hdr += b;
+  if (nrot > 0) { snprintf(b, sizeof(b), "<%3d;\"Angular deformation\";LENGTH;FLOAT;%2d;VECTOR;(%8d)>\n", 4, nbit, nrot); hdr += b; }
+  hdr += "DATABLOCKS:\n<1><2>\n{\"Part\";";
+  if (isup > 0) { snprintf(b, sizeof(b), "%d;", isup); hdr += b; } else hdr += ";";
+  if (user_id > 0) { snprintf(b, sizeof(b), "%d;", user_id); hdr += b; } else hdr += ";";
+  if (descr && *descr) { snprintf(b, sizeof(b), "\"%s\";\n", descr); hdr += b; } else hdr += ";\n";
+  hdr += "  [;\"Vectors\";\n";
+  auto block = [&](const char* name, bool compl_) {
+    if (nrot > 0) {
+      if (compl_) snprintf(b, sizeof(b), "    [;\"%s\";[;\"Re\";<%3d><%3d>][;\"Im\";<%3d><%3d>]]\n", name, 3, 4, 3, 4);
+      else snprintf(b, sizeof(b), "    [;\"%s\";<%3d><%3d>]\n", name, 3, 4);
+    } else {
+      if (compl_) snprintf(b, sizeof(b), "    [;\"%s\";[;\"Re\";<%3d>][;\"Im\";<%3d>]]\n", name, 3, 3);
+      else snprintf(b, sizeof(b), "    [;\"%s\";<%3d>]\n", name, 3);
+    }
+    hdr += b;
+  };
+  block("Dynamic response", false);
+  for (int j = 0; j < nMode; ++j) { char nm[32]; snprintf(nm, sizeof(nm), "Mode%3d", modeNum[(size_t)j]); block(nm, lComplex); }
+  hdr += "  ]\n}\n";
+  const long long nvalues = (long long)(ntra + nrot) * (1 + (long long)nMode * ncomp);
+  std::string path = file_name("rdbfile", ".frs");
+  {
+    const int inc = c.get_int("rdbinc");
+    if (inc > 0) {
+      const size_t dot = path.rfind('.'), sep = path.rfind('/');
+      char t[16];
+      snprintf(t, sizeof(t), "_%d", inc);
+      if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) path.insert(dot, t);
+      else path += t;
+    }
+  }
+  fsr_frs_writer* w = nullptr;
+  CHECK(fsr_frs_create_tagged(&w, path.c_str(), "#FEDEM modal data", 0, hdr.c_str(), nvalues * (nbit / 8)));
+  struct WGuard { fsr_frs_writer*& p; ~WGuard() { if (p) fsr_frs_finish(p); } } w_guard{w};
+  log.line("           --> Results database file: %s (%lld bytes per time step)", path.c_str(), 12 + nvalues * (nbit / 8));
+
+  // --- Time step loop
+  log.line("           --> Starting time loop");
+  const int nmodes_g = ngen + (lgrav ? 3 : 0), ndim = ndof2 + nmodes_g, ncols = 1 + nMode * ncomp, nall = (int)times.size();
+  std::vector<double> Q((size_t)ndim * ncols), sv((size_t)ncols * ndof), supTr(12), eig;
+  std::vector<double> rec_d(lDouble ? (size_t)nvalues : 0);
+  std::vector<float> rec_f(lDouble ? 0 : (size_t)nvalues);
+  int ndofs_tot = 0;
+  for (int i = 0; i < ntriads; ++i) ndofs_tot += tnd[(size_t)i];
+  eig.resize((size_t)std::max(ndofs_tot, 1) * ncomp);
+  std::vector<double> geig((size_t)std::max(ngen, 1) * ncomp);
+  int nerr = 0;
+  for (size_t it = 0; it < tsteps.size(); ++it) {
+    // ffr_setposition: the first key >= wanted - FLT_EPSILON, clamped to the ends (FFrResultContainer.C:953-1010)
+    int idx = -1;
+    if (nall > 0) {
+      const double wanted = tsteps[it];
+      if (times[0] > wanted) idx = 0;
+      else if (wanted > times[(size_t)nall - 1]) idx = nall - 1;
+      else idx = (int)(std::upper_bound(times.begin(), times.begin() + nall, wanted - 1.1920928955078125e-07) - times.begin());
+    }
+    if (idx < 0 || idx >= nall) { ++nerr; log.line(" *** Error: Error searching for results at time =%12.5E", tsteps[it]); continue; }
+    std::fill(Q.begin(), Q.end(), 0.0);
+    CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, idx, 1, Q.data(), ndim));
+    for (int j = 0; j < 12; ++j) supTr[(size_t)j] = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0;
+    if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, idx, 1, supTr.data(), 12, 12));
+    if (lgrav)   // g = matmul(grv, sup%supTr(:,1:3)) (modes.f90:364-367)
+      for (int j = 0; j < 3; ++j) Q[(size_t)ndof2 + ngen + j] = grv[0] * supTr[3 * j] + grv[1] * supTr[3 * j + 1] + grv[2] * supTr[3 * j + 2];
+    for (int j = 0; j < nMode; ++j) {   // readSupElModes
+      size_t off = 0;
+      for (int i = 0; i < ntriads; ++i) {
+        const int n = tnd[(size_t)i] * ncomp;
+        CHECK(fsr_frs_read(db, hm[(size_t)j * (ntriads + 1) + i], idx, 1, eig.data() + off, n, n));
+        off += (size_t)n;
+      }
+      if (ngen > 0) CHECK(fsr_frs_read(db, hm[(size_t)j * (ntriads + 1) + ntriads], idx, 1, geig.data(), ngen * ncomp, ngen * ncomp));
+      CHECK(fsr_build_mode_finit(ntriads, supTr.data(), tnd.data(), tfd.data(), eig.data(), ngen, gen_first, geig.data(), ncomp,
+                                 Q.data() + (size_t)ndim * (1 + j * ncomp), ndim));
+    }
+    CHECK(fsr_expand(part, Q.data(), ndim, ncols, sv.data()));
+    size_t n = 0;
+    auto put = [&](double x) { if (lDouble) rec_d[n++] = x; else rec_f[n++] = (float)x; };
+    for (int col = 0; col < ncols; ++col) {   // writeDisplacementDB: all translations, then all rotations, per component
+      const double* u = sv.data() + (size_t)col * ndof;
+      for (int i = 0; i < nnod; ++i) {
+        if (minex[(size_t)i] < 0) continue;
+        const int j0 = madof[(size_t)i] - 1;
+        put(u[j0]); put(u[j0 + 1]); put(u[j0 + 2]);
+      }
+      for (int i = 0; i < nnod; ++i) {
+        if (minex[(size_t)i] < 0 || madof[(size_t)i + 1] < madof[(size_t)i] + 6) continue;
+        const int j0 = madof[(size_t)i] - 1 + 3;
+        put(u[j0]); put(u[j0 + 1]); put(u[j0 + 2]);
+      }
+    }
+    CHECK(fsr_frs_write_step(w, stepno[(size_t)idx], times[(size_t)idx], lDouble ? (const void*)rec_d.data() : (const void*)rec_f.data()));
+    log.line("           --> ......Simulation time : %12.5E  (step %d, %d modes expanded)", times[(size_t)idx], stepno[(size_t)idx], nMode);
+  }
+  log.line("           --> Done time loop. Closing database files");
+  { fsr_frs_writer* x = w; w = nullptr; CHECK(fsr_frs_finish(x)); }
+  if (nerr) { log.line("\n    %s failed :-(", what); return -nerr; }
+  log.line("           ================>  END OF PROGRAM MODES  <================");
+  log.line("\n    %s successfully completed :-)  (%.2f s CPU)", what, (double)(clock() - log.t0) / CLOCKS_PER_SEC);
+  return 0;
+}
+
 extern "C" {
 
-int solveStress(void) { return run_program(false); }
-int solveGage(void) { return run_program(true); }
+int solveStress(void) { return run_program(0); }
+int solveGage(void) { return run_program(1); }
+int solveModes(void) { return run_program(2); }
 
 }  // extern "C"

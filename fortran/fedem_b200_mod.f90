@@ -542,6 +542,16 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_frs_create
 
+     function fsr_frs_create_tagged (w, path, tag, checksum, header_text, payload_bytes) &
+          &                         bind(C,name="fsr_frs_create_tagged") result(ierr)
+       import :: c_ptr, c_char, c_int, c_long_long
+       type(c_ptr)           , intent(out) :: w
+       character(kind=c_char), intent(in)  :: path(*), tag(*), header_text(*)
+       integer(c_int)        , value       :: checksum
+       integer(c_long_long)  , value       :: payload_bytes
+       integer(c_int) :: ierr
+     end function fsr_frs_create_tagged
+
      function fsr_frs_write_step (w, stepno, time, payload) bind(C,name="fsr_frs_write_step") result(n)
        import :: c_ptr, c_int, c_double
        type(c_ptr)   , value :: w, payload
@@ -770,6 +780,14 @@ module fedem_b200_mod
        import :: c_int
        integer(c_int) :: ierr
      end function solveGage
+
+     subroutine fsr_modes_define_options () bind(C,name="fsr_modes_define_options")
+     end subroutine fsr_modes_define_options
+
+     function solveModes () bind(C,name="solveModes") result(ierr)
+       import :: c_int
+       integer(c_int) :: ierr
+     end function solveModes
 
      subroutine fsr_cmdline_add_bool (name, value) bind(C,name="fsr_cmdline_add_bool")
        import :: c_char, c_int

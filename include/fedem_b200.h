@@ -356,6 +356,9 @@ int fsr_frs_reduced_history(fsr_frs *db, int sup_base_id, int ntriads, const int
 typedef struct fsr_frs_writer fsr_frs_writer;
 int fsr_frs_create(fsr_frs_writer **w, const char *path, int checksum, const char *header_text,
                    long long payload_bytes);
+/* the same with another file tag (openRDBfile's 4th argument): "#FEDEM modal data" for the fedem_modes results */
+int fsr_frs_create_tagged(fsr_frs_writer **w, const char *path, const char *tag, int checksum, const char *header_text,
+                          long long payload_bytes);
 int fsr_frs_write_step(fsr_frs_writer *w, int stepno, double time, const void *payload); /* returns steps written */
 int fsr_frs_finish(fsr_frs_writer *w);
 
@@ -476,6 +479,14 @@ int solveStress(void);
  * -fatigue > 0: rainflow + damage report of sigmaP(1) and the gage legs in the -resfile (reportDamage).
  * bin/fedem_gage is main() over initSolverArgs + solveGage. */
 int solveGage(void);
+/* solveModes (src/vpmStress/stressInterface.C:125-130, modesmain.C:15-56) runs subroutine modes (src/vpmStress/modes.f90):
+ * for every time listed in -recover_modes <t1 m1 m2 ..> <t2 ..> the dynamic response and the listed eigenmodes of the
+ * solver's modal results ("Eigenvectors|Mode n" of the part's triads and of the part) are expanded to all nodes (K1) and
+ * written as vector data to one modal results file (writeModesHeader / writeDisplacementDB "Vectors" grammar, file tag
+ * "#FEDEM modal data"); -damped = complex modes (Re / Im).  One file per mode (different mode lists per time,
+ * -energy_density, -write_nodes) and VTF export are not part of this build. */
+int solveModes(void);
+void fsr_modes_define_options(void);   /* the option table of fedem_modes (modesmain.C:22-52) */
 /* ffr_getnextstep (fedem-foundation/src/FFrLib/FFrExtractorInterface.f90:134-170) over a sorted key list:
  * indices of the time steps the stress loop visits for -statm start -stotm stop -tinc tinc; returns their
  * number (out may be NULL) */

@@ -13,7 +13,7 @@ def _declared_symbols():
     txt = open(os.path.join(ROOT, "include", "fedem_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     # fsr_* entry points + the exported names kept from the reference (stressInterface.C, solverInterface.C)
-    return sorted(set(re.findall(r"\b(fsr_[a-z0-9_]+|initSolverArgs|solveStress|solveGage|(?:get|save)Part[A-Za-z]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(fsr_[a-z0-9_]+|initSolverArgs|solveStress|solveGage|solveModes|(?:get|save)Part[A-Za-z]+)\s*\(", txt)))
 
 
 def test_header_symbols_are_exported():

@@ -320,3 +320,100 @@ def test_fedem_gage_with_gravitation_modes(oracle, tmp_path):
     V0 = oracle.rosette_history(b0, ros[0], case["Q"])
     V1 = oracle.rosette_history(b, ros[0], Q)
     assert np.abs(V1[:, 10:13] - V0[:, 10:13]).max() > 100 * 1.3e-7 * np.abs(V0[:, 10:13]).max()      # far above the file's float rounding
+
+
+def _write_modal_file(path, rng, triads, part_base, ngen, steps, times, nmodes, ncomp):
+    """A solver modal results file in the grammar of the reference's own (FFrTests/.../eigval_0001/ev_p_3.frs): Eigenvalues under
+    the Mechanism, "Eigenvectors|Mode  n" item groups (translational + angular components, global directions) under every
+    Triad and the component-mode part under the Part."""
+    from fedem_solvers_b200.frs import FrsWriter
+    hdr = " Module                  = fedem_solver;\nVARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n"
+    hdr += "<3;\"Eigenvalue\";ANGLE/TIME;FLOAT;64;SCALAR>\n<4;\"Eigenfrequency\";NONE/TIME;FLOAT;32;SCALAR>\n<5;\"Damping ratio\";NONE;FLOAT;32;SCALAR>\n"
+    nd = 3 * ncomp
+    hdr += f"<6;\"Translational deformation\";LENGTH;FLOAT;64;VECTOR;({nd})>\n<7;\"Angular deformation\";ANGLE;FLOAT;64;VECTOR;({nd})>\n"
+    hdr += f"<8;\"Generalized deformation\";NONE;FLOAT;64;VECTOR;({ngen * ncomp})>\n"
+    hdr += "[1;\"Eigenvalues\";\n" + "".join(f"  [;\"Mode{m + 1:3d}\";<3><4><5>]\n" for m in range(nmodes)) + "]\n"
+    hdr += "[2;\"Eigenvectors\";\n" + "".join(f"  [;\"Mode{m + 1:3d}\";<6><7>]\n" for m in range(nmodes)) + "]\n"
+    hdr += "[3;\"Eigenvectors\";\n" + "".join(f"  [;\"Mode{m + 1:3d}\";<8>]\n" for m in range(nmodes)) + "]\n"
+    hdr += "DATABLOCKS:\n<1><2>\n{\"Mechanism\";2;1;\"\";[1]}\n"
+    for bid, uid, _ in triads:
+        hdr += f"{{\"Triad\";{bid};{uid};\"\";[2]}}\n"
+    hdr += f"{{\"Part\";{part_base};2;\"\";[3]}}\n"
+    nbytes = nmodes * (8 + 4 + 4) + len(triads) * nmodes * 2 * nd * 8 + nmodes * ngen * ncomp * 8
+    data = {}
+    with FrsWriter(path, hdr, nbytes) as w:
+        for st, tm in zip(steps, times):
+            rec = b""
+            for m in range(nmodes):
+                rec += np.array([10.0 + m]).tobytes() + np.array([1.6 + m, 0.02], np.float32).tobytes()
+            tri = rng.standard_normal((len(triads), nmodes, 6 * ncomp))      # eigVec(6*ncomp): component l at [6*l, 6*l+6)
+            for t in range(len(triads)):
+                for m in range(nmodes):
+                    v = tri[t, m].reshape(ncomp, 6)
+                    # the file stores the translational variable (3 x ncomp) and then the angular one: readSupElModes reads n*iComp
+                    # values from the group and takes component l at offset n*(l-1), so write them in exactly that order
+                    rec += np.ascontiguousarray(tri[t, m]).tobytes()
+            gen = rng.standard_normal((nmodes, ngen * ncomp))
+            rec += gen.tobytes()
+            w.write_step(int(st), float(tm), np.frombuffer(rec, np.uint8))
+            data[int(st)] = (tri, gen)
+    return data
+
+
+@pytest.mark.parametrize("damped", [False, True])
+def test_fedem_modes_executable(oracle, tmp_path, damped):
+    """bin/fedem_modes: the dynamic response and two eigenmodes at two of the solver's time steps, expanded on the GPU and written as
+    vector data; read back and compared with the oracle's calcIntDisplacements of BuildFinit / readSupElModes columns."""
+    part = plate_part(5, 4, ngen=3, seed=51, tri_fraction=0.3, warp=0.02, n_ext=4)
+    nsteps = 12
+    case = _make_case(tmp_path, part, "plate", nsteps=nsteps)
+    sam = part.sam
+    ntriads, ngen, ncomp, nmodes = sam.ndof2 // 6, sam.ngen, 2 if damped else 1, 3
+    rng = np.random.default_rng(52)
+    triads = [(11 + i, 1 + i, "") for i in range(ntriads)]          # the ids _write_solver_file gives the triads
+    steps = [3, 8]
+    modal = _write_modal_file(str(tmp_path / "ev_p_1.frs"), rng, triads, case["base"], ngen, [case["stepno"][k] for k in steps],
+                              [case["times"][k] for k in steps], nmodes, ncomp)
+    exe = os.path.join(os.path.dirname(EXE), "fedem_modes")
+    sel = f"<<{case['times'][3]:.4f},1,3>,<{case['times'][8]:.4f},1,3>>"
+    args = [exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx", "-eigfile",
+            "plate_E.fmx", "-fsifile", "fedem_solver.fsi", "-frsfile", "<th_p_1.frs,ev_p_1.frs>", "-rdbfile", "modes.frs", "-double",
+            "-recover_modes", sel] + (["-damped"] if damped else [])
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Modal recovery successfully completed" in r.stdout
+    out = str(tmp_path / "modes_1.frs")
+    assert open(out, "rb").read(17) == b"#FEDEM modal data"
+    rd = FrsReader(out)
+    assert rd.nsteps == 2 and np.array_equal(rd.step_numbers, [case["stepno"][k] for k in steps])
+    b = oracle.bind_part(part)
+    nnod = sam.nnod
+    six = np.array([sam.madof[i + 1] - sam.madof[i] >= 6 for i in range(nnod)])
+
+    def vectors(sv):
+        tra = np.concatenate([sv[sam.madof[i] - 1: sam.madof[i] + 2] for i in range(nnod)])
+        rot = np.concatenate([sv[sam.madof[i] + 2: sam.madof[i] + 5] for i in range(nnod) if six[i]])
+        return tra, rot
+    for row, k in enumerate(steps):
+        tra, rot = vectors(oracle.expand(b, case["Q"][:, k]))
+        got = rd.read(rd.find("Vectors|Dynamic response|Translational deformation", "Part", case["base"]))[row]
+        assert got.shape == tra.shape and np.abs(got - tra).max() <= TOL * np.abs(tra).max()
+        got = rd.read(rd.find("Vectors|Dynamic response|Angular deformation", "Part", case["base"]))[row]
+        assert np.abs(got - rot).max() <= TOL * np.abs(rot).max()
+        tri, gen = modal[int(case["stepno"][k])]
+        tinv = case["sup"][k][:, :3].T
+        for m in (1, 3):
+            for l in range(ncomp):
+                q = np.zeros(sam.ndim)
+                for t in range(ntriads):
+                    e = tri[t, m - 1][6 * l: 6 * l + 6]
+                    q[6 * t: 6 * t + 3] = tinv @ e[:3]
+                    q[6 * t + 3: 6 * t + 6] = tinv @ e[3:]
+                q[sam.ndof2:] = gen[m - 1][ngen * l: ngen * (l + 1)]
+                tra, rot = vectors(oracle.expand(b, q))
+                sub = ("Re|" if l == 0 else "Im|") if damped else ""
+                got = rd.read(rd.find(f"Vectors|Mode{m:3d}|{sub}Translational deformation", "Part", case["base"]))[row]
+                assert np.abs(got - tra).max() <= TOL * np.abs(tra).max(), (k, m, l)
+                got = rd.read(rd.find(f"Vectors|Mode{m:3d}|{sub}Angular deformation", "Part", case["base"]))[row]
+                assert np.abs(got - rot).max() <= TOL * np.abs(rot).max(), (k, m, l)
+    assert rd.find("Vectors|Mode  2|Translational deformation", "Part", case["base"]) is None
