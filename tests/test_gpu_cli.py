@@ -417,3 +417,14 @@ def test_fedem_modes_executable(oracle, tmp_path, damped):
                 got = rd.read(rd.find(f"Vectors|Mode{m:3d}|{sub}Angular deformation", "Part", case["base"]))[row]
                 assert np.abs(got - rot).max() <= TOL * np.abs(rot).max(), (k, m, l)
     assert rd.find("Vectors|Mode  2|Translational deformation", "Part", case["base"]) is None
+    # the reference's own FFrExtractor finds the same arrays in the file (header grammar of writeModesHeader / writeNodesHeader)
+    from test_frs_cpu import RefFrs, REF_LIB
+    if os.path.exists(REF_LIB):
+        ref = RefFrs([out])
+        keys = ref.keys()
+        assert len(keys) == 2
+        for name in ("Vectors|Dynamic response|Angular deformation", f"Vectors|Mode  3|{'Im|' if damped else ''}Translational deformation"):
+            mine = rd.read(rd.find(name, "Part", case["base"]))
+            ok, theirs = ref.read(name, "Part", case["base"], keys, mine.shape[1])
+            assert ok == 2 and np.array_equal(theirs, mine), name
+        ref.close()
