@@ -307,3 +307,16 @@ def test_gage_executable_options_and_loud_failures(tmp_path):
     r = subprocess.run([exe, "-cwd", str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "FE data file must be specified through -linkfile" in r.stdout and "Strain gage recovery failed" in r.stdout
     assert os.path.exists(tmp_path / "fedem_gage.res")
+
+
+def test_modes_executable_options_and_loud_failures(tmp_path):
+    exe = os.path.join(os.path.dirname(EXE), "fedem_modes")
+    assert os.path.exists(exe), "build.sh did not produce bin/fedem_modes"
+    r = subprocess.run([exe, "-help"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0
+    for opt in ("-recover_modes", "-damped", "-energy_density", "-write_vector", "-write_nodes", "-linkfile", "-frsfile", "-rdbfile", "-double"):
+        assert opt + " " in r.stdout, opt
+    assert "-vmStress" not in r.stdout and "-rosfile" not in r.stdout
+    r = subprocess.run([exe, "-cwd", str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "FE data file must be specified through -linkfile" in r.stdout and "Modal recovery failed" in r.stdout
+    assert os.path.exists(tmp_path / "fedem_modes.res")
