@@ -9,13 +9,15 @@
  * Every function follows, statement by statement, the reference routine cited above it
  * (paths relative to the SAP-archive/fedem-solvers checkout).  The reference's Fortran cannot
  * be compiled in this image (no Fortran compiler), so this restatement is pinned by
- *   (1) the reference's own known-answer tests re-expressed in tests/ (testBmatrix.pf mat-vec),
+ *   (1) the reference's own known-answer tests re-expressed in tests/ (testBmatrix.pf mat-vec; the eight ElStress cases of
+ *       vpmStressTests/testThickShell.pf for the thick shells 31 / 32, passed at the reference's tolerance 1e-15),
  *   (2) the reference's own C++ (tensor invariants, cubicSolve, PVX / rainflow / S-N damage)
  *       compiled unmodified from /root/reference into oracle/_ref/ and compared bit-for-bit,
  *   (3) physics patch tests (rigid-body -> zero stress, uniform stretch, pure bending).
- * For the element types in the configs (11, 23, 24, 41) the reference holds NO unit-level
+ * For the element types in the configs (11, 23, 24, 41) and the other solids the reference holds NO unit-level
  * golden vector: parity for those is "unpinned by reference goldens" and
- * rests on this statement-level restatement.
+ * rests on this statement-level restatement; the thick shells (31, 32), the tensor invariants and the
+ * whole fatigue chain ARE pinned to the reference itself.
  *
  * Conventions: all index arrays are 1-based exactly as stored in the reference's .fsm file
  * (madof, mpmnpc, mmnpc, meqn, ...); matrices are Fortran column-major unless noted.
