@@ -141,13 +141,20 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam_in, const fsr_elmdata* el
   // The other (private, non-default) formulations are not built: elements of such a run get NO results, like any
   // unsupported type, and fedem_stress says so (stress_driver.cu).
   const int ffq = opt && opt->reserved[1] ? opt->reserved[1] - 1 : 2, fft = opt && opt->reserved[2] ? opt->reserved[2] - 1 : 1;
+  // -ffqStressForm 1 is STR22a with one Gauss point (:761-768,806-809): the quad operator builder takes the point count, so it
+  // is served as well as long as the part has no ANDES quads (which always use 2 x 2) next to the FFQ ones.
   std::vector<int> melcon_eff;
   fsr_sam sam_eff = *sam_in;
+  int quad_ngauss = 2;
   if (sam_in->melcon && sam_in->nel > 0) {
     melcon_eff.assign(sam_in->melcon, sam_in->melcon + sam_in->nel);
+    bool has24 = false, has22 = false;
+    for (int t : melcon_eff) { has24 |= t == 24; has22 |= t == 22; }
+    const bool ffq1 = ffq == 1 && has22 && !has24;
+    if (ffq1) quad_ngauss = 1;
     for (int& t : melcon_eff) {
       if (t == 21) t = fft == 1 ? 23 : 0;
-      else if (t == 22) t = ffq == 2 ? 24 : 0;
+      else if (t == 22) t = (ffq == 2 || ffq1) ? 24 : 0;
     }
     sam_eff.melcon = melcon_eff.data();
   }
@@ -182,6 +189,7 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam_in, const fsr_elmdata* el
   p->ndof2 = sam->ndof2; p->ngen = sam->ngen; p->neq = sam->neq; p->nceq = sam->nceq;
   p->ndim = sam->ndof2 + sam->ngen;
   p->stressForm = opt ? opt->stressForm : 0;
+  p->quad_ngauss = quad_ngauss;
   p->elem_order = opt ? opt->reserved[0] : 0;
   // ldk: multiple of 4 with ldk % 8 == 4 (bank-conflict-free fragment loads in K1)
   p->ldk = round_up(std::max(p->ndim, 1), 4);

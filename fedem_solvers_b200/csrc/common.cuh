@@ -127,6 +127,7 @@ struct fsr_part {
   int nrows_pad = 0;   // ndof padded to the K1 row tile
   int npts = 0;        // result points
   int stressForm = 0;
+  int quad_ngauss = 2;  // Gauss points per direction of the quad shell stress evaluation (1 only for legacy FFQ with -ffqStressForm 1)
   int elem_order = 0;  // 0 = elements processed in Morton order of their centroids (L2 reuse of shared
                        // nodes), 1 = SAM order.  Outputs are always in SAM order.
   int step_tile = 0;   // steps per device batch

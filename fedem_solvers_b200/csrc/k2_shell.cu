@@ -91,7 +91,7 @@ __global__ void build_quad_ops_kernel(int nelt, const int* __restrict__ elem,
                                       const double* __restrict__ xyz,
                                       const double* __restrict__ emod, const double* __restrict__ rny,
                                       const double* __restrict__ thk, double* __restrict__ Sfrag,
-                                      unsigned char* __restrict__ failed, double* __restrict__ aux)
+                                      unsigned char* __restrict__ failed, double* __restrict__ aux, int ngauss)
 {
   const int KT = 6;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,7 +172,8 @@ __global__ void build_quad_ops_kernel(int nelt, const int* __restrict__ elem,
     yl[k] = vdot(ey, d);
   }
   xl[0] = 0.0; yl[0] = 0.0;
-  const double gq = 1.0 / sqrt(3.0);
+  // ngauss = 1 (-ffqStressForm 1 of the legacy FFQ shell): STR22a evaluates at the centroid only and copies it to every node
+  const double gq = ngauss == 1 ? 0.0 : 1.0 / sqrt(3.0);
   double sx[4][4], sy[4][4];
   for (int gp = 0; gp < 4; ++gp) {
     double xi = (gp >> 1) ? gq : -gq, eta = (gp & 1) ? gq : -gq;
@@ -191,7 +192,7 @@ __global__ void build_quad_ops_kernel(int nelt, const int* __restrict__ elem,
     }
   }
   const double hh = (t + t + t + t) / 8.0;  // half thickness, sum(THK)/(2*nenod)
-  const double f1 = 0.5 + 0.5 * sqrt(3.0), f2 = 0.5 - 0.5 * sqrt(3.0);
+  const double f1 = ngauss == 1 ? 1.0 : 0.5 + 0.5 * sqrt(3.0), f2 = ngauss == 1 ? 0.0 : 0.5 - 0.5 * sqrt(3.0);
   // Gauss point closest to / farthest from node n: (iClose,jClose),(iFar,jFar) of STR22a
   const int gclose[4] = {0, 2, 3, 1}, gfar[4] = {3, 1, 0, 2};
 
@@ -800,7 +801,7 @@ int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
     if (rc) return rc;
     if (f.nelt > 0) {
       build_quad_ops_kernel<<<(f.nelt + 63) / 64, 64, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod,
-                                                            p->rny, p->thk, f.Sfrag, f.failed, f.aux);
+                                                            p->rny, p->thk, f.Sfrag, f.failed, f.aux, p->quad_ngauss);
       FSR_LAUNCH_CHECK();
       FSR_CUDA(cudaStreamSynchronize(s));
       cudaFree(d_conn);

@@ -404,10 +404,10 @@ static int run_program(int which)
     int nq = 0, nt = 0;
     for (int e = 0; e < nel; ++e) {
       if (elmid[(size_t)e] < 1) continue;
-      if (melcon[(size_t)e] == 22 && ffq != 2) ++nq;
+      if (melcon[(size_t)e] == 22 && ffq != 2 && ffq != 1) ++nq;
       if (melcon[(size_t)e] == 21 && fft != 1) ++nt;
     }
-    if (nq) log.line("  ** Warning: %d FFQ shells (type 22) get NO results: -ffqStressForm %d is not supported by this build (only the default, 2)", nq, ffq);
+    if (nq) log.line("  ** Warning: %d FFQ shells (type 22) get NO results: -ffqStressForm %d is not supported by this build (only 1 and the default, 2)", nq, ffq);
     if (nt) log.line("  ** Warning: %d FFT shells (type 21) get NO results: -fftStressForm %d is not supported by this build (only the default, 1)", nt, fft);
   }
 

@@ -78,9 +78,9 @@ typedef struct fsr_options {
                      L2 reuse of shared nodes), 1 = SAM order; results are in SAM order either way
                      [1]: -ffqStressForm + 1 (legacy FFQ4 shells, type 22), 0 = the default formulation 2
                      [2]: -fftStressForm + 1 (legacy FFT3 shells, type 21), 0 = the default formulation 1
-                     Types 21 / 22 are recovered for the default formulations only (then STR21 = STR23 and
-                     STR22 = STR24 statement by statement, elStressModule.f90:521-733); with another value
-                     those elements get no results */
+                     Type 21 is recovered for the default formulation (STR21 = STR23 statement by statement), type 22
+                     for formulations 2 (STR22 = STR24) and 1 (one Gauss point; parts without ANDES quads),
+                     elStressModule.f90:521-733; with another value those elements get no results */
 } fsr_options;
 
 /* Output selection bits = the -vmStress ... switches of stressmain.C:46-60 */

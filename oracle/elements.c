@@ -83,7 +83,13 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     ierr = orc_str23(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, S, SS, Sigma,
                      Epsil);
     break;
-  case 22: /* FFQ4 with the default -ffqStressForm 2: STR22 = pMatStiff + STR22a(2), the statements of STR24 (:675-686,717-722) */
+  case 22: /* FFQ4: STR22 = pMatStiff + STR22a(nGauss) for -ffqStressForm 1 / 2 (:675-686,717-722); 2 = the statements of STR24 */
+    *nenod = 4;
+    *nstrp = 8;
+    get_coor(iel, sam, ed, 4, x, y, z);
+    thk[0] = thk[1] = thk[2] = thk[3] = ed->thk[iel - 1];
+    ierr = orc_str22(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, S, SS, Sigma, Epsil);
+    break;
   case 24:
     *nenod = 4;
     *nstrp = 8;

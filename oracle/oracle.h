@@ -87,6 +87,12 @@ void orc_strain_disp_cst(int nndof, const double *xEl, const double *yEl, const 
 int orc_str24(const double xg[4], const double yg[4], const double zg[4], double emod,
               double rny, const double thk[4], double ev[24], double SR[24], double SS[24],
               double sigma[24], double epsil[24]);
+/* legacy FFQ shell (type 22) with -ffqStressForm 1 (1x1 Gauss point) or 2 (2x2, default); the form is a process-wide option
+ * like the reference's command-line argument */
+void orc_set_ffq_stress_form(int form);
+int orc_get_ffq_stress_form(void);
+int orc_str22(const double xg[4], const double yg[4], const double zg[4], double emod, double rny, const double thk[4],
+              double ev[24], double SR[24], double SS[24], double sigma[24], double epsil[24]);
 int orc_str23(const double xg[3], const double yg[3], const double zg[3], double emod,
               double rny, const double thk[3], const double ev[18], double SR[18],
               double SS[18], double sigma[18], double epsil[18]);

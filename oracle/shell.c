@@ -321,9 +321,13 @@ static void tra_strain(double eps[3], const double T_str[4])
   eps[2] = 2.0 * eps[2];
 }
 
-/* elStressModule.f90:738-849, nGauss = 2 only (the STR24 call).  Outputs column-major:
- * SR(6,4), SS(6,4), sigma(3,8), epsil(3,8). */
-static void str22a(const double *XG, const double *YG, const double *ZG, const double *THK,
+/* -ffqStressForm of the legacy FFQ shell (type 22): 2 = 2x2 Gauss points (default, what STR24 always uses), 1 = 1x1 */
+static int g_ffq_stress_form = 2;
+void orc_set_ffq_stress_form(int form) { g_ffq_stress_form = form; }
+int orc_get_ffq_stress_form(void) { return g_ffq_stress_form; }
+
+/* elStressModule.f90:738-849 (STR22a).  Outputs column-major: SR(6,4), SS(6,4), sigma(3,8), epsil(3,8). */
+static void str22a(int nGauss, const double *XG, const double *YG, const double *ZG, const double *THK,
                    const double Cmat[9], const double T_el[9], const double T_str[4],
                    const double *EV, double *SR, double *SS, double *sigma, double *epsil)
 {
@@ -335,10 +339,14 @@ static void str22a(const double *XG, const double *YG, const double *ZG, const d
   double gauss[2], hHalf, vld[nedof], B_L[3 * nedof], B_U[3 * nedof];
   double epsGU[2][2][3], epsGL[2][2][3], epsU[3], epsL[3], sigU[3], sigL[3];
   int i, j, n;
-  const int nGauss = 2;
 
-  gauss[0] = -1.0 / sqrt3;
-  gauss[1] = 1.0 / sqrt3;
+  if (nGauss == 1) {
+    gauss[0] = 0.0;
+    gauss[1] = 1.0;
+  } else {
+    gauss[0] = -1.0 / sqrt3;
+    gauss[1] = 1.0 / sqrt3;
+  }
 
   hHalf = (THK[0] + THK[1] + THK[2] + THK[3]) / (double)(2 * nenod);
   for (i = 1; i <= nGauss; i++)
@@ -368,8 +376,13 @@ static void str22a(const double *XG, const double *YG, const double *ZG, const d
   for (n = 1; n <= nenod; n++) {
     int i1 = iClose[n - 1], j1 = jClose[n - 1], i2 = iFar[n - 1], j2 = jFar[n - 1];
     for (int c = 0; c < 3; c++) {
-      epsU[c] = f1 * epsGU[i1 - 1][j1 - 1][c] + f2 * epsGU[i2 - 1][j2 - 1][c];
-      epsL[c] = f1 * epsGL[i1 - 1][j1 - 1][c] + f2 * epsGL[i2 - 1][j2 - 1][c];
+      if (nGauss == 1) {
+        epsU[c] = epsGU[0][0][c];
+        epsL[c] = epsGL[0][0][c];
+      } else {
+        epsU[c] = f1 * epsGU[i1 - 1][j1 - 1][c] + f2 * epsGU[i2 - 1][j2 - 1][c];
+        epsL[c] = f1 * epsGL[i1 - 1][j1 - 1][c] + f2 * epsGL[i2 - 1][j2 - 1][c];
+      }
     }
     for (int c = 0; c < 3; c++) {
       epsil[c + 3 * (n - 1)] = epsU[c];
@@ -392,9 +405,9 @@ static void str22a(const double *XG, const double *YG, const double *ZG, const d
 
 /* elStressModule.f90:1005-1078 (EF branch not taken: fedem_stress passes no nodal forces
  * unless -nodalForces).  EV is overwritten by its projection like the reference. */
-int orc_str24(const double xg[4], const double yg[4], const double zg[4], double emod,
-              double rny, const double thk[4], double ev[24], double SR[24], double SS[24],
-              double sigma[24], double epsil[24])
+static int str24_worker(int nGauss, const double xg[4], const double yg[4], const double zg[4], double emod,
+                        double rny, const double thk[4], double ev[24], double SR[24], double SS[24],
+                        double sigma[24], double epsil[24])
 {
   double Cmat[9], T_el[9], T_str[4], PMAT[24 * 24], tmp[24], V1[3], V2[3], V3[3];
   int ierr;
@@ -419,6 +432,22 @@ int orc_str24(const double xg[4], const double yg[4], const double zg[4], double
   ierr = orc_shell_stress_trans(V1, V3, T_str);
   if (ierr != 0) return ierr;
 
-  str22a(xg, yg, zg, thk, Cmat, T_el, T_str, ev, SR, SS, sigma, epsil);
+  str22a(nGauss, xg, yg, zg, thk, Cmat, T_el, T_str, ev, SR, SS, sigma, epsil);
   return 0;
+}
+
+int orc_str24(const double xg[4], const double yg[4], const double zg[4], double emod,
+              double rny, const double thk[4], double ev[24], double SR[24], double SS[24],
+              double sigma[24], double epsil[24])
+{
+  return str24_worker(2, xg, yg, zg, emod, rny, thk, ev, SR, SS, sigma, epsil);
+}
+
+/* STR22 (elStressModule.f90:640-733) for -ffqStressForm 1 or 2: the same projection (lStiffProj = .true.) and STR22a with 1x1 or
+ * 2x2 Gauss points; -ffqStressForm 0 (STR22b, Femlib nodal evaluation) is not restated: returns -99. */
+int orc_str22(const double xg[4], const double yg[4], const double zg[4], double emod, double rny, const double thk[4],
+              double ev[24], double SR[24], double SS[24], double sigma[24], double epsil[24])
+{
+  if (g_ffq_stress_form != 1 && g_ffq_stress_form != 2) return -99;
+  return str24_worker(g_ffq_stress_form, xg, yg, zg, emod, rny, thk, ev, SR, SS, sigma, epsil);
 }

@@ -365,9 +365,28 @@ def test_legacy_shells_default_formulations(oracle):
     assert set(np.unique(legacy.sam.melcon)) == {21, 22}
     vm = _check_part(oracle, legacy, nsteps=20, seed=8)
     assert np.array_equal(vm, ref_vm)
-    rec = StressRecovery(legacy, ffq_stress_form=1)      # FFQ quads drop out, the FFT triangles stay
+    rec = StressRecovery(legacy, ffq_stress_form=0)      # FFQ quads drop out (STR22b is not built), the FFT triangles stay
     assert rec.npts == 6 * int((legacy.sam.melcon == 21).sum())
     rec.close()
+    # -ffqStressForm 1: STR22a with one Gauss point, the centroid strain at every node
+    oracle.lib.orc_set_ffq_stress_form(1)
+    try:
+        b = oracle.bind_part(legacy)
+        Q = reduced_history(legacy.sam.ndim, 9, seed=9)
+        vm_o, mx_o, mn_o = oracle.recover_history(b, Q)
+        rec = StressRecovery(legacy, ffq_stress_form=1)
+        vm_g = rec.recover(Q)
+        assert rel_err(vm_g, vm_o) <= TOL
+        rec2 = StressRecovery(legacy)
+        assert rel_err(vm_g, rec2.recover(Q)) > 1e-3         # and it is a different formulation than the 2 x 2 one
+        rec2.close()
+        full = rec.calc_stresses(Q[:, 2])
+        ref = oracle.calc_stresses(b, oracle.expand(b, Q[:, 2]))
+        for key in ("stress", "strain", "sres"):
+            assert rel_err(full[key], ref[key]) <= TOL, key
+        rec.close()
+    finally:
+        oracle.lib.orc_set_ffq_stress_form(2)
 
 
 def test_edge_sizes(oracle):
