@@ -141,6 +141,7 @@ SYMBOLS = [
     ("fsr_rdb_path", C.c_int, [_P, C.c_char_p, C.c_int]),
     ("fsr_rdb_write_steps", C.c_int, [_P, _D, C.c_int, C.c_int, _I, _D, _D]),
     ("fsr_total_nodal_displacement", None, [_D, _D, C.c_int, _D, _D, _D]),
+    ("fsr_rdb_flush", C.c_int, [_P, _D, C.c_int]),
     ("fsr_rdb_close", C.c_int, [_P]),
     ("initSolverArgs", None, [C.c_int, C.POINTER(C.c_char_p)]),
     ("solveStress", C.c_int, []),

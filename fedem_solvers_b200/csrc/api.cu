@@ -3,6 +3,9 @@
 // kernels with fused envelope) per tile of steps.
 #include <cstdarg>
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -17,6 +20,19 @@ void set_error(const char* fmt, ...)
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int smem_opt_in(const void* kernel, size_t bytes)
+{
+  static std::mutex mtx;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  FSR_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mtx);
+  if (done.count({dev, kernel})) return FSR_OK;
+  FSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.insert({dev, kernel});
+  return FSR_OK;
 }
 
 static int nstrp_of(int type)

@@ -13,6 +13,9 @@ namespace fsr {
 
 void set_error(const char* fmt, ...);
 extern long long g_launches;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (primary context) attribute: set it once per
+// (current device, kernel), thread-safe (api.cu).  Returns FSR_OK or FSR_ERR_CUDA with the error text set.
+int smem_opt_in(const void* kernel, size_t bytes);
 
 #define FSR_CUDA(call)                                                              \
   do {                                                                              \

@@ -14,9 +14,17 @@
 // tiled transpose turns that into step-major float/double records, and the host only adds the 12-byte
 // step key (int32 step number + float64 time, writeTimeStepDB rdbModule.f90:669-736) in front of each.
 #include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
+#include <cstdlib>
 #include <ctime>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <sys/uio.h>
+#include <thread>
 #include <unistd.h>
 #include <vector>
 
@@ -40,100 +48,148 @@ __device__ __forceinline__ size_t frag_at2(int row, int col, int KT)
   return ((size_t)((row >> 3) * KT + (col >> 2)) << 5) + ((row & 7) << 2) + (col & 3);
 }
 
-// One thread per (result point, step); step is the fastest index so that the U reads of a warp are one
-// contiguous segment per DOF row and the record writes one contiguous segment per slot.
-// rec[slot * ldt + t].  layout: 0 = thin shells (operator row = comp*8 + point), 1 = solids (row = point*ncmp + comp),
+// The record kernel of every element family with stress points: one warp per element, a tile of 8 time steps at a time.
+//   (1) sigma rows (thick shells: also the strain rows of Efrag) = S_e . v_e with DMMA.8x8x4; the operator fragments are
+//       streamed from L1/L2 (one coalesced 256-byte load per fragment, the same bytes for all step tiles of the element),
+//       the element's DOF rows of U[dof][t] are read as 64-byte segments like in the von Mises kernels;
+//   (2) the accumulators go to shared memory as [row][step];
+//   (3) the lanes take (step, point) pairs with the point running fastest, form the strain tensor, von Mises, the principal
+//       values (FFa::cubicSolve branches, invariants.cuh) and max shear of whatever is selected, and store the values straight
+//       at their place in the STEP-MAJOR float/double record -- no slot-major staging, no transpose, and a store instruction
+//       of the warp covers contiguous bytes of one step record.
+// layout: 0 = thin shells (operator row = comp*8 + point), 1 = solids (row = point*ncmp + comp),
 // 2 = thick shells (rows as solids, strain from its own operator Efrag, zero stress resultants)
-__global__ void record_points_kernel(const double* __restrict__ U, size_t ldu, int nt, const double* __restrict__ Sfrag,
-                                     const int* __restrict__ edof, const long long* __restrict__ roff,
-                                     const unsigned char* __restrict__ failed, const double* __restrict__ aux, int naux,
-                                     const double* __restrict__ Efrag, int nelt, int nstrp, int ncmp, int nedof, int MT, int KT,
-                                     int layout, int nenod, RecLayout L, double* __restrict__ rec, size_t ldt)
+constexpr int kRecWarps = 4;
+constexpr int kRecLds = 9;   // shared-memory row stride in doubles (8 steps + 1: spreads the rows over the banks)
+
+template <class OUT_T>
+__global__ void __launch_bounds__(kRecWarps * 32)
+record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, const double* __restrict__ Sfrag,
+                          const double* __restrict__ Efrag, const int* __restrict__ edof, const long long* __restrict__ roff,
+                          const unsigned char* __restrict__ failed, const double* __restrict__ aux, int naux, int nelt, int nstrp,
+                          int ncmp, int MT, int KT, int layout, int nenod, RecLayout L, OUT_T* __restrict__ out, size_t ld_out)
 {
-  const int t = blockIdx.y * blockDim.x + threadIdx.x;
-  const long long ip = (long long)blockIdx.x * blockDim.y + threadIdx.y;
-  if (t >= nt || ip >= (long long)nelt * nstrp) return;
-  const int i = (int)(ip / nstrp), pnt = (int)(ip % nstrp);
+  extern __shared__ double rec_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int i = blockIdx.x * kRecWarps + warp;
+  if (i >= nelt) return;   // whole warp
   const long long base = roff[i];
   if (base < 0) return;
+  const int nrow = MT * 8;
+  double* sig_s = rec_smem + (size_t)warp * (layout == 2 ? 2 : 1) * nrow * kRecLds;
+  double* eps_s = sig_s + (size_t)nrow * kRecLds;   // thick shells only
   const int srsize = L.sr && layout != 1 ? 6 * nenod : 0;
   const int ptsize = (L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel;
-  double* out = rec + (size_t)(base + srsize + (long long)pnt * ptsize) * ldt + t;
-  double* srout = rec + (size_t)(base + 6 * pnt) * ldt + t;
-  if (failed[i]) {   // stressRoutines.f90:237-241,264-268: hugeVal for everything that is written
-    for (int k = 0; k < ptsize; ++k) out[(size_t)k * ldt] = kHuge;
-    if (srsize && pnt < nenod) for (int k = 0; k < 6; ++k) srout[(size_t)k * ldt] = kHuge;
-    return;
-  }
-  const double* S = Sfrag + (size_t)i * MT * KT * 32;
-  const int* ed = edof + (size_t)i * KT * 4;
-  double sig[6] = {0, 0, 0, 0, 0, 0}, eps[6] = {0, 0, 0, 0, 0, 0};
-  for (int c = 0; c < ncmp; ++c) {
-    const int row = layout == 0 ? c * 8 + pnt : pnt * ncmp + c;
-    double s = 0.0;
-    for (int col = 0; col < nedof; ++col) s += S[frag_at2(row, col, KT)] * U[(size_t)ed[col] * ldu + t];
-    sig[c] = s;
-  }
+  const bool bad = failed[i] != 0;
+  const double* S = Sfrag + (size_t)i * MT * KT * 32 + lane;
+  const double* Es = layout == 2 ? Efrag + (size_t)i * MT * KT * 32 + lane : nullptr;
   const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
-  if (layout == 2) {
-    const double* Es = Efrag + (size_t)i * MT * KT * 32;
-    for (int c = 0; c < ncmp; ++c) {
-      double s = 0.0;
-      for (int col = 0; col < nedof; ++col) s += Es[frag_at2(pnt * ncmp + c, col, KT)] * U[(size_t)ed[col] * ldu + t];
-      eps[c] = s;
+  const double th = layout == 0 ? aux[(size_t)i * naux + 2] : 0.0;
+  // B operand rows of this lane: element DOF 4*k + t4 (padding columns point at row 0, their operator entries are zero)
+  const double* up[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) up[k] = U + (k < KT ? (size_t)__ldg(edof + (size_t)i * KT * 4 + k * 4 + t4) * ldu : 0) + g;
+  const int npair = 8 * nstrp;
+
+  for (int t0 = 0; t0 < nt; t0 += 8) {
+    if (!bad) {
+      double b[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) b[k] = k < KT ? up[k][t0] : 0.0;   // U rows carry slack up to the padded tile
+      for (int m0 = 0; m0 < MT; m0 += 3) {   // three independent accumulator chains in flight
+        double c[3][2] = {{0, 0}, {0, 0}, {0, 0}}, d[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (k < KT) {
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm)
+              if (m0 + mm < MT) {
+                dmma884(c[mm][0], c[mm][1], __ldg(S + (size_t)((m0 + mm) * KT + k) * 32), b[k]);
+                if (Es) dmma884(d[mm][0], d[mm][1], __ldg(Es + (size_t)((m0 + mm) * KT + k) * 32), b[k]);
+              }
+          }
+        }
+#pragma unroll
+        for (int mm = 0; mm < 3; ++mm)
+          if (m0 + mm < MT) {
+            double* q = sig_s + ((m0 + mm) * 8 + g) * kRecLds + 2 * t4;
+            q[0] = c[mm][0]; q[1] = c[mm][1];
+            if (Es) { q += (size_t)nrow * kRecLds; q[0] = d[mm][0]; q[1] = d[mm][1]; }
+          }
+      }
     }
-  } else if (ncmp == 3) {
-    eps[0] = sig[0] / E - nu / E * sig[1];
-    eps[1] = -nu / E * sig[0] + sig[1] / E;
-    eps[2] = 0.5 * (2.0 * (1.0 + nu) / E * sig[2]);
-  } else {
-    eps[0] = (sig[0] - nu * (sig[1] + sig[2])) / E;
-    eps[1] = (sig[1] - nu * (sig[0] + sig[2])) / E;
-    eps[2] = (sig[2] - nu * (sig[0] + sig[1])) / E;
-    const double g2 = 2.0 * (1.0 + nu) / E;
-    eps[3] = 0.5 * g2 * sig[3]; eps[4] = 0.5 * g2 * sig[4]; eps[5] = 0.5 * g2 * sig[5];
-  }
-  int k = 0;
-  if (L.stress) for (int c = 0; c < ncmp; ++c) out[(size_t)(k++) * ldt] = sig[c];
-  if (L.strain) for (int c = 0; c < ncmp; ++c) out[(size_t)(k++) * ldt] = eps[c];
-  if (L.nsel) {
-    const int np = ncmp == 3 ? 2 : 3;
-    double r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, P[3] = {0, 0, 0};
-    if (L.mask & 0x01) r[0] = von_mises(ncmp, sig);
-    if (L.mask & 0x0e) { principal_values(ncmp, sig, P); r[1] = P[0]; r[2] = P[np - 1]; r[3] = 0.5 * (P[0] - P[np - 1]); }
-    if (L.mask & 0x10) r[4] = von_mises(ncmp, eps);
-    if (L.mask & 0xe0) { P[0] = P[1] = P[2] = 0.0; principal_values(ncmp, eps, P); r[5] = P[0]; r[6] = P[np - 1]; r[7] = 0.5 * (P[0] - P[np - 1]); }
-    for (int j = 0; j < 8; ++j) if (L.mask & (1 << j)) out[(size_t)(k++) * ldt] = r[j];
-  }
-  if (srsize && pnt < nenod && layout == 2)   // thick shells: SR = 0 (STR31 / STR32, elStressModule.f90:1174-1176, 1296-1298)
-    for (int k = 0; k < 6; ++k) srout[(size_t)k * ldt] = 0.0;
-  if (srsize && pnt < nenod && layout == 0) {   // shell stress resultants from the top and bottom stresses (k2_full.cu)
-    const double th = aux[(size_t)i * naux + 2];
-    for (int c = 0; c < 3; ++c) {
-      const int row = c * 8 + nenod + pnt;
-      double s = 0.0;
-      for (int col = 0; col < nedof; ++col) s += S[frag_at2(row, col, KT)] * U[(size_t)ed[col] * ldu + t];
-      srout[(size_t)c * ldt] = (sig[c] + s) * 0.5 * th;
-      srout[(size_t)(3 + c) * ldt] = (sig[c] - s) * 0.5 * th * th / 6.0;
+    __syncwarp();
+    for (int idx = lane; idx < npair; idx += 32) {
+      const int st = idx / nstrp, pnt = idx - st * nstrp;
+      const int t = t0 + st;
+      if (t >= nt) continue;
+      OUT_T* o = out + (size_t)t * ld_out + base + srsize + (long long)pnt * ptsize;
+      OUT_T* so = out + (size_t)t * ld_out + base + 6 * pnt;
+      if (bad) {   // stressRoutines.f90:237-241,264-268: hugeVal for everything that is written
+        for (int k = 0; k < ptsize; ++k) o[k] = (OUT_T)kHuge;
+        if (srsize && pnt < nenod) for (int k = 0; k < 6; ++k) so[k] = (OUT_T)kHuge;
+        continue;
+      }
+      double sig[6] = {0, 0, 0, 0, 0, 0}, eps[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < ncmp; ++c) sig[c] = sig_s[(layout == 0 ? c * 8 + pnt : pnt * ncmp + c) * kRecLds + st];
+      if (layout == 2) {
+        for (int c = 0; c < ncmp; ++c) eps[c] = eps_s[(pnt * ncmp + c) * kRecLds + st];
+      } else if (ncmp == 3) {   // isoMat2Dinv (isoMatModule.f90:41-57), tensorial shear (elStressModule.f90:244-248)
+        eps[0] = sig[0] / E - nu / E * sig[1];
+        eps[1] = -nu / E * sig[0] + sig[1] / E;
+        eps[2] = 0.5 * (2.0 * (1.0 + nu) / E * sig[2]);
+      } else {                  // isoMat3Dinv (isoMatModule.f90:95-120), tensorial shear (elStressModule.f90:249-251)
+        eps[0] = (sig[0] - nu * (sig[1] + sig[2])) / E;
+        eps[1] = (sig[1] - nu * (sig[0] + sig[2])) / E;
+        eps[2] = (sig[2] - nu * (sig[0] + sig[1])) / E;
+        const double g2 = 2.0 * (1.0 + nu) / E;
+        eps[3] = 0.5 * g2 * sig[3]; eps[4] = 0.5 * g2 * sig[4]; eps[5] = 0.5 * g2 * sig[5];
+      }
+      int k = 0;
+      if (L.stress) for (int c = 0; c < ncmp; ++c) o[k++] = (OUT_T)sig[c];
+      if (L.strain) for (int c = 0; c < ncmp; ++c) o[k++] = (OUT_T)eps[c];
+      if (L.nsel) {
+        const int np = ncmp == 3 ? 2 : 3;
+        double r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, P[3] = {0, 0, 0};
+        if (L.mask & 0x01) r[0] = von_mises(ncmp, sig);
+        if (L.mask & 0x0e) { principal_values(ncmp, sig, P); r[1] = P[0]; r[2] = P[np - 1]; r[3] = 0.5 * (P[0] - P[np - 1]); }
+        if (L.mask & 0x10) r[4] = von_mises(ncmp, eps);
+        if (L.mask & 0xe0) { P[0] = P[1] = P[2] = 0.0; principal_values(ncmp, eps, P); r[5] = P[0]; r[6] = P[np - 1]; r[7] = 0.5 * (P[0] - P[np - 1]); }
+        for (int j = 0; j < 8; ++j) if (L.mask & (1 << j)) o[k++] = (OUT_T)r[j];
+      }
+      if (srsize && pnt < nenod) {
+        if (layout == 2)   // thick shells: SR = 0 (STR31 / STR32, elStressModule.f90:1174-1176, 1296-1298)
+          for (int c = 0; c < 6; ++c) so[c] = (OUT_T)0.0;
+        else               // thin shells: from the top and bottom stresses of the node (STR22a :826-831, STR23 :976-979)
+          for (int c = 0; c < 3; ++c) {
+            const double bot = sig_s[(c * 8 + nenod + pnt) * kRecLds + st];
+            so[c] = (OUT_T)((sig[c] + bot) * 0.5 * th);
+            so[3 + c] = (OUT_T)((sig[c] - bot) * 0.5 * th * th / 6.0);
+          }
+      }
     }
+    __syncwarp();
   }
 }
 
 struct BeamOp12 { double S[12][12]; };
 
-// beam section forces SF(6,2) (STR11, elStressModule.f90:402-515): 12 rows per beam
+// beam section forces SF(6,2) (STR11, elStressModule.f90:402-515): 12 values per beam and step, written at their record
+// place; x = (beam, row) with the row fastest (contiguous record bytes), y = step
+template <class OUT_T>
 __global__ void record_beams_kernel(const double* __restrict__ U, size_t ldu, int nt, const BeamOp12* __restrict__ ops,
                                     const int* __restrict__ edof, const long long* __restrict__ roff,
-                                    const unsigned char* __restrict__ failed, int nelt, double* __restrict__ rec, size_t ldt)
+                                    const unsigned char* __restrict__ failed, int nelt, OUT_T* __restrict__ out, size_t ld_out)
 {
-  const int t = blockIdx.y * blockDim.x + threadIdx.x;
-  const long long ir = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const long long ir = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y * blockDim.y + threadIdx.y;
   if (t >= nt || ir >= (long long)nelt * 12) return;
   const int i = (int)(ir / 12), r = (int)(ir % 12);
   if (roff[i] < 0) return;
   double acc = 0.0;
   for (int c = 0; c < 12; ++c) acc += ops[i].S[r][c] * U[(size_t)edof[i * 12 + c] * ldu + t];
-  rec[(size_t)(roff[i] + r) * ldt + t] = failed[i] ? kHuge : acc;
+  out[(size_t)t * ld_out + roff[i] + r] = (OUT_T)(failed[i] ? kHuge : acc);
 }
 
 // ---- rotation utilities of src/vpmUtilities/rotationModule.f90 (vec_to_quat :393-428, quat_to_mat :478-497,
@@ -240,9 +296,11 @@ __global__ void record_nodes_kernel(const double* __restrict__ U, size_t ldu, in
   for (int d = 0; d < nd; ++d) rec[(size_t)(base + nd + d) * ldt + t] = ut[d];
 }
 
-// rec[slot][t] (double) -> out[t][slot] as float or double
+// rec[slot][t] (double) -> out[t * ld_out + slot] as float or double: the nodal part of the step records (the
+// displacement rows of U are step-fastest, the record is slot-fastest)
 template <class T>
-__global__ void record_transpose_kernel(const double* __restrict__ rec, size_t ldt, long long nslot, int nt, T* __restrict__ out)
+__global__ void record_transpose_kernel(const double* __restrict__ rec, size_t ldt, long long nslot, int nt, T* __restrict__ out,
+                                        size_t ld_out)
 {
   __shared__ double tile[32][33];
   const long long s0 = (long long)blockIdx.x * 32;
@@ -256,7 +314,7 @@ __global__ void record_transpose_kernel(const double* __restrict__ rec, size_t l
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int t = t0 + j;
     const long long s = s0 + threadIdx.x;
-    if (s < nslot && t < nt) out[(size_t)t * nslot + s] = (T)tile[threadIdx.x][j];
+    if (s < nslot && t < nt) out[(size_t)t * ld_out + s] = (T)tile[threadIdx.x][j];
   }
 }
 
@@ -274,31 +332,131 @@ static void appendf(std::string& s, const char* fmt, ...)
 
 using namespace fsr;
 
+// Two record buffers on the device, two pinned ones on the host: while tile n is computed (stream of the part), tile n-1
+// crosses PCIe (copy stream) and tile n-2 goes to the file (writer thread, one writev per batch of step records).
+struct RdbJob { int buf = 0, nt = 0; std::vector<char> keys; };   // keys: nt x (int32 step number, float64 time)
+
 struct fsr_rdb {
   fsr_part* part = nullptr;
   FILE* f = nullptr;
+  int fd = -1;
   std::string header, path;
   RecLayout L{};
   int dbl = 0;
   long long nslot = 0;                 // values per step record
+  long long nslot_nodes = 0;           // the leading nodal values of the record (writeDisplacementDB)
   long long* roff[FAM_COUNT] = {};     // device: record slot of each family element (-1 = not written)
-  double* rec = nullptr;               // [nslot][tile] slot-major staging
-  void* out = nullptr;                 // [tile][nslot] float/double records
-  void* host = nullptr;                // pinned copy
-  int tile = 0;
+  double* rec = nullptr;               // [nslot_nodes][tile] slot-major staging of the nodal values
+  void* out[2] = {nullptr, nullptr};   // [tile][nslot] float/double step records
+  void* host[2] = {nullptr, nullptr};  // pinned copies
+  double* Qpin[2] = {nullptr, nullptr};// pinned staging of the caller's Q tile
+  double* dQ = nullptr;                // device Q tile
+  int ldq_cap = 0;
+  cudaEvent_t ev[2][4] = {};           // per buffer: compute start / done (part stream), copy start / done (copy stream)
+  cudaStream_t copy_stream = nullptr;
+  int tile = 0, next_buf = 0;
   long long steps_written = 0;
   long long* node_slot = nullptr;      // device [nnod] record slot of each node's displacements (-1 = none)
   int* madof = nullptr;                // device [nnod+1]
   double* supTr0 = nullptr;            // device [12] initial part position (total displacements)
   double* supTr = nullptr;             // device [tile][12]
+  double* supPin[2] = {nullptr, nullptr};
+  // writer thread
+  std::thread writer;
+  std::mutex mtx;
+  std::condition_variable cv;
+  std::deque<RdbJob> jobs;
+  bool busy[2] = {false, false};       // buffer handed to the writer and not yet on file
+  bool quit = false;
+  std::string werr;                    // first error of the writer thread
+  // accounting (fsr_rdb_timing)
+  double ms_compute = 0.0, ms_copy = 0.0, ms_disk = 0.0;
+  long long bytes_written = 0, tiles = 0;
+
+  void writer_main();
+  void drain()
+  {
+    std::unique_lock<std::mutex> lk(mtx);
+    cv.wait(lk, [&] { return jobs.empty() && !busy[0] && !busy[1]; });
+  }
   ~fsr_rdb()
   {
+    if (writer.joinable()) {
+      { std::lock_guard<std::mutex> lk(mtx); quit = true; }
+      cv.notify_all();
+      writer.join();
+    }
     if (f) fclose(f);
     for (auto& r : roff) cudaFree(r);
-    cudaFree(rec); cudaFree(out); cudaFree(node_slot); cudaFree(madof); cudaFree(supTr0); cudaFree(supTr);
-    if (host) cudaFreeHost(host);
+    cudaFree(rec); cudaFree(node_slot); cudaFree(madof); cudaFree(supTr0); cudaFree(supTr); cudaFree(dQ);
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(out[b]);
+      if (host[b]) cudaFreeHost(host[b]);
+      if (Qpin[b]) cudaFreeHost(Qpin[b]);
+      if (supPin[b]) cudaFreeHost(supPin[b]);
+      for (auto& e : ev[b]) if (e) cudaEventDestroy(e);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
+
+// The writer: waits for the device-to-host copy of a buffer, then appends its step records -- 12-byte key + payload per
+// step (writeTimeStepDB, rdbModule.f90:669-736) -- with writev, up to 512 steps per system call.
+void fsr_rdb::writer_main()
+{
+  cudaSetDevice(part->device);
+  const size_t vb = dbl ? 8 : 4, rec_bytes = vb * (size_t)nslot;
+  for (;;) {
+    RdbJob job;
+    {
+      std::unique_lock<std::mutex> lk(mtx);
+      cv.wait(lk, [&] { return quit || !jobs.empty(); });
+      if (jobs.empty()) return;
+      job = std::move(jobs.front());
+      jobs.pop_front();
+    }
+    std::string err;
+    if (cudaEventSynchronize(ev[job.buf][3]) != cudaSuccess) err = std::string("device error while recovering a tile of steps: ") + cudaGetErrorString(cudaGetLastError());
+    float a = 0.f, c = 0.f;
+    if (err.empty()) { cudaEventElapsedTime(&a, ev[job.buf][0], ev[job.buf][1]); cudaEventElapsedTime(&c, ev[job.buf][2], ev[job.buf][3]); }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<iovec> iov;
+    for (int t = 0; t < job.nt && err.empty();) {
+      const int n = std::min(512, job.nt - t);
+      iov.resize(2 * (size_t)n);
+      size_t want = 0;
+      for (int k = 0; k < n; ++k) {
+        iov[2 * k] = {job.keys.data() + 12 * (size_t)(t + k), 12};
+        iov[2 * k + 1] = {(char*)host[job.buf] + rec_bytes * (size_t)(t + k), rec_bytes};
+        want += 12 + rec_bytes;
+      }
+      size_t first = 0;
+      while (want > 0) {   // a short write continues where it stopped
+        const ssize_t w = writev(fd, iov.data() + first, (int)(iov.size() - first));
+        if (w < 0) { if (errno == EINTR) continue; err = path + ": write error: " + strerror(errno); break; }
+        want -= (size_t)w;
+        size_t left = (size_t)w;
+        while (left > 0 && first < iov.size()) {
+          if (left >= iov[first].iov_len) { left -= iov[first].iov_len; ++first; }
+          else { iov[first].iov_base = (char*)iov[first].iov_base + left; iov[first].iov_len -= left; left = 0; }
+        }
+      }
+      t += n;
+    }
+    const double disk = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
+      std::lock_guard<std::mutex> lk(mtx);
+      if (!err.empty() && werr.empty()) werr = err;
+      if (err.empty()) {
+        ms_compute += a; ms_copy += c; ms_disk += disk; ++tiles;
+        bytes_written += (long long)job.nt * (12 + (long long)rec_bytes);
+        steps_written += job.nt;
+      }
+      busy[job.buf] = false;
+    }
+    cv.notify_all();
+  }
+}
 
 namespace {
 
@@ -531,6 +689,36 @@ static int layout_from_options(const fsr_rdb_options* o, RecLayout& L)
 
 }  // namespace
 
+template <class OUT_T>
+static int launch_record_kernels(fsr_rdb* r, int nt, OUT_T* out, cudaStream_t s)
+{
+  fsr_part* p = r->part;
+  const size_t ld_out = (size_t)r->nslot;
+  for (int fi = 0; fi < FAM_COUNT; ++fi) {
+    FamilyData& f = p->fam[fi];
+    if (f.nelt == 0 || !r->roff[fi]) continue;
+    if (fi == FAM_BEAM) {
+      if (!r->L.sr) continue;
+      dim3 blk(96, 4), grd((unsigned)(((long long)f.nelt * 12 + 95) / 96), (nt + 3) / 4);
+      record_beams_kernel<OUT_T><<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, reinterpret_cast<const BeamOp12*>(f.Sfrag), f.edof,
+                                                     r->roff[fi], f.failed, f.nelt, out, ld_out);
+    } else {
+      if (f.nstrp == 0) continue;
+      if (!(r->L.stress || r->L.strain || r->L.nsel || (r->L.sr && f.ncmp == 3) || (r->L.sr && f.Efrag))) continue;
+      const int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : (fi == FAM_TRI6 || fi == FAM_QUAD8) ? 2 : 1;
+      if (f.KT > 16) { set_error("internal: operator of family %d has %d k-tiles", fi, f.KT); return FSR_ERR_LIMIT; }
+      const size_t smem = sizeof(double) * kRecWarps * (layout == 2 ? 2 : 1) * (size_t)f.MT * 8 * kRecLds;
+      if (smem > 48 * 1024)
+        if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<OUT_T>, 100 * 1024)) return rc;
+      record_points_dmma_kernel<OUT_T><<<(f.nelt + kRecWarps - 1) / kRecWarps, kRecWarps * 32, smem, s>>>(
+          p->U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag, f.edof, r->roff[fi], f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
+          f.MT, f.KT, layout, f.nenod, r->L, out, ld_out);
+    }
+    FSR_LAUNCH_CHECK();
+  }
+  return FSR_OK;
+}
+
 extern "C" {
 
 // Host only: the header text and record size for a part given by its element type codes (SAM melcon) and
@@ -608,23 +796,43 @@ int fsr_rdb_create(fsr_rdb** out, fsr_part* p, const char* path, const fsr_rdb_o
       set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
     }
   }
-  // step tile of the record buffers: bounded by the part's step tile and by ~1/4 of the free memory
+  // step tile of the record buffers: bounded by the part's step tile, by 1 GiB per buffer (two on the device, two pinned
+  // on the host) and by ~1/4 of the free device memory
+  r->nslot_nodes = 0;
+  for (int n = 0; n < p->nnod; ++n)
+    if (node_slot[(size_t)n] >= 0) {
+      const int nd = p->madof_host[(size_t)n + 1] - p->madof_host[(size_t)n] > 5 ? 6 : 3;
+      r->nslot_nodes = std::max(r->nslot_nodes, node_slot[(size_t)n] + (L.def > 1 ? 2 : 1) * nd);
+    }
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  const double per_step = (double)nslot * (8.0 + (r->dbl ? 8.0 : 4.0));
-  long long tile = (long long)(0.25 * (double)free_b / per_step);
-  tile = std::max<long long>(1, std::min<long long>(tile, p->step_tile));
-  if (tile >= 32) tile = tile / 32 * 32;
-  r->tile = (int)tile;
   const size_t vb = r->dbl ? 8 : 4;
-  if (cudaMalloc(&r->rec, sizeof(double) * (size_t)nslot * r->tile) != cudaSuccess ||
-      cudaMalloc(&r->out, vb * (size_t)nslot * r->tile) != cudaSuccess ||
-      cudaMallocHost(&r->host, vb * (size_t)nslot * r->tile) != cudaSuccess ||
-      (L.def > 1 && cudaMalloc(&r->supTr, sizeof(double) * 12 * r->tile) != cudaSuccess)) {
-    set_error("fsr_rdb_create: cannot allocate the record buffers (%lld values x %d steps)", nslot, r->tile);
+  const double per_step = 2.0 * (double)nslot * (double)vb + 8.0 * (double)r->nslot_nodes;
+  long long tile = (long long)(0.25 * (double)free_b / per_step);
+  tile = std::min<long long>(tile, (long long)((double)(1u << 30) / ((double)nslot * (double)vb)));
+  if (const char* e = getenv("FSR_RDB_TILE")) tile = std::max(1, atoi(e));   // tests: force several tiles per call
+  tile = std::max<long long>(1, std::min<long long>(tile, p->step_tile));
+  if (tile >= 8) tile = tile / 8 * 8;
+  r->tile = (int)tile;
+  bool ok = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b) {
+    ok = cudaMalloc(&r->out[b], vb * (size_t)nslot * r->tile) == cudaSuccess &&
+         cudaMallocHost(&r->host[b], vb * (size_t)nslot * r->tile) == cudaSuccess &&
+         (L.def <= 1 || cudaMallocHost(&r->supPin[b], sizeof(double) * 12 * r->tile) == cudaSuccess);
+    for (auto& e : r->ev[b]) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+  }
+  ok = ok && (r->nslot_nodes == 0 || cudaMalloc(&r->rec, sizeof(double) * (size_t)r->nslot_nodes * r->tile) == cudaSuccess) &&
+       (L.def <= 1 || cudaMalloc(&r->supTr, sizeof(double) * 12 * r->tile) == cudaSuccess);
+  if (!ok) {
+    set_error("fsr_rdb_create: cannot allocate the record buffers (%lld values x %d steps): %s", nslot, r->tile,
+              cudaGetErrorString(cudaGetLastError()));
     delete r;
     return FSR_ERR_ALLOC;
   }
+  // the header went through stdio; the step records go through the descriptor
+  if (fflush(r->f) != 0) { set_error("%s: write error", r->path.c_str()); delete r; return FSR_ERR_ARG; }
+  r->fd = fileno(r->f);
+  r->writer = std::thread(&fsr_rdb::writer_main, r);
   *out = r;
   return FSR_OK;
 }
@@ -657,66 +865,82 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
   int rc = ensure_batch_buffers(p, false);
   if (rc) return rc;
   cudaStream_t s = p->stream;
-  double* dQ = nullptr;
   const size_t vb = r->dbl ? 8 : 4;
+  if (ldq > r->ldq_cap) {   // Q staging, sized on first use (ldq is the caller's)
+    r->drain();
+    FSR_CUDA(cudaStreamSynchronize(s));
+    cudaFree(r->dQ); r->dQ = nullptr;
+    for (int b = 0; b < 2; ++b) { if (r->Qpin[b]) cudaFreeHost(r->Qpin[b]); r->Qpin[b] = nullptr; }
+    FSR_CUDA(cudaMalloc(&r->dQ, sizeof(double) * (size_t)ldq * r->tile));
+    for (int b = 0; b < 2; ++b) FSR_CUDA(cudaMallocHost(&r->Qpin[b], sizeof(double) * (size_t)ldq * r->tile));
+    r->ldq_cap = ldq;
+  }
   for (int t0 = 0; t0 < nsteps; t0 += r->tile) {
     const int nt = std::min(r->tile, nsteps - t0);
     const int nt_pad = (nt + 63) / 64 * 64;
-    if (!dQ) FSR_CUDA(cudaMalloc(&dQ, sizeof(double) * (size_t)ldq * r->tile));
-    FSR_CUDA(cudaMemcpyAsync(dQ, Q + (size_t)t0 * ldq, sizeof(double) * (size_t)ldq * nt, cudaMemcpyHostToDevice, s));
-    if ((rc = launch_pack_q(p, dQ, ldq, nt, nt_pad, s)) || (rc = launch_k1(p, nt_pad, s))) { cudaFree(dQ); return rc; }
-    const size_t ldt = (size_t)r->tile;
-    dim3 blk(32, 8);
-    if (r->L.def) {
-      if (r->L.def > 1) FSR_CUDA(cudaMemcpyAsync(r->supTr, sup_tr + (size_t)t0 * 12, sizeof(double) * 12 * nt, cudaMemcpyHostToDevice, s));
-      dim3 grd((p->nnod + 7) / 8, (nt + 31) / 32);
+    const int b = r->next_buf;
+    {   // buffer b is free again once the writer has put its previous content on file
+      std::unique_lock<std::mutex> lk(r->mtx);
+      r->cv.wait(lk, [&] { return !r->busy[b]; });
+      if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); return FSR_ERR_ARG; }
+    }
+    memcpy(r->Qpin[b], Q + (size_t)t0 * ldq, sizeof(double) * (size_t)ldq * nt);
+    FSR_CUDA(cudaEventRecord(r->ev[b][0], s));
+    FSR_CUDA(cudaMemcpyAsync(r->dQ, r->Qpin[b], sizeof(double) * (size_t)ldq * nt, cudaMemcpyHostToDevice, s));
+    if ((rc = launch_pack_q(p, r->dQ, ldq, nt, nt_pad, s)) || (rc = launch_k1(p, nt_pad, s))) return rc;
+    if (r->L.def) {   // nodal values: slot-major staging, then one tiled transpose into the leading part of the records
+      if (r->L.def > 1) {
+        memcpy(r->supPin[b], sup_tr + (size_t)t0 * 12, sizeof(double) * 12 * nt);
+        FSR_CUDA(cudaMemcpyAsync(r->supTr, r->supPin[b], sizeof(double) * 12 * nt, cudaMemcpyHostToDevice, s));
+      }
+      const size_t ldt = (size_t)r->tile;
+      dim3 blk(32, 8), grd((p->nnod + 7) / 8, (nt + 31) / 32);
       record_nodes_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, p->nnod, r->madof, r->node_slot, p->xyz, r->supTr,
                                               r->supTr0, r->L.def > 1, r->rec, ldt);
-      ++g_launches;
+      FSR_LAUNCH_CHECK();
+      dim3 tg((unsigned)((r->nslot_nodes + 31) / 32), (nt + 31) / 32);
+      if (r->dbl) record_transpose_kernel<double><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (double*)r->out[b], (size_t)r->nslot);
+      else record_transpose_kernel<float><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (float*)r->out[b], (size_t)r->nslot);
+      FSR_LAUNCH_CHECK();
     }
-    for (int fi = 0; fi < FAM_COUNT; ++fi) {
-      FamilyData& f = p->fam[fi];
-      if (f.nelt == 0) continue;
-      if (fi == FAM_BEAM) {
-        if (!r->L.sr) continue;
-        dim3 grd((unsigned)(((long long)f.nelt * 12 + 7) / 8), (nt + 31) / 32);
-        record_beams_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, reinterpret_cast<const BeamOp12*>(f.Sfrag), f.edof,
-                                                r->roff[fi], f.failed, f.nelt, r->rec, ldt);
-      } else {
-        if (f.nstrp == 0) continue;
-        dim3 grd((unsigned)(((long long)f.nelt * f.nstrp + 7) / 8), (nt + 31) / 32);
-        const int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : (fi == FAM_TRI6 || fi == FAM_QUAD8) ? 2 : 1;
-        record_points_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, f.Sfrag, f.edof, r->roff[fi], f.failed, f.aux,
-                                                 f.naux, f.Efrag, f.nelt, f.nstrp, f.ncmp, f.nenod * f.nndof, f.MT, f.KT, layout, f.nenod,
-                                                 r->L, r->rec, ldt);
-      }
-      ++g_launches;
-      if (cudaGetLastError() != cudaSuccess) { set_error("record kernel launch failed"); cudaFree(dQ); return FSR_ERR_CUDA; }
-    }
-    dim3 tb(32, 8), tg((unsigned)((r->nslot + 31) / 32), (nt + 31) / 32);
-    if (r->dbl) record_transpose_kernel<double><<<tg, tb, 0, s>>>(r->rec, ldt, r->nslot, nt, (double*)r->out);
-    else record_transpose_kernel<float><<<tg, tb, 0, s>>>(r->rec, ldt, r->nslot, nt, (float*)r->out);
-    ++g_launches;
-    if (cudaMemcpyAsync(r->host, r->out, vb * (size_t)r->nslot * nt, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess) {
-      set_error("fsr_rdb_write_steps: %s", cudaGetErrorString(cudaGetLastError()));
-      cudaFree(dQ);
-      return FSR_ERR_CUDA;
-    }
+    rc = r->dbl ? launch_record_kernels<double>(r, nt, (double*)r->out[b], s) : launch_record_kernels<float>(r, nt, (float*)r->out[b], s);
+    if (rc) return rc;
+    FSR_CUDA(cudaEventRecord(r->ev[b][1], s));
+    FSR_CUDA(cudaStreamWaitEvent(r->copy_stream, r->ev[b][1], 0));
+    FSR_CUDA(cudaEventRecord(r->ev[b][2], r->copy_stream));
+    FSR_CUDA(cudaMemcpyAsync(r->host[b], r->out[b], vb * (size_t)r->nslot * nt, cudaMemcpyDeviceToHost, r->copy_stream));
+    FSR_CUDA(cudaEventRecord(r->ev[b][3], r->copy_stream));
+    RdbJob job;
+    job.buf = b; job.nt = nt;
+    job.keys.resize(12 * (size_t)nt);
     for (int t = 0; t < nt; ++t) {
-      const int is = stepno[t0 + t];
-      const double tm = time[t0 + t];
-      if (fwrite(&is, 4, 1, r->f) != 1 || fwrite(&tm, 8, 1, r->f) != 1 ||
-          fwrite((const char*)r->host + vb * (size_t)r->nslot * t, vb, (size_t)r->nslot, r->f) != (size_t)r->nslot) {
-        set_error("%s: write error", r->path.c_str());
-        cudaFree(dQ);
-        return FSR_ERR_ARG;
-      }
-      ++r->steps_written;
+      memcpy(job.keys.data() + 12 * (size_t)t, &stepno[t0 + t], 4);
+      memcpy(job.keys.data() + 12 * (size_t)t + 4, &time[t0 + t], 8);
     }
+    {
+      std::lock_guard<std::mutex> lk(r->mtx);
+      r->busy[b] = true;
+      r->jobs.push_back(std::move(job));
+    }
+    r->cv.notify_all();
+    r->next_buf ^= 1;
   }
-  cudaFree(dQ);
   return FSR_OK;
+}
+
+// Waits until every record handed over so far is on file.  t (may be NULL): [0] device time of the tiles (H2D of Q, K1,
+// record kernels), [1] device-to-host copies, [2] file writes, all in ms and summed over the tiles (they overlap in wall
+// time), [3] bytes written, [4] tiles.  Returns the number of entries written or a negative error.
+int fsr_rdb_flush(fsr_rdb* r, double* t, int n)
+{
+  if (!r) { set_error("fsr_rdb_flush: null handle"); return FSR_ERR_ARG; }
+  r->drain();
+  std::lock_guard<std::mutex> lk(r->mtx);
+  if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); return FSR_ERR_ARG; }
+  const double v[5] = {r->ms_compute, r->ms_copy, r->ms_disk, (double)r->bytes_written, (double)r->tiles};
+  const int m = t ? std::min(n, 5) : 0;
+  for (int i = 0; i < m; ++i) t[i] = v[i];
+  return m;
 }
 
 void fsr_total_nodal_displacement(const double* x0, const double* u, int nd, const double* T, const double* T0, double* utot)
@@ -728,7 +952,17 @@ int fsr_rdb_close(fsr_rdb* r)
 {
   if (!r) return FSR_ERR_ARG;
   int rc = FSR_OK;
-  if (r->f && fclose(r->f) != 0) { set_error("%s: close error", r->path.c_str()); rc = FSR_ERR_ARG; }
+  r->drain();
+  if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); rc = FSR_ERR_ARG; }
+  {
+    std::lock_guard<std::mutex> lk(r->mtx);
+    r->quit = true;
+  }
+  r->cv.notify_all();
+  if (r->writer.joinable()) r->writer.join();
+  cudaSetDevice(r->part->device);
+  cudaStreamSynchronize(r->copy_stream);
+  if (r->f && fclose(r->f) != 0 && rc == FSR_OK) { set_error("%s: close error", r->path.c_str()); rc = FSR_ERR_ARG; }
   r->f = nullptr;
   delete r;
   return rc;

@@ -330,17 +330,13 @@ static size_t k1_smem_bytes(int ldk)
 int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nrows_pad, int nsteps_pad, size_t ldu,
                   cudaStream_t s)
 {
-  static bool attr_set = false;
   size_t smem = k1_smem_bytes(ldk);
   if (smem > 227 * 1024) {
     set_error("reduced dimension (padded %d) too large for the resident-K expansion kernel (needs %zu B smem)",
               ldk, smem);
     return FSR_ERR_LIMIT;
   }
-  if (!attr_set) {
-    FSR_CUDA(cudaFuncSetAttribute(k1_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  if (int rc = smem_opt_in((const void*)k1_expand_kernel, 227 * 1024)) return rc;
   if (nsteps_pad % K1_BN != 0 || nrows_pad % K1_BM != 0) {
     set_error("internal: K1 tile mismatch (%d rows, %d steps)", nrows_pad, nsteps_pad);
     return FSR_ERR_ARG;

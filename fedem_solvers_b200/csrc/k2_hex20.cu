@@ -387,12 +387,8 @@ int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
     FSR_LAUNCH_CHECK();
     return FSR_OK;
   }
-  static bool attr = false;
   const size_t smem = solid_smem_bytes<20>();
-  if (!attr) {
-    FSR_CUDA(cudaFuncSetAttribute(k2_solid_smem_vm_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  if (int rc = smem_opt_in((const void*)k2_solid_smem_vm_kernel<20>, smem)) return rc;
   k2_solid_smem_vm_kernel<20><<<f.nelt, 128, smem, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof,
                                                        f.ptoff, f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min);
   FSR_LAUNCH_CHECK();

@@ -590,23 +590,15 @@ int launch_family(fsr_part* p, int fam, int nsteps, int nsteps_pad, double* vm_d
   static const bool dense = getenv("FSR_THICK_DENSE") && atoi(getenv("FSR_THICK_DENSE")) != 0;
   if (!dense) {
     constexpr int NEN = NPT / 2;
-    static bool gattr = false;
     constexpr size_t gsmem = thick_gauss_smem<NEN>();
-    if (!gattr) {
-      FSR_CUDA(cudaFuncSetAttribute(k2_thick_gauss_vm_kernel<NEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      gattr = true;
-    }
+    if (int rc = smem_opt_in((const void*)k2_thick_gauss_vm_kernel<NEN>, gsmem)) return rc;
     k2_thick_gauss_vm_kernel<NEN><<<f.nelt, 128, gsmem, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.edof, f.ptoff,
                                                             f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min);
     FSR_LAUNCH_CHECK();
     return FSR_OK;
   }
-  static bool attr = false;
   constexpr size_t smem = dense6_smem<NPT, NCOL>();
-  if (!attr) {
-    FSR_CUDA(cudaFuncSetAttribute(k2_dense6_vm_kernel<NPT, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  if (int rc = smem_opt_in((const void*)k2_dense6_vm_kernel<NPT, NCOL>, smem)) return rc;
   k2_dense6_vm_kernel<NPT, NCOL><<<f.nelt, 128, smem, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff,
                                                           f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min);
   FSR_LAUNCH_CHECK();

@@ -273,12 +273,8 @@ static int launch_stream(fsr_fatigue_state* f, const double* hist, size_t ld, in
 {
   if (nsteps <= 0 || f->ngage == 0) return FSR_OK;
   const unsigned blocks = (unsigned)((f->ngage + K3_THREADS - 1) / K3_THREADS);
-  static bool attr = false;
-  if (!attr) {
-    FSR_CUDA(cudaFuncSetAttribute(k3_stream_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem(0)));
-    FSR_CUDA(cudaFuncSetAttribute(k3_stream_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem(0)));
-    attr = true;
-  }
+  if (layout == 0)
+    if (int rc = smem_opt_in((const void*)k3_stream_kernel<0, MODE>, k3_smem(0))) return rc;
   if (layout == 0)
     k3_stream_kernel<0, MODE><<<blocks, K3_THREADS, k3_smem(0), s>>>(f->st, hist, ld, f->ngage, step0, nsteps, f->gate,
                                                                      f->curve, f->edges, f->bin_size, f->nbins,

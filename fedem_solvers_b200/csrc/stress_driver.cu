@@ -17,7 +17,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <unistd.h>
 #include <vector>
 
@@ -352,6 +354,15 @@ static int run_program(int which)
   if (c.get_bool("help") || c.get_bool("helpAll")) { printf("%s", c.help_text(c.get_bool("helpAll")).c_str()); return 0; }
   if (c.get_bool("version")) { printf("%s B200 1.0\n", prog); return 0; }
 
+  // CUDA context creation (a few hundred ms on a B200) runs beside the parsing of the input files
+  using clk = std::chrono::steady_clock;
+  const clk::time_point t_start = clk::now();
+  auto since = [](clk::time_point t) { return std::chrono::duration<double>(clk::now() - t).count(); };
+  double t_context = 0.0;
+  const int device = c.get_int("device");
+  std::thread ctx_thread([&] { const clk::time_point t = clk::now(); if (cudaSetDevice(device) == cudaSuccess) cudaFree(nullptr); t_context = since(t); });
+  struct CtxJoin { std::thread& t; ~CtxJoin() { if (t.joinable()) t.join(); } } ctx_join{ctx_thread};
+
   Log log;
   log.open(file_name("resfile", gage ? "_gage.res" : modes ? "_modes.res" : "_stress.res"), gage ? "Strain Gage Recovery" : modes ? "Modal Recovery" : "Stress Recovery");
   log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : modes ? "MODES" : "STRESS");
@@ -361,6 +372,7 @@ static int run_program(int which)
   if (c.is_set("resStressFile")) log.line("  ** Note: residual stress import (-resStressFile) is not part of this build; ignored");
   if (c.is_set("VTFfile") && !c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
   if (c.get_bool("dumpDefNas")) log.line("  ** Note: Nastran deformation dump (-dumpDefNas) is not part of this build; ignored");
+  if (which == 0 && c.get_bool("nodalForces")) log.line("  ** Note: nodal force print-out (-nodalForces, stressRoutines.f90:128) is not part of this build; ignored");
 
   // --- Read the link file (ffl_init)
   const std::string linkfile = c.get_string("linkfile");
@@ -443,6 +455,9 @@ static int run_program(int which)
   const int nmodes = ngen + (lgrav ? 3 : 0);
 
   // --- the part on the device
+  const double t_parse = since(t_start);
+  if (ctx_thread.joinable()) ctx_thread.join();
+  const clk::time_point t_setup0 = clk::now();
   fsr_sam sam;
   memset(&sam, 0, sizeof(sam));
   sam.nnod = nnod; sam.nel = nel; sam.ndof = ndof; sam.ndof1 = ndof1; sam.ndof2 = ndof2; sam.ngen = nmodes; sam.neq = neq; sam.nceq = nceq;
@@ -484,6 +499,7 @@ static int run_program(int which)
     CHECK(fsr_set_recovery(part, ndof2 > 0 ? B.data() : nullptr, ndof1, nmodes > 0 ? E.data() : nullptr, ndof1));
   }
 
+  const double t_setup = since(t_setup0);
   // --- Open the solver results database (ffr_init) and select the time steps (ffr_getnextstep loop)
   log.line("           --> Reading solver result files");
   const std::vector<std::string> frs_files = file_list(c.get_string("frsfile"));
@@ -543,8 +559,11 @@ static int run_program(int which)
   std::vector<int> s_w(window);
   std::vector<double> sup_all;
   const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
+  const clk::time_point t_loop0 = clk::now();
+  double t_hist = 0.0;
   for (int w0 = 0; w0 < nsel; w0 += window) {
     const int nw = std::min(window, nsel - w0);
+    const clk::time_point t_h0 = clk::now();
     for (int k = 0; k < nw;) {   // runs of consecutive steps on file are read with one call
       int run = 1;
       while (k + run < nw && sel[w0 + k + run] == sel[w0 + k] + run) ++run;
@@ -562,6 +581,8 @@ static int run_program(int which)
         for (int j = 0; j < 3; ++j) g[j] = grv[0] * T[3 * j] + grv[1] * T[3 * j + 1] + grv[2] * T[3 * j + 2];
       }
     }
+    t_hist += since(t_h0);
+    // queued: the device, the PCIe copy and the file writer work on this window while the next one is read
     if (rdb) CHECK(fsr_rdb_write_steps(rdb, Q.data(), ndim, nw, s_w.data(), t_w.data(), supTr.data()));
     else CHECK(fsr_recover(part, Q.data(), ndim, nw, nullptr));
     log.line("           --> ......Simulation time : %12.5E  (%d of %d steps done)", t_w[nw - 1], w0 + nw, nsel);
@@ -571,8 +592,16 @@ static int run_program(int which)
     CHECK(fsr_get_envelope(part, mx.data(), mn.data()));
     log.line("           --> largest von Mises stress over all result points and steps: %g", *std::max_element(mx.begin(), mx.end()));
   }
+  double tp[5] = {0, 0, 0, 0, 0};
+  if (rdb) CHECK(fsr_rdb_flush(rdb, tp, 5));
+  const double t_loop = since(t_loop0);
   log.line("           --> Time loop done. Closing database files");
   if (rdb) { fsr_rdb* r = rdb; rdb = nullptr; CHECK(fsr_rdb_close(r)); }
+  // where the wall time went; the three pipeline stages overlap with each other and with the reading of the history
+  log.line("           --> Wall time %.3f s: input files %.3f (CUDA context %.3f beside it), part on device + B/E %.3f, time loop %.3f",
+           since(t_start), t_parse, t_context, t_setup, t_loop);
+  log.line("           --> Time loop: history read %.3f s | device (K1 + record kernels) %.3f s | device-to-host %.3f s | file %.3f s (%.1f MB in %d tiles)",
+           t_hist, 1e-3 * tp[0], 1e-3 * tp[1], 1e-3 * tp[2], 1e-6 * tp[3], (int)tp[4]);
   log.line("           ================>  END OF PROGRAM STRESS  <================");
   log.line("\n    Stress calculation successfully completed :-)  (%.2f s CPU)", (double)(clock() - log.t0) / CLOCKS_PER_SEC);
   return 0;

@@ -100,6 +100,12 @@ class StressRdb:
         check(self.lib.fsr_rdb_write_steps(self._h, _dp(Q), Q.shape[0], Q.shape[1], _ip(stepno), _dp(time), _dp(st)),
               "fsr_rdb_write_steps")
 
+    def flush(self):
+        """Waits for the pipeline (device -> PCIe -> file) to drain; returns where the time went."""
+        t = np.zeros(5, F64)
+        check(self.lib.fsr_rdb_flush(self._h, _dp(t), 5), "fsr_rdb_flush")
+        return dict(compute_ms=t[0], d2h_ms=t[1], disk_ms=t[2], bytes=int(t[3]), tiles=int(t[4]))
+
     def close(self):
         if self._h:
             check(self.lib.fsr_rdb_close(self._h), "fsr_rdb_close")

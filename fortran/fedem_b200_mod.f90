@@ -739,6 +739,14 @@ module fedem_b200_mod
        real(c_double), intent(out) :: utot(*)
      end subroutine fsr_total_nodal_displacement
 
+     function fsr_rdb_flush (rdb, t, n) bind(C,name="fsr_rdb_flush") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value     :: rdb
+       real(c_double), intent(out) :: t(*)
+       integer(c_int), value  :: n
+       integer(c_int) :: ierr
+     end function fsr_rdb_flush
+
      function fsr_rdb_close (rdb) bind(C,name="fsr_rdb_close") result(ierr)
        import :: c_ptr, c_int
        type(c_ptr), value :: rdb
