@@ -9,8 +9,8 @@ the host-side mirror of the reference's driver interface.  There is no CPU fallb
 """
 from ._lib import load_library, library_path, FsrError
 from .model import SamData, ElementData, PartModel
-from .recovery import StressRecovery, FatigueCounter, fatigue
+from .recovery import StressRecovery, GroupRecovery, Comm, FatigueCounter, fatigue, split_elements
 from .gage import Rosette, StrainGages
 
 __all__ = ["load_library", "library_path", "FsrError", "SamData", "ElementData", "PartModel",
-           "StressRecovery", "FatigueCounter", "fatigue", "Rosette", "StrainGages"]
+           "StressRecovery", "GroupRecovery", "Comm", "split_elements", "FatigueCounter", "fatigue", "Rosette", "StrainGages"]

@@ -64,6 +64,35 @@ SYMBOLS = [
     ("fsr_ndim", C.c_int, [_P]),
     ("fsr_recover", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
     ("fsr_recover_dev", C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    ("fsr_split_elements", C.c_int, [C.POINTER(FsrSam), C.POINTER(FsrElmData), C.c_int, _I]),
+    ("fsr_blockdef_create", C.c_int, [C.POINTER(_P), C.POINTER(FsrSam), C.POINTER(FsrElmData), C.POINTER(FsrOptions), C.c_int, C.c_int]),
+    ("fsr_blockdef_sam", C.POINTER(FsrSam), [_P]),
+    ("fsr_blockdef_elm", C.POINTER(FsrElmData), [_P]),
+    ("fsr_blockdef_info", C.c_int, [_P, _I, _I, _I]),
+    ("fsr_blockdef_destroy", None, [_P]),
+    ("fsr_part_create_block", C.c_int, [C.POINTER(_P), C.POINTER(FsrSam), C.POINTER(FsrElmData), C.POINTER(FsrOptions), C.c_int, C.c_int]),
+    ("fsr_block_info", C.c_int, [_P, _I]),
+    ("fsr_block_rows", C.c_int, [_P, _I, _I]),
+    ("fsr_set_recovery_parent", C.c_int, [_P, _D, C.c_int, _D, C.c_int]),
+    ("fsr_group_create", C.c_int, [C.POINTER(_P), C.POINTER(FsrSam), C.POINTER(FsrElmData), C.POINTER(FsrOptions), _I, C.c_int]),
+    ("fsr_group_set_recovery", C.c_int, [_P, _D, C.c_int, _D, C.c_int]),
+    ("fsr_group_num_blocks", C.c_int, [_P]),
+    ("fsr_group_num_result_points", C.c_int, [_P]),
+    ("fsr_group_ndim", C.c_int, [_P]),
+    ("fsr_group_block", _P, [_P, C.c_int]),
+    ("fsr_group_recover", C.c_int, [_P, _D, C.c_int, C.c_int, _D]),
+    ("fsr_group_synchronize", C.c_int, [_P]),
+    ("fsr_group_reset_envelope", C.c_int, [_P]),
+    ("fsr_group_get_envelope", C.c_int, [_P, _D, _D]),
+    ("fsr_group_last_timing", C.c_int, [_P, _D, C.c_int]),
+    ("fsr_group_timing_reset", C.c_int, [_P]),
+    ("fsr_group_destroy", None, [_P]),
+    ("fsr_comm_unique_id", C.c_int, [C.c_char_p, C.c_int]),
+    ("fsr_comm_init_rank", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    ("fsr_comm_broadcast", C.c_int, [_P, _P, C.c_longlong, C.c_int, _P]),
+    ("fsr_comm_gather_envelope", C.c_int, [_P, _P, _I, _I, _P, _P, C.c_int, _P]),
+    ("fsr_comm_destroy", None, [_P]),
+    ("fsr_nccl_version", C.c_int, []),
     ("fsr_reset_envelope", C.c_int, [_P]),
     ("fsr_get_envelope", C.c_int, [_P, _D, _D]),
     ("fsr_envelope_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
@@ -135,6 +164,7 @@ SYMBOLS = [
     ("fsr_fsi_triads", C.c_int, [_P, _I, _I, _I, _I, _D, _D]),
     ("fsr_fsi_read_rosettes", C.c_int, [C.c_char_p, C.c_int, C.POINTER(FsrRosette), _I, C.c_char_p, C.c_int, C.c_int]),
     ("fsr_rdb_create", C.c_int, [C.POINTER(_P), _P, C.c_char_p, C.POINTER(FsrRdbOptions)]),
+    ("fsr_rdb_create_group", C.c_int, [C.POINTER(_P), _P, C.c_char_p, C.POINTER(FsrRdbOptions)]),
     ("fsr_rdb_build_header", C.c_int, [C.c_int, _I, C.c_int, _I, C.POINTER(FsrRdbOptions), C.c_char_p, C.c_int, C.POINTER(C.c_longlong)]),
     ("fsr_rdb_step_bytes", C.c_longlong, [_P]),
     ("fsr_rdb_header", C.c_int, [_P, C.c_char_p, C.c_int]),

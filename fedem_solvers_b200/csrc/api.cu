@@ -35,7 +35,7 @@ int smem_opt_in(const void* kernel, size_t bytes)
   return FSR_OK;
 }
 
-static int nstrp_of(int type)
+int nstrp_of(int type)
 {
   switch (type) {
     case 21: case 23: return 6;
@@ -52,7 +52,7 @@ static int nstrp_of(int type)
   }
 }
 
-static bool supported_type(int type) { return type == 24 || type == 23 || type == 31 || type == 32 || (type >= 41 && type <= 46) || type == 11; }
+bool supported_type(int type) { return type == 24 || type == 23 || type == 31 || type == 32 || (type >= 41 && type <= 46) || type == 11; }
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
@@ -150,6 +150,22 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam_in, const fsr_elmdata* el
 {
   if (!out || !sam_in || !elm) { set_error("fsr_part_create: null argument"); return FSR_ERR_ARG; }
   *out = nullptr;
+  std::vector<int> melcon_eff;
+  int quad_ngauss = 2;
+  fsr_sam sam_eff = *sam_in;
+  if (sam_in->melcon && sam_in->nel > 0) {
+    effective_element_types(sam_in, opt, melcon_eff, quad_ngauss);
+    sam_eff.melcon = melcon_eff.data();
+  }
+  return part_create_mapped(out, &sam_eff, elm, opt, quad_ngauss);
+}
+
+}  // extern "C"
+
+namespace fsr {
+
+void effective_element_types(const fsr_sam* sam_in, const fsr_options* opt, std::vector<int>& melcon_eff, int& quad_ngauss)
+{
   // Legacy thin shells (types 21 FFT3 and 22 FFQ4, parts reduced with -useANDESformulation-): with the default stress
   // formulations of fedem_stress (stressmain.C:72-78: -fftStressForm 1, -ffqStressForm 2) STR21 runs exactly the statements of
   // STR23 (FTSA31 / FTSA32 / FTS38, elStressModule.f90:559-562,586-587 vs :935,953) and STR22 exactly those of STR24
@@ -159,22 +175,22 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam_in, const fsr_elmdata* el
   const int ffq = opt && opt->reserved[1] ? opt->reserved[1] - 1 : 2, fft = opt && opt->reserved[2] ? opt->reserved[2] - 1 : 1;
   // -ffqStressForm 1 is STR22a with one Gauss point (:761-768,806-809): the quad operator builder takes the point count, so it
   // is served as well as long as the part has no ANDES quads (which always use 2 x 2) next to the FFQ ones.
-  std::vector<int> melcon_eff;
-  fsr_sam sam_eff = *sam_in;
-  int quad_ngauss = 2;
-  if (sam_in->melcon && sam_in->nel > 0) {
-    melcon_eff.assign(sam_in->melcon, sam_in->melcon + sam_in->nel);
-    bool has24 = false, has22 = false;
-    for (int t : melcon_eff) { has24 |= t == 24; has22 |= t == 22; }
-    const bool ffq1 = ffq == 1 && has22 && !has24;
-    if (ffq1) quad_ngauss = 1;
-    for (int& t : melcon_eff) {
-      if (t == 21) t = fft == 1 ? 23 : 0;
-      else if (t == 22) t = (ffq == 2 || ffq1) ? 24 : 0;
-    }
-    sam_eff.melcon = melcon_eff.data();
+  quad_ngauss = 2;
+  melcon_eff.assign(sam_in->melcon, sam_in->melcon + sam_in->nel);
+  bool has24 = false, has22 = false;
+  for (int t : melcon_eff) { has24 |= t == 24; has22 |= t == 22; }
+  const bool ffq1 = ffq == 1 && has22 && !has24;
+  if (ffq1) quad_ngauss = 1;
+  for (int& t : melcon_eff) {
+    if (t == 21) t = fft == 1 ? 23 : 0;
+    else if (t == 22) t = (ffq == 2 || ffq1) ? 24 : 0;
   }
-  const fsr_sam* sam = &sam_eff;
+}
+
+// fsr_part_create after the legacy shell types were mapped (an element block takes the mapping of its parent part)
+int part_create_mapped(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, const fsr_options* opt, int quad_ngauss)
+{
+  *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
     set_error("no CUDA device available: this library has no CPU fallback");
@@ -279,6 +295,10 @@ int fsr_part_create(fsr_part** out, const fsr_sam* sam_in, const fsr_elmdata* el
   *out = p;
   return p->nfailed;
 }
+
+}  // namespace fsr
+
+extern "C" {
 
 void fsr_part_destroy(fsr_part* p)
 {

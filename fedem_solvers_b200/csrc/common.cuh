@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>   // types only: the library binds NCCL at run time (sharded.cu)
+
 #include "../../include/fedem_b200.h"
 
 namespace fsr {
@@ -169,7 +171,35 @@ struct fsr_part {
   cudaEvent_t evring[256][3] = {};  // per-tile event triplets: start, after K1, after K2
   int ntimed = 0;
   double* pinned = nullptr; size_t pinned_cap = 0;
+  // element block of a larger part (sharded.cu): the parent's element range, the block's first result point in the parent's
+  // result-point order, the parent's nodes (1-based) of the block's nodes and the rows (0-based) of the parent's B / E it keeps
+  bool is_block = false;
+  int blk_e0 = 0, blk_e1 = 0, blk_pt0 = 0, parent_ndof1 = 0, parent_nel = 0, parent_npts = 0;
+  std::vector<int> blk_nodes, blk_rows1;
 };
+
+// ---- one process, several GPUs ------------------------------------------------------------------------
+struct fsr_group {
+  int nblk = 0, ndim = 0, npts = 0, nel = 0, nnod = 0;
+  std::vector<int> madof_host, melcon_host, active_host;   // the parent part (results database header)
+  std::vector<fsr_part*> parts;
+  std::vector<int> devices, e_cut;
+  std::vector<ncclComm_t> comms;       // empty when nblk == 1
+  std::vector<cudaStream_t> streams;   // the blocks' own streams
+  std::vector<double*> Qdev;           // per device: the broadcast Q window
+  size_t q_cap = 0;
+  double* Qpin = nullptr;              // pinned staging of the caller's Q
+  size_t qpin_cap = 0;
+  cudaEvent_t q_ev = nullptr;          // the H2D copy out of Qpin has finished
+  double* env_root = nullptr;          // device 0: [2][npts] gathered envelopes in the parent's result-point order
+  double* env_pin = nullptr;           // pinned copy
+  std::vector<double*> env_blk;        // per device: [2][npts_b] contiguous copy of the block's envelopes (send buffer)
+  std::vector<double*> vm_blk;         // per device: von Mises history staging [tile][npts_b]
+  size_t vm_cap = 0;
+  double* vm_pin = nullptr;            // pinned [nblk slices] for the host history
+  size_t vm_pin_cap = 0;
+};
+
 
 namespace fsr {
 // k1_expand.cu
@@ -183,6 +213,11 @@ int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nro
                   cudaStream_t s);
 int launch_pack_q_raw(double* Qt, int ldk, const double* Q_dev, int ldq, int ndim, int nsteps, int nsteps_pad,
                       cudaStream_t s);
+// api.cu: result points per element type, types with a stress operator, the legacy shell type mapping of fsr_part_create
+int nstrp_of(int type);
+bool supported_type(int type);
+void effective_element_types(const fsr_sam* sam, const fsr_options* opt, std::vector<int>& melcon_eff, int& quad_ngauss);
+int part_create_mapped(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, const fsr_options* opt, int quad_ngauss);
 // api.cu: active elements of one type, in processing order (see fsr_part::elem_order)
 std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int type);
 // io_rdb.cu: the meta data lines of a results database header (openHeaderFiles)

@@ -332,28 +332,38 @@ static void appendf(std::string& s, const char* fmt, ...)
 
 using namespace fsr;
 
-// Two record buffers on the device, two pinned ones on the host: while tile n is computed (stream of the part), tile n-1
-// crosses PCIe (copy stream) and tile n-2 goes to the file (writer thread, one writev per batch of step records).
+// Two record buffers per device, two pinned ones on the host: while tile n is computed (stream of the part), tile n-1
+// crosses PCIe (copy stream) and tile n-2 goes to the file (writer thread + helpers, pwritev of whole batches of step
+// records).  With a group of element blocks (several GPUs) every device fills the slots of ITS elements -- a contiguous
+// range of the step record, blocks being contiguous element ranges -- and a strided device-to-host copy drops them at
+// their place of the full records in the shared pinned buffer: the merge costs nothing.
 struct RdbJob { int buf = 0, nt = 0; std::vector<char> keys; };   // keys: nt x (int32 step number, float64 time)
 
-struct fsr_rdb {
+struct RdbDev {
   fsr_part* part = nullptr;
+  long long slot0 = 0, nslot = 0;      // this device's slot range of the step record
+  long long* roff[fsr::FAM_COUNT] = {};// device: record slot (relative to slot0) of each family element, -1 = not written
+  void* out[2] = {nullptr, nullptr};   // [tile][nslot] float/double
+  double* dQ = nullptr;                // device Q tile
+  cudaEvent_t ev[2][4] = {};           // per buffer: compute start / done (part stream), copy start / done (copy stream)
+  cudaStream_t copy_stream = nullptr;
+};
+
+struct fsr_rdb {
+  std::vector<RdbDev> devs;
+  fsr_part* part = nullptr;            // devs[0].part
   FILE* f = nullptr;
   int fd = -1;
+  long long data_pos = 0;              // file offset of the next step record
   std::string header, path;
   RecLayout L{};
   int dbl = 0;
   long long nslot = 0;                 // values per step record
-  long long nslot_nodes = 0;           // the leading nodal values of the record (writeDisplacementDB)
-  long long* roff[FAM_COUNT] = {};     // device: record slot of each family element (-1 = not written)
+  long long nslot_nodes = 0;           // the leading nodal values of the record (writeDisplacementDB; single device only)
   double* rec = nullptr;               // [nslot_nodes][tile] slot-major staging of the nodal values
-  void* out[2] = {nullptr, nullptr};   // [tile][nslot] float/double step records
-  void* host[2] = {nullptr, nullptr};  // pinned copies
+  void* host[2] = {nullptr, nullptr};  // pinned step records
   double* Qpin[2] = {nullptr, nullptr};// pinned staging of the caller's Q tile
-  double* dQ = nullptr;                // device Q tile
   int ldq_cap = 0;
-  cudaEvent_t ev[2][4] = {};           // per buffer: compute start / done (part stream), copy start / done (copy stream)
-  cudaStream_t copy_stream = nullptr;
   int tile = 0, next_buf = 0;
   long long steps_written = 0;
   long long* node_slot = nullptr;      // device [nnod] record slot of each node's displacements (-1 = none)
@@ -369,7 +379,8 @@ struct fsr_rdb {
   bool busy[2] = {false, false};       // buffer handed to the writer and not yet on file
   bool quit = false;
   std::string werr;                    // first error of the writer thread
-  // accounting (fsr_rdb_timing)
+  int nwriters = 1;
+  // accounting (fsr_rdb_flush)
   double ms_compute = 0.0, ms_copy = 0.0, ms_disk = 0.0;
   long long bytes_written = 0, tiles = 0;
 
@@ -387,24 +398,63 @@ struct fsr_rdb {
       writer.join();
     }
     if (f) fclose(f);
-    for (auto& r : roff) cudaFree(r);
-    cudaFree(rec); cudaFree(node_slot); cudaFree(madof); cudaFree(supTr0); cudaFree(supTr); cudaFree(dQ);
+    for (RdbDev& d : devs) {
+      cudaSetDevice(d.part->device);
+      for (auto& r : d.roff) cudaFree(r);
+      cudaFree(d.dQ);
+      for (int b = 0; b < 2; ++b) {
+        cudaFree(d.out[b]);
+        for (auto& e : d.ev[b]) if (e) cudaEventDestroy(e);
+      }
+      if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+    }
+    if (part) cudaSetDevice(part->device);
+    cudaFree(rec); cudaFree(node_slot); cudaFree(madof); cudaFree(supTr0); cudaFree(supTr);
     for (int b = 0; b < 2; ++b) {
-      cudaFree(out[b]);
       if (host[b]) cudaFreeHost(host[b]);
       if (Qpin[b]) cudaFreeHost(Qpin[b]);
       if (supPin[b]) cudaFreeHost(supPin[b]);
-      for (auto& e : ev[b]) if (e) cudaEventDestroy(e);
     }
-    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
 
-// The writer: waits for the device-to-host copy of a buffer, then appends its step records -- 12-byte key + payload per
-// step (writeTimeStepDB, rdbModule.f90:669-736) -- with writev, up to 512 steps per system call.
+// steps [t0, t1) of a pinned buffer -> file at `pos`: 12-byte key + payload per step (writeTimeStepDB,
+// rdbModule.f90:669-736), up to 512 steps per pwritev
+static std::string write_step_range(int fd, long long pos, const char* keys, const char* payload, size_t rec_bytes, int t0, int t1,
+                                    const std::string& path)
+{
+  std::vector<iovec> iov;
+  for (int t = t0; t < t1;) {
+    const int n = std::min(512, t1 - t);
+    iov.resize(2 * (size_t)n);
+    size_t want = 0;
+    for (int k = 0; k < n; ++k) {
+      iov[2 * k] = {(void*)(keys + 12 * (size_t)(t + k)), 12};
+      iov[2 * k + 1] = {(void*)(payload + rec_bytes * (size_t)(t + k)), rec_bytes};
+      want += 12 + rec_bytes;
+    }
+    size_t first = 0;
+    long long off = pos + (long long)(t - t0) * (long long)(12 + rec_bytes);
+    while (want > 0) {   // a short write continues where it stopped
+      const ssize_t w = pwritev(fd, iov.data() + first, (int)std::min<size_t>(iov.size() - first, 1024), off);
+      if (w < 0) { if (errno == EINTR) continue; return path + ": write error: " + strerror(errno); }
+      want -= (size_t)w;
+      off += w;
+      size_t left = (size_t)w;
+      while (left > 0 && first < iov.size()) {
+        if (left >= iov[first].iov_len) { left -= iov[first].iov_len; ++first; }
+        else { iov[first].iov_base = (char*)iov[first].iov_base + left; iov[first].iov_len -= left; left = 0; }
+      }
+    }
+    t += n;
+  }
+  return std::string();
+}
+
+// The writer: waits for the device-to-host copies of a buffer, then appends its step records; the copy into the page cache
+// is what takes the time, so the steps of a tile are split over a few helper threads writing at their own file offsets.
 void fsr_rdb::writer_main()
 {
-  cudaSetDevice(part->device);
   const size_t vb = dbl ? 8 : 4, rec_bytes = vb * (size_t)nslot;
   for (;;) {
     RdbJob job;
@@ -416,32 +466,30 @@ void fsr_rdb::writer_main()
       jobs.pop_front();
     }
     std::string err;
-    if (cudaEventSynchronize(ev[job.buf][3]) != cudaSuccess) err = std::string("device error while recovering a tile of steps: ") + cudaGetErrorString(cudaGetLastError());
     float a = 0.f, c = 0.f;
-    if (err.empty()) { cudaEventElapsedTime(&a, ev[job.buf][0], ev[job.buf][1]); cudaEventElapsedTime(&c, ev[job.buf][2], ev[job.buf][3]); }
+    for (RdbDev& d : devs) {
+      if (d.nslot == 0) continue;
+      cudaSetDevice(d.part->device);
+      if (cudaEventSynchronize(d.ev[job.buf][3]) != cudaSuccess) { err = std::string("device error while recovering a tile of steps: ") + cudaGetErrorString(cudaGetLastError()); break; }
+      float ai = 0.f, ci = 0.f;
+      cudaEventElapsedTime(&ai, d.ev[job.buf][0], d.ev[job.buf][1]);
+      cudaEventElapsedTime(&ci, d.ev[job.buf][2], d.ev[job.buf][3]);
+      a = std::max(a, ai); c = std::max(c, ci);
+    }
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<iovec> iov;
-    for (int t = 0; t < job.nt && err.empty();) {
-      const int n = std::min(512, job.nt - t);
-      iov.resize(2 * (size_t)n);
-      size_t want = 0;
-      for (int k = 0; k < n; ++k) {
-        iov[2 * k] = {job.keys.data() + 12 * (size_t)(t + k), 12};
-        iov[2 * k + 1] = {(char*)host[job.buf] + rec_bytes * (size_t)(t + k), rec_bytes};
-        want += 12 + rec_bytes;
+    if (err.empty()) {
+      const int nw = std::max(1, std::min(nwriters, job.nt));
+      std::vector<std::string> errs((size_t)nw);
+      std::vector<std::thread> th;
+      const long long step_bytes = 12 + (long long)rec_bytes;
+      for (int w = 0; w < nw; ++w) {
+        const int ta = (int)((long long)job.nt * w / nw), tb = (int)((long long)job.nt * (w + 1) / nw);
+        auto work = [&, w, ta, tb] { errs[(size_t)w] = write_step_range(fd, data_pos + step_bytes * ta, job.keys.data(), (const char*)host[job.buf], rec_bytes, ta, tb, path); };
+        if (w + 1 < nw) th.emplace_back(work); else work();
       }
-      size_t first = 0;
-      while (want > 0) {   // a short write continues where it stopped
-        const ssize_t w = writev(fd, iov.data() + first, (int)(iov.size() - first));
-        if (w < 0) { if (errno == EINTR) continue; err = path + ": write error: " + strerror(errno); break; }
-        want -= (size_t)w;
-        size_t left = (size_t)w;
-        while (left > 0 && first < iov.size()) {
-          if (left >= iov[first].iov_len) { left -= iov[first].iov_len; ++first; }
-          else { iov[first].iov_base = (char*)iov[first].iov_base + left; iov[first].iov_len -= left; left = 0; }
-        }
-      }
-      t += n;
+      for (std::thread& t : th) t.join();
+      for (const std::string& e : errs) if (!e.empty() && err.empty()) err = e;
+      data_pos += step_bytes * job.nt;
     }
     const double disk = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     {
@@ -690,18 +738,18 @@ static int layout_from_options(const fsr_rdb_options* o, RecLayout& L)
 }  // namespace
 
 template <class OUT_T>
-static int launch_record_kernels(fsr_rdb* r, int nt, OUT_T* out, cudaStream_t s)
+static int launch_record_kernels(fsr_rdb* r, RdbDev& d, int nt, OUT_T* out, cudaStream_t s)
 {
-  fsr_part* p = r->part;
-  const size_t ld_out = (size_t)r->nslot;
+  fsr_part* p = d.part;
+  const size_t ld_out = (size_t)d.nslot;
   for (int fi = 0; fi < FAM_COUNT; ++fi) {
     FamilyData& f = p->fam[fi];
-    if (f.nelt == 0 || !r->roff[fi]) continue;
+    if (f.nelt == 0 || !d.roff[fi]) continue;
     if (fi == FAM_BEAM) {
       if (!r->L.sr) continue;
       dim3 blk(96, 4), grd((unsigned)(((long long)f.nelt * 12 + 95) / 96), (nt + 3) / 4);
       record_beams_kernel<OUT_T><<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, reinterpret_cast<const BeamOp12*>(f.Sfrag), f.edof,
-                                                     r->roff[fi], f.failed, f.nelt, out, ld_out);
+                                                     d.roff[fi], f.failed, f.nelt, out, ld_out);
     } else {
       if (f.nstrp == 0) continue;
       if (!(r->L.stress || r->L.strain || r->L.nsel || (r->L.sr && f.ncmp == 3) || (r->L.sr && f.Efrag))) continue;
@@ -711,11 +759,149 @@ static int launch_record_kernels(fsr_rdb* r, int nt, OUT_T* out, cudaStream_t s)
       if (smem > 48 * 1024)
         if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<OUT_T>, 100 * 1024)) return rc;
       record_points_dmma_kernel<OUT_T><<<(f.nelt + kRecWarps - 1) / kRecWarps, kRecWarps * 32, smem, s>>>(
-          p->U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag, f.edof, r->roff[fi], f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
+          p->U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag, f.edof, d.roff[fi], f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
           f.MT, f.KT, layout, f.nenod, r->L, out, ld_out);
     }
     FSR_LAUNCH_CHECK();
   }
+  return FSR_OK;
+}
+
+// common part of fsr_rdb_create / fsr_rdb_create_group: parts = the element blocks (one: the whole part), e_cut their
+// element ranges in the parent, the remaining arguments describe the parent
+static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const std::vector<int>& e_cut, int nnod, const int* madof,
+                      int nel, const int* melcon, const int* active, const char* path, const fsr_rdb_options* o)
+{
+  *out = nullptr;
+  RecLayout L;
+  int rc0 = layout_from_options(o, L);
+  if (rc0) return rc0;
+  if (L.def && parts.size() > 1) { set_error("nodal deformation output is written by a single device: create the results database on one part"); return FSR_ERR_ARG; }
+  std::string header;
+  std::vector<long long> slot, node_slot;
+  const long long nslot = build_header(nnod, madof, nel, melcon, active, o, L, header, slot, node_slot);
+  if (nslot == 0) { set_error("fsr_rdb_create: none of the active elements has the requested results"); return FSR_ERR_ARG; }
+
+  fsr_rdb* r = new fsr_rdb;
+  fsr_part* p = parts[0];
+  r->part = p; r->L = L; r->dbl = o->double_precision ? 1 : 0; r->nslot = nslot;
+  r->header = header;
+  // openRDBfile (rdbModule.f90:268-403): <name>_<rdbinc>.<ext>
+  r->path = path;
+  if (o->rdbinc > 0) {
+    const size_t dot = r->path.rfind('.');
+    const size_t sep = r->path.rfind('/');
+    char inc[16];
+    snprintf(inc, sizeof(inc), "_%d", o->rdbinc);
+    if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) r->path.insert(dot, inc);
+    else r->path += inc;
+  }
+  TaggedFile tf;
+  int rc = tf.open_write(r->path.c_str(), "#FEDEM response data", 0u);
+  if (rc) { delete r; return rc; }
+  if (fputs(r->header.c_str(), tf.f) < 0 || fputs("DATA:", tf.f) < 0) { set_error("%s: write error", r->path.c_str()); delete r; return FSR_ERR_ARG; }
+  r->f = tf.f;
+  tf.f = nullptr;
+  // slot range of every block: blocks are contiguous element ranges and slots ascend with the element number
+  r->devs.resize(parts.size());
+  const long long first_elem_slot = [&] { for (int e = 0; e < nel; ++e) if (slot[(size_t)e] >= 0) return slot[(size_t)e]; return nslot; }();
+  for (size_t ib = 0; ib < parts.size(); ++ib) {
+    RdbDev& d = r->devs[ib];
+    d.part = parts[ib];
+    long long s0 = -1, s1 = nslot;
+    for (int e = e_cut[ib]; e < e_cut[ib + 1] && s0 < 0; ++e) if (slot[(size_t)e] >= 0) s0 = slot[(size_t)e];
+    for (int e = e_cut[ib + 1]; e < nel; ++e) if (slot[(size_t)e] >= 0) { s1 = slot[(size_t)e]; break; }
+    d.slot0 = s0 < 0 ? s1 : s0;
+    d.nslot = s0 < 0 ? 0 : s1 - s0;
+    if (parts.size() == 1) { d.slot0 = 0; d.nslot = nslot; }   // the single device also owns the nodal values in front
+  }
+  (void)first_elem_slot;
+  // per device and family: record slot of each of its elements, relative to the device's range
+  for (size_t ib = 0; ib < parts.size(); ++ib) {
+    RdbDev& d = r->devs[ib];
+    if (cudaSetDevice(d.part->device) != cudaSuccess) { set_error("cudaSetDevice failed"); delete r; return FSR_ERR_CUDA; }
+    for (int fi = 0; fi < FAM_COUNT; ++fi) {
+      FamilyData& f = d.part->fam[fi];
+      if (f.nelt == 0) continue;
+      std::vector<int> elem((size_t)f.nelt);
+      if (cudaMemcpy(elem.data(), f.elem, sizeof(int) * f.nelt, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("fsr_rdb_create: cudaMemcpy failed"); delete r; return FSR_ERR_CUDA; }
+      std::vector<long long> ro((size_t)f.nelt);
+      for (int i = 0; i < f.nelt; ++i) {
+        const long long sl = slot[(size_t)e_cut[ib] + (size_t)elem[(size_t)i]];
+        ro[(size_t)i] = sl < 0 ? -1 : sl - d.slot0;
+      }
+      if (cudaMalloc(&d.roff[fi], sizeof(long long) * f.nelt) != cudaSuccess ||
+          cudaMemcpy(d.roff[fi], ro.data(), sizeof(long long) * f.nelt, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
+      }
+    }
+  }
+  cudaSetDevice(p->device);
+  if (L.def) {
+    if (cudaMalloc(&r->node_slot, sizeof(long long) * std::max(p->nnod, 1)) != cudaSuccess ||
+        cudaMalloc(&r->madof, sizeof(int) * (p->nnod + 1)) != cudaSuccess ||
+        cudaMemcpy(r->node_slot, node_slot.data(), sizeof(long long) * p->nnod, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(r->madof, p->madof_host.data(), sizeof(int) * (p->nnod + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
+    }
+    if (L.def > 1 && (cudaMalloc(&r->supTr0, sizeof(double) * 12) != cudaSuccess ||
+                      cudaMemcpy(r->supTr0, o->sup_tr_init, sizeof(double) * 12, cudaMemcpyHostToDevice) != cudaSuccess)) {
+      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
+    }
+  }
+  // step tile of the record buffers: bounded by the parts' step tile, by 1 GiB per pinned host buffer (two of them) and by
+  // ~1/4 of the free device memory
+  r->nslot_nodes = 0;
+  if (L.def)
+    for (int n = 0; n < p->nnod; ++n)
+      if (node_slot[(size_t)n] >= 0) {
+        const int nd = p->madof_host[(size_t)n + 1] - p->madof_host[(size_t)n] > 5 ? 6 : 3;
+        r->nslot_nodes = std::max(r->nslot_nodes, node_slot[(size_t)n] + (L.def > 1 ? 2 : 1) * nd);
+      }
+  const size_t vb = r->dbl ? 8 : 4;
+  long long tile = (long long)((double)(1u << 30) / ((double)nslot * (double)vb));
+  for (RdbDev& d : r->devs) {
+    size_t free_b = 0, total_b = 0;
+    cudaSetDevice(d.part->device);
+    cudaMemGetInfo(&free_b, &total_b);
+    const double per_step = 2.0 * (double)std::max<long long>(d.nslot, 1) * (double)vb + 8.0 * (double)r->nslot_nodes;
+    tile = std::min<long long>(tile, (long long)(0.25 * (double)free_b / per_step));
+    tile = std::min<long long>(tile, d.part->step_tile);
+  }
+  if (const char* e = getenv("FSR_RDB_TILE")) tile = std::min<long long>(std::max(1, atoi(e)), tile);   // tests: several tiles per call
+  tile = std::max<long long>(1, tile);
+  if (tile >= 8) tile = tile / 8 * 8;
+  r->tile = (int)tile;
+  bool ok = true;
+  for (RdbDev& d : r->devs) {
+    cudaSetDevice(d.part->device);
+    ok = ok && cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int b = 0; b < 2 && ok; ++b) {
+      ok = cudaMalloc(&d.out[b], vb * (size_t)std::max<long long>(d.nslot, 1) * r->tile) == cudaSuccess;
+      for (auto& e : d.ev[b]) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    }
+  }
+  cudaSetDevice(p->device);
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaHostAlloc(&r->host[b], vb * (size_t)nslot * r->tile, cudaHostAllocPortable) == cudaSuccess &&
+         (L.def <= 1 || cudaHostAlloc((void**)&r->supPin[b], sizeof(double) * 12 * r->tile, cudaHostAllocPortable) == cudaSuccess);
+  ok = ok && (r->nslot_nodes == 0 || cudaMalloc(&r->rec, sizeof(double) * (size_t)r->nslot_nodes * r->tile) == cudaSuccess) &&
+       (L.def <= 1 || cudaMalloc(&r->supTr, sizeof(double) * 12 * r->tile) == cudaSuccess);
+  if (!ok) {
+    set_error("fsr_rdb_create: cannot allocate the record buffers (%lld values x %d steps): %s", nslot, r->tile,
+              cudaGetErrorString(cudaGetLastError()));
+    delete r;
+    return FSR_ERR_ALLOC;
+  }
+  // the header went through stdio; the step records go through the descriptor at explicit offsets
+  if (fflush(r->f) != 0) { set_error("%s: write error", r->path.c_str()); delete r; return FSR_ERR_ARG; }
+  r->fd = fileno(r->f);
+  r->data_pos = (long long)ftello(r->f);
+  const unsigned hc = std::thread::hardware_concurrency();
+  r->nwriters = (int)std::max(1u, std::min(8u, hc / 2));
+  if (const char* e = getenv("FSR_RDB_WRITERS")) r->nwriters = std::max(1, atoi(e));
+  r->writer = std::thread(&fsr_rdb::writer_main, r);
+  *out = r;
   return FSR_OK;
 }
 
@@ -741,100 +927,15 @@ int fsr_rdb_build_header(int nnod, const int* madof, int nel, const int* melcon,
 int fsr_rdb_create(fsr_rdb** out, fsr_part* p, const char* path, const fsr_rdb_options* o)
 {
   if (!out || !p || !path || !o) { set_error("fsr_rdb_create: bad arguments"); return FSR_ERR_ARG; }
-  *out = nullptr;
-  RecLayout L;
-  int rc0 = layout_from_options(o, L);
-  if (rc0) return rc0;
   FSR_CUDA(cudaSetDevice(p->device));
-  std::string header;
-  std::vector<long long> slot, node_slot;
-  const long long nslot = build_header(p->nnod, p->madof_host.data(), p->nel, p->melcon_host.data(), p->active_host.data(), o, L,
-                                       header, slot, node_slot);
-  if (nslot == 0) { set_error("fsr_rdb_create: none of the active elements has the requested results"); return FSR_ERR_ARG; }
+  return rdb_create(out, {p}, {0, p->nel}, p->nnod, p->madof_host.data(), p->nel, p->melcon_host.data(), p->active_host.data(), path, o);
+}
 
-  fsr_rdb* r = new fsr_rdb;
-  r->part = p; r->L = L; r->dbl = o->double_precision ? 1 : 0; r->nslot = nslot;
-  r->header = header;
-  // openRDBfile (rdbModule.f90:268-403): <name>_<rdbinc>.<ext>
-  r->path = path;
-  if (o->rdbinc > 0) {
-    const size_t dot = r->path.rfind('.');
-    const size_t sep = r->path.rfind('/');
-    char inc[16];
-    snprintf(inc, sizeof(inc), "_%d", o->rdbinc);
-    if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) r->path.insert(dot, inc);
-    else r->path += inc;
-  }
-  TaggedFile tf;
-  int rc = tf.open_write(r->path.c_str(), "#FEDEM response data", 0u);
-  if (rc) { delete r; return rc; }
-  if (fputs(r->header.c_str(), tf.f) < 0 || fputs("DATA:", tf.f) < 0) { set_error("%s: write error", r->path.c_str()); delete r; return FSR_ERR_ARG; }
-  r->f = tf.f;
-  tf.f = nullptr;
-  // per family: record slot of each of its elements
-  for (int fi = 0; fi < FAM_COUNT; ++fi) {
-    FamilyData& f = p->fam[fi];
-    if (f.nelt == 0) continue;
-    std::vector<int> elem((size_t)f.nelt);
-    if (cudaMemcpy(elem.data(), f.elem, sizeof(int) * f.nelt, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("fsr_rdb_create: cudaMemcpy failed"); delete r; return FSR_ERR_CUDA; }
-    std::vector<long long> ro((size_t)f.nelt);
-    for (int i = 0; i < f.nelt; ++i) ro[(size_t)i] = slot[(size_t)elem[(size_t)i]];
-    if (cudaMalloc(&r->roff[fi], sizeof(long long) * f.nelt) != cudaSuccess ||
-        cudaMemcpy(r->roff[fi], ro.data(), sizeof(long long) * f.nelt, cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
-    }
-  }
-  if (L.def) {
-    if (cudaMalloc(&r->node_slot, sizeof(long long) * std::max(p->nnod, 1)) != cudaSuccess ||
-        cudaMalloc(&r->madof, sizeof(int) * (p->nnod + 1)) != cudaSuccess ||
-        cudaMemcpy(r->node_slot, node_slot.data(), sizeof(long long) * p->nnod, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(r->madof, p->madof_host.data(), sizeof(int) * (p->nnod + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
-    }
-    if (L.def > 1 && (cudaMalloc(&r->supTr0, sizeof(double) * 12) != cudaSuccess ||
-                      cudaMemcpy(r->supTr0, o->sup_tr_init, sizeof(double) * 12, cudaMemcpyHostToDevice) != cudaSuccess)) {
-      set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
-    }
-  }
-  // step tile of the record buffers: bounded by the part's step tile, by 1 GiB per buffer (two on the device, two pinned
-  // on the host) and by ~1/4 of the free device memory
-  r->nslot_nodes = 0;
-  for (int n = 0; n < p->nnod; ++n)
-    if (node_slot[(size_t)n] >= 0) {
-      const int nd = p->madof_host[(size_t)n + 1] - p->madof_host[(size_t)n] > 5 ? 6 : 3;
-      r->nslot_nodes = std::max(r->nslot_nodes, node_slot[(size_t)n] + (L.def > 1 ? 2 : 1) * nd);
-    }
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  const size_t vb = r->dbl ? 8 : 4;
-  const double per_step = 2.0 * (double)nslot * (double)vb + 8.0 * (double)r->nslot_nodes;
-  long long tile = (long long)(0.25 * (double)free_b / per_step);
-  tile = std::min<long long>(tile, (long long)((double)(1u << 30) / ((double)nslot * (double)vb)));
-  if (const char* e = getenv("FSR_RDB_TILE")) tile = std::max(1, atoi(e));   // tests: force several tiles per call
-  tile = std::max<long long>(1, std::min<long long>(tile, p->step_tile));
-  if (tile >= 8) tile = tile / 8 * 8;
-  r->tile = (int)tile;
-  bool ok = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-  for (int b = 0; b < 2 && ok; ++b) {
-    ok = cudaMalloc(&r->out[b], vb * (size_t)nslot * r->tile) == cudaSuccess &&
-         cudaMallocHost(&r->host[b], vb * (size_t)nslot * r->tile) == cudaSuccess &&
-         (L.def <= 1 || cudaMallocHost(&r->supPin[b], sizeof(double) * 12 * r->tile) == cudaSuccess);
-    for (auto& e : r->ev[b]) ok = ok && cudaEventCreate(&e) == cudaSuccess;
-  }
-  ok = ok && (r->nslot_nodes == 0 || cudaMalloc(&r->rec, sizeof(double) * (size_t)r->nslot_nodes * r->tile) == cudaSuccess) &&
-       (L.def <= 1 || cudaMalloc(&r->supTr, sizeof(double) * 12 * r->tile) == cudaSuccess);
-  if (!ok) {
-    set_error("fsr_rdb_create: cannot allocate the record buffers (%lld values x %d steps): %s", nslot, r->tile,
-              cudaGetErrorString(cudaGetLastError()));
-    delete r;
-    return FSR_ERR_ALLOC;
-  }
-  // the header went through stdio; the step records go through the descriptor
-  if (fflush(r->f) != 0) { set_error("%s: write error", r->path.c_str()); delete r; return FSR_ERR_ARG; }
-  r->fd = fileno(r->f);
-  r->writer = std::thread(&fsr_rdb::writer_main, r);
-  *out = r;
-  return FSR_OK;
+// the results database of a part recovered by a group of element blocks on several GPUs (no nodal deformation output)
+int fsr_rdb_create_group(fsr_rdb** out, fsr_group* g, const char* path, const fsr_rdb_options* o)
+{
+  if (!out || !g || !path || !o) { set_error("fsr_rdb_create_group: bad arguments"); return FSR_ERR_ARG; }
+  return rdb_create(out, g->parts, g->e_cut, g->nnod, g->madof_host.data(), g->nel, g->melcon_host.data(), g->active_host.data(), path, o);
 }
 
 long long fsr_rdb_step_bytes(const fsr_rdb* r) { return r ? 12 + r->nslot * (r->dbl ? 8 : 4) : 0; }
@@ -860,19 +961,26 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
   if (r->L.def > 1 && !sup_tr) { set_error("fsr_rdb_write_steps: total displacements need the part position matrix of every step"); return FSR_ERR_ARG; }
   fsr_part* p = r->part;
   if (ldq < p->ndim) { set_error("fsr_rdb_write_steps: ldq < ndim"); return FSR_ERR_ARG; }
-  if (!p->have_R) { set_error("fsr_rdb_write_steps: call fsr_set_recovery first"); return FSR_ERR_STATE; }
-  FSR_CUDA(cudaSetDevice(p->device));
-  int rc = ensure_batch_buffers(p, false);
-  if (rc) return rc;
-  cudaStream_t s = p->stream;
+  int rc;
+  for (RdbDev& d : r->devs) {
+    if (!d.part->have_R) { set_error("fsr_rdb_write_steps: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+    FSR_CUDA(cudaSetDevice(d.part->device));
+    if ((rc = ensure_batch_buffers(d.part, false))) return rc;
+  }
   const size_t vb = r->dbl ? 8 : 4;
   if (ldq > r->ldq_cap) {   // Q staging, sized on first use (ldq is the caller's)
     r->drain();
-    FSR_CUDA(cudaStreamSynchronize(s));
-    cudaFree(r->dQ); r->dQ = nullptr;
-    for (int b = 0; b < 2; ++b) { if (r->Qpin[b]) cudaFreeHost(r->Qpin[b]); r->Qpin[b] = nullptr; }
-    FSR_CUDA(cudaMalloc(&r->dQ, sizeof(double) * (size_t)ldq * r->tile));
-    for (int b = 0; b < 2; ++b) FSR_CUDA(cudaMallocHost(&r->Qpin[b], sizeof(double) * (size_t)ldq * r->tile));
+    for (RdbDev& d : r->devs) {
+      FSR_CUDA(cudaSetDevice(d.part->device));
+      FSR_CUDA(cudaStreamSynchronize(d.part->stream));
+      cudaFree(d.dQ); d.dQ = nullptr;
+      FSR_CUDA(cudaMalloc(&d.dQ, sizeof(double) * (size_t)ldq * r->tile));
+    }
+    for (int b = 0; b < 2; ++b) {
+      if (r->Qpin[b]) cudaFreeHost(r->Qpin[b]);
+      r->Qpin[b] = nullptr;
+      FSR_CUDA(cudaHostAlloc((void**)&r->Qpin[b], sizeof(double) * (size_t)ldq * r->tile, cudaHostAllocPortable));
+    }
     r->ldq_cap = ldq;
   }
   for (int t0 = 0; t0 < nsteps; t0 += r->tile) {
@@ -885,31 +993,37 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
       if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); return FSR_ERR_ARG; }
     }
     memcpy(r->Qpin[b], Q + (size_t)t0 * ldq, sizeof(double) * (size_t)ldq * nt);
-    FSR_CUDA(cudaEventRecord(r->ev[b][0], s));
-    FSR_CUDA(cudaMemcpyAsync(r->dQ, r->Qpin[b], sizeof(double) * (size_t)ldq * nt, cudaMemcpyHostToDevice, s));
-    if ((rc = launch_pack_q(p, r->dQ, ldq, nt, nt_pad, s)) || (rc = launch_k1(p, nt_pad, s))) return rc;
-    if (r->L.def) {   // nodal values: slot-major staging, then one tiled transpose into the leading part of the records
-      if (r->L.def > 1) {
-        memcpy(r->supPin[b], sup_tr + (size_t)t0 * 12, sizeof(double) * 12 * nt);
-        FSR_CUDA(cudaMemcpyAsync(r->supTr, r->supPin[b], sizeof(double) * 12 * nt, cudaMemcpyHostToDevice, s));
+    if (r->L.def > 1) memcpy(r->supPin[b], sup_tr + (size_t)t0 * 12, sizeof(double) * 12 * nt);
+    for (RdbDev& d : r->devs) {
+      if (d.nslot == 0) continue;
+      fsr_part* dp = d.part;
+      cudaStream_t s = dp->stream;
+      FSR_CUDA(cudaSetDevice(dp->device));
+      FSR_CUDA(cudaEventRecord(d.ev[b][0], s));
+      FSR_CUDA(cudaMemcpyAsync(d.dQ, r->Qpin[b], sizeof(double) * (size_t)ldq * nt, cudaMemcpyHostToDevice, s));
+      if ((rc = launch_pack_q(dp, d.dQ, ldq, nt, nt_pad, s)) || (rc = launch_k1(dp, nt_pad, s))) return rc;
+      if (r->L.def) {   // nodal values: slot-major staging, then one tiled transpose into the leading part of the records
+        if (r->L.def > 1) FSR_CUDA(cudaMemcpyAsync(r->supTr, r->supPin[b], sizeof(double) * 12 * nt, cudaMemcpyHostToDevice, s));
+        const size_t ldt = (size_t)r->tile;
+        dim3 blk(32, 8), grd((dp->nnod + 7) / 8, (nt + 31) / 32);
+        record_nodes_kernel<<<grd, blk, 0, s>>>(dp->U, (size_t)dp->step_tile, nt, dp->nnod, r->madof, r->node_slot, dp->xyz, r->supTr,
+                                                r->supTr0, r->L.def > 1, r->rec, ldt);
+        FSR_LAUNCH_CHECK();
+        dim3 tg((unsigned)((r->nslot_nodes + 31) / 32), (nt + 31) / 32);
+        if (r->dbl) record_transpose_kernel<double><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (double*)d.out[b], (size_t)d.nslot);
+        else record_transpose_kernel<float><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (float*)d.out[b], (size_t)d.nslot);
+        FSR_LAUNCH_CHECK();
       }
-      const size_t ldt = (size_t)r->tile;
-      dim3 blk(32, 8), grd((p->nnod + 7) / 8, (nt + 31) / 32);
-      record_nodes_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, p->nnod, r->madof, r->node_slot, p->xyz, r->supTr,
-                                              r->supTr0, r->L.def > 1, r->rec, ldt);
-      FSR_LAUNCH_CHECK();
-      dim3 tg((unsigned)((r->nslot_nodes + 31) / 32), (nt + 31) / 32);
-      if (r->dbl) record_transpose_kernel<double><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (double*)r->out[b], (size_t)r->nslot);
-      else record_transpose_kernel<float><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (float*)r->out[b], (size_t)r->nslot);
-      FSR_LAUNCH_CHECK();
+      rc = r->dbl ? launch_record_kernels<double>(r, d, nt, (double*)d.out[b], s) : launch_record_kernels<float>(r, d, nt, (float*)d.out[b], s);
+      if (rc) return rc;
+      FSR_CUDA(cudaEventRecord(d.ev[b][1], s));
+      FSR_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev[b][1], 0));
+      FSR_CUDA(cudaEventRecord(d.ev[b][2], d.copy_stream));
+      // this device's slot range of every step record of the tile
+      FSR_CUDA(cudaMemcpy2DAsync((char*)r->host[b] + vb * (size_t)d.slot0, vb * (size_t)r->nslot, d.out[b], vb * (size_t)d.nslot,
+                                 vb * (size_t)d.nslot, (size_t)nt, cudaMemcpyDeviceToHost, d.copy_stream));
+      FSR_CUDA(cudaEventRecord(d.ev[b][3], d.copy_stream));
     }
-    rc = r->dbl ? launch_record_kernels<double>(r, nt, (double*)r->out[b], s) : launch_record_kernels<float>(r, nt, (float*)r->out[b], s);
-    if (rc) return rc;
-    FSR_CUDA(cudaEventRecord(r->ev[b][1], s));
-    FSR_CUDA(cudaStreamWaitEvent(r->copy_stream, r->ev[b][1], 0));
-    FSR_CUDA(cudaEventRecord(r->ev[b][2], r->copy_stream));
-    FSR_CUDA(cudaMemcpyAsync(r->host[b], r->out[b], vb * (size_t)r->nslot * nt, cudaMemcpyDeviceToHost, r->copy_stream));
-    FSR_CUDA(cudaEventRecord(r->ev[b][3], r->copy_stream));
     RdbJob job;
     job.buf = b; job.nt = nt;
     job.keys.resize(12 * (size_t)nt);
@@ -960,8 +1074,6 @@ int fsr_rdb_close(fsr_rdb* r)
   }
   r->cv.notify_all();
   if (r->writer.joinable()) r->writer.join();
-  cudaSetDevice(r->part->device);
-  cudaStreamSynchronize(r->copy_stream);
   if (r->f && fclose(r->f) != 0 && rc == FSR_OK) { set_error("%s: close error", r->path.c_str()); rc = FSR_ERR_ARG; }
   r->f = nullptr;
   delete r;

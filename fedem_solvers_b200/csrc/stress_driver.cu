@@ -207,6 +207,7 @@ void fsr_stress_define_options(void)
   // B200 additions
   c.add("device", 0, "CUDA device ordinal");
   c.add("stepTile", 0, "Time steps per device batch (0 = from free device memory)");
+  c.add("gpus", 0, "Number of GPUs the elements of the part are spread over\n= 0: one per 100,000 elements, at most all visible ones");
   g_stress_options_defined = true;
 }
 
@@ -471,10 +472,29 @@ static int run_program(int which)
   memset(&po, 0, sizeof(po));
   po.device = c.get_int("device"); po.stressForm = c.get_int("stressForm"); po.step_tile = c.get_int("stepTile");
   if (!gage) { po.reserved[1] = c.get_int("ffqStressForm") + 1; po.reserved[2] = c.get_int("fftStressForm") + 1; }
+  // fedem_stress spreads the elements of the part over several GPUs (element blocks, sharded.cu) when the part is large;
+  // nodal deformation output needs all nodes on one device
+  int ngpu = 1;
+  if (which == 0) {
+    int nvis = 1;
+    cudaGetDeviceCount(&nvis);
+    ngpu = c.get_int("gpus");
+    if (ngpu <= 0) ngpu = std::max(1, std::min(nvis, nael / 100000));
+    if (ngpu > nvis) { log.line("  ** Note: -gpus %d but only %d GPU(s) visible", ngpu, nvis); ngpu = nvis; }
+    if (ngpu > 1 && c.get_bool("deformation")) { log.line("  ** Note: -deformation is written by one GPU: -gpus %d ignored", ngpu); ngpu = 1; }
+  }
   fsr_part* part = nullptr;
-  const int nfail = fsr_part_create(&part, &sam, &ed, &po);
+  fsr_group* group = nullptr;
+  int nfail;
+  if (ngpu > 1) {
+    std::vector<int> devs((size_t)ngpu);
+    for (int i = 0; i < ngpu; ++i) devs[(size_t)i] = (po.device + i) % ngpu;
+    nfail = fsr_group_create(&group, &sam, &ed, &po, devs.data(), ngpu);
+    if (nfail >= 0) log.line("           --> %d element blocks on %d GPUs", fsr_group_num_blocks(group), ngpu);
+  } else
+    nfail = fsr_part_create(&part, &sam, &ed, &po);
   if (nfail < 0) { log.line(" *** Error: %s", fsr_last_error()); log.line("\n    Stress calculation failed :-("); return nfail; }
-  struct PartGuard { fsr_part* p; ~PartGuard() { fsr_part_destroy(p); } } part_guard{part};
+  struct PartGuard { fsr_part*& p; fsr_group*& g; ~PartGuard() { if (p) fsr_part_destroy(p); if (g) fsr_group_destroy(g); } } part_guard{part, group};
   if (nfail > 0) log.line("  ** Warning: the stress operator of %d elements could not be formed; they get %g", nfail, kHuge);
 
   // --- Open the B-matrix and the generalized modes files (openBandEmatrices)
@@ -496,7 +516,8 @@ static int run_program(int which)
       if (strcmp(tag, "#FEDEM displacement matrix") != 0) FAIL("%s is not a displacement matrix file, tag=%s", dispfile.c_str(), tag);
       log.line("           --> Gravitation displacement modes read from %s", dispfile.c_str());
     }
-    CHECK(fsr_set_recovery(part, ndof2 > 0 ? B.data() : nullptr, ndof1, nmodes > 0 ? E.data() : nullptr, ndof1));
+    if (group) CHECK(fsr_group_set_recovery(group, ndof2 > 0 ? B.data() : nullptr, ndof1, nmodes > 0 ? E.data() : nullptr, ndof1));
+    else CHECK(fsr_set_recovery(part, ndof2 > 0 ? B.data() : nullptr, ndof1, nmodes > 0 ? E.data() : nullptr, ndof1));
   }
 
   const double t_setup = since(t_setup0);
@@ -544,7 +565,8 @@ static int run_program(int which)
     ro.part_base_id = isup; ro.part_user_id = user_id; ro.part_descr = descr_s.c_str();
     ro.model_file = model_file; ro.link_file = linkfile.c_str();
     ro.elmid = elmid.data(); ro.minex = minex.data(); ro.sup_tr_init = sup_pos;
-    CHECK(fsr_rdb_create(&rdb, part, file_name("rdbfile", ".frs").c_str(), &ro));
+    if (group) CHECK(fsr_rdb_create_group(&rdb, group, file_name("rdbfile", ".frs").c_str(), &ro));
+    else CHECK(fsr_rdb_create(&rdb, part, file_name("rdbfile", ".frs").c_str(), &ro));
     char path[1024];
     fsr_rdb_path(rdb, path, sizeof(path));
     log.line("           --> Results database file: %s (%lld bytes per time step)", path, fsr_rdb_step_bytes(rdb));
@@ -584,12 +606,14 @@ static int run_program(int which)
     t_hist += since(t_h0);
     // queued: the device, the PCIe copy and the file writer work on this window while the next one is read
     if (rdb) CHECK(fsr_rdb_write_steps(rdb, Q.data(), ndim, nw, s_w.data(), t_w.data(), supTr.data()));
+    else if (group) CHECK(fsr_group_recover(group, Q.data(), ndim, nw, nullptr));
     else CHECK(fsr_recover(part, Q.data(), ndim, nw, nullptr));
     log.line("           --> ......Simulation time : %12.5E  (%d of %d steps done)", t_w[nw - 1], w0 + nw, nsel);
   }
   if (!rdb && nsel > 0) {
-    std::vector<double> mx(std::max(fsr_num_result_points(part), 1)), mn(mx.size());
-    CHECK(fsr_get_envelope(part, mx.data(), mn.data()));
+    std::vector<double> mx(std::max(group ? fsr_group_num_result_points(group) : fsr_num_result_points(part), 1)), mn(mx.size());
+    if (group) CHECK(fsr_group_get_envelope(group, mx.data(), mn.data()));
+    else CHECK(fsr_get_envelope(part, mx.data(), mn.data()));
     log.line("           --> largest von Mises stress over all result points and steps: %g", *std::max_element(mx.begin(), mx.end()));
   }
   double tp[5] = {0, 0, 0, 0, 0};

@@ -75,7 +75,10 @@ class StressRdb:
         self._keep = []
         o = _options(mask, double, rdbinc, base_id, user_id, descr, model_file, link_file, elmid, minex, sup_tr_init,
                      self._keep)
-        check(self.lib.fsr_rdb_create(C.byref(self._h), recovery._h, os.fsencode(path), C.byref(o)), "fsr_rdb_create")
+        if hasattr(recovery, "nblocks"):   # GroupRecovery: element blocks on several GPUs fill their slots of every record
+            check(self.lib.fsr_rdb_create_group(C.byref(self._h), recovery._h, os.fsencode(path), C.byref(o)), "fsr_rdb_create_group")
+        else:
+            check(self.lib.fsr_rdb_create(C.byref(self._h), recovery._h, os.fsencode(path), C.byref(o)), "fsr_rdb_create")
         self.step_bytes = self.lib.fsr_rdb_step_bytes(self._h)
         buf = C.create_string_buffer(4096)
         self.lib.fsr_rdb_path(self._h, buf, 4096)

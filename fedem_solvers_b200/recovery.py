@@ -26,48 +26,89 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
 
 
+def c_part_structs(part: PartModel, keep):
+    """fsr_sam / fsr_elmdata views of a PartModel; `keep` collects the arrays the pointers refer to."""
+    s, e = part.sam, part.elm
+
+    def ci(a):
+        a = np.ascontiguousarray(a, I32)
+        keep.append(a)
+        return a
+
+    def cd(a):
+        a = np.ascontiguousarray(a, F64)
+        keep.append(a)
+        return a
+
+    sam = FsrSam(nnod=s.nnod, nel=s.nel, ndof=s.ndof, ndof1=s.ndof1, ndof2=s.ndof2, ngen=s.ngen,
+                 neq=s.neq, nceq=s.nceq, nmmnpc=len(s.mmnpc), nmmceq=len(s.mmceq))
+    sam.madof = _ip(ci(s.madof)); sam.msc = _ip(ci(s.msc)); sam.mpmnpc = _ip(ci(s.mpmnpc))
+    sam.mmnpc = _ip(ci(s.mmnpc)); sam.melcon = _ip(ci(s.melcon)); sam.mpmceq = _ip(ci(s.mpmceq))
+    sam.mmceq = _ip(ci(s.mmceq if len(s.mmceq) else np.zeros(1, I32)))
+    sam.ttcc = _dp(cd(s.ttcc if len(s.ttcc) else np.zeros(1)))
+    sam.meqn = _ip(ci(s.meqn)); sam.meqn1 = _ip(ci(s.meqn1 if s.ndof1 else np.zeros(1, I32)))
+    sam.meqn2 = _ip(ci(s.meqn2 if s.ndof2 else np.zeros(1, I32)))
+    elm = FsrElmData()
+    elm.xyz = _dp(cd(e.xyz)); elm.emod = _dp(cd(e.emod)); elm.rny = _dp(cd(e.rny)); elm.thk = _dp(cd(e.thk))
+    elm.elmid = _ip(ci(e.elmid)) if e.elmid is not None else None
+    elm.beam = _dp(cd(e.beam)) if e.beam is not None else None
+    return sam, elm
+
+
+def c_options(device=0, stress_form=0, step_tile=0, elem_order=0, ffq_stress_form=2, fft_stress_form=1):
+    opt = FsrOptions(device=device, stressForm=stress_form, step_tile=step_tile)
+    opt.reserved[0] = elem_order  # 0 = Morton order of element centroids, 1 = SAM order
+    opt.reserved[1] = ffq_stress_form + 1   # -ffqStressForm / -fftStressForm of the legacy shells (types 22 / 21)
+    opt.reserved[2] = fft_stress_form + 1
+    return opt
+
+
+def split_elements(part: PartModel, nblocks):
+    """fsr_split_elements: contiguous element ranges [(e0, e1), ...] of equal cost (native; host only)."""
+    lib = _lib.load_library()
+    keep = []
+    sam, elm = c_part_structs(part, keep)
+    cut = np.zeros(nblocks + 1, I32)
+    check(lib.fsr_split_elements(C.byref(sam), C.byref(elm), nblocks, _ip(cut)), "fsr_split_elements")
+    return [(int(cut[b]), int(cut[b + 1])) for b in range(nblocks)]
+
+
 class StressRecovery:
-    def __init__(self, part: PartModel, device=0, stress_form=0, step_tile=0, elem_order=0, ffq_stress_form=2, fft_stress_form=1):
+    """One FE part -- or, with `block=(e0, e1)`, the element block [e0, e1) of it (fsr_part_create_block: own nodes, all
+    external DOFs, the B / E rows of its nodes; results bit-identical to the parent's for its elements)."""
+
+    def __init__(self, part: PartModel, device=0, stress_form=0, step_tile=0, elem_order=0, ffq_stress_form=2, fft_stress_form=1,
+                 block=None):
         self._lib = _lib.load_library()
         self._h = C.c_void_p()
-        s, e = part.sam, part.elm
-        self._keep = []
-
-        def ci(a):
-            a = np.ascontiguousarray(a, I32)
-            self._keep.append(a)
-            return a
-
-        def cd(a):
-            a = np.ascontiguousarray(a, F64)
-            self._keep.append(a)
-            return a
-
-        sam = FsrSam(nnod=s.nnod, nel=s.nel, ndof=s.ndof, ndof1=s.ndof1, ndof2=s.ndof2, ngen=s.ngen,
-                     neq=s.neq, nceq=s.nceq, nmmnpc=len(s.mmnpc), nmmceq=len(s.mmceq))
-        sam.madof = _ip(ci(s.madof)); sam.msc = _ip(ci(s.msc)); sam.mpmnpc = _ip(ci(s.mpmnpc))
-        sam.mmnpc = _ip(ci(s.mmnpc)); sam.melcon = _ip(ci(s.melcon)); sam.mpmceq = _ip(ci(s.mpmceq))
-        sam.mmceq = _ip(ci(s.mmceq if len(s.mmceq) else np.zeros(1, I32)))
-        sam.ttcc = _dp(cd(s.ttcc if len(s.ttcc) else np.zeros(1)))
-        sam.meqn = _ip(ci(s.meqn)); sam.meqn1 = _ip(ci(s.meqn1 if s.ndof1 else np.zeros(1, I32)))
-        sam.meqn2 = _ip(ci(s.meqn2 if s.ndof2 else np.zeros(1, I32)))
-        elm = FsrElmData()
-        elm.xyz = _dp(cd(e.xyz)); elm.emod = _dp(cd(e.emod)); elm.rny = _dp(cd(e.rny)); elm.thk = _dp(cd(e.thk))
-        elm.elmid = _ip(ci(e.elmid)) if e.elmid is not None else None
-        elm.beam = _dp(cd(e.beam)) if e.beam is not None else None
-        opt = FsrOptions(device=device, stressForm=stress_form, step_tile=step_tile)
-        opt.reserved[0] = elem_order  # 0 = Morton order of element centroids, 1 = SAM order
-        opt.reserved[1] = ffq_stress_form + 1   # -ffqStressForm / -fftStressForm of the legacy shells (types 22 / 21)
-        opt.reserved[2] = fft_stress_form + 1
-        rc = self._lib.fsr_part_create(C.byref(self._h), C.byref(sam), C.byref(elm), C.byref(opt))
-        self.n_failed = check(rc, "fsr_part_create")
-        self._keep = []
+        s = part.sam
+        keep = []
+        sam, elm = c_part_structs(part, keep)
+        opt = c_options(device, stress_form, step_tile, elem_order, ffq_stress_form, fft_stress_form)
+        if block is None:
+            rc = self._lib.fsr_part_create(C.byref(self._h), C.byref(sam), C.byref(elm), C.byref(opt))
+            self.n_failed = check(rc, "fsr_part_create")
+        else:
+            rc = self._lib.fsr_part_create_block(C.byref(self._h), C.byref(sam), C.byref(elm), C.byref(opt), int(block[0]), int(block[1]))
+            self.n_failed = check(rc, "fsr_part_create_block")
+        del keep
         self.ndim = self._lib.fsr_ndim(self._h)
         self.npts = self._lib.fsr_num_result_points(self._h)
-        self.ndof = s.ndof
-        self.nel = s.nel
+        info = np.zeros(10, I32)
+        check(self._lib.fsr_block_info(self._h, _ip(info)), "fsr_block_info")
+        self.e0, self.e1, self.pt0 = int(info[0]), int(info[1]), int(info[2])
+        self.nnod, self.ndof1, self.parent_ndof1, self.parent_npts = int(info[4]), int(info[5]), int(info[6]), int(info[7])
+        self.is_block = block is not None
+        self.ndof = int(info[8])
+        self.nel = self.e1 - self.e0
         if part.B is not None or part.E is not None:
             self.open_B_and_E_matrices(part.B, part.E)
+
+    def block_rows(self):
+        """(rows of the parent's B / E kept by the block, 0-based; parent node numbers of its nodes, 1-based)"""
+        rows, nodes = np.zeros(max(self.ndof1, 1), I32), np.zeros(max(self.nnod, 1), I32)
+        check(self._lib.fsr_block_rows(self._h, _ip(rows), _ip(nodes)), "fsr_block_rows")
+        return rows[:self.ndof1], nodes[:self.nnod]
 
     # ---- openBandEmatrices (displacementModule.f90:645-790) --------------------------------
     def open_B_and_E_matrices(self, B, E):
@@ -75,7 +116,10 @@ class StressRecovery:
         E = np.asfortranarray(E, F64) if E is not None and E.size else None
         ldB = B.shape[0] if B is not None else 0
         ldE = E.shape[0] if E is not None else 0
-        check(self._lib.fsr_set_recovery(self._h, _dp(B), ldB, _dp(E), ldE), "fsr_set_recovery")
+        if self.is_block and max(ldB, ldE) == self.parent_ndof1 and self.parent_ndof1 != self.ndof1:
+            check(self._lib.fsr_set_recovery_parent(self._h, _dp(B), ldB, _dp(E), ldE), "fsr_set_recovery_parent")   # the parent's matrices
+        else:
+            check(self._lib.fsr_set_recovery(self._h, _dp(B), ldB, _dp(E), ldE), "fsr_set_recovery")
 
     # ---- stress.f90:361-435 time loop, batched ----------------------------------------------
     def recover(self, Q, want_history=True):
@@ -161,6 +205,97 @@ class StressRecovery:
             self.close()
         except Exception:
             pass
+
+
+class GroupRecovery:
+    """One part on several GPUs of this process (fsr_group_*): element blocks, Q broadcast and envelope gather with NCCL
+    inside the library.  devices: list of CUDA ordinals, or None for all visible ones."""
+
+    def __init__(self, part: PartModel, devices=None, stress_form=0, step_tile=0, elem_order=0, ffq_stress_form=2, fft_stress_form=1):
+        self._lib = _lib.load_library()
+        self._h = C.c_void_p()
+        keep = []
+        sam, elm = c_part_structs(part, keep)
+        opt = c_options(0, stress_form, step_tile, elem_order, ffq_stress_form, fft_stress_form)
+        dv = np.ascontiguousarray(devices, I32) if devices is not None else None
+        rc = self._lib.fsr_group_create(C.byref(self._h), C.byref(sam), C.byref(elm), C.byref(opt), _ip(dv), len(dv) if dv is not None else 0)
+        self.n_failed = check(rc, "fsr_group_create")
+        self.nblocks = self._lib.fsr_group_num_blocks(self._h)
+        self.npts = self._lib.fsr_group_num_result_points(self._h)
+        self.ndim = self._lib.fsr_group_ndim(self._h)
+        if part.B is not None or part.E is not None:
+            B = np.asfortranarray(part.B, F64) if part.B is not None and part.B.size else None
+            E = np.asfortranarray(part.E, F64) if part.E is not None and part.E.size else None
+            check(self._lib.fsr_group_set_recovery(self._h, _dp(B), B.shape[0] if B is not None else 0, _dp(E),
+                                                   E.shape[0] if E is not None else 0), "fsr_group_set_recovery")
+
+    def recover(self, Q, want_history=True):
+        Q = np.asfortranarray(Q, F64)
+        assert Q.shape[0] == self.ndim
+        vm = np.empty((Q.shape[1], self.npts), F64) if want_history else None
+        check(self._lib.fsr_group_recover(self._h, _dp(Q), Q.shape[0], Q.shape[1], _dp(vm)), "fsr_group_recover")
+        return vm
+
+    def synchronize(self):
+        check(self._lib.fsr_group_synchronize(self._h), "fsr_group_synchronize")
+
+    def reset_envelope(self):
+        check(self._lib.fsr_group_reset_envelope(self._h), "fsr_group_reset_envelope")
+
+    def envelope(self, out_max=None, out_min=None):
+        mx = out_max if out_max is not None else np.empty(self.npts, F64)
+        mn = out_min if out_min is not None else np.empty(self.npts, F64)
+        check(self._lib.fsr_group_get_envelope(self._h, _dp(mx), _dp(mn)), "fsr_group_get_envelope")
+        return mx, mn
+
+    def last_timing(self):
+        t = np.zeros(4, F64)
+        self._lib.fsr_group_last_timing(self._h, _dp(t), 4)
+        return dict(k1_ms=t[0], k2_ms=t[1], tiles=int(t[2]), balance=t[3])
+
+    def timing_reset(self):
+        self._lib.fsr_group_timing_reset(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.fsr_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Comm:
+    """One process per GPU: the library's own NCCL communicator (fsr_comm_*).  `exchange(id_bytes_or_None) -> id_bytes` is the
+    host's way of passing rank 0's 128-byte id to the other ranks (MPI_Bcast, torch.distributed.broadcast_object_list, ...)."""
+
+    def __init__(self, rank, world, device, exchange):
+        self._lib = _lib.load_library()
+        self._h = C.c_void_p()
+        self.rank, self.world = rank, world
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(self._lib.fsr_comm_unique_id(buf, 128), "fsr_comm_unique_id")
+        ident = exchange(bytes(buf.raw) if rank == 0 else None)
+        check(self._lib.fsr_comm_init_rank(C.byref(self._h), ident, rank, world, device), "fsr_comm_init_rank")
+
+    def broadcast(self, buf_ptr, count, root=0, stream=None):
+        check(self._lib.fsr_comm_broadcast(self._h, C.c_void_p(buf_ptr), int(count), root, C.c_void_p(stream) if stream else None),
+              "fsr_comm_broadcast")
+
+    def gather_envelope(self, rec, pt0, npts, max_ptr=None, min_ptr=None, root=0, stream=None):
+        pt0 = np.ascontiguousarray(pt0, I32); npts = np.ascontiguousarray(npts, I32)
+        check(self._lib.fsr_comm_gather_envelope(self._h, rec._h, _ip(pt0), _ip(npts), C.c_void_p(max_ptr) if max_ptr else None,
+                                                 C.c_void_p(min_ptr) if min_ptr else None, root, C.c_void_p(stream) if stream else None),
+              "fsr_comm_gather_envelope")
+
+    def close(self):
+        if self._h:
+            self._lib.fsr_comm_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def fatigue(hist, gate, curve, bin_size=0.0, nbins=0, device=0):

@@ -739,6 +739,15 @@ module fedem_b200_mod
        real(c_double), intent(out) :: utot(*)
      end subroutine fsr_total_nodal_displacement
 
+     function fsr_rdb_create_group (rdb, group, path, opt) bind(C,name="fsr_rdb_create_group") result(ierr)
+       import :: c_ptr, c_int, c_char, fsr_rdb_options
+       type(c_ptr), intent(out) :: rdb
+       type(c_ptr), value       :: group
+       character(kind=c_char), intent(in) :: path(*)
+       type(fsr_rdb_options), intent(in)  :: opt
+       integer(c_int) :: ierr
+     end function fsr_rdb_create_group
+
      function fsr_rdb_flush (rdb, t, n) bind(C,name="fsr_rdb_flush") result(ierr)
        import :: c_ptr, c_int, c_double
        type(c_ptr), value     :: rdb
@@ -752,6 +761,215 @@ module fedem_b200_mod
        type(c_ptr), value :: rdb
        integer(c_int) :: ierr
      end function fsr_rdb_close
+
+     ! ---- element blocks and multi-GPU (sharded.cu) ------------------------------------------
+     function fsr_split_elements (sam, elm, nblocks, e_cut) bind(C,name="fsr_split_elements") result(ierr)
+       import :: c_int, fsr_sam, fsr_elmdata
+       type(fsr_sam), intent(in)     :: sam
+       type(fsr_elmdata), intent(in) :: elm
+       integer(c_int), value         :: nblocks
+       integer(c_int), intent(out)   :: e_cut(*)
+       integer(c_int) :: ierr
+     end function fsr_split_elements
+
+     function fsr_blockdef_create (def, sam, elm, opt, e0, e1) bind(C,name="fsr_blockdef_create") result(ierr)
+       import :: c_ptr, c_int, fsr_sam, fsr_elmdata, fsr_options
+       type(c_ptr), intent(out)      :: def
+       type(fsr_sam), intent(in)     :: sam
+       type(fsr_elmdata), intent(in) :: elm
+       type(fsr_options), intent(in) :: opt
+       integer(c_int), value         :: e0, e1
+       integer(c_int) :: ierr
+     end function fsr_blockdef_create
+
+     function fsr_blockdef_sam (def) bind(C,name="fsr_blockdef_sam") result(p)
+       import :: c_ptr
+       type(c_ptr), value :: def
+       type(c_ptr) :: p   !< pointer to a fsr_sam, use c_f_pointer
+     end function fsr_blockdef_sam
+
+     function fsr_blockdef_elm (def) bind(C,name="fsr_blockdef_elm") result(p)
+       import :: c_ptr
+       type(c_ptr), value :: def
+       type(c_ptr) :: p   !< pointer to a fsr_elmdata
+     end function fsr_blockdef_elm
+
+     function fsr_blockdef_info (def, info, rows1, nodes) bind(C,name="fsr_blockdef_info") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: def
+       integer(c_int), intent(out) :: info(10), rows1(*), nodes(*)
+       integer(c_int) :: ierr
+     end function fsr_blockdef_info
+
+     subroutine fsr_blockdef_destroy (def) bind(C,name="fsr_blockdef_destroy")
+       import :: c_ptr
+       type(c_ptr), value :: def
+     end subroutine fsr_blockdef_destroy
+
+     function fsr_part_create_block (part, sam, elm, opt, e0, e1) bind(C,name="fsr_part_create_block") result(ierr)
+       import :: c_ptr, c_int, fsr_sam, fsr_elmdata, fsr_options
+       type(c_ptr), intent(out)      :: part
+       type(fsr_sam), intent(in)     :: sam
+       type(fsr_elmdata), intent(in) :: elm
+       type(fsr_options), intent(in) :: opt
+       integer(c_int), value         :: e0, e1   !< 0-based element range [e0, e1)
+       integer(c_int) :: ierr
+     end function fsr_part_create_block
+
+     function fsr_block_info (part, info) bind(C,name="fsr_block_info") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int), intent(out) :: info(10)
+       integer(c_int) :: ierr
+     end function fsr_block_info
+
+     function fsr_block_rows (part, rows1, nodes) bind(C,name="fsr_block_rows") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int), intent(out) :: rows1(*), nodes(*)
+       integer(c_int) :: ierr
+     end function fsr_block_rows
+
+     function fsr_set_recovery_parent (part, B, ldB, E, ldE) bind(C,name="fsr_set_recovery_parent") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: part
+       real(c_double), intent(in) :: B(*), E(*)
+       integer(c_int), value      :: ldB, ldE
+       integer(c_int) :: ierr
+     end function fsr_set_recovery_parent
+
+     function fsr_group_create (group, sam, elm, opt, devices, ndev) bind(C,name="fsr_group_create") result(ierr)
+       import :: c_ptr, c_int, fsr_sam, fsr_elmdata, fsr_options
+       type(c_ptr), intent(out)      :: group
+       type(fsr_sam), intent(in)     :: sam
+       type(fsr_elmdata), intent(in) :: elm
+       type(fsr_options), intent(in) :: opt
+       integer(c_int), intent(in)    :: devices(*)
+       integer(c_int), value         :: ndev
+       integer(c_int) :: ierr
+     end function fsr_group_create
+
+     function fsr_group_set_recovery (group, B, ldB, E, ldE) bind(C,name="fsr_group_set_recovery") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: group
+       real(c_double), intent(in) :: B(*), E(*)
+       integer(c_int), value      :: ldB, ldE
+       integer(c_int) :: ierr
+     end function fsr_group_set_recovery
+
+     function fsr_group_num_blocks (group) bind(C,name="fsr_group_num_blocks") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: group
+       integer(c_int) :: n
+     end function fsr_group_num_blocks
+
+     function fsr_group_num_result_points (group) bind(C,name="fsr_group_num_result_points") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: group
+       integer(c_int) :: n
+     end function fsr_group_num_result_points
+
+     function fsr_group_ndim (group) bind(C,name="fsr_group_ndim") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: group
+       integer(c_int) :: n
+     end function fsr_group_ndim
+
+     function fsr_group_block (group, b) bind(C,name="fsr_group_block") result(part)
+       import :: c_ptr, c_int
+       type(c_ptr), value    :: group
+       integer(c_int), value :: b
+       type(c_ptr) :: part
+     end function fsr_group_block
+
+     function fsr_group_recover (group, Q, ldq, nsteps, vm_hist) bind(C,name="fsr_group_recover") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: group
+       real(c_double), intent(in) :: Q(*)
+       integer(c_int), value      :: ldq, nsteps
+       type(c_ptr), value         :: vm_hist   !< c_loc of a real(c_double) array [npts,nsteps], or c_null_ptr
+       integer(c_int) :: ierr
+     end function fsr_group_recover
+
+     function fsr_group_synchronize (group) bind(C,name="fsr_group_synchronize") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: group
+       integer(c_int) :: ierr
+     end function fsr_group_synchronize
+
+     function fsr_group_reset_envelope (group) bind(C,name="fsr_group_reset_envelope") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: group
+       integer(c_int) :: ierr
+     end function fsr_group_reset_envelope
+
+     function fsr_group_get_envelope (group, vm_max, vm_min) bind(C,name="fsr_group_get_envelope") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: group
+       real(c_double), intent(out) :: vm_max(*), vm_min(*)
+       integer(c_int) :: ierr
+     end function fsr_group_get_envelope
+
+     function fsr_group_last_timing (group, t, n) bind(C,name="fsr_group_last_timing") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: group
+       real(c_double), intent(out) :: t(*)
+       integer(c_int), value :: n
+       integer(c_int) :: ierr
+     end function fsr_group_last_timing
+
+     function fsr_group_timing_reset (group) bind(C,name="fsr_group_timing_reset") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: group
+       integer(c_int) :: ierr
+     end function fsr_group_timing_reset
+
+     subroutine fsr_group_destroy (group) bind(C,name="fsr_group_destroy")
+       import :: c_ptr
+       type(c_ptr), value :: group
+     end subroutine fsr_group_destroy
+
+     function fsr_comm_unique_id (id, cap) bind(C,name="fsr_comm_unique_id") result(ierr)
+       import :: c_char, c_int
+       character(kind=c_char), intent(out) :: id(*)   !< 128 bytes
+       integer(c_int), value :: cap
+       integer(c_int) :: ierr
+     end function fsr_comm_unique_id
+
+     function fsr_comm_init_rank (comm, id, rank, world, device) bind(C,name="fsr_comm_init_rank") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr), intent(out) :: comm
+       character(kind=c_char), intent(in) :: id(*)
+       integer(c_int), value :: rank, world, device
+       integer(c_int) :: ierr
+     end function fsr_comm_init_rank
+
+     function fsr_comm_broadcast (comm, buf_dev, count, root, stream) bind(C,name="fsr_comm_broadcast") result(ierr)
+       import :: c_ptr, c_int, c_long_long
+       type(c_ptr), value :: comm, buf_dev, stream
+       integer(c_long_long), value :: count
+       integer(c_int), value :: root
+       integer(c_int) :: ierr
+     end function fsr_comm_broadcast
+
+     function fsr_comm_gather_envelope (comm, block, pt0, npts, vm_max_root_dev, vm_min_root_dev, root, stream) &
+          &   bind(C,name="fsr_comm_gather_envelope") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: comm, block, vm_max_root_dev, vm_min_root_dev, stream
+       integer(c_int), intent(in) :: pt0(*), npts(*)
+       integer(c_int), value :: root
+       integer(c_int) :: ierr
+     end function fsr_comm_gather_envelope
+
+     subroutine fsr_comm_destroy (comm) bind(C,name="fsr_comm_destroy")
+       import :: c_ptr
+       type(c_ptr), value :: comm
+     end subroutine fsr_comm_destroy
+
+     function fsr_nccl_version () bind(C,name="fsr_nccl_version") result(v)
+       import :: c_int
+       integer(c_int) :: v
+     end function fsr_nccl_version
 
      ! ---- the fedem_stress program (same exported names as the reference's stressInterface.C) --
      subroutine initSolverArgs (argc, argv) bind(C,name="initSolverArgs")

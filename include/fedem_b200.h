@@ -172,6 +172,78 @@ int fsr_expand(fsr_part *part, const double *Q, int ldq, int nsteps, double *U_h
  * CalcRosetteDisplacements (strainRosetteModule.f90:846) needs of the H_el rows of the rosette nodes. */
 int fsr_expand_rows(fsr_part *part, const double *Q, int ldq, int nsteps, const int *rows, int nrows, double *out);
 
+/* ---- element blocks and multi-GPU (one box, NCCL over NVLink / NVSwitch) ------------------------------------
+ * The reference recovers a part in one serial element loop, one process per part (stress.f90:126-128; in the solver
+ * stressRecoveryModule.f90:1021-1061 loops over the parts).  Elements are independent given the nodal displacements and
+ * result points belong to elements, so a part is cut into contiguous (SAM order) element blocks of equal cost; a block is
+ * a self-contained part handle: its own nodes, every external node (ndof2 and the reduced history Q stay the parent's),
+ * the masters of the constraint equations it depends on, the B / E rows of exactly those nodes.  Results of a block are
+ * bit-identical to the parent's for its elements.
+ *  fsr_split_elements      : e_cut[nblocks+1], 0-based element indices, block b = [e_cut[b], e_cut[b+1])
+ *  fsr_part_create_block   : like fsr_part_create for the elements [e0, e1) of the part given by sam / elm
+ *  fsr_block_info          : info[10] = e0, e1, first result point in the parent's order, result points, nodes, B/E rows of
+ *                            the block, B/E rows of the parent (ndof1), result points of the parent, nodal DOFs of the
+ *                            block, elements of the parent
+ *  fsr_block_rows          : rows1[ndof1 of the block] = rows (0-based) of the parent's B / E the block keeps, nodes[nnod of
+ *                            the block] = parent node numbers (1-based); either may be NULL
+ *  fsr_set_recovery_parent : fsr_set_recovery with the PARENT's B / E (ldB, ldE >= the parent's ndof1); the block picks its
+ *                            rows.  (fsr_set_recovery on a block handle expects the rows already gathered.) */
+int fsr_split_elements(const fsr_sam *sam, const fsr_elmdata *elm, int nblocks, int *e_cut);
+/* host only (no device needed): the SAM / element arrays of the block [e0, e1) for hosts that keep their own copy.  The
+ * pointers of fsr_blockdef_sam / _elm stay valid until fsr_blockdef_destroy; info[10], rows1, nodes as fsr_block_info /
+ * fsr_block_rows (any may be NULL). */
+typedef struct fsr_blockdef fsr_blockdef;
+int fsr_blockdef_create(fsr_blockdef **def, const fsr_sam *sam, const fsr_elmdata *elm, const fsr_options *opt,
+                        int e0, int e1);
+const fsr_sam *fsr_blockdef_sam(const fsr_blockdef *def);
+const fsr_elmdata *fsr_blockdef_elm(const fsr_blockdef *def);
+int fsr_blockdef_info(const fsr_blockdef *def, int *info, int *rows1, int *nodes);
+void fsr_blockdef_destroy(fsr_blockdef *def);
+int fsr_part_create_block(fsr_part **part, const fsr_sam *sam, const fsr_elmdata *elm, const fsr_options *opt,
+                          int e0, int e1);
+int fsr_block_info(const fsr_part *part, int *info);
+int fsr_block_rows(const fsr_part *part, int *rows1, int *nodes);
+int fsr_set_recovery_parent(fsr_part *part, const double *B, int ldB, const double *E, int ldE);
+
+/* One process, several GPUs: the blocks of one part on `devices` (NULL / ndev <= 0: all visible devices; ndev > 0 with
+ * devices == NULL: the first ndev).  fsr_group_recover copies Q to the first device, ncclBroadcast's it to the others and
+ * runs K1 + K2 of every block concurrently; vm_hist (optional) is [nsteps x npts] step-major in the PARENT's result-point
+ * order.  fsr_group_get_envelope gathers the per-block envelopes on the first device with ncclSend / ncclRecv (block b
+ * lands at its first result point: concatenation is the parent's order) and copies them to the host.  opt->device is
+ * ignored.  fsr_group_create returns the number of failed elements like fsr_part_create. */
+typedef struct fsr_group fsr_group;
+int fsr_group_create(fsr_group **group, const fsr_sam *sam, const fsr_elmdata *elm, const fsr_options *opt,
+                     const int *devices, int ndev);
+int fsr_group_set_recovery(fsr_group *group, const double *B, int ldB, const double *E, int ldE);
+int fsr_group_num_blocks(const fsr_group *group);
+int fsr_group_num_result_points(const fsr_group *group);
+int fsr_group_ndim(const fsr_group *group);
+fsr_part *fsr_group_block(fsr_group *group, int b); /* borrowed handle of block b */
+int fsr_group_recover(fsr_group *group, const double *Q, int ldq, int nsteps, double *vm_hist);
+int fsr_group_synchronize(fsr_group *group);
+int fsr_group_reset_envelope(fsr_group *group);
+int fsr_group_get_envelope(fsr_group *group, double *vm_max, double *vm_min); /* host [npts of the parent] each */
+/* t[0] = K1, t[1] = K2 device time (ms) of the slowest block since fsr_group_timing_reset, t[2] = tiles,
+ * t[3] = fastest / slowest block (load balance) */
+int fsr_group_last_timing(fsr_group *group, double *t, int n);
+int fsr_group_timing_reset(fsr_group *group);
+void fsr_group_destroy(fsr_group *group);
+
+/* One process per GPU (MPI or torchrun style hosts): a communicator over the ranks' devices.  Rank 0 calls
+ * fsr_comm_unique_id (128 bytes), the host passes the id to the other ranks by its own means, every rank calls
+ * fsr_comm_init_rank.  fsr_comm_broadcast sends the reduced history window from the root's device buffer to the same
+ * buffer on every rank; fsr_comm_gather_envelope sends this rank's block envelopes to the root, which receives block r at
+ * pt0[r] of its two [parent npts] device buffers (pt0 / npts [world]: fsr_block_info of every rank's block).  Both are
+ * asynchronous on `stream` (cudaStream_t as void*) -- pass the stream the block runs on. */
+typedef struct fsr_comm fsr_comm;
+int fsr_comm_unique_id(char *id, int cap);
+int fsr_comm_init_rank(fsr_comm **comm, const char *id, int rank, int world, int device);
+int fsr_comm_broadcast(fsr_comm *comm, double *buf_dev, long long count, int root, void *stream);
+int fsr_comm_gather_envelope(fsr_comm *comm, fsr_part *block, const int *pt0, const int *npts,
+                             double *vm_max_root_dev, double *vm_min_root_dev, int root, void *stream);
+void fsr_comm_destroy(fsr_comm *comm);
+int fsr_nccl_version(void); /* version code of the NCCL library bound at run time, < 0 if none */
+
 /* ---- strain gages + fatigue (fedem_gage path) ------------------------------------------------
  * Replaces ffp_addpoint / ffp_getdamage / ffp_getnumcycles
  * (fedem-foundation/src/FFpLib/FFpFatigue/FFpFatigue_F.C:37-141) for ngage independent scalar
@@ -447,6 +519,10 @@ typedef struct fsr_rdb_options {
 } fsr_rdb_options;
 typedef struct fsr_rdb fsr_rdb;
 int fsr_rdb_create(fsr_rdb **rdb, fsr_part *part, const char *path, const fsr_rdb_options *opt);
+/* the same for a part recovered by a group of element blocks on several GPUs: every device fills the record slots of its
+ * elements and a strided device-to-host copy drops them into the full step records (nodal deformation output is written
+ * by a single device only: use fsr_rdb_create for FSR_OUT_DEFORMATION) */
+int fsr_rdb_create_group(fsr_rdb **rdb, fsr_group *group, const char *path, const fsr_rdb_options *opt);
 /* host only: the header text and the bytes per step for a part given by its SAM element type codes (melcon)
  * and opt->elmid; header may be NULL to query the length, which is returned */
 int fsr_rdb_build_header(int nnod, const int *madof, int nel, const int *melcon, const fsr_rdb_options *opt,

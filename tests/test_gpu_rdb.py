@@ -201,3 +201,15 @@ def test_thick_shells_everything_double(oracle, tmp_path):
 def test_thick_shells_von_mises_float(oracle, tmp_path):
     part = thickshell_panel(2, 3, ngen=3, seed=14)
     _check(oracle, part, tmp_path, out_mask(vmStress=True, strain=True), False, nsteps=5)
+
+
+def test_pipeline_with_many_small_tiles(oracle, tmp_path, monkeypatch):
+    """record tiles of 8 steps: the double-buffered device / PCIe / writer-thread pipeline wraps around several times,
+    two writer helpers split the steps of a tile, the last tile of each call is ragged"""
+    monkeypatch.setenv("FSR_RDB_TILE", "8")
+    monkeypatch.setenv("FSR_RDB_WRITERS", "3")
+    part = plate_part(8, 7, ngen=5, seed=9, tri_fraction=0.4, warp=0.02)
+    mask = out_mask(SR=True, stress=True, strain=True, vmStress=True, maxPStress=True, deformation=True)
+    _check(oracle, part, tmp_path, mask, False, nsteps=45, total=True)
+    part = hex20_block(2, 1, 1, ngen=3, seed=10)
+    _check(oracle, part, tmp_path, out_mask(stress=True, vmStress=True, minPStress=True), True, nsteps=19)

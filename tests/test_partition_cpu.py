@@ -128,3 +128,73 @@ def test_gloo_world2_broadcast_and_gather():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0] and res[1] and res[2] > 0
+
+
+# ---- the native cut (libfedem_b200.so, sharded.cu) against the Python one above ---------------------------------
+def _native_blockdef(part, e0, e1):
+    import ctypes as C
+    from fedem_solvers_b200 import _lib
+    from fedem_solvers_b200.recovery import c_part_structs, c_options
+    lib = _lib.load_library()
+    keep = []
+    sam, elm = c_part_structs(part, keep)
+    opt = c_options()
+    h = C.c_void_p()
+    _lib.check(lib.fsr_blockdef_create(C.byref(h), C.byref(sam), C.byref(elm), C.byref(opt), e0, e1), "fsr_blockdef_create")
+    s, e = lib.fsr_blockdef_sam(h).contents, lib.fsr_blockdef_elm(h).contents
+    info = np.zeros(10, np.int32)
+    _lib.check(lib.fsr_blockdef_info(h, info.ctypes.data_as(_lib._I), None, None), "fsr_blockdef_info")
+    rows, nodes = np.zeros(max(info[5], 1), np.int32), np.zeros(max(info[4], 1), np.int32)
+    lib.fsr_blockdef_info(h, None, rows.ctypes.data_as(_lib._I), nodes.ctypes.data_as(_lib._I))
+
+    def arr(p, n):
+        return np.array(p[:n]) if n > 0 else np.zeros(0)
+    out = dict(nnod=s.nnod, nel=s.nel, ndof=s.ndof, ndof1=s.ndof1, ndof2=s.ndof2, ngen=s.ngen, neq=s.neq, nceq=s.nceq,
+               madof=arr(s.madof, s.nnod + 1), msc=arr(s.msc, s.ndof), mpmnpc=arr(s.mpmnpc, s.nel + 1), mmnpc=arr(s.mmnpc, s.nmmnpc),
+               melcon=arr(s.melcon, s.nel), mpmceq=arr(s.mpmceq, s.nceq + 1), mmceq=arr(s.mmceq, s.nmmceq), ttcc=arr(s.ttcc, s.nmmceq),
+               meqn=arr(s.meqn, s.ndof), meqn1=arr(s.meqn1, s.ndof1), meqn2=arr(s.meqn2, s.ndof2),
+               xyz=arr(e.xyz, 3 * s.nnod).reshape(-1, 3), emod=arr(e.emod, s.nel), rny=arr(e.rny, s.nel), thk=arr(e.thk, s.nel),
+               elmid=arr(e.elmid, s.nel) if e.elmid else None,
+               beam=arr(e.beam, 32 * s.nel).reshape(-1, 32) if e.beam else None,
+               info=info.copy(), rows1=rows[:info[5]].copy(), nodes=nodes[:info[4]].copy())
+    lib.fsr_blockdef_destroy(h)
+    return out
+
+
+@pytest.mark.parametrize("maker", ["plate", "tets"])
+def test_native_blocks_equal_python_sub_parts(maker):
+    """fsr_split_elements / fsr_blockdef_create (what fsr_part_create_block and fsr_group_create cut with) give exactly the
+    arrays of partition.split_elements / sub_part, which test_sub_parts_reproduce_parent checks against the oracle"""
+    from fedem_solvers_b200 import split_elements as native_split
+    if maker == "plate":
+        part = plate_part(9, 8, ngen=4, seed=3, tri_fraction=0.3, shuffle_eq=True, n_fixed=3, n_constraints=4, warp=0.02)
+    else:
+        part = tet10_block(3, 2, 2, ngen=4, seed=4, shuffle_eq=True, n_beams=5)
+    for nb in (1, 2, 3, 5):
+        assert native_split(part, nb) == split_elements(part, nb)
+    for e0, e1 in split_elements(part, 3) + [(0, 0), (part.sam.nel, part.sam.nel), (2, 3)]:
+        sp = sub_part(part, e0, e1)
+        nb = _native_blockdef(part, e0, e1)
+        s = sp.part.sam
+        for k in ("nnod", "nel", "ndof", "ndof1", "ndof2", "ngen", "neq", "nceq"):
+            assert nb[k] == getattr(s, k), (k, nb[k], getattr(s, k))
+        for k in ("madof", "msc", "mpmnpc", "mmnpc", "melcon", "mpmceq", "mmceq", "ttcc", "meqn", "meqn1", "meqn2"):
+            assert np.array_equal(nb[k], np.asarray(getattr(s, k))[:len(nb[k])]) and len(nb[k]) == len(getattr(s, k)), k
+        assert np.array_equal(nb["xyz"], sp.part.elm.xyz) and np.array_equal(nb["emod"], sp.part.elm.emod)
+        assert np.array_equal(nb["thk"], sp.part.elm.thk) and np.array_equal(nb["rny"], sp.part.elm.rny)
+        if sp.part.elm.elmid is not None and e1 > e0:
+            assert np.array_equal(nb["elmid"], sp.part.elm.elmid)
+        if sp.part.elm.beam is not None and e1 > e0:
+            assert np.array_equal(nb["beam"], sp.part.elm.beam)
+        assert np.array_equal(nb["rows1"], sp.rows1) and np.array_equal(nb["nodes"], sp.nodes)
+        assert tuple(nb["info"][:4]) == (e0, e1, sp.pt0, sp.npts) and nb["info"][6] == part.sam.ndof1
+        assert nb["info"][7] == int(part.nstrp().sum()) and nb["info"][8] == s.ndof and nb["info"][9] == part.sam.nel
+
+
+def test_native_split_skips_inactive_elements():
+    from fedem_solvers_b200 import split_elements as native_split
+    part = plate_part(12, 10, ngen=2, seed=5, tri_fraction=0.4, with_recovery=False)
+    part.elm.elmid = np.arange(1, part.sam.nel + 1, dtype=np.int32)
+    part.elm.elmid[:40] *= -1
+    for nb in (2, 4, 7):
+        assert native_split(part, nb) == split_elements(part, nb)
