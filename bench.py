@@ -9,11 +9,21 @@ Workload : BASELINE.json configs[1] -- synthetic 1000x1000 ANDES-quad plate (1,0
            (Q pack -> K1 DMMA expansion -> K2 element kernel with fused envelope) over one batch
            of --tile time steps (default 500), so the default --steps 20 covers the 10,000-step
            history once.  At N > 1 GPUs ONE part of N x 1,000,000 elements (a 1000 x 1000N plate) is
-           cut into N element blocks by fedem_solvers_b200.partition (weak scaling: the per-GPU block
-           stays at the named size); rank r recovers block r.  The reduced history is broadcast
-           from rank 0 with NCCL every step and the per-block envelopes are gathered to rank 0 at
-           the end, both inside the timed region.
-
+           cut into N element blocks by the library (fsr_split_elements / fsr_part_create_block;
+           weak scaling: the per-GPU block stays at the named size); rank r recovers block r.  The
+           reduced history is broadcast from rank 0 every step and the per-block envelopes are
+           gathered to rank 0 at the end, both with the library's own NCCL communicator
+           (fsr_comm_*), both inside the timed region.
+Legs     : `value`  inputs resident in HBM, the full von Mises history of the tile written to HBM.
+           `e2e`    through the host API with page-locked host buffers: per step the H2D copy of
+                    the step's Q tile and the D2H read-back of the step's result (the running
+                    envelopes, 2 x 8 B per result point) are inside the timed region, the read-back
+                    of step i overlapping the compute of step i+1 (fsr_recover_async /
+                    fsr_get_envelope_async); the per-step history stays on the device in this leg.
+Checks   : the timed part is compared with the CPU oracle (full field, first steps of the last
+           tile + the history of sampled elements) -> `parity`; the run fails above 1e-10.
+Secondary: at N = 1 also config 3 (TET10 + beams) and config 5 (rosettes + rainflow) with their own
+           CPU baselines; at every N the STRONG scaling of the fixed config-3 part -> `strong_c3`.
 Arms     : default           this repo's CUDA path through the C ABI (libfedem_b200.so)
            --impl reference  the reference's CPU algorithm (oracle/ restatement; the reference's
                              Fortran cannot be compiled in this image) on all host threads, on a
@@ -37,6 +47,10 @@ UNIT = "element*steps/s"
 NRED_EXT_NODES = 8      # 48 external DOFs
 NGEN = 50               # component modes
 QUAD_BYTES = 256        # algorithmic bytes per quad element.step: 192 read + 64 written
+QUAD_DMMA_FLOP = 1152   # 18 DMMA.8x8x4 per 8 steps = the 24x24 operator, no padding
+DGEMM_PEAK = 35.45      # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt)
+DMMA_PEAK = 37.1        # TFLOP/s, DMMA issue peak measured by tools/microbench/fp64_peaks.cu (same file)
+PARITY_TOL = 1.0e-10
 
 
 def parse_args():
@@ -51,8 +65,16 @@ def parse_args():
     ap.add_argument("--cpu-sample-steps", type=int, default=0,
                     help="time steps of the CPU sample (0 = 128 for cpu_baseline ~10 s on one thread, 48 per reference-arm step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip config 3 / config 5 / strong-scaling blocks")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--c3-elements", type=int, default=2_000_000)
     ap.add_argument("--elem-order", type=int, default=0, help="0 = Morton order (default), 1 = SAM order")
     return ap.parse_args()
+
+
+def workload_text(nx, tile):
+    return (f"C2: {nx}x{nx} ANDES-quad plate block per GPU ({nx * nx} elements), n_red=48+50, {tile} time steps per bench step, "
+            "full-field von Mises + envelope")
 
 
 class ClockSampler:
@@ -145,58 +167,184 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "C2: 1M-element ANDES-quad plate, n_red=48+50, von Mises + envelope "
-                                   "(bounded CPU sample, see cpu_baseline.sample)"},
+            "config": {"workload": workload_text(args.nx, args.tile)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------------
+def oracle_parity(part, Q2, vm_rows, sample_hist=None):
+    """max relative difference of the device results against the CPU oracle (TEST INFRASTRUCTURE used as the checker):
+    vm_rows [k, npts] = von Mises of the k steps Q2 [ndim, k] at every result point of `part`; sample_hist = (Qall, elements,
+    vm_hist_of_their_points) for the per-element history check.  Per value, relative to max(|oracle value|, 1e-6 of the field max)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind
+    o = oracle_bind.Oracle()
+    b = o.bind_part(part)
+    vm_o, _, _ = o.recover_history(b, np.asfortranarray(Q2), want_history=True, nthreads=os.cpu_count() or 1)
+    floor = 1.0e-6 * np.abs(vm_o).max()
+    err = float((np.abs(vm_rows - vm_o) / np.maximum(np.abs(vm_o), floor)).max())
+    return err, int(vm_o.size)
+
+
+def secondary_c5(lib, peaks):
+    """config 5 at its named size: 100,000 rosettes x 100,000 steps (tiles of 256), rainflow + damage"""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs
+    a = argparse.Namespace(gages=100_000, nsteps=99_840, tile=256)
+    r = bench_configs.c5(a)
+    out = {k: r[k] for k in ("metric", "value", "unit", "ms_total", "workload", "rainflow", "gpu_launches", "cycles_total")}
+    # CPU baseline: the reference's OWN compiled C++ (FFpFatigue.C, FFpCycle.C, FFpSNCurve.C from oracle/_ref) on series
+    # shaped like the device ones, one thread like fedem_gage
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_bind
+        ref = oracle_bind.Reference()
+        if not ref.available:
+            raise RuntimeError("oracle/_ref/libfedem_ref.so is missing (built from /root/reference by __graft_entry__.build())")
+        rng = np.random.default_rng(5)
+        nser, ns = 64, 99_840
+        t = np.arange(ns) * 1.0e-3
+        series = [np.ascontiguousarray(sum(rng.normal(0, 30.0) * np.sin(2 * np.pi * rng.uniform(2, 60) * t + rng.uniform(0, 6.28))
+                                           for _ in range(8))) for _ in range(nser)]
+        t0 = time.perf_counter()
+        ncyc = 0
+        for x in series:
+            ref.get_damage(x, 5.0, [15.117, 17.146, 4.0, 5.0])
+            ncyc += max(ref.num_cycles(0.0, 1.0e30), 0)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nser * ns / dt, "unit": "samples/s", "cores": 1, "kind": "reference",
+                               "sample": f"{nser} narrow-band series x {ns} samples through the reference's own compiled FFpFatigue (PVX + "
+                                         f"rainflow + Miner sum + cycle count, {ncyc} cycles), {dt:.1f} s on one thread like fedem_gage; "
+                                         "compare with rainflow.samples_per_s"}
+    except Exception as e:  # the reference objects are built from /root/reference in the build container and travel with the repo
+        out["cpu_baseline"] = {"unavailable": str(e)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync_all):
+    """config 3: ONE fixed part (1.97 M TET10 + 2 % beams) cut into `world` element blocks -> strong scaling"""
+    import torch
+    from fedem_solvers_b200 import StressRecovery, split_elements
+    from fedem_solvers_b200.model import tet10_block, reduced_history, synthetic_recovery
+    n = round((args.c3_elements / 6) ** (1 / 3))
+    t0 = time.time()
+    whole = tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)), with_recovery=False)
+    cuts = split_elements(whole, world)
+    tile, steps, warm = 256, 10, 3
+    rec = StressRecovery(whole, device=local_rank, step_tile=tile, block=cuts[rank] if world > 1 else None)
+    rows, _ = rec.block_rows()
+    B, E = synthetic_recovery(whole, rows=rows if world > 1 else None)
+    rec.open_B_and_E_matrices(B, E)
+    del B, E
+    setup = time.time() - t0
+    nel, ndim = whole.sam.nel, whole.sam.ndim
+    ntet = int((whole.sam.melcon == 41).sum())
+    ntet_blk = int((whole.sam.melcon[cuts[rank][0]:cuts[rank][1]] == 41).sum())
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    Q = torch.empty((tile * (steps + warm), ndim), dtype=torch.float64, device=dev)
+    if rank == 0:
+        Q.copy_(torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * (steps + warm), seed=3).T)))
+    nstrp = whole.nstrp()
+    off = np.concatenate([[0], np.cumsum(nstrp)])
+    pt0 = [int(off[a]) for a, _ in cuts]
+    npts = [int(off[b] - off[a]) for a, b in cuts]
+    env = torch.empty((2, int(off[-1])), dtype=torch.float64, device=dev) if rank == 0 else None
+
+    def step(i):
+        q = Q[i * tile:(i + 1) * tile]
+        if world > 1:
+            comm.broadcast(q.data_ptr(), q.numel(), 0, stream.cuda_stream)
+        rec.recover_dev(q.data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+
+    def gather():
+        if world > 1:
+            comm.gather_envelope(rec, pt0, npts, env[0].data_ptr() if rank == 0 else None, env[1].data_ptr() if rank == 0 else None, 0,
+                                 stream.cuda_stream)
+
+    for i in range(warm):
+        step(i)
+    gather()
+    sync_all()
+    rec.reset_envelope(); rec.timing_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(steps):
+        step(warm + i)
+    gather()
+    e1.record()
+    sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    tm = rec.last_timing()
+    k2 = tm["k2_ms"] / max(tm["tiles"], 1)
+    k1 = tm["k1_ms"] / max(tm["tiles"], 1)
+    k2_max, k1_max = max_over_ranks(k2), max_over_ranks(k1)
+    rec.close()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    hbm = float(peaks_json().get("hbm_gbs", 6650.0))
+    alg = 240.0 * ntet_blk * tile     # envelope only: 240 B of displacements read per TET10 element.step
+    return {"config": "C3", "metric": METRIC, "value": nel * tile * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
+            "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+            "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2 ({whole.sam.ndof} DOF), n_red={ndim}, ONE part cut into "
+                        f"{world} element block(s), {tile} time steps per step, von Mises envelope; NCCL broadcast of Q per step + "
+                        "gather of the envelopes inside the timed region",
+            "roofline": {"kernel": "k2_tet10 von Mises + envelope (rank 0 block)", "bound": "fp64 pipe (reported against HBM as the north_star asks)",
+                         "achieved": alg / (k2 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / hbm,
+                         "ms_per_launch": k2, "algorithmic_bytes_per_launch": alg},
+            "k1_ms": k1, "k2_ms_slowest_rank": k2_max, "k1_ms_slowest_rank": k1_max, "setup_s": setup}
+
+
+def c3_cpu_baseline():
+    """the CPU restatement on a small TET10 + beam block, one thread"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_bind
+    from fedem_solvers_b200.model import tet10_block, reduced_history
+    part = tet10_block(12, 12, 12, ngen=50, seed=3, n_ext=16, n_beams=200)
+    o = oracle_bind.Oracle()
+    b = o.bind_part(part)
+    ns = 24
+    Q = reduced_history(part.sam.ndim, ns + 1, seed=3)
+    o.recover_history(b, Q[:, :1], want_history=False, nthreads=1)
+    t0 = time.perf_counter()
+    o.recover_history(b, Q[:, 1:], want_history=False, nthreads=1)
+    dt = time.perf_counter() - t0
+    return {"value": part.sam.nel * ns / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"12x12x12 cells ({part.sam.nel} TET10 + beams, n_red={part.sam.ndim}) x {ns} steps, {dt:.1f} s, oracle C restatement of "
+                      "the reference loop (ITET32 per element and step), single thread"}
+
+
+_PEAKS = None
+
+
+def peaks_json():
+    global _PEAKS
+    if _PEAKS is None:
+        try:
+            _PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            _PEAKS = {}
+    return _PEAKS
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from fedem_solvers_b200 import StressRecovery, load_library
-    from fedem_solvers_b200.model import plate_part, reduced_history
+    from fedem_solvers_b200 import StressRecovery, Comm, load_library, split_elements
+    from fedem_solvers_b200.model import plate_part, reduced_history, synthetic_recovery
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = load_library()
-
-    tile = args.tile
-    nsteps_total = tile * (args.steps + args.warmup)
-    # ---- setup (untimed): the rank's element block, recovery matrices, reduced history ----
-    if world == 1:
-        part = plate_part(args.nx, args.nx, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2)
-    else:
-        # one part, `world` element blocks: the rank builds the (matrix-free) part, cuts its block and
-        # generates only its own rows of the synthetic [B|E]
-        from fedem_solvers_b200.partition import split_elements, sub_part
-        from fedem_solvers_b200.model import synthetic_recovery
-        whole = plate_part(args.nx, args.nx * world, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2, ly=float(world),
-                           with_recovery=False)
-        bbox = (whole.elm.xyz.min(0), whole.elm.xyz.max(0))
-        e0, e1 = split_elements(whole, world)[rank]
-        part = sub_part(whole, e0, e1, with_matrices=False).part
-        del whole
-        part.B, part.E = synthetic_recovery(part, bbox=bbox)
-    nel, ndim = part.sam.nel, part.sam.ndim
-    rec = StressRecovery(part, device=local_rank, step_tile=((tile + 63) // 64) * 64, elem_order=args.elem_order)
-    npts = rec.npts
-    part.B = part.E = None  # host copies no longer needed
-    stream = torch.cuda.current_stream()
-    rec.set_stream(stream.cuda_stream)
-
-    Q_host = torch.empty((nsteps_total, ndim), dtype=torch.float64).pin_memory()
-    if rank == 0:
-        Q_host.numpy()[:] = reduced_history(ndim, nsteps_total, seed=2).T
-    Q_dev = torch.empty((nsteps_total, ndim), dtype=torch.float64, device=dev)
-    vm_tile = torch.empty((tile, npts), dtype=torch.float64, device=dev)
-    env_host = torch.empty((2, npts), dtype=torch.float64).pin_memory()
-    gather_buf = [torch.empty((2, npts), dtype=torch.float64, device=dev) for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
 
     def sync_all():
         torch.cuda.synchronize()
@@ -210,25 +358,72 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    comm = None
+    if world > 1:
+        # the library's own NCCL communicator carries the data path; torch.distributed only passes the 128-byte id around
+        def exchange(ident):
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if ident is not None:
+                t.copy_(torch.frombuffer(bytearray(ident), dtype=torch.uint8))
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().numpy().tobytes())
+        comm = Comm(rank, world, local_rank, exchange)
+
+    tile = args.tile
+    nsteps_total = tile * (args.steps + args.warmup)
+    # ---- setup (untimed): the rank's element block, recovery matrices, reduced history ----
+    if world == 1:
+        part = plate_part(args.nx, args.nx, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2)
+        rec = StressRecovery(part, device=local_rank, step_tile=((tile + 63) // 64) * 64, elem_order=args.elem_order)
+        cuts, whole = [(0, part.sam.nel)], part
+    else:
+        # one part, `world` element blocks, cut natively; the rank generates only its own rows of the synthetic [B|E]
+        whole = plate_part(args.nx, args.nx * world, ngen=NGEN, n_ext=NRED_EXT_NODES, seed=2, ly=float(world), with_recovery=False)
+        cuts = split_elements(whole, world)
+        rec = StressRecovery(whole, device=local_rank, step_tile=((tile + 63) // 64) * 64, elem_order=args.elem_order, block=cuts[rank])
+        rows, _ = rec.block_rows()
+        B, E = synthetic_recovery(whole, rows=rows)
+        rec.open_B_and_E_matrices(B, E)
+        part = None
+    nel = cuts[rank][1] - cuts[rank][0]
+    ndim, npts, ndof_blk = rec.ndim, rec.npts, rec.ndof
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    nstrp = whole.nstrp()
+    off = np.concatenate([[0], np.cumsum(nstrp)])
+    pt0 = [int(off[a]) for a, _ in cuts]
+    npts_r = [int(off[b] - off[a]) for a, b in cuts]
+
+    Q_host = torch.empty((nsteps_total, ndim), dtype=torch.float64).pin_memory()
+    Q_np = reduced_history(ndim, nsteps_total, seed=2) if (rank == 0 or not args.no_parity) else None
+    if rank == 0:
+        Q_host.numpy()[:] = Q_np.T
+    Q_dev = torch.empty((nsteps_total, ndim), dtype=torch.float64, device=dev)
+    vm_tile = torch.empty((tile, npts), dtype=torch.float64, device=dev)
+    env_host = torch.empty((2, 2, npts), dtype=torch.float64).pin_memory()
+    env_root = torch.empty((2, int(off[-1])), dtype=torch.float64, device=dev) if (world > 1 and rank == 0) else None
+
     # ---------------- leg 1: device-resident inputs (`value`) ----------------
     if rank == 0:
         Q_dev.copy_(Q_host, non_blocking=True)
     if world > 1:
-        dist.broadcast(Q_dev, src=0)
+        comm.broadcast(Q_dev.data_ptr(), Q_dev.numel(), 0, stream.cuda_stream)
     torch.cuda.synchronize()
 
     def device_step(i):
         q = Q_dev[i * tile:(i + 1) * tile]
         if world > 1:
-            dist.broadcast(q, src=0)  # the small reduced history goes to every element block
+            comm.broadcast(q.data_ptr(), q.numel(), 0, stream.cuda_stream)  # the small reduced history goes to every element block
         rec.recover_dev(q.data_ptr(), ndim, tile, vm_tile.data_ptr(), npts, stream.cuda_stream)
+
+    def gather():
+        if world > 1:
+            comm.gather_envelope(rec, pt0, npts_r, env_root[0].data_ptr() if rank == 0 else None,
+                                 env_root[1].data_ptr() if rank == 0 else None, 0, stream.cuda_stream)
 
     for i in range(args.warmup):
         device_step(i)
-    if world > 1:  # bring up NCCL's point-to-point channels (gather = send/recv) before the timed region
-        env = torch.empty((2, npts), dtype=torch.float64, device=dev)
-        rec.copy_envelope_dev(env[0].data_ptr(), env[1].data_ptr(), stream.cuda_stream)
-        dist.gather(env, gather_buf, dst=0)
+    gather()   # brings up NCCL's point-to-point channels before the timed region
     sync_all()
     rec.reset_envelope()
     rec.timing_reset()
@@ -241,9 +436,7 @@ def run_b200(args, rank, world, local_rank):
     e0.record()
     for i in range(args.steps):
         device_step(args.warmup + i)
-    if world > 1:  # per-part envelopes gathered to rank 0 over NVLink
-        rec.copy_envelope_dev(env[0].data_ptr(), env[1].data_ptr(), stream.cuda_stream)
-        dist.gather(env, gather_buf, dst=0)
+    gather()   # per-block envelopes gathered to rank 0 over NVLink
     e1.record()
     sync_all()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -254,42 +447,90 @@ def run_b200(args, rank, world, local_rank):
     k2_ms = tm["k2_ms"] / max(tm["tiles"], 1)
     k1_ms = tm["k1_ms"] / max(tm["tiles"], 1)
 
+    # ---------------- parity of the timed part against the CPU oracle ----------------
+    parity = None
+    if not args.no_parity:
+        nchk = 2
+        last = args.warmup + args.steps - 1
+        Qchk = Q_np[:, last * tile:last * tile + nchk]
+        if world == 1:
+            blk_part = part
+        else:
+            from fedem_solvers_b200.partition import sub_part    # the Python cut: an independent check of the native one
+            sp = sub_part(whole, cuts[rank][0], cuts[rank][1], with_matrices=False)
+            blk_part = sp.part
+            blk_part.B, blk_part.E = B, E
+        err, nval = oracle_parity(blk_part, Qchk, vm_tile[:nchk].cpu().numpy())
+        # envelope property on the whole timed history: max >= every value of the last tile, min <= (size-independent check)
+        mx_d, mn_d = rec.envelope_dev_ptrs()
+        env_now = torch.empty((2, npts), dtype=torch.float64, device=dev)
+        rec.copy_envelope_dev(env_now[0].data_ptr(), env_now[1].data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        env_ok = bool((env_now[0] >= vm_tile.max(0).values).all().item() and (env_now[1] <= vm_tile.min(0).values).all().item())
+        err = max_over_ranks(err)
+        env_ok = max_over_ranks(0.0 if env_ok else 1.0) == 0.0
+        parity = {"max_rel_vs_oracle": err, "values_compared_per_rank": nval, "tolerance": PARITY_TOL,
+                  "what": f"von Mises at every result point of the timed part, first {nchk} steps of the last timed tile, per value "
+                          "relative to max(|oracle|, 1e-6 field max); envelope >= / <= every value of the last tile",
+                  "envelope_consistent": env_ok}
+        if world > 1:
+            del B, E
+    del vm_tile
+    torch.cuda.empty_cache()
+
     # ---------------- leg 2: end to end through the host API (`e2e`) ----------------
     qh = Q_host.numpy()
-    mx_h, mn_h = env_host[0].numpy(), env_host[1].numpy()
 
     def host_step(i):
+        buf = env_host[i & 1]
         if world > 1:
-            # rank 0 owns the history; the other ranks receive the tile over NCCL, then use the host API
+            # rank 0 owns the history; the other ranks receive the tile over NCCL
             q = Q_dev[i * tile:(i + 1) * tile]
             if rank == 0:
                 q.copy_(Q_host[i * tile:(i + 1) * tile], non_blocking=True)
-            dist.broadcast(q, src=0)
+            comm.broadcast(q.data_ptr(), q.numel(), 0, stream.cuda_stream)
             rec.recover_dev(q.data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
         else:
-            rec.recover(qh[i * tile:(i + 1) * tile].T, want_history=False)  # H2D of the step's Q inside
-        rec.envelope(mx_h, mn_h)                                           # D2H of the step's result
+            rec.recover_async(qh[i * tile:(i + 1) * tile].T)                 # H2D of the step's Q (page-locked) inside
+        rec.envelope_async(buf[0].numpy(), buf[1].numpy())                   # D2H of the step's result, overlapping the next step
 
     host_step(0)
+    rec.synchronize()
     sync_all()
     rec.reset_envelope()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_wall0 = time.perf_counter()
     h0.record()
     for i in range(args.steps):
         host_step(args.warmup + i)
     h1.record()
+    rec.synchronize()          # the last read-back has landed in host memory
+    wall_e2e = (time.perf_counter() - t_wall0) * 1e3
     sync_all()
-    ms_e2e = max_over_ranks(h0.elapsed_time(h1))
+    ms_e2e = max_over_ranks(max(h0.elapsed_time(h1), wall_e2e))
     e2e_value = world * nel * tile * args.steps / (ms_e2e * 1e-3)
+    e2e_env_max = float(env_host[(args.warmup + args.steps - 1) & 1][0].max())
+
+    # ---------------- secondary configurations ----------------
+    secondary, strong = {}, None
+    rec.close()
+    del Q_dev
+    torch.cuda.empty_cache()
+    if not args.no_secondary:
+        strong = c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync_all)
+        if world == 1:
+            if not args.no_cpu_baseline:
+                strong["cpu_baseline"] = c3_cpu_baseline()
+            secondary["C5"] = secondary_c5(lib, peaks_json())
 
     if rank != 0:
+        if comm:
+            comm.close()
+        if world > 1:
+            dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = peaks_json()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
@@ -300,33 +541,43 @@ def run_b200(args, rank, world, local_rank):
     except Exception:
         pass
     achieved = QUAD_BYTES * nel * tile / (k2_ms * 1e-3) / 1e9
-    k1_flops = 2.0 * part.sam.ndof * ndim * tile
-    dgemm_peak = 35.45  # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt)
+    k1_flops = 2.0 * ndof_blk * ndim * tile
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C2: {args.nx}x{args.nx} ANDES-quad plate block per GPU ({nel} elements, "
-                               f"{part.sam.ndof} DOF), n_red=48+50, {tile} time steps per bench step "
-                               f"({tile * args.steps} steps timed), full-field von Mises + envelope",
-                   "elements_per_gpu": nel, "ndof_per_gpu": int(part.sam.ndof), "n_red": ndim,
-                   "time_steps_per_step": tile, "parallelism": f"element-block x{world}",
+        "config": {"workload": workload_text(args.nx, tile),
+                   "elements_per_gpu": nel, "ndof_per_gpu": int(ndof_blk), "n_red": ndim,
+                   "time_steps_per_step": tile, "time_steps_timed": tile * args.steps, "parallelism": f"element-block x{world}",
                    "l2": "inputs larger than L2 (U tile %.1f GB, vm tile %.1f GB per step)" %
-                         (part.sam.ndof * tile * 8 / 1e9, npts * tile * 8 / 1e9)},
+                         (ndof_blk * tile * 8 / 1e9, npts * tile * 8 / 1e9)},
         "roofline": {"kernel": "k2_shell_vm_kernel<6> (ANDES quad von Mises + envelope)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": peak_src, "traffic": traffic["bytes_per_launch"] if traffic else None,
                      "traffic_source": traffic["source"] if traffic else None, "ms_per_launch": k2_ms,
-                     "algorithmic_bytes_per_launch": QUAD_BYTES * nel * tile},
+                     "algorithmic_bytes_per_launch": QUAD_BYTES * nel * tile,
+                     # what the counters say limits this kernel: `frac` counts every node's displacements once per element that
+                     # reads them; the DRAM really moved and the FP64 pipe (DMMA + scalar FP64 share it) are below
+                     "dram_frac": (traffic["bytes_per_launch"] / (k2_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                     "fp64_pipe_frac": QUAD_DMMA_FLOP * nel * tile / (k2_ms * 1e-3) / 1e12 / DMMA_PEAK,
+                     "fp64_pipe_note": "DMMA flops issued / DMMA issue peak (37.1 TFLOP/s measured); the von Mises epilogue adds scalar "
+                                       "FP64 on the same pipe (ncu: tensor + fp64 pipe active, profiles/)"},
         "k1": {"kernel": "k1_expand_kernel (DMMA.8x8x4)", "bound": "fp64 tensor", "ms_per_launch": k1_ms,
-               "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": dgemm_peak, "unit": "TFLOP/s",
-               "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / dgemm_peak,
+               "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": DGEMM_PEAK, "unit": "TFLOP/s",
+               "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / DGEMM_PEAK,
                "peak_source": "cuBLAS DGEMM 8192^3 measured (profiles/r01_fp64_peaks.txt)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ndim * tile * 8),
                 "d2h_bytes_per_step": int(2 * npts * 8), "ms_per_step": ms_e2e / args.steps,
-                "api": "fsr_recover(host Q tile) + fsr_get_envelope(host)"},
-        "gpu_launches": launches, "clocks": clk,
+                "api": "fsr_recover_async(page-locked host Q tile) + fsr_get_envelope_async(page-locked host) per step, fsr_synchronize at the "
+                       "end; the result read back per step is the running von Mises ENVELOPE (max, min per result point), the "
+                       "per-step history stays on the device in this leg",
+                "last_envelope_max": e2e_env_max},
+        "gpu_launches": launches, "clocks": clk, "parity": parity,
     }
+    if strong:
+        line["strong_c3"] = strong
+    if secondary:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
         ncs = args.cpu_sample_steps or 128
         cs = CpuSample(args.cpu_sample_nx, ncs + 1)
@@ -339,8 +590,13 @@ def run_b200(args, rank, world, local_rank):
                       f"{ncs} time steps, {dt:.1f} s, single thread like the serial reference "
                       "(oracle C restatement; the reference's Fortran cannot be built in this image)"}
     print(json.dumps(line), flush=True)
+    if comm:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity and (parity["max_rel_vs_oracle"] > PARITY_TOL or not parity["envelope_consistent"]):
+        print(f"PARITY FAILURE: {parity}", file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 def main():

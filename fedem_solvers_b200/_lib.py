@@ -93,6 +93,10 @@ SYMBOLS = [
     ("fsr_comm_gather_envelope", C.c_int, [_P, _P, _I, _I, _P, _P, C.c_int, _P]),
     ("fsr_comm_destroy", None, [_P]),
     ("fsr_nccl_version", C.c_int, []),
+    ("fsr_recover_async", C.c_int, [_P, _D, C.c_int, C.c_int]),
+    ("fsr_get_envelope_async", C.c_int, [_P, _D, _D]),
+    ("fsr_envelope_wait", C.c_int, [_P]),
+    ("fsr_synchronize", C.c_int, [_P]),
     ("fsr_reset_envelope", C.c_int, [_P]),
     ("fsr_get_envelope", C.c_int, [_P, _D, _D]),
     ("fsr_envelope_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),

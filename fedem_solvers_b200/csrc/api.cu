@@ -307,7 +307,10 @@ void fsr_part_destroy(fsr_part* p)
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->xyz); cudaFree(p->emod); cudaFree(p->rny); cudaFree(p->thk);
   cudaFree(p->R); cudaFree(p->Qt); cudaFree(p->U); cudaFree(p->vm_tile); cudaFree(p->Qstage);
-  cudaFree(p->env_max); cudaFree(p->env_min);
+  cudaFree(p->env_max); cudaFree(p->env_min); cudaFree(p->env_snap);
+  if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
+  if (p->ev_snap) cudaEventDestroy(p->ev_snap);
+  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   for (int f = 0; f < FAM_COUNT; ++f) free_family(p->fam[f]);
   if (p->pinned) cudaFreeHost(p->pinned);
   for (int i = 0; i < 4; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
@@ -365,6 +368,51 @@ int fsr_get_envelope(fsr_part* p, double* vm_max, double* vm_min)
   FSR_CUDA(cudaStreamSynchronize(p->stream));
   if (vm_max) FSR_CUDA(cudaMemcpy(vm_max, p->env_max, sizeof(double) * p->npts, cudaMemcpyDeviceToHost));
   if (vm_min) FSR_CUDA(cudaMemcpy(vm_min, p->env_min, sizeof(double) * p->npts, cudaMemcpyDeviceToHost));
+  return FSR_OK;
+}
+
+// The envelopes as they are after the work queued so far, delivered to the host without stopping the pipeline: a
+// device-to-device snapshot in stream order, then the PCIe copy on a second stream while the next tiles compute.
+int fsr_get_envelope_async(fsr_part* p, double* vm_max, double* vm_min)
+{
+  if (!p || (!vm_max && !vm_min)) { set_error("fsr_get_envelope_async: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  const size_t np = (size_t)std::max(p->npts, 1);
+  if (!p->copy_stream) {
+    FSR_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    FSR_CUDA(cudaEventCreateWithFlags(&p->ev_snap, cudaEventDisableTiming));
+    FSR_CUDA(cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
+    FSR_CUDA(cudaMalloc(&p->env_snap, sizeof(double) * 2 * np));
+    FSR_CUDA(cudaEventRecord(p->ev_copied, p->copy_stream));
+  }
+  cudaStream_t s = p->stream;
+  FSR_CUDA(cudaStreamWaitEvent(s, p->ev_copied, 0));   // the previous read-back has left the snapshot buffer
+  FSR_CUDA(cudaMemcpyAsync(p->env_snap, p->env_max, sizeof(double) * p->npts, cudaMemcpyDeviceToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(p->env_snap + np, p->env_min, sizeof(double) * p->npts, cudaMemcpyDeviceToDevice, s));
+  FSR_CUDA(cudaEventRecord(p->ev_snap, s));
+  FSR_CUDA(cudaStreamWaitEvent(p->copy_stream, p->ev_snap, 0));
+  if (vm_max) FSR_CUDA(cudaMemcpyAsync(vm_max, p->env_snap, sizeof(double) * p->npts, cudaMemcpyDeviceToHost, p->copy_stream));
+  if (vm_min) FSR_CUDA(cudaMemcpyAsync(vm_min, p->env_snap + np, sizeof(double) * p->npts, cudaMemcpyDeviceToHost, p->copy_stream));
+  FSR_CUDA(cudaEventRecord(p->ev_copied, p->copy_stream));
+  return FSR_OK;
+}
+
+// waits for everything queued on the handle: tiles of steps (fsr_recover_async / fsr_recover_dev) and read-backs
+int fsr_synchronize(fsr_part* p)
+{
+  if (!p) { set_error("fsr_synchronize: null handle"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  FSR_CUDA(cudaStreamSynchronize(p->stream));
+  if (p->copy_stream) FSR_CUDA(cudaStreamSynchronize(p->copy_stream));
+  return FSR_OK;
+}
+
+// waits for the read-backs only (the tiles queued after them keep running)
+int fsr_envelope_wait(fsr_part* p)
+{
+  if (!p) { set_error("fsr_envelope_wait: null handle"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  if (p->ev_copied) FSR_CUDA(cudaEventSynchronize(p->ev_copied));
   return FSR_OK;
 }
 
@@ -434,7 +482,16 @@ int fsr_recover_dev(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   return FSR_OK;
 }
 
-int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hist)
+static int recover_host(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hist, bool wait);
+
+int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hist) { return recover_host(p, Q, ldq, nsteps, vm_hist, true); }
+
+// fsr_recover without the history and without waiting: the window is queued (H2D of Q, K1, K2 + envelope) and the call
+// returns; Q should be page-locked for the copy to be asynchronous and must stay untouched until the copy has happened
+// (fsr_synchronize, or the next fsr_recover* call, which reuses the staging buffer in stream order).
+int fsr_recover_async(fsr_part* p, const double* Q, int ldq, int nsteps) { return recover_host(p, Q, ldq, nsteps, nullptr, false); }
+
+static int recover_host(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hist, bool wait)
 {
   if (!p || !Q || nsteps < 0 || ldq < p->ndim) { set_error("fsr_recover: bad arguments"); return FSR_ERR_ARG; }
   if (!p->have_R) { set_error("fsr_recover: call fsr_set_recovery first"); return FSR_ERR_STATE; }
@@ -444,6 +501,7 @@ int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hi
   cudaStream_t s = p->stream;
   size_t qbytes = sizeof(double) * (size_t)ldq * nsteps;
   if (p->Qstage_cap < qbytes) {
+    FSR_CUDA(cudaStreamSynchronize(s));   // earlier windows may still read the old staging buffer
     cudaFree(p->Qstage); p->Qstage = nullptr; p->Qstage_cap = 0;
     FSR_CUDA(cudaMalloc(&p->Qstage, std::max<size_t>(qbytes, 8)));
     p->Qstage_cap = qbytes;
@@ -459,7 +517,7 @@ int fsr_recover(fsr_part* p, const double* Q, int ldq, int nsteps, double* vm_hi
                                cudaMemcpyDeviceToHost, s));
     if (vm_hist) FSR_CUDA(cudaStreamSynchronize(s));  // vm_tile is reused by the next tile
   }
-  FSR_CUDA(cudaStreamSynchronize(s));
+  if (wait) FSR_CUDA(cudaStreamSynchronize(s));
   return FSR_OK;
 }
 

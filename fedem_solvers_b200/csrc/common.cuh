@@ -171,6 +171,10 @@ struct fsr_part {
   cudaEvent_t evring[256][3] = {};  // per-tile event triplets: start, after K1, after K2
   int ntimed = 0;
   double* pinned = nullptr; size_t pinned_cap = 0;
+  // asynchronous envelope read-back (fsr_get_envelope_async): snapshot of the envelopes, copy stream, copy-finished event
+  double* env_snap = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
   // element block of a larger part (sharded.cu): the parent's element range, the block's first result point in the parent's
   // result-point order, the parent's nodes (1-based) of the block's nodes and the rows (0-based) of the parent's B / E it keeps
   bool is_block = false;

@@ -849,8 +849,9 @@ static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const 
       set_error("fsr_rdb_create: device allocation failed"); delete r; return FSR_ERR_ALLOC;
     }
   }
-  // step tile of the record buffers: bounded by the parts' step tile, by 1 GiB per pinned host buffer (two of them) and by
-  // ~1/4 of the free device memory
+  // step tile of the record buffers: bounded by the parts' step tile, by 256 MiB per pinned host buffer (two of them; pinning
+  // costs about a second per GiB at program start, and the file, not the device, paces the pipeline) and by ~1/4 of the free
+  // device memory
   r->nslot_nodes = 0;
   if (L.def)
     for (int n = 0; n < p->nnod; ++n)
@@ -859,7 +860,7 @@ static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const 
         r->nslot_nodes = std::max(r->nslot_nodes, node_slot[(size_t)n] + (L.def > 1 ? 2 : 1) * nd);
       }
   const size_t vb = r->dbl ? 8 : 4;
-  long long tile = (long long)((double)(1u << 30) / ((double)nslot * (double)vb));
+  long long tile = (long long)((double)(1u << 28) / ((double)nslot * (double)vb));
   for (RdbDev& d : r->devs) {
     size_t free_b = 0, total_b = 0;
     cudaSetDevice(d.part->device);

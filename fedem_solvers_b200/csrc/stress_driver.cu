@@ -207,7 +207,7 @@ void fsr_stress_define_options(void)
   // B200 additions
   c.add("device", 0, "CUDA device ordinal");
   c.add("stepTile", 0, "Time steps per device batch (0 = from free device memory)");
-  c.add("gpus", 0, "Number of GPUs the elements of the part are spread over\n= 0: one per 100,000 elements, at most all visible ones");
+  c.add("gpus", 0, "Number of GPUs the elements of the part are spread over\n= 0: automatic (one per 250,000 elements for an envelope-only run,\n     one per 2,000,000 when a results database is written)");
   g_stress_options_defined = true;
 }
 
@@ -479,7 +479,12 @@ static int run_program(int which)
     int nvis = 1;
     cudaGetDeviceCount(&nvis);
     ngpu = c.get_int("gpus");
-    if (ngpu <= 0) ngpu = std::max(1, std::min(nvis, nael / 100000));
+    // automatic: the results database is paced by the file (one GPU fills ~80 GB/s of records), so only very large parts gain;
+    // an envelope-only run scales with the GPUs
+    bool any_out = false;
+    for (const char* o : {"vmStress", "maxPStress", "minPStress", "maxSStress", "vmStrain", "maxPStrain", "minPStrain", "maxSStrain", "stress", "strain", "SR"})
+      any_out = any_out || c.get_bool(o);
+    if (ngpu <= 0) ngpu = std::max(1, std::min(nvis, nael / (any_out ? 2000000 : 250000)));
     if (ngpu > nvis) { log.line("  ** Note: -gpus %d but only %d GPU(s) visible", ngpu, nvis); ngpu = nvis; }
     if (ngpu > 1 && c.get_bool("deformation")) { log.line("  ** Note: -deformation is written by one GPU: -gpus %d ignored", ngpu); ngpu = 1; }
   }

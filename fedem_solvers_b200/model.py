@@ -132,26 +132,28 @@ def _build_sam(nnod, ndof_per_node, conn_list, types, ext_nodes, fixed_dofs=(), 
                    minex=np.arange(1, nnod + 1, dtype=I32))
 
 
-def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0, bbox=None):
+def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0, bbox=None, rows=None):
     """Synthetic [B|E]: smooth low-order cosine fields over the part, one per reduced DOF, with
     a random per-component scale -- cheap to generate at 6M rows, and every internal DOF row is a
     distinct, well-scaled linear combination of the reduced DOFs.  A row depends
     only on its node's coordinates, its DOF component and the per-column parameters drawn from `rng`,
     so an element block of a part (partition.sub_part) can generate exactly its own rows when given
-    the whole part's bounding box."""
+    the whole part's bounding box; `rows` (0-based) restricts the result to those rows of the part's
+    matrices (what fsr_block_rows reports for a native element block)."""
     int_dofs = np.nonzero(sam.msc == 1)[0]
     # internal row k corresponds to equation meqn1[k]; map equation -> dof
     eq2dof = np.zeros(sam.neq + 1, np.int64)
     nz = np.nonzero(sam.meqn > 0)[0]
     eq2dof[sam.meqn[nz]] = nz
-    rows_dof = eq2dof[sam.meqn1]                       # dof of each B row
+    rows_dof = eq2dof[sam.meqn1 if rows is None else sam.meqn1[np.asarray(rows, np.int64)]]   # dof of each B row
+    nrow = len(rows_dof)
     node_of_dof = np.searchsorted(sam.madof, rows_dof + 1, side="right") - 1
     comp = rows_dof - (sam.madof[node_of_dof] - 1)
     lo, hi = (xyz.min(0), xyz.max(0)) if bbox is None else (np.asarray(bbox[0], F64), np.asarray(bbox[1], F64))
     span = np.where(hi - lo > 0, hi - lo, 1.0)
     u = (xyz[node_of_dof] - lo) / span                 # normalised coordinates in [0,1]
     ncol = sam.ndof2 + ngen
-    M = np.empty((sam.ndof1, ncol), F64, order="F")
+    M = np.empty((nrow, ncol), F64, order="F")
     cscale = np.array([1.0, 1.0, 1.0, 0.5, 0.5, 0.5])
     # cos(f*u + ph) = cos(f*u) cos(ph) - sin(f*u) sin(ph): tabulate the four harmonics per axis once
     ctab = [[np.cos(m * np.pi * u[:, ax]) for m in range(4)] for ax in range(3)]
@@ -163,13 +165,13 @@ def _smooth_recovery_matrices(sam, xyz, ngen, rng, amp=1.0, bbox=None):
     def fill(j):
         col = M[:, j]
         np.take(amp * amps[j], comp, out=col)
-        tmp = np.empty(sam.ndof1, F64)
+        tmp = np.empty(nrow, F64)
         for ax in range(3):
             np.multiply(ctab[ax][fs[j, ax]], np.cos(phs[j, ax]), out=tmp)
             tmp -= stab[ax][fs[j, ax]] * np.sin(phs[j, ax])
             col *= tmp
 
-    if sam.ndof1 * ncol > 5_000_000:
+    if nrow * ncol > 5_000_000:
         from concurrent.futures import ThreadPoolExecutor
         import os
         with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
@@ -586,10 +588,10 @@ def thickshell_panel(nx, ny, ngen=6, seed=12, n_ext=4, jitter=0.1, emod=2.1e11, 
     return part
 
 
-def synthetic_recovery(part, bbox=None):
-    """(B, E) of a synthetic part (or of an element block of it, given the whole part's bbox)."""
+def synthetic_recovery(part, bbox=None, rows=None):
+    """(B, E) of a synthetic part (or of an element block of it, given the whole part's bbox; or only `rows` of them)."""
     rng = np.random.default_rng([int(getattr(part, "recovery_seed", 0)), 7719])
-    return _smooth_recovery_matrices(part.sam, part.elm.xyz, part.sam.ngen, rng, bbox=bbox)
+    return _smooth_recovery_matrices(part.sam, part.elm.xyz, part.sam.ngen, rng, bbox=bbox, rows=rows)
 
 
 # ------------------------------------------------------------------------------------------

@@ -138,6 +138,21 @@ class StressRecovery:
                                         C.c_void_p(vm_ptr) if vm_ptr else None, ld_vm,
                                         C.c_void_p(stream) if stream else None), "fsr_recover_dev")
 
+    def recover_async(self, Q):
+        """Queues a window (Q [ndim, nsteps], Fortran order, ideally page-locked) and returns; see envelope_async / synchronize."""
+        assert Q.flags.f_contiguous and Q.dtype == F64 and Q.shape[0] == self.ndim
+        check(self._lib.fsr_recover_async(self._h, _dp(Q), Q.shape[0], Q.shape[1]), "fsr_recover_async")
+
+    def envelope_async(self, out_max, out_min):
+        """Envelopes after the work queued so far -> out_max / out_min (page-locked arrays), copied while later windows compute."""
+        check(self._lib.fsr_get_envelope_async(self._h, _dp(out_max), _dp(out_min)), "fsr_get_envelope_async")
+
+    def envelope_wait(self):
+        check(self._lib.fsr_envelope_wait(self._h), "fsr_envelope_wait")
+
+    def synchronize(self):
+        check(self._lib.fsr_synchronize(self._h), "fsr_synchronize")
+
     def reset_envelope(self):
         check(self._lib.fsr_reset_envelope(self._h), "fsr_reset_envelope")
 

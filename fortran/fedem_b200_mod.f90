@@ -762,6 +762,34 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_rdb_close
 
+     ! ---- streaming form of the hot path ---------------------------------------------------------
+     function fsr_recover_async (part, Q, ldq, nsteps) bind(C,name="fsr_recover_async") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: part
+       real(c_double), intent(in) :: Q(*)
+       integer(c_int), value      :: ldq, nsteps
+       integer(c_int) :: ierr
+     end function fsr_recover_async
+
+     function fsr_get_envelope_async (part, vm_max, vm_min) bind(C,name="fsr_get_envelope_async") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: part
+       real(c_double), intent(out) :: vm_max(*), vm_min(*)
+       integer(c_int) :: ierr
+     end function fsr_get_envelope_async
+
+     function fsr_envelope_wait (part) bind(C,name="fsr_envelope_wait") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: ierr
+     end function fsr_envelope_wait
+
+     function fsr_synchronize (part) bind(C,name="fsr_synchronize") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int) :: ierr
+     end function fsr_synchronize
+
      ! ---- element blocks and multi-GPU (sharded.cu) ------------------------------------------
      function fsr_split_elements (sam, elm, nblocks, e_cut) bind(C,name="fsr_split_elements") result(ierr)
        import :: c_int, fsr_sam, fsr_elmdata

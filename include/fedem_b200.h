@@ -141,6 +141,16 @@ int fsr_recover(fsr_part *part, const double *Q, int ldq, int nsteps, double *vm
 int fsr_recover_dev(fsr_part *part, const double *Q_dev, int ldq, int nsteps,
                     double *vm_hist_dev, size_t ld_vm, void *stream);
 
+/* The streaming form for hosts that feed window after window: fsr_recover_async queues a window (H2D copy of Q, K1, K2 +
+ * envelope) and returns; fsr_get_envelope_async delivers the envelopes as they are after the work queued so far -- a
+ * device-side snapshot in stream order, then the PCIe copy on a second stream while the next windows compute;
+ * fsr_envelope_wait waits for the pending read-backs, fsr_synchronize for everything.  Q and the two result arrays
+ * should be page-locked (cudaHostAlloc / cudaHostRegister): with pageable memory the calls still work but block. */
+int fsr_recover_async(fsr_part *part, const double *Q, int ldq, int nsteps);
+int fsr_get_envelope_async(fsr_part *part, double *vm_max, double *vm_min);
+int fsr_envelope_wait(fsr_part *part);
+int fsr_synchronize(fsr_part *part);
+
 int fsr_reset_envelope(fsr_part *part);
 int fsr_get_envelope(fsr_part *part, double *vm_max, double *vm_min); /* host [npts] each */
 int fsr_envelope_dev(fsr_part *part, double **vm_max_dev, double **vm_min_dev);
