@@ -105,7 +105,7 @@ std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const f
 static void free_family(FamilyData& f)
 {
   cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed); cudaFree(f.Gfrag); cudaFree(f.Efrag);
-  cudaFree(f.aux);
+  cudaFree(f.aux); cudaFree(f.sub[0]); cudaFree(f.sub[1]); cudaFree(f.fast);
   f = FamilyData();
 }
 

@@ -84,6 +84,11 @@ struct FamilyData {
   double* Gfrag = nullptr;      // solids: displacement-gradient operator in A-fragment order (k2_solid.cu)
   double* Efrag = nullptr;      // thick shells: strain operator, same shape as Sfrag (strain is not an isotropic function of
                                 // the global stress there, k2_thickshell.cu); NULL for every other family
+  // geometry fast path of a family (TET10: straight-sided elements, constant Jacobian): the family elements are split
+  // into sub[0] (fast path) and sub[1] (general kernel), indices into the family arrays; fast[] = per-element constants
+  int* sub[2] = {nullptr, nullptr};
+  int nsub[2] = {0, 0};
+  double* fast = nullptr;
 };
 
 }  // namespace fsr

@@ -56,7 +56,8 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
                                        const double* __restrict__ xyz, const double* __restrict__ emod,
                                        const double* __restrict__ rny, const Tet10Points* __restrict__ pts,
                                        double* __restrict__ Sfrag, unsigned char* __restrict__ failed,
-                                       double* __restrict__ aux, double* __restrict__ Gfrag)
+                                       double* __restrict__ aux, double* __restrict__ Gfrag,
+                                       double* __restrict__ fast /* [nelt][10]: J^-1 (row d, column j) + flag */)
 {
   const int KT = 8;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,6 +103,9 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
     I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
     I[2][1] = (J[2][0] * J[0][1] - J[2][1] * J[0][0]) / det;
     I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    if (gpt == 0)
+      for (int d = 0; d < 3; ++d)
+        for (int j = 0; j < 3; ++j) fast[(size_t)i * 10 + 3 * d + j] = I[d][j];
     for (int j = 0; j < 10; ++j) {
       const double bx = I[0][0] * d1[j] + I[0][1] * d2[j] + I[0][2] * d3[j];
       const double by = I[1][0] * d1[j] + I[1][1] * d2[j] + I[1][2] * d3[j];
@@ -125,6 +129,18 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
     for (int k = 0; k < 12 * 32; ++k) G[k] = 0.0;
   }
   failed[i] = ok ? 0 : 1;
+  // straight-sided element: every mid-edge node sits at the midpoint of its two corners (to 1e-13 of the edge length), so
+  // the Jacobian is constant and the displacement gradient is linear over the element (k2_tet10_affine_vm_kernel); only for
+  // the nodal evaluation (-stressForm 0), where evaluation point 0 is corner 0
+  const int mid[6][3] = {{1, 0, 2}, {3, 2, 4}, {5, 4, 0}, {6, 0, 9}, {7, 2, 9}, {8, 4, 9}};
+  bool affine = ok && npt == 10;
+  for (int m = 0; m < 6 && affine; ++m) {
+    const int q = mid[m][0], a = mid[m][1], b = mid[m][2];
+    const double ex = X[b] - X[a], ey = Y[b] - Y[a], ez = Z[b] - Z[a];
+    const double dx = X[q] - 0.5 * (X[a] + X[b]), dy = Y[q] - 0.5 * (Y[a] + Y[b]), dz = Z[q] - 0.5 * (Z[a] + Z[b]);
+    if (dx * dx + dy * dy + dz * dz > 1.0e-26 * (ex * ex + ey * ey + ez * ez)) affine = false;
+  }
+  fast[(size_t)i * 10 + 9] = affine ? 1.0 : 0.0;
 }
 
 // one warp per element; 8 m-tiles x 8 k-tiles of operator fragments live in registers
@@ -239,12 +255,14 @@ __global__ void __launch_bounds__(256, MINB)
 k2_tet10_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
                         const double* __restrict__ Gfrag, const double* __restrict__ aux, const int* __restrict__ edof,
                         const int* __restrict__ ptoff, const unsigned char* __restrict__ failed, int nelt,
-                        double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min)
+                        double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min,
+                        const int* __restrict__ list /* family elements to process, NULL = all */)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i >= nelt) return;
+  const int il = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (il >= nelt) return;
+  const int i = list ? __ldg(list + il) : il;
 
   double a[4][3];
   const double* gf = Gfrag + (size_t)i * 12 * 32 + lane;
@@ -369,6 +387,114 @@ k2_tet10_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, in
   }
 }
 
+// Straight-sided TET10 (constant Jacobian J, the common case away from curved boundaries): grad u is linear over the
+// element, so it is evaluated at the four corners only and averaged for the six mid-edge points -- exactly what the nodal
+// evaluation of ITET32 (itet.f:822-934) gives for such an element, up to rounding.  The natural derivatives at a corner are
+// three-point differences along the edges (rows of DN1031, itet.f:48-84, at L_a = 1):
+//     du/dL_j |corner a  =  g_j - g_4,   g_a = 3 u_a,   g_b = 4 u_mid(a,b) - u_b  (b != a)
+// and grad u = J^-1 . D with ONE 3x3 inverse per element.  No operator is streamed (80 bytes of constants per element instead
+// of 3 KB of fragments) and no tensor-core work is padded: ~500 FP64 operations per element.step instead of ~1,400.
+// One warp per element, lane = (corner k = lane / 8, step s = lane % 8): the lane evaluates corner k at step s, then the
+// mid-edge points in two rounds, fetching the partner corner's gradient with warp shuffles.
+__global__ void __launch_bounds__(256, 2)
+k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ fast,
+                          const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist,
+                          const int* __restrict__ list, double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
+                          double* __restrict__ env_min)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int il = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (il >= nlist) return;   // whole warp
+  const int i = __ldg(list + il);
+  const int k = lane >> 3, s = lane & 7;
+  // element nodes (0-based) of the corners L1..L4 and of the mid-edge node between two corners; mid(a,a) = corner a makes
+  // g_a = 4 u_a - u_a = 3 u_a fall out of the same expression
+  const int cn[4] = {0, 2, 4, 9};
+  const int mdn[4][4] = {{0, 1, 5, 6}, {1, 2, 3, 7}, {5, 3, 4, 8}, {6, 7, 8, 9}};
+  const int* ed = edof + (size_t)i * 32;
+  const double* Us = U + s;
+  int rc[4][3], rm[4][3];   // rows of U: corner ci / mid(k, ci), component c
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    const int nm = mdn[k][ci];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { rc[ci][c] = __ldg(ed + 3 * cn[ci] + c); rm[ci][c] = __ldg(ed + 3 * nm + c); }
+  }
+  double Ji[3][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Ji[d][j] = __ldg(fast + (size_t)i * 10 + 3 * d + j);
+  const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
+  const double mu2 = E / (1.0 + nu), mu1 = 0.5 * mu2;   // mid-edge points: vm(1/2 (Ha + Hb)) = 1/2 vm(Ha + Hb)
+  const size_t pt0 = (size_t)ptoff[i];
+  // result points of this lane: corner k; round 1 the mid node of edge (k, p1[k]); round 2 (k = 1, 2) of edge (k, 3)
+  const int p1 = k == 0 ? 1 : k == 1 ? 2 : 0;
+  const int pc = cn[k], pm1 = mdn[k][p1], pm2 = mdn[k][3];
+  const bool r2 = k == 1 || k == 2;
+  const int src1 = p1 * 8 + s, src2 = 24 + s;
+  double emax[3] = {0.0, 0.0, 0.0}, emin[3] = {kHuge, kHuge, kHuge};
+
+  for (int t0 = 0; t0 < nsteps_pad; t0 += 8) {
+    double H[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double gq[4];
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) gq[ci] = fma(4.0, Us[(size_t)rm[ci][c] * ldu + t0], -Us[(size_t)rc[ci][c] * ldu + t0]);
+      const double D0 = gq[0] - gq[3], D1 = gq[1] - gq[3], D2 = gq[2] - gq[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) H[c][d] = fma(Ji[d][2], D2, fma(Ji[d][1], D1, Ji[d][0] * D0));
+    }
+    const int t = t0 + s;
+    const bool live = t < nsteps;
+    double v = solid_vm_from_gradient(H, mu2);
+    if (live) {
+      if (vm) vm[(size_t)t * ld_vm + pt0 + pc] = v;
+      emax[0] = fmax(emax[0], v); emin[0] = fmin(emin[0], v);
+    }
+    double Hm[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Hm[c][d] = H[c][d] + __shfl_sync(0xffffffffu, H[c][d], src1);
+    v = solid_vm_from_gradient(Hm, mu1);
+    if (live) {
+      if (vm) vm[(size_t)t * ld_vm + pt0 + pm1] = v;
+      emax[1] = fmax(emax[1], v); emin[1] = fmin(emin[1], v);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Hm[c][d] = H[c][d] + __shfl_sync(0xffffffffu, H[c][d], src2);
+    if (r2) {
+      v = solid_vm_from_gradient(Hm, mu1);
+      if (live) {
+        if (vm) vm[(size_t)t * ld_vm + pt0 + pm2] = v;
+        emax[2] = fmax(emax[2], v); emin[2] = fmin(emin[2], v);
+      }
+    }
+  }
+  // fold the eight step lanes of each point, then into the stored envelope
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      emax[r] = fmax(emax[r], __shfl_xor_sync(0xffffffffu, emax[r], o));
+      emin[r] = fmin(emin[r], __shfl_xor_sync(0xffffffffu, emin[r], o));
+    }
+  }
+  if (s == 0 && nsteps > 0) {
+    const int pr[3] = {pc, pm1, pm2};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (r == 2 && !r2) continue;
+      if (emax[r] > env_max[pt0 + pr[r]]) env_max[pt0 + pr[r]] = emax[r];
+      if (emin[r] < env_min[pt0 + pr[r]]) env_min[pt0 + pr[r]] = emin[r];
+    }
+  }
+}
+
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
 {
   cudaStream_t s = p->stream;
@@ -429,6 +555,8 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
   FSR_CUDA(cudaMalloc(&f.Gfrag, sizeof(double) * (size_t)f.nelt * 12 * 32));
   FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, sizeof(double) * (size_t)f.nelt * 12 * 32, s));
+  FSR_CUDA(cudaMalloc(&f.fast, sizeof(double) * (size_t)f.nelt * 10));
+  FSR_CUDA(cudaMemsetAsync(f.fast, 0, sizeof(double) * (size_t)f.nelt * 10, s));
   FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
   FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
@@ -436,11 +564,25 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
   build_tet10_ops_kernel<<<(f.nelt + 63) / 64, 64, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny,
-                                                         d_pts, f.Sfrag, f.failed, f.aux, f.Gfrag);
+                                                         d_pts, f.Sfrag, f.failed, f.aux, f.Gfrag, f.fast);
   FSR_LAUNCH_CHECK();
   FSR_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_conn);
   cudaFree(d_pts);
+  // split the family into straight-sided elements (fast path) and the rest; FSR_TET10_AFFINE=0 sends all to the general kernel
+  {
+    std::vector<double> h((size_t)f.nelt * 10);
+    FSR_CUDA(cudaMemcpy(h.data(), f.fast, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    const bool use = !(getenv("FSR_TET10_AFFINE") && atoi(getenv("FSR_TET10_AFFINE")) == 0);
+    std::vector<int> lst[2];
+    for (int i = 0; i < f.nelt; ++i) lst[use && h[(size_t)i * 10 + 9] != 0.0 ? 0 : 1].push_back(i);
+    for (int k = 0; k < 2; ++k) {
+      f.nsub[k] = (int)lst[k].size();
+      if (f.nsub[k] == 0) continue;
+      FSR_CUDA(cudaMalloc(&f.sub[k], sizeof(int) * lst[k].size()));
+      FSR_CUDA(cudaMemcpy(f.sub[k], lst[k].data(), sizeof(int) * lst[k].size(), cudaMemcpyHostToDevice));
+    }
+  }
   return FSR_OK;
 }
 
@@ -455,14 +597,20 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
     k2_tet10_vm_kernel<<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
         p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
         ld_vm, p->env_max, p->env_min);
-  else if (getenv("FSR_TET10_OCC1"))
-    k2_tet10_grad_vm_kernel<1><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
-        ld_vm, p->env_max, p->env_min);
-  else
-    k2_tet10_grad_vm_kernel<2><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.aux, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
-        ld_vm, p->env_max, p->env_min);
+  else {
+    if (f.nsub[0] > 0) {
+      k2_tet10_affine_vm_kernel<<<(f.nsub[0] + warps - 1) / warps, warps * 32, 0, s>>>(
+          p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
+          p->env_min);
+      FSR_LAUNCH_CHECK();
+    }
+    if (f.nsub[1] > 0)
+      k2_tet10_grad_vm_kernel<2><<<(f.nsub[1] + warps - 1) / warps, warps * 32, 0, s>>>(
+          p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag, f.aux, f.edof, f.ptoff, f.failed, f.nsub[1], vm_dev,
+          ld_vm, p->env_max, p->env_min, f.sub[1]);
+    else
+      return FSR_OK;
+  }
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }

@@ -295,10 +295,13 @@ def beam_record(x1, x2, zdir, emod=2.1e11, gmod=8.0e10, area=1.0e-4, iy=2.0e-9, 
 
 
 def tet10_block(nx, ny, nz, ngen=10, seed=3, n_ext=4, jitter=0.05, emod=2.1e11, rny=0.3,
-                shuffle_eq=False, with_recovery=True, n_beams=0):
+                shuffle_eq=False, with_recovery=True, n_beams=0, curved="all"):
     """Structured block of nx*ny*nz hexahedral cells, each split into 6 ten-node tetrahedra
     (type 41), FEDEM node order: corners 1,3,5,10, mid-edges 2,4,6,7,8,9 (itet.f label 300).
-    Mid-edge nodes get a small jitter so edges are curved (non-constant Jacobians).  n_beams BEAM2
+    Mid-edge nodes get a small jitter so edges are curved (non-constant Jacobians): curved="all" every
+    mid-edge node (the worst case for the kernels), "surface" only those on the outer faces of the block
+    (what a mesher produces: mid-side nodes leave the chord only where they are snapped to curved CAD
+    surfaces; interior elements stay straight-sided), "none" no node.  n_beams BEAM2
     stiffeners (type 11) run along random cell edges; their nodes carry 6 DOFs like in a real model
     (the solids use the first three), some with eccentricities, shear-centre offsets and a rotated
     principal axis so that every branch of BEAM31 is exercised (config C3)."""
@@ -334,7 +337,15 @@ def tet10_block(nx, ny, nz, ngen=10, seed=3, n_ext=4, jitter=0.05, emod=2.1e11, 
     gi = np.stack([kk % NX, (kk // NX) % NY, kk // (NX * NY)], 1)
     xyz = gi / 2.0
     odd = (gi % 2).sum(1) > 0
-    xyz[odd] += rng.uniform(-jitter, jitter, (int(odd.sum()), 3)) * 0.5
+    shift = rng.uniform(-jitter, jitter, (int(odd.sum()), 3)) * 0.5
+    if curved == "surface":
+        on_surface = ((gi == 0) | (gi == np.array([NX - 1, NY - 1, NZ - 1]))).any(1)
+        shift[~on_surface[odd]] = 0.0
+    elif curved == "none":
+        shift[:] = 0.0
+    else:
+        assert curved == "all", curved
+    xyz[odd] += shift
     node_of = {int(k): i + 1 for i, k in enumerate(kk)}
 
     def nid(i, j, k):

@@ -1,6 +1,9 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
-seeded inputs.  Tolerance: BASELINE.json north_star -- <= 1e-10 relative on FP64 stresses
-(max|gpu - oracle| <= 1e-10 * max|oracle| per result quantity per part)."""
+seeded inputs.  Tolerance: BASELINE.json north_star -- <= 1e-10 relative on FP64 stresses, measured PER VALUE:
+|gpu - oracle| <= 1e-10 * max(|oracle value|, 1e-3 * max|oracle field|).  The floor is there because a stress component
+is a sum of ~24-60 products that partly cancel (rigid-body content of the element displacements): its absolute rounding
+error scales with the size of the terms, not of the result, so values far below the field maximum cannot be held to 1e-10
+of themselves by ANY summation order -- the oracle's included."""
 import numpy as np
 import pytest
 
@@ -11,8 +14,16 @@ pytestmark = pytest.mark.gpu
 TOL = 1.0e-10
 
 
+FLOOR = 1.0e-3
+
+
 def rel_err(a, b):
-    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+    """largest per-value relative difference, each value measured against max(|b|, FLOOR * max|b|)"""
+    a, b = np.asarray(a), np.asarray(b)
+    if b.size == 0:
+        return 0.0
+    scale = np.maximum(np.abs(b), max(FLOOR * np.abs(b).max(), 1e-300))
+    return float((np.abs(a - b) / scale).max())
 
 
 def _check_part(oracle, part, nsteps, seed, step_tile=0):
@@ -60,6 +71,34 @@ def test_quad_plate_multi_tile(oracle):
 def test_tet10_block_small(oracle):
     part = tet10_block(3, 2, 2, ngen=6, seed=5, shuffle_eq=True)
     _check_part(oracle, part, nsteps=21, seed=6)
+
+
+@pytest.mark.parametrize("curved", ["none", "surface"])
+def test_tet10_straight_sided_fast_path(oracle, curved):
+    """straight-sided TET10 (constant Jacobian) take k2_tet10_affine_vm_kernel: corner gradients from three-point
+    differences, mid-edge points by averaging; "surface" mixes them with curved elements (general DMMA kernel) in one part.
+    Ragged step count, several tiles, beams in between."""
+    part = tet10_block(4, 3, 3, ngen=6, seed=21, shuffle_eq=True, n_beams=5, curved=curved)
+    vm = _check_part(oracle, part, nsteps=150, seed=8, step_tile=64)
+    # the same part with the fast path switched off gives the same numbers to rounding
+    import os
+    os.environ["FSR_TET10_AFFINE"] = "0"
+    try:
+        rec = StressRecovery(part, step_tile=64)
+        vm2 = rec.recover(reduced_history(part.sam.ndim, 150, seed=8))
+        rec.close()
+    finally:
+        del os.environ["FSR_TET10_AFFINE"]
+    assert rel_err(vm, vm2) <= 1e-12
+    assert not np.array_equal(vm, vm2)        # ... but by a different kernel
+
+
+def test_tet10_rotated_skewed_straight_sided(oracle):
+    """fast path on a sheared and rotated block (J is not diagonal), nu close to incompressible"""
+    part = tet10_block(3, 3, 2, ngen=5, seed=22, curved="none", rny=0.49)
+    A = np.array([[0.9, 0.3, -0.2], [-0.1, 1.2, 0.4], [0.25, -0.15, 0.8]])
+    part.elm.xyz = part.elm.xyz @ A.T + np.array([3.0, -2.0, 1.0])
+    _check_part(oracle, part, nsteps=33, seed=9)
 
 
 def test_tri_quad_mixed_plate(oracle):

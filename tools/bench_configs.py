@@ -35,7 +35,7 @@ def c3(args):
     lib = load_library()
     n = round((args.elements / 6) ** (1 / 3))
     t0 = time.time()
-    part = tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)))
+    part = tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)), curved=args.curved)
     tile, steps, warm = args.tile, args.steps, 3
     rec = StressRecovery(part, device=0, step_tile=((tile + 63) // 64) * 64)
     setup = time.time() - t0
@@ -62,7 +62,7 @@ def c3(args):
     # envelope only: 240 B read per TET10 element.step (the 80 B of von Mises stay in registers -> envelope)
     alg = 240.0 * ntet * tile
     mx, mn = rec.envelope()
-    return {"config": "C3", "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
+    return {"config": "C3", "curved_elements": args.curved, "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
             "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
             "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2, {part.sam.ndof} DOF, n_red={ndim}, {tile} time "
                         f"steps per step, von Mises envelope (no per-step history kept)",
@@ -383,6 +383,7 @@ def main():
     ap.add_argument("--hex-elements", type=int, default=250_000)
     ap.add_argument("--gages", type=int, default=100_000)
     ap.add_argument("--nsteps", type=int, default=100_000)
+    ap.add_argument("--curved", default="all", choices=["all", "surface", "none"], help="c3: which TET10 mid-edge nodes leave the chord")
     args = ap.parse_args()
     for c in args.configs:
         print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick, "coat": ccoat, "tri": ctri}[c](args)), flush=True)
