@@ -66,6 +66,17 @@ __device__ __forceinline__ double sqrt_pos(double x)
   return x > 1.0e-290 ? y : 0.0;
 }
 
+// max / min of NON-NEGATIVE doubles (von Mises values, their radicands) on the integer pipe: IEEE order = integer order
+// there, and the FP64 pipe is the busy one in every K2 kernel
+__device__ __forceinline__ double max_nonneg(double a, double b)
+{
+  return __longlong_as_double(max(__double_as_longlong(a), __double_as_longlong(b)));
+}
+__device__ __forceinline__ double min_nonneg(double a, double b)
+{
+  return __longlong_as_double(min(__double_as_longlong(a), __double_as_longlong(b)));
+}
+
 // Element families handled by the K2 kernels.  A family fixes the operator shape:
 // MT m-tiles of 8 rows, KT k-tiles of 4 element DOFs.
 enum Family { FAM_QUAD = 0, FAM_TRI = 1, FAM_TET10 = 2, FAM_BEAM = 3, FAM_HEX20 = 4, FAM_HEX8 = 5, FAM_TET4 = 6, FAM_WEDG6 = 7, FAM_WEDG15 = 8, FAM_TRI6 = 9, FAM_QUAD8 = 10, FAM_COUNT = 11 };

@@ -17,6 +17,7 @@
 // banks per half-warp.  U row-major [nrows_pad][ldu] with t fastest: the K2 kernels read 8
 // consecutive steps of one DOF as one 64-byte segment.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -322,6 +323,92 @@ k1_expand_kernel(const double* __restrict__ R, const double* __restrict__ Qt, do
   }
 }
 
+// The same GEMM for reduced dimensions that do not fit the resident-K kernel (ldk > 108: superelements with many triads or
+// component modes): the K dimension is cut into slabs of 52 columns; a stage = the slab of the R row tile and of one 64-step
+// Q chunk, copied row by row with bulk TMA into one of two shared-memory buffers while the other is multiplied; the
+// accumulators of a chunk stay in registers across its slabs.  R is re-read once per step chunk (from L2 for the most part).
+constexpr int K1S_LS = 52;   // slab width, == 4 (mod 8) like ldk
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_expand_slab_kernel(const double* __restrict__ R, const double* __restrict__ Qt, double* __restrict__ U, int ldk, int nsteps_pad,
+                      size_t ldu)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sbuf = reinterpret_cast<double*>(smem_raw);                       // 2 x [K1_BM + K1_BN][K1S_LS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbuf + (size_t)2 * (K1_BM + K1_BN) * K1S_LS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const size_t row0 = (size_t)blockIdx.x * K1_BM;
+  const int nchunks = nsteps_pad / K1_BN;
+  const int nslab = (ldk + K1S_LS - 1) / K1S_LS;
+  const int nstage = nchunks * nslab;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int st) {   // warp 0 only
+    const int buf = st & 1, c = st / nslab, sl = st - c * nslab;
+    const int k0 = sl * K1S_LS, w = min(K1S_LS, ldk - k0);
+    double* dst = sbuf + (size_t)buf * (K1_BM + K1_BN) * K1S_LS;
+    if (lane == 0) mbar_expect_tx(&bars[buf], (uint32_t)((K1_BM + K1_BN) * w * sizeof(double)));
+    __syncwarp();
+    for (int r = lane; r < K1_BM + K1_BN; r += 32) {
+      const double* src = r < K1_BM ? R + (row0 + r) * ldk + k0 : Qt + ((size_t)c * K1_BN + (r - K1_BM)) * ldk + k0;
+      tma_load_1d(dst + (size_t)r * K1S_LS, src, (uint32_t)(w * sizeof(double)), &bars[buf]);
+    }
+  };
+  if (warp == 0) {
+    issue(0);
+    if (nstage > 1) issue(1);
+  }
+
+  double acc[4][4][2];
+  for (int st = 0; st < nstage; ++st) {
+    const int buf = st & 1, c = st / nslab, sl = st - c * nslab;
+    const int w = min(K1S_LS, ldk - sl * K1S_LS);
+    mbar_wait(&bars[buf], (uint32_t)((st >> 1) & 1));
+    if (sl == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    const double* sR = sbuf + (size_t)buf * (K1_BM + K1_BN) * K1S_LS;
+    const double* a_base = sR + (size_t)(wm * 32 + g) * K1S_LS + t4;
+    const double* b_base = sR + (size_t)(K1_BM + wn * 32 + g) * K1S_LS + t4;
+    const int ktiles = w >> 2;
+#pragma unroll 2
+    for (int kt = 0; kt < ktiles; ++kt) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = a_base[(size_t)i * 8 * K1S_LS + kt * 4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = b_base[(size_t)j * 8 * K1S_LS + kt * 4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (sl == nslab - 1) {
+      double* u_base = U + (row0 + wm * 32 + g) * ldu + (size_t)c * K1_BN + wn * 32 + 2 * t4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<double2*>(u_base + (size_t)i * 8 * ldu + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+    __syncthreads();   // the buffer is free again
+    if (warp == 0 && st + 2 < nstage) issue(st + 2);
+  }
+}
+
+static size_t k1_slab_smem_bytes() { return (size_t)2 * (K1_BM + K1_BN) * K1S_LS * sizeof(double) + 2 * sizeof(uint64_t) + 64; }
+
 static size_t k1_smem_bytes(int ldk)
 {
   return ((size_t)K1_BM * ldk + (size_t)2 * K1_BN * ldk) * sizeof(double) + 3 * sizeof(uint64_t) + 64;
@@ -331,18 +418,21 @@ int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nro
                   cudaStream_t s)
 {
   size_t smem = k1_smem_bytes(ldk);
-  if (smem > 227 * 1024) {
-    set_error("reduced dimension (padded %d) too large for the resident-K expansion kernel (needs %zu B smem)",
-              ldk, smem);
-    return FSR_ERR_LIMIT;
-  }
-  if (int rc = smem_opt_in((const void*)k1_expand_kernel, 227 * 1024)) return rc;
   if (nsteps_pad % K1_BN != 0 || nrows_pad % K1_BM != 0) {
     set_error("internal: K1 tile mismatch (%d rows, %d steps)", nrows_pad, nsteps_pad);
     return FSR_ERR_ARG;
   }
   unsigned blocks = (unsigned)(nrows_pad / K1_BM);
   if (blocks == 0) return FSR_OK;
+  // FSR_K1_SLAB=1 forces the K-slab kernel (tests); it is the only one for ldk > 108
+  static const bool force_slab = getenv("FSR_K1_SLAB") && atoi(getenv("FSR_K1_SLAB")) != 0;
+  if (smem > 227 * 1024 || force_slab) {
+    if (int rc = smem_opt_in((const void*)k1_expand_slab_kernel, k1_slab_smem_bytes())) return rc;
+    k1_expand_slab_kernel<<<blocks, K1_THREADS, k1_slab_smem_bytes(), s>>>(R, Qt, U, ldk, nsteps_pad, ldu);
+    FSR_LAUNCH_CHECK();
+    return FSR_OK;
+  }
+  if (int rc = smem_opt_in((const void*)k1_expand_kernel, 227 * 1024)) return rc;
   k1_expand_kernel<<<blocks, K1_THREADS, smem, s>>>(R, Qt, U, ldk, nsteps_pad, ldu);
   FSR_LAUNCH_CHECK();
   return FSR_OK;

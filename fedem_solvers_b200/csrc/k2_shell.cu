@@ -626,28 +626,29 @@ __device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const doubl
   for (int j = 0; j < KT; ++j)
 #pragma unroll
     for (int m = 0; m < 3; ++m) dmma884(c[m][0], c[m][1], a[m][j], b[j]);
-  // von Mises, FFaTensorTransforms.C:33-36: sqrt(s11^2 + s22^2 - s11*s22 + 3*s12^2)
+  // von Mises, FFaTensorTransforms.C:33-36: sqrt(s11^2 + s22^2 - s11*s22 + 3*s12^2).  Envelope only (WRITE_VM = false):
+  // the running max / min are kept on the radicand, which orders like its root; the root is taken once at the end.
   double q0 = fma(c[2][0] * 3.0, c[2][0], fma(-c[0][0], c[1][0], fma(c[1][0], c[1][0], c[0][0] * c[0][0])));
   double q1 = fma(c[2][1] * 3.0, c[2][1], fma(-c[0][1], c[1][1], fma(c[1][1], c[1][1], c[0][1] * c[0][1])));
-  double v0 = sqrt_pos(q0), v1 = sqrt_pos(q1);
+  // the form is positive semi-definite; rounding can leave -1e-17-relative, which must not reach the integer compares
+  if (!WRITE_VM) { q0 = fabs(q0); q1 = fabs(q1); }
+  const double v0 = WRITE_VM ? sqrt_pos(q0) : q0, v1 = WRITE_VM ? sqrt_pos(q1) : q1;
   const bool wr = ALL_LIVE || live;
   if (GUARD) {
     if (t0 < nsteps) {
       if (WRITE_VM && wr) *vmp0 = v0;
-      emax = v0 > emax ? v0 : emax;
-      emin = v0 < emin ? v0 : emin;
+      emax = max_nonneg(emax, v0);
+      emin = min_nonneg(emin, v0);
     }
     if (t0 + 1 < nsteps) {
       if (WRITE_VM && wr) *vmp1 = v1;
-      emax = v1 > emax ? v1 : emax;
-      emin = v1 < emin ? v1 : emin;
+      emax = max_nonneg(emax, v1);
+      emin = min_nonneg(emin, v1);
     }
   } else {
     if (WRITE_VM && wr) { *vmp0 = v0; *vmp1 = v1; }
-    const bool p = v0 > v1;
-    const double hi = p ? v0 : v1, lo = p ? v1 : v0;
-    emax = hi > emax ? hi : emax;
-    emin = lo < emin ? lo : emin;
+    emax = max_nonneg(emax, max_nonneg(v0, v1));
+    emin = min_nonneg(emin, min_nonneg(v0, v1));
   }
   if (WRITE_VM) { vmp0 += ld8; vmp1 += ld8; }
 }
@@ -730,6 +731,10 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
   emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, 1));
   emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 2));
   emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, 2));
+  if (!WRITE_VM) {   // radicand -> von Mises (kHuge: no step seen)
+    emax = sqrt_pos(emax);
+    emin = emin == kHuge ? kHuge : sqrt_pos(emin);
+  }
   if (live && t4 == 0 && nsteps > 0) {
     if (emax > env_max[pt]) env_max[pt] = emax;
     if (emin < env_min[pt]) env_min[pt] = emin;

@@ -238,14 +238,19 @@ k2_tet10_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
 // part drops out of von Mises: vm = 2 mu sqrt( ((exx-eyy)^2 + (eyy-ezz)^2 + (ezz-exx)^2)/2 + 3/4 (gxy^2 + gxz^2 + gyz^2) ),
 // the same number as FFaTensorTransforms::vonMises of the stress tensor up to rounding, at a third of the
 // FP64 instructions (DMMA and scalar FP64 share one pipe: every instruction here is wall time).
-__device__ __forceinline__ double solid_vm_from_gradient(const double (&H)[3][3], double mu2)
+__device__ __forceinline__ double solid_vm2_from_gradient(const double (&H)[3][3])   // (vm / 2 mu)^2 >= 0
 {
   const double a = H[0][0] - H[1][1], b = H[1][1] - H[2][2], c = H[2][2] - H[0][0];
   const double gxy = H[0][1] + H[1][0], gxz = H[0][2] + H[2][0], gyz = H[1][2] + H[2][1];
   const double dev = 0.5 * fma(a, a, fma(b, b, c * c));
   const double shr = fma(gxy, gxy, fma(gxz, gxz, gyz * gyz));
-  return mu2 * sqrt_pos(fma(0.75, shr, dev));
+  return fma(0.75, shr, dev);
 }
+__device__ __forceinline__ double solid_vm_from_gradient(const double (&H)[3][3], double mu2)
+{
+  return mu2 * sqrt_pos(solid_vm2_from_gradient(H));
+}
+
 
 // one warp per element: 4 m-tiles x 3 k-tiles of the gradient operator in registers, 36 DMMA per 8 steps.
 // Two 8-step tiles per loop trip: result points 0..7 are evaluated by their accumulator lanes after each tile,
@@ -396,30 +401,56 @@ k2_tet10_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, in
 // of 3 KB of fragments) and no tensor-core work is padded: ~500 FP64 operations per element.step instead of ~1,400.
 // One warp per element, lane = (corner k = lane / 8, step s = lane % 8): the lane evaluates corner k at step s, then the
 // mid-edge points in two rounds, fetching the partner corner's gradient with warp shuffles.
-__global__ void __launch_bounds__(256, 2)
+// The element's 30 displacement rows of a tile of 8 steps (30 x 64 bytes) are staged through shared memory with cp.async,
+// the tile after the current one always in flight (two buffers per warp): the lanes read their 24 operands from shared
+// memory, so no load latency sits inside the arithmetic and only 8 index registers are needed.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kAffWarps = 8;
+constexpr int kAffRows = 36;   // 12 node slots x 3 components, 64 bytes each
+
+// WRITE_VM = false (envelope only): the envelope is taken over the radicand (vm / 2 mu)^2, which orders like vm, and the
+// square root is taken once per result point at the end instead of once per step.
+template <bool WRITE_VM>
+__global__ void __launch_bounds__(kAffWarps * 32, 2)
 k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ fast,
                           const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist,
                           const int* __restrict__ list, double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
                           double* __restrict__ env_min)
 {
+  __shared__ __align__(16) double sU_all[kAffWarps][2][kAffRows * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int il = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int il = blockIdx.x * kAffWarps + warp;
   if (il >= nlist) return;   // whole warp
   const int i = __ldg(list + il);
   const int k = lane >> 3, s = lane & 7;
+  double (*sU)[kAffRows * 8] = sU_all[warp];
   // element nodes (0-based) of the corners L1..L4 and of the mid-edge node between two corners; mid(a,a) = corner a makes
-  // g_a = 4 u_a - u_a = 3 u_a fall out of the same expression
+  // g_a = 4 u_a - u_a = 3 u_a fall out of the same expression.  Shared-memory slot of a node: the two nodes that lanes of
+  // one half-warp (corners k, k+1) read with the same instruction sit in slots of different parity = different bank halves.
   const int cn[4] = {0, 2, 4, 9};
   const int mdn[4][4] = {{0, 1, 5, 6}, {1, 2, 3, 7}, {5, 3, 4, 8}, {6, 7, 8, 9}};
+  const int slot[10] = {0, 1, 2, 3, 8, 4, 5, 6, 7, 10};   // even: nodes 0 2 5 7 4 9, odd: nodes 1 3 6 8
   const int* ed = edof + (size_t)i * 32;
-  const double* Us = U + s;
-  int rc[4][3], rm[4][3];   // rows of U: corner ci / mid(k, ci), component c
+  // staging: chunk q = lane + 32 r (r < 4, q < 120) is 16 bytes: 2 steps of row q / 4 (node q / 12, component (q / 4) % 3)
+  const double* csrc[4];
+  int cdst[4];
 #pragma unroll
-  for (int ci = 0; ci < 4; ++ci) {
-    const int nm = mdn[k][ci];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { rc[ci][c] = __ldg(ed + 3 * cn[ci] + c); rm[ci][c] = __ldg(ed + 3 * nm + c); }
+  for (int r = 0; r < 4; ++r) {
+    const int q = lane + 32 * r, row = q >> 2;
+    const int node = row / 3, comp = row - 3 * node;
+    csrc[r] = q < 120 ? U + (size_t)__ldg(ed + row) * ldu + 2 * (q & 3) : nullptr;
+    cdst[r] = q < 120 ? (slot[node] * 3 + comp) * 8 + 2 * (q & 3) : 0;
   }
+  int ms[4];   // shared-memory offsets (doubles) of mid(k, ci), component 0, step s
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) ms[ci] = slot[mdn[k][ci]] * 24 + s;
   double Ji[3][3];
 #pragma unroll
   for (int d = 0; d < 3; ++d)
@@ -435,53 +466,71 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
   const int src1 = p1 * 8 + s, src2 = 24 + s;
   double emax[3] = {0.0, 0.0, 0.0}, emin[3] = {kHuge, kHuge, kHuge};
 
-  for (int t0 = 0; t0 < nsteps_pad; t0 += 8) {
+  auto stage = [&](int buf, int t0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r < 3 || lane < 24) cp_async16(&sU[buf][cdst[r]], csrc[r] + t0);
+    cp_async_commit();
+  };
+  stage(0, 0);
+  int buf = 0;
+  for (int t0 = 0; t0 < nsteps_pad; t0 += 8, buf ^= 1) {
+    if (t0 + 8 < nsteps_pad) { stage(buf ^ 1, t0 + 8); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncwarp();
+    const double* su = sU[buf];
     double H[3][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       double gq[4];
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) gq[ci] = fma(4.0, Us[(size_t)rm[ci][c] * ldu + t0], -Us[(size_t)rc[ci][c] * ldu + t0]);
+      for (int ci = 0; ci < 4; ++ci) gq[ci] = fma(4.0, su[ms[ci] + c * 8], -su[(slot[cn[ci]] * 3 + c) * 8 + s]);
       const double D0 = gq[0] - gq[3], D1 = gq[1] - gq[3], D2 = gq[2] - gq[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) H[c][d] = fma(Ji[d][2], D2, fma(Ji[d][1], D1, Ji[d][0] * D0));
     }
     const int t = t0 + s;
     const bool live = t < nsteps;
-    double v = solid_vm_from_gradient(H, mu2);
+    double v = WRITE_VM ? solid_vm_from_gradient(H, mu2) : solid_vm2_from_gradient(H);
     if (live) {
-      if (vm) vm[(size_t)t * ld_vm + pt0 + pc] = v;
-      emax[0] = fmax(emax[0], v); emin[0] = fmin(emin[0], v);
+      if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pc] = v;
+      emax[0] = max_nonneg(emax[0], v); emin[0] = min_nonneg(emin[0], v);
     }
     double Hm[3][3];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int d = 0; d < 3; ++d) Hm[c][d] = H[c][d] + __shfl_sync(0xffffffffu, H[c][d], src1);
-    v = solid_vm_from_gradient(Hm, mu1);
+    v = WRITE_VM ? solid_vm_from_gradient(Hm, mu1) : solid_vm2_from_gradient(Hm);
     if (live) {
-      if (vm) vm[(size_t)t * ld_vm + pt0 + pm1] = v;
-      emax[1] = fmax(emax[1], v); emin[1] = fmin(emin[1], v);
+      if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pm1] = v;
+      emax[1] = max_nonneg(emax[1], v); emin[1] = min_nonneg(emin[1], v);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int d = 0; d < 3; ++d) Hm[c][d] = H[c][d] + __shfl_sync(0xffffffffu, H[c][d], src2);
     if (r2) {
-      v = solid_vm_from_gradient(Hm, mu1);
+      v = WRITE_VM ? solid_vm_from_gradient(Hm, mu1) : solid_vm2_from_gradient(Hm);
       if (live) {
-        if (vm) vm[(size_t)t * ld_vm + pt0 + pm2] = v;
-        emax[2] = fmax(emax[2], v); emin[2] = fmin(emin[2], v);
+        if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pm2] = v;
+        emax[2] = max_nonneg(emax[2], v); emin[2] = min_nonneg(emin[2], v);
       }
     }
+    __syncwarp();   // everybody is done with this buffer before the next iteration refills it
   }
   // fold the eight step lanes of each point, then into the stored envelope
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
-      emax[r] = fmax(emax[r], __shfl_xor_sync(0xffffffffu, emax[r], o));
-      emin[r] = fmin(emin[r], __shfl_xor_sync(0xffffffffu, emin[r], o));
+      emax[r] = max_nonneg(emax[r], __shfl_xor_sync(0xffffffffu, emax[r], o));
+      emin[r] = min_nonneg(emin[r], __shfl_xor_sync(0xffffffffu, emin[r], o));
+    }
+    if (!WRITE_VM) {   // radicand -> von Mises; kHuge = no step seen
+      const double m = r == 0 ? mu2 : mu1;
+      emax[r] = m * sqrt_pos(emax[r]);
+      emin[r] = emin[r] == kHuge ? kHuge : m * sqrt_pos(emin[r]);
     }
   }
   if (s == 0 && nsteps > 0) {
@@ -599,9 +648,14 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
         ld_vm, p->env_max, p->env_min);
   else {
     if (f.nsub[0] > 0) {
-      k2_tet10_affine_vm_kernel<<<(f.nsub[0] + warps - 1) / warps, warps * 32, 0, s>>>(
-          p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
-          p->env_min);
+      if (vm_dev)
+        k2_tet10_affine_vm_kernel<true><<<(f.nsub[0] + warps - 1) / warps, warps * 32, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
+            p->env_min);
+      else
+        k2_tet10_affine_vm_kernel<false><<<(f.nsub[0] + warps - 1) / warps, warps * 32, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
+            p->env_min);
       FSR_LAUNCH_CHECK();
     }
     if (f.nsub[1] > 0)

@@ -52,7 +52,8 @@ def _check_part(oracle, part, nsteps, seed, step_tile=0):
     for k, name in enumerate(["vmStress", "maxPStress", "minPStress", "maxSStress", "vmStrain",
                               "maxPStrain", "minPStrain", "maxSStrain"]):
         e = rel_err(full["resmat"][:, k], ref["resmat"][:, k])
-        assert e <= 1e-9 if "P" in name else e <= TOL, (name, e)
+        # principal values and the max shear derived from them: trigonometric cubic, 1e-9
+        assert e <= (1e-9 if ("P" in name or "maxS" in name) else TOL), (name, e)
     rec.close()
     return vm_g
 
@@ -99,6 +100,15 @@ def test_tet10_rotated_skewed_straight_sided(oracle):
     A = np.array([[0.9, 0.3, -0.2], [-0.1, 1.2, 0.4], [0.25, -0.15, 0.8]])
     part.elm.xyz = part.elm.xyz @ A.T + np.array([3.0, -2.0, 1.0])
     _check_part(oracle, part, nsteps=33, seed=9)
+
+
+@pytest.mark.parametrize("ngen", [84, 110, 300])
+def test_large_reduced_dimension(oracle, ngen):
+    """ndof2 + ngen > 108 does not fit the resident-K expansion kernel: the K-slab kernel (52-column slabs, accumulators
+    kept across the slabs of a step chunk) takes over -- 3 slabs with a narrow last one / 4 slabs / 7 slabs"""
+    part = plate_part(7, 6, ngen=ngen, seed=31, n_ext=8, tri_fraction=0.3, n_constraints=2)
+    assert part.sam.ndim > 108
+    _check_part(oracle, part, nsteps=140, seed=7, step_tile=64)
 
 
 def test_tri_quad_mixed_plate(oracle):
