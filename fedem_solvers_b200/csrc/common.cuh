@@ -258,6 +258,10 @@ int launch_k2_shell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
                        cudaStream_t s);
 int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm,
                        cudaStream_t s);
+// k2_shell.cu: von Mises of a thin-shell family straight into float / double step records (results database, -vmStress only)
+template <class OUT_T>
+int launch_k2_shell_rec(fsr_part* p, int fam, const double* U, int nsteps, int nsteps_pad, const long long* roff, OUT_T* out, size_t ld_out,
+                        cudaStream_t s);
 int launch_beam_full(fsr_part* p, double* sres, cudaStream_t s);
 int launch_k2_full(fsr_part* p, double* resmat, double* stress, double* strain, double* sres,
                    cudaStream_t s);

@@ -62,12 +62,12 @@ __device__ __forceinline__ size_t frag_at2(int row, int col, int KT)
 constexpr int kRecWarps = 4;
 constexpr int kRecLds = 9;   // shared-memory row stride in doubles (8 steps + 1: spreads the rows over the banks)
 
-template <class OUT_T>
+template <int KT, class OUT_T>
 __global__ void __launch_bounds__(kRecWarps * 32)
 record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, const double* __restrict__ Sfrag,
                           const double* __restrict__ Efrag, const int* __restrict__ edof, const long long* __restrict__ roff,
                           const unsigned char* __restrict__ failed, const double* __restrict__ aux, int naux, int nelt, int nstrp,
-                          int ncmp, int MT, int KT, int layout, int nenod, RecLayout L, OUT_T* __restrict__ out, size_t ld_out)
+                          int ncmp, int MT, int layout, int nenod, RecLayout L, OUT_T* __restrict__ out, size_t ld_out)
 {
   extern __shared__ double rec_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,36 +87,51 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
   const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
   const double th = layout == 0 ? aux[(size_t)i * naux + 2] : 0.0;
   // B operand rows of this lane: element DOF 4*k + t4 (padding columns point at row 0, their operator entries are zero)
-  const double* up[16];
+  const double* up[KT];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) up[k] = U + (k < KT ? (size_t)__ldg(edof + (size_t)i * KT * 4 + k * 4 + t4) * ldu : 0) + g;
+  for (int k = 0; k < KT; ++k) up[k] = U + (size_t)__ldg(edof + (size_t)i * KT * 4 + k * 4 + t4) * ldu + g;
   const int npair = 8 * nstrp;
 
   for (int t0 = 0; t0 < nt; t0 += 8) {
     if (!bad) {
-      double b[16];
+      double b[KT];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) b[k] = k < KT ? up[k][t0] : 0.0;   // U rows carry slack up to the padded tile
-      for (int m0 = 0; m0 < MT; m0 += 3) {   // three independent accumulator chains in flight
-        double c[3][2] = {{0, 0}, {0, 0}, {0, 0}}, d[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+      for (int k = 0; k < KT; ++k) b[k] = up[k][t0];   // U rows carry slack up to the padded tile
+      // three m-tiles at a time (three independent accumulator chains); the fragment loads of a group carry no branches
+      // (the last group repeats the last m-tile instead of running short), so they are all in flight before the first DMMA
+      for (int m0 = 0; m0 < MT; m0 += 3) {
+        const double* Sm[3];
+        const double* Em[3];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          if (k < KT) {
-#pragma unroll
-            for (int mm = 0; mm < 3; ++mm)
-              if (m0 + mm < MT) {
-                dmma884(c[mm][0], c[mm][1], __ldg(S + (size_t)((m0 + mm) * KT + k) * 32), b[k]);
-                if (Es) dmma884(d[mm][0], d[mm][1], __ldg(Es + (size_t)((m0 + mm) * KT + k) * 32), b[k]);
-              }
-          }
+        for (int mm = 0; mm < 3; ++mm) {
+          const int mi = min(m0 + mm, MT - 1);
+          Sm[mm] = S + (size_t)mi * KT * 32;
+          Em[mm] = Es ? Es + (size_t)mi * KT * 32 : nullptr;
         }
+        double c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+#pragma unroll
+          for (int mm = 0; mm < 3; ++mm) dmma884(c[mm][0], c[mm][1], __ldg(Sm[mm] + k * 32), b[k]);
 #pragma unroll
         for (int mm = 0; mm < 3; ++mm)
           if (m0 + mm < MT) {
             double* q = sig_s + ((m0 + mm) * 8 + g) * kRecLds + 2 * t4;
             q[0] = c[mm][0]; q[1] = c[mm][1];
-            if (Es) { q += (size_t)nrow * kRecLds; q[0] = d[mm][0]; q[1] = d[mm][1]; }
           }
+        if (Es) {
+          double d[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+          for (int k = 0; k < KT; ++k)
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm) dmma884(d[mm][0], d[mm][1], __ldg(Em[mm] + k * 32), b[k]);
+#pragma unroll
+          for (int mm = 0; mm < 3; ++mm)
+            if (m0 + mm < MT) {
+              double* q = eps_s + ((m0 + mm) * 8 + g) * kRecLds + 2 * t4;
+              q[0] = d[mm][0]; q[1] = d[mm][1];
+            }
+        }
       }
     }
     __syncwarp();
@@ -345,7 +360,9 @@ struct RdbDev {
   long long* roff[fsr::FAM_COUNT] = {};// device: record slot (relative to slot0) of each family element, -1 = not written
   void* out[2] = {nullptr, nullptr};   // [tile][nslot] float/double
   double* dQ = nullptr;                // device Q tile
-  cudaEvent_t ev[2][4] = {};           // per buffer: compute start / done (part stream), copy start / done (copy stream)
+  cudaEvent_t ev[2][5] = {};           // per buffer: compute start / done (part stream), copy start / done (copy stream),
+                                       // [4] = expansion done (part stream; = start for the later record tiles of a chunk)
+  cudaEvent_t ev_q[2] = {};            // the H2D copy out of Qpin[k] has finished
   cudaStream_t copy_stream = nullptr;
 };
 
@@ -364,7 +381,8 @@ struct fsr_rdb {
   void* host[2] = {nullptr, nullptr};  // pinned step records
   double* Qpin[2] = {nullptr, nullptr};// pinned staging of the caller's Q tile
   int ldq_cap = 0;
-  int tile = 0, next_buf = 0;
+  int tile = 0, next_buf = 0;          // record tile: steps per pinned buffer
+  int ktile = 0, next_q = 0;           // expansion chunk: steps per K1 launch (>= tile; several record tiles read one U)
   long long steps_written = 0;
   long long* node_slot = nullptr;      // device [nnod] record slot of each node's displacements (-1 = none)
   int* madof = nullptr;                // device [nnod+1]
@@ -381,7 +399,7 @@ struct fsr_rdb {
   std::string werr;                    // first error of the writer thread
   int nwriters = 1;
   // accounting (fsr_rdb_flush)
-  double ms_compute = 0.0, ms_copy = 0.0, ms_disk = 0.0;
+  double ms_compute = 0.0, ms_copy = 0.0, ms_disk = 0.0, ms_k1 = 0.0;
   long long bytes_written = 0, tiles = 0;
 
   void writer_main();
@@ -405,6 +423,7 @@ struct fsr_rdb {
       for (int b = 0; b < 2; ++b) {
         cudaFree(d.out[b]);
         for (auto& e : d.ev[b]) if (e) cudaEventDestroy(e);
+        if (d.ev_q[b]) cudaEventDestroy(d.ev_q[b]);
       }
       if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     }
@@ -466,15 +485,16 @@ void fsr_rdb::writer_main()
       jobs.pop_front();
     }
     std::string err;
-    float a = 0.f, c = 0.f;
+    float a = 0.f, c = 0.f, k1 = 0.f;
     for (RdbDev& d : devs) {
       if (d.nslot == 0) continue;
       cudaSetDevice(d.part->device);
       if (cudaEventSynchronize(d.ev[job.buf][3]) != cudaSuccess) { err = std::string("device error while recovering a tile of steps: ") + cudaGetErrorString(cudaGetLastError()); break; }
-      float ai = 0.f, ci = 0.f;
+      float ai = 0.f, ci = 0.f, ki = 0.f;
       cudaEventElapsedTime(&ai, d.ev[job.buf][0], d.ev[job.buf][1]);
       cudaEventElapsedTime(&ci, d.ev[job.buf][2], d.ev[job.buf][3]);
-      a = std::max(a, ai); c = std::max(c, ci);
+      cudaEventElapsedTime(&ki, d.ev[job.buf][0], d.ev[job.buf][4]);
+      a = std::max(a, ai); c = std::max(c, ci); k1 = std::max(k1, ki);
     }
     const auto t0 = std::chrono::steady_clock::now();
     if (err.empty()) {
@@ -496,7 +516,7 @@ void fsr_rdb::writer_main()
       std::lock_guard<std::mutex> lk(mtx);
       if (!err.empty() && werr.empty()) werr = err;
       if (err.empty()) {
-        ms_compute += a; ms_copy += c; ms_disk += disk; ++tiles;
+        ms_compute += a; ms_copy += c; ms_disk += disk; ms_k1 += k1; ++tiles;
         bytes_written += (long long)job.nt * (12 + (long long)rec_bytes);
         steps_written += job.nt;
       }
@@ -738,29 +758,43 @@ static int layout_from_options(const fsr_rdb_options* o, RecLayout& L)
 }  // namespace
 
 template <class OUT_T>
-static int launch_record_kernels(fsr_rdb* r, RdbDev& d, int nt, OUT_T* out, cudaStream_t s)
+static int launch_record_kernels(fsr_rdb* r, RdbDev& d, int ts, int nt, OUT_T* out, cudaStream_t s)
 {
   fsr_part* p = d.part;
   const size_t ld_out = (size_t)d.nslot;
+  const double* U = p->U + ts;   // steps [ts, ts + nt) of the expanded chunk
   for (int fi = 0; fi < FAM_COUNT; ++fi) {
     FamilyData& f = p->fam[fi];
     if (f.nelt == 0 || !d.roff[fi]) continue;
     if (fi == FAM_BEAM) {
       if (!r->L.sr) continue;
       dim3 blk(96, 4), grd((unsigned)(((long long)f.nelt * 12 + 95) / 96), (nt + 3) / 4);
-      record_beams_kernel<OUT_T><<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, nt, reinterpret_cast<const BeamOp12*>(f.Sfrag), f.edof,
+      record_beams_kernel<OUT_T><<<grd, blk, 0, s>>>(U, (size_t)p->step_tile, nt, reinterpret_cast<const BeamOp12*>(f.Sfrag), f.edof,
                                                      d.roff[fi], f.failed, f.nelt, out, ld_out);
     } else {
       if (f.nstrp == 0) continue;
       if (!(r->L.stress || r->L.strain || r->L.nsel || (r->L.sr && f.ncmp == 3) || (r->L.sr && f.Efrag))) continue;
       const int layout = (fi == FAM_QUAD || fi == FAM_TRI) ? 0 : (fi == FAM_TRI6 || fi == FAM_QUAD8) ? 2 : 1;
-      if (f.KT > 16) { set_error("internal: operator of family %d has %d k-tiles", fi, f.KT); return FSR_ERR_LIMIT; }
+      // `-vmStress` alone on thin shells: the tuned von Mises kernel (operator fragments in registers) writes the records
+      if (layout == 0 && r->L.mask == 0x01 && !r->L.sr && !r->L.stress && !r->L.strain && !getenv("FSR_RDB_GENERIC")) {
+        if (int rc = launch_k2_shell_rec<OUT_T>(p, fi, U, nt, (nt + 7) / 8 * 8, d.roff[fi], out, ld_out, s)) return rc;
+        continue;
+      }
       const size_t smem = sizeof(double) * kRecWarps * (layout == 2 ? 2 : 1) * (size_t)f.MT * 8 * kRecLds;
-      if (smem > 48 * 1024)
-        if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<OUT_T>, 100 * 1024)) return rc;
-      record_points_dmma_kernel<OUT_T><<<(f.nelt + kRecWarps - 1) / kRecWarps, kRecWarps * 32, smem, s>>>(
-          p->U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag, f.edof, d.roff[fi], f.failed, f.aux, f.naux, f.nelt, f.nstrp, f.ncmp,
-          f.MT, f.KT, layout, f.nenod, r->L, out, ld_out);
+      const unsigned grid = (unsigned)((f.nelt + kRecWarps - 1) / kRecWarps);
+#define FSR_REC_LAUNCH(KTV)                                                                                                        \
+  case KTV:                                                                                                                        \
+    if (smem > 48 * 1024)                                                                                                          \
+      if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<KTV, OUT_T>, 100 * 1024)) return rc;                        \
+    record_points_dmma_kernel<KTV, OUT_T><<<grid, kRecWarps * 32, smem, s>>>(U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag, f.edof, \
+                                                                              d.roff[fi], f.failed, f.aux, f.naux, f.nelt, f.nstrp, \
+                                                                              f.ncmp, f.MT, layout, f.nenod, r->L, out, ld_out);   \
+    break;
+      switch (f.KT) {   // the k-tile counts of the element families (common.cuh): the k loop is unrolled at compile time
+        FSR_REC_LAUNCH(3) FSR_REC_LAUNCH(5) FSR_REC_LAUNCH(6) FSR_REC_LAUNCH(8) FSR_REC_LAUNCH(9) FSR_REC_LAUNCH(12) FSR_REC_LAUNCH(15)
+        default: set_error("internal: no record kernel for an operator with %d k-tiles (family %d)", f.KT, fi); return FSR_ERR_LIMIT;
+      }
+#undef FSR_REC_LAUNCH
     }
     FSR_LAUNCH_CHECK();
   }
@@ -870,9 +904,13 @@ static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const 
     tile = std::min<long long>(tile, d.part->step_tile);
   }
   if (const char* e = getenv("FSR_RDB_TILE")) tile = std::min<long long>(std::max(1, atoi(e)), tile);   // tests: several tiles per call
-  tile = std::max<long long>(1, tile);
+  tile = std::max<long long>(getenv("FSR_RDB_TILE") ? 1 : 8, tile);   // the record kernels work on 8 steps at a time
   if (tile >= 8) tile = tile / 8 * 8;
   r->tile = (int)tile;
+  // the expansion (K1) works on chunks of the parts' step tile; the record tiles of a chunk read the same U
+  r->ktile = 1 << 30;
+  for (RdbDev& d : r->devs) r->ktile = std::min(r->ktile, d.part->step_tile);
+  r->ktile = std::max(r->ktile / r->tile, 1) * r->tile;
   bool ok = true;
   for (RdbDev& d : r->devs) {
     cudaSetDevice(d.part->device);
@@ -880,14 +918,15 @@ static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const 
     for (int b = 0; b < 2 && ok; ++b) {
       ok = cudaMalloc(&d.out[b], vb * (size_t)std::max<long long>(d.nslot, 1) * r->tile) == cudaSuccess;
       for (auto& e : d.ev[b]) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&d.ev_q[b], cudaEventDisableTiming) == cudaSuccess;
     }
   }
   cudaSetDevice(p->device);
   for (int b = 0; b < 2 && ok; ++b)
     ok = cudaHostAlloc(&r->host[b], vb * (size_t)nslot * r->tile, cudaHostAllocPortable) == cudaSuccess &&
-         (L.def <= 1 || cudaHostAlloc((void**)&r->supPin[b], sizeof(double) * 12 * r->tile, cudaHostAllocPortable) == cudaSuccess);
+         (L.def <= 1 || cudaHostAlloc((void**)&r->supPin[b], sizeof(double) * 12 * r->ktile, cudaHostAllocPortable) == cudaSuccess);
   ok = ok && (r->nslot_nodes == 0 || cudaMalloc(&r->rec, sizeof(double) * (size_t)r->nslot_nodes * r->tile) == cudaSuccess) &&
-       (L.def <= 1 || cudaMalloc(&r->supTr, sizeof(double) * 12 * r->tile) == cudaSuccess);
+       (L.def <= 1 || cudaMalloc(&r->supTr, sizeof(double) * 12 * r->ktile) == cudaSuccess);
   if (!ok) {
     set_error("fsr_rdb_create: cannot allocate the record buffers (%lld values x %d steps): %s", nslot, r->tile,
               cudaGetErrorString(cudaGetLastError()));
@@ -975,85 +1014,100 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
       FSR_CUDA(cudaSetDevice(d.part->device));
       FSR_CUDA(cudaStreamSynchronize(d.part->stream));
       cudaFree(d.dQ); d.dQ = nullptr;
-      FSR_CUDA(cudaMalloc(&d.dQ, sizeof(double) * (size_t)ldq * r->tile));
+      FSR_CUDA(cudaMalloc(&d.dQ, sizeof(double) * (size_t)ldq * r->ktile));
     }
     for (int b = 0; b < 2; ++b) {
       if (r->Qpin[b]) cudaFreeHost(r->Qpin[b]);
       r->Qpin[b] = nullptr;
-      FSR_CUDA(cudaHostAlloc((void**)&r->Qpin[b], sizeof(double) * (size_t)ldq * r->tile, cudaHostAllocPortable));
+      FSR_CUDA(cudaHostAlloc((void**)&r->Qpin[b], sizeof(double) * (size_t)ldq * r->ktile, cudaHostAllocPortable));
     }
     r->ldq_cap = ldq;
   }
-  for (int t0 = 0; t0 < nsteps; t0 += r->tile) {
-    const int nt = std::min(r->tile, nsteps - t0);
-    const int nt_pad = (nt + 63) / 64 * 64;
-    const int b = r->next_buf;
-    {   // buffer b is free again once the writer has put its previous content on file
-      std::unique_lock<std::mutex> lk(r->mtx);
-      r->cv.wait(lk, [&] { return !r->busy[b]; });
-      if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); return FSR_ERR_ARG; }
+  for (int c0 = 0; c0 < nsteps; c0 += r->ktile) {   // expansion chunks
+    const int nc = std::min(r->ktile, nsteps - c0), nc_pad = (nc + 63) / 64 * 64;
+    const int qb = r->next_q;
+    for (RdbDev& d : r->devs) {   // the H2D copy of the chunk before the previous one has left this staging buffer
+      FSR_CUDA(cudaSetDevice(d.part->device));
+      FSR_CUDA(cudaEventSynchronize(d.ev_q[qb]));
     }
-    memcpy(r->Qpin[b], Q + (size_t)t0 * ldq, sizeof(double) * (size_t)ldq * nt);
-    if (r->L.def > 1) memcpy(r->supPin[b], sup_tr + (size_t)t0 * 12, sizeof(double) * 12 * nt);
-    for (RdbDev& d : r->devs) {
-      if (d.nslot == 0) continue;
-      fsr_part* dp = d.part;
-      cudaStream_t s = dp->stream;
-      FSR_CUDA(cudaSetDevice(dp->device));
-      FSR_CUDA(cudaEventRecord(d.ev[b][0], s));
-      FSR_CUDA(cudaMemcpyAsync(d.dQ, r->Qpin[b], sizeof(double) * (size_t)ldq * nt, cudaMemcpyHostToDevice, s));
-      if ((rc = launch_pack_q(dp, d.dQ, ldq, nt, nt_pad, s)) || (rc = launch_k1(dp, nt_pad, s))) return rc;
-      if (r->L.def) {   // nodal values: slot-major staging, then one tiled transpose into the leading part of the records
-        if (r->L.def > 1) FSR_CUDA(cudaMemcpyAsync(r->supTr, r->supPin[b], sizeof(double) * 12 * nt, cudaMemcpyHostToDevice, s));
-        const size_t ldt = (size_t)r->tile;
-        dim3 blk(32, 8), grd((dp->nnod + 7) / 8, (nt + 31) / 32);
-        record_nodes_kernel<<<grd, blk, 0, s>>>(dp->U, (size_t)dp->step_tile, nt, dp->nnod, r->madof, r->node_slot, dp->xyz, r->supTr,
-                                                r->supTr0, r->L.def > 1, r->rec, ldt);
-        FSR_LAUNCH_CHECK();
-        dim3 tg((unsigned)((r->nslot_nodes + 31) / 32), (nt + 31) / 32);
-        if (r->dbl) record_transpose_kernel<double><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (double*)d.out[b], (size_t)d.nslot);
-        else record_transpose_kernel<float><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (float*)d.out[b], (size_t)d.nslot);
-        FSR_LAUNCH_CHECK();
+    memcpy(r->Qpin[qb], Q + (size_t)c0 * ldq, sizeof(double) * (size_t)ldq * nc);
+    if (r->L.def > 1) memcpy(r->supPin[qb], sup_tr + (size_t)c0 * 12, sizeof(double) * 12 * nc);
+    bool first = true;
+    for (int ts = 0; ts < nc; ts += r->tile) {   // record tiles of the chunk
+      const int nt = std::min(r->tile, nc - ts);
+      const int b = r->next_buf;
+      {   // buffer b is free again once the writer has put its previous content on file
+        std::unique_lock<std::mutex> lk(r->mtx);
+        r->cv.wait(lk, [&] { return !r->busy[b]; });
+        if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); return FSR_ERR_ARG; }
       }
-      rc = r->dbl ? launch_record_kernels<double>(r, d, nt, (double*)d.out[b], s) : launch_record_kernels<float>(r, d, nt, (float*)d.out[b], s);
-      if (rc) return rc;
-      FSR_CUDA(cudaEventRecord(d.ev[b][1], s));
-      FSR_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev[b][1], 0));
-      FSR_CUDA(cudaEventRecord(d.ev[b][2], d.copy_stream));
-      // this device's slot range of every step record of the tile
-      FSR_CUDA(cudaMemcpy2DAsync((char*)r->host[b] + vb * (size_t)d.slot0, vb * (size_t)r->nslot, d.out[b], vb * (size_t)d.nslot,
-                                 vb * (size_t)d.nslot, (size_t)nt, cudaMemcpyDeviceToHost, d.copy_stream));
-      FSR_CUDA(cudaEventRecord(d.ev[b][3], d.copy_stream));
+      for (RdbDev& d : r->devs) {
+        if (d.nslot == 0) continue;
+        fsr_part* dp = d.part;
+        cudaStream_t s = dp->stream;
+        FSR_CUDA(cudaSetDevice(dp->device));
+        FSR_CUDA(cudaEventRecord(d.ev[b][0], s));
+        if (first) {
+          FSR_CUDA(cudaMemcpyAsync(d.dQ, r->Qpin[qb], sizeof(double) * (size_t)ldq * nc, cudaMemcpyHostToDevice, s));
+          if (r->L.def > 1) FSR_CUDA(cudaMemcpyAsync(r->supTr, r->supPin[qb], sizeof(double) * 12 * nc, cudaMemcpyHostToDevice, s));
+          FSR_CUDA(cudaEventRecord(d.ev_q[qb], s));
+          if ((rc = launch_pack_q(dp, d.dQ, ldq, nc, nc_pad, s)) || (rc = launch_k1(dp, nc_pad, s))) return rc;
+        }
+        FSR_CUDA(cudaEventRecord(d.ev[b][4], s));
+        if (r->L.def) {   // nodal values: slot-major staging, then one tiled transpose into the leading part of the records
+          const size_t ldt = (size_t)r->tile;
+          dim3 blk(32, 8), grd((dp->nnod + 7) / 8, (nt + 31) / 32);
+          record_nodes_kernel<<<grd, blk, 0, s>>>(dp->U + ts, (size_t)dp->step_tile, nt, dp->nnod, r->madof, r->node_slot, dp->xyz,
+                                                  r->supTr ? r->supTr + (size_t)12 * ts : nullptr, r->supTr0, r->L.def > 1, r->rec, ldt);
+          FSR_LAUNCH_CHECK();
+          dim3 tg((unsigned)((r->nslot_nodes + 31) / 32), (nt + 31) / 32);
+          if (r->dbl) record_transpose_kernel<double><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (double*)d.out[b], (size_t)d.nslot);
+          else record_transpose_kernel<float><<<tg, blk, 0, s>>>(r->rec, ldt, r->nslot_nodes, nt, (float*)d.out[b], (size_t)d.nslot);
+          FSR_LAUNCH_CHECK();
+        }
+        rc = r->dbl ? launch_record_kernels<double>(r, d, ts, nt, (double*)d.out[b], s) : launch_record_kernels<float>(r, d, ts, nt, (float*)d.out[b], s);
+        if (rc) return rc;
+        FSR_CUDA(cudaEventRecord(d.ev[b][1], s));
+        FSR_CUDA(cudaStreamWaitEvent(d.copy_stream, d.ev[b][1], 0));
+        FSR_CUDA(cudaEventRecord(d.ev[b][2], d.copy_stream));
+        // this device's slot range of every step record of the tile
+        FSR_CUDA(cudaMemcpy2DAsync((char*)r->host[b] + vb * (size_t)d.slot0, vb * (size_t)r->nslot, d.out[b], vb * (size_t)d.nslot,
+                                   vb * (size_t)d.nslot, (size_t)nt, cudaMemcpyDeviceToHost, d.copy_stream));
+        FSR_CUDA(cudaEventRecord(d.ev[b][3], d.copy_stream));
+      }
+      first = false;
+      RdbJob job;
+      job.buf = b; job.nt = nt;
+      job.keys.resize(12 * (size_t)nt);
+      for (int t = 0; t < nt; ++t) {
+        memcpy(job.keys.data() + 12 * (size_t)t, &stepno[c0 + ts + t], 4);
+        memcpy(job.keys.data() + 12 * (size_t)t + 4, &time[c0 + ts + t], 8);
+      }
+      {
+        std::lock_guard<std::mutex> lk(r->mtx);
+        r->busy[b] = true;
+        r->jobs.push_back(std::move(job));
+      }
+      r->cv.notify_all();
+      r->next_buf ^= 1;
     }
-    RdbJob job;
-    job.buf = b; job.nt = nt;
-    job.keys.resize(12 * (size_t)nt);
-    for (int t = 0; t < nt; ++t) {
-      memcpy(job.keys.data() + 12 * (size_t)t, &stepno[t0 + t], 4);
-      memcpy(job.keys.data() + 12 * (size_t)t + 4, &time[t0 + t], 8);
-    }
-    {
-      std::lock_guard<std::mutex> lk(r->mtx);
-      r->busy[b] = true;
-      r->jobs.push_back(std::move(job));
-    }
-    r->cv.notify_all();
-    r->next_buf ^= 1;
+    r->next_q ^= 1;
   }
   return FSR_OK;
 }
 
 // Waits until every record handed over so far is on file.  t (may be NULL): [0] device time of the tiles (H2D of Q, K1,
 // record kernels), [1] device-to-host copies, [2] file writes, all in ms and summed over the tiles (they overlap in wall
-// time), [3] bytes written, [4] tiles.  Returns the number of entries written or a negative error.
+// time), [3] bytes written, [4] tiles, [5] the part of [0] spent on the H2D copy + the expansion (K1).  Returns the number
+// of entries written or a negative error.
 int fsr_rdb_flush(fsr_rdb* r, double* t, int n)
 {
   if (!r) { set_error("fsr_rdb_flush: null handle"); return FSR_ERR_ARG; }
   r->drain();
   std::lock_guard<std::mutex> lk(r->mtx);
   if (!r->werr.empty()) { set_error("%s", r->werr.c_str()); return FSR_ERR_ARG; }
-  const double v[5] = {r->ms_compute, r->ms_copy, r->ms_disk, (double)r->bytes_written, (double)r->tiles};
-  const int m = t ? std::min(n, 5) : 0;
+  const double v[6] = {r->ms_compute, r->ms_copy, r->ms_disk, (double)r->bytes_written, (double)r->tiles, r->ms_k1};
+  const int m = t ? std::min(n, 6) : 0;
   for (int i = 0; i < m; ++i) t[i] = v[i];
   return m;
 }

@@ -616,9 +616,9 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
 // `live` = this lane's result point exists (triangles use 6 of the 8 rows of an m-tile).  Every lane
 // of the warp must reach every mma.sync, so dead lanes run the same loop and only their stores and
 // envelope updates are predicated off (ALL_LIVE = true for quads compiles the predicate away).
-template <int KT, bool WRITE_VM, bool GUARD, bool ALL_LIVE>
-__device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const double (&b)[KT], double*& vmp0,
-                                           double*& vmp1, size_t ld8, int t0, int nsteps, double& emax,
+template <int KT, bool WRITE_VM, bool GUARD, bool ALL_LIVE, class OUT_T, bool ENV>
+__device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const double (&b)[KT], OUT_T*& vmp0,
+                                           OUT_T*& vmp1, size_t ld8, int t0, int nsteps, double& emax,
                                            double& emin, bool live)
 {
   double c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -630,49 +630,60 @@ __device__ __forceinline__ void shell_tile(const double (&a)[3][KT], const doubl
   // the running max / min are kept on the radicand, which orders like its root; the root is taken once at the end.
   double q0 = fma(c[2][0] * 3.0, c[2][0], fma(-c[0][0], c[1][0], fma(c[1][0], c[1][0], c[0][0] * c[0][0])));
   double q1 = fma(c[2][1] * 3.0, c[2][1], fma(-c[0][1], c[1][1], fma(c[1][1], c[1][1], c[0][1] * c[0][1])));
-  // the form is positive semi-definite; rounding can leave -1e-17-relative, which must not reach the integer compares
-  if (!WRITE_VM) { q0 = fabs(q0); q1 = fabs(q1); }
   const double v0 = WRITE_VM ? sqrt_pos(q0) : q0, v1 = WRITE_VM ? sqrt_pos(q1) : q1;
   const bool wr = ALL_LIVE || live;
+  // compare / select (measured: 64-bit integer max / min on the ALU pipe costs more issue slots than three DSETP here)
   if (GUARD) {
     if (t0 < nsteps) {
-      if (WRITE_VM && wr) *vmp0 = v0;
-      emax = max_nonneg(emax, v0);
-      emin = min_nonneg(emin, v0);
+      if (WRITE_VM && wr) *vmp0 = (OUT_T)v0;
+      if (ENV) { emax = v0 > emax ? v0 : emax; emin = v0 < emin ? v0 : emin; }
     }
     if (t0 + 1 < nsteps) {
-      if (WRITE_VM && wr) *vmp1 = v1;
-      emax = max_nonneg(emax, v1);
-      emin = min_nonneg(emin, v1);
+      if (WRITE_VM && wr) *vmp1 = (OUT_T)v1;
+      if (ENV) { emax = v1 > emax ? v1 : emax; emin = v1 < emin ? v1 : emin; }
     }
   } else {
-    if (WRITE_VM && wr) { *vmp0 = v0; *vmp1 = v1; }
-    emax = max_nonneg(emax, max_nonneg(v0, v1));
-    emin = min_nonneg(emin, min_nonneg(v0, v1));
+    if (WRITE_VM && wr) { *vmp0 = (OUT_T)v0; *vmp1 = (OUT_T)v1; }
+    if (ENV) {
+      const bool p = v0 > v1;
+      const double hi = p ? v0 : v1, lo = p ? v1 : v0;
+      emax = hi > emax ? hi : emax;
+      emin = lo < emin ? lo : emin;
+    }
   }
   if (WRITE_VM) { vmp0 += ld8; vmp1 += ld8; }
 }
 
-template <int KT, bool WRITE_VM, bool ALL_LIVE>
+// OUT_T / ENV / roff: the same kernel writes the von Mises values of a `-vmStress` results database straight into the
+// step records (io_rdb.cu): OUT_T = float or double, column = record slot roff[i] + point instead of the result-point
+// number, no envelope.
+template <int KT, bool WRITE_VM, bool ALL_LIVE, class OUT_T = double, bool ENV = true>
 __global__ void __launch_bounds__(256, 2)
 k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad,
                    const double* __restrict__ Sfrag, const int* __restrict__ edof,
                    const int* __restrict__ ptoff, const unsigned char* __restrict__ failed,
-                   int nelt, int nstrp, double* __restrict__ vm, size_t ld_vm,
-                   double* __restrict__ env_max, double* __restrict__ env_min)
+                   int nelt, int nstrp, OUT_T* __restrict__ vm, size_t ld_vm,
+                   double* __restrict__ env_max, double* __restrict__ env_min, const long long* __restrict__ roff = nullptr)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int i = blockIdx.x * (blockDim.x >> 5) + warp;
   if (i >= nelt) return;  // whole warp
   const bool live = ALL_LIVE || g < nstrp;
-  const size_t pt = (size_t)ptoff[i] + (live ? g : 0);
+  size_t pt;
+  if (ENV)
+    pt = (size_t)ptoff[i] + (live ? g : 0);
+  else {
+    const long long r0 = roff[i];
+    if (r0 < 0) return;   // element not in the results database; whole warp
+    pt = (size_t)r0 + (live ? g : 0);
+  }
 
   if (failed[i]) {  // operator build failed: hugeVal results (stressRoutines.f90:264-268); whole warp
     if (live) {
       if (WRITE_VM)
-        for (int t = t4; t < nsteps; t += 4) vm[(size_t)t * ld_vm + pt] = kHuge;
-      if (t4 == 0 && nsteps > 0) { env_max[pt] = kHuge; if (kHuge < env_min[pt]) env_min[pt] = kHuge; }
+        for (int t = t4; t < nsteps; t += 4) vm[(size_t)t * ld_vm + pt] = (OUT_T)kHuge;
+      if (ENV && t4 == 0 && nsteps > 0) { env_max[pt] = kHuge; if (kHuge < env_min[pt]) env_min[pt] = kHuge; }
     }
     return;
   }
@@ -692,8 +703,8 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
 
   double emax = 0.0, emin = kHuge;  // neutral w.r.t. the stored envelope (max starts at 0)
   // lane owns point g at steps t0 = 8*tile + 2*t4 and t0 + 1
-  double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
-  double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
+  OUT_T* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
+  OUT_T* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
   const size_t ld8 = ld_vm * 8;
 
   const int ntiles = nsteps_pad >> 3;            // multiple of 8
@@ -708,21 +719,21 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
   for (; nt < nfull; nt += 4) {
 #pragma unroll
     for (int j = 0; j < KT; ++j) b1[j] = up[j][8];
-    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE, OUT_T, ENV>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
 #pragma unroll
     for (int j = 0; j < KT; ++j) b0[j] = up[j][16];
-    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE, OUT_T, ENV>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
 #pragma unroll
     for (int j = 0; j < KT; ++j) b1[j] = up[j][24];
-    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE, OUT_T, ENV>(a, b0, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
 #pragma unroll
     for (int j = 0; j < KT; ++j) { up[j] += 32; b0[j] = up[j][0]; }  // U rows carry 64 doubles of slack
-    shell_tile<KT, WRITE_VM, false, ALL_LIVE>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
+    shell_tile<KT, WRITE_VM, false, ALL_LIVE, OUT_T, ENV>(a, b1, vmp0, vmp1, ld8, 0, 0, emax, emin, live);
   }
   for (; nt < ntiles && nt * 8 < nsteps; ++nt) {  // ragged tail: guarded stores
 #pragma unroll
     for (int j = 0; j < KT; ++j) { up[j] += 8; b1[j] = up[j][0]; }
-    shell_tile<KT, WRITE_VM, true, ALL_LIVE>(a, b0, vmp0, vmp1, ld8, nt * 8 + 2 * t4, nsteps, emax, emin, live);
+    shell_tile<KT, WRITE_VM, true, ALL_LIVE, OUT_T, ENV>(a, b0, vmp0, vmp1, ld8, nt * 8 + 2 * t4, nsteps, emax, emin, live);
 #pragma unroll
     for (int j = 0; j < KT; ++j) b0[j] = b1[j];
   }
@@ -735,7 +746,7 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
     emax = sqrt_pos(emax);
     emin = emin == kHuge ? kHuge : sqrt_pos(emin);
   }
-  if (live && t4 == 0 && nsteps > 0) {
+  if (ENV && live && t4 == 0 && nsteps > 0) {
     if (emax > env_max[pt]) env_max[pt] = emax;
     if (emin < env_min[pt]) env_min[pt] = emin;
   }
@@ -850,6 +861,27 @@ static int launch_shell_family(fsr_part* p, FamilyData& f, int nsteps, int nstep
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }
+
+// von Mises of the family's elements into float / double step records: out[t * ld_out + roff[i] + point]
+template <class OUT_T>
+int launch_k2_shell_rec(fsr_part* p, int fam, const double* U, int nsteps, int nsteps_pad, const long long* roff, OUT_T* out, size_t ld_out,
+                        cudaStream_t s)
+{
+  FamilyData& f = p->fam[fam];
+  const int warps = 8;
+  if (f.nelt == 0) return FSR_OK;
+  const unsigned grid = (unsigned)((f.nelt + warps - 1) / warps);
+  if (fam == FAM_QUAD)
+    k2_shell_vm_kernel<6, true, true, OUT_T, false><<<grid, warps * 32, 0, s>>>(U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof,
+                                                                                f.ptoff, f.failed, f.nelt, f.nstrp, out, ld_out, nullptr, nullptr, roff);
+  else
+    k2_shell_vm_kernel<5, true, false, OUT_T, false><<<grid, warps * 32, 0, s>>>(U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof,
+                                                                                 f.ptoff, f.failed, f.nelt, f.nstrp, out, ld_out, nullptr, nullptr, roff);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+template int launch_k2_shell_rec<float>(fsr_part*, int, const double*, int, int, const long long*, float*, size_t, cudaStream_t);
+template int launch_k2_shell_rec<double>(fsr_part*, int, const double*, int, int, const long long*, double*, size_t, cudaStream_t);
 
 int launch_k2_shell_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s)
 {

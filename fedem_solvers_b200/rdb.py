@@ -105,9 +105,9 @@ class StressRdb:
 
     def flush(self):
         """Waits for the pipeline (device -> PCIe -> file) to drain; returns where the time went."""
-        t = np.zeros(5, F64)
-        check(self.lib.fsr_rdb_flush(self._h, _dp(t), 5), "fsr_rdb_flush")
-        return dict(compute_ms=t[0], d2h_ms=t[1], disk_ms=t[2], bytes=int(t[3]), tiles=int(t[4]))
+        t = np.zeros(6, F64)
+        check(self.lib.fsr_rdb_flush(self._h, _dp(t), 6), "fsr_rdb_flush")
+        return dict(compute_ms=t[0], d2h_ms=t[1], disk_ms=t[2], bytes=int(t[3]), tiles=int(t[4]), k1_ms=t[5])
 
     def close(self):
         if self._h:

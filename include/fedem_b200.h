@@ -548,7 +548,8 @@ int fsr_rdb_write_steps(fsr_rdb *rdb, const double *Q, int ldq, int nsteps, cons
  * crosses PCIe and tile n-2 is appended to the file by a writer thread.  fsr_rdb_flush waits until every record handed
  * over so far is on file and reports where the time went: t[0] = device time of the tiles (H2D of Q, K1, record
  * kernels), t[1] = device-to-host copies, t[2] = file writes -- milliseconds, each summed over the tiles (the three
- * overlap in wall time) -- t[3] = bytes written, t[4] = tiles.  t may be NULL.  Returns the entries written. */
+ * overlap in wall time) -- t[3] = bytes written, t[4] = tiles, t[5] = the part of t[0] spent on the H2D copy of Q and the
+ * expansion (K1).  t may be NULL.  Returns the entries written. */
 int fsr_rdb_flush(fsr_rdb *rdb, double *t, int n);
 /* calcTotalNodalDisplacement for one node on the host (the same code the record kernel runs): x0[3], u[nd],
  * nd = 3 or 6, T / T0 = current / initial 3x4 position matrices; utot[nd] */
