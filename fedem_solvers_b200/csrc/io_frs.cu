@@ -574,19 +574,31 @@ int fsr_frs_reduced_history(fsr_frs* db, int sup_base_id, int ntriads, const int
     return FSR_ERR_ARG;
   }
   // initiateTriadAndSupElTypeModule / displacementModule.f90:262-292: result pointers of the triads and the part
+  // readResponsePointers (displacementModule.f90:246-328): all found = go on; NONE found = a warning (ierr = 1) and the
+  // recovery is "based on local deformations relative to the modelling configuration of the part", i.e. the triads stay
+  // where the solver input file put them and finit = 0; only a PARTIAL set is an error
   std::vector<int> h((size_t)ntriads + 2, -1);
+  int nfound = 0, nfixed = 0;
   for (int i = 0; i < ntriads; ++i) {
     if (ndofs[i] == 6) h[(size_t)i] = fsr_frs_find(db, "Position matrix", "Triad", triad_base_id[i]);
     else if (ndofs[i] == 3) h[(size_t)i] = fsr_frs_find(db, "Position", "Triad", triad_base_id[i]);
-    else continue;
-    if (h[(size_t)i] < 0) { set_error("Error reading position for Triad {%d}: variable not found on the results file", triad_base_id[i]); return FSR_ERR_ARG; }
+    else { ++nfixed; continue; }
+    nfound += h[(size_t)i] >= 0;
   }
-  if ((h[(size_t)ntriads] = fsr_frs_find(db, "Position matrix", "Part", sup_base_id)) < 0) {
-    set_error("Error reading position matrix for Part {%d}: variable not found on the results file", sup_base_id);
-    return FSR_ERR_ARG;
+  nfound += (h[(size_t)ntriads] = fsr_frs_find(db, "Position matrix", "Part", sup_base_id)) >= 0;
+  if (ngen > 0) nfound += (h[(size_t)ntriads + 1] = fsr_frs_find(db, "Generalized displacement", "Part", sup_base_id)) >= 0;
+  if (nfound == 0) {
+    for (int s = 0; s < nsteps; ++s)
+      for (int k = 0; k < ldq; ++k) Q[(size_t)s * ldq + k] = 0.0;
+    set_error("No system-level response variables found. Stress recovery will be based on local deformations relative to the "
+              "modelling configuration of the part.");
+    return 1;   // warning, like ierr = 1 of readResponsePointers
   }
-  if (ngen > 0 && (h[(size_t)ntriads + 1] = fsr_frs_find(db, "Generalized displacement", "Part", sup_base_id)) < 0) {
-    set_error("Error reading generalized displacements for Part {%d}: variable not found on the results file", sup_base_id);
+  if (nfound + nfixed != ntriads + 1 + (ngen > 0 ? 1 : 0)) {
+    for (int i = 0; i < ntriads; ++i)
+      if (h[(size_t)i] < 0 && (ndofs[i] == 6 || ndofs[i] == 3)) { set_error("Cannot find position for Triad {%d} on the results file", triad_base_id[i]); return FSR_ERR_ARG; }
+    if (h[(size_t)ntriads] < 0) { set_error("Cannot find position matrix for Part {%d} on the results file", sup_base_id); return FSR_ERR_ARG; }
+    set_error("Cannot find generalized displacements for Part {%d} on the results file", sup_base_id);
     return FSR_ERR_ARG;
   }
   std::vector<double> sup((size_t)nsteps * 12), tri((size_t)nsteps * std::max(ntriads, 1) * 12, 0.0), gen((size_t)nsteps * std::max(ngen, 1));

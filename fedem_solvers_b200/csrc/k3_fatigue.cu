@@ -445,9 +445,16 @@ int fsr_fatigue_finish(fsr_fatigue_state* f, double* damage, int* ncycles, int* 
   if (status) FSR_CUDA(cudaMemcpyAsync(status, f->out_status, sizeof(int) * ng, cudaMemcpyDeviceToHost, s));
   if (bins && f->nbins > 0) FSR_CUDA(cudaMemcpyAsync(bins, f->out_bins, sizeof(int) * ng * f->nbins, cudaMemcpyDeviceToHost, s));
   FSR_CUDA(cudaStreamSynchronize(s));
-  // warning count = gages whose closure failed like the reference's or whose stack overflowed
+  // warning count = gages whose closure failed like the reference's or whose stack overflowed -- also when the caller
+  // did not ask for the status array
+  std::vector<int> st;
+  if (!status) {
+    st.resize(ng);
+    FSR_CUDA(cudaMemcpy(st.data(), f->out_status, sizeof(int) * ng, cudaMemcpyDeviceToHost));
+    status = st.data();
+  }
   int nwarn = 0;
-  if (status) for (size_t g = 0; g < ng; ++g) nwarn += status[g] != 0;
+  for (size_t g = 0; g < ng; ++g) nwarn += status[g] != 0;
   return nwarn;
 }
 

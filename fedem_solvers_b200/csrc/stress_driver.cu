@@ -588,6 +588,7 @@ static int run_program(int which)
   const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
   const clk::time_point t_loop0 = clk::now();
   double t_hist = 0.0;
+  bool warned_no_response = false;
   for (int w0 = 0; w0 < nsel; w0 += window) {
     const int nw = std::min(window, nsel - w0);
     const clk::time_point t_h0 = clk::now();
@@ -595,7 +596,9 @@ static int run_program(int which)
       int run = 1;
       while (k + run < nw && sel[w0 + k + run] == sel[w0 + k] + run) ++run;
       double* q0 = Q.data() + (size_t)k * ndim;
-      CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[w0 + k], run, q0, ndim));
+      const int rch = fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[w0 + k], run, q0, ndim);
+      CHECK(rch);
+      if (rch > 0 && !warned_no_response) { log.line("  ** Warning: %s", fsr_last_error()); warned_no_response = true; }
       if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, sel[w0 + k], run, supTr.data() + 12 * (size_t)k, 12, 12));
       k += run;
     }
@@ -825,8 +828,12 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
     for (int k = 0; k < nw;) {
       int run = 1;
       while (k + run < nw && sel[(size_t)(w0 + k + run)] == sel[(size_t)(w0 + k)] + run) ++run;
-      CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[(size_t)(w0 + k)], run,
-                                    Q.data() + (size_t)k * ndim, ndim));
+      {
+        const int rch = fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[(size_t)(w0 + k)], run,
+                                    Q.data() + (size_t)k * ndim, ndim);
+        CHECK(rch);
+        if (rch > 0 && w0 == 0 && k == 0) log.line("  ** Warning: %s", fsr_last_error());
+      }
       if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, sel[(size_t)(w0 + k)], run, supTr.data() + 12 * (size_t)k, 12, 12));
       k += run;
     }
@@ -883,7 +890,10 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
   if (iFatigue > 0 && nsel > 0) {
     log.line("           --> Time loop done. Performing fatigue calculation");
     const double to_mpa = c.get_double("stressToMPaScale"), gate = c.get_double("gate"), bin_size = c.get_double("binSize");
-    const double curve[4] = {c.get_double("loga1"), c.get_double("loga2"), c.get_double("m1"), 5.0};   // m2 = 5 (FFpSNCurve.H)
+    // m2: the reference has no command-line default for it -- reportDamage hands snCurve(4) of the rosette record to
+    // ffp_getdamage as it is, 0 when the record does not set it (strainGageModule.f90:157,811-816); same here, and the
+    // report below prints the value the computation used
+    const double curve[4] = {c.get_double("loga1"), c.get_double("loga2"), c.get_double("m1"), 0.0};
     const int nser = 4 * nros;
     std::vector<double> damage((size_t)nser);
     std::vector<int> ncyc((size_t)nser), status((size_t)nser), bins;
@@ -897,6 +907,23 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
       if (!open_end || nbins >= 65536) break;
       nbins *= 4;
     }
+    // status 1 = the reference's own closure failure (ffp_getdamage ignores it too, the cycles counted so far stand);
+    // status 2 = the turning-point stack of the series overflowed: its damage and cycle counts are NOT valid
+    int nclosure = 0, noverflow = 0;
+    for (int r = 0; r < nros; ++r)
+      for (int j = 0; j <= ros[(size_t)r].ngage; ++j) {
+        const int st = status[(size_t)(4 * r + j)];
+        if (st == 2) {
+          ++noverflow;
+          log.line(" *** Error: Rosette %d, %s: the rainflow residue exceeded the stack capacity; no damage / cycle counts for this series",
+                   ros[(size_t)r].id, j == 0 ? "max principal stress" : (std::string("gage ") + std::to_string(j)).c_str());
+        } else if (st == 1) {
+          ++nclosure;
+          log.line("  ** Warning: Rosette %d, %s: the rainflow residue did not close on three points (as in the reference, the cycles "
+                   "counted so far are kept)", ros[(size_t)r].id, j == 0 ? "max principal stress" : (std::string("gage ") + std::to_string(j)).c_str());
+        }
+      }
+    if (noverflow) log.line(" *** Error: %d series without fatigue results (marked -1 below)", noverflow);
     for (int r = 0; r < nros; ++r) {
       const fsr_rosette& R = ros[(size_t)r];
       const double g = R.gate > 0.0 ? R.gate : gate;

@@ -344,3 +344,19 @@ def test_eigenvector_groups_of_a_real_solver_file_and_mode_finit():
                 assert np.allclose(Q[k + 2:k + 5, l], tinv @ e[3:6], rtol=0, atol=1e-16)
         assert np.array_equal(Q[gfirst - 1:gfirst - 1 + ngen, l], gen[ngen * l: ngen * (l + 1)])
     assert lib.fsr_build_mode_finit(4, _dp(np.ascontiguousarray(sup.T.reshape(-1))), _ip(ndofs), _ip(first), _dp(tri), ngen, 23, _dp(gen), ncomp, _dp(Q), 24) < 0
+
+
+def test_no_system_level_response_is_a_warning_not_an_error(tmp_path):
+    """readResponsePointers (displacementModule.f90:292-303): when NONE of the position / generalized-displacement variables
+    is on the results files the reference warns and recovers from local deformations relative to the modelling configuration
+    (finit = 0); only a partial set is an error"""
+    rng = np.random.default_rng(3)
+    f1 = str(tmp_path / "th_p_1.frs")
+    triads, tr_undef, sup, tri, gen = _write_solver_file(f1, rng, 6, 3, 4)
+    rd = FrsReader(f1)
+    ndofs, first = np.array([6, 6, 6]), np.array([1, 7, 13])
+    Q = rd.reduced_history(500, [901, 902, 903], ndofs, first, tr_undef, 4, 19)       # nothing of this part is on the file
+    assert Q.shape == (22, 6) and not Q.any()
+    with pytest.raises(FsrError, match="Triad"):                                       # the part is there, one triad is not
+        rd.reduced_history(7, [triads[0][0], 902, triads[2][0]], ndofs, first, tr_undef, 4, 19)
+    rd.close()
