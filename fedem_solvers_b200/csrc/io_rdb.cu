@@ -62,13 +62,36 @@ __device__ __forceinline__ size_t frag_at2(int row, int col, int KT)
 constexpr int kRecWarps = 4;
 constexpr int kRecLds = 9;   // shared-memory row stride in doubles (8 steps + 1: spreads the rows over the banks)
 
-template <int KT, class OUT_T>
+// von Mises / principal values of one result point with the component count known at compile time (everything stays in
+// registers).  2-D: FFaTensorTransforms.C:33-36 and the quadratic branch of FFa::cubicSolve (FFaMath.C:117-133: P > 0 two
+// roots, P > -1e-64 a double root, else no result -> the zeros the caller put in, like the reference's stale values);
+// 3-D: the shared routines of invariants.cuh (trigonometric cubic with the reference's case analysis).
+template <int NCMP>
+__device__ __forceinline__ void rec_invariants(const double (&S)[NCMP], bool want_vm, bool want_p, double& vm, double& pmax, double& pmin)
+{
+  vm = pmax = pmin = 0.0;
+  if (NCMP == 3) {
+    if (want_vm) vm = sqrt_pos(fma(3.0 * S[2], S[2], fma(-S[0], S[1], fma(S[1], S[1], S[0] * S[0]))));
+    if (want_p) {
+      const double Cq = -(S[0] + S[1]), Dq = S[0] * S[1] - S[2] * S[2];
+      const double Pq = Cq * Cq - 4.0 * Dq;
+      if (Pq > 0.0) { const double Q = sqrt_pos(Pq); pmax = 0.5 * (Q - Cq); pmin = 0.5 * (-Cq - Q); }
+      else if (Pq > -1.0e-64) pmax = pmin = -0.5 * Cq;
+    }
+  } else {
+    if (want_vm) vm = von_mises(NCMP, S);
+    if (want_p) { double P[3] = {0.0, 0.0, 0.0}; principal_values(NCMP, S, P); pmax = P[0]; pmin = P[2]; }
+  }
+}
+
+template <int KT, int LAYOUT, class OUT_T>
 __global__ void __launch_bounds__(kRecWarps * 32)
 record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, const double* __restrict__ Sfrag,
                           const double* __restrict__ Efrag, const int* __restrict__ edof, const long long* __restrict__ roff,
                           const unsigned char* __restrict__ failed, const double* __restrict__ aux, int naux, int nelt, int nstrp,
-                          int ncmp, int MT, int layout, int nenod, RecLayout L, OUT_T* __restrict__ out, size_t ld_out)
+                          int MT, int nenod, RecLayout L, OUT_T* __restrict__ out, size_t ld_out)
 {
+  constexpr int NCMP = LAYOUT == 0 ? 3 : 6;
   extern __shared__ double rec_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
@@ -77,15 +100,18 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
   const long long base = roff[i];
   if (base < 0) return;
   const int nrow = MT * 8;
-  double* sig_s = rec_smem + (size_t)warp * (layout == 2 ? 2 : 1) * nrow * kRecLds;
+  double* sig_s = rec_smem + (size_t)warp * (LAYOUT == 2 ? 2 : 1) * nrow * kRecLds;
   double* eps_s = sig_s + (size_t)nrow * kRecLds;   // thick shells only
-  const int srsize = L.sr && layout != 1 ? 6 * nenod : 0;
-  const int ptsize = (L.stress ? ncmp : 0) + (L.strain ? ncmp : 0) + L.nsel;
+  const int srsize = L.sr && LAYOUT != 1 ? 6 * nenod : 0;
+  const int ptsize = (L.stress ? NCMP : 0) + (L.strain ? NCMP : 0) + L.nsel;
   const bool bad = failed[i] != 0;
   const double* S = Sfrag + (size_t)i * MT * KT * 32 + lane;
-  const double* Es = layout == 2 ? Efrag + (size_t)i * MT * KT * 32 + lane : nullptr;
+  const double* Es = LAYOUT == 2 ? Efrag + (size_t)i * MT * KT * 32 + lane : nullptr;
   const double E = aux[(size_t)i * naux], nu = aux[(size_t)i * naux + 1];
-  const double th = layout == 0 ? aux[(size_t)i * naux + 2] : 0.0;
+  const double th = LAYOUT == 0 ? aux[(size_t)i * naux + 2] : 0.0;
+  const double iE = 1.0 / E, g1 = (1.0 + nu) * iE;   // isoMat2Dinv / isoMat3Dinv (isoMatModule.f90:41-57,95-120); tensorial shear
+  const double srn = 0.5 * th, srm = 0.5 * th * th / 6.0;
+  const bool want_s = (L.mask & 0x0f) != 0, want_e = (L.mask & 0xf0) != 0 || L.strain;
   // B operand rows of this lane: element DOF 4*k + t4 (padding columns point at row 0, their operator entries are zero)
   const double* up[KT];
 #pragma unroll
@@ -106,7 +132,7 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
         for (int mm = 0; mm < 3; ++mm) {
           const int mi = min(m0 + mm, MT - 1);
           Sm[mm] = S + (size_t)mi * KT * 32;
-          Em[mm] = Es ? Es + (size_t)mi * KT * 32 : nullptr;
+          Em[mm] = LAYOUT == 2 ? Es + (size_t)mi * KT * 32 : nullptr;
         }
         double c[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
@@ -119,7 +145,7 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
             double* q = sig_s + ((m0 + mm) * 8 + g) * kRecLds + 2 * t4;
             q[0] = c[mm][0]; q[1] = c[mm][1];
           }
-        if (Es) {
+        if (LAYOUT == 2) {
           double d[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
           for (int k = 0; k < KT; ++k)
@@ -146,46 +172,60 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
         if (srsize && pnt < nenod) for (int k = 0; k < 6; ++k) so[k] = (OUT_T)kHuge;
         continue;
       }
-      double sig[6] = {0, 0, 0, 0, 0, 0}, eps[6] = {0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < ncmp; ++c) sig[c] = sig_s[(layout == 0 ? c * 8 + pnt : pnt * ncmp + c) * kRecLds + st];
-      if (layout == 2) {
-        for (int c = 0; c < ncmp; ++c) eps[c] = eps_s[(pnt * ncmp + c) * kRecLds + st];
-      } else if (ncmp == 3) {   // isoMat2Dinv (isoMatModule.f90:41-57), tensorial shear (elStressModule.f90:244-248)
-        eps[0] = sig[0] / E - nu / E * sig[1];
-        eps[1] = -nu / E * sig[0] + sig[1] / E;
-        eps[2] = 0.5 * (2.0 * (1.0 + nu) / E * sig[2]);
-      } else {                  // isoMat3Dinv (isoMatModule.f90:95-120), tensorial shear (elStressModule.f90:249-251)
-        eps[0] = (sig[0] - nu * (sig[1] + sig[2])) / E;
-        eps[1] = (sig[1] - nu * (sig[0] + sig[2])) / E;
-        eps[2] = (sig[2] - nu * (sig[0] + sig[1])) / E;
-        const double g2 = 2.0 * (1.0 + nu) / E;
-        eps[3] = 0.5 * g2 * sig[3]; eps[4] = 0.5 * g2 * sig[4]; eps[5] = 0.5 * g2 * sig[5];
+      double sig[NCMP], eps[NCMP];
+#pragma unroll
+      for (int c = 0; c < NCMP; ++c) sig[c] = sig_s[(LAYOUT == 0 ? c * 8 + pnt : pnt * NCMP + c) * kRecLds + st];
+      if (LAYOUT == 2) {
+#pragma unroll
+        for (int c = 0; c < NCMP; ++c) eps[c] = eps_s[(pnt * NCMP + c) * kRecLds + st];
+      } else if (NCMP == 3) {
+        eps[0] = (sig[0] - nu * sig[1]) * iE;
+        eps[1] = (sig[1] - nu * sig[0]) * iE;
+        eps[2] = g1 * sig[2];
+      } else {
+        eps[0] = (sig[0] - nu * (sig[1] + sig[2])) * iE;
+        eps[1] = (sig[1] - nu * (sig[0] + sig[2])) * iE;
+        eps[2] = (sig[2] - nu * (sig[0] + sig[1])) * iE;
+#pragma unroll
+        for (int c = 3; c < NCMP; ++c) eps[c] = g1 * sig[c];
       }
       int k = 0;
-      if (L.stress) for (int c = 0; c < ncmp; ++c) o[k++] = (OUT_T)sig[c];
-      if (L.strain) for (int c = 0; c < ncmp; ++c) o[k++] = (OUT_T)eps[c];
+      if (L.stress) {
+#pragma unroll
+        for (int c = 0; c < NCMP; ++c) o[k + c] = (OUT_T)sig[c];
+        k += NCMP;
+      }
+      if (L.strain) {
+#pragma unroll
+        for (int c = 0; c < NCMP; ++c) o[k + c] = (OUT_T)eps[c];
+        k += NCMP;
+      }
       if (L.nsel) {
-        const int np = ncmp == 3 ? 2 : 3;
-        double r[8] = {0, 0, 0, 0, 0, 0, 0, 0}, P[3] = {0, 0, 0};
-        if (L.mask & 0x01) r[0] = von_mises(ncmp, sig);
-        if (L.mask & 0x0e) { principal_values(ncmp, sig, P); r[1] = P[0]; r[2] = P[np - 1]; r[3] = 0.5 * (P[0] - P[np - 1]); }
-        if (L.mask & 0x10) r[4] = von_mises(ncmp, eps);
-        if (L.mask & 0xe0) { P[0] = P[1] = P[2] = 0.0; principal_values(ncmp, eps, P); r[5] = P[0]; r[6] = P[np - 1]; r[7] = 0.5 * (P[0] - P[np - 1]); }
-        for (int j = 0; j < 8; ++j) if (L.mask & (1 << j)) o[k++] = (OUT_T)r[j];
+        double r[8];
+        if (want_s) rec_invariants<NCMP>(sig, (L.mask & 0x01) != 0, (L.mask & 0x0e) != 0, r[0], r[1], r[2]);
+        if (L.mask & 0xf0) rec_invariants<NCMP>(eps, (L.mask & 0x10) != 0, (L.mask & 0xe0) != 0, r[4], r[5], r[6]);
+        r[3] = 0.5 * (r[1] - r[2]); r[7] = 0.5 * (r[5] - r[6]);   // maxshearvalue_ (FFaTensorTransforms.C:295)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (L.mask & (1 << j)) o[k++] = (OUT_T)r[j];
       }
       if (srsize && pnt < nenod) {
-        if (layout == 2)   // thick shells: SR = 0 (STR31 / STR32, elStressModule.f90:1174-1176, 1296-1298)
+        if (LAYOUT == 2) {   // thick shells: SR = 0 (STR31 / STR32, elStressModule.f90:1174-1176, 1296-1298)
+#pragma unroll
           for (int c = 0; c < 6; ++c) so[c] = (OUT_T)0.0;
-        else               // thin shells: from the top and bottom stresses of the node (STR22a :826-831, STR23 :976-979)
+        } else if (LAYOUT == 0) {   // thin shells: from the top and bottom stresses of the node (STR22a :826-831, STR23 :976-979)
+#pragma unroll
           for (int c = 0; c < 3; ++c) {
             const double bot = sig_s[(c * 8 + nenod + pnt) * kRecLds + st];
-            so[c] = (OUT_T)((sig[c] + bot) * 0.5 * th);
-            so[3 + c] = (OUT_T)((sig[c] - bot) * 0.5 * th * th / 6.0);
+            so[c] = (OUT_T)((sig[c] + bot) * srn);
+            so[3 + c] = (OUT_T)((sig[c] - bot) * srm);
           }
+        }
       }
     }
     __syncwarp();
   }
+  (void)want_e;
 }
 
 struct BeamOp12 { double S[12][12]; };
@@ -782,18 +822,22 @@ static int launch_record_kernels(fsr_rdb* r, RdbDev& d, int ts, int nt, OUT_T* o
       }
       const size_t smem = sizeof(double) * kRecWarps * (layout == 2 ? 2 : 1) * (size_t)f.MT * 8 * kRecLds;
       const unsigned grid = (unsigned)((f.nelt + kRecWarps - 1) / kRecWarps);
-#define FSR_REC_LAUNCH(KTV)                                                                                                        \
-  case KTV:                                                                                                                        \
+#define FSR_REC_LAUNCH(KTV, LAY)                                                                                                   \
+  if (f.KT == KTV && layout == LAY) {                                                                                              \
     if (smem > 48 * 1024)                                                                                                          \
-      if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<KTV, OUT_T>, 100 * 1024)) return rc;                        \
-    record_points_dmma_kernel<KTV, OUT_T><<<grid, kRecWarps * 32, smem, s>>>(U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag, f.edof, \
-                                                                              d.roff[fi], f.failed, f.aux, f.naux, f.nelt, f.nstrp, \
-                                                                              f.ncmp, f.MT, layout, f.nenod, r->L, out, ld_out);   \
-    break;
-      switch (f.KT) {   // the k-tile counts of the element families (common.cuh): the k loop is unrolled at compile time
-        FSR_REC_LAUNCH(3) FSR_REC_LAUNCH(5) FSR_REC_LAUNCH(6) FSR_REC_LAUNCH(8) FSR_REC_LAUNCH(9) FSR_REC_LAUNCH(12) FSR_REC_LAUNCH(15)
-        default: set_error("internal: no record kernel for an operator with %d k-tiles (family %d)", f.KT, fi); return FSR_ERR_LIMIT;
-      }
+      if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<KTV, LAY, OUT_T>, 100 * 1024)) return rc;                   \
+    record_points_dmma_kernel<KTV, LAY, OUT_T><<<grid, kRecWarps * 32, smem, s>>>(U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag,   \
+                                                                                   f.edof, d.roff[fi], f.failed, f.aux, f.naux,    \
+                                                                                   f.nelt, f.nstrp, f.MT, f.nenod, r->L, out, ld_out); \
+    launched = true;                                                                                                               \
+  }
+      // the (k-tile count, row layout) pairs of the element families (common.cuh): loops over both are unrolled at compile time
+      bool launched = false;
+      FSR_REC_LAUNCH(6, 0) FSR_REC_LAUNCH(5, 0)                                                   // ANDES quad, triangle
+      FSR_REC_LAUNCH(8, 1) FSR_REC_LAUNCH(15, 1) FSR_REC_LAUNCH(12, 1)                            // TET10, HEX20, WEDG15
+      FSR_REC_LAUNCH(6, 1) FSR_REC_LAUNCH(3, 1) FSR_REC_LAUNCH(5, 1)                              // HEX8, TET4, WEDG6
+      FSR_REC_LAUNCH(9, 2) FSR_REC_LAUNCH(12, 2)                                                  // TRI6, QUAD8 thick shells
+      if (!launched) { set_error("internal: no record kernel for an operator with %d k-tiles, layout %d (family %d)", f.KT, layout, fi); return FSR_ERR_LIMIT; }
 #undef FSR_REC_LAUNCH
     }
     FSR_LAUNCH_CHECK();

@@ -483,3 +483,58 @@ def test_expand_rows(oracle):
     bad = np.array([part.sam.ndof], np.int32)
     assert rec._lib.fsr_expand_rows(rec._h, _dp(Q), Q.shape[0], 1, _ip(bad), 1, _dp(out)) < 0
     rec.close()
+
+
+def _impose_field(part, field):
+    """Makes the nodal field `field` [nnod, 6] the expansion of the part: B = 0, one component mode whose shape is the
+    field at the internal DOFs, the external DOFs carry the field themselves.  Returns q = [finit; 1]."""
+    sam = part.sam
+    f = np.asarray(field, np.float64).ravel()
+    eq2dof = np.zeros(sam.neq + 1, np.int64)
+    nz = np.nonzero(sam.meqn > 0)[0]
+    eq2dof[sam.meqn[nz]] = nz
+    part.B = np.zeros((sam.ndof1, sam.ndof2), order="F")
+    part.E = np.asfortranarray(f[eq2dof[sam.meqn1]].reshape(-1, 1))
+    sam.ngen = 1
+    rec = StressRecovery(part)
+    probe = np.zeros((sam.ndim, sam.ndof2), order="F")
+    probe[:sam.ndof2] = np.eye(sam.ndof2)
+    U = rec.calc_int_displacements(probe)              # row j: unit external DOF j of finit
+    ext = U.argmax(1)
+    assert np.array_equal(np.sort(ext), np.nonzero(sam.msc == 2)[0]) and np.allclose(U.max(1), 1.0)
+    q = np.concatenate([f[ext], [1.0]])
+    Uf = rec.calc_int_displacements(q.reshape(-1, 1))[0]
+    assert np.abs(Uf - f).max() <= 1e-15 * np.abs(f).max()
+    return rec, q
+
+
+def test_closed_form_twist_and_shear_on_the_device():
+    """not via the oracle: a plate of ANDES quads, turned and moved in space, under (a) pure twist w = kappa x y and (b)
+    in-plane shear -- the device's von Mises is sqrt(3) G t kappa resp. sqrt(3) G gamma at EVERY result point; the full
+    result set gives tau_xy = -+ G t kappa on top / bottom and zero direct stresses"""
+    from scipy.spatial.transform import Rotation
+    t, E, nu = 0.012, 2.1e11, 0.3
+    G = E / (2 * (1 + nu))
+    R = Rotation.from_rotvec([0.4, -0.7, 0.2]).as_matrix()
+    for case in ("twist", "shear"):
+        part = plate_part(6, 5, ngen=1, seed=41, jitter=0.25, thickness=t, emod=E, rny=nu, with_recovery=False)
+        X0 = part.elm.xyz.copy()
+        kap, gam = 3.0e-2, 1.0e-3
+        fld = np.zeros((part.sam.nnod, 6))
+        if case == "twist":
+            fld[:, 2] = kap * X0[:, 0] * X0[:, 1]
+            fld[:, 3], fld[:, 4] = kap * X0[:, 0], -kap * X0[:, 1]
+            want = np.sqrt(3.0) * G * t * kap
+        else:
+            fld[:, 0], fld[:, 1] = 0.5 * gam * X0[:, 1], 0.5 * gam * X0[:, 0]
+            want = np.sqrt(3.0) * G * gam
+        part.elm.xyz = X0 @ R.T + np.array([2.0, -1.0, 0.5])
+        fld = np.hstack([fld[:, :3] @ R.T, fld[:, 3:] @ R.T])
+        rec, q = _impose_field(part, fld)
+        vm = rec.recover(np.tile(q.reshape(-1, 1), (1, 9)))
+        assert np.abs(vm - want).max() <= 1e-9 * want, (case, np.abs(vm - want).max() / want)
+        full = rec.calc_stresses(q)
+        assert np.abs(np.abs(full["stress"][:, 2]) - want / np.sqrt(3.0)).max() <= 1e-9 * want
+        assert np.abs(full["stress"][:, :2]).max() <= 1e-9 * want
+        assert np.abs(full["resmat"][:, 3] - want / np.sqrt(3.0)).max() <= 1e-8 * want      # max shear = |tau| for pure shear
+        rec.close()
