@@ -54,9 +54,10 @@ __device__ __forceinline__ size_t frag_at2(int row, int col, int KT)
 //       the element's DOF rows of U[dof][t] are read as 64-byte segments like in the von Mises kernels;
 //   (2) the accumulators go to shared memory as [row][step];
 //   (3) the lanes take (step, point) pairs with the point running fastest, form the strain tensor, von Mises, the principal
-//       values (FFa::cubicSolve branches, invariants.cuh) and max shear of whatever is selected, and store the values straight
-//       at their place in the STEP-MAJOR float/double record -- no slot-major staging, no transpose, and a store instruction
-//       of the warp covers contiguous bytes of one step record.
+//       values (FFa::cubicSolve branches, invariants.cuh) and max shear of whatever is selected and put the float/double
+//       values at their place of the element's piece of the step record -- in shared memory;
+//   (4) the eight record pieces (contiguous in the STEP-MAJOR records) go out with fully coalesced stores: no slot-major
+//       staging in HBM, no transpose kernel.
 // layout: 0 = thin shells (operator row = comp*8 + point), 1 = solids (row = point*ncmp + comp),
 // 2 = thick shells (rows as solids, strain from its own operator Efrag, zero stress resultants)
 constexpr int kRecWarps = 4;
@@ -100,10 +101,15 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
   const long long base = roff[i];
   if (base < 0) return;
   const int nrow = MT * 8;
-  double* sig_s = rec_smem + (size_t)warp * (LAYOUT == 2 ? 2 : 1) * nrow * kRecLds;
-  double* eps_s = sig_s + (size_t)nrow * kRecLds;   // thick shells only
   const int srsize = L.sr && LAYOUT != 1 ? 6 * nenod : 0;
   const int ptsize = (L.stress ? NCMP : 0) + (L.strain ? NCMP : 0) + L.nsel;
+  const int nval = srsize + nstrp * ptsize;          // values of this element in one step record
+  const int nval_pad = (nval + 1) & ~1;              // keeps the double rows 8-byte aligned behind float pieces
+  // per warp: [sig rows][eps rows (thick shells)] as doubles, then 8 record pieces of nval values
+  const size_t warp_doubles = (size_t)(LAYOUT == 2 ? 2 : 1) * nrow * kRecLds + ((size_t)8 * nval_pad * sizeof(OUT_T) + 7) / 8;
+  double* sig_s = rec_smem + (size_t)warp * warp_doubles;
+  double* eps_s = sig_s + (size_t)nrow * kRecLds;   // thick shells only
+  OUT_T* rec_s = reinterpret_cast<OUT_T*>(sig_s + (size_t)(LAYOUT == 2 ? 2 : 1) * nrow * kRecLds);
   const bool bad = failed[i] != 0;
   const double* S = Sfrag + (size_t)i * MT * KT * 32 + lane;
   const double* Es = LAYOUT == 2 ? Efrag + (size_t)i * MT * KT * 32 + lane : nullptr;
@@ -165,8 +171,8 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
       const int st = idx / nstrp, pnt = idx - st * nstrp;
       const int t = t0 + st;
       if (t >= nt) continue;
-      OUT_T* o = out + (size_t)t * ld_out + base + srsize + (long long)pnt * ptsize;
-      OUT_T* so = out + (size_t)t * ld_out + base + 6 * pnt;
+      OUT_T* o = rec_s + (size_t)st * nval_pad + srsize + pnt * ptsize;
+      OUT_T* so = rec_s + (size_t)st * nval_pad + 6 * pnt;
       if (bad) {   // stressRoutines.f90:237-241,264-268: hugeVal for everything that is written
         for (int k = 0; k < ptsize; ++k) o[k] = (OUT_T)kHuge;
         if (srsize && pnt < nenod) for (int k = 0; k < 6; ++k) so[k] = (OUT_T)kHuge;
@@ -222,6 +228,13 @@ record_points_dmma_kernel(const double* __restrict__ U, size_t ldu, int nt, cons
           }
         }
       }
+    }
+    __syncwarp();
+    // the element's piece of each of the 8 step records: contiguous, coalesced
+    for (int st = 0; st < 8 && t0 + st < nt; ++st) {
+      OUT_T* dst = out + (size_t)(t0 + st) * ld_out + base;
+      const OUT_T* src = rec_s + (size_t)st * nval_pad;
+      for (int j = lane; j < nval; j += 32) dst[j] = src[j];
     }
     __syncwarp();
   }
@@ -820,12 +833,15 @@ static int launch_record_kernels(fsr_rdb* r, RdbDev& d, int ts, int nt, OUT_T* o
         if (int rc = launch_k2_shell_rec<OUT_T>(p, fi, U, nt, (nt + 7) / 8 * 8, d.roff[fi], out, ld_out, s)) return rc;
         continue;
       }
-      const size_t smem = sizeof(double) * kRecWarps * (layout == 2 ? 2 : 1) * (size_t)f.MT * 8 * kRecLds;
+      const int srsz = r->L.sr && layout != 1 ? 6 * f.nenod : 0;
+      const int nvl = srsz + f.nstrp * ((r->L.stress ? f.ncmp : 0) + (r->L.strain ? f.ncmp : 0) + r->L.nsel);
+      const size_t smem = sizeof(double) * kRecWarps * ((layout == 2 ? 2 : 1) * (size_t)f.MT * 8 * kRecLds +
+                                                        ((size_t)8 * ((nvl + 1) & ~1) * sizeof(OUT_T) + 7) / 8);
       const unsigned grid = (unsigned)((f.nelt + kRecWarps - 1) / kRecWarps);
 #define FSR_REC_LAUNCH(KTV, LAY)                                                                                                   \
   if (f.KT == KTV && layout == LAY) {                                                                                              \
     if (smem > 48 * 1024)                                                                                                          \
-      if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<KTV, LAY, OUT_T>, 100 * 1024)) return rc;                   \
+      if (int rc = smem_opt_in((const void*)record_points_dmma_kernel<KTV, LAY, OUT_T>, 200 * 1024)) return rc;                   \
     record_points_dmma_kernel<KTV, LAY, OUT_T><<<grid, kRecWarps * 32, smem, s>>>(U, (size_t)p->step_tile, nt, f.Sfrag, f.Efrag,   \
                                                                                    f.edof, d.roff[fi], f.failed, f.aux, f.naux,    \
                                                                                    f.nelt, f.nstrp, f.MT, f.nenod, r->L, out, ld_out); \
