@@ -463,6 +463,37 @@ static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   return FSR_OK;
 }
 
+}  // extern "C"
+
+namespace fsr {
+// One converged step of the dynamics solver: q = [finit; vg] (host) -> expanded displacements and the von Mises stress
+// of every result point, queued on the part's stream (the running envelope takes the step along).  sv_host [ndof] and
+// vm_host [npts] should be page-locked; the caller synchronises (fsr_synchronize) before reading them.
+int step_enqueue(fsr_part* p, const double* q, double* sv_host, double* vm_host)
+{
+  if (!p->have_R) { set_error("recovery step: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, true);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  if (p->Qstage_cap < sizeof(double) * (size_t)p->ndim) {
+    FSR_CUDA(cudaStreamSynchronize(s));
+    cudaFree(p->Qstage); p->Qstage = nullptr; p->Qstage_cap = 0;
+    FSR_CUDA(cudaMalloc(&p->Qstage, sizeof(double) * (size_t)std::max(p->ndim, 1)));
+    p->Qstage_cap = sizeof(double) * (size_t)p->ndim;
+  }
+  FSR_CUDA(cudaMemcpyAsync(p->Qstage, q, sizeof(double) * p->ndim, cudaMemcpyHostToDevice, s));
+  if ((rc = run_tile(p, p->Qstage, p->ndim, 1, p->vm_tile, (size_t)p->npts, s, false))) return rc;
+  if (sv_host)   // column t = 0 of U[dof][t]
+    FSR_CUDA(cudaMemcpy2DAsync(sv_host, sizeof(double), p->U, sizeof(double) * p->step_tile, sizeof(double), (size_t)p->ndof,
+                               cudaMemcpyDeviceToHost, s));
+  if (vm_host && p->npts > 0) FSR_CUDA(cudaMemcpyAsync(vm_host, p->vm_tile, sizeof(double) * p->npts, cudaMemcpyDeviceToHost, s));
+  return FSR_OK;
+}
+}  // namespace fsr
+
+extern "C" {
+
 int fsr_recover_dev(fsr_part* p, const double* Q_dev, int ldq, int nsteps, double* vm_hist_dev,
                     size_t ld_vm, void* stream)
 {

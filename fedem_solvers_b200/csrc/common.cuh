@@ -238,6 +238,8 @@ int nstrp_of(int type);
 bool supported_type(int type);
 void effective_element_types(const fsr_sam* sam, const fsr_options* opt, std::vector<int>& melcon_eff, int& quad_ngauss);
 int part_create_mapped(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, const fsr_options* opt, int quad_ngauss);
+// api.cu: one solver step (solver_state.cu)
+int step_enqueue(fsr_part* p, const double* q, double* sv_host, double* vm_host);
 // api.cu: active elements of one type, in processing order (see fsr_part::elem_order)
 std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, int type);
 // io_rdb.cu: the meta data lines of a results database header (openHeaderFiles)

@@ -11,6 +11,7 @@
 // Here the same four entry points, under the same names, serve the parts registered with
 // fsr_recovery_register; fsr_recovery_update plays the solver's per-step recovery (expansion + von Mises on
 // the device for the step's reduced displacements).
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -23,6 +24,7 @@ struct Entry {
   fsr_part* part = nullptr;
   std::vector<int> minex;
   std::vector<double> sv, vms;
+  double *sv_pin = nullptr, *vm_pin = nullptr;   // page-locked landing buffers of the step's device results
   double step = 0.0, time = 0.0, dt = 0.0;
   bool have_state = false;
 };
@@ -40,23 +42,66 @@ int fsr_recovery_register(int base_id, fsr_part* part, const int* minex)
   e.sv.assign((size_t)part->ndof, 0.0);
   const int nvms = fsr_vms_size(part);
   e.vms.assign((size_t)(nvms > 0 ? nvms : 0), 0.0);
+  fsr_recovery_unregister(base_id);
+  FSR_CUDA(cudaSetDevice(part->device));
+  FSR_CUDA(cudaMallocHost(&e.sv_pin, sizeof(double) * (size_t)std::max(part->ndof, 1)));
+  FSR_CUDA(cudaMallocHost(&e.vm_pin, sizeof(double) * (size_t)std::max(part->npts, 1)));
   g_parts[base_id] = e;
   return FSR_OK;
 }
 
-int fsr_recovery_unregister(int base_id) { return g_parts.erase(base_id) ? FSR_OK : FSR_ERR_ARG; }
-
-// The solver's per-step recovery for one part: q = [finit; vg] of the step just converged.
-int fsr_recovery_update(int base_id, int step, double time, double time_step, const double* q)
+int fsr_recovery_unregister(int base_id)
 {
   auto it = g_parts.find(base_id);
-  if (it == g_parts.end() || !q) { set_error("fsr_recovery_update: unknown part %d", base_id); return FSR_ERR_ARG; }
-  Entry& e = it->second;
-  int rc = fsr_recover_step_full(e.part, q, nullptr, nullptr, nullptr, nullptr, e.sv.data());
-  if (rc < 0) return rc;
-  if (!e.vms.empty() && (rc = fsr_get_vms(e.part, q, e.vms.data(), (int)e.vms.size())) < 0) return rc;
-  e.step = (double)step; e.time = time; e.dt = time_step; e.have_state = true;
+  if (it == g_parts.end()) return FSR_ERR_ARG;
+  if (it->second.sv_pin) cudaFreeHost(it->second.sv_pin);
+  if (it->second.vm_pin) cudaFreeHost(it->second.vm_pin);
+  g_parts.erase(it);
   return FSR_OK;
+}
+
+// The solver's recovery of one converged step for SEVERAL parts (the loop over the parts of
+// stressRecoveryModule.f90:1021-1061): the expansion and the stress kernels of all parts are queued on their own streams /
+// devices first and waited for afterwards, so the parts of a mechanism overlap instead of running one after the other.
+// q[k] = [finit; vg] of part base_ids[k].  The parts' running von Mises envelopes take the step along.
+int fsr_recovery_update_parts(int nparts, const int* base_ids, int step, double time, double time_step, const double* const* q)
+{
+  if (nparts < 0 || (nparts > 0 && (!base_ids || !q))) { set_error("fsr_recovery_update_parts: bad arguments"); return FSR_ERR_ARG; }
+  std::vector<Entry*> es((size_t)nparts);
+  for (int k = 0; k < nparts; ++k) {
+    auto it = g_parts.find(base_ids[k]);
+    if (it == g_parts.end() || !q[k]) { set_error("fsr_recovery_update: unknown part %d", base_ids[k]); return FSR_ERR_ARG; }
+    es[(size_t)k] = &it->second;
+  }
+  for (int k = 0; k < nparts; ++k) {
+    const int rc = step_enqueue(es[(size_t)k]->part, q[k], es[(size_t)k]->sv_pin, es[(size_t)k]->vm_pin);
+    if (rc < 0) return rc;
+  }
+  for (int k = 0; k < nparts; ++k) {
+    Entry& e = *es[(size_t)k];
+    const fsr_part* p = e.part;
+    const int rc = fsr_synchronize(e.part);
+    if (rc < 0) return rc;
+    std::copy(e.sv_pin, e.sv_pin + p->ndof, e.sv.begin());
+    // the in-core vms layout (stressRoutines.f90:324-331): [iel, nenod, nstrp, vm(1..nstrp)] per element with stress points
+    size_t m = 0;
+    for (int iel = 0; iel < p->nel; ++iel) {
+      const int nstrp = p->ptoff_host[(size_t)iel + 1] - p->ptoff_host[(size_t)iel];
+      if (nstrp <= 0) continue;
+      e.vms[m++] = (double)(iel + 1);
+      e.vms[m++] = (double)p->nenod_host[(size_t)iel];
+      e.vms[m++] = (double)nstrp;
+      for (int i = 0; i < nstrp; ++i) e.vms[m++] = e.vm_pin[(size_t)p->ptoff_host[(size_t)iel] + i];
+    }
+    e.step = (double)step; e.time = time; e.dt = time_step; e.have_state = true;
+  }
+  return FSR_OK;
+}
+
+// The same for one part: q = [finit; vg] of the step just converged.
+int fsr_recovery_update(int base_id, int step, double time, double time_step, const double* q)
+{
+  return fsr_recovery_update_parts(1, &base_id, step, time, time_step, &q);
 }
 
 // partStateVectorSize (solverModule.f90:2183-2206): 3*nnod + 4, -1 for an unknown part, -999 before any part exists

@@ -1126,6 +1126,16 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_recovery_unregister
 
+     function fsr_recovery_update_parts (nparts, base_ids, istep, time, timeStep, q) &
+          &   bind(C,name="fsr_recovery_update_parts") result(ierr)
+       import :: c_int, c_double, c_ptr
+       integer(c_int), value      :: nparts, istep
+       integer(c_int), intent(in) :: base_ids(*)
+       real(c_double), value      :: time, timeStep
+       type(c_ptr)   , intent(in) :: q(*)      !< c_loc of every part's [finit; vg]
+       integer(c_int) :: ierr
+     end function fsr_recovery_update_parts
+
      function fsr_recovery_update (base_id, istep, time, timeStep, q) bind(C,name="fsr_recovery_update") result(ierr)
        import :: c_int, c_double
        integer(c_int), value      :: base_id, istep

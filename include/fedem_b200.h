@@ -614,6 +614,11 @@ int fsr_cmdline_is_set(const char *name);
 int fsr_recovery_register(int base_id, fsr_part *part, const int *minex);
 int fsr_recovery_unregister(int base_id);
 int fsr_recovery_update(int base_id, int step, double time, double time_step, const double *q);
+/* the same for several parts at once -- the loop over the parts of stressRecoveryModule.f90:1021-1061: the device work of
+ * all parts (each on its own stream / device) is queued first and waited for afterwards, so the parts of a mechanism
+ * overlap; q[k] = [finit; vg] of part base_ids[k] */
+int fsr_recovery_update_parts(int nparts, const int *base_ids, int step, double time, double time_step,
+                              const double *const *q);
 int getPartDeformationStateSize(int bid);
 int getPartStressStateSize(int bid);
 bool savePartDeformationState(int bid, double *data, int ndat);

@@ -285,8 +285,36 @@ def test_fedempy_part_state_entry_points(oracle):
         assert np.abs(s[k + 3:k + 3 + n] - ref["resmat"][p0:p0 + n, 0]).max() <= TOL * scale
         k += 3 + n
     assert k == ns
-    assert lib.fsr_recovery_unregister(31) == 0
-    rec.close()
+    # the loop over the parts of a mechanism in one call (stressRecoveryModule.f90:1021-1061): a second part, both queued
+    # before either is waited for; every part keeps its own state, and the running envelope has taken the steps along
+    part2 = tet10_block(2, 2, 2, ngen=3, seed=10, n_beams=3, curved="surface")
+    b2 = oracle.bind_part(part2)
+    rec2 = StressRecovery(part2)
+    assert lib.fsr_recovery_register(44, rec2._h, None) == 0
+    q1, q2 = np.ascontiguousarray(Q[:, 1]), np.ascontiguousarray(reduced_history(part2.sam.ndim, 2, seed=8)[:, 1])
+    ids = np.array([31, 44], np.int32)
+    qs = (_lib._D * 2)(q1.ctypes.data_as(_lib._D), q2.ctypes.data_as(_lib._D))
+    assert lib.fsr_recovery_update_parts(2, ids.ctypes.data_as(_lib._I), 13, 0.38, 0.005, qs) == 0
+    ns2 = lib.getPartStressStateSize(44)
+    s2 = np.zeros(ns2)
+    assert lib.savePartStressState(31, s.ctypes.data_as(_lib._D), ns) and lib.savePartStressState(44, s2.ctypes.data_as(_lib._D), ns2)
+    assert list(s[:4]) == [13.0, 0.38, 0.005, 31.0] and list(s2[:4]) == [13.0, 0.38, 0.005, 44.0]
+    for bb, qq, ss, pp in ((b, q1, s, part), (b2, q2, s2, part2)):
+        r = oracle.calc_stresses(bb, oracle.expand(bb, qq))
+        vm = np.concatenate([ss[k + 3:k + 3 + int(ss[k + 2])] for k in _vms_offsets(ss)])
+        assert np.abs(vm - r["resmat"][:, 0]).max() <= TOL * np.abs(r["resmat"][:, 0]).max()
+    mx, _ = rec.envelope()
+    want_mx = np.maximum(ref["resmat"][:, 0], oracle.calc_stresses(b, oracle.expand(b, q1))["resmat"][:, 0])
+    assert np.abs(mx - want_mx).max() <= TOL * np.abs(want_mx).max()
+    assert lib.fsr_recovery_unregister(31) == 0 and lib.fsr_recovery_unregister(44) == 0
+    rec.close(); rec2.close()
+
+
+def _vms_offsets(s):
+    k = 4
+    while k < len(s):
+        yield k
+        k += 3 + int(s[k + 2])
 
 
 def test_linear_solids_hex8_tet4_wedg6(oracle):
