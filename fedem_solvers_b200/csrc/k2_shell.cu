@@ -17,6 +17,8 @@
 //       (strainCoatModule.f90:159-166,410-420) fused into the same loop.
 // HBM-bound by design: per element and step 8*nedof bytes of displacements in, 8*nstrp bytes of
 // von Mises out; the operator (4.6 KB per quad) is read once per step tile.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fsr {
@@ -663,12 +665,14 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
                    const double* __restrict__ Sfrag, const int* __restrict__ edof,
                    const int* __restrict__ ptoff, const unsigned char* __restrict__ failed,
                    int nelt, int nstrp, OUT_T* __restrict__ vm, size_t ld_vm,
-                   double* __restrict__ env_max, double* __restrict__ env_min, const long long* __restrict__ roff = nullptr)
+                   double* __restrict__ env_max, double* __restrict__ env_min, const long long* __restrict__ roff = nullptr,
+                   const int* __restrict__ list = nullptr /* family elements to process, NULL = all */)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (i >= nelt) return;  // whole warp
+  const int il = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (il >= nelt) return;  // whole warp
+  const int i = list ? __ldg(list + il) : il;
   const bool live = ALL_LIVE || g < nstrp;
   size_t pt;
   if (ENV)
@@ -753,6 +757,142 @@ k2_shell_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nst
 }
 
 // ------------------------------------------------------------------------------------------
+// Flat quadrilaterals: membrane / bending split of the operator
+// ------------------------------------------------------------------------------------------
+// For a flat element the rigid-body projector changes nothing (the strain-displacement matrices annihilate the rigid modes by
+// themselves), the membrane strains see only the nodal TRANSLATIONS and the curvatures only the nodal ROTATIONS.  With
+// top / bottom = membrane +- bending the 24 x 24 operator splits into two 12-row x 12-column blocks,
+//     M = (S_top + S_bot) / 2  on the translation columns,   B = (S_top - S_bot) / 2  on the rotation columns,
+// and the off-diagonal blocks are rounding noise (checked per element against 1e-12 of the block they would add to; an
+// element that is not flat to that level, or warped, keeps the dense operator).  12 DMMA per 8 steps instead of 18.
+// Fragment layout per element: [M | B][m-tile][k-tile][lane]; m-tile 0 rows = xx at the 4 nodes, yy at the 4 nodes;
+// m-tile 1 rows = xy at the 4 nodes, twice; column k of a block = 3 * node + component.
+__global__ void build_quad_flat_kernel(int nelt, const double* __restrict__ Sfrag, const unsigned char* __restrict__ failed,
+                                       double* __restrict__ Ffrag, unsigned char* __restrict__ flat)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nelt) return;
+  const double* S = Sfrag + (size_t)i * 3 * 6 * 32;
+  double* F = Ffrag + (size_t)i * 12 * 32;
+  double keep[2] = {0.0, 0.0}, drop[2] = {0.0, 0.0};   // [0] translation columns, [1] rotation columns
+  for (int c = 0; c < 3; ++c)
+    for (int n = 0; n < 4; ++n)
+      for (int col = 0; col < 24; ++col) {
+        const double top = S[frag_index(c * 8 + n, col, 6)], bot = S[frag_index(c * 8 + 4 + n, col, 6)];
+        const double m = 0.5 * (top + bot), b = 0.5 * (top - bot);
+        const int rot = (col % 6) >= 3, k = 3 * (col / 6) + (col % 3);
+        if (!rot) { keep[0] = fmax(keep[0], fabs(m)); drop[0] = fmax(drop[0], fabs(b)); }
+        else      { keep[1] = fmax(keep[1], fabs(b)); drop[1] = fmax(drop[1], fabs(m)); }
+        const double v = rot ? b : m;
+        double* blk = F + (size_t)(rot ? 6 : 0) * 32;
+        if (c < 2) blk[frag_index(4 * c + n, k, 3)] = v;
+        else { blk[frag_index(8 + n, k, 3)] = v; blk[frag_index(12 + n, k, 3)] = v; }
+      }
+  flat[i] = !failed[i] && drop[0] <= 1.0e-12 * keep[0] && drop[1] <= 1.0e-12 * keep[1];
+}
+
+template <bool WRITE_VM, bool GUARD>
+__device__ __forceinline__ void quad_flat_tile(const double (&am)[2][3], const double (&ab)[2][3], const double (&bm)[3],
+                                               const double (&bb)[3], double sgn, double*& vmp0, double*& vmp1, size_t ld8, int t0,
+                                               int nsteps, double& emax, double& emin)
+{
+  double cm[2][2] = {{0, 0}, {0, 0}}, cb[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { dmma884(cm[m][0], cm[m][1], am[m][j], bm[j]); dmma884(cb[m][0], cb[m][1], ab[m][j], bb[j]); }
+  double v[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    // lanes g < 4 hold xx of node g (top point g), lanes g >= 4 yy of node g - 4 (bottom point g): the partner lane ^ 16
+    // holds the other direct stress of the same node; von Mises is symmetric in the two
+    const double own = fma(sgn, cb[0][q], cm[0][q]);
+    const double oth = fma(sgn, __shfl_xor_sync(0xffffffffu, cb[0][q], 16), __shfl_xor_sync(0xffffffffu, cm[0][q], 16));
+    const double sxy = fma(sgn, cb[1][q], cm[1][q]);
+    const double rad = fma(sxy * 3.0, sxy, fma(-own, oth, fma(oth, oth, own * own)));
+    v[q] = WRITE_VM ? sqrt_pos(rad) : rad;
+  }
+  if (GUARD) {
+    if (t0 < nsteps) { if (WRITE_VM) *vmp0 = v[0]; emax = v[0] > emax ? v[0] : emax; emin = v[0] < emin ? v[0] : emin; }
+    if (t0 + 1 < nsteps) { if (WRITE_VM) *vmp1 = v[1]; emax = v[1] > emax ? v[1] : emax; emin = v[1] < emin ? v[1] : emin; }
+  } else {
+    if (WRITE_VM) { *vmp0 = v[0]; *vmp1 = v[1]; }
+    const bool p = v[0] > v[1];
+    const double hi = p ? v[0] : v[1], lo = p ? v[1] : v[0];
+    emax = hi > emax ? hi : emax;
+    emin = lo < emin ? lo : emin;
+  }
+  if (WRITE_VM) { vmp0 += ld8; vmp1 += ld8; }
+}
+
+template <bool WRITE_VM>
+__global__ void __launch_bounds__(256, 2)
+k2_quad_flat_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Ffrag,
+                       const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist, const int* __restrict__ list,
+                       double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int il = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (il >= nlist) return;  // whole warp
+  const int i = __ldg(list + il);
+  const size_t pt = (size_t)ptoff[i] + g;
+  const double sgn = g < 4 ? 1.0 : -1.0;   // top = membrane + bending, bottom = membrane - bending
+
+  double am[2][3], ab[2][3];
+  const double* ff = Ffrag + (size_t)i * 12 * 32 + lane;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { am[m][j] = __ldg(ff + (size_t)(m * 3 + j) * 32); ab[m][j] = __ldg(ff + (size_t)(6 + m * 3 + j) * 32); }
+  // B operands: column k = 4 j + t4 of a block = component k % 3 of node k / 3
+  const double *upm[3], *upb[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int k = 4 * j + t4, d = 6 * (k / 3) + k % 3;
+    upm[j] = U + (size_t)__ldg(edof + (size_t)i * 24 + d) * ldu + g;
+    upb[j] = U + (size_t)__ldg(edof + (size_t)i * 24 + d + 3) * ldu + g;
+  }
+  double emax = 0.0, emin = kHuge;
+  double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
+  double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
+  const size_t ld8 = ld_vm * 8;
+  const int ntiles = nsteps_pad >> 3;
+  const int nfull = ((nsteps >> 3) >> 1) << 1;   // tiles (in pairs) with all 8 steps valid
+  double m0[3], r0[3], m1[3], r1[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { m0[j] = upm[j][0]; r0[j] = upb[j][0]; }
+  int nt = 0;
+  for (; nt < nfull; nt += 2) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { m1[j] = upm[j][8]; r1[j] = upb[j][8]; }
+    quad_flat_tile<WRITE_VM, false>(am, ab, m0, r0, sgn, vmp0, vmp1, ld8, 0, 0, emax, emin);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { upm[j] += 16; upb[j] += 16; m0[j] = upm[j][0]; r0[j] = upb[j][0]; }   // rows carry 64 doubles of slack
+    quad_flat_tile<WRITE_VM, false>(am, ab, m1, r1, sgn, vmp0, vmp1, ld8, 0, 0, emax, emin);
+  }
+  for (; nt < ntiles && nt * 8 < nsteps; ++nt) {  // ragged tail: guarded stores
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { upm[j] += 8; upb[j] += 8; m1[j] = upm[j][0]; r1[j] = upb[j][0]; }
+    quad_flat_tile<WRITE_VM, true>(am, ab, m0, r0, sgn, vmp0, vmp1, ld8, nt * 8 + 2 * t4, nsteps, emax, emin);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { m0[j] = m1[j]; r0[j] = r1[j]; }
+  }
+  emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
+  emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, 1));
+  emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 2));
+  emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, 2));
+  if (!WRITE_VM) {   // radicand -> von Mises (kHuge: no step seen)
+    emax = sqrt_pos(emax);
+    emin = emin == kHuge ? kHuge : sqrt_pos(emin);
+  }
+  if (t4 == 0 && nsteps > 0) {
+    if (emax > env_max[pt]) env_max[pt] = emax;
+    if (emin < env_min[pt]) env_min[pt] = emin;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static int upload_family(FamilyData& f, const std::vector<int>& elem, const std::vector<int>& conn,
@@ -821,6 +961,28 @@ int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
       FSR_LAUNCH_CHECK();
       FSR_CUDA(cudaStreamSynchronize(s));
       cudaFree(d_conn);
+      // flat elements: membrane / bending split (k2_quad_flat_vm_kernel); FSR_QUAD_FLAT=0 keeps the dense operator for all
+      if (p->quad_ngauss == 2 && !(getenv("FSR_QUAD_FLAT") && atoi(getenv("FSR_QUAD_FLAT")) == 0)) {
+        unsigned char* d_flat = nullptr;
+        FSR_CUDA(cudaMalloc(&f.fast, sizeof(double) * (size_t)f.nelt * 12 * 32));
+        FSR_CUDA(cudaMalloc(&d_flat, f.nelt));
+        build_quad_flat_kernel<<<(f.nelt + 63) / 64, 64, 0, s>>>(f.nelt, f.Sfrag, f.failed, f.fast, d_flat);
+        FSR_LAUNCH_CHECK();
+        std::vector<unsigned char> h((size_t)f.nelt);
+        FSR_CUDA(cudaMemcpyAsync(h.data(), d_flat, f.nelt, cudaMemcpyDeviceToHost, s));
+        FSR_CUDA(cudaStreamSynchronize(s));
+        cudaFree(d_flat);
+        std::vector<int> lst[2];
+        for (int i = 0; i < f.nelt; ++i) lst[h[(size_t)i] ? 0 : 1].push_back(i);
+        if (lst[0].empty()) { cudaFree(f.fast); f.fast = nullptr; }
+        else
+          for (int k = 0; k < 2; ++k) {
+            f.nsub[k] = (int)lst[k].size();
+            if (f.nsub[k] == 0) continue;
+            FSR_CUDA(cudaMalloc(&f.sub[k], sizeof(int) * lst[k].size()));
+            FSR_CUDA(cudaMemcpy(f.sub[k], lst[k].data(), sizeof(int) * lst[k].size(), cudaMemcpyHostToDevice));
+          }
+      }
     }
   }
   // ---- triangles (type 23) ----
@@ -850,14 +1012,29 @@ static int launch_shell_family(fsr_part* p, FamilyData& f, int nsteps, int nstep
 {
   const int warps = 8;
   if (f.nelt == 0) return FSR_OK;
+  int ngen = f.nelt;
+  const int* gen_list = nullptr;
+  if (KT == 6 && f.fast && f.nsub[0] > 0) {   // quads: the flat ones take the membrane / bending split
+    const unsigned grid = (unsigned)((f.nsub[0] + warps - 1) / warps);
+    if (vm_dev)
+      k2_quad_flat_vm_kernel<true><<<grid, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.edof, f.ptoff,
+                                                               f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min);
+    else
+      k2_quad_flat_vm_kernel<false><<<grid, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.edof, f.ptoff,
+                                                                f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min);
+    FSR_LAUNCH_CHECK();
+    ngen = f.nsub[1];
+    gen_list = f.sub[1];
+    if (ngen == 0) return FSR_OK;
+  }
   if (vm_dev)
-    k2_shell_vm_kernel<KT, true, ALL_LIVE><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, f.nstrp, vm_dev,
-        ld_vm, p->env_max, p->env_min);
+    k2_shell_vm_kernel<KT, true, ALL_LIVE><<<(ngen + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, ngen, f.nstrp, vm_dev,
+        ld_vm, p->env_max, p->env_min, nullptr, gen_list);
   else
-    k2_shell_vm_kernel<KT, false, ALL_LIVE><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(
-        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, f.nstrp, vm_dev,
-        ld_vm, p->env_max, p->env_min);
+    k2_shell_vm_kernel<KT, false, ALL_LIVE><<<(ngen + warps - 1) / warps, warps * 32, 0, s>>>(
+        p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, ngen, f.nstrp, vm_dev,
+        ld_vm, p->env_max, p->env_min, nullptr, gen_list);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }

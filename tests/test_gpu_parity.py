@@ -111,6 +111,25 @@ def test_large_reduced_dimension(oracle, ngen):
     _check_part(oracle, part, nsteps=140, seed=7, step_tile=64)
 
 
+def test_flat_and_warped_quads_in_one_part(oracle):
+    """flat quads take the membrane / bending split (12 DMMA per 8 steps), warped ones the dense operator; one part holds
+    both, turned in space so that no global direction is special; the two kernels agree to rounding on the flat ones"""
+    import os
+    from scipy.spatial.transform import Rotation
+    part = plate_part(11, 9, ngen=5, seed=33, jitter=0.2, warp=0.03, tri_fraction=0.15, shuffle_eq=True, n_constraints=2)
+    part.elm.xyz[part.elm.xyz[:, 0] < 0.55, 2] = 0.0        # the left half is flat
+    part.elm.xyz = part.elm.xyz @ Rotation.from_rotvec([0.3, 0.5, -0.4]).as_matrix().T + np.array([1.0, 2.0, 3.0])
+    vm = _check_part(oracle, part, nsteps=100, seed=12, step_tile=64)
+    os.environ["FSR_QUAD_FLAT"] = "0"
+    try:
+        rec = StressRecovery(part, step_tile=64)
+        vm2 = rec.recover(reduced_history(part.sam.ndim, 100, seed=12))
+        rec.close()
+    finally:
+        del os.environ["FSR_QUAD_FLAT"]
+    assert rel_err(vm, vm2) <= 1e-12 and not np.array_equal(vm, vm2)
+
+
 def test_tri_quad_mixed_plate(oracle):
     """ANDES triangles (type 23: two LU inversions per element, REAL*4 Gauss rule) mixed with quads"""
     part = plate_part(9, 8, ngen=6, seed=13, tri_fraction=0.5, shuffle_eq=True, n_fixed=3, n_constraints=2, warp=0.04)
