@@ -47,7 +47,7 @@ UNIT = "element*steps/s"
 NRED_EXT_NODES = 8      # 48 external DOFs
 NGEN = 50               # component modes
 QUAD_BYTES = 256        # algorithmic bytes per quad element.step: 192 read + 64 written
-QUAD_DMMA_FLOP = 1152   # 18 DMMA.8x8x4 per 8 steps = the 24x24 operator, no padding
+QUAD_DMMA_FLOP = {"dense": 1152, "flat": 768}   # per element.step: 18 DMMA.8x8x4 per 8 steps (24x24 operator) / 12 (membrane | bending blocks)
 DGEMM_PEAK = 35.45      # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt)
 DMMA_PEAK = 37.1        # TFLOP/s, DMMA issue peak measured by tools/microbench/fp64_peaks.cu (same file)
 PARITY_TOL = 1.0e-10
@@ -226,14 +226,17 @@ def secondary_c5(lib, peaks):
     return out
 
 
-def c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync_all):
-    """config 3: ONE fixed part (1.97 M TET10 + 2 % beams) cut into `world` element blocks -> strong scaling"""
+def c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync_all, curved="surface"):
+    """config 3: ONE fixed part (1.97 M TET10 + 2 % beams) cut into `world` element blocks -> strong scaling.
+    curved = which mid-edge nodes leave the chord of their edge: "surface" (default: the outer faces of the block, as a
+    mesher leaves it -- interior elements are straight-sided and take the constant-Jacobian kernel) or "all" (every
+    element curved: the worst case, all on the general DMMA kernel)."""
     import torch
     from fedem_solvers_b200 import StressRecovery, split_elements
     from fedem_solvers_b200.model import tet10_block, reduced_history, synthetic_recovery
     n = round((args.c3_elements / 6) ** (1 / 3))
     t0 = time.time()
-    whole = tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)), with_recovery=False)
+    whole = tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)), with_recovery=False, curved=curved)
     cuts = split_elements(whole, world)
     tile, steps, warm = 256, 10, 3
     rec = StressRecovery(whole, device=local_rank, step_tile=tile, block=cuts[rank] if world > 1 else None)
@@ -285,18 +288,21 @@ def c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync
     k2 = tm["k2_ms"] / max(tm["tiles"], 1)
     k1 = tm["k1_ms"] / max(tm["tiles"], 1)
     k2_max, k1_max = max_over_ranks(k2), max_over_ranks(k1)
+    fam = rec.family_counts().get("tet10", (0, 0, 0))
     rec.close()
     torch.cuda.empty_cache()
     if rank != 0:
         return None
     hbm = float(peaks_json().get("hbm_gbs", 6650.0))
     alg = 240.0 * ntet_blk * tile     # envelope only: 240 B of displacements read per TET10 element.step
-    return {"config": "C3", "metric": METRIC, "value": nel * tile * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
+    return {"config": "C3", "curved_elements": curved, "tet10_on_rank0": {"elements": fam[0], "straight_sided_kernel": fam[1], "general_kernel": fam[2]},
+            "metric": METRIC, "value": nel * tile * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
             "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
             "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2 ({whole.sam.ndof} DOF), n_red={ndim}, ONE part cut into "
                         f"{world} element block(s), {tile} time steps per step, von Mises envelope; NCCL broadcast of Q per step + "
                         "gather of the envelopes inside the timed region",
-            "roofline": {"kernel": "k2_tet10 von Mises + envelope (rank 0 block)", "bound": "fp64 pipe (reported against HBM as the north_star asks)",
+            "roofline": {"kernel": "k2_tet10_affine_vm_kernel + k2_tet10_grad_vm_kernel (rank 0 block)", "bound": "hbm",
+                         "bound_note": "FP64 pipe in fact; reported against HBM as the north_star asks",
                          "achieved": alg / (k2 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / hbm,
                          "ms_per_launch": k2, "algorithmic_bytes_per_launch": alg},
             "k1_ms": k1, "k2_ms_slowest_rank": k2_max, "k1_ms_slowest_rank": k1_max, "setup_s": setup}
@@ -387,6 +393,9 @@ def run_b200(args, rank, world, local_rank):
         part = None
     nel = cuts[rank][1] - cuts[rank][0]
     ndim, npts, ndof_blk = rec.ndim, rec.npts, rec.ndof
+    fam = rec.family_counts()
+    n_flat = fam.get("quad", (0, 0, 0))[1]
+    quad_path = "flat" if n_flat == nel else "dense"
     stream = torch.cuda.current_stream()
     rec.set_stream(stream.cuda_stream)
     nstrp = whole.nstrp()
@@ -522,6 +531,9 @@ def run_b200(args, rank, world, local_rank):
         if world == 1:
             if not args.no_cpu_baseline:
                 strong["cpu_baseline"] = c3_cpu_baseline()
+            worst = c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync_all, curved="all")
+            secondary["C3_all_elements_curved"] = {k: worst[k] for k in ("value", "unit", "ms_per_step", "curved_elements", "tet10_on_rank0", "roofline",
+                                                                          "k1_ms", "workload")}
             secondary["C5"] = secondary_c5(lib, peaks_json())
 
     if rank != 0:
@@ -533,11 +545,16 @@ def run_b200(args, rank, world, local_rank):
     peaks = peaks_json()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload
+    k2_name = "k2_quad_flat_vm_kernel" if quad_path == "flat" else "k2_shell_vm_kernel<6>"
+    traffic, k1_traffic = None, None   # measured DRAM bytes per launch, from the committed ncu captures of this workload
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k2_shell_vm_kernel<6>"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        t = tj[k2_name]
         if t["nx"] == args.nx and t["tile"] == tile:
             traffic = {"bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"]}
+        t = tj["k1_expand_kernel"]
+        if t["nx"] == args.nx and t["tile"] == tile:
+            k1_traffic = {"bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"]}
     except Exception:
         pass
     achieved = QUAD_BYTES * nel * tile / (k2_ms * 1e-3) / 1e9
@@ -551,21 +568,26 @@ def run_b200(args, rank, world, local_rank):
                    "time_steps_per_step": tile, "time_steps_timed": tile * args.steps, "parallelism": f"element-block x{world}",
                    "l2": "inputs larger than L2 (U tile %.1f GB, vm tile %.1f GB per step)" %
                          (ndof_blk * tile * 8 / 1e9, npts * tile * 8 / 1e9)},
-        "roofline": {"kernel": "k2_shell_vm_kernel<6> (ANDES quad von Mises + envelope)", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "peak_source": peak_src, "traffic": traffic["bytes_per_launch"] if traffic else None,
-                     "traffic_source": traffic["source"] if traffic else None, "ms_per_launch": k2_ms,
-                     "algorithmic_bytes_per_launch": QUAD_BYTES * nel * tile,
-                     # what the counters say limits this kernel: `frac` counts every node's displacements once per element that
-                     # reads them; the DRAM really moved and the FP64 pipe (DMMA + scalar FP64 share it) are below
-                     "dram_frac": (traffic["bytes_per_launch"] / (k2_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
-                     "fp64_pipe_frac": QUAD_DMMA_FLOP * nel * tile / (k2_ms * 1e-3) / 1e12 / DMMA_PEAK,
-                     "fp64_pipe_note": "DMMA flops issued / DMMA issue peak (37.1 TFLOP/s measured); the von Mises epilogue adds scalar "
-                                       "FP64 on the same pipe (ncu: tensor + fp64 pipe active, profiles/)"},
-        "k1": {"kernel": "k1_expand_kernel (DMMA.8x8x4)", "bound": "fp64 tensor", "ms_per_launch": k1_ms,
+        "k2": {"kernel": k2_name + " (ANDES quad von Mises + envelope" + (", membrane / bending split of flat elements)" if quad_path == "flat" else ")"),
+               "bound": "hbm",
+               "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+               "peak_source": peak_src, "traffic": traffic["bytes_per_launch"] if traffic else None,
+               "traffic_source": traffic["source"] if traffic else None, "ms_per_launch": k2_ms,
+               "algorithmic_bytes_per_launch": QUAD_BYTES * nel * tile,
+               # what the counters say limits this kernel: `frac` counts every node's displacements once per element that
+               # reads them (256 B per element.step, so it can pass 1 when L2 serves the node sharing); the DRAM
+               # really moved and the FP64 pipe (DMMA + scalar FP64 share it) are below
+               "dram_frac": (traffic["bytes_per_launch"] / (k2_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+               "fp64_pipe_frac": QUAD_DMMA_FLOP[quad_path] * nel * tile / (k2_ms * 1e-3) / 1e12 / DMMA_PEAK,
+               "fp64_pipe_note": "DMMA flops issued / DMMA issue peak (37.1 TFLOP/s measured); the von Mises epilogue adds scalar "
+                                 "FP64 on the same pipe (ncu: tensor + fp64 pipe active, profiles/)"},
+        "k1": {"kernel": "k1_expand_kernel (DMMA.8x8x4, bulk-TMA staged)", "bound": "tensor", "ms_per_launch": k1_ms,
                "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": DGEMM_PEAK, "unit": "TFLOP/s",
                "frac": k1_flops / (k1_ms * 1e-3) / 1e12 / DGEMM_PEAK,
-               "peak_source": "cuBLAS DGEMM 8192^3 measured (profiles/r01_fp64_peaks.txt)"},
+               "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json holds no FP64 figure",
+               "traffic": k1_traffic["bytes_per_launch"] if k1_traffic else None,
+               "traffic_source": k1_traffic["source"] if k1_traffic else None,
+               "algorithmic_flops_per_launch": k1_flops, "dmma_issue_peak_frac": k1_flops / (k1_ms * 1e-3) / 1e12 / DMMA_PEAK},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ndim * tile * 8),
                 "d2h_bytes_per_step": int(2 * npts * 8), "ms_per_step": ms_e2e / args.steps,
                 "api": "fsr_recover_async(page-locked host Q tile) + fsr_get_envelope_async(page-locked host) per step, fsr_synchronize at the "
@@ -573,7 +595,12 @@ def run_b200(args, rank, world, local_rank):
                        "per-step history stays on the device in this leg",
                 "last_envelope_max": e2e_env_max},
         "gpu_launches": launches, "clocks": clk, "parity": parity,
+        "element_paths": {k: {"elements": v[0], "fast_path": v[1], "general": v[2]} for k, v in fam.items()},
     }
+    # `roofline` = the kernel that takes the larger share of the step (the two are within a few percent of each other)
+    dom = "k1" if k1_ms >= k2_ms else "k2"
+    line["roofline"] = dict(line[dom], share_of_step=(k1_ms if dom == "k1" else k2_ms) / (k1_ms + k2_ms),
+                            other_kernel={"k1": "k2", "k2": "k1"}[dom])
     if strong:
         line["strong_c3"] = strong
     if secondary:

@@ -98,6 +98,7 @@ SYMBOLS = [
     ("fsr_envelope_wait", C.c_int, [_P]),
     ("fsr_synchronize", C.c_int, [_P]),
     ("fsr_recovery_update_parts", C.c_int, [C.c_int, _I, C.c_int, C.c_double, C.c_double, C.POINTER(_D)]),
+    ("fsr_family_counts", C.c_int, [_P, _I, C.c_int]),
     ("fsr_reset_envelope", C.c_int, [_P]),
     ("fsr_get_envelope", C.c_int, [_P, _D, _D]),
     ("fsr_envelope_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),

@@ -701,6 +701,22 @@ int fsr_get_vms(fsr_part* p, const double* q, double* vms, int nvms)
   return FSR_OK;
 }
 
+// counts[3 * f + 0..2] = elements of family f (enum Family of common.cuh: 0 quad, 1 tri, 2 TET10, 3 beam, 4 HEX20, 5 HEX8,
+// 6 TET4, 7 WEDG6, 8 WEDG15, 9 TRI6, 10 QUAD8), of which on the geometry fast path (flat quads, straight-sided TET10), of
+// which on the general kernel.  Returns the number of families.
+int fsr_family_counts(const fsr_part* p, int* counts, int cap)
+{
+  if (!p || !counts) { set_error("fsr_family_counts: bad arguments"); return FSR_ERR_ARG; }
+  for (int f = 0; f < FAM_COUNT && 3 * f + 2 < cap; ++f) {
+    const FamilyData& fd = p->fam[f];
+    const bool split = fd.nsub[0] + fd.nsub[1] > 0;
+    counts[3 * f] = fd.nelt;
+    counts[3 * f + 1] = split ? fd.nsub[0] : 0;
+    counts[3 * f + 2] = split ? fd.nsub[1] : fd.nelt;
+  }
+  return FAM_COUNT;
+}
+
 int fsr_last_timing(fsr_part* p, double* t_ms, int n)
 {
   if (!p || !t_ms) return FSR_ERR_ARG;

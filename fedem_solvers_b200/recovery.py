@@ -207,6 +207,13 @@ class StressRecovery:
         self._lib.fsr_last_timing(self._h, _dp(t), 3)
         return dict(k1_ms=t[0], k2_ms=t[1], tiles=int(t[2]))
 
+    def family_counts(self):
+        """{family: (elements, on the geometry fast path, on the general kernel)}"""
+        names = ["quad", "tri", "tet10", "beam", "hex20", "hex8", "tet4", "wedg6", "wedg15", "tri6", "quad8"]
+        c = np.zeros(3 * len(names), I32)
+        check(self._lib.fsr_family_counts(self._h, _ip(c), len(c)), "fsr_family_counts")
+        return {n: tuple(int(v) for v in c[3 * i:3 * i + 3]) for i, n in enumerate(names) if c[3 * i] > 0}
+
     def timing_reset(self):
         self._lib.fsr_timing_reset(self._h)
 

@@ -762,6 +762,14 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_rdb_close
 
+     function fsr_family_counts (part, counts, cap) bind(C,name="fsr_family_counts") result(nfam)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: part
+       integer(c_int), intent(out) :: counts(*)
+       integer(c_int), value :: cap
+       integer(c_int) :: nfam
+     end function fsr_family_counts
+
      ! ---- streaming form of the hot path ---------------------------------------------------------
      function fsr_recover_async (part, Q, ldq, nsteps) bind(C,name="fsr_recover_async") result(ierr)
        import :: c_ptr, c_int, c_double

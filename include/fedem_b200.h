@@ -634,6 +634,11 @@ long long fsr_kernel_launches(int reset);
  * events recorded on the stream the kernels were launched on; synchronises on the last event.
  * Returns the number of entries written. */
 int fsr_last_timing(fsr_part *part, double *t_ms, int n);
+/* counts[3 f + 0..2] = elements of family f (0 ANDES quad, 1 ANDES triangle, 2 TET10, 3 beam, 4 HEX20, 5 HEX8, 6 TET4,
+ * 7 WEDG6, 8 WEDG15, 9 TRI6, 10 QUAD8), of which on the geometry fast path (flat quads: membrane / bending split;
+ * straight-sided TET10: corner gradients), of which on the general kernel.  cap = entries of counts.  Returns the
+ * number of families. */
+int fsr_family_counts(const fsr_part *part, int *counts, int cap);
 int fsr_timing_reset(fsr_part *part);
 
 #ifdef __cplusplus
