@@ -250,6 +250,15 @@ __device__ __forceinline__ double solid_vm_from_gradient(const double (&H)[3][3]
 {
   return mu2 * sqrt_pos(solid_vm2_from_gradient(H));
 }
+// the same from the six engineering strains (exx, eyy, ezz, gxy, gxz, gyz), which are linear in the nodal displacements
+// like the gradient but only six numbers to pass between lanes
+__device__ __forceinline__ double solid_vm2_from_strain(const double (&e)[6])
+{
+  const double a = e[0] - e[1], b = e[1] - e[2], c = e[2] - e[0];
+  const double dev = 0.5 * fma(a, a, fma(b, b, c * c));
+  const double shr = fma(e[3], e[3], fma(e[4], e[4], e[5] * e[5]));
+  return fma(0.75, shr, dev);
+}
 
 
 // one warp per element: 4 m-tiles x 3 k-tiles of the gradient operator in registers, 36 DMMA per 8 steps.
@@ -491,27 +500,28 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
     }
     const int t = t0 + s;
     const bool live = t < nsteps;
-    double v = WRITE_VM ? solid_vm_from_gradient(H, mu2) : solid_vm2_from_gradient(H);
+    // only the symmetric part of the gradient enters von Mises: six strains per corner go between the lanes, not nine
+    const double e[6] = {H[0][0], H[1][1], H[2][2], H[0][1] + H[1][0], H[0][2] + H[2][0], H[1][2] + H[2][1]};
+    double rad = solid_vm2_from_strain(e);
+    double v = WRITE_VM ? mu2 * sqrt_pos(rad) : rad;
     if (live) {
       if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pc] = v;
       emax[0] = max_nonneg(emax[0], v); emin[0] = min_nonneg(emin[0], v);
     }
-    double Hm[3][3];
+    double em[6];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) Hm[c][d] = H[c][d] + __shfl_sync(0xffffffffu, H[c][d], src1);
-    v = WRITE_VM ? solid_vm_from_gradient(Hm, mu1) : solid_vm2_from_gradient(Hm);
+    for (int c = 0; c < 6; ++c) em[c] = e[c] + __shfl_sync(0xffffffffu, e[c], src1);
+    rad = solid_vm2_from_strain(em);
+    v = WRITE_VM ? mu1 * sqrt_pos(rad) : rad;
     if (live) {
       if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pm1] = v;
       emax[1] = max_nonneg(emax[1], v); emin[1] = min_nonneg(emin[1], v);
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) Hm[c][d] = H[c][d] + __shfl_sync(0xffffffffu, H[c][d], src2);
+    for (int c = 0; c < 6; ++c) em[c] = e[c] + __shfl_sync(0xffffffffu, e[c], src2);
     if (r2) {
-      v = WRITE_VM ? solid_vm_from_gradient(Hm, mu1) : solid_vm2_from_gradient(Hm);
+      rad = solid_vm2_from_strain(em);
+      v = WRITE_VM ? mu1 * sqrt_pos(rad) : rad;
       if (live) {
         if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pm2] = v;
         emax[2] = max_nonneg(emax[2], v); emin[2] = min_nonneg(emin[2], v);

@@ -30,17 +30,19 @@ def build_parts(scale, which="c4"):
     from fedem_solvers_b200.model import plate_part, tet10_block, hex20_block, linsolid_block
     if which == "c3":
         n = max(2, int(round((2_000_000 * scale / 6) ** (1.0 / 3.0))))
-        return [tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)))]
+        return [tet10_block(n, n, n, ngen=50, seed=3, n_ext=16, n_beams=max(1, int(0.02 * 6 * n ** 3)), with_recovery=False)]
+    # scale = 1: the part sizes SURVEY 8(d) names for config 4, {2 M, 1 M, 500 k, 250 k, 100 k, 50 k} elements
     s = scale ** 0.5
     c = scale ** (1.0 / 3.0)
     n = lambda v, f: max(2, int(round(v * f)))
+    kw = dict(with_recovery=False)      # every rank generates only the B / E rows of its own element blocks
     return [
-        plate_part(n(800, s), n(800, s), ngen=40, n_ext=8, seed=41),                          # 640 k ANDES quads
-        plate_part(n(500, s), n(500, s), ngen=30, n_ext=6, seed=42, tri_fraction=0.5),        # 250 k quads + 250 k... tris
-        tet10_block(n(44, c), n(44, c), n(44, c), ngen=30, seed=43, n_ext=8, n_beams=2000),   # 511 k TET10 + beams
-        hex20_block(n(36, c), n(36, c), n(36, c), ngen=20, seed=44, n_ext=8),                 # 47 k HEX20
-        linsolid_block(n(40, c), n(40, c), n(40, c), ngen=20, seed=45, n_ext=8),              # HEX8 / TET4 / WEDG6 mix
-        plate_part(n(120, s), n(120, s), ngen=10, n_ext=4, seed=46),                          # a small one: 14 k quads
+        plate_part(n(2000, s), n(1000, s), ngen=40, n_ext=8, seed=41, lx=2.0, **kw),                              # 2.00 M ANDES quads
+        tet10_block(n(55, c), n(55, c), n(55, c), ngen=30, seed=43, n_ext=8, n_beams=2000, curved="surface", **kw),   # 1.00 M TET10 + beams
+        plate_part(n(572, s), n(572, s), ngen=30, n_ext=6, seed=42, tri_fraction=0.5, **kw),                      # 0.50 M quads + triangles
+        hex20_block(n(63, c), n(63, c), n(63, c), ngen=20, seed=44, n_ext=8, **kw),                               # 0.25 M HEX20
+        linsolid_block(n(32, c), n(32, c), n(32, c), ngen=20, seed=45, n_ext=8, **kw),                            # 0.10 M HEX8 / TET4 / WEDG6
+        plate_part(n(224, s), n(224, s), ngen=10, n_ext=4, seed=46, **kw),                                        # 0.05 M quads
     ]
 
 
@@ -56,15 +58,24 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
     import torch.distributed as dist
-    from fedem_solvers_b200 import StressRecovery, load_library
-    from fedem_solvers_b200.model import reduced_history
-    from fedem_solvers_b200.partition import element_costs, plan_work, cost_fraction_to_elements, sub_part
+    from fedem_solvers_b200 import StressRecovery, Comm, load_library
+    from fedem_solvers_b200.model import reduced_history, synthetic_recovery
+    from fedem_solvers_b200.partition import element_costs, plan_work, cost_fraction_to_elements
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = load_library()
+    comm = None
+    if world > 1:   # the library's own NCCL communicator carries Q and the envelopes; torch.distributed passes the id around
+        def exchange(ident):
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if ident is not None:
+                t.copy_(torch.frombuffer(bytearray(ident), dtype=torch.uint8))
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().numpy().tobytes())
+        comm = Comm(rank, world, local_rank, exchange)
     t0 = time.time()
     parts = build_parts(args.scale, args.parts)          # every rank builds the (seeded, identical) parts and keeps only its pieces
     costs = []
@@ -78,10 +89,15 @@ def main():
         e0, e1 = cost_fraction_to_elements(parts[ip], f0, f1)
         if e1 <= e0:
             continue
-        blk = sub_part(parts[ip], e0, e1, with_matrices=True).part
-        rec = StressRecovery(blk, device=local_rank, step_tile=((tile + 63) // 64) * 64)
+        # native element block (fsr_part_create_block) + only its rows of the synthetic [B | E]
+        rec = StressRecovery(parts[ip], device=local_rank, step_tile=((tile + 63) // 64) * 64, block=(e0, e1))
+        rows, _ = rec.block_rows()
+        B, E = synthetic_recovery(parts[ip], rows=rows)
+        rec.open_B_and_E_matrices(B, E)
+        del B, E
         pieces.append(dict(part=ip, e0=e0, e1=e1, rec=rec, nel=e1 - e0, npts=rec.npts))
     nel_total = sum(p.sam.nel for p in parts)
+    part_sizes = [int(p.sam.nel) for p in parts]
     ndims = [p.sam.ndim for p in parts]
     del parts
     stream = torch.cuda.current_stream()
@@ -100,7 +116,7 @@ def main():
     def step(i):
         q = Q[i * tile:(i + 1) * tile]
         if world > 1:
-            dist.broadcast(q, src=0)
+            comm.broadcast(q.data_ptr(), q.numel(), 0, stream.cuda_stream)
         for pc in pieces:
             ip = pc["part"]
             qp = q[:, int(off[ip]):int(off[ip + 1])]      # [tile, ndim] view with row stride sum(ndim)
@@ -157,6 +173,7 @@ def main():
             "config": "C4" if args.parts == "c4" else "C3-sharded", "metric": "element_timestep_stress_evals_per_sec", "value": nel_total * tile * steps / (tot * 1e-3),
             "unit": "element*steps/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / steps, "dtype": "f64",
             "scaling": "strong",
+            "part_elements": part_sizes,
             "workload": (f"6 parts, {nel_total} elements in total (ANDES quads/triangles, TET10 + beams, HEX20, HEX8/TET4/WEDG6), "
                          if args.parts == "c4" else f"one part, {nel_total} elements (TET10 + 2 % beams), cut into element blocks, ") +
                         f"{tile} time steps per step, von Mises envelopes gathered to rank 0",
