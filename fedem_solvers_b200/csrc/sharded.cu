@@ -80,13 +80,14 @@ static NcclApi* nccl_api()
 
 // ---- the cut ----------------------------------------------------------------------------------------------
 // relative cost of one element.step = the K1 rows it brings (nodal DOFs x n_red, shared with the neighbours) + its K2
-// kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/r01b, r01f, r01i)
+// kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R2_bench.json, R2_bench_configs.json;
+// flat quads and straight-sided TET10, the common case; the same table as partition.py)
 static double element_cost(int type)
 {
   switch (type) {
-    case 24: case 22: return 86.0;
-    case 23: case 21: return 55.0;
-    case 41: return 144.0;
+    case 24: case 22: return 77.0;
+    case 23: case 21: return 57.0;
+    case 41: return 90.0;
     case 42: return 240.0;
     case 43: return 397.0;
     case 44: return 65.0;
