@@ -105,7 +105,7 @@ std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const f
 static void free_family(FamilyData& f)
 {
   cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed); cudaFree(f.Gfrag); cudaFree(f.Efrag);
-  cudaFree(f.aux); cudaFree(f.sub[0]); cudaFree(f.sub[1]); cudaFree(f.fast);
+  cudaFree(f.aux); cudaFree(f.sub[0]); cudaFree(f.sub[1]); cudaFree(f.sub[2]); cudaFree(f.fast); cudaFree(f.fast2);
   f = FamilyData();
 }
 
@@ -709,10 +709,10 @@ int fsr_family_counts(const fsr_part* p, int* counts, int cap)
   if (!p || !counts) { set_error("fsr_family_counts: bad arguments"); return FSR_ERR_ARG; }
   for (int f = 0; f < FAM_COUNT && 3 * f + 2 < cap; ++f) {
     const FamilyData& fd = p->fam[f];
-    const bool split = fd.nsub[0] + fd.nsub[1] > 0;
+    const bool split = fd.nsub[0] + fd.nsub[1] + fd.nsub[2] > 0;
     counts[3 * f] = fd.nelt;
     counts[3 * f + 1] = split ? fd.nsub[0] : 0;
-    counts[3 * f + 2] = split ? fd.nsub[1] : fd.nelt;
+    counts[3 * f + 2] = split ? fd.nsub[1] + fd.nsub[2] : fd.nelt;
   }
   return FAM_COUNT;
 }

@@ -97,9 +97,10 @@ struct FamilyData {
                                 // the global stress there, k2_thickshell.cu); NULL for every other family
   // geometry fast path of a family (TET10: straight-sided elements, constant Jacobian): the family elements are split
   // into sub[0] (fast path) and sub[1] (general kernel), indices into the family arrays; fast[] = per-element constants
-  int* sub[2] = {nullptr, nullptr};
-  int nsub[2] = {0, 0};
+  int* sub[3] = {nullptr, nullptr, nullptr};   // TET10: [2] = curved elements on the scalar kernel
+  int nsub[3] = {0, 0, 0};
   double* fast = nullptr;
+  double* fast2 = nullptr;      // TET10: J^-1 of the ten nodal evaluation points
 };
 
 }  // namespace fsr

@@ -57,7 +57,8 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
                                        const double* __restrict__ rny, const Tet10Points* __restrict__ pts,
                                        double* __restrict__ Sfrag, unsigned char* __restrict__ failed,
                                        double* __restrict__ aux, double* __restrict__ Gfrag,
-                                       double* __restrict__ fast /* [nelt][10]: J^-1 (row d, column j) + flag */)
+                                       double* __restrict__ fast /* [nelt][10]: J^-1 (row d, column j) + flag */,
+                                       double* __restrict__ fastJ /* [nelt][10][9]: J^-1 of every nodal evaluation point, or NULL */)
 {
   const int KT = 8;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,6 +107,9 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
     if (gpt == 0)
       for (int d = 0; d < 3; ++d)
         for (int j = 0; j < 3; ++j) fast[(size_t)i * 10 + 3 * d + j] = I[d][j];
+    if (fastJ)
+      for (int d = 0; d < 3; ++d)
+        for (int j = 0; j < 3; ++j) fastJ[((size_t)i * 10 + gpt) * 9 + 3 * d + j] = I[d][j];
     for (int j = 0; j < 10; ++j) {
       const double bx = I[0][0] * d1[j] + I[0][1] * d2[j] + I[0][2] * d3[j];
       const double by = I[1][0] * d1[j] + I[1][1] * d2[j] + I[1][2] * d3[j];
@@ -140,7 +144,8 @@ __global__ void build_tet10_ops_kernel(int nelt, const int* __restrict__ elem,
     const double dx = X[q] - 0.5 * (X[a] + X[b]), dy = Y[q] - 0.5 * (Y[a] + Y[b]), dz = Z[q] - 0.5 * (Z[a] + Z[b]);
     if (dx * dx + dy * dy + dz * dz > 1.0e-26 * (ex * ex + ey * ey + ez * ez)) affine = false;
   }
-  fast[(size_t)i * 10 + 9] = affine ? 1.0 : 0.0;
+  // 1 = straight-sided, 0 = curved (scalar kernel with ten inverses), -1 = operator build failed (general kernel: hugeVal)
+  fast[(size_t)i * 10 + 9] = affine ? 1.0 : ok ? 0.0 : -1.0;
 }
 
 // one warp per element; 8 m-tiles x 8 k-tiles of operator fragments live in registers
@@ -421,21 +426,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kAffWarps = 8;
 constexpr int kAffRows = 36;   // 12 node slots x 3 components, 64 bytes each
 
 // WRITE_VM = false (envelope only): the envelope is taken over the radicand (vm / 2 mu)^2, which orders like vm, and the
 // square root is taken once per result point at the end instead of once per step.
-template <bool WRITE_VM>
-__global__ void __launch_bounds__(kAffWarps * 32, 2)
+// CURVED = true: the same kernel for curved elements (nodal evaluation).  u is quadratic in the volume coordinates, so its
+// NATURAL derivatives D = du/dL are linear in them whatever the geometry: the three-point differences at the corners stay
+// exact and D at a mid-edge point is still the average of its two corners; only J^-1 differs from point to point
+// (fastJ: the ten inverses of ITET32's nodal evaluation, itet.f:822-934).  The lanes exchange D (nine numbers) instead of
+// the strains and keep the inverses of their three result points in registers, hence the smaller blocks.
+template <bool WRITE_VM, bool CURVED, int NW>
+__global__ void __launch_bounds__(NW * 32, CURVED ? 3 : 2)
 k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ fast,
                           const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist,
                           const int* __restrict__ list, double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
-                          double* __restrict__ env_min)
+                          double* __restrict__ env_min, const double* __restrict__ fastJ = nullptr)
 {
-  __shared__ __align__(16) double sU_all[kAffWarps][2][kAffRows * 8];
+  __shared__ __align__(16) double sU_all[NW][2][kAffRows * 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int il = blockIdx.x * kAffWarps + warp;
+  const int il = blockIdx.x * NW + warp;
   if (il >= nlist) return;   // whole warp
   const int i = __ldg(list + il);
   const int k = lane >> 3, s = lane & 7;
@@ -460,11 +469,6 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
   int ms[4];   // shared-memory offsets (doubles) of mid(k, ci), component 0, step s
 #pragma unroll
   for (int ci = 0; ci < 4; ++ci) ms[ci] = slot[mdn[k][ci]] * 24 + s;
-  double Ji[3][3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) Ji[d][j] = __ldg(fast + (size_t)i * 10 + 3 * d + j);
   const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
   const double mu2 = E / (1.0 + nu), mu1 = 0.5 * mu2;   // mid-edge points: vm(1/2 (Ha + Hb)) = 1/2 vm(Ha + Hb)
   const size_t pt0 = (size_t)ptoff[i];
@@ -473,6 +477,18 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
   const int pc = cn[k], pm1 = mdn[k][p1], pm2 = mdn[k][3];
   const bool r2 = k == 1 || k == 2;
   const int src1 = p1 * 8 + s, src2 = 24 + s;
+  double Ji[3][3], Jm1[3][3], Jm2[3][3];   // J^-1 (row d, column j): of the element, or of this lane's three result points
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (CURVED) {
+        Ji[d][j] = __ldg(fastJ + ((size_t)i * 10 + pc) * 9 + 3 * d + j);
+        Jm1[d][j] = __ldg(fastJ + ((size_t)i * 10 + pm1) * 9 + 3 * d + j);
+        Jm2[d][j] = __ldg(fastJ + ((size_t)i * 10 + pm2) * 9 + 3 * d + j);
+      } else
+        Ji[d][j] = __ldg(fast + (size_t)i * 10 + 3 * d + j);
+    }
   double emax[3] = {0.0, 0.0, 0.0}, emin[3] = {kHuge, kHuge, kHuge};
 
   auto stage = [&](int buf, int t0) {
@@ -488,15 +504,15 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
     else cp_async_wait<0>();
     __syncwarp();
     const double* su = sU[buf];
-    double H[3][3];
+    double H[3][3], D[3][3];   // D[c][j] = d u_c / d L_j at corner k
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       double gq[4];
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) gq[ci] = fma(4.0, su[ms[ci] + c * 8], -su[(slot[cn[ci]] * 3 + c) * 8 + s]);
-      const double D0 = gq[0] - gq[3], D1 = gq[1] - gq[3], D2 = gq[2] - gq[3];
+      D[c][0] = gq[0] - gq[3]; D[c][1] = gq[1] - gq[3]; D[c][2] = gq[2] - gq[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) H[c][d] = fma(Ji[d][2], D2, fma(Ji[d][1], D1, Ji[d][0] * D0));
+      for (int d = 0; d < 3; ++d) H[c][d] = fma(Ji[d][2], D[c][2], fma(Ji[d][1], D[c][1], Ji[d][0] * D[c][0]));
     }
     const int t = t0 + s;
     const bool live = t < nsteps;
@@ -509,16 +525,33 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
       emax[0] = max_nonneg(emax[0], v); emin[0] = min_nonneg(emin[0], v);
     }
     double em[6];
+    // strains of a mid-edge point: straight-sided = sum of the two corners' strains (the 1/2 sits in mu1); curved = its own
+    // J^-1 applied to the sum of the two corners' natural derivatives
+    auto mid_strains = [&](int src, const double (&Jm)[3][3]) {
+      if (!CURVED) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) em[c] = e[c] + __shfl_sync(0xffffffffu, e[c], src1);
+        for (int c = 0; c < 6; ++c) em[c] = e[c] + __shfl_sync(0xffffffffu, e[c], src);
+      } else {
+        double Hm[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double d0 = D[c][0] + __shfl_sync(0xffffffffu, D[c][0], src), d1 = D[c][1] + __shfl_sync(0xffffffffu, D[c][1], src),
+                       d2 = D[c][2] + __shfl_sync(0xffffffffu, D[c][2], src);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) Hm[c][d] = fma(Jm[d][2], d2, fma(Jm[d][1], d1, Jm[d][0] * d0));
+        }
+        em[0] = Hm[0][0]; em[1] = Hm[1][1]; em[2] = Hm[2][2];
+        em[3] = Hm[0][1] + Hm[1][0]; em[4] = Hm[0][2] + Hm[2][0]; em[5] = Hm[1][2] + Hm[2][1];
+      }
+    };
+    mid_strains(src1, Jm1);
     rad = solid_vm2_from_strain(em);
     v = WRITE_VM ? mu1 * sqrt_pos(rad) : rad;
     if (live) {
       if (WRITE_VM) vm[(size_t)t * ld_vm + pt0 + pm1] = v;
       emax[1] = max_nonneg(emax[1], v); emin[1] = min_nonneg(emin[1], v);
     }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) em[c] = e[c] + __shfl_sync(0xffffffffu, e[c], src2);
+    mid_strains(src2, Jm2);
     if (r2) {
       rad = solid_vm2_from_strain(em);
       v = WRITE_VM ? mu1 * sqrt_pos(rad) : rad;
@@ -616,6 +649,10 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, sizeof(double) * (size_t)f.nelt * 12 * 32, s));
   FSR_CUDA(cudaMalloc(&f.fast, sizeof(double) * (size_t)f.nelt * 10));
   FSR_CUDA(cudaMemsetAsync(f.fast, 0, sizeof(double) * (size_t)f.nelt * 10, s));
+  if (p->stressForm == 0) {   // nodal evaluation: the ten inverses of every element, for the curved ones
+    FSR_CUDA(cudaMalloc(&f.fast2, sizeof(double) * (size_t)f.nelt * 90));
+    FSR_CUDA(cudaMemsetAsync(f.fast2, 0, sizeof(double) * (size_t)f.nelt * 90, s));
+  }
   FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
   FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
@@ -623,7 +660,7 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
   build_tet10_ops_kernel<<<(f.nelt + 63) / 64, 64, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny,
-                                                         d_pts, f.Sfrag, f.failed, f.aux, f.Gfrag, f.fast);
+                                                         d_pts, f.Sfrag, f.failed, f.aux, f.Gfrag, f.fast, f.fast2);
   FSR_LAUNCH_CHECK();
   FSR_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_conn);
@@ -633,9 +670,14 @@ int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
     std::vector<double> h((size_t)f.nelt * 10);
     FSR_CUDA(cudaMemcpy(h.data(), f.fast, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
     const bool use = !(getenv("FSR_TET10_AFFINE") && atoi(getenv("FSR_TET10_AFFINE")) == 0);
-    std::vector<int> lst[2];
-    for (int i = 0; i < f.nelt; ++i) lst[use && h[(size_t)i * 10 + 9] != 0.0 ? 0 : 1].push_back(i);
-    for (int k = 0; k < 2; ++k) {
+    // FSR_TET10_CURVED=0 sends the curved ones to the DMMA gradient kernel instead of the scalar one (A/B, cross-check)
+    const bool use_curved = use && f.fast2 && !(getenv("FSR_TET10_CURVED") && atoi(getenv("FSR_TET10_CURVED")) == 0);
+    std::vector<int> lst[3];
+    for (int i = 0; i < f.nelt; ++i) {
+      const double fl = h[(size_t)i * 10 + 9];
+      lst[use && fl > 0.0 ? 0 : (use_curved && fl == 0.0) ? 2 : 1].push_back(i);
+    }
+    for (int k = 0; k < 3; ++k) {
       f.nsub[k] = (int)lst[k].size();
       if (f.nsub[k] == 0) continue;
       FSR_CUDA(cudaMalloc(&f.sub[k], sizeof(int) * lst[k].size()));
@@ -659,13 +701,24 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
   else {
     if (f.nsub[0] > 0) {
       if (vm_dev)
-        k2_tet10_affine_vm_kernel<true><<<(f.nsub[0] + warps - 1) / warps, warps * 32, 0, s>>>(
+        k2_tet10_affine_vm_kernel<true, false, 8><<<(f.nsub[0] + 7) / 8, 256, 0, s>>>(
             p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
             p->env_min);
       else
-        k2_tet10_affine_vm_kernel<false><<<(f.nsub[0] + warps - 1) / warps, warps * 32, 0, s>>>(
+        k2_tet10_affine_vm_kernel<false, false, 8><<<(f.nsub[0] + 7) / 8, 256, 0, s>>>(
             p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
             p->env_min);
+      FSR_LAUNCH_CHECK();
+    }
+    if (f.nsub[2] > 0) {   // curved elements, nodal evaluation: the scalar kernel with the ten inverses
+      if (vm_dev)
+        k2_tet10_affine_vm_kernel<true, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max,
+            p->env_min, f.fast2);
+      else
+        k2_tet10_affine_vm_kernel<false, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max,
+            p->env_min, f.fast2);
       FSR_LAUNCH_CHECK();
     }
     if (f.nsub[1] > 0)
