@@ -436,6 +436,58 @@ int fsr_envelope_dev(fsr_part* p, double** vm_max_dev, double** vm_min_dev)
   return FSR_OK;
 }
 
+// sv[t][dof] (step-major, what ffr_getData delivers per step) -> U[dof][t]
+__global__ void load_u_kernel(double* __restrict__ U, size_t ldu, const double* __restrict__ sv, int ndof, int nt)
+{
+  __shared__ double tile[32][33];
+  const int d0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int t = t0 + j, d = d0 + threadIdx.x;
+    if (t < nt && d < ndof) tile[j][threadIdx.x] = sv[(size_t)t * ndof + d];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int d = d0 + j, t = t0 + threadIdx.x;
+    if (t < nt && d < ndof) U[(size_t)d * ldu + t] = tile[threadIdx.x][j];
+  }
+}
+
+}  // extern "C"
+
+namespace fsr {
+// nodal displacements of nt steps (host, step-major [nt][ndof]) into U[dof][t] of the part: the place K1 would fill
+int upload_displacements(fsr_part* p, const double* sv_host, int nt, cudaStream_t s)
+{
+  int rc = ensure_batch_buffers(p, false);
+  if (rc) return rc;
+  const size_t need = sizeof(double) * (size_t)p->ndof * p->step_tile;
+  if (p->Qstage_cap < need) {
+    FSR_CUDA(cudaStreamSynchronize(s));
+    cudaFree(p->Qstage); p->Qstage = nullptr; p->Qstage_cap = 0;
+    FSR_CUDA(cudaMalloc(&p->Qstage, need));
+    p->Qstage_cap = need;
+  }
+  FSR_CUDA(cudaMemcpyAsync(p->Qstage, sv_host, sizeof(double) * (size_t)p->ndof * nt, cudaMemcpyHostToDevice, s));
+  dim3 blk(32, 8), grd((p->ndof + 31) / 32, (nt + 31) / 32);
+  load_u_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, p->Qstage, p->ndof, nt);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+}  // namespace fsr
+
+extern "C" {
+
+static int run_k2(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_t ld_vm, cudaStream_t s)
+{
+  int rc;
+  if ((rc = launch_k2_shell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_tet10_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_hex20_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_linsolid_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = launch_k2_wedg15_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  return launch_k2_thickshell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s);
+}
+
 // One tile of steps, everything on `s`.  vm_dev may be NULL (envelope only).
 static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, double* vm_dev, size_t ld_vm,
                     cudaStream_t s, bool timed)
@@ -453,13 +505,31 @@ static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   if ((rc = launch_pack_q(p, Q_dev, ldq, nsteps, nsteps_pad, s))) return rc;
   if ((rc = launch_k1(p, nsteps_pad, s))) return rc;
   if (ev) cudaEventRecord(ev[1], s);
-  if ((rc = launch_k2_shell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
-  if ((rc = launch_k2_tet10_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
-  if ((rc = launch_k2_hex20_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
-  if ((rc = launch_k2_linsolid_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
-  if ((rc = launch_k2_wedg15_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
-  if ((rc = launch_k2_thickshell_vm(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
+  if ((rc = run_k2(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if (ev) cudaEventRecord(ev[2], s);
+  return FSR_OK;
+}
+
+// calcStresses on nodal displacements that are already there (stress.f90:397, readIntDisplacements: the direct solution of a
+// linear analysis on the results files; no B / E matrices, no expansion): sv_hist [nsteps x ndof] step-major in nodal DOF order.
+// vm_hist as fsr_recover; the envelopes accumulate.
+int fsr_recover_displacements(fsr_part* p, const double* sv_hist, int nsteps, double* vm_hist)
+{
+  if (!p || !sv_hist || nsteps < 0) { set_error("fsr_recover_displacements: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(p->device));
+  int rc = ensure_batch_buffers(p, vm_hist != nullptr);
+  if (rc) return rc;
+  cudaStream_t s = p->stream;
+  for (int t0 = 0; t0 < nsteps; t0 += p->step_tile) {
+    const int nt = std::min(p->step_tile, nsteps - t0);
+    if ((rc = upload_displacements(p, sv_hist + (size_t)t0 * p->ndof, nt, s))) return rc;
+    if ((rc = run_k2(p, nt, round_up(nt, 64), vm_hist ? p->vm_tile : nullptr, (size_t)p->npts, s))) return rc;
+    if (vm_hist) {
+      FSR_CUDA(cudaMemcpyAsync(vm_hist + (size_t)t0 * p->npts, p->vm_tile, sizeof(double) * (size_t)nt * p->npts, cudaMemcpyDeviceToHost, s));
+      FSR_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  FSR_CUDA(cudaStreamSynchronize(s));
   return FSR_OK;
 }
 

@@ -239,6 +239,8 @@ int nstrp_of(int type);
 bool supported_type(int type);
 void effective_element_types(const fsr_sam* sam, const fsr_options* opt, std::vector<int>& melcon_eff, int& quad_ngauss);
 int part_create_mapped(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* elm, const fsr_options* opt, int quad_ngauss);
+// api.cu: nodal displacements of nt steps (host, [nt][ndof]) -> U[dof][t] (direct solution on the results files)
+int upload_displacements(fsr_part* p, const double* sv_host, int nt, cudaStream_t s);
 // api.cu: one solver step (solver_state.cu)
 int step_enqueue(fsr_part* p, const double* q, double* sv_host, double* vm_host);
 // api.cu: active elements of one type, in processing order (see fsr_part::elem_order)

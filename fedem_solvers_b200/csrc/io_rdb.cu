@@ -1054,16 +1054,36 @@ int fsr_rdb_path(const fsr_rdb* r, char* buf, int cap)
   return (int)r->path.size();
 }
 
+static int rdb_write(fsr_rdb* r, const double* Q, int ldq, const double* sv_hist, int nsteps, const int* stepno, const double* time,
+                     const double* sup_tr);
+
 int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const int* stepno, const double* time,
                         const double* sup_tr)
 {
-  if (!r || !r->f || !Q || nsteps < 0 || !stepno || !time) { set_error("fsr_rdb_write_steps: bad arguments"); return FSR_ERR_ARG; }
+  if (!Q) { set_error("fsr_rdb_write_steps: bad arguments"); return FSR_ERR_ARG; }
+  return rdb_write(r, Q, ldq, nullptr, nsteps, stepno, time, sup_tr);
+}
+
+// the same from nodal displacements that are already there (fsr_recover_displacements): sv_hist [nsteps x ndof] step-major
+int fsr_rdb_write_steps_displacements(fsr_rdb* r, const double* sv_hist, int nsteps, const int* stepno, const double* time,
+                                      const double* sup_tr)
+{
+  if (!sv_hist) { set_error("fsr_rdb_write_steps_displacements: bad arguments"); return FSR_ERR_ARG; }
+  if (r && r->devs.size() > 1) { set_error("fsr_rdb_write_steps_displacements: one device only (the element blocks of a group hold their own nodes)"); return FSR_ERR_ARG; }
+  return rdb_write(r, nullptr, 0, sv_hist, nsteps, stepno, time, sup_tr);
+}
+
+static int rdb_write(fsr_rdb* r, const double* Q, int ldq, const double* sv_hist, int nsteps, const int* stepno, const double* time,
+                     const double* sup_tr)
+{
+  if (!r || !r->f || nsteps < 0 || !stepno || !time) { set_error("fsr_rdb_write_steps: bad arguments"); return FSR_ERR_ARG; }
   if (r->L.def > 1 && !sup_tr) { set_error("fsr_rdb_write_steps: total displacements need the part position matrix of every step"); return FSR_ERR_ARG; }
   fsr_part* p = r->part;
-  if (ldq < p->ndim) { set_error("fsr_rdb_write_steps: ldq < ndim"); return FSR_ERR_ARG; }
+  if (Q && ldq < p->ndim) { set_error("fsr_rdb_write_steps: ldq < ndim"); return FSR_ERR_ARG; }
+  if (!Q) ldq = 1;
   int rc;
   for (RdbDev& d : r->devs) {
-    if (!d.part->have_R) { set_error("fsr_rdb_write_steps: call fsr_set_recovery first"); return FSR_ERR_STATE; }
+    if (Q && !d.part->have_R) { set_error("fsr_rdb_write_steps: call fsr_set_recovery first"); return FSR_ERR_STATE; }
     FSR_CUDA(cudaSetDevice(d.part->device));
     if ((rc = ensure_batch_buffers(d.part, false))) return rc;
   }
@@ -1090,7 +1110,7 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
       FSR_CUDA(cudaSetDevice(d.part->device));
       FSR_CUDA(cudaEventSynchronize(d.ev_q[qb]));
     }
-    memcpy(r->Qpin[qb], Q + (size_t)c0 * ldq, sizeof(double) * (size_t)ldq * nc);
+    if (Q) memcpy(r->Qpin[qb], Q + (size_t)c0 * ldq, sizeof(double) * (size_t)ldq * nc);
     if (r->L.def > 1) memcpy(r->supPin[qb], sup_tr + (size_t)c0 * 12, sizeof(double) * 12 * nc);
     bool first = true;
     for (int ts = 0; ts < nc; ts += r->tile) {   // record tiles of the chunk
@@ -1108,10 +1128,13 @@ int fsr_rdb_write_steps(fsr_rdb* r, const double* Q, int ldq, int nsteps, const 
         FSR_CUDA(cudaSetDevice(dp->device));
         FSR_CUDA(cudaEventRecord(d.ev[b][0], s));
         if (first) {
-          FSR_CUDA(cudaMemcpyAsync(d.dQ, r->Qpin[qb], sizeof(double) * (size_t)ldq * nc, cudaMemcpyHostToDevice, s));
+          if (Q) FSR_CUDA(cudaMemcpyAsync(d.dQ, r->Qpin[qb], sizeof(double) * (size_t)ldq * nc, cudaMemcpyHostToDevice, s));
           if (r->L.def > 1) FSR_CUDA(cudaMemcpyAsync(r->supTr, r->supPin[qb], sizeof(double) * 12 * nc, cudaMemcpyHostToDevice, s));
           FSR_CUDA(cudaEventRecord(d.ev_q[qb], s));
-          if ((rc = launch_pack_q(dp, d.dQ, ldq, nc, nc_pad, s)) || (rc = launch_k1(dp, nc_pad, s))) return rc;
+          if (Q) {
+            if ((rc = launch_pack_q(dp, d.dQ, ldq, nc, nc_pad, s)) || (rc = launch_k1(dp, nc_pad, s))) return rc;
+          } else if ((rc = upload_displacements(dp, sv_hist + (size_t)c0 * dp->ndof, nc, s)))   // pageable source: the copy is staged before the call returns
+            return rc;
         }
         FSR_CUDA(cudaEventRecord(d.ev[b][4], s));
         if (r->L.def) {   // nodal values: slot-major staging, then one tiled transpose into the leading part of the records

@@ -443,8 +443,15 @@ static int run_program(int which)
     fsr_fsi_close(fsi);
     if (gen_first - 1 != ndof2 || ngen_fsi != ngen)
       FAIL("Part %d: the solver input file gives %d triad DOFs + %d component modes, the SAM file %d + %d", isup, gen_first - 1, ngen_fsi, ndof2, ngen);
-  } else
-    FAIL("No solver input file (-fsifile): reading expanded displacements directly from the results database is not part of this build");
+  } else if (which != 0)
+    FAIL("%s needs the solver input file (-fsifile)", prog);
+  else {
+    // stress.f90:131-135: no supernodes, a direct solution is assumed to be on the results files
+    // ("Vectors|Dynamic response|Displacement" of the part, readDisplPointer / readIntDisplacements)
+    log.line("           --> No solver input file: the nodal displacements are read from the results database");
+    snprintf(descr, sizeof(descr), "%s", linkfile.c_str());
+  }
+  const bool direct = !have_fsi;
 
   // --- gravitation displacement modes (stress.f90:184-206): folded in as three extra "component modes"
   const bool want_grav = std::sqrt(grv[0] * grv[0] + grv[1] * grv[1] + grv[2] * grv[2]) > 1.0e-8 && c.is_set("dispfile");
@@ -487,6 +494,7 @@ static int run_program(int which)
     if (ngpu <= 0) ngpu = std::max(1, std::min(nvis, nael / (any_out ? 2000000 : 250000)));
     if (ngpu > nvis) { log.line("  ** Note: -gpus %d but only %d GPU(s) visible", ngpu, nvis); ngpu = nvis; }
     if (ngpu > 1 && c.get_bool("deformation")) { log.line("  ** Note: -deformation is written by one GPU: -gpus %d ignored", ngpu); ngpu = 1; }
+    if (ngpu > 1 && direct) { log.line("  ** Note: a direct solution is recovered by one GPU: -gpus %d ignored", ngpu); ngpu = 1; }
   }
   fsr_part* part = nullptr;
   fsr_group* group = nullptr;
@@ -502,9 +510,9 @@ static int run_program(int which)
   struct PartGuard { fsr_part*& p; fsr_group*& g; ~PartGuard() { if (p) fsr_part_destroy(p); if (g) fsr_group_destroy(g); } } part_guard{part, group};
   if (nfail > 0) log.line("  ** Warning: the stress operator of %d elements could not be formed; they get %g", nfail, kHuge);
 
-  // --- Open the B-matrix and the generalized modes files (openBandEmatrices)
-  if (!c.is_set("Bmatfile") && ndof2 > 0) log.line("  ** Note: -Bmatfile not given, using %s", file_name("Bmatfile", "_B.fmx").c_str());
-  {
+  // --- Open the B-matrix and the generalized modes files (openBandEmatrices); not needed for a direct solution
+  if (!direct && !c.is_set("Bmatfile") && ndof2 > 0) log.line("  ** Note: -Bmatfile not given, using %s", file_name("Bmatfile", "_B.fmx").c_str());
+  if (!direct) {
     std::vector<double> B((size_t)std::max(ndof1, 1) * std::max(ndof2, 1)), E((size_t)std::max(ndof1, 1) * std::max(nmodes, 1));
     char tag[64];
     int cs = 0, sp = 0;
@@ -586,6 +594,17 @@ static int run_program(int which)
   std::vector<int> s_w(window);
   std::vector<double> sup_all;
   const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
+  for (int k = 0; k < window; ++k)   // part position when the results files hold none: where the modelling put it
+    for (int j = 0; j < 12; ++j) supTr[12 * (size_t)k + j] = sup_pos[j];
+  int hdis = -1;
+  std::vector<double> SV;
+  if (direct) {
+    hdis = fsr_frs_find(db, "Vectors|Dynamic response|Displacement", "Part", isup);
+    if (hdis < 0) FAIL("No solver input file (-fsifile) and no nodal displacements of Part %d (Vectors|Dynamic response|Displacement) on the results files", isup);
+    if (fsr_frs_var_size(db, hdis) != ndof)
+      FAIL("Mismatch between length of wanted array: %d and actual variable size: %d (nodal displacements of Part %d)", ndof, fsr_frs_var_size(db, hdis), isup);
+    SV.resize((size_t)ndof * window);
+  }
   const clk::time_point t_loop0 = clk::now();
   double t_hist = 0.0;
   bool warned_no_response = false;
@@ -595,17 +614,21 @@ static int run_program(int which)
     for (int k = 0; k < nw;) {   // runs of consecutive steps on file are read with one call
       int run = 1;
       while (k + run < nw && sel[w0 + k + run] == sel[w0 + k] + run) ++run;
-      double* q0 = Q.data() + (size_t)k * ndim;
-      const int rch = fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[w0 + k], run, q0, ndim);
-      CHECK(rch);
-      if (rch > 0 && !warned_no_response) { log.line("  ** Warning: %s", fsr_last_error()); warned_no_response = true; }
+      if (direct)   // readIntDisplacements (displacementModule.f90:865-904)
+        CHECK(fsr_frs_read(db, hdis, sel[w0 + k], run, SV.data() + (size_t)k * ndof, ndof, ndof));
+      else {
+        double* q0 = Q.data() + (size_t)k * ndim;
+        const int rch = fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[w0 + k], run, q0, ndim);
+        CHECK(rch);
+        if (rch > 0 && !warned_no_response) { log.line("  ** Warning: %s", fsr_last_error()); warned_no_response = true; }
+      }
       if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, sel[w0 + k], run, supTr.data() + 12 * (size_t)k, 12, 12));
       k += run;
     }
     for (int k = 0; k < nw; ++k) {
       s_w[k] = stepno[sel[w0 + k]];
       t_w[k] = times[sel[w0 + k]];
-      if (lgrav) {   // g = matmul(grv, sup%supTr(:,1:3)) (stress.f90:412)
+      if (lgrav && !direct) {   // g = matmul(grv, sup%supTr(:,1:3)) (stress.f90:412)
         const double* T = supTr.data() + 12 * (size_t)k;
         double* g = Q.data() + (size_t)k * ndim + ndof2 + ngen;
         for (int j = 0; j < 3; ++j) g[j] = grv[0] * T[3 * j] + grv[1] * T[3 * j + 1] + grv[2] * T[3 * j + 2];
@@ -613,7 +636,10 @@ static int run_program(int which)
     }
     t_hist += since(t_h0);
     // queued: the device, the PCIe copy and the file writer work on this window while the next one is read
-    if (rdb) CHECK(fsr_rdb_write_steps(rdb, Q.data(), ndim, nw, s_w.data(), t_w.data(), supTr.data()));
+    if (direct) {
+      if (rdb) CHECK(fsr_rdb_write_steps_displacements(rdb, SV.data(), nw, s_w.data(), t_w.data(), supTr.data()));
+      else CHECK(fsr_recover_displacements(part, SV.data(), nw, nullptr));
+    } else if (rdb) CHECK(fsr_rdb_write_steps(rdb, Q.data(), ndim, nw, s_w.data(), t_w.data(), supTr.data()));
     else if (group) CHECK(fsr_group_recover(group, Q.data(), ndim, nw, nullptr));
     else CHECK(fsr_recover(part, Q.data(), ndim, nw, nullptr));
     log.line("           --> ......Simulation time : %12.5E  (%d of %d steps done)", t_w[nw - 1], w0 + nw, nsel);

@@ -770,6 +770,25 @@ module fedem_b200_mod
        integer(c_int) :: nfam
      end function fsr_family_counts
 
+     function fsr_recover_displacements (part, sv_hist, nsteps, vm_hist) bind(C,name="fsr_recover_displacements") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: part
+       real(c_double), intent(in) :: sv_hist(*)
+       integer(c_int), value      :: nsteps
+       type(c_ptr), value         :: vm_hist
+       integer(c_int) :: ierr
+     end function fsr_recover_displacements
+
+     function fsr_rdb_write_steps_displacements (rdb, sv_hist, nsteps, stepno, time, sup_tr) &
+          &   bind(C,name="fsr_rdb_write_steps_displacements") result(ierr)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value         :: rdb
+       real(c_double), intent(in) :: sv_hist(*), time(*), sup_tr(*)
+       integer(c_int), value      :: nsteps
+       integer(c_int), intent(in) :: stepno(*)
+       integer(c_int) :: ierr
+     end function fsr_rdb_write_steps_displacements
+
      ! ---- streaming form of the hot path ---------------------------------------------------------
      function fsr_recover_async (part, Q, ldq, nsteps) bind(C,name="fsr_recover_async") result(ierr)
        import :: c_ptr, c_int, c_double

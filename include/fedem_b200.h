@@ -151,6 +151,12 @@ int fsr_get_envelope_async(fsr_part *part, double *vm_max, double *vm_min);
 int fsr_envelope_wait(fsr_part *part);
 int fsr_synchronize(fsr_part *part);
 
+/* calcStresses on nodal displacements that are already there: what fedem_stress does without -fsifile, when the results
+ * files hold a direct solution ("Vectors|Dynamic response|Displacement" of the part, stress.f90:397 -> readIntDisplacements,
+ * displacementModule.f90:865-904).  No B / E matrices and no expansion: sv_hist is [nsteps x ndof] step-major in nodal DOF
+ * order (madof).  vm_hist as fsr_recover; the envelopes accumulate. */
+int fsr_recover_displacements(fsr_part *part, const double *sv_hist, int nsteps, double *vm_hist);
+
 int fsr_reset_envelope(fsr_part *part);
 int fsr_get_envelope(fsr_part *part, double *vm_max, double *vm_min); /* host [npts] each */
 int fsr_envelope_dev(fsr_part *part, double **vm_max_dev, double **vm_min_dev);
@@ -544,6 +550,9 @@ int fsr_rdb_path(const fsr_rdb *rdb, char *buf, int cap);    /* the actual file 
  * total displacements are written (opt->sup_tr_init given), else may be NULL */
 int fsr_rdb_write_steps(fsr_rdb *rdb, const double *Q, int ldq, int nsteps, const int *stepno,
                         const double *time, const double *sup_tr);
+/* the same from nodal displacements that are already there (fsr_recover_displacements): sv_hist [nsteps x ndof] */
+int fsr_rdb_write_steps_displacements(fsr_rdb *rdb, const double *sv_hist, int nsteps, const int *stepno,
+                                      const double *time, const double *sup_tr);
 /* fsr_rdb_write_steps is pipelined: it returns once the window is queued; while the device recovers tile n, tile n-1
  * crosses PCIe and tile n-2 is appended to the file by a writer thread.  fsr_rdb_flush waits until every record handed
  * over so far is on file and reports where the time went: t[0] = device time of the tiles (H2D of Q, K1, record

@@ -12,7 +12,8 @@ from fedem_solvers_b200.files import save_part, write_fmx
 from fedem_solvers_b200.frs import FrsReader
 from fedem_solvers_b200.fsi import SolverPart, write_fsi
 from fedem_solvers_b200.ftl import write_ftl
-from fedem_solvers_b200.model import plate_part, tet10_block, thickshell_panel
+from fedem_solvers_b200 import StressRecovery
+from fedem_solvers_b200.model import plate_part, tet10_block, thickshell_panel, reduced_history
 from test_frs_cpu import _write_solver_file, _build_finit_numpy
 from test_rdb_cpu import NAMES, NENOD, MEASURES
 
@@ -434,3 +435,56 @@ def test_fedem_modes_executable(oracle, tmp_path, damped):
             ok, theirs = ref.read(name, "Part", case["base"], keys, mine.shape[1])
             assert ok == 2 and np.array_equal(theirs, mine), name
         ref.close()
+
+
+def test_direct_solution_without_solver_input_file(oracle, tmp_path):
+    """fedem_stress without -fsifile (stress.f90:131-135,397): the results files hold the nodal displacements of the part
+    themselves ("Vectors|Dynamic response|Displacement", readIntDisplacements) -- no B / E matrices, no expansion, the element
+    kernels run on what was read; stresses, von Mises and the deformations come out as if the displacements had been expanded"""
+    from fedem_solvers_b200.frs import FrsWriter
+    part = plate_part(6, 5, ngen=3, seed=31, tri_fraction=0.3, warp=0.02)
+    sam = part.sam
+    base, ns = 77, 21
+    write_ftl(str(tmp_path / "plate.ftl"), part)
+    save_part(str(tmp_path / "plate"), part, checksum=99, part_id=base)
+    b = oracle.bind_part(part)
+    Q = reduced_history(sam.ndim, ns, seed=3)
+    SV = np.stack([oracle.expand(b, Q[:, s]) for s in range(ns)])          # any nodal displacement field will do
+    hdr = (" Module                  = fedem_solver;\nVARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n"
+           f"<3;\"Displacement\";LENGTH;FLOAT;64;VECTOR;({sam.ndof})>\n[1;\"Vectors\";\n  [;\"Dynamic response\";<3>]\n]\n"
+           f"DATABLOCKS:\n<1><2>\n{{\"Part\";{base};1;\"plate\";[1]}}\n")
+    with FrsWriter(str(tmp_path / "lin_p_1.frs"), hdr, 8 * sam.ndof) as w:
+        for s in range(ns):
+            w.write_step(s + 1, 0.05 * s, SV[s])
+    out = _run(tmp_path, ["-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-linkId", str(base), "-frsfile", "lin_p_1.frs", "-vmStress", "-stress",
+                          "-deformation", "-double", "-statm", "0", "-stotm", "10", "-tinc", "0", "-rdbfile", "res.frs", "-rdbinc", "0"])
+    assert "nodal displacements are read from the results database" in out
+    rd = FrsReader(str(tmp_path / "res.frs"))
+    assert rd.nsteps == ns
+    o = [oracle.calc_stresses(b, SV[s]) for s in range(ns)]
+    sc = np.abs(np.stack([x["stress"] for x in o])).max()
+    for e in (0, sam.nel // 2, sam.nel - 1):
+        t = int(sam.melcon[e])
+        name, nn = ("QUAD4", 4) if t == 24 else ("TRI3", 3)
+        pt = b["ptoff"][e] + nn          # first bottom point
+        got = rd.read(rd.find(f"Elements|{part.elm.elmid[e]}|{name}|Element nodes|Bottom|1|Stress", "Part", base))
+        assert np.abs(got - np.stack([x["stress"][pt, :3] for x in o])).max() <= TOL * sc
+        got = rd.read(rd.find(f"Elements|{part.elm.elmid[e]}|{name}|Element nodes|Bottom|1|Von Mises stress", "Part", base))
+        assert np.abs(got[:, 0] - np.array([x["resmat"][pt, 0] for x in o])).max() <= TOL * sc
+    n = 7
+    j0 = sam.madof[n] - 1
+    got = rd.read(rd.find(f"Nodes|{sam.minex[n]}|Dynamic response|Translational deformation", "Part", base))
+    assert np.abs(got - SV[:, j0:j0 + 3]).max() <= TOL * np.abs(SV).max()
+    rd.close()
+    # the library call behind it, with the history and the envelope
+    from fedem_solvers_b200 import _lib
+    part.B = part.E = None
+    rec = StressRecovery(part)
+    vm = np.zeros((ns, rec.npts))
+    _lib.check(rec._lib.fsr_recover_displacements(rec._h, np.ascontiguousarray(SV).ctypes.data_as(_lib._D), ns, vm.ctypes.data_as(_lib._D)),
+               "fsr_recover_displacements")
+    want = np.stack([x["resmat"][:, 0] for x in o])
+    assert np.abs(vm - want).max() <= TOL * np.abs(want).max()
+    mx, mn = rec.envelope()
+    assert np.abs(mx - want.max(0)).max() <= TOL * np.abs(want).max()
+    rec.close()
