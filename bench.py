@@ -46,8 +46,11 @@ METRIC = "element_timestep_stress_evals_per_sec"
 UNIT = "element*steps/s"
 NRED_EXT_NODES = 8      # 48 external DOFs
 NGEN = 50               # component modes
-QUAD_BYTES = 256        # algorithmic bytes per quad element.step: 192 read + 64 written
-QUAD_DMMA_FLOP = {"dense": 1152, "flat": 768}   # per element.step: 18 DMMA.8x8x4 per 8 steps (24x24 operator) / 12 (membrane | bending blocks)
+# algorithmic bytes per quad element.step: 24 nodal DOFs read (192 B) + 8 von Mises values written (64 B);
+# in the in-plane form of flat regions an element reads 16 values (u, v, theta1, theta2 of its four nodes): 128 + 64 B
+QUAD_BYTES = {"dense": 256, "flat": 256, "inplane": 192}
+# DMMA flop per element.step: 18 DMMA.8x8x4 per 8 steps (24x24 operator) / 12 (membrane | bending blocks) / 8 (in-plane blocks)
+QUAD_DMMA_FLOP = {"dense": 1152, "flat": 768, "inplane": 512}
 DGEMM_PEAK = 35.45      # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt)
 DMMA_PEAK = 37.1        # TFLOP/s, DMMA issue peak measured by tools/microbench/fp64_peaks.cu (same file)
 PARITY_TOL = 1.0e-10
@@ -395,7 +398,9 @@ def run_b200(args, rank, world, local_rank):
     ndim, npts, ndof_blk = rec.ndim, rec.npts, rec.ndof
     fam = rec.family_counts()
     n_flat = fam.get("quad", (0, 0, 0))[1]
-    quad_path = "flat" if n_flat == nel else "dense"
+    path = rec.vm_path_info()
+    quad_path = "inplane" if path["quads_inplane"] == nel else ("flat" if n_flat == nel else "dense")
+    k1_rows = path["inplane_rows"] + 128 * path["global_row_tiles"] if path["inplane_rows"] else ndof_blk
     stream = torch.cuda.current_stream()
     rec.set_stream(stream.cuda_stream)
     nstrp = whole.nstrp()
@@ -545,7 +550,7 @@ def run_b200(args, rank, world, local_rank):
     peaks = peaks_json()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    k2_name = "k2_quad_flat_vm_kernel" if quad_path == "flat" else "k2_shell_vm_kernel<6>"
+    k2_name = {"inplane": "k2_quad_planar_vm_kernel", "flat": "k2_quad_flat_vm_kernel", "dense": "k2_shell_vm_kernel<6>"}[quad_path]
     traffic, k1_traffic = None, None   # measured DRAM bytes per launch, from the committed ncu captures of this workload
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -557,8 +562,8 @@ def run_b200(args, rank, world, local_rank):
             k1_traffic = {"bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"]}
     except Exception:
         pass
-    achieved = QUAD_BYTES * nel * tile / (k2_ms * 1e-3) / 1e9
-    k1_flops = 2.0 * ndof_blk * ndim * tile
+    achieved = QUAD_BYTES[quad_path] * nel * tile / (k2_ms * 1e-3) / 1e9
+    k1_flops = 2.0 * k1_rows * ndim * tile
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -568,12 +573,15 @@ def run_b200(args, rank, world, local_rank):
                    "time_steps_per_step": tile, "time_steps_timed": tile * args.steps, "parallelism": f"element-block x{world}",
                    "l2": "inputs larger than L2 (U tile %.1f GB, vm tile %.1f GB per step)" %
                          (ndof_blk * tile * 8 / 1e9, npts * tile * 8 / 1e9)},
-        "k2": {"kernel": k2_name + " (ANDES quad von Mises + envelope" + (", membrane / bending split of flat elements)" if quad_path == "flat" else ")"),
+        "k2": {"kernel": k2_name + " (ANDES quad von Mises + envelope" +
+                         {"inplane": ", flat region: in-plane rows (u, v, theta1, theta2 per node) and two 12 x 8 operator blocks)",
+                          "flat": ", membrane / bending split of flat elements)", "dense": ")"}[quad_path],
                "bound": "hbm",
                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                "peak_source": peak_src, "traffic": traffic["bytes_per_launch"] if traffic else None,
                "traffic_source": traffic["source"] if traffic else None, "ms_per_launch": k2_ms,
-               "algorithmic_bytes_per_launch": QUAD_BYTES * nel * tile,
+               "algorithmic_bytes_per_launch": QUAD_BYTES[quad_path] * nel * tile,
+               "algorithmic_bytes_per_element_step": QUAD_BYTES[quad_path],
                # what the counters say limits this kernel: `frac` counts every node's displacements once per element that
                # reads them (256 B per element.step, so it can pass 1 when L2 serves the node sharing); the DRAM
                # really moved and the FP64 pipe (DMMA + scalar FP64 share it) are below
@@ -587,6 +595,9 @@ def run_b200(args, rank, world, local_rank):
                "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (profiles/r01_fp64_peaks.txt); MEASURED_PEAKS.json holds no FP64 figure",
                "traffic": k1_traffic["bytes_per_launch"] if k1_traffic else None,
                "traffic_source": k1_traffic["source"] if k1_traffic else None,
+               "rows_expanded": int(k1_rows), "rows_note": "nodal DOFs of the block" if quad_path != "inplane" else
+                                "4 in-plane rows per node (the rotation into the plane is folded into the recovery operator once) "
+                                f"instead of the {int(ndof_blk)} nodal DOFs; FSR_QUAD_PLANAR=0 gives the 6-row path",
                "algorithmic_flops_per_launch": k1_flops, "dmma_issue_peak_frac": k1_flops / (k1_ms * 1e-3) / 1e12 / DMMA_PEAK},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ndim * tile * 8),
                 "d2h_bytes_per_step": int(2 * npts * 8), "ms_per_step": ms_e2e / args.steps,
@@ -596,6 +607,7 @@ def run_b200(args, rank, world, local_rank):
                 "last_envelope_max": e2e_env_max},
         "gpu_launches": launches, "clocks": clk, "parity": parity,
         "element_paths": {k: {"elements": v[0], "fast_path": v[1], "general": v[2]} for k, v in fam.items()},
+        "vm_path": path,
     }
     # `roofline` = the kernel that takes the larger share of the step (the two are within a few percent of each other)
     dom = "k1" if k1_ms >= k2_ms else "k2"

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("fsr_synchronize", C.c_int, [_P]),
     ("fsr_recovery_update_parts", C.c_int, [C.c_int, _I, C.c_int, C.c_double, C.c_double, C.POINTER(_D)]),
     ("fsr_family_counts", C.c_int, [_P, _I, C.c_int]),
+    ("fsr_vm_path_info", C.c_int, [_P, C.POINTER(C.c_longlong), C.c_int]),
     ("fsr_recover_displacements", C.c_int, [_P, _D, C.c_int, _D]),
     ("fsr_rdb_write_steps_displacements", C.c_int, [_P, _D, C.c_int, _I, _D, _D]),
     ("fsr_reset_envelope", C.c_int, [_P]),

@@ -105,7 +105,7 @@ std::vector<int> elements_of_type(const fsr_part* p, const fsr_sam* sam, const f
 static void free_family(FamilyData& f)
 {
   cudaFree(f.elem); cudaFree(f.edof); cudaFree(f.ptoff); cudaFree(f.Sfrag); cudaFree(f.failed); cudaFree(f.Gfrag); cudaFree(f.Efrag);
-  cudaFree(f.aux); cudaFree(f.sub[0]); cudaFree(f.sub[1]); cudaFree(f.sub[2]); cudaFree(f.fast); cudaFree(f.fast2);
+  cudaFree(f.aux); cudaFree(f.sub[0]); cudaFree(f.sub[1]); cudaFree(f.sub[2]); cudaFree(f.fast); cudaFree(f.fast2); cudaFree(f.edof2);
   f = FamilyData();
 }
 
@@ -113,6 +113,7 @@ int ensure_batch_buffers(fsr_part* p, bool need_vm_tile)
 {
   if (!p->Qt) FSR_CUDA(cudaMalloc(&p->Qt, sizeof(double) * (size_t)p->step_tile * p->ldk));
   if (!p->U) FSR_CUDA(cudaMalloc(&p->U, sizeof(double) * ((size_t)p->nrows_pad * p->step_tile + 64)));  // +64: prefetch slack
+  if (p->planar && !p->Up) FSR_CUDA(cudaMalloc(&p->Up, sizeof(double) * ((size_t)p->np_rows_pad * p->step_tile + 64)));
   if (need_vm_tile && !p->vm_tile && p->npts > 0)
     FSR_CUDA(cudaMalloc(&p->vm_tile, sizeof(double) * (size_t)p->step_tile * p->npts));
   return FSR_OK;
@@ -307,6 +308,7 @@ void fsr_part_destroy(fsr_part* p)
   if (p->stream) cudaStreamSynchronize(p->stream);
   cudaFree(p->xyz); cudaFree(p->emod); cudaFree(p->rny); cudaFree(p->thk);
   cudaFree(p->R); cudaFree(p->Qt); cudaFree(p->U); cudaFree(p->vm_tile); cudaFree(p->Qstage);
+  cudaFree(p->Rp); cudaFree(p->Up); cudaFree(p->prow_src); cudaFree(p->prow_w); cudaFree(p->k1_tiles);
   cudaFree(p->env_max); cudaFree(p->env_min); cudaFree(p->env_snap);
   if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
   if (p->ev_snap) cudaEventDestroy(p->ev_snap);
@@ -327,7 +329,8 @@ int fsr_set_recovery(fsr_part* p, const double* B, int ldB, const double* E, int
   FSR_CUDA(cudaSetDevice(p->device));
   if (!p->sam_keep.valid) { set_error("fsr_set_recovery: SAM maps missing"); return FSR_ERR_STATE; }
   fsr_sam sam = p->sam_keep.view();
-  return build_row_operator(p, &sam, B, ldB, E, ldE);
+  if (int rc = build_row_operator(p, &sam, B, ldB, E, ldE)) return rc;
+  return build_planar_rows(p);
 }
 
 int fsr_set_stream(fsr_part* p, void* stream)
@@ -471,7 +474,7 @@ int upload_displacements(fsr_part* p, const double* sv_host, int nt, cudaStream_
   dim3 blk(32, 8), grd((p->ndof + 31) / 32, (nt + 31) / 32);
   load_u_kernel<<<grd, blk, 0, s>>>(p->U, (size_t)p->step_tile, p->Qstage, p->ndof, nt);
   FSR_LAUNCH_CHECK();
-  return FSR_OK;
+  return planar_rows_from_u(p, nt, s);   // the in-plane rows of flat shell regions
 }
 }  // namespace fsr
 
@@ -490,7 +493,7 @@ static int run_k2(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, size_
 
 // One tile of steps, everything on `s`.  vm_dev may be NULL (envelope only).
 static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, double* vm_dev, size_t ld_vm,
-                    cudaStream_t s, bool timed)
+                    cudaStream_t s, bool timed, bool full_u = false)
 {
   int nsteps_pad = round_up(nsteps, 64);
   int rc;
@@ -503,7 +506,7 @@ static int run_tile(fsr_part* p, const double* Q_dev, int ldq, int nsteps, doubl
   }
   if (ev) cudaEventRecord(ev[0], s);
   if ((rc = launch_pack_q(p, Q_dev, ldq, nsteps, nsteps_pad, s))) return rc;
-  if ((rc = launch_k1(p, nsteps_pad, s))) return rc;
+  if ((rc = launch_k1_vm(p, nsteps_pad, s, full_u))) return rc;
   if (ev) cudaEventRecord(ev[1], s);
   if ((rc = run_k2(p, nsteps, nsteps_pad, vm_dev, ld_vm, s))) return rc;
   if (ev) cudaEventRecord(ev[2], s);
@@ -553,7 +556,7 @@ int step_enqueue(fsr_part* p, const double* q, double* sv_host, double* vm_host)
     p->Qstage_cap = sizeof(double) * (size_t)p->ndim;
   }
   FSR_CUDA(cudaMemcpyAsync(p->Qstage, q, sizeof(double) * p->ndim, cudaMemcpyHostToDevice, s));
-  if ((rc = run_tile(p, p->Qstage, p->ndim, 1, p->vm_tile, (size_t)p->npts, s, false))) return rc;
+  if ((rc = run_tile(p, p->Qstage, p->ndim, 1, p->vm_tile, (size_t)p->npts, s, false, sv_host != nullptr))) return rc;
   if (sv_host)   // column t = 0 of U[dof][t]
     FSR_CUDA(cudaMemcpy2DAsync(sv_host, sizeof(double), p->U, sizeof(double) * p->step_tile, sizeof(double), (size_t)p->ndof,
                                cudaMemcpyDeviceToHost, s));
@@ -781,10 +784,28 @@ int fsr_family_counts(const fsr_part* p, int* counts, int cap)
     const FamilyData& fd = p->fam[f];
     const bool split = fd.nsub[0] + fd.nsub[1] + fd.nsub[2] > 0;
     counts[3 * f] = fd.nelt;
-    counts[3 * f + 1] = split ? fd.nsub[0] : 0;
-    counts[3 * f + 2] = split ? fd.nsub[1] + fd.nsub[2] : fd.nelt;
+    const int fast = f == FAM_QUAD ? fd.nsub[0] + fd.nsub[2] : fd.nsub[0];   // quads: flat, on global or in-plane rows
+    counts[3 * f + 1] = split ? fast : 0;
+    counts[3 * f + 2] = split ? fd.nsub[0] + fd.nsub[1] + fd.nsub[2] - fast : fd.nelt;
   }
   return FAM_COUNT;
+}
+
+// What the von Mises path of the part expands and where its quadrilaterals go: info[0] = rows of K1 per step tile (all nodal
+// DOFs, or with in-plane rows of flat shell regions: those rows + the 128-row tiles of R still read), [1] = nodal DOFs,
+// [2] = in-plane rows, [3] = row tiles of R still expanded, [4] = quadrilaterals in the in-plane form, [5] = flat
+// quadrilaterals on global rows, [6] = quadrilaterals on the dense operator.  Returns the number of entries filled.
+int fsr_vm_path_info(const fsr_part* p, long long* info, int cap)
+{
+  if (!p || !info) { set_error("fsr_vm_path_info: bad arguments"); return FSR_ERR_ARG; }
+  const FamilyData& q = p->fam[FAM_QUAD];
+  const bool split = q.nsub[0] + q.nsub[1] + q.nsub[2] > 0;
+  const long long v[7] = {p->planar ? (long long)p->np_rows_pad + 128LL * p->n_k1_tiles : (long long)p->nrows_pad, p->ndof,
+                          p->planar ? p->np_rows : 0, p->planar ? p->n_k1_tiles : p->nrows_pad / 128, q.nsub[2], q.nsub[0],
+                          split ? q.nsub[1] : q.nelt};
+  const int n = std::min(cap, 7);
+  for (int i = 0; i < n; ++i) info[i] = v[i];
+  return n;
 }
 
 int fsr_last_timing(fsr_part* p, double* t_ms, int n)

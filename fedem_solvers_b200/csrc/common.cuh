@@ -100,7 +100,8 @@ struct FamilyData {
   int* sub[3] = {nullptr, nullptr, nullptr};   // TET10: [2] = curved elements on the scalar kernel
   int nsub[3] = {0, 0, 0};
   double* fast = nullptr;
-  double* fast2 = nullptr;      // TET10: J^-1 of the ten nodal evaluation points
+  double* fast2 = nullptr;      // TET10: J^-1 of the ten nodal evaluation points; quads: operators of the in-plane form
+  int* edof2 = nullptr;         // quads, in-plane form: [nsub[2]][16] rows of Up (u, v, theta1, theta2 of the four nodes)
 };
 
 }  // namespace fsr
@@ -175,6 +176,17 @@ struct fsr_part {
   // per-batch buffers
   double* Qt = nullptr;     // [step_tile][ldk]
   double* U = nullptr;      // [nrows_pad][step_tile]  (row = nodal DOF, t fastest)
+  // Flat shell regions (k2_shell.cu, "in-plane form"): the nodes whose flat quadrilaterals all lie in one plane get four rows
+  // (u, v, theta1, theta2) in the axes of that plane instead of six global ones: Rp = W . R, Up = Rp . Q.  The von Mises
+  // path expands only these rows plus the 128-row tiles of R that some other element still reads (k1_tiles).
+  bool planar = false;
+  int np_rows = 0, np_rows_pad = 0;   // rows of Rp / Up
+  int* prow_src = nullptr;            // [np_rows][3] rows of R / U feeding a row of Rp / Up
+  double* prow_w = nullptr;           // [np_rows][3] their weights (a unit vector of the plane)
+  double* Rp = nullptr;               // [np_rows_pad][ldk]
+  double* Up = nullptr;               // [np_rows_pad][step_tile]
+  int* k1_tiles = nullptr;            // row tiles of R the von Mises path still needs
+  int n_k1_tiles = 0;
   double* vm_tile = nullptr;// [step_tile][npts] staging for host output
   double* Qstage = nullptr; // device copy of the caller's Q (host API)
   size_t Qstage_cap = 0;
@@ -229,9 +241,14 @@ int build_row_operator(fsr_part* p, const fsr_sam* sam, const double* B, int ldB
 int launch_pack_q(fsr_part* p, const double* Q_dev, int ldq, int nsteps, int nsteps_pad,
                   cudaStream_t s);
 int launch_k1(fsr_part* p, int nsteps_pad, cudaStream_t s);
+// the expansion of the von Mises path: with in-plane rows (fsr_part::planar) Up = Rp . Q and only the row tiles of U that are
+// still read; full_u = true expands all of U as well (the solver step hands the nodal displacements out)
+int launch_k1_vm(fsr_part* p, int nsteps_pad, cudaStream_t s, bool full_u);
+int build_planar_rows(fsr_part* p);                                   // Rp = W . R (after build_row_operator)
+int planar_rows_from_u(fsr_part* p, int nsteps_pad, cudaStream_t s);  // Up = W . U (displacements given, no expansion)
 // the same GEMM on any row-major operator: U[nrows_pad x ldu] = R[nrows_pad x ldk] . Qt[nsteps_pad x ldk]^T
 int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nrows_pad, int nsteps_pad, size_t ldu,
-                  cudaStream_t s);
+                  cudaStream_t s, const int* tiles = nullptr, int ntiles = 0);
 int launch_pack_q_raw(double* Qt, int ldk, const double* Q_dev, int ldq, int ndim, int nsteps, int nsteps_pad,
                       cudaStream_t s);
 // api.cu: result points per element type, types with a stress operator, the legacy shell type mapping of fsr_part_create

@@ -242,7 +242,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_expand_kernel(const double* __restrict__ R, const double* __restrict__ Qt, double* __restrict__ U,
-                 int ldk, int nsteps_pad, size_t ldu)
+                 int ldk, int nsteps_pad, size_t ldu, const int* __restrict__ tiles)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sR = reinterpret_cast<double*>(smem_raw);   // [K1_BM][ldk]
@@ -252,7 +252,7 @@ k1_expand_kernel(const double* __restrict__ R, const double* __restrict__ Qt, do
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
-  const size_t row0 = (size_t)blockIdx.x * K1_BM;
+  const size_t row0 = (size_t)(tiles ? __ldg(tiles + blockIdx.x) : (int)blockIdx.x) * K1_BM;
   const int nchunks = nsteps_pad / K1_BN;
   const uint32_t bytesR = (uint32_t)(K1_BM * ldk * sizeof(double));
   const uint32_t bytesQ = (uint32_t)(K1_BN * ldk * sizeof(double));
@@ -331,7 +331,7 @@ constexpr int K1S_LS = 52;   // slab width, == 4 (mod 8) like ldk
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_expand_slab_kernel(const double* __restrict__ R, const double* __restrict__ Qt, double* __restrict__ U, int ldk, int nsteps_pad,
-                      size_t ldu)
+                      size_t ldu, const int* __restrict__ tiles)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sbuf = reinterpret_cast<double*>(smem_raw);                       // 2 x [K1_BM + K1_BN][K1S_LS]
@@ -339,7 +339,7 @@ k1_expand_slab_kernel(const double* __restrict__ R, const double* __restrict__ Q
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int wm = warp & 3, wn = warp >> 2;
-  const size_t row0 = (size_t)blockIdx.x * K1_BM;
+  const size_t row0 = (size_t)(tiles ? __ldg(tiles + blockIdx.x) : (int)blockIdx.x) * K1_BM;
   const int nchunks = nsteps_pad / K1_BN;
   const int nslab = (ldk + K1S_LS - 1) / K1S_LS;
   const int nstage = nchunks * nslab;
@@ -415,25 +415,25 @@ static size_t k1_smem_bytes(int ldk)
 }
 
 int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nrows_pad, int nsteps_pad, size_t ldu,
-                  cudaStream_t s)
+                  cudaStream_t s, const int* tiles, int ntiles)
 {
   size_t smem = k1_smem_bytes(ldk);
   if (nsteps_pad % K1_BN != 0 || nrows_pad % K1_BM != 0) {
     set_error("internal: K1 tile mismatch (%d rows, %d steps)", nrows_pad, nsteps_pad);
     return FSR_ERR_ARG;
   }
-  unsigned blocks = (unsigned)(nrows_pad / K1_BM);
+  unsigned blocks = tiles ? (unsigned)ntiles : (unsigned)(nrows_pad / K1_BM);   // tiles: only these row tiles
   if (blocks == 0) return FSR_OK;
   // FSR_K1_SLAB=1 forces the K-slab kernel (tests); it is the only one for ldk > 108
   static const bool force_slab = getenv("FSR_K1_SLAB") && atoi(getenv("FSR_K1_SLAB")) != 0;
   if (smem > 227 * 1024 || force_slab) {
     if (int rc = smem_opt_in((const void*)k1_expand_slab_kernel, k1_slab_smem_bytes())) return rc;
-    k1_expand_slab_kernel<<<blocks, K1_THREADS, k1_slab_smem_bytes(), s>>>(R, Qt, U, ldk, nsteps_pad, ldu);
+    k1_expand_slab_kernel<<<blocks, K1_THREADS, k1_slab_smem_bytes(), s>>>(R, Qt, U, ldk, nsteps_pad, ldu, tiles);
     FSR_LAUNCH_CHECK();
     return FSR_OK;
   }
   if (int rc = smem_opt_in((const void*)k1_expand_kernel, 227 * 1024)) return rc;
-  k1_expand_kernel<<<blocks, K1_THREADS, smem, s>>>(R, Qt, U, ldk, nsteps_pad, ldu);
+  k1_expand_kernel<<<blocks, K1_THREADS, smem, s>>>(R, Qt, U, ldk, nsteps_pad, ldu, tiles);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }
@@ -441,6 +441,56 @@ int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nro
 int launch_k1(fsr_part* p, int nsteps_pad, cudaStream_t s)
 {
   return launch_k1_raw(p->R, p->Qt, p->U, p->ldk, p->nrows_pad, nsteps_pad, (size_t)p->step_tile, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// In-plane rows of flat shell regions (fsr_part::planar, set up by k2_shell.cu)
+// ------------------------------------------------------------------------------------------
+// out[r][c] = sum_j w[r][j] * in[src[r][j]][c]: the rows of R (once) or of U (displacements given) in the axes of the plane
+__global__ void combine_rows_kernel(double* __restrict__ out, size_t ld_out, const double* __restrict__ in, size_t ld_in,
+                                    const int* __restrict__ src, const double* __restrict__ w, int nrows, int ncols)
+{
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nrows * ncols) return;
+  const int r = (int)(idx / ncols), c = (int)(idx % ncols);
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) acc = fma(w[(size_t)r * 3 + j], in[(size_t)src[(size_t)r * 3 + j] * ld_in + c], acc);
+  out[(size_t)r * ld_out + c] = acc;
+}
+
+int build_planar_rows(fsr_part* p)
+{
+  if (!p->planar) return FSR_OK;
+  cudaStream_t s = p->stream;
+  if (!p->Rp) FSR_CUDA(cudaMalloc(&p->Rp, sizeof(double) * (size_t)p->np_rows_pad * p->ldk));
+  FSR_CUDA(cudaMemsetAsync(p->Rp, 0, sizeof(double) * (size_t)p->np_rows_pad * p->ldk, s));
+  const size_t total = (size_t)p->np_rows * p->ldk;
+  combine_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p->Rp, (size_t)p->ldk, p->R, (size_t)p->ldk, p->prow_src,
+                                                                      p->prow_w, p->np_rows, p->ldk);
+  FSR_LAUNCH_CHECK();
+  FSR_CUDA(cudaStreamSynchronize(s));
+  return FSR_OK;
+}
+
+int planar_rows_from_u(fsr_part* p, int nsteps_pad, cudaStream_t s)
+{
+  if (!p->planar) return FSR_OK;
+  const size_t total = (size_t)p->np_rows * nsteps_pad;
+  combine_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p->Up, (size_t)p->step_tile, p->U, (size_t)p->step_tile,
+                                                                      p->prow_src, p->prow_w, p->np_rows, nsteps_pad);
+  FSR_LAUNCH_CHECK();
+  return FSR_OK;
+}
+
+int launch_k1_vm(fsr_part* p, int nsteps_pad, cudaStream_t s, bool full_u)
+{
+  if (!p->planar) return launch_k1(p, nsteps_pad, s);
+  int rc = launch_k1_raw(p->Rp, p->Qt, p->Up, p->ldk, p->np_rows_pad, nsteps_pad, (size_t)p->step_tile, s);
+  if (rc) return rc;
+  if (full_u) return launch_k1(p, nsteps_pad, s);
+  if (p->n_k1_tiles == 0) return FSR_OK;
+  return launch_k1_raw(p->R, p->Qt, p->U, p->ldk, p->nrows_pad, nsteps_pad, (size_t)p->step_tile, s, p->k1_tiles, p->n_k1_tiles);
 }
 
 }  // namespace fsr

@@ -791,14 +791,14 @@ __global__ void build_quad_flat_kernel(int nelt, const double* __restrict__ Sfra
   flat[i] = !failed[i] && drop[0] <= 1.0e-12 * keep[0] && drop[1] <= 1.0e-12 * keep[1];
 }
 
-template <bool WRITE_VM, bool GUARD>
-__device__ __forceinline__ void quad_flat_tile(const double (&am)[2][3], const double (&ab)[2][3], const double (&bm)[3],
-                                               const double (&bb)[3], double sgn, double*& vmp0, double*& vmp1, size_t ld8, int t0,
+template <bool WRITE_VM, bool GUARD, int NK = 3>
+__device__ __forceinline__ void quad_flat_tile(const double (&am)[2][NK], const double (&ab)[2][NK], const double (&bm)[NK],
+                                               const double (&bb)[NK], double sgn, double*& vmp0, double*& vmp1, size_t ld8, int t0,
                                                int nsteps, double& emax, double& emin)
 {
   double cm[2][2] = {{0, 0}, {0, 0}}, cb[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
+  for (int j = 0; j < NK; ++j)
 #pragma unroll
     for (int m = 0; m < 2; ++m) { dmma884(cm[m][0], cm[m][1], am[m][j], bm[j]); dmma884(cb[m][0], cb[m][1], ab[m][j], bb[j]); }
   double v[2];
@@ -893,6 +893,122 @@ k2_quad_flat_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Flat quadrilaterals in flat regions: the in-plane form
+// ------------------------------------------------------------------------------------------
+// A flat element never sees the translation along its normal nor the rotation about it.  Where ALL flat quadrilaterals around
+// a node lie in one plane (decks, webs, panels: most nodes of a plated structure), the node gets a frame (a1, a2 in the plane)
+// and the recovery operator is rotated into it once: four rows (u, v, theta1, theta2) of Rp = W . R replace the six global
+// ones, so K1 expands 2/3 of the rows for such nodes and the element operator shrinks to two 12 x 8 blocks
+//     M' = M . [a1 a2] per node (translations),   B' = B . [a1 a2] per node (rotations):
+// 8 DMMA per 8 steps instead of 12 and four U rows per node instead of six.  The dropped columns (M . a3, B . a3) are checked
+// per element against 1e-12 of the kept ones; an element that fails, or has a node on a fold line, keeps the flat form above
+// on the global rows.  Fragment layout per element: [M' | B'][m-tile][k-tile][lane], column k of a block = 2 * node + (u|v).
+__global__ void build_quad_planar_kernel(int ncand, const int* __restrict__ celem, const int* __restrict__ cnode,
+                                         const double* __restrict__ frames, const double* __restrict__ Ffrag,
+                                         double* __restrict__ Pfrag, unsigned char* __restrict__ ok)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const double* F = Ffrag + (size_t)celem[c] * 12 * 32;
+  double* P = Pfrag + (size_t)c * 8 * 32;
+  double keep[2] = {0.0, 0.0}, drop[2] = {0.0, 0.0};
+  for (int n = 0; n < 4; ++n) {
+    const double* fr = frames + (size_t)cnode[(size_t)c * 4 + n] * 6;
+    const double a1[3] = {fr[0], fr[1], fr[2]}, a2[3] = {fr[3], fr[4], fr[5]};
+    const double a3[3] = {a1[1] * a2[2] - a1[2] * a2[1], a1[2] * a2[0] - a1[0] * a2[2], a1[0] * a2[1] - a1[1] * a2[0]};
+    for (int blk = 0; blk < 2; ++blk)
+      for (int r = 0; r < 16; ++r) {
+        double v[3];
+        for (int k = 0; k < 3; ++k) v[k] = F[(size_t)blk * 6 * 32 + frag_index(r, 3 * n + k, 3)];
+        const double pu = v[0] * a1[0] + v[1] * a1[1] + v[2] * a1[2];
+        const double pv = v[0] * a2[0] + v[1] * a2[1] + v[2] * a2[2];
+        const double pw = v[0] * a3[0] + v[1] * a3[1] + v[2] * a3[2];
+        P[(size_t)blk * 4 * 32 + frag_index(r, 2 * n, 2)] = pu;
+        P[(size_t)blk * 4 * 32 + frag_index(r, 2 * n + 1, 2)] = pv;
+        keep[blk] = fmax(keep[blk], fmax(fabs(pu), fabs(pv)));
+        drop[blk] = fmax(drop[blk], fabs(pw));
+      }
+  }
+  ok[c] = drop[0] <= 1.0e-12 * keep[0] && drop[1] <= 1.0e-12 * keep[1];
+}
+
+// edof2: [candidate][20] = rows of Up (u, v, theta1, theta2) of the four nodes, [16] = first result point of the element
+// (three CTAs per SM when the history is written: 80 registers without spills, measured 14.7 vs 16.0 ms; the envelope-only
+// variant would spill there and keeps two)
+template <bool WRITE_VM>
+__global__ void __launch_bounds__(256, WRITE_VM ? 3 : 2)
+k2_quad_planar_vm_kernel(const double* __restrict__ Up, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Pfrag,
+                         const int* __restrict__ edof2, int nlist, const int* __restrict__ list, double* __restrict__ vm,
+                         size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int il = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (il >= nlist) return;  // whole warp
+  const int c = __ldg(list + il);
+  const int* ed = edof2 + (size_t)c * 20;
+  const size_t pt = (size_t)__ldg(ed + 16) + g;
+  const double sgn = g < 4 ? 1.0 : -1.0;   // top = membrane + bending, bottom = membrane - bending
+
+  double am[2][2], ab[2][2];
+  const double* ff = Pfrag + (size_t)c * 8 * 32 + lane;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { am[m][j] = __ldg(ff + (size_t)(m * 2 + j) * 32); ab[m][j] = __ldg(ff + (size_t)(4 + m * 2 + j) * 32); }
+  // B operands: column k = 4 j + t4 of a block = in-plane component k % 2 of node k / 2
+  const double *upm[2], *upb[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = 4 * j + t4;
+    upm[j] = Up + (size_t)__ldg(ed + 4 * (k >> 1) + (k & 1)) * ldu;
+    upb[j] = Up + (size_t)__ldg(ed + 4 * (k >> 1) + 2 + (k & 1)) * ldu;
+  }
+  double emax = 0.0, emin = kHuge;
+  const int ntiles = nsteps_pad >> 3;
+  const int nfull = ((nsteps >> 3) >> 1) << 1;   // tiles (in pairs) with all 8 steps valid
+  {
+    double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
+    double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
+    const size_t ld8 = ld_vm * 8;
+    double m0[2], r0[2], m1[2], r1[2];
+    const double *qm[2] = {upm[0] + g, upm[1] + g}, *qb[2] = {upb[0] + g, upb[1] + g};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { m0[j] = qm[j][0]; r0[j] = qb[j][0]; }
+    for (int nt = 0; nt < nfull; nt += 2) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { m1[j] = qm[j][8]; r1[j] = qb[j][8]; }
+      quad_flat_tile<WRITE_VM, false, 2>(am, ab, m0, r0, sgn, vmp0, vmp1, ld8, 0, 0, emax, emin);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { qm[j] += 16; qb[j] += 16; m0[j] = qm[j][0]; r0[j] = qb[j][0]; }
+      quad_flat_tile<WRITE_VM, false, 2>(am, ab, m1, r1, sgn, vmp0, vmp1, ld8, 0, 0, emax, emin);
+    }
+  }
+  {   // ragged tail: one tile at a time, guarded stores
+    double* vmp0 = WRITE_VM ? vm + (size_t)(nfull * 8 + 2 * t4) * ld_vm + pt : nullptr;
+    double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
+    for (int nt = nfull; nt < ntiles && nt * 8 < nsteps; ++nt) {
+      double m0[2], r0[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { m0[j] = upm[j][(size_t)nt * 8 + g]; r0[j] = upb[j][(size_t)nt * 8 + g]; }
+      quad_flat_tile<WRITE_VM, true, 2>(am, ab, m0, r0, sgn, vmp0, vmp1, ld_vm * 8, nt * 8 + 2 * t4, nsteps, emax, emin);
+    }
+  }
+  emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 1));
+  emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, 1));
+  emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, 2));
+  emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, 2));
+  if (!WRITE_VM) {   // radicand -> von Mises (kHuge: no step seen)
+    emax = sqrt_pos(emax);
+    emin = emin == kHuge ? kHuge : sqrt_pos(emin);
+  }
+  if (t4 == 0 && nsteps > 0) {
+    if (emax > env_max[pt]) env_max[pt] = emax;
+    if (emin < env_min[pt]) env_min[pt] = emin;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static int upload_family(FamilyData& f, const std::vector<int>& elem, const std::vector<int>& conn,
@@ -942,6 +1058,157 @@ static int gather_family(const fsr_part* p, const fsr_sam* sam, const fsr_elmdat
   return FSR_OK;
 }
 
+// Which flat quadrilaterals take the in-plane form, the node frames, the rows of Rp / Up and the row tiles of R the von Mises
+// path still has to expand for everything else.  lst[0] = flat elements on entry; the ones that qualify move to lst[2]
+// (positions in the candidate arrays fast2 / edof2).
+static int setup_planar_quads(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm, FamilyData& f, const std::vector<int>& conn,
+                              const std::vector<int>& ptoff, std::vector<int> (&lst)[3], cudaStream_t s)
+{
+  const int nnod = sam->nnod;
+  const double* X = elm->xyz;
+  // the plane of every node: the normal of its first flat quadrilateral; -1 = its flat quadrilaterals are not coplanar
+  std::vector<signed char> state((size_t)nnod, 0);
+  std::vector<double> nrm((size_t)nnod * 3, 0.0);
+  for (int i : lst[0]) {
+    const int* nd = &conn[(size_t)i * 4];
+    double d1[3], d2[3], n[3];
+    for (int k = 0; k < 3; ++k) {
+      d1[k] = X[3 * (size_t)nd[2] + k] - X[3 * (size_t)nd[0] + k];
+      d2[k] = X[3 * (size_t)nd[3] + k] - X[3 * (size_t)nd[1] + k];
+    }
+    n[0] = d1[1] * d2[2] - d1[2] * d2[1]; n[1] = d1[2] * d2[0] - d1[0] * d2[2]; n[2] = d1[0] * d2[1] - d1[1] * d2[0];
+    const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!(len > 0.0)) { for (int k = 0; k < 4; ++k) state[(size_t)nd[k]] = -1; continue; }
+    int kmax = 0;   // one sign for both orientations of the plane (element blocks of a sharded part see other neighbours)
+    for (int k = 1; k < 3; ++k) if (std::fabs(n[k]) > std::fabs(n[kmax])) kmax = k;
+    const double sg = n[kmax] < 0.0 ? -1.0 / len : 1.0 / len;
+    for (int k = 0; k < 3; ++k) n[k] *= sg;
+    for (int k = 0; k < 4; ++k) {
+      const size_t j = (size_t)nd[k];
+      if (state[j] == 0) { state[j] = 1; for (int d = 0; d < 3; ++d) nrm[3 * j + d] = n[d]; }
+      else if (state[j] == 1) {
+        const double c = n[0] * nrm[3 * j] + n[1] * nrm[3 * j + 1] + n[2] * nrm[3 * j + 2];
+        if (1.0 - std::fabs(c) > 1.0e-10) state[j] = -1;
+      }
+    }
+  }
+  std::vector<int> celem, cnode;   // candidates: family index, nodes
+  for (int i : lst[0]) {
+    const int* nd = &conn[(size_t)i * 4];
+    if (state[(size_t)nd[0]] == 1 && state[(size_t)nd[1]] == 1 && state[(size_t)nd[2]] == 1 && state[(size_t)nd[3]] == 1) {
+      celem.push_back(i);
+      cnode.insert(cnode.end(), nd, nd + 4);
+    }
+  }
+  const int ncand = (int)celem.size();
+  if (ncand == 0) return FSR_OK;
+  // node frames: a1 = the global axis least aligned with the normal, projected into the plane; a2 = a3 x a1
+  std::vector<double> frames((size_t)nnod * 6, 0.0);
+  for (int j = 0; j < nnod; ++j) {
+    if (state[(size_t)j] != 1) continue;
+    const double* a3 = &nrm[3 * (size_t)j];
+    int k0 = 0;
+    for (int k = 1; k < 3; ++k) if (std::fabs(a3[k]) < std::fabs(a3[k0])) k0 = k;
+    double a1[3] = {-a3[k0] * a3[0], -a3[k0] * a3[1], -a3[k0] * a3[2]};
+    a1[k0] += 1.0;
+    const double len = std::sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]);
+    for (int k = 0; k < 3; ++k) a1[k] /= len;
+    double* fr = &frames[6 * (size_t)j];
+    fr[0] = a1[0]; fr[1] = a1[1]; fr[2] = a1[2];
+    fr[3] = a3[1] * a1[2] - a3[2] * a1[1]; fr[4] = a3[2] * a1[0] - a3[0] * a1[2]; fr[5] = a3[0] * a1[1] - a3[1] * a1[0];
+  }
+  int *d_celem = nullptr, *d_cnode = nullptr;
+  double* d_frames = nullptr;
+  unsigned char* d_ok = nullptr;
+  FSR_CUDA(cudaMalloc(&d_celem, sizeof(int) * celem.size()));
+  FSR_CUDA(cudaMalloc(&d_cnode, sizeof(int) * cnode.size()));
+  FSR_CUDA(cudaMalloc(&d_frames, sizeof(double) * frames.size()));
+  FSR_CUDA(cudaMalloc(&d_ok, (size_t)ncand));
+  FSR_CUDA(cudaMalloc(&f.fast2, sizeof(double) * (size_t)ncand * 8 * 32));
+  FSR_CUDA(cudaMemcpyAsync(d_celem, celem.data(), sizeof(int) * celem.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(d_cnode, cnode.data(), sizeof(int) * cnode.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemcpyAsync(d_frames, frames.data(), sizeof(double) * frames.size(), cudaMemcpyHostToDevice, s));
+  FSR_CUDA(cudaMemsetAsync(f.fast2, 0, sizeof(double) * (size_t)ncand * 8 * 32, s));
+  build_quad_planar_kernel<<<(ncand + 63) / 64, 64, 0, s>>>(ncand, d_celem, d_cnode, d_frames, f.fast, f.fast2, d_ok);
+  FSR_LAUNCH_CHECK();
+  std::vector<unsigned char> ok((size_t)ncand);
+  FSR_CUDA(cudaMemcpyAsync(ok.data(), d_ok, (size_t)ncand, cudaMemcpyDeviceToHost, s));
+  FSR_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_celem); cudaFree(d_cnode); cudaFree(d_frames); cudaFree(d_ok);
+  // rows of Rp / Up: four per node that some in-plane element reads, in node order
+  std::vector<int> prow((size_t)nnod, -1);
+  std::vector<unsigned char> is_planar((size_t)f.nelt, 0);
+  int nok = 0;
+  for (int c = 0; c < ncand; ++c) {
+    if (!ok[(size_t)c]) continue;
+    ++nok;
+    is_planar[(size_t)celem[(size_t)c]] = 1;
+    for (int k = 0; k < 4; ++k) prow[(size_t)cnode[(size_t)c * 4 + k]] = 0;
+  }
+  if (nok == 0) { cudaFree(f.fast2); f.fast2 = nullptr; return FSR_OK; }
+  int nrows = 0;
+  for (int j = 0; j < nnod; ++j)
+    if (prow[(size_t)j] == 0) { prow[(size_t)j] = nrows; nrows += 4; }
+  std::vector<int> src((size_t)nrows * 3);
+  std::vector<double> w((size_t)nrows * 3);
+  for (int j = 0; j < nnod; ++j) {
+    if (prow[(size_t)j] < 0) continue;
+    const int js = sam->madof[j] - 1;
+    for (int q = 0; q < 4; ++q)
+      for (int k = 0; k < 3; ++k) {
+        src[((size_t)prow[(size_t)j] + q) * 3 + k] = js + (q >= 2 ? 3 : 0) + k;
+        w[((size_t)prow[(size_t)j] + q) * 3 + k] = frames[6 * (size_t)j + (q & 1) * 3 + k];
+      }
+  }
+  std::vector<int> edof2((size_t)ncand * 20, 0), planar_list, flat_rest;
+  for (int c = 0; c < ncand; ++c) {
+    if (!ok[(size_t)c]) continue;
+    planar_list.push_back(c);
+    for (int k = 0; k < 4; ++k)
+      for (int q = 0; q < 4; ++q) edof2[(size_t)c * 20 + 4 * k + q] = prow[(size_t)cnode[(size_t)c * 4 + k]] + q;
+    edof2[(size_t)c * 20 + 16] = ptoff[(size_t)celem[(size_t)c]];
+  }
+  for (int i : lst[0])
+    if (!is_planar[(size_t)i]) flat_rest.push_back(i);
+  lst[0].swap(flat_rest);
+  lst[2].swap(planar_list);
+  // row tiles of R that anything but the in-plane quadrilaterals reads (every other active element of the part)
+  const int ntile = p->nrows_pad / 128;
+  std::vector<unsigned char> need((size_t)ntile, 0);
+  std::vector<unsigned char> planar_sam((size_t)sam->nel, 0);
+  {
+    std::vector<int> elem_host((size_t)f.nelt);
+    FSR_CUDA(cudaMemcpy(elem_host.data(), f.elem, sizeof(int) * (size_t)f.nelt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < f.nelt; ++i) planar_sam[(size_t)elem_host[(size_t)i]] = is_planar[(size_t)i];
+  }
+  for (int e = 0; e < sam->nel; ++e) {
+    if (planar_sam[(size_t)e] || (elm->elmid && elm->elmid[e] < 1)) continue;
+    for (int ip = sam->mpmnpc[e] - 1; ip < sam->mpmnpc[e + 1] - 1; ++ip) {
+      const int n = sam->mmnpc[ip] - 1;
+      if (n < 0 || n >= nnod) continue;
+      for (int d = sam->madof[n] - 1; d < sam->madof[n + 1] - 1; ++d) need[(size_t)(d / 128)] = 1;
+    }
+  }
+  std::vector<int> tiles;
+  for (int t = 0; t < ntile; ++t)
+    if (need[(size_t)t]) tiles.push_back(t);
+  p->planar = true;
+  p->np_rows = nrows;
+  p->np_rows_pad = (nrows + 127) / 128 * 128;
+  p->n_k1_tiles = (int)tiles.size();
+  FSR_CUDA(cudaMalloc(&p->prow_src, sizeof(int) * src.size()));
+  FSR_CUDA(cudaMalloc(&p->prow_w, sizeof(double) * w.size()));
+  FSR_CUDA(cudaMalloc(&f.edof2, sizeof(int) * edof2.size()));
+  FSR_CUDA(cudaMemcpy(p->prow_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
+  FSR_CUDA(cudaMemcpy(p->prow_w, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice));
+  FSR_CUDA(cudaMemcpy(f.edof2, edof2.data(), sizeof(int) * edof2.size(), cudaMemcpyHostToDevice));
+  if (!tiles.empty()) {
+    FSR_CUDA(cudaMalloc(&p->k1_tiles, sizeof(int) * tiles.size()));
+    FSR_CUDA(cudaMemcpy(p->k1_tiles, tiles.data(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice));
+  }
+  return FSR_OK;
+}
+
 int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
 {
   cudaStream_t s = p->stream;
@@ -972,16 +1239,20 @@ int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
         FSR_CUDA(cudaMemcpyAsync(h.data(), d_flat, f.nelt, cudaMemcpyDeviceToHost, s));
         FSR_CUDA(cudaStreamSynchronize(s));
         cudaFree(d_flat);
-        std::vector<int> lst[2];
+        std::vector<int> lst[3];
         for (int i = 0; i < f.nelt; ++i) lst[h[(size_t)i] ? 0 : 1].push_back(i);
         if (lst[0].empty()) { cudaFree(f.fast); f.fast = nullptr; }
-        else
-          for (int k = 0; k < 2; ++k) {
+        else {
+          // flat regions: in-plane rows and operators (FSR_QUAD_PLANAR=0 keeps the global rows for all)
+          if (!(getenv("FSR_QUAD_PLANAR") && atoi(getenv("FSR_QUAD_PLANAR")) == 0))
+            if ((rc = setup_planar_quads(p, sam, elm, f, conn, ptoff, lst, s))) return rc;
+          for (int k = 0; k < 3; ++k) {
             f.nsub[k] = (int)lst[k].size();
             if (f.nsub[k] == 0) continue;
             FSR_CUDA(cudaMalloc(&f.sub[k], sizeof(int) * lst[k].size()));
             FSR_CUDA(cudaMemcpy(f.sub[k], lst[k].data(), sizeof(int) * lst[k].size(), cudaMemcpyHostToDevice));
           }
+        }
       }
     }
   }
@@ -1014,7 +1285,21 @@ static int launch_shell_family(fsr_part* p, FamilyData& f, int nsteps, int nstep
   if (f.nelt == 0) return FSR_OK;
   int ngen = f.nelt;
   const int* gen_list = nullptr;
-  if (KT == 6 && f.fast && f.nsub[0] > 0) {   // quads: the flat ones take the membrane / bending split
+  if (KT == 6 && f.fast2 && f.nsub[2] > 0) {  // quads of flat regions: in-plane rows
+    const unsigned grid = (unsigned)((f.nsub[2] + warps - 1) / warps);
+    if (vm_dev)
+      k2_quad_planar_vm_kernel<true><<<grid, warps * 32, 0, s>>>(p->Up, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast2, f.edof2, f.nsub[2],
+                                                                 f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min);
+    else
+      k2_quad_planar_vm_kernel<false><<<grid, warps * 32, 0, s>>>(p->Up, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast2, f.edof2, f.nsub[2],
+                                                                  f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min);
+    FSR_LAUNCH_CHECK();
+  }
+  if (KT == 6 && f.fast && (f.nsub[0] > 0 || f.nsub[2] > 0)) {   // the other flat ones take the membrane / bending split on global rows
+    ngen = f.nsub[1];
+    gen_list = f.sub[1];
+  }
+  if (KT == 6 && f.fast && f.nsub[0] > 0) {
     const unsigned grid = (unsigned)((f.nsub[0] + warps - 1) / warps);
     if (vm_dev)
       k2_quad_flat_vm_kernel<true><<<grid, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.edof, f.ptoff,
@@ -1023,10 +1308,8 @@ static int launch_shell_family(fsr_part* p, FamilyData& f, int nsteps, int nstep
       k2_quad_flat_vm_kernel<false><<<grid, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.edof, f.ptoff,
                                                                 f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min);
     FSR_LAUNCH_CHECK();
-    ngen = f.nsub[1];
-    gen_list = f.sub[1];
-    if (ngen == 0) return FSR_OK;
   }
+  if (ngen == 0) return FSR_OK;
   if (vm_dev)
     k2_shell_vm_kernel<KT, true, ALL_LIVE><<<(ngen + warps - 1) / warps, warps * 32, 0, s>>>(
         p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, ngen, f.nstrp, vm_dev,

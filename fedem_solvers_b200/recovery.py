@@ -132,6 +132,15 @@ class StressRecovery:
         check(self._lib.fsr_recover(self._h, _dp(Q), Q.shape[0], nsteps, _dp(vm)), "fsr_recover")
         return vm
 
+    def recover_displacements(self, sv, want_history=True):
+        """calcStresses on nodal displacements that are already there (stress.f90:397 readIntDisplacements, the direct
+        solution on the results files): sv [nsteps, ndof].  Returns the von Mises history like recover."""
+        sv = np.ascontiguousarray(sv, F64)
+        assert sv.ndim == 2 and sv.shape[1] == self.ndof, (sv.shape, self.ndof)
+        vm = np.empty((sv.shape[0], self.npts), F64) if want_history else None
+        check(self._lib.fsr_recover_displacements(self._h, _dp(sv), sv.shape[0], _dp(vm)), "fsr_recover_displacements")
+        return vm
+
     def recover_dev(self, q_ptr, ldq, nsteps, vm_ptr=None, ld_vm=0, stream=None):
         """Device-pointer variant (torch tensors: pass .data_ptr()); asynchronous."""
         check(self._lib.fsr_recover_dev(self._h, C.c_void_p(q_ptr), ldq, nsteps,
@@ -213,6 +222,13 @@ class StressRecovery:
         c = np.zeros(3 * len(names), I32)
         check(self._lib.fsr_family_counts(self._h, _ip(c), len(c)), "fsr_family_counts")
         return {n: tuple(int(v) for v in c[3 * i:3 * i + 3]) for i, n in enumerate(names) if c[3 * i] > 0}
+
+    def vm_path_info(self):
+        """Rows the von Mises path expands per step tile and the split of the quadrilaterals (fsr_vm_path_info)."""
+        v = (C.c_longlong * 7)()
+        check(self._lib.fsr_vm_path_info(self._h, v, 7), "fsr_vm_path_info")
+        keys = ["k1_rows", "ndof", "inplane_rows", "global_row_tiles", "quads_inplane", "quads_flat", "quads_dense"]
+        return {k: int(x) for k, x in zip(keys, v)}
 
     def timing_reset(self):
         self._lib.fsr_timing_reset(self._h)

@@ -770,6 +770,14 @@ module fedem_b200_mod
        integer(c_int) :: nfam
      end function fsr_family_counts
 
+     function fsr_vm_path_info (part, info, cap) bind(C,name="fsr_vm_path_info") result(nfilled)
+       import :: c_ptr, c_int, c_long_long
+       type(c_ptr), value :: part
+       integer(c_long_long), intent(out) :: info(*)
+       integer(c_int), value :: cap
+       integer(c_int) :: nfilled
+     end function fsr_vm_path_info
+
      function fsr_recover_displacements (part, sv_hist, nsteps, vm_hist) bind(C,name="fsr_recover_displacements") result(ierr)
        import :: c_ptr, c_int, c_double
        type(c_ptr), value         :: part

@@ -648,6 +648,13 @@ int fsr_last_timing(fsr_part *part, double *t_ms, int n);
  * straight-sided TET10: corner gradients), of which on the general kernel.  cap = entries of counts.  Returns the
  * number of families. */
 int fsr_family_counts(const fsr_part *part, int *counts, int cap);
+/* What the von Mises path of the part expands (K1) and where its quadrilaterals go.  Nodes whose flat quadrilaterals all
+ * lie in one plane get four rows (u, v, theta1, theta2) in the axes of that plane instead of six global ones (the rotation
+ * is folded into the recovery operator once, fsr_set_recovery); FSR_QUAD_PLANAR=0 in the environment switches that off.
+ * info[0] = rows K1 expands per step tile, [1] = nodal DOFs of the part, [2] = in-plane rows, [3] = 128-row tiles of the
+ * global operator still expanded (read by other elements), [4] = quadrilaterals in the in-plane form, [5] = flat
+ * quadrilaterals on global rows, [6] = quadrilaterals on the dense operator.  Returns the number of entries written. */
+int fsr_vm_path_info(const fsr_part *part, long long *info, int cap);
 int fsr_timing_reset(fsr_part *part);
 
 #ifdef __cplusplus

@@ -130,6 +130,68 @@ def test_flat_and_warped_quads_in_one_part(oracle):
     assert rel_err(vm, vm2) <= 1e-12 and not np.array_equal(vm, vm2)
 
 
+def _folded_plate(nx=12, ny=7, angle=0.6, **kw):
+    """a plate folded along the node line x = lx / 2 and turned in space: two flat panels that share the fold nodes"""
+    from scipy.spatial.transform import Rotation
+    part = plate_part(nx, ny, **kw)
+    x = part.elm.xyz
+    xf = x[:, 0].max() / 2
+    right = x[:, 0] > xf + 1e-9
+    d = x[right, 0] - xf
+    x[right, 0] = xf + d * np.cos(angle)
+    x[right, 2] = d * np.sin(angle)
+    part.elm.xyz = x @ Rotation.from_rotvec([-0.4, 0.2, 0.7]).as_matrix().T + np.array([-2.0, 0.5, 1.0])
+    return part
+
+
+def test_quads_of_flat_regions_use_inplane_rows(oracle):
+    """nodes whose flat quads all lie in one plane get (u, v, theta1, theta2) rows in the axes of the plane (K1 expands 4
+    rows instead of 6, the element operator is two 12 x 8 blocks); the fold nodes, the triangles and their neighbours keep
+    the global rows.  Same numbers as the oracle and, to rounding, as the run with the in-plane form switched off."""
+    import os
+    part = _folded_plate(ngen=6, seed=61, jitter=0.0, tri_fraction=0.1, shuffle_eq=True, n_constraints=2)
+    nq = int((part.sam.melcon == 24).sum())
+    rec = StressRecovery(part, step_tile=64)
+    info = rec.vm_path_info()
+    rec.close()
+    assert info["quads_inplane"] > 0 and info["quads_flat"] > 0 and info["quads_dense"] == 0, info
+    assert info["quads_inplane"] + info["quads_flat"] == nq
+    assert info["inplane_rows"] % 4 == 0 and 0 < info["inplane_rows"] < 4 * part.sam.nnod
+    vm = _check_part(oracle, part, nsteps=100, seed=12, step_tile=64)
+    os.environ["FSR_QUAD_PLANAR"] = "0"
+    try:
+        rec = StressRecovery(part, step_tile=64)
+        assert rec.vm_path_info()["quads_inplane"] == 0 and rec.vm_path_info()["k1_rows"] >= part.sam.ndof
+        vm2 = rec.recover(reduced_history(part.sam.ndim, 100, seed=12))
+        rec.close()
+    finally:
+        del os.environ["FSR_QUAD_PLANAR"]
+    assert rel_err(vm, vm2) <= 1e-12 and not np.array_equal(vm, vm2)
+
+
+def test_inplane_rows_skip_the_global_expansion_of_a_flat_plate(oracle):
+    """a flat plate of quads only: no tile of the global operator is expanded on the von Mises path, K1 does 2/3 of the rows;
+    the displacement outputs (expand, the solver step) still come from the global operator"""
+    part = plate_part(40, 30, ngen=7, seed=62, jitter=0.1, shuffle_eq=True)
+    rec = StressRecovery(part, step_tile=64)
+    info = rec.vm_path_info()
+    assert info["quads_inplane"] == part.sam.nel and info["global_row_tiles"] == 0, info
+    assert info["inplane_rows"] == 4 * part.sam.nnod and info["k1_rows"] < info["ndof"]
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, 70, seed=3)
+    vm = rec.recover(Q)
+    sv = rec.calc_int_displacements(Q)
+    vm_o, _, _ = oracle.recover_history(b, Q)
+    assert rel_err(vm, vm_o) <= TOL
+    for t in (0, 33, 69):
+        assert rel_err(sv[t], oracle.expand(b, Q[:, t])) <= TOL
+    # the displacements given instead of the reduced history (direct solution): the in-plane rows come from U
+    rec.reset_envelope()
+    vm_d = rec.recover_displacements(sv)
+    assert rel_err(vm_d, vm_o) <= TOL
+    rec.close()
+
+
 def test_tri_quad_mixed_plate(oracle):
     """ANDES triangles (type 23: two LU inversions per element, REAL*4 Gauss rule) mixed with quads"""
     part = plate_part(9, 8, ngen=6, seed=13, tri_fraction=0.5, shuffle_eq=True, n_fixed=3, n_constraints=2, warp=0.04)

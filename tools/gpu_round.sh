@@ -13,7 +13,7 @@ timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 4 --warmup 3 $NOSEC > $O/${TAG}_ncu_launch_bench.log 2>&1
 # full captures: K1 + the quad kernel of the headline; TET10 kernels of config 3; the record kernel; K3
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k1_expand|k2_quad_flat|k2_shell_vm' -s 6 -c 4 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k1_expand|k2_quad_planar|k2_quad_flat|k2_shell_vm' -s 6 -c 4 \
     -o $O/${TAG}_k1_k2 -f python bench.py --steps 2 --warmup 3 $NOSEC > $O/${TAG}_ncu_k1_k2.log 2>&1
 if [ "$2" != "quick" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_tet10' -s 4 -c 4 \
