@@ -204,6 +204,11 @@ SYMBOLS = [
     ("fsr_cmdline_is_set", C.c_int, [C.c_char_p]),
     ("fsr_recovery_register", C.c_int, [C.c_int, _P, _I]),
     ("fsr_recovery_unregister", C.c_int, [C.c_int]),
+    ("fsr_recovery_options", C.c_int, [C.c_char_p]),
+    ("fsr_recovery_register_part", C.c_int, [C.c_int, C.c_int, C.c_char_p, _P, _I, _D]),
+    ("fsr_recovery_update_parts_save", C.c_int, [C.c_int, _I, C.c_int, C.c_double, C.c_double, C.POINTER(_D), C.POINTER(_D), C.c_int]),
+    ("fsr_recovery_close", C.c_int, []),
+    ("fsr_recovery_file", C.c_int, [C.c_int, C.c_char_p, C.c_int]),
     ("fsr_recovery_update", C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, _D]),
     ("getPartDeformationStateSize", C.c_int, [C.c_int]),
     ("getPartStressStateSize", C.c_int, [C.c_int]),

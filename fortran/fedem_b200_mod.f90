@@ -1171,6 +1171,47 @@ module fedem_b200_mod
        integer(c_int) :: ierr
      end function fsr_recovery_update_parts
 
+     function fsr_recovery_options (args) bind(C,name="fsr_recovery_options") result(ierr)
+       import :: c_char, c_int
+       character(kind=c_char), intent(in) :: args(*)   !< "-recovery 1 -partVMStress 3 ..." null-terminated
+       integer(c_int) :: ierr
+     end function fsr_recovery_options
+
+     function fsr_recovery_register_part (base_id, user_id, descr, part, minex, supTrInit) &
+          &   bind(C,name="fsr_recovery_register_part") result(ierr)
+       import :: c_char, c_int, c_double, c_ptr
+       integer(c_int), value      :: base_id, user_id
+       character(kind=c_char), intent(in) :: descr(*)
+       type(c_ptr), value         :: part
+       integer(c_int), intent(in) :: minex(*)
+       real(c_double), intent(in) :: supTrInit(*)   !< sup%supTrInit, 3x4 column-major
+       integer(c_int) :: ierr
+     end function fsr_recovery_register_part
+
+     function fsr_recovery_update_parts_save (nparts, base_ids, istep, time, timeStep, q, supTr, doSave) &
+          &   bind(C,name="fsr_recovery_update_parts_save") result(ierr)
+       import :: c_int, c_double, c_ptr
+       integer(c_int), value      :: nparts, istep
+       integer(c_int), intent(in) :: base_ids(*)
+       real(c_double), value      :: time, timeStep
+       type(c_ptr)   , intent(in) :: q(*)      !< c_loc of every part's [finit; vg]
+       type(c_ptr)   , intent(in) :: supTr(*)  !< c_loc of every part's sup%supTr (3x4)
+       integer(c_int), value      :: doSave
+       integer(c_int) :: ierr
+     end function fsr_recovery_update_parts_save
+
+     function fsr_recovery_close () bind(C,name="fsr_recovery_close") result(ierr)
+       import :: c_int
+       integer(c_int) :: ierr
+     end function fsr_recovery_close
+
+     function fsr_recovery_file (base_id, buf, cap) bind(C,name="fsr_recovery_file") result(length)
+       import :: c_char, c_int
+       integer(c_int), value :: base_id, cap
+       character(kind=c_char), intent(out) :: buf(*)
+       integer(c_int) :: length
+     end function fsr_recovery_file
+
      function fsr_recovery_update (base_id, istep, time, timeStep, q) bind(C,name="fsr_recovery_update") result(ierr)
        import :: c_int, c_double
        integer(c_int), value      :: base_id, istep

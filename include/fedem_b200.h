@@ -628,6 +628,26 @@ int fsr_recovery_update(int base_id, int step, double time, double time_step, co
  * overlap; q[k] = [finit; vg] of part base_ids[k] */
 int fsr_recovery_update_parts(int nparts, const int *base_ids, int step, double time, double time_step,
                               const double *const *q);
+/* The recovery switches of the dynamics solver (src/vpmSolver/solverInterface.C:447-452), given like on its command line:
+ *   -recovery N         1 = stress, 2 = gages, 3 = both; stress recovery runs for mod(N, 2) == 1 (stressRecoveryModule.f90:1025)
+ *   -partVMStress N     0 off, 1 von Mises to the frs file, 2 through the state array (savePartStressState), 3 both (:583,655)
+ *   -partDeformation N  0 off, 1 deformational displacements to the frs file, 2 / 3 total displacements as well (:1017,1183)
+ *   -frs3file NAME      one file, or <"a.frs","b.frs">: one per recovered part in registration order (:771-815,860-884)
+ *   -double, -modelfile NAME; other options are skipped.  Switches not named take the solver's defaults (0, 1, 1).
+ * The switches apply to the parts registered afterwards.  Without this call the registry keeps stress recovery and the
+ * state arrays on and writes no file.  fsr_recovery_register_part also names the part in the frs header (user_id, descr)
+ * and takes its initial position sup_tr_init [12] (column-major 3x4; NULL = no total displacements).
+ * fsr_recovery_update_parts_save is the per-step call with the solver's doSave flag (0 = recoverNotSave) and the parts'
+ * positions sup_tr[k] [12] at the step (NULL when no total displacements are written): the step is appended to the
+ * parts' frs files through the pipelined results-database writer.  fsr_recovery_close = closeRecovery: flushes and closes
+ * the files, empties the registry, resets the switches.  fsr_recovery_file: the frs file of a part (length, 0 = none). */
+int fsr_recovery_options(const char *args);
+int fsr_recovery_register_part(int base_id, int user_id, const char *descr, fsr_part *part, const int *minex,
+                               const double *sup_tr_init);
+int fsr_recovery_update_parts_save(int nparts, const int *base_ids, int step, double time, double time_step,
+                                   const double *const *q, const double *const *sup_tr, int do_save);
+int fsr_recovery_close(void);
+int fsr_recovery_file(int base_id, char *buf, int cap);
 int getPartDeformationStateSize(int bid);
 int getPartStressStateSize(int bid);
 bool savePartDeformationState(int bid, double *data, int ndat);

@@ -213,3 +213,73 @@ def test_pipeline_with_many_small_tiles(oracle, tmp_path, monkeypatch):
     _check(oracle, part, tmp_path, mask, False, nsteps=45, total=True)
     part = hex20_block(2, 1, 1, ngen=3, seed=10)
     _check(oracle, part, tmp_path, out_mask(stress=True, vmStress=True, minPStress=True), True, nsteps=19)
+
+
+def test_solver_recovery_switches_and_frs3_files(oracle, tmp_path):
+    """-recovery / -partVMStress / -partDeformation / -frs3file of the dynamics solver (solverInterface.C:447-452) over the
+    part registry: state arrays only for -partVMStress >= 2 (getStressSize: -1 otherwise), one frs file per recovered part
+    with the deformations and / or the von Mises stresses of every saved step (recoverAndSave), nothing for a step with
+    doSave off, nothing at all for an even -recovery."""
+    import ctypes as C
+    from fedem_solvers_b200 import _lib
+    lib = _lib.load_library()
+    parts = [plate_part(5, 4, ngen=3, seed=71, tri_fraction=0.3), tet10_block(2, 2, 1, ngen=2, seed=72, curved="surface")]
+    recs = [StressRecovery(p) for p in parts]
+    binds = [oracle.bind_part(p) for p in parts]
+    f1, f2 = str(tmp_path / "th_p1.frs"), str(tmp_path / "th_p2.frs")
+    opts = f'-recovery 3 -partVMStress 1 -partDeformation 1 -double -frs3file <"{f1}","{f2}">'
+    assert lib.fsr_recovery_options(opts.encode()) == 0
+    ids = np.array([11, 12], np.int32)
+    for k, (p, r) in enumerate(zip(parts, recs)):
+        mx = np.ascontiguousarray(p.sam.minex, np.int32)
+        assert lib.fsr_recovery_register_part(int(ids[k]), 100 + k, p.name.encode(), r._h, mx.ctypes.data_as(_lib._I), None) == 0, lib.fsr_last_error()
+    assert lib.getPartStressStateSize(11) == -1 and lib.getPartDeformationStateSize(11) == 3 * parts[0].sam.nnod + 4
+    buf = C.create_string_buffer(512)
+    assert lib.fsr_recovery_file(12, buf, 512) > 0 and buf.value.decode() == f2
+    Qs = [reduced_history(p.sam.ndim, 4, seed=73 + k) for k, p in enumerate(parts)]
+    saved = []
+    for s in range(4):
+        cols = [np.ascontiguousarray(Q[:, s]) for Q in Qs]
+        qs = (_lib._D * 2)(*[c.ctypes.data_as(_lib._D) for c in cols])
+        do_save = s != 2
+        assert lib.fsr_recovery_update_parts_save(2, ids.ctypes.data_as(_lib._I), 5 + s, 0.1 * s, 0.1, qs, None, int(do_save)) == 0, lib.fsr_last_error()
+        if do_save:
+            saved.append(s)
+    # the state of the last step is in core whether it was saved or not
+    d = np.zeros(3 * parts[0].sam.nnod + 4)
+    assert lib.savePartDeformationState(11, d.ctypes.data_as(_lib._D), len(d)) and d[0] == 8.0
+    assert lib.fsr_recovery_close() == 0
+    assert lib.getPartDeformationStateSize(11) == -999
+    for k, (p, b, path) in enumerate(zip(parts, binds, (f1, f2))):
+        rd = FrsReader(path)
+        assert rd.nsteps == len(saved) and list(rd.step_numbers) == [5 + s for s in saved]
+        svs = [oracle.expand(b, Qs[k][:, s]) for s in saved]
+        res = [oracle.calc_stresses(b, sv) for sv in svs]
+        scale = max(np.abs(np.stack(svs)).max(), 1e-300)
+        for n in (0, p.sam.nnod - 1):
+            h = rd.find(f"Nodes|{p.sam.minex[n]}|Dynamic response|Translational deformation", "Part", int(ids[k]))
+            assert h is not None
+            j0 = p.sam.madof[n] - 1
+            assert np.abs(rd.read(h) - np.stack([sv[j0:j0 + 3] for sv in svs])).max() <= TOL * scale
+        e = int(np.nonzero(p.sam.melcon > 20)[0][0])
+        t = int(p.sam.melcon[e])
+        side = "Top" if t < 40 else "Basic"
+        h = rd.find(f"Elements|{e + 1}|{NAMES[t]}|Element nodes|{side}|1|{MEASURES[0]}", "Part", int(ids[k]))
+        assert h is not None
+        pt = b["ptoff"][e]
+        want = np.stack([r["resmat"][pt, 0:1] for r in res])
+        assert np.abs(rd.read(h) - want).max() <= TOL * np.abs(np.stack([r["resmat"][:, 0] for r in res])).max()
+    # gages only: no stress recovery, no files, no state
+    assert lib.fsr_recovery_options(b"-recovery 2 -frs3file " + str(tmp_path / "none.frs").encode()) == 0
+    assert lib.fsr_recovery_register(11, recs[0]._h, None) == 0
+    q = np.ascontiguousarray(Qs[0][:, 0])
+    assert lib.fsr_recovery_update(11, 1, 0.0, 0.1, q.ctypes.data_as(_lib._D)) == 0
+    assert lib.getPartStressStateSize(11) == -1 and not os.path.exists(str(tmp_path / "none.frs"))
+    assert lib.fsr_recovery_close() == 0
+    # the library's own default again (no switches given): state arrays on
+    assert lib.fsr_recovery_register(11, recs[0]._h, None) == 0
+    assert lib.getPartStressStateSize(11) > 0
+    assert lib.fsr_recovery_close() == 0
+    assert lib.fsr_recovery_options(b"-partVMStress 7") < 0
+    for r in recs:
+        r.close()

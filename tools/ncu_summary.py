@@ -18,7 +18,12 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
            "launch__shared_mem_per_block_static", "launch__occupancy_limit_registers",
            "sm__cycles_elapsed.avg.per_second",
-           "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+           "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 
 
 def full(path):
