@@ -85,9 +85,9 @@ static NcclApi* nccl_api()
 static double element_cost(int type)
 {
   switch (type) {
-    case 24: case 22: return 77.0;
+    case 24: case 22: return 50.0;   // flat regions on in-plane rows (26 K1 + 24 K2); 77 on six global rows
     case 23: case 21: return 57.0;
-    case 41: return 90.0;
+    case 41: return 80.0;
     case 42: return 240.0;
     case 43: return 397.0;
     case 44: return 65.0;

@@ -37,9 +37,13 @@ class ShardedRecovery:
             mine = mine.to(device)
         if self.world == 1:
             return mine[0].cpu().numpy(), mine[1].cpu().numpy()
-        bufs = [torch.empty((2, c), dtype=torch.float64, device=mine.device) for c in counts] if self.rank == 0 else None
-        dist.gather(mine, bufs, dst=0)
+        # gather wants equal shapes on every rank: pad the blocks to the largest one
+        width = max(counts)
+        padded = torch.zeros((2, width), dtype=torch.float64, device=mine.device)
+        padded[:, :mine.shape[1]] = mine
+        bufs = [torch.empty((2, width), dtype=torch.float64, device=mine.device) for _ in counts] if self.rank == 0 else None
+        dist.gather(padded, bufs, dst=0)
         if self.rank != 0:
             return None, None
-        full = torch.cat(bufs, 1).cpu().numpy()
+        full = torch.cat([b[:, :c] for b, c in zip(bufs, counts)], 1).cpu().numpy()
         return full[0], full[1]
