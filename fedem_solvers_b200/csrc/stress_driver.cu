@@ -324,7 +324,7 @@ void initSolverArgs(int argc, char** argv)
 
 // subroutine stress (stress.f90:17-493) and subroutine gage (gage.f90:8-431) share everything up to the opened B and E
 // matrices and the time step selection: one body, `gage` switches the program specific parts.
-static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, const char* model_file,
+static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, int sup_user_id, const char* model_file,
                      const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
                      int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
@@ -368,7 +368,7 @@ static int run_program(int which)
   log.open(file_name("resfile", gage ? "_gage.res" : modes ? "_modes.res" : "_stress.res"), gage ? "Strain Gage Recovery" : modes ? "Modal Recovery" : "Stress Recovery");
   log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : modes ? "MODES" : "STRESS");
   if (gage) {
-    if (c.get_bool("writeAsciiFiles")) log.line("  ** Note: ASCII / DAC rosette files (-writeAsciiFiles) are not part of this build; ignored");
+    if (c.get_bool("writeAsciiFiles")) log.line("  ** Note: ASCII / DAC rosette result files (-writeAsciiFiles) are not part of this build; ignored");
   } else
   if (c.is_set("resStressFile")) log.line("  ** Note: residual stress import (-resStressFile) is not part of this build; ignored");
   if (c.is_set("VTFfile") && !c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
@@ -555,7 +555,7 @@ static int run_program(int which)
     return modes_part(c, log, what, part, db, isup, user_id, descr[0] ? descr : linkfile.c_str(), model_file, linkfile, madof, minex, ndof2, ngen, ntriads,
                       tb, tnd, tfd, tru, gen_first, stepno, times, lgrav, grv);
   if (gage)
-    return gage_part(c, log, what, part, ftl, db, isup, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
+    return gage_part(c, log, what, part, ftl, db, isup, user_id, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
                      sel, nsel, stepno, times, lgrav, grv, madof);
 
   // --- Initialize the stress results database (writeStressHeader)
@@ -708,7 +708,7 @@ static void glb_euler_zyx(const double* a, double* ang)
 // --------------------------------------------------------------------------------------------------------------------
 // The fedem_gage specific part (gage.f90:136-150,196-247,278-400): rosette input, Bcart on the GPU, results database
 // (saveStrainGageModule.f90:23-268), fatigue report (reportDamage, strainGageModule.f90:778-862).
-static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, const char* model_file,
+static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, int sup_user_id, const char* model_file,
                      const std::string& linkfile, const std::vector<int>& minex, const std::vector<double>& xyz, int ndof2, int ngen,
                      int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
@@ -719,21 +719,93 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
   log.line("           --> Initializing strain rosettes");
   const std::string rosfile = c.get_string("rosfile");
   if (rosfile.empty()) FAIL("No strain rosette input file (-rosfile)");
-  if (rosfile.size() < 4 || rosfile.compare(rosfile.size() - 4, 4, ".fsi") != 0)
-    FAIL("%s: only the .fsi rosette format (&STRAIN_ROSETTE records) is part of this build, not the old rosette definition format", rosfile.c_str());
-  const int nros = fsr_fsi_read_rosettes(rosfile.c_str(), isup, nullptr, nullptr, nullptr, 0, 0);
-  if (nros < 0) CHECK(nros);
-  log.line("               Number of &STRAIN_ROSETTE =%6d", nros);
+  const bool fsi_format = rosfile.size() >= 4 && rosfile.compare(rosfile.size() - 4, 4, ".fsi") == 0;   // gage.f90:138
+  constexpr int kDescr = 128;
+  std::vector<fsr_rosette> ros;
+  std::vector<int> ruser;
+  std::vector<char> rdescr;
+  int nros = 0;
+  if (fsi_format) {
+    nros = fsr_fsi_read_rosettes(rosfile.c_str(), isup, nullptr, nullptr, nullptr, 0, 0);
+    if (nros < 0) CHECK(nros);
+    log.line("               Number of &STRAIN_ROSETTE =%6d", nros);
+  } else {
+    // The old rosette definition file (ReadStrainGageOldData, strainGageModule.f90:246-476): free-format records
+    //   id type link nnod node_1..node_nnod zPos Xx Xy Xz Zx Zy Zz Emod nu      ('#' starts a comment, END / EOF ends the file)
+    // of which the ones of this part (link == the part's user id) are kept; type 1 single gage, 2 double (90 deg),
+    // 3 triple 60 deg, 4 triple 45 deg; a dummy base id idIn + link*1000 + rdbinc*10000000 names the rosette on the frs file.
+    FILE* fp = fopen(rosfile.c_str(), "r");
+    if (!fp) FAIL("Could not open the rosette definition file %s", rosfile.c_str());
+    std::vector<std::string> tok;
+    {
+      char lbuf[4096];
+      bool done = false;
+      while (!done && fgets(lbuf, sizeof(lbuf), fp)) {
+        if (char* hash = strchr(lbuf, '#')) *hash = 0;
+        for (char* t = strtok(lbuf, " \t\r\n,"); t; t = strtok(nullptr, " \t\r\n,")) {
+          if (!strncasecmp(t, "END", 3) || !strncasecmp(t, "EOF", 3)) { done = true; break; }
+          tok.push_back(t);
+        }
+      }
+      fclose(fp);
+    }
+    const int rdbinc = c.get_int("rdbinc");
+    size_t it = 0;
+    bool bad_file = false;
+    auto next_i = [&](int& v) { if (it >= tok.size()) { bad_file = true; v = 0; return; } char* e = nullptr; v = (int)strtol(tok[it].c_str(), &e, 10); if (*e) bad_file = true; ++it; };
+    auto next_d = [&](double& v) {
+      if (it >= tok.size()) { bad_file = true; v = 0.0; return; }
+      std::string t = tok[it++];
+      for (char& ch : t) if (ch == 'D' || ch == 'd') ch = 'e';   // Fortran exponents
+      char* e = nullptr; v = strtod(t.c_str(), &e); if (*e) bad_file = true;
+    };
+    while (it < tok.size() && !bad_file) {
+      int id, type, link, nn;
+      next_i(id); next_i(type); next_i(link); next_i(nn);
+      if (bad_file || nn < 3 || nn > 4) { bad_file = true; break; }
+      fsr_rosette R;
+      memset(&R, 0, sizeof(R));
+      R.numnod = nn;
+      for (int k = 0; k < nn; ++k) next_i(R.nodes[k]);
+      double xv[3], zv[3];
+      next_d(R.zpos);
+      for (int k = 0; k < 3; ++k) next_d(xv[k]);
+      for (int k = 0; k < 3; ++k) next_d(zv[k]);
+      next_d(R.emod); next_d(R.nu);
+      if (bad_file) break;
+      if (link != sup_user_id) continue;   // skip for all other links
+      const double lx = std::sqrt(xv[0] * xv[0] + xv[1] * xv[1] + xv[2] * xv[2]), lz = std::sqrt(zv[0] * zv[0] + zv[1] * zv[1] + zv[2] * zv[2]);
+      if (lx < 1000.0 * 2.2250738585072014e-308) FAIL("Undefined x-direction for rosette number:%8d", id);
+      if (lz < 1000.0 * 2.2250738585072014e-308) FAIL("Undefined z-direction for rosette number:%8d", id);
+      for (int k = 0; k < 3; ++k) { R.rpos[k] = xv[k] / lx; R.rpos[6 + k] = zv[k] / lz; }   // posInGl(:,1), posInGl(:,3); (:,2) and (:,4) follow below
+      const double pi = 3.14159265358979323846;
+      switch (type) {
+        case 1: R.ngage = 1; R.alpha_gages = 0.0; break;
+        case 2: R.ngage = 2; R.alpha_gages = pi / 2.0; break;
+        case 3: R.ngage = 3; R.alpha_gages = pi / 3.0; break;
+        case 4: R.ngage = 3; R.alpha_gages = pi / 4.0; break;
+        default: FAIL("Undefined rosette-type:%8d", type);
+      }
+      ++nros;
+      R.id = nros + link * 1000 + rdbinc * 10000000;
+      ros.push_back(R);
+      ruser.push_back(id);
+    }
+    if (bad_file) FAIL("Failed to read rosette definition file %s", rosfile.c_str());
+    rdescr.assign((size_t)std::max(nros, 1) * kDescr, 0);
+    log.line("               Number of strain rosettes on this link =%6d", nros);
+  }
   if (nros == 0) {
     log.line("  ** Note: No strain rosettes on this link");
     log.line("\n    %s successfully completed :-)", what);
     return 0;
   }
-  constexpr int kDescr = 128;
-  std::vector<fsr_rosette> ros((size_t)nros);
-  std::vector<int> ruser((size_t)nros);
-  std::vector<char> rdescr((size_t)nros * kDescr);
-  CHECK(fsr_fsi_read_rosettes(rosfile.c_str(), isup, ros.data(), ruser.data(), rdescr.data(), kDescr, nros));
+  if (fsi_format) {
+    ros.resize((size_t)nros);
+    ruser.resize((size_t)nros);
+    rdescr.resize((size_t)nros * kDescr);
+    CHECK(fsr_fsi_read_rosettes(rosfile.c_str(), isup, ros.data(), ruser.data(), rdescr.data(), kDescr, nros));
+  }
   for (int r = 0; r < nros; ++r) {
     fsr_rosette& R = ros[(size_t)r];
     int bad = 0;
@@ -752,6 +824,53 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
       log.line("  ** Note: Nodal ordering for Rosette %d has been swapped", R.id);
     }
   }
+  if (!fsi_format)
+    // calcElmCoordSystem with useElCoordSys = .false. (strainRosetteModule.f90:506-583, gage.f90:216-229): the rosette sits in
+    // the centroid of its nodes, takes the element's Z axis and the given X direction projected into the element plane
+    for (int r = 0; r < nros; ++r) {
+      fsr_rosette& R = ros[(size_t)r];
+      double X[4][3], T[9];
+      for (int k = 0; k < R.numnod; ++k) for (int d = 0; d < 3; ++d) X[k][d] = xyz[3 * (size_t)(R.nodes[k] - 1) + d];
+      if (shell_element_axes(R.numnod, X, T, T + 3, T + 6)) FAIL("Could not calculate coordinate system for Rosette %d. Check the rosette definition.", ruser[(size_t)r]);
+      for (int d = 0; d < 3; ++d) { double sum = 0.0; for (int k = 0; k < R.numnod; ++k) sum += X[k][d]; R.rpos[9 + d] = sum / R.numnod; }
+      double* P = R.rpos;   // columns X, Y, Z, origin
+      if (T[6] * P[6] + T[7] * P[7] + T[8] * P[8] < kEpsDiv0) FAIL("Could not calculate coordinate system for Rosette %d. Check the rosette definition.", ruser[(size_t)r]);
+      for (int d = 0; d < 3; ++d) P[6 + d] = T[6 + d];
+      P[3] = P[7] * P[2] - P[8] * P[1]; P[4] = P[8] * P[0] - P[6] * P[2]; P[5] = P[6] * P[1] - P[7] * P[0];   // Y = Z x X
+      P[0] = P[4] * P[8] - P[5] * P[7]; P[1] = P[5] * P[6] - P[3] * P[8]; P[2] = P[3] * P[7] - P[4] * P[6];   // X = Y x Z
+      // orthoNorm3 = mat_to_quat + quat_to_mat (rotationModule.f90:441-497,549-558); rten(i,j) = P[3 (j-1) + (i-1)]
+      auto M = [&](int i, int j) -> double { return P[3 * (j - 1) + (i - 1)]; };
+      double q[5] = {0, 0, 0, 0, 0};   // q[1..4]
+      const double trace = M(1, 1) + M(2, 2) + M(3, 3);
+      int imax = 1;
+      if (M(2, 2) > M(imax, imax)) imax = 2;
+      if (M(3, 3) > M(imax, imax)) imax = 3;
+      if (trace > M(imax, imax)) {
+        q[1] = std::sqrt(1.0 + trace) * 0.5;
+        q[2] = (M(3, 2) - M(2, 3)) / (4.0 * q[1]);
+        q[3] = (M(1, 3) - M(3, 1)) / (4.0 * q[1]);
+        q[4] = (M(2, 1) - M(1, 2)) / (4.0 * q[1]);
+      } else {
+        const int i = imax, j = imax % 3 + 1, k = (imax + 1) % 3 + 1;
+        q[i + 1] = std::sqrt(M(i, i) * 0.5 + (1.0 - trace) * 0.25);
+        q[1] = (M(k, j) - M(j, k)) / (4.0 * q[i + 1]);
+        q[j + 1] = (M(j, i) + M(i, j)) / (4.0 * q[i + 1]);
+        q[k + 1] = (M(k, i) + M(i, k)) / (4.0 * q[i + 1]);
+      }
+      const double qn = std::sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[4] * q[4]);
+      for (int k = 1; k <= 4; ++k) q[k] /= qn;
+      double Rm[3][3];
+      Rm[0][0] = 2.0 * (q[2] * q[2] + q[1] * q[1]) - 1.0;
+      Rm[1][1] = 2.0 * (q[3] * q[3] + q[1] * q[1]) - 1.0;
+      Rm[2][2] = 2.0 * (q[4] * q[4] + q[1] * q[1]) - 1.0;
+      Rm[0][1] = 2.0 * (q[2] * q[3] - q[4] * q[1]);
+      Rm[0][2] = 2.0 * (q[2] * q[4] + q[3] * q[1]);
+      Rm[1][2] = 2.0 * (q[3] * q[4] - q[2] * q[1]);
+      Rm[1][0] = 2.0 * (q[3] * q[2] + q[4] * q[1]);
+      Rm[2][0] = 2.0 * (q[4] * q[2] - q[3] * q[1]);
+      Rm[2][1] = 2.0 * (q[4] * q[3] + q[2] * q[1]);
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) P[3 * j + i] = Rm[i][j];
+    }
   if (c.get_bool("nullify_start_rosettestrains"))   // gage.f90:312-320: every rosette starts from zero strain at the first step
     for (fsr_rosette& R : ros) R.zero_init = 1;
   fsr_gages* gages = nullptr;
@@ -768,11 +887,13 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
          "<7;\"Gage strain\";NONE;FLOAT;32;SCALAR>\n<8;\"Gage stress\";NONE;FLOAT;32;SCALAR>\n";
   // .fsi format: InitStrainRosette is called with calcDisp = .true. (gage.f90:203-214), so every rosette carries its node
   // deformations (written with -deformation) and its position + Euler angles in the global system (always written)
-  const bool lDef = c.get_bool("deformation");
+  // (the old rosette definition format goes without calcDisp: none of the three)
+  const bool lDisp = fsi_format;
+  const bool lDef = lDisp && c.get_bool("deformation");
   int nv = 8;
-  const int idDef = lDef ? ++nv : 0, idPos = ++nv, idAng = ++nv;
+  const int idDef = lDef ? ++nv : 0, idPos = lDisp ? ++nv : 0, idAng = lDisp ? ++nv : 0;
   if (lDef) { char b[128]; snprintf(b, sizeof(b), "<%d;\"Deformation\";LENGTH;FLOAT;32;VEC3;(3);((\"d_x\",\"d_y\",\"d_z\"))>\n", idDef); hdr += b; }
-  { char b[256]; snprintf(b, sizeof(b), "<%d;\"Position\";LENGTH;FLOAT;32;VEC3;(3);((\"x\",\"y\",\"z\"))>\n<%d;\"Euler angles\";ANGLE;FLOAT;32;ROT3;(3);((\"eps_x\",\"eps_y\",\"eps_z\"))>\n", idPos, idAng); hdr += b; }
+  if (lDisp) { char b[256]; snprintf(b, sizeof(b), "<%d;\"Position\";LENGTH;FLOAT;32;VEC3;(3);((\"x\",\"y\",\"z\"))>\n<%d;\"Euler angles\";ANGLE;FLOAT;32;ROT3;(3);((\"eps_x\",\"eps_y\",\"eps_z\"))>\n", idPos, idAng); hdr += b; }
   int maxg = 0;
   for (const fsr_rosette& R : ros) maxg = std::max(maxg, R.ngage);
   for (int j = 1; j <= maxg; ++j) { char b[64]; snprintf(b, sizeof(b), "[%d;\"Gage %d\";<7><8>]\n", j, j); hdr += b; }
@@ -800,10 +921,9 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
     line += "<3><4><5><6>";
     for (int j = 1; j <= R.ngage; ++j) { snprintf(b, sizeof(b), "[%d]", j); line += b; }
     line += node_groups[(size_t)r];
-    snprintf(b, sizeof(b), "<%d><%d>", idPos, idAng);
-    line += b;
+    if (lDisp) { snprintf(b, sizeof(b), "<%d><%d>", idPos, idAng); line += b; }
     hdr += line + "}\n";
-    nval += 8 + 2 * R.ngage + (lDef ? 3 * R.numnod : 0) + 6;
+    nval += 8 + 2 * R.ngage + (lDef ? 3 * R.numnod : 0) + (lDisp ? 6 : 0);
   }
   // X0 and T0 of every rosette (InitStrainRosette, strainRosetteModule.f90:753-764): node coordinates and initial element axes
   std::vector<double> X0((size_t)nros * 12), T0((size_t)nros * 9);
@@ -867,7 +987,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
       for (int k = 0; k < nw; ++k) for (int j = 0; j < 3; ++j) Q[(size_t)k * ndim + ndof2 + ngen + j] = grv[j];
     if (iFatigue > 0) memcpy(Qall.data() + (size_t)w0 * ndim, Q.data(), sizeof(double) * (size_t)nw * ndim);
     CHECK(fsr_gage_recover(gages, Q.data(), ndim, nw, vals.data()));
-    CHECK(fsr_expand_rows(part, Q.data(), ndim, nw, urows.data(), nur, Uw.data()));   // node displacements for CalcRosetteDisplacements
+    if (lDisp) CHECK(fsr_expand_rows(part, Q.data(), ndim, nw, urows.data(), nur, Uw.data()));   // node displacements for CalcRosetteDisplacements
     for (int k = 0; k < nw; ++k) {   // writeStrainGageDB (saveStrainGageModule.f90:196-262)
       size_t n = 0;
       for (int r = 0; r < nros; ++r) {
@@ -877,6 +997,7 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
         recbuf[n++] = (float)v[10]; recbuf[n++] = (float)v[11]; recbuf[n++] = (float)v[12];
         for (int j = 0; j < ros[(size_t)r].ngage; ++j) { recbuf[n++] = (float)v[18 + j]; recbuf[n++] = (float)v[21 + j]; }
         // CalcRosetteDisplacements (strainRosetteModule.f90:814-873): node deformations, position and Euler angles of the rosette
+        if (!lDisp) continue;   // old rosette definition format: no rosette displacement state
         const fsr_rosette& R = ros[(size_t)r];
         const double* u = Uw.data() + (size_t)k * nur + 12 * (size_t)r;
         const double* S = &supTr[12 * (size_t)k];

@@ -488,3 +488,85 @@ def test_direct_solution_without_solver_input_file(oracle, tmp_path):
     mx, mn = rec.envelope()
     assert np.abs(mx - want.max(0)).max() <= TOL * np.abs(want).max()
     rec.close()
+
+
+def _ortho_norm3(M):
+    """orthoNorm3 = mat_to_quat + quat_to_mat (rotationModule.f90:441-497,549-558), restated for the check"""
+    q = np.zeros(5)
+    tr = M[0, 0] + M[1, 1] + M[2, 2]
+    imax = int(np.argmax([M[0, 0], M[1, 1], M[2, 2]])) + 1
+    m = lambda i, j: M[i - 1, j - 1]
+    if tr > m(imax, imax):
+        q[1] = np.sqrt(1.0 + tr) * 0.5
+        q[2], q[3], q[4] = (m(3, 2) - m(2, 3)) / (4 * q[1]), (m(1, 3) - m(3, 1)) / (4 * q[1]), (m(2, 1) - m(1, 2)) / (4 * q[1])
+    else:
+        i, j, k = imax, imax % 3 + 1, (imax + 1) % 3 + 1
+        q[i + 1] = np.sqrt(m(i, i) * 0.5 + (1.0 - tr) * 0.25)
+        q[1] = (m(k, j) - m(j, k)) / (4 * q[i + 1])
+        q[j + 1] = (m(j, i) + m(i, j)) / (4 * q[i + 1])
+        q[k + 1] = (m(k, i) + m(i, k)) / (4 * q[i + 1])
+    q /= np.sqrt((q[1:] ** 2).sum())
+    R = np.empty((3, 3))
+    R[0, 0] = 2 * (q[2] * q[2] + q[1] * q[1]) - 1; R[1, 1] = 2 * (q[3] * q[3] + q[1] * q[1]) - 1; R[2, 2] = 2 * (q[4] * q[4] + q[1] * q[1]) - 1
+    R[0, 1] = 2 * (q[2] * q[3] - q[4] * q[1]); R[0, 2] = 2 * (q[2] * q[4] + q[3] * q[1]); R[1, 2] = 2 * (q[3] * q[4] - q[2] * q[1])
+    R[1, 0] = 2 * (q[3] * q[2] + q[4] * q[1]); R[2, 0] = 2 * (q[4] * q[2] - q[3] * q[1]); R[2, 1] = 2 * (q[4] * q[3] + q[2] * q[1])
+    return R
+
+
+def test_fedem_gage_old_rosette_definition_file(oracle, tmp_path):
+    """-rosfile in the old free-format layout (ReadStrainGageOldData, strainGageModule.f90:246-476): id type link nnod nodes zPos
+    X Z Emod nu per rosette, '#' comments, END; rosettes of other links are skipped, the position matrix is recomputed from the
+    element (centroid, element Z, X projected into the plane, orthoNorm3), dummy base ids idIn + 1000 link + 1e7 rdbinc, and
+    the results database carries no rosette displacement state."""
+    from fedem_solvers_b200.model import rosettes_on_part
+    part = plate_part(6, 5, ngen=4, seed=41, tri_fraction=0.3, warp=0.02, n_ext=4)
+    part.sam.minex = (500 + 2 * np.arange(part.sam.nnod)).astype(np.int32)
+    nsteps = 60
+    case = _make_case(tmp_path, part, "plate", nsteps=nsteps)
+    ros = rosettes_on_part(part, 2, seed=42, rtype="TRIPLE_GAGE_45") + rosettes_on_part(part, 1, seed=43, rtype="TRIPLE_GAGE_60") \
+        + rosettes_on_part(part, 1, seed=44, rtype="DOUBLE_GAGE_90") + rosettes_on_part(part, 1, seed=45, rtype="SINGLE_GAGE")
+    tcode = {"SINGLE_GAGE": 1, "DOUBLE_GAGE_90": 2, "TRIPLE_GAGE_60": 3, "TRIPLE_GAGE_45": 4}
+    lines = ["# id type link nnod nodes... zPos Xx Xy Xz Zx Zy Zz Emod nu"]
+    given_x = []
+    for k, r in enumerate(ros):
+        x = 2.5 * r.rpos[:, 0] + (0.05 * r.rpos[:, 2] if k == 1 else 0.0)      # not unit; one with an out-of-plane part
+        z = 0.7 * r.rpos[:, 2]
+        given_x.append(x / np.linalg.norm(x))
+        ext = [int(part.sam.minex[n - 1]) for n in r.nodes]
+        lines.append(f"{900 + k} {tcode[r.type]} 2 {len(ext)} " + " ".join(map(str, ext)) + f" {r.zpos:.12e}  # comment")
+        lines.append("   " + " ".join(f"{v:.15e}" for v in x) + "   " + " ".join(f"{v:.15e}" for v in z) + f" {r.emod:.6e} {r.nu:.4f}")
+        if k == 0:   # a rosette of another part in between
+            lines.append(f"77 1 5 3 {ext[0]} {ext[1]} {ext[2]} 0.0 1 0 0 0 0 1 2.1D11 0.3")
+    lines.append("END")
+    lines.append("this is never read")
+    (tmp_path / "rosettes.dat").write_text("\n".join(lines) + "\n")
+    exe = os.path.join(os.path.dirname(EXE), "fedem_gage")
+    r = subprocess.run([exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx",
+                        "-eigfile", "plate_E.fmx", "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rosfile", "rosettes.dat",
+                        "-rdbfile", "gage.frs", "-rdbinc", "1", "-stotm", "100", "-deformation"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Number of strain rosettes on this link =     5" in r.stdout
+    rd = FrsReader(str(tmp_path / "gage_1.frs"))
+    assert rd.nsteps == nsteps
+    b = oracle.bind_part(part)
+    for k, ro in enumerate(ros):
+        base_id = (k + 1) + 2 * 1000 + 1 * 10000000
+        # the position matrix the program must have built
+        Z = ro.rpos[:, 2]
+        Y = np.cross(Z, given_x[k]); X = np.cross(Y, Z)
+        P = _ortho_norm3(np.stack([X, Y, Z], 1))
+        want = type(ro)(**{**ro.__dict__})
+        want.rpos = np.concatenate([P, ro.rpos[:, 3:4]], 1)
+        Vo = oracle.rosette_history(b, want, case["Q"])
+        ng = ro.to_c().ngage
+        sc_e, sc_s = np.abs(Vo[:, :3]).max(), np.abs(Vo[:, 10:13]).max()
+        h = rd.find("Strain tensor", "Strain rosette", base_id)
+        assert h is not None, (k, base_id)
+        eps = rd.read(h)
+        wante = Vo[:, :3].copy(); wante[:, 2] *= 0.5
+        assert np.abs(eps - wante).max() <= 1.3e-7 * sc_e, k
+        assert np.abs(rd.read(rd.find("Stress tensor", "Strain rosette", base_id)) - Vo[:, 10:13]).max() <= 1.3e-7 * sc_s
+        for j in range(ng):
+            assert np.abs(rd.read(rd.find(f"Gage {j + 1}|Gage strain", "Strain rosette", base_id))[:, 0] - Vo[:, 18 + j]).max() <= 1.3e-7 * sc_e
+        assert rd.find("Position", "Strain rosette", base_id) is None and rd.find("Euler angles", "Strain rosette", base_id) is None
+    assert rd.find("Strain tensor", "Strain rosette", 6 + 2000 + 10000000) is None
