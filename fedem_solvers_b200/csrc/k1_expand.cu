@@ -323,6 +323,114 @@ k1_expand_kernel(const double* __restrict__ R, const double* __restrict__ Qt, do
   }
 }
 
+// The same kernel without a CTA-wide barrier per step chunk: a warp that has finished chunk c arrives on the chunk buffer's
+// "empty" mbarrier and goes straight on to chunk c + 1 (already in shared memory); thread 0 alone waits for the eight arrivals
+// before it refills the buffer with chunk c + 2.  The accumulators of chunk c are kept in a second register set and stored
+// between the k-tiles of chunk c + 1, so the tensor pipe does not drain while the results go out (190 registers; one CTA per
+// SM has 255 to spend).
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_expand_pipe_kernel(const double* __restrict__ R, const double* __restrict__ Qt, double* __restrict__ U,
+                      int ldk, int nsteps_pad, size_t ldu, const int* __restrict__ tiles)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sR = reinterpret_cast<double*>(smem_raw);   // [K1_BM][ldk]
+  double* sQ = sR + (size_t)K1_BM * ldk;              // 2 x [K1_BN][ldk]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + (size_t)2 * K1_BN * ldk); // [0]=R, [1..2]=Q full, [3..4]=Q empty
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int wm = warp & 3, wn = warp >> 2;
+  const size_t row0 = (size_t)(tiles ? __ldg(tiles + blockIdx.x) : (int)blockIdx.x) * K1_BM;
+  const int nchunks = nsteps_pad / K1_BN;
+  const uint32_t bytesR = (uint32_t)(K1_BM * ldk * sizeof(double));
+  const uint32_t bytesQ = (uint32_t)(K1_BN * ldk * sizeof(double));
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], K1_THREADS / 32);
+    mbar_init(&bars[4], K1_THREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], bytesR);
+    const uint32_t q = bytesR / 4;
+    const unsigned char* srcR = reinterpret_cast<const unsigned char*>(R + row0 * ldk);
+    for (int i = 0; i < 4; ++i)
+      tma_load_1d(reinterpret_cast<unsigned char*>(sR) + (size_t)i * q, srcR + (size_t)i * q, q, &bars[0]);
+    for (int c = 0; c < 2 && c < nchunks; ++c) {
+      mbar_expect_tx(&bars[1 + c], bytesQ);
+      tma_load_1d(sQ + (size_t)c * K1_BN * ldk, Qt + (size_t)c * K1_BN * ldk, bytesQ, &bars[1 + c]);
+    }
+  }
+  mbar_wait(&bars[0], 0);
+
+  const double* a_base = sR + (size_t)(wm * 32 + g) * ldk + t4;
+  double* u_row = U + (row0 + wm * 32 + g) * ldu + wn * 32 + 2 * t4;
+  const int ktiles = ldk >> 2, kq = ktiles >> 2;
+  double acc[4][4][2], prev[4][4][2];
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    mbar_wait(&bars[1 + buf], (uint32_t)((c >> 1) & 1));
+    const double* b_base = sQ + (size_t)buf * K1_BN * ldk + (size_t)(wn * 32 + g) * ldk + t4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double* u_prev = u_row + (size_t)(c - 1) * K1_BN;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      const int k_end = part == 3 ? ktiles : (part + 1) * kq;
+#pragma unroll 2
+      for (int kt = part * kq; kt < k_end; ++kt) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = a_base[(size_t)i * 8 * ldk + kt * 4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = b_base[(size_t)j * 8 * ldk + kt * 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      if (c > 0) {   // a quarter of the previous chunk's results goes out between the k-tiles of this one
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<double2*>(u_prev + (size_t)part * 8 * ldu + j * 8) = make_double2(prev[part][j][0], prev[part][j][1]);
+      }
+    }
+    // this warp is done with the chunk buffer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[3 + buf]);
+    if (tid == 0 && c + 2 < nchunks) {
+      mbar_wait(&bars[3 + buf], (uint32_t)((c >> 1) & 1));   // all eight warps have left it
+      mbar_expect_tx(&bars[1 + buf], bytesQ);
+      tma_load_1d(sQ + (size_t)buf * K1_BN * ldk, Qt + (size_t)(c + 2) * K1_BN * ldk, bytesQ, &bars[1 + buf]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { prev[i][j][0] = acc[i][j][0]; prev[i][j][1] = acc[i][j][1]; }
+  }
+  if (nchunks > 0) {
+    double* u_prev = u_row + (size_t)(nchunks - 1) * K1_BN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<double2*>(u_prev + (size_t)i * 8 * ldu + j * 8) = make_double2(prev[i][j][0], prev[i][j][1]);
+  }
+}
+
 // The same GEMM for reduced dimensions that do not fit the resident-K kernel (ldk > 108: superelements with many triads or
 // component modes): the K dimension is cut into slabs of 52 columns; a stage = the slab of the R row tile and of one 64-step
 // Q chunk, copied row by row with bulk TMA into one of two shared-memory buffers while the other is multiplied; the
@@ -429,6 +537,14 @@ int launch_k1_raw(const double* R, const double* Qt, double* U, int ldk, int nro
   if (smem > 227 * 1024 || force_slab) {
     if (int rc = smem_opt_in((const void*)k1_expand_slab_kernel, k1_slab_smem_bytes())) return rc;
     k1_expand_slab_kernel<<<blocks, K1_THREADS, k1_slab_smem_bytes(), s>>>(R, Qt, U, ldk, nsteps_pad, ldu, tiles);
+    FSR_LAUNCH_CHECK();
+    return FSR_OK;
+  }
+  // FSR_K1_PIPE=0: the version with a CTA barrier per step chunk (kept for comparison)
+  static const bool pipe = !(getenv("FSR_K1_PIPE") && atoi(getenv("FSR_K1_PIPE")) == 0);
+  if (pipe) {
+    if (int rc = smem_opt_in((const void*)k1_expand_pipe_kernel, 227 * 1024)) return rc;
+    k1_expand_pipe_kernel<<<blocks, K1_THREADS, smem + 2 * sizeof(uint64_t), s>>>(R, Qt, U, ldk, nsteps_pad, ldu, tiles);
     FSR_LAUNCH_CHECK();
     return FSR_OK;
   }
