@@ -935,8 +935,15 @@ __global__ void build_quad_planar_kernel(int ncand, const int* __restrict__ cele
 // edof2: [candidate][20] = rows of Up (u, v, theta1, theta2) of the four nodes, [16] = first result point of the element
 // (three CTAs per SM when the history is written: 80 registers without spills, measured 14.7 vs 16.0 ms; the envelope-only
 // variant would spill there and keeps two)
-template <bool WRITE_VM>
-__global__ void __launch_bounds__(256, WRITE_VM ? 3 : 2)
+constexpr int kPlStages = 3;            // staged variant: 16-step pairs in flight per warp
+constexpr int kPlRow = 20;              // doubles per staged row: 16 steps + 4 of padding (conflict-free 8-byte fragment reads)
+__device__ __forceinline__ void pl_cp_async16(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <bool WRITE_VM, bool STAGED = false>
+__global__ void __launch_bounds__(256, (WRITE_VM || STAGED) ? 3 : 2)
 k2_quad_planar_vm_kernel(const double* __restrict__ Up, size_t ldu, int nsteps, int nsteps_pad, const double* __restrict__ Pfrag,
                          const int* __restrict__ edof2, int nlist, const int* __restrict__ list, double* __restrict__ vm,
                          size_t ld_vm, double* __restrict__ env_max, double* __restrict__ env_min)
@@ -967,7 +974,53 @@ k2_quad_planar_vm_kernel(const double* __restrict__ Up, size_t ldu, int nsteps, 
   double emax = 0.0, emin = kHuge;
   const int ntiles = nsteps_pad >> 3;
   const int nfull = ((nsteps >> 3) >> 1) << 1;   // tiles (in pairs) with all 8 steps valid
-  {
+  if (STAGED) {
+    // The sixteen U rows of the element, 16 steps at a time, go through shared memory with cp.async (kPlStages pairs in
+    // flight per warp, no registers tied up by the prefetch).  Staged row (blk * 2 + j) * 4 + t4 = the row lane t4 reads as
+    // B operand of k-tile j of block blk (0 membrane, 1 bending).
+    extern __shared__ __align__(16) double pl_smem[];
+    double* st = pl_smem + (size_t)warp * kPlStages * 16 * kPlRow;
+    // this lane copies four 16-byte pieces per pair: piece q = lane + 32 i -> staged row q / 8, steps 2 (q % 8)
+    const double* src[4];
+    int dst[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = lane + 32 * i, sr = q >> 3, c2 = (q & 7) * 2;
+      const int blk = sr >> 3, k = 4 * ((sr >> 2) & 1) + (sr & 3);
+      src[i] = Up + (size_t)__ldg(ed + 4 * (k >> 1) + 2 * blk + (k & 1)) * ldu + c2;
+      dst[i] = sr * kPlRow + c2;
+    }
+    const int npairs = nfull >> 1;
+    auto issue = [&](int pr) {
+      if (pr < npairs) {
+        double* d = st + (size_t)(pr % kPlStages) * 16 * kPlRow;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pl_cp_async16(d + dst[i], src[i] + (size_t)pr * 16);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int pr = 0; pr < kPlStages - 1; ++pr) issue(pr);
+    double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
+    double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
+    const size_t ld8 = ld_vm * 8;
+    for (int pr = 0; pr < npairs; ++pr) {
+      issue(pr + kPlStages - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kPlStages - 1) : "memory");
+      __syncwarp();
+      const double* d = st + (size_t)(pr % kPlStages) * 16 * kPlRow + t4 * kPlRow + g;
+      double ma[2], ra[2], mb[2], rb[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        ma[j] = d[(size_t)j * 4 * kPlRow];     mb[j] = d[(size_t)j * 4 * kPlRow + 8];
+        ra[j] = d[(size_t)(2 + j) * 4 * kPlRow]; rb[j] = d[(size_t)(2 + j) * 4 * kPlRow + 8];
+      }
+      quad_flat_tile<WRITE_VM, false, 2>(am, ab, ma, ra, sgn, vmp0, vmp1, ld8, 0, 0, emax, emin);
+      quad_flat_tile<WRITE_VM, false, 2>(am, ab, mb, rb, sgn, vmp0, vmp1, ld8, 0, 0, emax, emin);
+      __syncwarp();   // the stage is refilled by the next iteration's issue
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
     double* vmp0 = WRITE_VM ? vm + (size_t)(2 * t4) * ld_vm + pt : nullptr;
     double* vmp1 = WRITE_VM ? vmp0 + ld_vm : nullptr;
     const size_t ld8 = ld_vm * 8;
@@ -1287,7 +1340,19 @@ static int launch_shell_family(fsr_part* p, FamilyData& f, int nsteps, int nstep
   const int* gen_list = nullptr;
   if (KT == 6 && f.fast2 && f.nsub[2] > 0) {  // quads of flat regions: in-plane rows
     const unsigned grid = (unsigned)((f.nsub[2] + warps - 1) / warps);
-    if (vm_dev)
+    // U rows through shared memory with cp.async (default; measured 14.58 vs 14.78 ms with the history, 11.6 vs 11.9 without);
+    // FSR_PLANAR_STAGED=0 keeps the register prefetch
+    static const bool staged = !(getenv("FSR_PLANAR_STAGED") && atoi(getenv("FSR_PLANAR_STAGED")) == 0);
+    const size_t st_smem = sizeof(double) * warps * kPlStages * 16 * kPlRow;
+    if (staged && vm_dev) {
+      if (int rc = smem_opt_in((const void*)k2_quad_planar_vm_kernel<true, true>, st_smem)) return rc;
+      k2_quad_planar_vm_kernel<true, true><<<grid, warps * 32, st_smem, s>>>(p->Up, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast2, f.edof2,
+                                                                             f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min);
+    } else if (staged) {
+      if (int rc = smem_opt_in((const void*)k2_quad_planar_vm_kernel<false, true>, st_smem)) return rc;
+      k2_quad_planar_vm_kernel<false, true><<<grid, warps * 32, st_smem, s>>>(p->Up, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast2, f.edof2,
+                                                                              f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min);
+    } else if (vm_dev)
       k2_quad_planar_vm_kernel<true><<<grid, warps * 32, 0, s>>>(p->Up, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast2, f.edof2, f.nsub[2],
                                                                  f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min);
     else
