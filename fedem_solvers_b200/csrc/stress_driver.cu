@@ -334,7 +334,7 @@ static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fs
                       const char* model_file, const std::string& linkfile, const std::vector<int>& madof, const std::vector<int>& minex,
                       int ndof2, int ngen, int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                       const std::vector<double>& tru, int gen_first, const std::vector<int>& stepno, const std::vector<double>& times, bool lgrav,
-                      const double* grv);
+                      const double* grv, const std::vector<int>& melcon, const std::vector<int>& elmid);
 
 static int run_program(int which)
 {
@@ -553,7 +553,8 @@ static int run_program(int which)
   if (!modes) log.line("           --> %d of %d time steps selected in [%g, %g], increment %g", nsel, nall, statm, stotm, tinc);
   if (modes)
     return modes_part(c, log, what, part, db, isup, user_id, descr[0] ? descr : linkfile.c_str(), model_file, linkfile, madof, minex, ndof2, ngen, ntriads,
-                      tb, tnd, tfd, tru, gen_first, stepno, times, lgrav, grv);
+                      tb, tnd, tfd, tru, gen_first, stepno, times, lgrav, grv,
+                      std::vector<int>(melcon.begin(), melcon.begin() + nel), std::vector<int>(elmid.begin(), elmid.begin() + nel));
   if (gage)
     return gage_part(c, log, what, part, ftl, db, isup, user_id, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
                      sel, nsel, stepno, times, lgrav, grv, madof);
@@ -1132,36 +1133,43 @@ static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fs
                       const char* model_file, const std::string& linkfile, const std::vector<int>& madof, const std::vector<int>& minex,
                       int ndof2, int ngen, int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
                       const std::vector<double>& tru, int gen_first, const std::vector<int>& stepno, const std::vector<double>& times, bool lgrav,
-                      const double* grv)
+                      const double* grv, const std::vector<int>& melcon, const std::vector<int>& elmid)
 {
-  // --- -recover_modes <<t1,m1,m2,..>,<t2,..>> (convertModeOption, stressInterface.C:30-83)
+  // --- -recover_modes <<t1,m1,m2,..>,<t2,..>> (getModesToExpand, stressInterface.C:30-83): the union of the mode numbers in order
+  // of first appearance, processThisMode[step][mode]
   const std::string opt = c.get_string("recover_modes");
   const std::vector<std::string> tt = bracket_tokens(opt);
   if (tt.empty()) FAIL("fedem_modes: No time steps, check option -recover_modes \"%s\"", opt.c_str());
-  std::vector<double> tsteps;
+  const int nStep = (int)tt.size();
+  std::vector<double> tsteps((size_t)nStep, 0.0);
   std::vector<int> modeNum;
-  for (size_t i = 0; i < tt.size(); ++i) {
-    const std::vector<std::string> mt = bracket_tokens(tt[i]);
-    if (mt.size() < 2) FAIL("fedem_modes: No modes at time step %zu check sub-token \"%s\" in -recover_modes", i, tt[i].c_str());
-    tsteps.push_back(atof(mt[0].c_str()));
-    std::vector<int> here;
-    for (size_t j = 1; j < mt.size(); ++j) here.push_back(atoi(mt[j].c_str()));
-    if (i == 0) modeNum = here;
-    else {
-      std::vector<int> a = modeNum, b = here;
-      std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
-      if (a != b) FAIL("different mode lists at different times (one results file per mode, modes.f90:263-301) are not part of this build");
+  std::vector<std::vector<char>> process;   // [mode][step]
+  for (int i = 0; i < nStep; ++i) {
+    const std::vector<std::string> mt = bracket_tokens(tt[(size_t)i]);
+    if (mt.size() < 2) FAIL("fedem_modes: No modes at time step %d check sub-token \"%s\" in -recover_modes", i, tt[(size_t)i].c_str());
+    tsteps[(size_t)i] = atof(mt[0].c_str());
+    for (size_t j = 1; j < mt.size(); ++j) {
+      const int jMode = atoi(mt[j].c_str());
+      size_t k = 0;
+      while (k < modeNum.size() && modeNum[k] != jMode) ++k;
+      if (k == modeNum.size()) { modeNum.push_back(jMode); process.emplace_back((size_t)nStep, (char)0); }
+      process[k][(size_t)i] = 1;
     }
   }
   const int nMode = (int)modeNum.size();
-  if (c.get_bool("energy_density")) FAIL("-energy_density (one results file per mode with the scaled strain energy density) is not part of this build");
-  if (!c.get_bool("write_vector") || c.get_bool("write_nodes")) FAIL("only the vector form of the modal results (-write_vector without -write_nodes, the default) is part of this build");
   if (!c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
-  const bool lComplex = c.get_bool("damped"), lDouble = c.get_bool("double");
+  const bool lComplex = c.get_bool("damped"), lDouble = c.get_bool("double"), lEnergy = c.get_bool("energy_density");
   const int ncomp = lComplex ? 2 : 1, nnod = (int)madof.size() - 1, ndof = madof.back() - 1;
+
+  // --- initWriteDisp (saveStressModule.f90:79-108): vector form if asked for and possible, nodal form otherwise or on request
+  bool lVector = c.get_bool("write_vector"), lNodes = true;
+  for (int i = 0; i < nnod && lVector; ++i) if (madof[(size_t)i + 1] < madof[(size_t)i] + 3) lVector = false;
+  if (lVector) lNodes = c.get_bool("write_nodes");
+  bool all_processed = true;
+  for (const std::vector<char>& pm : process) for (char f : pm) all_processed = all_processed && f;
+  const bool multiFiles = lNodes || lEnergy || !all_processed;   // modes.f90:258-261
   int ntra = 0, nrot = 0;
   for (int i = 0; i < nnod; ++i) {
-    if (madof[(size_t)i + 1] < madof[(size_t)i] + 3) FAIL("node %d has fewer than 3 DOFs: the vector form is impossible (initWriteDisp) and the nodal form is not part of this build", minex[(size_t)i]);
     if (minex[(size_t)i] < 0) continue;   // internal beam nodes
     ntra += 3;
     if (madof[(size_t)i + 1] >= madof[(size_t)i] + 6) nrot += 3;
@@ -1180,77 +1188,224 @@ static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fs
   }
   const int hsup = fsr_frs_find(db, "Position matrix", "Part", isup);
 
-  // --- Writing result database headers (writeModesHeader)
+  // --- Writing result database headers (writeModesHeader :356-426: all shapes as vectors in one file; writeModeHeader :259-343: one
+  //     file for the dynamic response and one per mode, with the nodal form and / or the scaled strain energy density)
   log.line("           --> Writing result database headers");
-  const int nbit = lDouble ? 64 : 32;
-  std::string hdr = rdb_file_preamble("fedem_modes", model_file, linkfile.c_str(), "modes data base file");
-  hdr += "VARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n";
-  char b[512];
-  snprintf(b, sizeof(b), "<%3d;\"Translational deformation\";LENGTH;FLOAT;%2d;VECTOR;(%8d)>\n", 3, nbit, ntra); hdr += b;
-  if (nrot > 0) { snprintf(b, sizeof(b), "<%3d;\"Angular deformation\";LENGTH;FLOAT;%2d;VECTOR;(%8d)>\n", 4, nbit, nrot); hdr += b; }
-  hdr += "DATABLOCKS:\n<1><2>\n{\"Part\";";
-  if (isup > 0) { snprintf(b, sizeof(b), "%d;", isup); hdr += b; } else hdr += ";";
-  if (user_id > 0) { snprintf(b, sizeof(b), "%d;", user_id); hdr += b; } else hdr += ";";
-  if (descr && *descr) { snprintf(b, sizeof(b), "\"%s\";\n", descr); hdr += b; } else hdr += ";\n";
-  hdr += "  [;\"Vectors\";\n";
-  auto block = [&](const char* name, bool compl_) {
-    if (nrot > 0) {
-      if (compl_) snprintf(b, sizeof(b), "    [;\"%s\";[;\"Re\";<%3d><%3d>][;\"Im\";<%3d><%3d>]]\n", name, 3, 4, 3, 4);
-      else snprintf(b, sizeof(b), "    [;\"%s\";<%3d><%3d>]\n", name, 3, 4);
-    } else {
-      if (compl_) snprintf(b, sizeof(b), "    [;\"%s\";[;\"Re\";<%3d>][;\"Im\";<%3d>]]\n", name, 3, 3);
-      else snprintf(b, sizeof(b), "    [;\"%s\";<%3d>]\n", name, 3);
+  const int nbit = lDouble ? 64 : 32, nel = (int)melcon.size();
+  std::vector<int> ptoff((size_t)nel + 1, 0);
+  if (lEnergy) CHECK(fsr_result_point_offsets(part, ptoff.data()));
+  // one header: comps = 1 (dynamic response) or ncomp; vectors = the names of the [;"Vectors"; entries (single-file form: all of them);
+  // returns the number of values of a step record
+  auto make_header = [&](const std::vector<std::string>& names, const std::vector<bool>& compl_, bool nodes, bool vectors_wrapped, bool energy,
+                         std::string& hdr) -> long long {
+    std::string vard = rdb_file_preamble("fedem_modes", model_file, linkfile.c_str(), "modes data base file");
+    vard += "VARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n";
+    std::string item, datd = "DATABLOCKS:\n<1><2>\n{\"Part\";";
+    char b[512];
+    if (isup > 0) { snprintf(b, sizeof(b), "%d;", isup); datd += b; } else datd += ";";
+    if (user_id > 0) { snprintf(b, sizeof(b), "%d;", user_id); datd += b; } else datd += ";";
+    if (descr && *descr) { snprintf(b, sizeof(b), "\"%s\";\n", descr); datd += b; } else datd += ";\n";
+    int nvar = 2, nig = 0;
+    long long nval = 0;
+    const bool cx = compl_[0];
+    if (nodes) {   // writeNodesHeader :459-537 (iDef = 1)
+      int idDis = 0, idRot = 0, id3 = 0, id6 = 0;
+      datd += "  [;\"Nodes\";\n";
+      for (int i = 0; i < nnod; ++i) {
+        const int nd = madof[(size_t)i + 1] - madof[(size_t)i];
+        if (nd < 3) continue;
+        if (!idDis) { idDis = ++nvar; snprintf(b, sizeof(b), "<%3d;\"Translational deformation\";LENGTH;FLOAT;%2d;VEC3;(3);((\"d_x\",\"d_y\",\"d_z\"))>\n", idDis, nbit); vard += b; }
+        int ig;
+        if (nd > 5) {
+          if (!idRot) { idRot = ++nvar; snprintf(b, sizeof(b), "<%3d;\"Angular deformation\";ANGLE;FLOAT;%2d;ROT3;(3);((\"theta_x\",\"theta_y\",\"theta_z\"))>\n", idRot, nbit); vard += b; }
+          if (!id6) {
+            id6 = ++nig;
+            if (cx) snprintf(b, sizeof(b), "[%3d;\"%s\";[;\"Re\";<%3d><%3d>][;\"Im\";<%3d><%3d>]]\n", id6, names[0].c_str(), idDis, idRot, idDis, idRot);
+            else snprintf(b, sizeof(b), "[%3d;\"%s\";<%3d><%3d>]\n", id6, names[0].c_str(), idDis, idRot);
+            item += b;
+          }
+          ig = id6; nval += cx ? 12 : 6;
+        } else {
+          if (!id3) {
+            id3 = ++nig;
+            if (cx) snprintf(b, sizeof(b), "[%3d;\"%s\";[;\"Re\";<%3d>][;\"Im\";<%3d>]]\n", id3, names[0].c_str(), idDis, idDis);
+            else snprintf(b, sizeof(b), "[%3d;\"%s\";<%3d>]\n", id3, names[0].c_str(), idDis);
+            item += b;
+          }
+          ig = id3; nval += cx ? 6 : 3;
+        }
+        snprintf(b, sizeof(b), "    [;%8d;[%3d]]\n", minex[(size_t)i], ig); datd += b;
+      }
+      datd += "  ]\n";
     }
-    hdr += b;
+    if (lVector) {   // :538-588
+      int idDis = 0, idRot = 0;
+      if (vectors_wrapped) datd += "  [;\"Vectors\";\n";
+      for (size_t k = 0; k < names.size(); ++k) {
+        if (!idDis) { idDis = ++nvar; snprintf(b, sizeof(b), "<%3d;\"Translational deformation\";LENGTH;FLOAT;%2d;VECTOR;(%8d)>\n", idDis, nbit, ntra); vard += b; }
+        if (nrot > 0 && !idRot) { idRot = ++nvar; snprintf(b, sizeof(b), "<%3d;\"Angular deformation\";LENGTH;FLOAT;%2d;VECTOR;(%8d)>\n", idRot, nbit, nrot); vard += b; }
+        const char* name = names[k].c_str();
+        if (nrot > 0) {
+          if (compl_[k]) snprintf(b, sizeof(b), "    [;\"%s\";[;\"Re\";<%3d><%3d>][;\"Im\";<%3d><%3d>]]\n", name, idDis, idRot, idDis, idRot);
+          else snprintf(b, sizeof(b), "    [;\"%s\";<%3d><%3d>]\n", name, idDis, idRot);
+        } else {
+          if (compl_[k]) snprintf(b, sizeof(b), "    [;\"%s\";[;\"Re\";<%3d>][;\"Im\";<%3d>]]\n", name, idDis, idDis);
+          else snprintf(b, sizeof(b), "    [;\"%s\";<%3d>]\n", name, idDis);
+        }
+        datd += b;
+        nval += (long long)(ntra + nrot) * (compl_[k] ? 2 : 1);
+      }
+      if (vectors_wrapped) datd += "  ]\n";
+    }
+    if (energy) {   // writeElementsHeader with lStrRes(9) only (:625-752, shell groups :1158-1175, solid groups :1327-1338)
+      int idE = 0, ig[64] = {};
+      datd += "  [;\"Elements\";\n";
+      for (int e = 0; e < nel; ++e) {
+        if (elmid[(size_t)e] <= 0 || ptoff[(size_t)e + 1] == ptoff[(size_t)e]) continue;
+        const int t = melcon[(size_t)e], key = t == 23 ? 21 : t == 24 ? 22 : t;
+        const char* tn = nullptr;
+        int nelnod = 0;
+        bool shell = false;
+        switch (key) {
+          case 21: tn = "TRI3"; nelnod = 3; shell = true; break;
+          case 22: tn = "QUAD4"; nelnod = 4; shell = true; break;
+          case 31: tn = "TRI6"; nelnod = 6; shell = true; break;
+          case 32: tn = "QUAD8"; nelnod = 8; shell = true; break;
+          case 41: tn = "TET10"; nelnod = 10; break;
+          case 42: tn = "WEDG15"; nelnod = 15; break;
+          case 43: tn = "HEX20"; nelnod = 20; break;
+          case 44: tn = "HEX8"; nelnod = 8; break;
+          case 45: tn = "TET4"; nelnod = 4; break;
+          case 46: tn = "WEDG6"; nelnod = 6; break;
+          default: continue;
+        }
+        if (!ig[key]) {
+          ig[key] = ++nig;
+          if (!idE) { idE = ++nvar; snprintf(b, sizeof(b), "<%3d;\"Scaled strain energy density\";FORCE/AREA;FLOAT;%2d;SCALAR>\n", idE, nbit); vard += b; }
+          snprintf(b, sizeof(b), "[%3d;\"%s\";\n  [;\"Element nodes\";\n", ig[key], tn); item += b;
+          for (const char* side : {"Top", "Bottom", "Basic"}) {
+            if (shell == (side[1] == 'a')) continue;   // shells: Top + Bottom, solids: Basic
+            snprintf(b, sizeof(b), "    [;\"%s\";\n", side); item += b;
+            for (int i = 1; i <= nelnod; ++i) { snprintf(b, sizeof(b), "      [;%2d;<%3d>]\n", i, idE); item += b; }
+            item += "    ]\n";
+          }
+          item += "  ]\n]\n";
+        }
+        snprintf(b, sizeof(b), "    [;%8d;[%3d]]\n", elmid[(size_t)e], ig[key]); datd += b;
+        nval += ptoff[(size_t)e + 1] - ptoff[(size_t)e];
+      }
+      datd += "  ]\n";
+    }
+    datd += "}\n";
+    hdr = vard + item + datd;
+    return nval;
   };
-  block("Dynamic response", false);
-  for (int j = 0; j < nMode; ++j) { char nm[32]; snprintf(nm, sizeof(nm), "Mode%3d", modeNum[(size_t)j]); block(nm, lComplex); }
-  hdr += "  ]\n}\n";
-  const long long nvalues = (long long)(ntra + nrot) * (1 + (long long)nMode * ncomp);
-  std::string path = file_name("rdbfile", ".frs");
-  {
-    const int inc = c.get_int("rdbinc");
-    if (inc > 0) {
+  // openRDBfile (rdbModule.f90:300-318): every new file takes the next increment number
+  int next_inc = c.get_int("rdbinc");
+  if (multiFiles && next_inc <= 0) next_inc = 1;
+  const std::string base_path = file_name("rdbfile", ".frs");
+  auto next_path = [&]() {
+    std::string path = base_path;
+    if (next_inc > 0) {
       const size_t dot = path.rfind('.'), sep = path.rfind('/');
       char t[16];
-      snprintf(t, sizeof(t), "_%d", inc);
+      snprintf(t, sizeof(t), "_%d", next_inc++);
       if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) path.insert(dot, t);
       else path += t;
     }
+    return path;
+  };
+  struct OutFile { fsr_frs_writer* w = nullptr; long long nval = 0; };
+  std::vector<OutFile> files(multiFiles ? (size_t)nMode + 1 : 1);
+  struct WGuard { std::vector<OutFile>& f; ~WGuard() { for (OutFile& x : f) if (x.w) fsr_frs_finish(x.w); } } w_guard{files};
+  auto mode_name = [&](int j) { char nm[32]; snprintf(nm, sizeof(nm), "Mode%3d", modeNum[(size_t)j]); return std::string(nm); };
+  if (multiFiles) {
+    for (int f = 0; f <= nMode; ++f) {
+      if (f > 0 && std::find(process[(size_t)f - 1].begin(), process[(size_t)f - 1].end(), (char)1) == process[(size_t)f - 1].end()) {
+        log.line("  ** Note: Eigenmode%3d will not be expanded", modeNum[(size_t)f - 1]);
+        continue;
+      }
+      std::string hdr;
+      files[(size_t)f].nval = make_header({f == 0 ? std::string("Dynamic response") : mode_name(f - 1)}, {f > 0 && lComplex}, lNodes, true, f > 0 && lEnergy, hdr);
+      const std::string path = next_path();
+      CHECK(fsr_frs_create_tagged(&files[(size_t)f].w, path.c_str(), "#FEDEM modal data", 0, hdr.c_str(), files[(size_t)f].nval * (nbit / 8)));
+      log.line("           --> Results database file: %s (%lld bytes per time step)", path.c_str(), 12 + files[(size_t)f].nval * (nbit / 8));
+    }
+  } else {
+    std::vector<std::string> names{"Dynamic response"};
+    std::vector<bool> cx{false};
+    for (int j = 0; j < nMode; ++j) { names.push_back(mode_name(j)); cx.push_back(lComplex); }
+    std::string hdr;
+    files[0].nval = make_header(names, cx, false, true, false, hdr);
+    const std::string path = next_path();
+    CHECK(fsr_frs_create_tagged(&files[0].w, path.c_str(), "#FEDEM modal data", 0, hdr.c_str(), files[0].nval * (nbit / 8)));
+    log.line("           --> Results database file: %s (%lld bytes per time step)", path.c_str(), 12 + files[0].nval * (nbit / 8));
   }
-  fsr_frs_writer* w = nullptr;
-  CHECK(fsr_frs_create_tagged(&w, path.c_str(), "#FEDEM modal data", 0, hdr.c_str(), nvalues * (nbit / 8)));
-  struct WGuard { fsr_frs_writer*& p; ~WGuard() { if (p) fsr_frs_finish(p); } } w_guard{w};
-  log.line("           --> Results database file: %s (%lld bytes per time step)", path.c_str(), 12 + nvalues * (nbit / 8));
 
   // --- Time step loop
   log.line("           --> Starting time loop");
   const int nmodes_g = ngen + (lgrav ? 3 : 0), ndim = ndof2 + nmodes_g, ncols = 1 + nMode * ncomp, nall = (int)times.size();
   std::vector<double> Q((size_t)ndim * ncols), sv((size_t)ncols * ndof), supTr(12), eig;
-  std::vector<double> rec_d(lDouble ? (size_t)nvalues : 0);
-  std::vector<float> rec_f(lDouble ? 0 : (size_t)nvalues);
   int ndofs_tot = 0;
   for (int i = 0; i < ntriads; ++i) ndofs_tot += tnd[(size_t)i];
   eig.resize((size_t)std::max(ndofs_tot, 1) * ncomp);
-  std::vector<double> geig((size_t)std::max(ngen, 1) * ncomp);
+  std::vector<double> geig((size_t)std::max(ngen, 1) * ncomp), rec;
+  std::vector<float> rec_f;
+  const int npts = lEnergy ? fsr_num_result_points(part) : 0;
+  std::vector<double> sig(lEnergy ? (size_t)6 * std::max(npts, 1) : 0), eps(sig.size());
+  // writeDisplacementDB (:1437-1515) for the columns [col0, col0 + nc) of sv
+  auto put_displacements = [&](int col0, int nc, bool nodes) {
+    if (nodes)
+      for (int i = 0; i < nnod; ++i) {
+        const int j0 = madof[(size_t)i] - 1, nd = madof[(size_t)i + 1] - madof[(size_t)i];
+        if (nd < 3) continue;
+        for (int l = 0; l < nc; ++l) {
+          const double* u = sv.data() + (size_t)(col0 + l) * ndof + j0;
+          rec.insert(rec.end(), u, u + (nd > 5 ? 6 : 3));
+        }
+      }
+    if (lVector)
+      for (int l = 0; l < nc; ++l) {   // all translations, then all rotations, per component
+        const double* u = sv.data() + (size_t)(col0 + l) * ndof;
+        for (int i = 0; i < nnod; ++i) {
+          if (minex[(size_t)i] < 0) continue;
+          const int j0 = madof[(size_t)i] - 1;
+          rec.insert(rec.end(), u + j0, u + j0 + 3);
+        }
+        for (int i = 0; i < nnod; ++i) {
+          if (minex[(size_t)i] < 0 || madof[(size_t)i + 1] < madof[(size_t)i] + 6) continue;
+          const int j0 = madof[(size_t)i] - 1 + 3;
+          rec.insert(rec.end(), u + j0, u + j0 + 3);
+        }
+      }
+  };
+  auto write_record = [&](OutFile& f, int step, double time) -> int {
+    if ((long long)rec.size() != f.nval) { set_error("internal: modal record of %zu values, header says %lld", rec.size(), f.nval); return FSR_ERR_STATE; }
+    if (lDouble) return fsr_frs_write_step(f.w, step, time, rec.data());
+    rec_f.assign(rec.begin(), rec.end());
+    return fsr_frs_write_step(f.w, step, time, rec_f.data());
+  };
   int nerr = 0;
-  for (size_t it = 0; it < tsteps.size(); ++it) {
+  for (int it = 0; it < nStep; ++it) {
     // ffr_setposition: the first key >= wanted - FLT_EPSILON, clamped to the ends (FFrResultContainer.C:953-1010)
     int idx = -1;
     if (nall > 0) {
-      const double wanted = tsteps[it];
+      const double wanted = tsteps[(size_t)it];
       if (times[0] > wanted) idx = 0;
       else if (wanted > times[(size_t)nall - 1]) idx = nall - 1;
       else idx = (int)(std::upper_bound(times.begin(), times.begin() + nall, wanted - 1.1920928955078125e-07) - times.begin());
     }
-    if (idx < 0 || idx >= nall) { ++nerr; log.line(" *** Error: Error searching for results at time =%12.5E", tsteps[it]); continue; }
+    if (idx < 0 || idx >= nall) { ++nerr; log.line(" *** Error: Error searching for results at time =%12.5E", tsteps[(size_t)it]); continue; }
     std::fill(Q.begin(), Q.end(), 0.0);
     CHECK(fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, idx, 1, Q.data(), ndim));
     for (int j = 0; j < 12; ++j) supTr[(size_t)j] = (j == 0 || j == 4 || j == 8) ? 1.0 : 0.0;
     if (hsup >= 0) CHECK(fsr_frs_read(db, hsup, idx, 1, supTr.data(), 12, 12));
     if (lgrav)   // g = matmul(grv, sup%supTr(:,1:3)) (modes.f90:364-367)
       for (int j = 0; j < 3; ++j) Q[(size_t)ndof2 + ngen + j] = grv[0] * supTr[3 * j] + grv[1] * supTr[3 * j + 1] + grv[2] * supTr[3 * j + 2];
+    int nproc = 0;
     for (int j = 0; j < nMode; ++j) {   // readSupElModes
+      if (!process[(size_t)j][(size_t)it]) continue;
+      ++nproc;
       size_t off = 0;
       for (int i = 0; i < ntriads; ++i) {
         const int n = tnd[(size_t)i] * ncomp;
@@ -1262,26 +1417,46 @@ static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fs
                                  Q.data() + (size_t)ndim * (1 + j * ncomp), ndim));
     }
     CHECK(fsr_expand(part, Q.data(), ndim, ncols, sv.data()));
-    size_t n = 0;
-    auto put = [&](double x) { if (lDouble) rec_d[n++] = x; else rec_f[n++] = (float)x; };
-    for (int col = 0; col < ncols; ++col) {   // writeDisplacementDB: all translations, then all rotations, per component
-      const double* u = sv.data() + (size_t)col * ndof;
-      for (int i = 0; i < nnod; ++i) {
-        if (minex[(size_t)i] < 0) continue;
-        const int j0 = madof[(size_t)i] - 1;
-        put(u[j0]); put(u[j0 + 1]); put(u[j0 + 2]);
-      }
-      for (int i = 0; i < nnod; ++i) {
-        if (minex[(size_t)i] < 0 || madof[(size_t)i + 1] < madof[(size_t)i] + 6) continue;
-        const int j0 = madof[(size_t)i] - 1 + 3;
-        put(u[j0]); put(u[j0 + 1]); put(u[j0 + 2]);
+    const int step = stepno[(size_t)idx];
+    const double time = times[(size_t)idx];
+    if (!multiFiles) {
+      rec.clear();
+      put_displacements(0, ncols, false);
+      CHECK(write_record(files[0], step, time));
+    } else {
+      rec.clear();
+      put_displacements(0, 1, lNodes);
+      CHECK(write_record(files[0], step, time));
+      for (int j = 0; j < nMode; ++j) {
+        if (!process[(size_t)j][(size_t)it]) continue;
+        rec.clear();
+        put_displacements(1 + j * ncomp, ncomp, lNodes);
+        if (lEnergy) {
+          // calcStrainEnergyDensity (modesRoutines.f90:219-305): sum(sigma*epsilon) with the shear terms counted twice, of the (real part of
+          // the) mode shape, at every result point of every element in SAM order
+          CHECK(fsr_recover_step_full(part, Q.data() + (size_t)ndim * (1 + j * ncomp), nullptr, sig.data(), eps.data(), nullptr, nullptr));
+          for (int e = 0; e < nel; ++e) {
+            if (elmid[(size_t)e] <= 0) continue;
+            const int t = melcon[(size_t)e];
+            const bool plane = t >= 21 && t <= 24;
+            if (!plane && !(t == 31 || t == 32 || (t >= 41 && t <= 46))) continue;
+            for (int n = ptoff[(size_t)e]; n < ptoff[(size_t)e + 1]; ++n) {
+              const double *s = sig.data() + 6 * (size_t)n, *x = eps.data() + 6 * (size_t)n;
+              double v;
+              if (std::fabs(s[0]) >= 1.0e300) v = kHuge;   // stress calculation failed, write hugeVal
+              else if (plane) v = s[0] * x[0] + s[1] * x[1] + s[2] * x[2] + s[2] * x[2];
+              else v = s[0] * x[0] + s[1] * x[1] + s[2] * x[2] + 2.0 * (s[3] * x[3] + s[4] * x[4] + s[5] * x[5]);
+              rec.push_back(v);
+            }
+          }
+        }
+        CHECK(write_record(files[(size_t)j + 1], step, time));
       }
     }
-    CHECK(fsr_frs_write_step(w, stepno[(size_t)idx], times[(size_t)idx], lDouble ? (const void*)rec_d.data() : (const void*)rec_f.data()));
-    log.line("           --> ......Simulation time : %12.5E  (step %d, %d modes expanded)", times[(size_t)idx], stepno[(size_t)idx], nMode);
+    log.line("           --> ......Simulation time : %12.5E  (step %d, %d modes expanded)", time, step, nproc);
   }
   log.line("           --> Done time loop. Closing database files");
-  { fsr_frs_writer* x = w; w = nullptr; CHECK(fsr_frs_finish(x)); }
+  for (OutFile& f : files) if (f.w) { fsr_frs_writer* x = f.w; f.w = nullptr; CHECK(fsr_frs_finish(x)); }
   if (nerr) { log.line("\n    %s failed :-(", what); return -nerr; }
   log.line("           ================>  END OF PROGRAM MODES  <================");
   log.line("\n    %s successfully completed :-)  (%.2f s CPU)", what, (double)(clock() - log.t0) / CLOCKS_PER_SEC);

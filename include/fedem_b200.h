@@ -585,8 +585,10 @@ int solveGage(void);
  * for every time listed in -recover_modes <t1 m1 m2 ..> <t2 ..> the dynamic response and the listed eigenmodes of the
  * solver's modal results ("Eigenvectors|Mode n" of the part's triads and of the part) are expanded to all nodes (K1) and
  * written as vector data to one modal results file (writeModesHeader / writeDisplacementDB "Vectors" grammar, file tag
- * "#FEDEM modal data"); -damped = complex modes (Re / Im).  One file per mode (different mode lists per time,
- * -energy_density, -write_nodes) and VTF export are not part of this build. */
+ * "#FEDEM modal data"); -damped = complex modes (Re / Im).  Different mode lists per time, -write_nodes or -energy_density
+ * give one file for the dynamic response and one per mode instead (writeModeHeader :259-343, file increments in creation
+ * order), with the nodal form (writeNodesHeader :459-537) and the scaled strain energy density per result point
+ * (calcStrainEnergyDensity, modesRoutines.f90:219-305: one full K1 + K2 pass per mode).  VTF export is not part of this build. */
 int solveModes(void);
 void fsr_modes_define_options(void);   /* the option table of fedem_modes (modesmain.C:22-52) */
 /* ffr_getnextstep (fedem-foundation/src/FFrLib/FFrExtractorInterface.f90:134-170) over a sorted key list:

@@ -437,6 +437,77 @@ def test_fedem_modes_executable(oracle, tmp_path, damped):
         ref.close()
 
 
+def test_fedem_modes_one_file_per_mode_nodes_and_energy_density(oracle, tmp_path):
+    """modes.f90:258-301,428-452: different mode lists per time, -write_nodes and -energy_density give one results file for the dynamic
+    response and one per mode (file increments in creation order); the mode files hold records only for the times at which the mode was
+    asked for, the nodal form next to the vector form, and the scaled strain energy density (calcStrainEnergyDensity) per result point."""
+    part = plate_part(5, 4, ngen=3, seed=53, tri_fraction=0.3, warp=0.02, n_ext=4)
+    case = _make_case(tmp_path, part, "plate", nsteps=12)
+    sam = part.sam
+    ntriads, ngen, nmodes = sam.ndof2 // 6, sam.ngen, 3
+    rng = np.random.default_rng(54)
+    triads = [(11 + i, 1 + i, "") for i in range(ntriads)]
+    steps = [3, 8]
+    modal = _write_modal_file(str(tmp_path / "ev_p_1.frs"), rng, triads, case["base"], ngen, [case["stepno"][k] for k in steps],
+                              [case["times"][k] for k in steps], nmodes, 1)
+    exe = os.path.join(os.path.dirname(EXE), "fedem_modes")
+    sel = f"<<{case['times'][3]:.4f},2,1>,<{case['times'][8]:.4f},2,3>>"       # mode order of first appearance: 2, 1, 3
+    args = [exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx", "-eigfile",
+            "plate_E.fmx", "-fsifile", "fedem_solver.fsi", "-frsfile", "<th_p_1.frs,ev_p_1.frs>", "-rdbfile", "modes.frs", "-double",
+            "-rdbinc", "4", "-write_nodes", "-energy_density", "-recover_modes", sel]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    b = oracle.bind_part(part)
+    base = case["base"]
+
+    def mode_q(k, m):
+        tri, gen = modal[int(case["stepno"][k])]
+        tinv = case["sup"][k][:, :3].T
+        q = np.zeros(sam.ndim)
+        for t in range(ntriads):
+            e = tri[t, m - 1][:6]
+            q[6 * t: 6 * t + 3] = tinv @ e[:3]
+            q[6 * t + 3: 6 * t + 6] = tinv @ e[3:]
+        q[sam.ndof2:] = gen[m - 1][:ngen]
+        return q
+    # file 4 = dynamic response (both times), 5 = mode 2 (both), 6 = mode 1 (first time only), 7 = mode 3 (second time only)
+    expect = {4: (None, [3, 8]), 5: (2, [3, 8]), 6: (1, [3]), 7: (3, [8])}
+    for inc, (m, ks) in expect.items():
+        out = str(tmp_path / f"modes_{inc}.frs")
+        assert open(out, "rb").read(17) == b"#FEDEM modal data"
+        rd = FrsReader(out)
+        assert rd.nsteps == len(ks) and np.array_equal(rd.step_numbers, [case["stepno"][k] for k in ks]), inc
+        name = "Dynamic response" if m is None else f"Mode{m:3d}"
+        for row, k in enumerate(ks):
+            q = case["Q"][:, k] if m is None else mode_q(k, m)
+            sv = oracle.expand(b, q)
+            tra = np.concatenate([sv[sam.madof[i] - 1: sam.madof[i] + 2] for i in range(sam.nnod)])
+            got = rd.read(rd.find(f"Vectors|{name}|Translational deformation", "Part", base))[row]
+            assert np.abs(got - tra).max() <= TOL * np.abs(tra).max(), (inc, k)
+            for node in (0, sam.nnod // 2, sam.nnod - 1):       # the nodal form
+                j = sam.madof[node] - 1
+                got = rd.read(rd.find(f"Nodes|{int(sam.minex[node])}|{name}|Translational deformation", "Part", base))[row]
+                assert np.abs(got - sv[j:j + 3]).max() <= TOL * np.abs(tra).max(), (inc, k, node)
+                got = rd.read(rd.find(f"Nodes|{int(sam.minex[node])}|{name}|Angular deformation", "Part", base))[row]
+                assert np.abs(got - sv[j + 3:j + 6]).max() <= TOL * np.abs(sv).max(), (inc, k, node)
+            if m is None:
+                assert rd.find(f"Elements|{part.elm.elmid[0]}|QUAD4|Element nodes|Top|1|Scaled strain energy density", "Part", base) is None
+                continue
+            o = oracle.calc_stresses(b, sv)
+            dens = (o["stress"][:, :3] * o["strain"][:, :3]).sum(axis=1) + o["stress"][:, 2] * o["strain"][:, 2]
+            for e in (0, sam.nel // 2, sam.nel - 1):
+                t = int(sam.melcon[e])
+                tn, nn = ("QUAD4", 4) if t == 24 else ("TRI3", 3)
+                for side, off in (("Top", 0), ("Bottom", nn)):
+                    for i in range(nn):
+                        h = rd.find(f"Elements|{part.elm.elmid[e]}|{tn}|Element nodes|{side}|{i + 1}|Scaled strain energy density", "Part", base)
+                        assert h is not None, (inc, e, side, i)
+                        got = rd.read(h)[row]
+                        want = dens[b["ptoff"][e] + off + i]
+                        assert abs(got - want) <= 1e-9 * np.abs(dens).max(), (inc, e, side, i, got, want)
+    assert not os.path.exists(tmp_path / "modes_8.frs")
+
+
 def test_direct_solution_without_solver_input_file(oracle, tmp_path):
     """fedem_stress without -fsifile (stress.f90:131-135,397): the results files hold the nodal displacements of the part
     themselves ("Vectors|Dynamic response|Displacement", readIntDisplacements) -- no B / E matrices, no expansion, the element
