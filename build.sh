@@ -20,5 +20,6 @@ mkdir -p fedem_solvers_b200/bin
 g++ -O2 -o fedem_solvers_b200/bin/fedem_stress $SRC/stress_main.cpp -L$OUT -lfedem_b200 -Wl,-rpath,'$ORIGIN/../lib'
 g++ -O2 -o fedem_solvers_b200/bin/fedem_gage $SRC/gage_main.cpp -L$OUT -lfedem_b200 -Wl,-rpath,'$ORIGIN/../lib'
 g++ -O2 -o fedem_solvers_b200/bin/fedem_modes $SRC/modes_main.cpp -L$OUT -lfedem_b200 -Wl,-rpath,'$ORIGIN/../lib'
+g++ -O2 -o fedem_solvers_b200/bin/fedem_fpp $SRC/fpp_main.cpp -L$OUT -lfedem_b200 -Wl,-rpath,'$ORIGIN/../lib'
 make -s -C oracle all
 echo "built $OUT/libfedem_b200.so"

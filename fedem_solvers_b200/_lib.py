@@ -45,6 +45,12 @@ class FsrRdbOptions(C.Structure):
                 ("minex", C.POINTER(C.c_int)), ("sup_tr_init", C.POINTER(C.c_double))]
 
 
+class FsrStrainCoat(C.Structure):
+    _fields_ = [("id", C.c_int), ("nnod", C.c_int), ("npts", C.c_int), ("elm_id", C.c_int), ("nodes", C.c_int * 8),
+                ("mat_id", C.c_int * 3), ("res_set", C.c_int * 3), ("sn_curve", (C.c_int * 2) * 3),
+                ("emod", C.c_double * 3), ("nu", C.c_double * 3), ("zpos", C.c_double * 3), ("scf", C.c_double * 3)]
+
+
 class FsrOptions(C.Structure):
     _fields_ = [("device", C.c_int), ("stressForm", C.c_int), ("step_tile", C.c_int),
                 ("reserved", C.c_int * 5)]
@@ -167,6 +173,15 @@ SYMBOLS = [
     ("fsr_ftl_get_topology", C.c_int, [_P, C.c_int, _I, _I, _I]),
     ("fsr_ftl_get_elmdata", C.c_int, [_P, _D, _D, _D, _D, _I, _D, _I]),
     ("fsr_ftl_ext2int", C.c_int, [_P, C.c_int, C.c_int]),
+    ("fsr_ftl_num_strain_coats", C.c_int, [_P]),
+    ("fsr_ftl_get_strain_coats", C.c_int, [_P, C.POINTER(FsrStrainCoat), C.c_int]),
+    ("fsr_gage_set_coat_fatigue", C.c_int, [_P, _D]),
+    ("fsr_sn_read", C.c_int, [C.POINTER(_P), C.c_char_p]),
+    ("fsr_sn_free", None, [_P]),
+    ("fsr_sn_num_standards", C.c_int, [_P]),
+    ("fsr_sn_num_curves", C.c_int, [_P, C.c_int]),
+    ("fsr_sn_get", C.c_int, [_P, C.c_int, C.c_int, _I, _D, _D, _D, C.c_int]),
+    ("fsr_sn_value", C.c_double, [_P, C.c_int, C.c_int, C.c_double]),
     ("fsr_fsi_open", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int]),
     ("fsr_fsi_close", None, [_P]),
     ("fsr_fsi_part", C.c_int, [_P, _I, C.c_char_p, C.c_int, _I, _I, _D, _D, C.c_char_p, C.c_int]),
@@ -186,6 +201,8 @@ SYMBOLS = [
     ("solveStress", C.c_int, []),
     ("solveGage", C.c_int, []),
     ("solveModes", C.c_int, []),
+    ("solveFpp", C.c_int, []),
+    ("fsr_fpp_define_options", None, []),
     ("fsr_modes_define_options", None, []),
     ("fsr_gage_define_options", None, []),
     ("fsr_select_steps", C.c_int, [_D, C.c_int, C.c_double, C.c_double, C.c_double, _I, C.c_int]),

@@ -54,6 +54,8 @@ struct Elem {
   const ElmType* type = nullptr;
   std::vector<int> nodes;             // external ids as read; after resolve: indices into nodes_
   std::map<std::string, int> attr;    // attribute type -> id
+  std::vector<int> pstrc;             // strain coat elements: every {PSTRC id} in file order (multiple references allowed)
+  int fe = 0;                         // strain coat elements: {FE id}, the underlying finite element
   bool calc = true;
 };
 struct Field {                         // one LABEL{entries {REF id opts} ...} record
@@ -96,6 +98,8 @@ struct fsr_ftl {
   std::vector<Node> nodes;                 // sorted by id
   std::vector<Elem> elems;                 // sorted by id
   std::map<std::string, std::map<int, std::vector<double>>> attrs;
+  std::map<std::string, std::map<int, std::map<std::string, int>>> attr_refs;   // attribute -> the attributes it refers to
+  std::map<int, std::string> pstrc_name;                                         // PSTRC id -> "Bottom" / "Mid" / "Top"
   std::map<int, std::vector<int>> groups;  // id -> element ids
   std::vector<int> fe_nodes;               // indices of nodes with DOFs        (internal node number - 1)
   std::vector<int> fe_elems;               // indices of the finite elements    (internal element number - 1)
@@ -230,7 +234,9 @@ struct fsr_ftl {
           if (!r.second.first.empty() && r.first[0] != 'V' && r.first != "FE") {
             std::string key = r.first == "PBEAMORIENT" || r.first == "PBUSHORIENT" ? "PORIENT" : r.first;
             e.attr[key] = r.second.first.front();
-          }
+            if (key == "PSTRC") e.pstrc.push_back(r.second.first.front());
+          } else if (r.first == "FE" && !r.second.first.empty())
+            e.fe = r.second.first.front();
         elems.push_back(e);
       } else if (fl.label == "GROUP") {
         int id = 0;
@@ -251,6 +257,8 @@ struct fsr_ftl {
           else v.push_back(0.0);
         }
         attrs[key][id] = v;
+        for (auto& r : fl.refs) if (!r.second.first.empty()) attr_refs[key][id][r.first] = r.second.first.front();
+        if (key == "PSTRC" && fl.entries.size() > 1) pstrc_name[id] = fl.entries[1];
       }
       // visuals, loads, coordinate systems etc. are not on the recovery path and are skipped
     }
@@ -599,6 +607,82 @@ int fsr_ftl_get_elmdata(const fsr_ftl* h, double* emod, double* rny, double* rho
 }
 
 // ffl_ext2int (:716-737): internal number of a node (is_node != 0) or finite element; 0/-1 when absent
+// ffl_getnostrc (FFlLinkHandler_F.C:1753-1762): strain coat elements whose calculation flag is on
+int fsr_ftl_num_strain_coats(const fsr_ftl* h)
+{
+  if (!h) return FSR_ERR_ARG;
+  int n = 0;
+  for (const Elem& e : h->elems) if (e.type->cat == STRC && e.calc) ++n;
+  return n;
+}
+
+// ffl_getstraincoat (:1640-1701) + getStrainCoatAttributes (:1587-1630) for all strain coat elements in element order
+int fsr_ftl_get_strain_coats(const fsr_ftl* h, fsr_strain_coat* out, int cap)
+{
+  if (!h || (cap > 0 && !out)) { set_error("fsr_ftl_get_strain_coats: bad arguments"); return FSR_ERR_ARG; }
+  auto ref_of = [&](const char* type, int id, const char* to) -> int {
+    auto t = h->attr_refs.find(type);
+    if (t == h->attr_refs.end()) return 0;
+    auto a = t->second.find(id);
+    if (a == t->second.end()) return 0;
+    auto r = a->second.find(to);
+    return r == a->second.end() ? 0 : r->second;
+  };
+  auto values = [&](const char* type, int id) -> const std::vector<double>* {
+    auto t = h->attrs.find(type);
+    if (t == h->attrs.end()) return nullptr;
+    auto a = t->second.find(id);
+    return a == t->second.end() ? nullptr : &a->second;
+  };
+  int n = 0;
+  for (const Elem& e : h->elems) {
+    if (e.type->cat != STRC || !e.calc) continue;
+    if (n < cap) {
+      fsr_strain_coat& c = out[n];
+      memset(&c, 0, sizeof(c));
+      c.id = e.id;
+      // every second node of the 6- and 8-noded elements is skipped
+      for (size_t i = 0; i < e.nodes.size(); i += e.nodes.size() > 4 ? 2 : 1) {
+        auto it = h->ext2int_node.find(h->nodes[(size_t)e.nodes[i]].id);
+        c.nodes[c.nnod++] = it == h->ext2int_node.end() ? -1 : it->second;
+      }
+      const std::vector<double>* fat = nullptr;
+      { auto f = e.attr.find("PFATIGUE"); if (f != e.attr.end()) fat = values("PFATIGUE", f->second); }
+      for (int ps : e.pstrc) {
+        if (c.npts >= 3) { set_error("Invalid strain coat definition. Too many points: element %d", e.id); return FSR_ERR_ARG; }
+        const int k = c.npts++;
+        c.sn_curve[k][0] = c.sn_curve[k][1] = -1;
+        auto nm = h->pstrc_name.find(ps);
+        std::string name = nm == h->pstrc_name.end() ? "" : nm->second;
+        for (char& ch : name) ch = (char)toupper((unsigned char)ch);
+        c.res_set[k] = name == "BOTTOM" ? 1 : name == "MID" ? 2 : name == "TOP" ? 3 : 0;
+        if (const int mid = ref_of("PSTRC", ps, "PMAT"))
+          if (const std::vector<double>* m = values("PMAT", mid)) {
+            c.mat_id[k] = mid;
+            c.emod[k] = m->size() > 0 ? (*m)[0] : 0.0;
+            c.nu[k] = m->size() > 2 ? (*m)[2] : 0.0;
+          }
+        if (const int hid = ref_of("PSTRC", ps, "PHEIGHT")) {
+          if (const std::vector<double>* hv = values("PHEIGHT", hid)) c.zpos[k] = hv->empty() ? 0.0 : (*hv)[0];
+        } else if (const int tid = ref_of("PSTRC", ps, "PTHICKREF")) {
+          const std::vector<double>* tr = values("PTHICKREF", tid);
+          const int thid = ref_of("PTHICKREF", tid, "PTHICK");
+          const std::vector<double>* th = thid ? values("PTHICK", thid) : nullptr;
+          if (tr && th && !th->empty()) c.zpos[k] = (*th)[0] * (tr->empty() ? 0.0 : (*tr)[0]);
+        }
+        if (fat) {
+          c.sn_curve[k][0] = fat->size() > 0 ? (int)(*fat)[0] : 0;
+          c.sn_curve[k][1] = fat->size() > 1 ? (int)(*fat)[1] : 0;
+          c.scf[k] = fat->size() > 2 ? (*fat)[2] : 0.0;
+        }
+      }
+      c.elm_id = e.fe;
+    }
+    ++n;
+  }
+  return n;
+}
+
 int fsr_ftl_ext2int(const fsr_ftl* h, int is_node, int id)
 {
   if (!h || id <= 0) return 0;

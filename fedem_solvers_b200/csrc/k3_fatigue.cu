@@ -325,9 +325,10 @@ int fsr_fatigue_set_gage_params(fsr_fatigue_state* f, const double* gate, const 
     std::vector<double> c5((size_t)5 * f->ngage);
     for (int g = 0; g < f->ngage; ++g) {
       const double* c = curve + 4 * (size_t)g;
-      if (c[3] == c[2]) { set_error("gage %d: S-N slopes m1 == m2", g); return FSR_ERR_ARG; }
+      if (c[3] == c[2] && c[0] != c[1]) { set_error("gage %d: S-N slopes m1 == m2", g); return FSR_ERR_ARG; }
       for (int k = 0; k < 4; ++k) c5[5 * (size_t)g + k] = c[k];
-      c5[5 * (size_t)g + 4] = (c[3] * c[0] - c[2] * c[1]) / (c[3] - c[2]);  // FFpSNCurve.C:12-15
+      // FFpSNCurve.C:12-15; twice the same line = a one-segment curve of the S-N library: always the second segment
+      c5[5 * (size_t)g + 4] = c[3] == c[2] ? -kHuge : (c[3] * c[0] - c[2] * c[1]) / (c[3] - c[2]);
     }
     FSR_CUDA(cudaMemcpy(f->curve, c5.data(), sizeof(double) * c5.size(), cudaMemcpyHostToDevice));
   }

@@ -36,7 +36,7 @@ struct fsr_gages {
   double* hist = nullptr;     // [4*nros][tile] fatigue series, gage-major
   double* values = nullptr;   // [tile][nros][NVAL] staging for host output
   double* Qstage = nullptr; size_t Qstage_cap = 0;
-  double* cmat = nullptr;     // [nros][4]: C11, C12, C33, unused
+  double* cmat = nullptr;     // [nros][4]: C11, C12, C33, strain coat SCF (0 = strain gage: fatigue series of sigmaP(1))
   double* tg = nullptr;       // [nros][9] Teps_NfromC of up to three legs
   double* eps0 = nullptr;     // [nros][3] epsCInit
   int* ngage = nullptr;       // [nros]
@@ -120,7 +120,9 @@ __device__ __forceinline__ void gage_point(const double* __restrict__ eps, size_
   double radius = sqrt(d12 * d12 + 4.0 * s[2] * s[2]) * 0.5;
   const double sp1 = origo + radius, sp2 = origo - radius, tmax = radius;
   // fatigue series: sigmaP(1) and the leg stresses in MPa (strainGageModule.f90:711-716)
-  hist[(size_t)(4 * r) * ld_hist + t] = sp1 * to_mpa;
+  // strain coats: the signed abs-max principal stress in MPa times the stress concentration factor (strainCoatModule.f90:385-400)
+  const double scf = cmat[4 * r + 3];
+  hist[(size_t)(4 * r) * ld_hist + t] = scf != 0.0 ? (fabs(sp1) > fabs(sp2) ? sp1 : sp2) * to_mpa * scf : sp1 * to_mpa;
 #pragma unroll
   for (int i = 0; i < 3; ++i) hist[(size_t)(4 * r + 1 + i) * ld_hist + t] = sg[i] * to_mpa;
   if (WANT) {
@@ -513,6 +515,18 @@ int fsr_gage_recover(fsr_gages* g, const double* Q, int ldq, int nsteps, double*
     }
   }
   FSR_CUDA(cudaStreamSynchronize(s));
+  return FSR_OK;
+}
+
+int fsr_gage_set_coat_fatigue(fsr_gages* g, const double* scf)
+{
+  if (!g) { set_error("fsr_gage_set_coat_fatigue: bad arguments"); return FSR_ERR_ARG; }
+  FSR_CUDA(cudaSetDevice(g->device));
+  std::vector<double> z((size_t)std::max(g->nros, 1), 0.0);
+  if (scf) std::copy(scf, scf + g->nros, z.begin());
+  FSR_CUDA(cudaStreamSynchronize(g->stream));
+  if (g->nros > 0)
+    FSR_CUDA(cudaMemcpy2D(g->cmat + 3, 4 * sizeof(double), z.data(), sizeof(double), sizeof(double), (size_t)g->nros, cudaMemcpyHostToDevice));
   return FSR_OK;
 }
 

@@ -31,7 +31,7 @@ using namespace fsr;
 namespace {
 
 CmdLine g_cmd;
-bool g_stress_options_defined = false, g_gage_options_defined = false, g_modes_options_defined = false;
+bool g_stress_options_defined = false, g_gage_options_defined = false, g_modes_options_defined = false, g_fpp_options_defined = false;
 
 std::string strip_ext_add(const std::string& link, const char* suffix)
 {
@@ -308,12 +308,71 @@ void fsr_modes_define_options(void)
   g_modes_options_defined = true;
 }
 
+// The option table of fedem_fpp: the standard options + fppmain.C:21-68.
+void fsr_fpp_define_options(void)
+{
+  CmdLine& c = g_cmd;
+  c.add("fao", "", "Read additional options from this file");
+  c.add("fco", "", "Read calculation options from this file");
+  c.add("fop", "", "Read output options from this file");
+  c.add("cwd", "", "Change working directory");
+  c.add("help", false, "Print out this help text");
+  c.add("helpAll", false, "Print out this help text\nincluding the private options, if any", false);
+  c.add("version", false, "Print out program version");
+  c.add("debug", 0, "Debug print switch");
+  c.add("terminal", 6, "File unit number for terminal output");
+  c.add("consolemsg", false, "Output error messages to console");
+  c.add("Bramsize", -1, "In-core size (MB) of displacement recovery matrix\n< 0: Use the same as in the reducer (default)\n= 0: Store full matrix in core");
+  c.add("dmramsize", -1, "Same as -Bramsize but in terms of double words", false);
+  c.add("linkId", 0, "Link base-ID number");
+  c.add("linkfile", "", "Name of link input file");
+  c.add("Bmatfile", "", "Name of B-matrix file");
+  c.add("eigfile", "", "Name of eigenvector file");
+  c.add("dispfile", "", "Name of gravitation displacement file");
+  c.add("resfile", "", "Name of result output file");
+  c.add("samfile", "", "Name of SAM data file");
+  c.add("fsifile", "fedem_solver.fsi", "Name of solver input file");
+  c.add("resStressFile", "", "Name of residual stress input file");
+  c.add("resStressSet", "", "Name of residual stress set");
+  c.add("frsfile", "", "Name of solver results database file");
+  c.add("fppfile", "", "Name of fpp output file");
+  c.add("rdbfile", "", "Name of strain coat results database file");
+  c.add("rdbinc", 1, "Increment number for the results database file");
+  c.add("double", false, "Save results in double precision");
+  c.add("writeHistory", false, "Write history frs-files instead", false);
+  c.add("oldRange", false, "Use old stress/strain range meassures", false);
+  c.add("group", "", "List of element groups to do calculations for");
+  c.add("blockSize", 2000, "Max number of elements processed together");
+  c.add("BufSizeInc", 20, "Buffer increment size");
+  c.add("PVXGate", 10.0, "Gate value for the Peak Valley extraction\n(MPa or microns depending on HistDataType)");
+  c.add("biAxialGate", 10.0, "Gate value for the biaxiality calculation");
+  c.add("angleBins", 541, "Number of bins in search for most popular angle");
+  c.add("HistXMin", -100.0, "Histogram min X-value");
+  c.add("HistXMax", 100.0, "Histogram max X-value");
+  c.add("HistYMin", -100.0, "Histogram min Y-value");
+  c.add("HistYMax", 100.0, "Histogram max Y-value");
+  c.add("HistXBins", 64, "Histogram number of X-bins");
+  c.add("HistYBins", 64, "Histogram number of Y-bins");
+  c.add("HistDataType", 0, "Histogram data type\n= 0: None\n= 1: Signed abs max stress\n= 2: Signed abs max strain");
+  c.add("surface", 0, "Surface selection option\n= 0: All element surfaces\n= 1: Bottom shell surfaces only\n= 2: Middle shell surfaces only\n= 3: Top shell surfaces only");
+  c.add("SNfile", "", "Name of SN-curve definition file");
+  c.add("stressToMPaScale", 1.0e-6, "Stress convertion factor to MPa");
+  c.add("statm", 0.0, "Start time");
+  c.add("stotm", 1.0, "Stop time");
+  c.add("tinc", 0.0, "Time increment (= 0.0: process all time steps)");
+  // B200 additions
+  c.add("device", 0, "CUDA device ordinal");
+  c.add("stepTile", 0, "Time steps per device batch (0 = from free device memory)");
+  g_fpp_options_defined = true;
+}
+
 void initSolverArgs(int argc, char** argv)
 {
   g_cmd = CmdLine();
   g_cmd.init(argc, argv);
   g_gage_options_defined = false;
   g_modes_options_defined = false;
+  g_fpp_options_defined = false;
   fsr_stress_define_options();
 }
 
@@ -330,6 +389,11 @@ static int gage_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr
                      const std::vector<double>& tru, int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno,
                      const std::vector<double>& times, bool lgrav, const double* grv, const std::vector<int>& madof);
 
+static int fpp_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, int user_id, const char* descr,
+                    const char* model_file, const std::string& linkfile, const std::vector<double>& xyz, int ndof2, int ngen, int ntriads,
+                    const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd, const std::vector<double>& tru,
+                    int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno, const std::vector<double>& times,
+                    bool lgrav, const double* grv, const std::vector<int>& madof);
 static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_frs* db, int isup, int user_id, const char* descr,
                       const char* model_file, const std::string& linkfile, const std::vector<int>& madof, const std::vector<int>& minex,
                       int ndof2, int ngen, int ntriads, const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd,
@@ -338,13 +402,15 @@ static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fs
 
 static int run_program(int which)
 {
-  const bool gage = which == 1, modes = which == 2;
-  const char* what = gage ? "Strain gage recovery" : modes ? "Modal recovery" : "Stress calculation";
-  const char* prog = gage ? "fedem_gage" : modes ? "fedem_modes" : "fedem_stress";
+  const bool gage = which == 1, modes = which == 2, fpp = which == 3;
+  const char* what = gage ? "Strain gage recovery" : modes ? "Modal recovery" : fpp ? "Strain coat calculation" : "Stress calculation";
+  const char* prog = gage ? "fedem_gage" : modes ? "fedem_modes" : fpp ? "fedem_fpp" : "fedem_stress";
   if (gage) {
-    if (!g_gage_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_modes_options_defined = false; fsr_gage_define_options(); }
+    if (!g_gage_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_modes_options_defined = g_fpp_options_defined = false; fsr_gage_define_options(); }
   } else if (modes) {
-    if (!g_modes_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_gage_options_defined = false; fsr_modes_define_options(); }
+    if (!g_modes_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_gage_options_defined = g_fpp_options_defined = false; fsr_modes_define_options(); }
+  } else if (fpp) {
+    if (!g_fpp_options_defined) { g_cmd.clear_options(); g_stress_options_defined = g_gage_options_defined = g_modes_options_defined = false; fsr_fpp_define_options(); }
   } else if (!g_stress_options_defined)
     fsr_stress_define_options();
   CmdLine& c = g_cmd;
@@ -365,14 +431,15 @@ static int run_program(int which)
   struct CtxJoin { std::thread& t; ~CtxJoin() { if (t.joinable()) t.join(); } } ctx_join{ctx_thread};
 
   Log log;
-  log.open(file_name("resfile", gage ? "_gage.res" : modes ? "_modes.res" : "_stress.res"), gage ? "Strain Gage Recovery" : modes ? "Modal Recovery" : "Stress Recovery");
-  log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : modes ? "MODES" : "STRESS");
+  log.open(file_name("resfile", gage ? "_gage.res" : modes ? "_modes.res" : fpp ? "_fpp.res" : "_stress.res"),
+           gage ? "Strain Gage Recovery" : modes ? "Modal Recovery" : fpp ? "Damage Recovery" : "Stress Recovery");
+  log.line("\n           ================> START OF PROGRAM %s <================", gage ? "GAGE" : modes ? "MODES" : fpp ? "FPP" : "STRESS");
   if (gage) {
     if (c.get_bool("writeAsciiFiles")) log.line("  ** Note: ASCII / DAC rosette result files (-writeAsciiFiles) are not part of this build; ignored");
   } else
-  if (c.is_set("resStressFile")) log.line("  ** Note: residual stress import (-resStressFile) is not part of this build; ignored");
-  if (c.is_set("VTFfile") && !c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
-  if (c.get_bool("dumpDefNas")) log.line("  ** Note: Nastran deformation dump (-dumpDefNas) is not part of this build; ignored");
+  if (!modes && c.is_set("resStressFile")) log.line("  ** Note: residual stress import (-resStressFile) is not part of this build; ignored");
+  if (!fpp && c.is_set("VTFfile") && !c.get_string("VTFfile").empty()) log.line("  ** Note: VTF export (-VTFfile) is not part of this build; ignored");
+  if (!fpp && c.get_bool("dumpDefNas")) log.line("  ** Note: Nastran deformation dump (-dumpDefNas) is not part of this build; ignored");
   if (which == 0 && c.get_bool("nodalForces")) log.line("  ** Note: nodal force print-out (-nodalForces, stressRoutines.f90:128) is not part of this build; ignored");
 
   // --- Read the link file (ffl_init)
@@ -382,7 +449,7 @@ static int run_program(int which)
   fsr_ftl* ftl = nullptr;
   CHECK(fsr_ftl_open(&ftl, linkfile.c_str()));
   struct FtlGuard { fsr_ftl* p; ~FtlGuard() { fsr_ftl_close(p); } } ftl_guard{ftl};
-  const std::string groups = c.get_string("group");
+  const std::string groups = modes ? std::string() : c.get_string("group");
   if (!groups.empty()) CHECK(fsr_ftl_activate_groups(ftl, groups.c_str()));
   int fsz[12];
   const int nael = fsr_ftl_sizes(ftl, fsz);
@@ -478,7 +545,8 @@ static int run_program(int which)
   fsr_options po;
   memset(&po, 0, sizeof(po));
   po.device = c.get_int("device"); po.stressForm = c.get_int("stressForm"); po.step_tile = c.get_int("stepTile");
-  if (!gage) { po.reserved[1] = c.get_int("ffqStressForm") + 1; po.reserved[2] = c.get_int("fftStressForm") + 1; }
+  if (!gage && !fpp) { po.reserved[1] = c.get_int("ffqStressForm") + 1; po.reserved[2] = c.get_int("fftStressForm") + 1; }
+  if (fpp) po.stressForm = 0;
   // fedem_stress spreads the elements of the part over several GPUs (element blocks, sharded.cu) when the part is large;
   // nodal deformation output needs all nodes on one device
   int ngpu = 1;
@@ -555,6 +623,9 @@ static int run_program(int which)
     return modes_part(c, log, what, part, db, isup, user_id, descr[0] ? descr : linkfile.c_str(), model_file, linkfile, madof, minex, ndof2, ngen, ntriads,
                       tb, tnd, tfd, tru, gen_first, stepno, times, lgrav, grv,
                       std::vector<int>(melcon.begin(), melcon.begin() + nel), std::vector<int>(elmid.begin(), elmid.begin() + nel));
+  if (fpp)
+    return fpp_part(c, log, what, part, ftl, db, isup, user_id, descr[0] ? descr : linkfile.c_str(), model_file, linkfile, xyz, ndof2, ngen, ntriads, tb, tnd,
+                    tfd, tru, gen_first, sel, nsel, stepno, times, lgrav, grv, madof);
   if (gage)
     return gage_part(c, log, what, part, ftl, db, isup, user_id, model_file, linkfile, minex, xyz, ndof2, ngen, ntriads, tb, tnd, tfd, tru, gen_first,
                      sel, nsel, stepno, times, lgrav, grv, madof);
@@ -667,7 +738,7 @@ static int run_program(int which)
 }
 
 // getShellElementAxes (src/vpmStress/strainAndStressUtils.f90:339-434) for 3 or 4 nodes X[k][3]; axes V1, V2, V3.  Returns 0 if ok.
-static int shell_element_axes(int n, const double (*X)[3], double* V1, double* V2, double* V3)
+static int shell_element_axes(int n, const double (*X)[3], double* V1, double* V2, double* V3, bool globalize = false)
 {
   auto cross = [](const double* a, const double* b, double* c) { c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0]; };
   auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
@@ -683,7 +754,16 @@ static int shell_element_axes(int n, const double (*X)[3], double* V1, double* V
   if (vn <= eps2) return 2;
   vn = std::sqrt(vn);
   for (int k = 0; k < 3; ++k) V3[k] /= vn;
-  if (n == 4) {
+  if (globalize) {   // getGlobalizedX (:297-336): the global X axis (or Y when the normal is close to it) projected into the element plane
+    if (std::fabs(V3[1]) > 0.01 || std::fabs(V3[2]) > 0.01) {
+      V1[0] = V3[1] * V3[1] + V3[2] * V3[2]; V1[1] = -V3[0] * V3[1]; V1[2] = -V3[0] * V3[2];
+    } else {
+      V2[0] = -V3[1] * V3[0]; V2[1] = V3[0] * V3[0] + V3[2] * V3[2]; V2[2] = -V3[1] * V3[2];
+      cross(V2, V3, V1);
+    }
+    const double l2 = dot(V1, V1);
+    for (int k = 0; k < 3; ++k) V1[k] = l2 > eps2 ? V1[k] / std::sqrt(l2) : 0.0;
+  } else if (n == 4) {
     for (int k = 0; k < 3; ++k) V1[k] = X[1][k] - X[0][k];
     cross(V3, V1, V2);
     cross(V2, V3, V1);
@@ -1463,10 +1543,539 @@ static int modes_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fs
   return 0;
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// S-N curve library file (FFpSNCurveLib::readSNCurves / read, FFpSNCurveLib.C:132-277)
+namespace {
+struct SnCurve {
+  std::string name;
+  int std_id = 0;
+  std::vector<double> loga, m, logN0;
+  double thk_exp = 0.0;
+};
+// FFaTokenizer::createTokens (FFaTokenizer.C:132-189) with '<' '>' ',' on a string that starts with the entry-begin character
+std::vector<std::string> ffa_tokens(const std::string& s)
+{
+  std::vector<std::string> out;
+  std::string token;
+  int sub = 0;
+  bool text = false;
+  for (size_t i = 0; i < s.size(); ++i) {
+    const int ch = (unsigned char)s[i];
+    if (!text && (ch == '<' || ch == '[' || ch == '{')) ++sub;
+    if (ch == '"') text = !text;
+    if (!(sub == 1 && ch == '"')) {
+      if (text) token += (char)ch;
+      else if (sub > 1 || (ch != ',' && ch != '<' && ch != '>')) { if (!isspace(ch)) token += (char)ch; }
+    }
+    if (!text && sub == 1 && (ch == ',' || ch == '>')) { out.push_back(token); token.clear(); }
+    if (!text && (ch == '>' || ch == ']' || ch == '}')) --sub;
+    if (sub == 0) break;
+  }
+  return out;
+}
+}  // namespace
+
+struct fsr_sn_lib {
+  std::vector<std::pair<std::string, std::vector<SnCurve>>> stds;
+  const SnCurve* curve(int is, int ic) const
+  {
+    if (is < 0 || (size_t)is >= stds.size() || ic < 0 || (size_t)ic >= stds[(size_t)is].second.size()) return nullptr;
+    return &stds[(size_t)is].second[(size_t)ic];
+  }
+};
+
+extern "C" {
+
+int fsr_sn_read(fsr_sn_lib** lib, const char* path)
+{
+  if (!lib || !path) { set_error("fsr_sn_read: bad arguments"); return FSR_ERR_ARG; }
+  *lib = nullptr;
+  FILE* f = fopen(path, "r");
+  if (!f) { set_error("Can't open S-N curves file %s", path); return FSR_ERR_ARG; }
+  std::string text;
+  { char buf[4096]; size_t n; while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n); }
+  fclose(f);
+  fsr_sn_lib* L = new fsr_sn_lib;
+  size_t i = 0;
+  auto skip_line = [&] { while (i < text.size() && text[i] != '\n') ++i; if (i < text.size()) ++i; };
+  while (i < text.size()) {
+    while (i < text.size() && isspace((unsigned char)text[i])) ++i;   // ignore leading white-space
+    if (i >= text.size()) break;
+    if (text[i] == '#') { skip_line(); continue; }                   // comment lines
+    if (text[i] != '<') { skip_line(); continue; }                   // "Invalid leading character": the rest of the line is ignored
+    // one entry: up to the matching end character (quoted text does not count)
+    size_t j = i;
+    int depth = 0;
+    bool quoted = false;
+    for (; j < text.size(); ++j) {
+      const char ch = text[j];
+      if (ch == '"') quoted = !quoted;
+      if (quoted) continue;
+      if (ch == '<' || ch == '[' || ch == '{') ++depth;
+      else if (ch == '>' || ch == ']' || ch == '}') { if (--depth == 0) break; }
+    }
+    const std::vector<std::string> st = ffa_tokens(text.substr(i, j + 1 - i));
+    i = j < text.size() ? j + 1 : j;
+    if (st.empty()) { delete L; set_error("%s: empty S-N curve standard entry", path); return FSR_ERR_ARG; }
+    std::vector<SnCurve> curves;
+    const int std_id = st.size() > 1 ? atoi(st[1].c_str()) : -1;
+    for (size_t k = 2; k < st.size(); ++k) {
+      const std::vector<std::string> ct = ffa_tokens(st[k]);
+      SnCurve cv;
+      cv.std_id = std_id;
+      if (std_id == 0) {        // NorSok: name, <values>, thickness exponent
+        if (ct.size() != 3) continue;
+        cv.thk_exp = atof(ct[2].c_str());
+      } else if (std_id == 1) { // British: name, <values>
+        if (ct.size() != 2) continue;
+      } else
+        break;                  // unknown curve standard: the rest of the entry is skipped
+      cv.name = ct[0];
+      const std::vector<std::string> vt = ffa_tokens(ct[1]);
+      bool valid = vt.size() % 2 == 0;
+      double loga0 = 0.0, m0 = 0.0, logN0 = 0.0;
+      for (size_t q = 0; q < vt.size() && valid; q += 2) {
+        const double loga1 = atof(vt[q].c_str()), m1 = atof(vt[q + 1].c_str());
+        if (m1 < 0.0) valid = false;
+        else if (q > 0 && std_id == 0) {   // intersection between the last two line segments
+          if (m1 == m0) valid = false;
+          else if (loga1 == loga0) continue;   // coincident lines are ignored
+          else {
+            const double logN1 = (m1 * loga0 - m0 * loga1) / (m1 - m0);
+            if (logN1 > loga1 || (q > 2 && logN1 < logN0)) valid = false;
+            cv.logN0.push_back(logN1);
+            logN0 = logN1;
+          }
+        }
+        cv.loga.push_back(loga1);
+        cv.m.push_back(m1);
+        loga0 = loga1;
+        m0 = m1;
+      }
+      if (valid) curves.push_back(cv);
+    }
+    if (!curves.empty()) L->stds.push_back({st[0], curves});
+  }
+  *lib = L;
+  return FSR_OK;
+}
+
+void fsr_sn_free(fsr_sn_lib* lib) { delete lib; }
+int fsr_sn_num_standards(const fsr_sn_lib* lib) { return lib ? (int)lib->stds.size() : 0; }
+int fsr_sn_num_curves(const fsr_sn_lib* lib, int is) { return lib && is >= 0 && (size_t)is < lib->stds.size() ? (int)lib->stds[(size_t)is].second.size() : 0; }
+
+int fsr_sn_get(const fsr_sn_lib* lib, int is, int ic, int* std_id, double* loga, double* m, double* logN0, int cap)
+{
+  const SnCurve* cv = lib ? lib->curve(is, ic) : nullptr;
+  if (!cv) { set_error("S-N curve index (%d, %d) is out of range", is, ic); return FSR_ERR_ARG; }
+  if (std_id) *std_id = cv->std_id;
+  const int n = (int)cv->loga.size();
+  for (int k = 0; k < n && k < cap; ++k) {
+    if (loga) loga[k] = cv->loga[(size_t)k];
+    if (m) m[k] = cv->m[(size_t)k];
+    if (logN0 && (size_t)k < cv->logN0.size()) logN0[k] = cv->logN0[(size_t)k];
+  }
+  return n;
+}
+
+// FFpSNCurveNorSok::getValue / FFpSNCurveBritish::getValue (FFpSNCurve.C:22-47)
+double fsr_sn_value(const fsr_sn_lib* lib, int is, int ic, double sr)
+{
+  const SnCurve* cv = lib ? lib->curve(is, ic) : nullptr;
+  if (!cv || cv->loga.empty()) return -1.0;
+  if (cv->std_id == 1) return cv->loga.size() > 1 ? pow(10.0, cv->loga[0] - cv->loga[1] * cv->m[1] - cv->m[0] * log10(sr)) : -1.0;
+  const size_t n = cv->logN0.size();
+  if (cv->loga.size() <= n) return -1.0;
+  for (size_t k = 0; k < n; ++k) {
+    const double logN = cv->loga[k] - cv->m[k] * log10(sr);
+    if (logN < cv->logN0[k]) return pow(10.0, logN);
+  }
+  return pow(10.0, cv->loga[n] - cv->m[n] * log10(sr));
+}
+
+}  // extern "C"
+
+// --------------------------------------------------------------------------------------------------------------------
+// The fedem_fpp specific part (fpp.f90:127-142,206-520): strain coat elements of the FE part as rosettes in their element systems,
+// running summary (and rainflow damage) on the GPU, the strain coat results database (saveStrainCoatModule.f90).
+static int fpp_part(CmdLine& c, Log& log, const char* what, fsr_part* part, fsr_ftl* ftl, fsr_frs* db, int isup, int user_id, const char* descr,
+                    const char* model_file, const std::string& linkfile, const std::vector<double>& xyz, int ndof2, int ngen, int ntriads,
+                    const std::vector<int>& tb, const std::vector<int>& tnd, const std::vector<int>& tfd, const std::vector<double>& tru,
+                    int gen_first, const std::vector<int>& sel, int nsel, const std::vector<int>& stepno, const std::vector<double>& times,
+                    bool lgrav, const double* grv, const std::vector<int>& madof)
+{
+  (void)madof;
+  const int iprint = c.get_int("debug"), iSurface = c.get_int("surface"), angBinSize = c.get_int("angleBins"), fppType = c.get_int("HistDataType");
+  const bool oldRange = c.get_bool("oldRange"), writeHistory = c.get_bool("writeHistory"), lDouble = c.get_bool("double");
+  const double pvxGate = (double)(float)c.get_double("PVXGate"), biAxialGate = c.get_double("biAxialGate"), toMPa = c.get_double("stressToMPaScale");
+  const double startTime = c.get_double("statm"), stopTime = c.get_double("stotm");
+  if (fppType < 0) FAIL("-HistDataType %d asks for the nCode FPP plug-in (-fppfile), which is not part of this build", fppType);
+  if (angBinSize < 2) FAIL("Invalid value on option -angleBins: %d", angBinSize);
+
+  const int nStrainCoatTotal = fsr_ftl_num_strain_coats(ftl);
+  if (nStrainCoatTotal < 1) FAIL("Link does not contain any strain coat elements");
+  log.line("               Number of strain coats =%6d", nStrainCoatTotal);
+  std::vector<fsr_strain_coat> coats((size_t)nStrainCoatTotal);
+  CHECK(fsr_ftl_get_strain_coats(ftl, coats.data(), nStrainCoatTotal));
+
+  // fatigueInit (fatigueModule.f90:14-37): the S-N curve library
+  fsr_sn_lib* sn = nullptr;
+  struct SnGuard { fsr_sn_lib*& p; ~SnGuard() { fsr_sn_free(p); } } sn_guard{sn};
+  if (fppType > 0) {
+    if (fsr_sn_read(&sn, c.get_string("SNfile").c_str()) < 0) {
+      log.line(" *** Error: %s", fsr_last_error());
+      FAIL("Failure in fatigue initialization");
+    }
+  }
+
+  // --- initiateStrainCoats (strainCoatModule.f90:172-312) + calcElmCoordSystem with useElCoordSys (strainRosetteModule.f90:506-567):
+  //     one rosette per kept result set, in the centroid of the coat nodes, axes = the globalized element axes
+  struct Point { int coat, set, mat, sn[2]; double scf, zpos; bool fat; };
+  std::vector<fsr_rosette> ros;
+  std::vector<Point> pts;
+  std::vector<int> first_pt((size_t)nStrainCoatTotal + 1, 0), coat_fpp((size_t)nStrainCoatTotal, 0);
+  bool haveSNdata = false;
+  int ndegenerate = 0;
+  for (int i = 0; i < nStrainCoatTotal; ++i) {
+    const fsr_strain_coat& k = coats[(size_t)i];
+    first_pt[(size_t)i] = (int)pts.size();
+    if (k.nnod < 3 || k.nnod > 4) FAIL("Invalid strain coat definition. Too many nodes or points: %d %d (element %d)", k.nnod, k.npts, k.id);
+    for (int j = 0; j < k.nnod; ++j) if (k.nodes[j] < 1) FAIL("Non-existing node referenced by strain coat element %d", k.id);
+    int snmin = 0;
+    for (int j = 0; j < k.npts; ++j) snmin = std::min(snmin, std::min(k.sn_curve[j][0], k.sn_curve[j][1]));
+    coat_fpp[(size_t)i] = (k.npts > 0 && snmin >= 0) ? fppType : 0;
+    double X[4][3], T[9];
+    for (int j = 0; j < k.nnod; ++j) for (int d = 0; d < 3; ++d) X[j][d] = xyz[3 * (size_t)(k.nodes[j] - 1) + d];
+    if (shell_element_axes(k.nnod, X, T, T + 3, T + 6, true)) { ++ndegenerate; continue; }   // degenerated strain coat element, just ignore it
+    for (int j = 0; j < k.npts; ++j) {
+      if (iSurface > 0 && iSurface != k.res_set[j]) continue;
+      fsr_rosette R;
+      memset(&R, 0, sizeof(R));
+      R.id = i + 1;
+      R.numnod = k.nnod;
+      for (int q = 0; q < k.nnod; ++q) R.nodes[q] = k.nodes[q];
+      for (int d = 0; d < 3; ++d) {
+        R.rpos[d] = T[d]; R.rpos[3 + d] = T[3 + d]; R.rpos[6 + d] = T[6 + d];
+        double sum = 0.0;
+        for (int q = 0; q < k.nnod; ++q) sum += X[q][d];
+        R.rpos[9 + d] = sum / k.nnod;
+      }
+      R.zpos = k.zpos[j]; R.emod = k.emod[j]; R.nu = k.nu[j];
+      Point P;
+      P.coat = i; P.set = k.res_set[j]; P.mat = k.mat_id[j]; P.sn[0] = k.sn_curve[j][0]; P.sn[1] = k.sn_curve[j][1]; P.scf = k.scf[j]; P.zpos = k.zpos[j];
+      P.fat = coat_fpp[(size_t)i] > 0;
+      if (P.fat) {
+        haveSNdata = true;
+        // ffp_calcDamage (FFpFatigue_F.C:53-78): the curve of the S-N library; one or two line segments (British: one line)
+        int std_id = 0;
+        double la[2], mm[2], ln0[2];
+        const int nseg = fsr_sn_get(sn, P.sn[0], P.sn[1], &std_id, la, mm, ln0, 2);
+        if (nseg < 1) { log.line(" *** Error: %s", fsr_last_error()); FAIL("Failure in damage calculation: Strain coat %d has no valid S-N curve", k.id); }
+        if (std_id == 1) {
+          if (nseg < 2) FAIL("Failure in damage calculation: British S-N curve (%d, %d) lacks its second parameter pair", P.sn[0], P.sn[1]);
+          R.sncurve[0] = R.sncurve[1] = la[0] - la[1] * mm[1]; R.sncurve[2] = R.sncurve[3] = mm[0];
+        } else if (nseg == 1) { R.sncurve[0] = R.sncurve[1] = la[0]; R.sncurve[2] = R.sncurve[3] = mm[0]; }
+        else if (nseg == 2) { R.sncurve[0] = la[0]; R.sncurve[1] = la[1]; R.sncurve[2] = mm[0]; R.sncurve[3] = mm[1]; }
+        else FAIL("S-N curve (%d, %d) has %d line segments; curves with more than two are not part of this build", P.sn[0], P.sn[1], nseg);
+      }
+      ros.push_back(R);
+      pts.push_back(P);
+    }
+  }
+  first_pt[(size_t)nStrainCoatTotal] = (int)pts.size();
+  const int npt = (int)pts.size();
+  if (ndegenerate) log.line("  ** Warning: %d degenerated strain coat elements are ignored", ndegenerate);
+  if (npt == 0) FAIL("No strain coat result points to process (check the -surface option)");
+  static const char* kSet[4] = {"Basic", "Bottom", "Mid", "Top"};
+  if (iprint > 0) {   // printStrainCoatInput (strainCoatModule.f90:550-596)
+    log.line("\n\n     STRAIN COAT PROPERTY SUMMARY\n     --------------------------------------------------------------------------");
+    log.line("     Strain Coat  Result set  Z-position  Material Group  S-N curve  SCF factor");
+    for (int i = 0; i < nStrainCoatTotal; ++i)
+      for (int q = first_pt[(size_t)i]; q < first_pt[(size_t)i + 1]; ++q) {
+        const Point& P = pts[(size_t)q];
+        if (q == first_pt[(size_t)i]) log.line("%8d%8d%10s%14.5E%10d%11d%3d%12.3f", i + 1, coats[(size_t)i].id, kSet[P.set & 3], P.zpos, P.mat, P.sn[0], P.sn[1], P.scf);
+        else log.line("              %12s%14.5E%10d%11d%3d%12.3f", kSet[P.set & 3], P.zpos, P.mat, P.sn[0], P.sn[1], P.scf);
+      }
+    log.line("    ---------------------------------------------------------------------------\n");
+  }
+
+  // --- the reduced history of the selected steps, read once (readSupElDisplacements + BuildFinit); every block of coats runs over it
+  log.line("           --> Reading the reduced history of %d time steps", nsel);
+  const int ndim = ndof2 + ngen + (lgrav ? 3 : 0);
+  std::vector<double> Qall((size_t)ndim * std::max(nsel, 1), 0.0);
+  for (int k = 0; k < nsel;) {
+    int run = 1;
+    while (k + run < nsel && sel[(size_t)(k + run)] == sel[(size_t)k] + run) ++run;
+    const int rch = fsr_frs_reduced_history(db, isup, ntriads, tb.data(), tnd.data(), tfd.data(), tru.data(), ngen, gen_first, sel[(size_t)k], run,
+                                            Qall.data() + (size_t)k * ndim, ndim);
+    CHECK(rch);
+    if (rch > 0 && k == 0) log.line("  ** Warning: %s", fsr_last_error());
+    k += run;
+  }
+  if (lgrav)   // the strains of the static gravitation deflection vgii = dis1Expand(V . g) (fpp.f90:170-192), as in fedem_gage
+    for (int k = 0; k < nsel; ++k) for (int j = 0; j < 3; ++j) Qall[(size_t)k * ndim + ndof2 + ngen + j] = grv[j];
+
+  // --- Element block loop: blocks of whole coats, bounded by the device memory of the angle bins (5 x 8 bytes per bin and point)
+  std::vector<double> env((size_t)8 * npt), summary((size_t)6 * npt), damage((size_t)npt, 0.0);
+  std::vector<int> nbiax((size_t)npt, 0);
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const long long per_pt = 44LL * (angBinSize - 1) + 4096;
+  const int max_pts = (int)std::max<long long>(1024, std::min<long long>(1 << 20, (long long)(free_b / 4) / per_pt));
+  const int nbit = lDouble ? 64 : 32;
+  int next_inc = c.get_int("rdbinc");
+  const std::string base_path = file_name("rdbfile", ".frs");
+  auto next_path = [&]() {   // openRDBfile (rdbModule.f90:300-318)
+    std::string path = base_path;
+    if (next_inc > 0) {
+      const size_t dot = path.rfind('.'), sep = path.rfind('/');
+      char t[16];
+      snprintf(t, sizeof(t), "_%d", next_inc++);
+      if (dot != std::string::npos && dot > 0 && (sep == std::string::npos || dot > sep)) path.insert(dot, t);
+      else path += t;
+    }
+    return path;
+  };
+  // the header files of rdbModule (ivard, iitem, idatd) with the ids of saveStrainCoatModule (id(15), idSTRC(4,0:3))
+  struct Header {
+    std::string vard, item, datd;
+    int nvar = 2, nig = 0, id[16] = {}, idSTRC[5][4] = {};
+    long long nval = 0;
+  };
+  auto begin_header = [&](Header& H) {
+    H = Header();
+    H.vard = rdb_file_preamble("fedem_fpp", model_file, linkfile.c_str(), "strain coat data base file");
+    H.vard += "VARIABLES:\n<1;\"Time step number\";NONE;INT;32;NUMBER>\n<2;\"Physical time\";TIME;FLOAT;64;SCALAR>\n";
+    H.datd = "DATABLOCKS:\n<1><2>\n{\"Part\";";
+    char b[512];
+    if (isup > 0) { snprintf(b, sizeof(b), "%d;", isup); H.datd += b; } else H.datd += ";";
+    if (user_id > 0) { snprintf(b, sizeof(b), "%d;", user_id); H.datd += b; } else H.datd += ";";
+    if (descr && *descr) { snprintf(b, sizeof(b), "\"%s\";\n", descr); H.datd += b; } else H.datd += ";\n";
+    H.datd += "  [;\"Elements\";\n";
+  };
+  // writeStrainCoatHeader (saveStrainCoatModule.f90:172-330) for the coats [c0, c1)
+  auto add_coats = [&](Header& H, int c0, int c1, bool hist) -> int {
+    char b[256];
+    auto vardef = [&](int k, const char* name, const char* unit) {
+      int& idv = H.id[k];
+      if (idv > 0) return;
+      if (idv < 0) { idv = -idv; return; }
+      idv = ++H.nvar;
+      snprintf(b, sizeof(b), "<%d;\"%s\";%s;FLOAT;%2d;SCALAR>\n", idv, name, unit, nbit); H.vard += b;
+    };
+    auto itemgroup = [&](int& idg, int nvar, int rset) {
+      H.nval += nvar;
+      if (idg > 0) return;
+      idg = ++H.nig;
+      snprintf(b, sizeof(b), "[%d;\"%s\";", idg, kSet[rset]); H.item += b;
+      for (int k = 1; k <= nvar; ++k) if (H.id[k] > 0) { snprintf(b, sizeof(b), "<%d>", H.id[k]); H.item += b; }
+      H.item += "]\n";
+    };
+    for (int i = c0; i < c1; ++i) {
+      const int q0 = first_pt[(size_t)i], q1 = first_pt[(size_t)i + 1];
+      if (q1 == q0) continue;   // empty strain coat (switched off with -surface, or degenerated)
+      std::string vars;
+      for (int q = q0; q < q1; ++q) {
+        const Point& P = pts[(size_t)q];
+        if (P.set < 0 || P.set > 3) { set_error("writeStrainCoatHeader: invalid result set"); return FSR_ERR_STATE; }
+        int itemG = 1;
+        if (hist) {
+          static const char* nm[10] = {"Max principal stress", "Min principal stress", "Signed abs max stress", "Max shear stress", "Von Mises stress",
+                                       "Max principal strain", "Min principal strain", "Signed abs max strain", "Max shear strain", "Von Mises strain"};
+          for (int k = 0; k < 10; ++k) vardef(k + 1, nm[k], k < 5 ? "FORCE/AREA" : "NONE");
+          itemgroup(H.idSTRC[1][P.set], 10, P.set);
+        } else {
+          vardef(1, "Max principal stress", "FORCE/AREA"); vardef(2, "Max shear stress", "FORCE/AREA");
+          vardef(3, "Max stress range", "FORCE/AREA"); vardef(4, "Max von Mises stress", "FORCE/AREA");
+          vardef(5, "Max principal strain", "NONE"); vardef(6, "Max shear strain", "NONE");
+          vardef(7, "Max strain range", "NONE"); vardef(8, "Max von Mises strain", "NONE");
+          if (coat_fpp[(size_t)i] > 0) {
+            itemG = 2;
+            vardef(9, "Damage", "NONE"); vardef(10, "Life (equnits)", "TIME"); vardef(11, "Life (repeats)", "NONE");
+          } else {
+            for (int k = 9; k <= 11; ++k) H.id[k] = -std::abs(H.id[k]);
+            H.nval -= 3;
+          }
+          vardef(12, "Angle spread", "ANGLE"); vardef(13, "Most popular angle", "ANGLE");
+          if (nbiax[(size_t)q] > 0) {
+            itemG += 2;
+            vardef(14, "Mean bi-axiality", "NONE"); vardef(15, "Biaxiality standard deviation", "NONE");
+            itemgroup(H.idSTRC[itemG][P.set], 15, P.set);
+          } else
+            itemgroup(H.idSTRC[itemG][P.set], 13, P.set);
+        }
+        snprintf(b, sizeof(b), "[%d]", H.idSTRC[itemG][P.set]); vars += b;
+      }
+      snprintf(b, sizeof(b), "    [;%8d;[;\"%s\";[;\"Element\";%s]]]\n", coats[(size_t)i].id, coats[(size_t)i].nnod == 3 ? "STRCT3" : "STRCQ4", vars.c_str());
+      H.datd += b;
+    }
+    return FSR_OK;
+  };
+  Header Hsum;
+  if (!writeHistory) { log.line("           --> Initializing result database headers"); begin_header(Hsum); }
+  std::vector<double> record;   // the one summary record, block after block
+
+  std::vector<double> vals;
+  for (int c0 = 0; c0 < nStrainCoatTotal;) {
+    int c1 = c0;
+    while (c1 < nStrainCoatTotal && (c1 == c0 || first_pt[(size_t)c1 + 1] - first_pt[(size_t)c0] <= max_pts)) ++c1;
+    const int p0 = first_pt[(size_t)c0], np = first_pt[(size_t)c1] - p0;
+    log.line("               Processing elements%8d  to%8d  of total%8d elements", c0 + 1, c1, nStrainCoatTotal);
+    if (np > 0) {
+      log.line("           --> Computing strain-displ matrices");
+      fsr_gages* gages = nullptr;
+      CHECK(fsr_gage_create(&gages, part, ros.data() + p0, np));
+      struct GagesGuard { fsr_gages* p; ~GagesGuard() { fsr_gage_destroy(p); } } gages_guard{gages};
+      fsr_frs_writer* hw = nullptr;
+      struct HGuard { fsr_frs_writer*& p; ~HGuard() { if (p) fsr_frs_finish(p); } } h_guard{hw};
+      if (writeHistory) {   // writeHistoryHeader (saveStrainCoatModule.f90:27-62): one file per block
+        log.line("           --> Writing result database headers");
+        Header H;
+        begin_header(H);
+        CHECK(add_coats(H, c0, c1, true));
+        H.datd += "  ]\n}\n";
+        const std::string path = next_path();
+        CHECK(fsr_frs_create_tagged(&hw, path.c_str(), "#FEDEM strain coat data", 0, (H.vard + H.item + H.datd).c_str(), H.nval * (nbit / 8)));
+        log.line("           --> Results database file: %s (%lld bytes per time step)", path.c_str(), 12 + H.nval * (nbit / 8));
+      }
+      log.line("           --> Starting time loop");
+      CHECK(fsr_coat_begin(gages, angBinSize, biAxialGate));
+      if (!writeHistory) CHECK(fsr_coat_feed(gages, Qall.data(), ndim, nsel));
+      else {
+        // calcStrainCoatData + writeHistoryDB / writeRosetteDB (:332-398): sigmaP(3), tauMax, sigmaVM, epsP(3), gammaMax, epsVM per result point
+        const int window = 256;
+        vals.resize((size_t)window * np * FSR_GAGE_NVAL);
+        std::vector<double> rec_d((size_t)10 * np);
+        std::vector<float> rec_f((size_t)10 * np);
+        for (int w0 = 0; w0 < nsel; w0 += window) {
+          const int nw = std::min(window, nsel - w0);
+          CHECK(fsr_coat_feed(gages, Qall.data() + (size_t)w0 * ndim, ndim, nw));
+          CHECK(fsr_gage_recover(gages, Qall.data() + (size_t)w0 * ndim, ndim, nw, vals.data()));
+          for (int k = 0; k < nw; ++k) {
+            size_t n = 0;
+            for (int r = 0; r < np; ++r) {
+              const double* v = vals.data() + ((size_t)k * np + r) * FSR_GAGE_NVAL;
+              const double out[10] = {v[13], v[14], v[15], v[16], v[17], v[3], v[4], v[5], v[6], v[7]};
+              for (double x : out) { rec_d[n] = x; rec_f[n] = (float)x; ++n; }
+            }
+            CHECK(fsr_frs_write_step(hw, stepno[(size_t)sel[(size_t)(w0 + k)]], times[(size_t)sel[(size_t)(w0 + k)]],
+                                     lDouble ? (const void*)rec_d.data() : (const void*)rec_f.data()));
+          }
+        }
+      }
+      // fsr_coat_end returns [8][np] / [6][np] blocks: fetch them block-wise and scatter into the part-wide arrays
+      {
+        std::vector<double> e8((size_t)8 * np), s6((size_t)6 * np);
+        std::vector<int> nb((size_t)np);
+        CHECK(fsr_coat_end(gages, e8.data(), s6.data(), nb.data()));
+        for (int r = 0; r < np; ++r) {
+          for (int k = 0; k < 8; ++k) env[(size_t)k * npt + p0 + r] = e8[(size_t)k * np + r];
+          for (int k = 0; k < 6; ++k) summary[(size_t)k * npt + p0 + r] = s6[(size_t)k * np + r];
+          nbiax[(size_t)(p0 + r)] = nb[(size_t)r];
+        }
+      }
+      log.line("           --> Time loop done. Closing fpp processors");
+      if (hw) { fsr_frs_writer* x = hw; hw = nullptr; CHECK(fsr_frs_finish(x)); }
+      bool any_fat = false;
+      for (int r = 0; r < np; ++r) any_fat = any_fat || pts[(size_t)(p0 + r)].fat;
+      if (any_fat && nsel > 0) {
+        // fatigueAddPoint + fatigueDamage (fatigueModule.f90:40-118): PVX + rainflow + Miner sum of fatValue on the point's S-N curve
+        std::vector<double> scf((size_t)np);
+        for (int r = 0; r < np; ++r) scf[(size_t)r] = pts[(size_t)(p0 + r)].fat ? pts[(size_t)(p0 + r)].scf : 1.0;
+        CHECK(fsr_gage_set_coat_fatigue(gages, scf.data()));
+        const double curve[4] = {15.117, 17.146, 4.0, 5.0};
+        std::vector<double> dmg((size_t)4 * np);
+        std::vector<int> ncyc((size_t)4 * np), status((size_t)4 * np);
+        const int nw = fsr_gage_fatigue(gages, Qall.data(), ndim, nsel, toMPa, pvxGate, curve, 1.0, 0, dmg.data(), ncyc.data(), nullptr, status.data());
+        CHECK(nw);
+        for (int r = 0; r < np; ++r) {
+          const Point& P = pts[(size_t)(p0 + r)];
+          if (!P.fat) continue;
+          if (status[4 * (size_t)r] == 2) FAIL("Failure in damage calculation: Strain coat %d (turning point stack exhausted)", coats[(size_t)P.coat].id);
+          damage[(size_t)(p0 + r)] = P.scf == 0.0 ? 0.0 : dmg[4 * (size_t)r];
+        }
+      }
+    }
+    if (!writeHistory) {
+      // writeElementsHeader + writeElementsDB / writeStrainCoatDB (:141-170,400-558) of this block
+      CHECK(add_coats(Hsum, c0, c1, false));
+      const double time = stopTime - startTime;
+      for (int q = p0; q < p0 + np; ++q) {
+        const Point& P = pts[(size_t)q];
+        auto E = [&](int k) { return env[(size_t)k * npt + q]; };   // epsMax, epsMin, sigMax, sigMin, gammaMax, tauMax, vmeMax, vmsMax
+        auto S = [&](int k) { return summary[(size_t)k * npt + q]; };
+        record.push_back(std::fabs(E(2)) > std::fabs(E(3)) ? E(2) : E(3));
+        record.push_back(E(5));
+        record.push_back(oldRange ? E(2) - E(3) : S(0));
+        record.push_back(E(7));
+        record.push_back(std::fabs(E(0)) > std::fabs(E(1)) ? E(0) : E(1));
+        record.push_back(E(4));
+        record.push_back(oldRange ? E(0) - E(1) : S(1));
+        record.push_back(E(6));
+        if (coat_fpp[(size_t)P.coat] > 0) {
+          const double d = damage[(size_t)q];
+          if (d > 0.0) { record.push_back(d); record.push_back(time / d); record.push_back(1.0 / d); }
+          else { record.push_back(1.0e20); record.push_back(1.0e20); record.push_back(1.0e20); }   // no damage = infinite life
+        }
+        record.push_back(S(3));
+        record.push_back(S(2));
+        if (nbiax[(size_t)q] > 0) { record.push_back(S(4)); record.push_back(S(5)); }
+      }
+    }
+    c0 = c1;
+  }
+  if (iprint > 0) {   // printStrainCoatData (strainCoatModule.f90:599-666)
+    log.line("\n\n     STRAIN COAT RECOVERY SUMMARY\n     ------------------------   --------------- Stress --------------   --------------- Strain --------------"
+             "   ------ Biaxiality ------   - Principal dir. angle -");
+    log.line("     Strain Coat  Result set      Max P1      Max shear  Max von Mises    Max P1      Max shear  Max von Mises     Mean      Std. Dev."
+             "      Most popular    spread");
+    for (int i = 0; i < nStrainCoatTotal; ++i) {
+      for (int q = first_pt[(size_t)i]; q < first_pt[(size_t)i + 1]; ++q) {
+        const Point& P = pts[(size_t)q];
+        auto E = [&](int k) { return env[(size_t)k * npt + q]; };
+        auto S = [&](int k) { return summary[(size_t)k * npt + q]; };
+        char head[40];
+        if (q == first_pt[(size_t)i]) snprintf(head, sizeof(head), "%8d%8d%10s", i + 1, coats[(size_t)i].id, kSet[P.set & 3]);
+        else snprintf(head, sizeof(head), "              %12s", kSet[P.set & 3]);
+        log.line("%s    %13.5E%13.5E%13.5E %13.5E%13.5E%13.5E %13.5E%13.5E %13.5f%13.5f", head, E(2), E(5), E(7), E(0), E(4), E(6), S(4), S(5), S(2), S(3));
+      }
+      if (coat_fpp[(size_t)i] > 0 && first_pt[(size_t)i + 1] > first_pt[(size_t)i]) {
+        std::string l = "                    Damage =  ";
+        char b[32];
+        for (int q = first_pt[(size_t)i]; q < first_pt[(size_t)i + 1]; ++q) { snprintf(b, sizeof(b), "%13.5E", damage[(size_t)q]); l += b; }
+        log.line("%s", l.c_str());
+      }
+    }
+    log.line("    ---------------------------------------------------------------------------------------------------------------------------------------------------------------\n");
+  }
+  log.line("           --> Block loop done. Closing database files");
+  if (!haveSNdata && fppType > 0)
+    log.line("  ** Warning: None of the element groups processed were assigned an S-N curve.\n"
+             "              Damage and Life contour plots are therefore not created for this part.");
+  if (!writeHistory) {   // finalizeStrainCoatHeader (:118-138) + the one record (writeTimeStepDB(rdb,1,stopTime), fpp.f90:222)
+    if ((long long)record.size() != Hsum.nval) FAIL("internal: strain coat summary record of %zu values, header says %lld", record.size(), Hsum.nval);
+    Hsum.datd += "  ]\n}\n";
+    const std::string path = next_path();
+    fsr_frs_writer* w = nullptr;
+    CHECK(fsr_frs_create_tagged(&w, path.c_str(), "#FEDEM strain coat data", 0, (Hsum.vard + Hsum.item + Hsum.datd).c_str(), Hsum.nval * (nbit / 8)));
+    int rcw;
+    if (lDouble) rcw = fsr_frs_write_step(w, 1, stopTime, record.data());
+    else { std::vector<float> rf(record.begin(), record.end()); rcw = fsr_frs_write_step(w, 1, stopTime, rf.data()); }
+    const int rcf = fsr_frs_finish(w);
+    CHECK(rcw);
+    CHECK(rcf);
+    log.line("           --> Results database file: %s (%lld values)", path.c_str(), Hsum.nval);
+  }
+  log.line("           ================>  END OF PROGRAM FPP  <================");
+  log.line("\n    %s successfully completed :-)  (%.2f s CPU)", what, (double)(clock() - log.t0) / CLOCKS_PER_SEC);
+  return 0;
+}
+
 extern "C" {
 
 int solveStress(void) { return run_program(0); }
 int solveGage(void) { return run_program(1); }
 int solveModes(void) { return run_program(2); }
+int solveFpp(void) { return run_program(3); }
 
 }  // extern "C"

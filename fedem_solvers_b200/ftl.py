@@ -89,13 +89,28 @@ class FtlPart:
     def ext2int(self, ident, node=True):
         return int(self.lib.fsr_ftl_ext2int(self.h, int(node), int(ident)))
 
+    def strain_coats(self):
+        """ffl_getnostrc + ffl_getstraincoat for every strain coat element: list of dicts."""
+        n = check(self.lib.fsr_ftl_num_strain_coats(self.h), "fsr_ftl_num_strain_coats")
+        arr = (_lib.FsrStrainCoat * max(n, 1))()
+        check(self.lib.fsr_ftl_get_strain_coats(self.h, arr, n), "fsr_ftl_get_strain_coats")
+        out = []
+        for c in arr[:n]:
+            out.append(dict(id=c.id, nodes=list(c.nodes[:c.nnod]), npts=c.npts, elm_id=c.elm_id, mat_id=list(c.mat_id[:c.npts]),
+                            res_set=list(c.res_set[:c.npts]), sn_curve=[tuple(c.sn_curve[k]) for k in range(c.npts)],
+                            emod=list(c.emod[:c.npts]), nu=list(c.nu[:c.npts]), zpos=list(c.zpos[:c.npts]), scf=list(c.scf[:c.npts])))
+        return out
+
 
 def _fmt(v):
     return repr(float(v))
 
 
-def write_ftl(path, part, groups=None, rho=7850.0, comments=True):
+def write_ftl(path, part, groups=None, rho=7850.0, comments=True, strain_coats=None):
     """Writes `part` (model.PartModel) as an .ftl file.  groups: {id: [external element ids]}.
+    strain_coats: list of dicts {id, elm (0-based element index of the shell underneath), sets: [(name, height or None)],
+    fatigue: (snStd, snIdx, scf) or None}: one STRCT3 / STRCQ4 element on the shell's nodes with a PSTRC per result set
+    (height given: PHEIGHT, else PTHICKREF +-0.5 to the shell's PTHICK) as FFlFedemWriter / the strain coat creator write them.
     Node ids = minex, element ids = elmid (or 1..nel); external nodes (all DOFs status 2) get status 1,
     nodes with suppressed DOFs the negative bit mask of FFlNode::isFixed."""
     sam, elm = part.sam, part.elm
@@ -148,6 +163,38 @@ def write_ftl(path, part, groups=None, rho=7850.0, comments=True):
             if t in (21, 22, 23, 24, 31, 32):
                 refs.insert(0, f"{{PTHICK {key(thks, (float(elm.thk[e]),))}}}")
         out.append(f"{NAMES[t]}{{{int(ids[e])} {' '.join(map(str, nodes))} {' '.join(refs)}}}")
+    coat_lines, pstrc, prefs, pheights, pfats = [], [], {}, {}, {}
+    for sc in strain_coats or []:
+        e = int(sc["elm"])
+        t = int(sam.melcon[e])
+        nodes = [int(minex[k - 1]) for k in sam.mmnpc[sam.mpmnpc[e] - 1: sam.mpmnpc[e + 1] - 1]]
+        nu = float(elm.rny[e])
+        m = key(mats, (float(elm.emod[e]), float(elm.emod[e]) / (2 * (1 + nu)), nu, rho))
+        refs = []
+        for name, height in sc["sets"]:
+            if height is not None:
+                sub = f"{{PHEIGHT {key(pheights, (float(height),))}}}"
+            else:
+                fac = {"Bottom": -0.5, "Mid": 0.0, "Top": 0.5}[name]
+                sub = f"{{PTHICKREF {key(prefs, (fac, key(thks, (float(elm.thk[e]),))))}}}"
+            pstrc.append((len(pstrc) + 1, name, m, sub))
+            refs.append(f"{{PSTRC {len(pstrc)}}}")
+        if sc.get("fatigue") is not None:
+            refs.append(f"{{PFATIGUE {key(pfats, tuple(sc['fatigue']))}}}")
+        refs.append(f"{{FE {int(ids[e])}}}")
+        coat_lines.append(f"{'STRCT3' if len(nodes) == 3 else 'STRCQ4'}{{{int(sc['id'])} {' '.join(map(str, nodes))} {' '.join(refs)}}}")
+    if coat_lines:
+        if comments:
+            out += ["#", "# Strain coat elements", "#"]
+        out += coat_lines
+        for i, name, m, sub in pstrc:
+            out.append(f"PSTRC{{{i} \"{name}\" {{PMAT {m}}} {sub}}}")
+        for (fac, th), i in prefs.items():
+            out.append(f"PTHICKREF{{{i} {_fmt(fac)} {{PTHICK {th}}}}}")
+        for (h,), i in pheights.items():
+            out.append(f"PHEIGHT{{{i} {_fmt(h)}}}")
+        for (a, b, scf), i in pfats.items():
+            out.append(f"PFATIGUE{{{i} {int(a)} {int(b)} {_fmt(scf)}}}")
     for title, name, table in (("Material properties", "PMAT", mats), ("Shell thicknesses", "PTHICK", thks),
                                ("Beam cross sections", "PBEAMSECTION", secs), ("Orientation vectors", "PORIENT", oris),
                                ("Beam eccentricities", "PBEAMECCENT", eccs), ("Beam pin flags", "PBEAMPIN", pins),

@@ -48,6 +48,14 @@ module fedem_b200_mod
      real(c_double) :: sncurve(4)
   end type fsr_rosette
 
+  !> struct fsr_strain_coat: one strain coat element as ffl_getstraincoat delivers it
+  type, bind(C) :: fsr_strain_coat
+     integer(c_int) :: id, nnod, npts, elm_id
+     integer(c_int) :: nodes(8)
+     integer(c_int) :: mat_id(3), res_set(3), sn_curve(2,3)
+     real(c_double) :: emod(3), nu(3), zpos(3), scf(3)
+  end type fsr_strain_coat
+
   !> struct fsr_rdb_options: what writeStressHeader takes from the command line and from sup%id
   type, bind(C) :: fsr_rdb_options
      integer(c_int) :: out_mask, double_precision, rdbinc, part_base_id, part_user_id
@@ -309,6 +317,55 @@ module fedem_b200_mod
        type(c_ptr), value :: env, summary, nbiax   ! real(c_double) env(nros,8), summary(nros,6), integer(c_int) nbiax(nros), or c_null_ptr
        integer(c_int) :: ierr
      end function fsr_coat_end
+
+     function fsr_gage_set_coat_fatigue (gages, scf) bind(C,name="fsr_gage_set_coat_fatigue") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: gages
+       type(c_ptr), value :: scf   ! real(c_double) scf(nros), or c_null_ptr
+       integer(c_int) :: ierr
+     end function fsr_gage_set_coat_fatigue
+
+     function fsr_sn_read (lib, path) bind(C,name="fsr_sn_read") result(ierr)
+       import :: c_ptr, c_int, c_char
+       type(c_ptr), intent(out) :: lib
+       character(kind=c_char), intent(in) :: path(*)
+       integer(c_int) :: ierr
+     end function fsr_sn_read
+
+     subroutine fsr_sn_free (lib) bind(C,name="fsr_sn_free")
+       import :: c_ptr
+       type(c_ptr), value :: lib
+     end subroutine fsr_sn_free
+
+     function fsr_sn_num_standards (lib) bind(C,name="fsr_sn_num_standards") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: lib
+       integer(c_int) :: n
+     end function fsr_sn_num_standards
+
+     function fsr_sn_num_curves (lib, std_index) bind(C,name="fsr_sn_num_curves") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr)   , value :: lib
+       integer(c_int), value :: std_index
+       integer(c_int) :: n
+     end function fsr_sn_num_curves
+
+     function fsr_sn_get (lib, std_index, curve_index, std_id, loga, m, logN0, cap) bind(C,name="fsr_sn_get") result(nseg)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value       :: lib
+       integer(c_int), value       :: std_index, curve_index, cap
+       integer(c_int), intent(out) :: std_id
+       real(c_double), intent(out) :: loga(*), m(*), logN0(*)
+       integer(c_int) :: nseg
+     end function fsr_sn_get
+
+     function fsr_sn_value (lib, std_index, curve_index, s) bind(C,name="fsr_sn_value") result(n)
+       import :: c_ptr, c_int, c_double
+       type(c_ptr)   , value :: lib
+       integer(c_int), value :: std_index, curve_index
+       real(c_double), value :: s
+       real(c_double) :: n
+     end function fsr_sn_value
 
      ! ---- fatigue (ffp_addpoint / ffp_getdamage / ffp_getnumcycles) ---------------------------
      function fsr_fatigue (device, hist, ngage, nsteps, gate, curve, bin_size, nbins, damage, &
@@ -630,6 +687,20 @@ module fedem_b200_mod
        integer(c_int), value :: is_node, id
        integer(c_int) :: intid
      end function fsr_ftl_ext2int
+
+     function fsr_ftl_num_strain_coats (ftl) bind(C,name="fsr_ftl_num_strain_coats") result(n)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: ftl
+       integer(c_int) :: n
+     end function fsr_ftl_num_strain_coats
+
+     function fsr_ftl_get_strain_coats (ftl, coats, cap) bind(C,name="fsr_ftl_get_strain_coats") result(n)
+       import :: c_ptr, c_int, fsr_strain_coat
+       type(c_ptr)          , value       :: ftl
+       type(fsr_strain_coat), intent(out) :: coats(*)
+       integer(c_int)       , value       :: cap
+       integer(c_int) :: n
+     end function fsr_ftl_get_strain_coats
 
      ! ---- solver input file (.fsi): replaces readSolverData ----------------------------------
      function fsr_fsi_open (fsi, path, part_base_id) bind(C,name="fsr_fsi_open") result(ierr)
@@ -1077,6 +1148,14 @@ module fedem_b200_mod
        import :: c_int
        integer(c_int) :: ierr
      end function solveModes
+
+     subroutine fsr_fpp_define_options () bind(C,name="fsr_fpp_define_options")
+     end subroutine fsr_fpp_define_options
+
+     function solveFpp () bind(C,name="solveFpp") result(ierr)
+       import :: c_int
+       integer(c_int) :: ierr
+     end function solveFpp
 
      subroutine fsr_cmdline_add_bool (name, value) bind(C,name="fsr_cmdline_add_bool")
        import :: c_char, c_int

@@ -370,6 +370,26 @@ int fsr_coat_begin(fsr_gages *gages, int angle_bins /* -angleBins, 541 */, doubl
 int fsr_coat_feed(fsr_gages *gages, const double *Q, int ldq, int nsteps);
 int fsr_coat_feed_dev(fsr_gages *gages, const double *Q_dev, int ldq, int nsteps, void *stream);
 int fsr_coat_end(fsr_gages *gages, double *env, double *summary, int *nbiax);
+/* Fatigue of strain coat result points (fatigueAddPoint / fatigueDamage, src/vpmStress/fatigueModule.f90:40-118, with
+ * calcStrainCoatData's fatValue = sigmaP(3) * toMPaScale * SCF, strainCoatModule.f90:385-400): after this call the first fatigue
+ * series of every rosette (fsr_gage_fatigue*: series 4 r) is the SIGNED ABS-MAX principal stress times to_mpa times scf[r]
+ * instead of the largest principal stress.  scf [nros]; NULL switches back. */
+int fsr_gage_set_coat_fatigue(fsr_gages *gages, const double *scf);
+
+/* S-N curve library file of fedem_fpp -SNfile (FFpSNCurveLib::readSNCurves / read, fedem-foundation/src/FFpLib/FFpFatigue/
+ * FFpSNCurveLib.C:132-277): entries <standard name, standard id (0 NorSok, 1 British), <curve name, <loga1, m1, loga2, m2, ..>
+ * [, thickness exponent]>, ..>, '#' comment lines.  Curves failing the reference's validity checks are dropped, standards
+ * without a valid curve too, so (std_index, curve_index) address the same curves as FFpSNCurveLib::getCurve.
+ *  fsr_sn_get : nseg line segments (loga[k], m[k], k < nseg <= cap) and for NorSok the nseg - 1 intersections logN0; returns
+ *               nseg, or < 0 when the indices are out of range.  std_id may be NULL.
+ *  fsr_sn_value : FFpSNCurve::getValue, cycles to failure at stress range s (FFpSNCurve.C:22-47); < 0 = no such curve. */
+typedef struct fsr_sn_lib fsr_sn_lib;
+int fsr_sn_read(fsr_sn_lib **lib, const char *path);
+void fsr_sn_free(fsr_sn_lib *lib);
+int fsr_sn_num_standards(const fsr_sn_lib *lib);
+int fsr_sn_num_curves(const fsr_sn_lib *lib, int std_index);
+int fsr_sn_get(const fsr_sn_lib *lib, int std_index, int curve_index, int *std_id, double *loga, double *m, double *logN0, int cap);
+double fsr_sn_value(const fsr_sn_lib *lib, int std_index, int curve_index, double s);
 
 /* ---- file formats and history assembly on the drop-in surface (host only) -------------------
  * Tagged binary files as written by writeTagDB / read by readTagDB (src/vpmUtilities/binaryDB.c:
@@ -481,6 +501,21 @@ int fsr_ftl_get_topology(const fsr_ftl *ftl, int use_andes, int *melcon, int *mp
 int fsr_ftl_get_elmdata(const fsr_ftl *ftl, double *emod, double *rny, double *rho, double *thk, int *elmid,
                         double *beam, int *status);
 int fsr_ftl_ext2int(const fsr_ftl *ftl, int is_node, int id); /* ffl_ext2int (:716-737) */
+/* Strain coat elements of the FE part (STRCT3 / STRCQ4 / STRCT6 / STRCQ8 with their PSTRC result sets, PFATIGUE data and the
+ * {FE id} reference to the underlying finite element) as ffl_getstraincoat delivers them one by one (FFlLinkHandler_F.C:1587-1701):
+ * nodes = internal node numbers (1-based; every second node of the 6- and 8-noded elements is skipped, < 0 = non-existing node),
+ * per result set k < npts: res_set 1 / 2 / 3 = "Bottom" / "Mid" / "Top" (0 = other), material id, E, nu of the PSTRC's PMAT, zpos =
+ * PHEIGHT height or PTHICKREF factor * PTHICK thickness, sn_curve = {snCurveStd, snCurveIndex} of the PFATIGUE (-1, -1 without
+ * one) and its stress concentration factor.  fsr_ftl_num_strain_coats = ffl_getnostrc (:1753-1762, calculation flag on);
+ * fsr_ftl_get_strain_coats fills at most cap entries in element order and returns the total count. */
+typedef struct fsr_strain_coat {
+  int id, nnod, npts, elm_id;
+  int nodes[8];
+  int mat_id[3], res_set[3], sn_curve[3][2];
+  double emod[3], nu[3], zpos[3], scf[3];
+} fsr_strain_coat;
+int fsr_ftl_num_strain_coats(const fsr_ftl *ftl);
+int fsr_ftl_get_strain_coats(const fsr_ftl *ftl, fsr_strain_coat *out, int cap);
 
 /* ---- solver input file (.fsi) -----------------------------------------------------------------------
  * Replaces readSolverData (src/vpmStress/displacementModule.f90:138-229 -> InitiateSupEls1/InitiateTriads/
@@ -590,6 +625,17 @@ int solveGage(void);
  * order), with the nodal form (writeNodesHeader :459-537) and the scaled strain energy density per result point
  * (calcStrainEnergyDensity, modesRoutines.f90:219-305: one full K1 + K2 pass per mode).  VTF export is not part of this build. */
 int solveModes(void);
+/* solveFpp (src/vpmStress/stressInterface.C:117-124, fppmain.C:15-72) runs subroutine fpp (src/vpmStress/fpp.f90): the strain coat
+ * elements of the FE part (-surface selects the result sets) become rosettes in their element coordinate systems
+ * (initiateStrainCoats, strainCoatModule.f90:172-312; InitStrainRosette with useElCoordSys); over the selected time steps the
+ * running envelopes, angle bins and biaxiality sums (calcStrainCoatData) and, with -HistDataType 1 and S-N curves assigned
+ * (PFATIGUE + -SNfile), rainflow damage of the signed abs-max principal stress; ONE summary record per run on the strain coat
+ * results database (saveStrainCoatModule.f90: file tag "#FEDEM strain coat data", step 1 at the stop time), the tables of
+ * printStrainCoatInput / printStrainCoatData in the -resfile with -debug > 0.  -writeHistory gives the per-step history form
+ * instead (writeHistoryHeader / writeHistoryDB).  Not part of this build: the nCode FPP plug-in (-HistDataType < 0, -fppfile;
+ * FT_HAS_FPPINTERFACE) and residual stress import.  bin/fedem_fpp is main() over initSolverArgs + solveFpp. */
+int solveFpp(void);
+void fsr_fpp_define_options(void);     /* the option table of fedem_fpp (fppmain.C:21-68) */
 void fsr_modes_define_options(void);   /* the option table of fedem_modes (modesmain.C:22-52) */
 /* ffr_getnextstep (fedem-foundation/src/FFrLib/FFrExtractorInterface.f90:134-170) over a sorted key list:
  * indices of the time steps the stress loop visits for -statm start -stotm stop -tinc tinc; returns their

@@ -18,6 +18,8 @@
 #include "FFlLib/FFlIOAdaptors/FFlReaders.H"
 #include "FFlLib/FFlIOAdaptors/FFlVTFWriter.H"
 #include "FFlLib/FFlLinkHandler.H"
+#include "FFpLib/FFpFatigue/FFpSNCurve.H"
+#include "FFpLib/FFpFatigue/FFpSNCurveLib.H"
 
 // ---- stubs for off-path parts --------------------------------------------------------------------
 namespace FedemAdmin { const char* getCopyrightString() { return "checker build"; } }
@@ -75,5 +77,23 @@ int ref_ffl_load(const char* path, const char* groups)
 }
 
 void ref_ffl_release() { const int all = 0; ffl_release_(all); }
+
+// the reference's S-N curve library reader (FFpSNCurveLib.C), as ffp_initfatigue / ffp_calcdamage use it
+int ref_sn_read(const char* path) { return FFpSNCurveLib::instance()->readSNCurves(path) ? 1 : 0; }
+int ref_sn_num_standards() { return (int)FFpSNCurveLib::instance()->getNoCurveStds(); }
+int ref_sn_num_curves(int is) { return (int)FFpSNCurveLib::instance()->getNoCurves(is); }
+int ref_sn_get(int is, int ic, int* std_id, double* loga, double* m, int cap)
+{
+  FFpSNCurve* c = FFpSNCurveLib::instance()->getCurve((long int)is, (long int)ic);
+  if (!c) return -1;
+  *std_id = (int)c->getStdId();
+  for (size_t k = 0; k < c->loga.size() && (int)k < cap; k++) { loga[k] = c->loga[k]; m[k] = c->m[k]; }
+  return (int)c->loga.size();
+}
+double ref_sn_value(int is, int ic, double s)
+{
+  FFpSNCurve* c = FFpSNCurveLib::instance()->getCurve((long int)is, (long int)ic);
+  return c ? c->getValue(s) : -1.0;
+}
 
 }  // extern "C"

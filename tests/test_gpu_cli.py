@@ -508,6 +508,158 @@ def test_fedem_modes_one_file_per_mode_nodes_and_energy_density(oracle, tmp_path
     assert not os.path.exists(tmp_path / "modes_8.frs")
 
 
+def _globalized_axes(X):
+    """getShellElementAxes with doGlobalize (strainAndStressUtils.f90:297-434)"""
+    n = np.cross(X[2] - X[0], X[3] - X[1]) if len(X) == 4 else np.cross(X[1] - X[0], X[2] - X[0])
+    n = n / np.linalg.norm(n)
+    if abs(n[1]) > 0.01 or abs(n[2]) > 0.01:
+        v1 = np.array([n[1] ** 2 + n[2] ** 2, -n[0] * n[1], -n[0] * n[2]])
+    else:
+        v1 = np.cross(np.array([-n[1] * n[0], n[0] ** 2 + n[2] ** 2, -n[1] * n[2]]), n)
+    v1 = v1 / np.linalg.norm(v1)
+    return v1, np.cross(n, v1), n
+
+
+@pytest.mark.parametrize("surface", [0, 3])
+def test_fedem_fpp_executable(oracle, tmp_path, surface):
+    """bin/fedem_fpp (fpp.f90): strain coat elements of the FE part -> rosettes in the element systems -> running envelopes, angle
+    bins, biaxiality and rainflow damage on the GPU -> ONE summary record on the strain coat results database.  Every value read back
+    and compared with the oracle's calcRosetteStrains / calcStrainCoatData / calcAngleData restatement and its PVX + rainflow + Miner
+    sum on the S-N curve of the library file."""
+    import ctypes as C
+    from oracle_bind import _dp
+    from test_fpp_cpu import SN_TEXT, coats_for
+    from fedem_solvers_b200.gage import Rosette
+    part = plate_part(6, 5, ngen=3, seed=81, tri_fraction=0.3, warp=0.02, n_ext=4)
+    ns = 400
+    case = _make_case(tmp_path, part, "plate", nsteps=ns)
+    coats = coats_for(part)
+    write_ftl(str(tmp_path / "plate.ftl"), part, strain_coats=coats)
+    open(tmp_path / "curves.fsn", "w").write(SN_TEXT)
+    sam, base = part.sam, case["base"]
+    b = oracle.bind_part(part)
+    # oracle side first: the gates are set from the response so that both the biaxiality gate and the PVX gate bite
+    to_mpa = 1.0e-6
+    curves = {(0, 0): (15.117, 17.146, 4.0, 5.0), (0, 1): (12.592, 16.320, 3.0, 5.0), (1, 0): (12.1818 - 0.2095 * 2.0,) * 2 + (3.0, 3.0),
+              (1, 1): (12.0128 - 0.2509 * 2.0,) * 2 + (3.0, 3.0)}
+    want = {}
+    for sc in coats:
+        e = sc["elm"]
+        nodes = [int(k) for k in sam.mmnpc[sam.mpmnpc[e] - 1: sam.mpmnpc[e + 1] - 1]]
+        X = part.elm.xyz[np.array(nodes) - 1]
+        v1, v2, v3 = _globalized_axes(X)
+        for name, h in sc["sets"]:
+            if surface and {"Bottom": 1, "Mid": 2, "Top": 3}[name] != surface:
+                continue
+            z = h if h is not None else {"Bottom": -0.5, "Top": 0.5}[name] * float(part.elm.thk[e])
+            r = Rosette(id=1, nodes=nodes, rpos=np.stack([v1, v2, v3, X.mean(0)], 1), type="SINGLE_GAGE", zpos=z, emod=float(part.elm.emod[e]),
+                        nu=float(part.elm.rny[e]))
+            want[(sc["id"], name)] = oracle.rosette_history(b, r, case["Q"])
+    smax = max(np.abs(v[:, 15]).max() for v in want.values())
+    bgate = 0.3 * float(np.median([np.abs(v[:, 15]).max() for v in want.values()]))
+    pvx = 0.05 * smax * to_mpa
+    exe = os.path.join(os.path.dirname(EXE), "fedem_fpp")
+    args = [exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx", "-eigfile", "plate_E.fmx",
+            "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rdbfile", "coat.frs", "-rdbinc", "2", "-double", "-debug", "1",
+            "-statm", "0", "-stotm", "100", "-HistDataType", "1", "-SNfile", "curves.fsn", "-PVXGate", repr(pvx), "-biAxialGate", repr(bgate),
+            "-stressToMPaScale", repr(to_mpa), "-angleBins", "181", "-surface", str(surface)]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Strain coat calculation successfully completed" in r.stdout and "STRAIN COAT RECOVERY SUMMARY" in r.stdout
+    out = str(tmp_path / "coat_2.frs")
+    assert open(out, "rb").read(23) == b"#FEDEM strain coat data"
+    rd = FrsReader(out)
+    assert rd.nsteps == 1 and rd.step_numbers[0] == 1 and rd.times[0] == 100.0
+    f = oracle.lib.orc_coat_summary
+    f.restype = C.c_int
+    pvx_used = float(np.float32(pvx))          # -PVXGate is a float option (fppmain.C:47, ffa_cmdlinearg_getfloat)
+    n_damaged = n_biax = 0
+    for (cid, name), v in want.items():
+        sc = coats[cid - 1000]
+        nn = len(sam.mmnpc[sam.mpmnpc[sc["elm"]] - 1: sam.mpmnpc[sc["elm"] + 1] - 1])
+        tn = "STRCT3" if nn == 3 else "STRCQ4"
+        env, summ = np.zeros(8), np.zeros(6)
+        nb = f(_dp(np.ascontiguousarray(v)), ns, 181, C.c_double(bgate), _dp(env), _dp(summ), None)
+
+        def val(var):
+            h = rd.find(f"Elements|{cid}|{tn}|Element|{name}|{var}", "Part", base)
+            return None if h is None else float(rd.read(h)[0, 0])
+        sc_s, sc_e = np.abs(v[:, 13:16]).max(), np.abs(v[:, 3:6]).max()
+        # env: epsMax, epsMin, sigMax, sigMin, gammaMax, tauMax, vmeMax, vmsMax; summ: stress range, strain range, popAngle, angSpread, mean, std
+        assert abs(val("Max principal stress") - (env[2] if abs(env[2]) > abs(env[3]) else env[3])) <= TOL * sc_s
+        assert abs(val("Max shear stress") - env[5]) <= TOL * sc_s and abs(val("Max von Mises stress") - env[7]) <= TOL * sc_s
+        assert abs(val("Max stress range") - summ[0]) <= TOL * sc_s and abs(val("Max strain range") - summ[1]) <= TOL * sc_e
+        assert abs(val("Max principal strain") - (env[0] if abs(env[0]) > abs(env[1]) else env[1])) <= TOL * sc_e
+        assert abs(val("Max shear strain") - env[4]) <= TOL * sc_e and abs(val("Max von Mises strain") - env[6]) <= TOL * sc_e
+        assert val("Most popular angle") == summ[2] and val("Angle spread") == summ[3]
+        if nb > 0:
+            assert abs(val("Mean bi-axiality") - summ[4]) <= 1e-9 and abs(val("Biaxiality standard deviation") - summ[5]) <= 1e-9
+            n_biax += 1
+        else:
+            assert val("Mean bi-axiality") is None
+        if sc["fatigue"] is None:
+            assert val("Damage") is None and val("Life (repeats)") is None
+        else:
+            a, bb, scf = sc["fatigue"]
+            dmg, ncyc, _, ok = oracle.series_fatigue(v[:, 15] * to_mpa * scf, pvx_used, curves[(a, bb)])
+            assert ok
+            got = val("Damage")
+            if dmg > 0:
+                assert abs(got - dmg) <= 1e-9 * dmg and abs(val("Life (repeats)") - 1.0 / dmg) <= 1e-9 / dmg
+                assert abs(val("Life (equnits)") - 100.0 / dmg) <= 1e-9 * 100.0 / dmg
+                n_damaged += 1
+            else:
+                assert got == 1.0e20 and val("Life (repeats)") == 1.0e20
+    assert n_damaged >= 3 and n_biax >= 3
+    # the reference's own FFrExtractor reads the file (header grammar of saveStrainCoatModule)
+    from test_frs_cpu import RefFrs, REF_LIB
+    if os.path.exists(REF_LIB):
+        ref = RefFrs([out])
+        keys = ref.keys()
+        assert len(keys) == 1
+        (cid, name), v = next(iter(want.items()))
+        nn = len(sam.mmnpc[sam.mpmnpc[coats[cid - 1000]["elm"]] - 1: sam.mpmnpc[coats[cid - 1000]["elm"] + 1] - 1])
+        var = f"Elements|{cid}|{'STRCT3' if nn == 3 else 'STRCQ4'}|Element|{name}|Max von Mises stress"
+        mine = rd.read(rd.find(var, "Part", base))
+        ok, theirs = ref.read(var, "Part", base, keys, 1)
+        assert ok == 1 and np.array_equal(theirs, mine)
+        ref.close()
+
+
+def test_fedem_fpp_history_files(oracle, tmp_path):
+    """-writeHistory: per-step records of sigmaP(1:3), tauMax, sigmaVM, epsP(1:3), gammaMax, epsVM of every coat result point
+    (writeHistoryHeader / writeRosetteDB)"""
+    from test_fpp_cpu import coats_for
+    from fedem_solvers_b200.gage import Rosette
+    part = plate_part(5, 4, ngen=2, seed=83, tri_fraction=0.3, warp=0.02, n_ext=4)
+    ns = 30
+    case = _make_case(tmp_path, part, "plate", nsteps=ns)
+    coats = coats_for(part, every=3)
+    write_ftl(str(tmp_path / "plate.ftl"), part, strain_coats=coats)
+    sam, base = part.sam, case["base"]
+    exe = os.path.join(os.path.dirname(EXE), "fedem_fpp")
+    args = [exe, "-cwd", str(tmp_path), "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-Bmatfile", "plate_B.fmx", "-eigfile", "plate_E.fmx",
+            "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs", "-rdbfile", "coat.frs", "-double", "-statm", "0", "-stotm", "100", "-writeHistory"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rd = FrsReader(str(tmp_path / "coat_1.frs"))
+    assert rd.nsteps == ns
+    b = oracle.bind_part(part)
+    sc = coats[1]
+    e = sc["elm"]
+    nodes = [int(k) for k in sam.mmnpc[sam.mpmnpc[e] - 1: sam.mpmnpc[e + 1] - 1]]
+    X = part.elm.xyz[np.array(nodes) - 1]
+    v1, v2, v3 = _globalized_axes(X)
+    rr = Rosette(id=1, nodes=nodes, rpos=np.stack([v1, v2, v3, X.mean(0)], 1), type="SINGLE_GAGE", zpos=0.5 * float(part.elm.thk[e]),
+                 emod=float(part.elm.emod[e]), nu=float(part.elm.rny[e]))
+    v = oracle.rosette_history(b, rr, case["Q"])
+    tn = "STRCT3" if len(nodes) == 3 else "STRCQ4"
+    for var, col in (("Max principal stress", 13), ("Min principal stress", 14), ("Signed abs max stress", 15), ("Max shear stress", 16),
+                     ("Von Mises stress", 17), ("Max principal strain", 3), ("Signed abs max strain", 5), ("Max shear strain", 6), ("Von Mises strain", 7)):
+        got = rd.read(rd.find(f"Elements|{sc['id']}|{tn}|Element|Top|{var}", "Part", base))[:, 0]
+        assert np.abs(got - v[:, col]).max() <= TOL * np.abs(v[:, col]).max(), var
+
+
 def test_direct_solution_without_solver_input_file(oracle, tmp_path):
     """fedem_stress without -fsifile (stress.f90:131-135,397): the results files hold the nodal displacements of the part
     themselves ("Vectors|Dynamic response|Displacement", readIntDisplacements) -- no B / E matrices, no expansion, the element
