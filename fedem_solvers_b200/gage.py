@@ -194,6 +194,11 @@ class StrainGages:
         out["nBiAxial"] = nb
         return out
 
+    def set_coat_fatigue(self, scf=None):
+        """fedem_fpp's fatigue series: signed abs-max principal stress * to_mpa * scf[r] as series 4 r (None: back to sigmaP(1))."""
+        a = None if scf is None else np.ascontiguousarray(scf, F64)
+        check(self._lib.fsr_gage_set_coat_fatigue(self._h, _dp(a)), "fsr_gage_set_coat_fatigue")
+
     def recover_dev(self, q_ptr, ldq, nsteps, values_ptr=None, stream=None):
         check(self._lib.fsr_gage_recover_dev(self._h, C.c_void_p(q_ptr), ldq, nsteps,
                                              C.c_void_p(values_ptr) if values_ptr else None,
