@@ -171,8 +171,9 @@ void effective_element_types(const fsr_sam* sam_in, const fsr_options* opt, std:
   // formulations of fedem_stress (stressmain.C:72-78: -fftStressForm 1, -ffqStressForm 2) STR21 runs exactly the statements of
   // STR23 (FTSA31 / FTSA32 / FTS38, elStressModule.f90:559-562,586-587 vs :935,953) and STR22 exactly those of STR24
   // (pMatStiff projection + STR22a with 2 x 2 Gauss points, :675-686,717-722 vs :1039-1076), so they join those families.
-  // The other (private, non-default) formulations are not built: elements of such a run get NO results, like any
-  // unsupported type, and fedem_stress says so (stress_driver.cu).
+  // Of the other (private, non-default) formulations -ffqStressForm 1 and -fftStressForm 0 / 2 are served below; FFQ elements of a
+  // run with -ffqStressForm 0 (STR22b: the Femlib nodal evaluation FQS32) get NO results, like any unsupported type, and
+  // fedem_stress says so (stress_driver.cu).
   const int ffq = opt && opt->reserved[1] ? opt->reserved[1] - 1 : 2, fft = opt && opt->reserved[2] ? opt->reserved[2] - 1 : 1;
   // -ffqStressForm 1 is STR22a with one Gauss point (:761-768,806-809): the quad operator builder takes the point count, so it
   // is served as well as long as the part has no ANDES quads (which always use 2 x 2) next to the FFQ ones.
@@ -182,8 +183,14 @@ void effective_element_types(const fsr_sam* sam_in, const fsr_options* opt, std:
   for (int t : melcon_eff) { has24 |= t == 24; has22 |= t == 22; }
   const bool ffq1 = ffq == 1 && has22 && !has24;
   if (ffq1) quad_ngauss = 1;
+  // -fftStressForm 0 / 2 is STR21 on FTS31 / FTS32 (:559-566,586-592): the triangle operator builder has that membrane formulation
+  // too, for a part whose triangles are all FFT3 (bit 8 of quad_ngauss carries the switch to part_create_mapped)
+  bool has23 = false, has21 = false;
+  for (int t : melcon_eff) { has23 |= t == 23; has21 |= t == 21; }
+  const bool fft_legacy = fft != 1 && has21 && !has23;
+  if (fft_legacy) quad_ngauss |= 0x100;
   for (int& t : melcon_eff) {
-    if (t == 21) t = fft == 1 ? 23 : 0;
+    if (t == 21) t = (fft == 1 || fft_legacy) ? 23 : 0;
     else if (t == 22) t = (ffq == 2 || ffq1) ? 24 : 0;
   }
 }
@@ -222,7 +229,8 @@ int part_create_mapped(fsr_part** out, const fsr_sam* sam, const fsr_elmdata* el
   p->ndof2 = sam->ndof2; p->ngen = sam->ngen; p->neq = sam->neq; p->nceq = sam->nceq;
   p->ndim = sam->ndof2 + sam->ngen;
   p->stressForm = opt ? opt->stressForm : 0;
-  p->quad_ngauss = quad_ngauss;
+  p->quad_ngauss = quad_ngauss & 0xff;
+  p->tri_legacy = (quad_ngauss >> 8) & 1;
   p->elem_order = opt ? opt->reserved[0] : 0;
   // ldk: multiple of 4 with ldk % 8 == 4 (bank-conflict-free fragment loads in K1)
   p->ldk = round_up(std::max(p->ndim, 1), 4);

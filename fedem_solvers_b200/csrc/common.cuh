@@ -150,6 +150,7 @@ struct fsr_part {
   int nrows_pad = 0;   // ndof padded to the K1 row tile
   int npts = 0;        // result points
   int stressForm = 0;
+  int tri_legacy = 0;   // 1 = the triangles are legacy FFT3 shells recovered with -fftStressForm 0 / 2 (FTS31 / FTS32 instead of FTSA31 / FTSA32)
   int quad_ngauss = 2;  // Gauss points per direction of the quad shell stress evaluation (1 only for legacy FFQ with -ffqStressForm 1)
   int elem_order = 0;  // 0 = elements processed in Morton order of their centroids (L2 reuse of shared
                        // nodes), 1 = SAM order.  Outputs are always in SAM order.

@@ -511,6 +511,126 @@ __device__ bool tri_bending_kappa(double* AKB, const double* Ei, const double* x
   return true;
 }
 
+// ---- legacy FFT3 shell with -fftStressForm 0 / 2 (STR21 -> FTS31 / FTS32, fts.f:7-292) ---------------------------------
+// The membrane part is the Bergan / Felippa triangle of tmrf.f: TMRF31 / SM3MH (:7-55,151-303) deliver the higher-order
+// strain-displacement relation HH(3,9) through a 9 x 9 Crout factorisation with implicit row scaling (LUFACT :304-388, LUSOLV
+// :389-473 in its row-storage form), TMRF32 (:474-634) the centroid stress matrix DM (L'/A + BH HH).
+__device__ static bool tmrf_lufact9(double* A, int* perm, double* V)
+{
+#define A_(i, j) A[(i) + 9 * (j)]
+  for (int i = 0; i < 9; ++i) {
+    double y = 0.0;
+    for (int j = 0; j < 9; ++j) y += A_(i, j) * A_(i, j);
+    V[i] = y > 0.0 ? sqrt(1.0 / y) : 0.0;
+  }
+  for (int k = 0; k < 9; ++k) {
+    perm[k] = k;
+    if (V[k] <= 0.0) continue;
+    int l = k;
+    double x = 0.0;
+    for (int i = k; i < 9; ++i) {
+      double y = 0.0;
+      for (int j = 0; j < k; ++j) y += A_(i, j) * A_(j, k);
+      A_(i, k) -= y;
+      y = fabs(V[i] * A_(i, k));
+      if (y > x) { x = y; l = i; }
+    }
+    if (l != k) {
+      for (int j = 0; j < 9; ++j) { const double y = A_(k, j); A_(k, j) = A_(l, j); A_(l, j) = y; }
+      V[l] = V[k];
+      perm[k] = l;
+    }
+    if (x <= 2.0e-16) return false;   // MACTOL
+    x = 1.0 / A_(k, k);
+    A_(k, k) = x;
+    for (int j = k + 1; j < 9; ++j) {
+      double y = 0.0;
+      for (int i = 0; i < k; ++i) y += A_(k, i) * A_(i, j);
+      A_(k, j) = (A_(k, j) - y) * x;
+    }
+  }
+  return true;
+}
+
+// HH [3][9] (row r, column j at HH[r + 3 j]; columns u1 v1 u2 v2 u3 v3 th1 th2 th3) and the centroid matrix SMM[3][9] of FTS32,
+// which is handed the plane stress matrix Dm where TMRF32 expects the membrane rigidity and adds the columns of HH to those of
+// the lumping matrix (node order u1 v1 th1 ..) as they come -- both as in the reference.
+__device__ static bool tri_legacy_membrane(double (*SMM)[9], const double* Dm /* 3x3 column-major */, const double* X, const double* Y,
+                                           double alpha)
+{
+  const double area2 = (Y[1] - Y[0]) * (X[0] - X[2]) - (X[1] - X[0]) * (Y[0] - Y[2]);
+  if (area2 <= 1.0e-16) return false;
+  const double x0 = (X[0] + X[1] + X[2]) / 3.0, y0 = (Y[0] + Y[1] + Y[2]) / 3.0, area = 0.5 * area2, c = 1. / sqrt(area);
+  double xc[3], yc[3], xm[3], ym[3], GT[81], HH[27], T[9], BH[9];
+  int perm[9];
+  for (int i = 0; i < 3; ++i) { xc[i] = c * (X[i] - x0); yc[i] = c * (Y[i] - y0); }
+  xm[0] = 0.5 * (xc[1] + xc[2]); xm[1] = 0.5 * (xc[2] + xc[0]); xm[2] = 0.5 * (xc[0] + xc[1]);
+  ym[0] = 0.5 * (yc[1] + yc[2]); ym[1] = 0.5 * (yc[2] + yc[0]); ym[2] = 0.5 * (yc[0] + yc[1]);
+  for (int i = 0; i < 81; ++i) GT[i] = 0.0;
+  for (int i = 0; i < 27; ++i) HH[i] = 0.0;
+#define G_(i, j) GT[(i) + 9 * (j)]
+  for (int j = 0; j < 3; ++j) {
+    const double dx = xm[j] - xc[j], dy = ym[j] - yc[j], dl = sqrt(dx * dx + dy * dy), cj = dx / dl, sj = dy / dl;
+    const double a1 = -0.5 * sj * (cj * cj), a2 = 0.5 * (cj * cj * cj), b2 = -0.5 * (sj * sj * sj), b3 = 0.5 * (sj * sj) * cj;
+    const double a3 = -(b2 + a1 + a1), b1 = -(b3 + b3 + a2);
+    G_(0, 2 * j) = 1.; G_(1, 2 * j + 1) = 1.;
+    G_(2, 2 * j) = -yc[j]; G_(2, 2 * j + 1) = xc[j]; G_(2, j + 6) = c;
+    G_(3, 2 * j) = xc[j]; G_(5, 2 * j) = yc[j]; G_(4, 2 * j + 1) = yc[j]; G_(5, 2 * j + 1) = xc[j];
+    HH[j + 3 * (j + 6)] = 1.;
+    for (int i = 0; i < 3; ++i) {
+      const double xi = xc[i], yi = yc[i];
+      G_(j + 6, 2 * i) = a1 * xi * xi + 2. * a2 * xi * yi + a3 * yi * yi;
+      G_(j + 6, 2 * i + 1) = b1 * xi * xi + 2. * b2 * xi * yi + b3 * yi * yi;
+      G_(j + 6, i + 6) = -c * (cj * xi + sj * yi);
+    }
+    BH[0 + 3 * j] = c * (2 * a1 * xc[j] + a2 * yc[j]);
+    BH[1 + 3 * j] = c * (b2 * xc[j] + 2 * b3 * yc[j]);
+    BH[2 + 3 * j] = c * (-4 * b3 * xc[j] - 4 * a1 * yc[j]);
+  }
+#undef G_
+  if (!tmrf_lufact9(GT, perm, T)) return false;
+  // LUSOLV(GT,9,9,IPERM,HH,3,-3): the three right hand sides are the rows of HH
+  for (int i = 0; i < 9; ++i) {
+    const int k = perm[i];
+    if (k != i) for (int r = 0; r < 3; ++r) { const double t = HH[r + 3 * i]; HH[r + 3 * i] = HH[r + 3 * k]; HH[r + 3 * k] = t; }
+  }
+  for (int r = 0; r < 3; ++r) {
+    HH[r] = HH[r] * GT[0];
+    for (int i = 0; i < 8; ++i) {
+      double sum = 0.0;
+      for (int k = 0; k <= i; ++k) sum -= GT[(i + 1) + 9 * k] * HH[r + 3 * k];
+      HH[r + 3 * (i + 1)] = (HH[r + 3 * (i + 1)] + sum) * GT[(i + 1) + 9 * (i + 1)];
+    }
+    for (int i = 7; i >= 0; --i) {
+      double sum = 0.0;
+      for (int k = 1; k <= 8 - i; ++k) sum -= GT[i + 9 * (i + k)] * HH[r + 3 * (i + k)];
+      HH[r + 3 * i] += sum;
+    }
+  }
+#undef A_
+  // TMRF32: lumping matrix L (9 x 3) in node order, TM = L'/A + BH HH, SM = Dm TM
+  const double x21 = X[1] - X[0], x12 = -x21, x32 = X[2] - X[1], x23 = -x32, x13 = X[0] - X[2], x31 = -x13;
+  const double y21 = Y[1] - Y[0], y12 = -y21, y32 = Y[2] - Y[1], y23 = -y32, y13 = Y[0] - Y[2], y31 = -y13;
+  double L[9][3] = {{0.5 * y23, 0.0, 0.5 * x32}, {0.0, 0.5 * x32, 0.5 * y23}, {0.0, 0.0, 0.0},
+                    {0.5 * y31, 0.0, 0.5 * x13}, {0.0, 0.5 * x13, 0.5 * y31}, {0.0, 0.0, 0.0},
+                    {0.5 * y12, 0.0, 0.5 * x21}, {0.0, 0.5 * x21, 0.5 * y12}, {0.0, 0.0, 0.0}};
+  if (alpha > 0.0) {
+    L[2][0] = 0.5 * (y23 * (y13 - y21) * alpha / 6); L[2][1] = 0.5 * (x32 * (x31 - x12) * alpha / 6); L[2][2] = 0.5 * ((x31 * y13 - x12 * y21) * alpha / 3);
+    L[5][0] = 0.5 * (y31 * (y21 - y32) * alpha / 6); L[5][1] = 0.5 * (x13 * (x12 - x23) * alpha / 6); L[5][2] = 0.5 * ((x12 * y21 - x23 * y32) * alpha / 3);
+    L[8][0] = 0.5 * (y12 * (y32 - y13) * alpha / 6); L[8][1] = 0.5 * (x21 * (x23 - x31) * alpha / 6); L[8][2] = 0.5 * ((x23 * y32 - x31 * y13) * alpha / 3);
+  }
+  for (int i = 0; i < 9; ++i) {
+    double tm[3];
+    for (int j = 0; j < 3; ++j) {
+      double sh = 0.0;
+      for (int k = 0; k < 3; ++k) sh += BH[j + 3 * k] * HH[k + 3 * i];
+      tm[j] = (1. / area) * L[i][j] + sh;
+    }
+    for (int j = 0; j < 3; ++j) SMM[j][i] = Dm[j] * tm[0] + Dm[j + 3] * tm[1] + Dm[j + 6] * tm[2];
+  }
+  return true;
+}
+
 // One thread per triangle: STR23 (src/vpmStress/elStressModule.f90:901-999) as a 6-point x 3-component
 // x 18-DOF operator.  FTSA31 (ftsa.f:53-104) gives the two kappa matrices, FTSA32 (:196-260) their
 // centroid stress matrices with ZZ = 1./3. in REAL*4, FTS38 (fts.f:446-490) the split of the nodal
@@ -520,7 +640,7 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
                                      const double* __restrict__ xyz, const double* __restrict__ emod,
                                      const double* __restrict__ rny, const double* __restrict__ thk,
                                      double* __restrict__ Sfrag, unsigned char* __restrict__ failed,
-                                     double* __restrict__ aux)
+                                     double* __restrict__ aux, int legacy)
 {
   const int KT = 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,7 +668,7 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
   const double xl[3] = {0., L21, L31 * cosg}, yl[3] = {0., 0., L31 * sing};
   const double th[3] = {t, t, t};
   double AKM[63], AKB[81];
-  if (ok) ok = tri_membrane_kappa(AKM, Ei, xl, yl, (t + t + t) / 3.);
+  if (ok && !legacy) ok = tri_membrane_kappa(AKM, Ei, xl, yl, (t + t + t) / 3.);
   if (ok) ok = tri_bending_kappa(AKB, Ei, xl, yl, th);
   // output-system rotation from the triangle axes (x along 1->2, not projected)
   V3 ex = d21, ez = vcross(d21, d31);
@@ -561,16 +681,24 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
   if (!ok) { failed[i] = 1; return; }  // Sfrag was zeroed by the caller
 
   // centroid stress matrices (HLST32, hlst.f:330-352; TEBA32, nyteba.f:333-364), ZZ = REAL*4 1./3.
-  const double zz = (double)(1.f / 3.f);
+  // legacy FFT3 formulation (-fftStressForm 0 / 2): FTS32 with ZZ = 1/3 in double precision, membrane matrix of TMRF32 on the
+  // plane stress matrix E itself (elStressModule.f90:589-591 passes E where FTS32 expects t * E)
+  const double zz = legacy ? 1.0 / 3.0 : (double)(1.f / 3.f);
   const double x0 = (xl[0] + xl[1] + xl[2]) / 3., y0 = (yl[0] + yl[1] + yl[2]) / 3.;
   double rx = 0., ry = 0.;
   for (int k = 0; k < 3; ++k) { rx += (xl[k] - x0) * zz; ry += (yl[k] - y0) * zz; }
   double SMM[3][9], SMB[3][9];
+  if (legacy) {
+    const double Dm[9] = {C11, nu * C11, 0., nu * C11, C11, 0., 0., 0., 0.5 * E / (1.0 + nu)};
+    if (!tri_legacy_membrane(SMM, Dm, xl, yl, 1.5)) { failed[i] = 1; return; }
+  }
   for (int j = 0; j < 9; ++j) {
-    const double* a = AKM + 7 * j;
-    SMM[0][j] = a[0] + rx * a[3] + ry * a[5];
-    SMM[1][j] = a[1] + rx * a[4] + ry * a[6];
-    SMM[2][j] = a[2] - ry * a[3] - rx * a[6];
+    if (!legacy) {
+      const double* a = AKM + 7 * j;
+      SMM[0][j] = a[0] + rx * a[3] + ry * a[5];
+      SMM[1][j] = a[1] + rx * a[4] + ry * a[6];
+      SMM[2][j] = a[2] - ry * a[3] - rx * a[6];
+    }
     for (int r = 0; r < 3; ++r) SMB[r][j] = zz * AKB[3 * r + 9 * j] + zz * AKB[3 * r + 1 + 9 * j] + zz * AKB[3 * r + 2 + 9 * j];
   }
   // direction cosines (DIRC30): rows = local x (1->2), y, z; every row renormalised
@@ -1321,7 +1449,7 @@ int build_shell_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
     if (rc) return rc;
     if (f.nelt > 0) {
       build_tri_ops_kernel<<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny,
-                                                           p->thk, f.Sfrag, f.failed, f.aux);
+                                                           p->thk, f.Sfrag, f.failed, f.aux, p->tri_legacy);
       FSR_LAUNCH_CHECK();
       FSR_CUDA(cudaStreamSynchronize(s));
       cudaFree(d_conn);

@@ -482,13 +482,15 @@ static int run_program(int which)
   if (which == 0) {   // legacy thin shells are recovered for the default stress formulations only (fsr_part_create): say so loudly otherwise
     const int ffq = c.get_int("ffqStressForm"), fft = c.get_int("fftStressForm");
     int nq = 0, nt = 0;
+    bool has23 = false;
+    for (int e = 0; e < nel; ++e) has23 = has23 || melcon[(size_t)e] == 23;
     for (int e = 0; e < nel; ++e) {
       if (elmid[(size_t)e] < 1) continue;
       if (melcon[(size_t)e] == 22 && ffq != 2 && ffq != 1) ++nq;
-      if (melcon[(size_t)e] == 21 && fft != 1) ++nt;
+      if (melcon[(size_t)e] == 21 && fft != 1 && has23) ++nt;   // FTS31 / FTS32 is served for parts whose triangles are all FFT3
     }
     if (nq) log.line("  ** Warning: %d FFQ shells (type 22) get NO results: -ffqStressForm %d is not supported by this build (only 1 and the default, 2)", nq, ffq);
-    if (nt) log.line("  ** Warning: %d FFT shells (type 21) get NO results: -fftStressForm %d is not supported by this build (only the default, 1)", nt, fft);
+    if (nt) log.line("  ** Warning: %d FFT shells (type 21) get NO results: -fftStressForm %d next to ANDES triangles (type 23) in one part is not supported by this build", nt, fft);
   }
 
   // --- Read superelement data from the solver input file (readSolverData)

@@ -80,6 +80,10 @@ int orc_el_stress(int iel, int ieltyp, const orc_sam *sam, const orc_elmdata *ed
     *nstrp = 6;
     get_coor(iel, sam, ed, 3, x, y, z);
     thk[0] = thk[1] = thk[2] = ed->thk[iel - 1];
+    if (ieltyp == 21 && orc_get_fft_stress_form() != 1) {
+      ierr = orc_str21_legacy(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, S, SS, Sigma, Epsil);
+      break;
+    }
     ierr = orc_str23(x, y, z, ed->emod[iel - 1], ed->rny[iel - 1], thk, V, S, SS, Sigma,
                      Epsil);
     break;

@@ -91,6 +91,11 @@ int orc_str24(const double xg[4], const double yg[4], const double zg[4], double
  * like the reference's command-line argument */
 void orc_set_ffq_stress_form(int form);
 int orc_get_ffq_stress_form(void);
+void orc_set_fft_stress_form(int form);
+int orc_get_fft_stress_form(void);
+int orc_str21_legacy(const double xg[3], const double yg[3], const double zg[3], double emod,
+                     double rny, const double thk[3], const double ev[18], double SR[18],
+                     double SS[18], double sigma[18], double epsil[18]);
 int orc_str22(const double xg[4], const double yg[4], const double zg[4], double emod, double rny, const double thk[4],
               double ev[24], double SR[24], double SS[24], double sigma[24], double epsil[24]);
 int orc_str23(const double xg[3], const double yg[3], const double zg[3], double emod,

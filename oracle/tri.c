@@ -442,6 +442,266 @@ static void fts38(double *VML, double *VBL, const double *V, const double *X, co
   }
 }
 
+/* tmrf.f:304-388 (LUFACT): Crout factorisation with implicit row scaling, A(NA,*) column-major, diagonal stored inverted */
+static int lufact9(double *A, int *IPERM, double *V)
+{
+  const int N = 9;
+  const double MACTOL = 2.0e-16;
+#define A_(i, j) A[((i) - 1) + 9 * ((j) - 1)]
+  for (int I = 1; I <= N; I++) {
+    double Y = 0.0;
+    for (int J = 1; J <= N; J++) Y = Y + A_(I, J) * A_(I, J);
+    V[I - 1] = Y > 0.0 ? sqrt(1.0 / Y) : 0.0;
+  }
+  for (int K = 1; K <= N; K++) {
+    IPERM[K - 1] = K;
+    if (V[K - 1] <= 0.0) continue;
+    int L = K;
+    double X = 0.0;
+    for (int I = K; I <= N; I++) {
+      double Y = 0.0;
+      for (int J = 1; J <= K - 1; J++) Y = Y + A_(I, J) * A_(J, K);
+      A_(I, K) = A_(I, K) - Y;
+      Y = fabs(V[I - 1] * A_(I, K));
+      if (Y > X) { X = Y; L = I; }
+    }
+    if (L != K) {
+      for (int J = 1; J <= N; J++) { double Y = A_(K, J); A_(K, J) = A_(L, J); A_(L, J) = Y; }
+      V[L - 1] = V[K - 1];
+      IPERM[K - 1] = L;
+    }
+    if (X <= MACTOL) return N - (K - 1);
+    X = 1.0 / A_(K, K);
+    A_(K, K) = X;
+    for (int J = K + 1; J <= N; J++) {
+      double Y = 0.0;
+      for (int I = 1; I <= K - 1; I++) Y = Y + A_(K, I) * A_(I, J);
+      A_(K, J) = (A_(K, J) - Y) * X;
+    }
+  }
+  return 0;
+}
+
+/* tmrf.f:389-473 (LUSOLV) for the call LUSOLV(GT,9,9,IPERM,HH,3,-3): three right hand sides stored as ROWS of B(3,9) */
+static void lusolv9_rows(const double *A, const int *IPERM, double *B)
+{
+  const int N = 9;
+#define B_(j, i) B[((j) - 1) + 3 * ((i) - 1)]
+  for (int I = 1; I <= N; I++) {
+    const int K = IPERM[I - 1];
+    if (K != I)
+      for (int J = 1; J <= 3; J++) { double T = B_(J, I); B_(J, I) = B_(J, K); B_(J, K) = T; }
+  }
+  for (int J = 1; J <= 3; J++) {
+    B_(J, 1) = B_(J, 1) * A_(1, 1);
+    for (int I = 1; I <= N - 1; I++) {
+      double SUM = 0.0;
+      for (int K = 1; K <= I; K++) SUM = SUM - A_(I + 1, K) * B_(J, K);
+      B_(J, I + 1) = (B_(J, I + 1) + SUM) * A_(I + 1, I + 1);
+    }
+    for (int I = N - 1; I >= 1; I--) {
+      double SUM = 0.0;
+      for (int K = 1; K <= N - I; K++) SUM = SUM - A_(I, I + K) * B_(J, I + K);
+      B_(J, I) = B_(J, I) + SUM;
+    }
+  }
+#undef B_
+#undef A_
+}
+
+/* The HH(3,9) output of TMRF31 / SM3MH (tmrf.f:7-55,151-303) as FTS31 calls it (IAT = 0: one triangle, BETA > 0): the
+ * higher-order strain-displacement relation of the Bergan / Felippa membrane triangle; columns in SM3MH's own DOF order
+ * (u1 v1 u2 v2 u3 v3 th1 th2 th3).  The stiffness part of the routine does not feed the stresses and is left out. */
+static int tmrf31_hh(double *HH, const double *X, const double *Y)
+{
+  double GT[81], T[9], XC[3], YC[3], XM[3], YM[3];
+  int IPERM[9];
+  const double AREA2 = (Y[1] - Y[0]) * (X[0] - X[2]) - (X[1] - X[0]) * (Y[0] - Y[2]);
+  if (AREA2 <= 1.0e-16) return -1; /* NEGA_AREA / ZERO_AREA */
+  const double X0 = (X[0] + X[1] + X[2]) / 3.0, Y0 = (Y[0] + Y[1] + Y[2]) / 3.0;
+  const double AREA = 0.5 * AREA2;
+  const double C = 1. / sqrt(AREA);
+  for (int i = 0; i < 3; i++) { XC[i] = C * (X[i] - X0); YC[i] = C * (Y[i] - Y0); }
+  XM[0] = 0.5 * (XC[1] + XC[2]); XM[1] = 0.5 * (XC[2] + XC[0]); XM[2] = 0.5 * (XC[0] + XC[1]);
+  YM[0] = 0.5 * (YC[1] + YC[2]); YM[1] = 0.5 * (YC[2] + YC[0]); YM[2] = 0.5 * (YC[0] + YC[1]);
+#define GT_(i, j) GT[((i) - 1) + 9 * ((j) - 1)]
+#define HH_(i, j) HH[((i) - 1) + 3 * ((j) - 1)]
+  /* only rows 1..6 of GT are zeroed (tmrf.f:206-212); rows 7..9 are fully assigned below */
+  for (int I = 1; I <= 9; I++) {
+    for (int J = 1; J <= 6; J++) GT_(J, I) = 0.;
+    HH_(1, I) = 0.; HH_(2, I) = 0.; HH_(3, I) = 0.;
+  }
+  for (int J = 1; J <= 3; J++) {
+    const double DX = XM[J - 1] - XC[J - 1], DY = YM[J - 1] - YC[J - 1];
+    const double DL = sqrt(DX * DX + DY * DY);
+    const double CJ = DX / DL, SJ = DY / DL;
+    const double A1J = -0.5 * SJ * (CJ * CJ), A2J = 0.5 * (CJ * CJ * CJ), B2J = -0.5 * (SJ * SJ * SJ), B3J = 0.5 * (SJ * SJ) * CJ;
+    const double A3J = -(B2J + A1J + A1J), B1J = -(B3J + B3J + A2J);
+    GT_(1, 2 * J - 1) = 1.;
+    GT_(2, 2 * J) = 1.;
+    GT_(3, 2 * J - 1) = -YC[J - 1];
+    GT_(3, 2 * J) = XC[J - 1];
+    GT_(3, J + 6) = C;
+    GT_(4, 2 * J - 1) = XC[J - 1];
+    GT_(6, 2 * J - 1) = YC[J - 1];
+    GT_(5, 2 * J) = YC[J - 1];
+    GT_(6, 2 * J) = XC[J - 1];
+    HH_(J, J + 6) = 1.;
+    for (int I = 1; I <= 3; I++) {
+      const double XI = XC[I - 1], YI = YC[I - 1];
+      GT_(J + 6, 2 * I - 1) = A1J * XI * XI + 2. * A2J * XI * YI + A3J * YI * YI;
+      GT_(J + 6, 2 * I) = B1J * XI * XI + 2. * B2J * XI * YI + B3J * YI * YI;
+      GT_(J + 6, I + 6) = -C * (CJ * XI + SJ * YI);
+    }
+  }
+  if (lufact9(GT, IPERM, T) != 0) return -2; /* SINGULAR_G */
+  lusolv9_rows(GT, IPERM, HH);
+#undef GT_
+#undef HH_
+  return 0;
+}
+
+/* tmrf.f:474-634 (TMRF32): the centroid stress matrix SM(3,9) = DM * (L'/AREA + BH * HH).  L and TMB run over the DOFs in node
+ * order (u1 v1 th1 u2 ..) while the columns of HH come in SM3MH's order (u1 v1 u2 v2 u3 v3 th1 th2 th3): the reference adds the
+ * two column by column as they are, and so does this restatement. */
+static int tmrf32(const double *HH, const double *X, const double *Y, const double *DM, double ALPHA, double *SM)
+{
+  double L[27], TMB[27], TMH[27], BH[9], TM[27], XC[3], YC[3], XM[3], YM[3];
+  const double X21 = X[1] - X[0], X12 = -X21, X32 = X[2] - X[1], X23 = -X32, X13 = X[0] - X[2], X31 = -X13;
+  const double Y21 = Y[1] - Y[0], Y12 = -Y21, Y32 = Y[2] - Y[1], Y23 = -Y32, Y13 = Y[0] - Y[2], Y31 = -Y13;
+  const double AREA = 0.5 * (Y21 * X13 - X21 * Y13);
+  if (AREA <= 1.0e-16) return -1;
+#define L_(i, j) L[((i) - 1) + 9 * ((j) - 1)]
+  for (int i = 0; i < 27; i++) L[i] = 0.0; /* rows 3, 6, 9 are only set for ALPHA > 0 (always, here) */
+  L_(1, 1) = 0.5 * Y23; L_(2, 1) = 0.5 * 0.0; L_(4, 1) = 0.5 * Y31; L_(5, 1) = 0.5 * 0.0; L_(7, 1) = 0.5 * Y12; L_(8, 1) = 0.5 * 0.0;
+  L_(1, 2) = 0.5 * 0.0; L_(2, 2) = 0.5 * X32; L_(4, 2) = 0.5 * 0.0; L_(5, 2) = 0.5 * X13; L_(7, 2) = 0.5 * 0.0; L_(8, 2) = 0.5 * X21;
+  L_(1, 3) = 0.5 * X32; L_(2, 3) = 0.5 * Y23; L_(4, 3) = 0.5 * X13; L_(5, 3) = 0.5 * Y31; L_(7, 3) = 0.5 * X21; L_(8, 3) = 0.5 * Y12;
+  if (ALPHA > 0.0) {
+    L_(3, 1) = 0.5 * (Y23 * (Y13 - Y21) * ALPHA / 6);
+    L_(3, 2) = 0.5 * (X32 * (X31 - X12) * ALPHA / 6);
+    L_(3, 3) = 0.5 * ((X31 * Y13 - X12 * Y21) * ALPHA / 3);
+    L_(6, 1) = 0.5 * (Y31 * (Y21 - Y32) * ALPHA / 6);
+    L_(6, 2) = 0.5 * (X13 * (X12 - X23) * ALPHA / 6);
+    L_(6, 3) = 0.5 * ((X12 * Y21 - X23 * Y32) * ALPHA / 3);
+    L_(9, 1) = 0.5 * (Y12 * (Y32 - Y13) * ALPHA / 6);
+    L_(9, 2) = 0.5 * (X21 * (X23 - X31) * ALPHA / 6);
+    L_(9, 3) = 0.5 * ((X23 * Y32 - X31 * Y13) * ALPHA / 3);
+  }
+  for (int I = 1; I <= 9; I++)
+    for (int J = 1; J <= 3; J++) TMB[(J - 1) + 3 * (I - 1)] = (1. / AREA) * L_(I, J);
+#undef L_
+  const double X0 = (X[0] + X[1] + X[2]) / 3.0, Y0 = (Y[0] + Y[1] + Y[2]) / 3.0;
+  const double C = 1. / sqrt(AREA);
+  for (int i = 0; i < 3; i++) { XC[i] = C * (X[i] - X0); YC[i] = C * (Y[i] - Y0); }
+  XM[0] = 0.5 * (XC[1] + XC[2]); XM[1] = 0.5 * (XC[2] + XC[0]); XM[2] = 0.5 * (XC[0] + XC[1]);
+  YM[0] = 0.5 * (YC[1] + YC[2]); YM[1] = 0.5 * (YC[2] + YC[0]); YM[2] = 0.5 * (YC[0] + YC[1]);
+  for (int J = 1; J <= 3; J++) {
+    const double DX = XM[J - 1] - XC[J - 1], DY = YM[J - 1] - YC[J - 1];
+    const double DL = sqrt(DX * DX + DY * DY);
+    const double CJ = DX / DL, SJ = DY / DL;
+    const double A1J = -0.5 * SJ * (CJ * CJ), A2J = 0.5 * (CJ * CJ * CJ), B2J = -0.5 * (SJ * SJ * SJ), B3J = 0.5 * (SJ * SJ) * CJ;
+    BH[0 + 3 * (J - 1)] = C * (2 * A1J * XC[J - 1] + A2J * YC[J - 1]);
+    BH[1 + 3 * (J - 1)] = C * (B2J * XC[J - 1] + 2 * B3J * YC[J - 1]);
+    BH[2 + 3 * (J - 1)] = C * (-4 * B3J * XC[J - 1] - 4 * A1J * YC[J - 1]);
+  }
+  for (int I = 0; I < 9; I++)
+    for (int J = 0; J < 3; J++) {
+      double S = 0.0;
+      for (int K = 0; K < 3; K++) S = S + BH[J + 3 * K] * HH[K + 3 * I];
+      TMH[J + 3 * I] = S;
+    }
+  for (int i = 0; i < 27; i++) TM[i] = TMB[i] + TMH[i];
+  for (int I = 0; I < 9; I++)
+    for (int J = 0; J < 3; J++) {
+      double S = 0.0;
+      for (int K = 0; K < 3; K++) S = S + DM[J + 3 * K] * TM[K + 3 * I];
+      SM[J + 3 * I] = S;
+    }
+  return 0;
+}
+
+/* TEST HOOK: the centroid membrane stress matrix of the TMRF triangle, SM(3,9) over (u1 v1 th1 u2 v2 th2 u3 v3 th3), from the two
+ * routines above.  reorder = 0: exactly what FTS32 computes (HH columns taken as they come); reorder = 1: HH columns first moved to
+ * the node order TMRF32's lumping matrix uses -- the consistent element, which must reproduce every constant strain state.  The
+ * closed-form test on the latter checks the restatement of HH and BH without a compiled reference. */
+int orc_tmrf_centroid_matrix(const double XL[3], const double YL[3], const double DM[9], double alpha, int reorder, double SM[27])
+{
+  double HH[27], H2[27];
+  if (tmrf31_hh(HH, XL, YL) < 0) return -1;
+  if (reorder) {
+    static const int LST[9] = {1, 2, 4, 5, 7, 8, 3, 6, 9};
+    for (int j = 0; j < 9; j++)
+      for (int r = 0; r < 3; r++) H2[r + 3 * (LST[j] - 1)] = HH[r + 3 * j];
+    memcpy(HH, H2, sizeof(HH));
+  }
+  return tmrf32(HH, XL, YL, DM, alpha, SM);
+}
+
+/* -fftStressForm of the legacy FFT shell (type 21): 1 = FTSA31 / FTSA32 (default, the statements of STR23), anything else =
+ * FTS31 / FTS32 (elStressModule.f90:559-566,586-592) */
+static int g_fft_stress_form = 1;
+void orc_set_fft_stress_form(int form) { g_fft_stress_form = form; }
+int orc_get_fft_stress_form(void) { return g_fft_stress_form; }
+
+/* STR21 with -fftStressForm /= 1 (elStressModule.f90:521-633): FTS31 (fts.f:7-213) delivers HH (membrane, TMRF31 with ALPHA = 1.5,
+ * BETA = 0.5) and the kappa matrix AKB of TEBA31; FTS32 (fts.f:214-292) the centroid stress matrices, called with the plane stress
+ * matrix E where it expects the membrane rigidity t * E -- kept as the reference has it; ZZ = 1/3 in double precision here. */
+int orc_str21_legacy(const double xg[3], const double yg[3], const double zg[3], double emod,
+                     double rny, const double thk[3], const double ev[18], double SR[18],
+                     double SS[18], double sigma[18], double epsil[18])
+{
+  double E[9], HH[27], AKB[81], ESMM[27], ESMB[27], VML[9], VBL[9], RMF[3], RBF[3];
+  double VX[3], VY[3], VZ[3], T_str[4], XL[3], YL[3], ZZ[3];
+  const double ALPHA = 1.5;
+  int ierr;
+
+  orc_iso_mat2d(emod, rny, E);
+  local_xy(xg, yg, zg, XL, YL);
+  if (tmrf31_hh(HH, XL, YL) < 0) return 1;
+  if (teba31(AKB, E, XL, YL, thk) < 0) return 1;
+
+  ierr = orc_shell_element_axes(3, xg, yg, zg, VX, VY, VZ);
+  if (ierr != 0) return ierr;
+  ierr = orc_shell_stress_trans(VX, VZ, T_str);
+  if (ierr != 0) return ierr;
+
+  for (int i = 0; i < 3; i++) ZZ[i] = 1.0 / 3.0;
+  local_xy(xg, yg, zg, XL, YL);
+  if (tmrf32(HH, XL, YL, E, ALPHA, ESMM) < 0) return 1;
+  teba32(ESMB, AKB, ZZ);
+
+  fts38(VML, VBL, ev, xg, yg, zg);
+  for (int i = 0; i < 3; i++) {
+    double sm = 0.0, sb = 0.0;
+    for (int j = 0; j < 9; j++) {
+      sm += ESMM[i + 3 * j] * VML[j];
+      sb += ESMB[i + 3 * j] * VBL[j];
+    }
+    RMF[i] = sm;
+    RBF[i] = sb;
+  }
+  orc_rotate2d(RMF, T_str, RMF);
+  orc_rotate2d(RBF, T_str, RBF);
+  for (int n = 0; n < 3; n++)
+    for (int c = 0; c < 3; c++) {
+      SR[c + 6 * n] = RMF[c];
+      SR[3 + c + 6 * n] = RBF[c];
+      SS[c + 6 * n] = 0.0;
+      SS[3 + c + 6 * n] = 0.0;
+    }
+  for (int i = 0; i < 3; i++)
+    for (int c = 0; c < 3; c++) {
+      sigma[c + 3 * i] = (RMF[c] + RBF[c] * 6.0 / thk[i]) / thk[i];
+      sigma[c + 3 * (3 + i)] = (RMF[c] - RBF[c] * 6.0 / thk[i]) / thk[i];
+    }
+  orc_iso_mat2d_inv(emod, rny, E);
+  for (int p = 0; p < 6; p++)
+    for (int r = 0; r < 3; r++)
+      epsil[r + 3 * p] = E[r] * sigma[3 * p] + E[r + 3] * sigma[1 + 3 * p] +
+                         E[r + 6] * sigma[2 + 3 * p];
+  return 0;
+}
+
 /* elStressModule.f90:901-999.  SR(6,3), sigma(3,6), epsil(3,6) column-major. */
 int orc_str23(const double xg[3], const double yg[3], const double zg[3], double emod,
               double rny, const double thk[3], const double ev[18], double SR[18],

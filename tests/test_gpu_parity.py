@@ -547,6 +547,42 @@ def test_legacy_shells_default_formulations(oracle):
         oracle.lib.orc_set_ffq_stress_form(2)
 
 
+def test_legacy_fft_shell_private_formulations(oracle):
+    """type 21 with -fftStressForm 0 / 2: STR21 on FTS31 / FTS32 (Bergan / Felippa membrane triangle of tmrf.f + TEBA bending), the
+    reference's statements including its two oddities (plane stress matrix where the membrane rigidity is expected, HH columns added
+    in their own order); von Mises history, stresses, strains and stress resultants against the oracle's restatement"""
+    legacy = plate_part(6, 5, ngen=4, seed=23, tri_fraction=1.0, warp=0.02)
+    legacy.sam.melcon = legacy.sam.melcon - 2
+    assert set(np.unique(legacy.sam.melcon)) == {21}
+    Q = reduced_history(legacy.sam.ndim, 11, seed=10)
+    rec1 = StressRecovery(legacy)
+    vm_default = rec1.recover(Q)
+    rec1.close()
+    for form in (0, 2):
+        oracle.lib.orc_set_fft_stress_form(form)
+        try:
+            b = oracle.bind_part(legacy)
+            vm_o, mx_o, mn_o = oracle.recover_history(b, Q)
+            rec = StressRecovery(legacy, fft_stress_form=form)
+            assert rec.npts == 6 * legacy.sam.nel
+            vm_g = rec.recover(Q)
+            assert rel_err(vm_g, vm_o) <= TOL
+            assert rel_err(vm_g, vm_default) > 1e-3        # a different formulation than FTSA31 / FTSA32
+            full = rec.calc_stresses(Q[:, 3])
+            ref = oracle.calc_stresses(b, oracle.expand(b, Q[:, 3]))
+            for key in ("stress", "strain", "sres"):
+                assert rel_err(full[key], ref[key]) <= TOL, key
+            rec.close()
+        finally:
+            oracle.lib.orc_set_fft_stress_form(1)
+    # next to ANDES triangles in one part the private formulation is not served: those FFT shells get no results
+    mixed = plate_part(6, 5, ngen=4, seed=23, tri_fraction=1.0, warp=0.02)
+    mixed.sam.melcon[::2] = 21
+    rec = StressRecovery(mixed, fft_stress_form=0)
+    assert rec.npts == 6 * int((mixed.sam.melcon == 23).sum())
+    rec.close()
+
+
 def test_edge_sizes(oracle):
     """ragged / empty inputs: one step, zero steps, no component modes, a part whose elements are all outside the selection"""
     part = plate_part(5, 4, ngen=0, seed=18, tri_fraction=0.5)            # no generalized DOFs: E matrix absent
