@@ -667,8 +667,14 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
   const double sing = a1 <= 0.0 ? 0. : sqrt(a1);
   const double xl[3] = {0., L21, L31 * cosg}, yl[3] = {0., 0., L31 * sing};
   const double th[3] = {t, t, t};
-  double AKM[63], AKB[81];
+  double AKM[63], AKB[81], SMM[3][9], SMB[3][9];
   if (ok && !legacy) ok = tri_membrane_kappa(AKM, Ei, xl, yl, (t + t + t) / 3.);
+  if (ok && legacy) {
+    // legacy FFT3 formulation (-fftStressForm 0 / 2): membrane matrix of TMRF32 on the plane stress matrix E itself
+    // (elStressModule.f90:589-591 passes E where FTS32 expects t * E)
+    const double Dm[9] = {C11, nu * C11, 0., nu * C11, C11, 0., 0., 0., 0.5 * E / (1.0 + nu)};
+    ok = tri_legacy_membrane(SMM, Dm, xl, yl, 1.5);
+  }
   if (ok) ok = tri_bending_kappa(AKB, Ei, xl, yl, th);
   // output-system rotation from the triangle axes (x along 1->2, not projected)
   V3 ex = d21, ez = vcross(d21, d31);
@@ -681,17 +687,11 @@ __global__ void build_tri_ops_kernel(int nelt, const int* __restrict__ elem, con
   if (!ok) { failed[i] = 1; return; }  // Sfrag was zeroed by the caller
 
   // centroid stress matrices (HLST32, hlst.f:330-352; TEBA32, nyteba.f:333-364), ZZ = REAL*4 1./3.
-  // legacy FFT3 formulation (-fftStressForm 0 / 2): FTS32 with ZZ = 1/3 in double precision, membrane matrix of TMRF32 on the
-  // plane stress matrix E itself (elStressModule.f90:589-591 passes E where FTS32 expects t * E)
+  // legacy FFT3 formulation: FTS32 with ZZ = 1/3 in double precision
   const double zz = legacy ? 1.0 / 3.0 : (double)(1.f / 3.f);
   const double x0 = (xl[0] + xl[1] + xl[2]) / 3., y0 = (yl[0] + yl[1] + yl[2]) / 3.;
   double rx = 0., ry = 0.;
   for (int k = 0; k < 3; ++k) { rx += (xl[k] - x0) * zz; ry += (yl[k] - y0) * zz; }
-  double SMM[3][9], SMB[3][9];
-  if (legacy) {
-    const double Dm[9] = {C11, nu * C11, 0., nu * C11, C11, 0., 0., 0., 0.5 * E / (1.0 + nu)};
-    if (!tri_legacy_membrane(SMM, Dm, xl, yl, 1.5)) { failed[i] = 1; return; }
-  }
   for (int j = 0; j < 9; ++j) {
     if (!legacy) {
       const double* a = AKM + 7 * j;
