@@ -99,36 +99,6 @@ struct CycleSink {
   FSR_HD void init() { damage = 0.0; max_range = 0.0; ncycles = 0; }
 };
 
-// access policies for the spilled part of the rainflow stack (entry j of a series at spill[j * stride])
-struct SpillDirect {
-  FSR_HD double load(const double* spill, size_t stride, int j) { return spill[(size_t)j * stride]; }
-  FSR_HD void store(double* spill, size_t stride, int j, double v) { spill[(size_t)j * stride] = v; }
-};
-// write-through window of the topmost NEAR spilled entries in fast memory (shared memory on the device): slot j % NEAR at
-// c[(j % NEAR) * cstride]; entries [lo, top of the spill) are valid.  The stack only changes at its top, so a miss (j < lo) refills
-// one slot and moves the window down; stores move it up.
-template <int NEAR>
-struct SpillWindow {
-  double* c;
-  int cstride, lo;
-  FSR_HD double load(const double* spill, size_t stride, int j)
-  {
-    double* slot = c + (size_t)(j % NEAR) * cstride;
-    if (j >= lo) return *slot;
-    const double v = spill[(size_t)j * stride];
-    *slot = v;
-    lo = j;
-    return v;
-  }
-  FSR_HD void store(double* spill, size_t stride, int j, double v)
-  {
-    spill[(size_t)j * stride] = v;
-    c[(size_t)(j % NEAR) * cstride] = v;
-    if (lo > j) lo = j;
-    else if (j - lo >= NEAR) lo = j - NEAR + 1;
-  }
-};
-
 struct Rainflow {
   double s0, s1, s2;  // s2 = top of stack
   int n;              // points on the stack (registers + spill)
@@ -148,15 +118,9 @@ struct Rainflow {
   // registers hold the top min(n,3) points right-aligned: n=1: s2; n=2: s1,s2; n>=3: s0,s1,s2
   FSR_HD void append(double v, double* spill, size_t stride, int cap)
   {
-    SpillDirect d;
-    append(v, spill, stride, cap, d);
-  }
-  template <class Cache>
-  FSR_HD void append(double v, double* spill, size_t stride, int cap, Cache& cache)
-  {
     if (n >= 3) {
       if (n - 3 >= cap) { overflow = 1; return; }
-      cache.store(spill, stride, n - 3, s0);
+      spill[(size_t)(n - 3) * stride] = s0;
     }
     s0 = s1; s1 = s2; s2 = v;
     ++n;
@@ -167,34 +131,26 @@ struct Rainflow {
   template <class Count>
   FSR_HD void push(double v, double gate, double* spill, size_t stride, int cap, Count&& count)
   {
-    SpillDirect d;
-    push(v, gate, spill, stride, cap, count, d);
-  }
-  // the same with the accesses to the spilled part of the stack going through `cache` (the device kernel keeps the entries next to
-  // the register-held top in shared memory: the rules pop and push at the top, so nearly every refill is served from there)
-  template <class Count, class Cache>
-  FSR_HD void push(double v, double gate, double* spill, size_t stride, int cap, Count&& count, Cache& cache)
-  {
     while (n >= 3) {
       const double r0 = s1 - s0, r1 = s2 - s1, r2 = v - s2;
       if (r0 * r1 > 0.0) {            // point 1 is not a turning point (FFpFatigue.C:227-237)
         s1 = s0;                      // survivors: s0, s2
         --n;
-        s0 = n >= 3 ? cache.load(spill, stride, n - 3) : 0.0;
+        s0 = n >= 3 ? spill[(size_t)(n - 3) * stride] : 0.0;
       } else if (r1 * r2 > 0.0) {     // point 2 is not a turning point (:238-247)
         s2 = s1; s1 = s0;             // survivors: s0, s1
         --n;
-        s0 = n >= 3 ? cache.load(spill, stride, n - 3) : 0.0;
+        s0 = n >= 3 ? spill[(size_t)(n - 3) * stride] : 0.0;
       } else if (fabs(r0) >= fabs(r1) && fabs(r2) >= fabs(r1)) {  // a genuine cycle (:248-264)
         if (fabs(r1) > gate) count(s1, s2);
         s2 = s0;                      // survivor: s0
         n -= 2;
-        s1 = n >= 2 ? cache.load(spill, stride, n - 2) : 0.0;
-        s0 = n >= 3 ? cache.load(spill, stride, n - 3) : 0.0;
+        s1 = n >= 2 ? spill[(size_t)(n - 2) * stride] : 0.0;
+        s0 = n >= 3 ? spill[(size_t)(n - 3) * stride] : 0.0;
       } else
         break;
     }
-    append(v, spill, stride, cap, cache);
+    append(v, spill, stride, cap);
   }
 };
 

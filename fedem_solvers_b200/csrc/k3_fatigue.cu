@@ -35,7 +35,6 @@ constexpr int K3_THREADS = 128;
 constexpr int K3_CHUNK = 32;
 constexpr int K3_TPCAP = 8;  // turning points a gage may queue between two convergent rainflow passes
 constexpr int K3_QCAP = 4;   // closed cycles a gage may queue between two convergent damage evaluations
-constexpr int K3_NEAR = 4;   // spilled rainflow stack entries next to the register-held top that are kept in shared memory
 
 }  // namespace fsr
 
@@ -152,14 +151,10 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
   // rainflow stack consumes them at the end of the chunk in a loop every lane of the warp runs together, so the three
   // state machines (PVX, rainflow, damage) are three tight loops instead of one interleaved, divergent one.
   __shared__ double q_tp[MODE == 1 ? K3_TPCAP : 1][K3_THREADS];
-  // the refills of the register-held stack top after a removed point / counted cycle are dependent global loads in the middle of
-  // the rule loop: the K3_NEAR entries below the registers live in shared memory (write-through, state stays in HBM between tiles)
-  __shared__ double rf_near[MODE == 1 ? K3_NEAR : 1][K3_THREADS];
-  SpillWindow<K3_NEAR> near{&rf_near[0][threadIdx.x], K3_THREADS, 0x7fffffff};
   int qt = 0;
   auto emit = [&](double v) {
     if (qt == K3_TPCAP) {   // queue full: drain in order (divergent, rare)
-      for (int k = 0; k < K3_TPCAP; ++k) s.rf.push(q_tp[k][threadIdx.x], p.gate, myspill, stride, cap, count, near);
+      for (int k = 0; k < K3_TPCAP; ++k) s.rf.push(q_tp[k][threadIdx.x], p.gate, myspill, stride, cap, count);
       qt = 0;
     }
     q_tp[qt][threadIdx.x] = v; ++qt;
@@ -169,7 +164,7 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     for (int k = 0; k < m; ++k)
-      if (k < qt) s.rf.push(q_tp[k][threadIdx.x], p.gate, myspill, stride, cap, count, near);
+      if (k < qt) s.rf.push(q_tp[k][threadIdx.x], p.gate, myspill, stride, cap, count);
     qt = 0;
     flush();
     if (s.rf.overflow) { s.status = 2; idle = true; }
