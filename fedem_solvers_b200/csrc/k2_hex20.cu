@@ -56,7 +56,8 @@ __device__ void hex20_dn(double xi, double et, double ze, double* dx, double* de
 __global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, const int* __restrict__ conn,
                                        const double* __restrict__ xyz, const double* __restrict__ emod,
                                        const double* __restrict__ rny, int stressForm, double* __restrict__ Sfrag,
-                                       unsigned char* __restrict__ failed, double* __restrict__ aux, double* __restrict__ Gfrag)
+                                       unsigned char* __restrict__ failed, double* __restrict__ aux, double* __restrict__ Gfrag,
+                                       double* __restrict__ fastJ /* [nelt][20][9]: J^-1 of the nodal evaluation points, or NULL */)
 {
   constexpr int KT = 15, MT = 15;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,6 +104,9 @@ __global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, c
     I[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det;
     I[2][1] = (J[2][0] * J[0][1] - J[2][1] * J[0][0]) / det;
     I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+    if (fastJ && stressForm == 0)
+      for (int d = 0; d < 3; ++d)
+        for (int j = 0; j < 3; ++j) fastJ[((size_t)i * 20 + q) * 9 + 3 * d + j] = I[d][j];
     for (int j = 0; j < 20; ++j) {
       const double bx = I[0][0] * dx[j] + I[0][1] * de[j] + I[0][2] * dz[j];
       const double by = I[1][0] * dx[j] + I[1][1] * de[j] + I[1][2] * dz[j];
@@ -129,6 +133,8 @@ __global__ void build_hex20_ops_kernel(int nelt, const int* __restrict__ elem, c
   if (!ok) {
     for (int k = 0; k < MT * KT * 32; ++k) S[k] = 0.0;
     for (int k = 0; k < 9 * 5 * 32; ++k) G[k] = 0.0;
+    if (fastJ)
+      for (int k = 0; k < 180; ++k) fastJ[(size_t)i * 180 + k] = 0.0;
   }
   failed[i] = ok ? 0 : 1;
 }
@@ -234,6 +240,171 @@ k2_bigsolid_grad_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps,
       if (emax[pb] > env_max[pt]) env_max[pt] = emax[pb];
       if (emin[pb] < env_min[pt]) env_min[pt] = emin[pb];
     }
+  }
+}
+
+// ---- nodal evaluation in natural coordinates, lane = time step ------------------------------------------------------------
+// At a NODE of the serendipity element most shape-function derivatives vanish: a corner sees the three nodes of each of
+// its three edges, a mid-edge node the two ends of its edge and the eight nodes of the two faces that meet there -- 288
+// non-zero entries of the 20 x 3 x 20 table instead of 1,200.  So for -stressForm 0 the NATURAL derivatives
+// D[c][j] = d u_c / d xi_j are formed from those entries with compile-time coefficients (-3/2, 2, -1/2, +-1/2, 1) and the
+// inverse Jacobian of the point (fastJ [elem][20][9], row d, column j, from the operator builder) turns them into the
+// gradient: 864 + 540 FMA per element.step against 3,600 in the dense gradient operator (4,320 issued with its padding),
+// and 1.4 KB of constants per element instead of 11.5 KB of fragments.  Lane = time step (tiles of 32): the 60 nodal
+// displacements of a step sit in registers, every row of U is read as one 256-byte segment per warp, no shared-memory
+// staging.  The 20 x 32 values of a tile are turned through shared memory: lanes 0..19 fold the envelope of one result
+// point each, and the history goes out as 160-byte pieces of the step records.
+__host__ __device__ constexpr int hex20_nat(int i, int axis)
+{
+  constexpr int hx[20] = {-1, 0, 1, 1, 1, 0, -1, -1, -1, 1, 1, -1, -1, 0, 1, 1, 1, 0, -1, -1};
+  constexpr int he[20] = {-1, -1, -1, 0, 1, 1, 1, 0, -1, -1, 1, 1, -1, -1, -1, 0, 1, 1, 1, 0};
+  constexpr int hz[20] = {-1, -1, -1, -1, -1, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1};
+  return axis == 0 ? hx[i] : axis == 1 ? he[i] : hz[i];
+}
+// d N_j / d xi_d at node p (DN2031, ihex.f:2433-2545, evaluated at the node coordinates)
+__host__ __device__ constexpr double hex20_dn_node(int p, int d, int j)
+{
+  const double xi = hex20_nat(p, 0), et = hex20_nat(p, 1), ze = hex20_nat(p, 2);
+  const double a = hex20_nat(j, 0), b = hex20_nat(j, 1), c = hex20_nat(j, 2);
+  if (a != 0.0 && b != 0.0 && c != 0.0)
+    return d == 0 ? .125 * a * (1. + et * b) * (1. + ze * c) * (2. * xi * a + et * b + ze * c - 1.)
+         : d == 1 ? .125 * b * (1. + xi * a) * (1. + ze * c) * (xi * a + 2. * et * b + ze * c - 1.)
+                  : .125 * c * (1. + xi * a) * (1. + et * b) * (xi * a + et * b + 2. * ze * c - 1.);
+  if (a == 0.0)
+    return d == 0 ? -.5 * xi * (1. + et * b) * (1. + ze * c) : d == 1 ? .25 * b * (1. - xi * xi) * (1. + ze * c) : .25 * c * (1. - xi * xi) * (1. + et * b);
+  if (b == 0.0)
+    return d == 0 ? .25 * a * (1. - et * et) * (1. + ze * c) : d == 1 ? -.5 * et * (1. + xi * a) * (1. + ze * c) : .25 * c * (1. + xi * a) * (1. - et * et);
+  return d == 0 ? .25 * a * (1. + et * b) * (1. - ze * ze) : d == 1 ? .25 * b * (1. + xi * a) * (1. - ze * ze) : -.5 * ze * (1. + xi * a) * (1. + et * b);
+}
+
+template <int P>
+struct Hex20NodeRow {   // the coefficients of result point P as compile-time constants
+  double c[3][20];
+  constexpr Hex20NodeRow() : c{}
+  {
+    for (int d = 0; d < 3; ++d)
+      for (int j = 0; j < 20; ++j) c[d][j] = hex20_dn_node(P, d, j);
+  }
+};
+
+template <int P>
+__device__ __forceinline__ double hex20_point_vm2(const double (&u)[20][3], const double (&J)[3][3])
+{
+  constexpr Hex20NodeRow<P> R{};
+  double D[3][3];   // D[c][j]
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    bool first = true;
+#pragma unroll
+    for (int n = 0; n < 20; ++n) {
+      if (R.c[j][n] != 0.0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) D[c][j] = first ? R.c[j][n] * u[n][c] : fma(R.c[j][n], u[n][c], D[c][j]);
+        first = false;
+      }
+    }
+  }
+  double H[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) H[c][d] = fma(J[d][2], D[c][2], fma(J[d][1], D[c][1], J[d][0] * D[c][0]));
+  const double da = H[0][0] - H[1][1], db = H[1][1] - H[2][2], dc = H[2][2] - H[0][0];
+  const double gxy = H[1][0] + H[0][1], gxz = H[2][0] + H[0][2], gyz = H[2][1] + H[1][2];
+  const double dev = 0.5 * fma(da, da, fma(db, db, dc * dc));
+  const double shr = fma(gxy, gxy, fma(gxz, gxz, gyz * gyz));
+  return fma(0.75, shr, dev);   // (vm / 2 mu)^2
+}
+
+__device__ __forceinline__ void hex20_load_J(const double* __restrict__ fJ, int p, double (&J)[3][3])
+{
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) J[d][j] = __ldg(fJ + p * 9 + 3 * d + j);
+}
+
+// the inverse of point P + 1 is fetched (warp-uniform loads, L1) before the arithmetic of point P
+template <int P, bool WRITE_VM>
+__device__ __forceinline__ void hex20_points(const double (&u)[20][3], const double* __restrict__ fJ, const double (&J)[3][3], double mu2,
+                                             bool bad, double* sv)
+{
+  if constexpr (P < 20) {
+    double Jn[3][3];
+    if constexpr (P + 1 < 20) hex20_load_J(fJ, P + 1, Jn);
+    double v = hex20_point_vm2<P>(u, J);
+    if (WRITE_VM) v = mu2 * sqrt_pos(v);
+    if (bad) v = kHuge;
+    sv[P * 33] = v;
+    hex20_points<P + 1, WRITE_VM>(u, fJ, Jn, mu2, bad, sv);
+  }
+}
+
+template <bool WRITE_VM, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+k2_hex20_steplane_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, const double* __restrict__ fastJ,
+                            const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff,
+                            const unsigned char* __restrict__ failed, int nelt, double* __restrict__ vm, size_t ld_vm,
+                            double* __restrict__ env_max, double* __restrict__ env_min)
+{
+  __shared__ double sv_all[NW][20 * 33];
+  __shared__ unsigned so_all[NW][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * NW + warp;
+  if (i >= nelt) return;   // whole warp
+  double* sv = sv_all[warp];
+  // row offsets of the element's 60 DOFs in units of 64 doubles (ldu is a multiple of 64: 32 bits are enough for any U),
+  // kept in shared memory: one broadcast LDS + one IMAD.WIDE per load
+  unsigned* so = so_all[warp];
+  const unsigned ldu64 = (unsigned)(ldu >> 6);
+  if (lane < 30) {
+    const int2 e2 = __ldg(reinterpret_cast<const int2*>(edof + (size_t)i * 60) + lane);
+    so[2 * lane] = (unsigned)e2.x * ldu64;
+    so[2 * lane + 1] = (unsigned)e2.y * ldu64;
+  }
+  __syncwarp();
+  const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
+  const double mu2 = E / (1.0 + nu);
+  const bool bad = failed[i] != 0;
+  const size_t pt0 = (size_t)ptoff[i];
+  const double* fJ = fastJ + (size_t)i * 180;
+  double emax = 0.0, emin = kHuge;   // lanes 0..19: result point = lane
+  for (int t0 = 0; t0 < nsteps; t0 += 32) {
+    // lanes past the last step repeat it: no predicates, no zero fill (their values are not scanned below)
+    const double* Ut = U + min(t0 + lane, nsteps - 1);
+    double u[20][3];
+#pragma unroll
+    for (int n = 0; n < 20; ++n)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) u[n][c] = __ldg(Ut + ((size_t)so[3 * n + c] << 6));
+    double J0[3][3];
+    hex20_load_J(fJ, 0, J0);
+    hex20_points<0, WRITE_VM>(u, fJ, J0, mu2, bad, sv + lane);
+    __syncwarp();
+    const int ns = min(32, nsteps - t0);
+    if (lane < 20) {
+      const double* row = sv + lane * 33;
+      for (int s = 0; s < ns; ++s) {
+        const double v = row[s];
+        emax = max_nonneg(emax, v); emin = min_nonneg(emin, v);
+      }
+    }
+    if (WRITE_VM) {
+#pragma unroll
+      for (int r = 0; r < 20; ++r) {
+        const int idx = lane + 32 * r, s = idx / 20, p = idx - 20 * s;
+        if (s < ns) vm[(size_t)(t0 + s) * ld_vm + pt0 + p] = sv[p * 33 + s];
+      }
+    }
+    __syncwarp();
+  }
+  if (lane < 20 && nsteps > 0) {
+    if (!WRITE_VM && !bad) {   // radicand -> von Mises
+      emax = mu2 * sqrt_pos(emax);
+      emin = mu2 * sqrt_pos(emin);
+    }
+    if (emax > env_max[pt0 + lane]) env_max[pt0 + lane] = emax;
+    if (emin < env_min[pt0 + lane]) env_min[pt0 + lane] = emin;
   }
 }
 
@@ -359,6 +530,10 @@ int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMalloc(&f.aux, sizeof(double) * (size_t)f.nelt * f.naux));
   FSR_CUDA(cudaMalloc(&f.Gfrag, sizeof(double) * (size_t)f.nelt * 9 * 5 * 32));
   FSR_CUDA(cudaMemsetAsync(f.Gfrag, 0, sizeof(double) * (size_t)f.nelt * 9 * 5 * 32, s));
+  if (p->stressForm == 0) {   // nodal evaluation: the twenty inverses of every element for the natural-coordinate kernel
+    FSR_CUDA(cudaMalloc(&f.fast2, sizeof(double) * (size_t)f.nelt * 180));
+    FSR_CUDA(cudaMemsetAsync(f.fast2, 0, sizeof(double) * (size_t)f.nelt * 180, s));
+  }
   FSR_CUDA(cudaMalloc(&d_conn, sizeof(int) * conn.size()));
   FSR_CUDA(cudaMemcpyAsync(f.elem, elem.data(), sizeof(int) * elem.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemcpyAsync(f.edof, edof.data(), sizeof(int) * edof.size(), cudaMemcpyHostToDevice, s));
@@ -366,7 +541,7 @@ int build_hex20_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* el
   FSR_CUDA(cudaMemcpyAsync(d_conn, conn.data(), sizeof(int) * conn.size(), cudaMemcpyHostToDevice, s));
   FSR_CUDA(cudaMemsetAsync(f.Sfrag, 0, sizeof(double) * (size_t)f.nelt * f.MT * f.KT * 32, s));
   build_hex20_ops_kernel<<<(f.nelt + 31) / 32, 32, 0, s>>>(f.nelt, f.elem, d_conn, p->xyz, p->emod, p->rny, p->stressForm,
-                                                         f.Sfrag, f.failed, f.aux, f.Gfrag);
+                                                         f.Sfrag, f.failed, f.aux, f.Gfrag, f.fast2);
   FSR_LAUNCH_CHECK();
   FSR_CUDA(cudaStreamSynchronize(s));
   cudaFree(d_conn);
@@ -379,6 +554,21 @@ int launch_k2_hex20_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
   if (f.nelt == 0) return FSR_OK;
   // FSR_HEX20_DENSE=1 selects the dense 120x60 shared-memory formulation (A/B timing, cross-check)
   static const bool dense = getenv("FSR_HEX20_DENSE") && atoi(getenv("FSR_HEX20_DENSE")) != 0;
+  // tiles of 32 steps and more, nodal evaluation: natural-coordinate form, lane = step (FSR_HEX20_STEPLANE=0: A/B, cross-check)
+  const bool steplane = !(getenv("FSR_HEX20_STEPLANE") && atoi(getenv("FSR_HEX20_STEPLANE")) == 0);
+  if (!dense && steplane && f.fast2 && nsteps >= 32) {
+    constexpr int NW = 4;
+    const int grid = (f.nelt + NW - 1) / NW;
+    const bool b3 = getenv("FSR_HEX20_MINB") && atoi(getenv("FSR_HEX20_MINB")) == 3;   // A/B: 168 registers, 12 warps per SM
+#define FSR_HEX20_SL(W, B)                                                                                                      \
+  k2_hex20_steplane_vm_kernel<W, NW, B><<<grid, NW * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, f.fast2, f.aux, f.edof, f.ptoff, \
+                                                                 f.failed, f.nelt, vm_dev, ld_vm, p->env_max, p->env_min)
+    if (vm_dev) { if (b3) FSR_HEX20_SL(true, 3); else FSR_HEX20_SL(true, 2); }
+    else { if (b3) FSR_HEX20_SL(false, 3); else FSR_HEX20_SL(false, 2); }
+#undef FSR_HEX20_SL
+    FSR_LAUNCH_CHECK();
+    return FSR_OK;
+  }
   if (!dense) {
     const int warps = 4;
     k2_bigsolid_grad_vm_kernel<3, 5, 20, 20><<<(f.nelt + warps - 1) / warps, warps * 32, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Gfrag,

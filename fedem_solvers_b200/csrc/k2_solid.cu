@@ -587,6 +587,170 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
   }
 }
 
+// The same scalar formulation with lane = TIME STEP (tiles of 32 steps): every lane holds the 30 nodal displacements of its
+// own step in registers, so a row of U is read as ONE 256-byte segment per warp, nothing goes through shared memory or
+// shuffles on the way to the strains (the (corner, step) kernel above spends 24 LDS + 18 SHFL per lane and tile and is
+// LSU-bound), and the envelope of the ten result points lives in registers.  When the history is written, the 10 x 32
+// values of a tile are turned through shared memory so that each step record receives its ten points as one 80-byte piece.
+// Used for tiles of at least 32 steps; shorter tiles stay on the (corner, step) kernel.
+template <bool WRITE_VM, bool CURVED, int NW>
+__global__ void __launch_bounds__(NW * 32, CURVED ? 3 : 4)
+k2_tet10_steplane_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, const double* __restrict__ fast,
+                            const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist,
+                            const int* __restrict__ list, double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
+                            double* __restrict__ env_min, const double* __restrict__ fastJ)
+{
+  __shared__ double sv_all[NW][10 * 33];
+  __shared__ unsigned so_all[CURVED ? 1 : NW][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int il = blockIdx.x * NW + warp;
+  if (il >= nlist) return;   // whole warp
+  const int i = __ldg(list + il);
+  double* sv = sv_all[warp];
+  constexpr int cn[4] = {0, 2, 4, 9};
+  constexpr int mdn[4][4] = {{0, 1, 5, 6}, {1, 2, 3, 7}, {5, 3, 4, 8}, {6, 7, 8, 9}};
+  constexpr int edge[6][3] = {{0, 1, 1}, {1, 2, 3}, {0, 2, 5}, {0, 3, 6}, {1, 3, 7}, {2, 3, 8}};   // corners a, b -> node
+  const int* ed = edof + (size_t)i * 32;
+  // row offsets in units of 64 doubles (ldu is a multiple of 64): 32 bits are enough for any U, one LEA pair per load
+  const unsigned ldu64 = (unsigned)(ldu >> 6);
+  // (kept in shared memory by the straight-sided variant: one broadcast LDS + one IMAD.WIDE per load; the curved one
+  // re-reads the row numbers)
+  unsigned* eoff = so_all[CURVED ? 0 : warp];
+  if (!CURVED) {
+    if (lane < 30) eoff[lane] = (unsigned)__ldg(ed + lane) * ldu64;
+    __syncwarp();
+  }
+  const double E = __ldg(aux + (size_t)i * 2), nu = __ldg(aux + (size_t)i * 2 + 1);
+  const double mu2 = E / (1.0 + nu), mu1 = 0.5 * mu2;
+  const size_t pt0 = (size_t)ptoff[i];
+  double Ji[3][3];
+  if (!CURVED) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Ji[d][j] = __ldg(fast + (size_t)i * 10 + 3 * d + j);
+  }
+  const double* fJ = CURVED ? fastJ + (size_t)i * 90 : nullptr;
+  double emax = 0.0, emin = kHuge;   // lanes 0..29: result point lane % 10, steps 11 (lane / 10) .. + 10 of every tile
+
+  for (int t0 = 0; t0 < nsteps; t0 += 32) {
+    // lanes past the last step repeat it: no predicates, no zero fill, and a repeated value does not move an envelope
+    const double* Ut = U + min(t0 + lane, nsteps - 1);
+    double u[10][3];
+    if (!CURVED) {
+#pragma unroll
+      for (int n = 0; n < 10; ++n)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) u[n][c] = __ldg(Ut + ((size_t)eoff[3 * n + c] << 6));
+    } else {   // predicated loads keep ptxas from front-loading the 90 inverses on top of these (it spills 1 KB otherwise)
+      const bool live = t0 + lane < nsteps;
+#pragma unroll
+      for (int n = 0; n < 10; ++n)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) u[n][c] = live ? __ldg(Ut + ((size_t)((unsigned)__ldg(ed + 3 * n + c) * ldu64) << 6)) : 0.0;
+    }
+    double v[10];
+    // D[a][c][j] = d u_c / d L_j at corner a (three-point differences, see above)
+    double D[4][3][3];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double gq[4];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) gq[ci] = fma(4.0, u[mdn[a][ci]][c], -u[cn[ci]][c]);
+        D[a][c][0] = gq[0] - gq[3]; D[a][c][1] = gq[1] - gq[3]; D[a][c][2] = gq[2] - gq[3];
+      }
+    auto strains = [&](const double (&Dp)[3][3], const double (&J)[3][3], double (&e)[6]) {
+      double H[3][3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) H[c][d] = fma(J[d][2], Dp[c][2], fma(J[d][1], Dp[c][1], J[d][0] * Dp[c][0]));
+      e[0] = H[0][0]; e[1] = H[1][1]; e[2] = H[2][2];
+      e[3] = H[0][1] + H[1][0]; e[4] = H[0][2] + H[2][0]; e[5] = H[1][2] + H[2][1];
+    };
+    auto loadJ = [&](int node, double (&J)[3][3]) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) J[d][j] = __ldg(fJ + node * 9 + 3 * d + j);
+    };
+    if (!CURVED) {
+      double e[4][6];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        strains(D[a], Ji, e[a]);
+        v[cn[a]] = solid_vm2_from_strain(e[a]);
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double em[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) em[c] = e[edge[q][0]][c] + e[edge[q][1]][c];
+        v[edge[q][2]] = solid_vm2_from_strain(em);
+      }
+    } else {
+      double J[3][3], e[6];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        loadJ(cn[a], J);
+        strains(D[a], J, e);
+        v[cn[a]] = solid_vm2_from_strain(e);
+      }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        double Dm[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) Dm[c][j] = D[edge[q][0]][c][j] + D[edge[q][1]][c][j];
+        loadJ(edge[q][2], J);
+        strains(Dm, J, e);
+        v[edge[q][2]] = solid_vm2_from_strain(e);
+      }
+    }
+    // corners carry 2 mu, mid-edge points (sums of two corners) mu.  The 10 x 32 values of the tile are turned through shared
+    // memory: three lanes per result point fold its envelope (11 steps each), the history goes out as 80-byte pieces of the
+    // step records
+#pragma unroll
+    for (int p = 0; p < 10; ++p) {
+      const bool corner = p == 0 || p == 2 || p == 4 || p == 9;
+      sv[p * 33 + lane] = WRITE_VM ? (corner ? mu2 : mu1) * sqrt_pos(v[p]) : v[p];
+    }
+    __syncwarp();
+    const int ns1 = min(32, nsteps - t0) - 1;   // last live step of the tile: the scan repeats it instead of reading past it
+    if (lane < 30) {
+      const int pl = lane % 10, s0 = 11 * (lane / 10);
+      const double* row = sv + pl * 33;
+#pragma unroll
+      for (int q = 0; q < 11; ++q) {
+        const double x = row[min(s0 + q, ns1)];
+        emax = max_nonneg(emax, x); emin = min_nonneg(emin, x);
+      }
+    }
+    if (WRITE_VM) {
+#pragma unroll
+      for (int r = 0; r < 10; ++r) {
+        const int idx = lane + 32 * r, s = idx / 10, p = idx - 10 * s;
+        if (s <= ns1) vm[(size_t)(t0 + s) * ld_vm + pt0 + p] = sv[p * 33 + s];
+      }
+    }
+    __syncwarp();
+  }
+  emax = max_nonneg(emax, max_nonneg(__shfl_down_sync(0xffffffffu, emax, 10), __shfl_down_sync(0xffffffffu, emax, 20)));
+  emin = min_nonneg(emin, min_nonneg(__shfl_down_sync(0xffffffffu, emin, 10), __shfl_down_sync(0xffffffffu, emin, 20)));
+  if (lane < 10 && nsteps > 0) {
+    if (!WRITE_VM) {   // radicand -> von Mises
+      const double m = (lane == 0 || lane == 2 || lane == 4 || lane == 9) ? mu2 : mu1;
+      emax = m * sqrt_pos(emax);
+      emin = m * sqrt_pos(emin);
+    }
+    if (emax > env_max[pt0 + lane]) env_max[pt0 + lane] = emax;
+    if (emin < env_min[pt0 + lane]) env_min[pt0 + lane] = emin;
+  }
+}
+
 int build_solid_operators(fsr_part* p, const fsr_sam* sam, const fsr_elmdata* elm)
 {
   cudaStream_t s = p->stream;
@@ -699,7 +863,28 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
         p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.Sfrag, f.edof, f.ptoff, f.failed, f.nelt, vm_dev,
         ld_vm, p->env_max, p->env_min);
   else {
-    if (f.nsub[0] > 0) {
+    // tiles of 32 steps and more: lane = step (FSR_TET10_STEPLANE=0 keeps the (corner, step) kernels, A/B and cross-check)
+    const bool steplane = !(getenv("FSR_TET10_STEPLANE") && atoi(getenv("FSR_TET10_STEPLANE")) == 0);
+    const bool sl = steplane && nsteps >= 32;
+    if (sl && f.nsub[0] > 0) {
+      if (vm_dev)
+        k2_tet10_steplane_vm_kernel<true, false, 4><<<(f.nsub[0] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min, nullptr);
+      else
+        k2_tet10_steplane_vm_kernel<false, false, 4><<<(f.nsub[0] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min, nullptr);
+      FSR_LAUNCH_CHECK();
+    }
+    if (sl && f.nsub[2] > 0) {
+      if (vm_dev)
+        k2_tet10_steplane_vm_kernel<true, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min, f.fast2);
+      else
+        k2_tet10_steplane_vm_kernel<false, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min, f.fast2);
+      FSR_LAUNCH_CHECK();
+    }
+    if (!sl && f.nsub[0] > 0) {
       if (vm_dev)
         k2_tet10_affine_vm_kernel<true, false, 8><<<(f.nsub[0] + 7) / 8, 256, 0, s>>>(
             p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max,
@@ -710,7 +895,7 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
             p->env_min);
       FSR_LAUNCH_CHECK();
     }
-    if (f.nsub[2] > 0) {   // curved elements, nodal evaluation: the scalar kernel with the ten inverses
+    if (!sl && f.nsub[2] > 0) {   // curved elements, nodal evaluation: the scalar kernel with the ten inverses
       if (vm_dev)
         k2_tet10_affine_vm_kernel<true, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
             p->U, (size_t)p->step_tile, nsteps, nsteps_pad, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max,

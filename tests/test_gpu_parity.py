@@ -253,6 +253,61 @@ def test_hex20_block(oracle):
     _check_part(oracle, part, nsteps=27, seed=7)
 
 
+def _envelope_only_matches(oracle, part, nsteps, seed, step_tile):
+    """envelope-only run (the kernels keep the envelope on the von Mises radicand there) against the oracle's history"""
+    b = oracle.bind_part(part)
+    Q = reduced_history(part.sam.ndim, nsteps, seed=seed)
+    vm_o, mx_o, mn_o = oracle.recover_history(b, Q)
+    rec = StressRecovery(part, step_tile=step_tile)
+    rec.recover(Q, want_history=False)
+    mx, mn = rec.envelope()
+    rec.close()
+    assert rel_err(mx, mx_o) <= TOL and rel_err(mn, mn_o) <= TOL
+
+
+def test_hex20_natural_coordinate_kernel(oracle):
+    """tiles of 32 steps and more take k2_hex20_steplane_vm_kernel (the 288 non-zero natural derivatives at the nodes with
+    compile-time coefficients, J^-1 per result point, lane = time step); curved (jittered) elements, several tiles, the
+    ragged last tile (22 steps) on the DMMA gradient kernel; the same run with the kernel switched off agrees to rounding."""
+    import os
+    part = hex20_block(3, 2, 2, ngen=5, seed=6, shuffle_eq=True)
+    vm = _check_part(oracle, part, nsteps=150, seed=7, step_tile=64)
+    os.environ["FSR_HEX20_STEPLANE"] = "0"
+    try:
+        rec = StressRecovery(part, step_tile=64)
+        vm2 = rec.recover(reduced_history(part.sam.ndim, 150, seed=7))
+        rec.close()
+    finally:
+        del os.environ["FSR_HEX20_STEPLANE"]
+    assert rel_err(vm, vm2) <= 1e-11
+    assert not np.array_equal(vm[:64], vm2[:64])   # ... by a different kernel
+    assert np.array_equal(vm[128:], vm2[128:])     # the short last tile stays on the gradient kernel
+    _envelope_only_matches(oracle, part, nsteps=97, seed=8, step_tile=0)
+    # a sheared, rotated block: the inverses are full matrices
+    part = hex20_block(2, 2, 2, ngen=4, seed=16, rny=0.45)
+    A = np.array([[0.9, 0.3, -0.2], [-0.1, 1.2, 0.4], [0.25, -0.15, 0.8]])
+    part.elm.xyz = part.elm.xyz @ A.T + np.array([3.0, -2.0, 1.0])
+    _check_part(oracle, part, nsteps=45, seed=9)
+
+
+@pytest.mark.parametrize("curved", ["none", "all"])
+def test_tet10_step_lane_kernel(oracle, curved):
+    """tiles of 32 steps and more take k2_tet10_steplane_vm_kernel (lane = time step); cross-check against the
+    (corner, step) kernels and the envelope-only mode"""
+    import os
+    part = tet10_block(3, 3, 2, ngen=5, seed=31, shuffle_eq=True, curved=curved)
+    vm = _check_part(oracle, part, nsteps=100, seed=4, step_tile=0)
+    os.environ["FSR_TET10_STEPLANE"] = "0"
+    try:
+        rec = StressRecovery(part)
+        vm2 = rec.recover(reduced_history(part.sam.ndim, 100, seed=4))
+        rec.close()
+    finally:
+        del os.environ["FSR_TET10_STEPLANE"]
+    assert rel_err(vm, vm2) <= 1e-11
+    _envelope_only_matches(oracle, part, nsteps=77, seed=5, step_tile=0)
+
+
 def test_hex20_gauss_extrapolation(oracle):
     import ctypes as C
     from oracle_bind import _dp, _D

@@ -66,7 +66,7 @@ def c3(args):
             "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
             "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2, {part.sam.ndof} DOF, n_red={ndim}, {tile} time "
                         f"steps per step, von Mises envelope (no per-step history kept)",
-            "roofline": {"kernel": "k2_tet10_vm_kernel (dense 60x30)" if os.environ.get("FSR_TET10_DENSE") else "k2_tet10_grad_vm_kernel", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK,
+            "roofline": {"kernel": "k2_tet10_vm_kernel (dense 60x30)" if os.environ.get("FSR_TET10_DENSE") else "k2_tet10_affine_vm_kernel (lane = corner x step)" if os.environ.get("FSR_TET10_STEPLANE") == "0" else "k2_tet10_steplane_vm_kernel (lane = step)", "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK,
                          "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch": k2,
                          "algorithmic_bytes_per_launch": alg,
                          "dmma_tflops_issued": (4096.0 if os.environ.get("FSR_TET10_DENSE") else 2304.0) * ntet * tile / (k2 * 1e-3) / 1e12},
@@ -75,7 +75,7 @@ def c3(args):
 
 
 def chex(args):
-    """HEX20 block (type 43, named by the north_star): von Mises envelope, gradient-form kernel."""
+    """HEX20 block (type 43, named by the north_star): von Mises envelope."""
     import torch
     from fedem_solvers_b200 import StressRecovery, load_library
     from fedem_solvers_b200.model import hex20_block, reduced_history
@@ -108,7 +108,7 @@ def chex(args):
             "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
             "workload": f"{n}x{n}x{n} HEX20 ({nel} elements, {part.sam.ndof} DOF), n_red={ndim}, {tile} time steps per step, "
                         "von Mises envelope",
-            "roofline": {"kernel": "k2_hex20_grad_vm_kernel" if not os.environ.get("FSR_HEX20_DENSE") else "k2_solid_smem_vm_kernel<20>",
+            "roofline": {"kernel": "k2_solid_smem_vm_kernel<20>" if os.environ.get("FSR_HEX20_DENSE") else "k2_bigsolid_grad_vm_kernel (DMMA gradient form)" if os.environ.get("FSR_HEX20_STEPLANE") == "0" else "k2_hex20_steplane_vm_kernel (natural derivatives at the nodes, lane = step)",
                          "bound": "hbm", "achieved": alg / (k2 * 1e-3) / 1e9, "peak": HBM_PEAK, "unit": "GB/s",
                          "frac": alg / (k2 * 1e-3) / 1e9 / HBM_PEAK, "ms_per_launch": k2, "algorithmic_bytes_per_launch": alg},
             "k1": {"ms_per_launch": k1, "tflops": 2.0 * part.sam.ndof * ndim * tile / (k1 * 1e-3) / 1e12, "peak": DGEMM_PEAK},
