@@ -192,6 +192,14 @@ def oracle_parity(part, Q2, vm_rows, sample_hist=None):
     return err, int(vm_o.size)
 
 
+def secondary_hex20():
+    """the 20-node hexahedron the north_star names beside the TET10: 250,000 elements x 256 steps per step, von Mises envelope"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs
+    r = bench_configs.chex(argparse.Namespace(hex_elements=250_000, tile=256, steps=10))
+    return {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "workload", "roofline", "k1", "gpu_launches")}
+
+
 def secondary_c5(lib, peaks):
     """config 5 at its named size: 100,000 rosettes x 100,000 steps (tiles of 256), rainflow + damage"""
     import torch
@@ -304,7 +312,7 @@ def c3_block(args, rank, world, local_rank, comm, dev, lib, max_over_ranks, sync
             "workload": f"{n}x{n}x{n} cells -> {ntet} TET10 + {nel - ntet} BEAM2 ({whole.sam.ndof} DOF), n_red={ndim}, ONE part cut into "
                         f"{world} element block(s), {tile} time steps per step, von Mises envelope; NCCL broadcast of Q per step + "
                         "gather of the envelopes inside the timed region",
-            "roofline": {"kernel": "k2_tet10_affine_vm_kernel + k2_tet10_grad_vm_kernel (rank 0 block)", "bound": "hbm",
+            "roofline": {"kernel": "k2_tet10_steplane_vm_kernel, straight-sided + curved launches (rank 0 block)", "bound": "hbm",
                          "bound_note": "FP64 pipe in fact; reported against HBM as the north_star asks",
                          "achieved": alg / (k2 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": alg / (k2 * 1e-3) / 1e9 / hbm,
                          "ms_per_launch": k2, "algorithmic_bytes_per_launch": alg},
@@ -540,6 +548,7 @@ def run_b200(args, rank, world, local_rank):
             secondary["C3_all_elements_curved"] = {k: worst[k] for k in ("value", "unit", "ms_per_step", "curved_elements", "tet10_on_rank0", "roofline",
                                                                           "k1_ms", "workload")}
             secondary["C5"] = secondary_c5(lib, peaks_json())
+            secondary["HEX20"] = secondary_hex20()
 
     if rank != 0:
         if comm:

@@ -32,7 +32,7 @@ struct GageState {
 };
 
 constexpr int K3_THREADS = 128;
-constexpr int K3_CHUNK = 32;
+constexpr int K3_CHUNK = 32;   // steps staged per pass of a block (FSR_K3_CHUNK=16: half the tile, more blocks per SM)
 constexpr int K3_TPCAP = 8;  // turning points a gage may queue between two convergent rainflow passes
 constexpr int K3_QCAP = 4;   // closed cycles a gage may queue between two convergent damage evaluations
 
@@ -79,23 +79,26 @@ __global__ void k3_init_kernel(GageState* st, int ngage, int* bins, int nbins)
   for (int k = 0; k < nbins; ++k) bins[(size_t)k * ngage + g] = 0;
 }
 
-// Stages the 32-step x 128-gage block starting at (g0, t0) of a gage-major history into
-// tile[step][gage] (row padded to 129 doubles: conflict-free both ways).
+// Stages the CHUNK-step x 128-gage block starting at (g0, t0) of a gage-major history into
+// tile[step][gage] (row padded to 129 doubles: conflict-free both ways).  A warp instruction copies CHUNK consecutive
+// steps of 32 / CHUNK gages.
+template <int CHUNK>
 __device__ __forceinline__ void stage_tile(double* tile, const double* __restrict__ hist, size_t ld, int g0,
                                            int ngage, int t0, int t1)
 {
+  constexpr int GPI = 32 / CHUNK;   // gages per instruction
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int t = t0 + lane;
+  const int ts = lane & (CHUNK - 1), t = t0 + ts, sub = lane / CHUNK;
 #pragma unroll 8
-  for (int r = 0; r < 32; ++r) {
-    const int gl = warp * 32 + r, g = g0 + gl;
-    if (g < ngage && t < t1) cp_async8(tile + lane * (K3_THREADS + 1) + gl, hist + (size_t)g * ld + t);
+  for (int r = 0; r < 32 / GPI; ++r) {
+    const int gl = warp * 32 + r * GPI + sub, g = g0 + gl;
+    if (g < ngage && t < t1) cp_async8(tile + ts * (K3_THREADS + 1) + gl, hist + (size_t)g * ld + t);
   }
 }
 
 // MODE 0: locate the first turning point (early exit once every gage of the block has one);
 // MODE 1: PVX main loop + rainflow + damage.  hist points at the sample of global step `step0`.
-template <int LAYOUT, int MODE>
+template <int LAYOUT, int MODE, int CHUNK>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, size_t ld, int ngage, int step0,
                  int nsteps, const double* __restrict__ gate_g, const double* __restrict__ curve_g,
@@ -179,19 +182,19 @@ k3_stream_kernel(GageState* __restrict__ st, const double* __restrict__ hist, si
   };
 
   if (LAYOUT == 0) {
-    const int nchunks = (nsteps + K3_CHUNK - 1) / K3_CHUNK;
+    const int nchunks = (nsteps + CHUNK - 1) / CHUNK;
     // One staging buffer per block: the kernel is latency bound (a divergent state machine per lane), so the shared
     // memory goes to occupancy -- five blocks per SM hide each other's staging waits -- rather than to double buffering
     // inside a block (r01l profile: 2 blocks/SM, 12 % of the warp slots active with two 33 KB buffers).
     for (int c = 0; c < nchunks; ++c) {
-      stage_tile(tiles, hist, ld, g0, ngage, c * K3_CHUNK, nsteps);
+      stage_tile<CHUNK>(tiles, hist, ld, g0, ngage, c * CHUNK, nsteps);
       cp_async_commit();
       cp_async_wait<0>();
       __syncthreads();
-      const int tn = min(K3_CHUNK, nsteps - c * K3_CHUNK);
+      const int tn = min(CHUNK, nsteps - c * CHUNK);
       const double* col = tiles + threadIdx.x;
       if (!idle)
-        for (int k = 0; k < tn && !idle; ++k) consume(step0 + c * K3_CHUNK + k, col[k * (K3_THREADS + 1)]);
+        for (int k = 0; k < tn && !idle; ++k) consume(step0 + c * CHUNK + k, col[k * (K3_THREADS + 1)]);
       if (MODE == 1) drain();
       // every gage of the block located: nothing left to read in this pass
       if (MODE == 0 && __syncthreads_and(idle)) break;
@@ -265,7 +268,7 @@ k3_finish_kernel(GageState* __restrict__ st, int ngage, const double* __restrict
     }
 }
 
-static size_t k3_smem(int layout) { return layout == 0 ? sizeof(double) * K3_CHUNK * (K3_THREADS + 1) : 0; }
+static size_t k3_smem(int layout, int chunk) { return layout == 0 ? sizeof(double) * chunk * (K3_THREADS + 1) : 0; }
 
 template <int MODE>
 static int launch_stream(fsr_fatigue_state* f, const double* hist, size_t ld, int layout, int step0, int nsteps,
@@ -273,16 +276,21 @@ static int launch_stream(fsr_fatigue_state* f, const double* hist, size_t ld, in
 {
   if (nsteps <= 0 || f->ngage == 0) return FSR_OK;
   const unsigned blocks = (unsigned)((f->ngage + K3_THREADS - 1) / K3_THREADS);
-  if (layout == 0)
-    if (int rc = smem_opt_in((const void*)k3_stream_kernel<0, MODE>, k3_smem(0))) return rc;
-  if (layout == 0)
-    k3_stream_kernel<0, MODE><<<blocks, K3_THREADS, k3_smem(0), s>>>(f->st, hist, ld, f->ngage, step0, nsteps, f->gate,
-                                                                     f->curve, f->edges, f->bin_size, f->nbins,
-                                                                     f->spillA, f->cap, f->bins, f->pending);
-  else
-    k3_stream_kernel<1, MODE><<<blocks, K3_THREADS, 0, s>>>(f->st, hist, ld, f->ngage, step0, nsteps, f->gate, f->curve,
-                                                            f->edges, f->bin_size, f->nbins, f->spillA, f->cap, f->bins,
-                                                            f->pending);
+  static const int chunk = (getenv("FSR_K3_CHUNK") && atoi(getenv("FSR_K3_CHUNK")) == 32) ? 32 : 16;
+  if (layout == 0 && chunk == 16) {
+    if (int rc = smem_opt_in((const void*)k3_stream_kernel<0, MODE, 16>, k3_smem(0, 16))) return rc;
+    k3_stream_kernel<0, MODE, 16><<<blocks, K3_THREADS, k3_smem(0, 16), s>>>(f->st, hist, ld, f->ngage, step0, nsteps, f->gate,
+                                                                             f->curve, f->edges, f->bin_size, f->nbins,
+                                                                             f->spillA, f->cap, f->bins, f->pending);
+  } else if (layout == 0) {
+    if (int rc = smem_opt_in((const void*)k3_stream_kernel<0, MODE, 32>, k3_smem(0, 32))) return rc;
+    k3_stream_kernel<0, MODE, 32><<<blocks, K3_THREADS, k3_smem(0, 32), s>>>(f->st, hist, ld, f->ngage, step0, nsteps, f->gate,
+                                                                             f->curve, f->edges, f->bin_size, f->nbins,
+                                                                             f->spillA, f->cap, f->bins, f->pending);
+  } else
+    k3_stream_kernel<1, MODE, 32><<<blocks, K3_THREADS, 0, s>>>(f->st, hist, ld, f->ngage, step0, nsteps, f->gate, f->curve,
+                                                                f->edges, f->bin_size, f->nbins, f->spillA, f->cap, f->bins,
+                                                                f->pending);
   FSR_LAUNCH_CHECK();
   return FSR_OK;
 }

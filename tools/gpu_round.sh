@@ -16,8 +16,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k1_expand|k2_quad_planar|k2_quad_flat|k2_shell_vm' -s 6 -c 4 \
     -o $O/${TAG}_k1_k2 -f python bench.py --steps 2 --warmup 3 $NOSEC > $O/${TAG}_ncu_k1_k2.log 2>&1
 if [ "$2" != "quick" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_tet10' -s 4 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2_tet10' -s 6 -c 2 \
     -o $O/${TAG}_tet10 -f python tools/bench_configs.py c3 --curved surface --steps 2 > $O/${TAG}_ncu_tet10.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k2_hex20_steplane' -s 3 -c 1 \
+    -o $O/${TAG}_hex20 -f python tools/bench_configs.py hex20 --steps 2 > $O/${TAG}_ncu_hex20.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'record_points_dmma' -s 2 -c 2 \
     -o $O/${TAG}_record -f python tools/bench_record.py --only all --steps 64 > $O/${TAG}_ncu_record.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k3_stream_kernel|gage_post_kernel' -s 8 -c 4 \
