@@ -53,6 +53,22 @@ FSR_HD double sn_norsok(double s, const FatigueParams& p)
   return pow(10.0, logN);
 }
 
+// Damage of one cycle, 1 / getValue(s) (FFpFatigue.C:381-396).  On the device the general pow(10, x) (an extended-precision
+// log + exp, ~3x the instructions of everything else a cycle costs) is replaced by exp10(-x): one logarithm, one exponential,
+// no division.  The branch is decided on the same logN as the reference; the value differs from 1 / pow(10, logN) by a few
+// ulp (every term of the Miner sum is positive, so the sum keeps that relative error; the tests hold 1e-10).
+FSR_HD double sn_norsok_damage(double s, const FatigueParams& p)
+{
+#ifdef __CUDA_ARCH__
+  const double ls = log10(s);
+  double logN = p.loga1 - p.m1 * ls;
+  if (!(logN < p.logN0)) logN = p.loga2 - p.m2 * ls;
+  return exp10(-logN);
+#else
+  return 1.0 / sn_norsok(s, p);
+#endif
+}
+
 // ---- locateFirstTP (FFpFatigue.C:129-163), one sample at a time -----------------------------
 struct PvxLocate {
   double deltaTP, vTP, vMin, vMax, xprev;
@@ -201,7 +217,7 @@ FSR_HD void count_cycle(double a, double b, const FatigueParams& p, CycleSink& s
   const double range = fabs(a - b);  // FFpCycle::range with toMPaScale = 1
   ++sink.ncycles;
   if (range > sink.max_range) sink.max_range = range;
-  sink.damage += 1.0 / sn_norsok(range, p);
+  sink.damage += sn_norsok_damage(range, p);
   if (bins && p.nbins > 0) {
     double q = range / p.bin_size;
     int k = q < (double)p.nbins ? (int)q : p.nbins;

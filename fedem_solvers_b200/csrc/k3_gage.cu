@@ -149,15 +149,61 @@ __device__ __forceinline__ void gage_point(const double* __restrict__ eps, size_
   }
 }
 
-// fatigue pass: no result record, one thread per (rosette, step), step fastest (coalesced eps reads and hist writes)
-__global__ void gage_post_kernel(const double* __restrict__ eps, size_t ldu, int nros, int nsteps,
-                                 const double* __restrict__ cmat, const double* __restrict__ tg,
-                                 const double* __restrict__ eps0, const int* __restrict__ ngage, double to_mpa,
-                                 double* __restrict__ hist, size_t ld_hist)
+// fatigue pass: no result record.  One thread per (rosette, PAIR of steps), steps fastest: the three strain rows are read and the
+// four series rows written as 16-byte accesses, the rosette's constants (13 doubles) are fetched once per pair; same arithmetic
+// per step as gage_point.  An odd last step takes the scalar path.
+__global__ void __launch_bounds__(256)
+gage_post_kernel(const double* __restrict__ eps, size_t ldu, int nros, int nsteps,
+                 const double* __restrict__ cmat, const double* __restrict__ tg,
+                 const double* __restrict__ eps0, const int* __restrict__ ngage, double to_mpa,
+                 double* __restrict__ hist, size_t ld_hist)
 {
+  const unsigned npair = (unsigned)(nsteps + 1) >> 1;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)nros * nsteps) return;
-  gage_point<false>(eps, ldu, (int)(idx / nsteps), (int)(idx % nsteps), cmat, tg, eps0, ngage, to_mpa, hist, ld_hist, nullptr);
+  if (idx >= (size_t)nros * npair) return;
+  const int r = (int)(idx / npair), t = 2 * (int)(idx - (size_t)r * npair);
+  if (t + 1 >= nsteps || ((ldu | ld_hist) & 1)) {
+    gage_point<false>(eps, ldu, r, t, cmat, tg, eps0, ngage, to_mpa, hist, ld_hist, nullptr);
+    if (t + 1 < nsteps) gage_point<false>(eps, ldu, r, t + 1, cmat, tg, eps0, ngage, to_mpa, hist, ld_hist, nullptr);
+    return;
+  }
+  double2 e[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double2 x = *reinterpret_cast<const double2*>(eps + (size_t)(3 * r + j) * ldu + t);
+    const double e0 = __ldg(eps0 + 3 * r + j);
+    e[j] = make_double2(x.x + e0, x.y + e0);
+  }
+  const double C11 = __ldg(cmat + 4 * r), C12 = __ldg(cmat + 4 * r + 1), C33 = __ldg(cmat + 4 * r + 2), scf = __ldg(cmat + 4 * r + 3);
+  const int ng = __ldg(ngage + r);
+  double2 s[3];
+  s[0] = make_double2(C11 * e[0].x + C12 * e[1].x, C11 * e[0].y + C12 * e[1].y);
+  s[1] = make_double2(C12 * e[0].x + C11 * e[1].x, C12 * e[0].y + C11 * e[1].y);
+  s[2] = make_double2(C33 * e[2].x, C33 * e[2].y);
+  double2 sg[3] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    if (i < ng) {
+      const double T0 = __ldg(tg + 9 * r + 3 * i), T1 = __ldg(tg + 9 * r + 3 * i + 1), T2 = __ldg(tg + 9 * r + 3 * i + 2);
+      sg[i] = make_double2(T0 * s[0].x + T1 * s[1].x + T2 * s[2].x, T0 * s[0].y + T1 * s[1].y + T2 * s[2].y);
+    }
+  double2 h0;
+  {
+    const double origo = (s[0].x + s[1].x) * 0.5, d12 = s[0].x - s[1].x;
+    const double radius = sqrt(d12 * d12 + 4.0 * s[2].x * s[2].x) * 0.5;
+    const double sp1 = origo + radius, sp2 = origo - radius;
+    h0.x = scf != 0.0 ? (fabs(sp1) > fabs(sp2) ? sp1 : sp2) * to_mpa * scf : sp1 * to_mpa;
+  }
+  {
+    const double origo = (s[0].y + s[1].y) * 0.5, d12 = s[0].y - s[1].y;
+    const double radius = sqrt(d12 * d12 + 4.0 * s[2].y * s[2].y) * 0.5;
+    const double sp1 = origo + radius, sp2 = origo - radius;
+    h0.y = scf != 0.0 ? (fabs(sp1) > fabs(sp2) ? sp1 : sp2) * to_mpa * scf : sp1 * to_mpa;
+  }
+  *reinterpret_cast<double2*>(hist + (size_t)(4 * r) * ld_hist + t) = h0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    *reinterpret_cast<double2*>(hist + (size_t)(4 * r + 1 + i) * ld_hist + t) = make_double2(sg[i].x * to_mpa, sg[i].y * to_mpa);
 }
 
 // result-record pass: a block takes 32 steps x 4 rosettes, the records are staged in shared memory and written out as contiguous
@@ -332,7 +378,8 @@ static int gage_tile(fsr_gages* g, const double* Q_dev, int ldq, int nsteps, dou
   }
   const size_t total = (size_t)g->nros * nsteps;
   if (total > 0 && !values_dev) {
-    gage_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g->eps, (size_t)g->tile, g->nros, nsteps, g->cmat,
+    const size_t pairs = (size_t)g->nros * ((nsteps + 1) / 2);
+    gage_post_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(g->eps, (size_t)g->tile, g->nros, nsteps, g->cmat,
                                                                     g->tg, g->eps0, g->ngage, g->to_mpa, g->hist,
                                                                     (size_t)g->tile);
     FSR_LAUNCH_CHECK();
