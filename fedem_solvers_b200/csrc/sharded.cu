@@ -80,16 +80,16 @@ static NcclApi* nccl_api()
 
 // ---- the cut ----------------------------------------------------------------------------------------------
 // relative cost of one element.step = the K1 rows it brings (nodal DOFs x n_red, shared with the neighbours) + its K2
-// kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R2_bench.json, R2_bench_configs.json;
+// kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R4_bench.json, R4_bench_configs.json;
 // flat quads and straight-sided TET10, the common case; the same table as partition.py)
 static double element_cost(int type)
 {
   switch (type) {
     case 24: case 22: return 50.0;   // flat regions on in-plane rows (26 K1 + 24 K2); 77 on six global rows
     case 23: case 21: return 57.0;
-    case 41: return 80.0;
+    case 41: return 54.0;    // 23 K1 + 31 K2 (step-lane kernel)
     case 42: return 240.0;
-    case 43: return 397.0;
+    case 43: return 212.0;   // 63 K1 + 149 K2 (step-lane kernel)
     case 44: return 65.0;
     case 45: return 35.0;
     case 46: return 55.0;

@@ -17,11 +17,11 @@ I32 = np.int32
 F64 = np.float64
 
 # relative cost of one element.step = K1 rows it brings (nodal DOFs x n_red, shared with neighbours)
-# + its K2 kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R2_bench.json,
-# R2_bench_configs.json: quad 26 + 24 (flat regions on in-plane rows; 39 + 38 on six global rows), TET10 24 + 56 (scalar kernels),
-# HEX20 66 + 331, triangles 59; the other types scaled by their DMMA counts).  The same table lives in csrc/sharded.cu
-# (fsr_split_elements).
-ELEMENT_COST = {24: 50.0, 22: 50.0, 23: 57.0, 21: 57.0, 41: 80.0, 42: 240.0, 43: 397.0, 44: 65.0, 45: 35.0, 46: 55.0, 11: 3.0, 31: 216.0, 32: 308.0}
+# + its K2 kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R4_bench.json,
+# R4_bench_configs.json: quad 26 + 24 (flat regions on in-plane rows; 39 + 38 on six global rows), TET10 23 + 31 (step-lane
+# kernel), HEX20 63 + 149 (step-lane kernel), triangles 58; the other types scaled by their DMMA counts).  The same table lives
+# in csrc/sharded.cu (fsr_split_elements).
+ELEMENT_COST = {24: 50.0, 22: 50.0, 23: 57.0, 21: 57.0, 41: 54.0, 42: 240.0, 43: 212.0, 44: 65.0, 45: 35.0, 46: 55.0, 11: 3.0, 31: 216.0, 32: 308.0}
 NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 31: 12, 32: 16, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
 
 
