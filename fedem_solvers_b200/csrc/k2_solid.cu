@@ -593,8 +593,8 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
 // LSU-bound), and the envelope of the ten result points lives in registers.  When the history is written, the 10 x 32
 // values of a tile are turned through shared memory so that each step record receives its ten points as one 80-byte piece.
 // Used for tiles of at least 32 steps; shorter tiles stay on the (corner, step) kernel.
-template <bool WRITE_VM, bool CURVED, int NW>
-__global__ void __launch_bounds__(NW * 32, CURVED ? 3 : 4)
+template <bool WRITE_VM, bool CURVED, int NW, int MINB = (CURVED ? 3 : 4)>
+__global__ void __launch_bounds__(NW * 32, MINB)
 k2_tet10_steplane_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, const double* __restrict__ fast,
                             const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist,
                             const int* __restrict__ list, double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
@@ -866,24 +866,22 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
     // tiles of 32 steps and more: lane = step (FSR_TET10_STEPLANE=0 keeps the (corner, step) kernels, A/B and cross-check)
     const bool steplane = !(getenv("FSR_TET10_STEPLANE") && atoi(getenv("FSR_TET10_STEPLANE")) == 0);
     const bool sl = steplane && nsteps >= 32;
+    // FSR_TET10_MINB=5: one more block per SM (96 registers, ~40 spilled doubles per tile through L1) -- A/B
+    const bool mb = getenv("FSR_TET10_MINB") && atoi(getenv("FSR_TET10_MINB")) == 5;
+#define FSR_TET10_SL(W, C, B, N, LIST, FJ)                                                                                        \
+  k2_tet10_steplane_vm_kernel<W, C, 4, B><<<((N) + 3) / 4, 128, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, \
+                                                                        f.ptoff, (N), (LIST), vm_dev, ld_vm, p->env_max, p->env_min, FJ)
     if (sl && f.nsub[0] > 0) {
-      if (vm_dev)
-        k2_tet10_steplane_vm_kernel<true, false, 4><<<(f.nsub[0] + 3) / 4, 128, 0, s>>>(
-            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min, nullptr);
-      else
-        k2_tet10_steplane_vm_kernel<false, false, 4><<<(f.nsub[0] + 3) / 4, 128, 0, s>>>(
-            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min, nullptr);
+      if (vm_dev) { if (mb) FSR_TET10_SL(true, false, 5, f.nsub[0], f.sub[0], nullptr); else FSR_TET10_SL(true, false, 4, f.nsub[0], f.sub[0], nullptr); }
+      else { if (mb) FSR_TET10_SL(false, false, 5, f.nsub[0], f.sub[0], nullptr); else FSR_TET10_SL(false, false, 4, f.nsub[0], f.sub[0], nullptr); }
       FSR_LAUNCH_CHECK();
     }
     if (sl && f.nsub[2] > 0) {
-      if (vm_dev)
-        k2_tet10_steplane_vm_kernel<true, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
-            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min, f.fast2);
-      else
-        k2_tet10_steplane_vm_kernel<false, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
-            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min, f.fast2);
+      if (vm_dev) { if (mb) FSR_TET10_SL(true, true, 4, f.nsub[2], f.sub[2], f.fast2); else FSR_TET10_SL(true, true, 3, f.nsub[2], f.sub[2], f.fast2); }
+      else { if (mb) FSR_TET10_SL(false, true, 4, f.nsub[2], f.sub[2], f.fast2); else FSR_TET10_SL(false, true, 3, f.nsub[2], f.sub[2], f.fast2); }
       FSR_LAUNCH_CHECK();
     }
+#undef FSR_TET10_SL
     if (!sl && f.nsub[0] > 0) {
       if (vm_dev)
         k2_tet10_affine_vm_kernel<true, false, 8><<<(f.nsub[0] + 7) / 8, 256, 0, s>>>(
