@@ -422,10 +422,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -597,11 +593,8 @@ k2_tet10_affine_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, 
 // LSU-bound), and the envelope of the ten result points lives in registers.  When the history is written, the 10 x 32
 // values of a tile are turned through shared memory so that each step record receives its ten points as one 80-byte piece.
 // Used for tiles of at least 32 steps; shorter tiles stay on the (corner, step) kernel.
-// STAGED: the 30 rows of the NEXT tile are fetched with cp.async (8 bytes per lane and row: each lane copies and later reads only
-// its own step, so no barrier is involved) into a 7.5 KB buffer per warp while the current tile is computed; the buffer is free
-// again as soon as the current tile sits in registers.
-template <bool WRITE_VM, bool CURVED, int NW, int MINB = (CURVED ? 3 : 4), bool STAGED = false>
-__global__ void __launch_bounds__(NW * 32, MINB)
+template <bool WRITE_VM, bool CURVED, int NW>
+__global__ void __launch_bounds__(NW * 32, CURVED ? 3 : 4)
 k2_tet10_steplane_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps, const double* __restrict__ fast,
                             const double* __restrict__ aux, const int* __restrict__ edof, const int* __restrict__ ptoff, int nlist,
                             const int* __restrict__ list, double* __restrict__ vm, size_t ld_vm, double* __restrict__ env_max,
@@ -609,13 +602,11 @@ k2_tet10_steplane_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps
 {
   __shared__ double sv_all[NW][10 * 33];
   __shared__ unsigned so_all[CURVED ? 1 : NW][32];
-  __shared__ double stg_all[STAGED ? NW : 1][STAGED ? 30 * 32 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int il = blockIdx.x * NW + warp;
   if (il >= nlist) return;   // whole warp
   const int i = __ldg(list + il);
   double* sv = sv_all[warp];
-  double* stg = stg_all[STAGED ? warp : 0] + (STAGED ? lane : 0);
   constexpr int cn[4] = {0, 2, 4, 9};
   constexpr int mdn[4][4] = {{0, 1, 5, 6}, {1, 2, 3, 7}, {5, 3, 4, 8}, {6, 7, 8, 9}};
   constexpr int edge[6][3] = {{0, 1, 1}, {1, 2, 3}, {0, 2, 5}, {0, 3, 6}, {1, 3, 7}, {2, 3, 8}};   // corners a, b -> node
@@ -641,29 +632,12 @@ k2_tet10_steplane_vm_kernel(const double* __restrict__ U, size_t ldu, int nsteps
   }
   const double* fJ = CURVED ? fastJ + (size_t)i * 90 : nullptr;
   double emax = 0.0, emin = kHuge;   // lanes 0..29: result point lane % 10, steps 11 (lane / 10) .. + 10 of every tile
-  auto prefetch = [&](int t0) {
-    const double* Ut = U + min(t0 + lane, nsteps - 1);
-#pragma unroll
-    for (int k = 0; k < 30; ++k) {
-      const unsigned ro = CURVED ? (unsigned)__ldg(ed + k) * ldu64 : eoff[k];
-      cp_async8(stg + k * 32, Ut + ((size_t)ro << 6));
-    }
-    cp_async_commit();
-  };
-  if (STAGED && nsteps > 0) prefetch(0);
 
   for (int t0 = 0; t0 < nsteps; t0 += 32) {
     // lanes past the last step repeat it: no predicates, no zero fill, and a repeated value does not move an envelope
     const double* Ut = U + min(t0 + lane, nsteps - 1);
     double u[10][3];
-    if (STAGED) {
-      cp_async_wait<0>();
-#pragma unroll
-      for (int n = 0; n < 10; ++n)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) u[n][c] = stg[(3 * n + c) * 32];
-      if (t0 + 32 < nsteps) prefetch(t0 + 32);
-    } else if (!CURVED) {
+    if (!CURVED) {
 #pragma unroll
       for (int n = 0; n < 10; ++n)
 #pragma unroll
@@ -892,38 +866,24 @@ int launch_k2_tet10_vm(fsr_part* p, int nsteps, int nsteps_pad, double* vm_dev, 
     // tiles of 32 steps and more: lane = step (FSR_TET10_STEPLANE=0 keeps the (corner, step) kernels, A/B and cross-check)
     const bool steplane = !(getenv("FSR_TET10_STEPLANE") && atoi(getenv("FSR_TET10_STEPLANE")) == 0);
     const bool sl = steplane && nsteps >= 32;
-    // FSR_TET10_MINB=5: one more block per SM (96 registers, ~40 spilled doubles per tile through L1) -- A/B
-    const bool mb = getenv("FSR_TET10_MINB") && atoi(getenv("FSR_TET10_MINB")) == 5;
-    // FSR_TET10_STAGED=1: next tile prefetched through shared memory with cp.async -- A/B
-    const bool stg = getenv("FSR_TET10_STAGED") && atoi(getenv("FSR_TET10_STAGED")) != 0;
-#define FSR_TET10_SL(W, C, B, N, LIST, FJ)                                                                                        \
-  k2_tet10_steplane_vm_kernel<W, C, 4, B><<<((N) + 3) / 4, 128, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, \
-                                                                        f.ptoff, (N), (LIST), vm_dev, ld_vm, p->env_max, p->env_min, FJ)
-#define FSR_TET10_SLS(W, C, B, N, LIST, FJ)                                                                                             \
-  k2_tet10_steplane_vm_kernel<W, C, 4, B, true><<<((N) + 3) / 4, 128, 0, s>>>(p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, \
-                                                                              f.ptoff, (N), (LIST), vm_dev, ld_vm, p->env_max, p->env_min, FJ)
-    if (sl && stg) {
-      if (f.nsub[0] > 0) {
-        if (vm_dev) FSR_TET10_SLS(true, false, 4, f.nsub[0], f.sub[0], nullptr); else FSR_TET10_SLS(false, false, 4, f.nsub[0], f.sub[0], nullptr);
-        FSR_LAUNCH_CHECK();
-      }
-      if (f.nsub[2] > 0) {
-        if (vm_dev) FSR_TET10_SLS(true, true, 3, f.nsub[2], f.sub[2], f.fast2); else FSR_TET10_SLS(false, true, 3, f.nsub[2], f.sub[2], f.fast2);
-        FSR_LAUNCH_CHECK();
-      }
-    }
-    if (sl && !stg && f.nsub[0] > 0) {
-      if (vm_dev) { if (mb) FSR_TET10_SL(true, false, 5, f.nsub[0], f.sub[0], nullptr); else FSR_TET10_SL(true, false, 4, f.nsub[0], f.sub[0], nullptr); }
-      else { if (mb) FSR_TET10_SL(false, false, 5, f.nsub[0], f.sub[0], nullptr); else FSR_TET10_SL(false, false, 4, f.nsub[0], f.sub[0], nullptr); }
+    if (sl && f.nsub[0] > 0) {
+      if (vm_dev)
+        k2_tet10_steplane_vm_kernel<true, false, 4><<<(f.nsub[0] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min, nullptr);
+      else
+        k2_tet10_steplane_vm_kernel<false, false, 4><<<(f.nsub[0] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[0], f.sub[0], vm_dev, ld_vm, p->env_max, p->env_min, nullptr);
       FSR_LAUNCH_CHECK();
     }
-    if (sl && !stg && f.nsub[2] > 0) {
-      if (vm_dev) { if (mb) FSR_TET10_SL(true, true, 4, f.nsub[2], f.sub[2], f.fast2); else FSR_TET10_SL(true, true, 3, f.nsub[2], f.sub[2], f.fast2); }
-      else { if (mb) FSR_TET10_SL(false, true, 4, f.nsub[2], f.sub[2], f.fast2); else FSR_TET10_SL(false, true, 3, f.nsub[2], f.sub[2], f.fast2); }
+    if (sl && f.nsub[2] > 0) {
+      if (vm_dev)
+        k2_tet10_steplane_vm_kernel<true, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min, f.fast2);
+      else
+        k2_tet10_steplane_vm_kernel<false, true, 4><<<(f.nsub[2] + 3) / 4, 128, 0, s>>>(
+            p->U, (size_t)p->step_tile, nsteps, f.fast, f.aux, f.edof, f.ptoff, f.nsub[2], f.sub[2], vm_dev, ld_vm, p->env_max, p->env_min, f.fast2);
       FSR_LAUNCH_CHECK();
     }
-#undef FSR_TET10_SL
-#undef FSR_TET10_SLS
     if (!sl && f.nsub[0] > 0) {
       if (vm_dev)
         k2_tet10_affine_vm_kernel<true, false, 8><<<(f.nsub[0] + 7) / 8, 256, 0, s>>>(

@@ -308,35 +308,6 @@ def test_tet10_step_lane_kernel(oracle, curved):
     _envelope_only_matches(oracle, part, nsteps=77, seed=5, step_tile=0)
 
 
-@pytest.mark.parametrize("switch", ["FSR_TET10_STAGED=1", "FSR_TET10_MINB=5"])
-def test_tet10_step_lane_variants(oracle, switch):
-    """the A/B variants of the step-lane kernel (next tile prefetched with cp.async through shared memory; one more block
-    per SM) do the same arithmetic: identical histories and envelopes, with and without the history written, on a ragged
-    number of steps and a part that mixes straight-sided and curved elements"""
-    import os
-    part = tet10_block(3, 3, 3, ngen=5, seed=33, shuffle_eq=True, curved="surface")
-    Q = reduced_history(part.sam.ndim, 109, seed=6)
-    rec = StressRecovery(part)
-    vm = rec.recover(Q)
-    mx, mn = rec.envelope()
-    rec.close()
-    key, val = switch.split("=")
-    os.environ[key] = val
-    try:
-        rec = StressRecovery(part)
-        vm2 = rec.recover(Q)
-        mx2, mn2 = rec.envelope()
-        rec.close()
-        rec = StressRecovery(part)
-        rec.recover(Q, want_history=False)
-        mx3, mn3 = rec.envelope()
-        rec.close()
-    finally:
-        del os.environ[key]
-    assert np.array_equal(vm, vm2) and np.array_equal(mx, mx2) and np.array_equal(mn, mn2)
-    assert rel_err(mx3, mx) <= 1e-14 and rel_err(mn3, mn) <= 1e-14
-
-
 def test_hex20_gauss_extrapolation(oracle):
     import ctypes as C
     from oracle_bind import _dp, _D
