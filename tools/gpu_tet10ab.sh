@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of the step-lane TET10 kernel variants on config 3 (bench_configs c3): default, cp.async-staged prefetch, one more block per SM.
+# A/B of step-lane TET10 kernel variants on config 3 (R4 visit; the cp.async-staged and 96-register variants it switched on were
+# measured slower and removed again -- see DESIGN.md section 10; kept as the record of how the numbers were taken).
 TAG=${1:-R4ab}
 O=gpurun_out
 mkdir -p $O
