@@ -23,6 +23,8 @@
 #include <deque>
 #include <mutex>
 #include <string>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/uio.h>
 #include <thread>
 #include <unistd.h>
@@ -424,6 +426,7 @@ struct fsr_rdb {
   fsr_part* part = nullptr;            // devs[0].part
   FILE* f = nullptr;
   int fd = -1;
+  int mfd = -1;                        // second descriptor (O_RDWR) for the mapped writes, -1 = pwritev path
   long long data_pos = 0;              // file offset of the next step record
   std::string header, path;
   RecLayout L{};
@@ -468,6 +471,7 @@ struct fsr_rdb {
       cv.notify_all();
       writer.join();
     }
+    if (mfd >= 0) close(mfd);
     if (f) fclose(f);
     for (RdbDev& d : devs) {
       cudaSetDevice(d.part->device);
@@ -523,6 +527,41 @@ static std::string write_step_range(int fd, long long pos, const char* keys, con
   return std::string();
 }
 
+// The same records through a shared mapping of the file: the file is extended to the end of the tile, the window is mapped and
+// `nthreads` threads copy equal BYTE ranges of the record stream (12-byte key + payload per step) into it.  write() / pwritev()
+// hold the inode lock while they copy into the page cache, so concurrent writers to one file do not add up; page faults on a
+// shared mapping do (per-VMA locks), and the copy is what the file stage consists of.  Returns "!" when the mapping cannot be
+// set up (the caller falls back to pwritev), an error text, or nothing.
+static std::string write_steps_mapped(int mfd, long long pos, const char* keys, const char* payload, size_t rec_bytes, int nt,
+                                      int nthreads, const std::string& path)
+{
+  const long long step_bytes = 12 + (long long)rec_bytes, total = step_bytes * nt;
+  if (total == 0) return std::string();
+  if (ftruncate(mfd, pos + total) != 0) return "!";
+  const long long page = sysconf(_SC_PAGESIZE), map0 = pos / page * page;
+  const size_t len = (size_t)(pos + total - map0);
+  char* m = (char*)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, mfd, (off_t)map0);
+  if (m == MAP_FAILED) return "!";
+  char* base = m + (pos - map0);
+  auto copy_range = [&](long long a, long long b) {   // bytes [a, b) of the record stream
+    while (a < b) {
+      const long long t = a / step_bytes, o = a - t * step_bytes;
+      const long long n = std::min(b - a, (o < 12 ? 12 : step_bytes) - o);
+      memcpy(base + a, o < 12 ? keys + 12 * t + o : payload + rec_bytes * (size_t)t + (o - 12), (size_t)n);
+      a += n;
+    }
+  };
+  const int nw = (int)std::max<long long>(1, std::min<long long>(nthreads, total >> 20));   // at least 1 MiB per thread
+  std::vector<std::thread> th;
+  for (int w = 0; w < nw; ++w) {
+    const long long a = total * w / nw, b = total * (w + 1) / nw;
+    if (w + 1 < nw) th.emplace_back(copy_range, a, b); else copy_range(a, b);
+  }
+  for (std::thread& t : th) t.join();
+  if (munmap(m, len) != 0) return path + ": write error: " + strerror(errno);
+  return std::string();
+}
+
 // The writer: waits for the device-to-host copies of a buffer, then appends its step records; the copy into the page cache
 // is what takes the time, so the steps of a tile are split over a few helper threads writing at their own file offsets.
 void fsr_rdb::writer_main()
@@ -550,7 +589,13 @@ void fsr_rdb::writer_main()
       a = std::max(a, ai); c = std::max(c, ci); k1 = std::max(k1, ki);
     }
     const auto t0 = std::chrono::steady_clock::now();
-    if (err.empty()) {
+    bool mapped = false;
+    if (err.empty() && mfd >= 0) {
+      const std::string e = write_steps_mapped(mfd, data_pos, job.keys.data(), (const char*)host[job.buf], rec_bytes, job.nt, nwriters, path);
+      if (e == "!") { close(mfd); mfd = -1; }   // no mapping on this file system: pwritev from here on
+      else { mapped = true; err = e; if (err.empty()) data_pos += (12 + (long long)rec_bytes) * job.nt; }
+    }
+    if (err.empty() && !mapped) {
       const int nw = std::max(1, std::min(nwriters, job.nt));
       std::vector<std::string> errs((size_t)nw);
       std::vector<std::thread> th;
@@ -1000,6 +1045,8 @@ static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const 
   const unsigned hc = std::thread::hardware_concurrency();
   r->nwriters = (int)std::max(1u, std::min(8u, hc / 2));
   if (const char* e = getenv("FSR_RDB_WRITERS")) r->nwriters = std::max(1, atoi(e));
+  // FSR_RDB_MMAP=1: step records copied into a shared mapping of the file by the helper threads instead of pwritev (A/B)
+  if (getenv("FSR_RDB_MMAP") && atoi(getenv("FSR_RDB_MMAP")) != 0) r->mfd = open(r->path.c_str(), O_RDWR);
   r->writer = std::thread(&fsr_rdb::writer_main, r);
   *out = r;
   return FSR_OK;

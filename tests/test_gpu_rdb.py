@@ -215,6 +215,20 @@ def test_pipeline_with_many_small_tiles(oracle, tmp_path, monkeypatch):
     _check(oracle, part, tmp_path, out_mask(stress=True, vmStress=True, minPStress=True), True, nsteps=19)
 
 
+def test_pipeline_with_mapped_file_writes(oracle, tmp_path, monkeypatch):
+    """FSR_RDB_MMAP=1: the step records are copied into a shared mapping of the file by the helper threads (byte ranges that
+    cut through keys and records) instead of pwritev; same files, checked value by value like every other case"""
+    monkeypatch.setenv("FSR_RDB_MMAP", "1")
+    monkeypatch.setenv("FSR_RDB_TILE", "8")
+    monkeypatch.setenv("FSR_RDB_WRITERS", "3")
+    part = plate_part(8, 7, ngen=5, seed=9, tri_fraction=0.4, warp=0.02)
+    mask = out_mask(SR=True, stress=True, strain=True, vmStress=True, maxPStress=True, deformation=True)
+    _check(oracle, part, tmp_path, mask, False, nsteps=45, total=True)
+    monkeypatch.delenv("FSR_RDB_TILE")
+    part = hex20_block(2, 1, 1, ngen=3, seed=10)
+    _check(oracle, part, tmp_path, out_mask(stress=True, vmStress=True, minPStress=True), True, nsteps=19)
+
+
 def test_solver_recovery_switches_and_frs3_files(oracle, tmp_path):
     """-recovery / -partVMStress / -partDeformation / -frs3file of the dynamics solver (solverInterface.C:447-452) over the
     part registry: state arrays only for -partVMStress >= 2 (getStressSize: -1 otherwise), one frs file per recovered part

@@ -65,11 +65,11 @@ def parse_log(text):
     return out
 
 
-def run(exe, d, opts, rdbfile, stotm=1.0e9):
+def run(exe, d, opts, rdbfile, stotm=1.0e9, env=None):
     cmd = [exe, "-cwd", d, "-linkfile", "plate.ftl", "-samfile", "plate_SAM.fsm", "-fsifile", "fedem_solver.fsi", "-frsfile", "th_p_1.frs",
            "-rdbfile", rdbfile, "-statm", "0", "-stotm", repr(stotm), "-tinc", "0"] + opts
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, **(env or {})))
     wall = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError(r.stdout[-2000:] + r.stderr[-2000:])
@@ -116,6 +116,8 @@ def main():
     ap.add_argument("--all-steps", type=int, default=200, help="time steps of the every-measure run (its file is 14x larger per step)")
     ap.add_argument("--shm", action="store_true", help="also write the results database to /dev/shm (no disk in the way)")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--writer-ab", action="store_true", help="every -vmStress run twice: pwritev helpers and FSR_RDB_MMAP=1 (mapped file)")
+    ap.add_argument("--skip-all", action="store_true", help="no every-measure run")
     args = ap.parse_args()
     exe = os.path.join(ROOT, "fedem_solvers_b200", "bin", "fedem_stress")
     d = args.dir or tempfile.mkdtemp(prefix="bench_cli_")
@@ -129,18 +131,21 @@ def main():
         targets = [("disk", os.path.join(d, "plate.frs"))]
         if args.shm and os.path.isdir("/dev/shm"):
             targets.append(("shm", "/dev/shm/bench_cli_plate.frs"))
-        for where, rdbfile in targets:
-            wall, split = run(exe, d, ["-vmStress"], rdbfile)
+        variants = [("pwritev", {"FSR_RDB_MMAP": "0"}), ("mmap", {"FSR_RDB_MMAP": "1"})] if args.writer_ab else [("default", {})]
+        for where, rdbfile, (wname, wenv) in [(a, b, v) for a, b in targets for v in variants]:
+            wall, split = run(exe, d, ["-vmStress"], rdbfile, env=wenv)
             out = rdbfile.replace(".frs", "_1.frs")
-            line = dict(common, config="cli-vmStress", results_database=where, steps=args.steps, value=nel * args.steps / wall, seconds_wall=wall,
+            line = dict(common, config="cli-vmStress", results_database=where, writer=wname, steps=args.steps, value=nel * args.steps / wall, seconds_wall=wall,
                         split=split, file_mb=os.path.getsize(out) / 1e6,
                         workload=f"bin/fedem_stress -vmStress: {args.nx}x{args.ny} ANDES quads, n_red={part.sam.ndim}, {args.steps} steps -> .frs on {where}")
-            if not args.no_parity and where == "disk":
+            if not args.no_parity and where == "disk" and wname != "pwritev":
                 line["parity_max_rel_vs_oracle_float_file"] = check_parity(d, part, base, hist, out, args.steps)
             print(json.dumps(line), flush=True)
             os.remove(out)
         # every measure + tensors + stress resultants (J2: the full-output path), fewer steps
         ns = min(args.all_steps, args.steps)
+        if args.skip_all:
+            return
         wall, split = run(exe, d, ALL, os.path.join(d, "plate_all.frs"), stotm=0.001 * (ns - 1) + 0.0005)
         out = os.path.join(d, "plate_all_1.frs")
         print(json.dumps(dict(common, config="cli-all-measures", results_database="disk", steps=ns, value=nel * ns / wall, seconds_wall=wall,
