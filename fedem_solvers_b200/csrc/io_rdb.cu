@@ -543,7 +543,15 @@ static std::string write_steps_mapped(int mfd, long long pos, const char* keys, 
   char* m = (char*)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, mfd, (off_t)map0);
   if (m == MAP_FAILED) return "!";
   char* base = m + (pos - map0);
+  static const bool populate = !(getenv("FSR_RDB_POPULATE") && atoi(getenv("FSR_RDB_POPULATE")) == 0);
   auto copy_range = [&](long long a, long long b) {   // bytes [a, b) of the record stream
+#ifdef MADV_POPULATE_WRITE
+    if (populate) {   // the pages of this thread's range in one call instead of one fault per 4 KiB (Linux >= 5.14; ignored otherwise)
+      char* p0 = (char*)((uintptr_t)(base + a) / (uintptr_t)page * (uintptr_t)page);
+      if (p0 < m) p0 = m;
+      madvise(p0, (size_t)(base + b - p0), MADV_POPULATE_WRITE);
+    }
+#endif
     while (a < b) {
       const long long t = a / step_bytes, o = a - t * step_bytes;
       const long long n = std::min(b - a, (o < 12 ? 12 : step_bytes) - o);

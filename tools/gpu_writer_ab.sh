@@ -3,7 +3,7 @@
 TAG=${1:-R4wr}
 O=gpurun_out
 mkdir -p $O
-timeout 300 python -m pytest tests/test_gpu_rdb.py -m gpu -x -q -k "pipeline" > $O/${TAG}_pytest.log 2>&1; echo "rc=$?" >> $O/${TAG}_pytest.log
+timeout 300 python -m pytest tests/test_gpu_rdb.py -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "rc=$?" >> $O/${TAG}_pytest.log
 timeout 600 python tools/bench_cli.py --nx 500 --ny 500 --steps 2000 --shm --writer-ab --skip-all > $O/${TAG}_cli.json 2> $O/${TAG}_cli.err
 tail -3 $O/${TAG}_pytest.log; tail -3 $O/${TAG}_cli.err
 python - $O/${TAG}_cli.json <<'P'
