@@ -25,6 +25,7 @@
 #include <string>
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/statvfs.h>
 #include <sys/uio.h>
 #include <thread>
 #include <unistd.h>
@@ -537,21 +538,17 @@ static std::string write_steps_mapped(int mfd, long long pos, const char* keys, 
 {
   const long long step_bytes = 12 + (long long)rec_bytes, total = step_bytes * nt;
   if (total == 0) return std::string();
+  // a full file system would show up as SIGBUS inside the copy: ask first (ftruncate only makes a hole)
+  struct statvfs vfs;
+  if (fstatvfs(mfd, &vfs) == 0 && (unsigned long long)vfs.f_bavail * vfs.f_frsize < (unsigned long long)total + (1ull << 20))
+    return path + ": write error: " + strerror(ENOSPC);
   if (ftruncate(mfd, pos + total) != 0) return "!";
   const long long page = sysconf(_SC_PAGESIZE), map0 = pos / page * page;
   const size_t len = (size_t)(pos + total - map0);
   char* m = (char*)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, mfd, (off_t)map0);
   if (m == MAP_FAILED) return "!";
   char* base = m + (pos - map0);
-  static const bool populate = !(getenv("FSR_RDB_POPULATE") && atoi(getenv("FSR_RDB_POPULATE")) == 0);
   auto copy_range = [&](long long a, long long b) {   // bytes [a, b) of the record stream
-#ifdef MADV_POPULATE_WRITE
-    if (populate) {   // the pages of this thread's range in one call instead of one fault per 4 KiB (Linux >= 5.14; ignored otherwise)
-      char* p0 = (char*)((uintptr_t)(base + a) / (uintptr_t)page * (uintptr_t)page);
-      if (p0 < m) p0 = m;
-      madvise(p0, (size_t)(base + b - p0), MADV_POPULATE_WRITE);
-    }
-#endif
     while (a < b) {
       const long long t = a / step_bytes, o = a - t * step_bytes;
       const long long n = std::min(b - a, (o < 12 ? 12 : step_bytes) - o);
@@ -1053,8 +1050,10 @@ static int rdb_create(fsr_rdb** out, const std::vector<fsr_part*>& parts, const 
   const unsigned hc = std::thread::hardware_concurrency();
   r->nwriters = (int)std::max(1u, std::min(8u, hc / 2));
   if (const char* e = getenv("FSR_RDB_WRITERS")) r->nwriters = std::max(1, atoi(e));
-  // FSR_RDB_MMAP=1: step records copied into a shared mapping of the file by the helper threads instead of pwritev (A/B)
-  if (getenv("FSR_RDB_MMAP") && atoi(getenv("FSR_RDB_MMAP")) != 0) r->mfd = open(r->path.c_str(), O_RDWR);
+  // step records copied into a shared mapping of the file by the helper threads (measured: 16 GB in 2.2 s on tmpfs, 3.4 s on the
+  // container's disk, against 4.2 s / 4.1 s with pwritev; MADV_POPULATE_WRITE and 16 threads measured slower);
+  // FSR_RDB_MMAP=0 keeps pwritev, which is also the fallback when the file cannot be mapped
+  if (!(getenv("FSR_RDB_MMAP") && atoi(getenv("FSR_RDB_MMAP")) == 0)) r->mfd = open(r->path.c_str(), O_RDWR);
   r->writer = std::thread(&fsr_rdb::writer_main, r);
   *out = r;
   return FSR_OK;

@@ -215,10 +215,11 @@ def test_pipeline_with_many_small_tiles(oracle, tmp_path, monkeypatch):
     _check(oracle, part, tmp_path, out_mask(stress=True, vmStress=True, minPStress=True), True, nsteps=19)
 
 
-def test_pipeline_with_mapped_file_writes(oracle, tmp_path, monkeypatch):
-    """FSR_RDB_MMAP=1: the step records are copied into a shared mapping of the file by the helper threads (byte ranges that
-    cut through keys and records) instead of pwritev; same files, checked value by value like every other case"""
-    monkeypatch.setenv("FSR_RDB_MMAP", "1")
+def test_pipeline_with_pwritev_file_writes(oracle, tmp_path, monkeypatch):
+    """FSR_RDB_MMAP=0: the step records go out with pwritev from the helper threads instead of copies into a shared mapping of
+    the file (the default, and what every other case runs: byte ranges that cut through keys and records); same files, checked
+    value by value like every other case"""
+    monkeypatch.setenv("FSR_RDB_MMAP", "0")
     monkeypatch.setenv("FSR_RDB_TILE", "8")
     monkeypatch.setenv("FSR_RDB_WRITERS", "3")
     part = plate_part(8, 7, ngen=5, seed=9, tri_fraction=0.4, warp=0.02)

@@ -131,9 +131,7 @@ def main():
         targets = [("disk", os.path.join(d, "plate.frs"))]
         if args.shm and os.path.isdir("/dev/shm"):
             targets.append(("shm", "/dev/shm/bench_cli_plate.frs"))
-        variants = [("pwritev", {"FSR_RDB_MMAP": "0"}), ("mmap", {"FSR_RDB_MMAP": "1"}),
-                    ("mmap-nopopulate", {"FSR_RDB_MMAP": "1", "FSR_RDB_POPULATE": "0"}),
-                    ("mmap-16", {"FSR_RDB_MMAP": "1", "FSR_RDB_WRITERS": "16"})] if args.writer_ab else [("default", {})]
+        variants = [("pwritev", {"FSR_RDB_MMAP": "0"}), ("mmap", {"FSR_RDB_MMAP": "1"})] if args.writer_ab else [("default", {})]
         for where, rdbfile, (wname, wenv) in [(a, b, v) for a, b in targets for v in variants]:
             wall, split = run(exe, d, ["-vmStress"], rdbfile, env=wenv)
             out = rdbfile.replace(".frs", "_1.frs")
