@@ -166,6 +166,18 @@ def main():
         dist.all_gather(allt, t)
     else:
         allt = [t]
+    # the library's own per-piece K1 / K2 times (CUDA events on the part's stream): what the cost table is calibrated with
+    mine_t = []
+    for pc in pieces:
+        lt = pc["rec"].last_timing()
+        nt = max(1, int(lt["tiles"]))   # sums over the timed tiles of the ring
+        mine_t.append(dict(part=pc["part"], elements=int(pc["nel"]), k1_ms=round(float(lt["k1_ms"]) / nt, 4), k2_ms=round(float(lt["k2_ms"]) / nt, 4),
+                           ps_per_element_step=round(1e9 * float(lt["k1_ms"] + lt["k2_ms"]) / nt / max(1, pc["nel"] * tile), 2)))
+    piece_t = [None] * world
+    if world > 1:
+        dist.all_gather_object(piece_t, mine_t)
+    else:
+        piece_t = [mine_t]
     if rank == 0:
         comp = [float(x[0]) for x in allt]
         tot = max(float(x[1]) for x in allt)
@@ -178,6 +190,7 @@ def main():
                          if args.parts == "c4" else f"one part, {nel_total} elements (TET10 + 2 % beams), cut into element blocks, ") +
                         f"{tile} time steps per step, von Mises envelopes gathered to rank 0",
             "rank_compute_ms_per_step": [c / steps for c in comp],
+            "pieces_per_rank": piece_t,
             "load_imbalance": max(comp) / (sum(comp) / len(comp)) - 1.0,
             "planned_load_share": [float(l / sum(loads)) for l in loads],
             "plan": [[(ip, round(f0, 4), round(f1, 4)) for ip, f0, f1 in it] for it in items],
