@@ -166,12 +166,26 @@ def main():
         dist.all_gather(allt, t)
     else:
         allt = [t]
+    # one more (untimed) step with an event between the pieces: the stream time each piece really takes, gaps included
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(pieces) + 2)]
+    qx = Q[(warm + steps - 1) * tile:(warm + steps) * tile]
+    evs[0].record()
+    if world > 1:
+        comm.broadcast(qx.data_ptr(), qx.numel(), 0, stream.cuda_stream)
+    evs[1].record()
+    for k, pc in enumerate(pieces):
+        ip = pc["part"]
+        pc["rec"].recover_dev(qx[:, int(off[ip]):int(off[ip + 1])].data_ptr(), int(off[-1]), tile, None, 0, stream.cuda_stream)
+        evs[k + 2].record()
+    torch.cuda.synchronize()
+    bracket = [evs[k + 1].elapsed_time(evs[k + 2]) for k in range(len(pieces))]
+    bcast_ms = evs[0].elapsed_time(evs[1])
     # the library's own per-piece K1 / K2 times (CUDA events on the part's stream): what the cost table is calibrated with
     mine_t = []
     for pc in pieces:
         lt = pc["rec"].last_timing()
         nt = max(1, int(lt["tiles"]))   # sums over the timed tiles of the ring
-        mine_t.append(dict(part=pc["part"], elements=int(pc["nel"]), k1_ms=round(float(lt["k1_ms"]) / nt, 4), k2_ms=round(float(lt["k2_ms"]) / nt, 4),
+        mine_t.append(dict(part=pc["part"], elements=int(pc["nel"]), stream_ms=round(bracket[len(mine_t)], 4), bcast_ms=round(bcast_ms, 4), k1_ms=round(float(lt["k1_ms"]) / nt, 4), k2_ms=round(float(lt["k2_ms"]) / nt, 4),
                            ps_per_element_step=round(1e9 * float(lt["k1_ms"] + lt["k2_ms"]) / nt / max(1, pc["nel"] * tile), 2)))
     piece_t = [None] * world
     if world > 1:
