@@ -113,14 +113,23 @@ def main():
         Q.copy_(torch.from_numpy(np.ascontiguousarray(Qh)))
     setup = time.time() - t0
 
-    def step(i):
+    step_ev = []   # (before the broadcast, after it, after the pieces) of every timed step
+
+    def step(i, timed=False):
         q = Q[i * tile:(i + 1) * tile]
+        if timed:
+            step_ev.append([torch.cuda.Event(enable_timing=True) for _ in range(3)])
+            step_ev[-1][0].record()
         if world > 1:
             comm.broadcast(q.data_ptr(), q.numel(), 0, stream.cuda_stream)
+        if timed:
+            step_ev[-1][1].record()
         for pc in pieces:
             ip = pc["part"]
             qp = q[:, int(off[ip]):int(off[ip + 1])]      # [tile, ndim] view with row stride sum(ndim)
             pc["rec"].recover_dev(qp.data_ptr(), int(off[-1]), tile, None, 0, stream.cuda_stream)
+        if timed:
+            step_ev[-1][2].record()
 
     state = {}
 
@@ -152,7 +161,7 @@ def main():
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     for i in range(steps):
-        step(warm + i)
+        step(warm + i, timed=True)
     e1.record()
     gather()
     e2.record()
@@ -187,6 +196,8 @@ def main():
         nt = max(1, int(lt["tiles"]))   # sums over the timed tiles of the ring
         mine_t.append(dict(part=pc["part"], elements=int(pc["nel"]), stream_ms=round(bracket[len(mine_t)], 4), bcast_ms=round(bcast_ms, 4), k1_ms=round(float(lt["k1_ms"]) / nt, 4), k2_ms=round(float(lt["k2_ms"]) / nt, 4),
                            ps_per_element_step=round(1e9 * float(lt["k1_ms"] + lt["k2_ms"]) / nt / max(1, pc["nel"] * tile), 2)))
+    mine_t.append(dict(steps_bcast_ms=[round(e[0].elapsed_time(e[1]), 3) for e in step_ev],
+                       steps_pieces_ms=[round(e[1].elapsed_time(e[2]), 3) for e in step_ev]))
     piece_t = [None] * world
     if world > 1:
         dist.all_gather_object(piece_t, mine_t)
