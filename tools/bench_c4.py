@@ -159,6 +159,12 @@ def main():
         pc["rec"].timing_reset()
     lib.fsr_kernel_launches(1)
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    # the envelope resets above are synchronous host-to-device copies whose length depends on the rank's pieces: every rank
+    # starts its clock only when all of them are through (without this the ranks with small pieces spent the head start waiting
+    # at the first broadcast -- 34 ms of 270 at N = 2, read as an 8 % "load imbalance" in the lines before R4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0.record()
     for i in range(steps):
         step(warm + i, timed=True)
