@@ -231,9 +231,35 @@ static int make_block(const fsr_sam* s, const fsr_elmdata* el, const int* melcon
 static int split_elements(const fsr_sam* sam, const fsr_elmdata* elm, int nblocks, int* e_cut)
 {
   const int nel = sam->nel;
+  // a quadrilateral that shares a node with any other element type leaves the in-plane path (such nodes keep their six global
+  // rows): 77 instead of 50 (config 4's mixed plate: 64.8 ps measured = 2/3 x 58 + 1/3 x 77; the same rule as partition.py)
+  std::vector<char> mixed_node;
+  bool any_quad = false, any_other = false;
+  for (int e = 0; e < nel; ++e) {
+    const bool q = sam->melcon[e] == 24 || sam->melcon[e] == 22;
+    any_quad = any_quad || q; any_other = any_other || !q;
+  }
+  if (any_quad && any_other && sam->mpmnpc && sam->mmnpc) {
+    mixed_node.assign((size_t)sam->nnod + 1, 0);
+    for (int e = 0; e < nel; ++e)
+      if (sam->melcon[e] != 24 && sam->melcon[e] != 22)
+        for (int ip = sam->mpmnpc[e] - 1; ip < sam->mpmnpc[e + 1] - 1; ++ip) {
+          const int n = sam->mmnpc[ip];
+          if (n >= 1 && n <= sam->nnod) mixed_node[(size_t)n] = 1;
+        }
+  }
+  auto cost_of = [&](int e) {
+    const int t = sam->melcon[e];
+    if (!mixed_node.empty() && (t == 24 || t == 22))
+      for (int ip = sam->mpmnpc[e] - 1; ip < sam->mpmnpc[e + 1] - 1; ++ip) {
+        const int n = sam->mmnpc[ip];
+        if (n >= 1 && n <= sam->nnod && mixed_node[(size_t)n]) return 77.0;
+      }
+    return element_cost(t);
+  };
   std::vector<double> cum((size_t)nel + 1, 0.0);
   for (int e = 0; e < nel; ++e)
-    cum[(size_t)e + 1] = cum[(size_t)e] + ((elm && elm->elmid && elm->elmid[e] < 1) ? 0.0 : element_cost(sam->melcon[e]));
+    cum[(size_t)e + 1] = cum[(size_t)e] + ((elm && elm->elmid && elm->elmid[e] < 1) ? 0.0 : cost_of(e));
   const double total = cum[(size_t)nel];
   e_cut[0] = 0;
   for (int b = 1; b < nblocks; ++b) {

@@ -25,16 +25,36 @@ ELEMENT_COST = {24: 50.0, 22: 50.0, 23: 57.0, 21: 57.0, 41: 54.0, 42: 240.0, 43:
 NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 31: 12, 32: 16, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
 
 
-def element_costs(melcon):
+QUAD_GLOBAL_ROWS_COST = 77.0   # a quadrilateral on six global rows per node (39 K1 + 38 K2): see element_costs
+
+
+def element_costs(melcon, mpmnpc=None, mmnpc=None):
+    """Cost of every element by its type code.  With the connectivity (SAM mpmnpc / mmnpc, 1-based) a quadrilateral that shares
+    a node with any other element type (triangles, beams, solids) is charged QUAD_GLOBAL_ROWS_COST: such nodes keep their six
+    global rows, so the quadrilateral leaves the in-plane path (measured on config 4's mixed plate: 64.8 ps per element.step
+    for 2/3 triangles + 1/3 quadrilaterals = 2/3 x 58 + 1/3 x 77; the plain table said 53.5 and the rank that got the plate
+    ran 18 % longer than the others).  Fold lines inside an all-quadrilateral mesh are not looked for."""
+    melcon = np.asarray(melcon)
     c = np.zeros(len(melcon), F64)
     for t, v in ELEMENT_COST.items():
         c[melcon == t] = v
+    if mpmnpc is not None and mmnpc is not None:
+        isq = (melcon == 24) | (melcon == 22)
+        if isq.any() and not isq.all():
+            mp = np.asarray(mpmnpc, np.int64) - 1
+            nodes = np.asarray(mmnpc, np.int64) - 1
+            owner = np.repeat(np.arange(len(melcon)), np.diff(mp))
+            mixed = np.zeros(int(nodes.max()) + 1, bool)
+            mixed[nodes[~isq[owner]]] = True
+            touched = np.zeros(len(melcon), bool)
+            np.logical_or.at(touched, owner, mixed[nodes])
+            c[isq & touched] = QUAD_GLOBAL_ROWS_COST
     return c
 
 
 def split_elements(part, nblocks):
     """Contiguous (SAM order) element ranges [(e0, e1), ...] of equal summed cost."""
-    cost = element_costs(part.sam.melcon)
+    cost = element_costs(part.sam.melcon, part.sam.mpmnpc, part.sam.mmnpc)
     if part.elm.elmid is not None:
         cost = np.where(part.elm.elmid < 1, 0.0, cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
@@ -167,7 +187,7 @@ def plan_work(part_costs, nranks):
 
 def cost_fraction_to_elements(part, f0, f1):
     """Element range [e0, e1) of `part` covering the cost fractions [f0, f1) (see plan_work)."""
-    cost = element_costs(part.sam.melcon)
+    cost = element_costs(part.sam.melcon, part.sam.mpmnpc, part.sam.mmnpc)
     if part.elm.elmid is not None:
         cost = np.where(part.elm.elmid < 1, 0.0, cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])

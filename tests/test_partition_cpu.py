@@ -55,6 +55,27 @@ def test_split_balances_cost():
         assert max(loads) <= 1.02 * (cost.sum() / n) + cost.max()
 
 
+def test_quads_next_to_other_element_types_cost_the_global_row_path():
+    """a quadrilateral that shares a node with a triangle is charged the six-global-rows cost (it leaves the in-plane path);
+    an all-quadrilateral plate and a solid part are charged by type alone"""
+    from fedem_solvers_b200.partition import ELEMENT_COST, QUAD_GLOBAL_ROWS_COST
+    part = plate_part(12, 10, ngen=2, seed=2, tri_fraction=0.3, with_recovery=False)
+    s = part.sam
+    c = element_costs(s.melcon, s.mpmnpc, s.mmnpc)
+    tri_nodes = set()
+    for e in np.nonzero(s.melcon == 23)[0]:
+        tri_nodes.update(s.mmnpc[s.mpmnpc[e] - 1:s.mpmnpc[e + 1] - 1].tolist())
+    nq_global = 0
+    for e in np.nonzero(s.melcon == 24)[0]:
+        touches = bool(tri_nodes.intersection(s.mmnpc[s.mpmnpc[e] - 1:s.mpmnpc[e + 1] - 1].tolist()))
+        assert c[e] == (QUAD_GLOBAL_ROWS_COST if touches else ELEMENT_COST[24])
+        nq_global += touches
+    assert 0 < nq_global and np.all(c[s.melcon == 23] == ELEMENT_COST[23])
+    plain = plate_part(6, 5, ngen=2, seed=2, with_recovery=False).sam
+    assert np.all(element_costs(plain.melcon, plain.mpmnpc, plain.mmnpc) == ELEMENT_COST[24])
+    assert np.array_equal(element_costs(s.melcon), np.where(s.melcon == 24, ELEMENT_COST[24], ELEMENT_COST[23]))
+
+
 def test_plan_work_config4():
     """six parts of {2M, 1M, 500k, 250k, 100k, 50k} elements on 8 GPUs: divisible-load packing"""
     from fedem_solvers_b200.partition import cost_fraction_to_elements
