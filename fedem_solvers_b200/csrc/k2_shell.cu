@@ -1351,8 +1351,6 @@ static int setup_planar_quads(fsr_part* p, const fsr_sam* sam, const fsr_elmdata
   }
   for (int i : lst[0])
     if (!is_planar[(size_t)i]) flat_rest.push_back(i);
-  lst[0].swap(flat_rest);
-  lst[2].swap(planar_list);
   // row tiles of R that anything but the in-plane quadrilaterals reads (every other active element of the part)
   const int ntile = p->nrows_pad / 128;
   std::vector<unsigned char> need((size_t)ntile, 0);
@@ -1373,6 +1371,19 @@ static int setup_planar_quads(fsr_part* p, const fsr_sam* sam, const fsr_elmdata
   std::vector<int> tiles;
   for (int t = 0; t < ntile; ++t)
     if (need[(size_t)t]) tiles.push_back(t);
+  // Is it worth it?  The in-plane form saves ~14 ps of K2 per quadrilateral and step (24 instead of 38 on the global rows,
+  // profiles/R4) and costs the expansion of its own rows, ~0.068 ps per row, step and reduced DOF, minus the row tiles of R
+  // nobody reads any more.  A plate of quadrilaterals frees every tile (C2: 4 M rows instead of 6 M); quadrilaterals
+  // scattered among triangles free none and K1 would expand 4 + 6 rows per node (config 4's mixed plate: K1 at 30 instead
+  // of 18 ps per element.step).  FSR_QUAD_PLANAR=2 takes the in-plane form wherever it applies.
+  {
+    const double extra_rows = (double)nrows - 128.0 * (double)(ntile - (int)tiles.size());
+    const double k1_cost = 0.068 * (double)std::max(p->ndim, 1) * extra_rows, k2_gain = 14.0 * (double)nok;
+    const bool force = getenv("FSR_QUAD_PLANAR") && atoi(getenv("FSR_QUAD_PLANAR")) == 2;
+    if (!force && k1_cost > k2_gain) { cudaFree(f.fast2); f.fast2 = nullptr; return FSR_OK; }
+  }
+  lst[0].swap(flat_rest);
+  lst[2].swap(planar_list);
   p->planar = true;
   p->np_rows = nrows;
   p->np_rows_pad = (nrows + 127) / 128 * 128;

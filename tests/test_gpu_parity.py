@@ -151,13 +151,17 @@ def test_quads_of_flat_regions_use_inplane_rows(oracle):
     import os
     part = _folded_plate(ngen=6, seed=61, jitter=0.0, tri_fraction=0.1, shuffle_eq=True, n_constraints=2)
     nq = int((part.sam.melcon == 24).sum())
-    rec = StressRecovery(part, step_tile=64)
-    info = rec.vm_path_info()
-    rec.close()
-    assert info["quads_inplane"] > 0 and info["quads_flat"] > 0 and info["quads_dense"] == 0, info
-    assert info["quads_inplane"] + info["quads_flat"] == nq
-    assert info["inplane_rows"] % 4 == 0 and 0 < info["inplane_rows"] < 4 * part.sam.nnod
-    vm = _check_part(oracle, part, nsteps=100, seed=12, step_tile=64)
+    os.environ["FSR_QUAD_PLANAR"] = "2"    # wherever it applies: the cost rule may leave so small a part on the global rows
+    try:
+        rec = StressRecovery(part, step_tile=64)
+        info = rec.vm_path_info()
+        rec.close()
+        assert info["quads_inplane"] > 0 and info["quads_flat"] > 0 and info["quads_dense"] == 0, info
+        assert info["quads_inplane"] + info["quads_flat"] == nq
+        assert info["inplane_rows"] % 4 == 0 and 0 < info["inplane_rows"] < 4 * part.sam.nnod
+        vm = _check_part(oracle, part, nsteps=100, seed=12, step_tile=64)
+    finally:
+        del os.environ["FSR_QUAD_PLANAR"]
     os.environ["FSR_QUAD_PLANAR"] = "0"
     try:
         rec = StressRecovery(part, step_tile=64)
@@ -190,6 +194,28 @@ def test_inplane_rows_skip_the_global_expansion_of_a_flat_plate(oracle):
     vm_d = rec.recover_displacements(sv)
     assert rel_err(vm_d, vm_o) <= TOL
     rec.close()
+
+
+def test_inplane_rows_only_where_they_pay(oracle):
+    """flat quadrilaterals scattered among triangles: every row tile of R is still read by the triangles, the in-plane rows
+    would come on top (4 + 6 rows per node in K1) and cost more than the smaller quad operator saves, so the part stays on
+    the global rows; FSR_QUAD_PLANAR=2 takes the in-plane form anyway, same numbers to rounding"""
+    import os
+    part = plate_part(20, 16, ngen=40, seed=71, jitter=0.0, tri_fraction=0.5, shuffle_eq=True)
+    rec = StressRecovery(part, step_tile=64)
+    info = rec.vm_path_info()
+    rec.close()
+    assert info["quads_inplane"] == 0 and info["quads_flat"] == int((part.sam.melcon == 24).sum()), info
+    vm = _check_part(oracle, part, nsteps=70, seed=13, step_tile=64)
+    os.environ["FSR_QUAD_PLANAR"] = "2"
+    try:
+        rec = StressRecovery(part, step_tile=64)
+        assert rec.vm_path_info()["quads_inplane"] > 0
+        vm2 = rec.recover(reduced_history(part.sam.ndim, 70, seed=13))
+        rec.close()
+    finally:
+        del os.environ["FSR_QUAD_PLANAR"]
+    assert rel_err(vm, vm2) <= 1e-12
 
 
 def test_tri_quad_mixed_plate(oracle):

@@ -195,6 +195,40 @@ def ctri(args):
             "gpu_launches": int(lib.fsr_kernel_launches(0))}
 
 
+def cmixed(args):
+    """Config 4's mixed plate (half of the cells split into triangles, flat): quadrilaterals scattered among triangles; the
+    library's cost rule decides between the in-plane rows and the global rows (FSR_QUAD_PLANAR=2 forces the in-plane form)."""
+    import torch
+    from fedem_solvers_b200 import StressRecovery, load_library
+    from fedem_solvers_b200.model import plate_part, reduced_history
+    lib = load_library()
+    part = plate_part(572, 572, ngen=30, n_ext=6, seed=42, tri_fraction=0.5)
+    tile, steps, warm = args.tile, args.steps, 3
+    rec = StressRecovery(part, device=0, step_tile=((tile + 63) // 64) * 64)
+    nel, ndim = part.sam.nel, part.sam.ndim
+    stream = torch.cuda.current_stream()
+    rec.set_stream(stream.cuda_stream)
+    Q = torch.from_numpy(np.ascontiguousarray(reduced_history(ndim, tile * (steps + warm), seed=3).T)).to(torch.device("cuda", 0))
+    for i in range(warm):
+        rec.recover_dev(Q[i * tile:(i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    torch.cuda.synchronize()
+    rec.reset_envelope(); rec.timing_reset(); lib.fsr_kernel_launches(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        rec.recover_dev(Q[(warm + i) * tile:(warm + i + 1) * tile].data_ptr(), ndim, tile, None, 0, stream.cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tm = rec.last_timing()
+    k2, k1 = tm["k2_ms"] / max(tm["tiles"], 1), tm["k1_ms"] / max(tm["tiles"], 1)
+    return {"config": "MIXED", "metric": "element_timestep_stress_evals_per_sec", "value": nel * tile * steps / (ms * 1e-3),
+            "unit": "element*steps/s", "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "dtype": "f64",
+            "workload": f"572x572 cells -> {nel} ANDES triangles + quadrilaterals ({part.sam.ndof} DOF), n_red={ndim}, {tile} time steps per step, von Mises envelope",
+            "ps_per_element_step": 1e9 * (ms / steps) / (nel * tile), "k1_ms": k1, "k2_ms": k2, "vm_path": rec.vm_path_info(),
+            "quad_planar_env": os.environ.get("FSR_QUAD_PLANAR", ""), "gpu_launches": int(lib.fsr_kernel_launches(0))}
+
+
 def c5(args):
     import torch
     from fedem_solvers_b200 import StressRecovery, StrainGages, load_library
@@ -386,7 +420,7 @@ def main():
     ap.add_argument("--curved", default="all", choices=["all", "surface", "none"], help="c3: which TET10 mid-edge nodes leave the chord")
     args = ap.parse_args()
     for c in args.configs:
-        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick, "coat": ccoat, "tri": ctri}[c](args)), flush=True)
+        print(json.dumps({"c1": c1, "c1cli": c1cli, "c3": c3, "c5": c5, "hex20": chex, "thick": cthick, "coat": ccoat, "tri": ctri, "mixed": cmixed}[c](args)), flush=True)
 
 
 if __name__ == "__main__":
