@@ -79,23 +79,24 @@ static NcclApi* nccl_api()
   } while (0)
 
 // ---- the cut ----------------------------------------------------------------------------------------------
-// relative cost of one element.step = the K1 rows it brings (nodal DOFs x n_red, shared with the neighbours) + its K2
-// kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R4_bench.json, R4_bench_configs.json;
-// flat quads and straight-sided TET10, the common case; the same table as partition.py)
-static double element_cost(int type)
+// relative cost of one element.step = the K1 rows it brings (nodal DOFs x n_red, shared with the neighbours) + its K2 kernel,
+// in measured picoseconds per element.step on B200 (profiles/R4_bench.json, R4_bench_configs.json, the per-piece times of
+// R5_bench_c4_n8.json); the K1 share is quoted at n_red = 98 and scales with the reduced dimension f = n_red / 98.  Flat quads
+// and straight-sided TET10, the common case; the same table as partition.py (ELEMENT_K1 / ELEMENT_K2).
+static double element_cost(int type, double f)
 {
   switch (type) {
-    case 24: case 22: return 50.0;   // flat regions on in-plane rows (26 K1 + 24 K2); 77 on six global rows
-    case 23: case 21: return 57.0;
-    case 41: return 54.0;    // 23 K1 + 31 K2 (step-lane kernel)
-    case 42: return 240.0;
-    case 43: return 212.0;   // 63 K1 + 149 K2 (step-lane kernel)
-    case 44: return 65.0;
-    case 45: return 35.0;
-    case 46: return 55.0;
-    case 11: return 3.0;
-    case 31: return 216.0;
-    case 32: return 308.0;
+    case 24: case 22: return 24.0 + 26.0 * f;   // flat regions on in-plane rows; 38 + 39 f on six global rows
+    case 23: case 21: return 37.0 + 20.0 * f;
+    case 41: return 31.0 + 23.0 * f;     // step-lane kernel
+    case 42: return 170.0 + 70.0 * f;
+    case 43: return 149.0 + 63.0 * f;    // step-lane kernel
+    case 44: return 67.0 + 14.0 * f;
+    case 45: return 36.0 + 8.0 * f;
+    case 46: return 57.0 + 12.0 * f;
+    case 11: return 2.0 + 1.0 * f;
+    case 31: return 160.0 + 56.0 * f;
+    case 32: return 230.0 + 78.0 * f;
     default: return 0.0;
   }
 }
@@ -232,7 +233,8 @@ static int split_elements(const fsr_sam* sam, const fsr_elmdata* elm, int nblock
 {
   const int nel = sam->nel;
   // a quadrilateral that shares a node with any other element type leaves the in-plane path (such nodes keep their six global
-  // rows): 77 instead of 50 (config 4's mixed plate: 64.8 ps measured = 2/3 x 58 + 1/3 x 77; the same rule as partition.py)
+  // rows): 38 + 39 f instead of 24 + 26 f (config 4's mixed plate; the same rule as partition.py)
+  const double fred = (double)(sam->ndof2 + sam->ngen) / 98.0;
   std::vector<char> mixed_node;
   bool any_quad = false, any_other = false;
   for (int e = 0; e < nel; ++e) {
@@ -253,9 +255,9 @@ static int split_elements(const fsr_sam* sam, const fsr_elmdata* elm, int nblock
     if (!mixed_node.empty() && (t == 24 || t == 22))
       for (int ip = sam->mpmnpc[e] - 1; ip < sam->mpmnpc[e + 1] - 1; ++ip) {
         const int n = sam->mmnpc[ip];
-        if (n >= 1 && n <= sam->nnod && mixed_node[(size_t)n]) return 77.0;
+        if (n >= 1 && n <= sam->nnod && mixed_node[(size_t)n]) return 38.0 + 39.0 * fred;
       }
-    return element_cost(t);
+    return element_cost(t, fred);
   };
   std::vector<double> cum((size_t)nel + 1, 0.0);
   for (int e = 0; e < nel; ++e)

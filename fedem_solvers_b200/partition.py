@@ -16,28 +16,34 @@ from .model import SamData, ElementData, PartModel
 I32 = np.int32
 F64 = np.float64
 
-# relative cost of one element.step = K1 rows it brings (nodal DOFs x n_red, shared with neighbours)
-# + its K2 kernel, in measured picoseconds per element.step on B200 at n_red ~ 100 (profiles/R4_bench.json,
-# R4_bench_configs.json: quad 26 + 24 (flat regions on in-plane rows; 39 + 38 on six global rows), TET10 23 + 31 (step-lane
-# kernel), HEX20 63 + 149 (step-lane kernel), triangles 58; the other types scaled by their DMMA counts).  The same table lives
-# in csrc/sharded.cu (fsr_split_elements).
-ELEMENT_COST = {24: 50.0, 22: 50.0, 23: 57.0, 21: 57.0, 41: 54.0, 42: 240.0, 43: 212.0, 44: 65.0, 45: 35.0, 46: 55.0, 11: 3.0, 31: 216.0, 32: 308.0}
+# relative cost of one element.step = the K1 rows it brings (nodal DOFs x n_red, shared with the neighbours) + its K2 kernel, in
+# measured picoseconds per element.step on B200 (profiles/R4_bench.json, R4_bench_configs.json, the per-piece times of
+# R5_bench_c4_n8.json).  The K1 share is quoted at n_red = 98 and scales with the reduced dimension of the part: quad 26 + 24
+# (flat regions on in-plane rows; 39 + 38 on six global rows), TET10 23 + 31 and HEX20 63 + 149 (step-lane kernels), triangles
+# 20 + 37; linear solids 4.2 + 44.4 measured on config 4's mix at n_red = 44; the other types scaled by their DMMA counts.  With the scaling the six
+# parts of config 4 (n_red 34 ... 88) come out within 5 % of their measured times (the small ones within 11 %).  The same table
+# lives in csrc/sharded.cu (fsr_split_elements).
+ELEMENT_K1 = {24: 26.0, 22: 26.0, 23: 20.0, 21: 20.0, 41: 23.0, 42: 70.0, 43: 63.0, 44: 14.0, 45: 8.0, 46: 12.0, 11: 1.0, 31: 56.0, 32: 78.0}
+ELEMENT_K2 = {24: 24.0, 22: 24.0, 23: 37.0, 21: 37.0, 41: 31.0, 42: 170.0, 43: 149.0, 44: 67.0, 45: 36.0, 46: 57.0, 11: 2.0, 31: 160.0, 32: 230.0}
+ELEMENT_COST = {t: ELEMENT_K1[t] + ELEMENT_K2[t] for t in ELEMENT_K1}   # at n_red = 98
 NSTRP = {11: 0, 21: 6, 23: 6, 22: 8, 24: 8, 31: 12, 32: 16, 41: 10, 42: 15, 43: 20, 44: 8, 45: 4, 46: 6}
+N_RED_REF = 98.0
+
+QUAD_GLOBAL_ROWS_K1, QUAD_GLOBAL_ROWS_K2 = 39.0, 38.0   # a quadrilateral on six global rows per node: see element_costs
+QUAD_GLOBAL_ROWS_COST = QUAD_GLOBAL_ROWS_K1 + QUAD_GLOBAL_ROWS_K2
 
 
-QUAD_GLOBAL_ROWS_COST = 77.0   # a quadrilateral on six global rows per node (39 K1 + 38 K2): see element_costs
-
-
-def element_costs(melcon, mpmnpc=None, mmnpc=None):
-    """Cost of every element by its type code.  With the connectivity (SAM mpmnpc / mmnpc, 1-based) a quadrilateral that shares
-    a node with any other element type (triangles, beams, solids) is charged QUAD_GLOBAL_ROWS_COST: such nodes keep their six
-    global rows, so the quadrilateral leaves the in-plane path (measured on config 4's mixed plate: 64.8 ps per element.step
-    for 2/3 triangles + 1/3 quadrilaterals = 2/3 x 58 + 1/3 x 77; the plain table said 53.5 and the rank that got the plate
-    ran 18 % longer than the others).  Fold lines inside an all-quadrilateral mesh are not looked for."""
+def element_costs(melcon, mpmnpc=None, mmnpc=None, n_red=None):
+    """Cost of every element by its type code; n_red (the part's reduced dimension, SAM ndim) scales the K1 share.  With the
+    connectivity (SAM mpmnpc / mmnpc, 1-based) a quadrilateral that shares a node with any other element type (triangles,
+    beams, solids) is charged the six-global-rows cost: the in-plane form does not pay where other elements read the global
+    rows of the same nodes anyway (config 4's mixed plate, profiles/R5_bench_mixed_plate.json).  Fold lines inside an
+    all-quadrilateral mesh are not looked for."""
     melcon = np.asarray(melcon)
+    f = 1.0 if n_red is None else float(n_red) / N_RED_REF
     c = np.zeros(len(melcon), F64)
-    for t, v in ELEMENT_COST.items():
-        c[melcon == t] = v
+    for t in ELEMENT_K1:
+        c[melcon == t] = ELEMENT_K2[t] + ELEMENT_K1[t] * f
     if mpmnpc is not None and mmnpc is not None:
         isq = (melcon == 24) | (melcon == 22)
         if isq.any() and not isq.all():
@@ -48,13 +54,13 @@ def element_costs(melcon, mpmnpc=None, mmnpc=None):
             mixed[nodes[~isq[owner]]] = True
             touched = np.zeros(len(melcon), bool)
             np.logical_or.at(touched, owner, mixed[nodes])
-            c[isq & touched] = QUAD_GLOBAL_ROWS_COST
+            c[isq & touched] = QUAD_GLOBAL_ROWS_K2 + QUAD_GLOBAL_ROWS_K1 * f
     return c
 
 
 def split_elements(part, nblocks):
     """Contiguous (SAM order) element ranges [(e0, e1), ...] of equal summed cost."""
-    cost = element_costs(part.sam.melcon, part.sam.mpmnpc, part.sam.mmnpc)
+    cost = element_costs(part.sam.melcon, part.sam.mpmnpc, part.sam.mmnpc, part.sam.ndim)
     if part.elm.elmid is not None:
         cost = np.where(part.elm.elmid < 1, 0.0, cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
@@ -187,7 +193,7 @@ def plan_work(part_costs, nranks):
 
 def cost_fraction_to_elements(part, f0, f1):
     """Element range [e0, e1) of `part` covering the cost fractions [f0, f1) (see plan_work)."""
-    cost = element_costs(part.sam.melcon, part.sam.mpmnpc, part.sam.mmnpc)
+    cost = element_costs(part.sam.melcon, part.sam.mpmnpc, part.sam.mmnpc, part.sam.ndim)
     if part.elm.elmid is not None:
         cost = np.where(part.elm.elmid < 1, 0.0, cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])

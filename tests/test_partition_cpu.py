@@ -74,6 +74,11 @@ def test_quads_next_to_other_element_types_cost_the_global_row_path():
     plain = plate_part(6, 5, ngen=2, seed=2, with_recovery=False).sam
     assert np.all(element_costs(plain.melcon, plain.mpmnpc, plain.mmnpc) == ELEMENT_COST[24])
     assert np.array_equal(element_costs(s.melcon), np.where(s.melcon == 24, ELEMENT_COST[24], ELEMENT_COST[23]))
+    # the K1 share scales with the reduced dimension of the part (quoted at n_red = 98)
+    from fedem_solvers_b200.partition import ELEMENT_K1, ELEMENT_K2
+    half = element_costs(s.melcon, n_red=49)
+    assert np.allclose(half, np.where(s.melcon == 24, ELEMENT_K2[24] + 0.5 * ELEMENT_K1[24], ELEMENT_K2[23] + 0.5 * ELEMENT_K1[23]), rtol=1e-15)
+    assert all(abs(ELEMENT_COST[t] - (ELEMENT_K1[t] + ELEMENT_K2[t])) == 0 for t in ELEMENT_COST)
 
 
 def test_plan_work_config4():

@@ -80,7 +80,7 @@ def main():
     parts = build_parts(args.scale, args.parts)          # every rank builds the (seeded, identical) parts and keeps only its pieces
     costs = []
     for p in parts:
-        c = element_costs(p.sam.melcon, p.sam.mpmnpc, p.sam.mmnpc)
+        c = element_costs(p.sam.melcon, p.sam.mpmnpc, p.sam.mmnpc, p.sam.ndim)
         costs.append(float(c.sum()))
     items, loads = plan_work(costs, world)
     tile, steps, warm = args.tile, args.steps, args.warmup
