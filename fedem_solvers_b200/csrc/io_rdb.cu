@@ -538,10 +538,10 @@ static std::string write_steps_mapped(int mfd, long long pos, const char* keys, 
 {
   const long long step_bytes = 12 + (long long)rec_bytes, total = step_bytes * nt;
   if (total == 0) return std::string();
-  // a full file system would show up as SIGBUS inside the copy: ask first (ftruncate only makes a hole)
+  // a full file system would show up as SIGBUS inside the copy (ftruncate only makes a hole): ask first, and leave a tile
+  // that may not fit -- or a file system that does not say -- to pwritev, which reports ENOSPC properly
   struct statvfs vfs;
-  if (fstatvfs(mfd, &vfs) == 0 && (unsigned long long)vfs.f_bavail * vfs.f_frsize < (unsigned long long)total + (1ull << 20))
-    return path + ": write error: " + strerror(ENOSPC);
+  if (fstatvfs(mfd, &vfs) != 0 || (unsigned long long)vfs.f_bavail * vfs.f_frsize < (unsigned long long)total + (1ull << 20)) return "!";
   if (ftruncate(mfd, pos + total) != 0) return "!";
   const long long page = sysconf(_SC_PAGESIZE), map0 = pos / page * page;
   const size_t len = (size_t)(pos + total - map0);
