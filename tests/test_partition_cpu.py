@@ -107,7 +107,7 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     import oracle_bind
-    from fedem_solvers_b200.distributed import ShardedRecovery
+    from fedem_solvers_b200.partition import ShardedRecovery
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
