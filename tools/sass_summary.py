@@ -2,7 +2,7 @@
 """Opcode histogram of the hot kernels from the built objects (cuobjdump -sass), the evidence for DMMA / bulk-TMA / cp.async use.
    python tools/sass_summary.py > profiles/RNN_sass.txt      (run after build.sh; no GPU needed)"""
 import collections, re, subprocess, sys
-KERNELS = [("build/k1_expand.o", "k1_expand_kernel"), ("build/k1_expand.o", "k1_expand_slab_kernel"),
+KERNELS = [("build/k1_expand.o", "k1_expand_pipe_kernel"), ("build/k1_expand.o", "k1_expand_kernel"), ("build/k1_expand.o", "k1_expand_slab_kernel"),
            ("build/k2_shell.o", "k2_quad_planar_vm_kernel"), ("build/k2_shell.o", "k2_quad_flat_vm_kernel"),
            ("build/k2_shell.o", "k2_shell_vm_kernel"), ("build/k2_solid.o", "k2_tet10_steplane_vm_kernel"),
            ("build/k2_solid.o", "k2_tet10_affine_vm_kernel"), ("build/k2_hex20.o", "k2_hex20_steplane_vm_kernel"),
