@@ -22,8 +22,9 @@ Legs     : `value`  inputs resident in HBM, the full von Mises history of the ti
                     fsr_get_envelope_async); the per-step history stays on the device in this leg.
 Checks   : the timed part is compared with the CPU oracle (full field, first steps of the last
            tile + the history of sampled elements) -> `parity`; the run fails above 1e-10.
-Secondary: at N = 1 also config 3 (TET10 + beams) and config 5 (rosettes + rainflow) with their own
-           CPU baselines; at every N the STRONG scaling of the fixed config-3 part -> `strong_c3`.
+Secondary: at N = 1 also config 3 with every element curved, config 5 (rosettes + rainflow, the
+           reference's own compiled fatigue code as CPU arm) and the HEX20 kernel -> `secondary`; at
+           every N the STRONG scaling of the fixed config-3 part (TET10 + beams) -> `strong_c3`.
 Arms     : default           this repo's CUDA path through the C ABI (libfedem_b200.so)
            --impl reference  the reference's CPU algorithm (oracle/ restatement; the reference's
                              Fortran cannot be compiled in this image) on all host threads, on a
